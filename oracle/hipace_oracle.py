@@ -1,0 +1,1195 @@
+"""CPU oracle: a NumPy/SciPy fp64 restatement of the HiPACE++ per-zeta-slice quasi-static PIC loop.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import it.  The product path
+(hipace_b200/ + libhpb200.so) never calls into this file.
+
+Parity status: PINNED.  tests/test_oracle_golden.py checks the checksums this oracle produces
+against the reference's own golden files
+  tests/checksum/benchmarks_json/linear_wake.normalized.1Rank.json   (rtol 1e-9)
+  tests/checksum/benchmarks_json/blowout_wake_explicit.2Rank.json    (rtol 1e-9)
+(copies of the numbers are committed under tests/golden/ with the script that extracted them).
+
+Each function cites the reference file:line (relative to /root/reference/src) it restates.
+Scope: level 0, explicit Bx/By solver, depos_order_xy = 2,
+depos_derivative_type = 2, Dirichlet field boundary, no laser, no ionization, no MR,
+fixed_ppc beams, u_std = 0 plasma (no RNG anywhere).
+
+Array convention: every slice component is a 2-D array a[j + g, i + g] (x fastest) over the
+grown box [-g, n-1+g]^2, g = 2 guard cells (fields/Fields.cpp:63-64).
+"""
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+try:  # SciPy is only needed for the Poisson solve
+    from scipy.fft import dstn as _dstn
+except Exception:  # pragma: no cover
+    _dstn = None
+
+G = 2  # guard cells for depos_order_xy = 2: (order+1)/2 + 1, fields/Fields.cpp:63-64
+
+
+# --------------------------------------------------------------------------------------------
+# Input deck (subset of AMReX ParmParse + HiPACE++ parser, utils/Parser.H:316-395)
+# --------------------------------------------------------------------------------------------
+
+_CONST_SI = dict(clight=299792458.0, epsilon0=8.8541878128e-12, mu0=1.25663706212e-06,
+                 q_e=1.602176634e-19, m_e=9.1093837015e-31, m_p=1.67262192369e-27,
+                 hbar=1.054571817e-34, r_e=2.817940326204929e-15, pi=math.pi)
+
+
+def parse_deck(text: str, overrides: dict | None = None) -> dict:
+    """'prefix.key = v1 v2 ...' lines, '#' comments; later entries win (like CLI overrides)."""
+    deck: dict[str, list[str]] = {}
+    for raw in text.splitlines():
+        line = raw.split('#', 1)[0].strip()
+        if not line or '=' not in line:
+            continue
+        key, val = line.split('=', 1)
+        toks = re.findall(r'"[^"]*"|\S+', val.strip())
+        deck[key.strip()] = [t.strip('"') for t in toks]
+    for k, v in (overrides or {}).items():
+        deck[k] = [str(t) for t in (v if isinstance(v, (list, tuple)) else str(v).split())]
+    return deck
+
+
+def _eval(expr: str, deck: dict, extra: dict | None = None) -> float:
+    """Math-parser stand-in: numbers, + - * / ^, my_constants.*, built-in constants."""
+    env = dict(_CONST_SI)
+    env.update({f: getattr(math, f) for f in ('sqrt', 'exp', 'sin', 'cos', 'log', 'tanh')})
+    for k, v in deck.items():
+        if k.startswith('my_constants.'):
+            env[k.split('.', 1)[1]] = _eval(v[0], {kk: vv for kk, vv in deck.items() if kk != k})
+    env.update(extra or {})
+    return float(eval(expr.replace('^', '**'), {'__builtins__': {}}, env))
+
+
+def _get(deck, key, default=None, n=None, typ=float, alt=None):
+    v = deck.get(key)
+    if v is None and alt is not None:
+        v = deck.get(alt)
+    if v is None:
+        return default
+    if typ is str:
+        return v[0] if n is None else v
+    vals = [typ(_eval(t, deck)) for t in v]
+    return vals[0] if n is None else vals
+
+
+@dataclass
+class PhysConst:
+    """utils/Constants.H:54-81"""
+    c: float
+    ep0: float
+    mu0: float
+    q_e: float
+    m_e: float
+    m_p: float
+
+    @staticmethod
+    def make(normalized: bool) -> 'PhysConst':
+        if normalized:
+            return PhysConst(1., 1., 1., 1., 1., 1836.15267343)
+        s = _CONST_SI
+        return PhysConst(s['clight'], s['epsilon0'], s['mu0'], s['q_e'], s['m_e'], s['m_p'])
+
+
+# --------------------------------------------------------------------------------------------
+# Shape factors (particles/particles_utils/ShapeFactors.H)
+# --------------------------------------------------------------------------------------------
+
+def shape_order2(xmid):
+    """compute_single_shape_factor<false,2>, ShapeFactors.H:165-174.
+    Returns (S[3,P], leftmost cell[P])."""
+    xfloor = np.floor(xmid + 0.5)
+    xint = xmid - xfloor
+    s = np.stack([0.5 * (0.5 - xint) * (0.5 - xint),
+                  0.75 - xint * xint,
+                  0.5 * (0.5 + xint) * (0.5 + xint)])
+    return s, xfloor.astype(np.int64) - 1
+
+
+def dshape_centered_order2(xmid):
+    """single_derivative_shape_factor<2,2>, ShapeFactors.H:405-430.
+    Returns (S[5,P], dS[5,P] (already '-sdx'), leftmost cell[P])."""
+    xm = xmid + 0.5
+    xfloor = np.floor(xm)
+    xint = xm - xfloor
+    x2 = xint * xint
+    z = np.zeros_like(xint)
+    s = np.stack([z,
+                  0.5 * x2 - xint + 0.5,
+                  -x2 + xint + 0.5,
+                  0.5 * x2,
+                  z])
+    sdx = np.stack([-0.25 * x2 + 0.5 * xint - 0.25,
+                    0.5 * x2 - 0.5 * xint - 0.25,
+                    0.25 - 0.5 * xint,
+                    -0.5 * x2 + 0.5 * xint + 0.25,
+                    0.25 * x2])
+    return s, -sdx, xfloor.astype(np.int64) - 2
+
+
+def dshape_nodal_order2(xmid):
+    """single_derivative_shape_factor<1,2>, ShapeFactors.H:305-329.
+    Returns (S[4,P], dS[4,P] (already '-sdx'), leftmost cell[P])."""
+    xfloor = np.floor(xmid)
+    xint = xmid - xfloor
+    x2 = xint * xint
+    lo = xint < 0.5
+    z = np.zeros_like(xint)
+    s = np.stack([np.where(lo, 0.5 * x2 - 0.5 * xint + 0.125, z),
+                  np.where(lo, 0.75 - x2, 0.5 * x2 - 1.5 * xint + 1.125),
+                  np.where(lo, 0.5 * x2 + 0.5 * xint + 0.125, -x2 + 2 * xint - 0.25),
+                  np.where(lo, z, 0.5 * x2 - 0.5 * xint + 0.125)])
+    sdx = np.stack([-0.5 * x2 + xint - 0.5,
+                    1.5 * x2 - 2 * xint,
+                    -1.5 * x2 + xint + 0.5,
+                    0.5 * x2])
+    return s, -sdx, xfloor.astype(np.int64) - 1
+
+
+# --------------------------------------------------------------------------------------------
+# Geometry and field storage
+# --------------------------------------------------------------------------------------------
+
+@dataclass
+class Geometry:
+    nx: int
+    ny: int
+    nz: int
+    lo: tuple
+    hi: tuple
+
+    @property
+    def dx(self):
+        return (self.hi[0] - self.lo[0]) / self.nx
+
+    @property
+    def dy(self):
+        return (self.hi[1] - self.lo[1]) / self.ny
+
+    @property
+    def dz(self):
+        return (self.hi[2] - self.lo[2]) / self.nz
+
+    def pos_offset(self, d):
+        """GetPosOffset, fields/Fields.H:71-77, with the grown box [-g, n-1+g] (or the valid box:
+        both give lo + dx/2 up to round-off; we follow the formula literally)."""
+        n = (self.nx, self.ny, self.nz)[d]
+        dd = (self.dx, self.dy, self.dz)[d]
+        g = G if d < 2 else 0
+        return 0.5 * (self.lo[d] + self.hi[d] - dd * ((-g) + (n - 1 + g)))
+
+
+# component names of the explicit solver, allocation order of fields/Fields.cpp:70-122
+EXPLICIT_COMPS = (
+    ('Next', ('jx_beam', 'jy_beam')),
+    ('This', ('chi', 'Sy', 'Sx', 'ExmBy', 'EypBx', 'Ez', 'Bx', 'By', 'Bz', 'Psi',
+              'jx_beam', 'jy_beam', 'jz_beam', 'jx', 'jy', 'rhomjz')),
+    ('Previous', ('jx_beam', 'jy_beam')),
+    ('RhomJzIons', ('rhomjz',)),
+)
+
+
+def component_map(deposit_rho=False, neutral_background=True):
+    comps = {}
+    n = 0
+    for sl, names in EXPLICIT_COMPS:
+        if sl == 'RhomJzIons' and not neutral_background:
+            continue
+        for nm in names:
+            comps[(sl, nm)] = n
+            n += 1
+        if sl == 'This' and deposit_rho:
+            comps[('This', 'rho')] = n
+            n += 1
+    return comps, n
+
+
+# --------------------------------------------------------------------------------------------
+# Species
+# --------------------------------------------------------------------------------------------
+
+@dataclass
+class Plasma:
+    name: str
+    charge: float
+    mass: float
+    ppc: tuple
+    density: object            # callable(x, y, z) -> array
+    neutralize_background: bool = True
+    max_qsa_weighting_factor: float = 35.
+    n_subcycles: int = 1
+    radius: float = math.inf
+    hollow_core_radius: float = 0.
+    min_density: float = 0.
+    u_mean: tuple = (0., 0., 0.)
+    # SoA, PlasmaIdx order particles/plasma/PlasmaParticleContainer.H:21-46
+    x: np.ndarray = None
+    y: np.ndarray = None
+    w: np.ndarray = None
+    ux: np.ndarray = None
+    uy: np.ndarray = None
+    psi: np.ndarray = None
+    x_prev: np.ndarray = None
+    y_prev: np.ndarray = None
+    ux_half: np.ndarray = None
+    uy_half: np.ndarray = None
+    psi_half: np.ndarray = None
+    valid: np.ndarray = None     # id sign (valid/invalid)
+
+
+@dataclass
+class Beam:
+    name: str
+    charge: float
+    mass: float
+    ppc: tuple
+    profile: str
+    density: float
+    zmin: float
+    zmax: float
+    radius: float
+    position_mean: tuple = (0., 0., 0.)
+    position_std: tuple = (0., 0., 0.)
+    u_mean: tuple = (0., 0., 0.)
+    min_density: float = 0.
+    n_subcycles: int = 10
+    slices: dict = field(default_factory=dict)   # islice -> dict of arrays
+    next_id: int = 1
+
+
+# --------------------------------------------------------------------------------------------
+# Kernels
+# --------------------------------------------------------------------------------------------
+
+def _scatter(arr, jj, ii, vals):
+    """arr[jj+G, ii+G] += vals, duplicates accumulated (Gpu::Atomic::Add semantics).
+    np.bincount sums in a fixed order, so the oracle itself is deterministic."""
+    ny_t, nx_t = arr.shape
+    flat = (jj + G) * nx_t + (ii + G)
+    arr += np.bincount(flat.ravel(), weights=vals.ravel(), minlength=arr.size).reshape(arr.shape)
+
+
+def deposit_current(pl: Plasma, F: dict, geom: Geometry, pc: PhysConst, normalized: bool,
+                    *, jx=None, jy=None, rho=None, chi=None, rhomjz=None, flip_charge=False):
+    """::DepositCurrent, particles/deposition/PlasmaDepositCurrent.cpp:22-257 (jz not needed by
+    the explicit solver).  Arguments jx.. are the destination arrays or None (the reference's -1).
+    Returns the number of QSA-violating particles killed in this call (:197-204)."""
+    charge = -pl.charge if flip_charge else pl.charge                       # :40
+    invvol = 1.0 if normalized else 1.0 / (geom.dx * geom.dy * geom.dz)     # :71-73 (lev 0)
+    x_off, y_off = geom.pos_offset(0), geom.pos_offset(1)
+    dx_inv, dy_inv = 1.0 / geom.dx, 1.0 / geom.dy
+    clightinv = 1.0 / pc.c
+    charge_invvol = charge * invvol
+    charge_mu0_mass_ratio = charge * pc.mu0 / pl.mass
+
+    v = pl.valid
+    psi_inv = 1.0 / pl.psi
+    vx_c = pl.ux * psi_inv
+    vy_c = pl.uy * psi_inv
+    gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * clightinv * clightinv
+                       + vy_c * vy_c * clightinv * clightinv + 1.0)         # :190-195
+    bad = v & ((gamma_psi < 0.0) | (gamma_psi > pl.max_qsa_weighting_factor) | (psi_inv < 0.0))
+    n_bad = int(bad.sum())
+    if n_bad:
+        pl.w[bad] = 0.0
+        pl.valid[bad] = False
+    sel = pl.valid.copy()
+    if not sel.any():
+        return n_bad
+    xmid = (pl.x[sel] - x_off) * dx_inv
+    ymid = (pl.y[sel] - y_off) * dy_inv
+    sx, i0 = shape_order2(xmid)
+    sy, j0 = shape_order2(ymid)
+    q_invvol = charge_invvol * pl.w[sel]
+    psi_inv, vx_c, vy_c, gamma_psi = psi_inv[sel], vx_c[sel], vy_c[sel], gamma_psi[sel]
+    ii = np.stack([i0 + ix for iy in range(3) for ix in range(3)])
+    jj = np.stack([j0 + iy for iy in range(3) for ix in range(3)])
+    cd = np.stack([q_invvol * sx[ix] * sy[iy] for iy in range(3) for ix in range(3)])  # :218
+    if jx is not None:
+        _scatter(jx, jj, ii, cd * vx_c)
+        _scatter(jy, jj, ii, cd * vy_c)
+    if rho is not None:
+        _scatter(rho, jj, ii, cd * gamma_psi)
+    if chi is not None:
+        _scatter(chi, jj, ii, cd * charge_mu0_mass_ratio * psi_inv)
+    if rhomjz is not None:
+        _scatter(rhomjz, jj, ii, cd)
+    return n_bad
+
+
+def beam_deposit(bs: dict, beam: Beam, geom: Geometry, pc: PhysConst, normalized: bool,
+                 *, jxb=None, jyb=None, jzb=None):
+    """DepositCurrentSlice, particles/deposition/BeamDepositCurrent.cpp:21-195 (lev 0)."""
+    if bs is None or bs['x'].size == 0:
+        return
+    invvol = 1.0 if normalized else 1.0 / (geom.dx * geom.dy * geom.dz)     # :72-82
+    x_off, y_off = geom.pos_offset(0), geom.pos_offset(1)
+    clightsq = 1.0 / (pc.c * pc.c)
+    ux, uy, uz = bs['ux'], bs['uy'], bs['uz']
+    gaminv = 1.0 / np.sqrt(1.0 + ux * ux * clightsq + uy * uy * clightsq + uz * uz * clightsq)
+    wq = beam.charge * bs['w'] * invvol
+    sx, i0 = shape_order2((bs['x'] - x_off) / geom.dx)
+    sy, j0 = shape_order2((bs['y'] - y_off) / geom.dy)
+    ii = np.stack([i0 + ix for iy in range(3) for ix in range(3)])
+    jj = np.stack([j0 + iy for iy in range(3) for ix in range(3)])
+    ss = np.stack([sx[ix] * sy[iy] for iy in range(3) for ix in range(3)])
+    v = bs['valid']
+    ii, jj, ss = ii[:, v], jj[:, v], ss[:, v]
+    if jxb is not None:
+        _scatter(jxb, jj, ii, ss * (wq * ux * gaminv)[v])
+        _scatter(jyb, jj, ii, ss * (wq * uy * gaminv)[v])
+    if jzb is not None:
+        _scatter(jzb, jj, ii, ss * (wq * uz * gaminv)[v])
+
+
+def poisson_eigenvalues(nx, ny, dx, dy):
+    """m_eigenvalue_matrix incl. DST normalisation,
+    fields/fft_poisson_solver/FFTPoissonSolverDirichletFast.cpp:224-248."""
+    sx = np.sin((np.arange(nx) + 1) * (math.pi / (2.0 * (nx + 1)))) ** 2
+    sy = np.sin((np.arange(ny) + 1) * (math.pi / (2.0 * (ny + 1)))) ** 2
+    norm_fac = 0.5 / (2 * ((nx + 1) * (ny + 1)))
+    return norm_fac / (-4.0 * (sx[None, :] / (dx * dx) + sy[:, None] / (dy * dy)))
+
+
+def poisson_dirichlet(rhs, eig):
+    """FFTPoissonSolverDirichletFast::SolvePoissonEquation (:286-328) ==
+    FFTPoissonSolverDirichletDirect (FFTW RODFT00): lhs = DST2D(DST2D(rhs) * eig).
+    scipy dstn(type=1) is FFTW's unnormalised RODFT00 (y_k = 2 sum x_j sin(pi (j+1)(k+1)/(n+1)))."""
+    return _dstn(_dstn(rhs, type=1) * eig, type=1)
+
+
+def _ddx(a, dx):
+    """derivative<x> on the valid box, fields/Fields.cpp:223-235: (f[i+1]-f[i-1]) * 0.5/dx"""
+    return (a[G:-G, G + 1:a.shape[1] - G + 1] - a[G:-G, G - 1:a.shape[1] - G - 1]) * (0.5 / dx)
+
+
+def _ddy(a, dy):
+    return (a[G + 1:a.shape[0] - G + 1, G:-G] - a[G - 1:a.shape[0] - G - 1, G:-G]) * (0.5 / dy)
+
+
+def solve_poisson_psi_ez_bz(F, geom: Geometry, pc: PhysConst, eig):
+    """Fields::SolvePoissonPsiExmByEypBxEzBz, fields/Fields.cpp:840-957 (lev 0, Dirichlet)."""
+    dx, dy = geom.dx, geom.dy
+    T = lambda n: F[('This', n)]
+    T('Psi')[G:-G, G:-G] = poisson_dirichlet((-1.0 / pc.ep0) * T('rhomjz')[G:-G, G:-G], eig)
+    f = 1.0 / (pc.ep0 * pc.c)
+    T('Ez')[G:-G, G:-G] = poisson_dirichlet(f * _ddx(T('jx'), dx) + f * _ddy(T('jy'), dy), eig)
+    T('Bz')[G:-G, G:-G] = poisson_dirichlet(pc.mu0 * _ddy(T('jx'), dy)
+                                            + (-pc.mu0) * _ddx(T('jy'), dx), eig)
+    # ExmBy / EypBx on the box grown by g-1 = 1 (:931-956)
+    psi = T('Psi')
+    s = slice(G - 1, -(G - 1))
+    ny_t, nx_t = psi.shape
+    T('ExmBy')[s, s] = -(psi[G - 1:ny_t - G + 1, G:nx_t - G + 2]
+                         - psi[G - 1:ny_t - G + 1, G - 2:nx_t - G]) * (0.5 / dx)
+    T('EypBx')[s, s] = -(psi[G:ny_t - G + 2, G - 1:nx_t - G + 1]
+                         - psi[G - 2:ny_t - G, G - 1:nx_t - G + 1]) * (0.5 / dy)
+
+
+def init_sxsy_with_beam(F, geom: Geometry, pc: PhysConst):
+    """Hipace::InitializeSxSyWithBeam, Hipace.cpp:744-790 (valid box)."""
+    dx, dy, dz = geom.dx, geom.dy, geom.dz
+    jzb = F[('This', 'jz_beam')]
+    ny_t, nx_t = jzb.shape
+    v = (slice(G, -G), slice(G, -G))
+    dx_jzb = (jzb[G:-G, G + 1:nx_t - G + 1] - jzb[G:-G, G - 1:nx_t - G - 1]) / (2.0 * dx)
+    dy_jzb = (jzb[G + 1:ny_t - G + 1, G:-G] - jzb[G - 1:ny_t - G - 1, G:-G]) / (2.0 * dy)
+    dz_jxb = (F[('Previous', 'jx_beam')][v] - F[('Next', 'jx_beam')][v]) / (2.0 * dz)
+    dz_jyb = (F[('Previous', 'jy_beam')][v] - F[('Next', 'jy_beam')][v]) / (2.0 * dz)
+    F[('This', 'Sy')][v] = pc.mu0 * (-dy_jzb + dz_jyb)
+    F[('This', 'Sx')][v] = -pc.mu0 * (-dx_jzb + dz_jxb)
+
+
+def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized: bool):
+    """::ExplicitDeposition, particles/deposition/ExplicitDeposition.cpp:20-263
+    (depos_order 2, derivative_type 2, no laser)."""
+    sel = pl.valid
+    if not sel.any():
+        return
+    invvol = 1.0 if normalized else 1.0 / (geom.dx * geom.dy * geom.dz)
+    x_off, y_off = geom.pos_offset(0), geom.pos_offset(1)
+    dx_inv, dy_inv = 1.0 / geom.dx, 1.0 / geom.dy
+    clight_inv = 1.0 / pc.c
+    a_clight = pc.c
+    charge_invvol_mu0 = pl.charge * invvol * pc.mu0
+    q_mass_ratio = pl.charge / pl.mass
+
+    psi_inv = 1.0 / pl.psi[sel]
+    vx = pl.ux[sel] * psi_inv * clight_inv
+    vy = pl.uy[sel] * psi_inv * clight_inv
+    cdm = charge_invvol_mu0 * pl.w[sel]
+    xmid = (pl.x[sel] - x_off) * dx_inv
+    ymid = (pl.y[sel] - y_off) * dy_inv
+    gamma_psi = 0.5 * (psi_inv * psi_inv + vx * vx + vy * vy + 1.0)           # :177-182
+    sx, dsx, i0 = dshape_centered_order2(xmid)
+    sy, dsy, j0 = dshape_centered_order2(ymid)
+    Bz, Ez = F[('This', 'Bz')], F[('This', 'Ez')]
+    ExmBy, EypBx = F[('This', 'ExmBy')], F[('This', 'EypBx')]
+    Sy, Sx = F[('This', 'Sy')], F[('This', 'Sx')]
+    ii_l, jj_l, sy_l, sx_l = [], [], [], []
+    for iy in range(5):
+        for ix in range(5):
+            if ix in (0, 4) and iy in (0, 4):
+                continue                                                      # :193-198
+            i, j = i0 + ix, j0 + iy
+            shx, shdx, shy, shdy = sx[ix], dsx[ix], sy[iy], dsy[iy]
+            Bz_v, Ez_v = Bz[j + G, i + G], Ez[j + G, i + G]
+            ExmBy_v, EypBx_v = ExmBy[j + G, i + G], EypBx[j + G, i + G]
+            val_sy = cdm * (                                                   # :228-242
+                - shx * shy * (
+                    - Bz_v * vx
+                    + (Ez_v * vy
+                       + ExmBy_v * (- vx * vy)
+                       + EypBx_v * (gamma_psi - vy * vy)) * clight_inv
+                ) * q_mass_ratio * psi_inv
+                + (- shdx * shy * dx_inv * (- vx * vy)
+                   - shx * shdy * dy_inv * (gamma_psi - vy * vy - 1.0)) * a_clight)
+            val_sx = cdm * (                                                   # :244-258
+                + shx * shy * (
+                    + Bz_v * vy
+                    + (Ez_v * vx
+                       + ExmBy_v * (gamma_psi - vx * vx)
+                       + EypBx_v * (- vx * vy)) * clight_inv
+                ) * q_mass_ratio * psi_inv
+                + (+ shdx * shy * dx_inv * (gamma_psi - vx * vx - 1.0)
+                   + shx * shdy * dy_inv * (- vx * vy)) * a_clight)
+            ii_l.append(i); jj_l.append(j); sy_l.append(val_sy); sx_l.append(val_sx)
+    ii, jj = np.stack(ii_l), np.stack(jj_l)
+    _scatter(Sy, jj, ii, np.stack(sy_l))
+    _scatter(Sx, jj, ii, np.stack(sx_l))
+
+
+# ---- hpmg (mg_solver/HpMultiGrid.cpp), system type 1 ---------------------------------------
+
+class MultiGrid1:
+    """hpmg::MultiGrid with system_type 1: solves  lap(phi) - acf*phi = rhs  for two components
+    sharing acf, Dirichlet 0 (cell-centred: at the cell face, :163-182; nodal: at nodes 0, n+1).
+
+    Level arrays are indexed [j, i] over m_domain[ilev] (:1054-1072): cell-centred for even n
+    (0..n-1), nodal for odd n (nodes 0..n+1 where 0 and n+1 are boundary nodes held at 0).
+    The CPU (gsrb_cached :594-740) and CUDA (gsrb_shared :413-590, bottomsolve_gpu :854-1033)
+    paths compute the same values as whole-array red-black sweeps, which is what we do here.
+    """
+
+    def __init__(self, dx, dy, nx, ny):
+        assert nx % 2 == ny % 2, 'HpMultiGrid.cpp:1051-1052'
+        self.dx, self.dy = dx, dy
+        self.cc = (nx % 2 == 0)
+        if self.cc:
+            sizes = [(ny, nx)]
+            minw = 2
+            while True:                                 # coarsenable(2, min_width) :1065-1072
+                h, w = sizes[-1]
+                if h % 2 == 0 and w % 2 == 0 and h >= 2 * minw and w >= 2 * minw:
+                    sizes.append((h // 2, w // 2))
+                else:
+                    break
+        else:
+            # nodal box 0..n+1 (n+2 points); coarsenable if hi even and npts >= 2*4
+            sizes = [(ny + 2, nx + 2)]
+            while True:
+                h, w = sizes[-1]
+                if (h - 1) % 2 == 0 and (w - 1) % 2 == 0 and h >= 8 and w >= 8:
+                    sizes.append(((h - 1) // 2 + 1, (w - 1) // 2 + 1))
+                else:
+                    break
+        self.sizes = sizes
+        self.nlev = len(sizes)
+        self.acf = [np.zeros(s) for s in sizes]
+        self.res = [None] + [np.zeros((2,) + s) for s in sizes[1:]]
+        self.cor = [np.zeros((2,) + s) for s in sizes]
+        self.rescor = [np.zeros((2,) + s) for s in sizes]
+        self.n_vcycles_last = 0
+
+    # -- helpers -------------------------------------------------------------------------
+    def _valid(self, a):
+        return a if self.cc else a[..., 1:-1, 1:-1]
+
+    def _masks(self, shape):
+        ny, nx = shape
+        j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing='ij')
+        return (i + j)
+
+    def _lap_offdiag(self, phi, facx, facy):
+        """sum of neighbour terms as in gs1 (:265-292) and the matching diagonal c0 modifier."""
+        ny, nx = phi.shape[-2:]
+        p = np.zeros(phi.shape[:-2] + (ny + 2, nx + 2))
+        p[..., 1:-1, 1:-1] = phi
+        lapx = facx * (p[..., 1:-1, :-2] + p[..., 1:-1, 2:])
+        lapy = facy * (p[..., :-2, 1:-1] + p[..., 2:, 1:-1])
+        if self.cc:
+            lapx[..., :, 0] = facx * (4. / 3.) * phi[..., :, 1]
+            lapx[..., :, -1] = facx * (4. / 3.) * phi[..., :, -2]
+            lapy[..., 0, :] = facy * (4. / 3.) * phi[..., 1, :]
+            lapy[..., -1, :] = facy * (4. / 3.) * phi[..., -2, :]
+        return lapx + lapy
+
+    def _c0(self, acf, facx, facy):
+        c0 = -(acf + 2.0 * (facx + facy))
+        if self.cc:
+            c0 = c0.copy()
+            c0[:, 0] -= 2.0 * facx
+            c0[:, -1] -= 2.0 * facx
+            c0[0, :] -= 2.0 * facy
+            c0[-1, :] -= 2.0 * facy
+        return c0
+
+    def gsrb(self, phi, rhs, acf, facx, facy, nsweeps, first_color=0):
+        """nsweeps red-black half-sweeps, colour (i+j+icolor)%2==0 (:367-404, :521-548).
+        phi[2, ny, nx] over the level box; for nodal only the interior is updated."""
+        if self.cc:
+            par = self._masks(phi.shape[-2:])
+            c0_inv = 1.0 / self._c0(acf, facx, facy)
+            for ic in range(first_color, first_color + nsweeps):
+                m = ((par + ic) % 2 == 0)
+                lap = self._lap_offdiag(phi, facx, facy)
+                new = (rhs - lap) * c0_inv
+                phi[:, m] = new[:, m]
+        else:
+            ny, nx = phi.shape[-2:]
+            j, i = np.meshgrid(np.arange(1, ny - 1), np.arange(1, nx - 1), indexing='ij')
+            par = i + j
+            c0_inv = 1.0 / self._c0(acf[1:-1, 1:-1], facx, facy)
+            for ic in range(first_color, first_color + nsweeps):
+                m = ((par + ic) % 2 == 0)
+                lap = (facx * (phi[:, 1:-1, :-2] + phi[:, 1:-1, 2:])
+                       + facy * (phi[:, :-2, 1:-1] + phi[:, 2:, 1:-1]))
+                new = (rhs[:, 1:-1, 1:-1] - lap) * c0_inv
+                inner = phi[:, 1:-1, 1:-1]
+                inner[:, m] = new[:, m]
+        return phi
+
+    def residual(self, phi, rhs, acf, facx, facy):
+        """residual1 (:184-190): rhs + acf*phi - laplacian(phi), laplacian as :163-182."""
+        out = np.zeros_like(phi)
+        if self.cc:
+            lap = -2.0 * (facx + facy) * phi
+            lx = self._lap_offdiag_x(phi, facx)
+            ly = self._lap_offdiag_y(phi, facy)
+            lap = lap + lx
+            lap = lap + ly
+            out[:] = rhs + acf * phi - lap
+        else:
+            inner = phi[:, 1:-1, 1:-1]
+            lap = -2.0 * (facx + facy) * inner
+            lap = lap + facx * (phi[:, 1:-1, :-2] + phi[:, 1:-1, 2:])
+            lap = lap + facy * (phi[:, :-2, 1:-1] + phi[:, 2:, 1:-1])
+            out[:, 1:-1, 1:-1] = rhs[:, 1:-1, 1:-1] + acf[1:-1, 1:-1] * inner - lap
+        return out
+
+    def _lap_offdiag_x(self, phi, facx):
+        lx = np.empty_like(phi)
+        lx[..., :, 1:-1] = facx * (phi[..., :, :-2] + phi[..., :, 2:])
+        lx[..., :, 0] = facx * ((4. / 3.) * phi[..., :, 1] - 2.0 * phi[..., :, 0])
+        lx[..., :, -1] = facx * ((4. / 3.) * phi[..., :, -2] - 2.0 * phi[..., :, -1])
+        return lx
+
+    def _lap_offdiag_y(self, phi, facy):
+        ly = np.empty_like(phi)
+        ly[..., 1:-1, :] = facy * (phi[..., :-2, :] + phi[..., 2:, :])
+        ly[..., 0, :] = facy * ((4. / 3.) * phi[..., 1, :] - 2.0 * phi[..., 0, :])
+        ly[..., -1, :] = facy * ((4. / 3.) * phi[..., -2, :] - 2.0 * phi[..., -1, :])
+        return ly
+
+    def restrict(self, fine):
+        """restrict_cc (:29-37) / restrict_nd (:39-52)"""
+        if self.cc:
+            return 0.25 * (fine[..., 0::2, 0::2] + fine[..., 0::2, 1::2]
+                           + fine[..., 1::2, 0::2] + fine[..., 1::2, 1::2])
+        nyc = (fine.shape[-2] - 1) // 2 + 1
+        nxc = (fine.shape[-1] - 1) // 2 + 1
+        crse = np.zeros(fine.shape[:-2] + (nyc, nxc))
+        c = lambda dj, di: fine[..., 2 + dj:fine.shape[-2] - 2 + dj + 1:2,
+                                2 + di:fine.shape[-1] - 2 + di + 1:2]
+        crse[..., 1:-1, 1:-1] = (1. / 16.) * (
+            c(-1, -1) + 2. * c(-1, 0) + c(-1, 1)
+            + 2. * c(0, -1) + 4. * c(0, 0) + 2. * c(0, 1)
+            + c(1, -1) + 2. * c(1, 0) + c(1, 1))
+        return crse
+
+    def interp_add(self, fine, crse):
+        """interpcpy_cc / interpcpy_nd (:88-121): returns fine + I(crse)"""
+        if self.cc:
+            return fine + np.repeat(np.repeat(crse, 2, axis=-2), 2, axis=-1)
+        out = fine.copy()
+        ny, nx = fine.shape[-2:]
+        I = np.zeros_like(fine)
+        I[..., 0::2, 0::2] = crse
+        I[..., 1::2, 0::2] = (crse[..., :-1, :] + crse[..., 1:, :]) * 0.5
+        I[..., 0::2, 1::2] = (crse[..., :, :-1] + crse[..., :, 1:]) * 0.5
+        I[..., 1::2, 1::2] = (crse[..., :-1, :-1] + crse[..., 1:, :-1]
+                              + crse[..., :-1, 1:] + crse[..., 1:, 1:]) * 0.25
+        out[..., 1:-1, 1:-1] += I[..., 1:-1, 1:-1]
+        return out
+
+    # -- solve1 ----------------------------------------------------------------------------
+    def solve1(self, sol, rhs, acf, tol_rel=1e-4, tol_abs=np.finfo(float).tiny, maxiter=200):
+        """solve1 (:1169-1190) + solve_doit (:1307-1427) + vcycle (:1429-1512) +
+        bottomsolve (:1514-1594).  sol[2,ny,nx], rhs[2,ny,nx], acf[ny,nx] are *valid-box*
+        arrays (the caller strips the guard cells = center_box, HpMultiGrid.H:168-175).
+        sol is the initial guess and is overwritten."""
+        dx, dy = self.dx, self.dy
+
+        def emb(a):      # valid-box array -> level-0 box
+            if self.cc:
+                return a
+            out = np.zeros(a.shape[:-2] + self.sizes[0])
+            out[..., 1:-1, 1:-1] = a
+            return out
+        self.acf[0] = emb(np.array(acf, dtype=float))
+        for l in range(1, self.nlev):                        # average_down_acoef :1640-1700
+            self.acf[l] = self.restrict(self.acf[l - 1])
+        rhs0 = emb(rhs)
+        fac = lambda l: (1.0 / ((dx * (1 << l)) ** 2), 1.0 / ((dy * (1 << l)) ** 2))
+
+        def gsrb4_res(phi_in, r, l, zero_init, do_res):
+            fx, fy = fac(l)
+            phi = np.zeros_like(r) if zero_init else phi_in.copy()
+            self.gsrb(phi, r, self.acf[l], fx, fy, 4)
+            rr = self.residual(phi, r, self.acf[l], fx, fy) if do_res else None
+            return phi, rr
+
+        sol0 = emb(sol)
+        self.cor[0], self.rescor[0] = gsrb4_res(sol0, rhs0, 0, False, True)     # :1326-1327
+        resnorm0 = np.abs(self._valid(self.rescor[0])).max()
+        rhsnorm0 = np.abs(self._valid(rhs0)).max()
+        max_norm = max(rhsnorm0, resnorm0)
+        res_target = max(tol_abs, max(tol_rel, 1e-16) * max_norm)               # :1361
+        self.n_vcycles_last = 0
+        if resnorm0 > res_target:
+            converged = False
+            for it in range(maxiter):
+                self._vcycle(sol0, rhs0, gsrb4_res, fac)
+                self.n_vcycles_last = it + 1
+                norminf = np.abs(self.rescor[0]).max()
+                if norminf <= res_target:
+                    converged = True
+                    break
+                if norminf > 1e20 * max_norm:
+                    raise RuntimeError('hpmg failing so lets stop here')
+            if not converged:
+                raise RuntimeError('hpmg failed')
+        sol[...] = self._valid(self.cor[0])                                    # :1419-1426
+        return sol
+
+    def _vcycle(self, sol0, rhs0, gsrb4_res, fac):
+        nl = self.nlev
+        for l in range(0, nl - 1):
+            if l > 0:
+                self.cor[l], self.rescor[l] = gsrb4_res(None, self.res[l], l, True, True)
+            self.res[l + 1] = self.restrict(self.rescor[l])
+        # bottom: 16 sweeps (numsweeps = max(16, (len.max()+1)/2*2), :1587; coarsest len <= 5)
+        l = nl - 1
+        fx, fy = fac(l)
+        nsw = max(16, (max(self.sizes[l]) + 1) // 2 * 2)
+        self.cor[l] = np.zeros_like(self.res[l])
+        self.gsrb(self.cor[l], self.res[l], self.acf[l], fx, fy, nsw)
+        for l in range(nl - 2, -1, -1):
+            self.rescor[l] = self.interp_add(self.cor[l], self.cor[l + 1])
+            if l == 0:
+                new, _ = gsrb4_res(self.rescor[0], rhs0, 0, False, False)
+                sol0[...] = new
+            else:
+                self.cor[l], _ = gsrb4_res(self.rescor[l], self.res[l], l, False, False)
+        self.cor[0], self.rescor[0] = gsrb4_res(sol0, rhs0, 0, False, True)     # :1501-1503
+
+
+# ---- gather + push ------------------------------------------------------------------------
+
+def _momentum_push(ux, uy, psi_inv, ExmBy, EypBx, Ez, Bx_c, By_c, Bz, clight_inv, qmc):
+    """PlasmaMomentumPush<Real>, particles/pusher/PushPlasmaParticles.H:39-75 (no laser)."""
+    gamma_psi = 0.5 * psi_inv * psi_inv * (1.0 + ux * ux * (clight_inv * clight_inv)
+                                           + uy * uy * (clight_inv * clight_inv)) + 0.5
+    dz_ux = qmc * (gamma_psi * ExmBy + By_c + (uy * Bz) * psi_inv)
+    dz_uy = qmc * (gamma_psi * EypBx - Bx_c - (ux * Bz) * psi_inv)
+    dz_psi = qmc * clight_inv * ((ux * ExmBy + uy * EypBx) * clight_inv * psi_inv - Ez)
+    return dz_ux, dz_uy, dz_psi
+
+
+def _momentum_push_dual(ux, uxe, uy, uye, pi, pie, ExmBy, EypBx, Ez, Bx_c, By_c, Bz,
+                        clight_inv, qmc):
+    """PlasmaMomentumPush<DualNumber> epsilon parts; arithmetic follows utils/DualNumbers.H:13-43
+    operator by operator (Real*Dual promotes the Real to a Dual with epsilon 0)."""
+    c2 = clight_inv * clight_inv
+
+    def mul(a, ae, b, be):
+        return a * b, ae * b + a * be
+
+    def add(a, ae, b, be):
+        return a + b, ae + be
+
+    def sub(a, ae, b, be):
+        return a - b, ae - be
+    z = 0.0
+    # gamma_psi = 0.5*psi_inv*psi_inv*(1 + Aabssq + ux*ux*c2 + uy*uy*c2) + 0.5
+    t, te = mul(0.5, z, pi, pie)
+    t, te = mul(t, te, pi, pie)
+    uxx, uxxe = mul(ux, uxe, ux, uxe)
+    uxx, uxxe = mul(uxx, uxxe, c2, z)
+    uyy, uyye = mul(uy, uye, uy, uye)
+    uyy, uyye = mul(uyy, uyye, c2, z)
+    s, se = add(1.0 + 0.0, z, uxx, uxxe)
+    s, se = add(s, se, uyy, uyye)
+    gp, gpe = mul(t, te, s, se)
+    gp, gpe = add(gp, gpe, 0.5, z)
+    # dz_ux = qmc*(gamma_psi*ExmBy + By_c + (uy*Bz)*psi_inv) - 0*psi_inv
+    a, ae = mul(gp, gpe, ExmBy, z)
+    a, ae = add(a, ae, By_c, z)
+    b, be = mul(uy, uye, Bz, z)
+    b, be = mul(b, be, pi, pie)
+    a, ae = add(a, ae, b, be)
+    dux, duxe = mul(qmc, z, a, ae)
+    # dz_uy = qmc*(gamma_psi*EypBx - Bx_c - (ux*Bz)*psi_inv)
+    a, ae = mul(gp, gpe, EypBx, z)
+    a, ae = sub(a, ae, Bx_c, z)
+    b, be = mul(ux, uxe, Bz, z)
+    b, be = mul(b, be, pi, pie)
+    a, ae = sub(a, ae, b, be)
+    duy, duye = mul(qmc, z, a, ae)
+    # dz_psi = qmc*clight_inv*((ux*ExmBy + uy*EypBx)*clight_inv*psi_inv - Ez)
+    a, ae = mul(ux, uxe, ExmBy, z)
+    b, be = mul(uy, uye, EypBx, z)
+    a, ae = add(a, ae, b, be)
+    a, ae = mul(a, ae, clight_inv, z)
+    a, ae = mul(a, ae, pi, pie)
+    a, ae = sub(a, ae, Ez, z)
+    dps, dpse = mul(qmc * clight_inv, z, a, ae)
+    return duxe, duye, dpse
+
+
+def gather_fields(xp, yp, F, geom: Geometry):
+    """doGatherShapeN<2>, particles/particles_utils/FieldGather.H:45-96"""
+    x_off, y_off = geom.pos_offset(0), geom.pos_offset(1)
+    dx_inv, dy_inv = 1.0 / geom.dx, 1.0 / geom.dy
+    x = (xp - x_off) * dx_inv
+    y = (yp - y_off) * dy_inv
+    sx, dsx, i0 = dshape_nodal_order2(x)
+    sy, dsy, j0 = dshape_nodal_order2(y)
+    Psi, Ez, Bx, By, Bz = (F[('This', n)] for n in ('Psi', 'Ez', 'Bx', 'By', 'Bz'))
+    ExmByp = np.zeros_like(xp); EypBxp = np.zeros_like(xp); Ezp = np.zeros_like(xp)
+    Bxp = np.zeros_like(xp); Byp = np.zeros_like(xp); Bzp = np.zeros_like(xp)
+    for iy in range(4):
+        for ix in range(4):
+            i, j = i0 + ix + G, j0 + iy + G
+            psi_v = Psi[j, i]
+            ExmByp += (dsx[ix] * sy[iy]) * psi_v * dx_inv
+            EypBxp += (sx[ix] * dsy[iy]) * psi_v * dy_inv
+            w = sx[ix] * sy[iy]
+            Ezp += w * Ez[j, i]
+            Bxp += w * Bx[j, i]
+            Byp += w * By[j, i]
+            Bzp += w * Bz[j, i]
+    return ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp
+
+
+def enforce_bc(x, y, ux, uy, lo, hi, kind):
+    """EnforceBC, particles/pusher/GetAndSetPosition.H:29-99.  Returns 'invalid' mask."""
+    out = (x < lo[0]) | (y < lo[1]) | (x > hi[0]) | (y > hi[1])
+    invalid = np.zeros_like(out)
+    if not out.any():
+        return invalid
+    len_x, len_y = hi[0] - lo[0], hi[1] - lo[1]
+    if kind == 'Periodic':
+        xn = np.fmod(x[out] - lo[0], len_x); xn = np.where(xn < 0, xn + len_x, xn) + lo[0]
+        yn = np.fmod(y[out] - lo[1], len_y); yn = np.where(yn < 0, yn + len_y, yn) + lo[1]
+        x[out], y[out] = xn, yn
+    elif kind == 'Reflecting':
+        xn = np.fmod(x[out] - lo[0], 2 * len_x); xn = np.where(xn < 0, xn + 2 * len_x, xn) + lo[0]
+        fx = xn > hi[0]
+        xn = np.where(fx, 2 * hi[0] - xn, xn)
+        yn = np.fmod(y[out] - lo[1], 2 * len_y); yn = np.where(yn < 0, yn + 2 * len_y, yn) + lo[1]
+        fy = yn > hi[1]
+        yn = np.where(fy, 2 * hi[1] - yn, yn)
+        x[out], y[out] = xn, yn
+        uxo, uyo = ux[out], uy[out]
+        ux[out] = np.where(fx, -uxo, uxo)
+        uy[out] = np.where(fy, -uyo, uyo)
+    else:  # Absorbing
+        invalid = out
+    return invalid
+
+
+def advance_plasma_particles(pl: Plasma, F, geom: Geometry, pc: PhysConst, bc_kind: str,
+                             bc_lo, bc_hi, temp_slice=False):
+    """AdvancePlasmaParticles, particles/pusher/PlasmaParticleAdvance.cpp:29-217 (leap-frog,
+    lev 0, no laser, no ionization)."""
+    sel = np.nonzero(pl.valid)[0]
+    if sel.size == 0:
+        return
+    clight, clight_inv = pc.c, 1.0 / pc.c
+    qmc = pl.charge / (pl.mass * pc.c)
+    dz = geom.dz / pl.n_subcycles
+    nsub = 4
+    sdz = dz / nsub
+    for _ in range(pl.n_subcycles):
+        if sel.size == 0:
+            break
+        xp = pl.x_prev[sel].copy()
+        yp = pl.y_prev[sel].copy()
+        ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp = gather_fields(xp, yp, F, geom)
+        Bxp = Bxp * clight
+        Byp = Byp * clight
+        ux, uy, psi = pl.ux_half[sel].copy(), pl.uy_half[sel].copy(), pl.psi_half[sel].copy()
+
+        def substep(ux, uy, psi):
+            psi_inv = 1.0 / psi
+            dux, duy, dps = _momentum_push(ux, uy, psi_inv, ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp,
+                                           clight_inv, qmc)
+            duxe, duye, dpse = _momentum_push_dual(
+                ux, dux, uy, duy, psi_inv, -psi_inv * psi_inv * dps,
+                ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp, clight_inv, qmc)
+            ux = ux + (sdz * dux + 0.5 * sdz * sdz * duxe)
+            uy = uy + (sdz * duy + 0.5 * sdz * sdz * duye)
+            psi = psi + (sdz * dps + 0.5 * sdz * sdz * dpse)
+            return ux, uy, psi
+        for _i in range(nsub):                                                  # :148-168
+            ux, uy, psi = substep(ux, uy, psi)
+        xp = xp + dz * clight_inv * (ux * (1.0 / psi))                           # :173-174
+        yp = yp + dz * clight_inv * (uy * (1.0 / psi))
+        invalid = enforce_bc(xp, yp, ux, uy, bc_lo, bc_hi, bc_kind)             # :176
+        if invalid.any():
+            dead = sel[invalid]
+            pl.w[dead] = 0.0
+            pl.valid[dead] = False
+            keep = ~invalid
+            sel, xp, yp, ux, uy, psi = sel[keep], xp[keep], yp[keep], ux[keep], uy[keep], psi[keep]
+            ExmByp, EypBxp, Ezp = ExmByp[keep], EypBxp[keep], Ezp[keep]
+            Bxp, Byp, Bzp = Bxp[keep], Byp[keep], Bzp[keep]
+        pl.x[sel], pl.y[sel] = xp, yp
+        if not temp_slice:
+            pl.ux_half[sel], pl.uy_half[sel], pl.psi_half[sel] = ux, uy, psi
+            pl.x_prev[sel], pl.y_prev[sel] = xp, yp
+        for _i in range(nsub // 2):                                             # :194-214
+            ux, uy, psi = substep(ux, uy, psi)
+        pl.ux[sel], pl.uy[sel], pl.psi[sel] = ux, uy, psi
+
+
+# --------------------------------------------------------------------------------------------
+# Initialisation
+# --------------------------------------------------------------------------------------------
+
+def init_plasma(pl: Plasma, geom: Geometry, pc: PhysConst, normalized: bool, bc_lo, bc_hi,
+                c_t: float = 0.0):
+    """PlasmaParticleContainer::InitParticles, particles/plasma/PlasmaParticleContainerInit.cpp:
+    17-316 (GPU order: ppc index outermost, cells x-fastest; no fine patch, u_std = 0)."""
+    dx, dy, dz = geom.dx, geom.dy, geom.dz
+    ppcx, ppcy = pl.ppc
+    nppc = ppcx * ppcy
+    scale = 0.0 if nppc <= 0 else (1.0 / nppc if normalized else dx * dy * dz / nppc)   # :40-41
+    ilo, ihi, jlo, jhi = 0, geom.nx - 1, 0, geom.ny - 1
+    if pl.radius != math.inf:                                                  # :70-82
+        ilo = max(ilo, int(round((-pl.radius - geom.lo[0]) / dx - 2)))
+        jlo = max(jlo, int(round((-pl.radius - geom.lo[1]) / dy - 2)))
+        ihi = min(ihi, int(round((pl.radius - geom.lo[0]) / dx + 2)))
+        jhi = min(jhi, int(round((pl.radius - geom.lo[1]) / dy + 2)))
+    jj, ii = np.meshgrid(np.arange(jlo, jhi + 1), np.arange(ilo, ihi + 1), indexing='ij')
+    ii, jj = ii.ravel().astype(float), jj.ravel().astype(float)
+    xs, ys, ws = [], [], []
+    for i_part in range(nppc):
+        rx = (0.5 + (i_part % ppcx)) / ppcx                                    # ParticleUtil.H:72-80
+        ry = (0.5 + (i_part // ppcx)) / ppcy
+        x = geom.lo[0] + (ii + rx) * dx
+        y = geom.lo[1] + (jj + ry) * dy
+        rsq = x * x + y * y
+        dens = np.broadcast_to(np.asarray(pl.density(x, y, c_t), dtype=float), x.shape)
+        keep = ~((x >= bc_hi[0]) | (x < bc_lo[0]) | (y >= bc_hi[1]) | (y < bc_lo[1])
+                 | (rsq > pl.radius * pl.radius)
+                 | (rsq < pl.hollow_core_radius * pl.hollow_core_radius)
+                 | (dens <= pl.min_density))                                     # :162-166
+        xs.append(x[keep]); ys.append(y[keep]); ws.append(dens[keep] * scale)
+    pl.x = np.concatenate(xs); pl.y = np.concatenate(ys); pl.w = np.concatenate(ws)
+    n = pl.x.size
+    u = pl.u_mean
+    pl.ux = np.full(n, u[0] * pc.c); pl.uy = np.full(n, u[1] * pc.c)
+    pl.psi = np.full(n, math.sqrt(1.0 + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) - u[2])
+    pl.x_prev, pl.y_prev = pl.x.copy(), pl.y.copy()
+    pl.ux_half, pl.uy_half, pl.psi_half = pl.ux.copy(), pl.uy.copy(), pl.psi.copy()
+    pl.valid = np.ones(n, dtype=bool)
+
+
+def beam_density(beam: Beam, x, y, z):
+    """GetInitialDensity, particles/profiles/GetInitialDensity.H:33-51"""
+    if beam.profile == 'gaussian':
+        dxn = (x - beam.position_mean[0]) / beam.position_std[0]
+        dyn = (y - beam.position_mean[1]) / beam.position_std[1]
+        dzn = (z - beam.position_mean[2]) / beam.position_std[2]
+        return beam.density * np.exp(-0.5 * dxn * dxn) * np.exp(-0.5 * dyn * dyn) \
+            * np.exp(-0.5 * dzn * dzn)
+    if beam.profile == 'flattop':
+        return np.full_like(x, beam.density)
+    raise NotImplementedError(beam.profile)
+
+
+def init_beam_slice(beam: Beam, islice: int, geom: Geometry, pc: PhysConst, normalized: bool):
+    """BeamParticleContainer::InitBeamFixedPPCSlice,
+    particles/beam/BeamParticleContainerInit.cpp:198-346 (random_ppc = 0 0 0, u_std = 0)."""
+    dx, dy, dz = geom.dx, geom.dy, geom.dz
+    px, py, pz = beam.ppc
+    nppc = px * py * pz
+    scale = 1.0 / nppc if normalized else dx * dy * dz / nppc
+    jj, ii = np.meshgrid(np.arange(geom.ny), np.arange(geom.nx), indexing='ij')
+    ii, jj = ii.ravel().astype(float), jj.ravel().astype(float)
+    cols = []
+    for i_part in range(nppc):
+        ix_p = i_part // (py * pz)                                   # ParticleUtil.H:49-63
+        iy_p = (i_part % (py * pz)) % py
+        iz_p = (i_part % (py * pz)) // py
+        x = geom.lo[0] + (ii + (0.5 + ix_p) / px) * dx
+        y = geom.lo[1] + (jj + (0.5 + iy_p) / py) * dy
+        z = np.full_like(x, geom.lo[2] + (islice + (0.5 + iz_p) / pz) * dz)
+        xm, ym = beam.position_mean[0], beam.position_mean[1]
+        keep = ~((z >= beam.zmax) | (z < beam.zmin)
+                 | (((x - xm) * (x - xm) + (y - ym) * (y - ym)) > beam.radius * beam.radius))
+        dens = beam_density(beam, x, y, z)
+        keep &= ~(dens <= beam.min_density)
+        cols.append((keep, x, y, z, dens * scale))
+    # particle order: cell-major (x fastest), i_part inner (:298-345)
+    keep = np.stack([c[0] for c in cols], axis=1).ravel()
+    pick = lambda k: np.stack([c[k] for c in cols], axis=1).ravel()[keep]
+    n = int(keep.sum())
+    bs = dict(x=pick(1), y=pick(2), z=pick(3), w=np.abs(pick(4)),
+              ux=np.full(n, beam.u_mean[0] * pc.c), uy=np.full(n, beam.u_mean[1] * pc.c),
+              uz=np.full(n, beam.u_mean[2] * pc.c),
+              id=np.arange(beam.next_id, beam.next_id + n, dtype=np.int64),
+              valid=np.ones(n, dtype=bool))
+    beam.next_id += n
+    return bs
+
+
+# --------------------------------------------------------------------------------------------
+# Driver (Hipace.cpp:393-728)
+# --------------------------------------------------------------------------------------------
+
+class Simulation:
+    def __init__(self, deck_text: str, overrides: dict | None = None):
+        d = self.deck = parse_deck(deck_text, overrides)
+        self.normalized = bool(_get(d, 'hipace.normalized_units', 0, typ=int))
+        self.pc = PhysConst.make(self.normalized)
+        n = _get(d, 'amr.n_cell', n=3, typ=int)
+        lo = _get(d, 'geometry.prob_lo', n=3)
+        hi = _get(d, 'geometry.prob_hi', n=3)
+        self.geom = Geometry(n[0], n[1], n[2], tuple(lo), tuple(hi))
+        assert _get(d, 'hipace.depos_order_xy', 2, typ=int) == 2, 'oracle scope: order 2'
+        assert _get(d, 'hipace.depos_derivative_type', 2, typ=int) == 2
+        assert _get(d, 'hipace.bxby_solver', 'explicit', typ=str) == 'explicit'
+        assert _get(d, 'boundary.field', typ=str) == 'Dirichlet', 'oracle scope: Dirichlet'
+        self.bc_kind = _get(d, 'boundary.particle', typ=str)
+        self.bc_lo = _get(d, 'boundary.particle_lo', [lo[0], lo[1]], n=2)
+        self.bc_hi = _get(d, 'boundary.particle_hi', [hi[0], hi[1]], n=2)
+        self.max_step = _get(d, 'max_step', 0, typ=int)
+        self.dt = _get(d, 'hipace.dt', 0.0)
+        self.mg_tol_rel = _get(d, 'hipace.MG_tolerance_rel', 1e-4)
+        self.mg_tol_abs = _get(d, 'hipace.MG_tolerance_abs', np.finfo(float).tiny)
+        fd = d.get('diagnostic.field_data', [])
+        self.deposit_rho = ('rho' in fd) or bool(_get(d, 'hipace.deposit_rho', 0, typ=int))
+        self.do_beam_jx_jy = bool(_get(d, 'hipace.do_beam_jx_jy_deposition', 1, typ=int))
+
+        self.plasmas = []
+        names = d.get('plasmas.names', ['no_plasma'])
+        if names[0] != 'no_plasma':
+            for nm in names:
+                self.plasmas.append(self._read_plasma(nm))
+        self.beams = []
+        bnames = d.get('beams.names', ['no_beam'])
+        if bnames[0] != 'no_beam':
+            for nm in bnames:
+                self.beams.append(self._read_beam(nm))
+        self.any_neutral = any(p.neutralize_background for p in self.plasmas)
+        self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral)
+        g = self.geom
+        self.F = {k: np.zeros((g.ny + 2 * G, g.nx + 2 * G)) for k in self.comps}
+        self.eig = poisson_eigenvalues(g.nx, g.ny, g.dx, g.dy)
+        self.mg = MultiGrid1(g.dx, g.dy, g.nx, g.ny)
+        self.checksums = {}
+        self.n_plasma_pushed = 0
+        self.mg_cycles = []
+        self.n_qsa_violation = 0
+        self.slice_hook = None        # callable(sim, islice, stage) for tests
+
+    # -- deck readers ----------------------------------------------------------------------
+    def _species_charge_mass(self, pre, default_element=None):
+        d, pc = self.deck, self.pc
+        el = _get(d, pre + '.element', default_element, typ=str)
+        charge = mass = 0.0
+        if el == 'electron':
+            charge, mass = -pc.q_e, pc.m_e
+        elif el == 'positron':
+            charge, mass = pc.q_e, pc.m_e
+        elif el == 'proton':
+            charge, mass = pc.q_e, pc.m_p
+        elif el:
+            raise NotImplementedError('element ' + el)
+        charge = _get(d, pre + '.charge', charge)
+        mass = _get(d, pre + '.mass', mass)
+        return charge, mass
+
+    def _read_plasma(self, nm):
+        """PlasmaParticleContainer::ReadParameters, particles/plasma/PlasmaParticleContainer.cpp:27-170"""
+        d = self.deck
+        charge, mass = self._species_charge_mass(nm)
+        expr = _get(d, nm + '.density(x,y,z)', None, typ=str, alt='plasmas.density(x,y,z)') or '0.'
+        code = compile(expr.replace('^', '**'), '<density>', 'eval')
+        env = dict(_CONST_SI)
+        env.update({f: getattr(np, f) for f in ('sqrt', 'exp', 'sin', 'cos', 'log', 'tanh')})
+        for k, v in d.items():
+            if k.startswith('my_constants.'):
+                env[k.split('.', 1)[1]] = _eval(v[0], {kk: vv for kk, vv in d.items() if kk != k})
+
+        def density(x, y, z, _code=code, _env=env):
+            return eval(_code, {'__builtins__': {}}, dict(_env, x=x, y=y, z=z))
+        ppc = _get(d, nm + '.ppc', n=2, typ=int, alt='plasmas.ppc')
+        return Plasma(
+            name=nm, charge=charge, mass=mass, ppc=tuple(ppc), density=density,
+            neutralize_background=bool(_get(d, nm + '.neutralize_background', 1, typ=int,
+                                            alt='plasmas.neutralize_background')),
+            max_qsa_weighting_factor=_get(d, nm + '.max_qsa_weighting_factor', 35.,
+                                          alt='plasmas.max_qsa_weighting_factor'),
+            n_subcycles=_get(d, nm + '.n_subcycles', 1, typ=int, alt='plasmas.n_subcycles'),
+            radius=_get(d, nm + '.radius', math.inf, alt='plasmas.radius'),
+            hollow_core_radius=_get(d, nm + '.hollow_core_radius', 0., alt='plasmas.hollow_core_radius'),
+            min_density=_get(d, nm + '.min_density', 0., alt='plasmas.min_density'),
+            u_mean=tuple(_get(d, nm + '.u_mean', [0., 0., 0.], n=3)))
+
+    def _read_beam(self, nm):
+        """BeamParticleContainer::ReadParameters/InitData (fixed_ppc),
+        particles/beam/BeamParticleContainer.cpp:41-143"""
+        d = self.deck
+        assert _get(d, nm + '.injection_type', typ=str) == 'fixed_ppc', 'oracle scope: fixed_ppc'
+        charge, mass = self._species_charge_mass(nm, 'electron')
+        return Beam(
+            name=nm, charge=charge, mass=mass, ppc=tuple(_get(d, nm + '.ppc', [1, 1, 1], n=3, typ=int)),
+            profile=_get(d, nm + '.profile', typ=str), density=abs(_get(d, nm + '.density')),
+            zmin=_get(d, nm + '.zmin'), zmax=_get(d, nm + '.zmax'), radius=_get(d, nm + '.radius'),
+            position_mean=tuple(_get(d, nm + '.position_mean', [0., 0., 0.], n=3)),
+            position_std=tuple(_get(d, nm + '.position_std', [0., 0., 0.], n=3)),
+            u_mean=tuple(_get(d, nm + '.u_mean', [0., 0., 0.], n=3)),
+            min_density=abs(_get(d, nm + '.min_density', 0.)),
+            n_subcycles=_get(d, nm + '.n_subcycles', 10, typ=int))
+
+    # -- slice loop ------------------------------------------------------------------------
+    def T(self, name):
+        return self.F[('This', name)]
+
+    def begin_step(self):
+        """Hipace::Evolve up to the slice loop, Hipace.cpp:401-475"""
+        for a in self.F.values():
+            a[...] = 0.0                                          # ResetAllQuantities :730-742
+        for pl in self.plasmas:
+            init_plasma(pl, self.geom, self.pc, self.normalized, self.bc_lo, self.bc_hi)
+        for pl in self.plasmas:                                   # :468-470, MultiPlasma.cpp:106-118
+            if pl.neutralize_background:
+                deposit_current(pl, self.F, self.geom, self.pc, self.normalized,
+                                rhomjz=self.F[('RhomJzIons', 'rhomjz')], flip_charge=True)
+
+    def beam_slice(self, beam: Beam, islice: int):
+        if islice < 0:
+            return None
+        if islice not in beam.slices:
+            beam.slices[islice] = init_beam_slice(beam, islice, self.geom, self.pc, self.normalized)
+        return beam.slices[islice]
+
+    def solve_one_slice(self, islice: int):
+        """Hipace::SolveOneSlice, Hipace.cpp:556-728 (explicit branch)."""
+        F, g, pc, nrm = self.F, self.geom, self.pc, self.normalized
+        T = self.T
+        for b in self.beams:
+            self.beam_slice(b, islice)
+        # InitializeSlices, fields/Fields.cpp:535-586
+        for nm in ('chi', 'Sy', 'Sx', 'ExmBy', 'EypBx', 'jz_beam', 'rhomjz'):
+            T(nm)[...] = 0.0
+        F[('Next', 'jx_beam')][...] = 0.0
+        F[('Next', 'jy_beam')][...] = 0.0
+        if self.deposit_rho:
+            T('rho')[...] = 0.0
+        # plasma deposit (:609-610)
+        for pl in self.plasmas:
+            self.n_qsa_violation += deposit_current(
+                pl, F, g, pc, nrm, jx=T('jx'), jy=T('jy'),
+                rho=T('rho') if self.deposit_rho else None, chi=T('chi'), rhomjz=T('rhomjz'))
+        # beam deposit on This: jz_beam (:613-614)
+        for b in self.beams:
+            beam_deposit(self.beam_slice(b, islice), b, g, pc, nrm, jzb=T('jz_beam'))
+        # AddRhoIons, fields/Fields.cpp:606-615
+        if self.any_neutral:
+            T('rhomjz')[...] += F[('RhomJzIons', 'rhomjz')]
+            if self.deposit_rho:
+                T('rho')[...] += F[('RhomJzIons', 'rhomjz')]
+        if self.slice_hook:
+            self.slice_hook(self, islice, 'deposited')
+        solve_poisson_psi_ez_bz(F, g, pc, self.eig)                               # :633
+        # Next-slice beam jx/jy (:639-657)
+        if self.do_beam_jx_jy:
+            for b in self.beams:
+                if islice - 1 >= 0:
+                    beam_deposit(self.beam_slice(b, islice - 1), b, g, pc, nrm,
+                                 jxb=F[('Next', 'jx_beam')], jyb=F[('Next', 'jy_beam')])
+        init_sxsy_with_beam(F, g, pc)                                             # :660
+        for pl in self.plasmas:
+            explicit_deposition(pl, F, g, pc, nrm)                                # :663
+        if self.slice_hook:
+            self.slice_hook(self, islice, 'sources')
+        # ExplicitMGSolveBxBy, Hipace.cpp:793-933
+        v = (slice(G, -G), slice(G, -G))
+        sol = np.stack([T('Bx')[v], T('By')[v]])
+        rhs = np.stack([T('Sy')[v], T('Sx')[v]])
+        self.mg.solve1(sol, rhs, T('chi')[v], self.mg_tol_rel, self.mg_tol_abs, 200)
+        T('Bx')[v], T('By')[v] = sol[0], sol[1]
+        self.mg_cycles.append(self.mg.n_vcycles_last)
+        if self.slice_hook:
+            self.slice_hook(self, islice, 'fields')
+        self._accumulate_checksums(islice)                                        # :691
+        for pl in self.plasmas:                                                   # :699-701
+            self.n_plasma_pushed += pl.x.size
+            advance_plasma_particles(pl, F, g, pc, self.bc_kind, self.bc_lo, self.bc_hi)
+        assert self.dt == 0.0, 'oracle scope: beam push only for dt = 0 (identity)'
+        if self.slice_hook:
+            self.slice_hook(self, islice, 'pushed')
+        # ShiftSlices, fields/Fields.cpp:588-604
+        F[('Previous', 'jx_beam')][...] = T('jx_beam')
+        F[('Previous', 'jy_beam')][...] = T('jy_beam')
+        T('jx_beam')[...] = F[('Next', 'jx_beam')]
+        T('jy_beam')[...] = F[('Next', 'jy_beam')]
+        T('jx')[...] = F[('Next', 'jx_beam')]
+        T('jy')[...] = F[('Next', 'jy_beam')]
+
+    def _accumulate_checksums(self, islice):
+        """checksum of a field = sum|Q| over the last iteration's valid cells,
+        tests/checksum/backend/openpmd_backend.py:40-45 (diag copy fields/Fields.cpp:413-533
+        is the identity for an uncoarsened xyz diagnostic)."""
+        for (sl, nm), a in self.F.items():
+            if sl == 'This':
+                self.checksums[nm] = self.checksums.get(nm, 0.0) + float(np.abs(a[G:-G, G:-G]).sum())
+
+    def evolve(self, nslices: int | None = None):
+        """Run step 0 (for dt = 0 every later step repeats it, Hipace.cpp:401-507).
+        nslices limits the slice loop (from the head) for bounded tests/benchmarks."""
+        self.checksums = {}
+        self.begin_step()
+        g = self.geom
+        stop = -1 if nslices is None else max(-1, g.nz - 1 - nslices)
+        for isl in range(g.nz - 1, stop, -1):
+            self.solve_one_slice(isl)
+        return self.checksums
+
+    def beam_checksums(self):
+        out = {}
+        for b in self.beams:
+            for isl in range(self.geom.nz):
+                self.beam_slice(b, isl)
+            cat = lambda k: np.concatenate([b.slices[i][k] for i in sorted(b.slices)])
+            n = cat('x').size
+            out[b.name] = dict(
+                charge=abs(b.charge) * n, mass=abs(b.mass) * n, id=int(np.abs(cat('id')).sum()),
+                x=float(np.abs(cat('x')).sum()), y=float(np.abs(cat('y')).sum()),
+                z=float(np.abs(cat('z')).sum()), ux=float(np.abs(cat('ux')).sum()),
+                uy=float(np.abs(cat('uy')).sum()), uz=float(np.abs(cat('uz')).sum()),
+                w=float(np.abs(cat('w')).sum()))
+        return out

@@ -1,0 +1,28 @@
+#!/usr/bin/env python3
+"""Extract the reference's golden checksums for the hot path into tests/golden/.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+The reference's goldens are the pinned known answers for the oracle:
+  tests/checksum/benchmarks_json/linear_wake.normalized.1Rank.json
+  tests/checksum/benchmarks_json/blowout_wake_explicit.2Rank.json
+Their decks + overrides (tests/linear_wake.normalized.1Rank.sh:32-35,
+tests/blowout_wake_explicit.2Rank.sh:32-35) are restated in examples/ of this repo.
+"""
+import json, os
+REF = '/root/reference/tests/checksum/benchmarks_json'
+OUT = os.path.dirname(os.path.abspath(__file__))
+CASES = {
+    'linear_wake.normalized.1Rank': dict(
+        deck='examples/linear_wake_normalized.in',
+        overrides={'diagnostic.field_data': 'all rho'}, rtol_cpu=1e-12, rtol_cuda=1e-7),
+    'blowout_wake_explicit.2Rank': dict(
+        deck='examples/blowout_wake_normalized.in',
+        overrides={'max_step': 1}, rtol_cpu=1e-9, rtol_cuda=1e-9,
+        skip=['Sy', 'Sx', 'chi']),
+}
+for name, meta in CASES.items():
+    gold = json.load(open(os.path.join(REF, name + '.json')))
+    json.dump(dict(meta, source=f'tests/checksum/benchmarks_json/{name}.json', checksums=gold),
+              open(os.path.join(OUT, name + '.json'), 'w'), indent=1, sort_keys=True)
+    print('wrote', name)

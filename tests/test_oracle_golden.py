@@ -1,0 +1,36 @@
+"""The oracle must reproduce the reference's own golden checksums.
+
+This pins oracle/hipace_oracle.py to the reference: every later CUDA parity test compares
+against an oracle that is itself anchored here.  rtol 1e-9 is the reference's default
+checksum tolerance (tests/checksum/checksumAPI.py:46); we actually agree to ~1e-13.
+"""
+import json
+import os
+
+import pytest
+
+from oracle.hipace_oracle import Simulation
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+RTOL = 1e-9
+
+
+def _run(case, repo_root):
+    meta = json.load(open(os.path.join(GOLD, case + '.json')))
+    deck = open(os.path.join(repo_root, meta['deck'])).read()
+    sim = Simulation(deck, meta['overrides'])
+    cs = sim.evolve()
+    return meta, sim, cs
+
+
+@pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank'])
+def test_oracle_matches_reference_golden(case, repo_root):
+    meta, sim, cs = _run(case, repo_root)
+    gold = meta['checksums']
+    for name, want in gold['lev=0'].items():
+        got = cs[name]
+        assert abs(got - want) <= RTOL * abs(want) + 1e-40, (name, got, want)
+    bc = sim.beam_checksums()['beam']
+    for name, want in gold['beam'].items():
+        assert abs(bc[name] - want) <= RTOL * abs(want) + 1e-40, (name, bc[name], want)
+    assert sim.n_qsa_violation == 0
