@@ -1,0 +1,131 @@
+// Shared device helpers for the hpb200 hot path (sm_100a, fp64).
+// Shape-factor arithmetic follows src/particles/particles_utils/ShapeFactors.H of the reference
+// (order 2 only: the default hipace.depos_order_xy and the one every BASELINE config uses).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/hpb200.h"
+
+#define HPB_G HPB_NGUARD
+
+#define HPB_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            hpb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            return HPB_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+void hpb_set_error(const char *fmt, ...);
+void hpb_count_launch(hpb_ctx *ctx, int n = 1);
+
+// validity flag = top bit of idcpu (AMReX >= 24 ParticleIDWrapper packing)
+#define HPB_ID_VALID_BIT (uint64_t(1) << 63)
+__host__ __device__ inline bool hpb_is_valid(uint64_t idcpu) { return (idcpu >> 63) != 0; }
+__host__ __device__ inline uint64_t hpb_make_invalid(uint64_t idcpu) { return idcpu & ~HPB_ID_VALID_BIT; }
+__host__ __device__ inline uint64_t hpb_make_idcpu(uint64_t id, uint32_t cpu)
+{
+    return HPB_ID_VALID_BIT | (id << 24) | cpu;
+}
+
+// Array3 view: a(i,j,n) over the grown box
+struct SliceView {
+    double *p;
+    int lo_x, lo_y;
+    long jstride, nstride;
+    __host__ __device__ inline double *comp(int n) const { return p + n * nstride; }
+    __host__ __device__ inline long idx(int i, int j) const
+    {
+        return (long)(i - lo_x) + (long)(j - lo_y) * jstride;
+    }
+    __device__ inline double &operator()(int i, int j, int n) const { return p[idx(i, j) + n * nstride]; }
+};
+inline SliceView make_view(const hpb_slice &s)
+{
+    SliceView v;
+    v.p = s.p; v.lo_x = s.lo_x; v.lo_y = s.lo_y; v.jstride = s.jstride; v.nstride = s.nstride;
+    return v;
+}
+
+// ---- shape factors, order 2 ----------------------------------------------------------------
+
+// compute_single_shape_factor<false,2>, ShapeFactors.H:165-174: returns leftmost cell
+__device__ __forceinline__ int shape2(double xmid, double s[3])
+{
+    const double xfloor = floor(xmid + 0.5);
+    const double xint = xmid - xfloor;
+    s[0] = 0.5 * (0.5 - xint) * (0.5 - xint);
+    s[1] = 0.75 - xint * xint;
+    s[2] = 0.5 * (0.5 + xint) * (0.5 + xint);
+    return (int)xfloor - 1;
+}
+
+// single_derivative_shape_factor<2,2> (centred derivative), ShapeFactors.H:405-430
+// ds[] already carries the minus sign ("-sdx"). Returns leftmost cell of the 5-point stencil.
+__device__ __forceinline__ int dshape2_centered(double xmid, double s[5], double ds[5])
+{
+    xmid += 0.5;
+    const double xfloor = floor(xmid);
+    const double xint = xmid - xfloor;
+    const double xint_2 = xint * xint;
+    s[0] = 0.;
+    s[1] = 0.5 * xint_2 - xint + 0.5;
+    s[2] = -xint_2 + xint + 0.5;
+    s[3] = 0.5 * xint_2;
+    s[4] = 0.;
+    ds[0] = -(-0.25 * xint_2 + 0.5 * xint - 0.25);
+    ds[1] = -(0.5 * xint_2 - 0.5 * xint - 0.25);
+    ds[2] = -(0.25 - 0.5 * xint);
+    ds[3] = -(-0.5 * xint_2 + 0.5 * xint + 0.25);
+    ds[4] = -(0.25 * xint_2);
+    return (int)xfloor - 2;
+}
+
+// single_derivative_shape_factor<1,2> (nodal derivative), ShapeFactors.H:305-329
+__device__ __forceinline__ int dshape2_nodal(double xmid, double s[4], double ds[4])
+{
+    const double xfloor = floor(xmid);
+    const double xint = xmid - xfloor;
+    const double xint_2 = xint * xint;
+    const bool lo = xint < 0.5;
+    s[0] = lo ? 0.5 * xint_2 - 0.5 * xint + 0.125 : 0.;
+    s[1] = lo ? 0.75 - xint_2 : 0.5 * xint_2 - 1.5 * xint + 1.125;
+    s[2] = lo ? 0.5 * xint_2 + 0.5 * xint + 0.125 : -xint_2 + 2. * xint - 0.25;
+    s[3] = lo ? 0. : 0.5 * xint_2 - 0.5 * xint + 0.125;
+    ds[0] = -(-0.5 * xint_2 + xint - 0.5);
+    ds[1] = -(1.5 * xint_2 - 2. * xint);
+    ds[2] = -(-1.5 * xint_2 + xint + 0.5);
+    ds[3] = -(0.5 * xint_2);
+    return (int)xfloor - 1;
+}
+
+// fp64 reduction without return value (RED.E.ADD.F64 on sm_100a)
+__device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+// ---- the context ---------------------------------------------------------------------------
+struct MGLevel {
+    int nx, ny;            // points in the level box (cells if cc, nodes incl. boundary if nodal)
+    double *acf, *res, *cor, *rescor;   // res/cor/rescor: 2 comps, comp stride nx*ny
+};
+
+struct hpb_ctx {
+    hpb_geom g;
+    cudaStream_t stream;
+    long n_launch;
+    // Poisson (poisson.cu)
+    int fftN;                 // nx + 1
+    int nrad; int radices[32];
+    double2 *d_root;          // exp(-2 pi i t / N), t = 0..N-1
+    double *d_sinx;           // sin(pi j / N), j = 0..N-1
+    double *d_tri_m, *d_tri_c;  // Thomas tables [ny][nx]
+    double *d_spec;           // 3 * nx * ny spectral scratch
+    double *d_stage;          // 3 * nx * ny staging (rhs)
+    // Multigrid (mg.cu)
+    int mg_cc; int mg_nlev;
+    MGLevel mg[32];
+    double *d_mg_norm;        // [0]=res norm, [1]=rhs norm
+    double *h_mg_norm;        // pinned
+    // misc
+    int *d_scalar_i;          // scratch ints
+};

@@ -1,0 +1,57 @@
+// hpb_ctx life cycle and error reporting.
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+int hpb_poisson_init(hpb_ctx *ctx);
+void hpb_poisson_free(hpb_ctx *ctx);
+int hpb_mg_init(hpb_ctx *ctx);
+void hpb_mg_free(hpb_ctx *ctx);
+
+static thread_local char g_err[1024] = "";
+
+void hpb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void hpb_count_launch(hpb_ctx *ctx, int n) { ctx->n_launch += n; }
+
+extern "C" const char *hpb_last_error(void) { return g_err; }
+extern "C" const char *hpb_version(void) { return "hpb200 0.1 (sm_100a, fp64)"; }
+
+extern "C" int hpb_create(hpb_ctx **out, const hpb_geom *geom, void *stream)
+{
+    if (!out || !geom || geom->nx < 2 || geom->ny < 2) {
+        hpb_set_error("hpb_create: bad arguments");
+        return HPB_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        hpb_set_error("hpb_create: no CUDA device (this library has no CPU fallback)");
+        return HPB_ERR_CUDA;
+    }
+    hpb_ctx *ctx = new hpb_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->g = *geom;
+    ctx->stream = (cudaStream_t)stream;
+    int rc = hpb_poisson_init(ctx);
+    if (rc == HPB_OK) rc = hpb_mg_init(ctx);
+    if (rc == HPB_OK && cudaMalloc(&ctx->d_scalar_i, 16 * sizeof(int)) != cudaSuccess) rc = HPB_ERR_CUDA;
+    if (rc != HPB_OK) { delete ctx; return rc; }
+    *out = ctx;
+    return HPB_OK;
+}
+
+extern "C" void hpb_destroy(hpb_ctx *ctx)
+{
+    if (!ctx) return;
+    hpb_poisson_free(ctx);
+    hpb_mg_free(ctx);
+    cudaFree(ctx->d_scalar_i);
+    delete ctx;
+}

@@ -1,0 +1,220 @@
+// Slice housekeeping and stencil kernels (all HBM/L2-bandwidth bound, one thread per cell,
+// x fastest => coalesced).  Restates src/fields/Fields.cpp:535-615 (InitializeSlices,
+// ShiftSlices, AddRhoIons), :880-956 (RHS assembly, ExmBy/EypBx) and src/Hipace.cpp:744-790.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct CompList { int n; int c[12]; };
+struct CompPairs { int n; int dst[8]; int src[8]; };
+
+// grown box, flat
+__global__ void k_zero(SliceView a, CompList cl, long ntot)
+{
+    const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= ntot) return;
+    for (int n = 0; n < cl.n; ++n) a.comp(cl.c[n])[o] = 0.0;
+}
+
+__global__ void k_copy(SliceView a, CompPairs cp, long ntot)
+{
+    const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= ntot) return;
+    double v[8];
+    for (int n = 0; n < cp.n; ++n) v[n] = a.comp(cp.src[n])[o];
+    for (int n = 0; n < cp.n; ++n) a.comp(cp.dst[n])[o] = v[n];
+}
+
+__global__ void k_add(SliceView a, CompPairs cp, long ntot)
+{
+    const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= ntot) return;
+    for (int n = 0; n < cp.n; ++n) a.comp(cp.dst[n])[o] += a.comp(cp.src[n])[o];
+}
+
+// RHS of the three Poisson equations into staging [3][ny][nx] (Fields.cpp:886-912)
+__global__ void k_poisson_rhs(SliceView a, int c_rhomjz, int c_jx, int c_jy, int nx, int ny,
+                              double *stage, double f_psi, double f_ez, double mu0,
+                              double dx_inv_half, double dy_inv_half)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx) return;
+    const long o = a.idx(i, j);
+    const double *jx = a.comp(c_jx), *jy = a.comp(c_jy);
+    const long js = a.jstride;
+    const double dx_jx = (jx[o + 1] - jx[o - 1]) * dx_inv_half;
+    const double dy_jy = (jy[o + js] - jy[o - js]) * dy_inv_half;
+    const double dy_jx = (jx[o + js] - jx[o - js]) * dy_inv_half;
+    const double dx_jy = (jy[o + 1] - jy[o - 1]) * dx_inv_half;
+    const long s = (long)j * nx + i;
+    const long n = (long)nx * ny;
+    stage[s] = f_psi * a.comp(c_rhomjz)[o];
+    stage[s + n] = f_ez * dx_jx + f_ez * dy_jy;
+    stage[s + 2 * n] = mu0 * dy_jx + (-mu0) * dx_jy;
+}
+
+// ExmBy = -d/dx Psi, EypBx = -d/dy Psi on the box grown by g-1 (Fields.cpp:931-956)
+__global__ void k_exmby_eypbx(SliceView a, int c_psi, int c_exmby, int c_eypbx, int nx, int ny,
+                              double dx_inv_half, double dy_inv_half)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - (HPB_G - 1);
+    const int j = (int)blockIdx.y - (HPB_G - 1);
+    if (i >= nx + (HPB_G - 1)) return;
+    const long o = a.idx(i, j);
+    const double *psi = a.comp(c_psi);
+    const long js = a.jstride;
+    a.comp(c_exmby)[o] = -(psi[o + 1] - psi[o - 1]) * dx_inv_half;
+    a.comp(c_eypbx)[o] = -(psi[o + js] - psi[o - js]) * dy_inv_half;
+}
+
+// Hipace::InitializeSxSyWithBeam (Hipace.cpp:775-788), valid box
+__global__ void k_sxsy_from_beam(SliceView a, int c_sx, int c_sy, int c_next_jxb, int c_next_jyb,
+                                 int c_jzb, int c_prev_jxb, int c_prev_jyb, int nx, int ny,
+                                 double mu0, double dx, double dy, double dz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx) return;
+    const long o = a.idx(i, j);
+    const long js = a.jstride;
+    const double *jzb = a.comp(c_jzb);
+    const double dx_jzb = (jzb[o + 1] - jzb[o - 1]) / (2.0 * dx);
+    const double dy_jzb = (jzb[o + js] - jzb[o - js]) / (2.0 * dy);
+    const double dz_jxb = (a.comp(c_prev_jxb)[o] - a.comp(c_next_jxb)[o]) / (2.0 * dz);
+    const double dz_jyb = (a.comp(c_prev_jyb)[o] - a.comp(c_next_jyb)[o]) / (2.0 * dz);
+    a.comp(c_sy)[o] = mu0 * (-dy_jzb + dz_jyb);
+    a.comp(c_sx)[o] = -mu0 * (-dx_jzb + dz_jxb);
+}
+
+// sum|Q| over the valid box; fixed-order block tree + one atomic per block
+__global__ void k_abs_sum(SliceView a, int c, int nx, int ny, double *out)
+{
+    __shared__ double sm[kThreads];
+    double acc = 0.0;
+    const double *p = a.comp(c);
+    for (long s = (long)blockIdx.x * blockDim.x + threadIdx.x; s < (long)nx * ny;
+         s += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(s / nx), i = (int)(s - (long)j * nx);
+        acc += fabs(p[a.idx(i, j)]);
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = kThreads / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, sm[0]);
+}
+
+inline unsigned nb(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+}  // namespace
+
+// exposed to poisson.cu (fused driver)
+int hpb_launch_poisson_rhs(hpb_ctx *ctx, const hpb_slice &sl, const int *comps)
+{
+    const hpb_geom &g = ctx->g;
+    dim3 grid((g.nx + kThreads - 1) / kThreads, g.ny);
+    k_poisson_rhs<<<grid, kThreads, 0, ctx->stream>>>(
+        make_view(sl), comps[HPB_C_RHOMJZ], comps[HPB_C_JX], comps[HPB_C_JY], g.nx, g.ny,
+        ctx->d_stage, -1.0 / g.ep0, 1.0 / (g.ep0 * g.c), g.mu0, 0.5 * (1.0 / g.dx),
+        0.5 * (1.0 / g.dy));
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+int hpb_launch_exmby_eypbx(hpb_ctx *ctx, const hpb_slice &sl, const int *comps)
+{
+    const hpb_geom &g = ctx->g;
+    const int gx = g.nx + 2 * (HPB_G - 1), gy = g.ny + 2 * (HPB_G - 1);
+    dim3 grid((gx + kThreads - 1) / kThreads, gy);
+    k_exmby_eypbx<<<grid, kThreads, 0, ctx->stream>>>(
+        make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.nx, g.ny,
+        0.5 * (1.0 / g.dx), 0.5 * (1.0 / g.dy));
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_fields_initialize_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps)
+{
+    if (!ctx || !comps) return HPB_ERR_ARG;
+    // Fields::InitializeSlices, explicit branch (Fields.cpp:551-560, 578-580)
+    CompList cl;
+    cl.n = 0;
+    const int names[] = {HPB_C_CHI, HPB_C_SY, HPB_C_SX, HPB_C_EXMBY, HPB_C_EYPBX, HPB_C_JZ_BEAM,
+                         HPB_C_RHOMJZ, HPB_C_NEXT_JX_BEAM, HPB_C_NEXT_JY_BEAM, HPB_C_RHO};
+    for (int k : names) if (comps[k] >= 0) cl.c[cl.n++] = comps[k];
+    const long ntot = (long)sl.jstride * sl.ny_tot;
+    k_zero<<<nb(ntot), kThreads, 0, ctx->stream>>>(make_view(sl), cl, ntot);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_fields_add_rho_ions(hpb_ctx *ctx, hpb_slice sl, const int *comps)
+{
+    if (!ctx || !comps) return HPB_ERR_ARG;
+    if (comps[HPB_C_IONS_RHOMJZ] < 0) return HPB_OK;     // Fields.cpp:609
+    CompPairs cp;
+    cp.n = 0;
+    cp.dst[cp.n] = comps[HPB_C_RHOMJZ]; cp.src[cp.n++] = comps[HPB_C_IONS_RHOMJZ];
+    if (comps[HPB_C_RHO] >= 0) { cp.dst[cp.n] = comps[HPB_C_RHO]; cp.src[cp.n++] = comps[HPB_C_IONS_RHOMJZ]; }
+    const long ntot = (long)sl.jstride * sl.ny_tot;
+    k_add<<<nb(ntot), kThreads, 0, ctx->stream>>>(make_view(sl), cp, ntot);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_fields_shift_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps)
+{
+    if (!ctx || !comps) return HPB_ERR_ARG;
+    // Fields::ShiftSlices, explicit branch (Fields.cpp:596-599): Previous <- This (jx_beam,
+    // jy_beam), then This{jx_beam,jy_beam,jx,jy} <- Next{jx_beam,jy_beam,jx_beam,jy_beam}.
+    // One kernel: all sources are read before any destination is written.
+    CompPairs cp;
+    cp.n = 6;
+    cp.dst[0] = comps[HPB_C_PREV_JX_BEAM]; cp.src[0] = comps[HPB_C_JX_BEAM];
+    cp.dst[1] = comps[HPB_C_PREV_JY_BEAM]; cp.src[1] = comps[HPB_C_JY_BEAM];
+    cp.dst[2] = comps[HPB_C_JX_BEAM];      cp.src[2] = comps[HPB_C_NEXT_JX_BEAM];
+    cp.dst[3] = comps[HPB_C_JY_BEAM];      cp.src[3] = comps[HPB_C_NEXT_JY_BEAM];
+    cp.dst[4] = comps[HPB_C_JX];           cp.src[4] = comps[HPB_C_NEXT_JX_BEAM];
+    cp.dst[5] = comps[HPB_C_JY];           cp.src[5] = comps[HPB_C_NEXT_JY_BEAM];
+    const long ntot = (long)sl.jstride * sl.ny_tot;
+    k_copy<<<nb(ntot), kThreads, 0, ctx->stream>>>(make_view(sl), cp, ntot);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_fields_sxsy_from_beam(hpb_ctx *ctx, hpb_slice sl, const int *comps)
+{
+    if (!ctx || !comps) return HPB_ERR_ARG;
+    const hpb_geom &g = ctx->g;
+    dim3 grid((g.nx + kThreads - 1) / kThreads, g.ny);
+    k_sxsy_from_beam<<<grid, kThreads, 0, ctx->stream>>>(
+        make_view(sl), comps[HPB_C_SX], comps[HPB_C_SY], comps[HPB_C_NEXT_JX_BEAM],
+        comps[HPB_C_NEXT_JY_BEAM], comps[HPB_C_JZ_BEAM], comps[HPB_C_PREV_JX_BEAM],
+        comps[HPB_C_PREV_JY_BEAM], g.nx, g.ny, g.mu0, g.dx, g.dy, g.dz);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_abs_sum(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out)
+{
+    if (!ctx || c < 0 || !d_out) return HPB_ERR_ARG;
+    const hpb_geom &g = ctx->g;
+    const long n = (long)g.nx * g.ny;
+    unsigned blocks = nb(n);
+    if (blocks > 592) blocks = 592;
+    k_abs_sum<<<blocks, kThreads, 0, ctx->stream>>>(make_view(sl), c, g.nx, g.ny, d_out);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}

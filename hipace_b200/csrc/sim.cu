@@ -1,0 +1,1008 @@
+// Slice-loop driver: Hipace::Hipace / InitData / Evolve / SolveOneSlice restated over the
+// hpb_* kernel seams (src/Hipace.cpp:74-295 constructor + InitData, :393-554 Evolve,
+// :556-728 SolveOneSlice, explicit-solver branch, level 0).
+//
+// Everything lives on the device between hpb_sim_create() and the host-buffer queries; the host
+// only enqueues kernels.  Plasma is re-created every time step (Hipace.cpp:450) by a device
+// kernel that evaluates the deck's density expression; fixed_ppc beams are created for all
+// slices at once (the reference creates them slice by slice on the head rank at step 0,
+// src/particles/beam/BeamParticleContainerInit.cpp:198-346 -- same particles, same order, same
+// ids because our storage order is the head-first processing order).
+#include "common.cuh"
+#include "deck.hpp"
+#include <cub/cub.cuh>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <memory>
+#include <string>
+#include <vector>
+
+using hpb::Deck;
+using hpb::RpnInstr;
+
+namespace {
+
+struct DevRpn { int n; RpnInstr code[hpb::kMaxRpn]; };
+
+__device__ double rpn_eval(const DevRpn &p, double x, double y, double z)
+{
+    double st[24];
+    int sp = 0;
+    for (int k = 0; k < p.n; ++k) {
+        const RpnInstr c = p.code[k];
+        switch (c.op) {
+        case hpb::OP_CONST: st[sp++] = c.val; break;
+        case hpb::OP_VAR: st[sp++] = c.var == 0 ? x : (c.var == 1 ? y : z); break;
+        case hpb::OP_ADD: --sp; st[sp - 1] += st[sp]; break;
+        case hpb::OP_SUB: --sp; st[sp - 1] -= st[sp]; break;
+        case hpb::OP_MUL: --sp; st[sp - 1] *= st[sp]; break;
+        case hpb::OP_DIV: --sp; st[sp - 1] /= st[sp]; break;
+        case hpb::OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+        case hpb::OP_LT: --sp; st[sp - 1] = st[sp - 1] < st[sp] ? 1.0 : 0.0; break;
+        case hpb::OP_GT: --sp; st[sp - 1] = st[sp - 1] > st[sp] ? 1.0 : 0.0; break;
+        case hpb::OP_MIN: --sp; st[sp - 1] = fmin(st[sp - 1], st[sp]); break;
+        case hpb::OP_MAX: --sp; st[sp - 1] = fmax(st[sp - 1], st[sp]); break;
+        case hpb::OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+        case hpb::OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+        case hpb::OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+        case hpb::OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
+        case hpb::OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+        case hpb::OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
+        case hpb::OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
+        case hpb::OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+        }
+    }
+    return sp > 0 ? st[sp - 1] : 0.0;
+}
+
+// ---- plasma: PlasmaParticleContainer::InitParticles (PlasmaParticleContainerInit.cpp:17-316) ----
+struct PlasmaInitArgs {
+    int ilo, jlo, ncx, ncy;       // candidate cell box
+    int ppcx, ppcy;
+    double plo_x, plo_y, dx, dy;
+    double blo_x, blo_y, bhi_x, bhi_y;
+    double radius_sq, hollow_sq, min_density, c_t, scale;
+    double ux0, uy0, psi0;
+};
+
+__device__ __forceinline__ bool plasma_candidate(const PlasmaInitArgs &a, const DevRpn &dens,
+                                                 long idx, double &x, double &y, double &d)
+{
+    const long ncell = (long)a.ncx * a.ncy;
+    const int i_part = (int)(idx / ncell);
+    const long cell = idx - (long)i_part * ncell;
+    const int j = (int)(cell / a.ncx) + a.jlo, i = (int)(cell % a.ncx) + a.ilo;
+    const double rx = (0.5 + (i_part % a.ppcx)) / a.ppcx;       // ParticleUtil.H:72-80
+    const double ry = (0.5 + (i_part / a.ppcx)) / a.ppcy;
+    x = a.plo_x + (i + rx) * a.dx;
+    y = a.plo_y + (j + ry) * a.dy;
+    const double rsq = x * x + y * y;
+    if (x >= a.bhi_x || x < a.blo_x || y >= a.bhi_y || y < a.blo_y || rsq > a.radius_sq ||
+        rsq < a.hollow_sq)
+        return false;
+    d = rpn_eval(dens, x, y, a.c_t);
+    return !(d <= a.min_density);
+}
+
+__global__ void k_plasma_flag(PlasmaInitArgs a, DevRpn dens, long ncand, unsigned *flag)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncand) return;
+    double x, y, d;
+    flag[idx] = plasma_candidate(a, dens, idx, x, y, d) ? 1u : 0u;
+}
+
+__global__ void k_plasma_fill(PlasmaInitArgs a, DevRpn dens, long ncand, const unsigned *flag,
+                              const unsigned *offs, hpb_plasma pl)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncand || !flag[idx]) return;
+    double x, y, d;
+    plasma_candidate(a, dens, idx, x, y, d);
+    const long p = offs[idx];
+    pl.r[HPB_X][p] = x;
+    pl.r[HPB_Y][p] = y;
+    pl.r[HPB_W][p] = d * a.scale;
+    pl.r[HPB_UX][p] = a.ux0;
+    pl.r[HPB_UY][p] = a.uy0;
+    pl.r[HPB_PSI][p] = a.psi0;
+    pl.r[HPB_X_PREV][p] = x;
+    pl.r[HPB_Y_PREV][p] = y;
+    pl.r[HPB_UX_HALF][p] = a.ux0;
+    pl.r[HPB_UY_HALF][p] = a.uy0;
+    pl.r[HPB_PSI_HALF][p] = a.psi0;
+    pl.idcpu[p] = hpb_make_idcpu(1, 0);       // id 1, cpu (= MR level) 0, :283-284
+}
+
+// ---- beam: InitBeamFixedPPCSlice for all slices (BeamParticleContainerInit.cpp:198-346) ----
+struct BeamInitArgs {
+    int ilo, jlo, ncx, ncy, nz;
+    int ppcx, ppcy, ppcz;
+    double plo_x, plo_y, plo_z, dx, dy, dz;
+    double x_mean, y_mean, z_mean, sx, sy, sz;
+    double zmin, zmax, radius_sq, density, min_density, scale;
+    int profile;                  // 0 gaussian, 1 flattop
+    double ux0, uy0, uz0;
+};
+
+__device__ __forceinline__ bool beam_candidate(const BeamInitArgs &a, long idx, double &x,
+                                               double &y, double &z, double &d)
+{
+    const int nppc = a.ppcx * a.ppcy * a.ppcz;
+    const long per_slice = (long)a.ncx * a.ncy * nppc;
+    const int s = (int)(idx / per_slice);            // storage slot: head slice first
+    const int islice = a.nz - 1 - s;
+    long rem = idx - (long)s * per_slice;
+    const long cell = rem / nppc;
+    const int i_part = (int)(rem - cell * nppc);
+    const int j = (int)(cell / a.ncx) + a.jlo, i = (int)(cell % a.ncx) + a.ilo;
+    const int pyz = a.ppcy * a.ppcz;
+    const int ix_p = i_part / pyz, iy_p = (i_part % pyz) % a.ppcy, iz_p = (i_part % pyz) / a.ppcy;
+    x = a.plo_x + (i + (0.5 + ix_p) / a.ppcx) * a.dx;
+    y = a.plo_y + (j + (0.5 + iy_p) / a.ppcy) * a.dy;
+    z = a.plo_z + (islice + (0.5 + iz_p) / a.ppcz) * a.dz;
+    if (z >= a.zmax || z < a.zmin ||
+        ((x - a.x_mean) * (x - a.x_mean) + (y - a.y_mean) * (y - a.y_mean)) > a.radius_sq)
+        return false;
+    if (a.profile == 0) {                            // GetInitialDensity.H:33-51
+        const double dxn = (x - a.x_mean) / a.sx, dyn = (y - a.y_mean) / a.sy,
+                     dzn = (z - a.z_mean) / a.sz;
+        d = a.density * exp(-0.5 * dxn * dxn) * exp(-0.5 * dyn * dyn) * exp(-0.5 * dzn * dzn);
+    } else {
+        d = a.density;
+    }
+    return !(d <= a.min_density);
+}
+
+__global__ void k_beam_flag(BeamInitArgs a, long ncand, unsigned *flag)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncand) return;
+    double x, y, z, d;
+    flag[idx] = beam_candidate(a, idx, x, y, z, d) ? 1u : 0u;
+}
+
+__global__ void k_beam_fill(BeamInitArgs a, long ncand, const unsigned *flag, const unsigned *offs,
+                            hpb_beam_slice b, uint64_t first_id)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncand || !flag[idx]) return;
+    double x, y, z, d;
+    beam_candidate(a, idx, x, y, z, d);
+    const long p = offs[idx];
+    b.x[p] = x; b.y[p] = y; b.z[p] = z;
+    b.w[p] = fabs(d * a.scale);
+    b.ux[p] = a.ux0; b.uy[p] = a.uy0; b.uz[p] = a.uz0;
+    b.idcpu[p] = hpb_make_idcpu(first_id + (uint64_t)p, 0);
+}
+
+// offsets of the slice slots: slot_off[s] = offs[s * per_slice], slot_off[nslots] = total
+__global__ void k_slot_offsets(const unsigned *flag, const unsigned *offs, long per_slice,
+                               int nslots, long ncand, long *slot_off)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nslots) return;
+    if (s == nslots) slot_off[s] = ncand > 0 ? (long)offs[ncand - 1] + flag[ncand - 1] : 0;
+    else slot_off[s] = offs[(long)s * per_slice];
+}
+
+__global__ void k_count_valid(const uint64_t *idcpu, long np, unsigned long long *out)
+{
+    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool v = ip < np && hpb_is_valid(idcpu[ip]);
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+__global__ void k_valid_bytes(const uint64_t *idcpu, long np, uint8_t *out)
+{
+    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip < np) out[ip] = hpb_is_valid(idcpu[ip]) ? 1 : 0;
+}
+
+struct Species {
+    std::string name;
+    double charge = 0, mass = 0;
+    int ppc[2] = {1, 1};
+    DevRpn density;
+    bool neutralize = true;
+    double max_qsa = 35.;
+    int n_subcycles = 1;
+    double radius = INFINITY, hollow = 0., min_density = 0.;
+    double u_mean[3] = {0, 0, 0};
+    hpb_plasma d = {};
+    long capacity = 0;
+};
+
+struct BeamSp {
+    std::string name;
+    double charge = 0, mass = 0;
+    int ppc[3] = {1, 1, 1};
+    int profile = 0;
+    double density = 0, zmin = 0, zmax = 0, radius = 0, min_density = 0;
+    double pos_mean[3] = {0, 0, 0}, pos_std[3] = {0, 0, 0}, u_mean[3] = {0, 0, 0};
+    hpb_beam_slice d = {};        // whole beam, slot-major (slot s = slice nz-1-s)
+    std::vector<long> slot_off;   // nz + 1
+    bool initialised = false;
+};
+
+void species_charge_mass(const Deck &dk, const hpb_geom &g, const std::string &pre,
+                         const std::string &def_el, double &charge, double &mass)
+{
+    const double m_p = g.normalized ? 1836.15267343 : 1.67262192369e-27;
+    const std::string el = dk.str(pre + ".element", def_el);
+    charge = mass = 0.;
+    if (el == "electron") { charge = -g.q_e; mass = g.m_e; }
+    else if (el == "positron") { charge = g.q_e; mass = g.m_e; }
+    else if (el == "proton") { charge = g.q_e; mass = m_p; }
+    else if (!el.empty()) throw std::runtime_error("unsupported element '" + el + "'");
+    charge = dk.num(pre + ".charge", charge);
+    mass = dk.num(pre + ".mass", mass);
+}
+
+inline unsigned nb256(long n) { return (unsigned)((n + 255) / 256); }
+
+}  // namespace
+
+struct hpb_sim {
+    Deck deck;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    hpb_geom g = {};
+    int nz = 0;
+    double prob_lo[3], prob_hi[3];
+    double bc_lo[2], bc_hi[2];
+    int particle_bc = HPB_BC_PERIODIC;
+    int max_step = 0;
+    double dt = 0.;
+    double mg_tol_rel = 1e-4, mg_tol_abs = DBL_MIN;
+    bool deposit_rho = false, do_beam_jx_jy = true, any_neutral = false;
+    hpb_ctx *ctx = nullptr;
+    hpb_slice sl = {};
+    int comps[HPB_C_COUNT];
+    std::vector<std::pair<std::string, std::string>> comp_names;   // (which_slice, name) by index
+    std::vector<Species> plasmas;
+    std::vector<BeamSp> beams;
+    // scratch for init
+    unsigned *d_flag = nullptr, *d_offs = nullptr;
+    long scan_cap = 0;
+    void *d_cub = nullptr;
+    size_t cub_bytes = 0;
+    // diagnostics
+    double *d_checksum = nullptr;       // ncomp
+    int *d_nqsa = nullptr;
+    unsigned long long *d_count = nullptr;
+    bool opt_checksums = true, opt_profile = false;
+    hpb_sim_stats stats = {};
+    std::vector<int> mg_iters;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> pev;
+    int cur_step = -1;
+};
+
+namespace {
+
+#define SIM_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            hpb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            return HPB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+int ensure_scan(hpb_sim *s, long n)
+{
+    if (n > 0x7fffffffL) { hpb_set_error("init: too many candidate particles"); return HPB_ERR_UNSUPPORTED; }
+    if (n <= s->scan_cap) return HPB_OK;
+    cudaFree(s->d_flag); cudaFree(s->d_offs); cudaFree(s->d_cub);
+    s->d_flag = s->d_offs = nullptr; s->d_cub = nullptr;
+    SIM_CUDA(cudaMalloc(&s->d_flag, sizeof(unsigned) * n));
+    SIM_CUDA(cudaMalloc(&s->d_offs, sizeof(unsigned) * n));
+    s->cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, s->cub_bytes, s->d_flag, s->d_offs, (int)n, s->stream);
+    SIM_CUDA(cudaMalloc(&s->d_cub, s->cub_bytes));
+    s->scan_cap = n;
+    return HPB_OK;
+}
+
+int read_deck(hpb_sim *s)
+{
+    const Deck &d = s->deck;
+    hpb_geom &g = s->g;
+    g.normalized = (int)d.num("hipace.normalized_units", 0);
+    if (g.normalized) { g.c = g.ep0 = g.mu0 = g.q_e = g.m_e = 1.0; }       // Constants.H:54-81
+    else { g.c = 299792458.; g.ep0 = 8.8541878128e-12; g.mu0 = 1.25663706212e-06;
+           g.q_e = 1.602176634e-19; g.m_e = 9.1093837015e-31; }
+    const auto nc = d.nums("amr.n_cell", {});
+    const auto lo = d.nums("geometry.prob_lo", {}), hi = d.nums("geometry.prob_hi", {});
+    if (nc.size() != 3 || lo.size() != 3 || hi.size() != 3)
+        throw std::runtime_error("amr.n_cell / geometry.prob_lo / geometry.prob_hi need 3 values");
+    g.nx = (int)nc[0]; g.ny = (int)nc[1]; s->nz = (int)nc[2];
+    for (int k = 0; k < 3; ++k) { s->prob_lo[k] = lo[k]; s->prob_hi[k] = hi[k]; }
+    g.dx = (hi[0] - lo[0]) / g.nx; g.dy = (hi[1] - lo[1]) / g.ny; g.dz = (hi[2] - lo[2]) / s->nz;
+    // GetPosOffset with the grown fab box [-g, n-1+g] (Fields.H:71-77)
+    g.x_off = 0.5 * (lo[0] + hi[0] - g.dx * ((-HPB_G) + (g.nx - 1 + HPB_G)));
+    g.y_off = 0.5 * (lo[1] + hi[1] - g.dy * ((-HPB_G) + (g.ny - 1 + HPB_G)));
+    if ((int)d.num("hipace.depos_order_xy", 2) != 2)
+        throw std::runtime_error("only hipace.depos_order_xy = 2 is supported");
+    if ((int)d.num("hipace.depos_derivative_type", 2) != 2)
+        throw std::runtime_error("only hipace.depos_derivative_type = 2 is supported");
+    if (d.str("hipace.bxby_solver", "explicit") != "explicit")
+        throw std::runtime_error("only hipace.bxby_solver = explicit is supported");
+    if (d.str("boundary.field", "") != "Dirichlet")
+        throw std::runtime_error("only boundary.field = Dirichlet is supported");
+    const std::string pbc = d.str("boundary.particle", "");
+    if (pbc == "Periodic") s->particle_bc = HPB_BC_PERIODIC;
+    else if (pbc == "Reflecting") s->particle_bc = HPB_BC_REFLECTING;
+    else if (pbc == "Absorbing") s->particle_bc = HPB_BC_ABSORBING;
+    else throw std::runtime_error("boundary.particle must be Periodic, Reflecting or Absorbing");
+    const auto blo = d.nums("boundary.particle_lo", {lo[0], lo[1]});
+    const auto bhi = d.nums("boundary.particle_hi", {hi[0], hi[1]});
+    s->bc_lo[0] = blo[0]; s->bc_lo[1] = blo[1]; s->bc_hi[0] = bhi[0]; s->bc_hi[1] = bhi[1];
+    s->max_step = (int)d.num("max_step", 0);
+    s->dt = d.num("hipace.dt", 0.);
+    s->mg_tol_rel = d.num("hipace.MG_tolerance_rel", 1e-4);
+    s->mg_tol_abs = d.num("hipace.MG_tolerance_abs", DBL_MIN);
+    s->deposit_rho = (int)d.num("hipace.deposit_rho", 0) != 0;
+    for (auto &t : d.strs("diagnostic.field_data")) if (t == "rho") s->deposit_rho = true;
+    s->do_beam_jx_jy = (int)d.num("hipace.do_beam_jx_jy_deposition", 1) != 0;
+
+    auto pn = d.strs("plasmas.names");
+    if (!pn.empty() && pn[0] != "no_plasma") {
+        for (auto &nm : pn) {
+            Species sp;
+            sp.name = nm;
+            species_charge_mass(d, g, nm, "", sp.charge, sp.mass);
+            std::string expr = d.str(nm + ".density(x,y,z)", "", "plasmas.density(x,y,z)");
+            if (expr.empty()) expr = "0.";
+            else {      // the value may contain blanks: re-join the tokens
+                auto v = d.find(nm + ".density(x,y,z)", "plasmas.density(x,y,z)");
+                expr.clear();
+                for (auto &t : *v) expr += t;
+            }
+            std::vector<RpnInstr> code;
+            d.compile(expr, {"x", "y", "z"}, code);
+            sp.density.n = (int)code.size();
+            for (size_t k = 0; k < code.size(); ++k) sp.density.code[k] = code[k];
+            const auto ppc = d.nums(nm + ".ppc", {}, "plasmas.ppc");
+            if (ppc.size() != 2) throw std::runtime_error(nm + ".ppc needs 2 values");
+            sp.ppc[0] = (int)ppc[0]; sp.ppc[1] = (int)ppc[1];
+            sp.neutralize = (int)d.num(nm + ".neutralize_background", 1, "plasmas.neutralize_background") != 0;
+            sp.max_qsa = d.num(nm + ".max_qsa_weighting_factor", 35., "plasmas.max_qsa_weighting_factor");
+            sp.n_subcycles = (int)d.num(nm + ".n_subcycles", 1, "plasmas.n_subcycles");
+            sp.radius = d.num(nm + ".radius", INFINITY, "plasmas.radius");
+            sp.hollow = d.num(nm + ".hollow_core_radius", 0., "plasmas.hollow_core_radius");
+            sp.min_density = d.num(nm + ".min_density", 0., "plasmas.min_density");
+            const auto um = d.nums(nm + ".u_mean", {0., 0., 0.});
+            for (int k = 0; k < 3 && k < (int)um.size(); ++k) sp.u_mean[k] = um[k];
+            const auto us = d.nums(nm + ".u_std", {0., 0., 0.});
+            for (double v : us)
+                if (v != 0.) throw std::runtime_error("plasma u_std != 0 needs AMReX's RNG stream: unsupported");
+            s->plasmas.push_back(sp);
+            s->any_neutral = s->any_neutral || sp.neutralize;
+        }
+    }
+    auto bn = d.strs("beams.names");
+    if (!bn.empty() && bn[0] != "no_beam") {
+        for (auto &nm : bn) {
+            BeamSp b;
+            b.name = nm;
+            if (d.str(nm + ".injection_type", "") != "fixed_ppc")
+                throw std::runtime_error("only beam injection_type = fixed_ppc is supported (others need AMReX's RNG)");
+            species_charge_mass(d, g, nm, "electron", b.charge, b.mass);
+            const auto ppc = d.nums(nm + ".ppc", {1., 1., 1.});
+            for (int k = 0; k < 3 && k < (int)ppc.size(); ++k) b.ppc[k] = (int)ppc[k];
+            const std::string prof = d.str(nm + ".profile", "");
+            if (prof == "gaussian") b.profile = 0;
+            else if (prof == "flattop") b.profile = 1;
+            else throw std::runtime_error("beam profile must be gaussian or flattop");
+            b.density = fabs(d.num(nm + ".density", 0.));
+            b.zmin = d.num(nm + ".zmin", -INFINITY); b.zmax = d.num(nm + ".zmax", INFINITY);
+            b.radius = d.num(nm + ".radius", INFINITY);
+            b.min_density = fabs(d.num(nm + ".min_density", 0.));
+            const auto pm = d.nums(nm + ".position_mean", {0., 0., 0.});
+            const auto ps = d.nums(nm + ".position_std", {0., 0., 0.});
+            const auto um = d.nums(nm + ".u_mean", {0., 0., 0.});
+            for (int k = 0; k < 3; ++k) {
+                if (k < (int)pm.size()) b.pos_mean[k] = pm[k];
+                if (k < (int)ps.size()) b.pos_std[k] = ps[k];
+                if (k < (int)um.size()) b.u_mean[k] = um[k];
+            }
+            const auto us = d.nums(nm + ".u_std", {0., 0., 0.});
+            for (double v : us)
+                if (v != 0.) throw std::runtime_error("beam u_std != 0 needs AMReX's RNG stream: unsupported");
+            s->beams.push_back(b);
+        }
+    }
+    return HPB_OK;
+}
+
+// component table, allocation order of Fields::AllocData (Fields.cpp:70-122), explicit solver
+void build_components(hpb_sim *s)
+{
+    for (int k = 0; k < HPB_C_COUNT; ++k) s->comps[k] = -1;
+    int n = 0;
+    auto add = [&](int id, const char *which, const char *name) {
+        s->comps[id] = n++;
+        s->comp_names.emplace_back(which, name);
+    };
+    add(HPB_C_NEXT_JX_BEAM, "Next", "jx_beam"); add(HPB_C_NEXT_JY_BEAM, "Next", "jy_beam");
+    add(HPB_C_CHI, "This", "chi"); add(HPB_C_SY, "This", "Sy"); add(HPB_C_SX, "This", "Sx");
+    add(HPB_C_EXMBY, "This", "ExmBy"); add(HPB_C_EYPBX, "This", "EypBx"); add(HPB_C_EZ, "This", "Ez");
+    add(HPB_C_BX, "This", "Bx"); add(HPB_C_BY, "This", "By"); add(HPB_C_BZ, "This", "Bz");
+    add(HPB_C_PSI, "This", "Psi"); add(HPB_C_JX_BEAM, "This", "jx_beam");
+    add(HPB_C_JY_BEAM, "This", "jy_beam"); add(HPB_C_JZ_BEAM, "This", "jz_beam");
+    add(HPB_C_JX, "This", "jx"); add(HPB_C_JY, "This", "jy"); add(HPB_C_RHOMJZ, "This", "rhomjz");
+    if (s->deposit_rho) add(HPB_C_RHO, "This", "rho");
+    add(HPB_C_PREV_JX_BEAM, "Previous", "jx_beam"); add(HPB_C_PREV_JY_BEAM, "Previous", "jy_beam");
+    if (s->any_neutral) add(HPB_C_IONS_RHOMJZ, "RhomJzIons", "rhomjz");
+    s->sl.ncomp = n;
+}
+
+int init_plasma(hpb_sim *s, Species &sp, double c_t)
+{
+    const hpb_geom &g = s->g;
+    PlasmaInitArgs a;
+    int ilo = 0, ihi = g.nx - 1, jlo = 0, jhi = g.ny - 1;
+    if (std::isfinite(sp.radius)) {      // :70-82
+        ilo = std::max(ilo, (int)lround((-sp.radius - s->prob_lo[0]) / g.dx - 2));
+        jlo = std::max(jlo, (int)lround((-sp.radius - s->prob_lo[1]) / g.dy - 2));
+        ihi = std::min(ihi, (int)lround((sp.radius - s->prob_lo[0]) / g.dx + 2));
+        jhi = std::min(jhi, (int)lround((sp.radius - s->prob_lo[1]) / g.dy + 2));
+    }
+    a.ilo = ilo; a.jlo = jlo; a.ncx = std::max(0, ihi - ilo + 1); a.ncy = std::max(0, jhi - jlo + 1);
+    a.ppcx = sp.ppc[0]; a.ppcy = sp.ppc[1];
+    const int nppc = a.ppcx * a.ppcy;
+    a.plo_x = s->prob_lo[0]; a.plo_y = s->prob_lo[1]; a.dx = g.dx; a.dy = g.dy;
+    a.blo_x = s->bc_lo[0]; a.blo_y = s->bc_lo[1]; a.bhi_x = s->bc_hi[0]; a.bhi_y = s->bc_hi[1];
+    a.radius_sq = sp.radius * sp.radius; a.hollow_sq = sp.hollow * sp.hollow;
+    a.min_density = sp.min_density; a.c_t = c_t;
+    a.scale = nppc <= 0 ? 0. : (g.normalized ? 1. / nppc : g.dx * g.dy * g.dz / nppc);   // :40-41
+    a.ux0 = sp.u_mean[0] * g.c; a.uy0 = sp.u_mean[1] * g.c;
+    a.psi0 = sqrt(1. + sp.u_mean[0] * sp.u_mean[0] + sp.u_mean[1] * sp.u_mean[1]
+                  + sp.u_mean[2] * sp.u_mean[2]) - sp.u_mean[2];
+    const long ncand = (long)a.ncx * a.ncy * nppc;
+    sp.d.np = 0;
+    if (ncand == 0) return HPB_OK;
+    int rc = ensure_scan(s, ncand);
+    if (rc) return rc;
+    k_plasma_flag<<<nb256(ncand), 256, 0, s->stream>>>(a, sp.density, ncand, s->d_flag);
+    size_t tb = s->cub_bytes;
+    SIM_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tb, s->d_flag, s->d_offs, (int)ncand, s->stream));
+    unsigned last[2];
+    SIM_CUDA(cudaMemcpyAsync(&last[0], s->d_flag + ncand - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaMemcpyAsync(&last[1], s->d_offs + ncand - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    const long np = (long)last[0] + last[1];
+    if (np > sp.capacity) {
+        for (int k = 0; k < HPB_PLASMA_NREAL; ++k) { cudaFree(sp.d.r[k]); sp.d.r[k] = nullptr; }
+        cudaFree(sp.d.idcpu); sp.d.idcpu = nullptr;
+        for (int k = 0; k < HPB_PLASMA_NREAL; ++k) SIM_CUDA(cudaMalloc(&sp.d.r[k], sizeof(double) * np));
+        SIM_CUDA(cudaMalloc(&sp.d.idcpu, sizeof(uint64_t) * np));
+        sp.capacity = np;
+    }
+    sp.d.np = np;
+    if (np > 0)
+        k_plasma_fill<<<nb256(ncand), 256, 0, s->stream>>>(a, sp.density, ncand, s->d_flag, s->d_offs, sp.d);
+    SIM_CUDA(cudaGetLastError());
+    return HPB_OK;
+}
+
+int init_beam(hpb_sim *s, BeamSp &b)
+{
+    const hpb_geom &g = s->g;
+    BeamInitArgs a;
+    int ilo = 0, ihi = g.nx - 1, jlo = 0, jhi = g.ny - 1;
+    if (std::isfinite(b.radius)) {   // bounding box of the radius cut: a superset, order preserved
+        ilo = std::max(ilo, (int)floor((b.pos_mean[0] - b.radius - s->prob_lo[0]) / g.dx) - 2);
+        jlo = std::max(jlo, (int)floor((b.pos_mean[1] - b.radius - s->prob_lo[1]) / g.dy) - 2);
+        ihi = std::min(ihi, (int)ceil((b.pos_mean[0] + b.radius - s->prob_lo[0]) / g.dx) + 2);
+        jhi = std::min(jhi, (int)ceil((b.pos_mean[1] + b.radius - s->prob_lo[1]) / g.dy) + 2);
+    }
+    a.ilo = ilo; a.jlo = jlo; a.ncx = std::max(0, ihi - ilo + 1); a.ncy = std::max(0, jhi - jlo + 1);
+    a.nz = s->nz;
+    a.ppcx = b.ppc[0]; a.ppcy = b.ppc[1]; a.ppcz = b.ppc[2];
+    const int nppc = a.ppcx * a.ppcy * a.ppcz;
+    a.plo_x = s->prob_lo[0]; a.plo_y = s->prob_lo[1]; a.plo_z = s->prob_lo[2];
+    a.dx = g.dx; a.dy = g.dy; a.dz = g.dz;
+    a.x_mean = b.pos_mean[0]; a.y_mean = b.pos_mean[1]; a.z_mean = b.pos_mean[2];
+    a.sx = b.pos_std[0]; a.sy = b.pos_std[1]; a.sz = b.pos_std[2];
+    a.zmin = b.zmin; a.zmax = b.zmax; a.radius_sq = b.radius * b.radius;
+    a.density = b.density; a.min_density = b.min_density;
+    a.scale = g.normalized ? 1. / nppc : g.dx * g.dy * g.dz / nppc;
+    a.profile = b.profile;
+    a.ux0 = b.u_mean[0] * g.c; a.uy0 = b.u_mean[1] * g.c; a.uz0 = b.u_mean[2] * g.c;
+    const long per_slice = (long)a.ncx * a.ncy * nppc;
+    const long ncand = per_slice * s->nz;
+    b.slot_off.assign(s->nz + 1, 0);
+    b.d.np = 0;
+    b.initialised = true;
+    if (ncand == 0) return HPB_OK;
+    int rc = ensure_scan(s, ncand);
+    if (rc) return rc;
+    k_beam_flag<<<nb256(ncand), 256, 0, s->stream>>>(a, ncand, s->d_flag);
+    size_t tb = s->cub_bytes;
+    SIM_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tb, s->d_flag, s->d_offs, (int)ncand, s->stream));
+    long *d_so = nullptr;
+    SIM_CUDA(cudaMalloc(&d_so, sizeof(long) * (s->nz + 1)));
+    k_slot_offsets<<<nb256(s->nz + 1), 256, 0, s->stream>>>(s->d_flag, s->d_offs, per_slice, s->nz, ncand, d_so);
+    SIM_CUDA(cudaMemcpyAsync(b.slot_off.data(), d_so, sizeof(long) * (s->nz + 1), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(d_so);
+    const long np = b.slot_off[s->nz];
+    double **arrs[7] = {&b.d.x, &b.d.y, &b.d.z, &b.d.w, &b.d.ux, &b.d.uy, &b.d.uz};
+    for (auto p : arrs) { cudaFree(*p); *p = nullptr; }
+    cudaFree(b.d.idcpu); b.d.idcpu = nullptr;
+    if (np > 0) {
+        for (auto p : arrs) SIM_CUDA(cudaMalloc(p, sizeof(double) * np));
+        SIM_CUDA(cudaMalloc(&b.d.idcpu, sizeof(uint64_t) * np));
+        b.d.np = np;
+        k_beam_fill<<<nb256(ncand), 256, 0, s->stream>>>(a, ncand, s->d_flag, s->d_offs, b.d, 1);
+    }
+    SIM_CUDA(cudaGetLastError());
+    return HPB_OK;
+}
+
+// view of the beam particles of slice islice (empty for islice < 0)
+hpb_beam_slice beam_slice_view(const hpb_sim *s, const BeamSp &b, int islice)
+{
+    hpb_beam_slice v = {};
+    if (islice < 0 || islice >= s->nz || b.d.np == 0) return v;
+    const int slot = s->nz - 1 - islice;
+    const long o = b.slot_off[slot], n = b.slot_off[slot + 1] - o;
+    v.x = b.d.x + o; v.y = b.d.y + o; v.z = b.d.z + o; v.w = b.d.w + o;
+    v.ux = b.d.ux + o; v.uy = b.d.uy + o; v.uz = b.d.uz + o; v.idcpu = b.d.idcpu + o;
+    v.np = n;
+    return v;
+}
+
+enum { ST_DEPOSIT = 0, ST_POISSON, ST_EXPLICIT, ST_MG, ST_PUSH, ST_OTHER, ST_N };
+
+struct StageTimer {
+    hpb_sim *s; double *acc;
+    cudaEvent_t a, b;
+    StageTimer(hpb_sim *s_, int st) : s(s_), acc(nullptr)
+    {
+        if (!s->opt_profile) return;
+        static double *slots[ST_N];
+        slots[ST_DEPOSIT] = &s->stats.ms_deposit; slots[ST_POISSON] = &s->stats.ms_poisson;
+        slots[ST_EXPLICIT] = &s->stats.ms_explicit; slots[ST_MG] = &s->stats.ms_mg;
+        slots[ST_PUSH] = &s->stats.ms_push; slots[ST_OTHER] = &s->stats.ms_other;
+        acc = slots[st];
+        a = s->pev[0]; b = s->pev[1];
+        cudaEventRecord(a, s->stream);
+    }
+    ~StageTimer()
+    {
+        if (!acc) return;
+        cudaEventRecord(b, s->stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        *acc += ms;
+    }
+};
+
+int begin_step(hpb_sim *s, int step)
+{
+    // ResetAllQuantities (Hipace.cpp:730-742)
+    SIM_CUDA(cudaMemsetAsync(s->sl.p, 0, sizeof(double) * s->sl.nstride * s->sl.ncomp, s->stream));
+    SIM_CUDA(cudaMemsetAsync(s->d_checksum, 0, sizeof(double) * s->sl.ncomp, s->stream));
+    const double c_t = s->g.c * (s->dt * step);
+    for (auto &sp : s->plasmas) {                                    // Hipace.cpp:450
+        int rc = init_plasma(s, sp, c_t);
+        if (rc) return rc;
+    }
+    for (auto &b : s->beams)
+        if (!b.initialised) { int rc = init_beam(s, b); if (rc) return rc; }
+    // DepositNeutralizingBackground (Hipace.cpp:468-470, MultiPlasma.cpp:106-118)
+    for (auto &sp : s->plasmas) {
+        if (!sp.neutralize) continue;
+        int rc = hpb_deposit_current(s->ctx, sp.d, s->sl, -sp.charge, sp.mass, -1, -1, -1, -1,
+                                     s->comps[HPB_C_IONS_RHOMJZ], sp.max_qsa, s->d_nqsa);
+        if (rc) return rc;
+    }
+    s->cur_step = step;
+    return HPB_OK;
+}
+
+// Hipace::SolveOneSlice, explicit branch (Hipace.cpp:556-728)
+int solve_one_slice(hpb_sim *s, int islice)
+{
+    hpb_ctx *ctx = s->ctx;
+    const int *C = s->comps;
+    int rc;
+    {
+        StageTimer t(s, ST_OTHER);
+        if ((rc = hpb_fields_initialize_slices(ctx, s->sl, C))) return rc;              // :598-600
+    }
+    {
+        StageTimer t(s, ST_DEPOSIT);
+        for (auto &sp : s->plasmas)                                                     // :609-610
+            if ((rc = hpb_deposit_current(ctx, sp.d, s->sl, sp.charge, sp.mass, C[HPB_C_JX],
+                                          C[HPB_C_JY], C[HPB_C_RHO], C[HPB_C_CHI],
+                                          C[HPB_C_RHOMJZ], sp.max_qsa, s->d_nqsa))) return rc;
+    }
+    {
+        StageTimer t(s, ST_OTHER);
+        for (auto &b : s->beams)                                                        // :613-614
+            if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice), s->sl, b.charge, -1, -1,
+                                       C[HPB_C_JZ_BEAM]))) return rc;
+        if ((rc = hpb_fields_add_rho_ions(ctx, s->sl, C))) return rc;                   // :626
+    }
+    {
+        StageTimer t(s, ST_POISSON);
+        if ((rc = hpb_fields_solve_psi_ez_bz(ctx, s->sl, C))) return rc;                // :633
+    }
+    {
+        StageTimer t(s, ST_OTHER);
+        if (s->do_beam_jx_jy)                                                           // :639-657
+            for (auto &b : s->beams)
+                if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice - 1), s->sl, b.charge,
+                                           C[HPB_C_NEXT_JX_BEAM], C[HPB_C_NEXT_JY_BEAM], -1))) return rc;
+        if ((rc = hpb_fields_sxsy_from_beam(ctx, s->sl, C))) return rc;                 // :660
+    }
+    {
+        StageTimer t(s, ST_EXPLICIT);
+        for (auto &sp : s->plasmas)                                                     // :663
+            if ((rc = hpb_explicit_deposition(ctx, sp.d, s->sl, sp.charge, sp.mass, C))) return rc;
+    }
+    {
+        StageTimer t(s, ST_MG);
+        int iters = 0;                                                                  // :666
+        if ((rc = hpb_mg_solve1(ctx, s->sl, C[HPB_C_BX], C[HPB_C_SY], C[HPB_C_CHI], s->mg_tol_rel,
+                                s->mg_tol_abs, 200, &iters))) return rc;
+        s->stats.n_mg_vcycles += iters;
+        s->mg_iters.push_back(iters);
+    }
+    if (s->opt_checksums) {                                                             // :681-691
+        StageTimer t(s, ST_OTHER);
+        for (int c = 0; c < s->sl.ncomp; ++c)
+            if (s->comp_names[c].first == "This")
+                if ((rc = hpb_abs_sum(ctx, s->sl, c, s->d_checksum + c))) return rc;
+    }
+    {
+        StageTimer t(s, ST_PUSH);
+        for (auto &sp : s->plasmas) {                                                   // :699-701
+            s->stats.n_plasma_pushed += (double)sp.d.np;
+            if ((rc = hpb_advance_plasma_particles(ctx, sp.d, s->sl, sp.charge, sp.mass, sp.n_subcycles,
+                                                   0, s->particle_bc, s->bc_lo, s->bc_hi, C))) return rc;
+        }
+    }
+    for (auto &b : s->beams) s->stats.n_beam_pushed += (double)beam_slice_view(s, b, islice).np;
+    {
+        StageTimer t(s, ST_OTHER);
+        if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;                   // :721
+    }
+    s->stats.n_cells_updated += (double)s->g.nx * s->g.ny;
+    s->stats.n_slices += 1;
+    return HPB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overrides, int device)
+{
+    if (!out || !deck) return HPB_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        hpb_set_error("hpb_sim_create: no CUDA device (this library has no CPU fallback)");
+        return HPB_ERR_CUDA;
+    }
+    std::unique_ptr<hpb_sim> s(new hpb_sim());
+    try {
+        s->deck.parse(deck);
+        if (overrides) s->deck.parse(overrides);
+        read_deck(s.get());
+    } catch (const std::exception &e) {
+        hpb_set_error("deck: %s", e.what());
+        return HPB_ERR_PARSE;
+    }
+    s->device = device;
+    SIM_CUDA(cudaSetDevice(device));
+    SIM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    build_components(s.get());
+    int rc = hpb_create(&s->ctx, &s->g, (void *)s->stream);
+    if (rc) return rc;
+    hpb_slice &sl = s->sl;
+    sl.lo_x = sl.lo_y = -HPB_G;
+    sl.nx_tot = s->g.nx + 2 * HPB_G; sl.ny_tot = s->g.ny + 2 * HPB_G;
+    sl.jstride = sl.nx_tot; sl.nstride = (long)sl.nx_tot * sl.ny_tot;
+    SIM_CUDA(cudaMalloc(&sl.p, sizeof(double) * sl.nstride * sl.ncomp));
+    SIM_CUDA(cudaMemset(sl.p, 0, sizeof(double) * sl.nstride * sl.ncomp));
+    SIM_CUDA(cudaMalloc(&s->d_checksum, sizeof(double) * sl.ncomp));
+    SIM_CUDA(cudaMemset(s->d_checksum, 0, sizeof(double) * sl.ncomp));
+    SIM_CUDA(cudaMalloc(&s->d_nqsa, sizeof(int)));
+    SIM_CUDA(cudaMemset(s->d_nqsa, 0, sizeof(int)));
+    SIM_CUDA(cudaMalloc(&s->d_count, sizeof(unsigned long long)));
+    SIM_CUDA(cudaEventCreate(&s->ev0));
+    SIM_CUDA(cudaEventCreate(&s->ev1));
+    s->pev.resize(2);
+    for (auto &e : s->pev) SIM_CUDA(cudaEventCreate(&e));
+    *out = s.release();
+    return HPB_OK;
+}
+
+extern "C" void hpb_sim_destroy(hpb_sim *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    for (auto &sp : s->plasmas) {
+        for (int k = 0; k < HPB_PLASMA_NREAL; ++k) cudaFree(sp.d.r[k]);
+        cudaFree(sp.d.idcpu);
+    }
+    for (auto &b : s->beams) {
+        cudaFree(b.d.x); cudaFree(b.d.y); cudaFree(b.d.z); cudaFree(b.d.w);
+        cudaFree(b.d.ux); cudaFree(b.d.uy); cudaFree(b.d.uz); cudaFree(b.d.idcpu);
+    }
+    cudaFree(s->sl.p); cudaFree(s->d_checksum); cudaFree(s->d_nqsa); cudaFree(s->d_count);
+    cudaFree(s->d_flag); cudaFree(s->d_offs); cudaFree(s->d_cub);
+    hpb_destroy(s->ctx);
+    cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+    for (auto &e : s->pev) cudaEventDestroy(e);
+    cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int hpb_sim_begin_step(hpb_sim *s, int step)
+{
+    if (!s) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    return begin_step(s, step);
+}
+
+extern "C" int hpb_sim_solve_one_slice(hpb_sim *s, int islice)
+{
+    if (!s || islice < 0 || islice >= s->nz) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    return solve_one_slice(s, islice);
+}
+
+extern "C" int hpb_sim_evolve(hpb_sim *s, int step_begin, int step_end, int n_slices)
+{
+    if (!s || step_end < step_begin) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    s->stats = hpb_sim_stats();
+    s->mg_iters.clear();
+    SIM_CUDA(cudaMemsetAsync(s->d_nqsa, 0, sizeof(int), s->stream));
+    const long launches0 = s->ctx->n_launch;
+    double loop_ms = 0.;
+    for (int step = step_begin; step <= step_end; ++step) {
+        int rc = begin_step(s, step);
+        if (rc) return rc;
+        const int stop = (n_slices > 0) ? std::max(-1, s->nz - 1 - n_slices) : -1;
+        SIM_CUDA(cudaEventRecord(s->ev0, s->stream));
+        for (int isl = s->nz - 1; isl > stop; --isl) {               // Hipace.cpp:478-480
+            rc = solve_one_slice(s, isl);
+            if (rc) return rc;
+        }
+        SIM_CUDA(cudaEventRecord(s->ev1, s->stream));
+        SIM_CUDA(cudaEventSynchronize(s->ev1));
+        float ms = 0.f;
+        SIM_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        loop_ms += ms;
+    }
+    s->stats.slice_loop_ms = loop_ms;
+    s->stats.n_kernel_launches = s->ctx->n_launch - launches0;
+    int nq = 0;
+    SIM_CUDA(cudaMemcpy(&nq, s->d_nqsa, sizeof(int), cudaMemcpyDeviceToHost));
+    s->stats.n_qsa_violation = nq;
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_geometry(hpb_sim *s, int n_cell[3], double prob_lo[3], double prob_hi[3])
+{
+    if (!s) return HPB_ERR_ARG;
+    if (n_cell) { n_cell[0] = s->g.nx; n_cell[1] = s->g.ny; n_cell[2] = s->nz; }
+    for (int k = 0; k < 3; ++k) {
+        if (prob_lo) prob_lo[k] = s->prob_lo[k];
+        if (prob_hi) prob_hi[k] = s->prob_hi[k];
+    }
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_ncomp(hpb_sim *s) { return s ? s->sl.ncomp : -1; }
+
+extern "C" int hpb_sim_comp_index(hpb_sim *s, const char *which_slice, const char *name)
+{
+    if (!s || !which_slice || !name) return -1;
+    for (size_t c = 0; c < s->comp_names.size(); ++c)
+        if (s->comp_names[c].first == which_slice && s->comp_names[c].second == name) return (int)c;
+    return -1;
+}
+
+extern "C" int hpb_sim_get_field(hpb_sim *s, int comp, double *h_out)
+{
+    if (!s || comp < 0 || comp >= s->sl.ncomp || !h_out) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    SIM_CUDA(cudaMemcpy(h_out, s->sl.p + comp * s->sl.nstride, sizeof(double) * s->sl.nstride,
+                        cudaMemcpyDeviceToHost));
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_set_field(hpb_sim *s, int comp, const double *h_in)
+{
+    if (!s || comp < 0 || comp >= s->sl.ncomp || !h_in) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    SIM_CUDA(cudaMemcpy(s->sl.p + comp * s->sl.nstride, h_in, sizeof(double) * s->sl.nstride,
+                        cudaMemcpyHostToDevice));
+    return HPB_OK;
+}
+
+extern "C" long hpb_sim_plasma_np(hpb_sim *s, int species)
+{
+    if (!s || species < 0 || species >= (int)s->plasmas.size()) return -1;
+    return s->plasmas[species].d.np;
+}
+
+extern "C" int hpb_sim_get_plasma_real(hpb_sim *s, int species, int idx, double *h_out)
+{
+    if (!s || species < 0 || species >= (int)s->plasmas.size() || idx < 0 ||
+        idx >= HPB_PLASMA_NREAL || !h_out) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    const Species &sp = s->plasmas[species];
+    if (sp.d.np > 0)
+        SIM_CUDA(cudaMemcpy(h_out, sp.d.r[idx], sizeof(double) * sp.d.np, cudaMemcpyDeviceToHost));
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_get_plasma_valid(hpb_sim *s, int species, uint8_t *h_out)
+{
+    if (!s || species < 0 || species >= (int)s->plasmas.size() || !h_out) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    const Species &sp = s->plasmas[species];
+    if (sp.d.np == 0) return HPB_OK;
+    uint8_t *d = nullptr;
+    SIM_CUDA(cudaMalloc(&d, sp.d.np));
+    k_valid_bytes<<<nb256(sp.d.np), 256, 0, s->stream>>>(sp.d.idcpu, sp.d.np, d);
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    SIM_CUDA(cudaMemcpy(h_out, d, sp.d.np, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_checksum_count(hpb_sim *s)
+{
+    if (!s) return -1;
+    int n = 0;
+    for (auto &c : s->comp_names) n += (c.first == "This");
+    return n;
+}
+
+extern "C" const char *hpb_sim_checksum_name(hpb_sim *s, int k)
+{
+    if (!s) return nullptr;
+    int n = 0;
+    for (auto &c : s->comp_names)
+        if (c.first == "This") { if (n == k) return c.second.c_str(); ++n; }
+    return nullptr;
+}
+
+extern "C" int hpb_sim_get_checksums(hpb_sim *s, double *h_out)
+{
+    if (!s || !h_out) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<double> all(s->sl.ncomp);
+    SIM_CUDA(cudaMemcpy(all.data(), s->d_checksum, sizeof(double) * s->sl.ncomp, cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (size_t c = 0; c < s->comp_names.size(); ++c)
+        if (s->comp_names[c].first == "This") h_out[n++] = all[c];
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_get_beam_checksums(hpb_sim *s, int beam, double h_out[9])
+{
+    if (!s || beam < 0 || beam >= (int)s->beams.size() || !h_out) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    BeamSp &b = s->beams[beam];
+    if (!b.initialised) { int rc = init_beam(s, b); if (rc) return rc; SIM_CUDA(cudaStreamSynchronize(s->stream)); }
+    const long np = b.d.np;
+    for (int k = 0; k < 9; ++k) h_out[k] = 0.;
+    if (np == 0) return HPB_OK;
+    std::vector<double> h(np);
+    double *arrs[7] = {b.d.x, b.d.y, b.d.z, b.d.ux, b.d.uy, b.d.uz, b.d.w};
+    for (int k = 0; k < 7; ++k) {
+        SIM_CUDA(cudaMemcpy(h.data(), arrs[k], sizeof(double) * np, cudaMemcpyDeviceToHost));
+        long double acc = 0;
+        for (long p = 0; p < np; ++p) acc += fabs(h[p]);
+        h_out[k] = (double)acc;
+    }
+    std::vector<uint64_t> id(np);
+    SIM_CUDA(cudaMemcpy(id.data(), b.d.idcpu, sizeof(uint64_t) * np, cudaMemcpyDeviceToHost));
+    long double ids = 0;
+    for (long p = 0; p < np; ++p) ids += (long double)((id[p] & ~HPB_ID_VALID_BIT) >> 24);
+    h_out[7] = (double)ids;
+    h_out[8] = (double)np;
+    return HPB_OK;
+}
+
+extern "C" long hpb_sim_beam_np(hpb_sim *s, int beam)
+{
+    if (!s || beam < 0 || beam >= (int)s->beams.size()) return -1;
+    BeamSp &b = s->beams[beam];
+    if (!b.initialised) {
+        if (cudaSetDevice(s->device) != cudaSuccess || init_beam(s, b) != HPB_OK) return -1;
+        cudaStreamSynchronize(s->stream);
+    }
+    return b.d.np;
+}
+
+// Host <-> device transfer of a whole beam (the role of MultiBuffer::get_data / put_data with
+// host staging buffers, src/utils/MultiBuffer.cpp:444-609, and of beam.injection_type =
+// from_file).  h_real: 7 arrays x y z w ux uy uz of np doubles; h_idcpu: np; h_slot_off: nz+1
+// offsets, slot s = slice nz-1-s.  Asynchronous on the simulation stream when the host memory
+// is pinned; hpb_sim_evolve orders itself after an upload.
+extern "C" int hpb_sim_get_beam(hpb_sim *s, int beam, double *const h_real[7], uint64_t *h_idcpu,
+                                long *h_slot_off)
+{
+    if (!s || beam < 0 || beam >= (int)s->beams.size() || !h_real) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    const long np = hpb_sim_beam_np(s, beam);
+    if (np < 0) return HPB_ERR_CUDA;
+    BeamSp &b = s->beams[beam];
+    double *arrs[7] = {b.d.x, b.d.y, b.d.z, b.d.w, b.d.ux, b.d.uy, b.d.uz};
+    for (int k = 0; k < 7 && np > 0; ++k)
+        SIM_CUDA(cudaMemcpyAsync(h_real[k], arrs[k], sizeof(double) * np, cudaMemcpyDeviceToHost, s->stream));
+    if (h_idcpu && np > 0)
+        SIM_CUDA(cudaMemcpyAsync(h_idcpu, b.d.idcpu, sizeof(uint64_t) * np, cudaMemcpyDeviceToHost, s->stream));
+    if (h_slot_off) memcpy(h_slot_off, b.slot_off.data(), sizeof(long) * (s->nz + 1));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_set_beam(hpb_sim *s, int beam, const double *const h_real[7],
+                                const uint64_t *h_idcpu, const long *h_slot_off)
+{
+    if (!s || beam < 0 || beam >= (int)s->beams.size() || !h_real || !h_idcpu || !h_slot_off)
+        return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    BeamSp &b = s->beams[beam];
+    const long np = h_slot_off[s->nz];
+    double **arrs[7] = {&b.d.x, &b.d.y, &b.d.z, &b.d.w, &b.d.ux, &b.d.uy, &b.d.uz};
+    if (!b.initialised || np != b.d.np) {
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+        for (auto p : arrs) { cudaFree(*p); *p = nullptr; }
+        cudaFree(b.d.idcpu); b.d.idcpu = nullptr;
+        if (np > 0) {
+            for (auto p : arrs) SIM_CUDA(cudaMalloc(p, sizeof(double) * np));
+            SIM_CUDA(cudaMalloc(&b.d.idcpu, sizeof(uint64_t) * np));
+        }
+        b.d.np = np;
+    }
+    b.slot_off.assign(h_slot_off, h_slot_off + s->nz + 1);
+    b.initialised = true;
+    for (int k = 0; k < 7 && np > 0; ++k)
+        SIM_CUDA(cudaMemcpyAsync(*arrs[k], h_real[k], sizeof(double) * np, cudaMemcpyHostToDevice, s->stream));
+    if (np > 0)
+        SIM_CUDA(cudaMemcpyAsync(b.d.idcpu, h_idcpu, sizeof(uint64_t) * np, cudaMemcpyHostToDevice, s->stream));
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_get_stats(hpb_sim *s, hpb_sim_stats *out)
+{
+    if (!s || !out) return HPB_ERR_ARG;
+    *out = s->stats;
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
+{
+    if (!s || !key) return HPB_ERR_ARG;
+    const std::string k(key);
+    if (k == "checksums") s->opt_checksums = value != 0.;
+    else if (k == "profile") s->opt_profile = value != 0.;
+    else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }
+    return HPB_OK;
+}

@@ -1,0 +1,219 @@
+/* hpb200.h -- C-ABI of the B200-native per-zeta-slice quasi-static PIC hot path.
+ *
+ * Two layers:
+ *
+ *  (1) KERNEL SEAMS.  One entry point per reference call seam of Hipace::SolveOneSlice
+ *      (src/Hipace.cpp:556-728).  All pointers are DEVICE pointers, every call only enqueues work
+ *      on the stream given to hpb_create(), returns 0 on success / non-zero on error (the
+ *      reference aborts instead, amrex::Abort), and never synchronises unless stated.
+ *      The caller owns field and particle memory (as Fields::m_slices / the AMReX particle
+ *      tiles do in the reference); the context owns solver scratch.
+ *
+ *  (2) SLICE-LOOP DRIVER.  hpb_sim_* runs a HiPACE++ input deck through the same call order
+ *      as Hipace::Evolve (src/Hipace.cpp:393-554) with HOST buffers at the boundary; this is
+ *      what the command-line driver and bench.py's end-to-end leg call.
+ *
+ * Memory layouts (identical to what an AMReX build of the reference holds):
+ *   slice array : component-major, p[(i - lo_x) + (j - lo_y)*jstride + n*nstride], box
+ *                 [-g, n-1+g]^2 with g = 2 guard cells (src/utils/GPUUtil.H:98-182,
+ *                 src/fields/Fields.cpp:63-64,169-174)
+ *   plasma      : pure SoA in PlasmaIdx order (src/particles/plasma/PlasmaParticleContainer.H:
+ *                 21-46): x y w ux uy psi x_prev y_prev ux_half_step uy_half_step psi_half_step,
+ *                 plus a 64-bit idcpu whose top bit is the validity flag (AMReX >= 24 packing)
+ *   beam slice  : SoA x y z w ux uy uz + idcpu (src/particles/beam/BeamParticleContainer.H)
+ */
+#ifndef HPB200_H_
+#define HPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPB_OK 0
+#define HPB_ERR_ARG 1
+#define HPB_ERR_CUDA 2
+#define HPB_ERR_UNSUPPORTED 3
+#define HPB_ERR_MG_DIVERGED 4      /* hpmg "failing so lets stop here", HpMultiGrid.cpp:1399-1416 */
+#define HPB_ERR_PARSE 5
+
+#define HPB_NGUARD 2               /* (depos_order_xy+1)/2 + 1 for order 2, Fields.cpp:63-64 */
+#define HPB_PLASMA_NREAL 11
+
+/* PlasmaIdx, PlasmaParticleContainer.H:21-46 */
+enum { HPB_X = 0, HPB_Y, HPB_W, HPB_UX, HPB_UY, HPB_PSI, HPB_X_PREV, HPB_Y_PREV,
+       HPB_UX_HALF, HPB_UY_HALF, HPB_PSI_HALF };
+
+/* ParticleBoundary, src/Hipace.H */
+enum { HPB_BC_REFLECTING = 0, HPB_BC_PERIODIC = 1, HPB_BC_ABSORBING = 2 };
+
+typedef struct hpb_ctx hpb_ctx;     /* solver scratch, plans, stream; one per (nx, ny) */
+typedef struct hpb_sim hpb_sim;     /* slice-loop driver state */
+
+/* Array3 view of the slice MultiFab (src/utils/GPUUtil.H:98-147) */
+typedef struct {
+    double *p;                      /* device */
+    int lo_x, lo_y;                 /* -g, -g */
+    int nx_tot, ny_tot;             /* nx + 2g, ny + 2g */
+    long jstride, nstride;          /* nx_tot, nx_tot*ny_tot (or padded) */
+    int ncomp;
+} hpb_slice;
+
+/* plasma particle tile: ParticleTileData of PlasmaParticleContainer */
+typedef struct {
+    double *r[HPB_PLASMA_NREAL];    /* device, PlasmaIdx order */
+    uint64_t *idcpu;                /* device */
+    long np;
+} hpb_plasma;
+
+/* per-slice beam tile (BeamIdx: x y z w ux uy uz) */
+typedef struct {
+    double *x, *y, *z, *w, *ux, *uy, *uz;   /* device */
+    uint64_t *idcpu;                         /* device */
+    long np;
+} hpb_beam_slice;
+
+/* geometry + PhysConst (src/fields/Fields.H:71-77 GetPosOffset, src/utils/Constants.H:54-81) */
+typedef struct {
+    int nx, ny;
+    double dx, dy, dz;
+    double x_off, y_off;            /* x = i*dx + x_off, GetPosOffset with the grown fab box */
+    double c, ep0, mu0, q_e, m_e;
+    int normalized;                 /* hipace.normalized_units */
+} hpb_geom;
+
+/* ---------------------------------------------------------------------------------------- */
+/* (1) kernel seams                                                                         */
+/* ---------------------------------------------------------------------------------------- */
+
+/* stream: a cudaStream_t passed as void* (NULL = legacy default stream).  Replaces the solver
+ * objects built in Fields::AllocData (Fields.cpp:179-208) and Hipace::ExplicitMGSolveBxBy
+ * (Hipace.cpp:914-918). */
+int hpb_create(hpb_ctx **out, const hpb_geom *geom, void *stream);
+void hpb_destroy(hpb_ctx *ctx);
+const char *hpb_last_error(void);
+const char *hpb_version(void);
+
+/* ::DepositCurrent (src/particles/deposition/PlasmaDepositCurrent.cpp:22-257).  Component
+ * indices < 0 mean "do not deposit" exactly as the reference's -1 (:53-58).  d_n_qsa_violation:
+ * device int incremented once per particle killed by the QSA check (:197-204); may be NULL. */
+int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                        int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz,
+                        double max_qsa_weighting_factor, int *d_n_qsa_violation);
+
+/* beam ::DepositCurrentSlice (src/particles/deposition/BeamDepositCurrent.cpp:21-195) */
+int hpb_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, double charge,
+                     int c_jx, int c_jy, int c_jz);
+
+/* Fields::InitializeSlices / AddRhoIons / ShiftSlices (src/fields/Fields.cpp:535-615):
+ * comps[] is the component table in the order of hpb_comp below. */
+int hpb_fields_initialize_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+int hpb_fields_add_rho_ions(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+int hpb_fields_shift_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+
+/* FFTPoissonSolver::SolvePoissonEquation (src/fields/fft_poisson_solver/FFTPoissonSolver.H:26-57,
+ * ...DirichletFast.cpp:286-328): laplace(lhs) = rhs with lhs = 0 at the first guard cell.
+ * d_rhs: nbatch contiguous nx*ny staging areas; c_lhs[b]: destination component of solve b. */
+int hpb_poisson_solve(hpb_ctx *ctx, const double *d_rhs, hpb_slice sl, const int *c_lhs,
+                      int nbatch);
+
+/* Fields::SolvePoissonPsiExmByEypBxEzBz (src/fields/Fields.cpp:840-957): RHS assembly + three
+ * Poisson solves + ExmBy/EypBx stencil, fused. */
+int hpb_fields_solve_psi_ez_bz(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+
+/* Hipace::InitializeSxSyWithBeam (src/Hipace.cpp:744-790) */
+int hpb_fields_sxsy_from_beam(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+
+/* ::ExplicitDeposition (src/particles/deposition/ExplicitDeposition.cpp:20-263) */
+int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge,
+                            double mass, const int *comps);
+
+/* hpmg::MultiGrid::solve1 (src/mg_solver/HpMultiGrid.H:64-66, .cpp:1169-1190): solves
+ * laplace(sol) - acf*sol = rhs for the two adjacent components (c_sol, c_sol+1) with rhs
+ * (c_rhs, c_rhs+1); sol holds the initial guess.  h_iters (host, may be NULL) receives the
+ * number of V-cycles; this call synchronises the stream when h_iters != NULL. */
+int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, int c_acf,
+                  double tol_rel, double tol_abs, int max_iters, int *h_iters);
+
+/* AdvancePlasmaParticles (src/particles/pusher/PlasmaParticleAdvance.cpp:29-305) */
+int hpb_advance_plasma_particles(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge,
+                                 double mass, int n_subcycles, int temp_slice, int particle_bc,
+                                 const double bc_lo[2], const double bc_hi[2], const int *comps);
+
+/* sum|Q| over the valid box of component c -> d_out[0] += ...   (checksum of
+ * tests/checksum/backend/openpmd_backend.py:40-45, one slice at a time) */
+int hpb_abs_sum(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out);
+
+/* component table passed as "comps" above (names of src/fields/Fields.cpp:70-122) */
+enum hpb_comp {
+    HPB_C_NEXT_JX_BEAM = 0, HPB_C_NEXT_JY_BEAM,
+    HPB_C_CHI, HPB_C_SY, HPB_C_SX, HPB_C_EXMBY, HPB_C_EYPBX, HPB_C_EZ, HPB_C_BX, HPB_C_BY,
+    HPB_C_BZ, HPB_C_PSI, HPB_C_JX_BEAM, HPB_C_JY_BEAM, HPB_C_JZ_BEAM, HPB_C_JX, HPB_C_JY,
+    HPB_C_RHOMJZ, HPB_C_RHO /* -1 if not allocated */,
+    HPB_C_PREV_JX_BEAM, HPB_C_PREV_JY_BEAM,
+    HPB_C_IONS_RHOMJZ /* -1 if no neutralising background */,
+    HPB_C_COUNT
+};
+
+/* ---------------------------------------------------------------------------------------- */
+/* (2) slice-loop driver: Hipace::Hipace / InitData / Evolve / SolveOneSlice                */
+/* ---------------------------------------------------------------------------------------- */
+
+/* deck: HiPACE++ input-deck text (ParmParse syntax); overrides: extra "key = value" lines
+ * appended after it (the reference takes them on the command line). device: CUDA ordinal. */
+int hpb_sim_create(hpb_sim **out, const char *deck, const char *overrides, int device);
+void hpb_sim_destroy(hpb_sim *sim);
+
+/* Hipace::Evolve for time steps [step_begin, step_end] on this rank (all slices, or only the
+ * first n_slices from the head if n_slices > 0).  Blocks until the device is idle. */
+int hpb_sim_evolve(hpb_sim *sim, int step_begin, int step_end, int n_slices);
+
+/* finer control for tests: begin a time step (plasma re-init + neutralising background,
+ * Hipace.cpp:403-475), then one Hipace::SolveOneSlice per call. */
+int hpb_sim_begin_step(hpb_sim *sim, int step);
+int hpb_sim_solve_one_slice(hpb_sim *sim, int islice);
+
+/* queries (host buffers) */
+int hpb_sim_geometry(hpb_sim *sim, int n_cell[3], double prob_lo[3], double prob_hi[3]);
+int hpb_sim_ncomp(hpb_sim *sim);
+int hpb_sim_comp_index(hpb_sim *sim, const char *which_slice, const char *name); /* -1 if absent */
+/* copy one component of the current slice array (with guard cells, (ny+2g)*(nx+2g) doubles) */
+int hpb_sim_get_field(hpb_sim *sim, int comp, double *h_out);
+int hpb_sim_set_field(hpb_sim *sim, int comp, const double *h_in);
+long hpb_sim_plasma_np(hpb_sim *sim, int species);
+/* copy one PlasmaIdx real component / the validity flags of a species to the host */
+int hpb_sim_get_plasma_real(hpb_sim *sim, int species, int idx, double *h_out);
+int hpb_sim_get_plasma_valid(hpb_sim *sim, int species, uint8_t *h_out);
+/* checksums accumulated over the slices of the last step: sum|Q| per This-slice component,
+ * in component order; names via hpb_sim_checksum_name. */
+int hpb_sim_checksum_count(hpb_sim *sim);
+const char *hpb_sim_checksum_name(hpb_sim *sim, int k);
+int hpb_sim_get_checksums(hpb_sim *sim, double *h_out);
+/* beam checksums of the last step: x y z ux uy uz w (sum|.|), id sum, count */
+int hpb_sim_get_beam_checksums(hpb_sim *sim, int beam, double h_out[9]);
+/* Whole-beam host <-> device transfer: the role of MultiBuffer::get_data / put_data with host
+ * staging buffers (src/utils/MultiBuffer.cpp:444-609) and of beam.injection_type = from_file.
+ * h_real: 7 host arrays x y z w ux uy uz (np doubles each), h_idcpu: np, h_slot_off: nz+1
+ * offsets with slot s = slice nz-1-s (head slice first).  Copies run on the simulation stream
+ * (asynchronously if the host memory is pinned); get synchronises before returning. */
+long hpb_sim_beam_np(hpb_sim *sim, int beam);
+int hpb_sim_get_beam(hpb_sim *sim, int beam, double *const h_real[7], uint64_t *h_idcpu,
+                     long *h_slot_off);
+int hpb_sim_set_beam(hpb_sim *sim, int beam, const double *const h_real[7],
+                     const uint64_t *h_idcpu, const long *h_slot_off);
+/* performance counters of Hipace.cpp:509-553 and solver statistics */
+typedef struct {
+    double n_plasma_pushed, n_beam_pushed, n_cells_updated;
+    double slice_loop_ms;           /* device time of the slice loop(s) of the last evolve */
+    long n_slices, n_mg_vcycles, n_qsa_violation, n_kernel_launches;
+    double ms_deposit, ms_poisson, ms_explicit, ms_mg, ms_push, ms_other; /* if profiling on */
+} hpb_sim_stats;
+int hpb_sim_get_stats(hpb_sim *sim, hpb_sim_stats *out);
+int hpb_sim_set_option(hpb_sim *sim, const char *key, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPB200_H_ */
