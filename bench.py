@@ -1,0 +1,315 @@
+#!/usr/bin/env python3
+"""bench.py -- slices/s of the per-zeta-slice quasi-static PIC loop on the blowout_wake deck.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (N ranks: time-step pipeline)
+  python bench.py --impl reference --steps K --warmup W    CPU restatement of the reference path
+
+A "step" is one whole time step = nz zeta-slices of the deck (Hipace::Evolve body,
+src/Hipace.cpp:401-507): plasma re-initialisation + neutralising background + nz x SolveOneSlice.
+Workload = BASELINE.json configs[2] (the configuration the metric is quoted on):
+blowout_wake, normalised units, 1024 x 1024 transverse x 1024 zeta, ppc 4 (plasma.ppc = 2 2),
+fixed_ppc gaussian beam, explicit Bx/By solver, order-2 shapes.  Synthetic, deterministic, no RNG.
+
+Timed region of `value`: K time steps, inputs resident in HBM, CUDA events on the simulation
+stream (hpb_sim_evolve records them), barrier + synchronize on both sides, max over ranks.
+`e2e`: the same K steps through the public API with HOST buffers -- every step uploads the
+whole beam from pinned host memory (the role of MultiBuffer::get_data) and reads back the beam
+and the field checksums -- timed by wall clock around the calls.
+Working set per slice (177 MB slice array + 419 MB particles) exceeds the 126 MB L2, so no
+explicit L2 flush is needed between timed iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'slices_per_sec'
+UNIT = 'slices/s'
+
+
+def deck_and_overrides(nxy, nz, ppc):
+    deck = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    ov = {'amr.n_cell': f'{nxy} {nxy} {nz}', 'plasma.ppc': f'{ppc} {ppc}'}
+    return deck, ov
+
+
+def workload_name(nxy, nz, ppc):
+    return f'blowout_wake_explicit normalized {nxy}x{nxy}x{nz} ppc={ppc * ppc} (BASELINE configs[2])'
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '200', '-i', str(self.gpu)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(',') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, smax = [], set(), None
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in rows:
+            try:
+                r = [t.strip() for t in r]
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            sm.sort()
+            out = {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                   'samples': len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU restatement (oracle) -- cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(nxy, nz, ppc, steps, warmup, sample_slices):
+    """Time the CPU restatement of the reference algorithm (oracle/) on this box's host cores.
+    Each step is a bounded sample: `sample_slices` consecutive slices of the same deck starting
+    at the beam head (the reference cannot be built here: AMReX/FFTW/MPI absent)."""
+    from oracle import cport
+    deck, ov = deck_and_overrides(nxy, nz, ppc)
+    sim = cport.Simulation(deck, ov)
+    sim.begin_step()
+    isl = sim.nz - 1 - sim.first_beam_slot()       # start where the beam begins: representative work
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for _ in range(sample_slices):
+            sim.solve_one_slice(isl)
+            isl -= 1
+        times.append(time.perf_counter() - t0)
+    tt = sum(times[warmup:])
+    return dict(value=steps * sample_slices / tt, seconds=tt, cores=sim.threads,
+                sample=f'{sample_slices} slices/step x {steps} steps of the {nxy}x{nxy} ppc={ppc * ppc} '
+                       f'deck from the beam head (slice {sim.nz - 1 - sim.first_beam_slot()} down), '
+                       f'C/OpenMP port of the oracle, {sim.threads} threads'), tt / steps
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--nxy', type=int, default=1024)
+    ap.add_argument('--nz', type=int, default=1024)
+    ap.add_argument('--ppc', type=int, default=2, help='per direction (2 -> ppc 4)')
+    ap.add_argument('--cpu-sample-slices', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-profile', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    K, W = args.steps, max(args.warmup, 0)
+    cfg = {'workload': workload_name(args.nxy, args.nz, args.ppc), 'nx': args.nxy, 'ny': args.nxy,
+           'nz': args.nz, 'ppc': args.ppc * args.ppc, 'units': 'normalized',
+           'solver': 'explicit (FFT/DST Poisson x3 + multigrid BxBy)',
+           'l2_policy': 'working set per slice (~600 MB) > L2 (126 MB); no flush needed',
+           'parallelism': f'time-step pipeline x{world}' if world > 1 else 'single GPU'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        base, sec_per_step = cpu_arm(args.nxy, args.nz, args.ppc, K, max(W, 1), args.cpu_sample_slices)
+        line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT,
+                'n_gpus': args.gpus, 'steps': K, 'warmup': W, 'ms_per_step': 1e3 * sec_per_step,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic', 'config': cfg,
+                'cpu_baseline': {'value': base['value'], 'unit': UNIT, 'cores': base['cores'],
+                                 'kind': 'port', 'sample': base['sample']},
+                'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import hipace_b200 as hp
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    deck, ov = deck_and_overrides(args.nxy, args.nz, args.ppc)
+    sim = hp.Simulation(deck, ov, device=local_rank)
+    sim.set_option('checksums', 0)
+    if world > 1:
+        sim.pipeline_init(rank, world, dist)
+
+    # ---- device-resident leg ---------------------------------------------------------------
+    # rank r owns time steps r, r+world, ... (Hipace.cpp:401); K steps per rank (weak scaling)
+    def run_steps(first, count):
+        ms = 0.0
+        launches = 0
+        for k in range(count):
+            step = (first + k) * world + rank
+            sim.evolve(step, step)
+            st = sim.stats()
+            ms += st['slice_loop_ms']
+            launches += st['n_kernel_launches']
+        return ms, launches
+
+    run_steps(0, W)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, launches = run_steps(W, K)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    st_last = sim.stats()
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    # whole-job time: pipelined ranks overlap, so the job time is the wall time between the
+    # barriers (max over ranks); on one GPU it equals the device time of the slice loops
+    job_ms = wall_ms_max if world > 1 else dev_ms_max
+    total_slices = K * args.nz * world
+    value = total_slices / (job_ms * 1e-3)
+    n_pushed = st_last['n_plasma_pushed'] + st_last['n_beam_pushed']
+    ns_per_push = (dev_ms / K) * 1e6 / max(n_pushed, 1)
+
+    # ---- end-to-end leg (host buffers) -----------------------------------------------------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        npb = sim.beam_np()
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+        host = {'real': pin((7, max(npb, 1)), torch.float64), 'idcpu': pin((max(npb, 1),), torch.int64).view(np.uint64),
+                'slot_off': np.zeros(args.nz + 1, dtype=np.int64)}
+        sim.get_beam(host)
+        sim.set_option('checksums', 1)
+        h2d = 7 * 8 * npb + 8 * npb
+        d2h = h2d + 8 * len(sim.checksums())
+
+        def e2e_step(step):
+            sim.set_beam(host)                 # H2D: this step's beam from pinned host memory
+            cs = sim.evolve(step, step)        # plasma init + nz slices; D2H of the checksums
+            sim.get_beam(host)                 # D2H: the beam after the step
+            return cs
+        e2e_step(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(K):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {'value': K * args.nz / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3 * e2e_s / K,
+               'api': 'hipace_b200.Simulation.set_beam/evolve/get_beam -> hpb_sim_* C-ABI'}
+        sim.set_option('checksums', 0)
+
+    # ---- per-stage profile + roofline of the dominant kernel (extra, untimed pass) -----------
+    roofline = None
+    stages = None
+    if not args.no_profile and rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+        sim.set_option('profile', 1)
+        sim.evolve(0, 0)
+        sp = sim.stats()
+        sim.set_option('profile', 0)
+        nsl = sp['n_slices']
+        P = sp['n_plasma_pushed'] / nsl
+        Gc = (args.nxy + 4) ** 2
+        # algorithmic bytes per launch, SURVEY.md 8(d)
+        alg = {'deposit': 56 * P + 4 * 8 * Gc, 'explicit': 56 * P + 8 * 8 * Gc, 'push': 128 * P + 5 * 8 * Gc}
+        stages = {k: sp['ms_' + k] / nsl for k in ('deposit', 'poisson', 'explicit', 'mg', 'push', 'other')}
+        stages['mg_vcycles_per_slice'] = sp['n_mg_vcycles'] / nsl
+        dom = max(alg, key=lambda k: stages[k])
+        ach = alg[dom] / (stages[dom] * 1e-3) / 1e9
+        roofline = {'kernel': {'deposit': 'k_deposit_current', 'explicit': 'k_explicit_deposition',
+                               'push': 'k_advance_plasma'}[dom],
+                    'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                    'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': alg[dom], 'avg_launch_ms': stages[dom],
+                    'all': {k: {'GBps': alg[k] / (stages[k] * 1e-3) / 1e9, 'ms': stages[k]} for k in alg}}
+
+    # ---- CPU baseline (rank 0, N = 1) -----------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            base, _ = cpu_arm(args.nxy, args.nz, args.ppc, 2, 1, args.cpu_sample_slices)
+            cpu_baseline = {'value': base['value'], 'unit': UNIT, 'cores': base['cores'], 'kind': 'port',
+                            'sample': base['sample']}
+        except Exception as e:      # the baseline is a report, never a dependency of the GPU path
+            cpu_baseline = {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port',
+                            'sample': f'unavailable: {type(e).__name__}: {e}'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+                'ms_per_step': job_ms / K, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+                'ns_per_particle_step': ns_per_push, 'ms_per_slice': job_ms / (K * args.nz) * world,
+                'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
+                'stage_ms_per_slice': stages, 'cpu_baseline': cpu_baseline,
+                'wall_ms_per_step': wall_ms_max / K}
+        print(json.dumps(line))
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
