@@ -106,7 +106,7 @@ __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr
 // ---- the context ---------------------------------------------------------------------------
 struct MGLevel {
     int nx, ny;            // points in the level box (cells if cc, nodes incl. boundary if nodal)
-    double *acf, *res, *cor, *rescor;   // res/cor/rescor: 2 comps, comp stride nx*ny
+    double *acf, *c0i, *res, *cor, *rescor;   // res/cor/rescor: 2 comps, comp stride nx*ny
 };
 
 struct hpb_ctx {
@@ -116,13 +116,16 @@ struct hpb_ctx {
     // Poisson (poisson.cu)
     int fftN;                 // nx + 1
     int nrad; int radices[32];
+    double *d_cs_cos[32], *d_cs_sin[32];         // per odd-prime stage: DFT-p cos / sin tables
     double2 *d_root;          // exp(-2 pi i t / N), t = 0..N-1
-    double *d_sinx;           // sin(pi j / N), j = 0..N-1
-    double *d_tri_m, *d_tri_c;  // Thomas tables [ny][nx]
+    double *d_sinf;           // 1 / (2 sin(pi (i+1) / N)), i = 0..nx-1
+    int th_L, th_C, th_last_base;                // partitioned Thomas: chunk length, chunks
+    double *d_tri_m, *d_tri_c, *d_tri_p, *d_tri_q;   // chunk-local pivots and spikes [row][nx]
+    double *d_red_pe, *d_red_pf, *d_red_b, *d_red_inv, *d_red_del;   // reduced system [C-1][nx]
     double *d_spec;           // 3 * nx * ny spectral scratch
-    double *d_stage;          // 3 * nx * ny staging (rhs)
+    double *d_iface;          // 4 * 3 * C * nx chunk-interface values
     // Multigrid (mg.cu)
-    int mg_cc; int mg_nlev;
+    int mg_cc; int mg_nlev; int mg_lc;   // mg_lc: first level solved by the single-CTA kernel
     MGLevel mg[32];
     double *d_mg_norm;        // [0]=res norm, [1]=rhs norm
     double *h_mg_norm;        // pinned

@@ -34,28 +34,6 @@ __global__ void k_add(SliceView a, CompPairs cp, long ntot)
     for (int n = 0; n < cp.n; ++n) a.comp(cp.dst[n])[o] += a.comp(cp.src[n])[o];
 }
 
-// RHS of the three Poisson equations into staging [3][ny][nx] (Fields.cpp:886-912)
-__global__ void k_poisson_rhs(SliceView a, int c_rhomjz, int c_jx, int c_jy, int nx, int ny,
-                              double *stage, double f_psi, double f_ez, double mu0,
-                              double dx_inv_half, double dy_inv_half)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i >= nx) return;
-    const long o = a.idx(i, j);
-    const double *jx = a.comp(c_jx), *jy = a.comp(c_jy);
-    const long js = a.jstride;
-    const double dx_jx = (jx[o + 1] - jx[o - 1]) * dx_inv_half;
-    const double dy_jy = (jy[o + js] - jy[o - js]) * dy_inv_half;
-    const double dy_jx = (jx[o + js] - jx[o - js]) * dy_inv_half;
-    const double dx_jy = (jy[o + 1] - jy[o - 1]) * dx_inv_half;
-    const long s = (long)j * nx + i;
-    const long n = (long)nx * ny;
-    stage[s] = f_psi * a.comp(c_rhomjz)[o];
-    stage[s + n] = f_ez * dx_jx + f_ez * dy_jy;
-    stage[s + 2 * n] = mu0 * dy_jx + (-mu0) * dx_jy;
-}
-
 // ExmBy = -d/dx Psi, EypBx = -d/dy Psi on the box grown by g-1 (Fields.cpp:931-956)
 __global__ void k_exmby_eypbx(SliceView a, int c_psi, int c_exmby, int c_eypbx, int nx, int ny,
                               double dx_inv_half, double dy_inv_half)
@@ -114,19 +92,6 @@ inline unsigned nb(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 }  // namespace
 
 // exposed to poisson.cu (fused driver)
-int hpb_launch_poisson_rhs(hpb_ctx *ctx, const hpb_slice &sl, const int *comps)
-{
-    const hpb_geom &g = ctx->g;
-    dim3 grid((g.nx + kThreads - 1) / kThreads, g.ny);
-    k_poisson_rhs<<<grid, kThreads, 0, ctx->stream>>>(
-        make_view(sl), comps[HPB_C_RHOMJZ], comps[HPB_C_JX], comps[HPB_C_JY], g.nx, g.ny,
-        ctx->d_stage, -1.0 / g.ep0, 1.0 / (g.ep0 * g.c), g.mu0, 0.5 * (1.0 / g.dx),
-        0.5 * (1.0 / g.dy));
-    hpb_count_launch(ctx);
-    HPB_CUDA_CHECK(cudaGetLastError());
-    return HPB_OK;
-}
-
 int hpb_launch_exmby_eypbx(hpb_ctx *ctx, const hpb_slice &sl, const int *comps)
 {
     const hpb_geom &g = ctx->g;

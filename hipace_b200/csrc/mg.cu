@@ -4,10 +4,16 @@
 // hpmg::MultiGrid system type 1 (src/mg_solver/HpMultiGrid.cpp: gs1 :265-292, residual1 :184-190,
 // restrict :29-52, interp :88-121, solve_doit :1307-1427, vcycle :1429-1512, bottomsolve
 // :1514-1594) because the answer depends on where the iteration stops (tol_rel = 1e-4).
-// Compiled with -fmad=false so that every level operator is bit-identical to the oracle.
+// Compiled with -fmad=false so that every level operator rounds exactly like the oracle.
 //
-// Kernels: one shared-memory tile kernel does 4 red-black Gauss-Seidel half-sweeps (+ residual)
-// per launch: tile 64x32 with a 4/5-cell halo so the shrunken interior is exact.
+// B200 formulation: every level operator pair of the V-cycle is ONE shared-memory tile kernel
+//   down:  cor = GSRB^4(0; res)            + residual + restriction -> res[l+1]      (k_smooth<0,1>)
+//   up:    cor = GSRB^4(cor + I(cor[l+1]))  (interpolation fused into the tile load)   (k_smooth<2,0>)
+//   top:   cor0 = GSRB^4(sol) + residual + restriction -> res[1] + max-norm            (k_smooth<1,1>)
+// with a 4/5/6-cell halo so that the shrunken interior is exact, and all levels of <= 34x34
+// points run inside a single 1024-thread CTA (k_coarse).  chi is used in place as the level-0
+// coefficient.  A V-cycle is ~2 + 2*(tile levels) + 1 launches instead of ~40, and the level-0
+// traffic drops from 24 to 15 planes.
 #include "common.cuh"
 #include <math.h>
 #include <float.h>
@@ -30,38 +36,12 @@ struct LevelGeom {
 constexpr int CX = 64, CY = 32;       // compute region of a tile
 constexpr int AX = CX + 2, AY = CY + 2;
 constexpr int NT = 256;
+constexpr int kCoarseMax = 34;        // levels with <= 34 x 34 points run in k_coarse
+constexpr int kCoarseThreads = 1024;
 
-__device__ __forceinline__ void gs1(double *ph, int li, int lj, int i, int j, const LevelGeom &g,
-                                    double rhs, double acf)
-{
-    // ph: smem plane [AY][AX]; (li, lj) local index of cell (i, j)
-    double lap;
-    double c0 = -(acf + 2.0 * (g.facx + g.facy));
-    const double *c = ph + lj * AX + li;
-    if (g.cc && i == g.vlo) {
-        lap = g.facx * (4. / 3.) * c[1];
-        c0 -= 2.0 * g.facx;
-    } else if (g.cc && i == g.vhix) {
-        lap = g.facx * (4. / 3.) * c[-1];
-        c0 -= 2.0 * g.facx;
-    } else {
-        lap = g.facx * (c[-1] + c[1]);
-    }
-    if (g.cc && j == g.vlo) {
-        lap += g.facy * (4. / 3.) * c[AX];
-        c0 -= 2.0 * g.facy;
-    } else if (g.cc && j == g.vhiy) {
-        lap += g.facy * (4. / 3.) * c[-AX];
-        c0 -= 2.0 * g.facy;
-    } else {
-        lap += g.facy * (c[-AX] + c[AX]);
-    }
-    const double c0_inv = 1.0 / c0;
-    ph[lj * AX + li] = (rhs - lap) * c0_inv;
-}
-
-__device__ __forceinline__ double residual1(const double *ph, int li, int lj, int i, int j,
-                                            const LevelGeom &g, double rhs, double acf)
+// residual1 (:184-190) with the boundary-modified laplacian (:163-182); ph: smem plane
+__device__ __forceinline__ double residual_smem(const double *ph, int li, int lj, int i, int j,
+                                                const LevelGeom &g, double rhs, double acf)
 {
     const double *c = ph + lj * AX + li;
     double lap = -2.0 * (g.facx + g.facy) * c[0];
@@ -74,45 +54,70 @@ __device__ __forceinline__ double residual1(const double *ph, int li, int lj, in
     return rhs + acf * c[0] - lap;
 }
 
-// phi_out = GSRB^4(phi_in or 0); optionally res = rhs + acf*phi - lap(phi)
-template <bool ZERO_INIT, bool DO_RES>
-__global__ void __launch_bounds__(NT)
-k_gsrb4(LevelGeom g, V2 phi_in, V2 rhs, const double *__restrict__ acf, long acf_rs, V2 phi_out,
-        V2 res, int nbx)
+// I(crse)(i, j): interpcpy_cc / interpcpy_nd (:88-121)
+__device__ __forceinline__ double interp_at(const V2 &crse, int i, int j, int n, int cc)
 {
-    constexpr int EO = DO_RES ? 4 : 3;            // edge offset (HpMultiGrid.cpp:427)
-    constexpr int FX = CX - 2 * EO, FY = CY - 2 * EO;
-    __shared__ double sm[2][AY * AX];
+    const int ic = i >> 1, jc = j >> 1;
+    if (cc) return crse.at(ic, jc, n);
+    const bool io = (ic * 2 != i), jo = (jc * 2 != j);
+    if (io && jo) return (crse.at(ic, jc, n) + crse.at(ic + 1, jc, n) + crse.at(ic, jc + 1, n)
+                          + crse.at(ic + 1, jc + 1, n)) * 0.25;
+    if (io) return (crse.at(ic, jc, n) + crse.at(ic + 1, jc, n)) * 0.5;
+    if (jo) return (crse.at(ic, jc, n) + crse.at(ic, jc + 1, n)) * 0.5;
+    return crse.at(ic, jc, n);
+}
 
+// One tile: phi = GSRB^4(init); optional residual -> restricted into res_c (+ max-norms).
+//   INIT 0: phi = 0;  1: phi = phi_in;  2: phi = phi_in + I(crse)
+//   RES: rescor = rhs + acf*phi - lap(phi) is restricted on the fly (restrict_cc / restrict_nd)
+//        into res_c; norm[0] = max|rescor| and norm[1] = max|rhs| if norm != nullptr.
+template <int INIT, bool RES>
+__global__ void __launch_bounds__(NT)
+k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
+         V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO)
+{
+    __shared__ double sm[2][AY * AX];
+    const int FX = CX - 2 * EO, FY = CY - 2 * EO;
     const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
-    // local (1,1) is compute cell (0,0) of the tile; final region starts EO further in
-    const int ox = bx * FX - EO + g.vlo;          // global index of compute cell 0
+    const int ox = bx * FX - EO + g.vlo;          // level index of compute cell (0, 0)
     const int oy = by * FY - EO + g.vlo;
 
     for (int s = threadIdx.x; s < AX * AY; s += NT) {
         const int lj = s / AX, li = s - lj * AX;
         const int i = ox - 1 + li, j = oy - 1 + lj;
         double v0 = 0., v1 = 0.;
-        if (!ZERO_INIT && i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy) {
+        if (INIT != 0 && i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy) {
             v0 = phi_in.at(i, j, 0);
             v1 = phi_in.at(i, j, 1);
+            if (INIT == 2) {
+                v0 = v0 + interp_at(crse, i, j, 0, g.cc);
+                v1 = v1 + interp_at(crse, i, j, 1, g.cc);
+            }
         }
         sm[0][s] = v0;
         sm[1][s] = v1;
     }
     // every thread owns 4 vertical pairs: columns tx, tx+32; row pairs 2*(ty + 8b)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    double r0[4][2], r1[4][2], ac[4][2];
+    double r0[4][2], r1[4][2], ci[4][2], ac[4][2];
+    unsigned okmask = 0;
+    const double fx43 = g.facx * (4. / 3.), fy43 = g.facy * (4. / 3.);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        const int ci = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+        const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int i = ox + ci, j = oy + cj + h;
+            const int i = ox + cix, j = oy + cj + h;
             const bool ok = i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy;
+            okmask |= (ok ? 1u : 0u) << (2 * p + h);
             r0[p][h] = ok ? rhs.at(i, j, 0) : 0.;
             r1[p][h] = ok ? rhs.at(i, j, 1) : 0.;
-            ac[p][h] = ok ? acf[i + (long)j * acf_rs] : 0.;
+            const double a = ok ? acf[i + (long)j * acf_rs] : 0.;
+            ac[p][h] = a;
+            double c0 = -(a + 2.0 * (g.facx + g.facy));                 // gs1 :265-292
+            if (g.cc && (i == g.vlo || i == g.vhix)) c0 -= 2.0 * g.facx;
+            if (g.cc && (j == g.vlo || j == g.vhiy)) c0 -= 2.0 * g.facy;
+            ci[p][h] = 1.0 / c0;
         }
     }
     __syncthreads();
@@ -120,160 +125,280 @@ k_gsrb4(LevelGeom g, V2 phi_in, V2 rhs, const double *__restrict__ acf, long acf
     for (int icolor = 0; icolor < 4; ++icolor) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const int ci = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
-            const int i = ox + ci;
+            const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+            const int i = ox + cix;
             const int sh = (i + oy + cj + icolor) & 1;
             const int j = oy + cj + sh;
-            if (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy) {
-                const double a = sh ? ac[p][1] : ac[p][0];
-                gs1(sm[0], ci + 1, cj + sh + 1, i, j, g, sh ? r0[p][1] : r0[p][0], a);
-                gs1(sm[1], ci + 1, cj + sh + 1, i, j, g, sh ? r1[p][1] : r1[p][0], a);
+            if ((okmask >> (2 * p + sh)) & 1u) {
+                // boundary cells (cell-centred): one neighbour is the zero halo, the other is
+                // weighted 4/3 -- identical to the branches of gs1
+                const double cxw = (g.cc && (i == g.vlo || i == g.vhix)) ? fx43 : g.facx;
+                const double cyw = (g.cc && (j == g.vlo || j == g.vhiy)) ? fy43 : g.facy;
+                const int o = (cj + sh + 1) * AX + cix + 1;
+                const double rr0 = sh ? r0[p][1] : r0[p][0], rr1 = sh ? r1[p][1] : r1[p][0];
+                const double cinv = sh ? ci[p][1] : ci[p][0];
+                double *c = sm[0] + o;
+                double lap = cxw * (c[-1] + c[1]) + cyw * (c[-AX] + c[AX]);
+                c[0] = (rr0 - lap) * cinv;
+                c = sm[1] + o;
+                lap = cxw * (c[-1] + c[1]) + cyw * (c[-AX] + c[AX]);
+                c[0] = (rr1 - lap) * cinv;
             }
         }
         __syncthreads();
     }
+    double rs0[4][2], rs1[4][2];
+    double nres = 0., nrhs = 0.;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        const int ci = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+        const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int i = ox + ci, j = oy + cj + h;
-            if (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy &&
-                ci >= EO && ci < CX - EO && cj + h >= EO && cj + h < CY - EO) {
-                if (DO_RES) {
-                    res.at(i, j, 0) = residual1(sm[0], ci + 1, cj + h + 1, i, j, g, r0[p][h], ac[p][h]);
-                    res.at(i, j, 1) = residual1(sm[1], ci + 1, cj + h + 1, i, j, g, r1[p][h], ac[p][h]);
-                }
-                phi_out.at(i, j, 0) = sm[0][(cj + h + 1) * AX + ci + 1];
-                phi_out.at(i, j, 1) = sm[1][(cj + h + 1) * AX + ci + 1];
+            const int i = ox + cix, j = oy + cj + h;
+            const bool ok = (okmask >> (2 * p + h)) & 1u;
+            rs0[p][h] = rs1[p][h] = 0.;
+            // the residual is exact one ring further out than the owned region (needed by the
+            // nodal full-weighting restriction)
+            if (RES && ok && cix >= EO - 1 && cix < CX - EO + 1 && cj + h >= EO - 1 && cj + h < CY - EO + 1) {
+                rs0[p][h] = residual_smem(sm[0], cix + 1, cj + h + 1, i, j, g, r0[p][h], ac[p][h]);
+                rs1[p][h] = residual_smem(sm[1], cix + 1, cj + h + 1, i, j, g, r1[p][h], ac[p][h]);
             }
+            if (ok && cix >= EO && cix < CX - EO && cj + h >= EO && cj + h < CY - EO) {
+                phi_out.at(i, j, 0) = sm[0][(cj + h + 1) * AX + cix + 1];
+                phi_out.at(i, j, 1) = sm[1][(cj + h + 1) * AX + cix + 1];
+                if (RES) {
+                    nres = fmax(nres, fmax(fabs(rs0[p][h]), fabs(rs1[p][h])));
+                    nrhs = fmax(nrhs, fmax(fabs(r0[p][h]), fabs(r1[p][h])));
+                }
+            }
+        }
+    }
+    if (!RES) return;
+    __syncthreads();                   // everyone is done reading phi from shared memory
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            sm[0][(cj + h + 1) * AX + cix + 1] = rs0[p][h];
+            sm[1][(cj + h + 1) * AX + cix + 1] = rs1[p][h];
+        }
+    }
+    __syncthreads();
+    // restriction of the owned region [X0, X0 + FX) x [Y0, Y0 + FY) (level indices)
+    const int X0 = ox + EO, Y0 = oy + EO;
+    // coarse points owned by this tile: cc: fine cells (2I, 2I+1); nodal: fine node 2I
+    const int I0 = (X0 + 1) >> 1, J0 = (Y0 + 1) >> 1;
+    const int I1 = (X0 + FX + 1) >> 1, J1 = (Y0 + FY + 1) >> 1;     // exclusive
+    const int nI = I1 - I0, nJ = J1 - J0;
+    for (int s = threadIdx.x; s < nI * nJ; s += NT) {
+        const int J = J0 + s / nI, I = I0 + s % nI;
+        if (I < gc.vlo || I > gc.vhix || J < gc.vlo || J > gc.vhiy) continue;
+        const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;         // smem index of fine (2I, 2J)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            const double *f = sm[n] + lj * AX + li;
+            double v;
+            if (g.cc) {
+                v = 0.25 * (f[0] + f[1] + f[AX] + f[AX + 1]);
+            } else {
+                v = (1. / 16.) * (f[-AX - 1] + 2. * f[-AX] + f[-AX + 1]
+                                  + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                                  + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
+            }
+            res_c.at(I, J, n) = v;
+        }
+    }
+    if (norm) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nres = fmax(nres, __shfl_xor_sync(0xffffffffu, nres, o));
+            nrhs = fmax(nrhs, __shfl_xor_sync(0xffffffffu, nrhs, o));
+        }
+        if (tx == 0) {
+            // bit pattern of non-negative doubles is monotone: exact, order-independent max
+            atomicMax((unsigned long long *)&norm[0], (unsigned long long)__double_as_longlong(nres));
+            atomicMax((unsigned long long *)&norm[1], (unsigned long long)__double_as_longlong(nrhs));
         }
     }
 }
 
-// plain red-black half-sweeps in global memory by a single CTA (coarsest level: <= 5x5 points)
-__global__ void k_bottom(LevelGeom g, V2 phi, V2 rhs, const double *acf, int nsweeps)
+// ---- single-CTA part of the V-cycle: all levels with <= 34 x 34 points -------------------------
+struct CoarseLevel {
+    LevelGeom g;
+    double *acf, *c0i, *res, *cor, *rescor;      // res/cor/rescor: 2 comps, comp stride nx*ny
+};
+struct CoarseArgs { int nl; int nsweeps_bottom; CoarseLevel L[12]; };
+
+__device__ void c_gsrb(const CoarseLevel &L, double *phi, const double *rhs, int nsweeps)
 {
+    const LevelGeom &g = L.g;
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
-    for (int s = threadIdx.x; s < g.nx * g.ny; s += blockDim.x) {
-        phi.p[s] = 0.;
-        phi.p[s + phi.cs] = 0.;
-    }
-    __syncthreads();
+    const int ncell = nvx * nvy;
+    const long cs = (long)g.nx * g.ny;
+    const double fx43 = g.facx * (4. / 3.), fy43 = g.facy * (4. / 3.);
     for (int is = 0; is < nsweeps; ++is) {
-        for (int s = threadIdx.x; s < nvx * nvy; s += blockDim.x) {
-            const int j = s / nvx + g.vlo, i = s % nvx + g.vlo;
+        for (int s = threadIdx.x; s < 2 * ncell; s += blockDim.x) {
+            const int n = s >= ncell, cell = s - n * ncell;
+            const int j = cell / nvx + g.vlo, i = cell % nvx + g.vlo;
             if (((i + j + is) & 1) == 0) {
-                const double a = acf[i + (long)j * g.nx];
-                for (int n = 0; n < 2; ++n) {
-                    auto P = [&](int ii, int jj) -> double {
-                        // nodal boundary nodes are stored (and stay) zero; cc never reads outside
-                        return phi.at(ii, jj, n);
-                    };
-                    double lap;
-                    double c0 = -(a + 2.0 * (g.facx + g.facy));
-                    if (g.cc && i == g.vlo) { lap = g.facx * (4. / 3.) * P(i + 1, j); c0 -= 2.0 * g.facx; }
-                    else if (g.cc && i == g.vhix) { lap = g.facx * (4. / 3.) * P(i - 1, j); c0 -= 2.0 * g.facx; }
-                    else lap = g.facx * (P(i - 1, j) + P(i + 1, j));
-                    if (g.cc && j == g.vlo) { lap += g.facy * (4. / 3.) * P(i, j + 1); c0 -= 2.0 * g.facy; }
-                    else if (g.cc && j == g.vhiy) { lap += g.facy * (4. / 3.) * P(i, j - 1); c0 -= 2.0 * g.facy; }
-                    else lap += g.facy * (P(i, j - 1) + P(i, j + 1));
-                    const double c0_inv = 1.0 / c0;
-                    phi.at(i, j, n) = (rhs.at(i, j, n) - lap) * c0_inv;
-                }
+                const long o = i + (long)j * g.nx;
+                const double *c = phi + n * cs + o;
+                double lap;
+                if (g.cc && i == g.vlo) lap = fx43 * c[1];
+                else if (g.cc && i == g.vhix) lap = fx43 * c[-1];
+                else lap = g.facx * (c[-1] + c[1]);
+                if (g.cc && j == g.vlo) lap += fy43 * c[g.nx];
+                else if (g.cc && j == g.vhiy) lap += fy43 * c[-g.nx];
+                else lap += g.facy * (c[-g.nx] + c[g.nx]);
+                phi[n * cs + o] = (rhs[n * cs + o] - lap) * L.c0i[o];
             }
         }
         __syncthreads();
     }
 }
 
-// crse = R(fine) over the valid coarse points, ncomp components
-__global__ void k_restrict(LevelGeom gc, V2 crse, V2 fine, int ncomp)
+__device__ void c_residual(const CoarseLevel &L, double *res, const double *phi, const double *rhs)
+{
+    const LevelGeom &g = L.g;
+    const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
+    const int ncell = nvx * nvy;
+    const long cs = (long)g.nx * g.ny;
+    for (int s = threadIdx.x; s < 2 * ncell; s += blockDim.x) {
+        const int n = s >= ncell, cell = s - n * ncell;
+        const int j = cell / nvx + g.vlo, i = cell % nvx + g.vlo;
+        const long o = i + (long)j * g.nx;
+        const double *c = phi + n * cs + o;
+        double lap = -2.0 * (g.facx + g.facy) * c[0];
+        if (g.cc && i == g.vlo) lap += g.facx * ((4. / 3.) * c[1] - 2.0 * c[0]);
+        else if (g.cc && i == g.vhix) lap += g.facx * ((4. / 3.) * c[-1] - 2.0 * c[0]);
+        else lap += g.facx * (c[-1] + c[1]);
+        if (g.cc && j == g.vlo) lap += g.facy * ((4. / 3.) * c[g.nx] - 2.0 * c[0]);
+        else if (g.cc && j == g.vhiy) lap += g.facy * ((4. / 3.) * c[-g.nx] - 2.0 * c[0]);
+        else lap += g.facy * (c[-g.nx] + c[g.nx]);
+        res[n * cs + o] = rhs[n * cs + o] + L.acf[o] * c[0] - lap;
+    }
+    __syncthreads();
+}
+
+// crse(ncomp comps) = R(fine)
+__device__ void c_restrict(const LevelGeom &gc, double *crse, const LevelGeom &gf, const double *fine,
+                           int ncomp)
+{
+    const int nvx = gc.vhix - gc.vlo + 1, nvy = gc.vhiy - gc.vlo + 1;
+    const int ncell = nvx * nvy;
+    const long ccs = (long)gc.nx * gc.ny, fcs = (long)gf.nx * gf.ny;
+    for (int s = threadIdx.x; s < ncomp * ncell; s += blockDim.x) {
+        const int n = s / ncell, cell = s - n * ncell;
+        const int j = cell / nvx + gc.vlo, i = cell % nvx + gc.vlo;
+        const double *f = fine + n * fcs + (2 * i) + (long)(2 * j) * gf.nx;
+        const int w = gf.nx;
+        double v;
+        if (gc.cc) v = 0.25 * (f[0] + f[1] + f[w] + f[w + 1]);
+        else v = (1. / 16.) * (f[-w - 1] + 2. * f[-w] + f[-w + 1] + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                               + f[w - 1] + 2. * f[w] + f[w + 1]);
+        crse[n * ccs + i + (long)j * gc.nx] = v;
+    }
+    __syncthreads();
+}
+
+__device__ void c_interp_add(const CoarseLevel &Lf, double *fine, const CoarseLevel &Lc, double *crse)
+{
+    const LevelGeom &g = Lf.g;
+    const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
+    const int ncell = nvx * nvy;
+    const long cs = (long)g.nx * g.ny;
+    V2 cv{crse, Lc.g.nx, (long)Lc.g.nx * Lc.g.ny};
+    for (int s = threadIdx.x; s < 2 * ncell; s += blockDim.x) {
+        const int n = s >= ncell, cell = s - n * ncell;
+        const int j = cell / nvx + g.vlo, i = cell % nvx + g.vlo;
+        const long o = n * cs + i + (long)j * g.nx;
+        fine[o] = fine[o] + interp_at(cv, i, j, n, g.cc);
+    }
+    __syncthreads();
+}
+
+__device__ void c_zero(double *p, long n)
+{
+    for (long s = threadIdx.x; s < n; s += blockDim.x) p[s] = 0.;
+    __syncthreads();
+}
+
+// levels L[0..nl-1] (L[0] = first single-CTA level): in res[0]; out cor[0]
+__global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A)
+{
+    const int nl = A.nl;
+    for (int l = 0; l < nl - 1; ++l) {
+        const CoarseLevel &L = A.L[l];
+        const long n = (long)L.g.nx * L.g.ny;
+        c_zero(L.cor, 2 * n);
+        c_gsrb(L, L.cor, L.res, 4);
+        c_residual(L, L.rescor, L.cor, L.res);
+        c_restrict(A.L[l + 1].g, A.L[l + 1].res, L.g, L.rescor, 2);
+    }
+    {
+        const CoarseLevel &L = A.L[nl - 1];
+        c_zero(L.cor, 2 * (long)L.g.nx * L.g.ny);
+        c_gsrb(L, L.cor, L.res, A.nsweeps_bottom);
+    }
+    for (int l = nl - 2; l >= 0; --l) {
+        c_interp_add(A.L[l], A.L[l].cor, A.L[l + 1], A.L[l + 1].cor);
+        c_gsrb(A.L[l], A.L[l].cor, A.L[l].res, 4);
+    }
+}
+
+// average_down_acoef (:1640-1700) for the single-CTA levels + their 1/c0 tables.
+// L[0].acf must already hold the restriction from the last tile level (or be level 1's input).
+__global__ void __launch_bounds__(kCoarseThreads) k_coarse_setup(CoarseArgs A, LevelGeom gfine,
+                                                                  const double *acf_fine, long fine_rs)
+{
+    // restrict into L[0] from the finer (tile) level with an arbitrary row stride
+    {
+        const LevelGeom &gc = A.L[0].g;
+        const int nvx = gc.vhix - gc.vlo + 1, nvy = gc.vhiy - gc.vlo + 1;
+        for (int s = threadIdx.x; s < nvx * nvy; s += blockDim.x) {
+            const int j = s / nvx + gc.vlo, i = s % nvx + gc.vlo;
+            const double *f = acf_fine + (2 * i) + (long)(2 * j) * fine_rs;
+            const long w = fine_rs;
+            double v;
+            if (gc.cc) v = 0.25 * (f[0] + f[1] + f[w] + f[w + 1]);
+            else v = (1. / 16.) * (f[-w - 1] + 2. * f[-w] + f[-w + 1] + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                                   + f[w - 1] + 2. * f[w] + f[w + 1]);
+            A.L[0].acf[i + (long)j * gc.nx] = v;
+        }
+        __syncthreads();
+        (void)gfine;
+    }
+    for (int l = 1; l < A.nl; ++l) c_restrict(A.L[l].g, A.L[l].acf, A.L[l - 1].g, A.L[l - 1].acf, 1);
+    for (int l = 0; l < A.nl; ++l) {
+        const LevelGeom &g = A.L[l].g;
+        const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
+        for (int s = threadIdx.x; s < nvx * nvy; s += blockDim.x) {
+            const int j = s / nvx + g.vlo, i = s % nvx + g.vlo;
+            const long o = i + (long)j * g.nx;
+            double c0 = -(A.L[l].acf[o] + 2.0 * (g.facx + g.facy));
+            if (g.cc && (i == g.vlo || i == g.vhix)) c0 -= 2.0 * g.facx;
+            if (g.cc && (j == g.vlo || j == g.vhiy)) c0 -= 2.0 * g.facy;
+            A.L[l].c0i[o] = 1.0 / c0;
+        }
+    }
+}
+
+// crse = R(fine), 1 component, arbitrary fine row stride (coefficient average-down on tile levels)
+__global__ void k_restrict_acf(LevelGeom gc, double *crse, const double *fine, long fine_rs)
 {
     const int nvx = gc.vhix - gc.vlo + 1;
     const long nv = (long)nvx * (gc.vhiy - gc.vlo + 1);
     const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nv) return;
     const int j = (int)(s / nvx) + gc.vlo, i = (int)(s % nvx) + gc.vlo;
-    for (int n = 0; n < ncomp; ++n) {
-        if (gc.cc) {
-            crse.at(i, j, n) = 0.25 * (fine.at(2 * i, 2 * j, n) + fine.at(2 * i + 1, 2 * j, n)
-                                       + fine.at(2 * i, 2 * j + 1, n) + fine.at(2 * i + 1, 2 * j + 1, n));
-        } else {
-            crse.at(i, j, n) = (1. / 16.) * (fine.at(2 * i - 1, 2 * j - 1, n)
-                               + 2. * fine.at(2 * i, 2 * j - 1, n)
-                               + fine.at(2 * i + 1, 2 * j - 1, n)
-                               + 2. * fine.at(2 * i - 1, 2 * j, n)
-                               + 4. * fine.at(2 * i, 2 * j, n)
-                               + 2. * fine.at(2 * i + 1, 2 * j, n)
-                               + fine.at(2 * i - 1, 2 * j + 1, n)
-                               + 2. * fine.at(2 * i, 2 * j + 1, n)
-                               + fine.at(2 * i + 1, 2 * j + 1, n));
-        }
-    }
-}
-
-// fine_out = fine_in + I(crse) over the valid fine points
-__global__ void k_interp_add(LevelGeom gf, V2 fine_in, V2 crse, V2 fine_out)
-{
-    const int nvx = gf.vhix - gf.vlo + 1;
-    const long nv = (long)nvx * (gf.vhiy - gf.vlo + 1);
-    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nv) return;
-    const int j = (int)(s / nvx) + gf.vlo, i = (int)(s % nvx) + gf.vlo;
-    const int ic = i >> 1, jc = j >> 1;
-    for (int n = 0; n < 2; ++n) {
-        double add;
-        if (gf.cc) {
-            add = crse.at(ic, jc, n);
-        } else {
-            const bool io = (ic * 2 != i), jo = (jc * 2 != j);
-            if (io && jo) add = (crse.at(ic, jc, n) + crse.at(ic + 1, jc, n) + crse.at(ic, jc + 1, n)
-                                 + crse.at(ic + 1, jc + 1, n)) * 0.25;
-            else if (io) add = (crse.at(ic, jc, n) + crse.at(ic + 1, jc, n)) * 0.5;
-            else if (jo) add = (crse.at(ic, jc, n) + crse.at(ic, jc + 1, n)) * 0.5;
-            else add = crse.at(ic, jc, n);
-        }
-        fine_out.at(i, j, n) = fine_in.at(i, j, n) + add;
-    }
-}
-
-__global__ void k_copy_acf(LevelGeom g, double *dst, const double *src, long src_rs)
-{
-    const int nvx = g.vhix - g.vlo + 1;
-    const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
-    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nv) return;
-    const int j = (int)(s / nvx) + g.vlo, i = (int)(s % nvx) + g.vlo;
-    dst[i + (long)j * g.nx] = src[i + (long)j * src_rs];
-}
-
-// max|a| (2 comps) and optionally max|b| over the valid box -> out[0], out[1] (uint64 atomicMax
-// on the bit pattern of non-negative doubles: order-independent, exact)
-__global__ void k_norms(LevelGeom g, V2 a, V2 b, int do_b, double *out)
-{
-    __shared__ double sa[256], sb[256];
-    const int nvx = g.vhix - g.vlo + 1;
-    const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
-    double ma = 0., mb = 0.;
-    for (long s = (long)blockIdx.x * blockDim.x + threadIdx.x; s < nv; s += (long)gridDim.x * blockDim.x) {
-        const int j = (int)(s / nvx) + g.vlo, i = (int)(s % nvx) + g.vlo;
-        ma = fmax(ma, fmax(fabs(a.at(i, j, 0)), fabs(a.at(i, j, 1))));
-        if (do_b) mb = fmax(mb, fmax(fabs(b.at(i, j, 0)), fabs(b.at(i, j, 1))));
-    }
-    sa[threadIdx.x] = ma; sb[threadIdx.x] = mb;
-    __syncthreads();
-    for (int st = 128; st > 0; st >>= 1) {
-        if ((int)threadIdx.x < st) {
-            sa[threadIdx.x] = fmax(sa[threadIdx.x], sa[threadIdx.x + st]);
-            sb[threadIdx.x] = fmax(sb[threadIdx.x], sb[threadIdx.x + st]);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        atomicMax((unsigned long long *)&out[0], (unsigned long long)__double_as_longlong(sa[0]));
-        if (do_b) atomicMax((unsigned long long *)&out[1], (unsigned long long)__double_as_longlong(sb[0]));
-    }
+    const double *f = fine + (2 * i) + (long)(2 * j) * fine_rs;
+    const long w = fine_rs;
+    double v;
+    if (gc.cc) v = 0.25 * (f[0] + f[1] + f[w] + f[w + 1]);
+    else v = (1. / 16.) * (f[-w - 1] + 2. * f[-w] + f[-w + 1] + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                           + f[w - 1] + 2. * f[w] + f[w + 1]);
+    crse[i + (long)j * gc.nx] = v;
 }
 
 __global__ void k_copy2(LevelGeom g, V2 dst, V2 src)
@@ -306,19 +431,41 @@ V2 lvl_view(const hpb_ctx *ctx, int l, double *p)
     V2 v; v.p = p; v.rs = ctx->mg[l].nx; v.cs = (long)ctx->mg[l].nx * ctx->mg[l].ny; return v;
 }
 
-template <bool Z, bool R>
-void launch_gsrb4(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 rhs, const double *acf, long acf_rs,
-                  V2 out, V2 res)
+template <int INIT, bool RES>
+void launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, const double *acf,
+                   long acf_rs, V2 out, const LevelGeom &gc, V2 res_c, double *norm)
 {
-    constexpr int EO = R ? 4 : 3;
+    // owned region must start on even indices relative to vlo for the fused restriction;
+    // cc needs 1 extra ring for the residual (EO 4), nodal full weighting one more (EO 5)
+    const int EO = RES ? (g.cc ? 4 : 5) : 3;
     const int FX = CX - 2 * EO, FY = CY - 2 * EO;
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
-    k_gsrb4<Z, R><<<nbx * nby, NT, 0, ctx->stream>>>(g, in, rhs, acf, acf_rs, out, res, nbx);
+    k_smooth<INIT, RES><<<nbx * nby, NT, 0, ctx->stream>>>(g, in, crse, rhs, acf, acf_rs, out, gc,
+                                                           res_c, norm, nbx, EO);
     hpb_count_launch(ctx);
 }
 
 inline unsigned nb(long n) { return (unsigned)((n + 255) / 256); }
+
+CoarseArgs coarse_args(hpb_ctx *ctx)
+{
+    CoarseArgs A;
+    const int lc = ctx->mg_lc, nl = ctx->mg_nlev;
+    A.nl = nl - lc;
+    for (int l = lc; l < nl; ++l) {
+        CoarseLevel &L = A.L[l - lc];
+        L.g = level_geom(ctx, l);
+        L.acf = ctx->mg[l].acf; L.c0i = ctx->mg[l].c0i; L.res = ctx->mg[l].res;
+        L.cor = ctx->mg[l].cor; L.rescor = ctx->mg[l].rescor;
+    }
+    const LevelGeom gb = level_geom(ctx, nl - 1);
+    int nsw = 16;
+    const int mx = gb.nx > gb.ny ? gb.nx : gb.ny;
+    if ((mx + 1) / 2 * 2 > nsw) nsw = (mx + 1) / 2 * 2;       // HpMultiGrid.cpp:1587
+    A.nsweeps_bottom = nsw;
+    return A;
+}
 
 }  // namespace
 
@@ -342,16 +489,30 @@ int hpb_mg_init(hpb_ctx *ctx)
         if (ctx->mg_cc) { w /= 2; h /= 2; } else { w = (w - 1) / 2 + 1; h = (h - 1) / 2 + 1; }
     }
     ctx->mg_nlev = nl;
+    if (nl < 2) {
+        hpb_set_error("hpmg: a %d x %d grid cannot be coarsened (HpMultiGrid.cpp:1085-1090)", nx, ny);
+        return HPB_ERR_UNSUPPORTED;
+    }
+    // first level handled by the single-CTA kernel (>= 1: level 0 always uses the tile kernels)
+    int lc = 1;
+    while (lc < nl - 1 && (ctx->mg[lc].nx > kCoarseMax || ctx->mg[lc].ny > kCoarseMax)) ++lc;
+    if (nl - lc > 12) lc = nl - 12;
+    if (ctx->mg[lc].nx * ctx->mg[lc].ny > 4 * kCoarseMax * kCoarseMax) {
+        hpb_set_error("hpmg: coarsest level %d x %d is too large for the single-block solve",
+                      ctx->mg[lc].nx, ctx->mg[lc].ny);
+        return HPB_ERR_UNSUPPORTED;
+    }
+    ctx->mg_lc = lc;
     for (int l = 0; l < nl; ++l) {
         const size_t n = (size_t)ctx->mg[l].nx * ctx->mg[l].ny;
-        HPB_CUDA_CHECK(cudaMalloc(&ctx->mg[l].acf, n * sizeof(double)));
-        HPB_CUDA_CHECK(cudaMalloc(&ctx->mg[l].res, 2 * n * sizeof(double)));
-        HPB_CUDA_CHECK(cudaMalloc(&ctx->mg[l].cor, 2 * n * sizeof(double)));
-        HPB_CUDA_CHECK(cudaMalloc(&ctx->mg[l].rescor, 2 * n * sizeof(double)));
-        HPB_CUDA_CHECK(cudaMemset(ctx->mg[l].acf, 0, n * sizeof(double)));
-        HPB_CUDA_CHECK(cudaMemset(ctx->mg[l].res, 0, 2 * n * sizeof(double)));
-        HPB_CUDA_CHECK(cudaMemset(ctx->mg[l].cor, 0, 2 * n * sizeof(double)));
-        HPB_CUDA_CHECK(cudaMemset(ctx->mg[l].rescor, 0, 2 * n * sizeof(double)));
+        double **arrs[5] = {&ctx->mg[l].acf, &ctx->mg[l].c0i, &ctx->mg[l].res, &ctx->mg[l].cor,
+                            &ctx->mg[l].rescor};
+        const size_t mult[5] = {1, 1, 2, 2, 2};
+        for (int k = 0; k < 5; ++k) {
+            if (l == 0 && (k == 0 || k == 1 || k == 2)) { *arrs[k] = nullptr; continue; }  // chi / rhs in place
+            HPB_CUDA_CHECK(cudaMalloc(arrs[k], mult[k] * n * sizeof(double)));
+            HPB_CUDA_CHECK(cudaMemset(*arrs[k], 0, mult[k] * n * sizeof(double)));
+        }
     }
     HPB_CUDA_CHECK(cudaMalloc(&ctx->d_mg_norm, 2 * sizeof(double)));
     HPB_CUDA_CHECK(cudaMallocHost(&ctx->h_mg_norm, 2 * sizeof(double)));
@@ -361,57 +522,46 @@ int hpb_mg_init(hpb_ctx *ctx)
 void hpb_mg_free(hpb_ctx *ctx)
 {
     for (int l = 0; l < ctx->mg_nlev; ++l) {
-        cudaFree(ctx->mg[l].acf); cudaFree(ctx->mg[l].res); cudaFree(ctx->mg[l].cor);
-        cudaFree(ctx->mg[l].rescor);
+        cudaFree(ctx->mg[l].acf); cudaFree(ctx->mg[l].c0i); cudaFree(ctx->mg[l].res);
+        cudaFree(ctx->mg[l].cor); cudaFree(ctx->mg[l].rescor);
     }
     cudaFree(ctx->d_mg_norm);
     cudaFreeHost(ctx->h_mg_norm);
 }
 
-static int mg_vcycle(hpb_ctx *ctx, V2 sol, V2 rhs0)
+// one V-cycle (:1429-1512).  On entry: cur = cor0 (level-0 iterate after 4 sweeps), res[1] holds
+// the restricted residual of cor0.  On exit the same invariants hold for the new cor0, and
+// d_mg_norm[0] holds max|rescor0|.  tmp is the second level-0 buffer.
+static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, long chi_rs)
 {
-    const int nl = ctx->mg_nlev;
-    for (int l = 0; l < nl - 1; ++l) {
-        const LevelGeom g = level_geom(ctx, l);
-        if (l > 0) {
-            launch_gsrb4<true, true>(ctx, g, V2{}, lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf,
-                                     g.nx, lvl_view(ctx, l, ctx->mg[l].cor),
-                                     lvl_view(ctx, l, ctx->mg[l].rescor));
-        }
-        const LevelGeom gc = level_geom(ctx, l + 1);
-        const long nv = (long)(gc.vhix - gc.vlo + 1) * (gc.vhiy - gc.vlo + 1);
-        k_restrict<<<nb(nv), 256, 0, ctx->stream>>>(gc, lvl_view(ctx, l + 1, ctx->mg[l + 1].res),
-                                                    lvl_view(ctx, l, ctx->mg[l].rescor), 2);
-        hpb_count_launch(ctx);
+    const int lc = ctx->mg_lc;
+    const V2 none{};
+    const LevelGeom gnone{};
+    for (int l = 1; l < lc; ++l) {                 // down, tile levels
+        const LevelGeom g = level_geom(ctx, l), gc = level_geom(ctx, l + 1);
+        launch_smooth<0, true>(ctx, g, none, none, lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf,
+                               g.nx, lvl_view(ctx, l, ctx->mg[l].cor), gc,
+                               lvl_view(ctx, l + 1, ctx->mg[l + 1].res), nullptr);
     }
-    {
-        const int l = nl - 1;
+    k_coarse<<<1, kCoarseThreads, 0, ctx->stream>>>(coarse_args(ctx));
+    hpb_count_launch(ctx);
+    // up, tile levels: cor[l] <- GSRB^4(cor[l] + I(cor[l+1])); double-buffered through rescor[l]
+    double *up_prev = ctx->mg[lc].cor;
+    for (int l = lc - 1; l >= 1; --l) {
         const LevelGeom g = level_geom(ctx, l);
-        int nsw = 16;
-        const int mx = g.nx > g.ny ? g.nx : g.ny;
-        if ((mx + 1) / 2 * 2 > nsw) nsw = (mx + 1) / 2 * 2;       // HpMultiGrid.cpp:1587
-        k_bottom<<<1, 64, 0, ctx->stream>>>(g, lvl_view(ctx, l, ctx->mg[l].cor),
-                                            lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf, nsw);
-        hpb_count_launch(ctx);
+        launch_smooth<2, false>(ctx, g, lvl_view(ctx, l, ctx->mg[l].cor), lvl_view(ctx, l + 1, up_prev),
+                                lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf, g.nx,
+                                lvl_view(ctx, l, ctx->mg[l].rescor), gnone, none, nullptr);
+        up_prev = ctx->mg[l].rescor;
     }
-    for (int l = nl - 2; l >= 0; --l) {
-        const LevelGeom g = level_geom(ctx, l);
-        const long nv = (long)(g.vhix - g.vlo + 1) * (g.vhiy - g.vlo + 1);
-        k_interp_add<<<nb(nv), 256, 0, ctx->stream>>>(g, lvl_view(ctx, l, ctx->mg[l].cor),
-                                                      lvl_view(ctx, l + 1, ctx->mg[l + 1].cor),
-                                                      lvl_view(ctx, l, ctx->mg[l].rescor));
-        hpb_count_launch(ctx);
-        if (l == 0)
-            launch_gsrb4<false, false>(ctx, g, lvl_view(ctx, 0, ctx->mg[0].rescor), rhs0,
-                                       ctx->mg[0].acf, g.nx, sol, V2{});
-        else
-            launch_gsrb4<false, false>(ctx, g, lvl_view(ctx, l, ctx->mg[l].rescor),
-                                       lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf, g.nx,
-                                       lvl_view(ctx, l, ctx->mg[l].cor), V2{});
-    }
-    const LevelGeom g0 = level_geom(ctx, 0);
-    launch_gsrb4<false, true>(ctx, g0, sol, rhs0, ctx->mg[0].acf, g0.nx,
-                              lvl_view(ctx, 0, ctx->mg[0].cor), lvl_view(ctx, 0, ctx->mg[0].rescor));
+    const LevelGeom g0 = level_geom(ctx, 0), g1 = level_geom(ctx, 1);
+    // sol = GSRB^4(cor0 + I(cor[1]))  ->  tmp
+    launch_smooth<2, false>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs, tmp, gnone, none,
+                            nullptr);
+    // cor0 = GSRB^4(sol), rescor0 = rhs - L cor0 -> res[1], norm   (:1501-1503)
+    HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, 2 * sizeof(double), ctx->stream));
+    launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, cur, g1,
+                           lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm);
     return HPB_OK;
 }
 
@@ -426,27 +576,33 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     V2 sol{v.comp(c_sol) + v.idx(sh, sh), v.jstride, v.nstride};
     V2 rhs{v.comp(c_rhs) + v.idx(sh, sh), v.jstride, v.nstride};
     const double *chi = v.comp(c_acf) + v.idx(sh, sh);
-    const int nl = ctx->mg_nlev;
-    const LevelGeom g0 = level_geom(ctx, 0);
+    const long chi_rs = v.jstride;
+    const int nl = ctx->mg_nlev, lc = ctx->mg_lc;
+    const LevelGeom g0 = level_geom(ctx, 0), g1 = level_geom(ctx, 1);
     const long nv0 = (long)(g0.vhix - g0.vlo + 1) * (g0.vhiy - g0.vlo + 1);
+    const V2 none{};
+    (void)nl;
 
-    // acf[0] <- chi, then average down (solve1 :1177-1187, average_down_acoef :1640-1700)
-    k_copy_acf<<<nb(nv0), 256, 0, ctx->stream>>>(g0, ctx->mg[0].acf, chi, v.jstride);
-    hpb_count_launch(ctx);
-    for (int l = 1; l < nl; ++l) {
+    // average_down_acoef (:1640-1700); level 0 uses chi in place (solve1 :1177-1187)
+    const double *fine = chi;
+    long fine_rs = chi_rs;
+    for (int l = 1; l < lc; ++l) {
         const LevelGeom gc = level_geom(ctx, l);
         const long nv = (long)(gc.vhix - gc.vlo + 1) * (gc.vhiy - gc.vlo + 1);
-        V2 c{ctx->mg[l].acf, gc.nx, 0}, f{ctx->mg[l - 1].acf, ctx->mg[l - 1].nx, 0};
-        k_restrict<<<nb(nv), 256, 0, ctx->stream>>>(gc, c, f, 1);
+        k_restrict_acf<<<nb(nv), 256, 0, ctx->stream>>>(gc, ctx->mg[l].acf, fine, fine_rs);
         hpb_count_launch(ctx);
+        fine = ctx->mg[l].acf;
+        fine_rs = gc.nx;
     }
-    // cor0 = GSRB^4(sol), rescor0 = rhs - L(cor0)   (:1326-1327)
-    launch_gsrb4<false, true>(ctx, g0, sol, rhs, ctx->mg[0].acf, g0.nx,
-                              lvl_view(ctx, 0, ctx->mg[0].cor), lvl_view(ctx, 0, ctx->mg[0].rescor));
-    HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, 2 * sizeof(double), ctx->stream));
-    unsigned nbn = nb(nv0); if (nbn > 592) nbn = 592;
-    k_norms<<<nbn, 256, 0, ctx->stream>>>(g0, lvl_view(ctx, 0, ctx->mg[0].rescor), rhs, 1, ctx->d_mg_norm);
+    k_coarse_setup<<<1, kCoarseThreads, 0, ctx->stream>>>(coarse_args(ctx), level_geom(ctx, lc - 1),
+                                                          fine, fine_rs);
     hpb_count_launch(ctx);
+
+    // cor0 = GSRB^4(sol), rescor0 = rhs - L(cor0)   (:1326-1327), fused with its restriction
+    V2 cur = lvl_view(ctx, 0, ctx->mg[0].cor);
+    HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, 2 * sizeof(double), ctx->stream));
+    launch_smooth<1, true>(ctx, g0, sol, none, rhs, chi, chi_rs, cur, g1,
+                           lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm);
     HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_norm, ctx->d_mg_norm, 2 * sizeof(double),
                                    cudaMemcpyDeviceToHost, ctx->stream));
     HPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -457,12 +613,9 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     if (!(resnorm0 <= res_target)) {
         bool converged = false;
         for (int it = 0; it < max_iters; ++it) {
-            mg_vcycle(ctx, sol, rhs);
+            int rc = mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs);     // sol is the scratch iterate
+            if (rc) return rc;
             iters = it + 1;
-            HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, sizeof(double), ctx->stream));
-            k_norms<<<nbn, 256, 0, ctx->stream>>>(g0, lvl_view(ctx, 0, ctx->mg[0].rescor), rhs, 0,
-                                                  ctx->d_mg_norm);
-            hpb_count_launch(ctx);
             HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_norm, ctx->d_mg_norm, sizeof(double),
                                            cudaMemcpyDeviceToHost, ctx->stream));
             HPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -479,7 +632,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
         }
     }
     // sol <- cor0 on the valid box (:1419-1426)
-    k_copy2<<<nb(nv0), 256, 0, ctx->stream>>>(g0, sol, lvl_view(ctx, 0, ctx->mg[0].cor));
+    k_copy2<<<nb(nv0), 256, 0, ctx->stream>>>(g0, sol, cur);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     if (h_iters) *h_iters = iters;

@@ -3,16 +3,20 @@
 // DST2D(DST2D(rhs) * eigenvalue) (src/fields/fft_poisson_solver/FFTPoissonSolverDirichletFast.cpp:
 // 224-248, 286-328; identical maths in ...DirichletDirect.cpp:87-139).
 //
-// B200-native formulation (not the reference's 4 cuFFT calls + 5 helper kernels):
-//   1. rows:    Rhat[j][k] = DST-I_x(rhs[j][:])            one CTA per PAIR of rows; the two real
-//               rows ride in the real/imaginary lanes of ONE complex FFT of length N = nx+1 held
-//               in shared memory (mixed-radix Stockham, any N: 1025 = 5*5*41, 1024 = 4^5, ...)
-//   2. columns: for every x-mode k solve the constant-coefficient tridiagonal system in y
-//               (phi[j-1] - 2 phi[j] + phi[j+1])/dy^2 + lambda_k phi[j] = Rhat[j][k]
-//               lambda_k = -4 sin^2(pi (k+1) / (2 (nx+1))) / dx^2      (Thomas, pivots tabulated)
-//   3. rows:    phi[j][:] = DST-I_x(phihat[j][:]) / (2 (nx+1))   written straight into the slice
-// Two 1-D transform passes instead of four, no transposes, no dependence on ny+1 being smooth.
-// The three solves of a slice (Psi, Ez, Bz) are batched into each launch (grid.y = batch).
+// B200-native formulation (not the reference's 4 cuFFT calls + 5 helper kernels per solve):
+//   K1 rows:   Rhat[j][k] = DST-I_x(rhs[j][:]).  One CTA per PAIR of rows: the two real rows ride
+//              in the real / imaginary lanes of ONE complex FFT of length N = nx+1 held in shared
+//              memory (Stockham, radix 4/2/3/5 + any odd prime factor: 1025 = 5*5*41), with the
+//              pre-differencing / sine-factor post-processing of the (n+1)-point DST trick.  The
+//              RHS assembly of Fields::SolvePoissonPsiExmByEypBxEzBz is fused into the row load.
+//   K2,K3:     for every x-mode k the constant-coefficient tridiagonal system in y
+//                (phi[j-1] - 2 phi[j] + phi[j+1])/dy^2 + lambda_k phi[j] = Rhat[j][k]
+//              is solved by the partition method: independent Thomas solves on chunks of rows
+//              (nx * nchunk * 3 threads, pivots tabulated), then a small reduced system for the
+//              chunk-interface values; the interface correction is applied in the load of K4.
+//   K4 rows:   phi[j][:] = DST-I_x(phihat[j][:]) / (2 (nx+1)), written straight into the slice.
+// Two transform passes instead of four, no transposes, and the three solves of a slice
+// (Psi, Ez, Bz) are batched into every launch (grid.y = batch).
 #include "common.cuh"
 #include <math.h>
 #include <vector>
@@ -22,46 +26,58 @@ namespace {
 constexpr int kFftThreads = 256;
 constexpr int kMaxRad = 32;
 
-struct FftPlan { int N; int nrad; int rad[kMaxRad]; };
+struct FftPlan {
+    int N; int nrad; int rad[kMaxRad];
+    const double *cs_cos[kMaxRad];     // per prime stage: cos(2 pi t b / p), [b = 0..h][t = 1..h]
+    const double *cs_sin[kMaxRad];
+};
 struct OutPtrs { double *p[4]; };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
-// One Stockham stage of radix r: every thread produces output elements
-//   out[(j-k) r + k + b Ns] = sum_t in[j + t N/r] * w_N^{ t (k + b Ns) N/(Ns r) }
-__device__ __forceinline__ void fft_stage_generic(const double2 *__restrict__ in,
-                                                  double2 *__restrict__ out,
-                                                  const double2 *__restrict__ root, int N, int Ns,
-                                                  int r)
+// Stockham stage of radix r with Ns = product of the previous radices:
+//   out[(j-k) r + k + b Ns] = sum_t ( in[j + t N/r] w_N^{t k N/(Ns r)} ) w_r^{t b},  k = j mod Ns
+
+__device__ __forceinline__ void fft_stage_r2(const double2 *__restrict__ in, double2 *__restrict__ out,
+                                             const double2 *__restrict__ root, int N, int Ns)
 {
-    const int Nr = N / r;
-    const int blk = Ns * r;
-    const int tw = N / blk;
-    for (int e = threadIdx.x; e < N; e += blockDim.x) {
-        const int q = e / blk, rem = e - q * blk;
-        const int b = rem / Ns, k = rem - b * Ns;
-        const int j = q * Ns + k;
-        const int step = (k + b * Ns) * tw;
-        double2 acc = in[j];
-        int idx = step;
-        for (int t = 1; t < r; ++t) {
-            const double2 w = __ldg(&root[idx]);
-            const double2 v = in[j + t * Nr];
-            acc.x += v.x * w.x - v.y * w.y;
-            acc.y += v.x * w.y + v.y * w.x;
-            idx += step;
-            if (idx >= N) idx -= N;
-        }
-        out[e] = acc;
+    const int Nr = N >> 1, tw = N / (Ns * 2);
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+        const int k = j % Ns;
+        double2 v0 = in[j], v1 = in[j + Nr];
+        if (k) v1 = cmul(v1, __ldg(&root[k * tw]));
+        const int o = (j - k) * 2 + k;
+        out[o] = cadd(v0, v1);
+        out[o + Ns] = csub(v0, v1);
+    }
+}
+
+__device__ __forceinline__ void fft_stage_r3(const double2 *__restrict__ in, double2 *__restrict__ out,
+                                             const double2 *__restrict__ root, int N, int Ns)
+{
+    const int Nr = N / 3, tw = N / (Ns * 3);
+    const double c1 = -0.5, s1 = 0.86602540378443864676;
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+        const int k = j % Ns;
+        double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr];
+        if (k) { v1 = cmul(v1, __ldg(&root[k * tw])); v2 = cmul(v2, __ldg(&root[2 * k * tw])); }
+        const double2 a = cadd(v1, v2), d = csub(v1, v2);
+        const double2 P = make_double2(v0.x + c1 * a.x, v0.y + c1 * a.y);
+        const double2 Q = make_double2(s1 * d.x, s1 * d.y);
+        const int o = (j - k) * 3 + k;
+        out[o] = cadd(v0, a);
+        out[o + Ns] = make_double2(P.x + Q.y, P.y - Q.x);          // P - iQ
+        out[o + 2 * Ns] = make_double2(P.x - Q.y, P.y + Q.x);      // P + iQ
     }
 }
 
 // radix-4 stage, one butterfly per thread iteration (4 inputs read once)
-__device__ __forceinline__ void fft_stage_r4(const double2 *__restrict__ in,
-                                             double2 *__restrict__ out,
+__device__ __forceinline__ void fft_stage_r4(const double2 *__restrict__ in, double2 *__restrict__ out,
                                              const double2 *__restrict__ root, int N, int Ns)
 {
     const int Nr = N >> 2;
@@ -74,157 +90,281 @@ __device__ __forceinline__ void fft_stage_r4(const double2 *__restrict__ in,
             v2 = cmul(v2, __ldg(&root[2 * k * tw]));
             v3 = cmul(v3, __ldg(&root[3 * k * tw]));
         }
-        // DFT-4 with w = -i
-        const double2 s02 = make_double2(v0.x + v2.x, v0.y + v2.y);
-        const double2 d02 = make_double2(v0.x - v2.x, v0.y - v2.y);
-        const double2 s13 = make_double2(v1.x + v3.x, v1.y + v3.y);
-        const double2 d13 = make_double2(v1.x - v3.x, v1.y - v3.y);
+        const double2 s02 = cadd(v0, v2), d02 = csub(v0, v2), s13 = cadd(v1, v3), d13 = csub(v1, v3);
         const int o = (j - k) * 4 + k;
-        out[o] = make_double2(s02.x + s13.x, s02.y + s13.y);
+        out[o] = cadd(s02, s13);
         out[o + Ns] = make_double2(d02.x + d13.y, d02.y - d13.x);       // d02 - i d13
-        out[o + 2 * Ns] = make_double2(s02.x - s13.x, s02.y - s13.y);
+        out[o + 2 * Ns] = csub(s02, s13);
         out[o + 3 * Ns] = make_double2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
     }
 }
 
-// DST-I along x of two rows per CTA.
-//   in : rows of length nx, row stride in_rs, batch stride in_bs
-//   out: rows of length nx at out.p[batch] + row*out_rs (first element = cell 0)
-__global__ void __launch_bounds__(kFftThreads)
-k_dst_rows(const double *__restrict__ in, long in_rs, long in_bs, OutPtrs out, long out_rs,
-           int nx, int ny, FftPlan plan, const double2 *__restrict__ root,
-           const double *__restrict__ sinx, double scale)
+__device__ __forceinline__ void fft_stage_r5(const double2 *__restrict__ in, double2 *__restrict__ out,
+                                             const double2 *__restrict__ root, int N, int Ns)
 {
-    extern __shared__ double2 smem[];
-    const int N = plan.N;
-    double2 *buf0 = smem;
-    double2 *buf1 = smem + N;
-    __shared__ double2 partial[kFftThreads];
-
-    const int ja = 2 * blockIdx.x;
-    const int jb = ja + 1;
-    const bool has_b = jb < ny;
-    const double *row_a = in + (long)blockIdx.y * in_bs + (long)ja * in_rs;
-    const double *row_b = row_a + in_rs;
-
-    // stage a_j (a_0 = 0, a_j = x_{j-1})
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        double2 v = make_double2(0., 0.);
-        if (j > 0) {
-            v.x = row_a[j - 1];
-            if (has_b) v.y = row_b[j - 1];
+    const int Nr = N / 5, tw = N / (Ns * 5);
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
+        const int k = j % Ns;
+        double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr], v3 = in[j + 3 * Nr], v4 = in[j + 4 * Nr];
+        if (k) {
+            v1 = cmul(v1, __ldg(&root[k * tw]));
+            v2 = cmul(v2, __ldg(&root[2 * k * tw]));
+            v3 = cmul(v3, __ldg(&root[3 * k * tw]));
+            v4 = cmul(v4, __ldg(&root[4 * k * tw]));
         }
-        buf1[j] = v;
-    }
-    __syncthreads();
-    // auxiliary sequence y_j = sin(pi j/N) (a_j + a_{N-j}) + (a_j - a_{N-j})/2
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        double2 y = make_double2(0., 0.);
-        if (j > 0) {
-            const double2 a = buf1[j], ar = buf1[N - j];
-            const double s = __ldg(&sinx[j]);
-            y.x = s * (a.x + ar.x) + 0.5 * (a.x - ar.x);
-            y.y = s * (a.y + ar.y) + 0.5 * (a.y - ar.y);
-        }
-        buf0[j] = y;
-    }
-    __syncthreads();
-    // complex FFT of length N (forward, e^{-2 pi i jk/N})
-    double2 *src = buf0, *dst = buf1;
-    int Ns = 1;
-    for (int s = 0; s < plan.nrad; ++s) {
-        const int r = plan.rad[s];
-        if (r == 4) fft_stage_r4(src, dst, root, N, Ns);
-        else fft_stage_generic(src, dst, root, N, Ns, r);
-        __syncthreads();
-        double2 *t = src; src = dst; dst = t;
-        Ns *= r;
-    }
-    // split the two real transforms:  Ya = (Z_k + conj Z_{N-k})/2, Yb = (Z_k - conj Z_{N-k})/(2i)
-    // F_{2k} = -Im Y_k ; F_{2k+1} = F_{2k-1} + Re Y_k, F_1 = Re Y_0 / 2
-    // dst[k]      <- (Re Ya_k, Re Yb_k)   (to be prefix-summed),  k = 0..M-1
-    // src reuse is not possible (still read) so evens go to registers -> written after the scan
-    const int M = (N + 1) / 2;             // number of odd outputs F_1, F_3, ...  (2k+1 <= N-1)
-    const int chunk = (M + blockDim.x - 1) / blockDim.x;
-    const int k0 = threadIdx.x * chunk;
-    double2 run = make_double2(0., 0.);
-    for (int c = 0; c < chunk; ++c) {
-        const int k = k0 + c;
-        if (k < M) {
-            const double2 Z = src[k];
-            const double2 Zr = src[k == 0 ? 0 : N - k];
-            double2 re = make_double2(0.5 * (Z.x + Zr.x), 0.5 * (Z.y + Zr.y));  // Re Ya, Re Yb
-            if (k == 0) { re.x *= 0.5; re.y *= 0.5; }
-            run.x += re.x;
-            run.y += re.y;
-            dst[k] = run;                  // chunk-local inclusive scan
-        }
-    }
-    partial[threadIdx.x] = run;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over the per-thread totals
-    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
-        double2 add = make_double2(0., 0.);
-        if ((int)threadIdx.x >= off) add = partial[threadIdx.x - off];
-        __syncthreads();
-        partial[threadIdx.x].x += add.x;
-        partial[threadIdx.x].y += add.y;
-        __syncthreads();
-    }
-    const double2 base = threadIdx.x == 0 ? make_double2(0., 0.) : partial[threadIdx.x - 1];
-    double *out_a = out.p[blockIdx.y] + (long)ja * out_rs;
-    double *out_b = out_a + out_rs;
-    const double sc = 2.0 * scale;
-    // odd F_{2k+1} -> output index m = 2k
-    for (int c = 0; c < chunk; ++c) {
-        const int k = k0 + c;
-        if (k < M && 2 * k < nx) {
-            const double2 v = dst[k];
-            out_a[2 * k] = sc * (v.x + base.x);
-            if (has_b) out_b[2 * k] = sc * (v.y + base.y);
-        }
-    }
-    // even F_{2k} = -Im Y_k -> output index m = 2k-1,  k = 1..(N-1)/2
-    for (int k = threadIdx.x + 1; 2 * k <= N - 1; k += blockDim.x) {
-        const double2 Z = src[k];
-        const double2 Zr = src[N - k];
-        // Im Ya = (Z.y - Zr.y)/2 ; Yb = (Z - conj Zr)/(2i): Im Yb = -(Z.x - Zr.x)/2
-        out_a[2 * k - 1] = sc * (-0.5 * (Z.y - Zr.y));
-        if (has_b) out_b[2 * k - 1] = sc * (0.5 * (Z.x - Zr.x));
+        const double2 a1 = cadd(v1, v4), a2 = cadd(v2, v3), d1 = csub(v1, v4), d2 = csub(v2, v3);
+        const double2 P1 = make_double2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
+        const double2 P2 = make_double2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
+        const double2 Q1 = make_double2(s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y);
+        const double2 Q2 = make_double2(s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y);
+        const int o = (j - k) * 5 + k;
+        out[o] = make_double2(v0.x + a1.x + a2.x, v0.y + a1.y + a2.y);
+        out[o + Ns] = make_double2(P1.x + Q1.y, P1.y - Q1.x);
+        out[o + 4 * Ns] = make_double2(P1.x - Q1.y, P1.y + Q1.x);
+        out[o + 2 * Ns] = make_double2(P2.x + Q2.y, P2.y - Q2.x);
+        out[o + 3 * Ns] = make_double2(P2.x - Q2.y, P2.y + Q2.x);
     }
 }
 
-// Thomas solve along y for every x-mode; in place on spec[batch][j][k]
+// any odd prime radix p = 2h+1.  Two sub-steps through `tmp` (N entries):
+//   A: x_t = in[j + t Nr] w^{t k tw};  U[t][j] = x_t + x_{p-t},  V[t][j] = x_t - x_{p-t},  X0[j]
+//   B: X_b = x0 + sum_t U_t cos(2 pi t b/p) - i sum_t V_t sin(2 pi t b/p),  X_{p-b} = conj-sign
+// Result is written back into `in` (no buffer swap for this stage).
+__device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double2 *__restrict__ tmp,
+                                                const double2 *__restrict__ root, int N, int Ns, int p,
+                                                const double *__restrict__ tcos,
+                                                const double *__restrict__ tsin)
+{
+    const int Nr = N / p, h = (p - 1) / 2, tw = N / (Ns * p);
+    for (int e = threadIdx.x; e < Nr * h; e += blockDim.x) {
+        const int t = e / Nr + 1, j = e - (t - 1) * Nr;
+        const int k = j % Ns;
+        double2 a = in[j + t * Nr], b = in[j + (p - t) * Nr];
+        if (k) {
+            a = cmul(a, __ldg(&root[(int)(((long)t * k * tw) % N)]));
+            b = cmul(b, __ldg(&root[(int)(((long)(p - t) * k * tw) % N)]));
+        }
+        tmp[(t - 1) * Nr + j] = cadd(a, b);
+        tmp[(h + t - 1) * Nr + j] = csub(a, b);
+    }
+    for (int j = threadIdx.x; j < Nr; j += blockDim.x) tmp[2 * h * Nr + j] = in[j];
+    __syncthreads();
+    for (int e = threadIdx.x; e < Nr * (h + 1); e += blockDim.x) {
+        const int b = e / Nr, j = e - b * Nr;
+        const int k = j % Ns;
+        const double2 x0 = tmp[2 * h * Nr + j];
+        double2 P = x0, Q = make_double2(0., 0.);
+        const double *cc = tcos + b * h, *ss = tsin + b * h;
+#pragma unroll 4
+        for (int t = 0; t < h; ++t) {
+            const double c = __ldg(&cc[t]), s = __ldg(&ss[t]);
+            const double2 u = tmp[t * Nr + j], v = tmp[(h + t) * Nr + j];
+            P.x += c * u.x; P.y += c * u.y;
+            Q.x += s * v.x; Q.y += s * v.y;
+        }
+        const int o = (j - k) * p + k;
+        in[o + b * Ns] = make_double2(P.x + Q.y, P.y - Q.x);                    // P - iQ
+        if (b) in[o + (p - b) * Ns] = make_double2(P.x - Q.y, P.y + Q.x);       // P + iQ
+    }
+}
+
+// forward complex FFT of length N on shared memory; returns the buffer holding the result
+__device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const FftPlan &plan,
+                                             const double2 *__restrict__ root)
+{
+    const int N = plan.N;
+    int Ns = 1;
+    for (int s = 0; s < plan.nrad; ++s) {
+        const int r = plan.rad[s];
+        bool swap = true;
+        if (r == 4) fft_stage_r4(src, dst, root, N, Ns);
+        else if (r == 2) fft_stage_r2(src, dst, root, N, Ns);
+        else if (r == 5) fft_stage_r5(src, dst, root, N, Ns);
+        else if (r == 3) fft_stage_r3(src, dst, root, N, Ns);
+        else { fft_stage_prime(src, dst, root, N, Ns, r, plan.cs_cos[s], plan.cs_sin[s]); swap = false; }
+        __syncthreads();
+        if (swap) { double2 *t = src; src = dst; dst = t; }
+        Ns *= r;
+    }
+    return src;
+}
+
+// ---- row sources ---------------------------------------------------------------------------
+struct SrcStage {            // plain rows: in[b][j][i]
+    const double *in; long rs, bs;
+    __device__ __forceinline__ double get(int b, int j, int i) const { return in[(long)b * bs + (long)j * rs + i]; }
+};
+struct SrcFields {           // RHS of the three Poisson equations (Fields.cpp:886-912)
+    SliceView a; int c_rhomjz, c_jx, c_jy;
+    double f_psi, f_ez, mu0, dx_inv_half, dy_inv_half;
+    __device__ __forceinline__ double get(int b, int j, int i) const
+    {
+        const long o = a.idx(i, j);
+        if (b == 0) return f_psi * a.comp(c_rhomjz)[o];
+        const double *jx = a.comp(c_jx), *jy = a.comp(c_jy);
+        const long js = a.jstride;
+        if (b == 1) {
+            const double dx_jx = (jx[o + 1] - jx[o - 1]) * dx_inv_half;
+            const double dy_jy = (jy[o + js] - jy[o - js]) * dy_inv_half;
+            return f_ez * dx_jx + f_ez * dy_jy;
+        }
+        const double dy_jx = (jx[o + js] - jx[o - js]) * dy_inv_half;
+        const double dx_jy = (jy[o + 1] - jy[o - 1]) * dx_inv_half;
+        return mu0 * dy_jx + (-mu0) * dx_jy;
+    }
+};
+struct SrcSpec {             // chunk-local Thomas solution + interface correction
+    const double *y; long rs, bs;             // spec[b][j][k]
+    const double *xl, *xr;                    // [b][chunk][k]
+    const double *tp, *tq;                    // spike tables [table row][k]
+    int L, C, nx, last_base;                  // table row of the last chunk's first row
+    __device__ __forceinline__ double get(int b, int j, int i) const
+    {
+        const int c = j / L, r = j - c * L;
+        const int tr = (c == C - 1) ? last_base + r : r;
+        const long ci = ((long)b * C + c) * nx + i;
+        return y[(long)b * bs + (long)j * rs + i] + xl[ci] * __ldg(&tp[(long)tr * nx + i])
+               + xr[ci] * __ldg(&tq[(long)tr * nx + i]);
+    }
+};
+
+// DST-I along x of two rows per CTA (unnormalised, FFTW RODFT00 convention, times `scale`).
+template <class Src>
+__global__ void __launch_bounds__(kFftThreads)
+k_dst_rows(Src src, OutPtrs out, long out_rs, int nx, int ny, FftPlan plan,
+           const double2 *__restrict__ root, const double *__restrict__ sinf, double scale)
+{
+    extern __shared__ double2 smem[];
+    const int N = plan.N, n = nx;
+    double2 *buf0 = smem;
+    double2 *buf1 = smem + N;
+    const int b = blockIdx.y;
+    const int ja = 2 * blockIdx.x, jb = ja + 1;
+    const bool has_b = jb < ny;
+
+    // stage the two real rows: xs[q] = (x_a[q], x_b[q]), q = 0..n-1, padded by two zero entries on
+    // each side so that the differencing below needs no bounds checks
+    double2 *xs = buf1 + 2;
+    for (int q = threadIdx.x; q < n; q += blockDim.x)
+        xs[q] = make_double2(src.get(b, ja, q), has_b ? src.get(b, jb, q) : 0.);
+    if (threadIdx.x < 2) { buf1[threadIdx.x] = make_double2(0., 0.); }
+    // N = n + 1 entries in buf1: indices n+2.. are beyond; the reads below touch xs[-2..n-1] only
+    __syncthreads();
+    // W[i] = (x[2i] - x[2i-2]) + i x[2i-1]  (x[-1] = x[-2]... = 0 handled explicitly), i = 0..nh;
+    // V = W_a + i W_b with Hermitian extension; buf0 <- conj(V) so that the forward FFT below is
+    // the backward (C2R) transform of the (n+1)-point DST trick
+    const int nh = (n + 1) / 2;
+    for (int i = threadIdx.x; i <= nh; i += blockDim.x) {
+        double2 re, im;      // .x: row a, .y: row b
+        if (i == 0) {
+            re = make_double2(2. * xs[0].x, 2. * xs[0].y);
+            im = make_double2(0., 0.);
+        } else if (i == nh) {
+            if (n & 1) {
+                re = make_double2(-2. * xs[2 * i - 2].x, -2. * xs[2 * i - 2].y);
+                im = make_double2(0., 0.);
+            } else {
+                re = make_double2(-xs[2 * i - 2].x, -xs[2 * i - 2].y);
+                im = xs[2 * i - 1];
+            }
+        } else {
+            re = csub(xs[2 * i], xs[2 * i - 2]);
+            im = xs[2 * i - 1];
+        }
+        // W_a = re.x + i im.x, W_b = re.y + i im.y
+        buf0[i] = make_double2(re.x - im.y, -(im.x + re.y));               // conj(V[i])
+        if (i > 0 && N - i > nh) buf0[N - i] = make_double2(re.x + im.y, im.x - re.y);   // conj(V[N-i])
+    }
+    __syncthreads();
+    const double2 *F = fft_smem(buf0, buf1, plan, root);
+    // z_a = Re F, z_b = -Im F;  out[i] = 0.5 (z[n-i] - z[i+1] + (z[i+1] + z[n-i]) sinf[i])
+    double *out_a = out.p[b] + (long)ja * out_rs;
+    double *out_b = out_a + out_rs;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 za = F[i + 1], zb = F[n - i];
+        const double sf = __ldg(&sinf[i]);
+        out_a[i] = scale * (0.5 * (zb.x - za.x + (za.x + zb.x) * sf));
+        if (has_b) out_b[i] = scale * (0.5 * (-zb.y + za.y - (za.y + zb.y) * sf));
+    }
+}
+
+// K2: chunk-local Thomas solve along y for every x-mode; in place on spec[batch][j][k].
+// Thread = (k, chunk, batch).  Writes the first / last local value of each chunk to yf / ye.
 __global__ void __launch_bounds__(128)
-k_tridiag_y(double *__restrict__ spec, const double *__restrict__ tm,
-            const double *__restrict__ tc, int nx, int ny, double a)
+k_thomas_local(double *__restrict__ spec, const double *__restrict__ tm, const double *__restrict__ tc,
+               double *__restrict__ yf, double *__restrict__ ye, int nx, int ny, int L, int C,
+               int last_base, double a)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nx) return;
-    double *d = spec + (long)blockIdx.y * nx * ny + k;
-    const double *m = tm + k, *c = tc + k;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int j0 = c * L, len = min(L, ny - j0);
+    const int tr0 = (c == C - 1) ? last_base : 0;
+    double *d = spec + (long)b * nx * ny + (long)j0 * nx + k;
+    const double *m = tm + (long)tr0 * nx + k, *cc = tc + (long)tr0 * nx + k;
     constexpr int U = 8;
     double prev = 0.0;
-    int j = 0;
-    for (; j + U <= ny; j += U) {
+    int r = 0;
+    for (; r + U <= len; r += U) {
         double rv[U], mv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { rv[u] = d[(long)(j + u) * nx]; mv[u] = __ldg(&m[(long)(j + u) * nx]); }
+        for (int u = 0; u < U; ++u) { rv[u] = d[(long)(r + u) * nx]; mv[u] = __ldg(&m[(long)(r + u) * nx]); }
 #pragma unroll
-        for (int u = 0; u < U; ++u) { prev = (rv[u] - a * prev) * mv[u]; d[(long)(j + u) * nx] = prev; }
+        for (int u = 0; u < U; ++u) { prev = (rv[u] - a * prev) * mv[u]; d[(long)(r + u) * nx] = prev; }
     }
-    for (; j < ny; ++j) { prev = (d[(long)j * nx] - a * prev) * __ldg(&m[(long)j * nx]); d[(long)j * nx] = prev; }
-    // back substitution: phi_j = d_j - c_j phi_{j+1}
-    double phi = prev;     // j = ny-1
-    j = ny - 2;
-    for (; j - (U - 1) >= 0; j -= U) {
+    for (; r < len; ++r) { prev = (d[(long)r * nx] - a * prev) * __ldg(&m[(long)r * nx]); d[(long)r * nx] = prev; }
+    double phi = prev;
+    const long ci = ((long)b * C + c) * nx + k;
+    ye[ci] = phi;
+    r = len - 2;
+    for (; r - (U - 1) >= 0; r -= U) {
         double dv[U], cv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { dv[u] = d[(long)(j - u) * nx]; cv[u] = __ldg(&c[(long)(j - u) * nx]); }
+        for (int u = 0; u < U; ++u) { dv[u] = d[(long)(r - u) * nx]; cv[u] = __ldg(&cc[(long)(r - u) * nx]); }
 #pragma unroll
-        for (int u = 0; u < U; ++u) { phi = dv[u] - cv[u] * phi; d[(long)(j - u) * nx] = phi; }
+        for (int u = 0; u < U; ++u) { phi = dv[u] - cv[u] * phi; d[(long)(r - u) * nx] = phi; }
     }
-    for (; j >= 0; --j) { phi = d[(long)j * nx] - __ldg(&c[(long)j * nx]) * phi; d[(long)j * nx] = phi; }
+    for (; r >= 0; --r) { phi = d[(long)r * nx] - __ldg(&cc[(long)r * nx]) * phi; d[(long)r * nx] = phi; }
+    yf[ci] = phi;
+}
+
+// K3: reduced system for the chunk-interface values.  Thread = (k, batch).
+//   in : yf[c] = first, ye[c] = last chunk-local value
+//   out: xl[c] = value of the row just below chunk c (0 for c = 0), xr[c] = row just above (0 for last)
+// (yf is overwritten by xl's data flow: xl/xr alias separate arrays)
+__global__ void __launch_bounds__(128)
+k_thomas_reduced(const double *__restrict__ yf, const double *__restrict__ ye, double *__restrict__ xl,
+                 double *__restrict__ xr, const double *__restrict__ t_pe, const double *__restrict__ t_pf,
+                 const double *__restrict__ t_b, const double *__restrict__ t_inv,
+                 const double *__restrict__ t_del, int nx, int C)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nx) return;
+    const int b = blockIdx.y;
+    const long base = (long)b * C * nx + k;
+    // forward: A_c -> xl[c+1], gamma_c -> xr[c]
+    double alpha = 0.0;
+    for (int c = 0; c < C - 1; ++c) {
+        const long t = (long)c * nx + k;
+        const double A = ye[base + (long)c * nx] + __ldg(&t_pe[t]) * alpha;
+        const double gam = (yf[base + (long)(c + 1) * nx] + __ldg(&t_pf[t]) * A) * __ldg(&t_inv[t]);
+        alpha = A + __ldg(&t_b[t]) * gam;
+        xl[base + (long)(c + 1) * nx] = A;
+        xr[base + (long)c * nx] = gam;
+    }
+    // backward: v_c = gamma_c + delta_c v_{c+1};  u_c = A_c + B_c v_c
+    double v = 0.0;
+    xr[base + (long)(C - 1) * nx] = 0.0;
+    xl[base] = 0.0;
+    for (int c = C - 2; c >= 0; --c) {
+        const long t = (long)c * nx + k;
+        v = xr[base + (long)c * nx] + __ldg(&t_del[t]) * v;
+        const double u = xl[base + (long)(c + 1) * nx] + __ldg(&t_b[t]) * v;
+        xr[base + (long)c * nx] = v;
+        xl[base + (long)(c + 1) * nx] = u;
+    }
 }
 
 void factorize(int N, FftPlan &plan)
@@ -232,16 +372,54 @@ void factorize(int N, FftPlan &plan)
     plan.N = N;
     plan.nrad = 0;
     int n = N;
-    const int pref[] = {4, 2, 3, 5, 7};
+    const int pref[] = {4, 2, 3, 5};
     for (int r : pref)
         while (n % r == 0) { plan.rad[plan.nrad++] = r; n /= r; }
-    for (int p = 11; n > 1; p += 2)
+    for (int p = 7; n > 1; p += 2)
         while (n % p == 0) { plan.rad[plan.nrad++] = p; n /= p; }
+    // small radices last would also work; Stockham stages are order independent
+}
+
+template <class T>
+int upload(T **dptr, const std::vector<T> &h)
+{
+    HPB_CUDA_CHECK(cudaMalloc(dptr, sizeof(T) * h.size()));
+    HPB_CUDA_CHECK(cudaMemcpy(*dptr, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+    return HPB_OK;
+}
+
+FftPlan make_plan(const hpb_ctx *ctx)
+{
+    FftPlan plan;
+    plan.N = ctx->fftN; plan.nrad = ctx->nrad;
+    for (int i = 0; i < plan.nrad; ++i) {
+        plan.rad[i] = ctx->radices[i];
+        plan.cs_cos[i] = ctx->d_cs_cos[i];
+        plan.cs_sin[i] = ctx->d_cs_sin[i];
+    }
+    return plan;
+}
+
+template <class Src>
+int launch_rows(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, int nbatch, double scale)
+{
+    const int nx = ctx->g.nx, ny = ctx->g.ny, N = ctx->fftN;
+    const size_t smem = 2 * sizeof(double2) * (size_t)(N + 4);
+    static bool attr_set = false;       // per instantiation; the limit covers every supported N
+    if (!attr_set) {
+        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            220 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((ny + 1) / 2, nbatch);
+    k_dst_rows<Src><<<grid, kFftThreads, smem, ctx->stream>>>(src, out, out_rs, nx, ny, make_plan(ctx),
+                                                              ctx->d_root, ctx->d_sinf, scale);
+    hpb_count_launch(ctx);
+    return HPB_OK;
 }
 
 }  // namespace
 
-int hpb_launch_poisson_rhs(hpb_ctx *ctx, const hpb_slice &sl, const int *comps);
 int hpb_launch_exmby_eypbx(hpb_ctx *ctx, const hpb_slice &sl, const int *comps);
 
 int hpb_poisson_init(hpb_ctx *ctx)
@@ -252,94 +430,174 @@ int hpb_poisson_init(hpb_ctx *ctx)
     FftPlan plan;
     factorize(N, plan);
     ctx->nrad = plan.nrad;
-    for (int i = 0; i < plan.nrad; ++i) ctx->radices[i] = plan.rad[i];
-    std::vector<double2> root(N);
-    std::vector<double> sinx(N);
     const long double pi = 3.14159265358979323846264338327950288L;
+    for (int i = 0; i < plan.nrad; ++i) {
+        ctx->radices[i] = plan.rad[i];
+        ctx->d_cs_cos[i] = ctx->d_cs_sin[i] = nullptr;
+        const int p = plan.rad[i];
+        if (p > 5) {
+            const int h = (p - 1) / 2;
+            std::vector<double> tc((size_t)(h + 1) * h), ts((size_t)(h + 1) * h);
+            for (int b = 0; b <= h; ++b)
+                for (int t = 1; t <= h; ++t) {
+                    const long tb = ((long)t * b) % p;
+                    tc[(size_t)b * h + t - 1] = (double)cosl(2.0L * pi * tb / p);
+                    ts[(size_t)b * h + t - 1] = (double)sinl(2.0L * pi * tb / p);
+                }
+            int rc = upload(&ctx->d_cs_cos[i], tc); if (rc) return rc;
+            rc = upload(&ctx->d_cs_sin[i], ts); if (rc) return rc;
+        }
+    }
+    std::vector<double2> root(N);
+    std::vector<double> sinf(nx);
     for (int t = 0; t < N; ++t) {
         root[t].x = (double)cosl(-2.0L * pi * t / N);
         root[t].y = (double)sinl(-2.0L * pi * t / N);
-        sinx[t] = (double)sinl(pi * t / N);
     }
-    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_root, sizeof(double2) * N));
-    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_sinx, sizeof(double) * N));
-    HPB_CUDA_CHECK(cudaMemcpy(ctx->d_root, root.data(), sizeof(double2) * N, cudaMemcpyHostToDevice));
-    HPB_CUDA_CHECK(cudaMemcpy(ctx->d_sinx, sinx.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
-    // Thomas pivots: b_k = -2/dy^2 + lambda_k, a = 1/dy^2
-    const double a = 1.0 / (g.dy * g.dy);
-    std::vector<double> tm((size_t)nx * ny), tc((size_t)nx * ny);
+    for (int i = 0; i < nx; ++i) sinf[i] = (double)(1.0L / (2.0L * sinl(pi * (i + 1) / N)));
+    int rc = upload(&ctx->d_root, root); if (rc) return rc;
+    rc = upload(&ctx->d_sinf, sinf); if (rc) return rc;
+
+    // ---- partitioned Thomas tables ----------------------------------------------------------
+    int L = (ny + 31) / 32;
+    if (L < 4) L = 4;
+    if (L > ny) L = ny;
+    const int C = (ny + L - 1) / L;
+    const int Llast = ny - (C - 1) * L;
+    const bool two_types = (Llast != L);
+    const int nrows = L + (two_types ? Llast : 0);
+    ctx->th_L = L; ctx->th_C = C; ctx->th_last_base = two_types ? L : 0;
+    const long double a = 1.0L / ((long double)g.dy * g.dy);
+    std::vector<double> tm((size_t)nrows * nx), tc((size_t)nrows * nx), tp((size_t)nrows * nx), tq((size_t)nrows * nx);
+    const int nif = C > 1 ? C - 1 : 1;
+    std::vector<double> t_pe((size_t)nif * nx, 0.), t_pf((size_t)nif * nx, 0.), t_b((size_t)nif * nx, 0.),
+        t_inv((size_t)nif * nx, 1.), t_del((size_t)nif * nx, 0.);
+    std::vector<long double> m(L), cp(L), sp(L), sq(L);
     for (int k = 0; k < nx; ++k) {
         const long double s = sinl(pi * (k + 1) / (2.0L * (nx + 1)));
-        const double b = (double)(-2.0L / ((long double)g.dy * g.dy)
-                                  - 4.0L * s * s / ((long double)g.dx * g.dx));
-        double cp = 0.0;
-        for (int j = 0; j < ny; ++j) {
-            const double m = 1.0 / (b - a * cp);
-            cp = a * m;
-            tm[(size_t)j * nx + k] = m;
-            tc[(size_t)j * nx + k] = cp;
+        const long double bdiag = -2.0L * a - 4.0L * s * s / ((long double)g.dx * g.dx);
+        long double pE[2], qE[2], pF[2], qF[2];
+        for (int type = 0; type < (two_types ? 2 : 1); ++type) {
+            const int len = type == 0 ? L : Llast;
+            const int base = type == 0 ? 0 : L;
+            long double c_prev = 0.0L;
+            for (int r = 0; r < len; ++r) {
+                // pivots in double arithmetic order of the kernel: m = 1/(b - a c'), c' = a m
+                m[r] = 1.0L / (bdiag - a * c_prev);
+                cp[r] = a * m[r];
+                c_prev = cp[r];
+                tm[(size_t)(base + r) * nx + k] = (double)m[r];
+                tc[(size_t)(base + r) * nx + k] = (double)cp[r];
+            }
+            // spikes: p = T^{-1}(-a e_0), q = T^{-1}(-a e_{len-1})
+            long double prev = 0.0L;
+            for (int r = 0; r < len; ++r) { const long double d = (r == 0 ? -a : 0.0L); prev = (d - a * prev) * m[r]; sp[r] = prev; }
+            for (int r = len - 2; r >= 0; --r) sp[r] = sp[r] - cp[r] * sp[r + 1];
+            prev = 0.0L;
+            for (int r = 0; r < len; ++r) { const long double d = (r == len - 1 ? -a : 0.0L); prev = (d - a * prev) * m[r]; sq[r] = prev; }
+            for (int r = len - 2; r >= 0; --r) sq[r] = sq[r] - cp[r] * sq[r + 1];
+            for (int r = 0; r < len; ++r) {
+                tp[(size_t)(base + r) * nx + k] = (double)sp[r];
+                tq[(size_t)(base + r) * nx + k] = (double)sq[r];
+            }
+            pF[type] = sp[0]; qF[type] = sq[0]; pE[type] = sp[len - 1]; qE[type] = sq[len - 1];
+        }
+        if (!two_types) { pE[1] = pE[0]; qE[1] = qE[0]; pF[1] = pF[0]; qF[1] = qF[0]; }
+        long double beta = 0.0L;
+        for (int c = 0; c < C - 1; ++c) {
+            // interface between chunk c (always a full chunk) and chunk c+1 (last one may be short)
+            const int tn = (c + 1 == C - 1) ? 1 : 0;
+            const long double B = qE[0] + pE[0] * beta;
+            const long double inv = 1.0L / (1.0L - pF[tn] * B);
+            const long double del = qF[tn] * inv;
+            beta = B * del;
+            const size_t t = (size_t)c * nx + k;
+            t_pe[t] = (double)pE[0]; t_pf[t] = (double)pF[tn]; t_b[t] = (double)B;
+            t_inv[t] = (double)inv; t_del[t] = (double)del;
         }
     }
+    if ((rc = upload(&ctx->d_tri_m, tm))) return rc;
+    if ((rc = upload(&ctx->d_tri_c, tc))) return rc;
+    if ((rc = upload(&ctx->d_tri_p, tp))) return rc;
+    if ((rc = upload(&ctx->d_tri_q, tq))) return rc;
+    if ((rc = upload(&ctx->d_red_pe, t_pe))) return rc;
+    if ((rc = upload(&ctx->d_red_pf, t_pf))) return rc;
+    if ((rc = upload(&ctx->d_red_b, t_b))) return rc;
+    if ((rc = upload(&ctx->d_red_inv, t_inv))) return rc;
+    if ((rc = upload(&ctx->d_red_del, t_del))) return rc;
     const size_t bytes = sizeof(double) * (size_t)nx * ny;
-    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_tri_m, bytes));
-    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_tri_c, bytes));
-    HPB_CUDA_CHECK(cudaMemcpy(ctx->d_tri_m, tm.data(), bytes, cudaMemcpyHostToDevice));
-    HPB_CUDA_CHECK(cudaMemcpy(ctx->d_tri_c, tc.data(), bytes, cudaMemcpyHostToDevice));
     HPB_CUDA_CHECK(cudaMalloc(&ctx->d_spec, 3 * bytes));
-    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_stage, 3 * bytes));
-    const size_t smem = 2 * sizeof(double2) * (size_t)N;
-    if (smem > 200 * 1024) {
+    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_iface, 4 * 3 * sizeof(double) * (size_t)C * nx));
+    HPB_CUDA_CHECK(cudaMemset(ctx->d_iface, 0, 4 * 3 * sizeof(double) * (size_t)C * nx));
+    const size_t smem = 2 * sizeof(double2) * (size_t)(N + 4);
+    if (smem > 220 * 1024) {
         hpb_set_error("poisson: nx = %d too large for the shared-memory row FFT", nx);
         return HPB_ERR_UNSUPPORTED;
     }
-    HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
     return HPB_OK;
 }
 
 void hpb_poisson_free(hpb_ctx *ctx)
 {
-    cudaFree(ctx->d_root); cudaFree(ctx->d_sinx); cudaFree(ctx->d_tri_m); cudaFree(ctx->d_tri_c);
-    cudaFree(ctx->d_spec); cudaFree(ctx->d_stage);
+    cudaFree(ctx->d_root); cudaFree(ctx->d_sinf); cudaFree(ctx->d_tri_m); cudaFree(ctx->d_tri_c);
+    cudaFree(ctx->d_tri_p); cudaFree(ctx->d_tri_q); cudaFree(ctx->d_red_pe); cudaFree(ctx->d_red_pf);
+    cudaFree(ctx->d_red_b); cudaFree(ctx->d_red_inv); cudaFree(ctx->d_red_del);
+    cudaFree(ctx->d_spec); cudaFree(ctx->d_iface);
+    for (int i = 0; i < ctx->nrad; ++i) { cudaFree(ctx->d_cs_cos[i]); cudaFree(ctx->d_cs_sin[i]); }
+}
+
+// K2 + K3 + K4 on ctx->d_spec (already holding the row transforms of nbatch right-hand sides)
+static int poisson_finish(hpb_ctx *ctx, hpb_slice sl, const int *c_lhs, int nbatch)
+{
+    const hpb_geom &g = ctx->g;
+    const int nx = g.nx, ny = g.ny, N = ctx->fftN, L = ctx->th_L, C = ctx->th_C;
+    const long plane = (long)nx * ny;
+    const long ifn = 3L * C * nx;
+    double *yf = ctx->d_iface, *ye = yf + ifn, *xl = ye + ifn, *xr = xl + ifn;
+    dim3 g2((nx + 127) / 128, C, nbatch);
+    k_thomas_local<<<g2, 128, 0, ctx->stream>>>(ctx->d_spec, ctx->d_tri_m, ctx->d_tri_c, yf, ye, nx, ny, L, C,
+                                                ctx->th_last_base, 1.0 / (g.dy * g.dy));
+    dim3 g3((nx + 127) / 128, nbatch);
+    k_thomas_reduced<<<g3, 128, 0, ctx->stream>>>(yf, ye, xl, xr, ctx->d_red_pe, ctx->d_red_pf, ctx->d_red_b,
+                                                  ctx->d_red_inv, ctx->d_red_del, nx, C);
+    hpb_count_launch(ctx, 2);
+    SliceView v = make_view(sl);
+    OutPtrs o2;
+    for (int b = 0; b < 4; ++b) o2.p[b] = v.comp(c_lhs[b < nbatch ? b : 0]) + v.idx(0, 0);
+    SrcSpec ss{ctx->d_spec, nx, plane, xl, xr, ctx->d_tri_p, ctx->d_tri_q, L, C, nx, ctx->th_last_base};
+    int rc = launch_rows(ctx, ss, o2, sl.jstride, nbatch, 1.0 / (2.0 * N));
+    if (rc) return rc;
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
 }
 
 extern "C" int hpb_poisson_solve(hpb_ctx *ctx, const double *d_rhs, hpb_slice sl, const int *c_lhs,
                                  int nbatch)
 {
     if (!ctx || !d_rhs || !c_lhs || nbatch < 1 || nbatch > 3) return HPB_ERR_ARG;
-    const hpb_geom &g = ctx->g;
-    const int nx = g.nx, ny = g.ny, N = ctx->fftN;
-    FftPlan plan;
-    plan.N = N; plan.nrad = ctx->nrad;
-    for (int i = 0; i < plan.nrad; ++i) plan.rad[i] = ctx->radices[i];
-    const size_t smem = 2 * sizeof(double2) * (size_t)N;
+    const int nx = ctx->g.nx, ny = ctx->g.ny;
     const long plane = (long)nx * ny;
-    dim3 grid((ny + 1) / 2, nbatch);
     OutPtrs o1;
     for (int b = 0; b < 4; ++b) o1.p[b] = ctx->d_spec + (b < nbatch ? b : 0) * plane;
-    k_dst_rows<<<grid, kFftThreads, smem, ctx->stream>>>(d_rhs, nx, plane, o1, nx, nx, ny, plan,
-                                                         ctx->d_root, ctx->d_sinx, 1.0);
-    dim3 gridt((nx + 127) / 128, nbatch);
-    k_tridiag_y<<<gridt, 128, 0, ctx->stream>>>(ctx->d_spec, ctx->d_tri_m, ctx->d_tri_c, nx, ny,
-                                                1.0 / (g.dy * g.dy));
-    SliceView v = make_view(sl);
-    OutPtrs o2;
-    for (int b = 0; b < 4; ++b) o2.p[b] = v.comp(c_lhs[b < nbatch ? b : 0]) + v.idx(0, 0);
-    k_dst_rows<<<grid, kFftThreads, smem, ctx->stream>>>(ctx->d_spec, nx, plane, o2, sl.jstride,
-                                                         nx, ny, plan, ctx->d_root, ctx->d_sinx,
-                                                         1.0 / (2.0 * N));
-    hpb_count_launch(ctx, 3);
-    HPB_CUDA_CHECK(cudaGetLastError());
-    return HPB_OK;
+    SrcStage st{d_rhs, nx, plane};
+    int rc = launch_rows(ctx, st, o1, nx, nbatch, 1.0);
+    if (rc) return rc;
+    return poisson_finish(ctx, sl, c_lhs, nbatch);
 }
 
 extern "C" int hpb_fields_solve_psi_ez_bz(hpb_ctx *ctx, hpb_slice sl, const int *comps)
 {
     if (!ctx || !comps) return HPB_ERR_ARG;
-    int rc = hpb_launch_poisson_rhs(ctx, sl, comps);
+    const hpb_geom &g = ctx->g;
+    const long plane = (long)g.nx * g.ny;
+    OutPtrs o1;
+    for (int b = 0; b < 4; ++b) o1.p[b] = ctx->d_spec + (b < 3 ? b : 0) * plane;
+    SrcFields sf{make_view(sl), comps[HPB_C_RHOMJZ], comps[HPB_C_JX], comps[HPB_C_JY],
+                 -1.0 / g.ep0, 1.0 / (g.ep0 * g.c), g.mu0, 0.5 * (1.0 / g.dx), 0.5 * (1.0 / g.dy)};
+    int rc = launch_rows(ctx, sf, o1, g.nx, 3, 1.0);
     if (rc) return rc;
     const int lhs[3] = {comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BZ]};
-    rc = hpb_poisson_solve(ctx, ctx->d_stage, sl, lhs, 3);
+    rc = poisson_finish(ctx, sl, lhs, 3);
     if (rc) return rc;
     return hpb_launch_exmby_eypbx(ctx, sl, comps);
 }

@@ -76,9 +76,10 @@ __device__ __forceinline__ bool plasma_candidate(const PlasmaInitArgs &a, const 
     const int j = (int)(cell / a.ncx) + a.jlo, i = (int)(cell % a.ncx) + a.ilo;
     const double rx = (0.5 + (i_part % a.ppcx)) / a.ppcx;       // ParticleUtil.H:72-80
     const double ry = (0.5 + (i_part / a.ppcx)) / a.ppcy;
-    x = a.plo_x + (i + rx) * a.dx;
-    y = a.plo_y + (j + ry) * a.dy;
-    const double rsq = x * x + y * y;
+    // separate multiply and add (no FMA contraction): positions are bit-identical to a CPU build
+    x = __dadd_rn(a.plo_x, __dmul_rn(i + rx, a.dx));
+    y = __dadd_rn(a.plo_y, __dmul_rn(j + ry, a.dy));
+    const double rsq = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
     if (x >= a.bhi_x || x < a.blo_x || y >= a.bhi_y || y < a.blo_y || rsq > a.radius_sq ||
         rsq < a.hollow_sq)
         return false;
@@ -140,11 +141,11 @@ __device__ __forceinline__ bool beam_candidate(const BeamInitArgs &a, long idx, 
     const int j = (int)(cell / a.ncx) + a.jlo, i = (int)(cell % a.ncx) + a.ilo;
     const int pyz = a.ppcy * a.ppcz;
     const int ix_p = i_part / pyz, iy_p = (i_part % pyz) % a.ppcy, iz_p = (i_part % pyz) / a.ppcy;
-    x = a.plo_x + (i + (0.5 + ix_p) / a.ppcx) * a.dx;
-    y = a.plo_y + (j + (0.5 + iy_p) / a.ppcy) * a.dy;
-    z = a.plo_z + (islice + (0.5 + iz_p) / a.ppcz) * a.dz;
-    if (z >= a.zmax || z < a.zmin ||
-        ((x - a.x_mean) * (x - a.x_mean) + (y - a.y_mean) * (y - a.y_mean)) > a.radius_sq)
+    x = __dadd_rn(a.plo_x, __dmul_rn(i + (0.5 + ix_p) / a.ppcx, a.dx));
+    y = __dadd_rn(a.plo_y, __dmul_rn(j + (0.5 + iy_p) / a.ppcy, a.dy));
+    z = __dadd_rn(a.plo_z, __dmul_rn(islice + (0.5 + iz_p) / a.ppcz, a.dz));
+    const double xr = x - a.x_mean, yr = y - a.y_mean;
+    if (z >= a.zmax || z < a.zmin || __dadd_rn(__dmul_rn(xr, xr), __dmul_rn(yr, yr)) > a.radius_sq)
         return false;
     if (a.profile == 0) {                            // GetInitialDensity.H:33-51
         const double dxn = (x - a.x_mean) / a.sx, dyn = (y - a.y_mean) / a.sy,

@@ -1035,7 +1035,8 @@ class Simulation:
         """PlasmaParticleContainer::ReadParameters, particles/plasma/PlasmaParticleContainer.cpp:27-170"""
         d = self.deck
         charge, mass = self._species_charge_mass(nm)
-        expr = _get(d, nm + '.density(x,y,z)', None, typ=str, alt='plasmas.density(x,y,z)') or '0.'
+        toks = _get(d, nm + '.density(x,y,z)', None, n=-1, typ=str, alt='plasmas.density(x,y,z)')
+        expr = ' '.join(toks) if toks else '0.'        # the expression may contain blanks
         code = compile(expr.replace('^', '**'), '<density>', 'eval')
         env = dict(_CONST_SI)
         env.update({f: getattr(np, f) for f in ('sqrt', 'exp', 'sin', 'cos', 'log', 'tanh')})
