@@ -497,11 +497,7 @@ int hpb_mg_init(hpb_ctx *ctx)
     int lc = 1;
     while (lc < nl - 1 && (ctx->mg[lc].nx > kCoarseMax || ctx->mg[lc].ny > kCoarseMax)) ++lc;
     if (nl - lc > 12) lc = nl - 12;
-    if (ctx->mg[lc].nx * ctx->mg[lc].ny > 4 * kCoarseMax * kCoarseMax) {
-        hpb_set_error("hpmg: coarsest level %d x %d is too large for the single-block solve",
-                      ctx->mg[lc].nx, ctx->mg[lc].ny);
-        return HPB_ERR_UNSUPPORTED;
-    }
+    // (grids that stop coarsening early leave a large 'coarse' level: k_coarse loops over it)
     ctx->mg_lc = lc;
     for (int l = 0; l < nl; ++l) {
         const size_t n = (size_t)ctx->mg[l].nx * ctx->mg[l].ny;

@@ -10,6 +10,7 @@
 //   src/particles/pusher/PlasmaParticleAdvance.cpp:92-217, PushPlasmaParticles.H:39-75,
 //   src/utils/DualNumbers.H:13-43, src/particles/pusher/GetAndSetPosition.H:29-99
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -31,51 +32,118 @@ PlasmaPtrs to_ptrs(const hpb_plasma &pl)
 // -------------------------------------------------------------------------------------------
 // DepositCurrent
 // -------------------------------------------------------------------------------------------
+// Warp-aggregated scatter.  Plasma particles keep the lattice order of InitParticles (cells
+// x-fastest), so the 32 lanes of a warp usually sit in 32 consecutive cells of one row and their
+// 3-wide stencils overlap: a lane whose left / right neighbour lane is exactly one cell to the
+// left / right (and on the same rows) takes over that neighbour's contribution to its own centre
+// column through warp shuffles.  An aligned particle then issues 3 fp64 reductions per component
+// (its centre column) instead of 9; unaligned pairs fall back to their own reductions, so the
+// result is the same sum for any particle order.
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kDepOwn = 30;      // particles deposited per warp (lanes 1..30)
+constexpr int kExplOwn = 28;     // explicit deposition: lanes 2..29
+
+template <bool JXY, bool RHO, bool CHI, bool RMJ>
 __global__ void __launch_bounds__(kThreads)
 k_deposit_current(PlasmaPtrs pl, SliceView a, int c_jx, int c_jy, int c_rho, int c_chi,
                   int c_rhomjz, double x_off, double y_off, double dx_inv, double dy_inv,
                   double clightinv, double charge_invvol, double charge_mu0_mass_ratio,
                   double max_qsa, int *n_qsa_violation)
 {
-    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= pl.np) return;
-    const uint64_t idcpu = pl.idcpu[ip];
-    if (!hpb_is_valid(idcpu)) return;
-
-    const double psi_inv = 1.0 / pl.r[HPB_PSI][ip];
-    const double xp = pl.r[HPB_X][ip];
-    const double yp = pl.r[HPB_Y][ip];
-    const double vx_c = pl.r[HPB_UX][ip] * psi_inv;
-    const double vy_c = pl.r[HPB_UY][ip] * psi_inv;
-    const double q_invvol = charge_invvol * pl.r[HPB_W][ip];
-
-    const double gamma_psi = 0.5 * (psi_inv * psi_inv
-                                    + vx_c * vx_c * clightinv * clightinv
-                                    + vy_c * vy_c * clightinv * clightinv + 1.0);
-    if (gamma_psi < 0.0 || gamma_psi > max_qsa || psi_inv < 0.0) {
-        // QSA violation: discard the particle (PlasmaDepositCurrent.cpp:197-204)
-        if (n_qsa_violation) atomicAdd(n_qsa_violation, 1);
-        pl.r[HPB_W][ip] = 0.0;
-        pl.idcpu[ip] = hpb_make_invalid(idcpu);
-        return;
+    // warps overlap by one lane on each side: lanes 0 and 31 only feed their neighbours, so an
+    // aligned run of particles never pays for warp-edge columns
+    const int lane = threadIdx.x & 31;
+    const long warp = (long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long ip = warp * kDepOwn - 1 + lane;
+    const bool owner = lane >= 1 && lane <= kDepOwn;
+    bool active = ip >= 0 && ip < pl.np;
+    uint64_t idcpu = 0;
+    double psi_inv = 1., vx_c = 0., vy_c = 0., q_invvol = 0., gamma_psi = 1.;
+    double sx[3] = {0., 0., 0.}, sy[3] = {0., 0., 0.};
+    int i0 = 0, j0 = 0;
+    if (active) {
+        // all seven streams are requested before the first use (one HBM round trip, not two)
+        idcpu = pl.idcpu[ip];
+        const double psi = pl.r[HPB_PSI][ip];
+        const double xp = pl.r[HPB_X][ip];
+        const double yp = pl.r[HPB_Y][ip];
+        const double ux = pl.r[HPB_UX][ip];
+        const double uy = pl.r[HPB_UY][ip];
+        const double w = pl.r[HPB_W][ip];
+        active = hpb_is_valid(idcpu);
+        psi_inv = 1.0 / psi;
+        vx_c = ux * psi_inv;
+        vy_c = uy * psi_inv;
+        q_invvol = charge_invvol * w;
+        gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * clightinv * clightinv
+                           + vy_c * vy_c * clightinv * clightinv + 1.0);
+        if (active && (gamma_psi < 0.0 || gamma_psi > max_qsa || psi_inv < 0.0)) {
+            // QSA violation: discard the particle (PlasmaDepositCurrent.cpp:197-204)
+            if (owner) {
+                if (n_qsa_violation) atomicAdd(n_qsa_violation, 1);
+                pl.r[HPB_W][ip] = 0.0;
+                pl.idcpu[ip] = hpb_make_invalid(idcpu);
+            }
+            active = false;
+        }
+        if (active) {
+            i0 = shape2((xp - x_off) * dx_inv, sx);
+            j0 = shape2((yp - y_off) * dy_inv, sy);
+        } else {
+            q_invvol = 0.;
+        }
     }
-    double sx[3], sy[3];
-    const int i0 = shape2((xp - x_off) * dx_inv, sx);
-    const int j0 = shape2((yp - y_off) * dy_inv, sy);
+    // centre column; inactive lanes get a sentinel that never aligns with a neighbour
+    const int cc = active ? i0 + 1 : -(1 << 28) - 3 * lane;
+    const int cL = __shfl_up_sync(kFull, cc, 1), jL = __shfl_up_sync(kFull, j0, 1);
+    const int cR = __shfl_down_sync(kFull, cc, 1), jR = __shfl_down_sync(kFull, j0, 1);
+    const bool L_ok = active && lane > 0 && cL == cc - 1 && jL == j0;
+    const bool R_ok = active && lane < 31 && cR == cc + 1 && jR == j0;
+
     const double chi_fac = charge_mu0_mass_ratio * psi_inv;
+    // per-row weights of the three stencil columns
+    double P0[3], P1[3], P2[3], PL[3], PR[3];
 #pragma unroll
     for (int iy = 0; iy < 3; ++iy) {
+        P0[iy] = q_invvol * sx[0] * sy[iy];
+        P1[iy] = q_invvol * sx[1] * sy[iy];
+        P2[iy] = q_invvol * sx[2] * sy[iy];
+        PL[iy] = __shfl_up_sync(kFull, P2[iy], 1);       // right column of the left neighbour
+        PR[iy] = __shfl_down_sync(kFull, P0[iy], 1);     // left column of the right neighbour
+        if (!L_ok) PL[iy] = 0.;
+        if (!R_ok) PR[iy] = 0.;
+    }
+    // per-component multipliers: own, left neighbour's, right neighbour's
+    const double vxL = __shfl_up_sync(kFull, vx_c, 1), vxR = __shfl_down_sync(kFull, vx_c, 1);
+    const double vyL = __shfl_up_sync(kFull, vy_c, 1), vyR = __shfl_down_sync(kFull, vy_c, 1);
+    const double gpL = RHO ? __shfl_up_sync(kFull, gamma_psi, 1) : 0., gpR = RHO ? __shfl_down_sync(kFull, gamma_psi, 1) : 0.;
+    const double cfL = CHI ? __shfl_up_sync(kFull, chi_fac, 1) : 0., cfR = CHI ? __shfl_down_sync(kFull, chi_fac, 1) : 0.;
+    if (!active || !owner) return;
+
+    double *jx = JXY ? a.comp(c_jx) : nullptr, *jy = JXY ? a.comp(c_jy) : nullptr;
+    double *rho = RHO ? a.comp(c_rho) : nullptr, *chi = CHI ? a.comp(c_chi) : nullptr;
+    double *rmj = RMJ ? a.comp(c_rhomjz) : nullptr;
 #pragma unroll
-        for (int ix = 0; ix < 3; ++ix) {
-            const double cd = q_invvol * sx[ix] * sy[iy];
-            const long o = a.idx(i0 + ix, j0 + iy);
-            if (c_jx >= 0) {
-                red_add(a.comp(c_jx) + o, cd * vx_c);
-                red_add(a.comp(c_jy) + o, cd * vy_c);
-            }
-            if (c_rho >= 0) red_add(a.comp(c_rho) + o, cd * gamma_psi);
-            if (c_chi >= 0) red_add(a.comp(c_chi) + o, cd * chi_fac);
-            if (c_rhomjz >= 0) red_add(a.comp(c_rhomjz) + o, cd);
+    for (int iy = 0; iy < 3; ++iy) {
+        const long o = a.idx(cc, j0 + iy);
+        if (JXY) {
+            red_add(jx + o, P1[iy] * vx_c + PL[iy] * vxL + PR[iy] * vxR);
+            red_add(jy + o, P1[iy] * vy_c + PL[iy] * vyL + PR[iy] * vyR);
+        }
+        if (RHO) red_add(rho + o, P1[iy] * gamma_psi + PL[iy] * gpL + PR[iy] * gpR);
+        if (CHI) red_add(chi + o, P1[iy] * chi_fac + PL[iy] * cfL + PR[iy] * cfR);
+        if (RMJ) red_add(rmj + o, P1[iy] + PL[iy] + PR[iy]);
+        if (!L_ok) {
+            if (JXY) { red_add(jx + o - 1, P0[iy] * vx_c); red_add(jy + o - 1, P0[iy] * vy_c); }
+            if (RHO) red_add(rho + o - 1, P0[iy] * gamma_psi);
+            if (CHI) red_add(chi + o - 1, P0[iy] * chi_fac);
+            if (RMJ) red_add(rmj + o - 1, P0[iy]);
+        }
+        if (!R_ok) {
+            if (JXY) { red_add(jx + o + 1, P2[iy] * vx_c); red_add(jy + o + 1, P2[iy] * vy_c); }
+            if (RHO) red_add(rho + o + 1, P2[iy] * gamma_psi);
+            if (CHI) red_add(chi + o + 1, P2[iy] * chi_fac);
+            if (RMJ) red_add(rmj + o + 1, P2[iy]);
         }
     }
 }
@@ -117,57 +185,207 @@ k_beam_deposit(BeamPtrs b, SliceView a, int c_jx, int c_jy, int c_jz, double x_o
 // -------------------------------------------------------------------------------------------
 // ExplicitDeposition (order 2, centred derivative: 5x5 stencil minus corners)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+// Same warp aggregation, 5 columns wide: lane l owns the centre column of its particle for the 5
+// stencil rows, loads the 4 field values of those 5 cells ONCE and adds the contributions of the
+// particles of lanes l-2..l+2 whenever they are aligned (d cells to the side, same rows) using
+// shuffled particle scalars; columns that no aligned neighbour owns are scattered by the particle
+// itself.  An aligned particle costs 20 field loads + 10 reductions instead of 84 + 42.
+// The per-cell expression is ExplicitDeposition.cpp:228-258 with the particle-only factors
+// hoisted:  Sy += -ss hq Fy + sd1 gy1 + sd2 gy2,  Sx += ss hq Fx + sd1 gx1 + sd2 gx2.
+
+// y part of single_derivative_shape_factor<2,2> from the in-cell offset (ShapeFactors.H:405-430)
+__device__ __forceinline__ void dshape2_centered_frac(double xint, double s[5], double ds[5])
+{
+    const double xint_2 = xint * xint;
+    s[0] = 0.;
+    s[1] = 0.5 * xint_2 - xint + 0.5;
+    s[2] = -xint_2 + xint + 0.5;
+    s[3] = 0.5 * xint_2;
+    s[4] = 0.;
+    ds[0] = -(-0.25 * xint_2 + 0.5 * xint - 0.25);
+    ds[1] = -(0.5 * xint_2 - 0.5 * xint - 0.25);
+    ds[2] = -(0.25 - 0.5 * xint);
+    ds[3] = -(-0.5 * xint_2 + 0.5 * xint + 0.25);
+    ds[4] = -(0.25 * xint_2);
+}
+
+// particle-only factors for one stencil column (weights wx = shx[ix], wdx = shdx[ix]):
+//   Sy(cell) += shy (A Fy + B) + shdy C,    Sx(cell) += shy (Ap Fx + Bp) + shdy Cp
+//   Fy = -Bz vx + (Ez vy + ExmBy a3 + EypBx a4)/c,   Fx = Bz vy + (Ez vx + ExmBy a5 + EypBx a3)/c
+struct ExplCol { double A, B, C, Ap, Bp, Cp; };
+struct ExplPart { double vx, vy, a3, a4, a5, hq, gy1, gy2, gx1, gx2; };
+
+__device__ __forceinline__ ExplPart expl_part(double vx, double vy, double gamma_psi, double cdm,
+                                              double psi_inv, double q_mass_ratio, double a_clight)
+{
+    ExplPart e;
+    e.vx = vx; e.vy = vy;
+    e.a3 = -vx * vy;
+    e.a4 = gamma_psi - vy * vy;
+    e.a5 = gamma_psi - vx * vx;
+    e.hq = cdm * (q_mass_ratio * psi_inv);
+    const double cc = cdm * a_clight;
+    e.gy1 = -e.a3 * cc;              // -shdx shy/dx (-vx vy) c
+    e.gy2 = -(e.a4 - 1.0) * cc;      // -shx shdy/dy (gamma_psi - vy^2 - 1) c
+    e.gx1 = (e.a5 - 1.0) * cc;       // +shdx shy/dx (gamma_psi - vx^2 - 1) c
+    e.gx2 = e.a3 * cc;               // +shx shdy/dy (-vx vy) c
+    return e;
+}
+__device__ __forceinline__ ExplCol expl_col(const ExplPart &e, double wx, double wdx, double dx_inv,
+                                            double dy_inv)
+{
+    ExplCol k;
+    const double wxd = wdx * dx_inv, wxy = wx * dy_inv;
+    k.A = -wx * e.hq;  k.B = wxd * e.gy1;  k.C = wxy * e.gy2;
+    k.Ap = wx * e.hq;  k.Bp = wxd * e.gx1; k.Cp = wxy * e.gx2;
+    return k;
+}
+__device__ __forceinline__ void expl_cell(const ExplCol &k, double vx, double vy, double a3,
+                                          double a4, double a5, double shy, double shdy, double Bz,
+                                          double Ez, double ExmBy, double EypBx, double clight_inv,
+                                          double &sy_out, double &sx_out)
+{
+    const double Fy = -Bz * vx + (Ez * vy + ExmBy * a3 + EypBx * a4) * clight_inv;
+    const double Fx = Bz * vy + (Ez * vx + ExmBy * a5 + EypBx * a3) * clight_inv;
+    sy_out += shy * (k.A * Fy + k.B) + shdy * k.C;
+    sx_out += shy * (k.Ap * Fx + k.Bp) + shdy * k.Cp;
+}
+
+template <int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB)
 k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, int c_ez,
                       int c_exmby, int c_eypbx, double x_off, double y_off, double dx_inv,
                       double dy_inv, double a_clight, double clight_inv,
                       double charge_invvol_mu0, double q_mass_ratio)
 {
-    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= pl.np) return;
-    if (!hpb_is_valid(pl.idcpu[ip])) return;
+    // warps overlap by two lanes on each side (see k_deposit_current)
+    const int lane = threadIdx.x & 31;
+    const long warp = (long)blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
+    const long ip = warp * kExplOwn - 2 + lane;
+    const bool owner = lane >= 2 && lane < 2 + kExplOwn;
+    bool active = ip >= 0 && ip < pl.np;
 
-    const double psi_inv = 1.0 / pl.r[HPB_PSI][ip];
-    const double xp = pl.r[HPB_X][ip];
-    const double yp = pl.r[HPB_Y][ip];
-    const double vx = pl.r[HPB_UX][ip] * psi_inv * clight_inv;
-    const double vy = pl.r[HPB_UY][ip] * psi_inv * clight_inv;
-    const double cdm = charge_invvol_mu0 * pl.r[HPB_W][ip];
-    const double gamma_psi = 0.5 * (psi_inv * psi_inv + vx * vx + vy * vy + 1.0);
-
-    double sx[5], dsx[5], sy[5], dsy[5];
-    const int i0 = dshape2_centered((xp - x_off) * dx_inv, sx, dsx);
-    const int j0 = dshape2_centered((yp - y_off) * dy_inv, sy, dsy);
+    double vx = 0., vy = 0., gamma_psi = 1., yint = 0.;
+    double sx[5] = {0., 0., 0., 0., 0.}, dsx[5] = {0., 0., 0., 0., 0.};
+    ExplPart e = {};
+    int i0 = 0, j0 = 0;
+    if (active) {
+        const uint64_t idcpu = pl.idcpu[ip];
+        const double psi = pl.r[HPB_PSI][ip];
+        const double xp = pl.r[HPB_X][ip];
+        const double yp = pl.r[HPB_Y][ip];
+        const double ux = pl.r[HPB_UX][ip];
+        const double uy = pl.r[HPB_UY][ip];
+        const double w = pl.r[HPB_W][ip];
+        active = hpb_is_valid(idcpu);
+        if (active) {
+            const double psi_inv = 1.0 / psi;
+            vx = ux * psi_inv * clight_inv;
+            vy = uy * psi_inv * clight_inv;
+            const double cdm = charge_invvol_mu0 * w;
+            gamma_psi = 0.5 * (psi_inv * psi_inv + vx * vx + vy * vy + 1.0);
+            i0 = dshape2_centered((xp - x_off) * dx_inv, sx, dsx);
+            const double ym = (yp - y_off) * dy_inv + 0.5;
+            const double yfl = floor(ym);
+            yint = ym - yfl;
+            j0 = (int)yfl - 2;
+            e = expl_part(vx, vy, gamma_psi, cdm, psi_inv, q_mass_ratio, a_clight);
+        }
+    }
+    const int cc = active ? i0 + 2 : -(1 << 28) - 7 * lane;      // centre column / sentinel
     const double *Bz = a.comp(c_bz), *Ez = a.comp(c_ez);
     const double *ExmBy = a.comp(c_exmby), *EypBx = a.comp(c_eypbx);
     double *Sy = a.comp(c_sy), *Sx = a.comp(c_sx);
-    const double qp = q_mass_ratio * psi_inv;
+
+    // The field-dependent part carries the plain shape factor shx*shy, which vanishes on the
+    // outer ring of the 5x5 stencil (s[0] = s[4] = 0): only rows 1..3 of the owned column need
+    // the fields, and only the sources one cell to the side contribute through them.
+    double fBz[3], fEz[3], fEx[3], fEy[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        fBz[r] = fEz[r] = fEx[r] = fEy[r] = 0.;
+        if (active && owner) {
+            const long o = a.idx(cc, j0 + 1 + r);
+            fBz[r] = Bz[o]; fEz[r] = Ez[o]; fEx[r] = ExmBy[o]; fEy[r] = EypBx[o];
+        }
+    }
+    double accy[5] = {0., 0., 0., 0., 0.}, accx[5] = {0., 0., 0., 0., 0.};
+    unsigned absorbed = 0;      // bit ix set: my column ix is deposited by the lane that owns it
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) {
+        // source = lane + d; its column 2 - d is my centre column
+        const int src = lane + d;
+        const int srcl = src < 0 ? 0 : (src > 31 ? 31 : src);
+        const ExplCol mine = expl_col(e, sx[2 - d], dsx[2 - d], dx_inv, dy_inv);
+        if (d == -2 || d == 2) {
+            // outer column of the source (shx = 0): only the shdx*shy terms survive, rows 1..3
+            const int c_s = __shfl_sync(kFull, cc, srcl), j_s = __shfl_sync(kFull, j0, srcl);
+            const double B = __shfl_sync(kFull, mine.B, srcl), Bp = __shfl_sync(kFull, mine.Bp, srcl);
+            const double yint_s = __shfl_sync(kFull, yint, srcl);
+            const bool ok = active && owner && src >= 0 && src <= 31 && c_s == cc + d && j_s == j0;
+            if (ok) {
+                absorbed |= 1u << (2 + d);
+                double shy[5], shdy[5];
+                dshape2_centered_frac(yint_s, shy, shdy);
+#pragma unroll
+                for (int r = 1; r <= 3; ++r) { accy[r] += shy[r] * B; accx[r] += shy[r] * Bp; }
+            }
+        } else {
+            ExplCol k;
+            double vx_s, vy_s, gp_s, yint_s;
+            bool ok;
+            if (d == 0) {
+                k = mine; vx_s = vx; vy_s = vy; gp_s = gamma_psi; yint_s = yint; ok = active && owner;
+            } else {
+                const int c_s = __shfl_sync(kFull, cc, srcl), j_s = __shfl_sync(kFull, j0, srcl);
+                k.A = __shfl_sync(kFull, mine.A, srcl);   k.B = __shfl_sync(kFull, mine.B, srcl);
+                k.C = __shfl_sync(kFull, mine.C, srcl);   k.Ap = -k.A;
+                k.Bp = __shfl_sync(kFull, mine.Bp, srcl); k.Cp = __shfl_sync(kFull, mine.Cp, srcl);
+                vx_s = __shfl_sync(kFull, vx, srcl);      vy_s = __shfl_sync(kFull, vy, srcl);
+                gp_s = __shfl_sync(kFull, gamma_psi, srcl);
+                yint_s = __shfl_sync(kFull, yint, srcl);
+                ok = active && owner && src >= 0 && src <= 31 && c_s == cc + d && j_s == j0;
+                if (ok) absorbed |= 1u << (2 + d);
+            }
+            if (ok) {
+                const double a3 = -vx_s * vy_s, a4 = gp_s - vy_s * vy_s, a5 = gp_s - vx_s * vx_s;
+                double shy[5], shdy[5];
+                dshape2_centered_frac(yint_s, shy, shdy);
+                accy[0] += shdy[0] * k.C; accx[0] += shdy[0] * k.Cp;      // shy[0] = shy[4] = 0
+                accy[4] += shdy[4] * k.C; accx[4] += shdy[4] * k.Cp;
+#pragma unroll
+                for (int r = 1; r <= 3; ++r)
+                    expl_cell(k, vx_s, vy_s, a3, a4, a5, shy[r], shdy[r], fBz[r - 1], fEz[r - 1],
+                              fEx[r - 1], fEy[r - 1], clight_inv, accy[r], accx[r]);
+            }
+        }
+    }
+    if (!active || !owner) return;
 #pragma unroll
     for (int iy = 0; iy < 5; ++iy) {
+        const long o = a.idx(cc, j0 + iy);
+        red_add(Sy + o, accy[iy]);
+        red_add(Sx + o, accx[iy]);
+    }
+    if (absorbed == 0x1bu) return;       // columns 0, 1, 3, 4 all owned by aligned neighbours
+    // scatter the columns nobody owns (same expressions, fields read at the target cells)
+    double shy[5], shdy[5];
+    dshape2_centered_frac(yint, shy, shdy);
+#pragma unroll 1
+    for (int ix = 0; ix < 5; ++ix) {
+        if (ix == 2 || ((absorbed >> ix) & 1u)) continue;
+        const double wx = ix == 0 ? sx[0] : ix == 1 ? sx[1] : ix == 3 ? sx[3] : sx[4];
+        const double wdx = ix == 0 ? dsx[0] : ix == 1 ? dsx[1] : ix == 3 ? dsx[3] : dsx[4];
+        const ExplCol k = expl_col(e, wx, wdx, dx_inv, dy_inv);
 #pragma unroll
-        for (int ix = 0; ix < 5; ++ix) {
+        for (int iy = 0; iy < 5; ++iy) {
             if ((ix == 0 || ix == 4) && (iy == 0 || iy == 4)) continue;
             const long o = a.idx(i0 + ix, j0 + iy);
-            const double shx = sx[ix], shdx = dsx[ix], shy = sy[iy], shdy = dsy[iy];
-            const double Bz_v = Bz[o], Ez_v = Ez[o], ExmBy_v = ExmBy[o], EypBx_v = EypBx[o];
-            red_add(Sy + o, cdm * (
-                - shx * shy * (
-                    - Bz_v * vx
-                    + ( Ez_v * vy
-                    + ExmBy_v * (          - vx * vy)
-                    + EypBx_v * (gamma_psi - vy * vy) ) * clight_inv
-                ) * qp
-                + ( - shdx * shy * dx_inv * ( - vx * vy )
-                    - shx * shdy * dy_inv * ( gamma_psi - vy * vy - 1.0 )) * a_clight));
-            red_add(Sx + o, cdm * (
-                + shx * shy * (
-                    + Bz_v * vy
-                    + ( Ez_v * vx
-                    + ExmBy_v * (gamma_psi - vx * vx)
-                    + EypBx_v * (          - vx * vy) ) * clight_inv
-                ) * qp
-                + ( + shdx * shy * dx_inv * ( gamma_psi - vx * vx - 1.0 )
-                    + shx * shdy * dy_inv * ( - vx * vy )) * a_clight));
+            double vy_ = 0., vx_ = 0.;
+            expl_cell(k, e.vx, e.vy, e.a3, e.a4, e.a5, shy[iy], shdy[iy], Bz[o], Ez[o], ExmBy[o],
+                      EypBx[o], clight_inv, vy_, vx_);
+            red_add(Sy + o, vy_);
+            red_add(Sx + o, vx_);
         }
     }
 }
@@ -236,7 +454,8 @@ __device__ __forceinline__ bool enforce_bc(double &x, double &y, double &ux, dou
     return false;
 }
 
-__global__ void __launch_bounds__(kThreads)
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int c_by, int c_bz,
                  double x_off, double y_off, double dx_inv, double dy_inv, double clight,
                  double qmc, double dz, int n_subcycles, int temp_slice, int bc, double lox,
@@ -244,15 +463,20 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
 {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= pl.np) return;
+    // request every input stream before the first use (one HBM round trip)
     const uint64_t idcpu = pl.idcpu[ip];
+    double xp0 = pl.r[HPB_X_PREV][ip];
+    double yp0 = pl.r[HPB_Y_PREV][ip];
+    double ux0 = pl.r[HPB_UX_HALF][ip];
+    double uy0 = pl.r[HPB_UY_HALF][ip];
+    double psi0 = pl.r[HPB_PSI_HALF][ip];
     if (!hpb_is_valid(idcpu)) return;
     const double clight_inv = 1.0 / clight;
     const double *Psi = a.comp(c_psi), *Ez = a.comp(c_ez), *Bx = a.comp(c_bx);
     const double *By = a.comp(c_by), *Bz = a.comp(c_bz);
 
     for (int isc = 0; isc < n_subcycles; ++isc) {
-        double xp = pl.r[HPB_X_PREV][ip];
-        double yp = pl.r[HPB_Y_PREV][ip];
+        double xp = xp0, yp = yp0;
         // doGatherShapeN<2>, FieldGather.H:45-96
         double sx[4], dsx[4], sy[4], dsy[4];
         const int i0 = dshape2_nodal((xp - x_off) * dx_inv, sx, dsx);
@@ -278,9 +502,7 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
 
         constexpr int nsub = 4;
         const double sdz = dz / nsub;
-        double ux = pl.r[HPB_UX_HALF][ip];
-        double uy = pl.r[HPB_UY_HALF][ip];
-        double psi = pl.r[HPB_PSI_HALF][ip];
+        double ux = ux0, uy = uy0, psi = psi0;
 #pragma unroll 1
         for (int isub = 0; isub < nsub; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
 
@@ -299,6 +521,7 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
             pl.r[HPB_PSI_HALF][ip] = psi;
             pl.r[HPB_X_PREV][ip] = xp;
             pl.r[HPB_Y_PREV][ip] = yp;
+            xp0 = xp; yp0 = yp; ux0 = ux; uy0 = uy; psi0 = psi;
         }
 #pragma unroll 1
         for (int isub = 0; isub < nsub / 2; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
@@ -324,10 +547,23 @@ extern "C" int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, do
     const hpb_geom &g = ctx->g;
     // invvol: 1 in normalised units at lev 0, 1/(dx dy dz) in SI (PlasmaDepositCurrent.cpp:71-73)
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
-    k_deposit_current<<<nblocks(pl.np), kThreads, 0, ctx->stream>>>(
-        to_ptrs(pl), make_view(sl), c_jx, c_jy, c_rho, c_chi, c_rhomjz, g.x_off, g.y_off,
-        1.0 / g.dx, 1.0 / g.dy, 1.0 / g.c, charge * invvol, charge * g.mu0 / mass, max_qsa,
-        d_n_qsa_violation);
+    if ((c_jx >= 0) != (c_jy >= 0)) { hpb_set_error("deposit: jx and jy go together"); return HPB_ERR_ARG; }
+    const int mask = (c_jx >= 0 ? 8 : 0) | (c_rho >= 0 ? 4 : 0) | (c_chi >= 0 ? 2 : 0) | (c_rhomjz >= 0 ? 1 : 0);
+#define HPB_DEP(M)                                                                                \
+    case M:                                                                                       \
+        k_deposit_current<((M) & 8) != 0, ((M) & 4) != 0, ((M) & 2) != 0, ((M) & 1) != 0>         \
+            <<<(unsigned)((pl.np + kDepOwn * (kThreads / 32) - 1) / (kDepOwn * (kThreads / 32))), \
+               kThreads, 0, ctx->stream>>>(                                                       \
+                to_ptrs(pl), make_view(sl), c_jx, c_jy, c_rho, c_chi, c_rhomjz, g.x_off, g.y_off, \
+                1.0 / g.dx, 1.0 / g.dy, 1.0 / g.c, charge * invvol, charge * g.mu0 / mass,        \
+                max_qsa, d_n_qsa_violation);                                                      \
+        break;
+    switch (mask) {
+        HPB_DEP(1) HPB_DEP(2) HPB_DEP(3) HPB_DEP(4) HPB_DEP(5) HPB_DEP(6) HPB_DEP(7) HPB_DEP(8)
+        HPB_DEP(9) HPB_DEP(10) HPB_DEP(11) HPB_DEP(12) HPB_DEP(13) HPB_DEP(14) HPB_DEP(15)
+    default: return HPB_OK;      // nothing to deposit
+    }
+#undef HPB_DEP
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
@@ -357,10 +593,21 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     if (pl.np == 0) return HPB_OK;
     const hpb_geom &g = ctx->g;
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
-    k_explicit_deposition<<<nblocks(pl.np), kThreads, 0, ctx->stream>>>(
-        to_ptrs(pl), make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ],
-        comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.x_off, g.y_off, 1.0 / g.dx,
-        1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass);
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("HPB_EXPL_VARIANT"); variant = e ? atoi(e) : 4; }
+#define HPB_LAUNCH_EXPL(NT, MB)                                                                    \
+    k_explicit_deposition<NT, MB><<<(unsigned)((pl.np + kExplOwn * (NT / 32) - 1) / (kExplOwn * (NT / 32))), \
+                                    NT, 0, ctx->stream>>>(                                        \
+        to_ptrs(pl), make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ],             \
+        comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.x_off, g.y_off, 1.0 / g.dx,     \
+        1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass)
+    if (variant == 2) HPB_LAUNCH_EXPL(256, 2);
+    else if (variant == 3) HPB_LAUNCH_EXPL(128, 3);
+    else if (variant == 5) HPB_LAUNCH_EXPL(128, 6);
+    else if (variant == 6) HPB_LAUNCH_EXPL(128, 8);
+    else if (variant == 1) HPB_LAUNCH_EXPL(256, 1);
+    else HPB_LAUNCH_EXPL(128, 5);
+#undef HPB_LAUNCH_EXPL
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
@@ -374,11 +621,18 @@ extern "C" int hpb_advance_plasma_particles(hpb_ctx *ctx, hpb_plasma pl, hpb_sli
     if (!ctx || !comps || !bc_lo || !bc_hi || n_subcycles < 1) return HPB_ERR_ARG;
     if (pl.np == 0) return HPB_OK;
     const hpb_geom &g = ctx->g;
-    k_advance_plasma<<<nblocks(pl.np), kThreads, 0, ctx->stream>>>(
-        to_ptrs(pl), make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],
-        comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,
-        charge / (mass * g.c), g.dz / n_subcycles, n_subcycles, temp_slice, particle_bc,
-        bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1]);
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("HPB_PUSH_VARIANT"); variant = e ? atoi(e) : 3; }
+#define HPB_LAUNCH_PUSH(MB)                                                                       \
+    k_advance_plasma<MB><<<nblocks(pl.np), kThreads, 0, ctx->stream>>>(                          \
+        to_ptrs(pl), make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],           \
+        comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
+        charge / (mass * g.c), g.dz / n_subcycles, n_subcycles, temp_slice, particle_bc,         \
+        bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1])
+    if (variant == 3) HPB_LAUNCH_PUSH(3);
+    else if (variant == 4) HPB_LAUNCH_PUSH(4);
+    else HPB_LAUNCH_PUSH(2);
+#undef HPB_LAUNCH_PUSH
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
