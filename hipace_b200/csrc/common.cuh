@@ -125,10 +125,14 @@ struct hpb_ctx {
     double *d_spec;           // 3 * nx * ny spectral scratch
     double *d_iface;          // 4 * 3 * C * nx chunk-interface values
     // Multigrid (mg.cu)
-    int mg_cc; int mg_nlev; int mg_lc;   // mg_lc: first level solved by the single-CTA kernel
+    int mg_cc; int mg_nlev; int mg_lc; int mg_coarse_smem;   // mg_lc: first level solved by the single-CTA kernel
     MGLevel mg[32];
-    double *d_mg_norm;        // [0]=res norm, [1]=rhs norm
-    double *h_mg_norm;        // pinned
+    double *d_mg_norm;        // [0]=res norm, [1]=rhs norm (atomicMax accumulators)
+    double *d_mg_state;       // target, max_norm, last norm
+    int *d_mg_istate;         // done, V-cycles, failed
+    double *h_mg_norm;        // pinned copies
+    int *h_mg_istate;
+    int mg_last_iters;        // V-cycles of the previous solve = speculation depth of the next
     // misc
     int *d_scalar_i;          // scratch ints
 };

@@ -74,9 +74,10 @@ __device__ __forceinline__ double interp_at(const V2 &crse, int i, int j, int n,
 template <int INIT, bool RES>
 __global__ void __launch_bounds__(NT)
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
-         V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO)
+         V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO, const int *done)
 {
     __shared__ double sm[2][AY * AX];
+    if (done && *done) return;      // converged: the speculatively enqueued V-cycle is a no-op
     const int FX = CX - 2 * EO, FY = CY - 2 * EO;
     const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
     const int ox = bx * FX - EO + g.vlo;          // level index of compute cell (0, 0)
@@ -324,9 +325,68 @@ __device__ void c_zero(double *p, long n)
     __syncthreads();
 }
 
-// levels L[0..nl-1] (L[0] = first single-CTA level): in res[0]; out cor[0]
-__global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A)
+// levels L[0..nl-1] (L[0] = first single-CTA level): in res[0]; out cor[0].
+// All level arrays live in shared memory for the duration of the kernel (a phase is then bounded
+// by shared-memory latency instead of an L2 round trip); acf / 1/c0 are copied in from the tables
+// k_coarse_setup made, res[0] comes from the last tile level and cor[0] goes back to it.
+__global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const int *done)
 {
+    extern __shared__ double csm[];
+    __shared__ CoarseLevel S[12];
+    if (*done) return;
+    const int nl = A.nl;
+    if (threadIdx.x == 0) {
+        double *p = csm;
+        for (int l = 0; l < nl; ++l) {
+            const long n = (long)A.L[l].g.nx * A.L[l].g.ny;
+            S[l].g = A.L[l].g;
+            S[l].acf = p; p += n;
+            S[l].c0i = p; p += n;
+            S[l].res = p; p += 2 * n;
+            S[l].cor = p; p += 2 * n;
+            S[l].rescor = p; p += 2 * n;
+        }
+    }
+    __syncthreads();
+    for (int l = 0; l < nl; ++l) {
+        const long n = (long)S[l].g.nx * S[l].g.ny;
+        for (long s = threadIdx.x; s < n; s += blockDim.x) {
+            S[l].acf[s] = A.L[l].acf[s];
+            S[l].c0i[s] = A.L[l].c0i[s];
+            if (l == 0) { S[0].res[s] = A.L[0].res[s]; S[0].res[n + s] = A.L[0].res[n + s]; }
+            else { S[l].res[s] = 0.; S[l].res[n + s] = 0.; }      // boundary nodes stay 0
+        }
+    }
+    __syncthreads();
+    for (int l = 0; l < nl - 1; ++l) {
+        const CoarseLevel &L = S[l];
+        const long n = (long)L.g.nx * L.g.ny;
+        c_zero(L.cor, 2 * n);
+        c_zero(L.rescor, 2 * n);
+        c_gsrb(L, L.cor, L.res, 4);
+        c_residual(L, L.rescor, L.cor, L.res);
+        c_restrict(S[l + 1].g, S[l + 1].res, L.g, L.rescor, 2);
+    }
+    {
+        const CoarseLevel &L = S[nl - 1];
+        c_zero(L.cor, 2 * (long)L.g.nx * L.g.ny);
+        c_gsrb(L, L.cor, L.res, A.nsweeps_bottom);
+    }
+    for (int l = nl - 2; l >= 0; --l) {
+        c_interp_add(S[l], S[l].cor, S[l + 1], S[l + 1].cor);
+        c_gsrb(S[l], S[l].cor, S[l].res, 4);
+    }
+    {
+        const long n = (long)S[0].g.nx * S[0].g.ny;
+        for (long s = threadIdx.x; s < 2 * n; s += blockDim.x) A.L[0].cor[s] = S[0].cor[s];
+    }
+}
+
+// fallback when the single-CTA levels do not fit in shared memory: same algorithm on the global
+// arrays (coherent within one CTA after __syncthreads)
+__global__ void __launch_bounds__(kCoarseThreads) k_coarse_global(CoarseArgs A, const int *done)
+{
+    if (*done) return;
     const int nl = A.nl;
     for (int l = 0; l < nl - 1; ++l) {
         const CoarseLevel &L = A.L[l];
@@ -412,6 +472,31 @@ __global__ void k_copy2(LevelGeom g, V2 dst, V2 src)
     dst.at(i, j, 1) = src.at(i, j, 1);
 }
 
+// convergence bookkeeping on the device (solve_doit :1354-1416)
+//   st[0] = res_target, st[1] = max_norm, st[2] = last norm;  ist[0] = done, ist[1] = V-cycles,
+//   ist[2] = failed.  norm[] is reset for the next accumulation.
+__global__ void k_mg_check(int mode, double *norm, double *st, int *ist, double tol_rel, double tol_abs)
+{
+    if (mode == 0) {
+        const double resnorm0 = norm[0], rhsnorm0 = norm[1];
+        const double max_norm = rhsnorm0 >= resnorm0 ? rhsnorm0 : resnorm0;
+        st[0] = fmax(tol_abs, fmax(tol_rel, 1.e-16) * max_norm);      // :1361
+        st[1] = max_norm;
+        st[2] = resnorm0;
+        ist[0] = (resnorm0 <= st[0]) ? 1 : 0;
+        ist[1] = 0;
+        ist[2] = 0;
+    } else if (!ist[0]) {
+        const double norminf = norm[0];
+        st[2] = norminf;
+        ist[1] += 1;
+        if (norminf <= st[0]) ist[0] = 1;
+        else if (norminf > 1.e20 * st[1] || norminf != norminf) { ist[0] = 1; ist[2] = 1; }
+    }
+    norm[0] = 0.;
+    norm[1] = 0.;
+}
+
 LevelGeom level_geom(const hpb_ctx *ctx, int l)
 {
     LevelGeom g;
@@ -433,7 +518,7 @@ V2 lvl_view(const hpb_ctx *ctx, int l, double *p)
 
 template <int INIT, bool RES>
 void launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, const double *acf,
-                   long acf_rs, V2 out, const LevelGeom &gc, V2 res_c, double *norm)
+                   long acf_rs, V2 out, const LevelGeom &gc, V2 res_c, double *norm, const int *done)
 {
     // owned region must start on even indices relative to vlo for the fused restriction;
     // cc needs 1 extra ring for the residual (EO 4), nodal full weighting one more (EO 5)
@@ -442,7 +527,7 @@ void launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, con
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
     k_smooth<INIT, RES><<<nbx * nby, NT, 0, ctx->stream>>>(g, in, crse, rhs, acf, acf_rs, out, gc,
-                                                           res_c, norm, nbx, EO);
+                                                           res_c, norm, nbx, EO, done);
     hpb_count_launch(ctx);
 }
 
@@ -499,6 +584,16 @@ int hpb_mg_init(hpb_ctx *ctx)
     if (nl - lc > 12) lc = nl - 12;
     // (grids that stop coarsening early leave a large 'coarse' level: k_coarse loops over it)
     ctx->mg_lc = lc;
+    {
+        size_t bytes = 0;
+        for (int l = lc; l < nl; ++l) bytes += 8 * sizeof(double) * (size_t)ctx->mg[l].nx * ctx->mg[l].ny;
+        ctx->mg_coarse_smem = 0;
+        if (bytes <= 200 * 1024) {
+            HPB_CUDA_CHECK(cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                200 * 1024));
+            ctx->mg_coarse_smem = (int)bytes;
+        }
+    }
     for (int l = 0; l < nl; ++l) {
         const size_t n = (size_t)ctx->mg[l].nx * ctx->mg[l].ny;
         double **arrs[5] = {&ctx->mg[l].acf, &ctx->mg[l].c0i, &ctx->mg[l].res, &ctx->mg[l].cor,
@@ -511,7 +606,13 @@ int hpb_mg_init(hpb_ctx *ctx)
         }
     }
     HPB_CUDA_CHECK(cudaMalloc(&ctx->d_mg_norm, 2 * sizeof(double)));
-    HPB_CUDA_CHECK(cudaMallocHost(&ctx->h_mg_norm, 2 * sizeof(double)));
+    HPB_CUDA_CHECK(cudaMemset(ctx->d_mg_norm, 0, 2 * sizeof(double)));
+    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_mg_state, 4 * sizeof(double)));
+    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_mg_istate, 4 * sizeof(int)));
+    HPB_CUDA_CHECK(cudaMemset(ctx->d_mg_istate, 0, 4 * sizeof(int)));
+    HPB_CUDA_CHECK(cudaMallocHost(&ctx->h_mg_norm, 4 * sizeof(double)));
+    HPB_CUDA_CHECK(cudaMallocHost(&ctx->h_mg_istate, 4 * sizeof(int)));
+    ctx->mg_last_iters = 2;
     return HPB_OK;
 }
 
@@ -521,25 +622,30 @@ void hpb_mg_free(hpb_ctx *ctx)
         cudaFree(ctx->mg[l].acf); cudaFree(ctx->mg[l].c0i); cudaFree(ctx->mg[l].res);
         cudaFree(ctx->mg[l].cor); cudaFree(ctx->mg[l].rescor);
     }
-    cudaFree(ctx->d_mg_norm);
-    cudaFreeHost(ctx->h_mg_norm);
+    cudaFree(ctx->d_mg_norm); cudaFree(ctx->d_mg_state); cudaFree(ctx->d_mg_istate);
+    cudaFreeHost(ctx->h_mg_norm); cudaFreeHost(ctx->h_mg_istate);
 }
 
 // one V-cycle (:1429-1512).  On entry: cur = cor0 (level-0 iterate after 4 sweeps), res[1] holds
 // the restricted residual of cor0.  On exit the same invariants hold for the new cor0, and
 // d_mg_norm[0] holds max|rescor0|.  tmp is the second level-0 buffer.
-static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, long chi_rs)
+static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, long chi_rs,
+                     double tol_rel, double tol_abs)
 {
     const int lc = ctx->mg_lc;
     const V2 none{};
     const LevelGeom gnone{};
+    const int *done = ctx->d_mg_istate;
     for (int l = 1; l < lc; ++l) {                 // down, tile levels
         const LevelGeom g = level_geom(ctx, l), gc = level_geom(ctx, l + 1);
         launch_smooth<0, true>(ctx, g, none, none, lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf,
                                g.nx, lvl_view(ctx, l, ctx->mg[l].cor), gc,
-                               lvl_view(ctx, l + 1, ctx->mg[l + 1].res), nullptr);
+                               lvl_view(ctx, l + 1, ctx->mg[l + 1].res), nullptr, done);
     }
-    k_coarse<<<1, kCoarseThreads, 0, ctx->stream>>>(coarse_args(ctx));
+    if (ctx->mg_coarse_smem > 0)
+        k_coarse<<<1, kCoarseThreads, ctx->mg_coarse_smem, ctx->stream>>>(coarse_args(ctx), done);
+    else
+        k_coarse_global<<<1, kCoarseThreads, 0, ctx->stream>>>(coarse_args(ctx), done);
     hpb_count_launch(ctx);
     // up, tile levels: cor[l] <- GSRB^4(cor[l] + I(cor[l+1])); double-buffered through rescor[l]
     double *up_prev = ctx->mg[lc].cor;
@@ -547,17 +653,18 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
         const LevelGeom g = level_geom(ctx, l);
         launch_smooth<2, false>(ctx, g, lvl_view(ctx, l, ctx->mg[l].cor), lvl_view(ctx, l + 1, up_prev),
                                 lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf, g.nx,
-                                lvl_view(ctx, l, ctx->mg[l].rescor), gnone, none, nullptr);
+                                lvl_view(ctx, l, ctx->mg[l].rescor), gnone, none, nullptr, done);
         up_prev = ctx->mg[l].rescor;
     }
     const LevelGeom g0 = level_geom(ctx, 0), g1 = level_geom(ctx, 1);
     // sol = GSRB^4(cor0 + I(cor[1]))  ->  tmp
     launch_smooth<2, false>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs, tmp, gnone, none,
-                            nullptr);
+                            nullptr, done);
     // cor0 = GSRB^4(sol), rescor0 = rhs - L cor0 -> res[1], norm   (:1501-1503)
-    HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, 2 * sizeof(double), ctx->stream));
     launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, cur, g1,
-                           lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm);
+                           lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, done);
+    k_mg_check<<<1, 1, 0, ctx->stream>>>(1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
+    hpb_count_launch(ctx);
     return HPB_OK;
 }
 
@@ -596,37 +703,42 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
 
     // cor0 = GSRB^4(sol), rescor0 = rhs - L(cor0)   (:1326-1327), fused with its restriction
     V2 cur = lvl_view(ctx, 0, ctx->mg[0].cor);
-    HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, 2 * sizeof(double), ctx->stream));
     launch_smooth<1, true>(ctx, g0, sol, none, rhs, chi, chi_rs, cur, g1,
-                           lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm);
-    HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_norm, ctx->d_mg_norm, 2 * sizeof(double),
-                                   cudaMemcpyDeviceToHost, ctx->stream));
-    HPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    const double resnorm0 = ctx->h_mg_norm[0], rhsnorm0 = ctx->h_mg_norm[1];
-    const double max_norm = rhsnorm0 >= resnorm0 ? rhsnorm0 : resnorm0;
-    const double res_target = fmax(tol_abs, fmax(tol_rel, 1.e-16) * max_norm);      // :1361
+                           lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, nullptr);
+    k_mg_check<<<1, 1, 0, ctx->stream>>>(0, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
+    hpb_count_launch(ctx);
+    // Speculative V-cycles: as many as the previous solve needed, enqueued without a host round
+    // trip; each kernel is a no-op once the device-side test (:1391) has passed.  One
+    // synchronisation then tells us whether more are needed.
+    int enq = 0;
+    const int n_pred = ctx->mg_last_iters < 1 ? 1 : (ctx->mg_last_iters > max_iters ? max_iters : ctx->mg_last_iters);
+    for (; enq < n_pred; ++enq) {
+        int rc = mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs, tol_rel, tol_abs);     // sol is the scratch iterate
+        if (rc) return rc;
+    }
     int iters = 0;
-    if (!(resnorm0 <= res_target)) {
-        bool converged = false;
-        for (int it = 0; it < max_iters; ++it) {
-            int rc = mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs);     // sol is the scratch iterate
-            if (rc) return rc;
-            iters = it + 1;
-            HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_norm, ctx->d_mg_norm, sizeof(double),
-                                           cudaMemcpyDeviceToHost, ctx->stream));
-            HPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            const double norminf = ctx->h_mg_norm[0];
-            if (norminf <= res_target) { converged = true; break; }
-            if (norminf > 1.e20 * max_norm || norminf != norminf) {
-                hpb_set_error("hpmg failing so lets stop here (resid/max_norm = %g)", norminf / max_norm);
-                return HPB_ERR_MG_DIVERGED;
-            }
+    while (true) {
+        HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_istate, ctx->d_mg_istate, 4 * sizeof(int),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_norm, ctx->d_mg_state, 3 * sizeof(double),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        HPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        iters = ctx->h_mg_istate[1];
+        if (ctx->h_mg_istate[2]) {
+            hpb_set_error("hpmg failing so lets stop here (resid/max_norm = %g)",
+                          ctx->h_mg_norm[2] / ctx->h_mg_norm[1]);
+            return HPB_ERR_MG_DIVERGED;
         }
-        if (!converged) {
+        if (ctx->h_mg_istate[0]) break;
+        if (enq >= max_iters) {
             hpb_set_error("hpmg failed to converge after %d iterations", max_iters);
             return HPB_ERR_MG_DIVERGED;
         }
+        int rc = mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs, tol_rel, tol_abs);
+        if (rc) return rc;
+        ++enq;
     }
+    ctx->mg_last_iters = iters;
     // sol <- cor0 on the valid box (:1419-1426)
     k_copy2<<<nb(nv0), 256, 0, ctx->stream>>>(g0, sol, cur);
     hpb_count_launch(ctx);
