@@ -35,7 +35,7 @@ struct LevelGeom {
 
 constexpr int CX = 64, CY = 32;       // compute region of a tile
 constexpr int AX = CX + 2, AY = CY + 2;
-constexpr int NT = 256;
+constexpr int NT = 512;
 constexpr int kCoarseMax = 34;        // levels with <= 34 x 34 points run in k_coarse
 constexpr int kCoarseThreads = 1024;
 
@@ -71,8 +71,10 @@ __device__ __forceinline__ double interp_at(const V2 &crse, int i, int j, int n,
 //   INIT 0: phi = 0;  1: phi = phi_in;  2: phi = phi_in + I(crse)
 //   RES: rescor = rhs + acf*phi - lap(phi) is restricted on the fly (restrict_cc / restrict_nd)
 //        into res_c; norm[0] = max|rescor| and norm[1] = max|rhs| if norm != nullptr.
+// 512 threads per 64x32 tile: thread (tx, ty) owns the vertical cell pairs (tx, 2ty) and
+// (tx+32, 2ty), so that every thread updates exactly one cell of each pair per half-sweep.
 template <int INIT, bool RES>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
          V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO, const int *done)
 {
@@ -82,30 +84,37 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
     const int ox = bx * FX - EO + g.vlo;          // level index of compute cell (0, 0)
     const int oy = by * FY - EO + g.vlo;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty = 0..15
 
-    for (int s = threadIdx.x; s < AX * AY; s += NT) {
-        const int lj = s / AX, li = s - lj * AX;
-        const int i = ox - 1 + li, j = oy - 1 + lj;
-        double v0 = 0., v1 = 0.;
-        if (INIT != 0 && i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy) {
-            v0 = phi_in.at(i, j, 0);
-            v1 = phi_in.at(i, j, 1);
-            if (INIT == 2) {
-                v0 = v0 + interp_at(crse, i, j, 0, g.cc);
-                v1 = v1 + interp_at(crse, i, j, 1, g.cc);
+    // tile load (with halo): lane -> columns tx, tx+32, tx+64; warp -> rows ty, ty+16, ty+32.
+    // All loads are independent and issued before the first use.
+    double v0[3][3], v1[3][3];
+    {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int lj = ty + 16 * a, li = tx + 32 * c;
+                const int i = ox - 1 + li, j = oy - 1 + lj;
+                v0[a][c] = 0.; v1[a][c] = 0.;
+                if (INIT != 0 && lj < AY && li < AX && i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy) {
+                    v0[a][c] = phi_in.at(i, j, 0);
+                    v1[a][c] = phi_in.at(i, j, 1);
+                    if (INIT == 2) {
+                        v0[a][c] = v0[a][c] + interp_at(crse, i, j, 0, g.cc);
+                        v1[a][c] = v1[a][c] + interp_at(crse, i, j, 1, g.cc);
+                    }
+                }
             }
         }
-        sm[0][s] = v0;
-        sm[1][s] = v1;
     }
-    // every thread owns 4 vertical pairs: columns tx, tx+32; row pairs 2*(ty + 8b)
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    double r0[4][2], r1[4][2], ci[4][2], ac[4][2];
+    double r0[2][2], r1[2][2], ci[2][2];
     unsigned okmask = 0;
     const double fx43 = g.facx * (4. / 3.), fy43 = g.facy * (4. / 3.);
+    const int cj = 2 * ty;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+    for (int p = 0; p < 2; ++p) {
+        const int cix = tx + 32 * p;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int i = ox + cix, j = oy + cj + h;
@@ -114,19 +123,26 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             r0[p][h] = ok ? rhs.at(i, j, 0) : 0.;
             r1[p][h] = ok ? rhs.at(i, j, 1) : 0.;
             const double a = ok ? acf[i + (long)j * acf_rs] : 0.;
-            ac[p][h] = a;
             double c0 = -(a + 2.0 * (g.facx + g.facy));                 // gs1 :265-292
             if (g.cc && (i == g.vlo || i == g.vhix)) c0 -= 2.0 * g.facx;
             if (g.cc && (j == g.vlo || j == g.vhiy)) c0 -= 2.0 * g.facy;
             ci[p][h] = 1.0 / c0;
         }
     }
+    // (the rhs / acf loads above are in flight together with the tile loads)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int lj = ty + 16 * a, li = tx + 32 * c;
+            if (lj < AY && li < AX) { sm[0][lj * AX + li] = v0[a][c]; sm[1][lj * AX + li] = v1[a][c]; }
+        }
     __syncthreads();
-#pragma unroll 1
+#pragma unroll
     for (int icolor = 0; icolor < 4; ++icolor) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+        for (int p = 0; p < 2; ++p) {
+            const int cix = tx + 32 * p;
             const int i = ox + cix;
             const int sh = (i + oy + cj + icolor) & 1;
             const int j = oy + cj + sh;
@@ -139,20 +155,20 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
                 const double rr0 = sh ? r0[p][1] : r0[p][0], rr1 = sh ? r1[p][1] : r1[p][0];
                 const double cinv = sh ? ci[p][1] : ci[p][0];
                 double *c = sm[0] + o;
-                double lap = cxw * (c[-1] + c[1]) + cyw * (c[-AX] + c[AX]);
-                c[0] = (rr0 - lap) * cinv;
-                c = sm[1] + o;
-                lap = cxw * (c[-1] + c[1]) + cyw * (c[-AX] + c[AX]);
-                c[0] = (rr1 - lap) * cinv;
+                double *e = sm[1] + o;
+                const double lap0 = cxw * (c[-1] + c[1]) + cyw * (c[-AX] + c[AX]);
+                const double lap1 = cxw * (e[-1] + e[1]) + cyw * (e[-AX] + e[AX]);
+                c[0] = (rr0 - lap0) * cinv;
+                e[0] = (rr1 - lap1) * cinv;
             }
         }
         __syncthreads();
     }
-    double rs0[4][2], rs1[4][2];
+    double rs0[2][2], rs1[2][2];
     double nres = 0., nrhs = 0.;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+    for (int p = 0; p < 2; ++p) {
+        const int cix = tx + 32 * p;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int i = ox + cix, j = oy + cj + h;
@@ -161,8 +177,9 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             // the residual is exact one ring further out than the owned region (needed by the
             // nodal full-weighting restriction)
             if (RES && ok && cix >= EO - 1 && cix < CX - EO + 1 && cj + h >= EO - 1 && cj + h < CY - EO + 1) {
-                rs0[p][h] = residual_smem(sm[0], cix + 1, cj + h + 1, i, j, g, r0[p][h], ac[p][h]);
-                rs1[p][h] = residual_smem(sm[1], cix + 1, cj + h + 1, i, j, g, r1[p][h], ac[p][h]);
+                const double a = acf[i + (long)j * acf_rs];
+                rs0[p][h] = residual_smem(sm[0], cix + 1, cj + h + 1, i, j, g, r0[p][h], a);
+                rs1[p][h] = residual_smem(sm[1], cix + 1, cj + h + 1, i, j, g, r1[p][h], a);
             }
             if (ok && cix >= EO && cix < CX - EO && cj + h >= EO && cj + h < CY - EO) {
                 phi_out.at(i, j, 0) = sm[0][(cj + h + 1) * AX + cix + 1];
@@ -177,8 +194,8 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     if (!RES) return;
     __syncthreads();                   // everyone is done reading phi from shared memory
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int cix = tx + 32 * (p & 1), cj = 2 * (ty + 8 * (p >> 1));
+    for (int p = 0; p < 2; ++p) {
+        const int cix = tx + 32 * p;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             sm[0][(cj + h + 1) * AX + cix + 1] = rs0[p][h];
@@ -191,23 +208,24 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     // coarse points owned by this tile: cc: fine cells (2I, 2I+1); nodal: fine node 2I
     const int I0 = (X0 + 1) >> 1, J0 = (Y0 + 1) >> 1;
     const int I1 = (X0 + FX + 1) >> 1, J1 = (Y0 + FY + 1) >> 1;     // exclusive
-    const int nI = I1 - I0, nJ = J1 - J0;
-    for (int s = threadIdx.x; s < nI * nJ; s += NT) {
-        const int J = J0 + s / nI, I = I0 + s % nI;
-        if (I < gc.vlo || I > gc.vhix || J < gc.vlo || J > gc.vhiy) continue;
-        const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;         // smem index of fine (2I, 2J)
+    // thread (tx, ty) -> coarse point (I0 + tx, J0 + ty): FX/2 <= 28 columns, FY/2 <= 12 rows
+    {
+        const int I = I0 + tx, J = J0 + ty;
+        if (I < I1 && J < J1 && I >= gc.vlo && I <= gc.vhix && J >= gc.vlo && J <= gc.vhiy) {
+            const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;         // smem index of fine (2I, 2J)
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
-            const double *f = sm[n] + lj * AX + li;
-            double v;
-            if (g.cc) {
-                v = 0.25 * (f[0] + f[1] + f[AX] + f[AX + 1]);
-            } else {
-                v = (1. / 16.) * (f[-AX - 1] + 2. * f[-AX] + f[-AX + 1]
-                                  + 2. * f[-1] + 4. * f[0] + 2. * f[1]
-                                  + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
+            for (int n = 0; n < 2; ++n) {
+                const double *f = sm[n] + lj * AX + li;
+                double v;
+                if (g.cc) {
+                    v = 0.25 * (f[0] + f[1] + f[AX] + f[AX + 1]);
+                } else {
+                    v = (1. / 16.) * (f[-AX - 1] + 2. * f[-AX] + f[-AX + 1]
+                                      + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                                      + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
+                }
+                res_c.at(I, J, n) = v;
             }
-            res_c.at(I, J, n) = v;
         }
     }
     if (norm) {
@@ -216,7 +234,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             nres = fmax(nres, __shfl_xor_sync(0xffffffffu, nres, o));
             nrhs = fmax(nrhs, __shfl_xor_sync(0xffffffffu, nrhs, o));
         }
-        if (tx == 0) {
+        if (tx == 0 && (nres > 0. || nrhs > 0.)) {
             // bit pattern of non-negative doubles is monotone: exact, order-independent max
             atomicMax((unsigned long long *)&norm[0], (unsigned long long)__double_as_longlong(nres));
             atomicMax((unsigned long long *)&norm[1], (unsigned long long)__double_as_longlong(nrhs));
@@ -326,59 +344,196 @@ __device__ void c_zero(double *p, long n)
 }
 
 // levels L[0..nl-1] (L[0] = first single-CTA level): in res[0]; out cor[0].
-// All level arrays live in shared memory for the duration of the kernel (a phase is then bounded
-// by shared-memory latency instead of an L2 round trip); acf / 1/c0 are copied in from the tables
-// k_coarse_setup made, res[0] comes from the last tile level and cor[0] goes back to it.
+// All level arrays live in shared memory for the duration of the kernel and thread (tx, ty) of the
+// 32x32 CTA owns the point (vlo + tx, vlo + ty) of every level, with its rhs, 1/c0 and stencil
+// weights in registers for the duration of a level visit: a half-sweep is then 4 shared-memory
+// loads, 7 flops and a barrier per component -- the V-cycle below level `lc` is latency bound and
+// this keeps the dependent chain per phase short.
+struct SLevel {
+    int nx, ny, vlo, vhix, vhiy, n;
+    double facx, facy;
+    int o_acf, o_c0i, o_res, o_cor, o_rescor;      // offsets into the dynamic shared array
+};
+
+struct SCell {         // per-thread view of its point on one level
+    bool ok, hl, hr, hd, hu;       // has a left / right / lower / upper neighbour inside the level box
+    int o, par;
+    double r0, r1, c0i, cxw, cyw;
+};
+
+__device__ __forceinline__ SCell s_cell(const SLevel &L, const double *sm, int cc)
+{
+    SCell c;
+    const int i = L.vlo + (threadIdx.x & 31), j = L.vlo + (threadIdx.x >> 5);
+    c.ok = i <= L.vhix && j <= L.vhiy;
+    c.o = i + j * L.nx;
+    c.par = (i + j) & 1;
+    c.r0 = c.r1 = c.c0i = 0.;
+    c.cxw = (cc && (i == L.vlo || i == L.vhix)) ? L.facx * (4. / 3.) : L.facx;
+    c.cyw = (cc && (j == L.vlo || j == L.vhiy)) ? L.facy * (4. / 3.) : L.facy;
+    // cell-centred level arrays carry no ghost ring: the missing neighbour counts as 0
+    c.hl = !(cc && i == L.vlo); c.hr = !(cc && i == L.vhix);
+    c.hd = !(cc && j == L.vlo); c.hu = !(cc && j == L.vhiy);
+    if (c.ok) { c.r0 = sm[L.o_res + c.o]; c.r1 = sm[L.o_res + L.n + c.o]; c.c0i = sm[L.o_c0i + c.o]; }
+    return c;
+}
+
+// half-sweeps is = first..last-1 on cor (boundary / exterior points hold 0: the zero neighbour and
+// the 4/3 weight reproduce the branches of gs1 exactly)
+__device__ __forceinline__ void s_sweeps(const SLevel &L, const SCell &c, double *sm, int first, int last)
+{
+    double *p0 = sm + L.o_cor + c.o, *p1 = p0 + L.n;
+    const int w = L.nx;
+    for (int is = first; is < last; ++is) {
+        if (c.ok && ((c.par + is) & 1) == 0) {
+            const double l0 = c.hl ? p0[-1] : 0., r0 = c.hr ? p0[1] : 0.;
+            const double d0 = c.hd ? p0[-w] : 0., u0 = c.hu ? p0[w] : 0.;
+            const double l1 = c.hl ? p1[-1] : 0., r1 = c.hr ? p1[1] : 0.;
+            const double d1 = c.hd ? p1[-w] : 0., u1 = c.hu ? p1[w] : 0.;
+            const double lap0 = c.cxw * (l0 + r0) + c.cyw * (d0 + u0);
+            const double lap1 = c.cxw * (l1 + r1) + c.cyw * (d1 + u1);
+            p0[0] = (c.r0 - lap0) * c.c0i;
+            p1[0] = (c.r1 - lap1) * c.c0i;
+        }
+        __syncthreads();
+    }
+}
+
+// cor = GSRB^n(0): the first half-sweep of a zero field is rhs / c0 on its colour
+__device__ __forceinline__ void s_sweeps_from_zero(const SLevel &L, const SCell &c, double *sm, int n)
+{
+    if (c.ok) {
+        const bool first = (c.par & 1) == 0;
+        sm[L.o_cor + c.o] = first ? (c.r0 - 0.) * c.c0i : 0.;
+        sm[L.o_cor + L.n + c.o] = first ? (c.r1 - 0.) * c.c0i : 0.;
+    }
+    __syncthreads();
+    s_sweeps(L, c, sm, 1, n);
+}
+
+__device__ __forceinline__ void s_residual(const SLevel &L, const SCell &c, double *sm, int cc)
+{
+    if (c.ok) {
+        const int w = L.nx;
+        const int i = L.vlo + (threadIdx.x & 31), j = L.vlo + (threadIdx.x >> 5);
+        const double a = sm[L.o_acf + c.o];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            const double *p = sm + L.o_cor + n * L.n + c.o;
+            double lap = -2.0 * (L.facx + L.facy) * p[0];
+            if (cc && i == L.vlo) lap += L.facx * ((4. / 3.) * p[1] - 2.0 * p[0]);
+            else if (cc && i == L.vhix) lap += L.facx * ((4. / 3.) * p[-1] - 2.0 * p[0]);
+            else lap += L.facx * (p[-1] + p[1]);
+            if (cc && j == L.vlo) lap += L.facy * ((4. / 3.) * p[w] - 2.0 * p[0]);
+            else if (cc && j == L.vhiy) lap += L.facy * ((4. / 3.) * p[-w] - 2.0 * p[0]);
+            else lap += L.facy * (p[-w] + p[w]);
+            sm[L.o_rescor + n * L.n + c.o] = (n ? c.r1 : c.r0) + a * p[0] - lap;
+        }
+    }
+    __syncthreads();
+}
+
+// res[coarse] = R(rescor[fine])
+__device__ __forceinline__ void s_restrict(const SLevel &Lc, const SLevel &Lf, double *sm, int cc)
+{
+    const int i = Lc.vlo + (threadIdx.x & 31), j = Lc.vlo + (threadIdx.x >> 5);
+    if (i <= Lc.vhix && j <= Lc.vhiy) {
+        const int w = Lf.nx;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            const double *f = sm + Lf.o_rescor + n * Lf.n + 2 * i + 2 * j * w;
+            double v;
+            if (cc) v = 0.25 * (f[0] + f[1] + f[w] + f[w + 1]);
+            else v = (1. / 16.) * (f[-w - 1] + 2. * f[-w] + f[-w + 1] + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                                   + f[w - 1] + 2. * f[w] + f[w + 1]);
+            sm[Lc.o_res + n * Lc.n + i + j * Lc.nx] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// cor[fine] += I(cor[coarse])
+__device__ __forceinline__ void s_interp_add(const SLevel &Lf, const SCell &c, const SLevel &Lc, double *sm, int cc)
+{
+    if (c.ok) {
+        const int i = Lf.vlo + (threadIdx.x & 31), j = Lf.vlo + (threadIdx.x >> 5);
+        const int ic = i >> 1, jc = j >> 1, wc = Lc.nx;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            const double *q = sm + Lc.o_cor + n * Lc.n + ic + jc * wc;
+            double add;
+            if (cc) add = q[0];
+            else {
+                const bool io = (ic * 2 != i), jo = (jc * 2 != j);
+                if (io && jo) add = (q[0] + q[1] + q[wc] + q[wc + 1]) * 0.25;
+                else if (io) add = (q[0] + q[1]) * 0.5;
+                else if (jo) add = (q[0] + q[wc]) * 0.5;
+                else add = q[0];
+            }
+            double *f = sm + Lf.o_cor + n * Lf.n + c.o;
+            f[0] = f[0] + add;
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const int *done)
 {
     extern __shared__ double csm[];
-    __shared__ CoarseLevel S[12];
+    __shared__ SLevel S[12];
     if (*done) return;
     const int nl = A.nl;
+    const int cc = A.L[0].g.cc;
     if (threadIdx.x == 0) {
-        double *p = csm;
+        int off = 0;
         for (int l = 0; l < nl; ++l) {
-            const long n = (long)A.L[l].g.nx * A.L[l].g.ny;
-            S[l].g = A.L[l].g;
-            S[l].acf = p; p += n;
-            S[l].c0i = p; p += n;
-            S[l].res = p; p += 2 * n;
-            S[l].cor = p; p += 2 * n;
-            S[l].rescor = p; p += 2 * n;
+            const LevelGeom &g = A.L[l].g;
+            SLevel &L = S[l];
+            L.nx = g.nx; L.ny = g.ny; L.vlo = g.vlo; L.vhix = g.vhix; L.vhiy = g.vhiy;
+            L.n = g.nx * g.ny; L.facx = g.facx; L.facy = g.facy;
+            L.o_acf = off; off += L.n;
+            L.o_c0i = off; off += L.n;
+            L.o_res = off; off += 2 * L.n;
+            L.o_cor = off; off += 2 * L.n;
+            L.o_rescor = off; off += 2 * L.n;
         }
     }
     __syncthreads();
     for (int l = 0; l < nl; ++l) {
-        const long n = (long)S[l].g.nx * S[l].g.ny;
-        for (long s = threadIdx.x; s < n; s += blockDim.x) {
-            S[l].acf[s] = A.L[l].acf[s];
-            S[l].c0i[s] = A.L[l].c0i[s];
-            if (l == 0) { S[0].res[s] = A.L[0].res[s]; S[0].res[n + s] = A.L[0].res[n + s]; }
-            else { S[l].res[s] = 0.; S[l].res[n + s] = 0.; }      // boundary nodes stay 0
+        const SLevel L = S[l];
+        for (int s = threadIdx.x; s < L.n; s += blockDim.x) {
+            csm[L.o_acf + s] = A.L[l].acf[s];
+            csm[L.o_c0i + s] = A.L[l].c0i[s];
+            csm[L.o_res + s] = l == 0 ? A.L[0].res[s] : 0.;             // boundary nodes stay 0
+            csm[L.o_res + L.n + s] = l == 0 ? A.L[0].res[L.n + s] : 0.;
+            csm[L.o_cor + s] = 0.;    csm[L.o_cor + L.n + s] = 0.;
+            csm[L.o_rescor + s] = 0.; csm[L.o_rescor + L.n + s] = 0.;
         }
     }
     __syncthreads();
+#pragma unroll 1
     for (int l = 0; l < nl - 1; ++l) {
-        const CoarseLevel &L = S[l];
-        const long n = (long)L.g.nx * L.g.ny;
-        c_zero(L.cor, 2 * n);
-        c_zero(L.rescor, 2 * n);
-        c_gsrb(L, L.cor, L.res, 4);
-        c_residual(L, L.rescor, L.cor, L.res);
-        c_restrict(S[l + 1].g, S[l + 1].res, L.g, L.rescor, 2);
+        const SLevel L = S[l];
+        const SCell c = s_cell(L, csm, cc);
+        s_sweeps_from_zero(L, c, csm, 4);
+        s_residual(L, c, csm, cc);
+        s_restrict(S[l + 1], L, csm, cc);
     }
     {
-        const CoarseLevel &L = S[nl - 1];
-        c_zero(L.cor, 2 * (long)L.g.nx * L.g.ny);
-        c_gsrb(L, L.cor, L.res, A.nsweeps_bottom);
+        const SLevel L = S[nl - 1];
+        const SCell c = s_cell(L, csm, cc);
+        s_sweeps_from_zero(L, c, csm, A.nsweeps_bottom);
     }
+#pragma unroll 1
     for (int l = nl - 2; l >= 0; --l) {
-        c_interp_add(S[l], S[l].cor, S[l + 1], S[l + 1].cor);
-        c_gsrb(S[l], S[l].cor, S[l].res, 4);
+        const SLevel L = S[l];
+        const SCell c = s_cell(L, csm, cc);
+        s_interp_add(L, c, S[l + 1], csm, cc);
+        s_sweeps(L, c, csm, 0, 4);
     }
     {
-        const long n = (long)S[0].g.nx * S[0].g.ny;
-        for (long s = threadIdx.x; s < 2 * n; s += blockDim.x) A.L[0].cor[s] = S[0].cor[s];
+        const SLevel L = S[0];
+        for (int s = threadIdx.x; s < 2 * L.n; s += blockDim.x) A.L[0].cor[s] = csm[L.o_cor + s];
     }
 }
 
@@ -588,7 +743,13 @@ int hpb_mg_init(hpb_ctx *ctx)
         size_t bytes = 0;
         for (int l = lc; l < nl; ++l) bytes += 8 * sizeof(double) * (size_t)ctx->mg[l].nx * ctx->mg[l].ny;
         ctx->mg_coarse_smem = 0;
-        if (bytes <= 200 * 1024) {
+        bool fits = true;       // one thread per valid point of a level
+        for (int l = lc; l < nl; ++l) {
+            const int vx = ctx->mg_cc ? ctx->mg[l].nx : ctx->mg[l].nx - 2;
+            const int vy = ctx->mg_cc ? ctx->mg[l].ny : ctx->mg[l].ny - 2;
+            if (vx > 32 || vy > 32) fits = false;
+        }
+        if (fits && bytes <= 200 * 1024) {
             HPB_CUDA_CHECK(cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 200 * 1024));
             ctx->mg_coarse_smem = (int)bytes;
