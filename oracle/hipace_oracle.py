@@ -8,12 +8,16 @@ Parity status: PINNED.  tests/test_oracle_golden.py checks the checksums this or
 against the reference's own golden files
   tests/checksum/benchmarks_json/linear_wake.normalized.1Rank.json   (rtol 1e-9)
   tests/checksum/benchmarks_json/blowout_wake_explicit.2Rank.json    (rtol 1e-9)
+  tests/checksum/benchmarks_json/beam_evolution.1Rank.json           (rtol 1e-9; 20 time steps with
+      dt = 3: pins the beam push, the external fields and the multi-step beam hand-off)
 (copies of the numbers are committed under tests/golden/ with the script that extracted them).
 
 Each function cites the reference file:line (relative to /root/reference/src) it restates.
 Scope: level 0, explicit Bx/By solver, depos_order_xy = 2,
 depos_derivative_type = 2, Dirichlet field boundary, no laser, no ionization, no MR,
-fixed_ppc beams, u_std = 0 plasma (no RNG anywhere).
+fixed_ppc beams, u_std = 0 plasma (no RNG anywhere).  Beam slippage between slices
+(particles/sorting/SliceSort.cpp) is restated but no golden of the reference exercises it with a
+deterministic beam: that one function is "parity unpinned" (property-tested only).
 
 Array convention: every slice component is a 2-D array a[j + g, i + g] (x fastest) over the
 grown box [-g, n-1+g]^2, g = 2 guard cells (fields/Fields.cpp:63-64).
@@ -261,6 +265,8 @@ class Beam:
     u_mean: tuple = (0., 0., 0.)
     min_density: float = 0.
     n_subcycles: int = 10
+    do_z_push: bool = True
+    external_fields: object = None   # callable(x, y, z, t) -> (Ex, Ey, Ez, Bx, By, Bz) or None
     slices: dict = field(default_factory=dict)   # islice -> dict of arrays
     next_id: int = 1
 
@@ -330,6 +336,9 @@ def beam_deposit(bs: dict, beam: Beam, geom: Geometry, pc: PhysConst, normalized
     """DepositCurrentSlice, particles/deposition/BeamDepositCurrent.cpp:21-195 (lev 0)."""
     if bs is None or bs['x'].size == 0:
         return
+    if bs.get('np', bs['x'].size) != bs['x'].size:      # getNumParticles excludes slipped (:100)
+        n = bs['np']
+        bs = {k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in bs.items()}
     invvol = 1.0 if normalized else 1.0 / (geom.dx * geom.dy * geom.dz)     # :72-82
     x_off, y_off = geom.pos_offset(0), geom.pos_offset(1)
     clightsq = 1.0 / (pc.c * pc.c)
@@ -872,6 +881,111 @@ def advance_plasma_particles(pl: Plasma, F, geom: Geometry, pc: PhysConst, bc_ki
         pl.ux[sel], pl.uy[sel], pl.psi[sel] = ux, uy, psi
 
 
+def advance_beam_slice(bs: dict, beam: Beam, F, geom: Geometry, pc: PhysConst, islice: int,
+                       dt_step: float, time: float, bc_kind: str, bc_lo, bc_hi):
+    """AdvanceBeamParticlesSlice, particles/pusher/BeamParticleAdvance.cpp:19-336 (lev 0, no
+    radiation reaction, no spin).  Pushes every particle of the slice INCLUDING the slipped ones
+    (:127), each from its own sub-cycle counter bs['nsub'] (:145, :333)."""
+    if bs is None or bs['x'].size == 0:
+        return
+    n_sub = beam.n_subcycles
+    dt = dt_step / n_sub                                                          # :32
+    clight, inv_clight = pc.c, 1.0 / pc.c
+    inv_c2 = 1.0 / (pc.c * pc.c)
+    cmr = beam.charge / beam.mass                                                 # :99
+    min_z = geom.lo[2] + islice * geom.dz                                         # :100
+    xp, yp, zp = bs['x'].copy(), bs['y'].copy(), bs['z'].copy()
+    ux, uy, uz = bs['ux'].copy(), bs['uy'].copy(), bs['uz'].copy()
+    nsub = bs['nsub'].copy()
+    alive = bs['valid'].copy()            # particles that still write back at the end
+    for it in range(n_sub):
+        act = alive & (nsub == it) & ~(zp < min_z)                                # :147-152
+        if not act.any():
+            continue
+        a = np.nonzero(act)[0]
+        x, y, z = xp[a], yp[a], zp[a]
+        vx, vy, vz = ux[a], uy[a], uz[a]
+        gammap_inv = 1.0 / np.sqrt(1.0 + (vx * vx + vy * vy + vz * vz) * inv_c2)  # :154-155
+        x = x + dt * 0.5 * vx * gammap_inv                                        # :159-160
+        y = y + dt * 0.5 * vy * gammap_inv
+        inv = enforce_bc(x, y, vx, vy, bc_lo, bc_hi, bc_kind)                     # :162
+        if inv.any():
+            dead = a[inv]
+            bs['w'][dead] = 0.0
+            bs['valid'][dead] = False
+            alive[dead] = False
+            k = ~inv
+            a, x, y, z, vx, vy, vz, gammap_inv = a[k], x[k], y[k], z[k], vx[k], vy[k], vz[k], gammap_inv[k]
+        ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp = gather_fields(x, y, F, geom)         # :192-194
+        if beam.external_fields is not None:                                      # ExternalFields.H:29-58
+            Ex, Ey, Ez_, Bx_, By_, Bz_ = beam.external_fields(x, y, z, time)
+            ExmByp = ExmByp + (Ex - clight * By_)
+            EypBxp = EypBxp + (Ey + clight * Bx_)
+            Ezp = Ezp + Ez_
+            Bxp = Bxp + Bx_
+            Byp = Byp + By_
+            Bzp = Bzp + Bz_
+        ux_next = vx + dt * cmr * (ExmByp + (clight - vz * gammap_inv) * Byp + vy * gammap_inv * Bzp)
+        uy_next = vy + dt * cmr * (EypBxp + (vz * gammap_inv - clight) * Bxp - vx * gammap_inv * Bzp)
+        ux_i = (ux_next + vx) * 0.5                                               # :208-211
+        uy_i = (uy_next + vy) * 0.5
+        uz_i = vz + dt * 0.5 * cmr * Ezp
+        gi_inv = 1.0 / np.sqrt(1.0 + (ux_i * ux_i + uy_i * uy_i + uz_i * uz_i) * inv_c2)
+        uz_next = vz + dt * cmr * (Ezp + (ux_i * Byp - uy_i * Bxp) * gi_inv)      # :240-242
+        gn_inv = 1.0 / np.sqrt(1.0 + (ux_next * ux_next + uy_next * uy_next + uz_next * uz_next) * inv_c2)
+        x = x + dt * 0.5 * ux_next * gn_inv                                       # :312-314
+        y = y + dt * 0.5 * uy_next * gn_inv
+        if beam.do_z_push:
+            z = z + dt * (uz_next * gn_inv - clight)
+        xp[a], yp[a], zp[a] = x, y, z
+        ux[a], uy[a], uz[a] = ux_next, uy_next, uz_next
+        nsub[a] += 1
+    a = np.nonzero(alive)[0]
+    x, y, vx, vy = xp[a], yp[a], ux[a], uy[a]
+    inv = enforce_bc(x, y, vx, vy, bc_lo, bc_hi, bc_kind)                         # :319
+    if inv.any():
+        dead = a[inv]
+        bs['w'][dead] = 0.0
+        bs['valid'][dead] = False
+        k = ~inv
+        a, x, y, vx, vy = a[k], x[k], y[k], vx[k], vy[k]
+    bs['x'][a], bs['y'][a], bs['z'][a] = x, y, zp[a]
+    bs['ux'][a], bs['uy'][a], bs['uz'][a] = vx, vy, uz[a]
+    bs['nsub'][a] = nsub[a]
+
+
+_BEAM_KEYS = ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id', 'valid', 'nsub')
+
+
+def empty_beam_slice():
+    bs = {k: np.zeros(0) for k in ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz')}
+    bs['id'] = np.zeros(0, dtype=np.int64)
+    bs['valid'] = np.zeros(0, dtype=bool)
+    bs['nsub'] = np.zeros(0, dtype=np.int64)
+    bs['np'] = 0
+    return bs
+
+
+def shift_slipped_particles(bs_this: dict, bs_next: dict | None, geom: Geometry, islice: int):
+    """shiftSlippedParticles, particles/sorting/SliceSort.cpp:13-67: drop invalid particles,
+    keep those with z >= min_z (stable order), append the others to the Next slice as 'slipped'
+    (they are pushed there with their remaining sub-cycles but not deposited, see
+    BeamParticleContainer.H:175-181).  PARITY UNPINNED (no deterministic golden slips)."""
+    if bs_this is None or bs_this['x'].size == 0:
+        return
+    min_z = geom.lo[2] + islice * geom.dz
+    v = bs_this['valid']
+    stay = v & (bs_this['z'] >= min_z)
+    slip = v & ~stay
+    if bs_next is not None and slip.any():
+        assert bs_next['x'].size == bs_next['np']          # SliceSort.cpp:45
+        for k in _BEAM_KEYS:
+            bs_next[k] = np.concatenate([bs_next[k], bs_this[k][slip]])
+    for k in _BEAM_KEYS:
+        bs_this[k] = bs_this[k][stay]
+    bs_this['np'] = int(stay.sum())
+
+
 # --------------------------------------------------------------------------------------------
 # Initialisation
 # --------------------------------------------------------------------------------------------
@@ -959,7 +1073,8 @@ def init_beam_slice(beam: Beam, islice: int, geom: Geometry, pc: PhysConst, norm
               ux=np.full(n, beam.u_mean[0] * pc.c), uy=np.full(n, beam.u_mean[1] * pc.c),
               uz=np.full(n, beam.u_mean[2] * pc.c),
               id=np.arange(beam.next_id, beam.next_id + n, dtype=np.int64),
-              valid=np.ones(n, dtype=bool))
+              valid=np.ones(n, dtype=bool), nsub=np.zeros(n, dtype=np.int64))
+    bs['np'] = n                 # particles without the slipped ones (BeamParticleContainer.H:175)
     beam.next_id += n
     return bs
 
@@ -1010,6 +1125,10 @@ class Simulation:
         self.mg = MultiGrid1(g.dx, g.dy, g.nx, g.ny)
         self.checksums = {}
         self.n_plasma_pushed = 0
+        self.n_beam_pushed = 0
+        self.step = 0
+        self.time = 0.0
+        self.beam_diag = {}
         self.mg_cycles = []
         self.n_qsa_violation = 0
         self.slice_hook = None        # callable(sim, islice, stage) for tests
@@ -1073,18 +1192,56 @@ class Simulation:
             position_std=tuple(_get(d, nm + '.position_std', [0., 0., 0.], n=3)),
             u_mean=tuple(_get(d, nm + '.u_mean', [0., 0., 0.], n=3)),
             min_density=abs(_get(d, nm + '.min_density', 0.)),
-            n_subcycles=_get(d, nm + '.n_subcycles', 10, typ=int))
+            n_subcycles=_get(d, nm + '.n_subcycles', 10, typ=int),
+            do_z_push=bool(_get(d, nm + '.do_z_push', 1, typ=int)),
+            external_fields=self._read_external_fields(nm))
+
+    def _read_external_fields(self, nm):
+        """external_E(x,y,z,t) / external_B(x,y,z,t), three expressions each,
+        particles/beam/BeamParticleContainer.cpp:71-88 (beam name first, then 'beams')"""
+        d = self.deck
+        exprs = []
+        used = False
+        for key in ('external_E(x,y,z,t)', 'external_B(x,y,z,t)'):
+            v = d.get(nm + '.' + key, d.get('beams.' + key))
+            if v is None:
+                exprs += ['0.', '0.', '0.']
+            else:
+                assert len(v) == 3, key + ' needs 3 expressions'
+                exprs += list(v)
+                used = True
+        if not used:
+            return None
+        env = dict(_CONST_SI)
+        env.update({f: getattr(np, f) for f in ('sqrt', 'exp', 'sin', 'cos', 'log', 'tanh')})
+        for k, v in d.items():
+            if k.startswith('my_constants.'):
+                env[k.split('.', 1)[1]] = _eval(v[0], {kk: vv for kk, vv in d.items() if kk != k})
+        codes = [compile(e.replace('^', '**'), '<external field>', 'eval') for e in exprs]
+
+        def fields(x, y, z, t, _codes=codes, _env=env):
+            loc = dict(_env, x=x, y=y, z=z, t=t)
+            return tuple(np.broadcast_to(np.asarray(eval(c, {'__builtins__': {}}, loc), dtype=float),
+                                         x.shape) for c in _codes)
+        return fields
 
     # -- slice loop ------------------------------------------------------------------------
     def T(self, name):
         return self.F[('This', name)]
 
-    def begin_step(self):
+    def begin_step(self, step: int = 0):
         """Hipace::Evolve up to the slice loop, Hipace.cpp:401-475"""
+        self.step = step
+        self.time = step * self.dt                                # :410, :434 (fixed dt)
+        self.beam_diag = {b.name: [] for b in self.beams}
         for a in self.F.values():
             a[...] = 0.0                                          # ResetAllQuantities :730-742
+        for b in self.beams:                                      # MultiBuffer: nsubcycles is not
+            for bs in b.slices.values():                          # communicated (BeamParticleContainer.H:35-37)
+                bs['nsub'][...] = 0
         for pl in self.plasmas:
-            init_plasma(pl, self.geom, self.pc, self.normalized, self.bc_lo, self.bc_hi)
+            init_plasma(pl, self.geom, self.pc, self.normalized, self.bc_lo, self.bc_hi,
+                        c_t=self.pc.c * self.time)
         for pl in self.plasmas:                                   # :468-470, MultiPlasma.cpp:106-118
             if pl.neutralize_background:
                 deposit_current(pl, self.F, self.geom, self.pc, self.normalized,
@@ -1147,10 +1304,20 @@ class Simulation:
         if self.slice_hook:
             self.slice_hook(self, islice, 'fields')
         self._accumulate_checksums(islice)                                        # :691
+        for b in self.beams:                                                      # :682-683 (before the push)
+            bs = self.beam_slice(b, islice)
+            n = bs['np']
+            self.beam_diag.setdefault(b.name, []).append(
+                {k: bs[k][:n].copy() for k in ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id')})
         for pl in self.plasmas:                                                   # :699-701
             self.n_plasma_pushed += pl.x.size
             advance_plasma_particles(pl, F, g, pc, self.bc_kind, self.bc_lo, self.bc_hi)
-        assert self.dt == 0.0, 'oracle scope: beam push only for dt = 0 (identity)'
+        for b in self.beams:                                                      # :707-709
+            bs = self.beam_slice(b, islice)
+            self.n_beam_pushed += bs['np']
+            advance_beam_slice(bs, b, F, g, pc, islice, self.dt, getattr(self, 'time', 0.0),
+                               self.bc_kind, self.bc_lo, self.bc_hi)
+            shift_slipped_particles(bs, self.beam_slice(b, islice - 1), g, islice)
         if self.slice_hook:
             self.slice_hook(self, islice, 'pushed')
         # ShiftSlices, fields/Fields.cpp:588-604
@@ -1169,23 +1336,29 @@ class Simulation:
             if sl == 'This':
                 self.checksums[nm] = self.checksums.get(nm, 0.0) + float(np.abs(a[G:-G, G:-G]).sum())
 
-    def evolve(self, nslices: int | None = None):
-        """Run step 0 (for dt = 0 every later step repeats it, Hipace.cpp:401-507).
-        nslices limits the slice loop (from the head) for bounded tests/benchmarks."""
-        self.checksums = {}
-        self.begin_step()
+    def evolve(self, nslices: int | None = None, step_begin: int = 0, step_end: int = 0):
+        """Run time steps step_begin..step_end (Hipace.cpp:401-507); the checksums returned are
+        those of the last one.  nslices limits the slice loop (from the head) for bounded
+        tests/benchmarks."""
         g = self.geom
         stop = -1 if nslices is None else max(-1, g.nz - 1 - nslices)
-        for isl in range(g.nz - 1, stop, -1):
-            self.solve_one_slice(isl)
+        for step in range(step_begin, step_end + 1):
+            self.checksums = {}
+            self.begin_step(step)
+            for isl in range(g.nz - 1, stop, -1):
+                self.solve_one_slice(isl)
         return self.checksums
 
     def beam_checksums(self):
         out = {}
         for b in self.beams:
-            for isl in range(self.geom.nz):
-                self.beam_slice(b, isl)
-            cat = lambda k: np.concatenate([b.slices[i][k] for i in sorted(b.slices)])
+            diag = self.beam_diag.get(b.name, [])
+            if len(diag) == self.geom.nz:      # state written by the last step's diagnostics
+                cat = lambda k, _d=diag: np.concatenate([t[k] for t in _d])
+            else:
+                for isl in range(self.geom.nz):
+                    self.beam_slice(b, isl)
+                cat = lambda k: np.concatenate([b.slices[i][k][:b.slices[i]['np']] for i in sorted(b.slices)])
             n = cat('x').size
             out[b.name] = dict(
                 charge=abs(b.charge) * n, mass=abs(b.mass) * n, id=int(np.abs(cat('id')).sum()),

@@ -6,6 +6,7 @@ Run in the build container only (needs /root/reference):
 The reference's goldens are the pinned known answers for the oracle:
   tests/checksum/benchmarks_json/linear_wake.normalized.1Rank.json
   tests/checksum/benchmarks_json/blowout_wake_explicit.2Rank.json
+  tests/checksum/benchmarks_json/beam_evolution.1Rank.json
 Their decks + overrides (tests/linear_wake.normalized.1Rank.sh:32-35,
 tests/blowout_wake_explicit.2Rank.sh:32-35) are restated in examples/ of this repo.
 """
@@ -20,6 +21,14 @@ CASES = {
         deck='examples/blowout_wake_normalized.in',
         overrides={'max_step': 1}, rtol_cpu=1e-9, rtol_cuda=1e-9,
         skip=['Sy', 'Sx', 'chi']),
+    # tests/beam_evolution.1Rank.sh:33-44 (hipace.tile_size / output_period / file_prefix dropped)
+    'beam_evolution.1Rank': dict(
+        deck='examples/beam_in_vacuum_normalized.in',
+        overrides={'amr.n_cell': '32 32 10', 'max_step': 20, 'geometry.prob_lo': '-2. -2. -2.',
+                   'geometry.prob_hi': '2. 2. 2.', 'hipace.dt': 3., 'beam.density': 1.e-8,
+                   'beam.radius': 1., 'beam.ppc': '4 4 1',
+                   'beams.external_E(x,y,z,t)': '.5*x .5*y 0.'},
+        rtol_cpu=1e-12, rtol_cuda=2e-6),
 }
 for name, meta in CASES.items():
     gold = json.load(open(os.path.join(REF, name + '.json')))

@@ -19,11 +19,13 @@ def _run(case, repo_root):
     meta = json.load(open(os.path.join(GOLD, case + '.json')))
     deck = open(os.path.join(repo_root, meta['deck'])).read()
     sim = Simulation(deck, meta['overrides'])
-    cs = sim.evolve()
+    # dt = 0 decks: every step repeats step 0, one step suffices; dt != 0: all max_step + 1 steps
+    cs = sim.evolve(step_end=sim.max_step if sim.dt != 0.0 else 0)
     return meta, sim, cs
 
 
-@pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank'])
+@pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank',
+                                  'beam_evolution.1Rank'])
 def test_oracle_matches_reference_golden(case, repo_root):
     meta, sim, cs = _run(case, repo_root)
     gold = meta['checksums']
