@@ -133,6 +133,7 @@ def main():
     ap.add_argument('--nxy', type=int, default=1024)
     ap.add_argument('--nz', type=int, default=1024)
     ap.add_argument('--ppc', type=int, default=2, help='per direction (2 -> ppc 4)')
+    ap.add_argument('--dt', type=float, default=0.0, help='hipace.dt (0: the beam is pushed but does not move)')
     ap.add_argument('--cpu-sample-slices', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -184,74 +185,83 @@ def main():
         torch.cuda.synchronize()
 
     deck, ov = deck_and_overrides(args.nxy, args.nz, args.ppc)
+    if args.dt:
+        ov['hipace.dt'] = args.dt
     sim = hp.Simulation(deck, ov, device=local_rank)
     sim.set_option('checksums', 0)
-    if world > 1:
-        sim.pipeline_init(rank, world, dist)
+    sim.pipeline_init(rank, world, dist)
 
     # ---- device-resident leg ---------------------------------------------------------------
-    # rank r owns time steps r, r+world, ... (Hipace.cpp:401); K steps per rank (weak scaling)
-    def run_steps(first, count):
-        ms = 0.0
-        launches = 0
-        for k in range(count):
-            step = (first + k) * world + rank
-            sim.evolve(step, step)
-            st = sim.stats()
-            ms += st['slice_loop_ms']
-            launches += st['n_kernel_launches']
-        return ms, launches
+    # rank r owns the time steps r, r + world, ... (Hipace.cpp:401); every rank runs `count`
+    # steps (weak scaling).  A run is self-contained: its last step hands nothing on, so the
+    # pipeline is drained when run() returns and the barriers around the timed region are safe.
+    def run_steps(count):
+        st = sim.run(count * world - 1, rank, world)
+        return st['slice_loop_ms'], st['n_kernel_launches'], st
 
-    run_steps(0, W)
+    run_steps(W)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
-    dev_ms, launches = run_steps(W, K)
+    sim.timer_start()
+    loop_ms, launches, st_last = run_steps(K)
+    dev_ms = sim.timer_stop()          # CUDA events on the simulation stream around the K steps
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    st_last = sim.stats()
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device='cuda')
+    tl = torch.tensor([float(launches)], dtype=torch.float64, device='cuda')
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
-    # whole-job time: pipelined ranks overlap, so the job time is the wall time between the
-    # barriers (max over ranks); on one GPU it equals the device time of the slice loops
-    job_ms = wall_ms_max if world > 1 else dev_ms_max
+    launches = int(tl[0])
+    job_ms = dev_ms_max               # whole job = the slowest rank's device time (incl. plasma init)
     total_slices = K * args.nz * world
     value = total_slices / (job_ms * 1e-3)
     n_pushed = st_last['n_plasma_pushed'] + st_last['n_beam_pushed']
-    ns_per_push = (dev_ms / K) * 1e6 / max(n_pushed, 1)
+    ns_per_push = dev_ms * 1e6 / max(n_pushed, 1) / world
 
     # ---- end-to-end leg (host buffers) -----------------------------------------------------
+    # N = 1: every step uploads its input beam from pinned host memory (MultiBuffer::get_data
+    # with host staging) and reads back the pushed beam + the field checksums.
+    # N > 1: the beam of step 0 comes from pinned host memory; later steps receive theirs from
+    # the upstream GPU over NVLink (that IS the public multi-GPU API); every step still reads
+    # back its pushed beam + checksums (the per-step diagnostic of a production run).
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         npb = sim.beam_np()
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
         host = {'real': pin((7, max(npb, 1)), torch.float64), 'idcpu': pin((max(npb, 1),), torch.int64).view(np.uint64),
                 'slot_off': np.zeros(args.nz + 1, dtype=np.int64)}
         sim.get_beam(host)
         sim.set_option('checksums', 1)
-        h2d = 7 * 8 * npb + 8 * npb
-        d2h = h2d + 8 * len(sim.checksums())
+        beam_bytes = 7 * 8 * npb + 8 * npb
+        ncs = len(sim.checksums())
+        from hipace_b200 import pipeline as pl
 
-        def e2e_step(step):
-            sim.set_beam(host)                 # H2D: this step's beam from pinned host memory
-            cs = sim.evolve(step, step)        # plasma init + nz slices; D2H of the checksums
-            sim.get_beam(host)                 # D2H: the beam after the step
-            return cs
-        e2e_step(0)
-        torch.cuda.synchronize()
+        def e2e_run(count):
+            max_step = count * world - 1
+            sim.set_option('max_step', max_step)
+            for step in pl.owned_steps(rank, world, max_step):
+                if world == 1 or step == 0:
+                    sim.set_beam(host)             # H2D: this step's beam from pinned host memory
+                sim.evolve(step, step)             # plasma init + nz slices; D2H of the checksums
+                sim.get_beam(host)                 # D2H: the beam after the step
+        e2e_run(1)
+        barrier()
         t0 = time.perf_counter()
-        for k in range(K):
-            e2e_step(k)
-        torch.cuda.synchronize()
+        e2e_run(K)
+        barrier()
         e2e_s = time.perf_counter() - t0
-        e2e = {'value': K * args.nz / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3 * e2e_s / K,
-               'api': 'hipace_b200.Simulation.set_beam/evolve/get_beam -> hpb_sim_* C-ABI'}
+        nsteps = K * world
+        h2d = beam_bytes if world == 1 else beam_bytes / nsteps
+        e2e = {'value': nsteps * args.nz / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': beam_bytes + 8 * ncs, 'ms_per_step': 1e3 * e2e_s / K,
+               'api': 'hipace_b200.Simulation.set_beam/evolve/get_beam -> hpb_sim_* C-ABI'
+                      + ('' if world == 1 else '; steps > 0 receive their beam from the upstream GPU (NCCL p2p)')}
         sim.set_option('checksums', 0)
 
     # ---- per-stage profile + roofline of the dominant kernel (extra, untimed pass) -----------
@@ -266,6 +276,7 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
         sim.set_option('profile', 1)
+        sim.set_option('max_step', 0)      # a lone step: nothing is handed downstream
         sim.evolve(0, 0)
         sp = sim.stats()
         sim.set_option('profile', 0)
@@ -300,11 +311,13 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': job_ms / K, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
-                'ns_per_particle_step': ns_per_push, 'ms_per_slice': job_ms / (K * args.nz) * world,
+                'ns_per_particle_step': ns_per_push, 'ms_per_slice': job_ms / (K * args.nz),
+                'slice_loop_ms_per_step_rank0': loop_ms / K,
                 'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
                 'stage_ms_per_slice': stages, 'cpu_baseline': cpu_baseline,
                 'wall_ms_per_step': wall_ms_max / K}
         print(json.dumps(line))
+    barrier()
     sim.close()
     if dist is not None:
         dist.destroy_process_group()

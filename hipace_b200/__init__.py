@@ -11,6 +11,9 @@ ctypes binding with the names of the reference seams it replaces:
   Context.advance_plasma_particles   AdvancePlasmaParticles             PlasmaParticleAdvance.cpp:29
   Context.poisson_solve(...)         FFTPoissonSolver::SolvePoissonEquation
   Context.mg_solve1(...)             hpmg::MultiGrid::solve1            HpMultiGrid.cpp:1169
+  Context.advance_beam_particles     AdvanceBeamParticlesSlice          BeamParticleAdvance.cpp:19
+  Context.beam_shift_slipped         shiftSlippedParticles              SliceSort.cpp:13
+  Simulation.pipeline_init(...)      MultiBuffer::initialize            MultiBuffer.cpp (NCCL p2p)
 
 There is NO CPU fallback: importing works without a GPU (so the symbol table can be checked), but
 every compute entry point needs a CUDA device and raises HpbError otherwise, and a missing
@@ -49,8 +52,12 @@ EXPORTS = (
     'hpb_sim_plasma_np', 'hpb_sim_get_plasma_real', 'hpb_sim_get_plasma_valid',
     'hpb_sim_checksum_count', 'hpb_sim_checksum_name', 'hpb_sim_get_checksums',
     'hpb_sim_get_beam_checksums', 'hpb_sim_get_stats', 'hpb_sim_set_option', 'hpb_sim_beam_np',
-    'hpb_sim_get_beam', 'hpb_sim_set_beam',
+    'hpb_sim_get_beam', 'hpb_sim_set_beam', 'hpb_extfields_create', 'hpb_extfields_destroy',
+    'hpb_advance_beam_particles', 'hpb_beam_shift_slipped', 'hpb_nccl_unique_id',
+    'hpb_sim_pipeline_init', 'hpb_sim_pipeline_message_bytes', 'hpb_sim_beam_slice_capacity',
+    'hpb_sim_timer_start', 'hpb_sim_timer_stop', 'hpb_sim_get_beam_packet',
 )
+NCCL_ID_BYTES = 128
 
 
 class HpbError(RuntimeError):
@@ -69,7 +76,7 @@ class hpb_plasma(C.Structure):
 
 class hpb_beam_slice(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'idcpu')] + \
-               [('np', C.c_long)]
+               [('np', C.c_long), ('d_np', C.c_void_p)]
 
 
 class hpb_geom(C.Structure):
@@ -149,6 +156,25 @@ def lib():
     L.hpb_sim_set_beam.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     L.hpb_sim_get_stats.argtypes = [C.c_void_p, C.POINTER(hpb_sim_stats)]
     L.hpb_sim_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.hpb_extfields_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_char_p)]
+    L.hpb_extfields_destroy.argtypes = [C.c_void_p]
+    L.hpb_extfields_destroy.restype = None
+    L.hpb_advance_beam_particles.argtypes = [
+        C.c_void_p, hpb_beam_slice, C.c_void_p, hpb_slice, C.c_double, C.c_double, C.c_int,
+        C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, DP, DP, IP, C.c_void_p, C.c_void_p,
+        C.c_void_p]
+    L.hpb_beam_shift_slipped.argtypes = [
+        C.c_void_p, hpb_beam_slice, C.c_void_p, C.c_double, C.c_void_p, hpb_beam_slice, C.c_void_p,
+        hpb_beam_slice, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hpb_sim_timer_start.argtypes = [C.c_void_p]
+    L.hpb_sim_timer_stop.argtypes = [C.c_void_p, DP]
+    L.hpb_sim_get_beam_packet.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.hpb_nccl_unique_id.argtypes = [C.c_char_p]
+    L.hpb_sim_pipeline_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+    L.hpb_sim_pipeline_message_bytes.argtypes = [C.c_void_p]
+    L.hpb_sim_pipeline_message_bytes.restype = C.c_long
+    L.hpb_sim_beam_slice_capacity.argtypes = [C.c_void_p, C.c_int]
+    L.hpb_sim_beam_slice_capacity.restype = C.c_long
     _lib = L
     return L
 
@@ -272,6 +298,55 @@ class Simulation:
         _check(self._L.hpb_sim_set_beam(self._h, beam, ptrs, host['idcpu'].ctypes.data,
                                         host['slot_off'].ctypes.data), 'hpb_sim_set_beam')
 
+    def beam_slice_capacity(self, beam: int = 0) -> int:
+        return self._L.hpb_sim_beam_slice_capacity(self._h, beam)
+
+    # -- time-step pipeline (MultiBuffer's role, NCCL point-to-point) ---------------------------
+    def pipeline_init(self, rank: int, world: int, dist=None):
+        """Join the ring of `world` GPUs: this rank owns the time steps rank, rank + world, ...
+        The ncclUniqueId of every edge r -> r+1 is created by rank r and exchanged through
+        torch.distributed (any backend; `dist` is the initialised torch.distributed module)."""
+        from . import pipeline as pl
+        self.rank, self.world = rank, world
+        if world == 1:
+            _check(self._L.hpb_sim_pipeline_init(self._h, 0, 1, None, None), 'hpb_sim_pipeline_init')
+            return
+        my_id = C.create_string_buffer(NCCL_ID_BYTES)
+        _check(self._L.hpb_nccl_unique_id(my_id), 'hpb_nccl_unique_id')
+        ids = pl.exchange_edge_ids(dist, rank, world, my_id.raw)
+        _check(self._L.hpb_sim_pipeline_init(self._h, rank, world, ids[pl.upstream(rank, world)],
+                                             ids[rank]), 'hpb_sim_pipeline_init')
+
+    def timer_start(self):
+        _check(self._L.hpb_sim_timer_start(self._h), 'hpb_sim_timer_start')
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.)
+        _check(self._L.hpb_sim_timer_stop(self._h, C.byref(ms)), 'hpb_sim_timer_stop')
+        return ms.value
+
+    def beam_packet(self, slot: int, beam: int = 0) -> np.ndarray:
+        """wire message of one slice packet of the current beam ring (uint8)"""
+        n = 64 + 64 * self.beam_slice_capacity(beam)
+        out = np.empty(n, dtype=np.uint8)
+        _check(self._L.hpb_sim_get_beam_packet(self._h, beam, slot, out.ctypes.data), 'hpb_sim_get_beam_packet')
+        return out
+
+    def pipeline_message_bytes(self) -> int:
+        return self._L.hpb_sim_pipeline_message_bytes(self._h)
+
+    def run(self, max_step: int, rank: int = 0, world: int = 1):
+        """Hipace::Evolve on this rank: the time steps rank, rank + world, ... <= max_step
+        (Hipace.cpp:401).  Returns the summed stats of the owned steps."""
+        from . import pipeline as pl
+        self.set_option('max_step', max_step)
+        tot = {}
+        for step in pl.owned_steps(rank, world, max_step):
+            self.evolve(step, step)
+            for k, v in self.stats().items():
+                tot[k] = tot.get(k, 0) + v
+        return tot
+
     def stats(self) -> dict:
         st = hpb_sim_stats()
         _check(self._L.hpb_sim_get_stats(self._h, C.byref(st)), 'hpb_sim_get_stats')
@@ -343,6 +418,45 @@ class Context:
         _check(self._L.hpb_advance_plasma_particles(self._h, pl, sl, charge, mass, n_subcycles,
                                                     int(temp_slice), BC[bc], lo, hi, comps),
                'hpb_advance_plasma_particles')
+
+    @staticmethod
+    def beam_view(reals, idcpu, counts=None, cap=None) -> hpb_beam_slice:
+        """reals: float64 CUDA tensor [7, cap] (x y z w ux uy uz); idcpu: int64 tensor [cap];
+        counts: int64 CUDA tensor [2] = (np, np incl. slipped) or None"""
+        b = hpb_beam_slice()
+        for k, nm in enumerate(('x', 'y', 'z', 'w', 'ux', 'uy', 'uz')):
+            setattr(b, nm, reals[k].data_ptr())
+        b.idcpu = idcpu.data_ptr()
+        b.np = reals.shape[1] if cap is None else cap
+        b.d_np = counts.data_ptr() if counts is not None else None
+        return b
+
+    def extfields(self, exprs):
+        """six expressions Ex Ey Ez Bx By Bz of (x, y, z, t) -> handle"""
+        arr = (C.c_char_p * 6)(*[e.encode() for e in exprs])
+        h = C.c_void_p()
+        _check(self._L.hpb_extfields_create(C.byref(h), arr), 'hpb_extfields_create')
+        return h
+
+    def advance_beam_particles(self, bm, nsub, sl, charge, mass, comps, *, n_subcycles=10, dt=0.,
+                               time=0., min_z=-1e300, do_z_push=True, bc='Periodic',
+                               bc_lo=(0., 0.), bc_hi=(0., 0.), ext=None, class_counts=None,
+                               checksum=None):
+        lo = (C.c_double * 2)(*bc_lo)
+        hi = (C.c_double * 2)(*bc_hi)
+        _check(self._L.hpb_advance_beam_particles(
+            self._h, bm, nsub.data_ptr(), sl, charge, mass, n_subcycles, dt, time, min_z,
+            int(do_z_push), BC[bc], lo, hi, comps, ext,
+            class_counts.data_ptr() if class_counts is not None else None,
+            checksum.data_ptr() if checksum is not None else None), 'hpb_advance_beam_particles')
+
+    def beam_shift_slipped(self, bm, nsub, min_z, class_counts, stay, stay_counts, nxt, next_counts,
+                           next_nsub, overflow):
+        _check(self._L.hpb_beam_shift_slipped(
+            self._h, bm, nsub.data_ptr(), min_z, class_counts.data_ptr(), stay,
+            stay_counts.data_ptr(), nxt, next_counts.data_ptr() if next_counts is not None else None,
+            next_nsub.data_ptr() if next_nsub is not None else None, overflow.data_ptr()),
+            'hpb_beam_shift_slipped')
 
     def poisson_solve(self, rhs, sl, c_lhs):
         """rhs: float64 CUDA tensor [nbatch, ny, nx]; c_lhs: destination components"""

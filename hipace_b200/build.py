@@ -28,6 +28,7 @@ SOURCES = {
     'poisson.cu': [],
     'mg.cu': ['-fmad=false'],
     'sim.cu': [],
+    'beam.cu': [],
     'pipeline.cu': [],
 }
 
@@ -69,7 +70,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = {s: f for s, f in SOURCES.items() if os.path.exists(os.path.join(CSRC, s))}
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda kv: _compile(*kv), srcs.items()))
-    cmd = [_nvcc()] + ARCH + ['-shared', '--cudart', 'shared', '-o', LIB] + objs
+    cmd = [_nvcc()] + ARCH + ['-shared', '--cudart', 'shared', '-o', LIB] + objs + ['-ldl']
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError('link failed:\n' + p.stdout + p.stderr)

@@ -100,6 +100,61 @@ __device__ __forceinline__ int dshape2_nodal(double xmid, double s[4], double ds
     return (int)xfloor - 1;
 }
 
+// doGatherShapeN<2> (src/particles/particles_utils/FieldGather.H:45-96): the six field values at
+// (xp, yp) from Psi, Ez, Bx, By, Bz with nodal-derivative shapes over 4 x 4 cells
+struct GatheredFields { double ExmBy, EypBx, Ez, Bx, By, Bz; };
+__device__ __forceinline__ GatheredFields gather_order2(const SliceView &a, int c_psi, int c_ez,
+                                                        int c_bx, int c_by, int c_bz, double x_off,
+                                                        double y_off, double dx_inv, double dy_inv,
+                                                        double xp, double yp)
+{
+    double sx[4], dsx[4], sy[4], dsy[4];
+    const int i0 = dshape2_nodal((xp - x_off) * dx_inv, sx, dsx);
+    const int j0 = dshape2_nodal((yp - y_off) * dy_inv, sy, dsy);
+    const double *Psi = a.comp(c_psi), *Ez = a.comp(c_ez), *Bx = a.comp(c_bx);
+    const double *By = a.comp(c_by), *Bz = a.comp(c_bz);
+    GatheredFields f = {0., 0., 0., 0., 0., 0.};
+#pragma unroll
+    for (int iy = 0; iy < 4; ++iy) {
+#pragma unroll
+        for (int ix = 0; ix < 4; ++ix) {
+            const long o = a.idx(i0 + ix, j0 + iy);
+            const double psi_v = Psi[o];
+            f.ExmBy += (dsx[ix] * sy[iy]) * psi_v * dx_inv;
+            f.EypBx += (sx[ix] * dsy[iy]) * psi_v * dy_inv;
+            const double w = sx[ix] * sy[iy];
+            f.Ez += w * Ez[o];
+            f.Bx += w * Bx[o];
+            f.By += w * By[o];
+            f.Bz += w * Bz[o];
+        }
+    }
+    return f;
+}
+
+// EnforceBC, src/particles/pusher/GetAndSetPosition.H:56-98.  Returns true if the particle
+// became invalid (absorbing boundary).
+__device__ __forceinline__ bool enforce_particle_bc(double &x, double &y, double &ux, double &uy,
+                                                    int bc, double lox, double loy, double hix,
+                                                    double hiy)
+{
+    if (x < lox || y < loy || x > hix || y > hiy) {
+        const double len_x = hix - lox, len_y = hiy - loy;
+        if (bc == HPB_BC_REFLECTING) {
+            x = fmod(x - lox, 2 * len_x); if (x < 0) x += 2 * len_x; x += lox;
+            if (x > hix) { x = 2 * hix - x; ux = -ux; }
+            y = fmod(y - loy, 2 * len_y); if (y < 0) y += 2 * len_y; y += loy;
+            if (y > hiy) { y = 2 * hiy - y; uy = -uy; }
+        } else if (bc == HPB_BC_PERIODIC) {
+            x = fmod(x - lox, len_x); if (x < 0) x += len_x; x += lox;
+            y = fmod(y - loy, len_y); if (y < 0) y += len_y; y += loy;
+        } else {
+            return true;
+        }
+    }
+    return false;
+}
+
 // fp64 reduction without return value (RED.E.ADD.F64 on sm_100a)
 __device__ __forceinline__ void red_add(double *addr, double v) { atomicAdd(addr, v); }
 

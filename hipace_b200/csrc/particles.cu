@@ -151,14 +151,15 @@ k_deposit_current(PlasmaPtrs pl, SliceView a, int c_jx, int c_jy, int c_rho, int
 // -------------------------------------------------------------------------------------------
 // beam DepositCurrentSlice
 // -------------------------------------------------------------------------------------------
-struct BeamPtrs { double *x, *y, *z, *w, *ux, *uy, *uz; uint64_t *idcpu; long np; };
+struct BeamPtrs { double *x, *y, *z, *w, *ux, *uy, *uz; uint64_t *idcpu; long np; const int64_t *d_np; };
 
 __global__ void __launch_bounds__(kThreads)
 k_beam_deposit(BeamPtrs b, SliceView a, int c_jx, int c_jy, int c_jz, double x_off, double y_off,
                double dx_inv, double dy_inv, double clightsq, double q_invvol)
 {
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= b.np) return;
+    // getNumParticles: the slipped particles behind d_np[0] are not deposited (BeamDepositCurrent.cpp:100)
+    if (ip >= b.np || (b.d_np && ip >= (long)b.d_np[0])) return;
     if (!hpb_is_valid(b.idcpu[ip])) return;
     const double ux = b.ux[ip], uy = b.uy[ip], uz = b.uz[ip];
     const double gaminv = 1.0 / sqrt(1.0 + ux * ux * clightsq + uy * uy * clightsq + uz * uz * clightsq);
@@ -577,7 +578,7 @@ extern "C" int hpb_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, d
     const hpb_geom &g = ctx->g;
     // BeamDepositCurrent.cpp:72-82: invvol = 1 in normalised units at lev 0
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
-    BeamPtrs b{bm.x, bm.y, bm.z, bm.w, bm.ux, bm.uy, bm.uz, bm.idcpu, bm.np};
+    BeamPtrs b{bm.x, bm.y, bm.z, bm.w, bm.ux, bm.uy, bm.uz, bm.idcpu, bm.np, bm.d_np};
     k_beam_deposit<<<nblocks(bm.np), kThreads, 0, ctx->stream>>>(
         b, make_view(sl), c_jx, c_jy, c_jz, g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy,
         1.0 / (g.c * g.c), charge * invvol);

@@ -8,54 +8,23 @@
 // slices at once (the reference creates them slice by slice on the head rank at step 0,
 // src/particles/beam/BeamParticleContainerInit.cpp:198-346 -- same particles, same order, same
 // ids because our storage order is the head-first processing order).
-#include "common.cuh"
-#include "deck.hpp"
+#include "sim.hpp"
 #include <cub/cub.cuh>
-#include <float.h>
-#include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <memory>
-#include <string>
-#include <vector>
+
+int hpb_advance_beam_impl(hpb_ctx *ctx, hpb_beam_slice bm, int *d_nsub, hpb_slice sl, double charge,
+                          double mass, int n_subcycles, double dt, double time, double min_z,
+                          int do_z_push, int particle_bc, const double bc_lo[2], const double bc_hi[2],
+                          const int *comps, const hpb_extfields *ext, int *d_class_counts,
+                          double *d_checksum, unsigned long long *d_n_pushed);   // beam.cu
 
 using hpb::Deck;
 using hpb::RpnInstr;
 
 namespace {
-
-struct DevRpn { int n; RpnInstr code[hpb::kMaxRpn]; };
-
-__device__ double rpn_eval(const DevRpn &p, double x, double y, double z)
-{
-    double st[24];
-    int sp = 0;
-    for (int k = 0; k < p.n; ++k) {
-        const RpnInstr c = p.code[k];
-        switch (c.op) {
-        case hpb::OP_CONST: st[sp++] = c.val; break;
-        case hpb::OP_VAR: st[sp++] = c.var == 0 ? x : (c.var == 1 ? y : z); break;
-        case hpb::OP_ADD: --sp; st[sp - 1] += st[sp]; break;
-        case hpb::OP_SUB: --sp; st[sp - 1] -= st[sp]; break;
-        case hpb::OP_MUL: --sp; st[sp - 1] *= st[sp]; break;
-        case hpb::OP_DIV: --sp; st[sp - 1] /= st[sp]; break;
-        case hpb::OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
-        case hpb::OP_LT: --sp; st[sp - 1] = st[sp - 1] < st[sp] ? 1.0 : 0.0; break;
-        case hpb::OP_GT: --sp; st[sp - 1] = st[sp - 1] > st[sp] ? 1.0 : 0.0; break;
-        case hpb::OP_MIN: --sp; st[sp - 1] = fmin(st[sp - 1], st[sp]); break;
-        case hpb::OP_MAX: --sp; st[sp - 1] = fmax(st[sp - 1], st[sp]); break;
-        case hpb::OP_NEG: st[sp - 1] = -st[sp - 1]; break;
-        case hpb::OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
-        case hpb::OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
-        case hpb::OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
-        case hpb::OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
-        case hpb::OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
-        case hpb::OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
-        case hpb::OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
-        }
-    }
-    return sp > 0 ? st[sp - 1] : 0.0;
-}
 
 // ---- plasma: PlasmaParticleContainer::InitParticles (PlasmaParticleContainerInit.cpp:17-316) ----
 struct PlasmaInitArgs {
@@ -166,17 +135,32 @@ __global__ void k_beam_flag(BeamInitArgs a, long ncand, unsigned *flag)
 }
 
 __global__ void k_beam_fill(BeamInitArgs a, long ncand, const unsigned *flag, const unsigned *offs,
-                            hpb_beam_slice b, uint64_t first_id)
+                            const long *slot_off, BeamRing ring, uint64_t first_id)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= ncand || !flag[idx]) return;
     double x, y, z, d;
     beam_candidate(a, idx, x, y, z, d);
-    const long p = offs[idx];
+    const long per_slice = (long)a.ncx * a.ncy * (a.ppcx * a.ppcy * a.ppcz);
+    const int slot = (int)(idx / per_slice);
+    const long gp = offs[idx];                 // global particle index = id - first_id
+    const long p = gp - slot_off[slot];
+    if (p >= ring.cap) return;
+    const hpb_beam_slice b = ring.view(slot);
     b.x[p] = x; b.y[p] = y; b.z[p] = z;
     b.w[p] = fabs(d * a.scale);
     b.ux[p] = a.ux0; b.uy[p] = a.uy0; b.uz[p] = a.uz0;
-    b.idcpu[p] = hpb_make_idcpu(first_id + (uint64_t)p, 0);
+    b.idcpu[p] = hpb_make_idcpu(first_id + (uint64_t)gp, 0);
+}
+
+__global__ void k_ring_set_counts(BeamRing ring, const long *slot_off)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ring.nslots) return;
+    int64_t *h = ring.hdr(s);
+    const long n = slot_off[s + 1] - slot_off[s];
+    h[0] = n; h[1] = n;
+    for (int k = 2; k < 8; ++k) h[k] = 0;
 }
 
 // offsets of the slice slots: slot_off[s] = offs[s * per_slice], slot_off[nslots] = total
@@ -203,32 +187,6 @@ __global__ void k_valid_bytes(const uint64_t *idcpu, long np, uint8_t *out)
     if (ip < np) out[ip] = hpb_is_valid(idcpu[ip]) ? 1 : 0;
 }
 
-struct Species {
-    std::string name;
-    double charge = 0, mass = 0;
-    int ppc[2] = {1, 1};
-    DevRpn density;
-    bool neutralize = true;
-    double max_qsa = 35.;
-    int n_subcycles = 1;
-    double radius = INFINITY, hollow = 0., min_density = 0.;
-    double u_mean[3] = {0, 0, 0};
-    hpb_plasma d = {};
-    long capacity = 0;
-};
-
-struct BeamSp {
-    std::string name;
-    double charge = 0, mass = 0;
-    int ppc[3] = {1, 1, 1};
-    int profile = 0;
-    double density = 0, zmin = 0, zmax = 0, radius = 0, min_density = 0;
-    double pos_mean[3] = {0, 0, 0}, pos_std[3] = {0, 0, 0}, u_mean[3] = {0, 0, 0};
-    hpb_beam_slice d = {};        // whole beam, slot-major (slot s = slice nz-1-s)
-    std::vector<long> slot_off;   // nz + 1
-    bool initialised = false;
-};
-
 void species_charge_mass(const Deck &dk, const hpb_geom &g, const std::string &pre,
                          const std::string &def_el, double &charge, double &mass)
 {
@@ -247,52 +205,7 @@ inline unsigned nb256(long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
 
-struct hpb_sim {
-    Deck deck;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    hpb_geom g = {};
-    int nz = 0;
-    double prob_lo[3], prob_hi[3];
-    double bc_lo[2], bc_hi[2];
-    int particle_bc = HPB_BC_PERIODIC;
-    int max_step = 0;
-    double dt = 0.;
-    double mg_tol_rel = 1e-4, mg_tol_abs = DBL_MIN;
-    bool deposit_rho = false, do_beam_jx_jy = true, any_neutral = false;
-    hpb_ctx *ctx = nullptr;
-    hpb_slice sl = {};
-    int comps[HPB_C_COUNT];
-    std::vector<std::pair<std::string, std::string>> comp_names;   // (which_slice, name) by index
-    std::vector<Species> plasmas;
-    std::vector<BeamSp> beams;
-    // scratch for init
-    unsigned *d_flag = nullptr, *d_offs = nullptr;
-    long scan_cap = 0;
-    void *d_cub = nullptr;
-    size_t cub_bytes = 0;
-    // diagnostics
-    double *d_checksum = nullptr;       // ncomp
-    int *d_nqsa = nullptr;
-    unsigned long long *d_count = nullptr;
-    bool opt_checksums = true, opt_profile = false;
-    hpb_sim_stats stats = {};
-    std::vector<int> mg_iters;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> pev;
-    int cur_step = -1;
-};
-
 namespace {
-
-#define SIM_CUDA(expr)                                                                        \
-    do {                                                                                      \
-        cudaError_t e_ = (expr);                                                              \
-        if (e_ != cudaSuccess) {                                                              \
-            hpb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
-            return HPB_ERR_CUDA;                                                              \
-        }                                                                                     \
-    } while (0)
 
 int ensure_scan(hpb_sim *s, long n)
 {
@@ -415,6 +328,21 @@ int read_deck(hpb_sim *s)
             const auto us = d.nums(nm + ".u_std", {0., 0., 0.});
             for (double v : us)
                 if (v != 0.) throw std::runtime_error("beam u_std != 0 needs AMReX's RNG stream: unsupported");
+            b.n_subcycles = (int)d.num(nm + ".n_subcycles", 10);
+            if (b.n_subcycles < 1) throw std::runtime_error(nm + ".n_subcycles must be >= 1");
+            b.do_z_push = (int)d.num(nm + ".do_z_push", 1) != 0;
+            if ((int)d.num(nm + ".do_radiation_reaction", 0) != 0 || (int)d.num(nm + ".do_spin_tracking", 0) != 0)
+                throw std::runtime_error("beam radiation reaction / spin tracking are not supported");
+            // external_E(x,y,z,t) / external_B(x,y,z,t): beam name first, then "beams"
+            const char *keys[2] = {"external_E(x,y,z,t)", "external_B(x,y,z,t)"};
+            for (int k = 0; k < 2; ++k) {
+                auto v = d.find(nm + "." + keys[k], std::string("beams.") + keys[k]);
+                for (int c = 0; c < 3; ++c) b.ext_expr[3 * k + c] = "0.";
+                if (!v) continue;
+                if (v->size() != 3) throw std::runtime_error(std::string(keys[k]) + " needs 3 expressions");
+                for (int c = 0; c < 3; ++c) b.ext_expr[3 * k + c] = (*v)[c];
+                b.use_ext = true;
+            }
             s->beams.push_back(b);
         }
     }
@@ -518,46 +446,46 @@ int init_beam(hpb_sim *s, BeamSp &b)
     a.ux0 = b.u_mean[0] * g.c; a.uy0 = b.u_mean[1] * g.c; a.uz0 = b.u_mean[2] * g.c;
     const long per_slice = (long)a.ncx * a.ncy * nppc;
     const long ncand = per_slice * s->nz;
-    b.slot_off.assign(s->nz + 1, 0);
-    b.d.np = 0;
-    b.initialised = true;
-    if (ncand == 0) return HPB_OK;
-    int rc = ensure_scan(s, ncand);
-    if (rc) return rc;
-    k_beam_flag<<<nb256(ncand), 256, 0, s->stream>>>(a, ncand, s->d_flag);
-    size_t tb = s->cub_bytes;
-    SIM_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tb, s->d_flag, s->d_offs, (int)ncand, s->stream));
-    long *d_so = nullptr;
-    SIM_CUDA(cudaMalloc(&d_so, sizeof(long) * (s->nz + 1)));
-    k_slot_offsets<<<nb256(s->nz + 1), 256, 0, s->stream>>>(s->d_flag, s->d_offs, per_slice, s->nz, ncand, d_so);
-    SIM_CUDA(cudaMemcpyAsync(b.slot_off.data(), d_so, sizeof(long) * (s->nz + 1), cudaMemcpyDeviceToHost, s->stream));
-    SIM_CUDA(cudaStreamSynchronize(s->stream));
-    cudaFree(d_so);
-    const long np = b.slot_off[s->nz];
-    double **arrs[7] = {&b.d.x, &b.d.y, &b.d.z, &b.d.w, &b.d.ux, &b.d.uy, &b.d.uz};
-    for (auto p : arrs) { cudaFree(*p); *p = nullptr; }
-    cudaFree(b.d.idcpu); b.d.idcpu = nullptr;
-    if (np > 0) {
-        for (auto p : arrs) SIM_CUDA(cudaMalloc(p, sizeof(double) * np));
-        SIM_CUDA(cudaMalloc(&b.d.idcpu, sizeof(uint64_t) * np));
-        b.d.np = np;
-        k_beam_fill<<<nb256(ncand), 256, 0, s->stream>>>(a, ncand, s->d_flag, s->d_offs, b.d, 1);
+    std::vector<long> slot_off(s->nz + 1, 0);
+    if (ncand > 0) {
+        int rc = ensure_scan(s, ncand);
+        if (rc) return rc;
+        k_beam_flag<<<nb256(ncand), 256, 0, s->stream>>>(a, ncand, s->d_flag);
+        size_t tb = s->cub_bytes;
+        SIM_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, tb, s->d_flag, s->d_offs, (int)ncand, s->stream));
+        k_slot_offsets<<<nb256(s->nz + 1), 256, 0, s->stream>>>(s->d_flag, s->d_offs, per_slice, s->nz, ncand,
+                                                                s->d_slot_off);
+        SIM_CUDA(cudaMemcpyAsync(slot_off.data(), s->d_slot_off, sizeof(long) * (s->nz + 1),
+                                 cudaMemcpyDeviceToHost, s->stream));
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+    } else {
+        SIM_CUDA(cudaMemsetAsync(s->d_slot_off, 0, sizeof(long) * (s->nz + 1), s->stream));
     }
+    // slice capacity: the largest initial slice + 25 % + 1024 for slipped particles, unless the
+    // deck fixes it (our addition: <beam>.slice_capacity); identical on every rank of a pipeline
+    long mx = 0;
+    for (int k = 0; k < s->nz; ++k) mx = std::max(mx, slot_off[k + 1] - slot_off[k]);
+    long cap = (long)s->deck.num(b.name + ".slice_capacity", (double)(mx + mx / 4 + 1024));
+    if (cap < mx) { hpb_set_error("beam %s: slice_capacity %ld < largest slice %ld", b.name.c_str(), cap, mx); return HPB_ERR_CAPACITY; }
+    int rc = hpb_beam_rings_alloc(s, b, cap);
+    if (rc) return rc;
+    const BeamRing &r = b.ring[b.cur];
+    k_ring_set_counts<<<nb256(s->nz), 256, 0, s->stream>>>(r, s->d_slot_off);
+    if (slot_off[s->nz] > 0)
+        k_beam_fill<<<nb256(ncand), 256, 0, s->stream>>>(a, ncand, s->d_flag, s->d_offs, s->d_slot_off, r, 1);
     SIM_CUDA(cudaGetLastError());
+    b.initialised = true;
+    b.from_host = false;
+    b.cs_valid = false;
     return HPB_OK;
 }
 
-// view of the beam particles of slice islice (empty for islice < 0)
+// view of the beam particles of slice islice in the current ring (empty for islice < 0)
 hpb_beam_slice beam_slice_view(const hpb_sim *s, const BeamSp &b, int islice)
 {
     hpb_beam_slice v = {};
-    if (islice < 0 || islice >= s->nz || b.d.np == 0) return v;
-    const int slot = s->nz - 1 - islice;
-    const long o = b.slot_off[slot], n = b.slot_off[slot + 1] - o;
-    v.x = b.d.x + o; v.y = b.d.y + o; v.z = b.d.z + o; v.w = b.d.w + o;
-    v.ux = b.d.ux + o; v.uy = b.d.uy + o; v.uz = b.d.uz + o; v.idcpu = b.d.idcpu + o;
-    v.np = n;
-    return v;
+    if (islice < 0 || islice >= s->nz || !b.ring[b.cur].base) return v;
+    return b.ring[b.cur].view(s->nz - 1 - islice);
 }
 
 enum { ST_DEPOSIT = 0, ST_POISSON, ST_EXPLICIT, ST_MG, ST_PUSH, ST_OTHER, ST_N };
@@ -597,8 +525,19 @@ int begin_step(hpb_sim *s, int step)
         int rc = init_plasma(s, sp, c_t);
         if (rc) return rc;
     }
-    for (auto &b : s->beams)
-        if (!b.initialised) { int rc = init_beam(s, b); if (rc) return rc; }
+    // beams: created at step 0 on the head rank (BeamParticleContainerInit.cpp), afterwards they
+    // arrive slice by slice from the previous time step (MultiBuffer::get_data) -- from the
+    // upstream rank in a pipeline, otherwise from the ring the previous step on this GPU filled
+    const bool recv = hpb_pipeline_receives(s, step);
+    for (auto &b : s->beams) {
+        if (!b.ring[0].base || (!recv && !b.initialised) || (!recv && step == 0 && !b.from_host)) {
+            int rc = init_beam(s, b);
+            if (rc) return rc;
+        }
+        SIM_CUDA(cudaMemsetAsync(b.d_cs, 0, 9 * sizeof(double), s->stream));
+        b.cs_valid = false;
+    }
+    if (hpb_pipeline_active(s)) { int rc = hpb_pipeline_begin_step(s, step); if (rc) return rc; }
     // DepositNeutralizingBackground (Hipace.cpp:468-470, MultiPlasma.cpp:106-118)
     for (auto &sp : s->plasmas) {
         if (!sp.neutralize) continue;
@@ -607,6 +546,14 @@ int begin_step(hpb_sim *s, int step)
         if (rc) return rc;
     }
     s->cur_step = step;
+    return HPB_OK;
+}
+
+// after the last slice of a step: the pushed beam becomes the current one
+int end_step(hpb_sim *s)
+{
+    for (auto &b : s->beams) { b.cur ^= 1; b.cs_valid = s->opt_checksums; b.initialised = true; }
+    if (hpb_pipeline_active(s)) return hpb_pipeline_end_step(s, s->cur_step);
     return HPB_OK;
 }
 
@@ -629,6 +576,7 @@ int solve_one_slice(hpb_sim *s, int islice)
     }
     {
         StageTimer t(s, ST_OTHER);
+        if (!s->beams.empty() && (rc = hpb_pipeline_wait_slice(s, islice))) return rc;  // :582-585
         for (auto &b : s->beams)                                                        // :613-614
             if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice), s->sl, b.charge, -1, -1,
                                        C[HPB_C_JZ_BEAM]))) return rc;
@@ -640,6 +588,7 @@ int solve_one_slice(hpb_sim *s, int islice)
     }
     {
         StageTimer t(s, ST_OTHER);
+        if (!s->beams.empty() && islice > 0 && (rc = hpb_pipeline_wait_slice(s, islice - 1))) return rc;   // :639-642
         if (s->do_beam_jx_jy)                                                           // :639-657
             for (auto &b : s->beams)
                 if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice - 1), s->sl, b.charge,
@@ -673,9 +622,26 @@ int solve_one_slice(hpb_sim *s, int islice)
                                                    0, s->particle_bc, s->bc_lo, s->bc_hi, C))) return rc;
         }
     }
-    for (auto &b : s->beams) s->stats.n_beam_pushed += (double)beam_slice_view(s, b, islice).np;
     {
+        // AdvanceBeamParticlesSlice + shiftSlippedParticles + MultiBuffer::put_data (:707-716)
         StageTimer t(s, ST_OTHER);
+        const int slot = s->nz - 1 - islice;
+        const double min_z = s->prob_lo[2] + islice * s->g.dz;
+        const double time = s->dt * s->cur_step;
+        for (auto &b : s->beams) {
+            const BeamRing &in = b.ring[b.cur], &out = b.ring[b.cur ^ 1];
+            const hpb_beam_slice bm = in.view(slot);
+            if ((rc = hpb_advance_beam_impl(ctx, bm, in.nsub(slot), s->sl, b.charge, b.mass, b.n_subcycles,
+                                            s->dt, time, min_z, b.do_z_push, s->particle_bc, s->bc_lo,
+                                            s->bc_hi, C, b.ext, b.d_class,
+                                            s->opt_checksums ? b.d_cs : nullptr, s->d_count))) return rc;
+            hpb_beam_slice next = {};
+            if (islice > 0) next = in.view(slot + 1);
+            if ((rc = hpb_beam_shift_slipped(ctx, bm, in.nsub(slot), min_z, b.d_class, out.view(slot),
+                                             out.hdr(slot), next, islice > 0 ? in.hdr(slot + 1) : nullptr,
+                                             islice > 0 ? in.nsub(slot + 1) : nullptr, s->d_overflow))) return rc;
+        }
+        if (!s->beams.empty() && (rc = hpb_pipeline_send_slice(s, islice, s->cur_step))) return rc;
         if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;                   // :721
     }
     s->stats.n_cells_updated += (double)s->g.nx * s->g.ny;
@@ -722,9 +688,22 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     SIM_CUDA(cudaMalloc(&s->d_nqsa, sizeof(int)));
     SIM_CUDA(cudaMemset(s->d_nqsa, 0, sizeof(int)));
     SIM_CUDA(cudaMalloc(&s->d_count, sizeof(unsigned long long)));
+    SIM_CUDA(cudaMemset(s->d_count, 0, sizeof(unsigned long long)));
+    SIM_CUDA(cudaMalloc(&s->d_overflow, sizeof(int)));
+    SIM_CUDA(cudaMemset(s->d_overflow, 0, sizeof(int)));
+    SIM_CUDA(cudaMalloc(&s->d_slot_off, sizeof(long) * (size_t)(s->nz + 1)));
+    for (auto &b : s->beams) {
+        SIM_CUDA(cudaMalloc(&b.d_cs, 9 * sizeof(double)));
+        SIM_CUDA(cudaMemset(b.d_cs, 0, 9 * sizeof(double)));
+        if (b.use_ext) {
+            const char *ex[6];
+            for (int k = 0; k < 6; ++k) ex[k] = b.ext_expr[k].c_str();
+            if ((rc = hpb_extfields_create(&b.ext, ex))) return rc;
+        }
+    }
     SIM_CUDA(cudaEventCreate(&s->ev0));
     SIM_CUDA(cudaEventCreate(&s->ev1));
-    s->pev.resize(2);
+    s->pev.resize(4);
     for (auto &e : s->pev) SIM_CUDA(cudaEventCreate(&e));
     *out = s.release();
     return HPB_OK;
@@ -739,10 +718,13 @@ extern "C" void hpb_sim_destroy(hpb_sim *s)
         for (int k = 0; k < HPB_PLASMA_NREAL; ++k) cudaFree(sp.d.r[k]);
         cudaFree(sp.d.idcpu);
     }
+    hpb_pipeline_destroy(s);
     for (auto &b : s->beams) {
-        cudaFree(b.d.x); cudaFree(b.d.y); cudaFree(b.d.z); cudaFree(b.d.w);
-        cudaFree(b.d.ux); cudaFree(b.d.uy); cudaFree(b.d.uz); cudaFree(b.d.idcpu);
+        hpb_beam_rings_free(b);
+        cudaFree(b.d_cs); cudaFree(b.d_stage); cudaFree(b.d_stage_off);
+        hpb_extfields_destroy(b.ext);
     }
+    cudaFree(s->d_overflow); cudaFree(s->d_slot_off);
     cudaFree(s->sl.p); cudaFree(s->d_checksum); cudaFree(s->d_nqsa); cudaFree(s->d_count);
     cudaFree(s->d_flag); cudaFree(s->d_offs); cudaFree(s->d_cub);
     hpb_destroy(s->ctx);
@@ -763,7 +745,9 @@ extern "C" int hpb_sim_solve_one_slice(hpb_sim *s, int islice)
 {
     if (!s || islice < 0 || islice >= s->nz) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
-    return solve_one_slice(s, islice);
+    int rc = solve_one_slice(s, islice);
+    if (rc == HPB_OK && islice == 0) rc = end_step(s);
+    return rc;
 }
 
 extern "C" int hpb_sim_evolve(hpb_sim *s, int step_begin, int step_end, int n_slices)
@@ -773,6 +757,7 @@ extern "C" int hpb_sim_evolve(hpb_sim *s, int step_begin, int step_end, int n_sl
     s->stats = hpb_sim_stats();
     s->mg_iters.clear();
     SIM_CUDA(cudaMemsetAsync(s->d_nqsa, 0, sizeof(int), s->stream));
+    SIM_CUDA(cudaMemsetAsync(s->d_count, 0, sizeof(unsigned long long), s->stream));
     const long launches0 = s->ctx->n_launch;
     double loop_ms = 0.;
     for (int step = step_begin; step <= step_end; ++step) {
@@ -785,6 +770,7 @@ extern "C" int hpb_sim_evolve(hpb_sim *s, int step_begin, int step_end, int n_sl
             if (rc) return rc;
         }
         SIM_CUDA(cudaEventRecord(s->ev1, s->stream));
+        if (stop == -1 && (rc = end_step(s))) return rc;
         SIM_CUDA(cudaEventSynchronize(s->ev1));
         float ms = 0.f;
         SIM_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
@@ -792,9 +778,18 @@ extern "C" int hpb_sim_evolve(hpb_sim *s, int step_begin, int step_end, int n_sl
     }
     s->stats.slice_loop_ms = loop_ms;
     s->stats.n_kernel_launches = s->ctx->n_launch - launches0;
-    int nq = 0;
-    SIM_CUDA(cudaMemcpy(&nq, s->d_nqsa, sizeof(int), cudaMemcpyDeviceToHost));
+    int nq = 0, ovf = 0;
+    unsigned long long nbp = 0;
+    SIM_CUDA(cudaMemcpyAsync(&nq, s->d_nqsa, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaMemcpyAsync(&ovf, s->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaMemcpyAsync(&nbp, s->d_count, sizeof(nbp), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
     s->stats.n_qsa_violation = nq;
+    s->stats.n_beam_pushed = (double)nbp;
+    if (ovf) {
+        hpb_set_error("a beam slice outgrew its packet capacity (raise <beam>.slice_capacity)");
+        return HPB_ERR_CAPACITY;
+    }
     return HPB_OK;
 }
 
@@ -906,38 +901,34 @@ extern "C" int hpb_sim_get_beam_checksums(hpb_sim *s, int beam, double h_out[9])
 {
     if (!s || beam < 0 || beam >= (int)s->beams.size() || !h_out) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
-    SIM_CUDA(cudaStreamSynchronize(s->stream));
     BeamSp &b = s->beams[beam];
-    if (!b.initialised) { int rc = init_beam(s, b); if (rc) return rc; SIM_CUDA(cudaStreamSynchronize(s->stream)); }
-    const long np = b.d.np;
-    for (int k = 0; k < 9; ++k) h_out[k] = 0.;
-    if (np == 0) return HPB_OK;
-    std::vector<double> h(np);
-    double *arrs[7] = {b.d.x, b.d.y, b.d.z, b.d.ux, b.d.uy, b.d.uz, b.d.w};
-    for (int k = 0; k < 7; ++k) {
-        SIM_CUDA(cudaMemcpy(h.data(), arrs[k], sizeof(double) * np, cudaMemcpyDeviceToHost));
-        long double acc = 0;
-        for (long p = 0; p < np; ++p) acc += fabs(h[p]);
-        h_out[k] = (double)acc;
-    }
-    std::vector<uint64_t> id(np);
-    SIM_CUDA(cudaMemcpy(id.data(), b.d.idcpu, sizeof(uint64_t) * np, cudaMemcpyDeviceToHost));
-    long double ids = 0;
-    for (long p = 0; p < np; ++p) ids += (long double)((id[p] & ~HPB_ID_VALID_BIT) >> 24);
-    h_out[7] = (double)ids;
-    h_out[8] = (double)np;
+    if (!b.ring[0].base) { int rc = init_beam(s, b); if (rc) return rc; }
+    // after a complete step with checksums on: the state the step's beam diagnostic saw (before
+    // the push, Hipace.cpp:682-683); otherwise the beam as it currently sits in the ring
+    if (!b.cs_valid) { int rc = hpb_beam_ring_checksum(s, b.ring[b.cur], b.d_cs); if (rc) return rc; }
+    SIM_CUDA(cudaMemcpyAsync(h_out, b.d_cs, 9 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
     return HPB_OK;
 }
 
 extern "C" long hpb_sim_beam_np(hpb_sim *s, int beam)
 {
     if (!s || beam < 0 || beam >= (int)s->beams.size()) return -1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return -1;
     BeamSp &b = s->beams[beam];
-    if (!b.initialised) {
-        if (cudaSetDevice(s->device) != cudaSuccess || init_beam(s, b) != HPB_OK) return -1;
-        cudaStreamSynchronize(s->stream);
-    }
-    return b.d.np;
+    if (!b.ring[0].base && init_beam(s, b) != HPB_OK) return -1;
+    std::vector<long> off;
+    if (hpb_beam_ring_counts(s, b.ring[b.cur], off) != HPB_OK) return -1;
+    return off[s->nz];
+}
+
+extern "C" long hpb_sim_beam_slice_capacity(hpb_sim *s, int beam)
+{
+    if (!s || beam < 0 || beam >= (int)s->beams.size()) return -1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return -1;
+    BeamSp &b = s->beams[beam];
+    if (!b.ring[0].base && init_beam(s, b) != HPB_OK) return -1;
+    return b.ring[0].cap;
 }
 
 // Host <-> device transfer of a whole beam (the role of MultiBuffer::get_data / put_data with
@@ -950,15 +941,13 @@ extern "C" int hpb_sim_get_beam(hpb_sim *s, int beam, double *const h_real[7], u
 {
     if (!s || beam < 0 || beam >= (int)s->beams.size() || !h_real) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
-    const long np = hpb_sim_beam_np(s, beam);
-    if (np < 0) return HPB_ERR_CUDA;
     BeamSp &b = s->beams[beam];
-    double *arrs[7] = {b.d.x, b.d.y, b.d.z, b.d.w, b.d.ux, b.d.uy, b.d.uz};
-    for (int k = 0; k < 7 && np > 0; ++k)
-        SIM_CUDA(cudaMemcpyAsync(h_real[k], arrs[k], sizeof(double) * np, cudaMemcpyDeviceToHost, s->stream));
-    if (h_idcpu && np > 0)
-        SIM_CUDA(cudaMemcpyAsync(h_idcpu, b.d.idcpu, sizeof(uint64_t) * np, cudaMemcpyDeviceToHost, s->stream));
-    if (h_slot_off) memcpy(h_slot_off, b.slot_off.data(), sizeof(long) * (s->nz + 1));
+    if (!b.ring[0].base) { int rc = init_beam(s, b); if (rc) return rc; }
+    std::vector<long> off;
+    int rc = hpb_beam_ring_counts(s, b.ring[b.cur], off);
+    if (rc) return rc;
+    if (h_slot_off) memcpy(h_slot_off, off.data(), sizeof(long) * (s->nz + 1));
+    if ((rc = hpb_beam_ring_gather(s, b, b.ring[b.cur], off, h_real, h_idcpu))) return rc;
     SIM_CUDA(cudaStreamSynchronize(s->stream));
     return HPB_OK;
 }
@@ -970,24 +959,23 @@ extern "C" int hpb_sim_set_beam(hpb_sim *s, int beam, const double *const h_real
         return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
     BeamSp &b = s->beams[beam];
-    const long np = h_slot_off[s->nz];
-    double **arrs[7] = {&b.d.x, &b.d.y, &b.d.z, &b.d.w, &b.d.ux, &b.d.uy, &b.d.uz};
-    if (!b.initialised || np != b.d.np) {
-        SIM_CUDA(cudaStreamSynchronize(s->stream));
-        for (auto p : arrs) { cudaFree(*p); *p = nullptr; }
-        cudaFree(b.d.idcpu); b.d.idcpu = nullptr;
-        if (np > 0) {
-            for (auto p : arrs) SIM_CUDA(cudaMalloc(p, sizeof(double) * np));
-            SIM_CUDA(cudaMalloc(&b.d.idcpu, sizeof(uint64_t) * np));
-        }
-        b.d.np = np;
+    long mx = 0;
+    for (int k = 0; k < s->nz; ++k) {
+        if (h_slot_off[k + 1] < h_slot_off[k]) { hpb_set_error("set_beam: slot offsets must not decrease"); return HPB_ERR_ARG; }
+        mx = std::max(mx, h_slot_off[k + 1] - h_slot_off[k]);
     }
-    b.slot_off.assign(h_slot_off, h_slot_off + s->nz + 1);
+    if (!b.ring[0].base || b.ring[0].cap < mx) {
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+        const long cap = (long)s->deck.num(b.name + ".slice_capacity", (double)(mx + mx / 4 + 1024));
+        if (cap < mx) { hpb_set_error("beam %s: slice_capacity %ld < largest slice %ld", b.name.c_str(), cap, mx); return HPB_ERR_CAPACITY; }
+        int rc = hpb_beam_rings_alloc(s, b, cap);
+        if (rc) return rc;
+    }
+    int rc = hpb_beam_ring_scatter(s, b, b.ring[b.cur], h_slot_off, h_real, h_idcpu);
+    if (rc) return rc;
     b.initialised = true;
-    for (int k = 0; k < 7 && np > 0; ++k)
-        SIM_CUDA(cudaMemcpyAsync(*arrs[k], h_real[k], sizeof(double) * np, cudaMemcpyHostToDevice, s->stream));
-    if (np > 0)
-        SIM_CUDA(cudaMemcpyAsync(b.d.idcpu, h_idcpu, sizeof(uint64_t) * np, cudaMemcpyHostToDevice, s->stream));
+    b.from_host = true;
+    b.cs_valid = false;
     return HPB_OK;
 }
 
@@ -998,12 +986,45 @@ extern "C" int hpb_sim_get_stats(hpb_sim *s, hpb_sim_stats *out)
     return HPB_OK;
 }
 
+extern "C" int hpb_sim_timer_start(hpb_sim *s)
+{
+    if (!s) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    SIM_CUDA(cudaEventRecord(s->pev[2], s->stream));
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_timer_stop(hpb_sim *s, double *ms)
+{
+    if (!s || !ms) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    SIM_CUDA(cudaEventRecord(s->pev[3], s->stream));
+    SIM_CUDA(cudaEventSynchronize(s->pev[3]));
+    float f = 0.f;
+    SIM_CUDA(cudaEventElapsedTime(&f, s->pev[2], s->pev[3]));
+    *ms = f;
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_get_beam_packet(hpb_sim *s, int beam, int slot, void *h_out)
+{
+    if (!s || beam < 0 || beam >= (int)s->beams.size() || slot < 0 || slot >= s->nz || !h_out) return HPB_ERR_ARG;
+    SIM_CUDA(cudaSetDevice(s->device));
+    BeamSp &b = s->beams[beam];
+    if (!b.ring[0].base) { int rc = init_beam(s, b); if (rc) return rc; }
+    const BeamRing &r = b.ring[b.cur];
+    SIM_CUDA(cudaMemcpyAsync(h_out, r.packet(slot), r.msg_bytes(), cudaMemcpyDeviceToHost, s->stream));
+    SIM_CUDA(cudaStreamSynchronize(s->stream));
+    return HPB_OK;
+}
+
 extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
 {
     if (!s || !key) return HPB_ERR_ARG;
     const std::string k(key);
     if (k == "checksums") s->opt_checksums = value != 0.;
     else if (k == "profile") s->opt_profile = value != 0.;
+    else if (k == "max_step") s->max_step = (int)value;
     else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }
     return HPB_OK;
 }

@@ -1,0 +1,150 @@
+// State of the slice-loop driver (hpb_sim), shared by sim.cu (Hipace::Evolve / SolveOneSlice),
+// beam.cu (beam rings) and pipeline.cu (NCCL time-step pipeline).
+#pragma once
+#include "common.cuh"
+#include "rpn.cuh"
+#include <float.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+// ---- beam slice packets -----------------------------------------------------------------------
+// A beam lives in two rings of nz fixed-capacity packets (slot s = slice nz-1-s, head first):
+// ring[cur] holds the beam of the time step being computed (locally initialised, left by the
+// previous step, or received from the upstream rank), ring[cur^1] receives the pushed slices
+// (next step's input / message to the downstream rank).  One packet:
+//   int64 hdr[8]   {np without slipped, np with slipped, step, time bits, 0...}   64 B
+//   uint64 idcpu[cap]; double x[cap] y z w ux uy uz                               64 B * cap
+//   int nsub[cap]   (BeamIdx::nsubcycles: never communicated, BeamParticleContainer.H:35-37)
+// The first 64 + 64*cap bytes are the wire message (MultiBuffer.cpp:611-728 layout: metadata,
+// idcpu, then the real components, each padded to the slice capacity).
+struct BeamRing {
+    char *base = nullptr;
+    long cap = 0;            // particles per packet
+    size_t stride = 0;       // bytes per packet
+    int nslots = 0;
+    __host__ __device__ size_t msg_bytes() const { return 64 + 64 * (size_t)cap; }
+    __host__ __device__ char *packet(int slot) const { return base + (size_t)slot * stride; }
+    __host__ __device__ int64_t *hdr(int slot) const { return (int64_t *)packet(slot); }
+    __host__ __device__ int *nsub(int slot) const { return (int *)(packet(slot) + msg_bytes()); }
+    __host__ __device__ hpb_beam_slice view(int slot) const
+    {
+        hpb_beam_slice v;
+        char *p = packet(slot) + 64;
+        v.idcpu = (uint64_t *)p;
+        double *r = (double *)(p + 8 * (size_t)cap);
+        v.x = r; v.y = r + cap; v.z = r + 2 * cap; v.w = r + 3 * cap;
+        v.ux = r + 4 * cap; v.uy = r + 5 * cap; v.uz = r + 6 * cap;
+        v.np = cap;
+        v.d_np = hdr(slot);
+        return v;
+    }
+};
+
+struct Species {
+    std::string name;
+    double charge = 0, mass = 0;
+    int ppc[2] = {1, 1};
+    DevRpn density;
+    bool neutralize = true;
+    double max_qsa = 35.;
+    int n_subcycles = 1;
+    double radius = INFINITY, hollow = 0., min_density = 0.;
+    double u_mean[3] = {0, 0, 0};
+    hpb_plasma d = {};
+    long capacity = 0;
+};
+
+struct BeamSp {
+    std::string name;
+    double charge = 0, mass = 0;
+    int ppc[3] = {1, 1, 1};
+    int profile = 0;
+    double density = 0, zmin = 0, zmax = 0, radius = 0, min_density = 0;
+    double pos_mean[3] = {0, 0, 0}, pos_std[3] = {0, 0, 0}, u_mean[3] = {0, 0, 0};
+    int n_subcycles = 10;
+    bool do_z_push = true;
+    std::string ext_expr[6];
+    bool use_ext = false;
+    hpb_extfields *ext = nullptr;
+    // device state
+    BeamRing ring[2];
+    int cur = 0;                  // ring[cur]: this step's beam
+    int *d_class = nullptr;       // per-256-particle-block {stay, slipped} counts of the last push
+    double *d_cs = nullptr;       // 9 checksum accumulators of the current step (pre-push state)
+    bool initialised = false;     // ring[cur] holds a beam
+    bool from_host = false;       // ... that came from hpb_sim_set_beam (not re-created at step 0)
+    bool cs_valid = false;        // d_cs holds a complete step
+    // staging for whole-beam host transfers
+    double *d_stage = nullptr; long stage_cap = 0; long *d_stage_off = nullptr;
+};
+
+struct hpb_pipeline;              // pipeline.cu
+
+struct hpb_sim {
+    hpb::Deck deck;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    hpb_geom g = {};
+    int nz = 0;
+    double prob_lo[3], prob_hi[3];
+    double bc_lo[2], bc_hi[2];
+    int particle_bc = HPB_BC_PERIODIC;
+    int max_step = 0;
+    double dt = 0.;
+    double mg_tol_rel = 1e-4, mg_tol_abs = DBL_MIN;
+    bool deposit_rho = false, do_beam_jx_jy = true, any_neutral = false;
+    hpb_ctx *ctx = nullptr;
+    hpb_slice sl = {};
+    int comps[HPB_C_COUNT];
+    std::vector<std::pair<std::string, std::string>> comp_names;   // (which_slice, name) by index
+    std::vector<Species> plasmas;
+    std::vector<BeamSp> beams;
+    // scratch for init
+    unsigned *d_flag = nullptr, *d_offs = nullptr;
+    long scan_cap = 0;
+    void *d_cub = nullptr;
+    long *d_slot_off = nullptr;         // nz + 1
+    size_t cub_bytes = 0;
+    // diagnostics
+    double *d_checksum = nullptr;       // ncomp
+    int *d_nqsa = nullptr;
+    int *d_overflow = nullptr;          // beam packet overflow flag
+    unsigned long long *d_count = nullptr;   // [0]: beam particles pushed (without slipped)
+    bool opt_checksums = true, opt_profile = false;
+    hpb_sim_stats stats = {};
+    std::vector<int> mg_iters;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> pev;
+    int cur_step = -1;
+    hpb_pipeline *pipe = nullptr;
+};
+
+#define SIM_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            hpb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            return HPB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+// beam.cu
+int hpb_beam_rings_alloc(hpb_sim *s, BeamSp &b, long cap);
+void hpb_beam_rings_free(BeamSp &b);
+int hpb_beam_ring_clear(hpb_sim *s, const BeamRing &r);
+int hpb_beam_ring_counts(hpb_sim *s, const BeamRing &r, std::vector<long> &slot_off);
+int hpb_beam_ring_checksum(hpb_sim *s, const BeamRing &r, double *d_out9);
+int hpb_beam_ring_gather(hpb_sim *s, BeamSp &b, const BeamRing &r, const std::vector<long> &slot_off,
+                         double *const h_real[7], uint64_t *h_idcpu);
+int hpb_beam_ring_scatter(hpb_sim *s, BeamSp &b, const BeamRing &r, const long *h_slot_off,
+                          const double *const h_real[7], const uint64_t *h_idcpu);
+
+// pipeline.cu
+void hpb_pipeline_destroy(hpb_sim *s);
+int hpb_pipeline_begin_step(hpb_sim *s, int step);          // post receives / order ring reuse
+int hpb_pipeline_wait_slice(hpb_sim *s, int islice);        // compute stream waits for slice islice
+int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step);
+int hpb_pipeline_end_step(hpb_sim *s, int step);
+bool hpb_pipeline_receives(const hpb_sim *s, int step);     // this step's beam comes from upstream
+bool hpb_pipeline_active(const hpb_sim *s);

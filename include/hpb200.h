@@ -38,6 +38,8 @@ extern "C" {
 #define HPB_ERR_UNSUPPORTED 3
 #define HPB_ERR_MG_DIVERGED 4      /* hpmg "failing so lets stop here", HpMultiGrid.cpp:1399-1416 */
 #define HPB_ERR_PARSE 5
+#define HPB_ERR_CAPACITY 6         /* a beam slice outgrew its packet (slipped particles) */
+#define HPB_ERR_NCCL 7
 
 #define HPB_NGUARD 2               /* (depos_order_xy+1)/2 + 1 for order 2, Fields.cpp:63-64 */
 #define HPB_PLASMA_NREAL 11
@@ -68,12 +70,22 @@ typedef struct {
     long np;
 } hpb_plasma;
 
-/* per-slice beam tile (BeamIdx: x y z w ux uy uz) */
+/* per-slice beam tile (BeamIdx: x y z w ux uy uz).  The particle counts may live on the device
+ * so that a slice can be pushed, re-binned and handed to the next rank without a host round
+ * trip: d_np (device, may be NULL) points to {number of particles without slipped ones, number
+ * including slipped ones} (BeamParticleContainer.H:175-181: getNumParticles /
+ * getNumParticlesIncludingSlipped); np is then only the capacity the kernels are launched for.
+ * With d_np == NULL both counts are np. */
 typedef struct {
     double *x, *y, *z, *w, *ux, *uy, *uz;   /* device */
     uint64_t *idcpu;                         /* device */
     long np;
+    const int64_t *d_np;                     /* device int64[2] or NULL */
 } hpb_beam_slice;
+
+/* beams.external_E(x,y,z,t) / external_B(x,y,z,t) (BeamParticleContainer.cpp:71-88,
+ * ExternalFields.H:29-58): six expressions Ex Ey Ez Bx By Bz compiled to device byte-code */
+typedef struct hpb_extfields hpb_extfields;
 
 /* geometry + PhysConst (src/fields/Fields.H:71-77 GetPosOffset, src/utils/Constants.H:54-81) */
 typedef struct {
@@ -106,6 +118,38 @@ int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge
 /* beam ::DepositCurrentSlice (src/particles/deposition/BeamDepositCurrent.cpp:21-195) */
 int hpb_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, double charge,
                      int c_jx, int c_jy, int c_jz);
+
+/* AdvanceBeamParticlesSlice (src/particles/pusher/BeamParticleAdvance.cpp:19-336; level 0, no
+ * radiation reaction, no spin).  Pushes the d_np[1] particles of the slice (slipped ones
+ * included) through n_subcycles sub-steps of dt/n_subcycles, stopping a particle once
+ * z < min_z (:147-152).  The first d_np[0] particles start at sub-cycle 0 (BeamIdx::nsubcycles
+ * is zeroed when a slice is unpacked, MultiBuffer.cpp:897-910), the slipped ones continue from
+ * their own counter d_nsubcycles[ip]; the counter reached is stored back for every particle.
+ * ext may be NULL.  d_class_counts (device, 2 ints per 256 particles of capacity, may be NULL)
+ * receives per block the number of valid particles that stay (z >= min_z) / slipped -- the
+ * input of hpb_beam_shift_slipped.  d_checksum (device, 9 doubles, may be NULL) accumulates
+ * sum|x| |y| |z| |ux| |uy| |uz| |w|, sum of ids and the count of the d_np[0] particles BEFORE
+ * the push (what the reference's beam diagnostic writes, Hipace.cpp:682-683). */
+int hpb_extfields_create(hpb_extfields **out, const char *const expr[6]);
+void hpb_extfields_destroy(hpb_extfields *ext);
+int hpb_advance_beam_particles(hpb_ctx *ctx, hpb_beam_slice bm, int *d_nsubcycles, hpb_slice sl,
+                               double charge, double mass, int n_subcycles, double dt,
+                               double time, double min_z, int do_z_push, int particle_bc,
+                               const double bc_lo[2], const double bc_hi[2], const int *comps,
+                               const hpb_extfields *ext, int *d_class_counts,
+                               double *d_checksum);
+
+/* shiftSlippedParticles (src/particles/sorting/SliceSort.cpp:13-67) fused with the packing of
+ * MultiBuffer::put_data (src/utils/MultiBuffer.cpp:730-905): invalid particles are dropped, the
+ * particles with z >= min_z go (stable order) to `stay` whose counts d_stay_np[0..1] are set,
+ * the others are appended to `next` behind its d_np[0] particles and d_next_np[1] is updated
+ * (next.idcpu == NULL: dropped, the reference's behaviour below the last slice).
+ * d_class_counts is the array filled by hpb_advance_beam_particles.  *d_overflow (device) is set
+ * to 1 if a destination capacity (stay.np / next.np) is exceeded. */
+int hpb_beam_shift_slipped(hpb_ctx *ctx, hpb_beam_slice bm, const int *d_nsubcycles, double min_z,
+                           const int *d_class_counts, hpb_beam_slice stay, int64_t *d_stay_np,
+                           hpb_beam_slice next, int64_t *d_next_np, int *d_next_nsubcycles,
+                           int *d_overflow);
 
 /* Fields::InitializeSlices / AddRhoIons / ShiftSlices (src/fields/Fields.cpp:535-615):
  * comps[] is the component table in the order of hpb_comp below. */
@@ -205,13 +249,42 @@ int hpb_sim_set_beam(hpb_sim *sim, int beam, const double *const h_real[7],
                      const uint64_t *h_idcpu, const long *h_slot_off);
 /* performance counters of Hipace.cpp:509-553 and solver statistics */
 typedef struct {
-    double n_plasma_pushed, n_beam_pushed, n_cells_updated;
+    double n_plasma_pushed, n_beam_pushed /* without slipped, BeamParticleAdvance.cpp:115-116 */,
+           n_cells_updated;
     double slice_loop_ms;           /* device time of the slice loop(s) of the last evolve */
     long n_slices, n_mg_vcycles, n_qsa_violation, n_kernel_launches;
     double ms_deposit, ms_poisson, ms_explicit, ms_mg, ms_push, ms_other; /* if profiling on */
 } hpb_sim_stats;
 int hpb_sim_get_stats(hpb_sim *sim, hpb_sim_stats *out);
+/* device-side stopwatch on the simulation stream: start records an event, stop records a second
+ * one, waits for it and returns the elapsed device time (bench.py's timed region) */
+int hpb_sim_timer_start(hpb_sim *sim);
+int hpb_sim_timer_stop(hpb_sim *sim, double *ms);
+/* raw wire message (hpb_sim_pipeline_message_bytes / n_beams bytes) of one slice packet of the
+ * current beam ring: what the downstream rank receives for slice nz-1-slot (tests) */
+int hpb_sim_get_beam_packet(hpb_sim *sim, int beam, int slot, void *h_out);
+/* options: "checksums" (0/1), "profile" (0/1), "max_step" (last time step of the run: the beam
+ * is handed on only while step + 1 <= max_step, Hipace.cpp:441-443) */
 int hpb_sim_set_option(hpb_sim *sim, const char *key, double value);
+
+/* ---------------------------------------------------------------------------------------- */
+/* (3) time-step pipeline over the GPUs of one box (the role of MultiBuffer, MPI replaced by  */
+/*     NCCL point-to-point over NVLink; src/utils/MultiBuffer.cpp, Hipace.cpp:401)            */
+/* ---------------------------------------------------------------------------------------- */
+/* Rank r of `world` owns the time steps r, r + world, ...; for every slice it receives the beam
+ * slice from rank r-1 (ring) and sends the pushed slice to rank r+1: one message per slice,
+ * header {np per beam, step, time} + idcpu + x y z w ux uy uz of each beam, MultiBuffer's layout
+ * (MultiBuffer.cpp:611-728) with a fixed per-slice capacity so that no count has to visit the
+ * host.  Each directed edge r -> r+1 is its own 2-rank NCCL communicator with its own stream.
+ * id_recv / id_send: ncclUniqueId bytes of the edges (r-1 -> r) and (r -> r+1), created with
+ * hpb_nccl_unique_id on the edge's sending rank and exchanged by the caller (any transport). */
+#define HPB_NCCL_ID_BYTES 128
+int hpb_nccl_unique_id(char out[HPB_NCCL_ID_BYTES]);
+int hpb_sim_pipeline_init(hpb_sim *sim, int rank, int world, const char *id_recv,
+                          const char *id_send);
+/* bytes of one slice message (all beams) and the slice capacity in particles of beam `beam` */
+long hpb_sim_pipeline_message_bytes(hpb_sim *sim);
+long hpb_sim_beam_slice_capacity(hpb_sim *sim, int beam);
 
 #ifdef __cplusplus
 }

@@ -124,10 +124,17 @@ class Simulation(O.Simulation):
             1.0 / g.dx, 1.0 / g.dy, 1.0 / pc.c, charge * invvol, charge * pc.mu0 / pl.mass,
             pl.max_qsa_weighting_factor)
 
-    def begin_step(self):
+    def begin_step(self, step=0):
+        self.step = step
+        self.time = step * self.dt
+        self.beam_diag = {b.name: [] for b in self.beams}
         self._arr[...] = 0.0
+        for b in self.beams:
+            for bs in b.slices.values():
+                bs['nsub'][...] = 0
         for pl in self.plasmas:
-            O.init_plasma(pl, self.geom, self.pc, self.normalized, self.bc_lo, self.bc_hi)
+            O.init_plasma(pl, self.geom, self.pc, self.normalized, self.bc_lo, self.bc_hi,
+                          c_t=self.pc.c * self.time)
         for pl in self.plasmas:
             if pl.neutralize_background:
                 self._deposit(pl, None, None, None, None, self.F[('RhomJzIons', 'rhomjz')], flip=True)
@@ -189,6 +196,11 @@ class Simulation(O.Simulation):
         if self.slice_hook:
             self.slice_hook(self, islice, 'fields')
         self._accumulate_checksums(islice)
+        for b in self.beams:
+            bs = self.beam_slice(b, islice)
+            n = bs['np']
+            self.beam_diag.setdefault(b.name, []).append(
+                {k: bs[k][:n].copy() for k in ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id')})
         bc = {'Reflecting': 0, 'Periodic': 1, 'Absorbing': 2}[self.bc_kind]
         for pl in self.plasmas:
             self.n_plasma_pushed += pl.x.size
@@ -199,7 +211,13 @@ class Simulation(O.Simulation):
                 _p(T('Bz')), g.nx, g.ny, self._xoff, self._yoff, 1.0 / g.dx, 1.0 / g.dy, pc.c,
                 pl.charge / (pl.mass * pc.c), g.dz / pl.n_subcycles, pl.n_subcycles, 0, bc,
                 self.bc_lo[0], self.bc_lo[1], self.bc_hi[0], self.bc_hi[1])
-        assert self.dt == 0.0
+        # the beam slice is ~1e-3 of the plasma work: NumPy restatement (hipace_oracle.py)
+        for b in self.beams:
+            bs = self.beam_slice(b, islice)
+            self.n_beam_pushed += bs['np']
+            O.advance_beam_slice(bs, b, F, g, pc, islice, self.dt, self.time, self.bc_kind,
+                                 self.bc_lo, self.bc_hi)
+            O.shift_slipped_particles(bs, self.beam_slice(b, islice - 1), g, islice)
         if self.slice_hook:
             self.slice_hook(self, islice, 'pushed')
         F[('Previous', 'jx_beam')][...] = T('jx_beam')

@@ -1,0 +1,109 @@
+"""GPU side of the time-step pipeline: the wire message the partition kernel packs, and (when the
+box has >= 2 GPUs) two NCCL ranks against a single-GPU run of the same deck."""
+import os
+import pickle
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OV = {'amr.n_cell': '48 48 20', 'hipace.dt': 4., 'beam.u_mean': '0. 0. 3.', 'beam.ppc': '1 1 2',
+      'beam.zmin': -3., 'beam.zmax': 3., 'beam.density': 0.5, 'beam.n_subcycles': 4,
+      'beam.radius': 3., 'max_step': 4}
+
+
+def _deck():
+    return open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+
+
+def test_wire_message_matches_host_packing():
+    """after 3 steps the packet of every slice == pipeline.pack_slice(oracle slice): header,
+    idcpu bits (ids, order, validity) bit-exact, the real components to 1e-9"""
+    import hipace_b200 as hp
+    from hipace_b200 import pipeline as pl
+    from oracle.hipace_oracle import Simulation as Oracle
+    ref = Oracle(_deck(), OV)
+    ref.evolve(step_end=2)
+    sim = hp.Simulation(_deck(), OV)
+    sim.evolve(0, 2)
+    cap = sim.beam_slice_capacity()
+    assert sim.pipeline_message_bytes() == pl.message_bytes(cap)
+    nz = sim.nz
+    nonempty = 0
+    for isl in range(nz):
+        got = sim.beam_packet(nz - 1 - isl)
+        bs = ref.beams[0].slices[isl]
+        n = bs['np']
+        want = pl.pack_slice({k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in bs.items()}, cap)
+        assert got[:16].view(np.int64).tolist() == [n, n]
+        assert np.array_equal(got[64:64 + 8 * cap].view(np.uint64)[:n], want[64:64 + 8 * cap].view(np.uint64)[:n])
+        g, w = pl.unpack_slice(got, cap), pl.unpack_slice(want, cap)
+        for k in pl.REAL_COMPS:
+            if n:
+                assert np.abs(g[k] - w[k]).max() <= 1e-9 * max(np.abs(w[k]).max(), 1e-300), (isl, k)
+        nonempty += n > 0
+    assert nonempty >= 8
+    sim.close()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import hipace_b200 as hp
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    sim = hp.Simulation(_deck(), OV, device=rank)
+    sim.pipeline_init(rank, world, dist)
+    sim.run(OV['max_step'], rank, world)
+    n = max(sim.beam_np(), 1)
+    host = {'real': np.zeros((7, n)), 'idcpu': np.zeros(n, dtype=np.uint64),
+            'slot_off': np.zeros(sim.nz + 1, dtype=np.int64)}
+    sim.get_beam(host)
+    pickle.dump({'cs': sim.checksums(), 'beam': host, 'bcs': sim.beam_checksums()},
+                open(os.path.join(out_dir, f'rank{rank}.pkl'), 'wb'))
+    torch.cuda.synchronize()
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_pipeline_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    import hipace_b200 as hp
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), d), nprocs=world, join=True)
+        res = [pickle.load(open(os.path.join(d, f'rank{r}.pkl'), 'rb')) for r in range(world)]
+    last = res[OV['max_step'] % world]
+    sim = hp.Simulation(_deck(), OV)
+    cs = sim.evolve(0, OV['max_step'])
+    n = max(sim.beam_np(), 1)
+    host = {'real': np.zeros((7, n)), 'idcpu': np.zeros(n, dtype=np.uint64),
+            'slot_off': np.zeros(sim.nz + 1, dtype=np.int64)}
+    sim.get_beam(host)
+    for k, v in cs.items():
+        assert abs(last['cs'][k] - v) <= 1e-9 * abs(v) + 1e-30, k
+    assert np.array_equal(last['beam']['slot_off'], host['slot_off'])
+    assert np.array_equal(last['beam']['idcpu'], host['idcpu'])
+    for k in range(7):
+        a, b = last['beam']['real'][k], host['real'][k]
+        assert np.abs(a - b).max() <= 1e-9 * max(np.abs(b).max(), 1e-300), k
+    sim.close()

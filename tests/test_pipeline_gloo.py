@@ -1,0 +1,138 @@
+"""The N > 1 path on CPU: two gloo ranks run the time-step pipeline protocol
+(hipace_b200/pipeline.py, the host-side statement of csrc/pipeline.cu) with the oracle as the
+compute engine, and must reproduce a single-process run of the same deck bit for bit --
+including beam particles that slip from one slice into the next between time steps.
+"""
+import os
+import pickle
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OV = {'amr.n_cell': '24 24 12', 'hipace.dt': 4., 'beam.u_mean': '0. 0. 3.', 'beam.ppc': '1 1 2',
+      'beam.zmin': -3., 'beam.zmax': 3., 'beam.density': 0.5, 'beam.n_subcycles': 4,
+      'beam.radius': 3., 'max_step': 4}
+CAP = 512
+KEYS = ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id')
+
+
+class OracleEngine:
+    def __init__(self, deck, ov):
+        from oracle.hipace_oracle import Simulation
+        self.sim = Simulation(deck, ov)
+        self.nz = self.sim.geom.nz
+
+    def begin_step(self, step):
+        self.sim.checksums = {}
+        self.sim.begin_step(step)
+
+    def solve_one_slice(self, isl):
+        self.sim.solve_one_slice(isl)
+
+    def put_beam_slice(self, ib, isl, bs):
+        self.sim.beams[ib].slices[isl] = bs
+
+    def take_beam_slice(self, ib, isl):
+        bs = self.sim.beams[ib].slices[isl]
+        assert bs['x'].size == bs['np']          # slipped particles were moved on
+        return bs
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from hipace_b200 import pipeline as pl
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    ids = pl.exchange_edge_ids(dist, rank, world, bytes([rank + 1]) * 128)
+    assert ids == [bytes([r + 1]) * 128 for r in range(world)]
+    deck = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    eng = OracleEngine(deck, OV)
+    pl.HostPipeline(dist, rank, world, 1, CAP).run(eng, OV['max_step'])
+    res = {'steps': list(pl.owned_steps(rank, world, OV['max_step'])),
+           'checksums': eng.sim.checksums,
+           'beam': {i: {k: bs[k][:bs['np']] for k in KEYS} for i, bs in eng.sim.beams[0].slices.items()}}
+    pickle.dump(res, open(os.path.join(out_dir, f'rank{rank}.pkl'), 'wb'))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pipeline_reproduces_serial_run():
+    import torch.multiprocessing as mp
+    from oracle.hipace_oracle import Simulation
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), d), nprocs=world, join=True)
+        res = [pickle.load(open(os.path.join(d, f'rank{r}.pkl'), 'rb')) for r in range(world)]
+    assert res[0]['steps'] == [0, 2, 4] and res[1]['steps'] == [1, 3]
+    deck = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    ref = Simulation(deck, OV)
+    ref.evolve(step_end=OV['max_step'])
+    last = res[OV['max_step'] % world]             # the rank that ran the last step
+    for k, v in ref.checksums.items():
+        assert last['checksums'][k] == v, k         # same arithmetic on both sides: bit-exact
+    nslip = 0
+    for isl, bs in ref.beams[0].slices.items():
+        n = bs['np']
+        got = last['beam'][isl]
+        for k in KEYS:
+            assert np.array_equal(got[k], bs[k][:n]), (isl, k)
+        nslip += n
+    assert nslip > 0
+
+
+def test_schedule_and_wire_layout():
+    from hipace_b200 import pipeline as pl
+    # every step is owned exactly once, in ring order
+    for world in (1, 2, 3, 8):
+        owners = {}
+        for r in range(world):
+            for s in pl.owned_steps(r, world, 20):
+                assert s not in owners
+                owners[s] = r
+        assert sorted(owners) == list(range(21))
+        for s in range(1, 21):
+            assert owners[s] == pl.downstream(owners[s - 1], world)
+            assert pl.upstream(owners[s], world) == owners[s - 1]
+        assert not pl.receives(0, world) and not pl.sends(20, world, 20)
+    # message = 64-byte header + idcpu[cap] + 7 real arrays [cap] (MultiBuffer.cpp:611-728)
+    rng = np.random.default_rng(0)
+    n, cap = 37, 64
+    bs = {k: rng.standard_normal(n) for k in pl.REAL_COMPS}
+    bs['id'] = np.arange(5, 5 + n)
+    bs['valid'] = rng.random(n) > 0.3
+    buf = pl.pack_slice(bs, cap)
+    assert buf.size == pl.message_bytes(cap) == 64 + 64 * cap
+    assert buf[:8].view(np.int64)[0] == n
+    assert np.array_equal(buf[64 + 8 * cap * 3:64 + 8 * cap * 4].view(np.float64)[:n], bs['z'])
+    back = pl.unpack_slice(buf, cap)
+    for k in pl.REAL_COMPS + ('id', 'valid'):
+        assert np.array_equal(back[k], bs[k]), k
+    assert (back['nsub'] == 0).all()
+    with pytest.raises(ValueError):
+        pl.pack_slice(bs, 16)
+
+
+def test_library_exports_every_declared_symbol():
+    """include/hpb200.h <-> libhpb200.so (no compute calls: there is no GPU here)"""
+    import re
+    import hipace_b200 as hp
+    hdr = open(os.path.join(ROOT, 'include', 'hpb200.h')).read()
+    declared = set(re.findall(r'\b(hpb_[a-z0-9_]+)\s*\(', hdr))
+    L = hp.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(hp.EXPORTS), declared ^ set(hp.EXPORTS)
