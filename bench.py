@@ -283,18 +283,33 @@ def main():
         nsl = sp['n_slices']
         P = sp['n_plasma_pushed'] / nsl
         Gc = (args.nxy + 4) ** 2
-        # algorithmic bytes per launch, SURVEY.md 8(d)
-        alg = {'deposit': 56 * P + 4 * 8 * Gc, 'explicit': 56 * P + 8 * 8 * Gc, 'push': 128 * P + 5 * 8 * Gc}
+        # algorithmic bytes per launch (particle kernels) / per slice (solver stages), SURVEY.md 8(d)
+        Nc = args.nxy ** 2
+        ncyc = sp['n_mg_vcycles'] / nsl
+        alg = {'deposit': 56 * P + 4 * 8 * Gc, 'explicit': 56 * P + 8 * 8 * Gc, 'push': 128 * P + 5 * 8 * Gc,
+               'poisson': 3 * 6 * 8 * Nc,                       # 3 solves x practical 3-pass model
+               'mg': (30 * ncyc + 17) * 8 * Gc}                 # hpmg finest-level model
         stages = {k: sp['ms_' + k] / nsl for k in ('deposit', 'poisson', 'explicit', 'mg', 'push', 'other')}
-        stages['mg_vcycles_per_slice'] = sp['n_mg_vcycles'] / nsl
-        dom = max(alg, key=lambda k: stages[k])
+        stages['mg_vcycles_per_slice'] = ncyc
+        kernel_of = {'deposit': 'k_deposit_current', 'explicit': 'k_explicit_deposition',
+                     'push': 'k_advance_plasma'}
+        dom = max(kernel_of, key=lambda k: stages[k])
         ach = alg[dom] / (stages[dom] * 1e-3) / 1e9
-        roofline = {'kernel': {'deposit': 'k_deposit_current', 'explicit': 'k_explicit_deposition',
-                               'push': 'k_advance_plasma'}[dom],
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+            if (tr.get('nxy'), tr.get('ppc')) == (args.nxy, args.ppc * args.ppc):
+                traffic = tr['kernels'].get(kernel_of[dom])
+                traffic_src = tr.get('source')
+        except Exception:
+            pass
+        roofline = {'kernel': kernel_of[dom],
                     'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': None, 'peak_source': peak_src,
+                    'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': alg[dom], 'avg_launch_ms': stages[dom],
-                    'all': {k: {'GBps': alg[k] / (stages[k] * 1e-3) / 1e9, 'ms': stages[k]} for k in alg}}
+                    'all': {k: {'GBps': alg[k] / (stages[k] * 1e-3) / 1e9, 'ms': stages[k],
+                                'frac': alg[k] / (stages[k] * 1e-3) / 1e9 / peak} for k in alg}}
 
     # ---- CPU baseline (rank 0, N = 1) -----------------------------------------------------------
     cpu_baseline = None

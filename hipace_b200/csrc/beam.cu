@@ -35,6 +35,7 @@ k_advance_beam(hpb_beam_slice b, int *__restrict__ nsub, SliceView a, int c_psi,
                const DevRpn *__restrict__ ext, int *__restrict__ class_counts,
                double *__restrict__ checksum, unsigned long long *__restrict__ n_pushed)
 {
+    hpb_pdl_prologue();
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long np = np_of(b, 0), np_tot = np_of(b, 1);
     int cls = 0;                 // 0 dropped / beyond the slice, 1 stays, 2 slipped
@@ -133,6 +134,7 @@ k_beam_partition(hpb_beam_slice b, const int *__restrict__ nsub, double min_z,
                  hpb_beam_slice next, int64_t *next_np,
                  int *__restrict__ next_nsub, int *overflow)
 {
+    hpb_pdl_prologue();
     __shared__ long s_base[2];
     __shared__ int s_warp[2][kBT / 32];
     const long np_tot = np_of(b, 1);
@@ -209,6 +211,7 @@ k_beam_partition(hpb_beam_slice b, const int *__restrict__ nsub, double min_z,
 // ---- ring maintenance ---------------------------------------------------------------------------
 __global__ void k_ring_clear(BeamRing r)
 {
+    hpb_pdl_prologue();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= r.nslots) return;
     int64_t *h = r.hdr(s);
@@ -217,6 +220,7 @@ __global__ void k_ring_clear(BeamRing r)
 
 __global__ void __launch_bounds__(kBT) k_ring_checksum(BeamRing r, double *out)
 {
+    hpb_pdl_prologue();
     const int s = blockIdx.y;
     const hpb_beam_slice b = r.view(s);
     const long n = np_of(b, 0);
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(kBT) k_ring_checksum(BeamRing r, double *out)
 template <bool GATHER>
 __global__ void __launch_bounds__(kBT) k_ring_copy(BeamRing r, const long *__restrict__ off, double *stage, long ntot)
 {
+    hpb_pdl_prologue();
     const int s = blockIdx.y;
     const hpb_beam_slice b = r.view(s);
     const long o = off[s], n = off[s + 1] - o;
@@ -317,7 +322,7 @@ int hpb_advance_beam_impl(hpb_ctx *ctx, hpb_beam_slice bm, int *d_nsub, hpb_slic
     if (bm.np == 0) return HPB_OK;
     const hpb_geom &g = ctx->g;
 #define HPB_ADV_BEAM(E)                                                                           \
-    k_advance_beam<E><<<nblk(bm.np), kBT, 0, ctx->stream>>>(                                      \
+    hpb_launch(k_advance_beam<E>, nblk(bm.np), kBT, 0, ctx->stream,                                       \
         bm, d_nsub, make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],            \
         comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
         charge / mass, n_subcycles, dt / n_subcycles, time, min_z, do_z_push, particle_bc,        \
@@ -350,7 +355,7 @@ extern "C" int hpb_beam_shift_slipped(hpb_ctx *ctx, hpb_beam_slice bm, const int
     if (!ctx || !d_class_counts || !d_stay_np || !d_overflow || !d_nsubcycles) return HPB_ERR_ARG;
     if (next.idcpu && !d_next_np) return HPB_ERR_ARG;
     const unsigned nb = bm.np > 0 ? nblk(bm.np) : 1;
-    k_beam_partition<<<nb, kBT, 0, ctx->stream>>>(bm, d_nsubcycles, min_z, d_class_counts, stay, d_stay_np,
+    hpb_launch(k_beam_partition, nb, kBT, 0, ctx->stream, bm, d_nsubcycles, min_z, d_class_counts, stay, d_stay_np,
                                                   next, d_next_np, d_next_nsubcycles, d_overflow);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
@@ -389,7 +394,7 @@ void hpb_beam_rings_free(BeamSp &b)
 
 int hpb_beam_ring_clear(hpb_sim *s, const BeamRing &r)
 {
-    k_ring_clear<<<(r.nslots + 255) / 256, 256, 0, s->stream>>>(r);
+    hpb_launch(k_ring_clear, (r.nslots + 255) / 256, 256, 0, s->stream, r);
     SIM_CUDA(cudaGetLastError());
     return HPB_OK;
 }
@@ -410,7 +415,7 @@ int hpb_beam_ring_checksum(hpb_sim *s, const BeamRing &r, double *d_out9)
 {
     SIM_CUDA(cudaMemsetAsync(d_out9, 0, 9 * sizeof(double), s->stream));
     dim3 grid(nblk(r.cap) < 64 ? nblk(r.cap) : 64, r.nslots);
-    k_ring_checksum<<<grid, kBT, 0, s->stream>>>(r, d_out9);
+    hpb_launch(k_ring_checksum, grid, kBT, 0, s->stream, r, d_out9);
     SIM_CUDA(cudaGetLastError());
     return HPB_OK;
 }
@@ -434,7 +439,7 @@ int hpb_beam_ring_gather(hpb_sim *s, BeamSp &b, const BeamRing &r, const std::ve
     SIM_CUDA(cudaMemcpyAsync(b.d_stage_off, slot_off.data(), sizeof(long) * (r.nslots + 1),
                              cudaMemcpyHostToDevice, s->stream));
     dim3 grid(nblk(r.cap) < 64 ? nblk(r.cap) : 64, r.nslots);
-    k_ring_copy<true><<<grid, kBT, 0, s->stream>>>(r, b.d_stage_off, b.d_stage, b.stage_cap);
+    hpb_launch(k_ring_copy<true>, grid, kBT, 0, s->stream, r, b.d_stage_off, b.d_stage, b.stage_cap);
     SIM_CUDA(cudaGetLastError());
     for (int k = 0; k < 7; ++k)
         SIM_CUDA(cudaMemcpyAsync(h_real[k], b.d_stage + (size_t)k * b.stage_cap, sizeof(double) * np,
@@ -462,7 +467,7 @@ int hpb_beam_ring_scatter(hpb_sim *s, BeamSp &b, const BeamRing &r, const long *
         SIM_CUDA(cudaMemcpyAsync(b.d_stage + 7 * (size_t)b.stage_cap, h_idcpu, sizeof(uint64_t) * np,
                                  cudaMemcpyHostToDevice, s->stream));
     dim3 grid(nblk(r.cap) < 64 ? nblk(r.cap) : 64, r.nslots);
-    k_ring_copy<false><<<grid, kBT, 0, s->stream>>>(r, b.d_stage_off, b.d_stage, b.stage_cap);
+    hpb_launch(k_ring_copy<false>, grid, kBT, 0, s->stream, r, b.d_stage_off, b.d_stage, b.stage_cap);
     SIM_CUDA(cudaGetLastError());
     return HPB_OK;
 }

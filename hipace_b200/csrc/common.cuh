@@ -20,6 +20,36 @@
 void hpb_set_error(const char *fmt, ...);
 void hpb_count_launch(hpb_ctx *ctx, int n = 1);
 
+// ---- programmatic dependent launch -----------------------------------------------------------
+// The slice loop is a strictly sequential chain of ~45 short kernels; with stream serialisation
+// every kernel pays the launch latency and the ramp-up of its predecessor's tail.  All hot-path
+// kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel signals
+// `launch_dependents` as its first instruction, so the CTAs of the next kernel become resident
+// while this one drains, and every kernel executes `griddepcontrol.wait` (= predecessor grid
+// complete and its memory visible) before it touches global memory.  Without the attribute
+// (HPB_PDL=0) both instructions are no-ops.
+__device__ __forceinline__ void hpb_pdl_prologue()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+bool hpb_pdl_enabled();
+
+template <class... KA, class... A>
+inline cudaError_t hpb_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, A &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = hpb_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<A &&>(args)...);
+}
+
 // validity flag = top bit of idcpu (AMReX >= 24 ParticleIDWrapper packing)
 #define HPB_ID_VALID_BIT (uint64_t(1) << 63)
 __host__ __device__ inline bool hpb_is_valid(uint64_t idcpu) { return (idcpu >> 63) != 0; }

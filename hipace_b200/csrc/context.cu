@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 int hpb_poisson_init(hpb_ctx *ctx);
@@ -20,6 +21,13 @@ void hpb_set_error(const char *fmt, ...)
 }
 
 void hpb_count_launch(hpb_ctx *ctx, int n) { ctx->n_launch += n; }
+
+bool hpb_pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("HPB_PDL"); on = e ? (atoi(e) != 0) : 1; }
+    return on != 0;
+}
 
 extern "C" const char *hpb_last_error(void) { return g_err; }
 extern "C" const char *hpb_version(void) { return "hpb200 0.1 (sm_100a, fp64)"; }

@@ -13,6 +13,7 @@ struct CompPairs { int n; int dst[8]; int src[8]; };
 // grown box, flat
 __global__ void k_zero(SliceView a, CompList cl, long ntot)
 {
+    hpb_pdl_prologue();
     const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= ntot) return;
     for (int n = 0; n < cl.n; ++n) a.comp(cl.c[n])[o] = 0.0;
@@ -20,6 +21,7 @@ __global__ void k_zero(SliceView a, CompList cl, long ntot)
 
 __global__ void k_copy(SliceView a, CompPairs cp, long ntot)
 {
+    hpb_pdl_prologue();
     const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= ntot) return;
     double v[8];
@@ -29,6 +31,7 @@ __global__ void k_copy(SliceView a, CompPairs cp, long ntot)
 
 __global__ void k_add(SliceView a, CompPairs cp, long ntot)
 {
+    hpb_pdl_prologue();
     const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= ntot) return;
     for (int n = 0; n < cp.n; ++n) a.comp(cp.dst[n])[o] += a.comp(cp.src[n])[o];
@@ -38,6 +41,7 @@ __global__ void k_add(SliceView a, CompPairs cp, long ntot)
 __global__ void k_exmby_eypbx(SliceView a, int c_psi, int c_exmby, int c_eypbx, int nx, int ny,
                               double dx_inv_half, double dy_inv_half)
 {
+    hpb_pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x - (HPB_G - 1);
     const int j = (int)blockIdx.y - (HPB_G - 1);
     if (i >= nx + (HPB_G - 1)) return;
@@ -48,15 +52,23 @@ __global__ void k_exmby_eypbx(SliceView a, int c_psi, int c_exmby, int c_eypbx, 
     a.comp(c_eypbx)[o] = -(psi[o + js] - psi[o - js]) * dy_inv_half;
 }
 
-// Hipace::InitializeSxSyWithBeam (Hipace.cpp:775-788), valid box
+// Hipace::InitializeSxSyWithBeam (Hipace.cpp:775-788) on the valid box; the guard cells are set to
+// zero (the state Fields::InitializeSlices leaves them in), so that Sx / Sy need no separate
+// zero-fill pass before this kernel.
 __global__ void k_sxsy_from_beam(SliceView a, int c_sx, int c_sy, int c_next_jxb, int c_next_jyb,
                                  int c_jzb, int c_prev_jxb, int c_prev_jyb, int nx, int ny,
                                  double mu0, double dx, double dy, double dz)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i >= nx) return;
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - HPB_G;
+    const int j = (int)blockIdx.y - HPB_G;
+    if (i >= nx + HPB_G) return;
     const long o = a.idx(i, j);
+    if (i < 0 || i >= nx || j < 0 || j >= ny) {
+        a.comp(c_sy)[o] = 0.0;
+        a.comp(c_sx)[o] = 0.0;
+        return;
+    }
     const long js = a.jstride;
     const double *jzb = a.comp(c_jzb);
     const double dx_jzb = (jzb[o + 1] - jzb[o - 1]) / (2.0 * dx);
@@ -67,9 +79,26 @@ __global__ void k_sxsy_from_beam(SliceView a, int c_sx, int c_sy, int c_next_jxb
     a.comp(c_sx)[o] = -mu0 * (-dx_jzb + dz_jxb);
 }
 
+// ShiftSlices + InitializeSlices of the next slice in one pass over the grown box
+struct ShiftInit {
+    int n_zero; int zero[8];
+    int n_copy; int dst[4]; int src[4];
+};
+__global__ void k_shift_init(SliceView a, ShiftInit si, long ntot)
+{
+    hpb_pdl_prologue();
+    const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= ntot) return;
+    double v[4];
+    for (int n = 0; n < si.n_copy; ++n) v[n] = a.comp(si.src[n])[o];
+    for (int n = 0; n < si.n_zero; ++n) a.comp(si.zero[n])[o] = 0.0;
+    for (int n = 0; n < si.n_copy; ++n) a.comp(si.dst[n])[o] = v[n];
+}
+
 // sum|Q| over the valid box; fixed-order block tree + one atomic per block
 __global__ void k_abs_sum(SliceView a, int c, int nx, int ny, double *out)
 {
+    hpb_pdl_prologue();
     __shared__ double sm[kThreads];
     double acc = 0.0;
     const double *p = a.comp(c);
@@ -97,7 +126,7 @@ int hpb_launch_exmby_eypbx(hpb_ctx *ctx, const hpb_slice &sl, const int *comps)
     const hpb_geom &g = ctx->g;
     const int gx = g.nx + 2 * (HPB_G - 1), gy = g.ny + 2 * (HPB_G - 1);
     dim3 grid((gx + kThreads - 1) / kThreads, gy);
-    k_exmby_eypbx<<<grid, kThreads, 0, ctx->stream>>>(
+    hpb_launch(k_exmby_eypbx, grid, kThreads, 0, ctx->stream, 
         make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.nx, g.ny,
         0.5 * (1.0 / g.dx), 0.5 * (1.0 / g.dy));
     hpb_count_launch(ctx);
@@ -115,7 +144,7 @@ extern "C" int hpb_fields_initialize_slices(hpb_ctx *ctx, hpb_slice sl, const in
                          HPB_C_RHOMJZ, HPB_C_NEXT_JX_BEAM, HPB_C_NEXT_JY_BEAM, HPB_C_RHO};
     for (int k : names) if (comps[k] >= 0) cl.c[cl.n++] = comps[k];
     const long ntot = (long)sl.jstride * sl.ny_tot;
-    k_zero<<<nb(ntot), kThreads, 0, ctx->stream>>>(make_view(sl), cl, ntot);
+    hpb_launch(k_zero, nb(ntot), kThreads, 0, ctx->stream, make_view(sl), cl, ntot);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
@@ -130,7 +159,7 @@ extern "C" int hpb_fields_add_rho_ions(hpb_ctx *ctx, hpb_slice sl, const int *co
     cp.dst[cp.n] = comps[HPB_C_RHOMJZ]; cp.src[cp.n++] = comps[HPB_C_IONS_RHOMJZ];
     if (comps[HPB_C_RHO] >= 0) { cp.dst[cp.n] = comps[HPB_C_RHO]; cp.src[cp.n++] = comps[HPB_C_IONS_RHOMJZ]; }
     const long ntot = (long)sl.jstride * sl.ny_tot;
-    k_add<<<nb(ntot), kThreads, 0, ctx->stream>>>(make_view(sl), cp, ntot);
+    hpb_launch(k_add, nb(ntot), kThreads, 0, ctx->stream, make_view(sl), cp, ntot);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
@@ -151,7 +180,39 @@ extern "C" int hpb_fields_shift_slices(hpb_ctx *ctx, hpb_slice sl, const int *co
     cp.dst[4] = comps[HPB_C_JX];           cp.src[4] = comps[HPB_C_NEXT_JX_BEAM];
     cp.dst[5] = comps[HPB_C_JY];           cp.src[5] = comps[HPB_C_NEXT_JY_BEAM];
     const long ntot = (long)sl.jstride * sl.ny_tot;
-    k_copy<<<nb(ntot), kThreads, 0, ctx->stream>>>(make_view(sl), cp, ntot);
+    hpb_launch(k_copy, nb(ntot), kThreads, 0, ctx->stream, make_view(sl), cp, ntot);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// Our addition (no reference counterpart as one call): Fields::ShiftSlices (Fields.cpp:596-599) of
+// this slice followed by Fields::InitializeSlices (:551-560, 578-580) and AddRhoIons (:606-615) of
+// the next one, as ONE pass.  The three (Previous, This, Next) planes of jx_beam / jy_beam are
+// rotated through the component table `comps` (in/out) instead of being copied; ExmBy / EypBx need
+// no zero-fill (k_exmby_eypbx rewrites every cell it ever wrote) and Sx / Sy get theirs from
+// k_sxsy_from_beam.  rhomjz starts from the ion background instead of 0 (+ AddRhoIons later).
+extern "C" int hpb_fields_shift_and_initialize(hpb_ctx *ctx, hpb_slice sl, int *comps)
+{
+    if (!ctx || !comps) return HPB_ERR_ARG;
+    // rotation: Previous <- This <- Next <- (old Previous, to be zeroed)
+    const int old_prev_x = comps[HPB_C_PREV_JX_BEAM], old_prev_y = comps[HPB_C_PREV_JY_BEAM];
+    comps[HPB_C_PREV_JX_BEAM] = comps[HPB_C_JX_BEAM]; comps[HPB_C_PREV_JY_BEAM] = comps[HPB_C_JY_BEAM];
+    comps[HPB_C_JX_BEAM] = comps[HPB_C_NEXT_JX_BEAM]; comps[HPB_C_JY_BEAM] = comps[HPB_C_NEXT_JY_BEAM];
+    comps[HPB_C_NEXT_JX_BEAM] = old_prev_x;           comps[HPB_C_NEXT_JY_BEAM] = old_prev_y;
+    ShiftInit si;
+    si.n_zero = 0; si.n_copy = 0;
+    for (int k : {HPB_C_CHI, HPB_C_JZ_BEAM, HPB_C_NEXT_JX_BEAM, HPB_C_NEXT_JY_BEAM})
+        si.zero[si.n_zero++] = comps[k];
+    si.dst[si.n_copy] = comps[HPB_C_JX]; si.src[si.n_copy++] = comps[HPB_C_JX_BEAM];
+    si.dst[si.n_copy] = comps[HPB_C_JY]; si.src[si.n_copy++] = comps[HPB_C_JY_BEAM];
+    for (int k : {HPB_C_RHOMJZ, HPB_C_RHO}) {
+        if (comps[k] < 0) continue;
+        if (comps[HPB_C_IONS_RHOMJZ] >= 0) { si.dst[si.n_copy] = comps[k]; si.src[si.n_copy++] = comps[HPB_C_IONS_RHOMJZ]; }
+        else si.zero[si.n_zero++] = comps[k];
+    }
+    const long ntot = (long)sl.jstride * sl.ny_tot;
+    hpb_launch(k_shift_init, nb(ntot), kThreads, 0, ctx->stream, make_view(sl), si, ntot);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
@@ -161,8 +222,8 @@ extern "C" int hpb_fields_sxsy_from_beam(hpb_ctx *ctx, hpb_slice sl, const int *
 {
     if (!ctx || !comps) return HPB_ERR_ARG;
     const hpb_geom &g = ctx->g;
-    dim3 grid((g.nx + kThreads - 1) / kThreads, g.ny);
-    k_sxsy_from_beam<<<grid, kThreads, 0, ctx->stream>>>(
+    dim3 grid((g.nx + 2 * HPB_G + kThreads - 1) / kThreads, g.ny + 2 * HPB_G);
+    hpb_launch(k_sxsy_from_beam, grid, kThreads, 0, ctx->stream, 
         make_view(sl), comps[HPB_C_SX], comps[HPB_C_SY], comps[HPB_C_NEXT_JX_BEAM],
         comps[HPB_C_NEXT_JY_BEAM], comps[HPB_C_JZ_BEAM], comps[HPB_C_PREV_JX_BEAM],
         comps[HPB_C_PREV_JY_BEAM], g.nx, g.ny, g.mu0, g.dx, g.dy, g.dz);
@@ -178,7 +239,7 @@ extern "C" int hpb_abs_sum(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out)
     const long n = (long)g.nx * g.ny;
     unsigned blocks = nb(n);
     if (blocks > 592) blocks = 592;
-    k_abs_sum<<<blocks, kThreads, 0, ctx->stream>>>(make_view(sl), c, g.nx, g.ny, d_out);
+    hpb_launch(k_abs_sum, blocks, kThreads, 0, ctx->stream, make_view(sl), c, g.nx, g.ny, d_out);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(NT, 2)
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
          V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO, const int *done)
 {
+    hpb_pdl_prologue();
     __shared__ double sm[2][AY * AX];
     if (done && *done) return;      // converged: the speculatively enqueued V-cycle is a no-op
     const int FX = CX - 2 * EO, FY = CY - 2 * EO;
@@ -479,6 +480,7 @@ __device__ __forceinline__ void s_interp_add(const SLevel &Lf, const SCell &c, c
 
 __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const int *done)
 {
+    hpb_pdl_prologue();
     extern __shared__ double csm[];
     __shared__ SLevel S[12];
     if (*done) return;
@@ -541,6 +543,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const i
 // arrays (coherent within one CTA after __syncthreads)
 __global__ void __launch_bounds__(kCoarseThreads) k_coarse_global(CoarseArgs A, const int *done)
 {
+    hpb_pdl_prologue();
     if (*done) return;
     const int nl = A.nl;
     for (int l = 0; l < nl - 1; ++l) {
@@ -567,6 +570,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_global(CoarseArgs A, 
 __global__ void __launch_bounds__(kCoarseThreads) k_coarse_setup(CoarseArgs A, LevelGeom gfine,
                                                                   const double *acf_fine, long fine_rs)
 {
+    hpb_pdl_prologue();
     // restrict into L[0] from the finer (tile) level with an arbitrary row stride
     {
         const LevelGeom &gc = A.L[0].g;
@@ -602,6 +606,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_setup(CoarseArgs A, L
 // crse = R(fine), 1 component, arbitrary fine row stride (coefficient average-down on tile levels)
 __global__ void k_restrict_acf(LevelGeom gc, double *crse, const double *fine, long fine_rs)
 {
+    hpb_pdl_prologue();
     const int nvx = gc.vhix - gc.vlo + 1;
     const long nv = (long)nvx * (gc.vhiy - gc.vlo + 1);
     const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,6 +623,7 @@ __global__ void k_restrict_acf(LevelGeom gc, double *crse, const double *fine, l
 
 __global__ void k_copy2(LevelGeom g, V2 dst, V2 src)
 {
+    hpb_pdl_prologue();
     const int nvx = g.vhix - g.vlo + 1;
     const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
     const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -632,6 +638,7 @@ __global__ void k_copy2(LevelGeom g, V2 dst, V2 src)
 //   ist[2] = failed.  norm[] is reset for the next accumulation.
 __global__ void k_mg_check(int mode, double *norm, double *st, int *ist, double tol_rel, double tol_abs)
 {
+    hpb_pdl_prologue();
     if (mode == 0) {
         const double resnorm0 = norm[0], rhsnorm0 = norm[1];
         const double max_norm = rhsnorm0 >= resnorm0 ? rhsnorm0 : resnorm0;
@@ -681,7 +688,7 @@ void launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, con
     const int FX = CX - 2 * EO, FY = CY - 2 * EO;
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
-    k_smooth<INIT, RES><<<nbx * nby, NT, 0, ctx->stream>>>(g, in, crse, rhs, acf, acf_rs, out, gc,
+    hpb_launch(k_smooth<INIT, RES>, nbx * nby, NT, 0, ctx->stream, g, in, crse, rhs, acf, acf_rs, out, gc,
                                                            res_c, norm, nbx, EO, done);
     hpb_count_launch(ctx);
 }
@@ -804,9 +811,9 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
                                lvl_view(ctx, l + 1, ctx->mg[l + 1].res), nullptr, done);
     }
     if (ctx->mg_coarse_smem > 0)
-        k_coarse<<<1, kCoarseThreads, ctx->mg_coarse_smem, ctx->stream>>>(coarse_args(ctx), done);
+        hpb_launch(k_coarse, 1, kCoarseThreads, ctx->mg_coarse_smem, ctx->stream, coarse_args(ctx), done);
     else
-        k_coarse_global<<<1, kCoarseThreads, 0, ctx->stream>>>(coarse_args(ctx), done);
+        hpb_launch(k_coarse_global, 1, kCoarseThreads, 0, ctx->stream, coarse_args(ctx), done);
     hpb_count_launch(ctx);
     // up, tile levels: cor[l] <- GSRB^4(cor[l] + I(cor[l+1])); double-buffered through rescor[l]
     double *up_prev = ctx->mg[lc].cor;
@@ -824,7 +831,7 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
     // cor0 = GSRB^4(sol), rescor0 = rhs - L cor0 -> res[1], norm   (:1501-1503)
     launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, cur, g1,
                            lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, done);
-    k_mg_check<<<1, 1, 0, ctx->stream>>>(1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
+    hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
     hpb_count_launch(ctx);
     return HPB_OK;
 }
@@ -853,12 +860,12 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     for (int l = 1; l < lc; ++l) {
         const LevelGeom gc = level_geom(ctx, l);
         const long nv = (long)(gc.vhix - gc.vlo + 1) * (gc.vhiy - gc.vlo + 1);
-        k_restrict_acf<<<nb(nv), 256, 0, ctx->stream>>>(gc, ctx->mg[l].acf, fine, fine_rs);
+        hpb_launch(k_restrict_acf, nb(nv), 256, 0, ctx->stream, gc, ctx->mg[l].acf, fine, fine_rs);
         hpb_count_launch(ctx);
         fine = ctx->mg[l].acf;
         fine_rs = gc.nx;
     }
-    k_coarse_setup<<<1, kCoarseThreads, 0, ctx->stream>>>(coarse_args(ctx), level_geom(ctx, lc - 1),
+    hpb_launch(k_coarse_setup, 1, kCoarseThreads, 0, ctx->stream, coarse_args(ctx), level_geom(ctx, lc - 1),
                                                           fine, fine_rs);
     hpb_count_launch(ctx);
 
@@ -866,7 +873,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     V2 cur = lvl_view(ctx, 0, ctx->mg[0].cor);
     launch_smooth<1, true>(ctx, g0, sol, none, rhs, chi, chi_rs, cur, g1,
                            lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, nullptr);
-    k_mg_check<<<1, 1, 0, ctx->stream>>>(0, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
+    hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 0, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
     hpb_count_launch(ctx);
     // Speculative V-cycles: as many as the previous solve needed, enqueued without a host round
     // trip; each kernel is a no-op once the device-side test (:1391) has passed.  One
@@ -901,7 +908,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     }
     ctx->mg_last_iters = iters;
     // sol <- cor0 on the valid box (:1419-1426)
-    k_copy2<<<nb(nv0), 256, 0, ctx->stream>>>(g0, sol, cur);
+    hpb_launch(k_copy2, nb(nv0), 256, 0, ctx->stream, g0, sol, cur);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     if (h_iters) *h_iters = iters;

@@ -43,6 +43,71 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kDepOwn = 30;      // particles deposited per warp (lanes 1..30)
 constexpr int kExplOwn = 28;     // explicit deposition: lanes 2..29
 
+// Scatter of one particle per lane with neighbour-lane aggregation.  Must be called by all 32
+// lanes.  active: the lane holds a particle to deposit; owner: the lane issues reductions (the
+// non-owner edge lanes of k_deposit_current only feed their neighbours).
+template <bool JXY, bool RHO, bool CHI, bool RMJ>
+__device__ __forceinline__ void
+deposit_aggregated(const SliceView &a, int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz,
+                   bool active, bool owner, int lane, int i0, int j0, const double sx[3],
+                   const double sy[3], double q_invvol, double vx_c, double vy_c, double gamma_psi,
+                   double chi_fac)
+{
+    // centre column; inactive lanes get a sentinel that never aligns with a neighbour
+    const int cc = active ? i0 + 1 : -(1 << 28) - 3 * lane;
+    const int cL = __shfl_up_sync(kFull, cc, 1), jL = __shfl_up_sync(kFull, j0, 1);
+    const int cR = __shfl_down_sync(kFull, cc, 1), jR = __shfl_down_sync(kFull, j0, 1);
+    const bool L_ok = active && lane > 0 && cL == cc - 1 && jL == j0;
+    const bool R_ok = active && lane < 31 && cR == cc + 1 && jR == j0;
+
+    // per-row weights of the three stencil columns
+    double P0[3], P1[3], P2[3], PL[3], PR[3];
+#pragma unroll
+    for (int iy = 0; iy < 3; ++iy) {
+        P0[iy] = q_invvol * sx[0] * sy[iy];
+        P1[iy] = q_invvol * sx[1] * sy[iy];
+        P2[iy] = q_invvol * sx[2] * sy[iy];
+        PL[iy] = __shfl_up_sync(kFull, P2[iy], 1);       // right column of the left neighbour
+        PR[iy] = __shfl_down_sync(kFull, P0[iy], 1);     // left column of the right neighbour
+        if (!L_ok) PL[iy] = 0.;
+        if (!R_ok) PR[iy] = 0.;
+    }
+    // per-component multipliers: own, left neighbour's, right neighbour's
+    const double vxL = __shfl_up_sync(kFull, vx_c, 1), vxR = __shfl_down_sync(kFull, vx_c, 1);
+    const double vyL = __shfl_up_sync(kFull, vy_c, 1), vyR = __shfl_down_sync(kFull, vy_c, 1);
+    const double gpL = RHO ? __shfl_up_sync(kFull, gamma_psi, 1) : 0., gpR = RHO ? __shfl_down_sync(kFull, gamma_psi, 1) : 0.;
+    const double cfL = CHI ? __shfl_up_sync(kFull, chi_fac, 1) : 0., cfR = CHI ? __shfl_down_sync(kFull, chi_fac, 1) : 0.;
+    if (!active || !owner) return;
+
+    double *jx = JXY ? a.comp(c_jx) : nullptr, *jy = JXY ? a.comp(c_jy) : nullptr;
+    double *rho = RHO ? a.comp(c_rho) : nullptr, *chi = CHI ? a.comp(c_chi) : nullptr;
+    double *rmj = RMJ ? a.comp(c_rhomjz) : nullptr;
+#pragma unroll
+    for (int iy = 0; iy < 3; ++iy) {
+        const long o = a.idx(cc, j0 + iy);
+        if (JXY) {
+            red_add(jx + o, P1[iy] * vx_c + PL[iy] * vxL + PR[iy] * vxR);
+            red_add(jy + o, P1[iy] * vy_c + PL[iy] * vyL + PR[iy] * vyR);
+        }
+        if (RHO) red_add(rho + o, P1[iy] * gamma_psi + PL[iy] * gpL + PR[iy] * gpR);
+        if (CHI) red_add(chi + o, P1[iy] * chi_fac + PL[iy] * cfL + PR[iy] * cfR);
+        if (RMJ) red_add(rmj + o, P1[iy] + PL[iy] + PR[iy]);
+        // a side column without an aligned neighbour lane is deposited by the particle itself
+        if (!L_ok) {
+            if (JXY) { red_add(jx + o - 1, P0[iy] * vx_c); red_add(jy + o - 1, P0[iy] * vy_c); }
+            if (RHO) red_add(rho + o - 1, P0[iy] * gamma_psi);
+            if (CHI) red_add(chi + o - 1, P0[iy] * chi_fac);
+            if (RMJ) red_add(rmj + o - 1, P0[iy]);
+        }
+        if (!R_ok) {
+            if (JXY) { red_add(jx + o + 1, P2[iy] * vx_c); red_add(jy + o + 1, P2[iy] * vy_c); }
+            if (RHO) red_add(rho + o + 1, P2[iy] * gamma_psi);
+            if (CHI) red_add(chi + o + 1, P2[iy] * chi_fac);
+            if (RMJ) red_add(rmj + o + 1, P2[iy]);
+        }
+    }
+}
+
 template <bool JXY, bool RHO, bool CHI, bool RMJ>
 __global__ void __launch_bounds__(kThreads)
 k_deposit_current(PlasmaPtrs pl, SliceView a, int c_jx, int c_jy, int c_rho, int c_chi,
@@ -50,6 +115,7 @@ k_deposit_current(PlasmaPtrs pl, SliceView a, int c_jx, int c_jy, int c_rho, int
                   double clightinv, double charge_invvol, double charge_mu0_mass_ratio,
                   double max_qsa, int *n_qsa_violation)
 {
+    hpb_pdl_prologue();
     // warps overlap by one lane on each side: lanes 0 and 31 only feed their neighbours, so an
     // aligned run of particles never pays for warp-edge columns
     const int lane = threadIdx.x & 31;
@@ -93,59 +159,9 @@ k_deposit_current(PlasmaPtrs pl, SliceView a, int c_jx, int c_jy, int c_rho, int
             q_invvol = 0.;
         }
     }
-    // centre column; inactive lanes get a sentinel that never aligns with a neighbour
-    const int cc = active ? i0 + 1 : -(1 << 28) - 3 * lane;
-    const int cL = __shfl_up_sync(kFull, cc, 1), jL = __shfl_up_sync(kFull, j0, 1);
-    const int cR = __shfl_down_sync(kFull, cc, 1), jR = __shfl_down_sync(kFull, j0, 1);
-    const bool L_ok = active && lane > 0 && cL == cc - 1 && jL == j0;
-    const bool R_ok = active && lane < 31 && cR == cc + 1 && jR == j0;
-
-    const double chi_fac = charge_mu0_mass_ratio * psi_inv;
-    // per-row weights of the three stencil columns
-    double P0[3], P1[3], P2[3], PL[3], PR[3];
-#pragma unroll
-    for (int iy = 0; iy < 3; ++iy) {
-        P0[iy] = q_invvol * sx[0] * sy[iy];
-        P1[iy] = q_invvol * sx[1] * sy[iy];
-        P2[iy] = q_invvol * sx[2] * sy[iy];
-        PL[iy] = __shfl_up_sync(kFull, P2[iy], 1);       // right column of the left neighbour
-        PR[iy] = __shfl_down_sync(kFull, P0[iy], 1);     // left column of the right neighbour
-        if (!L_ok) PL[iy] = 0.;
-        if (!R_ok) PR[iy] = 0.;
-    }
-    // per-component multipliers: own, left neighbour's, right neighbour's
-    const double vxL = __shfl_up_sync(kFull, vx_c, 1), vxR = __shfl_down_sync(kFull, vx_c, 1);
-    const double vyL = __shfl_up_sync(kFull, vy_c, 1), vyR = __shfl_down_sync(kFull, vy_c, 1);
-    const double gpL = RHO ? __shfl_up_sync(kFull, gamma_psi, 1) : 0., gpR = RHO ? __shfl_down_sync(kFull, gamma_psi, 1) : 0.;
-    const double cfL = CHI ? __shfl_up_sync(kFull, chi_fac, 1) : 0., cfR = CHI ? __shfl_down_sync(kFull, chi_fac, 1) : 0.;
-    if (!active || !owner) return;
-
-    double *jx = JXY ? a.comp(c_jx) : nullptr, *jy = JXY ? a.comp(c_jy) : nullptr;
-    double *rho = RHO ? a.comp(c_rho) : nullptr, *chi = CHI ? a.comp(c_chi) : nullptr;
-    double *rmj = RMJ ? a.comp(c_rhomjz) : nullptr;
-#pragma unroll
-    for (int iy = 0; iy < 3; ++iy) {
-        const long o = a.idx(cc, j0 + iy);
-        if (JXY) {
-            red_add(jx + o, P1[iy] * vx_c + PL[iy] * vxL + PR[iy] * vxR);
-            red_add(jy + o, P1[iy] * vy_c + PL[iy] * vyL + PR[iy] * vyR);
-        }
-        if (RHO) red_add(rho + o, P1[iy] * gamma_psi + PL[iy] * gpL + PR[iy] * gpR);
-        if (CHI) red_add(chi + o, P1[iy] * chi_fac + PL[iy] * cfL + PR[iy] * cfR);
-        if (RMJ) red_add(rmj + o, P1[iy] + PL[iy] + PR[iy]);
-        if (!L_ok) {
-            if (JXY) { red_add(jx + o - 1, P0[iy] * vx_c); red_add(jy + o - 1, P0[iy] * vy_c); }
-            if (RHO) red_add(rho + o - 1, P0[iy] * gamma_psi);
-            if (CHI) red_add(chi + o - 1, P0[iy] * chi_fac);
-            if (RMJ) red_add(rmj + o - 1, P0[iy]);
-        }
-        if (!R_ok) {
-            if (JXY) { red_add(jx + o + 1, P2[iy] * vx_c); red_add(jy + o + 1, P2[iy] * vy_c); }
-            if (RHO) red_add(rho + o + 1, P2[iy] * gamma_psi);
-            if (CHI) red_add(chi + o + 1, P2[iy] * chi_fac);
-            if (RMJ) red_add(rmj + o + 1, P2[iy]);
-        }
-    }
+    deposit_aggregated<JXY, RHO, CHI, RMJ>(a, c_jx, c_jy, c_rho, c_chi, c_rhomjz, active, owner, lane,
+                                           i0, j0, sx, sy, q_invvol, vx_c, vy_c, gamma_psi,
+                                           charge_mu0_mass_ratio * psi_inv);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -157,6 +173,7 @@ __global__ void __launch_bounds__(kThreads)
 k_beam_deposit(BeamPtrs b, SliceView a, int c_jx, int c_jy, int c_jz, double x_off, double y_off,
                double dx_inv, double dy_inv, double clightsq, double q_invvol)
 {
+    hpb_pdl_prologue();
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     // getNumParticles: the slipped particles behind d_np[0] are not deposited (BeamDepositCurrent.cpp:100)
     if (ip >= b.np || (b.d_np && ip >= (long)b.d_np[0])) return;
@@ -259,6 +276,7 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
                       double dy_inv, double a_clight, double clight_inv,
                       double charge_invvol_mu0, double q_mass_ratio)
 {
+    hpb_pdl_prologue();
     // warps overlap by two lanes on each side (see k_deposit_current)
     const int lane = threadIdx.x & 31;
     const long warp = (long)blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
@@ -455,29 +473,48 @@ __device__ __forceinline__ bool enforce_bc(double &x, double &y, double &ux, dou
     return false;
 }
 
-template <int MINB>
+// DEPOSIT: our fusion of AdvancePlasmaParticles (this slice) with ::DepositCurrent of the NEXT
+// slice (PlasmaDepositCurrent.cpp:155-246): the pushed x, y, ux, uy, psi are deposited straight
+// from registers into jx, jy, chi, rhomjz (which the caller has already shifted / initialised for
+// the next slice), saving the 56 B/particle re-read and one launch per slice.
+struct DepositArgs {
+    int c_jx, c_jy, c_chi, c_rhomjz;
+    double clightinv, charge_invvol, charge_mu0_mass_ratio, max_qsa;
+    int *n_qsa_violation;
+};
+
+template <int MINB, bool DEPOSIT>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int c_by, int c_bz,
                  double x_off, double y_off, double dx_inv, double dy_inv, double clight,
                  double qmc, double dz, int n_subcycles, int temp_slice, int bc, double lox,
-                 double loy, double hix, double hiy)
+                 double loy, double hix, double hiy, DepositArgs dep)
 {
+    hpb_pdl_prologue();
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= pl.np) return;
+    const bool in_range = ip < pl.np;
+    if (!DEPOSIT && !in_range) return;
     // request every input stream before the first use (one HBM round trip)
-    const uint64_t idcpu = pl.idcpu[ip];
-    double xp0 = pl.r[HPB_X_PREV][ip];
-    double yp0 = pl.r[HPB_Y_PREV][ip];
-    double ux0 = pl.r[HPB_UX_HALF][ip];
-    double uy0 = pl.r[HPB_UY_HALF][ip];
-    double psi0 = pl.r[HPB_PSI_HALF][ip];
-    if (!hpb_is_valid(idcpu)) return;
+    uint64_t idcpu = 0;
+    double xp0 = 0., yp0 = 0., ux0 = 0., uy0 = 0., psi0 = 1., wq = 0.;
+    if (in_range) {
+        idcpu = pl.idcpu[ip];
+        xp0 = pl.r[HPB_X_PREV][ip];
+        yp0 = pl.r[HPB_Y_PREV][ip];
+        ux0 = pl.r[HPB_UX_HALF][ip];
+        uy0 = pl.r[HPB_UY_HALF][ip];
+        psi0 = pl.r[HPB_PSI_HALF][ip];
+        if (DEPOSIT) wq = pl.r[HPB_W][ip];
+    }
+    bool valid = in_range && hpb_is_valid(idcpu);
+    if (!DEPOSIT && !valid) return;
     const double clight_inv = 1.0 / clight;
     const double *Psi = a.comp(c_psi), *Ez = a.comp(c_ez), *Bx = a.comp(c_bx);
     const double *By = a.comp(c_by), *Bz = a.comp(c_bz);
+    double xp = xp0, yp = yp0, ux = ux0, uy = uy0, psi = psi0;
 
-    for (int isc = 0; isc < n_subcycles; ++isc) {
-        double xp = xp0, yp = yp0;
+    for (int isc = 0; valid && isc < n_subcycles; ++isc) {
+        xp = xp0; yp = yp0;
         // doGatherShapeN<2>, FieldGather.H:45-96
         double sx[4], dsx[4], sy[4], dsy[4];
         const int i0 = dshape2_nodal((xp - x_off) * dx_inv, sx, dsx);
@@ -503,7 +540,7 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
 
         constexpr int nsub = 4;
         const double sdz = dz / nsub;
-        double ux = ux0, uy = uy0, psi = psi0;
+        ux = ux0; uy = uy0; psi = psi0;
 #pragma unroll 1
         for (int isub = 0; isub < nsub; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
 
@@ -512,7 +549,8 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
         if (enforce_bc(xp, yp, ux, uy, bc, lox, loy, hix, hiy)) {
             pl.r[HPB_W][ip] = 0.0;
             pl.idcpu[ip] = hpb_make_invalid(idcpu);
-            return;
+            valid = false;
+            break;
         }
         pl.r[HPB_X][ip] = xp;
         pl.r[HPB_Y][ip] = yp;
@@ -530,6 +568,34 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
         pl.r[HPB_UY][ip] = uy;
         pl.r[HPB_PSI][ip] = psi;
     }
+    if (!DEPOSIT) return;
+
+    // ::DepositCurrent of the pushed particle (same expressions as k_deposit_current)
+    const int lane = threadIdx.x & 31;
+    bool active = valid;
+    const double psi_inv = 1.0 / psi;
+    const double vx_c = ux * psi_inv, vy_c = uy * psi_inv;
+    double q_invvol = dep.charge_invvol * wq;
+    const double gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * dep.clightinv * dep.clightinv
+                                    + vy_c * vy_c * dep.clightinv * dep.clightinv + 1.0);
+    if (active && (gamma_psi < 0.0 || gamma_psi > dep.max_qsa || psi_inv < 0.0)) {
+        if (dep.n_qsa_violation) atomicAdd(dep.n_qsa_violation, 1);
+        pl.r[HPB_W][ip] = 0.0;
+        pl.idcpu[ip] = hpb_make_invalid(idcpu);
+        active = false;
+    }
+    double dsx3[3] = {0., 0., 0.}, dsy3[3] = {0., 0., 0.};
+    int di0 = 0, dj0 = 0;
+    if (active) {
+        di0 = shape2((xp - x_off) * dx_inv, dsx3);
+        dj0 = shape2((yp - y_off) * dy_inv, dsy3);
+    } else {
+        q_invvol = 0.;
+    }
+    deposit_aggregated<true, false, true, true>(a, dep.c_jx, dep.c_jy, -1, dep.c_chi, dep.c_rhomjz,
+                                                active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
+                                                vx_c, vy_c, gamma_psi,
+                                                dep.charge_mu0_mass_ratio * psi_inv);
 }
 
 inline unsigned nblocks(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
@@ -552,9 +618,9 @@ extern "C" int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, do
     const int mask = (c_jx >= 0 ? 8 : 0) | (c_rho >= 0 ? 4 : 0) | (c_chi >= 0 ? 2 : 0) | (c_rhomjz >= 0 ? 1 : 0);
 #define HPB_DEP(M)                                                                                \
     case M:                                                                                       \
-        k_deposit_current<((M) & 8) != 0, ((M) & 4) != 0, ((M) & 2) != 0, ((M) & 1) != 0>         \
-            <<<(unsigned)((pl.np + kDepOwn * (kThreads / 32) - 1) / (kDepOwn * (kThreads / 32))), \
-               kThreads, 0, ctx->stream>>>(                                                       \
+        hpb_launch(k_deposit_current<((M) & 8) != 0, ((M) & 4) != 0, ((M) & 2) != 0, ((M) & 1) != 0>, \
+               (unsigned)((pl.np + kDepOwn * (kThreads / 32) - 1) / (kDepOwn * (kThreads / 32))), \
+               kThreads, 0, ctx->stream,                                                        \
                 to_ptrs(pl), make_view(sl), c_jx, c_jy, c_rho, c_chi, c_rhomjz, g.x_off, g.y_off, \
                 1.0 / g.dx, 1.0 / g.dy, 1.0 / g.c, charge * invvol, charge * g.mu0 / mass,        \
                 max_qsa, d_n_qsa_violation);                                                      \
@@ -579,7 +645,7 @@ extern "C" int hpb_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, d
     // BeamDepositCurrent.cpp:72-82: invvol = 1 in normalised units at lev 0
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     BeamPtrs b{bm.x, bm.y, bm.z, bm.w, bm.ux, bm.uy, bm.uz, bm.idcpu, bm.np, bm.d_np};
-    k_beam_deposit<<<nblocks(bm.np), kThreads, 0, ctx->stream>>>(
+    hpb_launch(k_beam_deposit, nblocks(bm.np), kThreads, 0, ctx->stream, 
         b, make_view(sl), c_jx, c_jy, c_jz, g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy,
         1.0 / (g.c * g.c), charge * invvol);
     hpb_count_launch(ctx);
@@ -597,8 +663,8 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("HPB_EXPL_VARIANT"); variant = e ? atoi(e) : 4; }
 #define HPB_LAUNCH_EXPL(NT, MB)                                                                    \
-    k_explicit_deposition<NT, MB><<<(unsigned)((pl.np + kExplOwn * (NT / 32) - 1) / (kExplOwn * (NT / 32))), \
-                                    NT, 0, ctx->stream>>>(                                        \
+    hpb_launch(k_explicit_deposition<NT, MB>, (unsigned)((pl.np + kExplOwn * (NT / 32) - 1) / (kExplOwn * (NT / 32))), \
+                                    NT, 0, ctx->stream,                                         \
         to_ptrs(pl), make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ],             \
         comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.x_off, g.y_off, 1.0 / g.dx,     \
         1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass)
@@ -614,27 +680,66 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     return HPB_OK;
 }
 
-extern "C" int hpb_advance_plasma_particles(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
-                                            double charge, double mass, int n_subcycles,
-                                            int temp_slice, int particle_bc, const double bc_lo[2],
-                                            const double bc_hi[2], const int *comps)
+static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                          int n_subcycles, int temp_slice, int particle_bc, const double bc_lo[2],
+                          const double bc_hi[2], const int *comps, bool deposit, double max_qsa,
+                          int *d_n_qsa_violation)
 {
     if (!ctx || !comps || !bc_lo || !bc_hi || n_subcycles < 1) return HPB_ERR_ARG;
     if (pl.np == 0) return HPB_OK;
     const hpb_geom &g = ctx->g;
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("HPB_PUSH_VARIANT"); variant = e ? atoi(e) : 3; }
-#define HPB_LAUNCH_PUSH(MB)                                                                       \
-    k_advance_plasma<MB><<<nblocks(pl.np), kThreads, 0, ctx->stream>>>(                          \
+    DepositArgs dep = {};
+    if (deposit) {
+        const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
+        dep.c_jx = comps[HPB_C_JX]; dep.c_jy = comps[HPB_C_JY]; dep.c_chi = comps[HPB_C_CHI];
+        dep.c_rhomjz = comps[HPB_C_RHOMJZ];
+        dep.clightinv = 1.0 / g.c; dep.charge_invvol = charge * invvol;
+        dep.charge_mu0_mass_ratio = charge * g.mu0 / mass;
+        dep.max_qsa = max_qsa; dep.n_qsa_violation = d_n_qsa_violation;
+    }
+#define HPB_LAUNCH_PUSH(MB, DEP)                                                                  \
+    hpb_launch(k_advance_plasma<MB, DEP>, nblocks(pl.np), kThreads, 0, ctx->stream,               \
         to_ptrs(pl), make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],           \
         comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
         charge / (mass * g.c), g.dz / n_subcycles, n_subcycles, temp_slice, particle_bc,         \
-        bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1])
-    if (variant == 3) HPB_LAUNCH_PUSH(3);
-    else if (variant == 4) HPB_LAUNCH_PUSH(4);
-    else HPB_LAUNCH_PUSH(2);
+        bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep)
+    if (deposit) {
+        if (variant == 2) HPB_LAUNCH_PUSH(2, true);
+        else HPB_LAUNCH_PUSH(3, true);
+    } else {
+        if (variant == 3) HPB_LAUNCH_PUSH(3, false);
+        else if (variant == 4) HPB_LAUNCH_PUSH(4, false);
+        else HPB_LAUNCH_PUSH(2, false);
+    }
 #undef HPB_LAUNCH_PUSH
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
+}
+
+extern "C" int hpb_advance_plasma_particles(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
+                                            double charge, double mass, int n_subcycles,
+                                            int temp_slice, int particle_bc, const double bc_lo[2],
+                                            const double bc_hi[2], const int *comps)
+{
+    return advance_plasma(ctx, pl, sl, charge, mass, n_subcycles, temp_slice, particle_bc, bc_lo, bc_hi,
+                          comps, false, 0., nullptr);
+}
+
+extern "C" int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
+                                                        double charge, double mass, int n_subcycles,
+                                                        int particle_bc, const double bc_lo[2],
+                                                        const double bc_hi[2], const int *comps,
+                                                        double max_qsa_weighting_factor,
+                                                        int *d_n_qsa_violation)
+{
+    if (comps && (comps[HPB_C_JX] < 0 || comps[HPB_C_JY] < 0 || comps[HPB_C_CHI] < 0
+                  || comps[HPB_C_RHOMJZ] < 0 || comps[HPB_C_RHO] >= 0)) {
+        hpb_set_error("advance+deposit: needs jx, jy, chi, rhomjz and no rho component");
+        return HPB_ERR_UNSUPPORTED;
+    }
+    return advance_plasma(ctx, pl, sl, charge, mass, n_subcycles, 0, particle_bc, bc_lo, bc_hi, comps,
+                          true, max_qsa_weighting_factor, d_n_qsa_violation);
 }

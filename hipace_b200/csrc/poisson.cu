@@ -19,6 +19,7 @@
 // (Psi, Ez, Bz) are batched into every launch (grid.y = batch).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -40,6 +41,22 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
+// j / d and j % d for 0 <= j < 2^21 and a run-time divisor: a float reciprocal instead of the
+// ~20-instruction integer division sequence (the stage loops are instruction-issue bound)
+struct FastDiv {
+    int d; float inv;
+    __device__ __forceinline__ explicit FastDiv(int d_) : d(d_), inv(1.0f / (float)d_) {}
+    __device__ __forceinline__ int div(int j) const
+    {
+        int q = (int)(((float)j + 0.5f) * inv);
+        // the float estimate is off by at most one
+        const int r = j - q * d;
+        q += (r >= d) - (r < 0);
+        return q;
+    }
+    __device__ __forceinline__ int mod(int j) const { return j - div(j) * d; }
+};
+
 // Stockham stage of radix r with Ns = product of the previous radices:
 //   out[(j-k) r + k + b Ns] = sum_t ( in[j + t N/r] w_N^{t k N/(Ns r)} ) w_r^{t b},  k = j mod Ns
 
@@ -47,8 +64,9 @@ __device__ __forceinline__ void fft_stage_r2(const double2 *__restrict__ in, dou
                                              const double2 *__restrict__ root, int N, int Ns)
 {
     const int Nr = N >> 1, tw = N / (Ns * 2);
+    const FastDiv fd(Ns);
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = j % Ns;
+        const int k = fd.mod(j);
         double2 v0 = in[j], v1 = in[j + Nr];
         if (k) v1 = cmul(v1, __ldg(&root[k * tw]));
         const int o = (j - k) * 2 + k;
@@ -62,8 +80,9 @@ __device__ __forceinline__ void fft_stage_r3(const double2 *__restrict__ in, dou
 {
     const int Nr = N / 3, tw = N / (Ns * 3);
     const double c1 = -0.5, s1 = 0.86602540378443864676;
+    const FastDiv fd(Ns);
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = j % Ns;
+        const int k = fd.mod(j);
         double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr];
         if (k) { v1 = cmul(v1, __ldg(&root[k * tw])); v2 = cmul(v2, __ldg(&root[2 * k * tw])); }
         const double2 a = cadd(v1, v2), d = csub(v1, v2);
@@ -82,8 +101,9 @@ __device__ __forceinline__ void fft_stage_r4(const double2 *__restrict__ in, dou
 {
     const int Nr = N >> 2;
     const int tw = N / (Ns * 4);
+    const FastDiv fd(Ns);
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = j % Ns;
+        const int k = fd.mod(j);
         double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr], v3 = in[j + 3 * Nr];
         if (k) {
             v1 = cmul(v1, __ldg(&root[k * tw]));
@@ -105,8 +125,9 @@ __device__ __forceinline__ void fft_stage_r5(const double2 *__restrict__ in, dou
     const int Nr = N / 5, tw = N / (Ns * 5);
     const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
     const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+    const FastDiv fd(Ns);
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = j % Ns;
+        const int k = fd.mod(j);
         double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr], v3 = in[j + 3 * Nr], v4 = in[j + 4 * Nr];
         if (k) {
             v1 = cmul(v1, __ldg(&root[k * tw]));
@@ -138,13 +159,16 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
                                                 const double *__restrict__ tsin)
 {
     const int Nr = N / p, h = (p - 1) / 2, tw = N / (Ns * p);
+    const FastDiv fNr(Nr), fNs(Ns);
     for (int e = threadIdx.x; e < Nr * h; e += blockDim.x) {
-        const int t = e / Nr + 1, j = e - (t - 1) * Nr;
-        const int k = j % Ns;
+        const int tq = fNr.div(e);
+        const int t = tq + 1, j = e - tq * Nr;
+        const int k = fNs.mod(j);
         double2 a = in[j + t * Nr], b = in[j + (p - t) * Nr];
         if (k) {
-            a = cmul(a, __ldg(&root[(int)(((long)t * k * tw) % N)]));
-            b = cmul(b, __ldg(&root[(int)(((long)(p - t) * k * tw) % N)]));
+            // t k tw < p Ns N / (Ns p) = N: the twiddle index needs no reduction
+            a = cmul(a, __ldg(&root[t * k * tw]));
+            b = cmul(b, __ldg(&root[(p - t) * k * tw]));
         }
         tmp[(t - 1) * Nr + j] = cadd(a, b);
         tmp[(h + t - 1) * Nr + j] = csub(a, b);
@@ -152,8 +176,8 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) tmp[2 * h * Nr + j] = in[j];
     __syncthreads();
     for (int e = threadIdx.x; e < Nr * (h + 1); e += blockDim.x) {
-        const int b = e / Nr, j = e - b * Nr;
-        const int k = j % Ns;
+        const int b = fNr.div(e), j = e - b * Nr;
+        const int k = fNs.mod(j);
         const double2 x0 = tmp[2 * h * Nr + j];
         double2 P = x0, Q = make_double2(0., 0.);
         const double *cc = tcos + b * h, *ss = tsin + b * h;
@@ -231,11 +255,12 @@ struct SrcSpec {             // chunk-local Thomas solution + interface correcti
 };
 
 // DST-I along x of two rows per CTA (unnormalised, FFTW RODFT00 convention, times `scale`).
-template <class Src>
-__global__ void __launch_bounds__(kFftThreads)
+template <class Src, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB)
 k_dst_rows(Src src, OutPtrs out, long out_rs, int nx, int ny, FftPlan plan,
            const double2 *__restrict__ root, const double *__restrict__ sinf, double scale)
 {
+    hpb_pdl_prologue();
     extern __shared__ double2 smem[];
     const int N = plan.N, n = nx;
     double2 *buf0 = smem;
@@ -297,6 +322,7 @@ k_thomas_local(double *__restrict__ spec, const double *__restrict__ tm, const d
                double *__restrict__ yf, double *__restrict__ ye, int nx, int ny, int L, int C,
                int last_base, double a)
 {
+    hpb_pdl_prologue();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nx) return;
     const int c = blockIdx.y, b = blockIdx.z;
@@ -340,30 +366,67 @@ k_thomas_reduced(const double *__restrict__ yf, const double *__restrict__ ye, d
                  const double *__restrict__ t_b, const double *__restrict__ t_inv,
                  const double *__restrict__ t_del, int nx, int C)
 {
+    hpb_pdl_prologue();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nx) return;
     const int b = blockIdx.y;
     const long base = (long)b * C * nx + k;
+    // Both recurrences are short (C - 1 <= 31 steps) but every step needs six values from global
+    // memory: they are fetched U steps ahead (independent loads) so that the dependent chain
+    // only sees arithmetic.
+    constexpr int U = 8;
     // forward: A_c -> xl[c+1], gamma_c -> xr[c]
     double alpha = 0.0;
-    for (int c = 0; c < C - 1; ++c) {
-        const long t = (long)c * nx + k;
-        const double A = ye[base + (long)c * nx] + __ldg(&t_pe[t]) * alpha;
-        const double gam = (yf[base + (long)(c + 1) * nx] + __ldg(&t_pf[t]) * A) * __ldg(&t_inv[t]);
-        alpha = A + __ldg(&t_b[t]) * gam;
-        xl[base + (long)(c + 1) * nx] = A;
-        xr[base + (long)c * nx] = gam;
+    for (int c0 = 0; c0 < C - 1; c0 += U) {
+        double v_ye[U], v_yf[U], v_pe[U], v_pf[U], v_inv[U], v_b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u;
+            if (c < C - 1) {
+                const long t = (long)c * nx + k;
+                v_ye[u] = ye[base + (long)c * nx];
+                v_yf[u] = yf[base + (long)(c + 1) * nx];
+                v_pe[u] = __ldg(&t_pe[t]); v_pf[u] = __ldg(&t_pf[t]);
+                v_inv[u] = __ldg(&t_inv[t]); v_b[u] = __ldg(&t_b[t]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u;
+            if (c < C - 1) {
+                const double A = v_ye[u] + v_pe[u] * alpha;
+                const double gam = (v_yf[u] + v_pf[u] * A) * v_inv[u];
+                alpha = A + v_b[u] * gam;
+                xl[base + (long)(c + 1) * nx] = A;
+                xr[base + (long)c * nx] = gam;
+            }
+        }
     }
     // backward: v_c = gamma_c + delta_c v_{c+1};  u_c = A_c + B_c v_c
     double v = 0.0;
     xr[base + (long)(C - 1) * nx] = 0.0;
     xl[base] = 0.0;
-    for (int c = C - 2; c >= 0; --c) {
-        const long t = (long)c * nx + k;
-        v = xr[base + (long)c * nx] + __ldg(&t_del[t]) * v;
-        const double u = xl[base + (long)(c + 1) * nx] + __ldg(&t_b[t]) * v;
-        xr[base + (long)c * nx] = v;
-        xl[base + (long)(c + 1) * nx] = u;
+    for (int c0 = C - 2; c0 >= 0; c0 -= U) {
+        double v_g[U], v_a[U], v_del[U], v_b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 - u;
+            if (c >= 0) {
+                const long t = (long)c * nx + k;
+                v_g[u] = xr[base + (long)c * nx];
+                v_a[u] = xl[base + (long)(c + 1) * nx];
+                v_del[u] = __ldg(&t_del[t]); v_b[u] = __ldg(&t_b[t]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 - u;
+            if (c >= 0) {
+                v = v_g[u] + v_del[u] * v;
+                xr[base + (long)c * nx] = v;
+                xl[base + (long)(c + 1) * nx] = v_a[u] + v_b[u] * v;
+            }
+        }
     }
 }
 
@@ -400,22 +463,33 @@ FftPlan make_plan(const hpb_ctx *ctx)
     return plan;
 }
 
-template <class Src>
-int launch_rows(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, int nbatch, double scale)
+template <class Src, int NTHR, int MINB>
+int launch_rows_v(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, int nbatch, double scale)
 {
     const int nx = ctx->g.nx, ny = ctx->g.ny, N = ctx->fftN;
     const size_t smem = 2 * sizeof(double2) * (size_t)(N + 4);
     static bool attr_set = false;       // per instantiation; the limit covers every supported N
     if (!attr_set) {
-        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            220 * 1024));
+        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src, NTHR, MINB>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     dim3 grid((ny + 1) / 2, nbatch);
-    k_dst_rows<Src><<<grid, kFftThreads, smem, ctx->stream>>>(src, out, out_rs, nx, ny, make_plan(ctx),
-                                                              ctx->d_root, ctx->d_sinf, scale);
+    hpb_launch(k_dst_rows<Src, NTHR, MINB>, grid, NTHR, smem, ctx->stream, src, out, out_rs, nx, ny,
+               make_plan(ctx), ctx->d_root, ctx->d_sinf, scale);
     hpb_count_launch(ctx);
     return HPB_OK;
+}
+
+template <class Src>
+int launch_rows(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, int nbatch, double scale)
+{
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("HPB_FFT_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (variant == 1) return launch_rows_v<Src, 256, 6>(ctx, src, out, out_rs, nbatch, scale);
+    if (variant == 2) return launch_rows_v<Src, 128, 10>(ctx, src, out, out_rs, nbatch, scale);
+    if (variant == 3) return launch_rows_v<Src, 512, 2>(ctx, src, out, out_rs, nbatch, scale);
+    return launch_rows_v<Src, kFftThreads, 5>(ctx, src, out, out_rs, nbatch, scale);
 }
 
 }  // namespace
@@ -555,10 +629,10 @@ static int poisson_finish(hpb_ctx *ctx, hpb_slice sl, const int *c_lhs, int nbat
     const long ifn = 3L * C * nx;
     double *yf = ctx->d_iface, *ye = yf + ifn, *xl = ye + ifn, *xr = xl + ifn;
     dim3 g2((nx + 127) / 128, C, nbatch);
-    k_thomas_local<<<g2, 128, 0, ctx->stream>>>(ctx->d_spec, ctx->d_tri_m, ctx->d_tri_c, yf, ye, nx, ny, L, C,
+    hpb_launch(k_thomas_local, g2, 128, 0, ctx->stream, ctx->d_spec, ctx->d_tri_m, ctx->d_tri_c, yf, ye, nx, ny, L, C,
                                                 ctx->th_last_base, 1.0 / (g.dy * g.dy));
-    dim3 g3((nx + 127) / 128, nbatch);
-    k_thomas_reduced<<<g3, 128, 0, ctx->stream>>>(yf, ye, xl, xr, ctx->d_red_pe, ctx->d_red_pf, ctx->d_red_b,
+    dim3 g3((nx + 63) / 64, nbatch);
+    hpb_launch(k_thomas_reduced, g3, 64, 0, ctx->stream, yf, ye, xl, xr, ctx->d_red_pe, ctx->d_red_pf, ctx->d_red_b,
                                                   ctx->d_red_inv, ctx->d_red_del, nx, C);
     hpb_count_launch(ctx, 2);
     SliceView v = make_view(sl);

@@ -9,6 +9,7 @@
 // src/particles/beam/BeamParticleContainerInit.cpp:198-346 -- same particles, same order, same
 // ids because our storage order is the head-first processing order).
 #include "sim.hpp"
+#include <stdlib.h>
 #include <cub/cub.cuh>
 #include <stdio.h>
 #include <string.h>
@@ -357,6 +358,7 @@ void build_components(hpb_sim *s)
     auto add = [&](int id, const char *which, const char *name) {
         s->comps[id] = n++;
         s->comp_names.emplace_back(which, name);
+        s->comp_id.push_back(id);
     };
     add(HPB_C_NEXT_JX_BEAM, "Next", "jx_beam"); add(HPB_C_NEXT_JY_BEAM, "Next", "jy_beam");
     add(HPB_C_CHI, "This", "chi"); add(HPB_C_SY, "This", "Sy"); add(HPB_C_SX, "This", "Sx");
@@ -369,7 +371,11 @@ void build_components(hpb_sim *s)
     add(HPB_C_PREV_JX_BEAM, "Previous", "jx_beam"); add(HPB_C_PREV_JY_BEAM, "Previous", "jy_beam");
     if (s->any_neutral) add(HPB_C_IONS_RHOMJZ, "RhomJzIons", "rhomjz");
     s->sl.ncomp = n;
+    for (int k = 0; k < HPB_C_COUNT; ++k) s->comps0[k] = s->comps[k];
 }
+
+// physical plane of a logical component (they differ once the beam-current planes have rotated)
+inline int phys_comp(const hpb_sim *s, int logical) { return s->comps[s->comp_id[logical]]; }
 
 int init_plasma(hpb_sim *s, Species &sp, double c_t)
 {
@@ -520,6 +526,8 @@ int begin_step(hpb_sim *s, int step)
     // ResetAllQuantities (Hipace.cpp:730-742)
     SIM_CUDA(cudaMemsetAsync(s->sl.p, 0, sizeof(double) * s->sl.nstride * s->sl.ncomp, s->stream));
     SIM_CUDA(cudaMemsetAsync(s->d_checksum, 0, sizeof(double) * s->sl.ncomp, s->stream));
+    for (int k = 0; k < HPB_C_COUNT; ++k) s->comps[k] = s->comps0[k];
+    s->prepared = false;
     const double c_t = s->g.c * (s->dt * step);
     for (auto &sp : s->plasmas) {                                    // Hipace.cpp:450
         int rc = init_plasma(s, sp, c_t);
@@ -557,17 +565,24 @@ int end_step(hpb_sim *s)
     return HPB_OK;
 }
 
-// Hipace::SolveOneSlice, explicit branch (Hipace.cpp:556-728)
+// Hipace::SolveOneSlice, explicit branch (Hipace.cpp:556-728).
+// Reference order (opt_fuse = 0): InitializeSlices, DepositCurrent, ..., AdvancePlasmaParticles,
+// beam push, ShiftSlices.  Fused order (default): the beam push moves ahead of the plasma push
+// (they are independent), then ONE pass shifts the slices and initialises them for the next
+// slice, and the plasma push deposits the next slice's jx jy chi rhomjz from registers -- the
+// next call then starts at the beam deposit.
 int solve_one_slice(hpb_sim *s, int islice)
 {
     hpb_ctx *ctx = s->ctx;
     const int *C = s->comps;
     int rc;
-    {
-        StageTimer t(s, ST_OTHER);
-        if ((rc = hpb_fields_initialize_slices(ctx, s->sl, C))) return rc;              // :598-600
-    }
-    {
+    bool fuse = s->opt_fuse && C[HPB_C_RHO] < 0;
+    for (auto &sp : s->plasmas) if (sp.n_subcycles < 1) fuse = false;
+    if (!s->prepared) {
+        {
+            StageTimer t(s, ST_OTHER);
+            if ((rc = hpb_fields_initialize_slices(ctx, s->sl, C))) return rc;          // :598-600
+        }
         StageTimer t(s, ST_DEPOSIT);
         for (auto &sp : s->plasmas)                                                     // :609-610
             if ((rc = hpb_deposit_current(ctx, sp.d, s->sl, sp.charge, sp.mass, C[HPB_C_JX],
@@ -580,8 +595,10 @@ int solve_one_slice(hpb_sim *s, int islice)
         for (auto &b : s->beams)                                                        // :613-614
             if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice), s->sl, b.charge, -1, -1,
                                        C[HPB_C_JZ_BEAM]))) return rc;
-        if ((rc = hpb_fields_add_rho_ions(ctx, s->sl, C))) return rc;                   // :626
+        // a prepared slice started rhomjz from the ion background already
+        if (!s->prepared && (rc = hpb_fields_add_rho_ions(ctx, s->sl, C))) return rc;   // :626
     }
+    s->prepared = false;
     {
         StageTimer t(s, ST_POISSON);
         if ((rc = hpb_fields_solve_psi_ez_bz(ctx, s->sl, C))) return rc;                // :633
@@ -612,16 +629,25 @@ int solve_one_slice(hpb_sim *s, int islice)
         StageTimer t(s, ST_OTHER);
         for (int c = 0; c < s->sl.ncomp; ++c)
             if (s->comp_names[c].first == "This")
-                if ((rc = hpb_abs_sum(ctx, s->sl, c, s->d_checksum + c))) return rc;
+                if ((rc = hpb_abs_sum(ctx, s->sl, phys_comp(s, c), s->d_checksum + c))) return rc;
     }
-    {
+    auto push_plasma = [&](bool with_deposit) -> int {
         StageTimer t(s, ST_PUSH);
         for (auto &sp : s->plasmas) {                                                   // :699-701
             s->stats.n_plasma_pushed += (double)sp.d.np;
-            if ((rc = hpb_advance_plasma_particles(ctx, sp.d, s->sl, sp.charge, sp.mass, sp.n_subcycles,
-                                                   0, s->particle_bc, s->bc_lo, s->bc_hi, C))) return rc;
+            int r;
+            if (with_deposit)
+                r = hpb_advance_plasma_particles_and_deposit(ctx, sp.d, s->sl, sp.charge, sp.mass,
+                                                             sp.n_subcycles, s->particle_bc, s->bc_lo,
+                                                             s->bc_hi, s->comps, sp.max_qsa, s->d_nqsa);
+            else
+                r = hpb_advance_plasma_particles(ctx, sp.d, s->sl, sp.charge, sp.mass, sp.n_subcycles,
+                                                 0, s->particle_bc, s->bc_lo, s->bc_hi, s->comps);
+            if (r) return r;
         }
-    }
+        return HPB_OK;
+    };
+    if (!fuse && (rc = push_plasma(false))) return rc;
     {
         // AdvanceBeamParticlesSlice + shiftSlippedParticles + MultiBuffer::put_data (:707-716)
         StageTimer t(s, ST_OTHER);
@@ -642,7 +668,13 @@ int solve_one_slice(hpb_sim *s, int islice)
                                              islice > 0 ? in.nsub(slot + 1) : nullptr, s->d_overflow))) return rc;
         }
         if (!s->beams.empty() && (rc = hpb_pipeline_send_slice(s, islice, s->cur_step))) return rc;
-        if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;                   // :721
+        if (fuse) {
+            if ((rc = hpb_fields_shift_and_initialize(ctx, s->sl, s->comps))) return rc;
+        } else if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;            // :721
+    }
+    if (fuse) {
+        if ((rc = push_plasma(true))) return rc;
+        s->prepared = true;
     }
     s->stats.n_cells_updated += (double)s->g.nx * s->g.ny;
     s->stats.n_slices += 1;
@@ -672,6 +704,7 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
         return HPB_ERR_PARSE;
     }
     s->device = device;
+    if (const char *e = getenv("HPB_FUSE")) s->opt_fuse = atoi(e) != 0;       // tuning / A-B runs
     SIM_CUDA(cudaSetDevice(device));
     SIM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     build_components(s.get());
@@ -819,8 +852,8 @@ extern "C" int hpb_sim_get_field(hpb_sim *s, int comp, double *h_out)
     if (!s || comp < 0 || comp >= s->sl.ncomp || !h_out) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
     SIM_CUDA(cudaStreamSynchronize(s->stream));
-    SIM_CUDA(cudaMemcpy(h_out, s->sl.p + comp * s->sl.nstride, sizeof(double) * s->sl.nstride,
-                        cudaMemcpyDeviceToHost));
+    SIM_CUDA(cudaMemcpy(h_out, s->sl.p + phys_comp(s, comp) * s->sl.nstride,
+                        sizeof(double) * s->sl.nstride, cudaMemcpyDeviceToHost));
     return HPB_OK;
 }
 
@@ -829,8 +862,8 @@ extern "C" int hpb_sim_set_field(hpb_sim *s, int comp, const double *h_in)
     if (!s || comp < 0 || comp >= s->sl.ncomp || !h_in) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
     SIM_CUDA(cudaStreamSynchronize(s->stream));
-    SIM_CUDA(cudaMemcpy(s->sl.p + comp * s->sl.nstride, h_in, sizeof(double) * s->sl.nstride,
-                        cudaMemcpyHostToDevice));
+    SIM_CUDA(cudaMemcpy(s->sl.p + phys_comp(s, comp) * s->sl.nstride, h_in,
+                        sizeof(double) * s->sl.nstride, cudaMemcpyHostToDevice));
     return HPB_OK;
 }
 
@@ -1023,6 +1056,7 @@ extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
     if (!s || !key) return HPB_ERR_ARG;
     const std::string k(key);
     if (k == "checksums") s->opt_checksums = value != 0.;
+    else if (k == "fuse") s->opt_fuse = value != 0.;
     else if (k == "profile") s->opt_profile = value != 0.;
     else if (k == "max_step") s->max_step = (int)value;
     else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }

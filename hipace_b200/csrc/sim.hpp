@@ -96,8 +96,15 @@ struct hpb_sim {
     bool deposit_rho = false, do_beam_jx_jy = true, any_neutral = false;
     hpb_ctx *ctx = nullptr;
     hpb_slice sl = {};
-    int comps[HPB_C_COUNT];
-    std::vector<std::pair<std::string, std::string>> comp_names;   // (which_slice, name) by index
+    int comps[HPB_C_COUNT];             // enum hpb_comp -> physical plane (rotates in fused mode)
+    int comps0[HPB_C_COUNT];            // the table as built (identity order of comp_names)
+    std::vector<std::pair<std::string, std::string>> comp_names;   // (which_slice, name) by LOGICAL index
+    std::vector<int> comp_id;           // logical index -> enum hpb_comp
+    // fused slice transition (our addition, see hpb_fields_shift_and_initialize): the end of
+    // slice k shifts / initialises the planes for slice k-1 and the plasma push of slice k
+    // deposits jx jy chi rhomjz of slice k-1 from registers
+    bool opt_fuse = true;
+    bool prepared = false;              // the current slice was initialised + deposited by its predecessor
     std::vector<Species> plasmas;
     std::vector<BeamSp> beams;
     // scratch for init

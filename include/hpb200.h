@@ -186,6 +186,23 @@ int hpb_advance_plasma_particles(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, doub
                                  double mass, int n_subcycles, int temp_slice, int particle_bc,
                                  const double bc_lo[2], const double bc_hi[2], const int *comps);
 
+/* OUR ADDITIONS (no single reference call; used by the slice-loop driver, the seams above stay
+ * available and equivalent):
+ * hpb_fields_shift_and_initialize = Fields::ShiftSlices (Fields.cpp:596-599) of this slice +
+ *   Fields::InitializeSlices (:551-560) + AddRhoIons (:606-615) of the next one in ONE pass; the
+ *   Previous / This / Next planes of jx_beam, jy_beam are rotated through `comps` (in/out)
+ *   instead of copied.
+ * hpb_advance_plasma_particles_and_deposit = AdvancePlasmaParticles of this slice fused with
+ *   ::DepositCurrent (jx, jy, chi, rhomjz) of the next slice: the pushed particle is deposited
+ *   from registers.  Call after hpb_fields_shift_and_initialize. */
+int hpb_fields_shift_and_initialize(hpb_ctx *ctx, hpb_slice sl, int *comps);
+int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
+                                             double charge, double mass, int n_subcycles,
+                                             int particle_bc, const double bc_lo[2],
+                                             const double bc_hi[2], const int *comps,
+                                             double max_qsa_weighting_factor,
+                                             int *d_n_qsa_violation);
+
 /* sum|Q| over the valid box of component c -> d_out[0] += ...   (checksum of
  * tests/checksum/backend/openpmd_backend.py:40-45, one slice at a time) */
 int hpb_abs_sum(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out);

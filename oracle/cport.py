@@ -31,14 +31,32 @@ except Exception:  # pragma: no cover
     _dstn = None
 
 
+def _host_stamp():
+    """source hash + CPU model: -march=native code built on one host must not run on another"""
+    import hashlib
+    h = hashlib.sha256(open(_SRC, 'rb').read())
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith(('model name', 'flags')):
+                h.update(line.encode())
+                if line.startswith('flags'):
+                    break
+    except OSError:
+        pass
+    return h.hexdigest()
+
+
 def make_cport(force=False):
     os.makedirs(_OUT, exist_ok=True)
-    if (not force and os.path.exists(_LIB)
-            and os.path.getmtime(_LIB) >= os.path.getmtime(_SRC)):
+    stamp_file = _LIB + '.stamp'
+    stamp = _host_stamp()
+    if (not force and os.path.exists(_LIB) and os.path.exists(stamp_file)
+            and open(stamp_file).read() == stamp):
         return _LIB
     cmd = ['gcc', '-O3', '-march=native', '-fopenmp', '-ffp-contract=off', '-shared', '-fPIC',
            '-o', _LIB, _SRC, '-lm']
     subprocess.run(cmd, check=True)
+    open(stamp_file, 'w').write(stamp)
     return _LIB
 
 
@@ -53,8 +71,7 @@ def _p(a):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB):
-            make_cport()
+        make_cport()
         L = C.CDLL(_LIB)
         L.hpc_deposit_current.restype = C.c_long
         L.hpc_deposit_current.argtypes = [C.c_long] + [C.c_void_p] * 12 + [C.c_int, C.c_int] + [C.c_double] * 8
