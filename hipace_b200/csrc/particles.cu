@@ -473,6 +473,53 @@ __device__ __forceinline__ bool enforce_bc(double &x, double &y, double &ux, dou
     return false;
 }
 
+// ---- field gather -----------------------------------------------------------------------------
+// doGatherShapeN<2> (FieldGather.H:45-96) evaluated row by row: for each of the 4 stencil rows the
+// x-sums  sum_ix dSx Psi,  sum_ix Sx Psi,  sum_ix Sx {Ez,Bx,By,Bz}  are formed first and then
+// weighted with Sy / dSy -- 144 fused multiply-adds instead of the ~210 operations of the
+// cell-by-cell form (same sum up to fp64 re-association).
+// Ld(f, ix, iy) returns field f in {Psi, Ez, Bx, By, Bz} at stencil cell (ix, iy).
+template <class Ld>
+__device__ __forceinline__ PushFields gather_rows(const Ld &ld, const double sx[4], const double dsx[4],
+                                                  const double sy[4], const double dsy[4],
+                                                  double dx_inv, double dy_inv)
+{
+    PushFields f = {0., 0., 0., 0., 0., 0.};
+#pragma unroll
+    for (int iy = 0; iy < 4; ++iy) {
+        double a = 0., b = 0., e = 0., p = 0., q = 0., r = 0.;
+#pragma unroll
+        for (int ix = 0; ix < 4; ++ix) {
+            const double psi_v = ld(0, ix, iy);
+            a += dsx[ix] * psi_v;
+            b += sx[ix] * psi_v;
+            e += sx[ix] * ld(1, ix, iy);
+            p += sx[ix] * ld(2, ix, iy);
+            q += sx[ix] * ld(3, ix, iy);
+            r += sx[ix] * ld(4, ix, iy);
+        }
+        f.ExmBy += sy[iy] * a;
+        f.EypBx += dsy[iy] * b;
+        f.Ez += sy[iy] * e;
+        f.Bx_c += sy[iy] * p;
+        f.By_c += sy[iy] * q;
+        f.Bz += sy[iy] * r;
+    }
+    f.ExmBy *= dx_inv;
+    f.EypBx *= dy_inv;
+    return f;
+}
+
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // DEPOSIT: our fusion of AdvancePlasmaParticles (this slice) with ::DepositCurrent of the NEXT
 // slice (PlasmaDepositCurrent.cpp:155-246): the pushed x, y, ux, uy, psi are deposited straight
 // from registers into jx, jy, chi, rhomjz (which the caller has already shifted / initialised for
@@ -483,17 +530,29 @@ struct DepositArgs {
     int *n_qsa_violation;
 };
 
-template <int MINB, bool DEPOSIT>
-__global__ void __launch_bounds__(kThreads, MINB)
+// STAGE: warp-tile staging of the gathered fields.  The 32 particles of a warp are lattice
+// neighbours for most of the box (InitParticles order, x fastest), so their 4x4 gather stencils
+// cover a patch of ~35 x 4 cells.  Each warp finds the bounding box of its stencils
+// (warp min / max reductions); if it fits a kTW x kTH tile, the five field patches are fetched
+// with asynchronous copies (LDGSTS, no registers, all in flight at once: ONE L2 round trip
+// instead of ~8 register-limited batches of dependent 8-byte loads) into the warp's private
+// shared-memory tile and gathered from there.  Warps whose particles have dispersed (sheath,
+// trajectory crossing) fall back to direct loads, so the result never depends on the order.
+constexpr int kPushThreads = 128;
+constexpr int kTW = 40, kTH = 6;
+
+template <int MINB, bool DEPOSIT, bool STAGE>
+__global__ void __launch_bounds__(kPushThreads, MINB)
 k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int c_by, int c_bz,
                  double x_off, double y_off, double dx_inv, double dy_inv, double clight,
                  double qmc, double dz, int n_subcycles, int temp_slice, int bc, double lox,
                  double loy, double hix, double hiy, DepositArgs dep)
 {
+    __shared__ double s_tile[STAGE ? kPushThreads / 32 : 1][5][kTH][kTW];
     hpb_pdl_prologue();
     const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const bool in_range = ip < pl.np;
-    if (!DEPOSIT && !in_range) return;
     // request every input stream before the first use (one HBM round trip)
     uint64_t idcpu = 0;
     double xp0 = 0., yp0 = 0., ux0 = 0., uy0 = 0., psi0 = 1., wq = 0.;
@@ -507,71 +566,97 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
         if (DEPOSIT) wq = pl.r[HPB_W][ip];
     }
     bool valid = in_range && hpb_is_valid(idcpu);
-    if (!DEPOSIT && !valid) return;
     const double clight_inv = 1.0 / clight;
-    const double *Psi = a.comp(c_psi), *Ez = a.comp(c_ez), *Bx = a.comp(c_bx);
-    const double *By = a.comp(c_by), *Bz = a.comp(c_bz);
+    const double *F0 = a.comp(c_psi), *F1 = a.comp(c_ez), *F2 = a.comp(c_bx);
+    const double *F3 = a.comp(c_by), *F4 = a.comp(c_bz);
     double xp = xp0, yp = yp0, ux = ux0, uy = uy0, psi = psi0;
+    double (*tile)[kTH][kTW] = s_tile[STAGE ? (threadIdx.x >> 5) : 0];
 
-    for (int isc = 0; valid && isc < n_subcycles; ++isc) {
+    // every lane runs the loop (warp collectives inside); `valid` predicates the particle work
+    for (int isc = 0; isc < n_subcycles; ++isc) {
         xp = xp0; yp = yp0;
-        // doGatherShapeN<2>, FieldGather.H:45-96
         double sx[4], dsx[4], sy[4], dsy[4];
         const int i0 = dshape2_nodal((xp - x_off) * dx_inv, sx, dsx);
         const int j0 = dshape2_nodal((yp - y_off) * dy_inv, sy, dsy);
-        PushFields f = {0., 0., 0., 0., 0., 0.};
-#pragma unroll
-        for (int iy = 0; iy < 4; ++iy) {
-#pragma unroll
-            for (int ix = 0; ix < 4; ++ix) {
-                const long o = a.idx(i0 + ix, j0 + iy);
-                const double psi_v = Psi[o];
-                f.ExmBy += (dsx[ix] * sy[iy]) * psi_v * dx_inv;
-                f.EypBx += (sx[ix] * dsy[iy]) * psi_v * dy_inv;
-                const double w = sx[ix] * sy[iy];
-                f.Ez += w * Ez[o];
-                f.Bx_c += w * Bx[o];
-                f.By_c += w * By[o];
-                f.Bz += w * Bz[o];
+        bool staged = false;
+        int imin = 0, jmin = 0;
+        if (STAGE) {
+            const int big = 1 << 30;
+            imin = __reduce_min_sync(kFull, valid ? i0 : big);
+            jmin = __reduce_min_sync(kFull, valid ? j0 : big);
+            const int imax = __reduce_max_sync(kFull, valid ? i0 : -big);
+            const int jmax = __reduce_max_sync(kFull, valid ? j0 : -big);
+            const int ncol = imax - imin + 4, nrow = jmax - jmin + 4;
+            staged = imax >= imin && ncol <= kTW && nrow <= kTH;
+            if (staged) {
+                const long o0 = a.idx(imin, jmin);
+#pragma unroll 1
+                for (int r = 0; r < nrow; ++r) {
+                    const long orow = o0 + (long)r * a.jstride;
+                    for (int c = lane; c < ncol; c += 32) {
+                        cp_async_8(&tile[0][r][c], F0 + orow + c);
+                        cp_async_8(&tile[1][r][c], F1 + orow + c);
+                        cp_async_8(&tile[2][r][c], F2 + orow + c);
+                        cp_async_8(&tile[3][r][c], F3 + orow + c);
+                        cp_async_8(&tile[4][r][c], F4 + orow + c);
+                    }
+                }
+                cp_async_wait_all();
+                __syncwarp();
             }
         }
-        f.Bx_c *= clight;
-        f.By_c *= clight;
+        if (valid) {
+            PushFields f;
+            if (STAGE && staged) {
+                const double *t0 = &tile[0][j0 - jmin][i0 - imin];
+                f = gather_rows([&](int fi, int ix, int iy) { return t0[fi * (kTH * kTW) + iy * kTW + ix]; },
+                                sx, dsx, sy, dsy, dx_inv, dy_inv);
+            } else {
+                const long o = a.idx(i0, j0);
+                const long js = a.jstride;
+                f = gather_rows([&](int fi, int ix, int iy) {
+                        const double *F = fi == 0 ? F0 : fi == 1 ? F1 : fi == 2 ? F2 : fi == 3 ? F3 : F4;
+                        return F[o + iy * js + ix];
+                    }, sx, dsx, sy, dsy, dx_inv, dy_inv);
+            }
+            f.Bx_c *= clight;
+            f.By_c *= clight;
 
-        constexpr int nsub = 4;
-        const double sdz = dz / nsub;
-        ux = ux0; uy = uy0; psi = psi0;
+            constexpr int nsub = 4;
+            const double sdz = dz / nsub;
+            ux = ux0; uy = uy0; psi = psi0;
 #pragma unroll 1
-        for (int isub = 0; isub < nsub; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
+            for (int isub = 0; isub < nsub; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
 
-        xp += dz * clight_inv * (ux * (1.0 / psi));
-        yp += dz * clight_inv * (uy * (1.0 / psi));
-        if (enforce_bc(xp, yp, ux, uy, bc, lox, loy, hix, hiy)) {
-            pl.r[HPB_W][ip] = 0.0;
-            pl.idcpu[ip] = hpb_make_invalid(idcpu);
-            valid = false;
-            break;
-        }
-        pl.r[HPB_X][ip] = xp;
-        pl.r[HPB_Y][ip] = yp;
-        if (!temp_slice) {
-            pl.r[HPB_UX_HALF][ip] = ux;
-            pl.r[HPB_UY_HALF][ip] = uy;
-            pl.r[HPB_PSI_HALF][ip] = psi;
-            pl.r[HPB_X_PREV][ip] = xp;
-            pl.r[HPB_Y_PREV][ip] = yp;
-            xp0 = xp; yp0 = yp; ux0 = ux; uy0 = uy; psi0 = psi;
-        }
+            xp += dz * clight_inv * (ux * (1.0 / psi));
+            yp += dz * clight_inv * (uy * (1.0 / psi));
+            if (enforce_bc(xp, yp, ux, uy, bc, lox, loy, hix, hiy)) {
+                pl.r[HPB_W][ip] = 0.0;
+                pl.idcpu[ip] = hpb_make_invalid(idcpu);
+                valid = false;
+            } else {
+                pl.r[HPB_X][ip] = xp;
+                pl.r[HPB_Y][ip] = yp;
+                if (!temp_slice) {
+                    pl.r[HPB_UX_HALF][ip] = ux;
+                    pl.r[HPB_UY_HALF][ip] = uy;
+                    pl.r[HPB_PSI_HALF][ip] = psi;
+                    pl.r[HPB_X_PREV][ip] = xp;
+                    pl.r[HPB_Y_PREV][ip] = yp;
+                    xp0 = xp; yp0 = yp; ux0 = ux; uy0 = uy; psi0 = psi;
+                }
 #pragma unroll 1
-        for (int isub = 0; isub < nsub / 2; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
-        pl.r[HPB_UX][ip] = ux;
-        pl.r[HPB_UY][ip] = uy;
-        pl.r[HPB_PSI][ip] = psi;
+                for (int isub = 0; isub < nsub / 2; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
+                pl.r[HPB_UX][ip] = ux;
+                pl.r[HPB_UY][ip] = uy;
+                pl.r[HPB_PSI][ip] = psi;
+            }
+        }
+        if (STAGE && isc + 1 < n_subcycles) __syncwarp();     // the tile is rewritten next round
     }
     if (!DEPOSIT) return;
 
     // ::DepositCurrent of the pushed particle (same expressions as k_deposit_current)
-    const int lane = threadIdx.x & 31;
     bool active = valid;
     const double psi_inv = 1.0 / psi;
     const double vx_c = ux * psi_inv, vy_c = uy * psi_inv;
@@ -689,7 +774,7 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
     if (pl.np == 0) return HPB_OK;
     const hpb_geom &g = ctx->g;
     static int variant = -1;
-    if (variant < 0) { const char *e = getenv("HPB_PUSH_VARIANT"); variant = e ? atoi(e) : 3; }
+    if (variant < 0) { const char *e = getenv("HPB_PUSH_VARIANT"); variant = e ? atoi(e) : 0; }
     DepositArgs dep = {};
     if (deposit) {
         const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
@@ -699,19 +784,23 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         dep.charge_mu0_mass_ratio = charge * g.mu0 / mass;
         dep.max_qsa = max_qsa; dep.n_qsa_violation = d_n_qsa_violation;
     }
-#define HPB_LAUNCH_PUSH(MB, DEP)                                                                  \
-    hpb_launch(k_advance_plasma<MB, DEP>, nblocks(pl.np), kThreads, 0, ctx->stream,               \
+#define HPB_LAUNCH_PUSH(MB, DEP, STG)                                                             \
+    hpb_launch(k_advance_plasma<MB, DEP, STG>, (unsigned)((pl.np + kPushThreads - 1) / kPushThreads), \
+        kPushThreads, 0, ctx->stream,                                                             \
         to_ptrs(pl), make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],           \
         comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
         charge / (mass * g.c), g.dz / n_subcycles, n_subcycles, temp_slice, particle_bc,         \
         bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep)
+    // variants: 0 = staged gather, 5 blocks / SM (the shared-memory limit; default),
+    // 1 = direct loads only, 3 = staged with 128 registers
     if (deposit) {
-        if (variant == 2) HPB_LAUNCH_PUSH(2, true);
-        else HPB_LAUNCH_PUSH(3, true);
+        if (variant == 1) HPB_LAUNCH_PUSH(6, true, false);
+        else if (variant == 3) HPB_LAUNCH_PUSH(4, true, true);
+        else HPB_LAUNCH_PUSH(5, true, true);
     } else {
-        if (variant == 3) HPB_LAUNCH_PUSH(3, false);
-        else if (variant == 4) HPB_LAUNCH_PUSH(4, false);
-        else HPB_LAUNCH_PUSH(2, false);
+        if (variant == 1) HPB_LAUNCH_PUSH(6, false, false);
+        else if (variant == 3) HPB_LAUNCH_PUSH(4, false, true);
+        else HPB_LAUNCH_PUSH(5, false, true);
     }
 #undef HPB_LAUNCH_PUSH
     hpb_count_launch(ctx);
