@@ -71,96 +71,124 @@ __device__ __forceinline__ double interp_at(const V2 &crse, int i, int j, int n,
 //   INIT 0: phi = 0;  1: phi = phi_in;  2: phi = phi_in + I(crse)
 //   RES: rescor = rhs + acf*phi - lap(phi) is restricted on the fly (restrict_cc / restrict_nd)
 //        into res_c; norm[0] = max|rescor| and norm[1] = max|rhs| if norm != nullptr.
-// 512 threads per 64x32 tile: thread (tx, ty) owns the vertical cell pairs (tx, 2ty) and
-// (tx+32, 2ty), so that every thread updates exactly one cell of each pair per half-sweep.
+// 512 threads per 64x32 tile: thread (tx, ty) owns the vertical cell pairs (tx, 2ty), (tx, 2ty+1)
+// and the same 32 columns further right.  Of each pair exactly one cell has the colour of a
+// half-sweep, and which one is fixed per thread (parity of tx + tile origin): the per-cell
+// invariants (rhs, 1/c0, boundary weights, shared-memory offset) are sorted once into an "A"
+// set (updated by colours 0, 2) and a "B" set (colours 1, 3), so that a half-sweep is 8 shared
+// loads, 14 flops and 2 stores per cell and nothing else -- the kernel is instruction-issue
+// bound, not bandwidth bound.
+struct SmCell {
+    double r0, r1, cinv, wx, wy;
+    int o;              // shared-memory offset of the cell
+    bool ok;
+};
+
 template <int INIT, bool RES>
 __global__ void __launch_bounds__(NT, 2)
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
          V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO, const int *done)
 {
-    hpb_pdl_prologue();
     __shared__ double sm[2][AY * AX];
-    if (done && *done) return;      // converged: the speculatively enqueued V-cycle is a no-op
+    hpb_pdl_prologue();
+    // converged: the speculatively enqueued V-cycle is a no-op.  The flag is fetched here but only
+    // tested after the tile loads have been issued, so its L2 round trip is not serialised.
+    const int is_done = done ? *(const volatile int *)done : 0;
     const int FX = CX - 2 * EO, FY = CY - 2 * EO;
     const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
     const int ox = bx * FX - EO + g.vlo;          // level index of compute cell (0, 0)
     const int oy = by * FY - EO + g.vlo;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty = 0..15
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;       // ty = 0..15
+    // the whole tile (with its ring) lies strictly inside the valid range: no bounds or
+    // boundary-stencil cases anywhere (block-uniform)
+    const bool inner = ox - 1 > g.vlo && ox + CX < g.vhix && oy - 1 > g.vlo && oy + CY < g.vhiy;
 
-    // tile load (with halo): lane -> columns tx, tx+32, tx+64; warp -> rows ty, ty+16, ty+32.
-    // All loads are independent and issued before the first use.
-    double v0[3][3], v1[3][3];
-    {
+    // ---- tile load (with ring), linear over the AY x AX shared array; all loads are independent
+    constexpr int NLD = (AY * AX + NT - 1) / NT;
+    double v0[NLD], v1[NLD];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int lj = ty + 16 * a, li = tx + 32 * c;
-                const int i = ox - 1 + li, j = oy - 1 + lj;
-                v0[a][c] = 0.; v1[a][c] = 0.;
-                if (INIT != 0 && lj < AY && li < AX && i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy) {
-                    v0[a][c] = phi_in.at(i, j, 0);
-                    v1[a][c] = phi_in.at(i, j, 1);
-                    if (INIT == 2) {
-                        v0[a][c] = v0[a][c] + interp_at(crse, i, j, 0, g.cc);
-                        v1[a][c] = v1[a][c] + interp_at(crse, i, j, 1, g.cc);
-                    }
+    for (int k = 0; k < NLD; ++k) {
+        v0[k] = 0.; v1[k] = 0.;
+        if (INIT != 0) {
+            const int e = tid + k * NT;
+            const int lj = e / AX, li = e - lj * AX;
+            const int i = ox - 1 + li, j = oy - 1 + lj;
+            if (e < AY * AX && (inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy))) {
+                const long o = i + (long)j * phi_in.rs;
+                v0[k] = phi_in.p[o];
+                v1[k] = phi_in.p[o + phi_in.cs];
+                if (INIT == 2) {
+                    v0[k] = v0[k] + interp_at(crse, i, j, 0, g.cc);
+                    v1[k] = v1[k] + interp_at(crse, i, j, 1, g.cc);
                 }
             }
         }
     }
-    double r0[2][2], r1[2][2], ci[2][2];
-    unsigned okmask = 0;
-    const double fx43 = g.facx * (4. / 3.), fy43 = g.facy * (4. / 3.);
+    // ---- per-cell invariants of the four owned cells (p: column half, h: row of the pair)
     const int cj = 2 * ty;
+    const double fx43 = g.facx * (4. / 3.), fy43 = g.facy * (4. / 3.);
+    double r0[2][2], r1[2][2], ac[2][2], ci[2][2], wx[2][2], wy[2][2];
+    bool okc[2][2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        const int cix = tx + 32 * p;
+        const int i = ox + tx + 32 * p;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int i = ox + cix, j = oy + cj + h;
-            const bool ok = i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy;
-            okmask |= (ok ? 1u : 0u) << (2 * p + h);
-            r0[p][h] = ok ? rhs.at(i, j, 0) : 0.;
-            r1[p][h] = ok ? rhs.at(i, j, 1) : 0.;
+            const int j = oy + cj + h;
+            const bool ok = inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy);
+            okc[p][h] = ok;
+            const long o = i + (long)j * rhs.rs;
+            r0[p][h] = ok ? rhs.p[o] : 0.;
+            r1[p][h] = ok ? rhs.p[o + rhs.cs] : 0.;
             const double a = ok ? acf[i + (long)j * acf_rs] : 0.;
+            ac[p][h] = a;
             double c0 = -(a + 2.0 * (g.facx + g.facy));                 // gs1 :265-292
-            if (g.cc && (i == g.vlo || i == g.vhix)) c0 -= 2.0 * g.facx;
-            if (g.cc && (j == g.vlo || j == g.vhiy)) c0 -= 2.0 * g.facy;
+            const bool xb = !inner && g.cc && (i == g.vlo || i == g.vhix);
+            const bool yb = !inner && g.cc && (j == g.vlo || j == g.vhiy);
+            if (xb) c0 -= 2.0 * g.facx;
+            if (yb) c0 -= 2.0 * g.facy;
             ci[p][h] = 1.0 / c0;
+            // boundary cells (cell-centred): one neighbour is the zero halo, the other is
+            // weighted 4/3 -- identical to the branches of gs1
+            wx[p][h] = xb ? fx43 : g.facx;
+            wy[p][h] = yb ? fy43 : g.facy;
         }
     }
     // (the rhs / acf loads above are in flight together with the tile loads)
+    if (is_done) return;            // block-uniform; nothing has been written yet
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int k = 0; k < NLD; ++k) {
+        const int e = tid + k * NT;
+        if (e < AY * AX) { sm[0][e] = v0[k]; sm[1][e] = v1[k]; }
+    }
+    // colour 0 updates the cells with (i + j) even: h = par0 for both column halves
+    const int par0 = (ox + tx + oy) & 1;
+    SmCell A[2], B[2];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int lj = ty + 16 * a, li = tx + 32 * c;
-            if (lj < AY && li < AX) { sm[0][lj * AX + li] = v0[a][c]; sm[1][lj * AX + li] = v1[a][c]; }
-        }
+    for (int p = 0; p < 2; ++p) {
+        const int base = (cj + 1) * AX + tx + 32 * p + 1;
+        A[p].r0 = par0 ? r0[p][1] : r0[p][0];   B[p].r0 = par0 ? r0[p][0] : r0[p][1];
+        A[p].r1 = par0 ? r1[p][1] : r1[p][0];   B[p].r1 = par0 ? r1[p][0] : r1[p][1];
+        A[p].cinv = par0 ? ci[p][1] : ci[p][0]; B[p].cinv = par0 ? ci[p][0] : ci[p][1];
+        A[p].wx = par0 ? wx[p][1] : wx[p][0];   B[p].wx = par0 ? wx[p][0] : wx[p][1];
+        A[p].wy = par0 ? wy[p][1] : wy[p][0];   B[p].wy = par0 ? wy[p][0] : wy[p][1];
+        A[p].ok = par0 ? okc[p][1] : okc[p][0]; B[p].ok = par0 ? okc[p][0] : okc[p][1];
+        A[p].o = base + par0 * AX;              B[p].o = base + (par0 ^ 1) * AX;
+    }
     __syncthreads();
 #pragma unroll
     for (int icolor = 0; icolor < 4; ++icolor) {
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            const int cix = tx + 32 * p;
-            const int i = ox + cix;
-            const int sh = (i + oy + cj + icolor) & 1;
-            const int j = oy + cj + sh;
-            if ((okmask >> (2 * p + sh)) & 1u) {
-                // boundary cells (cell-centred): one neighbour is the zero halo, the other is
-                // weighted 4/3 -- identical to the branches of gs1
-                const double cxw = (g.cc && (i == g.vlo || i == g.vhix)) ? fx43 : g.facx;
-                const double cyw = (g.cc && (j == g.vlo || j == g.vhiy)) ? fy43 : g.facy;
-                const int o = (cj + sh + 1) * AX + cix + 1;
-                const double rr0 = sh ? r0[p][1] : r0[p][0], rr1 = sh ? r1[p][1] : r1[p][0];
-                const double cinv = sh ? ci[p][1] : ci[p][0];
-                double *c = sm[0] + o;
-                double *e = sm[1] + o;
-                const double lap0 = cxw * (c[-1] + c[1]) + cyw * (c[-AX] + c[AX]);
-                const double lap1 = cxw * (e[-1] + e[1]) + cyw * (e[-AX] + e[AX]);
-                c[0] = (rr0 - lap0) * cinv;
-                e[0] = (rr1 - lap1) * cinv;
+            const SmCell &q = (icolor & 1) ? B[p] : A[p];
+            if (q.ok) {
+                double *c = sm[0] + q.o;
+                double *e = sm[1] + q.o;
+                const double lap0 = q.wx * (c[-1] + c[1]) + q.wy * (c[-AX] + c[AX]);
+                const double lap1 = q.wx * (e[-1] + e[1]) + q.wy * (e[-AX] + e[AX]);
+                c[0] = (q.r0 - lap0) * q.cinv;
+                e[0] = (q.r1 - lap1) * q.cinv;
             }
         }
         __syncthreads();
@@ -170,21 +198,37 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int cix = tx + 32 * p;
+        const bool own_x = cix >= EO && cix < CX - EO;
+        const bool ring_x = cix >= EO - 1 && cix < CX - EO + 1;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int i = ox + cix, j = oy + cj + h;
-            const bool ok = (okmask >> (2 * p + h)) & 1u;
+            const bool ok = okc[p][h];
+            const int so = (cj + h + 1) * AX + cix + 1;
             rs0[p][h] = rs1[p][h] = 0.;
             // the residual is exact one ring further out than the owned region (needed by the
             // nodal full-weighting restriction)
-            if (RES && ok && cix >= EO - 1 && cix < CX - EO + 1 && cj + h >= EO - 1 && cj + h < CY - EO + 1) {
-                const double a = acf[i + (long)j * acf_rs];
-                rs0[p][h] = residual_smem(sm[0], cix + 1, cj + h + 1, i, j, g, r0[p][h], a);
-                rs1[p][h] = residual_smem(sm[1], cix + 1, cj + h + 1, i, j, g, r1[p][h], a);
+            if (RES && ok && ring_x && cj + h >= EO - 1 && cj + h < CY - EO + 1) {
+                if (inner) {
+                    // residual1 (:184-190), interior form -- same operation order as residual_smem
+                    const double *c = sm[0] + so, *e = sm[1] + so;
+                    double lap = -2.0 * (g.facx + g.facy) * c[0];
+                    lap += g.facx * (c[-1] + c[1]);
+                    lap += g.facy * (c[-AX] + c[AX]);
+                    rs0[p][h] = r0[p][h] + ac[p][h] * c[0] - lap;
+                    lap = -2.0 * (g.facx + g.facy) * e[0];
+                    lap += g.facx * (e[-1] + e[1]);
+                    lap += g.facy * (e[-AX] + e[AX]);
+                    rs1[p][h] = r1[p][h] + ac[p][h] * e[0] - lap;
+                } else {
+                    rs0[p][h] = residual_smem(sm[0], cix + 1, cj + h + 1, i, j, g, r0[p][h], ac[p][h]);
+                    rs1[p][h] = residual_smem(sm[1], cix + 1, cj + h + 1, i, j, g, r1[p][h], ac[p][h]);
+                }
             }
-            if (ok && cix >= EO && cix < CX - EO && cj + h >= EO && cj + h < CY - EO) {
-                phi_out.at(i, j, 0) = sm[0][(cj + h + 1) * AX + cix + 1];
-                phi_out.at(i, j, 1) = sm[1][(cj + h + 1) * AX + cix + 1];
+            if (ok && own_x && cj + h >= EO && cj + h < CY - EO) {
+                const long o = i + (long)j * phi_out.rs;
+                phi_out.p[o] = sm[0][so];
+                phi_out.p[o + phi_out.cs] = sm[1][so];
                 if (RES) {
                     nres = fmax(nres, fmax(fabs(rs0[p][h]), fabs(rs1[p][h])));
                     nrhs = fmax(nrhs, fmax(fabs(r0[p][h]), fabs(r1[p][h])));
@@ -214,6 +258,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
         const int I = I0 + tx, J = J0 + ty;
         if (I < I1 && J < J1 && I >= gc.vlo && I <= gc.vhix && J >= gc.vlo && J <= gc.vhiy) {
             const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;         // smem index of fine (2I, 2J)
+            const long oc = I + (long)J * res_c.rs;
 #pragma unroll
             for (int n = 0; n < 2; ++n) {
                 const double *f = sm[n] + lj * AX + li;
@@ -225,7 +270,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
                                       + 2. * f[-1] + 4. * f[0] + 2. * f[1]
                                       + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
                 }
-                res_c.at(I, J, n) = v;
+                res_c.p[oc + n * res_c.cs] = v;
             }
         }
     }
