@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -84,17 +85,23 @@ struct SmCell {
     bool ok;
 };
 
-template <int INIT, bool RES>
-__global__ void __launch_bounds__(NT, 2)
+// RH: the tile is 64 x (32 RH) cells (RH = 2: 8 cells per thread -- the per-thread set-up cost
+//     is amortised over twice the work).  NS: number of GSRB^4 groups applied back to back
+//     (NS = 2 fuses the last smoother of a V-cycle, sol = GSRB^4(cor0 + I(cor1)), with the first
+//     one of the next, cor0 = GSRB^4(sol), at the price of a 4-cell deeper halo).
+template <int INIT, bool RES, int RH, int NS>
+__global__ void __launch_bounds__(NT, RH == 2 ? 1 : 2)      // RH = 2: 8 cells of state per thread
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
          V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO, const int *done)
 {
-    __shared__ double sm[2][AY * AX];
+    constexpr int CYr = CY * RH, AYr = CYr + 2, NP = 2 * RH;
+    extern __shared__ double sm_dyn[];
+    double *const sm0 = sm_dyn, *const sm1 = sm_dyn + AYr * AX;
     hpb_pdl_prologue();
     // converged: the speculatively enqueued V-cycle is a no-op.  The flag is fetched here but only
     // tested after the tile loads have been issued, so its L2 round trip is not serialised.
     const int is_done = done ? *(const volatile int *)done : 0;
-    const int FX = CX - 2 * EO, FY = CY - 2 * EO;
+    const int FX = CX - 2 * EO, FY = CYr - 2 * EO;
     const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
     const int ox = bx * FX - EO + g.vlo;          // level index of compute cell (0, 0)
     const int oy = by * FY - EO + g.vlo;
@@ -102,10 +109,10 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     const int tx = tid & 31, ty = tid >> 5;       // ty = 0..15
     // the whole tile (with its ring) lies strictly inside the valid range: no bounds or
     // boundary-stencil cases anywhere (block-uniform)
-    const bool inner = ox - 1 > g.vlo && ox + CX < g.vhix && oy - 1 > g.vlo && oy + CY < g.vhiy;
+    const bool inner = ox - 1 > g.vlo && ox + CX < g.vhix && oy - 1 > g.vlo && oy + CYr < g.vhiy;
 
-    // ---- tile load (with ring), linear over the AY x AX shared array; all loads are independent
-    constexpr int NLD = (AY * AX + NT - 1) / NT;
+    // ---- tile load (with ring), linear over the AYr x AX shared array; all loads are independent
+    constexpr int NLD = (AYr * AX + NT - 1) / NT;
     double v0[NLD], v1[NLD];
 #pragma unroll
     for (int k = 0; k < NLD; ++k) {
@@ -114,7 +121,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             const int e = tid + k * NT;
             const int lj = e / AX, li = e - lj * AX;
             const int i = ox - 1 + li, j = oy - 1 + lj;
-            if (e < AY * AX && (inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy))) {
+            if (e < AYr * AX && (inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy))) {
                 const long o = i + (long)j * phi_in.rs;
                 v0[k] = phi_in.p[o];
                 v1[k] = phi_in.p[o + phi_in.cs];
@@ -125,17 +132,16 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             }
         }
     }
-    // ---- per-cell invariants of the four owned cells (p: column half, h: row of the pair)
-    const int cj = 2 * ty;
+    // ---- per-cell invariants of the owned cells: p = (row half, column half), h = row of the pair
     const double fx43 = g.facx * (4. / 3.), fy43 = g.facy * (4. / 3.);
-    double r0[2][2], r1[2][2], ac[2][2], ci[2][2], wx[2][2], wy[2][2];
-    bool okc[2][2];
+    double r0[NP][2], r1[NP][2], ac[NP][2], ci[NP][2], wx[NP][2], wy[NP][2];
+    bool okc[NP][2];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int i = ox + tx + 32 * p;
+    for (int p = 0; p < NP; ++p) {
+        const int i = ox + tx + 32 * (p & 1);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int j = oy + cj + h;
+            const int j = oy + 32 * (p >> 1) + 2 * ty + h;
             const bool ok = inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy);
             okc[p][h] = ok;
             const long o = i + (long)j * rhs.rs;
@@ -160,14 +166,14 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
 #pragma unroll
     for (int k = 0; k < NLD; ++k) {
         const int e = tid + k * NT;
-        if (e < AY * AX) { sm[0][e] = v0[k]; sm[1][e] = v1[k]; }
+        if (e < AYr * AX) { sm0[e] = v0[k]; sm1[e] = v1[k]; }
     }
-    // colour 0 updates the cells with (i + j) even: h = par0 for both column halves
+    // colour 0 updates the cells with (i + j) even: h = par0 for every p
     const int par0 = (ox + tx + oy) & 1;
-    SmCell A[2], B[2];
+    SmCell A[NP], B[NP];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int base = (cj + 1) * AX + tx + 32 * p + 1;
+    for (int p = 0; p < NP; ++p) {
+        const int base = (32 * (p >> 1) + 2 * ty + 1) * AX + tx + 32 * (p & 1) + 1;
         A[p].r0 = par0 ? r0[p][1] : r0[p][0];   B[p].r0 = par0 ? r0[p][0] : r0[p][1];
         A[p].r1 = par0 ? r1[p][1] : r1[p][0];   B[p].r1 = par0 ? r1[p][0] : r1[p][1];
         A[p].cinv = par0 ? ci[p][1] : ci[p][0]; B[p].cinv = par0 ? ci[p][0] : ci[p][1];
@@ -177,41 +183,45 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
         A[p].o = base + par0 * AX;              B[p].o = base + (par0 ^ 1) * AX;
     }
     __syncthreads();
+#pragma unroll 1
+    for (int is = 0; is < NS; ++is) {
 #pragma unroll
-    for (int icolor = 0; icolor < 4; ++icolor) {
+        for (int icolor = 0; icolor < 4; ++icolor) {
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const SmCell &q = (icolor & 1) ? B[p] : A[p];
-            if (q.ok) {
-                double *c = sm[0] + q.o;
-                double *e = sm[1] + q.o;
-                const double lap0 = q.wx * (c[-1] + c[1]) + q.wy * (c[-AX] + c[AX]);
-                const double lap1 = q.wx * (e[-1] + e[1]) + q.wy * (e[-AX] + e[AX]);
-                c[0] = (q.r0 - lap0) * q.cinv;
-                e[0] = (q.r1 - lap1) * q.cinv;
+            for (int p = 0; p < NP; ++p) {
+                const SmCell &q = (icolor & 1) ? B[p] : A[p];
+                if (q.ok) {
+                    double *c = sm0 + q.o;
+                    double *e = sm1 + q.o;
+                    const double lap0 = q.wx * (c[-1] + c[1]) + q.wy * (c[-AX] + c[AX]);
+                    const double lap1 = q.wx * (e[-1] + e[1]) + q.wy * (e[-AX] + e[AX]);
+                    c[0] = (q.r0 - lap0) * q.cinv;
+                    e[0] = (q.r1 - lap1) * q.cinv;
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
-    double rs0[2][2], rs1[2][2];
+    double rs0[NP][2], rs1[NP][2];
     double nres = 0., nrhs = 0.;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int cix = tx + 32 * p;
+    for (int p = 0; p < NP; ++p) {
+        const int cix = tx + 32 * (p & 1);
         const bool own_x = cix >= EO && cix < CX - EO;
         const bool ring_x = cix >= EO - 1 && cix < CX - EO + 1;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int i = ox + cix, j = oy + cj + h;
+            const int cjh = 32 * (p >> 1) + 2 * ty + h;
+            const int i = ox + cix, j = oy + cjh;
             const bool ok = okc[p][h];
-            const int so = (cj + h + 1) * AX + cix + 1;
+            const int so = (cjh + 1) * AX + cix + 1;
             rs0[p][h] = rs1[p][h] = 0.;
             // the residual is exact one ring further out than the owned region (needed by the
             // nodal full-weighting restriction)
-            if (RES && ok && ring_x && cj + h >= EO - 1 && cj + h < CY - EO + 1) {
+            if (RES && ok && ring_x && cjh >= EO - 1 && cjh < CYr - EO + 1) {
                 if (inner) {
                     // residual1 (:184-190), interior form -- same operation order as residual_smem
-                    const double *c = sm[0] + so, *e = sm[1] + so;
+                    const double *c = sm0 + so, *e = sm1 + so;
                     double lap = -2.0 * (g.facx + g.facy) * c[0];
                     lap += g.facx * (c[-1] + c[1]);
                     lap += g.facy * (c[-AX] + c[AX]);
@@ -221,14 +231,14 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
                     lap += g.facy * (e[-AX] + e[AX]);
                     rs1[p][h] = r1[p][h] + ac[p][h] * e[0] - lap;
                 } else {
-                    rs0[p][h] = residual_smem(sm[0], cix + 1, cj + h + 1, i, j, g, r0[p][h], ac[p][h]);
-                    rs1[p][h] = residual_smem(sm[1], cix + 1, cj + h + 1, i, j, g, r1[p][h], ac[p][h]);
+                    rs0[p][h] = residual_smem(sm0, cix + 1, cjh + 1, i, j, g, r0[p][h], ac[p][h]);
+                    rs1[p][h] = residual_smem(sm1, cix + 1, cjh + 1, i, j, g, r1[p][h], ac[p][h]);
                 }
             }
-            if (ok && own_x && cj + h >= EO && cj + h < CY - EO) {
+            if (ok && own_x && cjh >= EO && cjh < CYr - EO) {
                 const long o = i + (long)j * phi_out.rs;
-                phi_out.p[o] = sm[0][so];
-                phi_out.p[o + phi_out.cs] = sm[1][so];
+                phi_out.p[o] = sm0[so];
+                phi_out.p[o + phi_out.cs] = sm1[so];
                 if (RES) {
                     nres = fmax(nres, fmax(fabs(rs0[p][h]), fabs(rs1[p][h])));
                     nrhs = fmax(nrhs, fmax(fabs(r0[p][h]), fabs(r1[p][h])));
@@ -239,12 +249,13 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     if (!RES) return;
     __syncthreads();                   // everyone is done reading phi from shared memory
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int cix = tx + 32 * p;
+    for (int p = 0; p < NP; ++p) {
+        const int cix = tx + 32 * (p & 1);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            sm[0][(cj + h + 1) * AX + cix + 1] = rs0[p][h];
-            sm[1][(cj + h + 1) * AX + cix + 1] = rs1[p][h];
+            const int so = (32 * (p >> 1) + 2 * ty + h + 1) * AX + cix + 1;
+            sm0[so] = rs0[p][h];
+            sm1[so] = rs1[p][h];
         }
     }
     __syncthreads();
@@ -253,24 +264,26 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     // coarse points owned by this tile: cc: fine cells (2I, 2I+1); nodal: fine node 2I
     const int I0 = (X0 + 1) >> 1, J0 = (Y0 + 1) >> 1;
     const int I1 = (X0 + FX + 1) >> 1, J1 = (Y0 + FY + 1) >> 1;     // exclusive
-    // thread (tx, ty) -> coarse point (I0 + tx, J0 + ty): FX/2 <= 28 columns, FY/2 <= 12 rows
+    // thread (tx, ty) -> coarse points (I0 + tx, J0 + ty + 16 m): FX/2 <= 29 columns
     {
-        const int I = I0 + tx, J = J0 + ty;
-        if (I < I1 && J < J1 && I >= gc.vlo && I <= gc.vhix && J >= gc.vlo && J <= gc.vhiy) {
-            const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;         // smem index of fine (2I, 2J)
-            const long oc = I + (long)J * res_c.rs;
+        const int I = I0 + tx;
+        for (int J = J0 + ty; J < J1; J += NT / 32) {
+            if (I < I1 && I >= gc.vlo && I <= gc.vhix && J >= gc.vlo && J <= gc.vhiy) {
+                const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;     // smem index of fine (2I, 2J)
+                const long oc = I + (long)J * res_c.rs;
 #pragma unroll
-            for (int n = 0; n < 2; ++n) {
-                const double *f = sm[n] + lj * AX + li;
-                double v;
-                if (g.cc) {
-                    v = 0.25 * (f[0] + f[1] + f[AX] + f[AX + 1]);
-                } else {
-                    v = (1. / 16.) * (f[-AX - 1] + 2. * f[-AX] + f[-AX + 1]
-                                      + 2. * f[-1] + 4. * f[0] + 2. * f[1]
-                                      + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
+                for (int n = 0; n < 2; ++n) {
+                    const double *f = (n ? sm1 : sm0) + lj * AX + li;
+                    double v;
+                    if (g.cc) {
+                        v = 0.25 * (f[0] + f[1] + f[AX] + f[AX + 1]);
+                    } else {
+                        v = (1. / 16.) * (f[-AX - 1] + 2. * f[-AX] + f[-AX + 1]
+                                          + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                                          + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
+                    }
+                    res_c.p[oc + n * res_c.cs] = v;
                 }
-                res_c.p[oc + n * res_c.cs] = v;
             }
         }
     }
@@ -723,19 +736,29 @@ V2 lvl_view(const hpb_ctx *ctx, int l, double *p)
     V2 v; v.p = p; v.rs = ctx->mg[l].nx; v.cs = (long)ctx->mg[l].nx * ctx->mg[l].ny; return v;
 }
 
-template <int INIT, bool RES>
-void launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, const double *acf,
-                   long acf_rs, V2 out, const LevelGeom &gc, V2 res_c, double *norm, const int *done)
+template <int INIT, bool RES, int RH = 1, int NS = 1>
+int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, const double *acf,
+                  long acf_rs, V2 out, const LevelGeom &gc, V2 res_c, double *norm, const int *done)
 {
     // owned region must start on even indices relative to vlo for the fused restriction;
-    // cc needs 1 extra ring for the residual (EO 4), nodal full weighting one more (EO 5)
-    const int EO = RES ? (g.cc ? 4 : 5) : 3;
-    const int FX = CX - 2 * EO, FY = CY - 2 * EO;
+    // cc needs 1 extra ring for the residual (EO 4), nodal full weighting one more (EO 5);
+    // every further GSRB^4 group costs 4 more rings
+    // (FX, FY are even for any EO, so tile origins stay even)
+    const int EO = (RES ? (g.cc ? 4 : 5) : 3) + 4 * (NS - 1);
+    const int FX = CX - 2 * EO, FY = CY * RH - 2 * EO;
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
-    hpb_launch(k_smooth<INIT, RES>, nbx * nby, NT, 0, ctx->stream, g, in, crse, rhs, acf, acf_rs, out, gc,
-                                                           res_c, norm, nbx, EO, done);
+    const size_t smem = 2 * sizeof(double) * (size_t)(CY * RH + 2) * AX;
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_smooth<INIT, RES, RH, NS>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    hpb_launch(k_smooth<INIT, RES, RH, NS>, nbx * nby, NT, smem, ctx->stream, g, in, crse, rhs, acf,
+               acf_rs, out, gc, res_c, norm, nbx, EO, done);
     hpb_count_launch(ctx);
+    return HPB_OK;
 }
 
 inline unsigned nb(long n) { return (unsigned)((n + 255) / 256); }
@@ -842,8 +865,10 @@ void hpb_mg_free(hpb_ctx *ctx)
 // one V-cycle (:1429-1512).  On entry: cur = cor0 (level-0 iterate after 4 sweeps), res[1] holds
 // the restricted residual of cor0.  On exit the same invariants hold for the new cor0, and
 // d_mg_norm[0] holds max|rescor0|.  tmp is the second level-0 buffer.
+// fused = true: the two level-0 smoothers are ONE launch (8 half-sweeps, 64 x 64 tiles) that
+// reads cur and writes the new cor0 into tmp: the caller ping-pongs the two buffers.
 static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, long chi_rs,
-                     double tol_rel, double tol_abs)
+                     double tol_rel, double tol_abs, bool fused)
 {
     const int lc = ctx->mg_lc;
     const V2 none{};
@@ -870,12 +895,20 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
         up_prev = ctx->mg[l].rescor;
     }
     const LevelGeom g0 = level_geom(ctx, 0), g1 = level_geom(ctx, 1);
-    // sol = GSRB^4(cor0 + I(cor[1]))  ->  tmp
-    launch_smooth<2, false>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs, tmp, gnone, none,
-                            nullptr, done);
-    // cor0 = GSRB^4(sol), rescor0 = rhs - L cor0 -> res[1], norm   (:1501-1503)
-    launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, cur, g1,
-                           lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, done);
+    if (fused) {
+        // cor0' = GSRB^4(GSRB^4(cor0 + I(cor[1]))), rescor0 = rhs - L cor0' -> res[1], norm
+        int rc = launch_smooth<2, true, 2, 2>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs,
+                                              tmp, g1, lvl_view(ctx, 1, ctx->mg[1].res),
+                                              ctx->d_mg_norm, done);
+        if (rc) return rc;
+    } else {
+        // sol = GSRB^4(cor0 + I(cor[1]))  ->  tmp
+        launch_smooth<2, false>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs, tmp, gnone,
+                                none, nullptr, done);
+        // cor0 = GSRB^4(sol), rescor0 = rhs - L cor0 -> res[1], norm   (:1501-1503)
+        launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, cur, g1,
+                               lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, done);
+    }
     hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
     hpb_count_launch(ctx);
     return HPB_OK;
@@ -923,10 +956,23 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     // Speculative V-cycles: as many as the previous solve needed, enqueued without a host round
     // trip; each kernel is a no-op once the device-side test (:1391) has passed.  One
     // synchronisation then tells us whether more are needed.
+    static int fuse_env = -1;
+    if (fuse_env < 0) { const char *e = getenv("HPB_MG_FUSE"); fuse_env = e ? atoi(e) : 1; }
+    const bool fused = fuse_env != 0;
+    // fused: V-cycle k (1-based) reads buf[(k-1) % 2] and writes buf[k % 2], buf = {cor0 buffer, sol};
+    // the cycles that actually run are a prefix of the enqueued ones, so after `iters` executed
+    // cycles the iterate lives in buf[iters % 2].  Unfused: sol is only the scratch iterate.
+    const V2 buf[2] = {cur, sol};
     int enq = 0;
+    auto enqueue_cycle = [&]() -> int {
+        int rc = fused ? mg_vcycle(ctx, buf[enq & 1], buf[(enq + 1) & 1], rhs, chi, chi_rs, tol_rel, tol_abs, true)
+                       : mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs, tol_rel, tol_abs, false);
+        ++enq;
+        return rc;
+    };
     const int n_pred = ctx->mg_last_iters < 1 ? 1 : (ctx->mg_last_iters > max_iters ? max_iters : ctx->mg_last_iters);
-    for (; enq < n_pred; ++enq) {
-        int rc = mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs, tol_rel, tol_abs);     // sol is the scratch iterate
+    while (enq < n_pred) {
+        int rc = enqueue_cycle();
         if (rc) return rc;
     }
     int iters = 0;
@@ -947,14 +993,15 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
             hpb_set_error("hpmg failed to converge after %d iterations", max_iters);
             return HPB_ERR_MG_DIVERGED;
         }
-        int rc = mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs, tol_rel, tol_abs);
+        int rc = enqueue_cycle();
         if (rc) return rc;
-        ++enq;
     }
     ctx->mg_last_iters = iters;
-    // sol <- cor0 on the valid box (:1419-1426)
-    hpb_launch(k_copy2, nb(nv0), 256, 0, ctx->stream, g0, sol, cur);
-    hpb_count_launch(ctx);
+    // sol <- cor0 on the valid box (:1419-1426) unless the last executed cycle wrote it there
+    if (!fused || (iters & 1) == 0) {
+        hpb_launch(k_copy2, nb(nv0), 256, 0, ctx->stream, g0, sol, cur);
+        hpb_count_launch(ctx);
+    }
     HPB_CUDA_CHECK(cudaGetLastError());
     if (h_iters) *h_iters = iters;
     return HPB_OK;
