@@ -92,8 +92,11 @@ struct SmCell {
 template <int INIT, bool RES, int RH, int NS>
 __global__ void __launch_bounds__(NT, RH == 2 ? 1 : 2)      // RH = 2: 8 cells of state per thread
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
-         V2 phi_out, LevelGeom gc, V2 res_c, double *norm, int nbx, int EO, const int *done)
+         const double *__restrict__ c0i_in, double *__restrict__ c0i_out, V2 phi_out, LevelGeom gc,
+         V2 res_c, double *norm, int nbx, int EO, const int *done)
 {
+    // c0i_in: plane of 1 / c0 (row stride g.nx) written by an earlier launch of this solve -- the
+    // four fp64 divisions per thread are then loads; c0i_out: where the first launch stores it
     constexpr int CYr = CY * RH, AYr = CYr + 2, NP = 2 * RH;
     extern __shared__ double sm_dyn[];
     double *const sm0 = sm_dyn, *const sm1 = sm_dyn + AYr * AX;
@@ -147,14 +150,19 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             const long o = i + (long)j * rhs.rs;
             r0[p][h] = ok ? rhs.p[o] : 0.;
             r1[p][h] = ok ? rhs.p[o + rhs.cs] : 0.;
-            const double a = ok ? acf[i + (long)j * acf_rs] : 0.;
-            ac[p][h] = a;
-            double c0 = -(a + 2.0 * (g.facx + g.facy));                 // gs1 :265-292
             const bool xb = !inner && g.cc && (i == g.vlo || i == g.vhix);
             const bool yb = !inner && g.cc && (j == g.vlo || j == g.vhiy);
-            if (xb) c0 -= 2.0 * g.facx;
-            if (yb) c0 -= 2.0 * g.facy;
-            ci[p][h] = 1.0 / c0;
+            if (c0i_in) {
+                ci[p][h] = ok ? c0i_in[i + (long)j * g.nx] : 0.;
+                ac[p][h] = (RES && ok) ? acf[i + (long)j * acf_rs] : 0.;
+            } else {
+                const double a = ok ? acf[i + (long)j * acf_rs] : 0.;
+                ac[p][h] = a;
+                double c0 = -(a + 2.0 * (g.facx + g.facy));             // gs1 :265-292
+                if (xb) c0 -= 2.0 * g.facx;
+                if (yb) c0 -= 2.0 * g.facy;
+                ci[p][h] = 1.0 / c0;
+            }
             // boundary cells (cell-centred): one neighbour is the zero halo, the other is
             // weighted 4/3 -- identical to the branches of gs1
             wx[p][h] = xb ? fx43 : g.facx;
@@ -239,7 +247,8 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
                 const long o = i + (long)j * phi_out.rs;
                 phi_out.p[o] = sm0[so];
                 phi_out.p[o + phi_out.cs] = sm1[so];
-                if (RES) {
+                if (c0i_out) c0i_out[i + (long)j * g.nx] = ci[p][h];
+                if (RES && norm) {
                     nres = fmax(nres, fmax(fabs(rs0[p][h]), fabs(rs1[p][h])));
                     nrhs = fmax(nrhs, fmax(fabs(r0[p][h]), fabs(r1[p][h])));
                 }
@@ -662,7 +671,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse_setup(CoarseArgs A, L
 }
 
 // crse = R(fine), 1 component, arbitrary fine row stride (coefficient average-down on tile levels)
-__global__ void k_restrict_acf(LevelGeom gc, double *crse, const double *fine, long fine_rs)
+__global__ void k_restrict_acf(LevelGeom gc, double *crse, double *c0i, const double *fine, long fine_rs)
 {
     hpb_pdl_prologue();
     const int nvx = gc.vhix - gc.vlo + 1;
@@ -677,6 +686,11 @@ __global__ void k_restrict_acf(LevelGeom gc, double *crse, const double *fine, l
     else v = (1. / 16.) * (f[-w - 1] + 2. * f[-w] + f[-w + 1] + 2. * f[-1] + 4. * f[0] + 2. * f[1]
                            + f[w - 1] + 2. * f[w] + f[w + 1]);
     crse[i + (long)j * gc.nx] = v;
+    // 1 / c0 of the coarse level (gs1 :265-292), used by every smoother launch of this solve
+    double c0 = -(v + 2.0 * (gc.facx + gc.facy));
+    if (gc.cc && (i == gc.vlo || i == gc.vhix)) c0 -= 2.0 * gc.facx;
+    if (gc.cc && (j == gc.vlo || j == gc.vhiy)) c0 -= 2.0 * gc.facy;
+    c0i[i + (long)j * gc.nx] = 1.0 / c0;
 }
 
 __global__ void k_copy2(LevelGeom g, V2 dst, V2 src)
@@ -738,7 +752,8 @@ V2 lvl_view(const hpb_ctx *ctx, int l, double *p)
 
 template <int INIT, bool RES, int RH = 1, int NS = 1>
 int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, const double *acf,
-                  long acf_rs, V2 out, const LevelGeom &gc, V2 res_c, double *norm, const int *done)
+                  long acf_rs, const double *c0i_in, double *c0i_out, V2 out, const LevelGeom &gc,
+                  V2 res_c, double *norm, const int *done)
 {
     // owned region must start on even indices relative to vlo for the fused restriction;
     // cc needs 1 extra ring for the residual (EO 4), nodal full weighting one more (EO 5);
@@ -756,7 +771,7 @@ int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, cons
         attr_set = true;
     }
     hpb_launch(k_smooth<INIT, RES, RH, NS>, nbx * nby, NT, smem, ctx->stream, g, in, crse, rhs, acf,
-               acf_rs, out, gc, res_c, norm, nbx, EO, done);
+               acf_rs, c0i_in, c0i_out, out, gc, res_c, norm, nbx, EO, done);
     hpb_count_launch(ctx);
     return HPB_OK;
 }
@@ -836,7 +851,7 @@ int hpb_mg_init(hpb_ctx *ctx)
                             &ctx->mg[l].rescor};
         const size_t mult[5] = {1, 1, 2, 2, 2};
         for (int k = 0; k < 5; ++k) {
-            if (l == 0 && (k == 0 || k == 1 || k == 2)) { *arrs[k] = nullptr; continue; }  // chi / rhs in place
+            if (l == 0 && (k == 0 || k == 2)) { *arrs[k] = nullptr; continue; }  // chi / rhs in place
             HPB_CUDA_CHECK(cudaMalloc(arrs[k], mult[k] * n * sizeof(double)));
             HPB_CUDA_CHECK(cudaMemset(*arrs[k], 0, mult[k] * n * sizeof(double)));
         }
@@ -877,7 +892,7 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
     for (int l = 1; l < lc; ++l) {                 // down, tile levels
         const LevelGeom g = level_geom(ctx, l), gc = level_geom(ctx, l + 1);
         launch_smooth<0, true>(ctx, g, none, none, lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf,
-                               g.nx, lvl_view(ctx, l, ctx->mg[l].cor), gc,
+                               g.nx, ctx->mg[l].c0i, nullptr, lvl_view(ctx, l, ctx->mg[l].cor), gc,
                                lvl_view(ctx, l + 1, ctx->mg[l + 1].res), nullptr, done);
     }
     if (ctx->mg_coarse_smem > 0)
@@ -891,22 +906,24 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
         const LevelGeom g = level_geom(ctx, l);
         launch_smooth<2, false>(ctx, g, lvl_view(ctx, l, ctx->mg[l].cor), lvl_view(ctx, l + 1, up_prev),
                                 lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf, g.nx,
-                                lvl_view(ctx, l, ctx->mg[l].rescor), gnone, none, nullptr, done);
+                                ctx->mg[l].c0i, nullptr, lvl_view(ctx, l, ctx->mg[l].rescor), gnone, none,
+                                nullptr, done);
         up_prev = ctx->mg[l].rescor;
     }
     const LevelGeom g0 = level_geom(ctx, 0), g1 = level_geom(ctx, 1);
     if (fused) {
         // cor0' = GSRB^4(GSRB^4(cor0 + I(cor[1]))), rescor0 = rhs - L cor0' -> res[1], norm
         int rc = launch_smooth<2, true, 2, 2>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs,
-                                              tmp, g1, lvl_view(ctx, 1, ctx->mg[1].res),
+                                              ctx->mg[0].c0i, nullptr, tmp, g1,
+                                              lvl_view(ctx, 1, ctx->mg[1].res),
                                               ctx->d_mg_norm, done);
         if (rc) return rc;
     } else {
         // sol = GSRB^4(cor0 + I(cor[1]))  ->  tmp
-        launch_smooth<2, false>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs, tmp, gnone,
-                                none, nullptr, done);
+        launch_smooth<2, false>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs,
+                                ctx->mg[0].c0i, nullptr, tmp, gnone, none, nullptr, done);
         // cor0 = GSRB^4(sol), rescor0 = rhs - L cor0 -> res[1], norm   (:1501-1503)
-        launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, cur, g1,
+        launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, ctx->mg[0].c0i, nullptr, cur, g1,
                                lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, done);
     }
     hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
@@ -938,7 +955,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     for (int l = 1; l < lc; ++l) {
         const LevelGeom gc = level_geom(ctx, l);
         const long nv = (long)(gc.vhix - gc.vlo + 1) * (gc.vhiy - gc.vlo + 1);
-        hpb_launch(k_restrict_acf, nb(nv), 256, 0, ctx->stream, gc, ctx->mg[l].acf, fine, fine_rs);
+        hpb_launch(k_restrict_acf, nb(nv), 256, 0, ctx->stream, gc, ctx->mg[l].acf, ctx->mg[l].c0i, fine, fine_rs);
         hpb_count_launch(ctx);
         fine = ctx->mg[l].acf;
         fine_rs = gc.nx;
@@ -949,7 +966,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
 
     // cor0 = GSRB^4(sol), rescor0 = rhs - L(cor0)   (:1326-1327), fused with its restriction
     V2 cur = lvl_view(ctx, 0, ctx->mg[0].cor);
-    launch_smooth<1, true>(ctx, g0, sol, none, rhs, chi, chi_rs, cur, g1,
+    launch_smooth<1, true>(ctx, g0, sol, none, rhs, chi, chi_rs, nullptr, ctx->mg[0].c0i, cur, g1,
                            lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, nullptr);
     hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 0, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
     hpb_count_launch(ctx);
@@ -957,7 +974,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     // trip; each kernel is a no-op once the device-side test (:1391) has passed.  One
     // synchronisation then tells us whether more are needed.
     static int fuse_env = -1;
-    if (fuse_env < 0) { const char *e = getenv("HPB_MG_FUSE"); fuse_env = e ? atoi(e) : 1; }
+    if (fuse_env < 0) { const char *e = getenv("HPB_MG_FUSE"); fuse_env = e ? atoi(e) : 0; }
     const bool fused = fuse_env != 0;
     // fused: V-cycle k (1-based) reads buf[(k-1) % 2] and writes buf[k % 2], buf = {cor0 buffer, sol};
     // the cycles that actually run are a prefix of the enqueued ones, so after `iters` executed

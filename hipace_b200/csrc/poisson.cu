@@ -175,22 +175,36 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
     }
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) tmp[2 * h * Nr + j] = in[j];
     __syncthreads();
-    for (int e = threadIdx.x; e < Nr * (h + 1); e += blockDim.x) {
-        const int b = fNr.div(e), j = e - b * Nr;
+    // two outputs b per work item share the shared-memory reads of U_t, V_t
+    constexpr int BB = 2;
+    const int nbg = (h + BB) / BB;              // ceil((h + 1) / BB)
+    for (int e = threadIdx.x; e < Nr * nbg; e += blockDim.x) {
+        const int bg = fNr.div(e), j = e - bg * Nr;
+        const int b0 = bg * BB;
         const int k = fNs.mod(j);
         const double2 x0 = tmp[2 * h * Nr + j];
-        double2 P = x0, Q = make_double2(0., 0.);
-        const double *cc = tcos + b * h, *ss = tsin + b * h;
-#pragma unroll 4
+        double2 P[BB], Q[BB];
+#pragma unroll
+        for (int bb = 0; bb < BB; ++bb) { P[bb] = x0; Q[bb] = make_double2(0., 0.); }
+#pragma unroll 2
         for (int t = 0; t < h; ++t) {
-            const double c = __ldg(&cc[t]), s = __ldg(&ss[t]);
             const double2 u = tmp[t * Nr + j], v = tmp[(h + t) * Nr + j];
-            P.x += c * u.x; P.y += c * u.y;
-            Q.x += s * v.x; Q.y += s * v.y;
+#pragma unroll
+            for (int bb = 0; bb < BB; ++bb) {
+                const int b = min(b0 + bb, h);          // (a clamped duplicate is simply not stored)
+                const double c = __ldg(&tcos[b * h + t]), sn = __ldg(&tsin[b * h + t]);
+                P[bb].x += c * u.x; P[bb].y += c * u.y;
+                Q[bb].x += sn * v.x; Q[bb].y += sn * v.y;
+            }
         }
         const int o = (j - k) * p + k;
-        in[o + b * Ns] = make_double2(P.x + Q.y, P.y - Q.x);                    // P - iQ
-        if (b) in[o + (p - b) * Ns] = make_double2(P.x - Q.y, P.y + Q.x);       // P + iQ
+#pragma unroll
+        for (int bb = 0; bb < BB; ++bb) {
+            const int b = b0 + bb;
+            if (b > h) break;
+            in[o + b * Ns] = make_double2(P[bb].x + Q[bb].y, P[bb].y - Q[bb].x);                    // P - iQ
+            if (b) in[o + (p - b) * Ns] = make_double2(P[bb].x - Q[bb].y, P[bb].y + Q[bb].x);       // P + iQ
+        }
     }
 }
 
