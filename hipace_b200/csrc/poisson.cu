@@ -175,8 +175,9 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
     }
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) tmp[2 * h * Nr + j] = in[j];
     __syncthreads();
-    // two outputs b per work item share the shared-memory reads of U_t, V_t
-    constexpr int BB = 2;
+    // BB outputs b per work item share the shared-memory reads of U_t, V_t (BB > 1 measured slower:
+    // the extra accumulators spill at 6 CTAs / SM)
+    constexpr int BB = 1;
     const int nbg = (h + BB) / BB;              // ceil((h + 1) / BB)
     for (int e = threadIdx.x; e < Nr * nbg; e += blockDim.x) {
         const int bg = fNr.div(e), j = e - bg * Nr;
