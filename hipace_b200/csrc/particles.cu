@@ -525,6 +525,8 @@ __device__ __forceinline__ void cp_async_wait_all()
 // from registers into jx, jy, chi, rhomjz (which the caller has already shifted / initialised for
 // the next slice), saving the 56 B/particle re-read and one launch per slice.
 struct DepositArgs {
+    int exp_extra;      // TIMING EXPERIMENT ONLY (HPB_EXP_DEP12): two more 4-plane deposits into scratch
+    int cx[8];
     int c_jx, c_jy, c_chi, c_rhomjz;
     double clightinv, charge_invvol, charge_mu0_mass_ratio, max_qsa;
     int *n_qsa_violation;
@@ -681,6 +683,16 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
                                                 active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
                                                 vx_c, vy_c, gamma_psi,
                                                 dep.charge_mu0_mass_ratio * psi_inv);
+    if (dep.exp_extra) {
+        deposit_aggregated<true, false, true, true>(a, dep.cx[0], dep.cx[1], -1, dep.cx[2], dep.cx[3],
+                                                    active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
+                                                    vx_c * vy_c, vy_c * vy_c, gamma_psi,
+                                                    dep.charge_mu0_mass_ratio * psi_inv * vx_c);
+        deposit_aggregated<true, false, true, true>(a, dep.cx[4], dep.cx[5], -1, dep.cx[6], dep.cx[7],
+                                                    active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
+                                                    vx_c * vx_c, gamma_psi - vy_c, gamma_psi,
+                                                    dep.charge_mu0_mass_ratio * psi_inv * vy_c);
+    }
 }
 
 inline unsigned nblocks(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
@@ -783,6 +795,11 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         dep.clightinv = 1.0 / g.c; dep.charge_invvol = charge * invvol;
         dep.charge_mu0_mass_ratio = charge * g.mu0 / mass;
         dep.max_qsa = max_qsa; dep.n_qsa_violation = d_n_qsa_violation;
+        static int exp12 = -1;
+        if (exp12 < 0) { const char *e = getenv("HPB_EXP_DEP12"); exp12 = e ? atoi(e) : 0; }
+        dep.exp_extra = exp12;
+        const int cx[8] = {HPB_C_SY, HPB_C_SX, HPB_C_EXMBY, HPB_C_EYPBX, HPB_C_PSI, HPB_C_EZ, HPB_C_BZ, HPB_C_EXMBY};
+        for (int k = 0; k < 8; ++k) dep.cx[k] = comps[cx[k]];
     }
 #define HPB_LAUNCH_PUSH(MB, DEP, STG)                                                             \
     hpb_launch(k_advance_plasma<MB, DEP, STG>, (unsigned)((pl.np + kPushThreads - 1) / kPushThreads), \

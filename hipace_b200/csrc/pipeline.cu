@@ -77,9 +77,10 @@ struct hpb_pipeline {
     int rank = 0, world = 1;
     ncclComm_t comm_recv = nullptr, comm_send = nullptr;   // 2-rank comms: sender is rank 0, receiver rank 1
     cudaStream_t s_recv = nullptr, s_send = nullptr;
-    std::vector<cudaEvent_t> ev_recv, ev_ready;            // per slot
-    cudaEvent_t ev_step_done = nullptr, ev_sent_all = nullptr;
-    bool step_done_recorded = false, sent_recorded = false;
+    std::vector<cudaEvent_t> ev_recv, ev_ready, ev_sent;   // per slot
+    std::vector<char> sent_pending;                        // per slot: ev_sent[slot] guards the out ring
+    cudaEvent_t ev_step_done = nullptr;
+    bool step_done_recorded = false;
     bool receiving = false, sent_this_step = false;
     int posted = 0;                                        // slots with a receive posted this step
     int lookahead = 8;
@@ -128,19 +129,30 @@ extern "C" int hpb_sim_pipeline_init(hpb_sim *s, int rank, int world, const char
     }
     SIM_CUDA(cudaStreamCreateWithFlags(&p->s_recv, cudaStreamNonBlocking));
     SIM_CUDA(cudaStreamCreateWithFlags(&p->s_send, cudaStreamNonBlocking));
-    p->ev_recv.resize(s->nz); p->ev_ready.resize(s->nz);
+    p->ev_recv.resize(s->nz); p->ev_ready.resize(s->nz); p->ev_sent.resize(s->nz);
+    p->sent_pending.assign(s->nz, 0);
     for (auto &e : p->ev_recv) SIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : p->ev_ready) SIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : p->ev_sent) SIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SIM_CUDA(cudaEventCreateWithFlags(&p->ev_step_done, cudaEventDisableTiming));
-    SIM_CUDA(cudaEventCreateWithFlags(&p->ev_sent_all, cudaEventDisableTiming));
-    // connect both edges now (NCCL sets up its P2P channels on first use)
+    // connect both edges now: NCCL sets up its P2P channels on the first send / receive of a
+    // communicator, and that set-up BLOCKS THE HOST until the peer enters the matching call.  As
+    // for the communicators themselves the two edges of a rank are therefore connected in
+    // increasing edge index (rank 0: send on edge 0, then receive on edge R-1; every other rank:
+    // receive on edge r-1, then send on edge r) -- a chain, no cycle.
     char *d_hs = nullptr;
     SIM_CUDA(cudaMalloc(&d_hs, 512));
     SIM_CUDA(cudaMemset(d_hs, 0, 512));
-    HPB_NCCL(N->Send(d_hs, 256, ncclUint8, 1, p->comm_send, p->s_send));
-    HPB_NCCL(N->Recv(d_hs + 256, 256, ncclUint8, 0, p->comm_recv, p->s_recv));
-    SIM_CUDA(cudaStreamSynchronize(p->s_send));
-    SIM_CUDA(cudaStreamSynchronize(p->s_recv));
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool do_send = (pass == 0) == (e_send < e_recv);
+        if (do_send) {
+            HPB_NCCL(N->Send(d_hs, 256, ncclUint8, 1, p->comm_send, p->s_send));
+            SIM_CUDA(cudaStreamSynchronize(p->s_send));
+        } else {
+            HPB_NCCL(N->Recv(d_hs + 256, 256, ncclUint8, 0, p->comm_recv, p->s_recv));
+            SIM_CUDA(cudaStreamSynchronize(p->s_recv));
+        }
+    }
     cudaFree(d_hs);
     return HPB_OK;
 }
@@ -152,12 +164,18 @@ void hpb_pipeline_destroy(hpb_sim *s)
     NcclApi *N = nccl();
     if (p->s_recv) cudaStreamSynchronize(p->s_recv);
     if (p->s_send) cudaStreamSynchronize(p->s_send);
-    if (N && p->comm_recv) N->CommDestroy(p->comm_recv);
-    if (N && p->comm_send) N->CommDestroy(p->comm_send);
+    // ncclCommDestroy may wait for the peer of the communicator: tear the two edges down in the
+    // same global order (increasing edge index) in which they were built
+    const int e_send = p->rank, e_recv = (p->rank - 1 + p->world) % p->world;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool do_send = (pass == 0) == (e_send < e_recv);
+        if (do_send) { if (N && p->comm_send) N->CommDestroy(p->comm_send); }
+        else if (N && p->comm_recv) N->CommDestroy(p->comm_recv);
+    }
     for (auto &e : p->ev_recv) cudaEventDestroy(e);
     for (auto &e : p->ev_ready) cudaEventDestroy(e);
+    for (auto &e : p->ev_sent) cudaEventDestroy(e);
     if (p->ev_step_done) cudaEventDestroy(p->ev_step_done);
-    if (p->ev_sent_all) cudaEventDestroy(p->ev_sent_all);
     if (p->s_recv) cudaStreamDestroy(p->s_recv);
     if (p->s_send) cudaStreamDestroy(p->s_send);
     delete p;
@@ -197,10 +215,13 @@ int hpb_pipeline_begin_step(hpb_sim *s, int step)
     p->sent_this_step = false;
     p->posted = 0;
     if (!p->receiving) return HPB_OK;
-    // the ring we receive into was last read by the previous step's slice loop (as its input or,
-    // after the swap, as its send buffer): order the receives behind both
+    // We receive into the ring the previous owned step used as its INPUT (begin_step flips
+    // BeamSp::cur back when the other ring still holds slices being sent): it is free as soon as
+    // that step's slice loop is done.  The ring with the pending sends becomes this step's output
+    // ring; every slot of it is guarded by its own send-complete event (hpb_pipeline_wait_out_slot),
+    // so a rank never waits for the downstream rank to drain a whole step -- with a single
+    // "all sent" event two ranks ran their steps one after the other instead of pipelined.
     if (p->step_done_recorded) SIM_CUDA(cudaStreamWaitEvent(p->s_recv, p->ev_step_done, 0));
-    if (p->sent_recorded) SIM_CUDA(cudaStreamWaitEvent(p->s_recv, p->ev_sent_all, 0));
     return post_receives(s, p->lookahead);
 }
 
@@ -229,8 +250,31 @@ int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step)
         HPB_NCCL(N->Send(out.packet(slot), out.msg_bytes(), ncclUint8, 1, p->comm_send, p->s_send));
     }
     HPB_NCCL(N->GroupEnd());
+    SIM_CUDA(cudaEventRecord(p->ev_sent[slot], p->s_send));
+    p->sent_pending[slot] = 1;
     p->sent_this_step = true;
     return HPB_OK;
+}
+
+// the compute stream is about to overwrite slot `slot` of the output ring: the send of the slice
+// it held (previous owned step) must have left the buffer
+int hpb_pipeline_wait_out_slot(hpb_sim *s, int islice)
+{
+    hpb_pipeline *p = s->pipe;
+    if (!hpb_pipeline_active(s)) return HPB_OK;
+    const int slot = s->nz - 1 - islice;
+    if (p->sent_pending[slot]) {
+        SIM_CUDA(cudaStreamWaitEvent(s->stream, p->ev_sent[slot], 0));
+        p->sent_pending[slot] = 0;
+    }
+    return HPB_OK;
+}
+
+bool hpb_pipeline_out_ring_busy(const hpb_sim *s)
+{
+    if (!hpb_pipeline_active(s)) return false;
+    for (char c : s->pipe->sent_pending) if (c) return true;
+    return false;
 }
 
 int hpb_pipeline_end_step(hpb_sim *s, int step)
@@ -239,9 +283,5 @@ int hpb_pipeline_end_step(hpb_sim *s, int step)
     hpb_pipeline *p = s->pipe;
     SIM_CUDA(cudaEventRecord(p->ev_step_done, s->stream));
     p->step_done_recorded = true;
-    if (p->sent_this_step) {
-        SIM_CUDA(cudaEventRecord(p->ev_sent_all, p->s_send));
-        p->sent_recorded = true;
-    }
     return HPB_OK;
 }

@@ -537,7 +537,11 @@ int begin_step(hpb_sim *s, int step)
     // arrive slice by slice from the previous time step (MultiBuffer::get_data) -- from the
     // upstream rank in a pipeline, otherwise from the ring the previous step on this GPU filled
     const bool recv = hpb_pipeline_receives(s, step);
+    // end_step left BeamSp::cur on the ring this rank is still sending from: receive into the
+    // other one (the previous step's input) and reuse the sending ring, slot by slot, as output
+    const bool flip = recv && hpb_pipeline_out_ring_busy(s);
     for (auto &b : s->beams) {
+        if (flip && b.ring[0].base) b.cur ^= 1;
         if (!b.ring[0].base || (!recv && !b.initialised) || (!recv && step == 0 && !b.from_host)) {
             int rc = init_beam(s, b);
             if (rc) return rc;
@@ -654,6 +658,7 @@ int solve_one_slice(hpb_sim *s, int islice)
         const int slot = s->nz - 1 - islice;
         const double min_z = s->prob_lo[2] + islice * s->g.dz;
         const double time = s->dt * s->cur_step;
+        if (!s->beams.empty() && (rc = hpb_pipeline_wait_out_slot(s, islice))) return rc;
         for (auto &b : s->beams) {
             const BeamRing &in = b.ring[b.cur], &out = b.ring[b.cur ^ 1];
             const hpb_beam_slice bm = in.view(slot);

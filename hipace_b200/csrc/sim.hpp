@@ -152,6 +152,8 @@ void hpb_pipeline_destroy(hpb_sim *s);
 int hpb_pipeline_begin_step(hpb_sim *s, int step);          // post receives / order ring reuse
 int hpb_pipeline_wait_slice(hpb_sim *s, int islice);        // compute stream waits for slice islice
 int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step);
+int hpb_pipeline_wait_out_slot(hpb_sim *s, int islice);     // out-ring slot free (its last send left)
+bool hpb_pipeline_out_ring_busy(const hpb_sim *s);          // sends of the previous owned step pending
 int hpb_pipeline_end_step(hpb_sim *s, int step);
 bool hpb_pipeline_receives(const hpb_sim *s, int step);     // this step's beam comes from upstream
 bool hpb_pipeline_active(const hpb_sim *s);

@@ -60,6 +60,10 @@ def _free_port():
 
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
+    # a hung rank must never hold the GPU box: dump where it is stuck and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('HPB_TEST_WATCHDOG', '240')), exit=True)
+    log = lambda msg: print(f'[rank {rank}] {msg}', file=sys.stderr, flush=True)
     import torch
     import torch.distributed as dist
     import hipace_b200 as hp
@@ -67,9 +71,12 @@ def _worker(rank, world, port, out_dir):
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    log('process group up')
     sim = hp.Simulation(_deck(), OV, device=rank)
     sim.pipeline_init(rank, world, dist)
+    log('pipeline edges connected')
     sim.run(OV['max_step'], rank, world)
+    log('steps done')
     n = max(sim.beam_np(), 1)
     host = {'real': np.zeros((7, n)), 'idcpu': np.zeros(n, dtype=np.uint64),
             'slot_off': np.zeros(sim.nz + 1, dtype=np.int64)}
