@@ -109,6 +109,34 @@ def test_slice_by_slice_fields_and_particles(deck, ov, nsl, fuse, repo_root):
     sim.close()
 
 
+@pytest.mark.parametrize('fuse', [0, 1])
+def test_two_mobile_species_ion_motion(fuse, repo_root):
+    """two mobile species (electrons + light ions, no neutralising background; the
+    structure of the reference's inputs_ion_motion_SI with a deterministic beam) -- per-species
+    charge / mass through every particle kernel, both driver orders, vs the oracle: field
+    checksums of 70 slices and the full state of both species."""
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    text = _deck(repo_root, 'ion_motion_normalized.in')
+    nsl = 70
+    ref = Oracle(text, {})
+    want = ref.evolve(nsl)
+    sim = hp.Simulation(text, {})
+    sim.set_option('fuse', fuse)
+    got = sim.evolve(0, 0, nsl)
+    for k, w in want.items():
+        assert abs(got[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (k, got[k], w)
+    assert sim.stats()['n_qsa_violation'] == 0
+    for isp, o in enumerate(ref.plasmas):
+        p = sim.plasma(isp)
+        assert np.array_equal(p['valid'], o.valid)
+        v = o.valid
+        for nm, ov_ in (('x', o.x), ('y', o.y), ('ux', o.ux), ('uy', o.uy), ('psi', o.psi)):
+            scale = max(np.abs(ov_[v]).max(), 1e-300)
+            assert np.abs(p[nm][v] - ov_[v]).max() / scale <= 1e-9, (isp, nm)
+    sim.close()
+
+
 def test_plasma_init_is_bit_exact(repo_root):
     """particle count, order and positions right after InitParticles"""
     import hipace_b200 as hp
