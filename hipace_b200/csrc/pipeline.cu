@@ -232,7 +232,7 @@ int hpb_pipeline_wait_slice(hpb_sim *s, int islice)
     const int slot = s->nz - 1 - islice;
     int rc = post_receives(s, slot + 1 + p->lookahead);
     if (rc) return rc;
-    SIM_CUDA(cudaStreamWaitEvent(s->stream, p->ev_recv[slot], 0));
+    SIM_CUDA(cudaStreamWaitEvent(s->beam_stream ? s->beam_stream : s->stream, p->ev_recv[slot], 0));
     return HPB_OK;
 }
 
@@ -242,7 +242,7 @@ int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step)
     if (!hpb_pipeline_active(s) || step + 1 > s->max_step) return HPB_OK;     // Hipace.cpp:441-443
     NcclApi *N = nccl();
     const int slot = s->nz - 1 - islice;
-    SIM_CUDA(cudaEventRecord(p->ev_ready[slot], s->stream));
+    SIM_CUDA(cudaEventRecord(p->ev_ready[slot], s->beam_stream ? s->beam_stream : s->stream));
     SIM_CUDA(cudaStreamWaitEvent(p->s_send, p->ev_ready[slot], 0));
     HPB_NCCL(N->GroupStart());
     for (auto &b : s->beams) {
@@ -264,7 +264,7 @@ int hpb_pipeline_wait_out_slot(hpb_sim *s, int islice)
     if (!hpb_pipeline_active(s)) return HPB_OK;
     const int slot = s->nz - 1 - islice;
     if (p->sent_pending[slot]) {
-        SIM_CUDA(cudaStreamWaitEvent(s->stream, p->ev_sent[slot], 0));
+        SIM_CUDA(cudaStreamWaitEvent(s->beam_stream ? s->beam_stream : s->stream, p->ev_sent[slot], 0));
         p->sent_pending[slot] = 0;
     }
     return HPB_OK;

@@ -569,12 +569,76 @@ int end_step(hpb_sim *s)
     return HPB_OK;
 }
 
+// the kernel seams take their stream from the context: route a group of calls to another stream
+struct StreamScope {
+    hpb_sim *s; cudaStream_t old_ctx, old_beam;
+    StreamScope(hpb_sim *s_, cudaStream_t st) : s(s_), old_ctx(s_->ctx->stream), old_beam(s_->beam_stream)
+    {
+        s->ctx->stream = st; s->beam_stream = st;
+    }
+    ~StreamScope() { s->ctx->stream = old_ctx; s->beam_stream = old_beam; }
+};
+
+// beam jz of slice isl (Hipace.cpp:582-585, 613-614)
+int beam_deposit_jz(hpb_sim *s, int isl)
+{
+    int rc;
+    if (s->beams.empty() || isl < 0) return HPB_OK;
+    if ((rc = hpb_pipeline_wait_slice(s, isl))) return rc;
+    for (auto &b : s->beams)
+        if ((rc = hpb_beam_deposit(s->ctx, beam_slice_view(s, b, isl), s->sl, b.charge, -1, -1,
+                                   s->comps[HPB_C_JZ_BEAM]))) return rc;
+    return HPB_OK;
+}
+
+// beam jx, jy of slice isl - 1 into Next, then the Sx / Sy seed of slice isl (Hipace.cpp:639-660)
+int beam_next_and_sxsy(hpb_sim *s, int isl)
+{
+    int rc;
+    if (!s->beams.empty() && isl > 0 && (rc = hpb_pipeline_wait_slice(s, isl - 1))) return rc;
+    if (s->do_beam_jx_jy)
+        for (auto &b : s->beams)
+            if ((rc = hpb_beam_deposit(s->ctx, beam_slice_view(s, b, isl - 1), s->sl, b.charge,
+                                       s->comps[HPB_C_NEXT_JX_BEAM], s->comps[HPB_C_NEXT_JY_BEAM], -1))) return rc;
+    return hpb_fields_sxsy_from_beam(s->ctx, s->sl, s->comps);
+}
+
+// AdvanceBeamParticlesSlice + shiftSlippedParticles + MultiBuffer::put_data (Hipace.cpp:707-716)
+int beam_push_and_send(hpb_sim *s, int islice)
+{
+    int rc;
+    if (s->beams.empty()) return HPB_OK;
+    const int slot = s->nz - 1 - islice;
+    const double min_z = s->prob_lo[2] + islice * s->g.dz;
+    const double time = s->dt * s->cur_step;
+    if ((rc = hpb_pipeline_wait_out_slot(s, islice))) return rc;
+    for (auto &b : s->beams) {
+        const BeamRing &in = b.ring[b.cur], &out = b.ring[b.cur ^ 1];
+        const hpb_beam_slice bm = in.view(slot);
+        if ((rc = hpb_advance_beam_impl(s->ctx, bm, in.nsub(slot), s->sl, b.charge, b.mass, b.n_subcycles,
+                                        s->dt, time, min_z, b.do_z_push, s->particle_bc, s->bc_lo,
+                                        s->bc_hi, s->comps, b.ext, b.d_class,
+                                        s->opt_checksums ? b.d_cs : nullptr, s->d_count))) return rc;
+        hpb_beam_slice next = {};
+        if (islice > 0) next = in.view(slot + 1);
+        if ((rc = hpb_beam_shift_slipped(s->ctx, bm, in.nsub(slot), min_z, b.d_class, out.view(slot),
+                                         out.hdr(slot), next, islice > 0 ? in.hdr(slot + 1) : nullptr,
+                                         islice > 0 ? in.nsub(slot + 1) : nullptr, s->d_overflow))) return rc;
+    }
+    return hpb_pipeline_send_slice(s, islice, s->cur_step);
+}
+
 // Hipace::SolveOneSlice, explicit branch (Hipace.cpp:556-728).
-// Reference order (opt_fuse = 0): InitializeSlices, DepositCurrent, ..., AdvancePlasmaParticles,
-// beam push, ShiftSlices.  Fused order (default): the beam push moves ahead of the plasma push
-// (they are independent), then ONE pass shifts the slices and initialises them for the next
-// slice, and the plasma push deposits the next slice's jx jy chi rhomjz from registers -- the
-// next call then starts at the beam deposit.
+// Reference order (opt_fuse = 0): InitializeSlices, DepositCurrent, beam jz, Poisson, beam jx jy
+// (Next), Sx Sy seed, ExplicitDeposition, multigrid, AdvancePlasmaParticles, beam push, ShiftSlices.
+// Fused order (default), after the multigrid solve of slice k:
+//   main stream : shift + initialise the planes for slice k-1 (one pass), then the plasma push
+//                 of slice k, which deposits jx jy chi rhomjz of slice k-1 from registers;
+//   side stream : beam push / re-binning / hand-off of slice k, then the beam deposits and the
+//                 Sx, Sy seed of slice k-1 -- small latency-bound kernels that now run beside the
+//                 plasma push instead of in front of it.
+// The next call then starts at the Poisson solve.  (Without a side stream the same calls are
+// issued on the main stream in the same order.)
 int solve_one_slice(hpb_sim *s, int islice)
 {
     hpb_ctx *ctx = s->ctx;
@@ -582,39 +646,33 @@ int solve_one_slice(hpb_sim *s, int islice)
     int rc;
     bool fuse = s->opt_fuse && C[HPB_C_RHO] < 0;
     for (auto &sp : s->plasmas) if (sp.n_subcycles < 1) fuse = false;
-    if (!s->prepared) {
+    // (stage timers synchronise the main stream per stage: keep one stream when profiling)
+    const bool side = fuse && s->opt_side_stream && s->stream2 && !s->beams.empty() && !s->opt_profile;
+    const bool was_prepared = s->prepared;
+    if (!was_prepared) {
         {
             StageTimer t(s, ST_OTHER);
             if ((rc = hpb_fields_initialize_slices(ctx, s->sl, C))) return rc;          // :598-600
         }
-        StageTimer t(s, ST_DEPOSIT);
-        for (auto &sp : s->plasmas)                                                     // :609-610
-            if ((rc = hpb_deposit_current(ctx, sp.d, s->sl, sp.charge, sp.mass, C[HPB_C_JX],
-                                          C[HPB_C_JY], C[HPB_C_RHO], C[HPB_C_CHI],
-                                          C[HPB_C_RHOMJZ], sp.max_qsa, s->d_nqsa))) return rc;
-    }
-    {
+        {
+            StageTimer t(s, ST_DEPOSIT);
+            for (auto &sp : s->plasmas)                                                 // :609-610
+                if ((rc = hpb_deposit_current(ctx, sp.d, s->sl, sp.charge, sp.mass, C[HPB_C_JX],
+                                              C[HPB_C_JY], C[HPB_C_RHO], C[HPB_C_CHI],
+                                              C[HPB_C_RHOMJZ], sp.max_qsa, s->d_nqsa))) return rc;
+        }
         StageTimer t(s, ST_OTHER);
-        if (!s->beams.empty() && (rc = hpb_pipeline_wait_slice(s, islice))) return rc;  // :582-585
-        for (auto &b : s->beams)                                                        // :613-614
-            if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice), s->sl, b.charge, -1, -1,
-                                       C[HPB_C_JZ_BEAM]))) return rc;
-        // a prepared slice started rhomjz from the ion background already
-        if (!s->prepared && (rc = hpb_fields_add_rho_ions(ctx, s->sl, C))) return rc;   // :626
+        if ((rc = beam_deposit_jz(s, islice))) return rc;
+        if ((rc = hpb_fields_add_rho_ions(ctx, s->sl, C))) return rc;                   // :626
     }
     s->prepared = false;
     {
         StageTimer t(s, ST_POISSON);
         if ((rc = hpb_fields_solve_psi_ez_bz(ctx, s->sl, C))) return rc;                // :633
     }
-    {
+    if (!was_prepared) {
         StageTimer t(s, ST_OTHER);
-        if (!s->beams.empty() && islice > 0 && (rc = hpb_pipeline_wait_slice(s, islice - 1))) return rc;   // :639-642
-        if (s->do_beam_jx_jy)                                                           // :639-657
-            for (auto &b : s->beams)
-                if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice - 1), s->sl, b.charge,
-                                           C[HPB_C_NEXT_JX_BEAM], C[HPB_C_NEXT_JY_BEAM], -1))) return rc;
-        if ((rc = hpb_fields_sxsy_from_beam(ctx, s->sl, C))) return rc;                 // :660
+        if ((rc = beam_next_and_sxsy(s, islice))) return rc;
     }
     {
         StageTimer t(s, ST_EXPLICIT);
@@ -651,35 +709,40 @@ int solve_one_slice(hpb_sim *s, int islice)
         }
         return HPB_OK;
     };
-    if (!fuse && (rc = push_plasma(false))) return rc;
-    {
-        // AdvanceBeamParticlesSlice + shiftSlippedParticles + MultiBuffer::put_data (:707-716)
+    if (!fuse) {
+        if ((rc = push_plasma(false))) return rc;
         StageTimer t(s, ST_OTHER);
-        const int slot = s->nz - 1 - islice;
-        const double min_z = s->prob_lo[2] + islice * s->g.dz;
-        const double time = s->dt * s->cur_step;
-        if (!s->beams.empty() && (rc = hpb_pipeline_wait_out_slot(s, islice))) return rc;
-        for (auto &b : s->beams) {
-            const BeamRing &in = b.ring[b.cur], &out = b.ring[b.cur ^ 1];
-            const hpb_beam_slice bm = in.view(slot);
-            if ((rc = hpb_advance_beam_impl(ctx, bm, in.nsub(slot), s->sl, b.charge, b.mass, b.n_subcycles,
-                                            s->dt, time, min_z, b.do_z_push, s->particle_bc, s->bc_lo,
-                                            s->bc_hi, C, b.ext, b.d_class,
-                                            s->opt_checksums ? b.d_cs : nullptr, s->d_count))) return rc;
-            hpb_beam_slice next = {};
-            if (islice > 0) next = in.view(slot + 1);
-            if ((rc = hpb_beam_shift_slipped(ctx, bm, in.nsub(slot), min_z, b.d_class, out.view(slot),
-                                             out.hdr(slot), next, islice > 0 ? in.hdr(slot + 1) : nullptr,
-                                             islice > 0 ? in.nsub(slot + 1) : nullptr, s->d_overflow))) return rc;
-        }
-        if (!s->beams.empty() && (rc = hpb_pipeline_send_slice(s, islice, s->cur_step))) return rc;
-        if (fuse) {
+        if ((rc = beam_push_and_send(s, islice))) return rc;
+        if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;                   // :721
+    } else {
+        cudaStream_t bs = side ? s->stream2 : s->stream;
+        {
+            StageTimer t(s, ST_OTHER);
+            if (side) {     // fork: the beam push gathers this slice's fields
+                SIM_CUDA(cudaEventRecord(s->ev_fields, s->stream));
+                SIM_CUDA(cudaStreamWaitEvent(bs, s->ev_fields, 0));
+            }
+            {
+                StreamScope sc(s, bs);
+                if ((rc = beam_push_and_send(s, islice))) return rc;
+            }
             if ((rc = hpb_fields_shift_and_initialize(ctx, s->sl, s->comps))) return rc;
-        } else if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;            // :721
-    }
-    if (fuse) {
+            if (islice > 0) {
+                if (side) {     // the beam deposits of the next slice go into freshly zeroed planes
+                    SIM_CUDA(cudaEventRecord(s->ev_shift, s->stream));
+                    SIM_CUDA(cudaStreamWaitEvent(bs, s->ev_shift, 0));
+                }
+                StreamScope sc(s, bs);
+                if ((rc = beam_deposit_jz(s, islice - 1))) return rc;
+                if ((rc = beam_next_and_sxsy(s, islice - 1))) return rc;
+            }
+        }
         if ((rc = push_plasma(true))) return rc;
-        s->prepared = true;
+        if (side) {         // join: whatever follows on the main stream sees the side stream's work
+            SIM_CUDA(cudaEventRecord(s->ev_side, bs));
+            SIM_CUDA(cudaStreamWaitEvent(s->stream, s->ev_side, 0));
+        }
+        s->prepared = islice > 0;
     }
     s->stats.n_cells_updated += (double)s->g.nx * s->g.ny;
     s->stats.n_slices += 1;
@@ -741,6 +804,11 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     }
     SIM_CUDA(cudaEventCreate(&s->ev0));
     SIM_CUDA(cudaEventCreate(&s->ev1));
+    if (const char *e = getenv("HPB_SIDE_STREAM")) s->opt_side_stream = atoi(e) != 0;
+    SIM_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    SIM_CUDA(cudaEventCreateWithFlags(&s->ev_fields, cudaEventDisableTiming));
+    SIM_CUDA(cudaEventCreateWithFlags(&s->ev_shift, cudaEventDisableTiming));
+    SIM_CUDA(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
     s->pev.resize(4);
     for (auto &e : s->pev) SIM_CUDA(cudaEventCreate(&e));
     *out = s.release();
@@ -767,6 +835,10 @@ extern "C" void hpb_sim_destroy(hpb_sim *s)
     cudaFree(s->d_flag); cudaFree(s->d_offs); cudaFree(s->d_cub);
     hpb_destroy(s->ctx);
     cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+    if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
+    if (s->ev_fields) cudaEventDestroy(s->ev_fields);
+    if (s->ev_shift) cudaEventDestroy(s->ev_shift);
+    if (s->ev_side) cudaEventDestroy(s->ev_side);
     for (auto &e : s->pev) cudaEventDestroy(e);
     cudaStreamDestroy(s->stream);
     delete s;
@@ -1062,6 +1134,7 @@ extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
     const std::string k(key);
     if (k == "checksums") s->opt_checksums = value != 0.;
     else if (k == "fuse") s->opt_fuse = value != 0.;
+    else if (k == "side_stream") s->opt_side_stream = value != 0.;
     else if (k == "profile") s->opt_profile = value != 0.;
     else if (k == "max_step") s->max_step = (int)value;
     else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }

@@ -104,6 +104,12 @@ struct hpb_sim {
     // slice k shifts / initialises the planes for slice k-1 and the plasma push of slice k
     // deposits jx jy chi rhomjz of slice k-1 from registers
     bool opt_fuse = true;
+    // beam-side work of the fused order (beam push / re-binning / hand-off of this slice, beam
+    // deposits and the Sx, Sy seed of the next one) runs on a second stream beside the plasma push
+    bool opt_side_stream = true;
+    cudaStream_t stream2 = nullptr;
+    cudaStream_t beam_stream = nullptr;     // where the pipeline's per-slice waits / records go
+    cudaEvent_t ev_fields = nullptr, ev_shift = nullptr, ev_side = nullptr;
     bool prepared = false;              // the current slice was initialised + deposited by its predecessor
     std::vector<Species> plasmas;
     std::vector<BeamSp> beams;

@@ -56,9 +56,11 @@ def test_slice_by_slice_fields_and_particles(deck, ov, nsl, fuse, repo_root):
 
     fuse = 0: the reference's call order (InitializeSlices ... ShiftSlices), every component is
     comparable after the call.  fuse = 1 (the default driver): the end of a slice has already
-    shifted / re-initialised chi, jz_beam, rhomjz, jx, jy for the next slice and deposited the
-    pushed plasma into them, so only the solved fields are compared per slice -- the deposited
-    ones are covered through the fields of the following slice and the final particle state."""
+    shifted / re-initialised chi, jz_beam, rhomjz, jx, jy for the next slice, deposited the pushed
+    plasma into them and (on the side stream) seeded the next slice's Sx, Sy from the beam, so
+    only the solved fields are compared per slice -- the sources are covered through the fields
+    solved from them (Bx, By of the same slice, everything of the following one) and the final
+    particle state."""
     import hipace_b200 as hp
     from oracle.hipace_oracle import Simulation as Oracle
     text = _deck(repo_root, deck)
@@ -69,7 +71,7 @@ def test_slice_by_slice_fields_and_particles(deck, ov, nsl, fuse, repo_root):
     sim.begin_step(0)
     names = ['chi', 'Sy', 'Sx', 'ExmBy', 'EypBx', 'Ez', 'Bx', 'By', 'Bz', 'Psi', 'jx_beam',
              'jy_beam', 'jz_beam', 'jx', 'jy', 'rhomjz']
-    reset_by_fusion = ('chi', 'jz_beam', 'rhomjz')
+    reset_by_fusion = ('chi', 'jz_beam', 'rhomjz', 'Sy', 'Sx')      # Sx, Sy: already the next slice's beam seed
     nz = ref.geom.nz
     snap = {}
     ref.slice_hook = lambda s, isl, stage: snap.update(
