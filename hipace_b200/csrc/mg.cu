@@ -89,15 +89,19 @@ struct SmCell {
 //     is amortised over twice the work).  NS: number of GSRB^4 groups applied back to back
 //     (NS = 2 fuses the last smoother of a V-cycle, sol = GSRB^4(cor0 + I(cor1)), with the first
 //     one of the next, cor0 = GSRB^4(sol), at the price of a 4-cell deeper halo).
-template <int INIT, bool RES, int RH, int NS>
-__global__ void __launch_bounds__(NT, RH == 2 ? 1 : 2)      // RH = 2: 8 cells of state per thread
+// NTHR: 512 (two columns per thread) or 1024 (one column per thread: half the dependent work per
+//       thread -- used on the small levels, whose launches are latency bound, not throughput bound)
+template <int INIT, bool RES, int RH, int NS, int NTHR>
+__global__ void __launch_bounds__(NTHR, (RH == 2 || NTHR == 1024) ? 1 : 2)
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
          const double *__restrict__ c0i_in, double *__restrict__ c0i_out, V2 phi_out, LevelGeom gc,
          V2 res_c, double *norm, int nbx, int EO, const int *done)
 {
     // c0i_in: plane of 1 / c0 (row stride g.nx) written by an earlier launch of this solve -- the
     // four fp64 divisions per thread are then loads; c0i_out: where the first launch stores it
-    constexpr int CYr = CY * RH, AYr = CYr + 2, NP = 2 * RH;
+    constexpr int TXN = NTHR / 16;              // threads along x: 32 or 64
+    constexpr int CH = CX / TXN;                // column halves per thread: 2 or 1
+    constexpr int CYr = CY * RH, AYr = CYr + 2, NP = CH * RH;
     extern __shared__ double sm_dyn[];
     double *const sm0 = sm_dyn, *const sm1 = sm_dyn + AYr * AX;
     hpb_pdl_prologue();
@@ -109,19 +113,19 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     const int ox = bx * FX - EO + g.vlo;          // level index of compute cell (0, 0)
     const int oy = by * FY - EO + g.vlo;
     const int tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;       // ty = 0..15
+    const int tx = tid % TXN, ty = tid / TXN;     // ty = 0..15
     // the whole tile (with its ring) lies strictly inside the valid range: no bounds or
     // boundary-stencil cases anywhere (block-uniform)
     const bool inner = ox - 1 > g.vlo && ox + CX < g.vhix && oy - 1 > g.vlo && oy + CYr < g.vhiy;
 
     // ---- tile load (with ring), linear over the AYr x AX shared array; all loads are independent
-    constexpr int NLD = (AYr * AX + NT - 1) / NT;
+    constexpr int NLD = (AYr * AX + NTHR - 1) / NTHR;
     double v0[NLD], v1[NLD];
 #pragma unroll
     for (int k = 0; k < NLD; ++k) {
         v0[k] = 0.; v1[k] = 0.;
         if (INIT != 0) {
-            const int e = tid + k * NT;
+            const int e = tid + k * NTHR;
             const int lj = e / AX, li = e - lj * AX;
             const int i = ox - 1 + li, j = oy - 1 + lj;
             if (e < AYr * AX && (inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy))) {
@@ -141,10 +145,10 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     bool okc[NP][2];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const int i = ox + tx + 32 * (p & 1);
+        const int i = ox + tx + TXN * (p % CH);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int j = oy + 32 * (p >> 1) + 2 * ty + h;
+            const int j = oy + 32 * (p / CH) + 2 * ty + h;
             const bool ok = inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy);
             okc[p][h] = ok;
             const long o = i + (long)j * rhs.rs;
@@ -173,7 +177,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     if (is_done) return;            // block-uniform; nothing has been written yet
 #pragma unroll
     for (int k = 0; k < NLD; ++k) {
-        const int e = tid + k * NT;
+        const int e = tid + k * NTHR;
         if (e < AYr * AX) { sm0[e] = v0[k]; sm1[e] = v1[k]; }
     }
     // colour 0 updates the cells with (i + j) even: h = par0 for every p
@@ -181,7 +185,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     SmCell A[NP], B[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const int base = (32 * (p >> 1) + 2 * ty + 1) * AX + tx + 32 * (p & 1) + 1;
+        const int base = (32 * (p / CH) + 2 * ty + 1) * AX + tx + TXN * (p % CH) + 1;
         A[p].r0 = par0 ? r0[p][1] : r0[p][0];   B[p].r0 = par0 ? r0[p][0] : r0[p][1];
         A[p].r1 = par0 ? r1[p][1] : r1[p][0];   B[p].r1 = par0 ? r1[p][0] : r1[p][1];
         A[p].cinv = par0 ? ci[p][1] : ci[p][0]; B[p].cinv = par0 ? ci[p][0] : ci[p][1];
@@ -214,12 +218,12 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     double nres = 0., nrhs = 0.;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const int cix = tx + 32 * (p & 1);
+        const int cix = tx + TXN * (p % CH);
         const bool own_x = cix >= EO && cix < CX - EO;
         const bool ring_x = cix >= EO - 1 && cix < CX - EO + 1;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int cjh = 32 * (p >> 1) + 2 * ty + h;
+            const int cjh = 32 * (p / CH) + 2 * ty + h;
             const int i = ox + cix, j = oy + cjh;
             const bool ok = okc[p][h];
             const int so = (cjh + 1) * AX + cix + 1;
@@ -259,10 +263,10 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     __syncthreads();                   // everyone is done reading phi from shared memory
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        const int cix = tx + 32 * (p & 1);
+        const int cix = tx + TXN * (p % CH);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int so = (32 * (p >> 1) + 2 * ty + h + 1) * AX + cix + 1;
+            const int so = (32 * (p / CH) + 2 * ty + h + 1) * AX + cix + 1;
             sm0[so] = rs0[p][h];
             sm1[so] = rs1[p][h];
         }
@@ -273,10 +277,10 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     // coarse points owned by this tile: cc: fine cells (2I, 2I+1); nodal: fine node 2I
     const int I0 = (X0 + 1) >> 1, J0 = (Y0 + 1) >> 1;
     const int I1 = (X0 + FX + 1) >> 1, J1 = (Y0 + FY + 1) >> 1;     // exclusive
-    // thread (tx, ty) -> coarse points (I0 + tx, J0 + ty + 16 m): FX/2 <= 29 columns
+    // thread -> coarse points (I0 + lane, J0 + warp + m NTHR/32): FX/2 <= 29 columns
     {
-        const int I = I0 + tx;
-        for (int J = J0 + ty; J < J1; J += NT / 32) {
+        const int I = I0 + (tid & 31);
+        for (int J = J0 + (tid >> 5); J < J1; J += NTHR / 32) {
             if (I < I1 && I >= gc.vlo && I <= gc.vhix && J >= gc.vlo && J <= gc.vhiy) {
                 const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;     // smem index of fine (2I, 2J)
                 const long oc = I + (long)J * res_c.rs;
@@ -302,7 +306,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             nres = fmax(nres, __shfl_xor_sync(0xffffffffu, nres, o));
             nrhs = fmax(nrhs, __shfl_xor_sync(0xffffffffu, nrhs, o));
         }
-        if (tx == 0 && (nres > 0. || nrhs > 0.)) {
+        if ((tid & 31) == 0 && (nres > 0. || nrhs > 0.)) {
             // bit pattern of non-negative doubles is monotone: exact, order-independent max
             atomicMax((unsigned long long *)&norm[0], (unsigned long long)__double_as_longlong(nres));
             atomicMax((unsigned long long *)&norm[1], (unsigned long long)__double_as_longlong(nrhs));
@@ -750,6 +754,24 @@ V2 lvl_view(const hpb_ctx *ctx, int l, double *p)
     V2 v; v.p = p; v.rs = ctx->mg[l].nx; v.cs = (long)ctx->mg[l].nx * ctx->mg[l].ny; return v;
 }
 
+template <int INIT, bool RES, int RH, int NS, int NTHR>
+int launch_smooth_t(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, const double *acf,
+                    long acf_rs, const double *c0i_in, double *c0i_out, V2 out, const LevelGeom &gc,
+                    V2 res_c, double *norm, const int *done, int nbx, int nby, int EO)
+{
+    const size_t smem = 2 * sizeof(double) * (size_t)(CY * RH + 2) * AX;
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_smooth<INIT, RES, RH, NS, NTHR>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    hpb_launch(k_smooth<INIT, RES, RH, NS, NTHR>, nbx * nby, NTHR, smem, ctx->stream, g, in, crse, rhs,
+               acf, acf_rs, c0i_in, c0i_out, out, gc, res_c, norm, nbx, EO, done);
+    hpb_count_launch(ctx);
+    return HPB_OK;
+}
+
 template <int INIT, bool RES, int RH = 1, int NS = 1>
 int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, const double *acf,
                   long acf_rs, const double *c0i_in, double *c0i_out, V2 out, const LevelGeom &gc,
@@ -763,17 +785,14 @@ int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, cons
     const int FX = CX - 2 * EO, FY = CY * RH - 2 * EO;
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
-    const size_t smem = 2 * sizeof(double) * (size_t)(CY * RH + 2) * AX;
-    static bool attr_set = false;       // per instantiation
-    if (!attr_set) {
-        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_smooth<INIT, RES, RH, NS>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    hpb_launch(k_smooth<INIT, RES, RH, NS>, nbx * nby, NT, smem, ctx->stream, g, in, crse, rhs, acf,
-               acf_rs, c0i_in, c0i_out, out, gc, res_c, norm, nbx, EO, done);
-    hpb_count_launch(ctx);
-    return HPB_OK;
+    static int wide = -1;
+    if (wide < 0) { const char *e = getenv("HPB_MG_WIDE"); wide = e ? atoi(e) : 1; }
+    // levels whose tiles do not even fill the GPU once are latency bound: 1024 threads per tile
+    if (RH == 1 && NS == 1 && wide && nbx * nby <= 148)
+        return launch_smooth_t<INIT, RES, 1, 1, 1024>(ctx, g, in, crse, rhs, acf, acf_rs, c0i_in, c0i_out, out,
+                                                      gc, res_c, norm, done, nbx, nby, EO);
+    return launch_smooth_t<INIT, RES, RH, NS, NT>(ctx, g, in, crse, rhs, acf, acf_rs, c0i_in, c0i_out, out, gc,
+                                                  res_c, norm, done, nbx, nby, EO);
 }
 
 inline unsigned nb(long n) { return (unsigned)((n + 255) / 256); }

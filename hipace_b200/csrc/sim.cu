@@ -805,7 +805,13 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     SIM_CUDA(cudaEventCreate(&s->ev0));
     SIM_CUDA(cudaEventCreate(&s->ev1));
     if (const char *e = getenv("HPB_SIDE_STREAM")) s->opt_side_stream = atoi(e) != 0;
-    SIM_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    {
+        // highest priority: the side stream's small kernels must get CTA slots while the plasma
+        // push (tens of thousands of CTAs, launched at about the same time) is being dispatched
+        int least = 0, greatest = 0;
+        SIM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SIM_CUDA(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, greatest));
+    }
     SIM_CUDA(cudaEventCreateWithFlags(&s->ev_fields, cudaEventDisableTiming));
     SIM_CUDA(cudaEventCreateWithFlags(&s->ev_shift, cudaEventDisableTiming));
     SIM_CUDA(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
