@@ -416,28 +416,41 @@ __device__ void c_zero(double *p, long n)
 }
 
 // levels L[0..nl-1] (L[0] = first single-CTA level): in res[0]; out cor[0].
-// All level arrays live in shared memory for the duration of the kernel and thread (tx, ty) of the
-// 32x32 CTA owns the point (vlo + tx, vlo + ty) of every level, with its rhs, 1/c0 and stencil
-// weights in registers for the duration of a level visit: a half-sweep is then 4 shared-memory
-// loads, 7 flops and a barrier per component -- the V-cycle below level `lc` is latency bound and
-// this keeps the dependent chain per phase short.
+// All level arrays live in shared memory for the duration of the kernel.  The valid points of a
+// level are mapped compactly onto the first nvx*nvy threads (point = (t % nvx, t / nvx)), which
+// keep their rhs, 1/c0 and stencil weights in registers for the duration of a level visit: a
+// half-sweep is 4 shared-memory loads, 7 flops and a barrier per component.  This part of the
+// V-cycle is pure latency (~60 dependent phases), so every phase synchronises only the warps
+// that own points of the level: a named barrier over T_l = ceil32(nvx*nvy) threads, a
+// __syncwarp() for levels of <= 32 points (4x4 and 2x2: 27 of the 60 phases).  Threads without
+// points on a level skip it and wait at the barrier of the next finer level.
 struct SLevel {
     int nx, ny, vlo, vhix, vhiy, n;
+    int nvx, npts, T;              // valid width, valid points, participating threads (multiple of 32)
     double facx, facy;
     int o_acf, o_c0i, o_res, o_cor, o_rescor;      // offsets into the dynamic shared array
 };
 
+__device__ __forceinline__ void level_bar(int l, int T)
+{
+    if (T <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(l + 1), "r"(T) : "memory");
+}
+
 struct SCell {         // per-thread view of its point on one level
     bool ok, hl, hr, hd, hu;       // has a left / right / lower / upper neighbour inside the level box
-    int o, par;
+    int i, j, o, par;
     double r0, r1, c0i, cxw, cyw;
 };
 
 __device__ __forceinline__ SCell s_cell(const SLevel &L, const double *sm, int cc)
 {
     SCell c;
-    const int i = L.vlo + (threadIdx.x & 31), j = L.vlo + (threadIdx.x >> 5);
-    c.ok = i <= L.vhix && j <= L.vhiy;
+    const int t = threadIdx.x;
+    const int q = t / L.nvx;
+    c.i = L.vlo + (t - q * L.nvx); c.j = L.vlo + q;
+    c.ok = t < L.npts;
+    const int i = c.i, j = c.j;
     c.o = i + j * L.nx;
     c.par = (i + j) & 1;
     c.r0 = c.r1 = c.c0i = 0.;
@@ -452,7 +465,7 @@ __device__ __forceinline__ SCell s_cell(const SLevel &L, const double *sm, int c
 
 // half-sweeps is = first..last-1 on cor (boundary / exterior points hold 0: the zero neighbour and
 // the 4/3 weight reproduce the branches of gs1 exactly)
-__device__ __forceinline__ void s_sweeps(const SLevel &L, const SCell &c, double *sm, int first, int last)
+__device__ __forceinline__ void s_sweeps(const SLevel &L, int l, const SCell &c, double *sm, int first, int last)
 {
     double *p0 = sm + L.o_cor + c.o, *p1 = p0 + L.n;
     const int w = L.nx;
@@ -467,27 +480,27 @@ __device__ __forceinline__ void s_sweeps(const SLevel &L, const SCell &c, double
             p0[0] = (c.r0 - lap0) * c.c0i;
             p1[0] = (c.r1 - lap1) * c.c0i;
         }
-        __syncthreads();
+        level_bar(l, L.T);
     }
 }
 
 // cor = GSRB^n(0): the first half-sweep of a zero field is rhs / c0 on its colour
-__device__ __forceinline__ void s_sweeps_from_zero(const SLevel &L, const SCell &c, double *sm, int n)
+__device__ __forceinline__ void s_sweeps_from_zero(const SLevel &L, int l, const SCell &c, double *sm, int n)
 {
     if (c.ok) {
         const bool first = (c.par & 1) == 0;
         sm[L.o_cor + c.o] = first ? (c.r0 - 0.) * c.c0i : 0.;
         sm[L.o_cor + L.n + c.o] = first ? (c.r1 - 0.) * c.c0i : 0.;
     }
-    __syncthreads();
-    s_sweeps(L, c, sm, 1, n);
+    level_bar(l, L.T);
+    s_sweeps(L, l, c, sm, 1, n);
 }
 
-__device__ __forceinline__ void s_residual(const SLevel &L, const SCell &c, double *sm, int cc)
+__device__ __forceinline__ void s_residual(const SLevel &L, int l, const SCell &c, double *sm, int cc)
 {
     if (c.ok) {
         const int w = L.nx;
-        const int i = L.vlo + (threadIdx.x & 31), j = L.vlo + (threadIdx.x >> 5);
+        const int i = c.i, j = c.j;
         const double a = sm[L.o_acf + c.o];
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
@@ -502,14 +515,16 @@ __device__ __forceinline__ void s_residual(const SLevel &L, const SCell &c, doub
             sm[L.o_rescor + n * L.n + c.o] = (n ? c.r1 : c.r0) + a * p[0] - lap;
         }
     }
-    __syncthreads();
+    level_bar(l, L.T);
 }
 
-// res[coarse] = R(rescor[fine])
-__device__ __forceinline__ void s_restrict(const SLevel &Lc, const SLevel &Lf, double *sm, int cc)
+// res[coarse] = R(rescor[fine]); executed by the threads of the coarse level
+__device__ __forceinline__ void s_restrict(const SLevel &Lc, int lc, const SLevel &Lf, double *sm, int cc)
 {
-    const int i = Lc.vlo + (threadIdx.x & 31), j = Lc.vlo + (threadIdx.x >> 5);
-    if (i <= Lc.vhix && j <= Lc.vhiy) {
+    const int t = threadIdx.x;
+    if (t < Lc.npts) {
+        const int q = t / Lc.nvx;
+        const int i = Lc.vlo + (t - q * Lc.nvx), j = Lc.vlo + q;
         const int w = Lf.nx;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
@@ -521,14 +536,14 @@ __device__ __forceinline__ void s_restrict(const SLevel &Lc, const SLevel &Lf, d
             sm[Lc.o_res + n * Lc.n + i + j * Lc.nx] = v;
         }
     }
-    __syncthreads();
+    level_bar(lc, Lc.T);
 }
 
 // cor[fine] += I(cor[coarse])
-__device__ __forceinline__ void s_interp_add(const SLevel &Lf, const SCell &c, const SLevel &Lc, double *sm, int cc)
+__device__ __forceinline__ void s_interp_add(const SLevel &Lf, int l, const SCell &c, const SLevel &Lc, double *sm, int cc)
 {
     if (c.ok) {
-        const int i = Lf.vlo + (threadIdx.x & 31), j = Lf.vlo + (threadIdx.x >> 5);
+        const int i = c.i, j = c.j;
         const int ic = i >> 1, jc = j >> 1, wc = Lc.nx;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
@@ -546,24 +561,28 @@ __device__ __forceinline__ void s_interp_add(const SLevel &Lf, const SCell &c, c
             f[0] = f[0] + add;
         }
     }
-    __syncthreads();
+    level_bar(l, Lf.T);
 }
 
 __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const int *done)
 {
-    hpb_pdl_prologue();
     extern __shared__ double csm[];
     __shared__ SLevel S[12];
+    hpb_pdl_prologue();
     if (*done) return;
     const int nl = A.nl;
     const int cc = A.L[0].g.cc;
-    if (threadIdx.x == 0) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
         int off = 0;
         for (int l = 0; l < nl; ++l) {
             const LevelGeom &g = A.L[l].g;
             SLevel &L = S[l];
             L.nx = g.nx; L.ny = g.ny; L.vlo = g.vlo; L.vhix = g.vhix; L.vhiy = g.vhiy;
             L.n = g.nx * g.ny; L.facx = g.facx; L.facy = g.facy;
+            L.nvx = g.vhix - g.vlo + 1;
+            L.npts = L.nvx * (g.vhiy - g.vlo + 1);
+            L.T = (L.npts + 31) / 32 * 32;
             L.o_acf = off; off += L.n;
             L.o_c0i = off; off += L.n;
             L.o_res = off; off += 2 * L.n;
@@ -574,7 +593,7 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const i
     __syncthreads();
     for (int l = 0; l < nl; ++l) {
         const SLevel L = S[l];
-        for (int s = threadIdx.x; s < L.n; s += blockDim.x) {
+        for (int s = tid; s < L.n; s += blockDim.x) {
             csm[L.o_acf + s] = A.L[l].acf[s];
             csm[L.o_c0i + s] = A.L[l].c0i[s];
             csm[L.o_res + s] = l == 0 ? A.L[0].res[s] : 0.;             // boundary nodes stay 0
@@ -584,29 +603,35 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const i
         }
     }
     __syncthreads();
+    // down: a thread takes part in level l while tid < T_l (T is non-increasing with l)
 #pragma unroll 1
     for (int l = 0; l < nl - 1; ++l) {
         const SLevel L = S[l];
+        if (tid >= L.T) break;
         const SCell c = s_cell(L, csm, cc);
-        s_sweeps_from_zero(L, c, csm, 4);
-        s_residual(L, c, csm, cc);
-        s_restrict(S[l + 1], L, csm, cc);
+        s_sweeps_from_zero(L, l, c, csm, 4);
+        s_residual(L, l, c, csm, cc);
+        if (tid < S[l + 1].T) s_restrict(S[l + 1], l + 1, L, csm, cc);
     }
-    {
+    if (tid < S[nl - 1].T) {
         const SLevel L = S[nl - 1];
         const SCell c = s_cell(L, csm, cc);
-        s_sweeps_from_zero(L, c, csm, A.nsweeps_bottom);
+        s_sweeps_from_zero(L, nl - 1, c, csm, A.nsweeps_bottom);
     }
+    // up: the threads that sat out level l+1 meet the ones that worked on it at level l's barrier
 #pragma unroll 1
     for (int l = nl - 2; l >= 0; --l) {
         const SLevel L = S[l];
+        if (tid >= L.T) continue;
+        level_bar(l, L.T);
         const SCell c = s_cell(L, csm, cc);
-        s_interp_add(L, c, S[l + 1], csm, cc);
-        s_sweeps(L, c, csm, 0, 4);
+        s_interp_add(L, l, c, S[l + 1], csm, cc);
+        s_sweeps(L, l, c, csm, 0, 4);
     }
+    __syncthreads();
     {
         const SLevel L = S[0];
-        for (int s = threadIdx.x; s < 2 * L.n; s += blockDim.x) A.L[0].cor[s] = csm[L.o_cor + s];
+        for (int s = tid; s < 2 * L.n; s += blockDim.x) A.L[0].cor[s] = csm[L.o_cor + s];
     }
 }
 
@@ -786,8 +811,10 @@ int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, cons
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
     static int wide = -1;
-    if (wide < 0) { const char *e = getenv("HPB_MG_WIDE"); wide = e ? atoi(e) : 1; }
+    if (wide < 0) { const char *e = getenv("HPB_MG_WIDE"); wide = e ? atoi(e) : 0; }
     // levels whose tiles do not even fill the GPU once are latency bound: 1024 threads per tile
+    // (HPB_MG_WIDE=1; faster in isolation, but no gain in the un-profiled slice loop, where a
+    // 1024-thread x 62-register CTA leaves no room for the next kernel of the PDL chain: off)
     if (RH == 1 && NS == 1 && wide && nbx * nby <= 148)
         return launch_smooth_t<INIT, RES, 1, 1, 1024>(ctx, g, in, crse, rhs, acf, acf_rs, c0i_in, c0i_out, out,
                                                       gc, res_c, norm, done, nbx, nby, EO);
