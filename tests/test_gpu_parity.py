@@ -139,6 +139,41 @@ def test_two_mobile_species_ion_motion(fuse, repo_root):
     sim.close()
 
 
+def test_full_size_driver_orders_agree(repo_root):
+    """BASELINE configs[2] transverse size (1024 x 1024, ppc 4; the oracle would need minutes per
+    slice here): the reference call order, the fused order and the fused order with the side
+    stream must give the same physics -- field checksums of 48 slices through the beam head to
+    1e-9, particle validity bit-exact, particle state to 1e-9, identical multigrid V-cycle counts;
+    plus the invariant the domain offers: no particle is lost or invalidated (periodic boundary,
+    no QSA violation)."""
+    import hipace_b200 as hp
+    text = _deck(repo_root, 'blowout_wake_normalized.in')
+    ov = {'amr.n_cell': '1024 1024 1024', 'plasma.ppc': '2 2'}
+    nsl = 48
+    runs = {}
+    for name, opts in (('reference order', {'fuse': 0}), ('fused', {'fuse': 1, 'side_stream': 0}),
+                       ('fused + side stream', {'fuse': 1, 'side_stream': 1})):
+        sim = hp.Simulation(text, ov)
+        for k, v in opts.items():
+            sim.set_option(k, v)
+        cs = sim.evolve(0, 0, nsl)
+        p = sim.plasma()
+        st = sim.stats()
+        runs[name] = (cs, p, st)
+        sim.close()
+    cs0, p0, st0 = runs['reference order']
+    assert p0['x'].size == 4 * 1024 * 1024 and p0['valid'].all() and st0['n_qsa_violation'] == 0
+    for name in ('fused', 'fused + side stream'):
+        cs, p, st = runs[name]
+        for k, w in cs0.items():
+            assert abs(cs[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (name, k, cs[k], w)
+        assert np.array_equal(p['valid'], p0['valid']), name
+        for nm in ('x', 'y', 'ux', 'uy', 'psi', 'w'):
+            scale = max(np.abs(p0[nm]).max(), 1e-300)
+            assert np.abs(p[nm] - p0[nm]).max() / scale <= 1e-9, (name, nm)
+        assert st['n_mg_vcycles'] == st0['n_mg_vcycles'], name
+
+
 def test_plasma_init_is_bit_exact(repo_root):
     """particle count, order and positions right after InitParticles"""
     import hipace_b200 as hp
