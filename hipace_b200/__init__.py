@@ -56,7 +56,7 @@ EXPORTS = (
     'hpb_advance_beam_particles', 'hpb_beam_shift_slipped', 'hpb_nccl_unique_id',
     'hpb_sim_pipeline_init', 'hpb_sim_pipeline_message_bytes', 'hpb_sim_beam_slice_capacity',
     'hpb_sim_timer_start', 'hpb_sim_timer_stop', 'hpb_sim_get_beam_packet',
-    'hpb_fields_shift_and_initialize', 'hpb_advance_plasma_particles_and_deposit',
+    'hpb_fields_shift_and_initialize', 'hpb_advance_plasma_particles_and_deposit', 'hpb_deck_check',
 )
 NCCL_ID_BYTES = 128
 
@@ -194,6 +194,27 @@ def _overrides_text(overrides):
             v = ' '.join(str(t) for t in v)
         lines.append(f'{k} = {v}')
     return ('\n'.join(lines) + '\n').encode()
+
+
+def deck_check(deck: str, overrides: dict | None = None) -> dict:
+    """Host-only dry run of the input-deck parser (no GPU): what hpb_sim_create would run, or
+    HpbError with the same message (unsupported options abort like the reference's parser)."""
+    L = lib()
+    buf = C.create_string_buffer(8192)
+    L.hpb_deck_check.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    _check(L.hpb_deck_check(deck.encode(), _overrides_text(overrides), buf, len(buf)), 'hpb_deck_check')
+    out = {}
+    for kv in buf.value.decode().split(';'):
+        if '=' in kv:
+            k, v = kv.split('=', 1)
+            try:
+                out[k] = int(v)
+            except ValueError:
+                try:
+                    out[k] = float(v)
+                except ValueError:
+                    out[k] = v
+    return out
 
 
 class Simulation:

@@ -74,9 +74,18 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError('link failed:\n' + p.stdout + p.stderr)
+    # the command-line driver (C++ host over the C-ABI, the reference's `hipace inputs ...`)
+    os.makedirs(os.path.join(HERE, 'bin'), exist_ok=True)
+    exe = os.path.join(HERE, 'bin', 'hpb200_run')
+    cmd = ['g++', '-O2', '-std=c++17', '-I', os.path.join(ROOT, 'include'), os.path.join(CSRC, 'main.cpp'),
+           '-L', HERE, '-lhpb200', '-Wl,-rpath,$ORIGIN/..', '-Wl,-rpath,/usr/local/cuda/lib64',
+           '-L/usr/local/cuda/lib64', '-lcudart', '-o', exe]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError('driver link failed:\n' + p.stdout + p.stderr)
     open(stamp_file, 'w').write(stamp)
     if verbose:
-        print('built', LIB)
+        print('built', LIB, 'and', exe)
     return LIB
 
 

@@ -754,6 +754,51 @@ int solve_one_slice(hpb_sim *s, int islice)
 // ---------------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------------
+// Host-only: parse a deck exactly as hpb_sim_create does (same parser, same "unsupported"
+// errors) and describe what it would run -- needs no GPU, so the input-deck surface is testable
+// on any machine.  summary (may be NULL) receives "key=value;" pairs.
+extern "C" int hpb_deck_check(const char *deck, const char *overrides, char *summary, size_t n)
+{
+    if (!deck) return HPB_ERR_ARG;
+    hpb_sim s;
+    try {
+        s.deck.parse(deck);
+        if (overrides) s.deck.parse(overrides);
+        read_deck(&s);
+    } catch (const std::exception &e) {
+        hpb_set_error("deck: %s", e.what());
+        return HPB_ERR_PARSE;
+    }
+    if (summary && n) {
+        std::string o;
+        char b[256];
+        snprintf(b, sizeof b, "nx=%d;ny=%d;nz=%d;dx=%.17g;dy=%.17g;dz=%.17g;x_off=%.17g;y_off=%.17g;normalized=%d;"
+                 "particle_bc=%d;max_step=%d;dt=%.17g;mg_tol_rel=%.17g;deposit_rho=%d;",
+                 s.g.nx, s.g.ny, s.nz, s.g.dx, s.g.dy, s.g.dz, s.g.x_off, s.g.y_off, s.g.normalized,
+                 s.particle_bc, s.max_step, s.dt, s.mg_tol_rel, (int)s.deposit_rho);
+        o += b;
+        snprintf(b, sizeof b, "n_plasmas=%zu;n_beams=%zu;", s.plasmas.size(), s.beams.size());
+        o += b;
+        for (size_t k = 0; k < s.plasmas.size(); ++k) {
+            const Species &sp = s.plasmas[k];
+            snprintf(b, sizeof b, "plasma%zu.name=%s;plasma%zu.charge=%.17g;plasma%zu.mass=%.17g;plasma%zu.ppc=%dx%d;"
+                     "plasma%zu.neutralize=%d;plasma%zu.n_subcycles=%d;", k, sp.name.c_str(), k, sp.charge, k,
+                     sp.mass, k, sp.ppc[0], sp.ppc[1], k, (int)sp.neutralize, k, sp.n_subcycles);
+            o += b;
+        }
+        for (size_t k = 0; k < s.beams.size(); ++k) {
+            const BeamSp &bm = s.beams[k];
+            snprintf(b, sizeof b, "beam%zu.name=%s;beam%zu.charge=%.17g;beam%zu.mass=%.17g;beam%zu.ppc=%dx%dx%d;"
+                     "beam%zu.profile=%d;beam%zu.n_subcycles=%d;beam%zu.external_fields=%d;", k, bm.name.c_str(),
+                     k, bm.charge, k, bm.mass, k, bm.ppc[0], bm.ppc[1], bm.ppc[2], k, bm.profile, k,
+                     bm.n_subcycles, k, (int)bm.use_ext);
+            o += b;
+        }
+        snprintf(summary, n, "%s", o.c_str());
+    }
+    return HPB_OK;
+}
+
 extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overrides, int device)
 {
     if (!out || !deck) return HPB_ERR_ARG;

@@ -225,6 +225,9 @@ enum hpb_comp {
 /* deck: HiPACE++ input-deck text (ParmParse syntax); overrides: extra "key = value" lines
  * appended after it (the reference takes them on the command line). device: CUDA ordinal. */
 int hpb_sim_create(hpb_sim **out, const char *deck, const char *overrides, int device);
+/* host-only dry run of the deck parser (same code path and the same HPB_ERR_PARSE messages as
+ * hpb_sim_create; no GPU needed): summary receives "key=value;" pairs describing the run */
+int hpb_deck_check(const char *deck, const char *overrides, char *summary, size_t n);
 void hpb_sim_destroy(hpb_sim *sim);
 
 /* Hipace::Evolve for time steps [step_begin, step_end] on this rank (all slices, or only the

@@ -1,0 +1,86 @@
+"""Host logic without a GPU: the C++ input-deck parser behind hpb_sim_create (ParmParse subset +
+HiPACE++ expression parser, src/utils/Parser.H:316-395) against the oracle's reading of the same
+decks, and the 'unsupported' errors that stand in for the reference's aborts."""
+import glob
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DECKS = sorted(glob.glob(os.path.join(ROOT, 'examples', '*.in')))
+
+
+@pytest.mark.parametrize('path', DECKS, ids=[os.path.basename(p) for p in DECKS])
+def test_parser_agrees_with_oracle(path):
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    text = open(path).read()
+    got = hp.deck_check(text)
+    ref = Oracle(text, {})
+    g = ref.geom
+    assert (got['nx'], got['ny'], got['nz']) == (g.nx, g.ny, g.nz)
+    for k, w in (('dx', g.dx), ('dy', g.dy), ('dz', g.dz)):
+        assert got[k] == pytest.approx(w, rel=1e-15)
+    assert got['n_plasmas'] == len(ref.plasmas) and got['n_beams'] == len(ref.beams)
+    for k, p in enumerate(ref.plasmas):
+        assert got[f'plasma{k}.charge'] == pytest.approx(p.charge, rel=1e-15)
+        assert got[f'plasma{k}.mass'] == pytest.approx(p.mass, rel=1e-15)
+        assert got[f'plasma{k}.neutralize'] == int(p.neutralize_background)
+    for k, b in enumerate(ref.beams):
+        assert got[f'beam{k}.charge'] == pytest.approx(b.charge, rel=1e-15)
+        assert got[f'beam{k}.mass'] == pytest.approx(b.mass, rel=1e-15)
+
+
+def test_overrides_constants_and_expressions():
+    import hipace_b200 as hp
+    text = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    got = hp.deck_check(text, {'amr.n_cell': '1024 1023 7', 'plasma.ppc': '3 2', 'hipace.dt': '2.5*2',
+                               'my_constants.kp_inv': 2., 'geometry.prob_hi': '4*kp_inv 8. 6.'})
+    assert (got['nx'], got['ny'], got['nz']) == (1024, 1023, 7)
+    assert got['plasma0.ppc'] == '3x2' and got['dt'] == 5.0
+    assert got['dx'] == pytest.approx(16. / 1024, rel=1e-15)
+    # GetPosOffset with the grown box reduces to prob_lo + dx/2 (src/fields/Fields.H:71-77)
+    assert got['x_off'] == pytest.approx(-8. + 0.5 * got['dx'], rel=1e-14)
+
+
+@pytest.mark.parametrize('ov,msg', [
+    ({'beam.injection_type': 'fixed_weight'}, 'fixed_ppc'),
+    ({'hipace.depos_order_xy': 3}, 'depos_order_xy'),
+    ({'hipace.bxby_solver': 'predictor-corrector'}, 'explicit'),
+    ({'boundary.field': 'Periodic'}, 'Dirichlet'),
+    ({'plasma.u_std': '0. 0. 1e-3'}, 'RNG'),
+    ({'amr.n_cell': '64 64'}, '3 values'),
+    ({'beam.profile': 'parabolic'}, 'profile'),
+])
+def test_unsupported_options_fail_loudly(ov, msg):
+    import hipace_b200 as hp
+    text = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    with pytest.raises(hp.HpbError) as e:
+        hp.deck_check(text, ov)
+    assert msg in str(e.value)
+
+
+def test_no_gpu_means_error_not_fallback():
+    """the product path must fail loudly without a device (no CPU fallback)"""
+    import torch
+    import hipace_b200 as hp
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    text = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    with pytest.raises(hp.HpbError) as e:
+        hp.Simulation(text, {})
+    assert 'no CUDA device' in str(e.value)
+
+
+def test_command_line_driver_check_mode():
+    """hpb200_run (C++ host over the C-ABI, the reference's `hipace inputs key=value ...`)"""
+    import subprocess
+    from hipace_b200.build import build_library
+    build_library()
+    exe = os.path.join(ROOT, 'hipace_b200', 'bin', 'hpb200_run')
+    deck = os.path.join(ROOT, 'examples', 'linear_wake_normalized.in')
+    p = subprocess.run([exe, '--check', deck, 'amr.n_cell=64 64 64', 'max_step=3'], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert 'nx=64;ny=64;nz=64;' in p.stdout and 'max_step=3;' in p.stdout
+    p = subprocess.run([exe, '--check', deck, 'hipace.depos_order_xy=1'], capture_output=True, text=True)
+    assert p.returncode == 1 and 'depos_order_xy' in p.stderr

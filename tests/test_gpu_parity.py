@@ -253,3 +253,20 @@ def test_mg_solve1_matches_hpmg_oracle(nx, ny):
         err = np.abs(out[3 + k][v] - sol[k]).max() / np.abs(sol).max()
         assert err <= 1e-12, (k, err)
     ctx.close()
+
+
+def test_command_line_driver_reproduces_golden(repo_root):
+    """the C++ driver binary end to end: deck file + key=value overrides in, checksums out"""
+    import subprocess
+    meta = json.load(open(os.path.join(GOLD, 'linear_wake.normalized.1Rank.json')))
+    exe = os.path.join(repo_root, 'hipace_b200', 'bin', 'hpb200_run')
+    ov = [f'{k}={v}' for k, v in meta['overrides'].items() if k != 'max_step']
+    p = subprocess.run([exe, os.path.join(repo_root, meta['deck'])] + ov, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr + p.stdout
+    got = {}
+    for line in p.stdout.splitlines():
+        t = line.split()
+        if len(t) == 2 and line.startswith('  '):
+            got[t[0]] = float(t[1])
+    for name, want in meta['checksums']['lev=0'].items():
+        assert abs(got[name] - want) <= RTOL_SUM * abs(want) + 1e-40, (name, got[name], want)
