@@ -57,6 +57,7 @@ EXPORTS = (
     'hpb_sim_pipeline_init', 'hpb_sim_pipeline_message_bytes', 'hpb_sim_beam_slice_capacity',
     'hpb_sim_timer_start', 'hpb_sim_timer_stop', 'hpb_sim_get_beam_packet',
     'hpb_fields_shift_and_initialize', 'hpb_advance_plasma_particles_and_deposit', 'hpb_deck_check',
+    'hpb_set_plasma_lattice_hint',
 )
 NCCL_ID_BYTES = 128
 

@@ -220,4 +220,7 @@ struct hpb_ctx {
     int mg_last_iters;        // V-cycles of the previous solve = speculation depth of the next
     // misc
     int *d_scalar_i;          // scratch ints
+    // particle order hint (hpb_set_plasma_lattice_hint): the next particle-kernel calls see np =
+    // order_ppc passes of order_n lattice cells each (InitParticles order); 0 = unknown
+    long order_n; int order_ppc;
 };

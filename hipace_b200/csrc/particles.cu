@@ -20,13 +20,49 @@ struct PlasmaPtrs {
     double *r[HPB_PLASMA_NREAL];
     uint64_t *idcpu;
     long np;
+    long lat_n; int lat_ppc;        // lattice hint: np = lat_ppc passes of lat_n cells (0: none)
 };
 PlasmaPtrs to_ptrs(const hpb_plasma &pl)
 {
     PlasmaPtrs p;
     for (int i = 0; i < HPB_PLASMA_NREAL; ++i) p.r[i] = pl.r[i];
     p.idcpu = pl.idcpu; p.np = pl.np;
+    p.lat_n = 0; p.lat_ppc = 1;
     return p;
+}
+// with the lattice hint of the context (only if it describes exactly this particle array)
+PlasmaPtrs to_ptrs(const hpb_ctx *ctx, const hpb_plasma &pl)
+{
+    PlasmaPtrs p = to_ptrs(pl);
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("HPB_ORDER"); on = e ? atoi(e) : 0; }
+    if (on && ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np) {
+        p.lat_n = ctx->order_n; p.lat_ppc = ctx->order_ppc;
+    }
+    return p;
+}
+// Pass-interleaved thread -> particle map: warp w works on pass (w % ppc) of cell group (w / ppc).
+// `per_warp` consecutive cells are owned per warp, `lead` extra lanes in front of them (feed-only
+// neighbours of the aggregation).  Returns the particle index and whether the lane holds one.
+__device__ __forceinline__ long lattice_particle(const PlasmaPtrs &pl, long warp, int lane, int per_warp,
+                                                  int lead, bool &in_range)
+{
+    if (pl.lat_n <= 0) {
+        const long ip = warp * per_warp - lead + lane;
+        in_range = ip >= 0 && ip < pl.np;
+        return ip;
+    }
+    const long group = warp / pl.lat_ppc;
+    const int pass = (int)(warp - group * pl.lat_ppc);
+    const long cell = group * per_warp - lead + lane;
+    in_range = cell >= 0 && cell < pl.lat_n;
+    return (long)pass * pl.lat_n + cell;
+}
+// number of warps a launch needs
+inline long lattice_warps(const PlasmaPtrs &pl, int per_warp)
+{
+    if (pl.lat_n <= 0) return (pl.np + per_warp - 1) / per_warp;
+    return (pl.lat_n + per_warp - 1) / per_warp * pl.lat_ppc;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -296,9 +332,9 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
     // warps overlap by two lanes on each side (see k_deposit_current)
     const int lane = threadIdx.x & 31;
     const long warp = (long)blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
-    const long ip = warp * kExplOwn - 2 + lane;
+    bool active;
+    const long ip = lattice_particle(pl, warp, lane, kExplOwn, 2, active);
     const bool owner = lane >= 2 && lane < 2 + kExplOwn;
-    bool active = ip >= 0 && ip < pl.np;
 
     double vx = 0., vy = 0., gamma_psi = 1., yint = 0.;
     double sx[5] = {0., 0., 0., 0., 0.}, dsx[5] = {0., 0., 0., 0., 0.};
@@ -568,9 +604,10 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
 {
     __shared__ double s_tile[STAGE ? kPushThreads / 32 : 1][5][kTH][kTW];
     hpb_pdl_prologue();
-    const long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool in_range = ip < pl.np;
+    bool in_range;
+    const long ip = lattice_particle(pl, (long)blockIdx.x * (kPushThreads / 32) + (threadIdx.x >> 5), lane,
+                                     32, 0, in_range);
     // request every input stream before the first use (one HBM round trip)
     uint64_t idcpu = 0;
     double xp0 = 0., yp0 = 0., ux0 = 0., uy0 = 0., psi0 = 1., wq = 0.;
@@ -749,6 +786,14 @@ extern "C" int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, do
     return HPB_OK;
 }
 
+extern "C" int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc)
+{
+    if (!ctx || cells_per_pass < 0 || ppc < 0) return HPB_ERR_ARG;
+    ctx->order_n = cells_per_pass;
+    ctx->order_ppc = ppc;
+    return HPB_OK;
+}
+
 extern "C" int hpb_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, double charge,
                                 int c_jx, int c_jy, int c_jz)
 {
@@ -775,10 +820,12 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("HPB_EXPL_VARIANT"); variant = e ? atoi(e) : 4; }
+    const PlasmaPtrs pp = to_ptrs(ctx, pl);
+    const long nwarps = lattice_warps(pp, kExplOwn);
 #define HPB_LAUNCH_EXPL(NT, MB)                                                                    \
-    hpb_launch(k_explicit_deposition<NT, MB>, (unsigned)((pl.np + kExplOwn * (NT / 32) - 1) / (kExplOwn * (NT / 32))), \
+    hpb_launch(k_explicit_deposition<NT, MB>, (unsigned)((nwarps + (NT / 32) - 1) / (NT / 32)),    \
                                     NT, 0, ctx->stream,                                         \
-        to_ptrs(pl), make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ],             \
+        pp, make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ],             \
         comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.x_off, g.y_off, 1.0 / g.dx,     \
         1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass)
     if (variant == 2) HPB_LAUNCH_EXPL(256, 2);
@@ -817,10 +864,13 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         const int cx[8] = {HPB_C_SY, HPB_C_SX, HPB_C_EXMBY, HPB_C_EYPBX, HPB_C_PSI, HPB_C_EZ, HPB_C_BZ, HPB_C_EXMBY};
         for (int k = 0; k < 8; ++k) dep.cx[k] = comps[cx[k]];
     }
+    const PlasmaPtrs pp = to_ptrs(ctx, pl);
+    const long nwarps = lattice_warps(pp, 32);
 #define HPB_LAUNCH_PUSH(MB, DEP, STG)                                                             \
-    hpb_launch(k_advance_plasma<MB, DEP, STG>, (unsigned)((pl.np + kPushThreads - 1) / kPushThreads), \
+    hpb_launch(k_advance_plasma<MB, DEP, STG>,                                                    \
+        (unsigned)((nwarps + kPushThreads / 32 - 1) / (kPushThreads / 32)),                       \
         kPushThreads, 0, ctx->stream,                                                             \
-        to_ptrs(pl), make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],           \
+        pp, make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],           \
         comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
         charge / (mass * g.c), g.dz / n_subcycles, n_subcycles, temp_slice, particle_bc,         \
         bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep)

@@ -420,6 +420,8 @@ int init_plasma(hpb_sim *s, Species &sp, double c_t)
         sp.capacity = np;
     }
     sp.d.np = np;
+    sp.lattice_n = (np == ncand && nppc > 0) ? ncand / nppc : 0;
+    sp.lattice_ppc = nppc;
     if (np > 0)
         k_plasma_fill<<<nb256(ncand), 256, 0, s->stream>>>(a, sp.density, ncand, s->d_flag, s->d_offs, sp.d);
     SIM_CUDA(cudaGetLastError());
@@ -676,8 +678,11 @@ int solve_one_slice(hpb_sim *s, int islice)
     }
     {
         StageTimer t(s, ST_EXPLICIT);
-        for (auto &sp : s->plasmas)                                                     // :663
+        for (auto &sp : s->plasmas) {                                                   // :663
+            hpb_set_plasma_lattice_hint(ctx, sp.lattice_n, sp.lattice_ppc);
             if ((rc = hpb_explicit_deposition(ctx, sp.d, s->sl, sp.charge, sp.mass, C))) return rc;
+        }
+        hpb_set_plasma_lattice_hint(ctx, 0, 0);
     }
     {
         StageTimer t(s, ST_MG);
@@ -697,6 +702,7 @@ int solve_one_slice(hpb_sim *s, int islice)
         StageTimer t(s, ST_PUSH);
         for (auto &sp : s->plasmas) {                                                   // :699-701
             s->stats.n_plasma_pushed += (double)sp.d.np;
+            hpb_set_plasma_lattice_hint(ctx, sp.lattice_n, sp.lattice_ppc);
             int r;
             if (with_deposit)
                 r = hpb_advance_plasma_particles_and_deposit(ctx, sp.d, s->sl, sp.charge, sp.mass,
@@ -705,6 +711,7 @@ int solve_one_slice(hpb_sim *s, int islice)
             else
                 r = hpb_advance_plasma_particles(ctx, sp.d, s->sl, sp.charge, sp.mass, sp.n_subcycles,
                                                  0, s->particle_bc, s->bc_lo, s->bc_hi, s->comps);
+            hpb_set_plasma_lattice_hint(ctx, 0, 0);
             if (r) return r;
         }
         return HPB_OK;

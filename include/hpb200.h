@@ -196,6 +196,13 @@ int hpb_advance_plasma_particles(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, doub
  *   ::DepositCurrent (jx, jy, chi, rhomjz) of the next slice: the pushed particle is deposited
  *   from registers.  Call after hpb_fields_shift_and_initialize. */
 int hpb_fields_shift_and_initialize(hpb_ctx *ctx, hpb_slice sl, int *comps);
+/* Optional hint for the particle kernels that follow: the species' SoA holds `ppc` passes of
+ * `cells_per_pass` particles each in InitParticles order (pass outermost, cells x-fastest,
+ * PlasmaParticleContainerInit.cpp:189-316) with no particle filtered out.  The kernels then map
+ * consecutive warps to the SAME 32 cells of successive passes, so the slice planes a warp gathers
+ * from / reduces into are fetched from HBM once per slice instead of once per pass.  Results do
+ * not depend on it; cells_per_pass = 0 clears the hint. */
+int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc);
 int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
                                              double charge, double mass, int n_subcycles,
                                              int particle_bc, const double bc_lo[2],
