@@ -62,13 +62,31 @@ def parse_deck(text: str, overrides: dict | None = None) -> dict:
     return deck
 
 
-def _eval(expr: str, deck: dict, extra: dict | None = None) -> float:
-    """Math-parser stand-in: numbers, + - * / ^, my_constants.*, built-in constants."""
+def _constants(deck: dict) -> dict:
+    """my_constants.* may refer to each other in any order (utils/Parser.H:134-170): resolve by
+    repeated passes until nothing new can be evaluated"""
     env = dict(_CONST_SI)
     env.update({f: getattr(math, f) for f in ('sqrt', 'exp', 'sin', 'cos', 'log', 'tanh')})
-    for k, v in deck.items():
-        if k.startswith('my_constants.'):
-            env[k.split('.', 1)[1]] = _eval(v[0], {kk: vv for kk, vv in deck.items() if kk != k})
+    # (an expression may contain blanks: the deck reader split it into tokens)
+    todo = {k.split('.', 1)[1]: ' '.join(v) for k, v in deck.items() if k.startswith('my_constants.')}
+    while todo:
+        done = []
+        for name, expr in todo.items():
+            try:
+                env[name] = float(eval(expr.replace('^', '**'), {'__builtins__': {}}, env))
+                done.append(name)
+            except NameError:
+                pass
+        if not done:
+            raise ValueError('unresolvable my_constants: ' + ', '.join(todo))
+        for name in done:
+            del todo[name]
+    return env
+
+
+def _eval(expr: str, deck: dict, extra: dict | None = None) -> float:
+    """Math-parser stand-in: numbers, + - * / ^, my_constants.*, built-in constants."""
+    env = _constants(deck)
     env.update(extra or {})
     return float(eval(expr.replace('^', '**'), {'__builtins__': {}}, env))
 
@@ -201,7 +219,7 @@ EXPLICIT_COMPS = (
 )
 
 
-def component_map(deposit_rho=False, neutral_background=True):
+def component_map(deposit_rho=False, neutral_background=True, use_laser=False):
     comps = {}
     n = 0
     for sl, names in EXPLICIT_COMPS:
@@ -209,6 +227,9 @@ def component_map(deposit_rho=False, neutral_background=True):
             continue
         for nm in names:
             comps[(sl, nm)] = n
+            n += 1
+        if sl == 'This' and use_laser:                   # fields/Fields.cpp:98-101
+            comps[('This', 'aabs')] = n
             n += 1
         if sl == 'This' and deposit_rho:
             comps[('This', 'rho')] = n
@@ -275,6 +296,102 @@ class Beam:
 # Kernels
 # --------------------------------------------------------------------------------------------
 
+# ---- laser envelope (step 0 only: analytic envelope, |a|^2 on the field grid and the
+# ponderomotive terms of the particle kernels -- the envelope ADVANCE (hpmg type 2) is not restated)
+
+@dataclass
+class Laser:
+    name: str
+    a0: float = 0.0
+    w0: float = 0.0
+    cep: float = 0.0
+    propagation_angle_yz: float = 0.0
+    pft_yz: float = math.pi / 2.0
+    L0: float = 0.0
+    focal_distance: float = 0.0
+    position_mean: tuple = (0.0, 0.0, 0.0)
+
+
+def shape_order_n(xmid, order):
+    """compute_shape_factor<order> for order 0..2 (particles_utils/ShapeFactors.H:40-117):
+    weights and leftmost cell"""
+    if order == 0:
+        return [np.ones_like(xmid)], np.floor(xmid + 0.5).astype(np.int64)
+    if order == 1:
+        j = np.floor(xmid)
+        xint = xmid - j
+        return [1.0 - xint, xint], j.astype(np.int64)
+    if order == 2:
+        return shape_order2(xmid)
+    raise NotImplementedError('interp order 3')
+
+
+def laser_envelope_slice(lasers, lambda0, geom: 'Geometry', islice: int):
+    """MultiLaser::InitLaserSlice, gaussian branch, laser/MultiLaser.cpp:881-917 (laser grid =
+    field grid, the default of MakeLaserGeometry :58-118).  Complex array a[j, i], valid box."""
+    k0 = 2.0 * math.pi / lambda0
+    x = (np.arange(geom.nx) * geom.dx + geom.pos_offset(0))[None, :]
+    y = (np.arange(geom.ny) * geom.dy + geom.pos_offset(1))[:, None]
+    z = islice * geom.dz + geom.pos_offset(2)
+    env = np.zeros((geom.ny, geom.nx), dtype=complex)
+    for L in lasers:
+        xs, ys, zs = x - L.position_mean[0], y - L.position_mean[1], z - L.position_mean[2]
+        ang = L.propagation_angle_yz + (L.pft_yz - math.pi / 2.0)
+        yp = math.cos(ang) * ys - math.sin(ang) * zs
+        zp = math.sin(ang) * ys + math.cos(ang) * zs
+        diffract = 1.0 + 1j * (zp - L.focal_distance + L.position_mean[2] * math.cos(L.propagation_angle_yz)) \
+            * 2.0 / (k0 * L.w0 * L.w0)
+        inv_waist2 = 1.0 / (L.w0 * L.w0 * diffract)
+        prefactor = L.a0 / diffract
+        stc = prefactor * np.exp(-(zp * zp / (L.L0 * L.L0)))
+        arg = -(xs * xs + yp * yp) * inv_waist2
+        env = env + stc * np.exp(arg) * np.exp(1j * yp * k0 * L.propagation_angle_yz + L.cep)
+    return env
+
+
+def update_laser_aabs(env, aabs, geom: 'Geometry', interp_order: int):
+    """MultiLaser::UpdateLaserAabs, laser/MultiLaser.cpp:214-291: |a|^2 of the current envelope
+    interpolated (order interp_order) from the laser grid to the grown field slice"""
+    a2 = env.real * env.real + env.imag * env.imag                   # abssq
+    ii = np.arange(-G, geom.nx + G)
+    jj = np.arange(-G, geom.ny + G)
+    # same geometry for both grids: xmid = ((i dx + off) - off) / dx
+    xmid = ((ii * geom.dx + geom.pos_offset(0)) - geom.pos_offset(0)) * (1.0 / geom.dx)
+    ymid = ((jj * geom.dy + geom.pos_offset(1)) - geom.pos_offset(1)) * (1.0 / geom.dy)
+    sx, i0 = shape_order_n(xmid, interp_order)
+    sy, j0 = shape_order_n(ymid, interp_order)
+    out = np.zeros((geom.ny + 2 * G, geom.nx + 2 * G))
+    for iy in range(interp_order + 1):
+        for ix in range(interp_order + 1):
+            cx, cy = i0 + ix, j0 + iy
+            okx = (cx >= 0) & (cx <= geom.nx - 1)
+            oky = (cy >= 0) & (cy <= geom.ny - 1)
+            val = a2[np.clip(cy, 0, geom.ny - 1)[:, None], np.clip(cx, 0, geom.nx - 1)[None, :]]
+            w = (sy[iy] * oky)[:, None] * (sx[ix] * okx)[None, :]
+            out += w * val
+    aabs[...] = out
+
+
+def laser_gather(xp, yp, aabs, geom: 'Geometry', derivatives: bool):
+    """doLaserGatherShapeN<2>, particles_utils/FieldGather.H:162-222 (value only) and :236-283
+    (value + centred derivatives taken on the grid, then gathered)"""
+    x = (xp - geom.pos_offset(0)) * (1.0 / geom.dx)
+    y = (yp - geom.pos_offset(1)) * (1.0 / geom.dy)
+    sx, i0 = shape_order2(x)
+    sy, j0 = shape_order2(y)
+    dx_inv, dy_inv = 1.0 / geom.dx, 1.0 / geom.dy
+    A = np.zeros_like(xp); ADx = np.zeros_like(xp); ADy = np.zeros_like(xp)
+    for iy in range(3):
+        for ix in range(3):
+            i, j = i0 + ix + G, j0 + iy + G
+            w = sx[ix] * sy[iy]
+            A += w * aabs[j, i]
+            if derivatives:
+                ADx += w * 0.5 * dx_inv * (aabs[j, i + 1] - aabs[j, i - 1])
+                ADy += w * 0.5 * dy_inv * (aabs[j + 1, i] - aabs[j - 1, i])
+    return A, ADx, ADy
+
+
 def _scatter(arr, jj, ii, vals):
     """arr[jj+G, ii+G] += vals, duplicates accumulated (Gpu::Atomic::Add semantics).
     np.bincount sums in a fixed order, so the oracle itself is deterministic."""
@@ -284,7 +401,8 @@ def _scatter(arr, jj, ii, vals):
 
 
 def deposit_current(pl: Plasma, F: dict, geom: Geometry, pc: PhysConst, normalized: bool,
-                    *, jx=None, jy=None, rho=None, chi=None, rhomjz=None, flip_charge=False):
+                    *, jx=None, jy=None, rho=None, chi=None, rhomjz=None, flip_charge=False,
+                    aabs=None):
     """::DepositCurrent, particles/deposition/PlasmaDepositCurrent.cpp:22-257 (jz not needed by
     the explicit solver).  Arguments jx.. are the destination arrays or None (the reference's -1).
     Returns the number of QSA-violating particles killed in this call (:197-204)."""
@@ -300,7 +418,11 @@ def deposit_current(pl: Plasma, F: dict, geom: Geometry, pc: PhysConst, normaliz
     psi_inv = 1.0 / pl.psi
     vx_c = pl.ux * psi_inv
     vy_c = pl.uy * psi_inv
-    gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * clightinv * clightinv
+    Aabssqp = 0.0
+    if aabs is not None:                                                    # :182-187
+        laser_norm = (charge / pc.q_e) * (pc.m_e / pl.mass) * (charge / pc.q_e) * (pc.m_e / pl.mass)
+        Aabssqp = laser_gather(pl.x, pl.y, aabs, geom, False)[0] * laser_norm
+    gamma_psi = 0.5 * ((1.0 + 0.5 * Aabssqp) * psi_inv * psi_inv + vx_c * vx_c * clightinv * clightinv
                        + vy_c * vy_c * clightinv * clightinv + 1.0)         # :190-195
     bad = v & ((gamma_psi < 0.0) | (gamma_psi > pl.max_qsa_weighting_factor) | (psi_inv < 0.0))
     n_bad = int(bad.sum())
@@ -417,9 +539,9 @@ def init_sxsy_with_beam(F, geom: Geometry, pc: PhysConst):
     F[('This', 'Sx')][v] = -pc.mu0 * (-dx_jzb + dz_jxb)
 
 
-def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized: bool):
+def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized: bool, aabs=None):
     """::ExplicitDeposition, particles/deposition/ExplicitDeposition.cpp:20-263
-    (depos_order 2, derivative_type 2, no laser)."""
+    (depos_order 2, derivative_type 2; laser terms :167-175, :211-226, :234, :250)."""
     sel = pl.valid
     if not sel.any():
         return
@@ -437,7 +559,12 @@ def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized
     cdm = charge_invvol_mu0 * pl.w[sel]
     xmid = (pl.x[sel] - x_off) * dx_inv
     ymid = (pl.y[sel] - y_off) * dy_inv
-    gamma_psi = 0.5 * (psi_inv * psi_inv + vx * vx + vy * vy + 1.0)           # :177-182
+    Aabssqp = 0.0
+    laser_fac = (pc.m_e / pc.q_e) * (pc.m_e / pc.q_e)                         # :55
+    if aabs is not None:
+        Aabssqp = laser_gather(pl.x[sel], pl.y[sel], aabs, geom, False)[0] \
+            * (laser_fac * q_mass_ratio * q_mass_ratio)
+    gamma_psi = 0.5 * ((1.0 + 0.5 * Aabssqp) * psi_inv * psi_inv + vx * vx + vy * vy + 1.0)   # :177-182
     sx, dsx, i0 = dshape_centered_order2(xmid)
     sy, dsy, j0 = dshape_centered_order2(ymid)
     Bz, Ez = F[('This', 'Bz')], F[('This', 'Ez')]
@@ -452,12 +579,19 @@ def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized
             shx, shdx, shy, shdy = sx[ix], dsx[ix], sy[iy], dsy[iy]
             Bz_v, Ez_v = Bz[j + G, i + G], Ez[j + G, i + G]
             ExmBy_v, EypBx_v = ExmBy[j + G, i + G], EypBx[j + G, i + G]
+            ADx = ADy = 0.0
+            if aabs is not None:                                               # :215-226
+                nz_w = (shx * shy) != 0.0
+                ic, jc = np.where(nz_w, i, 0) + G, np.where(nz_w, j, 0) + G    # "avoid going outside"
+                ADx = np.where(nz_w, (aabs[jc, ic + 1] - aabs[jc, ic - 1]) * 0.5 * dx_inv * laser_fac * a_clight, 0.0)
+                ADy = np.where(nz_w, (aabs[jc + 1, ic] - aabs[jc - 1, ic]) * 0.5 * dy_inv * laser_fac * a_clight, 0.0)
             val_sy = cdm * (                                                   # :228-242
                 - shx * shy * (
                     - Bz_v * vx
                     + (Ez_v * vy
                        + ExmBy_v * (- vx * vy)
                        + EypBx_v * (gamma_psi - vy * vy)) * clight_inv
+                    - 0.25 * ADy * q_mass_ratio * psi_inv
                 ) * q_mass_ratio * psi_inv
                 + (- shdx * shy * dx_inv * (- vx * vy)
                    - shx * shdy * dy_inv * (gamma_psi - vy * vy - 1.0)) * a_clight)
@@ -467,6 +601,7 @@ def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized
                     + (Ez_v * vx
                        + ExmBy_v * (gamma_psi - vx * vx)
                        + EypBx_v * (- vx * vy)) * clight_inv
+                    - 0.25 * ADx * q_mass_ratio * psi_inv
                 ) * q_mass_ratio * psi_inv
                 + (+ shdx * shy * dx_inv * (gamma_psi - vx * vx - 1.0)
                    + shx * shdy * dy_inv * (- vx * vy)) * a_clight)
@@ -713,18 +848,20 @@ class MultiGrid1:
 
 # ---- gather + push ------------------------------------------------------------------------
 
-def _momentum_push(ux, uy, psi_inv, ExmBy, EypBx, Ez, Bx_c, By_c, Bz, clight_inv, qmc):
-    """PlasmaMomentumPush<Real>, particles/pusher/PushPlasmaParticles.H:39-75 (no laser)."""
-    gamma_psi = 0.5 * psi_inv * psi_inv * (1.0 + ux * ux * (clight_inv * clight_inv)
+def _momentum_push(ux, uy, psi_inv, ExmBy, EypBx, Ez, Bx_c, By_c, Bz, clight_inv, qmc,
+                   A=0.0, ADx=0.0, ADy=0.0):
+    """PlasmaMomentumPush<Real>, particles/pusher/PushPlasmaParticles.H:39-75
+    (A, ADx, ADy = Aabssq_norm, AabssqDx_norm, AabssqDy_norm; 0 without a laser)."""
+    gamma_psi = 0.5 * psi_inv * psi_inv * (1.0 + A + ux * ux * (clight_inv * clight_inv)
                                            + uy * uy * (clight_inv * clight_inv)) + 0.5
-    dz_ux = qmc * (gamma_psi * ExmBy + By_c + (uy * Bz) * psi_inv)
-    dz_uy = qmc * (gamma_psi * EypBx - Bx_c - (ux * Bz) * psi_inv)
+    dz_ux = qmc * (gamma_psi * ExmBy + By_c + (uy * Bz) * psi_inv) - ADx * psi_inv
+    dz_uy = qmc * (gamma_psi * EypBx - Bx_c - (ux * Bz) * psi_inv) - ADy * psi_inv
     dz_psi = qmc * clight_inv * ((ux * ExmBy + uy * EypBx) * clight_inv * psi_inv - Ez)
     return dz_ux, dz_uy, dz_psi
 
 
 def _momentum_push_dual(ux, uxe, uy, uye, pi, pie, ExmBy, EypBx, Ez, Bx_c, By_c, Bz,
-                        clight_inv, qmc):
+                        clight_inv, qmc, A=0.0, ADx=0.0, ADy=0.0):
     """PlasmaMomentumPush<DualNumber> epsilon parts; arithmetic follows utils/DualNumbers.H:13-43
     operator by operator (Real*Dual promotes the Real to a Dual with epsilon 0)."""
     c2 = clight_inv * clight_inv
@@ -745,7 +882,7 @@ def _momentum_push_dual(ux, uxe, uy, uye, pi, pie, ExmBy, EypBx, Ez, Bx_c, By_c,
     uxx, uxxe = mul(uxx, uxxe, c2, z)
     uyy, uyye = mul(uy, uye, uy, uye)
     uyy, uyye = mul(uyy, uyye, c2, z)
-    s, se = add(1.0 + 0.0, z, uxx, uxxe)
+    s, se = add(1.0 + A, z, uxx, uxxe)
     s, se = add(s, se, uyy, uyye)
     gp, gpe = mul(t, te, s, se)
     gp, gpe = add(gp, gpe, 0.5, z)
@@ -756,6 +893,8 @@ def _momentum_push_dual(ux, uxe, uy, uye, pi, pie, ExmBy, EypBx, Ez, Bx_c, By_c,
     b, be = mul(b, be, pi, pie)
     a, ae = add(a, ae, b, be)
     dux, duxe = mul(qmc, z, a, ae)
+    b, be = mul(ADx, z, pi, pie)
+    dux, duxe = sub(dux, duxe, b, be)
     # dz_uy = qmc*(gamma_psi*EypBx - Bx_c - (ux*Bz)*psi_inv)
     a, ae = mul(gp, gpe, EypBx, z)
     a, ae = sub(a, ae, Bx_c, z)
@@ -763,6 +902,8 @@ def _momentum_push_dual(ux, uxe, uy, uye, pi, pie, ExmBy, EypBx, Ez, Bx_c, By_c,
     b, be = mul(b, be, pi, pie)
     a, ae = sub(a, ae, b, be)
     duy, duye = mul(qmc, z, a, ae)
+    b, be = mul(ADy, z, pi, pie)
+    duy, duye = sub(duy, duye, b, be)
     # dz_psi = qmc*clight_inv*((ux*ExmBy + uy*EypBx)*clight_inv*psi_inv - Ez)
     a, ae = mul(ux, uxe, ExmBy, z)
     b, be = mul(uy, uye, EypBx, z)
@@ -827,7 +968,7 @@ def enforce_bc(x, y, ux, uy, lo, hi, kind):
 
 
 def advance_plasma_particles(pl: Plasma, F, geom: Geometry, pc: PhysConst, bc_kind: str,
-                             bc_lo, bc_hi, temp_slice=False):
+                             bc_lo, bc_hi, temp_slice=False, aabs=None):
     """AdvancePlasmaParticles, particles/pusher/PlasmaParticleAdvance.cpp:29-217 (leap-frog,
     lev 0, no laser, no ionization)."""
     sel = np.nonzero(pl.valid)[0]
@@ -846,15 +987,22 @@ def advance_plasma_particles(pl: Plasma, F, geom: Geometry, pc: PhysConst, bc_ki
         ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp = gather_fields(xp, yp, F, geom)
         Bxp = Bxp * clight
         Byp = Byp * clight
+        Ap = ADxp = ADyp = 0.0
+        if aabs is not None:                                                     # :123-133
+            laser_norm = (pl.charge / pc.q_e) * (pc.m_e / pl.mass) * (pl.charge / pc.q_e) * (pc.m_e / pl.mass)
+            Ap, ADxp, ADyp = laser_gather(xp, yp, aabs, geom, True)
+            Ap = Ap * (0.5 * laser_norm)
+            ADxp = ADxp * (0.25 * clight * laser_norm)
+            ADyp = ADyp * (0.25 * clight * laser_norm)
         ux, uy, psi = pl.ux_half[sel].copy(), pl.uy_half[sel].copy(), pl.psi_half[sel].copy()
 
         def substep(ux, uy, psi):
             psi_inv = 1.0 / psi
             dux, duy, dps = _momentum_push(ux, uy, psi_inv, ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp,
-                                           clight_inv, qmc)
+                                           clight_inv, qmc, Ap, ADxp, ADyp)
             duxe, duye, dpse = _momentum_push_dual(
                 ux, dux, uy, duy, psi_inv, -psi_inv * psi_inv * dps,
-                ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp, clight_inv, qmc)
+                ExmByp, EypBxp, Ezp, Bxp, Byp, Bzp, clight_inv, qmc, Ap, ADxp, ADyp)
             ux = ux + (sdz * dux + 0.5 * sdz * sdz * duxe)
             uy = uy + (sdz * duy + 0.5 * sdz * sdz * duye)
             psi = psi + (sdz * dps + 0.5 * sdz * sdz * dpse)
@@ -872,6 +1020,8 @@ def advance_plasma_particles(pl: Plasma, F, geom: Geometry, pc: PhysConst, bc_ki
             sel, xp, yp, ux, uy, psi = sel[keep], xp[keep], yp[keep], ux[keep], uy[keep], psi[keep]
             ExmByp, EypBxp, Ezp = ExmByp[keep], EypBxp[keep], Ezp[keep]
             Bxp, Byp, Bzp = Bxp[keep], Byp[keep], Bzp[keep]
+            if aabs is not None:
+                Ap, ADxp, ADyp = Ap[keep], ADxp[keep], ADyp[keep]
         pl.x[sel], pl.y[sel] = xp, yp
         if not temp_slice:
             pl.ux_half[sel], pl.uy_half[sel], pl.psi_half[sel] = ux, uy, psi
@@ -1118,7 +1268,33 @@ class Simulation:
             for nm in bnames:
                 self.beams.append(self._read_beam(nm))
         self.any_neutral = any(p.neutralize_background for p in self.plasmas)
-        self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral)
+        # lasers (laser/MultiLaser.cpp:26-56, laser/Laser.cpp:18-47): gaussian envelopes on the
+        # field grid; only what time step 0 needs (no envelope advance)
+        self.lasers = []
+        lnames = d.get('lasers.names', ['no_laser'])
+        self.use_laser = lnames[0] != 'no_laser'
+        if self.use_laser:
+            self.laser_lambda0 = _get(d, 'lasers.lambda0')
+            self.laser_interp_order = _get(d, 'lasers.interp_order', 1, typ=int)
+            for k in ('lasers.n_cell', 'lasers.patch_lo', 'lasers.patch_hi'):
+                if k in d:
+                    raise NotImplementedError('oracle scope: laser grid = field grid (' + k + ')')
+            for nm in lnames:
+                if _get(d, nm + '.init_type', 'gaussian', typ=str) != 'gaussian':
+                    raise NotImplementedError('oracle scope: gaussian lasers')
+                has_L0, has_tau = (nm + '.L0') in d, (nm + '.tau') in d
+                assert has_L0 != has_tau, 'specify exclusively L0 or tau'          # Laser.cpp:38-41
+                L0 = _get(d, nm + '.L0') if has_L0 else _get(d, nm + '.tau') * self.pc.c
+                self.lasers.append(Laser(
+                    name=nm, a0=_get(d, nm + '.a0', 0.0), w0=_get(d, nm + '.w0', 0.0),
+                    cep=_get(d, nm + '.CEP', 0.0),
+                    propagation_angle_yz=_get(d, nm + '.propagation_angle_yz', 0.0),
+                    pft_yz=_get(d, nm + '.PFT_yz', math.pi / 2.0), L0=L0,
+                    focal_distance=_get(d, nm + '.focal_distance', 0.0),
+                    position_mean=tuple(_get(d, nm + '.position_mean', [0., 0., 0.], n=3))))
+            if self.max_step > 0:
+                raise NotImplementedError('oracle scope: the laser envelope advance is not restated')
+        self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral, self.use_laser)
         g = self.geom
         self.F = {k: np.zeros((g.ny + 2 * G, g.nx + 2 * G)) for k in self.comps}
         self.eig = poisson_eigenvalues(g.nx, g.ny, g.dx, g.dy)
@@ -1157,11 +1333,8 @@ class Simulation:
         toks = _get(d, nm + '.density(x,y,z)', None, n=-1, typ=str, alt='plasmas.density(x,y,z)')
         expr = ' '.join(toks) if toks else '0.'        # the expression may contain blanks
         code = compile(expr.replace('^', '**'), '<density>', 'eval')
-        env = dict(_CONST_SI)
+        env = _constants(d)
         env.update({f: getattr(np, f) for f in ('sqrt', 'exp', 'sin', 'cos', 'log', 'tanh')})
-        for k, v in d.items():
-            if k.startswith('my_constants.'):
-                env[k.split('.', 1)[1]] = _eval(v[0], {kk: vv for kk, vv in d.items() if kk != k})
 
         def density(x, y, z, _code=code, _env=env):
             return eval(_code, {'__builtins__': {}}, dict(_env, x=x, y=y, z=z))
@@ -1267,11 +1440,19 @@ class Simulation:
         F[('Next', 'jy_beam')][...] = 0.0
         if self.deposit_rho:
             T('rho')[...] = 0.0
+        aabs = None
+        if self.use_laser:                                        # get_data :583, UpdateLaserAabs :603
+            env = laser_envelope_slice(self.lasers, self.laser_lambda0, g, islice)
+            update_laser_aabs(env, T('aabs'), g, self.laser_interp_order)
+            aabs = T('aabs')
+            self.checksums['laserEnvelope'] = self.checksums.get('laserEnvelope', 0.0) \
+                + float(np.abs(env).sum())
         # plasma deposit (:609-610)
         for pl in self.plasmas:
             self.n_qsa_violation += deposit_current(
                 pl, F, g, pc, nrm, jx=T('jx'), jy=T('jy'),
-                rho=T('rho') if self.deposit_rho else None, chi=T('chi'), rhomjz=T('rhomjz'))
+                rho=T('rho') if self.deposit_rho else None, chi=T('chi'), rhomjz=T('rhomjz'),
+                aabs=aabs)
         # beam deposit on This: jz_beam (:613-614)
         for b in self.beams:
             beam_deposit(self.beam_slice(b, islice), b, g, pc, nrm, jzb=T('jz_beam'))
@@ -1291,7 +1472,7 @@ class Simulation:
                                  jxb=F[('Next', 'jx_beam')], jyb=F[('Next', 'jy_beam')])
         init_sxsy_with_beam(F, g, pc)                                             # :660
         for pl in self.plasmas:
-            explicit_deposition(pl, F, g, pc, nrm)                                # :663
+            explicit_deposition(pl, F, g, pc, nrm, aabs=aabs)                     # :663
         if self.slice_hook:
             self.slice_hook(self, islice, 'sources')
         # ExplicitMGSolveBxBy, Hipace.cpp:793-933
@@ -1311,7 +1492,7 @@ class Simulation:
                 {k: bs[k][:n].copy() for k in ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id')})
         for pl in self.plasmas:                                                   # :699-701
             self.n_plasma_pushed += pl.x.size
-            advance_plasma_particles(pl, F, g, pc, self.bc_kind, self.bc_lo, self.bc_hi)
+            advance_plasma_particles(pl, F, g, pc, self.bc_kind, self.bc_lo, self.bc_hi, aabs=aabs)
         for b in self.beams:                                                      # :707-709
             bs = self.beam_slice(b, islice)
             self.n_beam_pushed += bs['np']

@@ -7,6 +7,7 @@ The reference's goldens are the pinned known answers for the oracle (SURVEY.md s
   tests/checksum/benchmarks_json/linear_wake.normalized.1Rank.json
   tests/checksum/benchmarks_json/blowout_wake_explicit.2Rank.json
   tests/checksum/benchmarks_json/beam_evolution.1Rank.json
+  tests/checksum/benchmarks_json/laser_blowout_wake_explicit.SI.1Rank.json  (SI units + laser, step 0)
 Their decks + overrides (tests/linear_wake.normalized.1Rank.sh:32-35,
 tests/blowout_wake_explicit.2Rank.sh:32-35) are restated in examples/ of this repo.
 """
@@ -29,6 +30,18 @@ CASES = {
                    'beam.radius': 1., 'beam.ppc': '4 4 1',
                    'beams.external_E(x,y,z,t)': '.5*x .5*y 0.'},
         rtol_cpu=1e-12, rtol_cuda=2e-6),
+    # tests/laser_blowout_wake_explicit.SI.1Rank.sh:23-36: SI units, no beam, gaussian laser; pins
+    # the SI code path, the laser initialisation, |a|^2 on the field grid and the ponderomotive terms
+    # of deposit / explicit deposition / push at time step 0 (the envelope advance is not exercised)
+    'laser_blowout_wake_explicit.SI.1Rank': dict(
+        deck='examples/blowout_wake_SI.in',
+        overrides={'max_step': 0, 'beams.names': 'no_beam',
+                   'geometry.prob_lo': '-20.*kp_inv -20.*kp_inv -7.5*kp_inv',
+                   'geometry.prob_hi': '20.*kp_inv 20.*kp_inv 6.*kp_inv',
+                   'lasers.names': 'laser', 'lasers.lambda0': '.8e-6', 'laser.a0': 4.5,
+                   'laser.position_mean': '0. 0. 0', 'laser.w0': '4.*kp_inv', 'laser.L0': '2.*kp_inv',
+                   'amr.n_cell': '128 128 100'},
+        rtol_cpu=1e-9, rtol_cuda=1e-9, skip=['Sy', 'Sx', 'chi']),
 }
 for name, meta in CASES.items():
     gold = json.load(open(os.path.join(REF, name + '.json')))

@@ -174,6 +174,24 @@ def test_full_size_driver_orders_agree(repo_root):
         assert st['n_mg_vcycles'] == st0['n_mg_vcycles'], name
 
 
+def test_si_units_deck_matches_oracle(repo_root):
+    """hipace.normalized_units = 0: the SI constants, invvol = 1/(dx dy dz) and the dx dy dz / ppc
+    weights through every kernel (the reference's examples/blowout_wake/inputs_SI restated).  The
+    oracle's SI path is pinned by the reference's laser_blowout_wake_explicit.SI.1Rank golden."""
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    text = _deck(repo_root, 'blowout_wake_SI.in')
+    nsl = 45
+    want = Oracle(text, {}).evolve(nsl)
+    for fuse in (0, 1):
+        sim = hp.Simulation(text, {})
+        sim.set_option('fuse', fuse)
+        got = sim.evolve(0, 0, nsl)
+        for k, w in want.items():
+            assert abs(got[k] - w) <= RTOL_SUM * abs(w) + 1e-300, (fuse, k, got[k], w)
+        sim.close()
+
+
 def test_plasma_init_is_bit_exact(repo_root):
     """particle count, order and positions right after InitParticles"""
     import hipace_b200 as hp
