@@ -252,7 +252,10 @@ private:
                 auto it = d->kv.find("my_constants." + name);
                 if (it != d->kv.end() && !it->second.empty()) {
                     if (++depth > 16) throw std::runtime_error("parser: recursive my_constants");
-                    emit(OP_CONST, 0, d->eval(it->second[0]));
+                    // the expression may contain blanks ("1. / kp_inv"): the reader split it
+                    std::string joined;
+                    for (auto &t : it->second) joined += t;
+                    emit(OP_CONST, 0, d->eval(joined));
                     return;
                 }
                 throw std::runtime_error("parser: unknown symbol '" + name + "' in '" + s + "'");

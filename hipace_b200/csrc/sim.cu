@@ -280,6 +280,7 @@ int read_deck(hpb_sim *s)
             }
             std::vector<RpnInstr> code;
             d.compile(expr, {"x", "y", "z"}, code);
+            { const double origin[3] = {0., 0., 0.}; sp.density0 = d.run(code, origin); }
             sp.density.n = (int)code.size();
             for (size_t k = 0; k < code.size(); ++k) sp.density.code[k] = code[k];
             const auto ppc = d.nums(nm + ".ppc", {}, "plasmas.ppc");
@@ -778,7 +779,7 @@ extern "C" int hpb_deck_check(const char *deck, const char *overrides, char *sum
     }
     if (summary && n) {
         std::string o;
-        char b[256];
+        char b[512];
         snprintf(b, sizeof b, "nx=%d;ny=%d;nz=%d;dx=%.17g;dy=%.17g;dz=%.17g;x_off=%.17g;y_off=%.17g;normalized=%d;"
                  "particle_bc=%d;max_step=%d;dt=%.17g;mg_tol_rel=%.17g;deposit_rho=%d;",
                  s.g.nx, s.g.ny, s.nz, s.g.dx, s.g.dy, s.g.dz, s.g.x_off, s.g.y_off, s.g.normalized,
@@ -789,8 +790,9 @@ extern "C" int hpb_deck_check(const char *deck, const char *overrides, char *sum
         for (size_t k = 0; k < s.plasmas.size(); ++k) {
             const Species &sp = s.plasmas[k];
             snprintf(b, sizeof b, "plasma%zu.name=%s;plasma%zu.charge=%.17g;plasma%zu.mass=%.17g;plasma%zu.ppc=%dx%d;"
-                     "plasma%zu.neutralize=%d;plasma%zu.n_subcycles=%d;", k, sp.name.c_str(), k, sp.charge, k,
-                     sp.mass, k, sp.ppc[0], sp.ppc[1], k, (int)sp.neutralize, k, sp.n_subcycles);
+                     "plasma%zu.neutralize=%d;plasma%zu.n_subcycles=%d;plasma%zu.density0=%.17g;", k,
+                     sp.name.c_str(), k, sp.charge, k, sp.mass, k, sp.ppc[0], sp.ppc[1], k, (int)sp.neutralize,
+                     k, sp.n_subcycles, k, sp.density0);
             o += b;
         }
         for (size_t k = 0; k < s.beams.size(); ++k) {

@@ -42,6 +42,7 @@ struct BeamRing {
 };
 
 struct Species {
+    double density0 = 0.;                        // density(0, 0, 0): reported by hpb_deck_check
     long lattice_n = 0; int lattice_ppc = 1;     // regular InitParticles lattice (nothing filtered): cells per pass, passes
     std::string name;
     double charge = 0, mass = 0;

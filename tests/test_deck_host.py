@@ -26,6 +26,8 @@ def test_parser_agrees_with_oracle(path):
         assert got[f'plasma{k}.charge'] == pytest.approx(p.charge, rel=1e-15)
         assert got[f'plasma{k}.mass'] == pytest.approx(p.mass, rel=1e-15)
         assert got[f'plasma{k}.neutralize'] == int(p.neutralize_background)
+        # (constants defined through other constants with blanks in the expression, SI deck)
+        assert got[f'plasma{k}.density0'] == pytest.approx(float(p.density(0., 0., 0.)), rel=1e-14)
     for k, b in enumerate(ref.beams):
         assert got[f'beam{k}.charge'] == pytest.approx(b.charge, rel=1e-15)
         assert got[f'beam{k}.mass'] == pytest.approx(b.mass, rel=1e-15)
