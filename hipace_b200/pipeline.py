@@ -42,6 +42,18 @@ def sends(step: int, world: int, max_step: int) -> bool:
     return world > 1 and step + 1 <= max_step
 
 
+def edge_order(rank: int, world: int):
+    """Order in which a rank touches its two ring edges whenever the operation BLOCKS THE HOST until
+    the peer of the edge enters the same call (ncclCommInitRank, the first ncclSend / ncclRecv of a
+    communicator, ncclCommDestroy): increasing edge index, edge e = (rank e -> rank e+1 mod world).
+    Returns [('send' | 'recv', edge), ...]; csrc/pipeline.cu follows exactly this rule.  With any
+    other order two ranks can each sit in a blocking call the other one has not reached yet (the
+    first 2-GPU run of this code dead-locked that way)."""
+    e_send, e_recv = rank, (rank - 1 + world) % world
+    ops = [('send', e_send), ('recv', e_recv)]
+    return sorted(ops, key=lambda o: o[1])
+
+
 def message_bytes(capacity: int) -> int:
     return HEADER_BYTES + 64 * capacity
 

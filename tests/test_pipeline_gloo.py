@@ -136,3 +136,30 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(hp.EXPORTS), declared ^ set(hp.EXPORTS)
+
+
+@pytest.mark.parametrize('world', [2, 3, 4, 8])
+def test_blocking_edge_order_cannot_deadlock(world):
+    """Rendezvous model of the blocking NCCL calls: a rank proceeds past an edge only when the
+    other end of that edge is at the same edge.  The ordering rule of pipeline.edge_order must
+    drain for every ring size; the naive "send first, then receive" order must not (it is the
+    dead-lock the first 2-GPU run hit), which shows the model can tell the difference."""
+    from hipace_b200 import pipeline as pl
+
+    def drains(order_of):
+        todo = {r: list(order_of(r)) for r in range(world)}
+        progress = True
+        while progress and any(todo.values()):
+            progress = False
+            for r in range(world):
+                if not todo[r]:
+                    continue
+                kind, e = todo[r][0]
+                peer = (e + 1) % world if kind == 'send' else e        # other end of edge e
+                if todo[peer] and todo[peer][0][1] == e and todo[peer][0][0] != kind:
+                    todo[r].pop(0); todo[peer].pop(0)
+                    progress = True
+        return not any(todo.values())
+
+    assert drains(lambda r: pl.edge_order(r, world))
+    assert not drains(lambda r: [('send', r), ('recv', (r - 1 + world) % world)])
