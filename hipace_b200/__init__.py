@@ -37,7 +37,7 @@ BC = {'Reflecting': 0, 'Periodic': 1, 'Absorbing': 2}
 # enum hpb_comp
 COMP_IDS = ('NEXT_JX_BEAM', 'NEXT_JY_BEAM', 'CHI', 'SY', 'SX', 'EXMBY', 'EYPBX', 'EZ', 'BX', 'BY',
             'BZ', 'PSI', 'JX_BEAM', 'JY_BEAM', 'JZ_BEAM', 'JX', 'JY', 'RHOMJZ', 'RHO',
-            'PREV_JX_BEAM', 'PREV_JY_BEAM', 'IONS_RHOMJZ')
+            'PREV_JX_BEAM', 'PREV_JY_BEAM', 'IONS_RHOMJZ', 'AABS')
 COMP = {n: i for i, n in enumerate(COMP_IDS)}
 
 # every symbol include/hpb200.h declares (tests check the library exports all of them)
@@ -57,7 +57,7 @@ EXPORTS = (
     'hpb_sim_pipeline_init', 'hpb_sim_pipeline_message_bytes', 'hpb_sim_beam_slice_capacity',
     'hpb_sim_timer_start', 'hpb_sim_timer_stop', 'hpb_sim_get_beam_packet',
     'hpb_fields_shift_and_initialize', 'hpb_advance_plasma_particles_and_deposit', 'hpb_deck_check',
-    'hpb_set_plasma_lattice_hint',
+    'hpb_set_plasma_lattice_hint', 'hpb_deposit_current_laser', 'hpb_laser_update_aabs',
 )
 NCCL_ID_BYTES = 128
 

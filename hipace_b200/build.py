@@ -30,6 +30,7 @@ SOURCES = {
     'sim.cu': [],
     'beam.cu': [],
     'pipeline.cu': [],
+    'laser.cu': [],
 }
 
 

@@ -162,6 +162,34 @@ __device__ __forceinline__ GatheredFields gather_order2(const SliceView &a, int 
     return f;
 }
 
+// doLaserGatherShapeN<2> (FieldGather.H:162-222, 236-283): |a|^2 at the particle with the plain
+// order-2 shape; DERIV: also its centred x / y differences taken on the grid and gathered
+template <bool DERIV>
+__device__ __forceinline__ void laser_gather(const SliceView &a, int c_aabs, double x_off, double y_off,
+                                             double dx_inv, double dy_inv, double xp, double yp,
+                                             double &A, double &ADx, double &ADy)
+{
+    double sx[3], sy[3];
+    const int i0 = shape2((xp - x_off) * dx_inv, sx);
+    const int j0 = shape2((yp - y_off) * dy_inv, sy);
+    const double *ab = a.comp(c_aabs);
+    const long js = a.jstride;
+    A = 0.; ADx = 0.; ADy = 0.;
+#pragma unroll
+    for (int iy = 0; iy < 3; ++iy) {
+#pragma unroll
+        for (int ix = 0; ix < 3; ++ix) {
+            const long o = a.idx(i0 + ix, j0 + iy);
+            const double w = sx[ix] * sy[iy];
+            A += w * ab[o];
+            if (DERIV) {
+                ADx += w * 0.5 * dx_inv * (ab[o + 1] - ab[o - 1]);
+                ADy += w * 0.5 * dy_inv * (ab[o + js] - ab[o - js]);
+            }
+        }
+    }
+}
+
 // EnforceBC, src/particles/pusher/GetAndSetPosition.H:56-98.  Returns true if the particle
 // became invalid (absorbing boundary).
 __device__ __forceinline__ bool enforce_particle_bc(double &x, double &y, double &ux, double &uy,

@@ -167,12 +167,12 @@ deposit_aggregated(const SliceView &a, int c_jx, int c_jy, int c_rho, int c_chi,
     }
 }
 
-template <bool JXY, bool RHO, bool CHI, bool RMJ>
+template <bool JXY, bool RHO, bool CHI, bool RMJ, bool LASER>
 __global__ void __launch_bounds__(kThreads)
 k_deposit_current(PlasmaPtrs pl, SliceView a, int c_jx, int c_jy, int c_rho, int c_chi,
                   int c_rhomjz, double x_off, double y_off, double dx_inv, double dy_inv,
                   double clightinv, double charge_invvol, double charge_mu0_mass_ratio,
-                  double max_qsa, int *n_qsa_violation)
+                  double max_qsa, int *n_qsa_violation, int c_aabs, double laser_norm)
 {
     hpb_pdl_prologue();
     // warps overlap by one lane on each side: lanes 0 and 31 only feed their neighbours, so an
@@ -200,8 +200,16 @@ k_deposit_current(PlasmaPtrs pl, SliceView a, int c_jx, int c_jy, int c_rho, int
         vx_c = ux * psi_inv;
         vy_c = uy * psi_inv;
         q_invvol = charge_invvol * w;
-        gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * clightinv * clightinv
-                           + vy_c * vy_c * clightinv * clightinv + 1.0);
+        if (LASER) {        // :182-195
+            double A, ADx, ADy;
+            laser_gather<false>(a, c_aabs, x_off, y_off, dx_inv, dy_inv, xp, yp, A, ADx, ADy);
+            gamma_psi = 0.5 * ((1.0 + 0.5 * (A * laser_norm)) * psi_inv * psi_inv
+                               + vx_c * vx_c * clightinv * clightinv
+                               + vy_c * vy_c * clightinv * clightinv + 1.0);
+        } else {
+            gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * clightinv * clightinv
+                               + vy_c * vy_c * clightinv * clightinv + 1.0);
+        }
         if (active && (gamma_psi < 0.0 || gamma_psi > max_qsa || psi_inv < 0.0)) {
             // QSA violation: discard the particle (PlasmaDepositCurrent.cpp:197-204)
             if (owner) {
@@ -317,23 +325,28 @@ __device__ __forceinline__ ExplCol expl_col(const ExplPart &e, double wx, double
     k.Ap = wx * e.hq;  k.Bp = wxd * e.gx1; k.Cp = wxy * e.gx2;
     return k;
 }
+// lasy / lasx: the ponderomotive term inside the field bracket, 0.25 AabssqD{y,x}(cell)
+// q_mass_ratio psi_inv(source) (ExplicitDeposition.cpp:234, 250); 0 without a laser
 __device__ __forceinline__ void expl_cell(const ExplCol &k, double vx, double vy, double a3,
                                           double a4, double a5, double shy, double shdy, double Bz,
                                           double Ez, double ExmBy, double EypBx, double clight_inv,
-                                          double &sy_out, double &sx_out)
+                                          double &sy_out, double &sx_out, double lasy = 0.,
+                                          double lasx = 0.)
 {
-    const double Fy = -Bz * vx + (Ez * vy + ExmBy * a3 + EypBx * a4) * clight_inv;
-    const double Fx = Bz * vy + (Ez * vx + ExmBy * a5 + EypBx * a3) * clight_inv;
+    const double Fy = -Bz * vx + (Ez * vy + ExmBy * a3 + EypBx * a4) * clight_inv - lasy;
+    const double Fx = Bz * vy + (Ez * vx + ExmBy * a5 + EypBx * a3) * clight_inv - lasx;
     sy_out += shy * (k.A * Fy + k.B) + shdy * k.C;
     sx_out += shy * (k.Ap * Fx + k.Bp) + shdy * k.Cp;
 }
 
-template <int NTHR, int MINB, bool LAT>
+struct ExplLaser { int c_aabs; double fac_c, a_norm; };     // laser_fac * c, laser_fac * q_mass_ratio^2
+
+template <int NTHR, int MINB, bool LAT, bool LASER>
 __global__ void __launch_bounds__(NTHR, MINB)
 k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, int c_ez,
                       int c_exmby, int c_eypbx, double x_off, double y_off, double dx_inv,
                       double dy_inv, double a_clight, double clight_inv,
-                      double charge_invvol_mu0, double q_mass_ratio)
+                      double charge_invvol_mu0, double q_mass_ratio, ExplLaser las)
 {
     hpb_pdl_prologue();
     // warps overlap by two lanes on each side (see k_deposit_current)
@@ -344,6 +357,7 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
     const bool owner = lane >= 2 && lane < 2 + kExplOwn;
 
     double vx = 0., vy = 0., gamma_psi = 1., yint = 0.;
+    double qp = 0.;             // 0.25 q_mass_ratio psi_inv (laser term factor of this particle)
     double sx[5] = {0., 0., 0., 0., 0.}, dsx[5] = {0., 0., 0., 0., 0.};
     ExplPart e = {};
     int i0 = 0, j0 = 0;
@@ -361,7 +375,14 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
             vx = ux * psi_inv * clight_inv;
             vy = uy * psi_inv * clight_inv;
             const double cdm = charge_invvol_mu0 * w;
-            gamma_psi = 0.5 * (psi_inv * psi_inv + vx * vx + vy * vy + 1.0);
+            if (LASER) {        // ExplicitDeposition.cpp:167-182
+                double A, ADx, ADy;
+                laser_gather<false>(a, las.c_aabs, x_off, y_off, dx_inv, dy_inv, xp, yp, A, ADx, ADy);
+                gamma_psi = 0.5 * ((1.0 + 0.5 * (A * las.a_norm)) * psi_inv * psi_inv + vx * vx + vy * vy + 1.0);
+                qp = 0.25 * q_mass_ratio * psi_inv;
+            } else {
+                gamma_psi = 0.5 * (psi_inv * psi_inv + vx * vx + vy * vy + 1.0);
+            }
             i0 = dshape2_centered((xp - x_off) * dx_inv, sx, dsx);
             const double ym = (yp - y_off) * dy_inv + 0.5;
             const double yfl = floor(ym);
@@ -379,12 +400,18 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
     // outer ring of the 5x5 stencil (s[0] = s[4] = 0): only rows 1..3 of the owned column need
     // the fields, and only the sources one cell to the side contribute through them.
     double fBz[3], fEz[3], fEx[3], fEy[3];
+    double fADx[3] = {0., 0., 0.}, fADy[3] = {0., 0., 0.};      // AabssqDx/Dy at the owned cells (:215-226)
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         fBz[r] = fEz[r] = fEx[r] = fEy[r] = 0.;
         if (active && owner) {
             const long o = a.idx(cc, j0 + 1 + r);
             fBz[r] = Bz[o]; fEz[r] = Ez[o]; fEx[r] = ExmBy[o]; fEy[r] = EypBx[o];
+            if (LASER) {
+                const double *ab = a.comp(las.c_aabs);
+                fADx[r] = (ab[o + 1] - ab[o - 1]) * 0.5 * dx_inv * las.fac_c;
+                fADy[r] = (ab[o + a.jstride] - ab[o - a.jstride]) * 0.5 * dy_inv * las.fac_c;
+            }
         }
     }
     double accy[5] = {0., 0., 0., 0., 0.}, accx[5] = {0., 0., 0., 0., 0.};
@@ -410,11 +437,12 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
             }
         } else {
             ExplCol k;
-            double vx_s, vy_s, gp_s, yint_s;
+            double vx_s, vy_s, gp_s, yint_s, qp_s = qp;
             bool ok;
             if (d == 0) {
                 k = mine; vx_s = vx; vy_s = vy; gp_s = gamma_psi; yint_s = yint; ok = active && owner;
             } else {
+                if (LASER) qp_s = __shfl_sync(kFull, qp, srcl);
                 const int c_s = __shfl_sync(kFull, cc, srcl), j_s = __shfl_sync(kFull, j0, srcl);
                 k.A = __shfl_sync(kFull, mine.A, srcl);   k.B = __shfl_sync(kFull, mine.B, srcl);
                 k.C = __shfl_sync(kFull, mine.C, srcl);   k.Ap = -k.A;
@@ -434,7 +462,8 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
 #pragma unroll
                 for (int r = 1; r <= 3; ++r)
                     expl_cell(k, vx_s, vy_s, a3, a4, a5, shy[r], shdy[r], fBz[r - 1], fEz[r - 1],
-                              fEx[r - 1], fEy[r - 1], clight_inv, accy[r], accx[r]);
+                              fEx[r - 1], fEy[r - 1], clight_inv, accy[r], accx[r],
+                              LASER ? fADy[r - 1] * qp_s : 0., LASER ? fADx[r - 1] * qp_s : 0.);
             }
         }
     }
@@ -460,8 +489,14 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
             if ((ix == 0 || ix == 4) && (iy == 0 || iy == 4)) continue;
             const long o = a.idx(i0 + ix, j0 + iy);
             double vy_ = 0., vx_ = 0.;
+            double lasy = 0., lasx = 0.;
+            if (LASER && wx * shy[iy] != 0.) {      // "avoid going outside of domain", :217
+                const double *ab = a.comp(las.c_aabs);
+                lasx = (ab[o + 1] - ab[o - 1]) * 0.5 * dx_inv * las.fac_c * qp;
+                lasy = (ab[o + a.jstride] - ab[o - a.jstride]) * 0.5 * dy_inv * las.fac_c * qp;
+            }
             expl_cell(k, e.vx, e.vy, e.a3, e.a4, e.a5, shy[iy], shdy[iy], Bz[o], Ez[o], ExmBy[o],
-                      EypBx[o], clight_inv, vy_, vx_);
+                      EypBx[o], clight_inv, vy_, vx_, lasy, lasx);
             red_add(Sy + o, vy_);
             red_add(Sx + o, vx_);
         }
@@ -483,29 +518,39 @@ __device__ __forceinline__ Dual operator-(Dual a, double b) { return {a.v - b, a
 
 struct PushFields { double ExmBy, EypBx, Ez, Bx_c, By_c, Bz; };
 
-// PlasmaMomentumPush<T>, PushPlasmaParticles.H:39-75 (laser terms are zero)
-template <class T>
+// Aabssq_norm, AabssqDx_norm, AabssqDy_norm of PushPlasmaParticles.H:32-34
+struct PushLaser { double A, ADx, ADy; };
+
+// PlasmaMomentumPush<T>, PushPlasmaParticles.H:39-75 (LASER = false: the laser terms are zero)
+template <class T, bool LASER>
 __device__ __forceinline__ void momentum_push(const T &ux, const T &uy, const T &psi_inv,
                                               const PushFields &f, double clight_inv, double qmc,
-                                              T &dz_ux, T &dz_uy, T &dz_psi)
+                                              T &dz_ux, T &dz_uy, T &dz_psi, const PushLaser &las)
 {
     const double c2 = clight_inv * clight_inv;
-    const T gamma_psi = 0.5 * psi_inv * psi_inv * (1.0 + ux * ux * c2 + uy * uy * c2) + 0.5;
-    dz_ux = qmc * (gamma_psi * f.ExmBy + f.By_c + (uy * f.Bz) * psi_inv);
-    dz_uy = qmc * (gamma_psi * f.EypBx - f.Bx_c - (ux * f.Bz) * psi_inv);
+    if (LASER) {
+        const T gamma_psi = 0.5 * psi_inv * psi_inv * ((1.0 + las.A) + ux * ux * c2 + uy * uy * c2) + 0.5;
+        dz_ux = qmc * (gamma_psi * f.ExmBy + f.By_c + (uy * f.Bz) * psi_inv) - las.ADx * psi_inv;
+        dz_uy = qmc * (gamma_psi * f.EypBx - f.Bx_c - (ux * f.Bz) * psi_inv) - las.ADy * psi_inv;
+    } else {
+        const T gamma_psi = 0.5 * psi_inv * psi_inv * (1.0 + ux * ux * c2 + uy * uy * c2) + 0.5;
+        dz_ux = qmc * (gamma_psi * f.ExmBy + f.By_c + (uy * f.Bz) * psi_inv);
+        dz_uy = qmc * (gamma_psi * f.EypBx - f.Bx_c - (ux * f.Bz) * psi_inv);
+    }
     dz_psi = (qmc * clight_inv) * ((ux * f.ExmBy + uy * f.EypBx) * clight_inv * psi_inv - f.Ez);
 }
 
+template <bool LASER>
 __device__ __forceinline__ void push_substep(double &ux, double &uy, double &psi,
                                              const PushFields &f, double clight_inv, double qmc,
-                                             double sdz)
+                                             double sdz, const PushLaser &las)
 {
     const double psi_inv = 1.0 / psi;
     double dz_ux, dz_uy, dz_psi;
-    momentum_push<double>(ux, uy, psi_inv, f, clight_inv, qmc, dz_ux, dz_uy, dz_psi);
+    momentum_push<double, LASER>(ux, uy, psi_inv, f, clight_inv, qmc, dz_ux, dz_uy, dz_psi, las);
     const Dual ux_d{ux, dz_ux}, uy_d{uy, dz_uy}, pi_d{psi_inv, -psi_inv * psi_inv * dz_psi};
     Dual d_ux, d_uy, d_psi;
-    momentum_push<Dual>(ux_d, uy_d, pi_d, f, clight_inv, qmc, d_ux, d_uy, d_psi);
+    momentum_push<Dual, LASER>(ux_d, uy_d, pi_d, f, clight_inv, qmc, d_ux, d_uy, d_psi, las);
     ux += sdz * dz_ux + 0.5 * sdz * sdz * d_ux.e;
     uy += sdz * dz_uy + 0.5 * sdz * sdz * d_uy.e;
     psi += sdz * dz_psi + 0.5 * sdz * sdz * d_psi.e;
@@ -602,12 +647,14 @@ struct DepositArgs {
 constexpr int kPushThreads = 128;
 constexpr int kTW = 40, kTH = 6;
 
-template <int MINB, bool DEPOSIT, bool STAGE, bool LAT>
+struct PushLaserArgs { int c_aabs; double norm; };      // (charge/q_e)^2 (m_e/mass)^2, PlasmaParticleAdvance.cpp:76-77
+
+template <int MINB, bool DEPOSIT, bool STAGE, bool LAT, bool LASER>
 __global__ void __launch_bounds__(kPushThreads, MINB)
 k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int c_by, int c_bz,
                  double x_off, double y_off, double dx_inv, double dy_inv, double clight,
                  double qmc, double dz, int n_subcycles, int temp_slice, int bc, double lox,
-                 double loy, double hix, double hiy, DepositArgs dep)
+                 double loy, double hix, double hiy, DepositArgs dep, PushLaserArgs lasa)
 {
     __shared__ double s_tile[STAGE ? kPushThreads / 32 : 1][5][kTH][kTW];
     hpb_pdl_prologue();
@@ -683,12 +730,19 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
             }
             f.Bx_c *= clight;
             f.By_c *= clight;
+            PushLaser las = {0., 0., 0.};
+            if (LASER) {        // PlasmaParticleAdvance.cpp:123-133
+                laser_gather<true>(a, lasa.c_aabs, x_off, y_off, dx_inv, dy_inv, xp, yp, las.A, las.ADx, las.ADy);
+                las.A *= 0.5 * lasa.norm;
+                las.ADx *= 0.25 * clight * lasa.norm;
+                las.ADy *= 0.25 * clight * lasa.norm;
+            }
 
             constexpr int nsub = 4;
             const double sdz = dz / nsub;
             ux = ux0; uy = uy0; psi = psi0;
 #pragma unroll 1
-            for (int isub = 0; isub < nsub; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
+            for (int isub = 0; isub < nsub; ++isub) push_substep<LASER>(ux, uy, psi, f, clight_inv, qmc, sdz, las);
 
             xp += dz * clight_inv * (ux * (1.0 / psi));
             yp += dz * clight_inv * (uy * (1.0 / psi));
@@ -708,7 +762,7 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
                     xp0 = xp; yp0 = yp; ux0 = ux; uy0 = uy; psi0 = psi;
                 }
 #pragma unroll 1
-                for (int isub = 0; isub < nsub / 2; ++isub) push_substep(ux, uy, psi, f, clight_inv, qmc, sdz);
+                for (int isub = 0; isub < nsub / 2; ++isub) push_substep<LASER>(ux, uy, psi, f, clight_inv, qmc, sdz, las);
                 st_stream(&pl.r[HPB_UX][ip], ux);
                 st_stream(&pl.r[HPB_UY][ip], uy);
                 st_stream(&pl.r[HPB_PSI][ip], psi);
@@ -762,9 +816,9 @@ inline unsigned nblocks(long n) { return (unsigned)((n + kThreads - 1) / kThread
 // ---------------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------------
-extern "C" int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge,
-                                   double mass, int c_jx, int c_jy, int c_rho, int c_chi,
-                                   int c_rhomjz, double max_qsa, int *d_n_qsa_violation)
+static int deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                           int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
+                           double max_qsa, int *d_n_qsa_violation)
 {
     if (!ctx) return HPB_ERR_ARG;
     if (pl.np == 0) return HPB_OK;
@@ -773,14 +827,18 @@ extern "C" int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, do
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     if ((c_jx >= 0) != (c_jy >= 0)) { hpb_set_error("deposit: jx and jy go together"); return HPB_ERR_ARG; }
     const int mask = (c_jx >= 0 ? 8 : 0) | (c_rho >= 0 ? 4 : 0) | (c_chi >= 0 ? 2 : 0) | (c_rhomjz >= 0 ? 1 : 0);
-#define HPB_DEP(M)                                                                                \
-    case M:                                                                                       \
-        hpb_launch(k_deposit_current<((M) & 8) != 0, ((M) & 4) != 0, ((M) & 2) != 0, ((M) & 1) != 0>, \
+    // (charge/q_e)^2 (m_e/mass)^2, PlasmaDepositCurrent.cpp:80-81
+    const double laser_norm = (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass);
+#define HPB_DEP_(M, LAS)                                                                          \
+        hpb_launch(k_deposit_current<((M) & 8) != 0, ((M) & 4) != 0, ((M) & 2) != 0, ((M) & 1) != 0, LAS>, \
                (unsigned)((pl.np + kDepOwn * (kThreads / 32) - 1) / (kDepOwn * (kThreads / 32))), \
                kThreads, 0, ctx->stream,                                                        \
                 to_ptrs(pl), make_view(sl), c_jx, c_jy, c_rho, c_chi, c_rhomjz, g.x_off, g.y_off, \
                 1.0 / g.dx, 1.0 / g.dy, 1.0 / g.c, charge * invvol, charge * g.mu0 / mass,        \
-                max_qsa, d_n_qsa_violation);                                                      \
+                max_qsa, d_n_qsa_violation, c_aabs, laser_norm)
+#define HPB_DEP(M)                                                                                \
+    case M:                                                                                       \
+        if (c_aabs >= 0) HPB_DEP_(M, true); else HPB_DEP_(M, false);                              \
         break;
     switch (mask) {
         HPB_DEP(1) HPB_DEP(2) HPB_DEP(3) HPB_DEP(4) HPB_DEP(5) HPB_DEP(6) HPB_DEP(7) HPB_DEP(8)
@@ -788,9 +846,27 @@ extern "C" int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, do
     default: return HPB_OK;      // nothing to deposit
     }
 #undef HPB_DEP
+#undef HPB_DEP_
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
+}
+
+extern "C" int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge,
+                                   double mass, int c_jx, int c_jy, int c_rho, int c_chi,
+                                   int c_rhomjz, double max_qsa, int *d_n_qsa_violation)
+{
+    return deposit_current(ctx, pl, sl, charge, mass, c_jx, c_jy, c_rho, c_chi, c_rhomjz, -1, max_qsa,
+                           d_n_qsa_violation);
+}
+
+extern "C" int hpb_deposit_current_laser(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge,
+                                         double mass, int c_jx, int c_jy, int c_rho, int c_chi,
+                                         int c_rhomjz, int c_aabs, double max_qsa,
+                                         int *d_n_qsa_violation)
+{
+    return deposit_current(ctx, pl, sl, charge, mass, c_jx, c_jy, c_rho, c_chi, c_rhomjz, c_aabs, max_qsa,
+                           d_n_qsa_violation);
 }
 
 extern "C" int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc)
@@ -827,16 +903,26 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("HPB_EXPL_VARIANT"); variant = e ? atoi(e) : 4; }
-    const PlasmaPtrs pp = to_ptrs(ctx, pl, 1);
+    // (the laser variant uses the plain particle order)
+    const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 1);
     const long nwarps = lattice_warps(pp, kExplOwn);
+    // laser: ExplicitDeposition.cpp:55 laser_fac = (m_e / q_e)^2, a0 is always normalised
+    ExplLaser las = {comps[HPB_C_AABS], 0., 0.};
+    if (las.c_aabs >= 0) {
+        const double laser_fac = (g.m_e / g.q_e) * (g.m_e / g.q_e);
+        las.fac_c = laser_fac * g.c;
+        las.a_norm = laser_fac * (charge / mass) * (charge / mass);
+    }
 #define HPB_LAUNCH_EXPL(NT, MB)                                                                    \
-    do { if (pp.lat_n > 0) HPB_LAUNCH_EXPL_(NT, MB, true); else HPB_LAUNCH_EXPL_(NT, MB, false); } while (0)
-#define HPB_LAUNCH_EXPL_(NT, MB, LAT)                                                              \
-    hpb_launch(k_explicit_deposition<NT, MB, LAT>, (unsigned)((nwarps + (NT / 32) - 1) / (NT / 32)), \
+    do { if (las.c_aabs >= 0) HPB_LAUNCH_EXPL_(128, 3, false, true);                               \
+         else if (pp.lat_n > 0) HPB_LAUNCH_EXPL_(NT, MB, true, false);                             \
+         else HPB_LAUNCH_EXPL_(NT, MB, false, false); } while (0)
+#define HPB_LAUNCH_EXPL_(NT, MB, LAT, LAS)                                                         \
+    hpb_launch(k_explicit_deposition<NT, MB, LAT, LAS>, (unsigned)((nwarps + (NT / 32) - 1) / (NT / 32)), \
                                     NT, 0, ctx->stream,                                         \
         pp, make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ],             \
         comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.x_off, g.y_off, 1.0 / g.dx,     \
-        1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass)
+        1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass, las)
     if (variant == 2) HPB_LAUNCH_EXPL(256, 2);
     else if (variant == 3) HPB_LAUNCH_EXPL(128, 3);
     else if (variant == 5) HPB_LAUNCH_EXPL(128, 6);
@@ -874,21 +960,29 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         const int cx[8] = {HPB_C_SY, HPB_C_SX, HPB_C_EXMBY, HPB_C_EYPBX, HPB_C_PSI, HPB_C_EZ, HPB_C_BZ, HPB_C_EXMBY};
         for (int k = 0; k < 8; ++k) dep.cx[k] = comps[cx[k]];
     }
-    const PlasmaPtrs pp = to_ptrs(ctx, pl, 2);
+    const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 2);
     const long nwarps = lattice_warps(pp, 32);
+    PushLaserArgs lasa = {comps[HPB_C_AABS], 0.};
+    if (lasa.c_aabs >= 0) {
+        if (deposit) { hpb_set_error("advance+deposit: not available with a laser"); return HPB_ERR_UNSUPPORTED; }
+        lasa.norm = (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass);
+    }
 #define HPB_LAUNCH_PUSH(MB, DEP, STG)                                                             \
-    do { if (pp.lat_n > 0) HPB_LAUNCH_PUSH_(MB, DEP, STG, true); else HPB_LAUNCH_PUSH_(MB, DEP, STG, false); } while (0)
-#define HPB_LAUNCH_PUSH_(MB, DEP, STG, LAT)                                                       \
-    hpb_launch(k_advance_plasma<MB, DEP, STG, LAT>,                                               \
+    do { if (pp.lat_n > 0) HPB_LAUNCH_PUSH_(MB, DEP, STG, true, false);                            \
+         else HPB_LAUNCH_PUSH_(MB, DEP, STG, false, false); } while (0)
+#define HPB_LAUNCH_PUSH_(MB, DEP, STG, LAT, LAS)                                                  \
+    hpb_launch(k_advance_plasma<MB, DEP, STG, LAT, LAS>,                                          \
         (unsigned)((nwarps + kPushThreads / 32 - 1) / (kPushThreads / 32)),                       \
         kPushThreads, 0, ctx->stream,                                                             \
         pp, make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],           \
         comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
         charge / (mass * g.c), g.dz / n_subcycles, n_subcycles, temp_slice, particle_bc,         \
-        bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep)
+        bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep, lasa)
     // variants: 0 = staged gather, 5 blocks / SM (the shared-memory limit; default),
     // 1 = direct loads only, 3 = staged with 128 registers
-    if (deposit) {
+    if (lasa.c_aabs >= 0) {
+        HPB_LAUNCH_PUSH_(4, false, true, false, true);      // laser: staged gather, plain order, 128 registers
+    } else if (deposit) {
         if (variant == 1) HPB_LAUNCH_PUSH(6, true, false);
         else if (variant == 3) HPB_LAUNCH_PUSH(4, true, true);
         else HPB_LAUNCH_PUSH(5, true, true);

@@ -301,6 +301,35 @@ int read_deck(hpb_sim *s)
             s->any_neutral = s->any_neutral || sp.neutralize;
         }
     }
+    // lasers (laser/MultiLaser.cpp:26-56, laser/Laser.cpp:18-47): gaussian envelopes on the field grid
+    auto ln = d.strs("lasers.names");
+    if (!ln.empty() && ln[0] != "no_laser") {
+        s->use_laser = true;
+        s->laser_lambda0 = d.num("lasers.lambda0", 0.);
+        s->laser_interp_order = (int)d.num("lasers.interp_order", 1);
+        if (s->laser_lambda0 <= 0.) throw std::runtime_error("lasers.lambda0 must be given");
+        for (const char *k : {"lasers.n_cell", "lasers.patch_lo", "lasers.patch_hi"})
+            if (d.find(k)) throw std::runtime_error(std::string(k) + ": only the default laser grid (= field grid) is supported");
+        if (s->max_step > 0)
+            throw std::runtime_error("lasers: the envelope advance (max_step > 0) is not implemented");
+        if ((int)ln.size() > HPB_MAX_LASERS) throw std::runtime_error("too many lasers");
+        for (auto &nm : ln) {
+            if (d.str(nm + ".init_type", "gaussian") != "gaussian")
+                throw std::runtime_error("laser init_type must be gaussian");
+            hpb_laser L = {};
+            L.a0 = d.num(nm + ".a0", 0.); L.w0 = d.num(nm + ".w0", 0.); L.cep = d.num(nm + ".CEP", 0.);
+            L.propagation_angle_yz = d.num(nm + ".propagation_angle_yz", 0.);
+            L.pft_yz = d.num(nm + ".PFT_yz", 1.5707963267948966);
+            const bool has_L0 = d.find(nm + ".L0") != nullptr, has_tau = d.find(nm + ".tau") != nullptr;
+            if (has_L0 == has_tau)                                  // Laser.cpp:38-41
+                throw std::runtime_error("specify exclusively either L0 or tau of laser " + nm);
+            L.L0 = has_L0 ? d.num(nm + ".L0", 0.) : d.num(nm + ".tau", 0.) * g.c;
+            L.focal_distance = d.num(nm + ".focal_distance", 0.);
+            const auto pm = d.nums(nm + ".position_mean", {0., 0., 0.});
+            for (int k = 0; k < 3 && k < (int)pm.size(); ++k) L.position_mean[k] = pm[k];
+            s->lasers.push_back(L);
+        }
+    }
     auto bn = d.strs("beams.names");
     if (!bn.empty() && bn[0] != "no_beam") {
         for (auto &nm : bn) {
@@ -369,6 +398,7 @@ void build_components(hpb_sim *s)
     add(HPB_C_JY_BEAM, "This", "jy_beam"); add(HPB_C_JZ_BEAM, "This", "jz_beam");
     add(HPB_C_JX, "This", "jx"); add(HPB_C_JY, "This", "jy"); add(HPB_C_RHOMJZ, "This", "rhomjz");
     if (s->deposit_rho) add(HPB_C_RHO, "This", "rho");
+    if (s->use_laser) add(HPB_C_AABS, "This", "aabs");
     add(HPB_C_PREV_JX_BEAM, "Previous", "jx_beam"); add(HPB_C_PREV_JY_BEAM, "Previous", "jy_beam");
     if (s->any_neutral) add(HPB_C_IONS_RHOMJZ, "RhomJzIons", "rhomjz");
     s->sl.ncomp = n;
@@ -528,7 +558,7 @@ int begin_step(hpb_sim *s, int step)
 {
     // ResetAllQuantities (Hipace.cpp:730-742)
     SIM_CUDA(cudaMemsetAsync(s->sl.p, 0, sizeof(double) * s->sl.nstride * s->sl.ncomp, s->stream));
-    SIM_CUDA(cudaMemsetAsync(s->d_checksum, 0, sizeof(double) * s->sl.ncomp, s->stream));
+    SIM_CUDA(cudaMemsetAsync(s->d_checksum, 0, sizeof(double) * (s->sl.ncomp + 1), s->stream));
     for (int k = 0; k < HPB_C_COUNT; ++k) s->comps[k] = s->comps0[k];
     s->prepared = false;
     const double c_t = s->g.c * (s->dt * step);
@@ -647,7 +677,7 @@ int solve_one_slice(hpb_sim *s, int islice)
     hpb_ctx *ctx = s->ctx;
     const int *C = s->comps;
     int rc;
-    bool fuse = s->opt_fuse && C[HPB_C_RHO] < 0;
+    bool fuse = s->opt_fuse && C[HPB_C_RHO] < 0 && !s->use_laser;
     for (auto &sp : s->plasmas) if (sp.n_subcycles < 1) fuse = false;
     // (stage timers synchronise the main stream per stage: keep one stream when profiling)
     const bool side = fuse && s->opt_side_stream && s->stream2 && !s->beams.empty() && !s->opt_profile;
@@ -657,12 +687,20 @@ int solve_one_slice(hpb_sim *s, int islice)
             StageTimer t(s, ST_OTHER);
             if ((rc = hpb_fields_initialize_slices(ctx, s->sl, C))) return rc;          // :598-600
         }
+        if (s->use_laser) {                                                             // :583, :603
+            StageTimer t(s, ST_OTHER);
+            const double z = islice * s->g.dz + (s->prob_lo[2] + 0.5 * s->g.dz);        // GetPosOffset(2)
+            if ((rc = hpb_laser_update_aabs(ctx, s->sl, C[HPB_C_AABS], s->lasers.data(), (int)s->lasers.size(),
+                                            s->laser_lambda0, s->laser_interp_order, z,
+                                            s->opt_checksums ? s->d_checksum + s->sl.ncomp : nullptr))) return rc;
+        }
         {
             StageTimer t(s, ST_DEPOSIT);
             for (auto &sp : s->plasmas)                                                 // :609-610
-                if ((rc = hpb_deposit_current(ctx, sp.d, s->sl, sp.charge, sp.mass, C[HPB_C_JX],
-                                              C[HPB_C_JY], C[HPB_C_RHO], C[HPB_C_CHI],
-                                              C[HPB_C_RHOMJZ], sp.max_qsa, s->d_nqsa))) return rc;
+                if ((rc = hpb_deposit_current_laser(ctx, sp.d, s->sl, sp.charge, sp.mass, C[HPB_C_JX],
+                                                    C[HPB_C_JY], C[HPB_C_RHO], C[HPB_C_CHI],
+                                                    C[HPB_C_RHOMJZ], C[HPB_C_AABS], sp.max_qsa,
+                                                    s->d_nqsa))) return rc;
         }
         StageTimer t(s, ST_OTHER);
         if ((rc = beam_deposit_jz(s, islice))) return rc;
@@ -785,7 +823,8 @@ extern "C" int hpb_deck_check(const char *deck, const char *overrides, char *sum
                  s.g.nx, s.g.ny, s.nz, s.g.dx, s.g.dy, s.g.dz, s.g.x_off, s.g.y_off, s.g.normalized,
                  s.particle_bc, s.max_step, s.dt, s.mg_tol_rel, (int)s.deposit_rho);
         o += b;
-        snprintf(b, sizeof b, "n_plasmas=%zu;n_beams=%zu;", s.plasmas.size(), s.beams.size());
+        snprintf(b, sizeof b, "n_plasmas=%zu;n_beams=%zu;n_lasers=%zu;", s.plasmas.size(), s.beams.size(),
+                 s.lasers.size());
         o += b;
         for (size_t k = 0; k < s.plasmas.size(); ++k) {
             const Species &sp = s.plasmas[k];
@@ -838,8 +877,8 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     sl.jstride = sl.nx_tot; sl.nstride = (long)sl.nx_tot * sl.ny_tot;
     SIM_CUDA(cudaMalloc(&sl.p, sizeof(double) * sl.nstride * sl.ncomp));
     SIM_CUDA(cudaMemset(sl.p, 0, sizeof(double) * sl.nstride * sl.ncomp));
-    SIM_CUDA(cudaMalloc(&s->d_checksum, sizeof(double) * sl.ncomp));
-    SIM_CUDA(cudaMemset(s->d_checksum, 0, sizeof(double) * sl.ncomp));
+    SIM_CUDA(cudaMalloc(&s->d_checksum, sizeof(double) * (sl.ncomp + 1)));     // + laserEnvelope
+    SIM_CUDA(cudaMemset(s->d_checksum, 0, sizeof(double) * (sl.ncomp + 1)));
     SIM_CUDA(cudaMalloc(&s->d_nqsa, sizeof(int)));
     SIM_CUDA(cudaMemset(s->d_nqsa, 0, sizeof(int)));
     SIM_CUDA(cudaMalloc(&s->d_count, sizeof(unsigned long long)));
@@ -1042,7 +1081,7 @@ extern "C" int hpb_sim_checksum_count(hpb_sim *s)
     if (!s) return -1;
     int n = 0;
     for (auto &c : s->comp_names) n += (c.first == "This");
-    return n;
+    return n + (s->use_laser ? 1 : 0);
 }
 
 extern "C" const char *hpb_sim_checksum_name(hpb_sim *s, int k)
@@ -1051,6 +1090,7 @@ extern "C" const char *hpb_sim_checksum_name(hpb_sim *s, int k)
     int n = 0;
     for (auto &c : s->comp_names)
         if (c.first == "This") { if (n == k) return c.second.c_str(); ++n; }
+    if (s->use_laser && n == k) return "laserEnvelope";
     return nullptr;
 }
 
@@ -1059,11 +1099,12 @@ extern "C" int hpb_sim_get_checksums(hpb_sim *s, double *h_out)
     if (!s || !h_out) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
     SIM_CUDA(cudaStreamSynchronize(s->stream));
-    std::vector<double> all(s->sl.ncomp);
-    SIM_CUDA(cudaMemcpy(all.data(), s->d_checksum, sizeof(double) * s->sl.ncomp, cudaMemcpyDeviceToHost));
+    std::vector<double> all(s->sl.ncomp + 1);
+    SIM_CUDA(cudaMemcpy(all.data(), s->d_checksum, sizeof(double) * (s->sl.ncomp + 1), cudaMemcpyDeviceToHost));
     int n = 0;
     for (size_t c = 0; c < s->comp_names.size(); ++c)
         if (s->comp_names[c].first == "This") h_out[n++] = all[c];
+    if (s->use_laser) h_out[n++] = all[s->sl.ncomp];
     return HPB_OK;
 }
 

@@ -105,6 +105,11 @@ struct hpb_sim {
     // fused slice transition (our addition, see hpb_fields_shift_and_initialize): the end of
     // slice k shifts / initialises the planes for slice k-1 and the plasma push of slice k
     // deposits jx jy chi rhomjz of slice k-1 from registers
+    // lasers (time step 0 only: analytic envelope + ponderomotive terms)
+    std::vector<hpb_laser> lasers;
+    double laser_lambda0 = 0.;
+    int laser_interp_order = 1;
+    bool use_laser = false;
     bool opt_fuse = true;
     // beam-side work of the fused order (beam push / re-binning / hand-off of this slice, beam
     // deposits and the Sx, Sy seed of the next one) runs on a second stream beside the plasma push

@@ -115,6 +115,26 @@ int hpb_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge
                         int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz,
                         double max_qsa_weighting_factor, int *d_n_qsa_violation);
 
+/* the same with a laser: c_aabs is the |a|^2 plane gathered for gamma/psi (:182-195); < 0 = none */
+int hpb_deposit_current_laser(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                              int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
+                              double max_qsa_weighting_factor, int *d_n_qsa_violation);
+
+/* Laser envelope at time step 0 (first part): MultiLaser::InitLaserSlice, gaussian
+ * branch (src/laser/MultiLaser.cpp:881-917) evaluated on the field grid (the default laser
+ * geometry, :58-118) + MultiLaser::UpdateLaserAabs (:214-291): component c_aabs of the slice
+ * receives |a|^2 interpolated with order interp_order, guard cells included.  lasers: HOST array.
+ * d_envelope_abs_sum (device, may be NULL) accumulates sum |a| over the slice (the laserEnvelope
+ * checksum).  With comps[HPB_C_AABS] >= 0, hpb_explicit_deposition and
+ * hpb_advance_plasma_particles apply the ponderomotive terms of ExplicitDeposition.cpp:167-250
+ * and PushPlasmaParticles.H:59-69.  The envelope ADVANCE (hpmg type 2) is not implemented. */
+typedef struct {
+    double a0, w0, cep, propagation_angle_yz, pft_yz, L0, focal_distance, position_mean[3];
+} hpb_laser;
+#define HPB_MAX_LASERS 4
+int hpb_laser_update_aabs(hpb_ctx *ctx, hpb_slice sl, int c_aabs, const hpb_laser *lasers, int nlasers,
+                          double lambda0, int interp_order, double z_slice, double *d_envelope_abs_sum);
+
 /* beam ::DepositCurrentSlice (src/particles/deposition/BeamDepositCurrent.cpp:21-195) */
 int hpb_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, double charge,
                      int c_jx, int c_jy, int c_jz);
@@ -222,6 +242,7 @@ enum hpb_comp {
     HPB_C_RHOMJZ, HPB_C_RHO /* -1 if not allocated */,
     HPB_C_PREV_JX_BEAM, HPB_C_PREV_JY_BEAM,
     HPB_C_IONS_RHOMJZ /* -1 if no neutralising background */,
+    HPB_C_AABS /* |a|^2 of the laser envelope on the field grid, -1 without a laser (Fields.cpp:98-101) */,
     HPB_C_COUNT
 };
 

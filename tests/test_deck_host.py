@@ -62,6 +62,18 @@ def test_unsupported_options_fail_loudly(ov, msg):
     assert msg in str(e.value)
 
 
+def test_laser_deck_is_accepted_for_step_zero_only():
+    import hipace_b200 as hp
+    import json
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'laser_blowout_wake_explicit.SI.1Rank.json')))
+    text = open(os.path.join(ROOT, meta['deck'])).read()
+    got = hp.deck_check(text, meta['overrides'])
+    assert got['n_lasers'] == 1 and got['n_beams'] == 0 and (got['nx'], got['nz']) == (128, 100)
+    with pytest.raises(hp.HpbError) as e:
+        hp.deck_check(text, dict(meta['overrides'], max_step=2))
+    assert 'envelope advance' in str(e.value)
+
+
 def test_no_gpu_means_error_not_fallback():
     """the product path must fail loudly without a device (no CPU fallback)"""
     import torch
