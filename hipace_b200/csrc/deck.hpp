@@ -75,8 +75,13 @@ struct Deck {
     }
     double num(const std::string &k, double def, const std::string &alt = "") const
     {
+        // a scalar: the whole right-hand side is ONE expression, blanks included ("0.01 * ne");
+        // the reference's getWithParser joins the tokens the same way (utils/Parser.H)
         auto v = find(k, alt);
-        return (v && !v->empty()) ? eval((*v)[0]) : def;
+        if (!v || v->empty()) return def;
+        std::string joined;
+        for (auto &t : *v) joined += t;
+        return eval(joined);
     }
     std::vector<double> nums(const std::string &k, const std::vector<double> &def,
                              const std::string &alt = "") const

@@ -1119,6 +1119,9 @@ extern "C" int hpb_sim_get_beam_checksums(hpb_sim *s, int beam, double h_out[9])
     if (!b.cs_valid) { int rc = hpb_beam_ring_checksum(s, b.ring[b.cur], b.d_cs); if (rc) return rc; }
     SIM_CUDA(cudaMemcpyAsync(h_out, b.d_cs, 9 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     SIM_CUDA(cudaStreamSynchronize(s->stream));
+    // momenta are stored as proper velocities u c (BeamParticleContainerInit.cpp:52-61); the
+    // reference's checksum reads them normalised to m c (openPMD-viewer): 1 in normalised units
+    for (int k = 3; k <= 5; ++k) h_out[k] *= 1.0 / s->g.c;
     return HPB_OK;
 }
 

@@ -99,8 +99,9 @@ def _get(deck, key, default=None, n=None, typ=float, alt=None):
         return default
     if typ is str:
         return v[0] if n is None else v
-    vals = [typ(_eval(t, deck)) for t in v]
-    return vals[0] if n is None else vals
+    if n is None:       # a scalar: the whole right-hand side is ONE expression, blanks included
+        return typ(_eval(' '.join(v), deck))                # (utils/Parser.H: getWithParser joins the tokens)
+    return [typ(_eval(t, deck)) for t in v]
 
 
 @dataclass
@@ -1541,10 +1542,13 @@ class Simulation:
                     self.beam_slice(b, isl)
                 cat = lambda k: np.concatenate([b.slices[i][k][:b.slices[i]['np']] for i in sorted(b.slices)])
             n = cat('x').size
+            # momenta are stored as proper velocities u c (BeamParticleContainerInit.cpp:52-61); the
+            # checksum reads them through openPMD-viewer, which normalises momentum to m c
+            ci = 1.0 / self.pc.c
             out[b.name] = dict(
                 charge=abs(b.charge) * n, mass=abs(b.mass) * n, id=int(np.abs(cat('id')).sum()),
                 x=float(np.abs(cat('x')).sum()), y=float(np.abs(cat('y')).sum()),
-                z=float(np.abs(cat('z')).sum()), ux=float(np.abs(cat('ux')).sum()),
-                uy=float(np.abs(cat('uy')).sum()), uz=float(np.abs(cat('uz')).sum()),
+                z=float(np.abs(cat('z')).sum()), ux=float(np.abs(cat('ux')).sum()) * ci,
+                uy=float(np.abs(cat('uy')).sum()) * ci, uz=float(np.abs(cat('uz')).sum()) * ci,
                 w=float(np.abs(cat('w')).sum()))
         return out

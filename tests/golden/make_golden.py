@@ -42,6 +42,18 @@ CASES = {
                    'laser.position_mean': '0. 0. 0', 'laser.w0': '4.*kp_inv', 'laser.L0': '2.*kp_inv',
                    'amr.n_cell': '128 128 100'},
         rtol_cpu=1e-9, rtol_cuda=1e-9, skip=['Sy', 'Sx', 'chi']),
+    # tests/laser_blowout_wake_explicit.1Rank.sh:23-36: the same in normalised units
+    'laser_blowout_wake_explicit.1Rank': dict(
+        deck='examples/blowout_wake_normalized.in',
+        overrides={'max_step': 0, 'beams.names': 'no_beam', 'geometry.prob_lo': '-20. -20. -7.5',
+                   'geometry.prob_hi': '20. 20. 6', 'lasers.names': 'laser', 'lasers.lambda0': '.8e-6',
+                   'laser.a0': 4.5, 'laser.position_mean': '0. 0. 0', 'laser.w0': 4, 'laser.L0': 2,
+                   'amr.n_cell': '128 128 100'},
+        rtol_cpu=1e-9, rtol_cuda=1e-9, skip=['Sy', 'Sx', 'chi']),
+    # tests/linear_wake.SI.1Rank.sh:30-34: SI units with a beam and the rho diagnostic
+    'linear_wake.SI.1Rank': dict(
+        deck='examples/linear_wake_SI.in', overrides={'diagnostic.field_data': 'all rho'},
+        rtol_cpu=1e-11, rtol_cuda=1e-7),
 }
 for name, meta in CASES.items():
     gold = json.load(open(os.path.join(REF, name + '.json')))

@@ -25,7 +25,8 @@ def _deck(repo_root, name):
 
 
 @pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank',
-                                  'laser_blowout_wake_explicit.SI.1Rank'])
+                                  'laser_blowout_wake_explicit.SI.1Rank',
+                                  'laser_blowout_wake_explicit.1Rank', 'linear_wake.SI.1Rank'])
 def test_slice_loop_matches_reference_golden(case, repo_root):
     import hipace_b200 as hp
     meta = json.load(open(os.path.join(GOLD, case + '.json')))

@@ -25,7 +25,8 @@ def _run(case, repo_root):
 
 
 @pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank',
-                                  'beam_evolution.1Rank', 'laser_blowout_wake_explicit.SI.1Rank'])
+                                  'beam_evolution.1Rank', 'laser_blowout_wake_explicit.SI.1Rank',
+                                  'laser_blowout_wake_explicit.1Rank', 'linear_wake.SI.1Rank'])
 def test_oracle_matches_reference_golden(case, repo_root):
     meta, sim, cs = _run(case, repo_root)
     gold = meta['checksums']
@@ -35,5 +36,6 @@ def test_oracle_matches_reference_golden(case, repo_root):
     if 'beam' in gold:
         bc = sim.beam_checksums()['beam']
         for name, want in gold['beam'].items():
-            assert abs(bc[name] - want) <= RTOL * abs(want) + 1e-40, (name, bc[name], want)
+            # (the reference's files hold charge, mass and positions to ~13 digits only)
+            assert abs(bc[name] - want) <= max(RTOL, 1e-12) * abs(want) + 1e-40, (name, bc[name], want)
     assert sim.n_qsa_violation == 0
