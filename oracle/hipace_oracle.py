@@ -373,6 +373,99 @@ def update_laser_aabs(env, aabs, geom: 'Geometry', interp_order: int):
     aabs[...] = out
 
 
+class LaserSlices:
+    """The nine complex work slices of MultiLaser (laser/MultiLaser.H:24-48, WhichLaserSlice):
+    time levels n-1, n, n+1 at slices j, j+1, j+2, on the valid laser box."""
+
+    def __init__(self, ny, nx):
+        z = lambda: np.zeros((ny, nx), dtype=complex)
+        self.nm1j00, self.nm1jp1, self.nm1jp2 = z(), z(), z()
+        self.n00j00, self.n00jp1, self.n00jp2 = z(), z(), z()
+        self.np1j00, self.np1jp1, self.np1jp2 = z(), z(), z()
+
+    def shift(self):
+        """MultiLaser::ShiftLaserSlices, laser/MultiLaser.cpp:180-212 (the j00 slots are then
+        refilled by MultiBuffer::get_data / InitSliceEnvelope)"""
+        self.nm1jp2, self.nm1jp1 = self.nm1jp1, self.nm1j00
+        self.n00jp2, self.n00jp1 = self.n00jp1, self.n00j00
+        self.np1jp2, self.np1jp1 = self.np1jp1, self.np1j00
+
+
+def laser_interpolate_chi(chi_field, chi_initial, geom: 'Geometry', interp_order: int):
+    """MultiLaser::InterpolateChi, laser/MultiLaser.cpp:334-407 for coinciding grids: chi of the
+    field slice inside the field box shrunk by 2 guard widths, the initial chi outside"""
+    ii, jj = np.arange(geom.nx), np.arange(geom.ny)
+    xmid = ((ii * geom.dx + geom.pos_offset(0)) - geom.pos_offset(0)) * (1.0 / geom.dx)
+    ymid = ((jj * geom.dy + geom.pos_offset(1)) - geom.pos_offset(1)) * (1.0 / geom.dy)
+    sx, i0 = shape_order_n(xmid, interp_order)
+    sy, j0 = shape_order_n(ymid, interp_order)
+    chi = np.zeros((geom.ny, geom.nx))
+    for iy in range(interp_order + 1):
+        for ix in range(interp_order + 1):
+            chi += (sy[iy][:, None] * sx[ix][None, :]) * chi_field[(j0 + iy + G)[:, None], (i0 + ix + G)[None, :]]
+    # field box [-G, n-1+G] grown by -2G -> [G, n-1-G]; laser index range where it ends (:368-371)
+    x_lo, x_hi, y_lo, y_hi = G, geom.nx - 1 - G, G, geom.ny - 1 - G
+    inside = ((jj >= y_lo) & (jj <= y_hi))[:, None] & ((ii >= x_lo) & (ii <= x_hi))[None, :]
+    return np.where(inside, chi, chi_initial)
+
+
+def laser_advance_fft(L: 'LaserSlices', chi, geom: 'Geometry', pc: 'PhysConst', lambda0, dt, step,
+                      use_phase=True):
+    """MultiLaser::AdvanceSliceFFT, laser/MultiLaser.cpp:609-801: A^{n+1}_j from the envelope
+    equation (Benedetti et al. 2017 discretisation), solved with a 2-D complex FFT"""
+    dx, dy, dz, c = geom.dx, geom.dy, geom.dz, pc.c
+    k0 = 2.0 * math.pi / lambda0
+    Ny, Nx = L.n00j00.shape
+    imid, jmid = (Nx + 1) // 2, (Ny + 1) // 2
+    tj00 = tjp1 = tjp2 = 0.0
+    if use_phase:                                                  # on-axis phase, :651-685
+        keep_x = [imid - 1, imid] if Nx % 2 == 0 else [imid]
+        keep_y = [jmid - 1, jmid] if Ny % 2 == 0 else [jmid]
+        ax = lambda a: a[np.ix_(keep_y, keep_x)].sum()
+        h0, h1, h2 = ax(L.n00j00), ax(L.n00jp1), ax(L.n00jp2)
+        tj00, tjp1, tjp2 = (math.atan2(h.imag, h.real) for h in (h0, h1, h2))
+    dt1, dt2 = tj00 - tjp1, tjp1 - tjp2
+    if dt1 < -1.5 * math.pi: dt1 += 2.0 * math.pi
+    if dt1 > 1.5 * math.pi: dt1 -= 2.0 * math.pi
+    if dt2 < -1.5 * math.pi: dt2 += 2.0 * math.pi
+    if dt2 > 1.5 * math.pi: dt2 -= 2.0 * math.pi
+    exp1 = np.exp(1j * (tj00 - tjp1))
+    exp2 = np.exp(1j * (tj00 - tjp2))
+    djn = (-3.0 * dt1 + dt2) / (2.0 * dz)
+
+    def lap(a):                                                    # 0 on the edge cells, :703-722
+        out = np.zeros_like(a)
+        out[1:-1, 1:-1] = (a[1:-1, 2:] + a[1:-1, :-2] - 2.0 * a[1:-1, 1:-1]) / (dx * dx) \
+            + (a[2:, 1:-1] + a[:-2, 1:-1] - 2.0 * a[1:-1, 1:-1]) / (dy * dy)
+        return out
+    an00j00 = L.n00j00
+    if step == 0:
+        rhs = (8.0 / (c * dt * dz) * (-L.np1jp1 + L.n00jp1) * exp1
+               + 2.0 / (c * dt * dz) * (L.np1jp2 - L.n00jp2) * exp2
+               + 2.0 * chi * an00j00
+               - lap(L.n00j00)
+               + (-6.0 / (c * dt * dz) + 4.0 * 1j * djn / (c * dt) + 1j * 4.0 * k0 / (c * dt)) * an00j00)
+        acoeff = 6.0 / (c * dt * dz) - 1j * 4.0 * (k0 + djn) / (c * dt)
+    else:
+        rhs = (4.0 / (c * dt * dz) * (-L.np1jp1 + L.nm1jp1) * exp1
+               + 1.0 / (c * dt * dz) * (L.np1jp2 - L.nm1jp2) * exp2
+               - 4.0 / (c * c * dt * dt) * an00j00
+               + 2.0 * chi * an00j00
+               - lap(L.nm1j00)
+               + (-3.0 / (c * dt * dz) + 2.0 * 1j * djn / (c * dt) + 2.0 / (c * c * dt * dt)
+                  + 1j * 2.0 * k0 / (c * dt)) * L.nm1j00)
+        acoeff = 3.0 / (c * dt * dz) + 2.0 / (c * c * dt * dt) - 1j * 2.0 * (k0 + djn) / (c * dt)
+    rhs_f = np.fft.fft2(rhs)
+    dkx = 2.0 * math.pi / (geom.hi[0] - geom.lo[0])
+    dky = 2.0 * math.pi / (geom.hi[1] - geom.lo[1])
+    ii, jj = np.arange(Nx), np.arange(Ny)
+    kx = np.where(ii < imid, dkx * ii, dkx * (ii - Nx))[None, :]
+    ky = np.where(jj < jmid, dky * jj, dky * (jj - Ny))[:, None]
+    den = kx * kx + ky * ky + acoeff
+    inv = np.where(np.abs(den) > 0.0, 1.0 / np.where(den == 0, 1.0, den), 0.0)
+    L.np1j00 = np.fft.ifft2(-rhs_f * inv)
+
+
 def laser_gather(xp, yp, aabs, geom: 'Geometry', derivatives: bool):
     """doLaserGatherShapeN<2>, particles_utils/FieldGather.H:162-222 (value only) and :236-283
     (value + centred derivatives taken on the grid, then gathered)"""
@@ -1243,8 +1336,12 @@ class Simulation:
         lo = _get(d, 'geometry.prob_lo', n=3)
         hi = _get(d, 'geometry.prob_hi', n=3)
         self.geom = Geometry(n[0], n[1], n[2], tuple(lo), tuple(hi))
-        assert _get(d, 'hipace.depos_order_xy', 2, typ=int) == 2, 'oracle scope: order 2'
+        nothing_deposits = d.get('plasmas.names', ['no_plasma'])[0] == 'no_plasma' \
+            and d.get('beams.names', ['no_beam'])[0] == 'no_beam'
+        assert _get(d, 'hipace.depos_order_xy', 2, typ=int) == 2 or nothing_deposits, 'oracle scope: order 2'
         assert _get(d, 'hipace.depos_derivative_type', 2, typ=int) == 2
+        self.diag_type = _get(d, 'diagnostic.diag_type', 'xyz', typ=str)
+        assert self.diag_type in ('xyz', 'xz'), 'oracle scope: xyz / xz field diagnostics'
         assert _get(d, 'hipace.bxby_solver', 'explicit', typ=str) == 'explicit'
         assert _get(d, 'boundary.field', typ=str) == 'Dirichlet', 'oracle scope: Dirichlet'
         self.bc_kind = _get(d, 'boundary.particle', typ=str)
@@ -1293,8 +1390,13 @@ class Simulation:
                     pft_yz=_get(d, nm + '.PFT_yz', math.pi / 2.0), L0=L0,
                     focal_distance=_get(d, nm + '.focal_distance', 0.0),
                     position_mean=tuple(_get(d, nm + '.position_mean', [0., 0., 0.], n=3))))
-            if self.max_step > 0:
-                raise NotImplementedError('oracle scope: the laser envelope advance is not restated')
+            self.laser_solver = _get(d, 'lasers.solver_type', 'multigrid', typ=str)
+            self.laser_use_phase = bool(_get(d, 'lasers.use_phase', 1, typ=int))
+            if self.max_step > 0 and self.laser_solver != 'fft':
+                raise NotImplementedError('oracle scope: the laser envelope advance is restated for '
+                                          'lasers.solver_type = fft only (hpmg type 2 is not)')
+            self.laser_store = {}           # islice -> (A^n, A^{n-1}) handed from step to step
+            self.laser_next = {}
         self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral, self.use_laser)
         g = self.geom
         self.F = {k: np.zeros((g.ny + 2 * G, g.nx + 2 * G)) for k in self.comps}
@@ -1416,6 +1518,16 @@ class Simulation:
         for pl in self.plasmas:
             init_plasma(pl, self.geom, self.pc, self.normalized, self.bc_lo, self.bc_hi,
                         c_t=self.pc.c * self.time)
+        if self.use_laser:                                        # :733-734, :452 SetInitialChi
+            g = self.geom
+            self.L = LaserSlices(g.ny, g.nx)
+            x = (np.arange(g.nx) * g.dx + g.pos_offset(0))[None, :] + np.zeros((g.ny, 1))
+            y = (np.arange(g.ny) * g.dy + g.pos_offset(1))[:, None] + np.zeros((1, g.nx))
+            self.laser_chi_initial = np.zeros((g.ny, g.nx))
+            for pl in self.plasmas:                               # laser/MultiLaser.cpp:293-332
+                self.laser_chi_initial += pl.density(x, y, self.pc.c * self.time) \
+                    * (pl.charge * pl.charge * self.pc.mu0 / pl.mass)
+            self.laser_next = {}
         for pl in self.plasmas:                                   # :468-470, MultiPlasma.cpp:106-118
             if pl.neutralize_background:
                 deposit_current(pl, self.F, self.geom, self.pc, self.normalized,
@@ -1442,12 +1554,16 @@ class Simulation:
         if self.deposit_rho:
             T('rho')[...] = 0.0
         aabs = None
-        if self.use_laser:                                        # get_data :583, UpdateLaserAabs :603
-            env = laser_envelope_slice(self.lasers, self.laser_lambda0, g, islice)
+        if self.use_laser:                                        # get_data :583 / :640, UpdateLaserAabs :603
+            if self.step == 0:
+                self.L.n00j00 = laser_envelope_slice(self.lasers, self.laser_lambda0, g, islice)
+            else:                                                 # MultiBuffer::unpack_data :913-923
+                self.L.n00j00, self.L.nm1j00 = (a.copy() for a in self.laser_store[islice])
+            env = self.L.n00j00
             update_laser_aabs(env, T('aabs'), g, self.laser_interp_order)
             aabs = T('aabs')
             self.checksums['laserEnvelope'] = self.checksums.get('laserEnvelope', 0.0) \
-                + float(np.abs(env).sum())
+                + float(np.abs(self._diag_rows(env, 0)).sum())
         # plasma deposit (:609-610)
         for pl in self.plasmas:
             self.n_qsa_violation += deposit_current(
@@ -1465,6 +1581,12 @@ class Simulation:
         if self.slice_hook:
             self.slice_hook(self, islice, 'deposited')
         solve_poisson_psi_ez_bz(F, g, pc, self.eig)                               # :633
+        if self.use_laser and self.dt != 0.0:                                     # :637 AdvanceSlice
+            chi = laser_interpolate_chi(T('chi'), self.laser_chi_initial, g, self.laser_interp_order)
+            laser_advance_fft(self.L, chi, g, pc, self.laser_lambda0, self.dt, self.step,
+                              self.laser_use_phase)
+            # MultiBuffer::pack_data :840-851: A^{n+1} and A^n of this slice go to the next step
+            self.laser_next[islice] = (self.L.np1j00.copy(), self.L.n00j00.copy())
         # Next-slice beam jx/jy (:639-657)
         if self.do_beam_jx_jy:
             for b in self.beams:
@@ -1509,6 +1631,18 @@ class Simulation:
         T('jy_beam')[...] = F[('Next', 'jy_beam')]
         T('jx')[...] = F[('Next', 'jx_beam')]
         T('jy')[...] = F[('Next', 'jy_beam')]
+        if self.use_laser:
+            self.L.shift()                                                        # :727
+
+    def _diag_rows(self, a, g):
+        """field diagnostic of one slice (fields/Fields.cpp:413-533): the valid box for 'xyz'; for
+        'xz' the order-1 interpolation to y = mid-domain (diagnostics/Diagnostic.cpp:393-407),
+        i.e. the mean of the two central rows (even ny) or the central row.  g = guard width of a."""
+        ny = a.shape[0] - 2 * g
+        v = a[g:g + ny, g:a.shape[1] - g]
+        if self.diag_type == 'xyz':
+            return v
+        return 0.5 * (v[ny // 2 - 1] + v[ny // 2]) if ny % 2 == 0 else v[ny // 2]
 
     def _accumulate_checksums(self, islice):
         """checksum of a field = sum|Q| over the last iteration's valid cells,
@@ -1516,7 +1650,7 @@ class Simulation:
         is the identity for an uncoarsened xyz diagnostic)."""
         for (sl, nm), a in self.F.items():
             if sl == 'This':
-                self.checksums[nm] = self.checksums.get(nm, 0.0) + float(np.abs(a[G:-G, G:-G]).sum())
+                self.checksums[nm] = self.checksums.get(nm, 0.0) + float(np.abs(self._diag_rows(a, G)).sum())
 
     def evolve(self, nslices: int | None = None, step_begin: int = 0, step_end: int = 0):
         """Run time steps step_begin..step_end (Hipace.cpp:401-507); the checksums returned are
@@ -1529,6 +1663,8 @@ class Simulation:
             self.begin_step(step)
             for isl in range(g.nz - 1, stop, -1):
                 self.solve_one_slice(isl)
+            if self.use_laser:
+                self.laser_store = self.laser_next
         return self.checksums
 
     def beam_checksums(self):

@@ -50,6 +50,11 @@ CASES = {
                    'laser.a0': 4.5, 'laser.position_mean': '0. 0. 0', 'laser.w0': 4, 'laser.L0': 2,
                    'amr.n_cell': '128 128 100'},
         rtol_cpu=1e-9, rtol_cuda=1e-9, skip=['Sy', 'Sx', 'chi']),
+    # tests/laser_evolution.SI.2Rank.sh:29-44: the envelope ADVANCE over 31 time steps in vacuum (the
+    # checksummed output is the one of the fft solver run), xz diagnostic
+    'laser_evolution.SI.2Rank': dict(
+        deck='examples/laser_vacuum_SI.in', overrides={'lasers.solver_type': 'fft'},
+        rtol_cpu=1e-12, rtol_cuda=1e-7),
     # tests/linear_wake.SI.1Rank.sh:30-34: SI units with a beam and the rho diagnostic
     'linear_wake.SI.1Rank': dict(
         deck='examples/linear_wake_SI.in', overrides={'diagnostic.field_data': 'all rho'},

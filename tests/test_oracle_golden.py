@@ -26,7 +26,8 @@ def _run(case, repo_root):
 
 @pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank',
                                   'beam_evolution.1Rank', 'laser_blowout_wake_explicit.SI.1Rank',
-                                  'laser_blowout_wake_explicit.1Rank', 'linear_wake.SI.1Rank'])
+                                  'laser_blowout_wake_explicit.1Rank', 'linear_wake.SI.1Rank',
+                                  'laser_evolution.SI.2Rank'])
 def test_oracle_matches_reference_golden(case, repo_root):
     meta, sim, cs = _run(case, repo_root)
     gold = meta['checksums']
