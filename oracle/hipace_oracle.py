@@ -940,6 +940,128 @@ class MultiGrid1:
         self.cor[0], self.rescor[0] = gsrb4_res(sol0, rhs0, 0, False, True)     # :1501-1503
 
 
+class MultiGrid2(MultiGrid1):
+    """hpmg::MultiGrid with system_type 2 (the laser envelope solver, laser/MultiLaser.cpp:598-606):
+    the complex system  lap(A) - (a_r + i a_i) A = rhs  as two coupled real components; gs2
+    (mg_solver/HpMultiGrid.cpp:296-334), residual2r / residual2i (:192-208); everything else (V-cycle,
+    transfer operators, stopping rule) is shared with type 1.  acf arrays are [2, ny, nx] = (a_r, a_i).
+    Not pinned by a golden of its own (the reference checksums only its fft-solver run): validated
+    against the pinned fft restatement to the multigrid tolerance (tests/test_oracle_golden.py)."""
+
+    def gsrb(self, phi, rhs, acf, facx, facy, nsweeps, first_color=0):
+        ar, ai = acf[0], acf[1]
+        if self.cc:
+            par = self._masks(phi.shape[-2:])
+            c0 = self._c0(np.zeros_like(ar), facx, facy)          # -2 (facx + facy) + boundary terms
+            sl = (slice(None), slice(None))
+        else:
+            ny, nx = phi.shape[-2:]
+            j, i = np.meshgrid(np.arange(1, ny - 1), np.arange(1, nx - 1), indexing='ij')
+            par = i + j
+            ar, ai = ar[1:-1, 1:-1], ai[1:-1, 1:-1]
+            c0 = -2.0 * (facx + facy) + np.zeros_like(ar)
+            sl = (slice(1, -1), slice(1, -1))
+        c_r, c_i = c0 - ar, -ai
+        cmag = 1.0 / (c_r * c_r + c_i * c_i)
+        c_r, c_i = c_r * cmag, c_i * cmag
+        for ic in range(first_color, first_color + nsweeps):
+            m = ((par + ic) % 2 == 0)
+            if self.cc:
+                lap = self._lap_offdiag(phi, facx, facy)
+            else:
+                lap = (facx * (phi[:, 1:-1, :-2] + phi[:, 1:-1, 2:])
+                       + facy * (phi[:, :-2, 1:-1] + phi[:, 2:, 1:-1]))
+            dr, di = rhs[0][sl] - lap[0], rhs[1][sl] - lap[1]
+            new_r = dr * c_r + di * c_i
+            new_i = di * c_r - dr * c_i
+            v = phi[(slice(None),) + sl]
+            v[0][m] = new_r[m]
+            v[1][m] = new_i[m]
+        return phi
+
+    def residual(self, phi, rhs, acf, facx, facy):
+        out = np.zeros_like(phi)
+        if self.cc:
+            lap = -2.0 * (facx + facy) * phi
+            lap = lap + self._lap_offdiag_x(phi, facx)
+            lap = lap + self._lap_offdiag_y(phi, facy)
+            out[0] = rhs[0] + acf[0] * phi[0] - acf[1] * phi[1] - lap[0]
+            out[1] = rhs[1] + acf[1] * phi[0] + acf[0] * phi[1] - lap[1]
+        else:
+            inner = phi[:, 1:-1, 1:-1]
+            lap = -2.0 * (facx + facy) * inner
+            lap = lap + facx * (phi[:, 1:-1, :-2] + phi[:, 1:-1, 2:])
+            lap = lap + facy * (phi[:, :-2, 1:-1] + phi[:, 2:, 1:-1])
+            ar, ai = acf[0][1:-1, 1:-1], acf[1][1:-1, 1:-1]
+            out[0, 1:-1, 1:-1] = rhs[0, 1:-1, 1:-1] + ar * inner[0] - ai * inner[1] - lap[0]
+            out[1, 1:-1, 1:-1] = rhs[1, 1:-1, 1:-1] + ai * inner[0] + ar * inner[1] - lap[1]
+        return out
+
+    def solve2(self, sol, rhs, acf_r, acf_i, tol_rel=1e-4, tol_abs=0.0, maxiter=200):
+        """solve2 (:1192-1296): acf_r / acf_i may be scalars or valid-box arrays"""
+        shape = sol.shape[-2:]
+        acf = np.stack([np.broadcast_to(np.asarray(acf_r, dtype=float), shape),
+                        np.broadcast_to(np.asarray(acf_i, dtype=float), shape)])
+        return self.solve1(sol, rhs, acf, tol_rel, tol_abs, maxiter)
+
+
+def laser_advance_mg(L: 'LaserSlices', chi, geom: 'Geometry', pc: 'PhysConst', lambda0, dt, step, mg,
+                     use_phase=True, do_avg_rhs=True, tol_rel=1e-4, tol_abs=0.0):
+    """MultiLaser::AdvanceSliceMG, laser/MultiLaser.cpp:429-607 (the default laser solver): the same
+    discretisation as the fft variant with chi treated per cell in the operator (do_avg_rhs) and
+    the Helmholtz system solved by hpmg type 2 from the previous slice's A^{n+1} as initial guess"""
+    dx, dy, dz, c = geom.dx, geom.dy, geom.dz, pc.c
+    k0 = 2.0 * math.pi / lambda0
+    Ny, Nx = L.n00j00.shape
+    imid, jmid = (Nx + 1) // 2, (Ny + 1) // 2
+    tj00 = tjp1 = tjp2 = 0.0
+    if use_phase:
+        keep_x = [imid - 1, imid] if Nx % 2 == 0 else [imid]
+        keep_y = [jmid - 1, jmid] if Ny % 2 == 0 else [jmid]
+        ax = lambda a: a[np.ix_(keep_y, keep_x)].sum()
+        h0, h1, h2 = ax(L.n00j00), ax(L.n00jp1), ax(L.n00jp2)
+        tj00, tjp1, tjp2 = (math.atan2(h.imag, h.real) for h in (h0, h1, h2))
+    dt1, dt2 = tj00 - tjp1, tjp1 - tjp2
+    if dt1 < -1.5 * math.pi: dt1 += 2.0 * math.pi
+    if dt1 > 1.5 * math.pi: dt1 -= 2.0 * math.pi
+    if dt2 < -1.5 * math.pi: dt2 += 2.0 * math.pi
+    if dt2 > 1.5 * math.pi: dt2 -= 2.0 * math.pi
+    exp1 = np.exp(1j * (tj00 - tjp1))
+    exp2 = np.exp(1j * (tj00 - tjp2))
+    djn = (-3.0 * dt1 + dt2) / (2.0 * dz)
+    if step == 0:
+        acoeff_real = 6.0 / (c * dt * dz)
+        acoeff_imag = -4.0 * (k0 + djn) / (c * dt)
+    else:
+        acoeff_real = 3.0 / (c * dt * dz) + 2.0 / (c * c * dt * dt)
+        acoeff_imag = -2.0 * (k0 + djn) / (c * dt)
+
+    def lap(a):
+        out = np.zeros_like(a)
+        out[1:-1, 1:-1] = (a[1:-1, 2:] + a[1:-1, :-2] - 2.0 * a[1:-1, 1:-1]) / (dx * dx) \
+            + (a[2:, 1:-1] + a[:-2, 1:-1] - 2.0 * a[1:-1, 1:-1]) / (dy * dy)
+        return out
+    an00j00 = L.n00j00
+    if step == 0:
+        rhs = (8.0 / (c * dt * dz) * (-L.np1jp1 + L.n00jp1) * exp1
+               + 2.0 / (c * dt * dz) * (L.np1jp2 - L.n00jp2) * exp2
+               - lap(L.n00j00)
+               + (-6.0 / (c * dt * dz) + 4.0 * 1j * djn / (c * dt) + 1j * 4.0 * k0 / (c * dt)) * an00j00)
+        rhs = rhs + (chi * an00j00 if do_avg_rhs else chi * an00j00 * 2.0)
+    else:
+        rhs = (4.0 / (c * dt * dz) * (-L.np1jp1 + L.nm1jp1) * exp1
+               + 1.0 / (c * dt * dz) * (L.np1jp2 - L.nm1jp2) * exp2
+               - 4.0 / (c * c * dt * dt) * an00j00
+               - lap(L.nm1j00)
+               + (-3.0 / (c * dt * dz) + 2.0 * 1j * djn / (c * dt) + 2.0 / (c * c * dt * dt)
+                  + 1j * 2.0 * k0 / (c * dt)) * L.nm1j00)
+        rhs = rhs + (chi * L.nm1j00 if do_avg_rhs else chi * an00j00 * 2.0)
+    acf_r = acoeff_real + chi if do_avg_rhs else acoeff_real
+    sol = np.stack([L.np1j00.real, L.np1j00.imag]).copy()          # initial guess: what np1j00 holds
+    mg.solve2(sol, np.stack([rhs.real, rhs.imag]), acf_r, acoeff_imag, tol_rel, tol_abs, 200)
+    L.np1j00 = sol[0] + 1j * sol[1]
+
+
 # ---- gather + push ------------------------------------------------------------------------
 
 def _momentum_push(ux, uy, psi_inv, ExmBy, EypBx, Ez, Bx_c, By_c, Bz, clight_inv, qmc,
@@ -1392,9 +1514,11 @@ class Simulation:
                     position_mean=tuple(_get(d, nm + '.position_mean', [0., 0., 0.], n=3))))
             self.laser_solver = _get(d, 'lasers.solver_type', 'multigrid', typ=str)
             self.laser_use_phase = bool(_get(d, 'lasers.use_phase', 1, typ=int))
-            if self.max_step > 0 and self.laser_solver != 'fft':
-                raise NotImplementedError('oracle scope: the laser envelope advance is restated for '
-                                          'lasers.solver_type = fft only (hpmg type 2 is not)')
+            assert self.laser_solver in ('fft', 'multigrid')
+            self.laser_mg_tol_rel = _get(d, 'lasers.MG_tolerance_rel', 1e-4)
+            self.laser_mg_tol_abs = _get(d, 'lasers.MG_tolerance_abs', 0.0)
+            self.laser_mg_avg_rhs = bool(_get(d, 'lasers.MG_average_rhs', 1, typ=int))
+            self.laser_mg = None
             self.laser_store = {}           # islice -> (A^n, A^{n-1}) handed from step to step
             self.laser_next = {}
         self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral, self.use_laser)
@@ -1583,8 +1707,15 @@ class Simulation:
         solve_poisson_psi_ez_bz(F, g, pc, self.eig)                               # :633
         if self.use_laser and self.dt != 0.0:                                     # :637 AdvanceSlice
             chi = laser_interpolate_chi(T('chi'), self.laser_chi_initial, g, self.laser_interp_order)
-            laser_advance_fft(self.L, chi, g, pc, self.laser_lambda0, self.dt, self.step,
-                              self.laser_use_phase)
+            if self.laser_solver == 'fft':
+                laser_advance_fft(self.L, chi, g, pc, self.laser_lambda0, self.dt, self.step,
+                                  self.laser_use_phase)
+            else:
+                if self.laser_mg is None:
+                    self.laser_mg = MultiGrid2(g.dx, g.dy, g.nx, g.ny)
+                laser_advance_mg(self.L, chi, g, pc, self.laser_lambda0, self.dt, self.step,
+                                 self.laser_mg, self.laser_use_phase, self.laser_mg_avg_rhs,
+                                 self.laser_mg_tol_rel, self.laser_mg_tol_abs)
             # MultiBuffer::pack_data :840-851: A^{n+1} and A^n of this slice go to the next step
             self.laser_next[islice] = (self.L.np1j00.copy(), self.L.n00j00.copy())
         # Next-slice beam jx/jy (:639-657)

@@ -40,3 +40,18 @@ def test_oracle_matches_reference_golden(case, repo_root):
             # (the reference's files hold charge, mass and positions to ~13 digits only)
             assert abs(bc[name] - want) <= max(RTOL, 1e-12) * abs(want) + 1e-40, (name, bc[name], want)
     assert sim.n_qsa_violation == 0
+
+
+def test_laser_multigrid_solver_agrees_with_pinned_fft_solver(repo_root):
+    """hpmg system type 2 (the reference's default laser solver) has no golden of its own -- the
+    reference checksums only its fft-solver run.  Its restatement must reproduce the pinned fft
+    restatement to the multigrid tolerance (1e-4 per solve; Dirichlet instead of periodic
+    transverse boundaries, irrelevant for a pulse that stays away from them)."""
+    deck = open(os.path.join(repo_root, 'examples', 'laser_vacuum_SI.in')).read()
+    out = {}
+    for solver in ('fft', 'multigrid'):
+        sim = Simulation(deck, {'lasers.solver_type': solver, 'max_step': 2})
+        out[solver] = sim.evolve(step_end=2)
+    for k in ('aabs', 'laserEnvelope'):
+        a, b = out['multigrid'][k], out['fft'][k]
+        assert abs(a - b) <= 1e-3 * abs(b), (k, a, b)
