@@ -35,7 +35,8 @@ try:  # SciPy is only needed for the Poisson solve
 except Exception:  # pragma: no cover
     _dstn = None
 
-G = 2  # guard cells for depos_order_xy = 2: (order+1)/2 + 1, fields/Fields.cpp:63-64
+G = 2  # guard cells of the DEFAULT depos_order_xy = 2 (Geometry.g holds the deck's; this constant
+       # is what the order-2-only C port and the CUDA parity tests index with)
 
 
 # --------------------------------------------------------------------------------------------
@@ -177,6 +178,104 @@ def dshape_nodal_order2(xmid):
     return s, -sdx, xfloor.astype(np.int64) - 1
 
 
+def _bspline_pieces(nmax=3):
+    """Polynomial pieces of the uniform B-spline B_n on the knots 0..n+1 (Cox-de Boor):
+    B_n(i + f) = P[n][i](f), 0 <= f < 1 -- the closed form behind every table of ShapeFactors.H,
+    S_n(x) = B_n(x + (n+1)/2).  Coefficients low order first."""
+    from numpy.polynomial import polynomial as npoly
+    P = {0: [np.array([1.0])]}
+    for n in range(1, nmax + 1):
+        P[n] = []
+        for i in range(n + 1):
+            acc = np.zeros(n + 1)
+            if i <= n - 1:
+                acc = npoly.polyadd(acc, npoly.polymul([i / n, 1.0 / n], P[n - 1][i]))
+            if i >= 1:
+                acc = npoly.polyadd(acc, npoly.polymul([(n + 1 - i) / n, -1.0 / n], P[n - 1][i - 1]))
+            P[n].append(acc)
+    return P
+
+
+_BP = _bspline_pieces()
+
+
+def _piece(n, i, f, deriv=False):
+    """B_n (or its derivative) on its piece i at local coordinate f; 0 outside the support"""
+    if i < 0 or i > n:
+        return np.zeros_like(f)
+    c = _BP[n][i]
+    if deriv:
+        c = c[1:] * np.arange(1, len(c))
+        if len(c) == 0:
+            return np.zeros_like(f)
+    out = np.full_like(f, c[-1])
+    for a in c[-2::-1]:
+        out = out * f + a
+    return out
+
+
+def _bspline_at(n, halves, xint, deriv=False):
+    """B_n at t = xint + halves/2, 0 <= xint < 1: a whole number of cells picks the piece outright;
+    a half-cell offset needs the one test the reference's tables have, xint < 0.5"""
+    if halves % 2 == 0:
+        return _piece(n, halves // 2, xint, deriv)
+    return np.where(xint < 0.5, _piece(n, (halves - 1) // 2, xint + 0.5, deriv),
+                    _piece(n, (halves + 1) // 2, xint - 0.5, deriv))
+
+
+def _cell_and_xint(m, xmid):
+    """leftmost cell of an order-m stencil and the in-cell coordinate it is counted from:
+    even m hang on the nearest cell (floor(xmid + 1/2)), odd m on floor(xmid)"""
+    xm = xmid + 0.5 if m % 2 == 0 else xmid
+    xfloor = np.floor(xm)
+    return xfloor.astype(np.int64) - (m // 2 if m % 2 == 0 else (m - 1) // 2), xm - xfloor
+
+
+def shape(order, xmid):
+    """compute_shape_factor<order> / compute_single_shape_factor<.,order>, ShapeFactors.H:40-117,
+    122-195: (weights[order+1, P], leftmost cell[P]).  Order 2 keeps the literal polynomials."""
+    if order == 2:
+        return shape_order2(xmid)
+    j0, xint = _cell_and_xint(order, xmid)
+    return np.stack([_bspline_at(order, 2 * (order - k), xint) for k in range(order + 1)]), j0
+
+
+def dshape(dtype, order, xmid):
+    """single_derivative_shape_factor<dtype, order>, ShapeFactors.H:211-466:
+    (S[m, P], dS[m, P] (the '-sdx' the reference returns), leftmost cell[P]), m = order+dtype+1.
+    The tables of the reference are, per cell at distance x = xmid - cell,
+      weight S_order(x) and
+      type 0 (analytic):  -S_order'(x)
+      type 1 (nodal):      S_order(x - 1/2) - S_order(x + 1/2)     (staggered difference)
+      type 2 (centred):   (S_order(x - 1) - S_order(x + 1)) / 2    (central difference)
+    with the stencil of order+1 for type 1 and the order's own stencil grown by one cell on both
+    sides for type 2.  Pinned to the reference's header itself in tests/test_oracle_refheaders.py."""
+    if order == 2 and dtype == 2:
+        return dshape_centered_order2(xmid)
+    if order == 2 and dtype == 1:
+        return dshape_nodal_order2(xmid)
+    m = order + 1 if dtype == 1 else order
+    e = 1 if dtype == 2 else 0
+    j0, xint = _cell_and_xint(m, xmid)
+    j0 = j0 - e
+    s, ds = [], []
+    for k in range(order + dtype + 1):
+        h = m + order + 2 * e - 2 * k          # t = x + (order+1)/2 = xint + h/2
+        s.append(_bspline_at(order, h, xint))
+        if dtype == 0:
+            ds.append(-_bspline_at(order, h, xint, deriv=True))
+        elif dtype == 1:
+            ds.append(_bspline_at(order, h - 1, xint) - _bspline_at(order, h + 1, xint))
+        else:
+            ds.append(0.5 * (_bspline_at(order, h - 2, xint) - _bspline_at(order, h + 2, xint)))
+    return np.stack(s), np.stack(ds), j0
+
+
+def n_guards(order):
+    """fields/Fields.cpp:63-64"""
+    return (order + 1) // 2 + 1
+
+
 # --------------------------------------------------------------------------------------------
 # Geometry and field storage
 # --------------------------------------------------------------------------------------------
@@ -188,6 +287,12 @@ class Geometry:
     nz: int
     lo: tuple
     hi: tuple
+    order: int = 2      # hipace.depos_order_xy
+    dtype: int = 2      # hipace.depos_derivative_type
+
+    @property
+    def g(self):
+        return n_guards(self.order)
 
     @property
     def dx(self):
@@ -206,7 +311,7 @@ class Geometry:
         both give lo + dx/2 up to round-off; we follow the formula literally)."""
         n = (self.nx, self.ny, self.nz)[d]
         dd = (self.dx, self.dy, self.dz)[d]
-        g = G if d < 2 else 0
+        g = self.g if d < 2 else 0
         return 0.5 * (self.lo[d] + self.hi[d] - dd * ((-g) + (n - 1 + g)))
 
 
@@ -354,6 +459,7 @@ def update_laser_aabs(env, aabs, geom: 'Geometry', interp_order: int):
     """MultiLaser::UpdateLaserAabs, laser/MultiLaser.cpp:214-291: |a|^2 of the current envelope
     interpolated (order interp_order) from the laser grid to the grown field slice"""
     a2 = env.real * env.real + env.imag * env.imag                   # abssq
+    G = geom.g
     ii = np.arange(-G, geom.nx + G)
     jj = np.arange(-G, geom.ny + G)
     # same geometry for both grids: xmid = ((i dx + off) - off) / dx
@@ -392,6 +498,7 @@ class LaserSlices:
 
 
 def laser_interpolate_chi(chi_field, chi_initial, geom: 'Geometry', interp_order: int):
+    G = geom.g
     """MultiLaser::InterpolateChi, laser/MultiLaser.cpp:334-407 for coinciding grids: chi of the
     field slice inside the field box shrunk by 2 guard widths, the initial chi outside"""
     ii, jj = np.arange(geom.nx), np.arange(geom.ny)
@@ -467,16 +574,17 @@ def laser_advance_fft(L: 'LaserSlices', chi, geom: 'Geometry', pc: 'PhysConst', 
 
 
 def laser_gather(xp, yp, aabs, geom: 'Geometry', derivatives: bool):
-    """doLaserGatherShapeN<2>, particles_utils/FieldGather.H:162-222 (value only) and :236-283
-    (value + centred derivatives taken on the grid, then gathered)"""
+    """doLaserGatherShapeN<order>, particles_utils/FieldGather.H:236-283 (value + centred
+    derivatives taken on the grid, then gathered) and :299-330 (value only)"""
+    G, n = geom.g, geom.order + 1
     x = (xp - geom.pos_offset(0)) * (1.0 / geom.dx)
     y = (yp - geom.pos_offset(1)) * (1.0 / geom.dy)
-    sx, i0 = shape_order2(x)
-    sy, j0 = shape_order2(y)
+    sx, i0 = shape(geom.order, x)
+    sy, j0 = shape(geom.order, y)
     dx_inv, dy_inv = 1.0 / geom.dx, 1.0 / geom.dy
     A = np.zeros_like(xp); ADx = np.zeros_like(xp); ADy = np.zeros_like(xp)
-    for iy in range(3):
-        for ix in range(3):
+    for iy in range(n):
+        for ix in range(n):
             i, j = i0 + ix + G, j0 + iy + G
             w = sx[ix] * sy[iy]
             A += w * aabs[j, i]
@@ -486,7 +594,7 @@ def laser_gather(xp, yp, aabs, geom: 'Geometry', derivatives: bool):
     return A, ADx, ADy
 
 
-def _scatter(arr, jj, ii, vals):
+def _scatter(arr, jj, ii, vals, G):
     """arr[jj+G, ii+G] += vals, duplicates accumulated (Gpu::Atomic::Add semantics).
     np.bincount sums in a fixed order, so the oracle itself is deterministic."""
     ny_t, nx_t = arr.shape
@@ -528,22 +636,23 @@ def deposit_current(pl: Plasma, F: dict, geom: Geometry, pc: PhysConst, normaliz
         return n_bad
     xmid = (pl.x[sel] - x_off) * dx_inv
     ymid = (pl.y[sel] - y_off) * dy_inv
-    sx, i0 = shape_order2(xmid)
-    sy, j0 = shape_order2(ymid)
+    sx, i0 = shape(geom.order, xmid)
+    sy, j0 = shape(geom.order, ymid)
     q_invvol = charge_invvol * pl.w[sel]
     psi_inv, vx_c, vy_c, gamma_psi = psi_inv[sel], vx_c[sel], vy_c[sel], gamma_psi[sel]
-    ii = np.stack([i0 + ix for iy in range(3) for ix in range(3)])
-    jj = np.stack([j0 + iy for iy in range(3) for ix in range(3)])
-    cd = np.stack([q_invvol * sx[ix] * sy[iy] for iy in range(3) for ix in range(3)])  # :218
+    n, G = geom.order + 1, geom.g
+    ii = np.stack([i0 + ix for iy in range(n) for ix in range(n)])
+    jj = np.stack([j0 + iy for iy in range(n) for ix in range(n)])
+    cd = np.stack([q_invvol * sx[ix] * sy[iy] for iy in range(n) for ix in range(n)])  # :218
     if jx is not None:
-        _scatter(jx, jj, ii, cd * vx_c)
-        _scatter(jy, jj, ii, cd * vy_c)
+        _scatter(jx, jj, ii, cd * vx_c, G)
+        _scatter(jy, jj, ii, cd * vy_c, G)
     if rho is not None:
-        _scatter(rho, jj, ii, cd * gamma_psi)
+        _scatter(rho, jj, ii, cd * gamma_psi, G)
     if chi is not None:
-        _scatter(chi, jj, ii, cd * charge_mu0_mass_ratio * psi_inv)
+        _scatter(chi, jj, ii, cd * charge_mu0_mass_ratio * psi_inv, G)
     if rhomjz is not None:
-        _scatter(rhomjz, jj, ii, cd)
+        _scatter(rhomjz, jj, ii, cd, G)
     return n_bad
 
 
@@ -561,18 +670,33 @@ def beam_deposit(bs: dict, beam: Beam, geom: Geometry, pc: PhysConst, normalized
     ux, uy, uz = bs['ux'], bs['uy'], bs['uz']
     gaminv = 1.0 / np.sqrt(1.0 + ux * ux * clightsq + uy * uy * clightsq + uz * uz * clightsq)
     wq = beam.charge * bs['w'] * invvol
-    sx, i0 = shape_order2((bs['x'] - x_off) / geom.dx)
-    sy, j0 = shape_order2((bs['y'] - y_off) / geom.dy)
-    ii = np.stack([i0 + ix for iy in range(3) for ix in range(3)])
-    jj = np.stack([j0 + iy for iy in range(3) for ix in range(3)])
-    ss = np.stack([sx[ix] * sy[iy] for iy in range(3) for ix in range(3)])
+    sx, i0 = shape(geom.order, (bs['x'] - x_off) / geom.dx)
+    sy, j0 = shape(geom.order, (bs['y'] - y_off) / geom.dy)
+    n, G = geom.order + 1, geom.g
+    ii = np.stack([i0 + ix for iy in range(n) for ix in range(n)])
+    jj = np.stack([j0 + iy for iy in range(n) for ix in range(n)])
+    ss = np.stack([sx[ix] * sy[iy] for iy in range(n) for ix in range(n)])
     v = bs['valid']
     ii, jj, ss = ii[:, v], jj[:, v], ss[:, v]
     if jxb is not None:
-        _scatter(jxb, jj, ii, ss * (wq * ux * gaminv)[v])
-        _scatter(jyb, jj, ii, ss * (wq * uy * gaminv)[v])
+        _scatter(jxb, jj, ii, ss * (wq * ux * gaminv)[v], G)
+        _scatter(jyb, jj, ii, ss * (wq * uy * gaminv)[v], G)
     if jzb is not None:
-        _scatter(jzb, jj, ii, ss * (wq * uz * gaminv)[v])
+        _scatter(jzb, jj, ii, ss * (wq * uz * gaminv)[v], G)
+
+
+def grid_current_deposit(jz, geom: Geometry, islice: int, peak, mean, std):
+    """GridCurrent::DepositCurrentSlice, utils/GridCurrent.cpp:25-70: an analytic gaussian current
+    density added to jz_beam on the valid box (cell centres plo + (i + 1/2) dx, z = plo + islice dz)"""
+    G = geom.g
+    z = geom.lo[2] + islice * geom.dz
+    dz_ = (z - mean[2]) / std[2]
+    long_f = math.exp(-0.5 * (dz_ * dz_))
+    x = geom.lo[0] + (np.arange(geom.nx) + 0.5) * geom.dx
+    y = geom.lo[1] + (np.arange(geom.ny) + 0.5) * geom.dy
+    ddx = ((x - mean[0]) / std[0])[None, :]
+    ddy = ((y - mean[1]) / std[1])[:, None]
+    jz[G:-G, G:-G] += peak * np.exp(-0.5 * (ddx * ddx + ddy * ddy)) * long_f
 
 
 def poisson_eigenvalues(nx, ny, dx, dy):
@@ -591,37 +715,35 @@ def poisson_dirichlet(rhs, eig):
     return _dstn(_dstn(rhs, type=1) * eig, type=1)
 
 
-def _ddx(a, dx):
+def _ddx(a, dx, G):
     """derivative<x> on the valid box, fields/Fields.cpp:223-235: (f[i+1]-f[i-1]) * 0.5/dx"""
     return (a[G:-G, G + 1:a.shape[1] - G + 1] - a[G:-G, G - 1:a.shape[1] - G - 1]) * (0.5 / dx)
 
 
-def _ddy(a, dy):
+def _ddy(a, dy, G):
     return (a[G + 1:a.shape[0] - G + 1, G:-G] - a[G - 1:a.shape[0] - G - 1, G:-G]) * (0.5 / dy)
 
 
 def solve_poisson_psi_ez_bz(F, geom: Geometry, pc: PhysConst, eig):
     """Fields::SolvePoissonPsiExmByEypBxEzBz, fields/Fields.cpp:840-957 (lev 0, Dirichlet)."""
-    dx, dy = geom.dx, geom.dy
+    dx, dy, G = geom.dx, geom.dy, geom.g
     T = lambda n: F[('This', n)]
     T('Psi')[G:-G, G:-G] = poisson_dirichlet((-1.0 / pc.ep0) * T('rhomjz')[G:-G, G:-G], eig)
     f = 1.0 / (pc.ep0 * pc.c)
-    T('Ez')[G:-G, G:-G] = poisson_dirichlet(f * _ddx(T('jx'), dx) + f * _ddy(T('jy'), dy), eig)
-    T('Bz')[G:-G, G:-G] = poisson_dirichlet(pc.mu0 * _ddy(T('jx'), dy)
-                                            + (-pc.mu0) * _ddx(T('jy'), dx), eig)
-    # ExmBy / EypBx on the box grown by g-1 = 1 (:931-956)
+    T('Ez')[G:-G, G:-G] = poisson_dirichlet(f * _ddx(T('jx'), dx, G) + f * _ddy(T('jy'), dy, G), eig)
+    T('Bz')[G:-G, G:-G] = poisson_dirichlet(pc.mu0 * _ddy(T('jx'), dy, G)
+                                            + (-pc.mu0) * _ddx(T('jy'), dx, G), eig)
+    # ExmBy / EypBx on the box grown by g-1, i.e. everything but the outermost ring (:931-956)
     psi = T('Psi')
-    s = slice(G - 1, -(G - 1))
     ny_t, nx_t = psi.shape
-    T('ExmBy')[s, s] = -(psi[G - 1:ny_t - G + 1, G:nx_t - G + 2]
-                         - psi[G - 1:ny_t - G + 1, G - 2:nx_t - G]) * (0.5 / dx)
-    T('EypBx')[s, s] = -(psi[G:ny_t - G + 2, G - 1:nx_t - G + 1]
-                         - psi[G - 2:ny_t - G, G - 1:nx_t - G + 1]) * (0.5 / dy)
+    s = (slice(1, ny_t - 1), slice(1, nx_t - 1))
+    T('ExmBy')[s] = -(psi[1:ny_t - 1, 2:nx_t] - psi[1:ny_t - 1, 0:nx_t - 2]) * (0.5 / dx)
+    T('EypBx')[s] = -(psi[2:ny_t, 1:nx_t - 1] - psi[0:ny_t - 2, 1:nx_t - 1]) * (0.5 / dy)
 
 
 def init_sxsy_with_beam(F, geom: Geometry, pc: PhysConst):
     """Hipace::InitializeSxSyWithBeam, Hipace.cpp:744-790 (valid box)."""
-    dx, dy, dz = geom.dx, geom.dy, geom.dz
+    dx, dy, dz, G = geom.dx, geom.dy, geom.dz, geom.g
     jzb = F[('This', 'jz_beam')]
     ny_t, nx_t = jzb.shape
     v = (slice(G, -G), slice(G, -G))
@@ -635,7 +757,8 @@ def init_sxsy_with_beam(F, geom: Geometry, pc: PhysConst):
 
 def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized: bool, aabs=None):
     """::ExplicitDeposition, particles/deposition/ExplicitDeposition.cpp:20-263
-    (depos_order 2, derivative_type 2; laser terms :167-175, :211-226, :234, :250)."""
+    (any depos_order 0..3 / derivative_type 0..2; laser terms :167-175, :211-226, :234, :250)."""
+    G, nst = geom.g, geom.order + geom.dtype + 1
     sel = pl.valid
     if not sel.any():
         return
@@ -659,15 +782,15 @@ def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized
         Aabssqp = laser_gather(pl.x[sel], pl.y[sel], aabs, geom, False)[0] \
             * (laser_fac * q_mass_ratio * q_mass_ratio)
     gamma_psi = 0.5 * ((1.0 + 0.5 * Aabssqp) * psi_inv * psi_inv + vx * vx + vy * vy + 1.0)   # :177-182
-    sx, dsx, i0 = dshape_centered_order2(xmid)
-    sy, dsy, j0 = dshape_centered_order2(ymid)
+    sx, dsx, i0 = dshape(geom.dtype, geom.order, xmid)
+    sy, dsy, j0 = dshape(geom.dtype, geom.order, ymid)
     Bz, Ez = F[('This', 'Bz')], F[('This', 'Ez')]
     ExmBy, EypBx = F[('This', 'ExmBy')], F[('This', 'EypBx')]
     Sy, Sx = F[('This', 'Sy')], F[('This', 'Sx')]
     ii_l, jj_l, sy_l, sx_l = [], [], [], []
-    for iy in range(5):
-        for ix in range(5):
-            if ix in (0, 4) and iy in (0, 4):
+    for iy in range(nst):
+        for ix in range(nst):
+            if geom.dtype == 2 and ix in (0, nst - 1) and iy in (0, nst - 1):
                 continue                                                      # :193-198
             i, j = i0 + ix, j0 + iy
             shx, shdx, shy, shdy = sx[ix], dsx[ix], sy[iy], dsy[iy]
@@ -701,8 +824,8 @@ def explicit_deposition(pl: Plasma, F, geom: Geometry, pc: PhysConst, normalized
                    + shx * shdy * dy_inv * (- vx * vy)) * a_clight)
             ii_l.append(i); jj_l.append(j); sy_l.append(val_sy); sx_l.append(val_sx)
     ii, jj = np.stack(ii_l), np.stack(jj_l)
-    _scatter(Sy, jj, ii, np.stack(sy_l))
-    _scatter(Sx, jj, ii, np.stack(sx_l))
+    _scatter(Sy, jj, ii, np.stack(sy_l), G)
+    _scatter(Sx, jj, ii, np.stack(sx_l), G)
 
 
 # ---- hpmg (mg_solver/HpMultiGrid.cpp), system type 1 ---------------------------------------
@@ -1132,18 +1255,20 @@ def _momentum_push_dual(ux, uxe, uy, uye, pi, pie, ExmBy, EypBx, Ez, Bx_c, By_c,
 
 
 def gather_fields(xp, yp, F, geom: Geometry):
-    """doGatherShapeN<2>, particles/particles_utils/FieldGather.H:45-96"""
+    """doGatherShapeN<order>, particles/particles_utils/FieldGather.H:45-96 (always the nodal
+    derivative shapes, whatever hipace.depos_derivative_type says)"""
+    G, nst = geom.g, geom.order + 2
     x_off, y_off = geom.pos_offset(0), geom.pos_offset(1)
     dx_inv, dy_inv = 1.0 / geom.dx, 1.0 / geom.dy
     x = (xp - x_off) * dx_inv
     y = (yp - y_off) * dy_inv
-    sx, dsx, i0 = dshape_nodal_order2(x)
-    sy, dsy, j0 = dshape_nodal_order2(y)
+    sx, dsx, i0 = dshape(1, geom.order, x)
+    sy, dsy, j0 = dshape(1, geom.order, y)
     Psi, Ez, Bx, By, Bz = (F[('This', n)] for n in ('Psi', 'Ez', 'Bx', 'By', 'Bz'))
     ExmByp = np.zeros_like(xp); EypBxp = np.zeros_like(xp); Ezp = np.zeros_like(xp)
     Bxp = np.zeros_like(xp); Byp = np.zeros_like(xp); Bzp = np.zeros_like(xp)
-    for iy in range(4):
-        for ix in range(4):
+    for iy in range(nst):
+        for ix in range(nst):
             i, j = i0 + ix + G, j0 + iy + G
             psi_v = Psi[j, i]
             ExmByp += (dsx[ix] * sy[iy]) * psi_v * dx_inv
@@ -1457,11 +1582,11 @@ class Simulation:
         n = _get(d, 'amr.n_cell', n=3, typ=int)
         lo = _get(d, 'geometry.prob_lo', n=3)
         hi = _get(d, 'geometry.prob_hi', n=3)
-        self.geom = Geometry(n[0], n[1], n[2], tuple(lo), tuple(hi))
-        nothing_deposits = d.get('plasmas.names', ['no_plasma'])[0] == 'no_plasma' \
-            and d.get('beams.names', ['no_beam'])[0] == 'no_beam'
-        assert _get(d, 'hipace.depos_order_xy', 2, typ=int) == 2 or nothing_deposits, 'oracle scope: order 2'
-        assert _get(d, 'hipace.depos_derivative_type', 2, typ=int) == 2
+        order = _get(d, 'hipace.depos_order_xy', 2, typ=int)
+        dtype = _get(d, 'hipace.depos_derivative_type', 2, typ=int)
+        assert 0 <= order <= 3 and 0 <= dtype <= 2
+        assert order != 0 or dtype != 0, 'Analytic derivative with depos_order=0 would vanish'  # Hipace.cpp:52-53
+        self.geom = Geometry(n[0], n[1], n[2], tuple(lo), tuple(hi), order, dtype)
         self.diag_type = _get(d, 'diagnostic.diag_type', 'xyz', typ=str)
         assert self.diag_type in ('xyz', 'xz'), 'oracle scope: xyz / xz field diagnostics'
         assert _get(d, 'hipace.bxby_solver', 'explicit', typ=str) == 'explicit'
@@ -1488,6 +1613,11 @@ class Simulation:
             for nm in bnames:
                 self.beams.append(self._read_beam(nm))
         self.any_neutral = any(p.neutralize_background for p in self.plasmas)
+        self.grid_current = None                                  # utils/GridCurrent.cpp:14-23
+        if _get(d, 'grid_current.use_grid_current', 0, typ=int):
+            self.grid_current = (_get(d, 'grid_current.peak_current_density'),
+                                 _get(d, 'grid_current.position_mean', n=3),
+                                 _get(d, 'grid_current.position_std', n=3))
         # lasers (laser/MultiLaser.cpp:26-56, laser/Laser.cpp:18-47): gaussian envelopes on the
         # field grid; only what time step 0 needs (no envelope advance)
         self.lasers = []
@@ -1523,7 +1653,7 @@ class Simulation:
             self.laser_next = {}
         self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral, self.use_laser)
         g = self.geom
-        self.F = {k: np.zeros((g.ny + 2 * G, g.nx + 2 * G)) for k in self.comps}
+        self.F = {k: np.zeros((g.ny + 2 * g.g, g.nx + 2 * g.g)) for k in self.comps}
         self.eig = poisson_eigenvalues(g.nx, g.ny, g.dx, g.dy)
         self.mg = MultiGrid1(g.dx, g.dy, g.nx, g.ny)
         self.checksums = {}
@@ -1702,6 +1832,8 @@ class Simulation:
             T('rhomjz')[...] += F[('RhomJzIons', 'rhomjz')]
             if self.deposit_rho:
                 T('rho')[...] += F[('RhomJzIons', 'rhomjz')]
+        if self.grid_current is not None:                                         # :629
+            grid_current_deposit(T('jz_beam'), g, islice, *self.grid_current)
         if self.slice_hook:
             self.slice_hook(self, islice, 'deposited')
         solve_poisson_psi_ez_bz(F, g, pc, self.eig)                               # :633
@@ -1730,7 +1862,7 @@ class Simulation:
         if self.slice_hook:
             self.slice_hook(self, islice, 'sources')
         # ExplicitMGSolveBxBy, Hipace.cpp:793-933
-        v = (slice(G, -G), slice(G, -G))
+        v = (slice(g.g, -g.g), slice(g.g, -g.g))
         sol = np.stack([T('Bx')[v], T('By')[v]])
         rhs = np.stack([T('Sy')[v], T('Sx')[v]])
         self.mg.solve1(sol, rhs, T('chi')[v], self.mg_tol_rel, self.mg_tol_abs, 200)
@@ -1781,7 +1913,7 @@ class Simulation:
         is the identity for an uncoarsened xyz diagnostic)."""
         for (sl, nm), a in self.F.items():
             if sl == 'This':
-                self.checksums[nm] = self.checksums.get(nm, 0.0) + float(np.abs(self._diag_rows(a, G)).sum())
+                self.checksums[nm] = self.checksums.get(nm, 0.0) + float(np.abs(self._diag_rows(a, self.geom.g)).sum())
 
     def evolve(self, nslices: int | None = None, step_begin: int = 0, step_end: int = 0):
         """Run time steps step_begin..step_end (Hipace.cpp:401-507); the checksums returned are

@@ -59,6 +59,43 @@ CASES = {
     'linear_wake.SI.1Rank': dict(
         deck='examples/linear_wake_SI.in', overrides={'diagnostic.field_data': 'all rho'},
         rtol_cpu=1e-11, rtol_cuda=1e-7),
+    # tests/gaussian_linear_wake.{normalized,SI}.1Rank.sh:32-43: gaussian fixed_ppc beam in the linear
+    # wake decks; pin Sy, Sx and chi too (nothing skipped)
+    'gaussian_linear_wake.normalized.1Rank': dict(
+        deck='examples/linear_wake_normalized.in',
+        overrides={'beam.profile': 'gaussian', 'beam.zmin': -5.9, 'beam.zmax': 5.9, 'beam.radius': 10,
+                   'beam.position_mean': '0. 0. 0', 'beam.position_std': '2 2 1.41',
+                   'geometry.prob_lo': '-10. -10. -6', 'geometry.prob_hi': '10. 10. 6',
+                   'diagnostic.field_data': 'all rho'}, rtol_cpu=1e-12, rtol_cuda=1e-7),
+    'gaussian_linear_wake.SI.1Rank': dict(
+        deck='examples/linear_wake_SI.in',
+        overrides={'beam.profile': 'gaussian', 'beam.zmin': '-59.e-6', 'beam.zmax': '59.e-6',
+                   'beam.radius': '100.e-6', 'beam.position_mean': '0. 0. 0',
+                   'beam.position_std': '20.e-6 20.e-6 14.1e-6',
+                   'geometry.prob_lo': '-100.e-6 -100.e-6 -60.e-6',
+                   'geometry.prob_hi': '100.e-6 100.e-6 60.e-6',
+                   'diagnostic.field_data': 'all rho'}, rtol_cpu=1e-11, rtol_cuda=1e-7),
+    # tests/beam_in_vacuum.{normalized,SI}.1Rank.sh:30-35: no plasma, ORDER-0 deposition, multigrid
+    # Bx/By on a non-square 512 x 768 grid, tolerance 1e-5; the SI deck has two beam species
+    'beam_in_vacuum.normalized.1Rank': dict(
+        deck='examples/beam_in_vacuum_normalized.in',
+        overrides={'hipace.depos_order_xy': 0, 'diagnostic.field_data': 'all rho',
+                   'hipace.MG_tolerance_rel': 1e-5}, rtol_cpu=1e-12, rtol_cuda=3e-5),
+    'beam_in_vacuum.SI.1Rank': dict(
+        deck='examples/beam_in_vacuum_SI.in',
+        overrides={'hipace.depos_order_xy': 0, 'diagnostic.field_data': 'all rho',
+                   'hipace.MG_tolerance_rel': 1e-5}, rtol_cpu=1e-12, rtol_cuda=2.5e-5),
+    # tests/grid_current.1Rank.sh:30-48: the analytic grid current added to jz_beam, order 0
+    # (max_step = 1 with dt = 0: step 1 repeats step 0)
+    'grid_current.1Rank': dict(
+        deck='examples/beam_in_vacuum_normalized.in',
+        overrides={'amr.n_cell': '32 32 32', 'max_step': 1, 'hipace.depos_order_xy': 0,
+                   'geometry.prob_lo': '-8. -8. -6.', 'geometry.prob_hi': '8. 8. 6.',
+                   'grid_current.use_grid_current': 1, 'grid_current.peak_current_density': 0.2,
+                   'grid_current.position_mean': '0. 0. 0.',
+                   'grid_current.position_std': '0.3 0.3 1.41', 'beam.profile': 'gaussian',
+                   'beam.position_std': '0.3 0.3 1.41', 'beam.density': 0.2, 'beam.radius': 1.,
+                   'beam.ppc': '1 1 1'}, rtol_cpu=1e-12, rtol_cuda=1e-5),
 }
 for name, meta in CASES.items():
     gold = json.load(open(os.path.join(REF, name + '.json')))

@@ -27,18 +27,21 @@ def _run(case, repo_root):
 @pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank',
                                   'beam_evolution.1Rank', 'laser_blowout_wake_explicit.SI.1Rank',
                                   'laser_blowout_wake_explicit.1Rank', 'linear_wake.SI.1Rank',
-                                  'laser_evolution.SI.2Rank'])
+                                  'laser_evolution.SI.2Rank',
+                                  'gaussian_linear_wake.normalized.1Rank', 'gaussian_linear_wake.SI.1Rank',
+                                  'beam_in_vacuum.normalized.1Rank', 'beam_in_vacuum.SI.1Rank',
+                                  'grid_current.1Rank'])
 def test_oracle_matches_reference_golden(case, repo_root):
     meta, sim, cs = _run(case, repo_root)
     gold = meta['checksums']
     for name, want in gold['lev=0'].items():
         got = cs[name]
         assert abs(got - want) <= RTOL * abs(want) + 1e-40, (name, got, want)
-    if 'beam' in gold:
-        bc = sim.beam_checksums()['beam']
-        for name, want in gold['beam'].items():
+    for species in (k for k in gold if k != 'lev=0'):          # one entry per beam species
+        bc = sim.beam_checksums()[species]
+        for name, want in gold[species].items():
             # (the reference's files hold charge, mass and positions to ~13 digits only)
-            assert abs(bc[name] - want) <= max(RTOL, 1e-12) * abs(want) + 1e-40, (name, bc[name], want)
+            assert abs(bc[name] - want) <= max(RTOL, 1e-12) * abs(want) + 1e-40, (species, name, bc[name], want)
     assert sim.n_qsa_violation == 0
 
 
