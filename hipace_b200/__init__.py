@@ -58,6 +58,7 @@ EXPORTS = (
     'hpb_sim_timer_start', 'hpb_sim_timer_stop', 'hpb_sim_get_beam_packet',
     'hpb_fields_shift_and_initialize', 'hpb_advance_plasma_particles_and_deposit', 'hpb_deck_check',
     'hpb_set_plasma_lattice_hint', 'hpb_deposit_current_laser', 'hpb_laser_update_aabs',
+    'hpb_set_deposition_order', 'hpb_fields_grid_current', 'hpb_sim_nguard',
 )
 NCCL_ID_BYTES = 128
 
@@ -234,6 +235,7 @@ class Simulation:
         self.prob_lo, self.prob_hi = tuple(lo), tuple(hi)
         self.nx, self.ny, self.nz = self.n_cell
         self.ncomp = self._L.hpb_sim_ncomp(self._h)
+        self.ng = self._L.hpb_sim_nguard(self._h)      # guard cells (2 for the default order)
 
     def close(self):
         if self._h:
@@ -268,14 +270,14 @@ class Simulation:
         c = self.comp_index(which_slice, name)
         if c < 0:
             raise KeyError((which_slice, name))
-        out = np.empty((self.ny + 2 * NGUARD, self.nx + 2 * NGUARD))
+        out = np.empty((self.ny + 2 * self.ng, self.nx + 2 * self.ng))
         _check(self._L.hpb_sim_get_field(self._h, c, out.ctypes.data), 'hpb_sim_get_field')
         return out
 
     def set_field(self, name: str, arr, which_slice: str = 'This'):
         c = self.comp_index(which_slice, name)
         a = np.ascontiguousarray(arr, dtype=np.float64)
-        assert a.shape == (self.ny + 2 * NGUARD, self.nx + 2 * NGUARD)
+        assert a.shape == (self.ny + 2 * self.ng, self.nx + 2 * self.ng)
         _check(self._L.hpb_sim_set_field(self._h, c, a.ctypes.data), 'hpb_sim_set_field')
 
     def plasma_np(self, species: int = 0) -> int:
@@ -401,10 +403,18 @@ class Context:
 
     # -- views over torch tensors ----------------------------------------------------------
     def slice_view(self, t) -> hpb_slice:
-        """t: float64 CUDA tensor [ncomp, ny + 2g, nx + 2g] (component-major slice array)"""
+        """t: float64 CUDA tensor [ncomp, ny + 2g, nx + 2g] (component-major slice array); g from
+        the tensor's shape (2 unless set_deposition_order chose another order)"""
         ncomp, ny_t, nx_t = t.shape
         assert t.is_cuda and t.is_contiguous() and str(t.dtype) == 'torch.float64'
-        return hpb_slice(t.data_ptr(), -NGUARD, -NGUARD, nx_t, ny_t, nx_t, nx_t * ny_t, ncomp)
+        g = (nx_t - self.nx) // 2
+        assert nx_t == self.nx + 2 * g and ny_t == self.ny + 2 * g
+        return hpb_slice(t.data_ptr(), -g, -g, nx_t, ny_t, nx_t, nx_t * ny_t, ncomp)
+
+    def set_deposition_order(self, order_xy: int, derivative_type: int = 2):
+        """hipace.depos_order_xy / hipace.depos_derivative_type for the particle kernels"""
+        _check(self._L.hpb_set_deposition_order(self._h, order_xy, derivative_type),
+               'hpb_set_deposition_order')
 
     @staticmethod
     def plasma_view(reals, idcpu) -> hpb_plasma:

@@ -9,6 +9,7 @@
 // partitioned into {stay, slipped, dropped} with a stable two-level prefix (block counts come out
 // of the push kernel itself) and packed into the wire layout by two launches and no host sync.
 #include "sim.hpp"
+#include "generic_order.cuh"
 #include <string.h>
 #include <memory>
 
@@ -26,7 +27,8 @@ __device__ __forceinline__ long np_of(const hpb_beam_slice &b, int which)
 }
 
 // ---- push -------------------------------------------------------------------------------------
-template <bool EXT>
+// ORDER = -2: the specialised order-2 gather of common.cuh; 0..3: the generic one (generic_order.cuh)
+template <bool EXT, int ORDER>
 __global__ void __launch_bounds__(kBT)
 k_advance_beam(hpb_beam_slice b, int *__restrict__ nsub, SliceView a, int c_psi, int c_ez, int c_bx,
                int c_by, int c_bz, double x_off, double y_off, double dx_inv, double dy_inv,
@@ -62,8 +64,13 @@ k_advance_beam(hpb_beam_slice b, int *__restrict__ nsub, SliceView a, int c_psi,
                 xp += dt * 0.5 * ux * gammap_inv;
                 yp += dt * 0.5 * uy * gammap_inv;
                 if (enforce_particle_bc(xp, yp, ux, uy, bc, lox, loy, hix, hiy)) { dead = true; break; }
-                GatheredFields f = gather_order2(a, c_psi, c_ez, c_bx, c_by, c_bz, x_off, y_off,
-                                                 dx_inv, dy_inv, xp, yp);
+                GatheredFields f;
+                if (ORDER < 0) {
+                    f = gather_order2(a, c_psi, c_ez, c_bx, c_by, c_bz, x_off, y_off, dx_inv, dy_inv, xp, yp);
+                } else {
+                    const GenGrid gr = {x_off, y_off, dx_inv, dy_inv};
+                    f = gen_gather<(ORDER < 0 ? 2 : ORDER)>(a, c_psi, c_ez, c_bx, c_by, c_bz, gr, xp, yp);
+                }
                 if (EXT) {
                     const double Ex = rpn_eval(ext[0], xp, yp, zp, time), Ey = rpn_eval(ext[1], xp, yp, zp, time);
                     const double Ez = rpn_eval(ext[2], xp, yp, zp, time), Bx = rpn_eval(ext[3], xp, yp, zp, time);
@@ -321,15 +328,21 @@ int hpb_advance_beam_impl(hpb_ctx *ctx, hpb_beam_slice bm, int *d_nsub, hpb_slic
     if (!ctx || !comps || !bc_lo || !bc_hi || !d_nsub || n_subcycles < 1) return HPB_ERR_ARG;
     if (bm.np == 0) return HPB_OK;
     const hpb_geom &g = ctx->g;
-#define HPB_ADV_BEAM(E)                                                                           \
-    hpb_launch(k_advance_beam<E>, nblk(bm.np), kBT, 0, ctx->stream,                                       \
+#define HPB_ADV_BEAM_(E, O)                                                                       \
+    hpb_launch(k_advance_beam<E, O>, nblk(bm.np), kBT, 0, ctx->stream,                                    \
         bm, d_nsub, make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EZ], comps[HPB_C_BX],            \
         comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
         charge / mass, n_subcycles, dt / n_subcycles, time, min_z, do_z_push, particle_bc,        \
         bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], ext ? ext->d_prog : nullptr, d_class_counts,      \
         d_checksum, d_n_pushed)
-    if (ext) HPB_ADV_BEAM(true); else HPB_ADV_BEAM(false);
+#define HPB_ADV_BEAM(O) do { if (ext) HPB_ADV_BEAM_(true, O); else HPB_ADV_BEAM_(false, O); } while (0)
+    if (!hpb_use_generic_order(ctx)) HPB_ADV_BEAM(-2);
+    else if (ctx->depos_order == 0) HPB_ADV_BEAM(0);
+    else if (ctx->depos_order == 1) HPB_ADV_BEAM(1);
+    else if (ctx->depos_order == 2) HPB_ADV_BEAM(2);
+    else HPB_ADV_BEAM(3);
 #undef HPB_ADV_BEAM
+#undef HPB_ADV_BEAM_
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;

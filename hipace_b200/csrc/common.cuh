@@ -192,7 +192,7 @@ __device__ __forceinline__ void laser_gather(const SliceView &a, int c_aabs, dou
 
 // EnforceBC, src/particles/pusher/GetAndSetPosition.H:56-98.  Returns true if the particle
 // became invalid (absorbing boundary).
-__device__ __forceinline__ bool enforce_particle_bc(double &x, double &y, double &ux, double &uy,
+__host__ __device__ __forceinline__ bool enforce_particle_bc(double &x, double &y, double &ux, double &uy,
                                                     int bc, double lox, double loy, double hix,
                                                     double hiy)
 {
@@ -251,4 +251,21 @@ struct hpb_ctx {
     // particle order hint (hpb_set_plasma_lattice_hint): the next particle-kernel calls see np =
     // order_ppc passes of order_n lattice cells each (InitParticles order); 0 = unknown
     long order_n; int order_ppc;
+    // hipace.depos_order_xy / hipace.depos_derivative_type (hpb_set_deposition_order; default 2 / 2:
+    // the specialised kernels of particles.cu.  Anything else: generic_order.cu)
+    int depos_order, depos_dtype;
+    int force_generic;        // run the generic kernels for the default order too (cross-check)
 };
+// true when the particle kernels must take the generic-order path
+bool hpb_use_generic_order(const hpb_ctx *ctx);
+// generic_order.cu: the entry points of particles.cu / beam.cu forward here in that case
+int hpb_gen_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                            int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
+                            double max_qsa, int *d_n_qsa_violation);
+int hpb_gen_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, double charge, int c_jx,
+                         int c_jy, int c_jz);
+int hpb_gen_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                                const int *comps);
+int hpb_gen_advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                           int n_subcycles, int temp_slice, int particle_bc, const double bc_lo[2],
+                           const double bc_hi[2], const int *comps);

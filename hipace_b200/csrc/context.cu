@@ -29,6 +29,27 @@ bool hpb_pdl_enabled()
     return on != 0;
 }
 
+bool hpb_use_generic_order(const hpb_ctx *ctx)
+{
+    static int force = -1;       // HPB_GENERIC=1: the generic kernels also for order 2 / centred (cross-check)
+    if (force < 0) { const char *e = getenv("HPB_GENERIC"); force = e ? (atoi(e) != 0) : 0; }
+    return force || ctx->force_generic || ctx->depos_order != 2 || ctx->depos_dtype != 2;
+}
+
+extern "C" int hpb_set_deposition_order(hpb_ctx *ctx, int order_xy, int derivative_type)
+{
+    // Hipace.cpp:49-53: orders 0..3, derivative types 0..2, "analytic derivative with order 0 would vanish"
+    if (!ctx || order_xy < 0 || order_xy > 3 || derivative_type < 0 || derivative_type > 2
+        || (order_xy == 0 && derivative_type == 0)) {
+        hpb_set_error("hpb_set_deposition_order: order %d / derivative type %d not allowed", order_xy,
+                      derivative_type);
+        return HPB_ERR_ARG;
+    }
+    ctx->depos_order = order_xy;
+    ctx->depos_dtype = derivative_type;
+    return HPB_OK;
+}
+
 extern "C" const char *hpb_last_error(void) { return g_err; }
 extern "C" const char *hpb_version(void) { return "hpb200 0.1 (sm_100a, fp64)"; }
 
@@ -47,6 +68,7 @@ extern "C" int hpb_create(hpb_ctx **out, const hpb_geom *geom, void *stream)
     memset(ctx, 0, sizeof(*ctx));
     ctx->g = *geom;
     ctx->stream = (cudaStream_t)stream;
+    ctx->depos_order = 2; ctx->depos_dtype = 2;
     int rc = hpb_poisson_init(ctx);
     if (rc == HPB_OK) rc = hpb_mg_init(ctx);
     if (rc == HPB_OK && cudaMalloc(&ctx->d_scalar_i, 16 * sizeof(int)) != cudaSuccess) rc = HPB_ERR_CUDA;

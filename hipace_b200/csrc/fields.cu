@@ -37,14 +37,16 @@ __global__ void k_add(SliceView a, CompPairs cp, long ntot)
     for (int n = 0; n < cp.n; ++n) a.comp(cp.dst[n])[o] += a.comp(cp.src[n])[o];
 }
 
-// ExmBy = -d/dx Psi, EypBx = -d/dy Psi on the box grown by g-1 (Fields.cpp:931-956)
+// ExmBy = -d/dx Psi, EypBx = -d/dy Psi on the box grown by g-1 (Fields.cpp:931-956).
+// G = guard cells of the slice: (depos_order_xy + 1) / 2 + 1 = 1, 2 (default order) or 3
+template <int G>
 __global__ void k_exmby_eypbx(SliceView a, int c_psi, int c_exmby, int c_eypbx, int nx, int ny,
                               double dx_inv_half, double dy_inv_half)
 {
     hpb_pdl_prologue();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x - (HPB_G - 1);
-    const int j = (int)blockIdx.y - (HPB_G - 1);
-    if (i >= nx + (HPB_G - 1)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - (G - 1);
+    const int j = (int)blockIdx.y - (G - 1);
+    if (i >= nx + (G - 1)) return;
     const long o = a.idx(i, j);
     const double *psi = a.comp(c_psi);
     const long js = a.jstride;
@@ -55,14 +57,15 @@ __global__ void k_exmby_eypbx(SliceView a, int c_psi, int c_exmby, int c_eypbx, 
 // Hipace::InitializeSxSyWithBeam (Hipace.cpp:775-788) on the valid box; the guard cells are set to
 // zero (the state Fields::InitializeSlices leaves them in), so that Sx / Sy need no separate
 // zero-fill pass before this kernel.
+template <int G>
 __global__ void k_sxsy_from_beam(SliceView a, int c_sx, int c_sy, int c_next_jxb, int c_next_jyb,
                                  int c_jzb, int c_prev_jxb, int c_prev_jyb, int nx, int ny,
                                  double mu0, double dx, double dy, double dz)
 {
     hpb_pdl_prologue();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x - HPB_G;
-    const int j = (int)blockIdx.y - HPB_G;
-    if (i >= nx + HPB_G) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - G;
+    const int j = (int)blockIdx.y - G;
+    if (i >= nx + G) return;
     const long o = a.idx(i, j);
     if (i < 0 || i >= nx || j < 0 || j >= ny) {
         a.comp(c_sy)[o] = 0.0;
@@ -77,6 +80,21 @@ __global__ void k_sxsy_from_beam(SliceView a, int c_sx, int c_sy, int c_next_jxb
     const double dz_jyb = (a.comp(c_prev_jyb)[o] - a.comp(c_next_jyb)[o]) / (2.0 * dz);
     a.comp(c_sy)[o] = mu0 * (-dy_jzb + dz_jyb);
     a.comp(c_sx)[o] = -mu0 * (-dx_jzb + dz_jxb);
+}
+
+// GridCurrent::DepositCurrentSlice (utils/GridCurrent.cpp:25-70): an analytic gaussian current
+// density added to jz_beam on the valid box; cell centres plo + (i + 1/2) dx
+__global__ void k_grid_current(SliceView a, int c_jz, int nx, int ny, double plo_x, double plo_y,
+                               double dx, double dy, double mx, double my, double sx, double sy,
+                               double amp)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx || j >= ny) return;
+    const double x = plo_x + (i + 0.5) * dx, y = plo_y + (j + 0.5) * dy;
+    const double ddx = (x - mx) / sx, ddy = (y - my) / sy;
+    a.comp(c_jz)[a.idx(i, j)] += amp * exp(-0.5 * (ddx * ddx + ddy * ddy));
 }
 
 // ShiftSlices + InitializeSlices of the next slice in one pass over the grown box
@@ -124,11 +142,31 @@ inline unsigned nb(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 int hpb_launch_exmby_eypbx(hpb_ctx *ctx, const hpb_slice &sl, const int *comps)
 {
     const hpb_geom &g = ctx->g;
-    const int gx = g.nx + 2 * (HPB_G - 1), gy = g.ny + 2 * (HPB_G - 1);
+    const int ng = -sl.lo_x;
+    if (ng < 1 || ng > 3 || sl.lo_y != sl.lo_x) { hpb_set_error("slice with %d guard cells", ng); return HPB_ERR_ARG; }
+    const int gx = g.nx + 2 * (ng - 1), gy = g.ny + 2 * (ng - 1);
     dim3 grid((gx + kThreads - 1) / kThreads, gy);
-    hpb_launch(k_exmby_eypbx, grid, kThreads, 0, ctx->stream, 
-        make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.nx, g.ny,
-        0.5 * (1.0 / g.dx), 0.5 * (1.0 / g.dy));
+#define HPB_EXMBY(G) hpb_launch(k_exmby_eypbx<G>, grid, kThreads, 0, ctx->stream,                   \
+        make_view(sl), comps[HPB_C_PSI], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.nx, g.ny,     \
+        0.5 * (1.0 / g.dx), 0.5 * (1.0 / g.dy))
+    if (ng == 2) HPB_EXMBY(2); else if (ng == 1) HPB_EXMBY(1); else HPB_EXMBY(3);
+#undef HPB_EXMBY
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_fields_grid_current(hpb_ctx *ctx, hpb_slice sl, int c_jz_beam, double peak,
+                                       const double mean[3], const double std[3], double plo_x,
+                                       double plo_y, double z)
+{
+    if (!ctx || c_jz_beam < 0 || !mean || !std) return HPB_ERR_ARG;
+    const hpb_geom &g = ctx->g;
+    const double delta_z = (z - mean[2]) / std[2];
+    const double long_pos_factor = exp(-0.5 * (delta_z * delta_z));
+    dim3 grid((g.nx + kThreads - 1) / kThreads, g.ny);
+    hpb_launch(k_grid_current, grid, kThreads, 0, ctx->stream, make_view(sl), c_jz_beam, g.nx, g.ny, plo_x,
+               plo_y, g.dx, g.dy, mean[0], mean[1], std[0], std[1], peak * long_pos_factor);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
@@ -222,11 +260,15 @@ extern "C" int hpb_fields_sxsy_from_beam(hpb_ctx *ctx, hpb_slice sl, const int *
 {
     if (!ctx || !comps) return HPB_ERR_ARG;
     const hpb_geom &g = ctx->g;
-    dim3 grid((g.nx + 2 * HPB_G + kThreads - 1) / kThreads, g.ny + 2 * HPB_G);
-    hpb_launch(k_sxsy_from_beam, grid, kThreads, 0, ctx->stream, 
-        make_view(sl), comps[HPB_C_SX], comps[HPB_C_SY], comps[HPB_C_NEXT_JX_BEAM],
-        comps[HPB_C_NEXT_JY_BEAM], comps[HPB_C_JZ_BEAM], comps[HPB_C_PREV_JX_BEAM],
-        comps[HPB_C_PREV_JY_BEAM], g.nx, g.ny, g.mu0, g.dx, g.dy, g.dz);
+    const int ng = -sl.lo_x;
+    if (ng < 1 || ng > 3 || sl.lo_y != sl.lo_x) { hpb_set_error("slice with %d guard cells", ng); return HPB_ERR_ARG; }
+    dim3 grid((g.nx + 2 * ng + kThreads - 1) / kThreads, g.ny + 2 * ng);
+#define HPB_SXSY(G) hpb_launch(k_sxsy_from_beam<G>, grid, kThreads, 0, ctx->stream,                 \
+        make_view(sl), comps[HPB_C_SX], comps[HPB_C_SY], comps[HPB_C_NEXT_JX_BEAM],              \
+        comps[HPB_C_NEXT_JY_BEAM], comps[HPB_C_JZ_BEAM], comps[HPB_C_PREV_JX_BEAM],              \
+        comps[HPB_C_PREV_JY_BEAM], g.nx, g.ny, g.mu0, g.dx, g.dy, g.dz)
+    if (ng == 2) HPB_SXSY(2); else if (ng == 1) HPB_SXSY(1); else HPB_SXSY(3);
+#undef HPB_SXSY
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;

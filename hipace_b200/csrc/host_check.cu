@@ -1,0 +1,203 @@
+// HOST harness for the __host__ __device__ arithmetic of the CUDA path (shapes.cuh, push_math.cuh,
+// generic_order.cuh): the very functions the kernels call, run on the CPU with a plain `+=` in place
+// of the fp64 RED.  Built into build/libhpb200_hostcheck.so by hipace_b200.build.build_host_check()
+// and driven by tests/test_device_math_host.py against the reference's own headers
+// (oracle/ref_headers.cpp) and the NumPy oracle.  This is a TEST artefact: it is not part of
+// libhpb200.so and nothing in the product loads it.
+#include "generic_order.cuh"
+
+namespace {
+struct HostAdd {
+    __host__ __device__ void operator()(double *p, double v) const { *p += v; }
+};
+SliceView view(double *planes, int nx_tot, int ny_tot, int g)
+{
+    SliceView v;
+    v.p = planes; v.lo_x = -g; v.lo_y = -g; v.jstride = nx_tot; v.nstride = (long)nx_tot * ny_tot;
+    return v;
+}
+}
+
+#define BY_ORDER(order, CALL)                                  \
+    switch (order) {                                           \
+    case 0: { constexpr int O = 0; CALL; } break;              \
+    case 1: { constexpr int O = 1; CALL; } break;              \
+    case 2: { constexpr int O = 2; CALL; } break;              \
+    case 3: { constexpr int O = 3; CALL; } break;              \
+    default: return 1;                                         \
+    }
+
+template <int O>
+static void shape_all(long n, const double *xmid, double *s, long *cell)
+{
+    for (long p = 0; p < n; ++p) {
+        double w[O + 1];
+        cell[p] = hpb_shape<O>(xmid[p], w);
+        for (int k = 0; k <= O; ++k) s[k * n + p] = w[k];
+    }
+}
+extern "C" int hc_shape(int order, long n, const double *xmid, double *s, long *cell)
+{
+    BY_ORDER(order, shape_all<O>(n, xmid, s, cell))
+    return 0;
+}
+
+template <int D, int O>
+static void dshape_all(long n, const double *xmid, double *s, double *ds, long *cell)
+{
+    for (long p = 0; p < n; ++p) {
+        double a[O + D + 1], b[O + D + 1];
+        cell[p] = hpb_dshape<D, O>(xmid[p], a, b);
+        for (int k = 0; k <= O + D; ++k) { s[k * n + p] = a[k]; ds[k * n + p] = b[k]; }
+    }
+}
+extern "C" int hc_dshape(int dtype, int order, long n, const double *xmid, double *s, double *ds, long *cell)
+{
+    if (dtype == 0) { BY_ORDER(order, (dshape_all<0, O>(n, xmid, s, ds, cell))) }
+    else if (dtype == 1) { BY_ORDER(order, (dshape_all<1, O>(n, xmid, s, ds, cell))) }
+    else if (dtype == 2) { BY_ORDER(order, (dshape_all<2, O>(n, xmid, s, ds, cell))) }
+    else return 1;
+    return 0;
+}
+
+// in: ux uy psi_inv ExmBy EypBx Ez Bx_c By_c Bz A ADx ADy; eps: epsilon parts of ux uy psi_inv.
+// out[9][n]: plain derivative (3), dual value (3), dual epsilon (3)
+extern "C" void hc_momentum_push(long n, const double *const *in, const double *const *eps, int laser,
+                                 double clight_inv, double qmc, double *out)
+{
+    for (long p = 0; p < n; ++p) {
+        const PushFields f = {in[3][p], in[4][p], in[5][p], in[6][p], in[7][p], in[8][p]};
+        const PushLaser las = {in[9][p], in[10][p], in[11][p]};
+        double a, b, c;
+        Dual da, db, dc;
+        const Dual ux{in[0][p], eps[0][p]}, uy{in[1][p], eps[1][p]}, pi{in[2][p], eps[2][p]};
+        if (laser) {
+            momentum_push<double, true>(in[0][p], in[1][p], in[2][p], f, clight_inv, qmc, a, b, c, las);
+            momentum_push<Dual, true>(ux, uy, pi, f, clight_inv, qmc, da, db, dc, las);
+        } else {
+            momentum_push<double, false>(in[0][p], in[1][p], in[2][p], f, clight_inv, qmc, a, b, c, las);
+            momentum_push<Dual, false>(ux, uy, pi, f, clight_inv, qmc, da, db, dc, las);
+        }
+        out[p] = a; out[n + p] = b; out[2 * n + p] = c;
+        out[3 * n + p] = da.v; out[4 * n + p] = db.v; out[5 * n + p] = dc.v;
+        out[6 * n + p] = da.e; out[7 * n + p] = db.e; out[8 * n + p] = dc.e;
+    }
+}
+
+struct HcGrid { int nx_tot, ny_tot, g; double x_off, y_off, dx_inv, dy_inv; };
+
+extern "C" int hc_gather(int order, long n, const double *xp, const double *yp, double *planes,
+                         const HcGrid *hg, const int *comps, double *out)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    const GenGrid gr = {hg->x_off, hg->y_off, hg->dx_inv, hg->dy_inv};
+    for (long p = 0; p < n; ++p) {
+        GatheredFields f;
+        BY_ORDER(order, (f = gen_gather<O>(a, comps[0], comps[1], comps[2], comps[3], comps[4], gr, xp[p], yp[p])))
+        out[p] = f.ExmBy; out[n + p] = f.EypBx; out[2 * n + p] = f.Ez;
+        out[3 * n + p] = f.Bx; out[4 * n + p] = f.By; out[5 * n + p] = f.Bz;
+    }
+    return 0;
+}
+
+extern "C" int hc_laser_gather(int order, long n, const double *xp, const double *yp, double *plane,
+                               const HcGrid *hg, double *out)
+{
+    const SliceView a = view(plane, hg->nx_tot, hg->ny_tot, hg->g);
+    const GenGrid gr = {hg->x_off, hg->y_off, hg->dx_inv, hg->dy_inv};
+    for (long p = 0; p < n; ++p) {
+        double A, Ax, Ay, A0, t0, t1;
+        BY_ORDER(order, (gen_laser_gather<O, true>(a, 0, gr, xp[p], yp[p], A, Ax, Ay),
+                         gen_laser_gather<O, false>(a, 0, gr, xp[p], yp[p], A0, t0, t1)))
+        out[p] = A; out[n + p] = Ax; out[2 * n + p] = Ay; out[3 * n + p] = A0;
+    }
+    return 0;
+}
+
+// plasma SoA: r[11] in PlasmaIdx order (hpb200.h), valid[] in/out (0/1)
+extern "C" long hc_deposit_current(int order, long n, double *const *r, unsigned char *valid,
+                                   double *planes, const HcGrid *hg, const int *c5,
+                                   const GenDepositPar *par)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    const GenGrid gr = {hg->x_off, hg->y_off, hg->dx_inv, hg->dy_inv};
+    long n_bad = 0;
+    for (long p = 0; p < n; ++p) {
+        if (!valid[p]) continue;
+        bool ok = true;
+        if (par->c_aabs >= 0) {
+            BY_ORDER(order, (ok = gen_deposit_current<O, true>(a, c5, gr, *par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p],
+                                                               r[HPB_UX][p], r[HPB_UY][p], r[HPB_PSI][p], HostAdd())))
+        } else {
+            BY_ORDER(order, (ok = gen_deposit_current<O, false>(a, c5, gr, *par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p],
+                                                                r[HPB_UX][p], r[HPB_UY][p], r[HPB_PSI][p], HostAdd())))
+        }
+        if (!ok) { ++n_bad; r[HPB_W][p] = 0.; valid[p] = 0; }
+    }
+    return n_bad;
+}
+
+extern "C" int hc_beam_deposit(int order, long n, const double *const *b7, const unsigned char *valid,
+                               double *planes, const HcGrid *hg, int c_jx, int c_jy, int c_jz,
+                               double clightsq, double q_invvol)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    const GenGrid gr = {hg->x_off, hg->y_off, hg->dx_inv, hg->dy_inv};
+    for (long p = 0; p < n; ++p) {
+        if (!valid[p]) continue;
+        // b7 = x y z w ux uy uz
+        BY_ORDER(order, (gen_beam_deposit<O>(a, c_jx, c_jy, c_jz, gr, clightsq, q_invvol, b7[0][p], b7[1][p],
+                                             b7[3][p], b7[4][p], b7[5][p], b7[6][p], HostAdd())))
+    }
+    return 0;
+}
+
+template <int O, int D>
+static void explicit_all(long n, double *const *r, const unsigned char *valid, const SliceView &a,
+                         const GenGrid &gr, const GenExplicitPar &par)
+{
+    for (long p = 0; p < n; ++p) {
+        if (!valid[p]) continue;
+        if (par.c_aabs >= 0)
+            gen_explicit_deposition<O, D, true>(a, gr, par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p], r[HPB_UX][p],
+                                                r[HPB_UY][p], r[HPB_PSI][p], HostAdd());
+        else
+            gen_explicit_deposition<O, D, false>(a, gr, par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p], r[HPB_UX][p],
+                                                 r[HPB_UY][p], r[HPB_PSI][p], HostAdd());
+    }
+}
+extern "C" int hc_explicit_deposition(int order, int dtype, long n, double *const *r,
+                                      const unsigned char *valid, double *planes, const HcGrid *hg,
+                                      const GenExplicitPar *par)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    const GenGrid gr = {hg->x_off, hg->y_off, hg->dx_inv, hg->dy_inv};
+    if (order == 0 && dtype == 0) return 1;
+    if (dtype == 0) { BY_ORDER(order, (explicit_all<(O == 0 ? 1 : O), 0>(n, r, valid, a, gr, *par))) }
+    else if (dtype == 1) { BY_ORDER(order, (explicit_all<O, 1>(n, r, valid, a, gr, *par))) }
+    else if (dtype == 2) { BY_ORDER(order, (explicit_all<O, 2>(n, r, valid, a, gr, *par))) }
+    else return 1;
+    return 0;
+}
+
+extern "C" int hc_advance_plasma(int order, long n, double *const *r, unsigned char *valid,
+                                 double *planes, const HcGrid *hg, const GenPushPar *par)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    const GenGrid gr = {hg->x_off, hg->y_off, hg->dx_inv, hg->dy_inv};
+    for (long p = 0; p < n; ++p) {
+        if (!valid[p]) continue;
+        double st[5] = {r[HPB_X_PREV][p], r[HPB_Y_PREV][p], r[HPB_UX_HALF][p], r[HPB_UY_HALF][p], r[HPB_PSI_HALF][p]};
+        double out[5] = {r[HPB_X][p], r[HPB_Y][p], r[HPB_UX][p], r[HPB_UY][p], r[HPB_PSI][p]};
+        bool alive = true;
+        if (par->c_aabs >= 0) { BY_ORDER(order, (alive = gen_advance_plasma<O, true>(a, gr, *par, st, out))) }
+        else { BY_ORDER(order, (alive = gen_advance_plasma<O, false>(a, gr, *par, st, out))) }
+        r[HPB_X][p] = out[0]; r[HPB_Y][p] = out[1]; r[HPB_UX][p] = out[2]; r[HPB_UY][p] = out[3]; r[HPB_PSI][p] = out[4];
+        if (!par->temp_slice) {
+            r[HPB_X_PREV][p] = st[0]; r[HPB_Y_PREV][p] = st[1]; r[HPB_UX_HALF][p] = st[2];
+            r[HPB_UY_HALF][p] = st[3]; r[HPB_PSI_HALF][p] = st[4];
+        }
+        if (!alive) { r[HPB_W][p] = 0.; valid[p] = 0; }
+    }
+    return 0;
+}

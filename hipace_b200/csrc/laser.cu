@@ -49,16 +49,17 @@ __device__ __forceinline__ int interp_shape(double xmid, int order, double w[3])
     return shape2(xmid, w);
 }
 
+template <int G>       // guard cells of the field slice
 __global__ void __launch_bounds__(256)
 k_laser_aabs(SliceView a, int c_aabs, LaserSet ls, int nx, int ny, double dx, double dy, double x_off,
              double y_off, int order, double z, double *abs_sum)
 {
     hpb_pdl_prologue();
     __shared__ double red[256];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x - HPB_G;
-    const int j = (int)blockIdx.y - HPB_G;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - G;
+    const int j = (int)blockIdx.y - G;
     double mag = 0.;
-    if (i < nx + HPB_G) {
+    if (i < nx + G) {
         // field cell -> position -> laser-grid coordinate (the two grids coincide)
         const double xmid = ((i * dx + x_off) - x_off) * (1.0 / dx);
         const double ymid = ((j * dy + y_off) - y_off) * (1.0 / dy);
@@ -105,9 +106,13 @@ extern "C" int hpb_laser_update_aabs(hpb_ctx *ctx, hpb_slice sl, int c_aabs, con
     ls.n = nlasers;
     for (int l = 0; l < nlasers; ++l) ls.L[l] = lasers[l];
     ls.k0 = 2.0 * 3.14159265358979323846 / lambda0;
-    dim3 grid((g.nx + 2 * HPB_G + 255) / 256, g.ny + 2 * HPB_G);
-    hpb_launch(k_laser_aabs, grid, 256, 0, ctx->stream, make_view(sl), c_aabs, ls, g.nx, g.ny, g.dx, g.dy,
-               g.x_off, g.y_off, interp_order, z_slice, d_envelope_abs_sum);
+    const int ng = -sl.lo_x;
+    if (ng < 1 || ng > 3 || sl.lo_y != sl.lo_x) { hpb_set_error("slice with %d guard cells", ng); return HPB_ERR_ARG; }
+    dim3 grid((g.nx + 2 * ng + 255) / 256, g.ny + 2 * ng);
+#define HPB_AABS(G) hpb_launch(k_laser_aabs<G>, grid, 256, 0, ctx->stream, make_view(sl), c_aabs, ls, g.nx, \
+                               g.ny, g.dx, g.dy, g.x_off, g.y_off, interp_order, z_slice, d_envelope_abs_sum)
+    if (ng == 2) HPB_AABS(2); else if (ng == 1) HPB_AABS(1); else HPB_AABS(3);
+#undef HPB_AABS
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;

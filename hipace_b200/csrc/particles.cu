@@ -10,6 +10,7 @@
 //   src/particles/pusher/PlasmaParticleAdvance.cpp:92-217, PushPlasmaParticles.H:39-75,
 //   src/utils/DualNumbers.H:13-43, src/particles/pusher/GetAndSetPosition.H:29-99
 #include "common.cuh"
+#include "push_math.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -506,56 +507,6 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
 // -------------------------------------------------------------------------------------------
 // gather + push
 // -------------------------------------------------------------------------------------------
-struct Dual { double v, e; };
-__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.e + b.e}; }
-__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.e - b.e}; }
-__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.e * b.v + a.v * b.e}; }
-__device__ __forceinline__ Dual operator*(Dual a, double b) { return {a.v * b, a.e * b}; }
-__device__ __forceinline__ Dual operator*(double a, Dual b) { return {a * b.v, a * b.e}; }
-__device__ __forceinline__ Dual operator+(Dual a, double b) { return {a.v + b, a.e}; }
-__device__ __forceinline__ Dual operator+(double a, Dual b) { return {a + b.v, b.e}; }
-__device__ __forceinline__ Dual operator-(Dual a, double b) { return {a.v - b, a.e}; }
-
-struct PushFields { double ExmBy, EypBx, Ez, Bx_c, By_c, Bz; };
-
-// Aabssq_norm, AabssqDx_norm, AabssqDy_norm of PushPlasmaParticles.H:32-34
-struct PushLaser { double A, ADx, ADy; };
-
-// PlasmaMomentumPush<T>, PushPlasmaParticles.H:39-75 (LASER = false: the laser terms are zero)
-template <class T, bool LASER>
-__device__ __forceinline__ void momentum_push(const T &ux, const T &uy, const T &psi_inv,
-                                              const PushFields &f, double clight_inv, double qmc,
-                                              T &dz_ux, T &dz_uy, T &dz_psi, const PushLaser &las)
-{
-    const double c2 = clight_inv * clight_inv;
-    if (LASER) {
-        const T gamma_psi = 0.5 * psi_inv * psi_inv * ((1.0 + las.A) + ux * ux * c2 + uy * uy * c2) + 0.5;
-        dz_ux = qmc * (gamma_psi * f.ExmBy + f.By_c + (uy * f.Bz) * psi_inv) - las.ADx * psi_inv;
-        dz_uy = qmc * (gamma_psi * f.EypBx - f.Bx_c - (ux * f.Bz) * psi_inv) - las.ADy * psi_inv;
-    } else {
-        const T gamma_psi = 0.5 * psi_inv * psi_inv * (1.0 + ux * ux * c2 + uy * uy * c2) + 0.5;
-        dz_ux = qmc * (gamma_psi * f.ExmBy + f.By_c + (uy * f.Bz) * psi_inv);
-        dz_uy = qmc * (gamma_psi * f.EypBx - f.Bx_c - (ux * f.Bz) * psi_inv);
-    }
-    dz_psi = (qmc * clight_inv) * ((ux * f.ExmBy + uy * f.EypBx) * clight_inv * psi_inv - f.Ez);
-}
-
-template <bool LASER>
-__device__ __forceinline__ void push_substep(double &ux, double &uy, double &psi,
-                                             const PushFields &f, double clight_inv, double qmc,
-                                             double sdz, const PushLaser &las)
-{
-    const double psi_inv = 1.0 / psi;
-    double dz_ux, dz_uy, dz_psi;
-    momentum_push<double, LASER>(ux, uy, psi_inv, f, clight_inv, qmc, dz_ux, dz_uy, dz_psi, las);
-    const Dual ux_d{ux, dz_ux}, uy_d{uy, dz_uy}, pi_d{psi_inv, -psi_inv * psi_inv * dz_psi};
-    Dual d_ux, d_uy, d_psi;
-    momentum_push<Dual, LASER>(ux_d, uy_d, pi_d, f, clight_inv, qmc, d_ux, d_uy, d_psi, las);
-    ux += sdz * dz_ux + 0.5 * sdz * sdz * d_ux.e;
-    uy += sdz * dz_uy + 0.5 * sdz * sdz * d_uy.e;
-    psi += sdz * dz_psi + 0.5 * sdz * sdz * d_psi.e;
-}
-
 // EnforceBC, GetAndSetPosition.H:56-98.  Returns true if the particle became invalid.
 __device__ __forceinline__ bool enforce_bc(double &x, double &y, double &ux, double &uy, int bc,
                                            double lox, double loy, double hix, double hiy)
@@ -826,6 +777,9 @@ static int deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double cha
     // invvol: 1 in normalised units at lev 0, 1/(dx dy dz) in SI (PlasmaDepositCurrent.cpp:71-73)
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     if ((c_jx >= 0) != (c_jy >= 0)) { hpb_set_error("deposit: jx and jy go together"); return HPB_ERR_ARG; }
+    if (hpb_use_generic_order(ctx))
+        return hpb_gen_deposit_current(ctx, pl, sl, charge, mass, c_jx, c_jy, c_rho, c_chi, c_rhomjz, c_aabs,
+                                       max_qsa, d_n_qsa_violation);
     const int mask = (c_jx >= 0 ? 8 : 0) | (c_rho >= 0 ? 4 : 0) | (c_chi >= 0 ? 2 : 0) | (c_rhomjz >= 0 ? 1 : 0);
     // (charge/q_e)^2 (m_e/mass)^2, PlasmaDepositCurrent.cpp:80-81
     const double laser_norm = (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass);
@@ -882,6 +836,7 @@ extern "C" int hpb_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, d
 {
     if (!ctx) return HPB_ERR_ARG;
     if (bm.np == 0 || (c_jx < 0 && c_jz < 0)) return HPB_OK;
+    if (hpb_use_generic_order(ctx)) return hpb_gen_beam_deposit(ctx, bm, sl, charge, c_jx, c_jy, c_jz);
     const hpb_geom &g = ctx->g;
     // BeamDepositCurrent.cpp:72-82: invvol = 1 in normalised units at lev 0
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
@@ -899,6 +854,7 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
 {
     if (!ctx || !comps) return HPB_ERR_ARG;
     if (pl.np == 0) return HPB_OK;
+    if (hpb_use_generic_order(ctx)) return hpb_gen_explicit_deposition(ctx, pl, sl, charge, mass, comps);
     const hpb_geom &g = ctx->g;
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     static int variant = -1;
@@ -943,6 +899,14 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
 {
     if (!ctx || !comps || !bc_lo || !bc_hi || n_subcycles < 1) return HPB_ERR_ARG;
     if (pl.np == 0) return HPB_OK;
+    if (hpb_use_generic_order(ctx)) {
+        if (deposit) {
+            hpb_set_error("advance+deposit: only for depos_order_xy = 2 with the centred derivative");
+            return HPB_ERR_UNSUPPORTED;
+        }
+        return hpb_gen_advance_plasma(ctx, pl, sl, charge, mass, n_subcycles, temp_slice, particle_bc, bc_lo,
+                                      bc_hi, comps);
+    }
     const hpb_geom &g = ctx->g;
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("HPB_PUSH_VARIANT"); variant = e ? atoi(e) : 0; }

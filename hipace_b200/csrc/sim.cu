@@ -239,12 +239,23 @@ int read_deck(hpb_sim *s)
     for (int k = 0; k < 3; ++k) { s->prob_lo[k] = lo[k]; s->prob_hi[k] = hi[k]; }
     g.dx = (hi[0] - lo[0]) / g.nx; g.dy = (hi[1] - lo[1]) / g.ny; g.dz = (hi[2] - lo[2]) / s->nz;
     // GetPosOffset with the grown fab box [-g, n-1+g] (Fields.H:71-77)
-    g.x_off = 0.5 * (lo[0] + hi[0] - g.dx * ((-HPB_G) + (g.nx - 1 + HPB_G)));
-    g.y_off = 0.5 * (lo[1] + hi[1] - g.dy * ((-HPB_G) + (g.ny - 1 + HPB_G)));
-    if ((int)d.num("hipace.depos_order_xy", 2) != 2)
-        throw std::runtime_error("only hipace.depos_order_xy = 2 is supported");
-    if ((int)d.num("hipace.depos_derivative_type", 2) != 2)
-        throw std::runtime_error("only hipace.depos_derivative_type = 2 is supported");
+    s->depos_order = (int)d.num("hipace.depos_order_xy", 2);
+    s->depos_dtype = (int)d.num("hipace.depos_derivative_type", 2);
+    if (s->depos_order < 0 || s->depos_order > 3 || s->depos_dtype < 0 || s->depos_dtype > 2)
+        throw std::runtime_error("hipace.depos_order_xy must be 0..3 and hipace.depos_derivative_type 0..2");
+    if (s->depos_order == 0 && s->depos_dtype == 0)                        // Hipace.cpp:52-53
+        throw std::runtime_error("Analytic derivative with depos_order=0 would vanish");
+    s->ng = HPB_NGUARD_OF(s->depos_order);
+    g.x_off = 0.5 * (lo[0] + hi[0] - g.dx * ((-s->ng) + (g.nx - 1 + s->ng)));
+    g.y_off = 0.5 * (lo[1] + hi[1] - g.dy * ((-s->ng) + (g.ny - 1 + s->ng)));
+    if ((int)d.num("grid_current.use_grid_current", 0)) {                  // GridCurrent.cpp:14-23
+        const auto m = d.nums("grid_current.position_mean", {}), sd = d.nums("grid_current.position_std", {});
+        if (m.size() != 3 || sd.size() != 3 || !d.has("grid_current.peak_current_density"))
+            throw std::runtime_error("grid_current needs peak_current_density, position_mean and position_std");
+        s->use_grid_current = true;
+        s->gc_peak = d.num("grid_current.peak_current_density", 0.);
+        for (int k = 0; k < 3; ++k) { s->gc_mean[k] = m[k]; s->gc_std[k] = sd[k]; }
+    }
     if (d.str("hipace.bxby_solver", "explicit") != "explicit")
         throw std::runtime_error("only hipace.bxby_solver = explicit is supported");
     if (d.str("boundary.field", "") != "Dirichlet")
@@ -677,7 +688,10 @@ int solve_one_slice(hpb_sim *s, int islice)
     hpb_ctx *ctx = s->ctx;
     const int *C = s->comps;
     int rc;
-    bool fuse = s->opt_fuse && C[HPB_C_RHO] < 0 && !s->use_laser;
+    // (the fused push + deposit exists for the default order only; the grid current is added
+    // between the beam deposit and the Poisson solve of the reference order)
+    bool fuse = s->opt_fuse && C[HPB_C_RHO] < 0 && !s->use_laser && !hpb_use_generic_order(ctx)
+                && !s->use_grid_current;
     for (auto &sp : s->plasmas) if (sp.n_subcycles < 1) fuse = false;
     // (stage timers synchronise the main stream per stage: keep one stream when profiling)
     const bool side = fuse && s->opt_side_stream && s->stream2 && !s->beams.empty() && !s->opt_profile;
@@ -705,6 +719,10 @@ int solve_one_slice(hpb_sim *s, int islice)
         StageTimer t(s, ST_OTHER);
         if ((rc = beam_deposit_jz(s, islice))) return rc;
         if ((rc = hpb_fields_add_rho_ions(ctx, s->sl, C))) return rc;                   // :626
+        if (s->use_grid_current)                                                        // :629
+            if ((rc = hpb_fields_grid_current(ctx, s->sl, C[HPB_C_JZ_BEAM], s->gc_peak, s->gc_mean, s->gc_std,
+                                              s->prob_lo[0], s->prob_lo[1],
+                                              s->prob_lo[2] + islice * s->g.dz))) return rc;
     }
     s->prepared = false;
     {
@@ -872,8 +890,9 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     int rc = hpb_create(&s->ctx, &s->g, (void *)s->stream);
     if (rc) return rc;
     hpb_slice &sl = s->sl;
-    sl.lo_x = sl.lo_y = -HPB_G;
-    sl.nx_tot = s->g.nx + 2 * HPB_G; sl.ny_tot = s->g.ny + 2 * HPB_G;
+    if ((rc = hpb_set_deposition_order(s->ctx, s->depos_order, s->depos_dtype))) return rc;
+    sl.lo_x = sl.lo_y = -s->ng;
+    sl.nx_tot = s->g.nx + 2 * s->ng; sl.ny_tot = s->g.ny + 2 * s->ng;
     sl.jstride = sl.nx_tot; sl.nstride = (long)sl.nx_tot * sl.ny_tot;
     SIM_CUDA(cudaMalloc(&sl.p, sizeof(double) * sl.nstride * sl.ncomp));
     SIM_CUDA(cudaMemset(sl.p, 0, sizeof(double) * sl.nstride * sl.ncomp));
@@ -1014,6 +1033,7 @@ extern "C" int hpb_sim_geometry(hpb_sim *s, int n_cell[3], double prob_lo[3], do
 }
 
 extern "C" int hpb_sim_ncomp(hpb_sim *s) { return s ? s->sl.ncomp : -1; }
+extern "C" int hpb_sim_nguard(hpb_sim *s) { return s ? s->ng : -1; }
 
 extern "C" int hpb_sim_comp_index(hpb_sim *s, const char *which_slice, const char *name)
 {
@@ -1238,6 +1258,7 @@ extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
     const std::string k(key);
     if (k == "checksums") s->opt_checksums = value != 0.;
     else if (k == "fuse") s->opt_fuse = value != 0.;
+    else if (k == "generic_order_kernels") s->ctx->force_generic = value != 0.;
     else if (k == "side_stream") s->opt_side_stream = value != 0.;
     else if (k == "profile") s->opt_profile = value != 0.;
     else if (k == "max_step") s->max_step = (int)value;

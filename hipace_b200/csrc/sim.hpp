@@ -92,6 +92,10 @@ struct hpb_sim {
     double prob_lo[3], prob_hi[3];
     double bc_lo[2], bc_hi[2];
     int particle_bc = HPB_BC_PERIODIC;
+    int depos_order = 2, depos_dtype = 2;         // hipace.depos_order_xy / depos_derivative_type
+    int ng = HPB_NGUARD;                          // guard cells of the slice, Fields.cpp:63-64
+    bool use_grid_current = false;                // utils/GridCurrent.cpp
+    double gc_peak = 0., gc_mean[3] = {0., 0., 0.}, gc_std[3] = {1., 1., 1.};
     int max_step = 0;
     double dt = 0.;
     double mg_tol_rel = 1e-4, mg_tol_abs = DBL_MIN;

@@ -41,7 +41,8 @@ extern "C" {
 #define HPB_ERR_CAPACITY 6         /* a beam slice outgrew its packet (slipped particles) */
 #define HPB_ERR_NCCL 7
 
-#define HPB_NGUARD 2               /* (depos_order_xy+1)/2 + 1 for order 2, Fields.cpp:63-64 */
+#define HPB_NGUARD 2               /* (depos_order_xy+1)/2 + 1 for the default order 2, Fields.cpp:63-64 */
+#define HPB_NGUARD_OF(order) (((order) + 1) / 2 + 1)
 #define HPB_PLASMA_NREAL 11
 
 /* PlasmaIdx, PlasmaParticleContainer.H:21-46 */
@@ -175,6 +176,12 @@ int hpb_beam_shift_slipped(hpb_ctx *ctx, hpb_beam_slice bm, const int *d_nsubcyc
  * comps[] is the component table in the order of hpb_comp below. */
 int hpb_fields_initialize_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps);
 int hpb_fields_add_rho_ions(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+/* GridCurrent::DepositCurrentSlice (src/utils/GridCurrent.cpp:25-70): jz_beam += peak *
+ * exp(-((x-mean_x)/std_x)^2/2 - ((y-mean_y)/std_y)^2/2 - ((z-mean_z)/std_z)^2/2) on the valid box,
+ * x = plo_x + (i + 1/2) dx, y likewise, z = prob_lo_z + islice dz (passed in) */
+int hpb_fields_grid_current(hpb_ctx *ctx, hpb_slice sl, int c_jz_beam, double peak_current_density,
+                            const double position_mean[3], const double position_std[3],
+                            double plo_x, double plo_y, double z);
 int hpb_fields_shift_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps);
 
 /* FFTPoissonSolver::SolvePoissonEquation (src/fields/fft_poisson_solver/FFTPoissonSolver.H:26-57,
@@ -223,6 +230,13 @@ int hpb_fields_shift_and_initialize(hpb_ctx *ctx, hpb_slice sl, int *comps);
  * from / reduces into are fetched from HBM once per slice instead of once per pass.  Results do
  * not depend on it; cells_per_pass = 0 clears the hint. */
 int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc);
+/* hipace.depos_order_xy (0..3) and hipace.depos_derivative_type (0 analytic, 1 nodal, 2 centred) for
+ * every particle kernel called with this context afterwards (Hipace.cpp:49-53; the reference selects
+ * them at compile time through CompileTimeOptions, e.g. ExplicitDeposition.cpp:62-67).  Default 2 / 2.
+ * The caller's slice must then carry (order_xy + 1) / 2 + 1 guard cells (Fields.cpp:63-64):
+ * hpb_slice.lo_x = lo_y = -guards.  The default has warp-aggregated, staged kernels; every other
+ * combination runs one-thread-per-particle kernels (csrc/generic_order.cu). */
+int hpb_set_deposition_order(hpb_ctx *ctx, int order_xy, int derivative_type);
 int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
                                              double charge, double mass, int n_subcycles,
                                              int particle_bc, const double bc_lo[2],
@@ -269,6 +283,8 @@ int hpb_sim_solve_one_slice(hpb_sim *sim, int islice);
 
 /* queries (host buffers) */
 int hpb_sim_geometry(hpb_sim *sim, int n_cell[3], double prob_lo[3], double prob_hi[3]);
+/* guard cells of the slice array: (hipace.depos_order_xy + 1) / 2 + 1 (Fields.cpp:63-64) */
+int hpb_sim_nguard(hpb_sim *sim);
 int hpb_sim_ncomp(hpb_sim *sim);
 int hpb_sim_comp_index(hpb_sim *sim, const char *which_slice, const char *name); /* -1 if absent */
 /* copy one component of the current slice array (with guard cells, (ny+2g)*(nx+2g) doubles) */

@@ -8,7 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # decks the oracle runs but the CUDA driver must refuse (with the reason), not mis-run
-ORACLE_ONLY = {'laser_vacuum_SI.in': 'depos_order_xy'}     # order 0 + the laser envelope advance
+ORACLE_ONLY = {'laser_vacuum_SI.in': 'envelope advance'}     # the laser envelope advance over time steps
 DECKS = sorted(p for p in glob.glob(os.path.join(ROOT, 'examples', '*.in'))
                if os.path.basename(p) not in ORACLE_ONLY)
 
@@ -42,10 +42,23 @@ def test_oracle_only_decks_are_refused(name, reason):
     with pytest.raises(hp.HpbError) as e:
         hp.deck_check(open(os.path.join(ROOT, 'examples', name)).read())
     assert reason in str(e.value)
-    # ... and with the order fixed, the next unsupported thing is named
-    with pytest.raises(hp.HpbError) as e:
-        hp.deck_check(open(os.path.join(ROOT, 'examples', name)).read(), {'hipace.depos_order_xy': 2})
-    assert 'envelope advance' in str(e.value)
+
+
+def test_deposition_orders_and_the_combination_the_reference_rejects():
+    import hipace_b200 as hp
+    text = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    for order in range(4):
+        for dtype in range(3):
+            ov = {'hipace.depos_order_xy': order, 'hipace.depos_derivative_type': dtype}
+            if (order, dtype) == (0, 0):          # Hipace.cpp:52-53
+                with pytest.raises(hp.HpbError) as e:
+                    hp.deck_check(text, ov)
+                assert 'would vanish' in str(e.value)
+            else:
+                hp.deck_check(text, ov)
+    for bad in ({'hipace.depos_order_xy': 4}, {'hipace.depos_derivative_type': 3}):
+        with pytest.raises(hp.HpbError):
+            hp.deck_check(text, bad)
 
 
 def test_overrides_constants_and_expressions():
@@ -62,7 +75,7 @@ def test_overrides_constants_and_expressions():
 
 @pytest.mark.parametrize('ov,msg', [
     ({'beam.injection_type': 'fixed_weight'}, 'fixed_ppc'),
-    ({'hipace.depos_order_xy': 3}, 'depos_order_xy'),
+    ({'hipace.depos_order_xy': 4}, 'depos_order_xy'),
     ({'hipace.bxby_solver': 'predictor-corrector'}, 'explicit'),
     ({'boundary.field': 'Periodic'}, 'Dirichlet'),
     ({'plasma.u_std': '0. 0. 1e-3'}, 'RNG'),
@@ -111,5 +124,5 @@ def test_command_line_driver_check_mode():
     p = subprocess.run([exe, '--check', deck, 'amr.n_cell=64 64 64', 'max_step=3'], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert 'nx=64;ny=64;nz=64;' in p.stdout and 'max_step=3;' in p.stdout
-    p = subprocess.run([exe, '--check', deck, 'hipace.depos_order_xy=1'], capture_output=True, text=True)
+    p = subprocess.run([exe, '--check', deck, 'hipace.depos_order_xy=5'], capture_output=True, text=True)
     assert p.returncode == 1 and 'depos_order_xy' in p.stderr
