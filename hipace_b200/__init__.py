@@ -59,6 +59,7 @@ EXPORTS = (
     'hpb_fields_shift_and_initialize', 'hpb_advance_plasma_particles_and_deposit', 'hpb_deck_check',
     'hpb_set_plasma_lattice_hint', 'hpb_deposit_current_laser', 'hpb_laser_update_aabs',
     'hpb_set_deposition_order', 'hpb_fields_grid_current', 'hpb_sim_nguard',
+    'hpb_beam_insitu_slice', 'hpb_insitu_write_beam',
 )
 NCCL_ID_BYTES = 128
 
@@ -196,6 +197,27 @@ def _overrides_text(overrides):
             v = ' '.join(str(t) for t in v)
         lines.append(f'{k} = {v}')
     return ('\n'.join(lines) + '\n').encode()
+
+
+def insitu_write_beam(path, time, step, charge, mass, z_lo, z_hi, density_factor, normalized, sums):
+    """hpb_insitu_write_beam (host only): append one in-situ record built from the raw per-slice
+    sums[23, n_slices] to `path` in the reference's NumPy-structured format"""
+    a = np.ascontiguousarray(sums, dtype=np.float64)
+    assert a.ndim == 2 and a.shape[0] == 23
+    L = lib()
+    L.hpb_insitu_write_beam.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int] + [C.c_double] * 5 + \
+        [C.c_int, C.c_void_p]
+    _check(L.hpb_insitu_write_beam(str(path).encode(), time, step, a.shape[1], charge, mass, z_lo, z_hi,
+                                   density_factor, int(normalized), a.ctypes.data), 'hpb_insitu_write_beam')
+
+
+def read_insitu(path):
+    """what tools/read_insitu_diagnostics.py of the reference does with one file: JSON dtype header,
+    then raw records"""
+    import json
+    raw = open(path, 'rb').read()
+    obj, off = json.JSONDecoder().raw_decode(raw.decode(errors='replace'))
+    return np.frombuffer(raw, dtype=np.dtype(obj), offset=off)
 
 
 def deck_check(deck: str, overrides: dict | None = None) -> dict:

@@ -5,6 +5,7 @@
 // (oracle/ref_headers.cpp) and the NumPy oracle.  This is a TEST artefact: it is not part of
 // libhpb200.so and nothing in the product loads it.
 #include "generic_order.cuh"
+#include "insitu.cuh"
 
 namespace {
 struct HostAdd {
@@ -200,4 +201,17 @@ extern "C" int hc_advance_plasma(int order, long n, double *const *r, unsigned c
         if (!alive) { r[HPB_W][p] = 0.; valid[p] = 0; }
     }
     return 0;
+}
+
+// the 23 raw in-situ sums of a beam slice (insitu.cuh), b7 = x y z w ux uy uz
+extern "C" void hc_beam_insitu(long n, const double *const *b7, const unsigned char *valid, double clight_inv,
+                               double radius_sq, double *out23)
+{
+    for (int k = 0; k < 23; ++k) out23[k] = 0.;
+    for (long p = 0; p < n; ++p) {
+        double t[23];
+        if (insitu_beam_terms(valid[p] != 0, b7[0][p], b7[1][p], b7[2][p], b7[4][p], b7[5][p], b7[6][p],
+                              b7[3][p], clight_inv, radius_sq, t))
+            for (int k = 0; k < 23; ++k) out23[k] += t[k];
+    }
 }

@@ -1,0 +1,159 @@
+// In-situ beam diagnostics: per-slice weighted moments of a beam slice reduced on the
+// device, and the host-side writer of the reference's NumPy-structured file format, so that
+// tools/read_insitu_diagnostics.py of the reference reads our files unchanged.
+//   BeamParticleContainer::InSituComputeDiags / InSituWriteToFile
+//       src/particles/beam/BeamParticleContainer.cpp:476-557, 596-732
+//   insitu_utils::DataNode / write_header / write_data      src/utils/InsituUtil.H:22-90
+#include "common.cuh"
+#include "insitu.cuh"
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int kT = 256;
+
+// one launch per beam slice: block tree reduction, then 23 atomics per block into the slice's record
+__global__ void __launch_bounds__(kT)
+k_beam_insitu(hpb_beam_slice b, double clight_inv, double radius_sq, double *__restrict__ rec, long stride)
+{
+    hpb_pdl_prologue();
+    __shared__ double red[kT / 32][23];
+    long np = b.np;
+    if (b.d_np) { const long n = (long)b.d_np[0]; if (n < np) np = n; }      // getNumParticles(This)
+    double acc[23];
+#pragma unroll
+    for (int k = 0; k < 23; ++k) acc[k] = 0.;
+    for (long ip = (long)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += (long)gridDim.x * blockDim.x) {
+        double t[23];
+        if (insitu_beam_terms(hpb_is_valid(b.idcpu[ip]), b.x[ip], b.y[ip], b.z[ip], b.ux[ip], b.uy[ip],
+                              b.uz[ip], b.w[ip], clight_inv, radius_sq, t)) {
+#pragma unroll
+            for (int k = 0; k < 23; ++k) acc[k] += t[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 23; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 23) {
+        double v = 0.;
+        for (int wq = 0; wq < kT / 32; ++wq) v += red[wq][threadIdx.x];
+        if (v != 0.) atomicAdd(rec + threadIdx.x * stride, v);
+    }
+}
+
+// ---- the file format -------------------------------------------------------------------------
+struct Node {
+    std::string name, format;        // format empty: a nested structured datatype
+    const void *data = nullptr;
+    size_t bytes = 0;
+    std::vector<Node> sub;
+};
+Node leaf(const char *name, const char *fmt, const void *data, size_t bytes, size_t count = 1)
+{
+    Node n;
+    n.name = name;
+    n.format = (count > 1 ? "(" + std::to_string(count) + ",)" : std::string()) + fmt;
+    n.data = data; n.bytes = bytes * count;
+    return n;
+}
+Node f8(const char *name, const double *p, size_t count = 1) { return leaf(name, "<f8", p, 8, count); }
+Node i4(const char *name, const int *p, size_t count = 1) { return leaf(name, "<i4", p, 4, count); }
+
+void header(const std::vector<Node> &nodes, std::string &out, const std::string &indent)
+{
+    out += indent + "{\n" + indent + "    \"names\": [\n";
+    for (size_t i = 0; i < nodes.size(); ++i)
+        out += indent + "        \"" + nodes[i].name + "\"" + (i + 1 == nodes.size() ? "\n" : ",\n");
+    out += indent + "    ],\n" + indent + "    \"formats\": [\n";
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        if (!nodes[i].format.empty()) out += indent + "        \"" + nodes[i].format + "\"";
+        else header(nodes[i].sub, out, "        ");
+        out += (i + 1 == nodes.size() ? "\n" : ",\n");
+    }
+    out += indent + "    ]\n" + indent + "}";
+}
+void payload(const std::vector<Node> &nodes, std::string &out)
+{
+    for (const Node &n : nodes) {
+        if (!n.format.empty()) out.append((const char *)n.data, n.bytes);
+        else payload(n.sub, out);
+    }
+}
+
+}  // namespace
+
+extern "C" int hpb_beam_insitu_slice(hpb_ctx *ctx, hpb_beam_slice bm, double insitu_radius,
+                                     double *d_record, long stride)
+{
+    if (!ctx || !d_record || stride < 1) return HPB_ERR_ARG;
+    if (bm.np == 0) return HPB_OK;
+    unsigned nb = (unsigned)((bm.np + kT - 1) / kT);
+    if (nb > 64) nb = 64;
+    hpb_launch(k_beam_insitu, nb, kT, 0, ctx->stream, bm, 1.0 / ctx->g.c, insitu_radius * insitu_radius,
+               d_record, stride);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// Host only (no GPU needed).  sums: [23][n_slices] RAW per-slice sums in the order of
+// insitu_beam_terms (sum w, sum w x, ..., Np).  Appends one record to `path`; writes the JSON
+// datatype header first when the file is empty (InSituWriteToFile :596-721).
+extern "C" int hpb_insitu_write_beam(const char *path, double time, int step, int n_slices, double charge,
+                                     double mass, double z_lo, double z_hi,
+                                     double normalized_density_factor, int is_normalized_units,
+                                     const double *sums)
+{
+    if (!path || !sums || n_slices < 1) return HPB_ERR_ARG;
+    const size_t ns = (size_t)n_slices;
+    std::vector<double> r(kInsituNReal * ns), tot(kInsituNReal, 0.);
+    std::vector<int> np(ns);
+    int np_tot = 0;
+    for (size_t s = ns; s-- > 0;) {          // slice by slice from the head, like the running sums (:548)
+        const double sw = sums[s];
+        const double sum_w_inv = sw <= 0. ? 0. : 1. / sw;                   // :542
+        for (int i = 0; i < kInsituNReal; ++i) {
+            const double v = sums[i * ns + s];
+            r[i * ns + s] = v * (i == 0 ? 1. : sum_w_inv);                  // :544-549
+            tot[i] += v;
+        }
+        np[s] = (int)sums[kInsituNReal * ns + s];
+        np_tot += np[s];
+    }
+    const double sum_w0 = tot[0];
+    for (int i = 1; i < kInsituNReal; ++i) tot[i] /= sum_w0;                // :655-675
+    static const char *names[kInsituNReal] = {"sum(w)", "[x]", "[x^2]", "[y]", "[y^2]", "[z]", "[z^2]",
+        "[ux]", "[ux^2]", "[uy]", "[uy^2]", "[uz]", "[uz^2]", "[x*ux]", "[y*uy]", "[z*uz]", "[x*uy]",
+        "[y*ux]", "[ux/uz]", "[uy/uz]", "[ga]", "[ga^2]"};
+    std::vector<Node> all = {f8("time", &time), i4("step", &step), i4("n_slices", &n_slices),
+                             f8("charge", &charge), f8("mass", &mass), f8("z_lo", &z_lo), f8("z_hi", &z_hi),
+                             f8("normalized_density_factor", &normalized_density_factor),
+                             i4("is_normalized_units", &is_normalized_units)};
+    for (int i = 1; i < kInsituNReal; ++i) all.push_back(f8(names[i], &r[i * ns], ns));
+    all.push_back(f8("sum(w)", &r[0], ns));
+    all.push_back(i4("Np", np.data(), ns));
+    Node avg; avg.name = "average";
+    for (int i = 1; i < kInsituNReal; ++i) avg.sub.push_back(f8(names[i], &tot[i]));
+    Node total; total.name = "total";
+    total.sub.push_back(f8("sum(w)", &tot[0]));
+    total.sub.push_back(i4("Np", &np_tot));
+    all.push_back(avg);
+    all.push_back(total);
+
+    FILE *f = fopen(path, "ab");
+    if (!f) { hpb_set_error("in-situ diagnostics: cannot open %s (does the directory exist?)", path); return HPB_ERR_ARG; }
+    std::string out;
+    fseek(f, 0, SEEK_END);
+    if (ftell(f) == 0) header(all, out, "");
+    payload(all, out);
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (fclose(f) != 0 || !ok) { hpb_set_error("in-situ diagnostics: error while writing %s", path); return HPB_ERR_ARG; }
+    return HPB_OK;
+}

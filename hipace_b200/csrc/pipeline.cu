@@ -87,6 +87,7 @@ struct hpb_pipeline {
 };
 
 bool hpb_pipeline_active(const hpb_sim *s) { return s->pipe && s->pipe->world > 1; }
+int hpb_pipeline_rank(const hpb_sim *s) { return s->pipe ? s->pipe->rank : 0; }
 
 // every time step but the first has an upstream (Hipace.cpp:410: step 0 starts from the initial
 // beam, later steps from MultiBuffer::get_data)

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 #include <stdio.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <algorithm>
 #include <memory>
 
@@ -373,6 +374,14 @@ int read_deck(hpb_sim *s)
             b.n_subcycles = (int)d.num(nm + ".n_subcycles", 10);
             if (b.n_subcycles < 1) throw std::runtime_error(nm + ".n_subcycles must be >= 1");
             b.do_z_push = (int)d.num(nm + ".do_z_push", 1) != 0;
+            // "<beam name> or beams" (queryWithParserAlt)
+            auto alt_num = [&](const char *key, double dflt) {
+                return d.has(nm + "." + key) ? d.num(nm + "." + key, dflt) : d.num(std::string("beams.") + key, dflt);
+            };
+            b.insitu_period = (int)alt_num("insitu_period", 0);
+            b.insitu_radius = alt_num("insitu_radius", INFINITY);
+            b.insitu_file_prefix = d.has(nm + ".insitu_file_prefix") ? d.str(nm + ".insitu_file_prefix", "")
+                                 : d.str("beams.insitu_file_prefix", "diags/insitu");
             if ((int)d.num(nm + ".do_radiation_reaction", 0) != 0 || (int)d.num(nm + ".do_spin_tracking", 0) != 0)
                 throw std::runtime_error("beam radiation reaction / spin tracking are not supported");
             // external_E(x,y,z,t) / external_B(x,y,z,t): beam name first, then "beams"
@@ -606,8 +615,10 @@ int begin_step(hpb_sim *s, int step)
 }
 
 // after the last slice of a step: the pushed beam becomes the current one
+int write_beam_insitu(hpb_sim *s);
 int end_step(hpb_sim *s)
 {
+    if (int rc = write_beam_insitu(s)) return rc;
     for (auto &b : s->beams) { b.cur ^= 1; b.cs_valid = s->opt_checksums; b.initialised = true; }
     if (hpb_pipeline_active(s)) return hpb_pipeline_end_step(s, s->cur_step);
     return HPB_OK;
@@ -647,6 +658,39 @@ int beam_next_and_sxsy(hpb_sim *s, int isl)
     return hpb_fields_sxsy_from_beam(s->ctx, s->sl, s->comps);
 }
 
+// utils::doDiagnostics (utils/IOUtil.cpp:75-82; no max_time in our decks)
+bool do_diagnostics(int period, int step, int max_step)
+{
+    return period > 0 && (step == max_step || step % period == 0);
+}
+
+// BeamParticleContainer::InSituWriteToFile at the end of a time step (Hipace.cpp:488)
+int write_beam_insitu(hpb_sim *s)
+{
+    for (auto &b : s->beams) {
+        if (!b.d_insitu || !do_diagnostics(b.insitu_period, s->cur_step, s->max_step)) continue;
+        std::vector<double> h(23 * (size_t)s->nz);
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+        if (s->stream2) SIM_CUDA(cudaStreamSynchronize(s->stream2));
+        SIM_CUDA(cudaMemcpy(h.data(), b.d_insitu, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        SIM_CUDA(cudaMemset(b.d_insitu, 0, sizeof(double) * h.size()));
+        // mkdir -p <prefix>; file <prefix>/reduced_<name>.<rank, 4 digits>.txt
+        std::string dir;
+        for (char ch : b.insitu_file_prefix + "/") {
+            if (ch == '/' && !dir.empty()) mkdir(dir.c_str(), 0777);
+            dir += ch;
+        }
+        char rank[16];
+        snprintf(rank, sizeof(rank), "%04d", hpb_pipeline_active(s) ? hpb_pipeline_rank(s) : 0);
+        const std::string path = b.insitu_file_prefix + "/reduced_" + b.name + "." + rank + ".txt";
+        const double ndf = s->g.normalized ? s->g.dx * s->g.dy * s->g.dz : 1.0;
+        int rc = hpb_insitu_write_beam(path.c_str(), s->dt * s->cur_step, s->cur_step, s->nz, b.charge, b.mass,
+                                       s->prob_lo[2], s->prob_hi[2], ndf, s->g.normalized, h.data());
+        if (rc) return rc;
+    }
+    return HPB_OK;
+}
+
 // AdvanceBeamParticlesSlice + shiftSlippedParticles + MultiBuffer::put_data (Hipace.cpp:707-716)
 int beam_push_and_send(hpb_sim *s, int islice)
 {
@@ -659,6 +703,14 @@ int beam_push_and_send(hpb_sim *s, int islice)
     for (auto &b : s->beams) {
         const BeamRing &in = b.ring[b.cur], &out = b.ring[b.cur ^ 1];
         const hpb_beam_slice bm = in.view(slot);
+        // in-situ diagnostics of the slice BEFORE the push (Hipace.cpp:680-681)
+        if (do_diagnostics(b.insitu_period, s->cur_step, s->max_step)) {
+            if (!b.d_insitu) {
+                SIM_CUDA(cudaMalloc(&b.d_insitu, sizeof(double) * 23 * (size_t)s->nz));
+                SIM_CUDA(cudaMemsetAsync(b.d_insitu, 0, sizeof(double) * 23 * (size_t)s->nz, s->ctx->stream));
+            }
+            if ((rc = hpb_beam_insitu_slice(s->ctx, bm, b.insitu_radius, b.d_insitu + islice, s->nz))) return rc;
+        }
         if ((rc = hpb_advance_beam_impl(s->ctx, bm, in.nsub(slot), s->sl, b.charge, b.mass, b.n_subcycles,
                                         s->dt, time, min_z, b.do_z_push, s->particle_bc, s->bc_lo,
                                         s->bc_hi, s->comps, b.ext, b.d_class,

@@ -66,6 +66,11 @@ struct BeamSp {
     double pos_mean[3] = {0, 0, 0}, pos_std[3] = {0, 0, 0}, u_mean[3] = {0, 0, 0};
     int n_subcycles = 10;
     bool do_z_push = true;
+    // in-situ diagnostics (BeamParticleContainer.cpp:61-63, 296-311)
+    int insitu_period = 0;
+    std::string insitu_file_prefix = "diags/insitu";
+    double insitu_radius = INFINITY;
+    double *d_insitu = nullptr;   // [23][nz] raw per-slice sums of the current step
     std::string ext_expr[6];
     bool use_ext = false;
     hpb_extfields *ext = nullptr;
@@ -174,3 +179,4 @@ bool hpb_pipeline_out_ring_busy(const hpb_sim *s);          // sends of the prev
 int hpb_pipeline_end_step(hpb_sim *s, int step);
 bool hpb_pipeline_receives(const hpb_sim *s, int step);     // this step's beam comes from upstream
 bool hpb_pipeline_active(const hpb_sim *s);
+int hpb_pipeline_rank(const hpb_sim *s);

@@ -160,6 +160,19 @@ int hpb_advance_beam_particles(hpb_ctx *ctx, hpb_beam_slice bm, int *d_nsubcycle
                                const hpb_extfields *ext, int *d_class_counts,
                                double *d_checksum);
 
+/* In-situ beam diagnostics.  hpb_beam_insitu_slice = the reduction of
+ * BeamParticleContainer::InSituComputeDiags (src/particles/beam/BeamParticleContainer.cpp:476-557)
+ * for one beam slice: d_record[k * stride] += the k-th of the 23 raw sums (sum w, sum w x, sum w x^2,
+ * ..., sum w gamma^2, Np; order of that file), i.e. with d_record = base + islice and stride =
+ * n_slices the array [23][n_slices] that hpb_insitu_write_beam takes.
+ * hpb_insitu_write_beam (HOST only, no GPU) = InSituWriteToFile (:596-732): normalises by sum(w),
+ * forms the averages / totals over slices and appends one record in the NumPy-structured format of
+ * src/utils/InsituUtil.H, which the reference's tools/read_insitu_diagnostics.py reads unchanged. */
+int hpb_beam_insitu_slice(hpb_ctx *ctx, hpb_beam_slice bm, double insitu_radius, double *d_record,
+                          long stride);
+int hpb_insitu_write_beam(const char *path, double time, int step, int n_slices, double charge,
+                          double mass, double z_lo, double z_hi, double normalized_density_factor,
+                          int is_normalized_units, const double *h_sums);
 /* shiftSlippedParticles (src/particles/sorting/SliceSort.cpp:13-67) fused with the packing of
  * MultiBuffer::put_data (src/utils/MultiBuffer.cpp:730-905): invalid particles are dropped, the
  * particles with z >= min_z go (stable order) to `stay` whose counts d_stay_np[0..1] are set,

@@ -1445,6 +1445,65 @@ def advance_beam_slice(bs: dict, beam: Beam, F, geom: Geometry, pc: PhysConst, i
     bs['nsub'][a] = nsub[a]
 
 
+INSITU_NAMES = ('sum(w)', '[x]', '[x^2]', '[y]', '[y^2]', '[z]', '[z^2]', '[ux]', '[ux^2]', '[uy]', '[uy^2]',
+                '[uz]', '[uz^2]', '[x*ux]', '[y*uy]', '[z*uz]', '[x*uy]', '[y*ux]', '[ux/uz]', '[uy/uz]',
+                '[ga]', '[ga^2]')
+
+
+def beam_insitu_sums(bs: dict, pc: PhysConst, radius=math.inf):
+    """BeamParticleContainer::InSituComputeDiags, particles/beam/BeamParticleContainer.cpp:476-557:
+    the 22 raw weighted sums + Np of one beam slice (getNumParticles: without the slipped ones)"""
+    out = np.zeros(23)
+    if bs is None or bs['x'].size == 0:
+        return out
+    n = bs.get('np', bs['x'].size)
+    x, y, z, w = bs['x'][:n], bs['y'][:n], bs['z'][:n], bs['w'][:n]
+    ci = 1.0 / pc.c
+    ux, uy, uz = bs['ux'][:n] * ci, bs['uy'][:n] * ci, bs['uz'][:n] * ci
+    sel = bs['valid'][:n] & ~(x * x + y * y > radius * radius)
+    x, y, z, w, ux, uy, uz = (a[sel] for a in (x, y, z, w, ux, uy, uz))
+    uz_inv = np.where(uz == 0.0, 0.0, 1.0 / np.where(uz == 0.0, 1.0, uz))
+    ga = np.sqrt(1.0 + ux * ux + uy * uy + uz * uz)
+    terms = (w, w * x, w * x * x, w * y, w * y * y, w * z, w * z * z, w * ux, w * ux * ux, w * uy,
+             w * uy * uy, w * uz, w * uz * uz, w * x * ux, w * y * uy, w * z * uz, w * x * uy, w * y * ux,
+             w * ux * uz_inv, w * uy * uz_inv, w * ga, w * ga * ga)
+    for k, t in enumerate(terms):
+        out[k] = t.sum()
+    out[22] = x.size
+    return out
+
+
+def insitu_beam_record(sums, time, step, charge, mass, z_lo, z_hi, density_factor, normalized):
+    """InSituWriteToFile, particles/beam/BeamParticleContainer.cpp:596-732: (numpy dtype, record)
+    of one time step from the raw sums[23, n_slices]; format of utils/InsituUtil.H"""
+    ns = sums.shape[1]
+    sw = sums[0]
+    sw_inv = np.where(sw <= 0.0, 0.0, 1.0 / np.where(sw <= 0.0, 1.0, sw))
+    per = sums[:22] * np.where(np.arange(22)[:, None] == 0, 1.0, sw_inv[None, :])
+    tot = np.zeros(22)
+    for isl in range(ns - 1, -1, -1):      # accumulated slice by slice from the head (:548)
+        tot += sums[:22, isl]
+    avg = tot / tot[0]
+    arr = [(nm, '<f8', (ns,)) for nm in INSITU_NAMES[1:]] + [('sum(w)', '<f8', (ns,)), ('Np', '<i4', (ns,))]
+    dt = np.dtype([('time', '<f8'), ('step', '<i4'), ('n_slices', '<i4'), ('charge', '<f8'), ('mass', '<f8'),
+                   ('z_lo', '<f8'), ('z_hi', '<f8'), ('normalized_density_factor', '<f8'),
+                   ('is_normalized_units', '<i4')] + arr
+                  + [('average', [(nm, '<f8') for nm in INSITU_NAMES[1:]]),
+                     ('total', [('sum(w)', '<f8'), ('Np', '<i4')])])
+    rec = np.zeros((), dtype=dt)
+    rec['time'], rec['step'], rec['n_slices'] = time, step, ns
+    rec['charge'], rec['mass'], rec['z_lo'], rec['z_hi'] = charge, mass, z_lo, z_hi
+    rec['normalized_density_factor'], rec['is_normalized_units'] = density_factor, int(normalized)
+    for k, nm in enumerate(INSITU_NAMES):
+        rec[nm] = per[k]
+        if k:
+            rec['average'][nm] = avg[k]
+    rec['Np'] = sums[22].astype(np.int32)
+    rec['total']['sum(w)'] = tot[0]
+    rec['total']['Np'] = int(sums[22].sum())
+    return dt, rec
+
+
 _BEAM_KEYS = ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id', 'valid', 'nsub')
 
 
@@ -1665,6 +1724,14 @@ class Simulation:
         self.mg_cycles = []
         self.n_qsa_violation = 0
         self.slice_hook = None        # callable(sim, islice, stage) for tests
+        # in-situ beam diagnostics ("<beam name> or beams", BeamParticleContainer.cpp:61-63)
+        self.insitu_period = {b.name: _get(d, b.name + '.insitu_period',
+                                           _get(d, 'beams.insitu_period', 0, typ=int), typ=int)
+                              for b in self.beams}
+        self.insitu_radius = {b.name: _get(d, b.name + '.insitu_radius',
+                                           _get(d, 'beams.insitu_radius', math.inf))
+                              for b in self.beams}
+        self.insitu, self.insitu_records = {}, {}
 
     # -- deck readers ----------------------------------------------------------------------
     def _species_charge_mass(self, pre, default_element=None):
@@ -1879,6 +1946,11 @@ class Simulation:
         for pl in self.plasmas:                                                   # :699-701
             self.n_plasma_pushed += pl.x.size
             advance_plasma_particles(pl, F, g, pc, self.bc_kind, self.bc_lo, self.bc_hi, aabs=aabs)
+        for b in self.beams:                                                      # :680-681
+            per = self.insitu_period.get(b.name, 0)
+            if per > 0 and (self.step == self.max_step or self.step % per == 0):
+                self.insitu.setdefault(b.name, np.zeros((23, g.nz)))[:, islice] = \
+                    beam_insitu_sums(self.beam_slice(b, islice), pc, self.insitu_radius.get(b.name, math.inf))
         for b in self.beams:                                                      # :707-709
             bs = self.beam_slice(b, islice)
             self.n_beam_pushed += bs['np']
@@ -1924,8 +1996,15 @@ class Simulation:
         for step in range(step_begin, step_end + 1):
             self.checksums = {}
             self.begin_step(step)
+            self.insitu = {}
             for isl in range(g.nz - 1, stop, -1):
                 self.solve_one_slice(isl)
+            for b in self.beams:                                                  # Hipace.cpp:488
+                if b.name in self.insitu:
+                    ndf = g.dx * g.dy * g.dz if self.normalized else 1.0
+                    self.insitu_records.setdefault(b.name, []).append(insitu_beam_record(
+                        self.insitu[b.name], self.dt * step, step, b.charge, b.mass, g.lo[2], g.hi[2],
+                        ndf, self.normalized)[1])
             if self.use_laser:
                 self.laser_store = self.laser_next
         return self.checksums
