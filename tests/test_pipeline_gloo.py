@@ -70,14 +70,19 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_pipeline_reproduces_serial_run():
+@pytest.mark.parametrize('world', [2, 3])
+def test_multi_rank_pipeline_reproduces_serial_run(world):
+    """world = 2: both neighbours of a rank are the same peer; world = 3: the smallest ring whose
+    upstream and downstream peers differ (the case 4 and 8 GPUs are)"""
     import torch.multiprocessing as mp
     from oracle.hipace_oracle import Simulation
-    world = 2
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, _free_port(), d), nprocs=world, join=True)
         res = [pickle.load(open(os.path.join(d, f'rank{r}.pkl'), 'rb')) for r in range(world)]
-    assert res[0]['steps'] == [0, 2, 4] and res[1]['steps'] == [1, 3]
+    if world == 2:
+        assert res[0]['steps'] == [0, 2, 4] and res[1]['steps'] == [1, 3]
+    else:
+        assert [r['steps'] for r in res] == [[0, 3], [1, 4], [2]]
     deck = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
     ref = Simulation(deck, OV)
     ref.evolve(step_end=OV['max_step'])
