@@ -325,9 +325,31 @@ EXPLICIT_COMPS = (
 )
 
 
-def component_map(deposit_rho=False, neutral_background=True, use_laser=False):
+PC_COMPS = (        # predictor-corrector solver, fields/Fields.cpp:124-163
+    ('Next', ('jx', 'jy')),
+    ('This', ('ExmBy', 'EypBx', 'Ez', 'Bx', 'By', 'Bz', 'Psi', 'jx', 'jy', 'jz', 'rhomjz')),
+    ('Previous', ('Bx', 'By', 'jx', 'jy')),
+    ('RhomJzIons', ('rhomjz',)),
+    ('PCIter', ('Bx', 'By')),
+    ('PCPrevIter', ('Bx', 'By')),
+)
+
+
+def component_map(deposit_rho=False, neutral_background=True, use_laser=False, explicit=True):
     comps = {}
     n = 0
+    if not explicit:
+        assert not use_laser, 'oracle scope: laser only with the explicit solver'
+        for sl, names in PC_COMPS:
+            if sl == 'RhomJzIons' and not neutral_background:
+                continue
+            for nm in names:
+                comps[(sl, nm)] = n
+                n += 1
+            if sl == 'This' and deposit_rho:
+                comps[('This', 'rho')] = n
+                n += 1
+        return comps, n
     for sl, names in EXPLICIT_COMPS:
         if sl == 'RhomJzIons' and not neutral_background:
             continue
@@ -604,7 +626,7 @@ def _scatter(arr, jj, ii, vals, G):
 
 def deposit_current(pl: Plasma, F: dict, geom: Geometry, pc: PhysConst, normalized: bool,
                     *, jx=None, jy=None, rho=None, chi=None, rhomjz=None, flip_charge=False,
-                    aabs=None):
+                    aabs=None, jz=None):
     """::DepositCurrent, particles/deposition/PlasmaDepositCurrent.cpp:22-257 (jz not needed by
     the explicit solver).  Arguments jx.. are the destination arrays or None (the reference's -1).
     Returns the number of QSA-violating particles killed in this call (:197-204)."""
@@ -647,6 +669,8 @@ def deposit_current(pl: Plasma, F: dict, geom: Geometry, pc: PhysConst, normaliz
     if jx is not None:
         _scatter(jx, jj, ii, cd * vx_c, G)
         _scatter(jy, jj, ii, cd * vy_c, G)
+    if jz is not None:                                                      # :223 (predictor-corrector)
+        _scatter(jz, jj, ii, cd * (gamma_psi - 1.0) * pc.c, G)
     if rho is not None:
         _scatter(rho, jj, ii, cd * gamma_psi, G)
     if chi is not None:
@@ -724,15 +748,64 @@ def _ddy(a, dy, G):
     return (a[G + 1:a.shape[0] - G + 1, G:-G] - a[G - 1:a.shape[0] - G - 1, G:-G]) * (0.5 / dy)
 
 
-def solve_poisson_psi_ez_bz(F, geom: Geometry, pc: PhysConst, eig):
-    """Fields::SolvePoissonPsiExmByEypBxEzBz, fields/Fields.cpp:840-957 (lev 0, Dirichlet)."""
+N_MULTIPOLE = 18      # fields/OpenBoundary.H: 1 + 2 * 18 coefficients
+
+
+def open_boundary_rhs(rhs, geom: Geometry, monopole: bool):
+    """Fields::SetBoundaryCondition for boundary.field = Open (fields/Fields.cpp:685-738) followed by
+    SetDirichletBoundaries (:628-673), offset = factor = 1 (FFTPoissonSolverDirichletFast.H:58-59).
+
+    The free-space potential of the sources inside 95 % of the largest centred circle,
+    phi(r) = dx dy / (4 pi) sum_s s ln |r - r_s|^2, is expanded about the origin: with z = x + i y
+    (both scaled by 3 / box diagonal) and the moments M_k = sum_s s z_s^k,
+        phi = dx dy / (4 pi) ( M_0 ln |z|^2 - 2 sum_{k=1..18} Re(M_k / z^k) / k ),
+    which is what the 37 real coefficients and the polynomial table of fields/OpenBoundary.H:39-156
+    spell out term by term.  Its value one cell outside every edge cell is the non-zero Dirichlet
+    value, folded into the right-hand side as -value / dx^2 (Van Loan).  Ez and Bz have no monopole."""
+    ny, nx = rhs.shape
+    dx, dy = geom.dx, geom.dy
+    off_x = 0.5 * (geom.lo[0] + geom.hi[0] - dx * (nx - 1))
+    off_y = 0.5 * (geom.lo[1] + geom.hi[1] - dy * (ny - 1))          # GetPosOffset of the valid box
+    scale = 3.0 / math.sqrt((geom.hi[0] - geom.lo[0]) ** 2 + (geom.hi[1] - geom.lo[1]) ** 2)
+    radius = min(abs(geom.lo[0]), abs(geom.hi[0]), abs(geom.lo[1]), abs(geom.hi[1]))
+    assert radius > 0.0, 'x = 0, y = 0 must be inside the box'
+    cutoff_sq = (0.95 * radius * scale) ** 2
+    x = ((np.arange(nx) * dx + off_x) * scale)[None, :]
+    y = ((np.arange(ny) * dy + off_y) * scale)[:, None]
+    inside = ~(x * x + y * y > cutoff_sq)
+    zs = (x + 1j * y)[inside]
+    sv = rhs[inside]
+    M = [np.sum(sv * zs ** k) for k in range(N_MULTIPOLE + 1)]
+    if not monopole:
+        M[0] = 0.0
+
+    def value(xd, yd):
+        z = (xd + 1j * yd) * scale
+        phi = np.real(M[0]) * np.log(np.abs(z) ** 2)
+        for k in range(1, N_MULTIPOLE + 1):
+            phi = phi - 2.0 * np.real(M[k] / z ** k) / k
+        return dx * dy / (4.0 * math.pi) * phi
+
+    out = rhs.copy()
+    xi = np.arange(nx) * dx + off_x
+    yj = np.arange(ny) * dy + off_y
+    out[0, :] += -value(xi, (0 - 1) * dy + off_y) / (dy * dy)             # j_lo edge
+    out[ny - 1, :] += -value(xi, (ny - 1 + 1) * dy + off_y) / (dy * dy)   # j_hi edge
+    out[:, 0] += -value((0 - 1) * dx + off_x, yj) / (dx * dx)             # i_lo edge
+    out[:, nx - 1] += -value((nx - 1 + 1) * dx + off_x, yj) / (dx * dx)   # i_hi edge
+    return out
+
+
+def solve_poisson_psi_ez_bz(F, geom: Geometry, pc: PhysConst, eig, open_bc=False):
+    """Fields::SolvePoissonPsiExmByEypBxEzBz, fields/Fields.cpp:840-957 (lev 0, Dirichlet or Open)."""
     dx, dy, G = geom.dx, geom.dy, geom.g
     T = lambda n: F[('This', n)]
-    T('Psi')[G:-G, G:-G] = poisson_dirichlet((-1.0 / pc.ep0) * T('rhomjz')[G:-G, G:-G], eig)
+    bc = (lambda r, mono: open_boundary_rhs(r, geom, mono)) if open_bc else (lambda r, mono: r)
+    T('Psi')[G:-G, G:-G] = poisson_dirichlet(bc((-1.0 / pc.ep0) * T('rhomjz')[G:-G, G:-G], True), eig)
     f = 1.0 / (pc.ep0 * pc.c)
-    T('Ez')[G:-G, G:-G] = poisson_dirichlet(f * _ddx(T('jx'), dx, G) + f * _ddy(T('jy'), dy, G), eig)
-    T('Bz')[G:-G, G:-G] = poisson_dirichlet(pc.mu0 * _ddy(T('jx'), dy, G)
-                                            + (-pc.mu0) * _ddx(T('jy'), dx, G), eig)
+    T('Ez')[G:-G, G:-G] = poisson_dirichlet(bc(f * _ddx(T('jx'), dx, G) + f * _ddy(T('jy'), dy, G), False), eig)
+    T('Bz')[G:-G, G:-G] = poisson_dirichlet(bc(pc.mu0 * _ddy(T('jx'), dy, G)
+                                               + (-pc.mu0) * _ddx(T('jy'), dx, G), False), eig)
     # ExmBy / EypBx on the box grown by g-1, i.e. everything but the outermost ring (:931-956)
     psi = T('Psi')
     ny_t, nx_t = psi.shape
@@ -1648,8 +1721,17 @@ class Simulation:
         self.geom = Geometry(n[0], n[1], n[2], tuple(lo), tuple(hi), order, dtype)
         self.diag_type = _get(d, 'diagnostic.diag_type', 'xyz', typ=str)
         assert self.diag_type in ('xyz', 'xz'), 'oracle scope: xyz / xz field diagnostics'
-        assert _get(d, 'hipace.bxby_solver', 'explicit', typ=str) == 'explicit'
-        assert _get(d, 'boundary.field', typ=str) == 'Dirichlet', 'oracle scope: Dirichlet'
+        solver = _get(d, 'hipace.bxby_solver', 'explicit', typ=str)
+        assert solver in ('explicit', 'predictor-corrector')
+        self.explicit = solver == 'explicit'
+        self.predcorr_tol = _get(d, 'hipace.predcorr_B_error_tolerance', 4e-2)      # Hipace.H:210-222
+        self.predcorr_max_iter = _get(d, 'hipace.predcorr_max_iterations', 30, typ=int)
+        self.predcorr_mix = _get(d, 'hipace.predcorr_B_mixing_factor', 0.05)
+        self.predcorr_iters = []
+        bf = _get(d, 'boundary.field', typ=str)
+        assert bf in ('Dirichlet', 'Open'), 'oracle scope: Dirichlet / Open field boundaries'
+        assert bf == 'Dirichlet' or not self.explicit, 'oracle scope: Open only with predictor-corrector'
+        self.open_bc = bf == 'Open'
         self.bc_kind = _get(d, 'boundary.particle', typ=str)
         self.bc_lo = _get(d, 'boundary.particle_lo', [lo[0], lo[1]], n=2)
         self.bc_hi = _get(d, 'boundary.particle_hi', [hi[0], hi[1]], n=2)
@@ -1710,7 +1792,8 @@ class Simulation:
             self.laser_mg = None
             self.laser_store = {}           # islice -> (A^n, A^{n-1}) handed from step to step
             self.laser_next = {}
-        self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral, self.use_laser)
+        self.comps, self.ncomp = component_map(self.deposit_rho, self.any_neutral, self.use_laser,
+                                               self.explicit)
         g = self.geom
         self.F = {k: np.zeros((g.ny + 2 * g.g, g.nx + 2 * g.g)) for k in self.comps}
         self.eig = poisson_eigenvalues(g.nx, g.ny, g.dx, g.dy)
@@ -1861,8 +1944,112 @@ class Simulation:
             beam.slices[islice] = init_beam_slice(beam, islice, self.geom, self.pc, self.normalized)
         return beam.slices[islice]
 
+    def _solve_one_slice_pc(self, islice: int):
+        """Hipace::SolveOneSlice with hipace.bxby_solver = predictor-corrector: Hipace.cpp:556-728
+        (the non-explicit branches) and PredictorCorrectorLoopToSolveBxBy, Hipace.cpp:935-1031"""
+        F, g, pc, nrm = self.F, self.geom, self.pc, self.normalized
+        T = self.T
+        G = g.g
+        v = (slice(G, -G), slice(G, -G))
+        for b in self.beams:
+            self.beam_slice(b, islice)
+        for nm in ('ExmBy', 'EypBx', 'jx', 'jy', 'jz', 'rhomjz'):                  # Fields.cpp:565-566
+            T(nm)[...] = 0.0
+        if self.deposit_rho:
+            T('rho')[...] = 0.0
+        for pl in self.plasmas:                                                   # :617-618
+            self.n_qsa_violation += deposit_current(
+                pl, F, g, pc, nrm, jx=T('jx'), jy=T('jy'), jz=T('jz'),
+                rho=T('rho') if self.deposit_rho else None, rhomjz=T('rhomjz'))
+        for b in self.beams:                                                      # :621-623
+            beam_deposit(self.beam_slice(b, islice), b, g, pc, nrm,
+                         jxb=T('jx') if self.do_beam_jx_jy else None,
+                         jyb=T('jy') if self.do_beam_jx_jy else None, jzb=T('jz'))
+        if self.any_neutral:                                                      # :626
+            T('rhomjz')[...] += F[('RhomJzIons', 'rhomjz')]
+            if self.deposit_rho:
+                T('rho')[...] += F[('RhomJzIons', 'rhomjz')]
+        if self.grid_current is not None:                                         # :629 (jz, GridCurrent.cpp:48-49)
+            grid_current_deposit(T('jz'), g, islice, *self.grid_current)
+        solve_poisson_psi_ez_bz(F, g, pc, self.eig, self.open_bc)                 # :633
+
+        def rel_error(a, b):                                                      # Fields.cpp:1227-1286
+            ax, ay, bx, by = F[(a, 'Bx')][v], F[(a, 'By')][v], F[(b, 'Bx')][v], F[(b, 'By')][v]
+            norm_b = np.sqrt(ax * ax + ay * ay).sum()
+            norm_d = np.sqrt((ax - bx) * (ax - bx) + (ay - by) * (ay - by)).sum()
+            return norm_d / norm_b if norm_b > 0.0 else 0.0
+
+        err = rel_error('Previous', 'PCPrevIter')                                 # :941-943
+        mix0 = math.exp(-0.5 * (err / (2.5 * self.predcorr_tol)) ** 2)            # Fields.cpp:1149-1170
+        for c in ('Bx', 'By'):
+            T(c)[...] = (1.0 + mix0) * F[('Previous', c)] + (-mix0) * F[('PCPrevIter', c)]
+            F[('PCIter', c)][...] = 0.0                                           # :951-955
+            F[('PCPrevIter', c)][...] = T(c)
+        bc = (lambda r: open_boundary_rhs(r, g, True)) if self.open_bc else (lambda r: r)
+        i_iter, err, err_prev = 0, 1.0, 1.0
+        while err > self.predcorr_tol and i_iter < self.predcorr_max_iter:        # :961-1010
+            i_iter += 1
+            for pl in self.plasmas:                                               # push to the temp slice
+                advance_plasma_particles(pl, F, g, pc, self.bc_kind, self.bc_lo, self.bc_hi, temp_slice=True)
+            for pl in self.plasmas:                                               # jx jy of the next slice
+                self.n_qsa_violation += deposit_current(pl, F, g, pc, nrm, jx=F[('Next', 'jx')],
+                                                        jy=F[('Next', 'jy')])
+            if self.do_beam_jx_jy and islice - 1 >= 0:
+                for b in self.beams:
+                    beam_deposit(self.beam_slice(b, islice - 1), b, g, pc, nrm,
+                                 jxb=F[('Next', 'jx')], jyb=F[('Next', 'jy')])
+            # SolvePoissonBxBy, Fields.cpp:1008-1078 -> PCIter
+            dz_jy = (F[('Previous', 'jy')][v] - F[('Next', 'jy')][v]) * (0.5 / g.dz)
+            dz_jx = (F[('Previous', 'jx')][v] - F[('Next', 'jx')][v]) * (0.5 / g.dz)
+            F[('PCIter', 'Bx')][v] = poisson_dirichlet(
+                bc(-pc.mu0 * _ddy(T('jz'), g.dy, G) + pc.mu0 * dz_jy), self.eig)
+            F[('PCIter', 'By')][v] = poisson_dirichlet(
+                bc(pc.mu0 * _ddx(T('jz'), g.dx, G) + (-pc.mu0) * dz_jx), self.eig)
+            err = rel_error('This', 'PCIter')
+            if i_iter == 1:
+                err_prev = err
+            # MixAndShiftBfields, Fields.cpp:1172-1225
+            if err != 0.0 or err_prev != 0.0:
+                w_it, w_prev = err_prev / (err + err_prev), err / (err + err_prev)
+            else:
+                w_it = w_prev = 0.5
+            for c in ('Bx', 'By'):
+                F[('PCPrevIter', c)][...] = w_it * F[('PCIter', c)] + w_prev * F[('PCPrevIter', c)]
+                T(c)[...] = (1.0 - self.predcorr_mix) * T(c) + self.predcorr_mix * F[('PCPrevIter', c)]
+                F[('PCPrevIter', c)][...] = F[('PCIter', c)]
+            F[('Next', 'jx')][...] = 0.0                                          # :996-999
+            F[('Next', 'jy')][...] = 0.0
+            err_prev = err
+        self.predcorr_iters.append(i_iter)
+        if self.slice_hook:
+            self.slice_hook(self, islice, 'fields')
+        for b in self.beams:                                                      # :682-683 (before the push)
+            bs = self.beam_slice(b, islice)
+            n = bs['np']
+            self.beam_diag.setdefault(b.name, []).append(
+                {k: bs[k][:n].copy() for k in ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id')})
+        self._accumulate_checksums(islice)
+        for pl in self.plasmas:
+            self.n_plasma_pushed += pl.x.size
+            advance_plasma_particles(pl, F, g, pc, self.bc_kind, self.bc_lo, self.bc_hi)
+        for b in self.beams:
+            bs = self.beam_slice(b, islice)
+            self.n_beam_pushed += bs['np']
+            advance_beam_slice(bs, b, F, g, pc, islice, self.dt, getattr(self, 'time', 0.0),
+                               self.bc_kind, self.bc_lo, self.bc_hi)
+            shift_slipped_particles(bs, self.beam_slice(b, islice - 1), g, islice)
+        if self.slice_hook:
+            self.slice_hook(self, islice, 'pushed')
+        for c in ('Bx', 'By'):                                                    # ShiftSlices, Fields.cpp:600-603
+            F[('PCPrevIter', c)][...] = F[('Previous', c)]
+            F[('Previous', c)][...] = T(c)
+        F[('Previous', 'jx')][...] = T('jx')
+        F[('Previous', 'jy')][...] = T('jy')
+
     def solve_one_slice(self, islice: int):
         """Hipace::SolveOneSlice, Hipace.cpp:556-728 (explicit branch)."""
+        if not self.explicit:
+            return self._solve_one_slice_pc(islice)
         F, g, pc, nrm = self.F, self.geom, self.pc, self.normalized
         T = self.T
         for b in self.beams:

@@ -96,6 +96,17 @@ CASES = {
                    'grid_current.position_std': '0.3 0.3 1.41', 'beam.profile': 'gaussian',
                    'beam.position_std': '0.3 0.3 1.41', 'beam.density': 0.2, 'beam.radius': 1.,
                    'beam.ppc': '1 1 1'}, rtol_cpu=1e-12, rtol_cuda=1e-5),
+    # tests/beam_in_vacuum_open_boundary.normalized.1Rank.sh:30-44: the PREDICTOR-CORRECTOR Bx/By solver
+    # with OPEN field boundaries (multipole expansion of the free-space potential, fields/OpenBoundary.H),
+    # off-centre beam, order 0, absorbing particle boundary
+    'beam_in_vacuum_open_boundary.normalized.1Rank': dict(
+        deck='examples/beam_in_vacuum_normalized.in',
+        overrides={'hipace.depos_order_xy': 0, 'hipace.bxby_solver': 'predictor-corrector',
+                   'hipace.predcorr_B_mixing_factor': 0.95, 'hipace.predcorr_max_iterations': 5,
+                   'boundary.field': 'Open', 'boundary.particle': 'Absorbing',
+                   'geometry.prob_lo': '-4. -4. -2.', 'geometry.prob_hi': '4. 4. 2.',
+                   'beam.position_mean': '2. -1. 0.', 'diagnostic.field_data': 'all rho'},
+        rtol_cpu=1e-9, rtol_cuda=1e-9),
 }
 for name, meta in CASES.items():
     gold = json.load(open(os.path.join(REF, name + '.json')))
