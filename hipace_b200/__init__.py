@@ -37,7 +37,9 @@ BC = {'Reflecting': 0, 'Periodic': 1, 'Absorbing': 2}
 # enum hpb_comp
 COMP_IDS = ('NEXT_JX_BEAM', 'NEXT_JY_BEAM', 'CHI', 'SY', 'SX', 'EXMBY', 'EYPBX', 'EZ', 'BX', 'BY',
             'BZ', 'PSI', 'JX_BEAM', 'JY_BEAM', 'JZ_BEAM', 'JX', 'JY', 'RHOMJZ', 'RHO',
-            'PREV_JX_BEAM', 'PREV_JY_BEAM', 'IONS_RHOMJZ', 'AABS')
+            'PREV_JX_BEAM', 'PREV_JY_BEAM', 'IONS_RHOMJZ', 'AABS',
+            'JZ', 'NEXT_JX', 'NEXT_JY', 'PREV_BX', 'PREV_BY', 'PREV_JX', 'PREV_JY',
+            'PCITER_BX', 'PCITER_BY', 'PCPREV_BX', 'PCPREV_BY')
 COMP = {n: i for i, n in enumerate(COMP_IDS)}
 
 # every symbol include/hpb200.h declares (tests check the library exports all of them)
@@ -59,7 +61,9 @@ EXPORTS = (
     'hpb_fields_shift_and_initialize', 'hpb_advance_plasma_particles_and_deposit', 'hpb_deck_check',
     'hpb_set_plasma_lattice_hint', 'hpb_deposit_current_laser', 'hpb_laser_update_aabs',
     'hpb_set_deposition_order', 'hpb_fields_grid_current', 'hpb_sim_nguard',
-    'hpb_beam_insitu_slice', 'hpb_insitu_write_beam',
+    'hpb_beam_insitu_slice', 'hpb_insitu_write_beam', 'hpb_fields_zero', 'hpb_deposit_current_jz',
+    'hpb_fields_bxby_rhs', 'hpb_fields_psi_ez_bz_rhs', 'hpb_fields_open_boundary',
+    'hpb_fields_rel_b_error', 'hpb_fields_lincomb2',
 )
 NCCL_ID_BYTES = 128
 

@@ -33,6 +33,7 @@ SOURCES = {
     'laser.cu': [],
     'generic_order.cu': [],
     'insitu.cu': [],
+    'pc_fields.cu': [],
 }
 
 
@@ -98,7 +99,7 @@ def build_host_check(force: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     lib = os.path.join(BUILD, 'libhpb200_hostcheck.so')
     deps = [os.path.join(CSRC, f) for f in ('host_check.cu', 'generic_order.cuh', 'push_math.cuh',
-                                            'shapes.cuh', 'common.cuh', 'insitu.cuh')]
+                                            'shapes.cuh', 'common.cuh', 'insitu.cuh', 'pc_fields.cuh')]
     deps.append(os.path.join(ROOT, 'include', 'hpb200.h'))
     if (not force and os.path.exists(lib)
             and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps)):

@@ -258,9 +258,11 @@ struct hpb_ctx {
 };
 // true when the particle kernels must take the generic-order path
 bool hpb_use_generic_order(const hpb_ctx *ctx);
+// fields.cu: ExmBy / EypBx from Psi (Fields.cpp:931-956), shared by the fused and the staged Poisson paths
+int hpb_launch_exmby_eypbx(hpb_ctx *ctx, const hpb_slice &sl, const int *comps);
 // generic_order.cu: the entry points of particles.cu / beam.cu forward here in that case
 int hpb_gen_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
-                            int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
+                            int c_jx, int c_jy, int c_jz, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
                             double max_qsa, int *d_n_qsa_violation);
 int hpb_gen_beam_deposit(hpb_ctx *ctx, hpb_beam_slice bm, hpb_slice sl, double charge, int c_jx,
                          int c_jy, int c_jz);

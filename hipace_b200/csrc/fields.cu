@@ -172,6 +172,21 @@ extern "C" int hpb_fields_grid_current(hpb_ctx *ctx, hpb_slice sl, int c_jz_beam
     return HPB_OK;
 }
 
+// setVal(0., ...) on a list of components (grown box)
+extern "C" int hpb_fields_zero(hpb_ctx *ctx, hpb_slice sl, const int *comp_list, int n)
+{
+    if (!ctx || !comp_list || n < 0 || n > 12) return HPB_ERR_ARG;
+    CompList cl;
+    cl.n = 0;
+    for (int k = 0; k < n; ++k) if (comp_list[k] >= 0) cl.c[cl.n++] = comp_list[k];
+    if (cl.n == 0) return HPB_OK;
+    const long ntot = (long)sl.jstride * sl.ny_tot;
+    hpb_launch(k_zero, nb(ntot), kThreads, 0, ctx->stream, make_view(sl), cl, ntot);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
 extern "C" int hpb_fields_initialize_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps)
 {
     if (!ctx || !comps) return HPB_ERR_ARG;

@@ -11,7 +11,7 @@ constexpr int kThreads = 128;
 struct RedAdd {
     __device__ __forceinline__ void operator()(double *p, double v) const { atomicAdd(p, v); }
 };
-struct Comps5 { int c[5]; };
+struct Comps6 { int c[6]; };       // jx jy jz rho chi rhomjz
 struct PlasmaSoA { double *r[HPB_PLASMA_NREAL]; uint64_t *idcpu; long np; };
 PlasmaSoA soa(const hpb_plasma &pl)
 {
@@ -24,7 +24,7 @@ inline unsigned nblocks(long n) { return (unsigned)((n + kThreads - 1) / kThread
 
 template <int ORDER, bool LASER>
 __global__ void __launch_bounds__(kThreads)
-k_gen_deposit_current(PlasmaSoA pl, SliceView a, Comps5 c, GenGrid gr, GenDepositPar par,
+k_gen_deposit_current(PlasmaSoA pl, SliceView a, Comps6 c, GenGrid gr, GenDepositPar par,
                       int *n_qsa_violation)
 {
     hpb_pdl_prologue();
@@ -125,14 +125,14 @@ int check_guards(const hpb_ctx *ctx, const hpb_slice &sl)
     }
 
 int hpb_gen_deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
-                            int c_jx, int c_jy, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
+                            int c_jx, int c_jy, int c_jz, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
                             double max_qsa, int *d_n_qsa_violation)
 {
     if (int rc = check_guards(ctx, sl)) return rc;
     const hpb_geom &g = ctx->g;
-    const Comps5 c = {{c_jx, c_jy, c_rho, c_chi, c_rhomjz}};
+    const Comps6 c = {{c_jx, c_jy, c_jz, c_rho, c_chi, c_rhomjz}};
     GenDepositPar par = {1.0 / g.c, charge * invvol_of(g), charge * g.mu0 / mass, max_qsa,
-                         (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass), c_aabs};
+                         (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass), c_aabs, g.c};
 #define HPB_CALL(LAS) hpb_launch(k_gen_deposit_current<O, LAS>, nblocks(pl.np), kThreads, 0, ctx->stream, \
                                  soa(pl), make_view(sl), c, grid_of(g), par, d_n_qsa_violation)
     if (c_aabs >= 0) { HPB_BY_ORDER(ctx->depos_order, HPB_CALL(true)) }

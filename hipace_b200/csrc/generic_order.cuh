@@ -45,15 +45,17 @@ HPB_HD void gen_laser_gather(const SliceView &a, int c_aabs, const GenGrid &gr, 
     }
 }
 
-// Plasma current deposition of one valid particle.  c[] = {jx, jy, rho, chi, rhomjz} (-1: skip).
+// Plasma current deposition of one valid particle.  c[] = {jx, jy, jz, rho, chi, rhomjz} (-1: skip;
+// jz is what the predictor-corrector solver needs, PlasmaDepositCurrent.cpp:223).
 // Returns false when the particle violates the quasi-static limits (nothing deposited; the caller
 // zeroes its weight, invalidates the id and counts it, PlasmaDepositCurrent.cpp:197-204).
 struct GenDepositPar {
     double clightinv, charge_invvol, charge_mu0_mass_ratio, max_qsa, laser_norm;
     int c_aabs;
+    double clight;
 };
 template <int ORDER, bool LASER, class Add>
-HPB_HD bool gen_deposit_current(const SliceView &a, const int c[5], const GenGrid &gr,
+HPB_HD bool gen_deposit_current(const SliceView &a, const int c[6], const GenGrid &gr,
                                 const GenDepositPar &p, double xp, double yp, double w, double ux,
                                 double uy, double psi, const Add &add)
 {
@@ -81,9 +83,10 @@ HPB_HD bool gen_deposit_current(const SliceView &a, const int c[5], const GenGri
             const long o = a.idx(i0 + ix, j0 + iy);
             const double cd = q_invvol * sx[ix] * sy[iy];
             if (c[0] >= 0) { add(a.comp(c[0]) + o, cd * vx_c); add(a.comp(c[1]) + o, cd * vy_c); }
-            if (c[2] >= 0) add(a.comp(c[2]) + o, cd * gamma_psi);
-            if (c[3] >= 0) add(a.comp(c[3]) + o, cd * chi_fac);
-            if (c[4] >= 0) add(a.comp(c[4]) + o, cd);
+            if (c[2] >= 0) add(a.comp(c[2]) + o, cd * (gamma_psi - 1.0) * p.clight);
+            if (c[3] >= 0) add(a.comp(c[3]) + o, cd * gamma_psi);
+            if (c[4] >= 0) add(a.comp(c[4]) + o, cd * chi_fac);
+            if (c[5] >= 0) add(a.comp(c[5]) + o, cd);
         }
     }
     return true;

@@ -6,6 +6,7 @@
 // libhpb200.so and nothing in the product loads it.
 #include "generic_order.cuh"
 #include "insitu.cuh"
+#include "pc_fields.cuh"
 
 namespace {
 struct HostAdd {
@@ -117,7 +118,7 @@ extern "C" int hc_laser_gather(int order, long n, const double *xp, const double
 
 // plasma SoA: r[11] in PlasmaIdx order (hpb200.h), valid[] in/out (0/1)
 extern "C" long hc_deposit_current(int order, long n, double *const *r, unsigned char *valid,
-                                   double *planes, const HcGrid *hg, const int *c5,
+                                   double *planes, const HcGrid *hg, const int *c6,
                                    const GenDepositPar *par)
 {
     const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
@@ -127,10 +128,10 @@ extern "C" long hc_deposit_current(int order, long n, double *const *r, unsigned
         if (!valid[p]) continue;
         bool ok = true;
         if (par->c_aabs >= 0) {
-            BY_ORDER(order, (ok = gen_deposit_current<O, true>(a, c5, gr, *par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p],
+            BY_ORDER(order, (ok = gen_deposit_current<O, true>(a, c6, gr, *par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p],
                                                                r[HPB_UX][p], r[HPB_UY][p], r[HPB_PSI][p], HostAdd())))
         } else {
-            BY_ORDER(order, (ok = gen_deposit_current<O, false>(a, c5, gr, *par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p],
+            BY_ORDER(order, (ok = gen_deposit_current<O, false>(a, c6, gr, *par, r[HPB_X][p], r[HPB_Y][p], r[HPB_W][p],
                                                                 r[HPB_UX][p], r[HPB_UY][p], r[HPB_PSI][p], HostAdd())))
         }
         if (!ok) { ++n_bad; r[HPB_W][p] = 0.; valid[p] = 0; }
@@ -214,4 +215,39 @@ extern "C" void hc_beam_insitu(long n, const double *const *b7, const unsigned c
                               b7[3][p], clight_inv, radius_sq, t))
             for (int k = 0; k < 23; ++k) out23[k] += t[k];
     }
+}
+
+// predictor-corrector right-hand sides into stage[2][ny][nx] (pc_fields.cuh)
+extern "C" void hc_bxby_rhs(double *planes, const HcGrid *hg, const BxByRhsPar *par, int nx, int ny, double *stage)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            double rbx, rby;
+            bxby_rhs_cell(a, *par, i, j, rbx, rby);
+            stage[(long)j * nx + i] = rbx;
+            stage[(long)nx * ny + (long)j * nx + i] = rby;
+        }
+}
+
+// Open boundary on one staging plane in place: moments, then the edge values
+extern "C" int hc_open_boundary(double *rhs, int nx, int ny, double dx, double dy, double lo_x, double hi_x,
+                                double lo_y, double hi_y, int monopole)
+{
+    OpenBcPar p;
+    if (!open_bc_par(nx, ny, dx, dy, lo_x, hi_x, lo_y, hi_y, p)) return 1;
+    double M[kMultipoleN];
+    for (int k = 0; k < kMultipoleN; ++k) M[k] = 0.;
+    for (long c = 0; c < (long)nx * ny; ++c) {
+        double t[kMultipoleN];
+        if (open_bc_source(p, c, rhs[c], t))
+            for (int k = 0; k < kMultipoleN; ++k) M[k] += t[k];
+    }
+    if (!monopole) M[0] = 0.;
+    for (int e = 0; e < 2 * (nx + ny); ++e) {
+        long cell;
+        const double v = open_bc_edge(p, e, M, cell);
+        rhs[cell] += v;
+    }
+    return 0;
 }

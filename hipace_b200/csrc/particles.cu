@@ -778,8 +778,8 @@ static int deposit_current(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double cha
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     if ((c_jx >= 0) != (c_jy >= 0)) { hpb_set_error("deposit: jx and jy go together"); return HPB_ERR_ARG; }
     if (hpb_use_generic_order(ctx))
-        return hpb_gen_deposit_current(ctx, pl, sl, charge, mass, c_jx, c_jy, c_rho, c_chi, c_rhomjz, c_aabs,
-                                       max_qsa, d_n_qsa_violation);
+        return hpb_gen_deposit_current(ctx, pl, sl, charge, mass, c_jx, c_jy, -1, c_rho, c_chi, c_rhomjz,
+                                       c_aabs, max_qsa, d_n_qsa_violation);
     const int mask = (c_jx >= 0 ? 8 : 0) | (c_rho >= 0 ? 4 : 0) | (c_chi >= 0 ? 2 : 0) | (c_rhomjz >= 0 ? 1 : 0);
     // (charge/q_e)^2 (m_e/mass)^2, PlasmaDepositCurrent.cpp:80-81
     const double laser_norm = (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass);
@@ -821,6 +821,20 @@ extern "C" int hpb_deposit_current_laser(hpb_ctx *ctx, hpb_plasma pl, hpb_slice 
 {
     return deposit_current(ctx, pl, sl, charge, mass, c_jx, c_jy, c_rho, c_chi, c_rhomjz, c_aabs, max_qsa,
                            d_n_qsa_violation);
+}
+
+// ::DepositCurrent with every destination of the reference (PlasmaDepositCurrent.cpp:53-58), jz
+// included: what the predictor-corrector solver deposits.  Always the one-thread-per-particle
+// kernels of generic_order.cu (the warp-aggregated kernels above have no jz variant).
+extern "C" int hpb_deposit_current_jz(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge,
+                                      double mass, int c_jx, int c_jy, int c_jz, int c_rho, int c_chi,
+                                      int c_rhomjz, int c_aabs, double max_qsa, int *d_n_qsa_violation)
+{
+    if (!ctx) return HPB_ERR_ARG;
+    if (pl.np == 0) return HPB_OK;
+    if ((c_jx >= 0) != (c_jy >= 0)) { hpb_set_error("deposit: jx and jy go together"); return HPB_ERR_ARG; }
+    return hpb_gen_deposit_current(ctx, pl, sl, charge, mass, c_jx, c_jy, c_jz, c_rho, c_chi, c_rhomjz, c_aabs,
+                                   max_qsa, d_n_qsa_violation);
 }
 
 extern "C" int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc)

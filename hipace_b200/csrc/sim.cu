@@ -257,10 +257,19 @@ int read_deck(hpb_sim *s)
         s->gc_peak = d.num("grid_current.peak_current_density", 0.);
         for (int k = 0; k < 3; ++k) { s->gc_mean[k] = m[k]; s->gc_std[k] = sd[k]; }
     }
-    if (d.str("hipace.bxby_solver", "explicit") != "explicit")
-        throw std::runtime_error("only hipace.bxby_solver = explicit is supported");
-    if (d.str("boundary.field", "") != "Dirichlet")
-        throw std::runtime_error("only boundary.field = Dirichlet is supported");
+    const std::string solver = d.str("hipace.bxby_solver", "explicit");
+    if (solver != "explicit" && solver != "predictor-corrector")
+        throw std::runtime_error("hipace.bxby_solver must be explicit or predictor-corrector");
+    s->explicit_solver = solver == "explicit";
+    s->predcorr_tol = d.num("hipace.predcorr_B_error_tolerance", 4e-2);
+    s->predcorr_max_iter = (int)d.num("hipace.predcorr_max_iterations", 30);
+    s->predcorr_mix = d.num("hipace.predcorr_B_mixing_factor", 0.05);
+    const std::string bfield = d.str("boundary.field", "");
+    if (bfield != "Dirichlet" && bfield != "Open")
+        throw std::runtime_error("only boundary.field = Dirichlet or Open is supported");
+    s->open_bc = bfield == "Open";
+    if (s->open_bc && s->explicit_solver)
+        throw std::runtime_error("boundary.field = Open is only available with hipace.bxby_solver = predictor-corrector");
     const std::string pbc = d.str("boundary.particle", "");
     if (pbc == "Periodic") s->particle_bc = HPB_BC_PERIODIC;
     else if (pbc == "Reflecting") s->particle_bc = HPB_BC_REFLECTING;
@@ -324,6 +333,8 @@ int read_deck(hpb_sim *s)
             if (d.find(k)) throw std::runtime_error(std::string(k) + ": only the default laser grid (= field grid) is supported");
         if (s->max_step > 0)
             throw std::runtime_error("lasers: the envelope advance (max_step > 0) is not implemented");
+        if (!s->explicit_solver)
+            throw std::runtime_error("lasers are only supported with hipace.bxby_solver = explicit");
         if ((int)ln.size() > HPB_MAX_LASERS) throw std::runtime_error("too many lasers");
         for (auto &nm : ln) {
             if (d.str(nm + ".init_type", "gaussian") != "gaussian")
@@ -410,6 +421,22 @@ void build_components(hpb_sim *s)
         s->comp_names.emplace_back(which, name);
         s->comp_id.push_back(id);
     };
+    if (!s->explicit_solver) {          // Fields.cpp:124-163
+        add(HPB_C_NEXT_JX, "Next", "jx"); add(HPB_C_NEXT_JY, "Next", "jy");
+        add(HPB_C_EXMBY, "This", "ExmBy"); add(HPB_C_EYPBX, "This", "EypBx"); add(HPB_C_EZ, "This", "Ez");
+        add(HPB_C_BX, "This", "Bx"); add(HPB_C_BY, "This", "By"); add(HPB_C_BZ, "This", "Bz");
+        add(HPB_C_PSI, "This", "Psi"); add(HPB_C_JX, "This", "jx"); add(HPB_C_JY, "This", "jy");
+        add(HPB_C_JZ, "This", "jz"); add(HPB_C_RHOMJZ, "This", "rhomjz");
+        if (s->deposit_rho) add(HPB_C_RHO, "This", "rho");
+        add(HPB_C_PREV_BX, "Previous", "Bx"); add(HPB_C_PREV_BY, "Previous", "By");
+        add(HPB_C_PREV_JX, "Previous", "jx"); add(HPB_C_PREV_JY, "Previous", "jy");
+        if (s->any_neutral) add(HPB_C_IONS_RHOMJZ, "RhomJzIons", "rhomjz");
+        add(HPB_C_PCITER_BX, "PCIter", "Bx"); add(HPB_C_PCITER_BY, "PCIter", "By");
+        add(HPB_C_PCPREV_BX, "PCPrevIter", "Bx"); add(HPB_C_PCPREV_BY, "PCPrevIter", "By");
+        s->sl.ncomp = n;
+        for (int k = 0; k < HPB_C_COUNT; ++k) s->comps0[k] = s->comps[k];
+        return;
+    }
     add(HPB_C_NEXT_JX_BEAM, "Next", "jx_beam"); add(HPB_C_NEXT_JY_BEAM, "Next", "jy_beam");
     add(HPB_C_CHI, "This", "chi"); add(HPB_C_SY, "This", "Sy"); add(HPB_C_SX, "This", "Sx");
     add(HPB_C_EXMBY, "This", "ExmBy"); add(HPB_C_EYPBX, "This", "EypBx"); add(HPB_C_EZ, "This", "Ez");
@@ -735,8 +762,159 @@ int beam_push_and_send(hpb_sim *s, int islice)
 //                 plasma push instead of in front of it.
 // The next call then starts at the Poisson solve.  (Without a side stream the same calls are
 // issued on the main stream in the same order.)
+// hipace.bxby_solver = predictor-corrector: Hipace::SolveOneSlice (the non-explicit branches of
+// Hipace.cpp:556-728) and PredictorCorrectorLoopToSolveBxBy (Hipace.cpp:935-1031), with
+// boundary.field = Dirichlet or Open.  Built from the validated kernels of the explicit path (push,
+// deposit, DST Poisson solves) plus the field kernels of pc_fields.cu.
+int solve_one_slice_pc(hpb_sim *s, int islice)
+{
+    hpb_ctx *ctx = s->ctx;
+    const int *C = s->comps;
+    const hpb_slice &sl = s->sl;
+    int rc;
+    auto open_bc = [&](double *plane, int monopole) -> int {
+        return s->open_bc ? hpb_fields_open_boundary(ctx, plane, monopole, s->prob_lo[0], s->prob_hi[0],
+                                                     s->prob_lo[1], s->prob_hi[1], s->d_pc_scal) : HPB_OK;
+    };
+    auto rel_error = [&](int ca, int cb, double &err) -> int {                  // Fields.cpp:1227-1286
+        int r = hpb_fields_rel_b_error(ctx, sl, ca, cb, s->d_pc_scal + 38);
+        if (r) return r;
+        double h[2];
+        SIM_CUDA(cudaMemcpyAsync(h, s->d_pc_scal + 38, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        SIM_CUDA(cudaStreamSynchronize(ctx->stream));
+        err = h[0] > 0. ? h[1] / h[0] : 0.;
+        return HPB_OK;
+    };
+    const long plane = (long)s->g.nx * s->g.ny;
+    {
+        StageTimer t(s, ST_OTHER);                                              // Fields.cpp:565-566
+        const int z[7] = {C[HPB_C_EXMBY], C[HPB_C_EYPBX], C[HPB_C_JX], C[HPB_C_JY], C[HPB_C_JZ],
+                          C[HPB_C_RHOMJZ], C[HPB_C_RHO]};
+        if ((rc = hpb_fields_zero(ctx, sl, z, 7))) return rc;
+    }
+    {
+        StageTimer t(s, ST_DEPOSIT);
+        for (auto &sp : s->plasmas)                                             // :617-618
+            if ((rc = hpb_deposit_current_jz(ctx, sp.d, sl, sp.charge, sp.mass, C[HPB_C_JX], C[HPB_C_JY],
+                                             C[HPB_C_JZ], C[HPB_C_RHO], -1, C[HPB_C_RHOMJZ], -1, sp.max_qsa,
+                                             s->d_nqsa))) return rc;
+    }
+    {
+        StageTimer t(s, ST_OTHER);
+        if (!s->beams.empty()) {                                                // :621-623
+            if ((rc = hpb_pipeline_wait_slice(s, islice))) return rc;
+            for (auto &b : s->beams)
+                if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice), sl, b.charge,
+                                           s->do_beam_jx_jy ? C[HPB_C_JX] : -1,
+                                           s->do_beam_jx_jy ? C[HPB_C_JY] : -1, C[HPB_C_JZ]))) return rc;
+        }
+        if ((rc = hpb_fields_add_rho_ions(ctx, sl, C))) return rc;              // :626
+        if (s->use_grid_current)                                                // :629
+            if ((rc = hpb_fields_grid_current(ctx, sl, C[HPB_C_JZ], s->gc_peak, s->gc_mean, s->gc_std,
+                                              s->prob_lo[0], s->prob_lo[1],
+                                              s->prob_lo[2] + islice * s->g.dz))) return rc;
+    }
+    {
+        StageTimer t(s, ST_POISSON);                                            // :633
+        if (!s->open_bc) {
+            if ((rc = hpb_fields_solve_psi_ez_bz(ctx, sl, C))) return rc;
+        } else {
+            if ((rc = hpb_fields_psi_ez_bz_rhs(ctx, sl, C, s->d_pc_rhs))) return rc;
+            for (int b = 0; b < 3; ++b)                 // Ez and Bz have no monopole (Fields.cpp:729-733)
+                if ((rc = open_bc(s->d_pc_rhs + b * plane, b == 0))) return rc;
+            const int lhs[3] = {C[HPB_C_PSI], C[HPB_C_EZ], C[HPB_C_BZ]};
+            if ((rc = hpb_poisson_solve(ctx, s->d_pc_rhs, sl, lhs, 3))) return rc;
+            if ((rc = hpb_launch_exmby_eypbx(ctx, sl, C))) return rc;
+        }
+    }
+    {
+        StageTimer t(s, ST_MG);         // (the stage slot of the Bx/By solve)
+        double err = 0.;
+        if ((rc = rel_error(C[HPB_C_PREV_BX], C[HPB_C_PCPREV_BX], err))) return rc;      // :941-943
+        const double q = err / (2.5 * s->predcorr_tol);
+        const double mix0 = exp(-0.5 * q * q);                                           // Fields.cpp:1149-1170
+        if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_BX], 1.0 + mix0, C[HPB_C_PREV_BX], -mix0,
+                                      C[HPB_C_PCPREV_BX]))) return rc;
+        if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_PCITER_BX], 0., C[HPB_C_BX], 0., C[HPB_C_BX]))) return rc;
+        if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_PCPREV_BX], 1., C[HPB_C_BX], 0., C[HPB_C_BX]))) return rc;
+        int i_iter = 0;
+        double err_prev = 1.0;
+        err = 1.0;
+        while (err > s->predcorr_tol && i_iter < s->predcorr_max_iter) {                 // :961-1010
+            ++i_iter;
+            for (auto &sp : s->plasmas) {                   // push to the temporary slice
+                hpb_set_plasma_lattice_hint(ctx, sp.lattice_n, sp.lattice_ppc);
+                rc = hpb_advance_plasma_particles(ctx, sp.d, sl, sp.charge, sp.mass, sp.n_subcycles, 1,
+                                                  s->particle_bc, s->bc_lo, s->bc_hi, C);
+                hpb_set_plasma_lattice_hint(ctx, 0, 0);
+                if (rc) return rc;
+            }
+            for (auto &sp : s->plasmas)                     // jx, jy of the next slice
+                if ((rc = hpb_deposit_current(ctx, sp.d, sl, sp.charge, sp.mass, C[HPB_C_NEXT_JX],
+                                              C[HPB_C_NEXT_JY], -1, -1, -1, sp.max_qsa, s->d_nqsa))) return rc;
+            if (s->do_beam_jx_jy && !s->beams.empty() && islice > 0) {
+                if ((rc = hpb_pipeline_wait_slice(s, islice - 1))) return rc;
+                for (auto &b : s->beams)
+                    if ((rc = hpb_beam_deposit(ctx, beam_slice_view(s, b, islice - 1), sl, b.charge,
+                                               C[HPB_C_NEXT_JX], C[HPB_C_NEXT_JY], -1))) return rc;
+            }
+            // SolvePoissonBxBy -> PCIter (Fields.cpp:1008-1078)
+            if ((rc = hpb_fields_bxby_rhs(ctx, sl, C, s->d_pc_rhs))) return rc;
+            if ((rc = open_bc(s->d_pc_rhs, 1))) return rc;
+            if ((rc = open_bc(s->d_pc_rhs + plane, 1))) return rc;
+            const int lhs[2] = {C[HPB_C_PCITER_BX], C[HPB_C_PCITER_BY]};
+            if ((rc = hpb_poisson_solve(ctx, s->d_pc_rhs, sl, lhs, 2))) return rc;
+            if ((rc = rel_error(C[HPB_C_BX], C[HPB_C_PCITER_BX], err))) return rc;
+            if (i_iter == 1) err_prev = err;
+            // MixAndShiftBfields (Fields.cpp:1172-1225)
+            double w_it = 0.5, w_prev = 0.5;
+            if (err != 0. || err_prev != 0.) { w_it = err_prev / (err + err_prev); w_prev = err / (err + err_prev); }
+            if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_PCPREV_BX], w_it, C[HPB_C_PCITER_BX], w_prev,
+                                          C[HPB_C_PCPREV_BX]))) return rc;
+            if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_BX], 1.0 - s->predcorr_mix, C[HPB_C_BX],
+                                          s->predcorr_mix, C[HPB_C_PCPREV_BX]))) return rc;
+            if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_PCPREV_BX], 1., C[HPB_C_PCITER_BX], 0.,
+                                          C[HPB_C_PCITER_BX]))) return rc;
+            const int z[2] = {C[HPB_C_NEXT_JX], C[HPB_C_NEXT_JY]};                      // :996-999
+            if ((rc = hpb_fields_zero(ctx, sl, z, 2))) return rc;
+            err_prev = err;
+        }
+        s->n_predcorr_iters += i_iter;
+        s->stats.n_mg_vcycles += i_iter;        // reported in the iteration slot of the statistics
+    }
+    if (s->opt_checksums) {
+        StageTimer t(s, ST_OTHER);
+        for (int c = 0; c < sl.ncomp; ++c)
+            if (s->comp_names[c].first == "This")
+                if ((rc = hpb_abs_sum(ctx, sl, phys_comp(s, c), s->d_checksum + c))) return rc;
+    }
+    {
+        StageTimer t(s, ST_PUSH);
+        for (auto &sp : s->plasmas) {
+            s->stats.n_plasma_pushed += (double)sp.d.np;
+            hpb_set_plasma_lattice_hint(ctx, sp.lattice_n, sp.lattice_ppc);
+            rc = hpb_advance_plasma_particles(ctx, sp.d, sl, sp.charge, sp.mass, sp.n_subcycles, 0,
+                                              s->particle_bc, s->bc_lo, s->bc_hi, C);
+            hpb_set_plasma_lattice_hint(ctx, 0, 0);
+            if (rc) return rc;
+        }
+    }
+    {
+        StageTimer t(s, ST_OTHER);
+        if ((rc = beam_push_and_send(s, islice))) return rc;
+        // ShiftSlices (Fields.cpp:600-603)
+        if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_PCPREV_BX], 1., C[HPB_C_PREV_BX], 0., C[HPB_C_PREV_BX]))) return rc;
+        if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_PREV_BX], 1., C[HPB_C_BX], 0., C[HPB_C_BX]))) return rc;
+        if ((rc = hpb_fields_lincomb2(ctx, sl, C[HPB_C_PREV_JX], 1., C[HPB_C_JX], 0., C[HPB_C_JX]))) return rc;
+    }
+    s->stats.n_cells_updated += (double)s->g.nx * s->g.ny;
+    s->stats.n_slices += 1;
+    return HPB_OK;
+}
+
 int solve_one_slice(hpb_sim *s, int islice)
 {
+    if (!s->explicit_solver) return solve_one_slice_pc(s, islice);
     hpb_ctx *ctx = s->ctx;
     const int *C = s->comps;
     int rc;
@@ -950,6 +1128,10 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     SIM_CUDA(cudaMemset(sl.p, 0, sizeof(double) * sl.nstride * sl.ncomp));
     SIM_CUDA(cudaMalloc(&s->d_checksum, sizeof(double) * (sl.ncomp + 1)));     // + laserEnvelope
     SIM_CUDA(cudaMemset(s->d_checksum, 0, sizeof(double) * (sl.ncomp + 1)));
+    if (!s->explicit_solver) {
+        SIM_CUDA(cudaMalloc(&s->d_pc_rhs, sizeof(double) * 3 * (size_t)s->g.nx * s->g.ny));
+        SIM_CUDA(cudaMalloc(&s->d_pc_scal, sizeof(double) * 40));
+    }
     SIM_CUDA(cudaMalloc(&s->d_nqsa, sizeof(int)));
     SIM_CUDA(cudaMemset(s->d_nqsa, 0, sizeof(int)));
     SIM_CUDA(cudaMalloc(&s->d_count, sizeof(unsigned long long)));

@@ -99,6 +99,14 @@ struct hpb_sim {
     int particle_bc = HPB_BC_PERIODIC;
     int depos_order = 2, depos_dtype = 2;         // hipace.depos_order_xy / depos_derivative_type
     int ng = HPB_NGUARD;                          // guard cells of the slice, Fields.cpp:63-64
+    // hipace.bxby_solver = predictor-corrector (Hipace.cpp:935-1031, Hipace.H:210-222) and
+    // boundary.field = Open (Fields.cpp:685-738)
+    bool explicit_solver = true, open_bc = false;
+    double predcorr_tol = 4e-2, predcorr_mix = 0.05;
+    int predcorr_max_iter = 30;
+    double *d_pc_rhs = nullptr;                   // 3 staging planes nx * ny
+    double *d_pc_scal = nullptr;                  // 38 multipole moments + 2 norms
+    long n_predcorr_iters = 0;
     bool use_grid_current = false;                // utils/GridCurrent.cpp
     double gc_peak = 0., gc_mean[3] = {0., 0., 0.}, gc_std[3] = {1., 1., 1.};
     int max_step = 0;

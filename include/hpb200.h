@@ -196,6 +196,34 @@ int hpb_fields_grid_current(hpb_ctx *ctx, hpb_slice sl, int c_jz_beam, double pe
                             const double position_mean[3], const double position_std[3],
                             double plo_x, double plo_y, double z);
 int hpb_fields_shift_slices(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+/* setVal(0., ...) on up to 12 components (entries < 0 are skipped), grown box */
+int hpb_fields_zero(hpb_ctx *ctx, hpb_slice sl, const int *comp_list, int n);
+
+/* ---- predictor-corrector Bx/By solver and open field boundaries ----------------
+ * hpb_deposit_current_jz: ::DepositCurrent with every destination incl. jz
+ *     (src/particles/deposition/PlasmaDepositCurrent.cpp:53-58, :223).
+ * hpb_fields_bxby_rhs: the two right-hand sides of Fields::SolvePoissonBxBy
+ *     (src/fields/Fields.cpp:1008-1078) into d_stage[2][ny][nx]; comps needs JZ, PREV_JX/JY, NEXT_JX/JY.
+ * hpb_fields_psi_ez_bz_rhs: the three right-hand sides of Fields.cpp:886-912 into d_stage[3][ny][nx]
+ *     (the Dirichlet path assembles them inside hpb_fields_solve_psi_ez_bz; the Open path needs them
+ *     in memory to fold the boundary values in).
+ * hpb_fields_open_boundary: Fields::SetBoundaryCondition for boundary.field = Open
+ *     (src/fields/Fields.cpp:685-738, SetDirichletBoundaries :628-673, src/fields/OpenBoundary.H): the
+ *     multipole moments of one staging plane and the free-space potential one cell outside every
+ *     edge, folded into the plane in place; monopole = 0 for Ez and Bz.  d_moments: 38 doubles.
+ * hpb_fields_rel_b_error: Fields::ComputeRelBFieldError (:1227-1286): d_out2 = {sum |B_a|,
+ *     sum |B_a - B_b|} over the valid box; c_* = the Bx component of an adjacent (Bx, By) pair.
+ * hpb_fields_lincomb2: MultiFab::LinComb on an adjacent component pair over the grown box,
+ *     dst = fa * A + fb * B (InitialBfieldGuess :1149-1170, MixAndShiftBfields :1172-1225, shifts). */
+int hpb_deposit_current_jz(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double charge, double mass,
+                           int c_jx, int c_jy, int c_jz, int c_rho, int c_chi, int c_rhomjz, int c_aabs,
+                           double max_qsa_weighting_factor, int *d_n_qsa_violation);
+int hpb_fields_bxby_rhs(hpb_ctx *ctx, hpb_slice sl, const int *comps, double *d_stage);
+int hpb_fields_psi_ez_bz_rhs(hpb_ctx *ctx, hpb_slice sl, const int *comps, double *d_stage);
+int hpb_fields_open_boundary(hpb_ctx *ctx, double *d_rhs, int monopole, double prob_lo_x,
+                             double prob_hi_x, double prob_lo_y, double prob_hi_y, double *d_moments);
+int hpb_fields_rel_b_error(hpb_ctx *ctx, hpb_slice sl, int c_bx_a, int c_bx_b, double *d_out2);
+int hpb_fields_lincomb2(hpb_ctx *ctx, hpb_slice sl, int c_dst, double fa, int c_a, double fb, int c_b);
 
 /* FFTPoissonSolver::SolvePoissonEquation (src/fields/fft_poisson_solver/FFTPoissonSolver.H:26-57,
  * ...DirichletFast.cpp:286-328): laplace(lhs) = rhs with lhs = 0 at the first guard cell.
@@ -270,6 +298,9 @@ enum hpb_comp {
     HPB_C_PREV_JX_BEAM, HPB_C_PREV_JY_BEAM,
     HPB_C_IONS_RHOMJZ /* -1 if no neutralising background */,
     HPB_C_AABS /* |a|^2 of the laser envelope on the field grid, -1 without a laser (Fields.cpp:98-101) */,
+    /* predictor-corrector solver only (Fields.cpp:124-163); -1 with the explicit solver */
+    HPB_C_JZ, HPB_C_NEXT_JX, HPB_C_NEXT_JY, HPB_C_PREV_BX, HPB_C_PREV_BY, HPB_C_PREV_JX, HPB_C_PREV_JY,
+    HPB_C_PCITER_BX, HPB_C_PCITER_BY, HPB_C_PCPREV_BX, HPB_C_PCPREV_BY,
     HPB_C_COUNT
 };
 

@@ -76,7 +76,8 @@ def test_overrides_constants_and_expressions():
 @pytest.mark.parametrize('ov,msg', [
     ({'beam.injection_type': 'fixed_weight'}, 'fixed_ppc'),
     ({'hipace.depos_order_xy': 4}, 'depos_order_xy'),
-    ({'hipace.bxby_solver': 'predictor-corrector'}, 'explicit'),
+    ({'hipace.bxby_solver': 'semi-implicit'}, 'bxby_solver'),
+    ({'boundary.field': 'Open'}, 'predictor-corrector'),
     ({'boundary.field': 'Periodic'}, 'Dirichlet'),
     ({'plasma.u_std': '0. 0. 1e-3'}, 'RNG'),
     ({'amr.n_cell': '64 64'}, '3 values'),

@@ -27,7 +27,7 @@ class HcGrid(C.Structure):
 class DepositPar(C.Structure):
     _fields_ = [('clightinv', C.c_double), ('charge_invvol', C.c_double),
                 ('charge_mu0_mass_ratio', C.c_double), ('max_qsa', C.c_double),
-                ('laser_norm', C.c_double), ('c_aabs', C.c_int)]
+                ('laser_norm', C.c_double), ('c_aabs', C.c_int), ('clight', C.c_double)]
 
 
 class ExplicitPar(C.Structure):
@@ -119,7 +119,7 @@ def _setup(order, dtype, laser, seed, si=False):
     geom = O.Geometry(24, 40, 8, (-3 * scale, -2 * scale, 0.0), (5 * scale, 7 * scale, 1 * scale), order, dtype)
     pc = O.PhysConst.make(not si)
     g = geom.g
-    names = ['chi', 'Sy', 'Sx', 'ExmBy', 'EypBx', 'Ez', 'Bx', 'By', 'Bz', 'Psi', 'jx', 'jy', 'rhomjz', 'rho', 'aabs']
+    names = ['chi', 'Sy', 'Sx', 'ExmBy', 'EypBx', 'Ez', 'Bx', 'By', 'Bz', 'Psi', 'jx', 'jy', 'rhomjz', 'rho', 'aabs', 'jz']
     fmag = 1e9 if si else 1.0
     F = {('This', nm): np.zeros((geom.ny + 2 * g, geom.nx + 2 * g)) for nm in names}
     for nm in ('ExmBy', 'EypBx', 'Ez', 'Psi'):
@@ -173,20 +173,21 @@ def test_device_deposit_current_matches_oracle(hc, order, laser, si):
     valid = np.ascontiguousarray(pl.valid.astype(np.uint8))
     planes = _planes(F, names)
     ix = {nm: k for k, nm in enumerate(names)}
-    c5 = (C.c_int * 5)(ix['jx'], ix['jy'], ix['rho'], ix['chi'], ix['rhomjz'])
+    c5 = (C.c_int * 6)(ix['jx'], ix['jy'], ix['jz'], ix['rho'], ix['chi'], ix['rhomjz'])
     invvol = 1.0 if not si else 1.0 / (geom.dx * geom.dy * geom.dz)
     norm = (pl.charge / pc.q_e) * (pc.m_e / pl.mass) * (pl.charge / pc.q_e) * (pc.m_e / pl.mass)
     par = DepositPar(1.0 / pc.c, pl.charge * invvol, pl.charge * pc.mu0 / pl.mass, 35.0, norm,
-                     ix['aabs'] if laser else -1)
+                     ix['aabs'] if laser else -1, pc.c)
     hg = _grid(geom)
     n_bad = hc.hc_deposit_current(order, C.c_long(pl.x.size), _ptrs(r), _dp(valid), _dp(planes),
                                   C.byref(hg), c5, C.byref(par))
     T = lambda nm: F[('This', nm)]
     want_bad = O.deposit_current(pl, F, geom, pc, not si, jx=T('jx'), jy=T('jy'), rho=T('rho'),
-                                 chi=T('chi'), rhomjz=T('rhomjz'), aabs=T('aabs') if laser else None)
+                                 chi=T('chi'), rhomjz=T('rhomjz'), aabs=T('aabs') if laser else None,
+                                 jz=T('jz'))
     assert n_bad == want_bad and want_bad > 0
     assert np.array_equal(valid.astype(bool), pl.valid)
-    for nm in ('jx', 'jy', 'rho', 'chi', 'rhomjz'):
+    for nm in ('jx', 'jy', 'jz', 'rho', 'chi', 'rhomjz'):
         assert _close(planes[ix[nm]], T(nm)), nm
 
 
@@ -315,11 +316,49 @@ def test_only_order_3_deposits_depend_on_the_summation_order(hc):
                                                    np.ones(n))] + [np.zeros(n) for _ in range(5)]
             valid = np.ones(n, dtype=np.uint8)
             planes = np.zeros((1, 32 + 2 * g, 32 + 2 * g))
-            c5 = (C.c_int * 5)(-1, -1, -1, -1, 0)
-            par = DepositPar(1.0, -1.0, -1.0, 35.0, 1.0, -1)
+            c5 = (C.c_int * 6)(-1, -1, -1, -1, -1, 0)
+            par = DepositPar(1.0, -1.0, -1.0, 35.0, 1.0, -1, 1.0)
             hg = _grid(geom)
             hc.hc_deposit_current(order, C.c_long(n), _ptrs(r), _dp(valid), _dp(planes), C.byref(hg), c5,
                                   C.byref(par))
             res.append(planes[0, g:-g, g:-g].copy())
         diff = np.abs(res[0] - res[1]).max()
         assert (diff == 0.0) if order < 3 else (0.0 < diff < 1e-15), (order, diff)
+
+
+class BxByRhsPar(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ('c_jz', 'c_prev_jx', 'c_prev_jy', 'c_next_jx', 'c_next_jy')] + \
+               [(k, C.c_double) for k in ('mu0', 'dx_inv_half', 'dy_inv_half', 'dz_inv_half')]
+
+
+def test_device_open_boundary_and_bxby_rhs_match_oracle(hc):
+    """pc_fields.cuh on the host: the multipole moments + edge values of boundary.field = Open and
+    the right-hand sides of SolvePoissonBxBy against the oracle (which the reference's
+    beam_in_vacuum_open_boundary golden pins)"""
+    rng = np.random.default_rng(12)
+    geom = O.Geometry(48, 36, 10, (-4.0, -3.0, -2.0), (5.0, 3.5, 2.0), 2, 2)
+    nx, ny = geom.nx, geom.ny
+    for monopole in (1, 0):
+        rhs = rng.normal(0, 1, (ny, nx))
+        want = O.open_boundary_rhs(rhs, geom, bool(monopole))
+        got = np.ascontiguousarray(rhs.copy())
+        assert hc.hc_open_boundary(_dp(got), nx, ny, C.c_double(geom.dx), C.c_double(geom.dy),
+                                   C.c_double(geom.lo[0]), C.c_double(geom.hi[0]), C.c_double(geom.lo[1]),
+                                   C.c_double(geom.hi[1]), monopole) == 0
+        assert np.abs(want - rhs).max() > 0                      # the edges did change
+        assert np.abs(got - want).max() <= 1e-11 * np.abs(want - rhs).max()
+        assert np.array_equal(got[1:-1, 1:-1], rhs[1:-1, 1:-1])  # ... and only the edges
+    g = geom.g
+    names = ['jz', 'pjx', 'pjy', 'njx', 'njy']
+    planes = np.ascontiguousarray(rng.normal(0, 1, (5, ny + 2 * g, nx + 2 * g)))
+    par = BxByRhsPar(0, 1, 2, 3, 4, 1.3, 0.5 / geom.dx, 0.5 / geom.dy, 0.5 / geom.dz)
+    stage = np.zeros((2, ny, nx))
+    hg = _grid(geom)
+    hc.hc_bxby_rhs(_dp(planes), C.byref(hg), C.byref(par), nx, ny, _dp(stage))
+    v = (slice(g, -g), slice(g, -g))
+    dz_jy = (planes[2][v] - planes[4][v]) * (0.5 / geom.dz)
+    dz_jx = (planes[1][v] - planes[3][v]) * (0.5 / geom.dz)
+    want_bx = -1.3 * O._ddy(planes[0], geom.dy, g) + 1.3 * dz_jy
+    want_by = 1.3 * O._ddx(planes[0], geom.dx, g) + (-1.3) * dz_jx
+    assert np.abs(stage[0] - want_bx).max() <= 1e-13 * np.abs(want_bx).max()
+    assert np.abs(stage[1] - want_by).max() <= 1e-13 * np.abs(want_by).max()
