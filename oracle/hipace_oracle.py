@@ -1736,7 +1736,18 @@ class Simulation:
         self.bc_lo = _get(d, 'boundary.particle_lo', [lo[0], lo[1]], n=2)
         self.bc_hi = _get(d, 'boundary.particle_hi', [hi[0], hi[1]], n=2)
         self.max_step = _get(d, 'max_step', 0, typ=int)
-        self.dt = _get(d, 'hipace.dt', 0.0)
+        # hipace.dt = adaptive (utils/AdaptiveTimeStep.cpp:17-60; defaults AdaptiveTimeStep.H:25-51)
+        self.adaptive_dt = str(d.get('hipace.dt', ['0'])[0]) == 'adaptive'
+        self.dt = 0.0 if self.adaptive_dt else _get(d, 'hipace.dt', 0.0)
+        self.nt_per_betatron = _get(d, 'hipace.nt_per_betatron', 20.0)
+        self.dt_max = _get(d, 'hipace.dt_max', math.inf)
+        self.adaptive_threshold_uz = _get(d, 'hipace.adaptive_threshold_uz', 2.0)
+        self.adaptive_density = _get(d, 'plasmas.adaptive_density', 0.0)
+        self.adaptive_phase_tolerance = _get(d, 'hipace.adaptive_phase_tolerance', 4e-4)
+        self.adaptive_phase_substeps = _get(d, 'hipace.adaptive_phase_substeps', 2000, typ=int)
+        self.adaptive_control_phase = bool(_get(d, 'hipace.adaptive_control_phase_advance', 1, typ=int))
+        assert not (self.adaptive_dt and _get(d, 'hipace.adaptive_gather_ez', 0, typ=int)), \
+            'oracle scope: hipace.adaptive_gather_ez = 0' 
         self.mg_tol_rel = _get(d, 'hipace.MG_tolerance_rel', 1e-4)
         self.mg_tol_abs = _get(d, 'hipace.MG_tolerance_abs', np.finfo(float).tiny)
         fd = d.get('diagnostic.field_data', [])
@@ -1912,7 +1923,14 @@ class Simulation:
     def begin_step(self, step: int = 0):
         """Hipace::Evolve up to the slice loop, Hipace.cpp:401-475"""
         self.step = step
-        self.time = step * self.dt                                # :410, :434 (fixed dt)
+        if self.adaptive_dt:                                      # :411, :420, :434
+            if step == 0:
+                self._adaptive_init()
+            self.time = 0.0 if step == 0 else self._next_time
+            self._adaptive_from_density()
+            self._next_time = self.time + self.dt
+        else:
+            self.time = step * self.dt                            # :410, :434 (fixed dt)
         self.beam_diag = {b.name: [] for b in self.beams}
         for a in self.F.values():
             a[...] = 0.0                                          # ResetAllQuantities :730-742
@@ -1936,6 +1954,86 @@ class Simulation:
             if pl.neutralize_background:
                 deposit_current(pl, self.F, self.geom, self.pc, self.normalized,
                                 rhomjz=self.F[('RhomJzIons', 'rhomjz')], flip_charge=True)
+
+    # ---- adaptive time step (utils/AdaptiveTimeStep.cpp), one rank ------------------------------
+    def _max_charge_density(self, z):
+        """MultiPlasma::maxChargeDensity, particles/plasma/MultiPlasma.cpp:63-73"""
+        m = abs(self.adaptive_density * self.pc.q_e)
+        for pl in self.plasmas:
+            m = max(m, abs(pl.charge * float(pl.density(0.0, 0.0, z))))
+        return m
+
+    def _adaptive_init(self):
+        """Hipace.cpp:275-279: the beam as specified in the deck (GatherMinUzSlice(initial), :96-106)"""
+        self._ts = {}
+        for b in self.beams:
+            u, us = b.u_mean[2], 0.0                               # u_std = 0 in the oracle's scope
+            self._ts[b.name] = dict(min_uz=u - 4.0 * us, sw=1.0, swu=u, swu2=u * u + us * us)
+        self._min_uz_mq = np.finfo(float).max
+        self._adaptive_from_min_uz(0.0)
+        self._adaptive_from_density(at=0.0)
+
+    def _adaptive_gather(self, islice):
+        """GatherMinUzSlice(false) after the push of a slice, :108-141"""
+        ci = 1.0 / self.pc.c
+        for b in self.beams:
+            bs = self.beam_slice(b, islice)
+            n = bs['np']
+            v = bs['valid'][:n]
+            w, uz = bs['w'][:n][v], bs['uz'][:n][v]
+            t = self._ts[b.name]
+            t['sw'] += w.sum()
+            t['swu'] += (w * uz * ci).sum()
+            t['swu2'] += (w * uz * uz * ci * ci).sum()
+            if uz.size:
+                t['min_uz'] = min(t['min_uz'], float((uz * ci).min()))
+
+    def _adaptive_from_min_uz(self, t_now):
+        """CalculateFromMinUz, :143-233 (one rank: no look-ahead over the pipeline)"""
+        new_dts, mq = [], []
+        for b in self.beams:
+            new_dt = self.dt
+            t = self._ts[b.name]
+            if b.charge == 0.0:
+                new_dts.append(new_dt); mq.append(np.finfo(float).max)
+                continue
+            mcr = b.mass / b.charge
+            assert t['sw'] != 0, 'The sum of all weights is 0'
+            mean = t['swu'] / t['sw']
+            sigma = math.sqrt(abs(t['swu2'] / t['sw'] - mean * mean))
+            chosen = min(max(mean - 4.0 * sigma, t['min_uz']), 1e30)
+            chosen = max(chosen, self.adaptive_threshold_uz)
+            mq.append(abs(chosen * mcr))
+            rho = self._max_charge_density(self.pc.c * t_now)
+            assert rho > 0.0, 'A >0 plasma density must be specified to use an adaptive time step.'
+            min_uz = max(chosen, 0.001 * self.adaptive_threshold_uz)
+            omega_b = math.sqrt(rho / (2.0 * abs(min_uz * mcr) * self.pc.ep0))
+            cand = 2.0 * math.pi / omega_b / self.nt_per_betatron
+            if min_uz > self.adaptive_threshold_uz:
+                new_dt = cand
+            new_dts.append(new_dt)
+        self._min_uz_mq = min(mq)
+        self.dt = min(min(new_dts), self.dt_max)
+
+    def _adaptive_from_density(self, at=None):
+        """CalculateFromDensity, :315-369: reset the gathered data; shorten dt if the betatron phase
+        advance over the step deviates from that of a uniform plasma"""
+        t0 = self.time if at is None else at
+        for t in self._ts.values():
+            t.update(min_uz=1e30, sw=0.0, swu=0.0, swu2=0.0)
+        if not self.adaptive_control_phase:
+            return
+        dt_sub = self.dt / self.adaptive_phase_substeps
+        pa = pa0 = 0.0
+        omgb0 = math.sqrt(self._max_charge_density(self.pc.c * t0) / (2.0 * self._min_uz_mq * self.pc.ep0))
+        for i in range(self.adaptive_phase_substeps):
+            omgb = math.sqrt(self._max_charge_density(self.pc.c * (t0 + i * dt_sub))
+                             / (2.0 * self._min_uz_mq * self.pc.ep0))
+            pa += omgb * dt_sub
+            pa0 += omgb0 * dt_sub
+            if abs(pa - pa0) > 2.0 * math.pi * self.adaptive_phase_tolerance / self.nt_per_betatron:
+                self.dt = i * dt_sub
+                return
 
     def beam_slice(self, beam: Beam, islice: int):
         if islice < 0:
@@ -2038,6 +2136,8 @@ class Simulation:
             advance_beam_slice(bs, b, F, g, pc, islice, self.dt, getattr(self, 'time', 0.0),
                                self.bc_kind, self.bc_lo, self.bc_hi)
             shift_slipped_particles(bs, self.beam_slice(b, islice - 1), g, islice)
+        if self.adaptive_dt:                                                      # :715
+            self._adaptive_gather(islice)
         if self.slice_hook:
             self.slice_hook(self, islice, 'pushed')
         for c in ('Bx', 'By'):                                                    # ShiftSlices, Fields.cpp:600-603
@@ -2144,6 +2244,8 @@ class Simulation:
             advance_beam_slice(bs, b, F, g, pc, islice, self.dt, getattr(self, 'time', 0.0),
                                self.bc_kind, self.bc_lo, self.bc_hi)
             shift_slipped_particles(bs, self.beam_slice(b, islice - 1), g, islice)
+        if self.adaptive_dt:                                                      # :715
+            self._adaptive_gather(islice)
         if self.slice_hook:
             self.slice_hook(self, islice, 'pushed')
         # ShiftSlices, fields/Fields.cpp:588-604
@@ -2186,6 +2288,8 @@ class Simulation:
             self.insitu = {}
             for isl in range(g.nz - 1, stop, -1):
                 self.solve_one_slice(isl)
+            if self.adaptive_dt and stop == -1:                                   # Hipace.cpp:482-483
+                self._adaptive_from_min_uz(self.time)
             for b in self.beams:                                                  # Hipace.cpp:488
                 if b.name in self.insitu:
                     ndf = g.dx * g.dy * g.dz if self.normalized else 1.0

@@ -107,6 +107,16 @@ CASES = {
                    'geometry.prob_lo': '-4. -4. -2.', 'geometry.prob_hi': '4. 4. 2.',
                    'beam.position_mean': '2. -1. 0.', 'diagnostic.field_data': 'all rho'},
         rtol_cpu=1e-9, rtol_cuda=1e-9),
+    # tests/adaptive_time_step.1Rank.sh:52-69 (the run whose output is checksummed: positive gradient):
+    # hipace.dt = adaptive over 20 steps, the beam gaining energy in an external Ez = z / 2
+    'adaptive_time_step.1Rank': dict(
+        deck='examples/beam_in_vacuum_normalized.in',
+        overrides={'amr.n_cell': '32 32 32', 'max_step': 20, 'geometry.prob_lo': '-2. -2. -2.',
+                   'geometry.prob_hi': '2. 2. 2.', 'hipace.dt': 'adaptive', 'beam.density': 1,
+                   'beam.radius': 1., 'beam.n_subcycles': 4, 'beam.ppc': '4 4 1',
+                   'beams.external_E(x,y,z,t)': '0. 0. .5*z', 'plasmas.adaptive_density': 1,
+                   'hipace.nt_per_betatron': 89.7597901025655},
+        rtol_cpu=1e-12, rtol_cuda=1e-5),
 }
 for name, meta in CASES.items():
     gold = json.load(open(os.path.join(REF, name + '.json')))

@@ -31,7 +31,8 @@ def _run(case, repo_root):
                                   'gaussian_linear_wake.normalized.1Rank', 'gaussian_linear_wake.SI.1Rank',
                                   'beam_in_vacuum.normalized.1Rank', 'beam_in_vacuum.SI.1Rank',
                                   'grid_current.1Rank',
-                                  'beam_in_vacuum_open_boundary.normalized.1Rank'])
+                                  'beam_in_vacuum_open_boundary.normalized.1Rank',
+                                  'adaptive_time_step.1Rank'])
 def test_oracle_matches_reference_golden(case, repo_root):
     meta, sim, cs = _run(case, repo_root)
     gold = meta['checksums']
