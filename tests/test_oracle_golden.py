@@ -20,7 +20,7 @@ def _run(case, repo_root):
     deck = open(os.path.join(repo_root, meta['deck'])).read()
     sim = Simulation(deck, meta['overrides'])
     # dt = 0 decks: every step repeats step 0, one step suffices; dt != 0: all max_step + 1 steps
-    cs = sim.evolve(step_end=sim.max_step if sim.dt != 0.0 else 0)
+    cs = sim.evolve(step_end=sim.max_step if (sim.dt != 0.0 or sim.adaptive_dt) else 0)
     return meta, sim, cs
 
 
