@@ -48,6 +48,52 @@ k_beam_insitu(hpb_beam_slice b, double clight_inv, double radius_sq, double *__r
     }
 }
 
+// GatherMinUzSlice of one beam slice after its push: acc[0] = min(acc[0], min uz / c), acc[1..3] += sums
+__device__ __forceinline__ void atomic_min_double(double *addr, double v)
+{
+    unsigned long long *a = (unsigned long long *)addr, old = *a;
+    while (__longlong_as_double((long long)old) > v) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__global__ void __launch_bounds__(kT)
+k_beam_min_uz(hpb_beam_slice b, double clight_inv, double *__restrict__ acc)
+{
+    hpb_pdl_prologue();
+    __shared__ double red[kT / 32][4];
+    long np = b.np;
+    if (b.d_np) { const long n = (long)b.d_np[0]; if (n < np) np = n; }      // getNumParticles(This)
+    double mn = 1e300, s1 = 0., s2 = 0., s3 = 0.;
+    for (long ip = (long)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += (long)gridDim.x * blockDim.x) {
+        double t[4];
+        if (adaptive_uz_terms(hpb_is_valid(b.idcpu[ip]), b.uz[ip], b.w[ip], clight_inv, t)) {
+            mn = fmin(mn, t[0]); s1 += t[1]; s2 += t[2]; s3 += t[3];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5][0] = mn; red[threadIdx.x >> 5][1] = s1;
+        red[threadIdx.x >> 5][2] = s2; red[threadIdx.x >> 5][3] = s3;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kT / 32; ++w) {
+            red[0][0] = fmin(red[0][0], red[w][0]);
+            red[0][1] += red[w][1]; red[0][2] += red[w][2]; red[0][3] += red[w][3];
+        }
+        atomic_min_double(acc, red[0][0]);
+        if (red[0][1] != 0.) { atomicAdd(acc + 1, red[0][1]); atomicAdd(acc + 2, red[0][2]); atomicAdd(acc + 3, red[0][3]); }
+    }
+}
+
 // ---- the file format -------------------------------------------------------------------------
 struct Node {
     std::string name, format;        // format empty: a nested structured datatype
@@ -98,6 +144,19 @@ extern "C" int hpb_beam_insitu_slice(hpb_ctx *ctx, hpb_beam_slice bm, double ins
     if (nb > 64) nb = 64;
     hpb_launch(k_beam_insitu, nb, kT, 0, ctx->stream, bm, 1.0 / ctx->g.c, insitu_radius * insitu_radius,
                d_record, stride);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// d_acc[4] = {min uz / c, sum w, sum w uz / c, sum w uz^2 / c^2}, accumulated over the slices of a step
+extern "C" int hpb_beam_min_uz_slice(hpb_ctx *ctx, hpb_beam_slice bm, double *d_acc)
+{
+    if (!ctx || !d_acc) return HPB_ERR_ARG;
+    if (bm.np == 0) return HPB_OK;
+    unsigned nb = (unsigned)((bm.np + kT - 1) / kT);
+    if (nb > 64) nb = 64;
+    hpb_launch(k_beam_min_uz, nb, kT, 0, ctx->stream, bm, 1.0 / ctx->g.c, d_acc);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;

@@ -7,6 +7,16 @@
 
 constexpr int kInsituNReal = 22;      // m_insitu_nrp; slot 22 of a record holds Np
 
+// AdaptiveTimeStep::GatherMinUzSlice (src/utils/AdaptiveTimeStep.cpp:121-141): one particle's
+// {uz / c (for the minimum), w, w uz / c, w uz^2 / c^2}; false for invalid particles
+HPB_HD bool adaptive_uz_terms(bool valid, double uz_c, double w, double clight_inv, double t[4])
+{
+    if (!valid) return false;
+    const double uz = uz_c * clight_inv;
+    t[0] = uz; t[1] = w; t[2] = w * uz; t[3] = w * uz * uz;
+    return true;
+}
+
 // out[23]: w, w x, w x^2, w y, w y^2, w z, w z^2, w ux, w ux^2, w uy, w uy^2, w uz, w uz^2, w x ux,
 // w y uy, w z uz, w x uy, w y ux, w ux/uz, w uy/uz, w gamma, w gamma^2, 1   (u = proper velocity / c).
 // Returns false (nothing to add) for invalid particles and particles outside the in-situ radius.

@@ -279,7 +279,20 @@ int read_deck(hpb_sim *s)
     const auto bhi = d.nums("boundary.particle_hi", {hi[0], hi[1]});
     s->bc_lo[0] = blo[0]; s->bc_lo[1] = blo[1]; s->bc_hi[0] = bhi[0]; s->bc_hi[1] = bhi[1];
     s->max_step = (int)d.num("max_step", 0);
-    s->dt = d.num("hipace.dt", 0.);
+    s->adaptive_dt = d.str("hipace.dt", "") == "adaptive";            // AdaptiveTimeStep.cpp:17-35
+    s->dt = s->adaptive_dt ? 0. : d.num("hipace.dt", 0.);
+    if (s->adaptive_dt) {
+        s->adp.nt_per_betatron = d.num("hipace.nt_per_betatron", 20.);
+        s->adp.dt_max = d.num("hipace.dt_max", INFINITY);
+        s->adp.threshold_uz = d.num("hipace.adaptive_threshold_uz", 2.);
+        s->adp.phase_tolerance = d.num("hipace.adaptive_phase_tolerance", 4e-4);
+        s->adp.phase_substeps = (int)d.num("hipace.adaptive_phase_substeps", 2000);
+        s->adp.control_phase = (int)d.num("hipace.adaptive_control_phase_advance", 1);
+        s->adp.c = g.c; s->adp.ep0 = g.ep0;
+        s->adaptive_density = d.num("plasmas.adaptive_density", 0.);
+        if ((int)d.num("hipace.adaptive_gather_ez", 0))
+            throw std::runtime_error("hipace.adaptive_gather_ez = 1 is not supported (the reference calls it buggy)");
+    }
     s->mg_tol_rel = d.num("hipace.MG_tolerance_rel", 1e-4);
     s->mg_tol_abs = d.num("hipace.MG_tolerance_abs", DBL_MIN);
     s->deposit_rho = (int)d.num("hipace.deposit_rho", 0) != 0;
@@ -302,6 +315,7 @@ int read_deck(hpb_sim *s)
             std::vector<RpnInstr> code;
             d.compile(expr, {"x", "y", "z"}, code);
             { const double origin[3] = {0., 0., 0.}; sp.density0 = d.run(code, origin); }
+            sp.density_host = code;
             sp.density.n = (int)code.size();
             for (size_t k = 0; k < code.size(); ++k) sp.density.code[k] = code[k];
             const auto ppc = d.nums(nm + ".ppc", {}, "plasmas.ppc");
@@ -382,6 +396,7 @@ int read_deck(hpb_sim *s)
             const auto us = d.nums(nm + ".u_std", {0., 0., 0.});
             for (double v : us)
                 if (v != 0.) throw std::runtime_error("beam u_std != 0 needs AMReX's RNG stream: unsupported");
+            b.u_mean_z = um.size() > 2 ? um[2] : 0.;
             b.n_subcycles = (int)d.num(nm + ".n_subcycles", 10);
             if (b.n_subcycles < 1) throw std::runtime_error(nm + ".n_subcycles must be >= 1");
             b.do_z_push = (int)d.num(nm + ".do_z_push", 1) != 0;
@@ -601,6 +616,26 @@ struct StageTimer {
     }
 };
 
+// CalculateFromMinUz (AdaptiveTimeStep.cpp:143-233) from the host copies BeamSp::ts
+int adaptive_from_min_uz(hpb_sim *s, double t_now, double rho)
+{
+    (void)t_now;
+    const int nb = (int)s->beams.size();
+    std::vector<double> ts(4 * nb), q(nb), m(nb);
+    for (int ib = 0; ib < nb; ++ib) {
+        for (int k = 0; k < 4; ++k) ts[4 * ib + k] = s->beams[ib].ts[k];
+        q[ib] = s->beams[ib].charge; m[ib] = s->beams[ib].mass;
+    }
+    double dt_out = s->dt, mq = s->min_uz_mq;
+    if (!adaptive_dt_from_min_uz(s->adp, nb, ts.data(), q.data(), m.data(), rho, s->dt, dt_out, mq)) {
+        hpb_set_error("adaptive time step: the sum of the beam weights is 0 or no plasma density > 0 is given "
+                      "(plasmas.adaptive_density)");
+        return HPB_ERR_ARG;
+    }
+    s->dt = dt_out; s->min_uz_mq = mq;
+    return HPB_OK;
+}
+
 int begin_step(hpb_sim *s, int step)
 {
     // ResetAllQuantities (Hipace.cpp:730-742)
@@ -608,7 +643,43 @@ int begin_step(hpb_sim *s, int step)
     SIM_CUDA(cudaMemsetAsync(s->d_checksum, 0, sizeof(double) * (s->sl.ncomp + 1), s->stream));
     for (int k = 0; k < HPB_C_COUNT; ++k) s->comps[k] = s->comps0[k];
     s->prepared = false;
-    const double c_t = s->g.c * (s->dt * step);
+    if (s->adaptive_dt) {                                            // Hipace.cpp:275-279, 411, 420, 434
+        if (hpb_pipeline_active(s)) {
+            hpb_set_error("hipace.dt = adaptive is not available with a multi-rank pipeline");
+            return HPB_ERR_UNSUPPORTED;
+        }
+        auto rho_at = [&](double z) {                                // MultiPlasma::maxChargeDensity
+            double m = fabs(s->adaptive_density * s->g.q_e);
+            for (auto &sp : s->plasmas) {
+                const double xyz[3] = {0., 0., z};
+                m = fmax(m, fabs(sp.charge * s->deck.run(sp.density_host, xyz)));
+            }
+            return m;
+        };
+        if (step == 0) {
+            if (s->beams.empty()) { hpb_set_error("adaptive time step: needs a beam"); return HPB_ERR_ARG; }
+            for (auto &b : s->beams) {                               // GatherMinUzSlice(initial)
+                b.ts[0] = b.u_mean_z; b.ts[1] = 1.; b.ts[2] = b.u_mean_z; b.ts[3] = b.u_mean_z * b.u_mean_z;
+            }
+            s->min_uz_mq = DBL_MAX;
+            int rc = adaptive_from_min_uz(s, 0., rho_at(0.));
+            if (rc) return rc;
+            s->dt = adaptive_dt_from_density(s->adp, s->min_uz_mq, 0., s->dt, rho_at);
+            s->time = 0.;
+        } else {
+            s->time = s->next_time;
+        }
+        s->dt = adaptive_dt_from_density(s->adp, s->min_uz_mq, s->time, s->dt, rho_at);
+        s->next_time = s->time + s->dt;
+        for (auto &b : s->beams) {                                   // CalculateFromDensity resets the data
+            b.ts[0] = 1e30; b.ts[1] = b.ts[2] = b.ts[3] = 0.;
+            if (!b.d_ts) SIM_CUDA(cudaMalloc(&b.d_ts, 4 * sizeof(double)));
+            SIM_CUDA(cudaMemcpyAsync(b.d_ts, b.ts, 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        }
+    } else {
+        s->time = s->dt * step;
+    }
+    const double c_t = s->g.c * s->time;
     for (auto &sp : s->plasmas) {                                    // Hipace.cpp:450
         int rc = init_plasma(s, sp, c_t);
         if (rc) return rc;
@@ -645,6 +716,19 @@ int begin_step(hpb_sim *s, int step)
 int write_beam_insitu(hpb_sim *s);
 int end_step(hpb_sim *s)
 {
+    if (s->adaptive_dt) {                                            // Hipace.cpp:482-483
+        for (auto &b : s->beams) {
+            SIM_CUDA(cudaStreamSynchronize(s->stream));
+            if (s->stream2) SIM_CUDA(cudaStreamSynchronize(s->stream2));
+            SIM_CUDA(cudaMemcpy(b.ts, b.d_ts, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        double rho = fabs(s->adaptive_density * s->g.q_e);
+        for (auto &sp : s->plasmas) {
+            const double xyz[3] = {0., 0., s->g.c * s->time};
+            rho = fmax(rho, fabs(sp.charge * s->deck.run(sp.density_host, xyz)));
+        }
+        if (int rc = adaptive_from_min_uz(s, s->time, rho)) return rc;
+    }
     if (int rc = write_beam_insitu(s)) return rc;
     for (auto &b : s->beams) { b.cur ^= 1; b.cs_valid = s->opt_checksums; b.initialised = true; }
     if (hpb_pipeline_active(s)) return hpb_pipeline_end_step(s, s->cur_step);
@@ -711,7 +795,7 @@ int write_beam_insitu(hpb_sim *s)
         snprintf(rank, sizeof(rank), "%04d", hpb_pipeline_active(s) ? hpb_pipeline_rank(s) : 0);
         const std::string path = b.insitu_file_prefix + "/reduced_" + b.name + "." + rank + ".txt";
         const double ndf = s->g.normalized ? s->g.dx * s->g.dy * s->g.dz : 1.0;
-        int rc = hpb_insitu_write_beam(path.c_str(), s->dt * s->cur_step, s->cur_step, s->nz, b.charge, b.mass,
+        int rc = hpb_insitu_write_beam(path.c_str(), s->time, s->cur_step, s->nz, b.charge, b.mass,
                                        s->prob_lo[2], s->prob_hi[2], ndf, s->g.normalized, h.data());
         if (rc) return rc;
     }
@@ -725,7 +809,7 @@ int beam_push_and_send(hpb_sim *s, int islice)
     if (s->beams.empty()) return HPB_OK;
     const int slot = s->nz - 1 - islice;
     const double min_z = s->prob_lo[2] + islice * s->g.dz;
-    const double time = s->dt * s->cur_step;
+    const double time = s->time;
     if ((rc = hpb_pipeline_wait_out_slot(s, islice))) return rc;
     for (auto &b : s->beams) {
         const BeamRing &in = b.ring[b.cur], &out = b.ring[b.cur ^ 1];
@@ -747,6 +831,8 @@ int beam_push_and_send(hpb_sim *s, int islice)
         if ((rc = hpb_beam_shift_slipped(s->ctx, bm, in.nsub(slot), min_z, b.d_class, out.view(slot),
                                          out.hdr(slot), next, islice > 0 ? in.hdr(slot + 1) : nullptr,
                                          islice > 0 ? in.nsub(slot + 1) : nullptr, s->d_overflow))) return rc;
+        // GatherMinUzSlice of the pushed slice without its slipped particles (Hipace.cpp:715)
+        if (s->adaptive_dt && (rc = hpb_beam_min_uz_slice(s->ctx, out.view(slot), b.d_ts))) return rc;
     }
     return hpb_pipeline_send_slice(s, islice, s->cur_step);
 }
@@ -1048,6 +1134,20 @@ int solve_one_slice(hpb_sim *s, int islice)
 // ---------------------------------------------------------------------------------------------
 // C-ABI
 // ---------------------------------------------------------------------------------------------
+// Host-only: the adaptive time step arithmetic (adaptive_dt.hpp) for a uniform plasma density,
+// so that the CPU tests can hold it to the oracle
+extern "C" int hpb_adaptive_dt_next(const hpb_adaptive_par *par, int nbeams, const double *ts,
+                                    const double *charge, const double *mass, double rho, double t_next,
+                                    double dt_in, double *dt_out, double *min_uz_mq)
+{
+    if (!par || !ts || !charge || !mass || !dt_out || !min_uz_mq) return HPB_ERR_ARG;
+    double dt = dt_in, mq = *min_uz_mq;
+    if (!adaptive_dt_from_min_uz(*par, nbeams, ts, charge, mass, rho, dt_in, dt, mq)) return HPB_ERR_ARG;
+    *dt_out = adaptive_dt_from_density(*par, mq, t_next, dt, [rho](double) { return rho; });
+    *min_uz_mq = mq;
+    return HPB_OK;
+}
+
 // Host-only: parse a deck exactly as hpb_sim_create does (same parser, same "unsupported"
 // errors) and describe what it would run -- needs no GPU, so the input-deck surface is testable
 // on any machine.  summary (may be NULL) receives "key=value;" pairs.

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "rpn.cuh"
+#include "adaptive_dt.hpp"
 #include <float.h>
 #include <math.h>
 #include <string>
@@ -43,6 +44,7 @@ struct BeamRing {
 
 struct Species {
     double density0 = 0.;                        // density(0, 0, 0): reported by hpb_deck_check
+    std::vector<hpb::RpnInstr> density_host;     // the density expression for host-side evaluation
     long lattice_n = 0; int lattice_ppc = 1;     // regular InitParticles lattice (nothing filtered): cells per pass, passes
     std::string name;
     double charge = 0, mass = 0;
@@ -67,6 +69,9 @@ struct BeamSp {
     int n_subcycles = 10;
     bool do_z_push = true;
     // in-situ diagnostics (BeamParticleContainer.cpp:61-63, 296-311)
+    double u_mean_z = 0.;                         // as in the deck (adaptive dt, AdaptiveTimeStep.cpp:96-106)
+    double ts[4] = {1e30, 0., 0., 0.};            // adaptive dt: min uz, sum w, sum w uz, sum w uz^2
+    double *d_ts = nullptr;
     int insitu_period = 0;
     std::string insitu_file_prefix = "diags/insitu";
     double insitu_radius = INFINITY;
@@ -107,6 +112,10 @@ struct hpb_sim {
     double *d_pc_rhs = nullptr;                   // 3 staging planes nx * ny
     double *d_pc_scal = nullptr;                  // 38 multipole moments + 2 norms
     long n_predcorr_iters = 0;
+    // hipace.dt = adaptive (utils/AdaptiveTimeStep.cpp)
+    bool adaptive_dt = false;
+    hpb_adaptive_par adp = {20., INFINITY, 2., 4e-4, 2000, 1, 1., 1.};
+    double adaptive_density = 0., min_uz_mq = DBL_MAX, time = 0., next_time = 0.;
     bool use_grid_current = false;                // utils/GridCurrent.cpp
     double gc_peak = 0., gc_mean[3] = {0., 0., 0.}, gc_std[3] = {1., 1., 1.};
     int max_step = 0;

@@ -173,6 +173,19 @@ int hpb_beam_insitu_slice(hpb_ctx *ctx, hpb_beam_slice bm, double insitu_radius,
 int hpb_insitu_write_beam(const char *path, double time, int step, int n_slices, double charge,
                           double mass, double z_lo, double z_hi, double normalized_density_factor,
                           int is_normalized_units, const double *h_sums);
+/* hipace.dt = adaptive (src/utils/AdaptiveTimeStep.cpp).  hpb_beam_min_uz_slice = GatherMinUzSlice
+ * (:108-141) of one pushed beam slice: d_acc[4] = {min uz/c, sum w, sum w uz/c, sum w uz^2/c^2}
+ * accumulated over the slices of a step.  hpb_adaptive_dt_next (HOST only) = CalculateFromMinUz
+ * (:143-233) followed by CalculateFromDensity (:315-369) for a uniform plasma charge density rho. */
+typedef struct {
+    double nt_per_betatron, dt_max, threshold_uz, phase_tolerance;
+    int phase_substeps, control_phase;
+    double c, ep0;
+} hpb_adaptive_par;
+int hpb_beam_min_uz_slice(hpb_ctx *ctx, hpb_beam_slice bm, double *d_acc);
+int hpb_adaptive_dt_next(const hpb_adaptive_par *par, int nbeams, const double *ts, const double *charge,
+                         const double *mass, double rho, double t_next, double dt_in, double *dt_out,
+                         double *min_uz_mq);
 /* shiftSlippedParticles (src/particles/sorting/SliceSort.cpp:13-67) fused with the packing of
  * MultiBuffer::put_data (src/utils/MultiBuffer.cpp:730-905): invalid particles are dropped, the
  * particles with z >= min_z go (stable order) to `stay` whose counts d_stay_np[0..1] are set,

@@ -65,3 +65,20 @@ def test_open_boundary_with_plasma_matches_oracle(repo_root):
     want = Oracle(deck, ov).evolve(25)
     _compare(got, want)
     sim.close()
+
+
+def test_adaptive_time_step_golden(repo_root):
+    """hipace.dt = adaptive on the GPU: the reference's adaptive_time_step.1Rank golden (20 steps)"""
+    import hipace_b200 as hp
+    meta = json.load(open(os.path.join(GOLD, 'adaptive_time_step.1Rank.json')))
+    ov = dict(meta['overrides'])
+    sim = hp.Simulation(open(os.path.join(repo_root, meta['deck'])).read(), ov)
+    cs = sim.evolve(0, int(ov['max_step']))
+    gold = meta['checksums']
+    for name, want in gold['lev=0'].items():
+        assert abs(cs[name] - want) <= 1e-8 * abs(want) + 1e-40, (name, cs[name], want)
+    bc = sim.beam_checksums(0)
+    for name, want in gold['beam'].items():
+        if name in bc:
+            assert abs(bc[name] - want) <= 1e-8 * abs(want) + 1e-40, (name, bc[name], want)
+    sim.close()

@@ -134,3 +134,50 @@ def test_cuda_insitu_files_match_oracle(repo_root, tmp_path):
                     assert got[k][nm][sub] == pytest.approx(r[nm][sub], rel=1e-10, abs=1e-300), (k, nm, sub)
             else:
                 assert np.allclose(got[k][nm], r[nm], rtol=1e-10, atol=1e-300), (k, nm)
+
+
+class _AdaptivePar(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ('nt_per_betatron', 'dt_max', 'threshold_uz', 'phase_tolerance')] + \
+               [('phase_substeps', C.c_int), ('control_phase', C.c_int), ('c', C.c_double), ('ep0', C.c_double)]
+
+
+def test_adaptive_time_step_host_logic_follows_the_oracle(repo_root):
+    """hpb_adaptive_dt_next (the C++ host arithmetic of hipace.dt = adaptive, csrc/adaptive_dt.hpp)
+    fed with the per-step beam data of the oracle run that reproduces the reference's
+    adaptive_time_step golden: the same sequence of time steps, bit for bit"""
+    import hipace_b200 as hp
+    import json
+    meta = json.load(open(os.path.join(repo_root, 'tests', 'golden', 'adaptive_time_step.1Rank.json')))
+    ov = dict(meta['overrides'], max_step=6)
+    sim = O.Simulation(open(os.path.join(repo_root, meta['deck'])).read(), ov)
+    log = []
+    orig = sim._adaptive_from_min_uz
+
+    def spy(t_now):
+        ts = {k: dict(v) for k, v in sim._ts.items()}
+        dt_in = sim.dt
+        orig(t_now)
+        log.append((ts, dt_in, sim.dt, sim._min_uz_mq))
+    sim._adaptive_from_min_uz = spy
+    dts = []
+    sim.slice_hook = lambda s, isl, stage: dts.append(s.dt) if (stage == 'pushed' and isl == 0) else None
+    sim.evolve(step_end=6)
+    L = hp.lib()
+    L.hpb_adaptive_dt_next.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_void_p] * 2
+    par = _AdaptivePar(sim.nt_per_betatron, sim.dt_max, sim.adaptive_threshold_uz, sim.adaptive_phase_tolerance,
+                       sim.adaptive_phase_substeps, 1, sim.pc.c, sim.pc.ep0)
+    assert len(log) == 8 and len(dts) == 7            # the initial call + one per step
+    for k, (ts, dt_in, dt_after_min_uz, mq_want) in enumerate(log):
+        t = ts['beam']
+        arr = np.array([t['min_uz'], t['sw'], t['swu'], t['swu2']])
+        q, m = np.array([sim.beams[0].charge]), np.array([sim.beams[0].mass])
+        dt_out, mq = C.c_double(0.), C.c_double(np.finfo(float).max)
+        rc = L.hpb_adaptive_dt_next(C.byref(par), 1, arr.ctypes.data, q.ctypes.data, m.ctypes.data,
+                                    abs(sim.adaptive_density * sim.pc.q_e), 0.0, dt_in, C.byref(dt_out), C.byref(mq))
+        assert rc == 0
+        assert mq.value == mq_want
+        # uniform density: the phase-advance control leaves dt as CalculateFromMinUz set it
+        assert dt_out.value == dt_after_min_uz
+        if k < len(dts):
+            assert dts[k] == dt_after_min_uz             # ... and that is the dt the next step ran with
+    assert len(set(dts)) == len(dts)                     # the step really adapts
