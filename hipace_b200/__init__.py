@@ -64,6 +64,7 @@ EXPORTS = (
     'hpb_beam_insitu_slice', 'hpb_insitu_write_beam', 'hpb_fields_zero', 'hpb_deposit_current_jz',
     'hpb_fields_bxby_rhs', 'hpb_fields_psi_ez_bz_rhs', 'hpb_fields_open_boundary',
     'hpb_fields_rel_b_error', 'hpb_fields_lincomb2', 'hpb_beam_min_uz_slice', 'hpb_adaptive_dt_next',
+    'hpb_abs_sum_xz',
 )
 NCCL_ID_BYTES = 128
 

@@ -134,6 +134,27 @@ __global__ void k_abs_sum(SliceView a, int c, int nx, int ny, double *out)
     if (threadIdx.x == 0) atomicAdd(out, sm[0]);
 }
 
+// the same for an xz diagnostic (diagnostics/Diagnostic.cpp:393-407, Fields::Copy with order-1
+// interpolation to y = mid-domain): the mean of the two central rows for even ny, else the central row
+__global__ void k_abs_sum_xz(SliceView a, int c, int nx, int ny, double *out)
+{
+    hpb_pdl_prologue();
+    __shared__ double sm[kThreads];
+    double acc = 0.0;
+    const double *p = a.comp(c);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        const double v = (ny % 2 == 0) ? 0.5 * (p[a.idx(i, ny / 2 - 1)] + p[a.idx(i, ny / 2)]) : p[a.idx(i, ny / 2)];
+        acc += fabs(v);
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = kThreads / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, sm[0]);
+}
+
 inline unsigned nb(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -284,6 +305,15 @@ extern "C" int hpb_fields_sxsy_from_beam(hpb_ctx *ctx, hpb_slice sl, const int *
         comps[HPB_C_PREV_JY_BEAM], g.nx, g.ny, g.mu0, g.dx, g.dy, g.dz)
     if (ng == 2) HPB_SXSY(2); else if (ng == 1) HPB_SXSY(1); else HPB_SXSY(3);
 #undef HPB_SXSY
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_abs_sum_xz(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out)
+{
+    if (!ctx || c < 0 || !d_out) return HPB_ERR_ARG;
+    hpb_launch(k_abs_sum_xz, 1, kThreads, 0, ctx->stream, make_view(sl), c, ctx->g.nx, ctx->g.ny, d_out);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;

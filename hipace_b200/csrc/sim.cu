@@ -297,6 +297,12 @@ int read_deck(hpb_sim *s)
     s->mg_tol_abs = d.num("hipace.MG_tolerance_abs", DBL_MIN);
     s->deposit_rho = (int)d.num("hipace.deposit_rho", 0) != 0;
     for (auto &t : d.strs("diagnostic.field_data")) if (t == "rho") s->deposit_rho = true;
+    {
+        const std::string dt_ = d.str("diagnostic.diag_type", "xyz");
+        if (dt_ != "xyz" && dt_ != "xz")
+            throw std::runtime_error("diagnostic.diag_type must be xyz or xz (the checksums follow it)");
+        s->diag_xz = dt_ == "xz";
+    }
     s->do_beam_jx_jy = (int)d.num("hipace.do_beam_jx_jy_deposition", 1) != 0;
 
     auto pn = d.strs("plasmas.names");
@@ -349,6 +355,7 @@ int read_deck(hpb_sim *s)
             throw std::runtime_error("lasers: the envelope advance (max_step > 0) is not implemented");
         if (!s->explicit_solver)
             throw std::runtime_error("lasers are only supported with hipace.bxby_solver = explicit");
+        if (s->diag_xz) throw std::runtime_error("lasers: only diagnostic.diag_type = xyz is supported (the laserEnvelope checksum)");
         if ((int)ln.size() > HPB_MAX_LASERS) throw std::runtime_error("too many lasers");
         for (auto &nm : ln) {
             if (d.str(nm + ".init_type", "gaussian") != "gaussian")
@@ -972,7 +979,7 @@ int solve_one_slice_pc(hpb_sim *s, int islice)
         StageTimer t(s, ST_OTHER);
         for (int c = 0; c < sl.ncomp; ++c)
             if (s->comp_names[c].first == "This")
-                if ((rc = hpb_abs_sum(ctx, sl, phys_comp(s, c), s->d_checksum + c))) return rc;
+                if ((rc = (s->diag_xz ? hpb_abs_sum_xz : hpb_abs_sum)(ctx, sl, phys_comp(s, c), s->d_checksum + c))) return rc;
     }
     {
         StageTimer t(s, ST_PUSH);
@@ -1069,7 +1076,7 @@ int solve_one_slice(hpb_sim *s, int islice)
         StageTimer t(s, ST_OTHER);
         for (int c = 0; c < s->sl.ncomp; ++c)
             if (s->comp_names[c].first == "This")
-                if ((rc = hpb_abs_sum(ctx, s->sl, phys_comp(s, c), s->d_checksum + c))) return rc;
+                if ((rc = (s->diag_xz ? hpb_abs_sum_xz : hpb_abs_sum)(ctx, s->sl, phys_comp(s, c), s->d_checksum + c))) return rc;
     }
     auto push_plasma = [&](bool with_deposit) -> int {
         StageTimer t(s, ST_PUSH);

@@ -113,6 +113,7 @@ struct hpb_sim {
     double *d_pc_scal = nullptr;                  // 38 multipole moments + 2 norms
     long n_predcorr_iters = 0;
     // hipace.dt = adaptive (utils/AdaptiveTimeStep.cpp)
+    bool diag_xz = false;                         // diagnostic.diag_type = xz
     bool adaptive_dt = false;
     hpb_adaptive_par adp = {20., INFINITY, 2., 4e-4, 2000, 1, 1., 1.};
     double adaptive_density = 0., min_uz_mq = DBL_MAX, time = 0., next_time = 0.;

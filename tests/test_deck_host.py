@@ -81,6 +81,7 @@ def test_overrides_constants_and_expressions():
     ({'boundary.field': 'Periodic'}, 'Dirichlet'),
     ({'plasma.u_std': '0. 0. 1e-3'}, 'RNG'),
     ({'amr.n_cell': '64 64'}, '3 values'),
+    ({'diagnostic.diag_type': 'yz'}, 'diag_type'),
     ({'beam.profile': 'parabolic'}, 'profile'),
 ])
 def test_unsupported_options_fail_loudly(ov, msg):

@@ -82,3 +82,17 @@ def test_adaptive_time_step_golden(repo_root):
         if name in bc:
             assert abs(bc[name] - want) <= 1e-8 * abs(want) + 1e-40, (name, bc[name], want)
     sim.close()
+
+
+def test_xz_diagnostic_checksums_match_oracle(repo_root):
+    """diagnostic.diag_type = xz: the checksums are those of the y = mid-domain line of every slice"""
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    deck = open(os.path.join(repo_root, 'examples', 'blowout_wake_normalized.in')).read()
+    for ncell in ('32 32 100', '33 33 100'):          # even ny: mean of two rows; odd ny: the central row
+        ov = {'amr.n_cell': ncell, 'diagnostic.diag_type': 'xz'}
+        sim = hp.Simulation(deck, ov)
+        got = sim.evolve(0, 0, 30)
+        want = Oracle(deck, ov).evolve(30)
+        _compare(got, want)
+        sim.close()
