@@ -64,7 +64,7 @@ EXPORTS = (
     'hpb_beam_insitu_slice', 'hpb_insitu_write_beam', 'hpb_fields_zero', 'hpb_deposit_current_jz',
     'hpb_fields_bxby_rhs', 'hpb_fields_psi_ez_bz_rhs', 'hpb_fields_open_boundary',
     'hpb_fields_rel_b_error', 'hpb_fields_lincomb2', 'hpb_beam_min_uz_slice', 'hpb_adaptive_dt_next',
-    'hpb_abs_sum_xz',
+    'hpb_abs_sum_xz', 'hpb_plasma_insitu_slice', 'hpb_insitu_write_plasma',
 )
 NCCL_ID_BYTES = 128
 
@@ -214,6 +214,17 @@ def insitu_write_beam(path, time, step, charge, mass, z_lo, z_hi, density_factor
         [C.c_int, C.c_void_p]
     _check(L.hpb_insitu_write_beam(str(path).encode(), time, step, a.shape[1], charge, mass, z_lo, z_hi,
                                    density_factor, int(normalized), a.ctypes.data), 'hpb_insitu_write_beam')
+
+
+def insitu_write_plasma(path, time, step, charge, mass, z_lo, z_hi, density_factor, normalized, sums):
+    """hpb_insitu_write_plasma (host only): raw per-slice sums[15, n_slices] -> one appended record"""
+    a = np.ascontiguousarray(sums, dtype=np.float64)
+    assert a.ndim == 2 and a.shape[0] == 15
+    L = lib()
+    L.hpb_insitu_write_plasma.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int] + [C.c_double] * 5 + \
+        [C.c_int, C.c_void_p]
+    _check(L.hpb_insitu_write_plasma(str(path).encode(), time, step, a.shape[1], charge, mass, z_lo, z_hi,
+                                     density_factor, int(normalized), a.ctypes.data), 'hpb_insitu_write_plasma')
 
 
 def read_insitu(path):

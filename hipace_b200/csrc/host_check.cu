@@ -251,3 +251,16 @@ extern "C" int hc_open_boundary(double *rhs, int nx, int ny, double dx, double d
     }
     return 0;
 }
+
+// the 15 raw in-situ sums of a plasma species (insitu.cuh); r[11] in PlasmaIdx order
+extern "C" void hc_plasma_insitu(long n, const double *const *r, const unsigned char *valid, double clight_inv,
+                                 double radius_sq, double *out15)
+{
+    for (int k = 0; k < 15; ++k) out15[k] = 0.;
+    for (long p = 0; p < n; ++p) {
+        double t[15];
+        if (insitu_plasma_terms(valid[p] != 0, r[HPB_X][p], r[HPB_Y][p], r[HPB_UX][p], r[HPB_UY][p], r[HPB_PSI][p],
+                                r[HPB_W][p], clight_inv, radius_sq, t))
+            for (int k = 0; k < 15; ++k) out15[k] += t[k];
+    }
+}

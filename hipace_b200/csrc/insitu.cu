@@ -48,6 +48,39 @@ k_beam_insitu(hpb_beam_slice b, double clight_inv, double radius_sq, double *__r
     }
 }
 
+// the plasma at the start of a slice: grid-stride over the SoA, 15 atomics per block
+struct PlasmaSoA5 { const double *x, *y, *w, *ux, *uy, *psi; const uint64_t *idcpu; long np; };
+__global__ void __launch_bounds__(kT)
+k_plasma_insitu(PlasmaSoA5 p, double clight_inv, double radius_sq, double *__restrict__ rec, long stride)
+{
+    hpb_pdl_prologue();
+    __shared__ double red[kT / 32][15];
+    double acc[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) acc[k] = 0.;
+    for (long ip = (long)blockIdx.x * blockDim.x + threadIdx.x; ip < p.np; ip += (long)gridDim.x * blockDim.x) {
+        double t[15];
+        if (insitu_plasma_terms(hpb_is_valid(p.idcpu[ip]), p.x[ip], p.y[ip], p.ux[ip], p.uy[ip], p.psi[ip],
+                                p.w[ip], clight_inv, radius_sq, t)) {
+#pragma unroll
+            for (int k = 0; k < 15; ++k) acc[k] += t[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 15) {
+        double v = 0.;
+        for (int wq = 0; wq < kT / 32; ++wq) v += red[wq][threadIdx.x];
+        if (v != 0.) atomicAdd(rec + threadIdx.x * stride, v);
+    }
+}
+
 // GatherMinUzSlice of one beam slice after its push: acc[0] = min(acc[0], min uz / c), acc[1..3] += sums
 __device__ __forceinline__ void atomic_min_double(double *addr, double v)
 {
@@ -146,6 +179,76 @@ extern "C" int hpb_beam_insitu_slice(hpb_ctx *ctx, hpb_beam_slice bm, double ins
                d_record, stride);
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_plasma_insitu_slice(hpb_ctx *ctx, hpb_plasma pl, double insitu_radius, double *d_record,
+                                       long stride)
+{
+    if (!ctx || !d_record || stride < 1) return HPB_ERR_ARG;
+    if (pl.np == 0) return HPB_OK;
+    unsigned nb = (unsigned)((pl.np + kT - 1) / kT);
+    if (nb > 1184) nb = 1184;         // 8 blocks per SM
+    const PlasmaSoA5 p = {pl.r[HPB_X], pl.r[HPB_Y], pl.r[HPB_W], pl.r[HPB_UX], pl.r[HPB_UY], pl.r[HPB_PSI],
+                          pl.idcpu, pl.np};
+    hpb_launch(k_plasma_insitu, nb, kT, 0, ctx->stream, p, 1.0 / ctx->g.c, insitu_radius * insitu_radius,
+               d_record, stride);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// Host only.  sums: [15][n_slices] RAW per-slice sums in the order of insitu_plasma_terms
+// (PlasmaParticleContainer::InSituWriteToFile, PlasmaParticleContainer.cpp:530-618)
+extern "C" int hpb_insitu_write_plasma(const char *path, double time, int step, int n_slices, double charge,
+                                       double mass, double z_lo, double z_hi,
+                                       double normalized_density_factor, int is_normalized_units,
+                                       const double *sums)
+{
+    if (!path || !sums || n_slices < 1) return HPB_ERR_ARG;
+    constexpr int NR = kPlasmaInsituNReal;
+    const size_t ns = (size_t)n_slices;
+    std::vector<double> r(NR * ns), tot(NR, 0.);
+    std::vector<int> np(ns);
+    int np_tot = 0;
+    for (size_t s = ns; s-- > 0;) {          // running sums from the head, like the beam's
+        const double sw = sums[s];
+        const double sum_w_inv = sw <= 0. ? 0. : 1. / sw;
+        for (int i = 0; i < NR; ++i) {
+            const double v = sums[i * ns + s];
+            r[i * ns + s] = v * ((i == 0 || i == NR - 1) ? 1. : sum_w_inv);      // :513-517
+            tot[i] += v;
+        }
+        np[s] = (int)sums[NR * ns + s];
+        np_tot += np[s];
+    }
+    const double sum_w0 = tot[0];
+    for (int i = 1; i < NR - 1; ++i) tot[i] /= sum_w0;
+    static const char *names[NR] = {"sum(w)", "[x]", "[x^2]", "[y]", "[y^2]", "[ux]", "[ux^2]", "[uy]", "[uy^2]",
+                                    "[uz]", "[uz^2]", "[ga]", "[ga^2]", "[(ga-1)*(1-vz)]"};
+    std::vector<Node> all = {f8("time", &time), i4("step", &step), i4("n_slices", &n_slices),
+                             f8("charge", &charge), f8("mass", &mass), f8("z_lo", &z_lo), f8("z_hi", &z_hi),
+                             f8("normalized_density_factor", &normalized_density_factor),
+                             i4("is_normalized_units", &is_normalized_units)};
+    for (int i = 1; i < NR; ++i) all.push_back(f8(names[i], &r[i * ns], ns));
+    all.push_back(f8("sum(w)", &r[0], ns));
+    all.push_back(i4("Np", np.data(), ns));
+    Node avg; avg.name = "average";
+    for (int i = 1; i < NR - 1; ++i) avg.sub.push_back(f8(names[i], &tot[i]));
+    Node total; total.name = "total";
+    total.sub.push_back(f8("sum(w)", &tot[0]));
+    total.sub.push_back(f8(names[NR - 1], &tot[NR - 1]));
+    total.sub.push_back(i4("Np", &np_tot));
+    all.push_back(avg);
+    all.push_back(total);
+    FILE *f = fopen(path, "ab");
+    if (!f) { hpb_set_error("in-situ diagnostics: cannot open %s (does the directory exist?)", path); return HPB_ERR_ARG; }
+    std::string out;
+    fseek(f, 0, SEEK_END);
+    if (ftell(f) == 0) header(all, out, "");
+    payload(all, out);
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (fclose(f) != 0 || !ok) { hpb_set_error("in-situ diagnostics: error while writing %s", path); return HPB_ERR_ARG; }
     return HPB_OK;
 }
 

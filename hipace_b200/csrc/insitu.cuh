@@ -7,6 +7,31 @@
 
 constexpr int kInsituNReal = 22;      // m_insitu_nrp; slot 22 of a record holds Np
 
+// PlasmaParticleContainer::InSituComputeDiags (src/particles/plasma/PlasmaParticleContainer.cpp:443-526):
+// out[15] = w', w' x, w' x^2, w' y, w' y^2, w' ux, w' ux^2, w' uy, w' uy^2, w' uz, w' uz^2, w' gamma,
+// w' gamma^2, w (gamma - 1), 1 with gamma = (1 + ux^2 + uy^2 + psi^2) / (2 psi), uz = gamma - psi,
+// w' = w gamma / psi
+constexpr int kPlasmaInsituNReal = 14;
+HPB_HD bool insitu_plasma_terms(bool valid, double x, double y, double ux_c, double uy_c, double psi,
+                                double w0, double clight_inv, double radius_sq, double out[15])
+{
+    const double ux = ux_c * clight_inv, uy = uy_c * clight_inv;
+    if (!valid || x * x + y * y > radius_sq) return false;
+    const double gamma = (1.0 + ux * ux + uy * uy + psi * psi) / (2.0 * psi);
+    const double uz = gamma - psi;
+    const double w = w0 * gamma / psi;
+    out[0] = w;
+    out[1] = w * x;   out[2] = w * x * x;
+    out[3] = w * y;   out[4] = w * y * y;
+    out[5] = w * ux;  out[6] = w * ux * ux;
+    out[7] = w * uy;  out[8] = w * uy * uy;
+    out[9] = w * uz;  out[10] = w * uz * uz;
+    out[11] = w * gamma; out[12] = w * gamma * gamma;
+    out[13] = w0 * (gamma - 1.0);
+    out[14] = 1.;
+    return true;
+}
+
 // AdaptiveTimeStep::GatherMinUzSlice (src/utils/AdaptiveTimeStep.cpp:121-141): one particle's
 // {uz / c (for the minimum), w, w uz / c, w uz^2 / c^2}; false for invalid particles
 HPB_HD bool adaptive_uz_terms(bool valid, double uz_c, double w, double clight_inv, double t[4])

@@ -330,6 +330,9 @@ int read_deck(hpb_sim *s)
             sp.neutralize = (int)d.num(nm + ".neutralize_background", 1, "plasmas.neutralize_background") != 0;
             sp.max_qsa = d.num(nm + ".max_qsa_weighting_factor", 35., "plasmas.max_qsa_weighting_factor");
             sp.n_subcycles = (int)d.num(nm + ".n_subcycles", 1, "plasmas.n_subcycles");
+            sp.insitu_period = (int)d.num(nm + ".insitu_period", 0, "plasmas.insitu_period");
+            sp.insitu_radius = d.num(nm + ".insitu_radius", INFINITY, "plasmas.insitu_radius");
+            sp.insitu_file_prefix = d.str(nm + ".insitu_file_prefix", "diags/plasma_insitu", "plasmas.insitu_file_prefix");
             sp.radius = d.num(nm + ".radius", INFINITY, "plasmas.radius");
             sp.hollow = d.num(nm + ".hollow_core_radius", 0., "plasmas.hollow_core_radius");
             sp.min_density = d.num(nm + ".min_density", 0., "plasmas.min_density");
@@ -782,9 +785,34 @@ bool do_diagnostics(int period, int step, int max_step)
     return period > 0 && (step == max_step || step % period == 0);
 }
 
-// BeamParticleContainer::InSituWriteToFile at the end of a time step (Hipace.cpp:488)
+// mkdir -p <prefix>; <prefix>/reduced_<name>.<rank, 4 digits>.txt
+std::string insitu_path(hpb_sim *s, const std::string &prefix, const std::string &name)
+{
+    std::string dir;
+    for (char ch : prefix + "/") {
+        if (ch == '/' && !dir.empty()) mkdir(dir.c_str(), 0777);
+        dir += ch;
+    }
+    char rank[16];
+    snprintf(rank, sizeof(rank), "%04d", hpb_pipeline_active(s) ? hpb_pipeline_rank(s) : 0);
+    return prefix + "/reduced_" + name + "." + rank + ".txt";
+}
+
+// Beam- and PlasmaParticleContainer::InSituWriteToFile at the end of a time step (Hipace.cpp:488-489)
 int write_beam_insitu(hpb_sim *s)
 {
+    for (auto &sp : s->plasmas) {
+        if (!sp.d_insitu || !do_diagnostics(sp.insitu_period, s->cur_step, s->max_step)) continue;
+        std::vector<double> h(15 * (size_t)s->nz);
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+        SIM_CUDA(cudaMemcpy(h.data(), sp.d_insitu, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        SIM_CUDA(cudaMemset(sp.d_insitu, 0, sizeof(double) * h.size()));
+        const double ndf = s->g.normalized ? s->g.dx * s->g.dy * s->g.dz : 1.0;
+        int rc = hpb_insitu_write_plasma(insitu_path(s, sp.insitu_file_prefix, sp.name).c_str(), s->time,
+                                         s->cur_step, s->nz, sp.charge, sp.mass, s->prob_lo[2], s->prob_hi[2],
+                                         ndf, s->g.normalized, h.data());
+        if (rc) return rc;
+    }
     for (auto &b : s->beams) {
         if (!b.d_insitu || !do_diagnostics(b.insitu_period, s->cur_step, s->max_step)) continue;
         std::vector<double> h(23 * (size_t)s->nz);
@@ -792,15 +820,7 @@ int write_beam_insitu(hpb_sim *s)
         if (s->stream2) SIM_CUDA(cudaStreamSynchronize(s->stream2));
         SIM_CUDA(cudaMemcpy(h.data(), b.d_insitu, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
         SIM_CUDA(cudaMemset(b.d_insitu, 0, sizeof(double) * h.size()));
-        // mkdir -p <prefix>; file <prefix>/reduced_<name>.<rank, 4 digits>.txt
-        std::string dir;
-        for (char ch : b.insitu_file_prefix + "/") {
-            if (ch == '/' && !dir.empty()) mkdir(dir.c_str(), 0777);
-            dir += ch;
-        }
-        char rank[16];
-        snprintf(rank, sizeof(rank), "%04d", hpb_pipeline_active(s) ? hpb_pipeline_rank(s) : 0);
-        const std::string path = b.insitu_file_prefix + "/reduced_" + b.name + "." + rank + ".txt";
+        const std::string path = insitu_path(s, b.insitu_file_prefix, b.name);
         const double ndf = s->g.normalized ? s->g.dx * s->g.dy * s->g.dz : 1.0;
         int rc = hpb_insitu_write_beam(path.c_str(), s->time, s->cur_step, s->nz, b.charge, b.mass,
                                        s->prob_lo[2], s->prob_hi[2], ndf, s->g.normalized, h.data());
@@ -1005,8 +1025,24 @@ int solve_one_slice_pc(hpb_sim *s, int islice)
     return HPB_OK;
 }
 
+// PlasmaParticleContainer::InSituComputeDiags at the start of a slice (Hipace.cpp:587)
+int plasma_insitu(hpb_sim *s, int islice)
+{
+    for (auto &sp : s->plasmas) {
+        if (!do_diagnostics(sp.insitu_period, s->cur_step, s->max_step)) continue;
+        if (!sp.d_insitu) {
+            SIM_CUDA(cudaMalloc(&sp.d_insitu, sizeof(double) * 15 * (size_t)s->nz));
+            SIM_CUDA(cudaMemsetAsync(sp.d_insitu, 0, sizeof(double) * 15 * (size_t)s->nz, s->ctx->stream));
+        }
+        int rc = hpb_plasma_insitu_slice(s->ctx, sp.d, sp.insitu_radius, sp.d_insitu + islice, s->nz);
+        if (rc) return rc;
+    }
+    return HPB_OK;
+}
+
 int solve_one_slice(hpb_sim *s, int islice)
 {
+    if (int rci = plasma_insitu(s, islice)) return rci;
     if (!s->explicit_solver) return solve_one_slice_pc(s, islice);
     hpb_ctx *ctx = s->ctx;
     const int *C = s->comps;
@@ -1015,6 +1051,9 @@ int solve_one_slice(hpb_sim *s, int islice)
     // between the beam deposit and the Poisson solve of the reference order)
     bool fuse = s->opt_fuse && C[HPB_C_RHO] < 0 && !s->use_laser && !hpb_use_generic_order(ctx)
                 && !s->use_grid_current;
+    // (plasma in-situ diagnostics see the particles before this slice's deposit may discard QSA
+    // violators: the fused order has deposited already)
+    for (auto &sp : s->plasmas) if (sp.insitu_period > 0) fuse = false;
     for (auto &sp : s->plasmas) if (sp.n_subcycles < 1) fuse = false;
     // (stage timers synchronise the main stream per stage: keep one stream when profiling)
     const bool side = fuse && s->opt_side_stream && s->stream2 && !s->beams.empty() && !s->opt_profile;

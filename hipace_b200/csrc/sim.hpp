@@ -45,6 +45,11 @@ struct BeamRing {
 struct Species {
     double density0 = 0.;                        // density(0, 0, 0): reported by hpb_deck_check
     std::vector<hpb::RpnInstr> density_host;     // the density expression for host-side evaluation
+    // in-situ diagnostics (PlasmaParticleContainer.H:164, 198, 215)
+    int insitu_period = 0;
+    std::string insitu_file_prefix = "diags/plasma_insitu";
+    double insitu_radius = INFINITY;
+    double *d_insitu = nullptr;                  // [15][nz] raw per-slice sums of the current step
     long lattice_n = 0; int lattice_ppc = 1;     // regular InitParticles lattice (nothing filtered): cells per pass, passes
     std::string name;
     double charge = 0, mass = 0;

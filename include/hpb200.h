@@ -173,6 +173,14 @@ int hpb_beam_insitu_slice(hpb_ctx *ctx, hpb_beam_slice bm, double insitu_radius,
 int hpb_insitu_write_beam(const char *path, double time, int step, int n_slices, double charge,
                           double mass, double z_lo, double z_hi, double normalized_density_factor,
                           int is_normalized_units, const double *h_sums);
+/* the same for a plasma species at the START of a slice (Hipace.cpp:587):
+ * PlasmaParticleContainer::InSituComputeDiags / InSituWriteToFile
+ * (src/particles/plasma/PlasmaParticleContainer.cpp:443-526, 530-618); 15 raw sums per slice */
+int hpb_plasma_insitu_slice(hpb_ctx *ctx, hpb_plasma pl, double insitu_radius, double *d_record,
+                            long stride);
+int hpb_insitu_write_plasma(const char *path, double time, int step, int n_slices, double charge,
+                            double mass, double z_lo, double z_hi, double normalized_density_factor,
+                            int is_normalized_units, const double *h_sums);
 /* hipace.dt = adaptive (src/utils/AdaptiveTimeStep.cpp).  hpb_beam_min_uz_slice = GatherMinUzSlice
  * (:108-141) of one pushed beam slice: d_acc[4] = {min uz/c, sum w, sum w uz/c, sum w uz^2/c^2}
  * accumulated over the slices of a step.  hpb_adaptive_dt_next (HOST only) = CalculateFromMinUz

@@ -1546,6 +1546,61 @@ def beam_insitu_sums(bs: dict, pc: PhysConst, radius=math.inf):
     return out
 
 
+PLASMA_INSITU_NAMES = ('sum(w)', '[x]', '[x^2]', '[y]', '[y^2]', '[ux]', '[ux^2]', '[uy]', '[uy^2]', '[uz]',
+                       '[uz^2]', '[ga]', '[ga^2]', '[(ga-1)*(1-vz)]')
+
+
+def plasma_insitu_sums(pl: 'Plasma', pc: PhysConst, radius=math.inf):
+    """PlasmaParticleContainer::InSituComputeDiags, particles/plasma/PlasmaParticleContainer.cpp:443-526"""
+    ci = 1.0 / pc.c
+    sel = pl.valid & ~(pl.x * pl.x + pl.y * pl.y > radius * radius)
+    x, y, psi, w0 = pl.x[sel], pl.y[sel], pl.psi[sel], pl.w[sel]
+    ux, uy = pl.ux[sel] * ci, pl.uy[sel] * ci
+    ga = (1.0 + ux * ux + uy * uy + psi * psi) / (2.0 * psi)
+    uz = ga - psi
+    w = w0 * ga / psi
+    terms = (w, w * x, w * x * x, w * y, w * y * y, w * ux, w * ux * ux, w * uy, w * uy * uy, w * uz,
+             w * uz * uz, w * ga, w * ga * ga, w0 * (ga - 1.0))
+    out = np.zeros(15)
+    for k, t in enumerate(terms):
+        out[k] = t.sum()
+    out[14] = x.size
+    return out
+
+
+def insitu_plasma_record(sums, time, step, charge, mass, z_lo, z_hi, density_factor, normalized):
+    """PlasmaParticleContainer::InSituWriteToFile, PlasmaParticleContainer.cpp:530-618"""
+    ns = sums.shape[1]
+    sw = sums[0]
+    sw_inv = np.where(sw <= 0.0, 0.0, 1.0 / np.where(sw <= 0.0, 1.0, sw))
+    keep = (np.arange(14) == 0) | (np.arange(14) == 13)
+    per = sums[:14] * np.where(keep[:, None], 1.0, sw_inv[None, :])
+    tot = np.zeros(14)
+    for isl in range(ns - 1, -1, -1):
+        tot += sums[:14, isl]
+    avg = tot / tot[0]
+    N = PLASMA_INSITU_NAMES
+    dt = np.dtype([('time', '<f8'), ('step', '<i4'), ('n_slices', '<i4'), ('charge', '<f8'), ('mass', '<f8'),
+                   ('z_lo', '<f8'), ('z_hi', '<f8'), ('normalized_density_factor', '<f8'),
+                   ('is_normalized_units', '<i4')] + [(nm, '<f8', (ns,)) for nm in N[1:]]
+                  + [('sum(w)', '<f8', (ns,)), ('Np', '<i4', (ns,)),
+                     ('average', [(nm, '<f8') for nm in N[1:13]]),
+                     ('total', [('sum(w)', '<f8'), (N[13], '<f8'), ('Np', '<i4')])])
+    rec = np.zeros((), dtype=dt)
+    rec['time'], rec['step'], rec['n_slices'] = time, step, ns
+    rec['charge'], rec['mass'], rec['z_lo'], rec['z_hi'] = charge, mass, z_lo, z_hi
+    rec['normalized_density_factor'], rec['is_normalized_units'] = density_factor, int(normalized)
+    for k, nm in enumerate(N):
+        rec[nm] = per[k]
+        if 1 <= k <= 12:
+            rec['average'][nm] = avg[k]
+    rec['Np'] = sums[14].astype(np.int32)
+    rec['total']['sum(w)'] = tot[0]
+    rec['total'][N[13]] = tot[13]
+    rec['total']['Np'] = int(sums[14].sum())
+    return dt, rec
+
+
 def insitu_beam_record(sums, time, step, charge, mass, z_lo, z_hi, density_factor, normalized):
     """InSituWriteToFile, particles/beam/BeamParticleContainer.cpp:596-732: (numpy dtype, record)
     of one time step from the raw sums[23, n_slices]; format of utils/InsituUtil.H"""
@@ -1826,6 +1881,13 @@ class Simulation:
                                            _get(d, 'beams.insitu_radius', math.inf))
                               for b in self.beams}
         self.insitu, self.insitu_records = {}, {}
+        self.plasma_insitu_period = {p.name: _get(d, p.name + '.insitu_period',
+                                                  _get(d, 'plasmas.insitu_period', 0, typ=int), typ=int)
+                                     for p in self.plasmas}
+        self.plasma_insitu_radius = {p.name: _get(d, p.name + '.insitu_radius',
+                                                  _get(d, 'plasmas.insitu_radius', math.inf))
+                                     for p in self.plasmas}
+        self.plasma_insitu, self.plasma_insitu_records = {}, {}
 
     # -- deck readers ----------------------------------------------------------------------
     def _species_charge_mass(self, pre, default_element=None):
@@ -2148,6 +2210,11 @@ class Simulation:
 
     def solve_one_slice(self, islice: int):
         """Hipace::SolveOneSlice, Hipace.cpp:556-728 (explicit branch)."""
+        for pl in self.plasmas:                                                   # :587
+            per = self.plasma_insitu_period.get(pl.name, 0)
+            if per > 0 and (self.step == self.max_step or self.step % per == 0):
+                self.plasma_insitu.setdefault(pl.name, np.zeros((15, self.geom.nz)))[:, islice] = \
+                    plasma_insitu_sums(pl, self.pc, self.plasma_insitu_radius.get(pl.name, math.inf))
         if not self.explicit:
             return self._solve_one_slice_pc(islice)
         F, g, pc, nrm = self.F, self.geom, self.pc, self.normalized
@@ -2285,7 +2352,7 @@ class Simulation:
         for step in range(step_begin, step_end + 1):
             self.checksums = {}
             self.begin_step(step)
-            self.insitu = {}
+            self.insitu, self.plasma_insitu = {}, {}
             for isl in range(g.nz - 1, stop, -1):
                 self.solve_one_slice(isl)
             if self.adaptive_dt and stop == -1:                                   # Hipace.cpp:482-483
@@ -2294,7 +2361,13 @@ class Simulation:
                 if b.name in self.insitu:
                     ndf = g.dx * g.dy * g.dz if self.normalized else 1.0
                     self.insitu_records.setdefault(b.name, []).append(insitu_beam_record(
-                        self.insitu[b.name], self.dt * step, step, b.charge, b.mass, g.lo[2], g.hi[2],
+                        self.insitu[b.name], self.time, step, b.charge, b.mass, g.lo[2], g.hi[2],
+                        ndf, self.normalized)[1])
+            for pl in self.plasmas:                                               # Hipace.cpp:489
+                if pl.name in self.plasma_insitu:
+                    ndf = g.dx * g.dy * g.dz if self.normalized else 1.0
+                    self.plasma_insitu_records.setdefault(pl.name, []).append(insitu_plasma_record(
+                        self.plasma_insitu[pl.name], self.time, step, pl.charge, pl.mass, g.lo[2], g.hi[2],
                         ndf, self.normalized)[1])
             if self.use_laser:
                 self.laser_store = self.laser_next
