@@ -65,6 +65,7 @@ EXPORTS = (
     'hpb_fields_bxby_rhs', 'hpb_fields_psi_ez_bz_rhs', 'hpb_fields_open_boundary',
     'hpb_fields_rel_b_error', 'hpb_fields_lincomb2', 'hpb_beam_min_uz_slice', 'hpb_adaptive_dt_next',
     'hpb_abs_sum_xz', 'hpb_plasma_insitu_slice', 'hpb_insitu_write_plasma',
+    'hpb_fields_insitu_slice', 'hpb_insitu_write_fields',
 )
 NCCL_ID_BYTES = 128
 
@@ -225,6 +226,17 @@ def insitu_write_plasma(path, time, step, charge, mass, z_lo, z_hi, density_fact
         [C.c_int, C.c_void_p]
     _check(L.hpb_insitu_write_plasma(str(path).encode(), time, step, a.shape[1], charge, mass, z_lo, z_hi,
                                      density_factor, int(normalized), a.ctypes.data), 'hpb_insitu_write_plasma')
+
+
+def insitu_write_fields(path, time, step, z_lo, z_hi, normalized, dxdydz, sums):
+    """hpb_insitu_write_fields (host only): raw per-slice sums[10, n_slices] -> one appended record"""
+    a = np.ascontiguousarray(sums, dtype=np.float64)
+    assert a.ndim == 2 and a.shape[0] == 10
+    L = lib()
+    L.hpb_insitu_write_fields.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                          C.c_int, C.c_double, C.c_void_p]
+    _check(L.hpb_insitu_write_fields(str(path).encode(), time, step, a.shape[1], z_lo, z_hi, int(normalized),
+                                     dxdydz, a.ctypes.data), 'hpb_insitu_write_fields')
 
 
 def read_insitu(path):

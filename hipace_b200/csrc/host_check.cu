@@ -264,3 +264,19 @@ extern "C" void hc_plasma_insitu(long n, const double *const *r, const unsigned 
             for (int k = 0; k < 15; ++k) out15[k] += t[k];
     }
 }
+
+// the 10 raw field in-situ sums over the valid box; comps7 = ExmBy EypBx Ez Bx By Bz jz_beam
+extern "C" void hc_field_insitu(double *planes, const HcGrid *hg, const int *comps7, int nx, int ny,
+                                double clight, double *out10)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    for (int k = 0; k < 10; ++k) out10[k] = 0.;
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            const long o = a.idx(i, j);
+            double t[10];
+            insitu_field_terms(a.comp(comps7[0])[o], a.comp(comps7[1])[o], a.comp(comps7[2])[o], a.comp(comps7[3])[o],
+                               a.comp(comps7[4])[o], a.comp(comps7[5])[o], a.comp(comps7[6])[o], clight, t);
+            for (int k = 0; k < 10; ++k) out10[k] += t[k];
+        }
+}

@@ -81,6 +81,42 @@ k_plasma_insitu(PlasmaSoA5 p, double clight_inv, double radius_sq, double *__res
     }
 }
 
+// the fields of a slice: 10 sums over the valid box
+struct FieldInsituComps { int exmby, eypbx, ez, bx, by, bz, jzb; };
+__global__ void __launch_bounds__(kT)
+k_field_insitu(SliceView a, FieldInsituComps c, int nx, int ny, double clight, double *__restrict__ rec,
+               long stride)
+{
+    hpb_pdl_prologue();
+    __shared__ double red[kT / 32][10];
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.;
+    const long n = (long)nx * ny;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(q / nx), i = (int)(q - (long)j * nx);
+        const long o = a.idx(i, j);
+        double t[10];
+        insitu_field_terms(a.comp(c.exmby)[o], a.comp(c.eypbx)[o], a.comp(c.ez)[o], a.comp(c.bx)[o],
+                           a.comp(c.by)[o], a.comp(c.bz)[o], a.comp(c.jzb)[o], clight, t);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] += t[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        double v = 0.;
+        for (int wq = 0; wq < kT / 32; ++wq) v += red[wq][threadIdx.x];
+        if (v != 0.) atomicAdd(rec + threadIdx.x * stride, v);
+    }
+}
+
 // GatherMinUzSlice of one beam slice after its push: acc[0] = min(acc[0], min uz / c), acc[1..3] += sums
 __device__ __forceinline__ void atomic_min_double(double *addr, double v)
 {
@@ -241,6 +277,58 @@ extern "C" int hpb_insitu_write_plasma(const char *path, double time, int step, 
     total.sub.push_back(i4("Np", &np_tot));
     all.push_back(avg);
     all.push_back(total);
+    FILE *f = fopen(path, "ab");
+    if (!f) { hpb_set_error("in-situ diagnostics: cannot open %s (does the directory exist?)", path); return HPB_ERR_ARG; }
+    std::string out;
+    fseek(f, 0, SEEK_END);
+    if (ftell(f) == 0) header(all, out, "");
+    payload(all, out);
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (fclose(f) != 0 || !ok) { hpb_set_error("in-situ diagnostics: error while writing %s", path); return HPB_ERR_ARG; }
+    return HPB_OK;
+}
+
+extern "C" int hpb_fields_insitu_slice(hpb_ctx *ctx, hpb_slice sl, const int *comps, double *d_record,
+                                       long stride)
+{
+    if (!ctx || !comps || !d_record || stride < 1) return HPB_ERR_ARG;
+    if (comps[HPB_C_JZ_BEAM] < 0) {
+        hpb_set_error("Must use explicit solver for field insitu diagnostic");       // Fields.cpp:1311-1312
+        return HPB_ERR_UNSUPPORTED;
+    }
+    const hpb_geom &g = ctx->g;
+    const FieldInsituComps c = {comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], comps[HPB_C_EZ], comps[HPB_C_BX],
+                                comps[HPB_C_BY], comps[HPB_C_BZ], comps[HPB_C_JZ_BEAM]};
+    unsigned nb = (unsigned)(((long)g.nx * g.ny + kT - 1) / kT);
+    if (nb > 592) nb = 592;
+    hpb_launch(k_field_insitu, nb, kT, 0, ctx->stream, make_view(sl), c, g.nx, g.ny, g.c, d_record, stride);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// Host only.  sums: [10][n_slices] RAW per-slice sums; every value is multiplied by dx dy dz
+// (Fields::InSituWriteToFile, src/fields/Fields.cpp:1349-1428)
+extern "C" int hpb_insitu_write_fields(const char *path, double time, int step, int n_slices, double z_lo,
+                                       double z_hi, int is_normalized_units, double dxdydz,
+                                       const double *sums)
+{
+    if (!path || !sums || n_slices < 1) return HPB_ERR_ARG;
+    const size_t ns = (size_t)n_slices;
+    std::vector<double> r(10 * ns), tot(10, 0.);
+    for (size_t s = ns; s-- > 0;)
+        for (int i = 0; i < 10; ++i) {
+            r[i * ns + s] = sums[i * ns + s] * dxdydz;                               // :1343-1346
+            tot[i] += r[i * ns + s];
+        }
+    static const char *names[10] = {"[Ex^2]", "[Ey^2]", "[Ez^2]", "[Bx^2]", "[By^2]", "[Bz^2]", "[ExmBy^2]",
+                                    "[EypBx^2]", "[jz_beam]", "[Ez*jz_beam]"};
+    std::vector<Node> all = {f8("time", &time), i4("step", &step), i4("n_slices", &n_slices), f8("z_lo", &z_lo),
+                             f8("z_hi", &z_hi), i4("is_normalized_units", &is_normalized_units)};
+    for (int i = 0; i < 10; ++i) all.push_back(f8(names[i], &r[i * ns], ns));
+    Node integ; integ.name = "integrated";
+    for (int i = 0; i < 10; ++i) integ.sub.push_back(f8(names[i], &tot[i]));
+    all.push_back(integ);
     FILE *f = fopen(path, "ab");
     if (!f) { hpb_set_error("in-situ diagnostics: cannot open %s (does the directory exist?)", path); return HPB_ERR_ARG; }
     std::string out;

@@ -32,6 +32,18 @@ HPB_HD bool insitu_plasma_terms(bool valid, double x, double y, double ux_c, dou
     return true;
 }
 
+// Fields::InSituComputeDiags (src/fields/Fields.cpp:1289-1347), one cell: Ex^2, Ey^2, Ez^2, Bx^2, By^2,
+// Bz^2, ExmBy^2, EypBx^2, jz_beam, Ez jz_beam
+HPB_HD void insitu_field_terms(double exmby, double eypbx, double ez, double bx, double by, double bz,
+                               double jzb, double clight, double out[10])
+{
+    const double ex = exmby + by * clight, ey = eypbx - bx * clight;
+    out[0] = ex * ex; out[1] = ey * ey; out[2] = ez * ez;
+    out[3] = bx * bx; out[4] = by * by; out[5] = bz * bz;
+    out[6] = exmby * exmby; out[7] = eypbx * eypbx;
+    out[8] = jzb; out[9] = ez * jzb;
+}
+
 // AdaptiveTimeStep::GatherMinUzSlice (src/utils/AdaptiveTimeStep.cpp:121-141): one particle's
 // {uz / c (for the minimum), w, w uz / c, w uz^2 / c^2}; false for invalid particles
 HPB_HD bool adaptive_uz_terms(bool valid, double uz_c, double w, double clight_inv, double t[4])

@@ -303,6 +303,10 @@ int read_deck(hpb_sim *s)
             throw std::runtime_error("diagnostic.diag_type must be xyz or xz (the checksums follow it)");
         s->diag_xz = dt_ == "xz";
     }
+    s->field_insitu_period = (int)d.num("fields.insitu_period", 0);
+    s->field_insitu_prefix = d.str("fields.insitu_file_prefix", "diags/field_insitu");
+    if (s->field_insitu_period > 0 && !s->explicit_solver)                     // Fields.cpp:1311-1312
+        throw std::runtime_error("Must use explicit solver for field insitu diagnostic");
     s->do_beam_jx_jy = (int)d.num("hipace.do_beam_jx_jy_deposition", 1) != 0;
 
     auto pn = d.strs("plasmas.names");
@@ -801,6 +805,16 @@ std::string insitu_path(hpb_sim *s, const std::string &prefix, const std::string
 // Beam- and PlasmaParticleContainer::InSituWriteToFile at the end of a time step (Hipace.cpp:488-489)
 int write_beam_insitu(hpb_sim *s)
 {
+    if (s->d_field_insitu && do_diagnostics(s->field_insitu_period, s->cur_step, s->max_step)) {   // :487
+        std::vector<double> h(10 * (size_t)s->nz);
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+        SIM_CUDA(cudaMemcpy(h.data(), s->d_field_insitu, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        SIM_CUDA(cudaMemset(s->d_field_insitu, 0, sizeof(double) * h.size()));
+        int rc = hpb_insitu_write_fields(insitu_path(s, s->field_insitu_prefix, "fields").c_str(), s->time,
+                                         s->cur_step, s->nz, s->prob_lo[2], s->prob_hi[2], s->g.normalized,
+                                         s->g.dx * s->g.dy * s->g.dz, h.data());
+        if (rc) return rc;
+    }
     for (auto &sp : s->plasmas) {
         if (!sp.d_insitu || !do_diagnostics(sp.insitu_period, s->cur_step, s->max_step)) continue;
         std::vector<double> h(15 * (size_t)s->nz);
@@ -1110,6 +1124,14 @@ int solve_one_slice(hpb_sim *s, int islice)
                                 s->mg_tol_abs, 200, &iters))) return rc;
         s->stats.n_mg_vcycles += iters;
         s->mg_iters.push_back(iters);
+    }
+    if (do_diagnostics(s->field_insitu_period, s->cur_step, s->max_step)) {             // :685
+        StageTimer t(s, ST_OTHER);
+        if (!s->d_field_insitu) {
+            SIM_CUDA(cudaMalloc(&s->d_field_insitu, sizeof(double) * 10 * (size_t)s->nz));
+            SIM_CUDA(cudaMemsetAsync(s->d_field_insitu, 0, sizeof(double) * 10 * (size_t)s->nz, ctx->stream));
+        }
+        if ((rc = hpb_fields_insitu_slice(ctx, s->sl, C, s->d_field_insitu + islice, s->nz))) return rc;
     }
     if (s->opt_checksums) {                                                             // :681-691
         StageTimer t(s, ST_OTHER);

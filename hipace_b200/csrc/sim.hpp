@@ -119,6 +119,9 @@ struct hpb_sim {
     long n_predcorr_iters = 0;
     // hipace.dt = adaptive (utils/AdaptiveTimeStep.cpp)
     bool diag_xz = false;                         // diagnostic.diag_type = xz
+    int field_insitu_period = 0;                  // fields.insitu_period (Fields.cpp:41-42)
+    std::string field_insitu_prefix = "diags/field_insitu";
+    double *d_field_insitu = nullptr;             // [10][nz]
     bool adaptive_dt = false;
     hpb_adaptive_par adp = {20., INFINITY, 2., 4e-4, 2000, 1, 1., 1.};
     double adaptive_density = 0., min_uz_mq = DBL_MAX, time = 0., next_time = 0.;

@@ -181,6 +181,11 @@ int hpb_plasma_insitu_slice(hpb_ctx *ctx, hpb_plasma pl, double insitu_radius, d
 int hpb_insitu_write_plasma(const char *path, double time, int step, int n_slices, double charge,
                             double mass, double z_lo, double z_hi, double normalized_density_factor,
                             int is_normalized_units, const double *h_sums);
+/* and for the fields of a slice once they are all computed (Hipace.cpp:685): Fields::InSituComputeDiags
+ * / InSituWriteToFile (src/fields/Fields.cpp:1289-1428); 10 raw sums per slice, explicit solver only */
+int hpb_fields_insitu_slice(hpb_ctx *ctx, hpb_slice sl, const int *comps, double *d_record, long stride);
+int hpb_insitu_write_fields(const char *path, double time, int step, int n_slices, double z_lo,
+                            double z_hi, int is_normalized_units, double dxdydz, const double *h_sums);
 /* hipace.dt = adaptive (src/utils/AdaptiveTimeStep.cpp).  hpb_beam_min_uz_slice = GatherMinUzSlice
  * (:108-141) of one pushed beam slice: d_acc[4] = {min uz/c, sum w, sum w uz/c, sum w uz^2/c^2}
  * accumulated over the slices of a step.  hpb_adaptive_dt_next (HOST only) = CalculateFromMinUz

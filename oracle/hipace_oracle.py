@@ -1601,6 +1601,41 @@ def insitu_plasma_record(sums, time, step, charge, mass, z_lo, z_hi, density_fac
     return dt, rec
 
 
+FIELD_INSITU_NAMES = ('[Ex^2]', '[Ey^2]', '[Ez^2]', '[Bx^2]', '[By^2]', '[Bz^2]', '[ExmBy^2]', '[EypBx^2]',
+                      '[jz_beam]', '[Ez*jz_beam]')
+
+
+def field_insitu_sums(F, geom: 'Geometry', pc: PhysConst):
+    """Fields::InSituComputeDiags, fields/Fields.cpp:1289-1347 (raw sums over the valid box)"""
+    G = geom.g
+    v = (slice(G, -G), slice(G, -G))
+    T = lambda n: F[('This', n)][v]
+    ex, ey = T('ExmBy') + T('By') * pc.c, T('EypBx') - T('Bx') * pc.c
+    terms = (ex * ex, ey * ey, T('Ez') ** 2, T('Bx') ** 2, T('By') ** 2, T('Bz') ** 2, T('ExmBy') ** 2,
+             T('EypBx') ** 2, T('jz_beam'), T('Ez') * T('jz_beam'))
+    return np.array([t.sum() for t in terms])
+
+
+def insitu_field_record(sums, time, step, z_lo, z_hi, normalized, dxdydz):
+    """Fields::InSituWriteToFile, fields/Fields.cpp:1349-1428"""
+    ns = sums.shape[1]
+    per = sums * dxdydz
+    tot = np.zeros(10)
+    for isl in range(ns - 1, -1, -1):
+        tot += per[:, isl]
+    N = FIELD_INSITU_NAMES
+    dt = np.dtype([('time', '<f8'), ('step', '<i4'), ('n_slices', '<i4'), ('z_lo', '<f8'), ('z_hi', '<f8'),
+                   ('is_normalized_units', '<i4')] + [(nm, '<f8', (ns,)) for nm in N]
+                  + [('integrated', [(nm, '<f8') for nm in N])])
+    rec = np.zeros((), dtype=dt)
+    rec['time'], rec['step'], rec['n_slices'] = time, step, ns
+    rec['z_lo'], rec['z_hi'], rec['is_normalized_units'] = z_lo, z_hi, int(normalized)
+    for k, nm in enumerate(N):
+        rec[nm] = per[k]
+        rec['integrated'][nm] = tot[k]
+    return dt, rec
+
+
 def insitu_beam_record(sums, time, step, charge, mass, z_lo, z_hi, density_factor, normalized):
     """InSituWriteToFile, particles/beam/BeamParticleContainer.cpp:596-732: (numpy dtype, record)
     of one time step from the raw sums[23, n_slices]; format of utils/InsituUtil.H"""
@@ -1888,6 +1923,10 @@ class Simulation:
                                                   _get(d, 'plasmas.insitu_radius', math.inf))
                                      for p in self.plasmas}
         self.plasma_insitu, self.plasma_insitu_records = {}, {}
+        self.field_insitu_period = _get(d, 'fields.insitu_period', 0, typ=int)
+        assert not (self.field_insitu_period and not self.explicit), \
+            'Must use explicit solver for field insitu diagnostic'
+        self.field_insitu, self.field_insitu_records = None, []
 
     # -- deck readers ----------------------------------------------------------------------
     def _species_charge_mass(self, pre, default_element=None):
@@ -2291,6 +2330,11 @@ class Simulation:
         self.mg_cycles.append(self.mg.n_vcycles_last)
         if self.slice_hook:
             self.slice_hook(self, islice, 'fields')
+        if self.field_insitu_period > 0 and (self.step == self.max_step
+                                             or self.step % self.field_insitu_period == 0):   # :685
+            if self.field_insitu is None:
+                self.field_insitu = np.zeros((10, g.nz))
+            self.field_insitu[:, islice] = field_insitu_sums(F, g, pc)
         self._accumulate_checksums(islice)                                        # :691
         for b in self.beams:                                                      # :682-683 (before the push)
             bs = self.beam_slice(b, islice)
@@ -2352,7 +2396,7 @@ class Simulation:
         for step in range(step_begin, step_end + 1):
             self.checksums = {}
             self.begin_step(step)
-            self.insitu, self.plasma_insitu = {}, {}
+            self.insitu, self.plasma_insitu, self.field_insitu = {}, {}, None
             for isl in range(g.nz - 1, stop, -1):
                 self.solve_one_slice(isl)
             if self.adaptive_dt and stop == -1:                                   # Hipace.cpp:482-483
@@ -2363,6 +2407,10 @@ class Simulation:
                     self.insitu_records.setdefault(b.name, []).append(insitu_beam_record(
                         self.insitu[b.name], self.time, step, b.charge, b.mass, g.lo[2], g.hi[2],
                         ndf, self.normalized)[1])
+            if self.field_insitu is not None:                                     # Hipace.cpp:487
+                self.field_insitu_records.append(insitu_field_record(
+                    self.field_insitu, self.time, step, g.lo[2], g.hi[2], self.normalized,
+                    g.dx * g.dy * g.dz)[1])
             for pl in self.plasmas:                                               # Hipace.cpp:489
                 if pl.name in self.plasma_insitu:
                     ndf = g.dx * g.dy * g.dz if self.normalized else 1.0

@@ -252,3 +252,71 @@ def test_cuda_plasma_insitu_matches_oracle(repo_root, tmp_path):
                 assert got[0][nm][sub] == pytest.approx(want[nm][sub], rel=1e-10, abs=1e-12), (nm, sub)
         else:
             assert np.allclose(got[0][nm], want[nm], rtol=1e-10, atol=1e-12), nm
+
+
+def test_field_insitu_writer_terms_and_oracle(tmp_path, repo_root):
+    import hipace_b200 as hp
+    from hipace_b200.build import build_host_check
+    rng = np.random.default_rng(8)
+    sums = rng.normal(0, 1, (10, 6))
+    path = tmp_path / 'reduced_fields.0000.txt'
+    for step in (0, 1):
+        hp.insitu_write_fields(path, 0.5 * step, step, -6.0, 6.0, True, 0.03, sums * (1 + step))
+    ours = hp.read_insitu(path)
+    for step in (0, 1):
+        dt, rec = O.insitu_field_record(sums * (1 + step), 0.5 * step, step, -6.0, 6.0, True, 0.03)
+        assert dt == ours.dtype and ours[step].tobytes() == rec.tobytes()
+    if os.path.isdir(REF_TOOLS):
+        sys.path.insert(0, REF_TOOLS)
+        import read_insitu_diagnostics as R
+        assert R.read_file(str(tmp_path / 'reduced_fields.*.txt')).tobytes() == ours.tobytes()
+    # device-side terms on the host against the oracle (SI magnitudes)
+    hc = C.CDLL(build_host_check())
+    geom = O.Geometry(20, 28, 8, (-1e-4, -1e-4, 0.0), (1e-4, 1.2e-4, 1e-5), 2, 2)
+    pc = O.PhysConst.make(False)
+    g = geom.g
+    names = ('ExmBy', 'EypBx', 'Ez', 'Bx', 'By', 'Bz', 'jz_beam')
+    F = {('This', nm): rng.normal(0, 1e9 if nm[0] == 'E' else (3.0 if nm[0] == 'B' else 1e12),
+                                  (geom.ny + 2 * g, geom.nx + 2 * g)) for nm in names}
+    want = O.field_insitu_sums(F, geom, pc)
+    planes = np.ascontiguousarray(np.stack([F[('This', nm)] for nm in names]))
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_device_math_host import HcGrid
+    hg = HcGrid(geom.nx + 2 * g, geom.ny + 2 * g, g, 0., 0., 1., 1.)
+    out = np.zeros(10)
+    hc.hc_field_insitu(planes.ctypes.data_as(C.c_void_p), C.byref(hg), (C.c_int * 7)(*range(7)), geom.nx, geom.ny,
+                       C.c_double(pc.c), out.ctypes.data_as(C.c_void_p))
+    assert np.abs(out - want).max() / np.abs(want).max() <= 1e-12
+    assert (np.abs(out - want) <= 1e-11 * np.abs(want) + 1e-12 * np.abs(want).max()).all()
+    # an oracle run: the beam loses energy to the wake, integral of Ez jz_beam < 0 for e- driver ... sign
+    deck = open(os.path.join(repo_root, 'examples', 'blowout_wake_normalized.in')).read()
+    sim = O.Simulation(deck, {'amr.n_cell': '32 32 100', 'fields.insitu_period': 1})
+    sim.evolve(step_end=0)
+    rec = sim.field_insitu_records[0]
+    assert rec['integrated']['[Ez^2]'] > 0 and rec['[jz_beam]'].shape == (100,)
+    # energy balance sign: the driver (charge -1, jz_beam < 0) is decelerated: E.j < 0 overall
+    assert rec['integrated']['[Ez*jz_beam]'] < 0
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason='first hardware run of the field in-situ reduction kernel')
+def test_cuda_field_insitu_matches_oracle(repo_root, tmp_path):
+    import hipace_b200 as hp
+    deck = open(os.path.join(repo_root, 'examples', 'blowout_wake_normalized.in')).read()
+    ov = {'amr.n_cell': '32 32 40', 'fields.insitu_period': 1,
+          'fields.insitu_file_prefix': str(tmp_path / 'f')}
+    sim = hp.Simulation(deck, ov)
+    sim.evolve(0, 0)
+    sim.close()
+    got = hp.read_insitu(tmp_path / 'f' / 'reduced_fields.0000.txt')
+    ref = O.Simulation(deck, ov)
+    ref.evolve(step_end=0)
+    want = ref.field_insitu_records[0]
+    assert got.shape == (1,) and got.dtype == want.dtype
+    scale = max(abs(want['integrated'][nm]) for nm in want['integrated'].dtype.names)
+    for nm in want.dtype.names:
+        if nm == 'integrated':
+            for sub in want[nm].dtype.names:
+                assert got[0][nm][sub] == pytest.approx(want[nm][sub], rel=1e-9, abs=1e-12 * scale), sub
+        else:
+            assert np.allclose(got[0][nm], want[nm], rtol=1e-9, atol=1e-12 * scale), nm
