@@ -1343,14 +1343,17 @@ extern "C" void hpb_sim_destroy(hpb_sim *s)
     for (auto &sp : s->plasmas) {
         for (int k = 0; k < HPB_PLASMA_NREAL; ++k) cudaFree(sp.d.r[k]);
         cudaFree(sp.d.idcpu);
+        cudaFree(sp.d_insitu);
     }
     hpb_pipeline_destroy(s);
     for (auto &b : s->beams) {
         hpb_beam_rings_free(b);
         cudaFree(b.d_cs); cudaFree(b.d_stage); cudaFree(b.d_stage_off);
+        cudaFree(b.d_insitu); cudaFree(b.d_ts);
         hpb_extfields_destroy(b.ext);
     }
     cudaFree(s->d_overflow); cudaFree(s->d_slot_off);
+    cudaFree(s->d_pc_rhs); cudaFree(s->d_pc_scal); cudaFree(s->d_field_insitu);
     cudaFree(s->sl.p); cudaFree(s->d_checksum); cudaFree(s->d_nqsa); cudaFree(s->d_count);
     cudaFree(s->d_flag); cudaFree(s->d_offs); cudaFree(s->d_cub);
     hpb_destroy(s->ctx);
