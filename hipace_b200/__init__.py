@@ -65,7 +65,7 @@ EXPORTS = (
     'hpb_fields_bxby_rhs', 'hpb_fields_psi_ez_bz_rhs', 'hpb_fields_open_boundary',
     'hpb_fields_rel_b_error', 'hpb_fields_lincomb2', 'hpb_beam_min_uz_slice', 'hpb_adaptive_dt_next',
     'hpb_abs_sum_xz', 'hpb_plasma_insitu_slice', 'hpb_insitu_write_plasma',
-    'hpb_fields_insitu_slice', 'hpb_insitu_write_fields',
+    'hpb_fields_insitu_slice', 'hpb_insitu_write_fields', 'hpb_debug_push_thread_map',
 )
 NCCL_ID_BYTES = 128
 

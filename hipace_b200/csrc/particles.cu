@@ -22,13 +22,14 @@ struct PlasmaPtrs {
     uint64_t *idcpu;
     long np;
     long lat_n; int lat_ppc;        // lattice hint: np = lat_ppc passes of lat_n cells (0: none)
+    int lat_mode;                   // 1: passes interleaved warp by warp, 2: CTA by CTA (experiment)
 };
 PlasmaPtrs to_ptrs(const hpb_plasma &pl)
 {
     PlasmaPtrs p;
     for (int i = 0; i < HPB_PLASMA_NREAL; ++i) p.r[i] = pl.r[i];
     p.idcpu = pl.idcpu; p.np = pl.np;
-    p.lat_n = 0; p.lat_ppc = 1;
+    p.lat_n = 0; p.lat_ppc = 1; p.lat_mode = 0;
     return p;
 }
 // with the lattice hint of the context (only if it describes exactly this particle array).
@@ -42,8 +43,14 @@ PlasmaPtrs to_ptrs(const hpb_ctx *ctx, const hpb_plasma &pl, int which)
     PlasmaPtrs p = to_ptrs(pl);
     static int on = -1;
     if (on < 0) { const char *e = getenv("HPB_ORDER"); on = e ? atoi(e) : 1; }
-    if ((on & which) && ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np) {
-        p.lat_n = ctx->order_n; p.lat_ppc = ctx->order_ppc;
+    // bits 4 / 8 (= which << 2): the same, interleaved CTA by CTA instead of warp by warp -- the next
+    // thing to measure for the push (ROADMAP.md): the ppc passes of a cell group then run in
+    // consecutive CTAs (co-resident on different SMs) instead of in the four warps of one CTA, so the
+    // planes are still fetched once but the fused deposit does not reduce into the same cells from
+    // within a CTA.  Not timed yet; results are identical by construction (a permutation of threads).
+    const bool cta = (on & (which << 2)) != 0 && which == 2;
+    if (((on & which) || cta) && ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np) {
+        p.lat_n = ctx->order_n; p.lat_ppc = ctx->order_ppc; p.lat_mode = cta ? 2 : 1;
     }
     return p;
 }
@@ -51,26 +58,37 @@ PlasmaPtrs to_ptrs(const hpb_ctx *ctx, const hpb_plasma &pl, int which)
 // `per_warp` consecutive cells are owned per warp, `lead` extra lanes in front of them (feed-only
 // neighbours of the aggregation).  Returns the particle index and whether the lane holds one.
 // LAT = false is the plain linear map (the code the kernels had before the hint existed).
-template <bool LAT>
-__device__ __forceinline__ long lattice_particle(const PlasmaPtrs &pl, long warp, int lane, int per_warp,
-                                                  int lead, bool &in_range)
+// LAT = 2 (UPW = warps per CTA): the same with whole CTAs as the interleaving unit -- CTA c works on
+// pass (c % ppc) of the UPW consecutive cell groups (c / ppc) * UPW ...
+template <int LAT, int UPW = 1>
+__host__ __device__ __forceinline__ long lattice_particle(const PlasmaPtrs &pl, long warp, int lane, int per_warp,
+                                                           int lead, bool &in_range)
 {
-    if (!LAT) {
+    if (LAT == 0) {
         const long ip = warp * per_warp - lead + lane;
         in_range = ip >= 0 && ip < pl.np;
         return ip;
     }
     const unsigned w = (unsigned)warp, ppc = (unsigned)pl.lat_ppc;      // 32-bit division only
+    if (LAT == 2) {
+        const unsigned unit = w / UPW, sub = w - unit * UPW;
+        const unsigned group = unit / ppc, pass = unit - group * ppc;
+        const long cell = ((long)group * UPW + sub) * per_warp - lead + lane;
+        in_range = cell >= 0 && cell < pl.lat_n;
+        return (long)pass * pl.lat_n + cell;
+    }
     const unsigned group = w / ppc, pass = w - group * ppc;
     const long cell = (long)group * per_warp - lead + lane;
     in_range = cell >= 0 && cell < pl.lat_n;
     return (long)pass * pl.lat_n + cell;
 }
-// number of warps a launch needs
-inline long lattice_warps(const PlasmaPtrs &pl, int per_warp)
+// number of warps a launch needs (upw: warps per CTA, only used by the CTA-interleaved map)
+inline long lattice_warps(const PlasmaPtrs &pl, int per_warp, int upw = 1)
 {
     if (pl.lat_n <= 0) return (pl.np + per_warp - 1) / per_warp;
-    return (pl.lat_n + per_warp - 1) / per_warp * pl.lat_ppc;
+    const long groups = (pl.lat_n + per_warp - 1) / per_warp;
+    if (pl.lat_mode == 2) return (groups + upw - 1) / upw * upw * pl.lat_ppc;
+    return groups * pl.lat_ppc;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -354,7 +372,7 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
     const int lane = threadIdx.x & 31;
     const long warp = (long)blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
     bool active;
-    const long ip = lattice_particle<LAT>(pl, warp, lane, kExplOwn, 2, active);
+    const long ip = lattice_particle<LAT ? 1 : 0>(pl, warp, lane, kExplOwn, 2, active);
     const bool owner = lane >= 2 && lane < 2 + kExplOwn;
 
     double vx = 0., vy = 0., gamma_psi = 1., yint = 0.;
@@ -600,7 +618,7 @@ constexpr int kTW = 40, kTH = 6;
 
 struct PushLaserArgs { int c_aabs; double norm; };      // (charge/q_e)^2 (m_e/mass)^2, PlasmaParticleAdvance.cpp:76-77
 
-template <int MINB, bool DEPOSIT, bool STAGE, bool LAT, bool LASER>
+template <int MINB, bool DEPOSIT, bool STAGE, int LAT, bool LASER>
 __global__ void __launch_bounds__(kPushThreads, MINB)
 k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int c_by, int c_bz,
                  double x_off, double y_off, double dx_inv, double dy_inv, double clight,
@@ -611,8 +629,8 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
     hpb_pdl_prologue();
     const int lane = threadIdx.x & 31;
     bool in_range;
-    const long ip = lattice_particle<LAT>(pl, (long)blockIdx.x * (kPushThreads / 32) + (threadIdx.x >> 5),
-                                          lane, 32, 0, in_range);
+    const long ip = lattice_particle<LAT, kPushThreads / 32>(pl, (long)blockIdx.x * (kPushThreads / 32) + (threadIdx.x >> 5),
+                                                             lane, 32, 0, in_range);
     // request every input stream before the first use (one HBM round trip)
     uint64_t idcpu = 0;
     double xp0 = 0., yp0 = 0., ux0 = 0., uy0 = 0., psi0 = 1., wq = 0.;
@@ -837,6 +855,31 @@ extern "C" int hpb_deposit_current_jz(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
                                    max_qsa, d_n_qsa_violation);
 }
 
+// TEST HOOK (host only): the thread -> particle map of the push kernel for a lattice of
+// cells_per_pass x ppc particles, mode 0 (linear), 1 (passes interleaved warp by warp) or 2 (CTA by
+// CTA).  out[w * 32 + lane] = particle index or -1; returns the number of warps (tests check that
+// every mode is a permutation of the particles).
+extern "C" long hpb_debug_push_thread_map(long cells_per_pass, int ppc, int mode, long *out, long out_len)
+{
+    PlasmaPtrs p;
+    for (int i = 0; i < HPB_PLASMA_NREAL; ++i) p.r[i] = nullptr;
+    p.idcpu = nullptr; p.np = cells_per_pass * ppc;
+    p.lat_n = mode ? cells_per_pass : 0; p.lat_ppc = ppc; p.lat_mode = mode;
+    const long nwarps = lattice_warps(p, 32, kPushThreads / 32);
+    if (!out) return nwarps;
+    if (out_len < nwarps * 32) return -1;
+    for (long w = 0; w < nwarps; ++w)
+        for (int lane = 0; lane < 32; ++lane) {
+            bool in_range = false;
+            long ip;
+            if (mode == 2) ip = lattice_particle<2, kPushThreads / 32>(p, w, lane, 32, 0, in_range);
+            else if (mode == 1) ip = lattice_particle<1>(p, w, lane, 32, 0, in_range);
+            else ip = lattice_particle<0>(p, w, lane, 32, 0, in_range);
+            out[w * 32 + lane] = in_range ? ip : -1;
+        }
+    return nwarps;
+}
+
 extern "C" int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc)
 {
     if (!ctx || cells_per_pass < 0 || ppc < 0) return HPB_ERR_ARG;
@@ -939,15 +982,16 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         for (int k = 0; k < 8; ++k) dep.cx[k] = comps[cx[k]];
     }
     const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 2);
-    const long nwarps = lattice_warps(pp, 32);
+    const long nwarps = lattice_warps(pp, 32, kPushThreads / 32);
     PushLaserArgs lasa = {comps[HPB_C_AABS], 0.};
     if (lasa.c_aabs >= 0) {
         if (deposit) { hpb_set_error("advance+deposit: not available with a laser"); return HPB_ERR_UNSUPPORTED; }
         lasa.norm = (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass);
     }
 #define HPB_LAUNCH_PUSH(MB, DEP, STG)                                                             \
-    do { if (pp.lat_n > 0) HPB_LAUNCH_PUSH_(MB, DEP, STG, true, false);                            \
-         else HPB_LAUNCH_PUSH_(MB, DEP, STG, false, false); } while (0)
+    do { if (pp.lat_n > 0 && pp.lat_mode == 2) HPB_LAUNCH_PUSH_(MB, DEP, STG, 2, false);           \
+         else if (pp.lat_n > 0) HPB_LAUNCH_PUSH_(MB, DEP, STG, 1, false);                          \
+         else HPB_LAUNCH_PUSH_(MB, DEP, STG, 0, false); } while (0)
 #define HPB_LAUNCH_PUSH_(MB, DEP, STG, LAT, LAS)                                                  \
     hpb_launch(k_advance_plasma<MB, DEP, STG, LAT, LAS>,                                          \
         (unsigned)((nwarps + kPushThreads / 32 - 1) / (kPushThreads / 32)),                       \
@@ -959,7 +1003,7 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
     // variants: 0 = staged gather, 5 blocks / SM (the shared-memory limit; default),
     // 1 = direct loads only, 3 = staged with 128 registers
     if (lasa.c_aabs >= 0) {
-        HPB_LAUNCH_PUSH_(4, false, true, false, true);      // laser: staged gather, plain order, 128 registers
+        HPB_LAUNCH_PUSH_(4, false, true, 0, true);          // laser: staged gather, plain order, 128 registers
     } else if (deposit) {
         if (variant == 1) HPB_LAUNCH_PUSH(6, true, false);
         else if (variant == 3) HPB_LAUNCH_PUSH(4, true, true);

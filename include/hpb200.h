@@ -297,6 +297,9 @@ int hpb_fields_shift_and_initialize(hpb_ctx *ctx, hpb_slice sl, int *comps);
  * from / reduces into are fetched from HBM once per slice instead of once per pass.  Results do
  * not depend on it; cells_per_pass = 0 clears the hint. */
 int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc);
+/* test hook, host only: the thread -> particle map the push kernel uses with that hint (mode 0 linear,
+ * 1 passes interleaved warp by warp, 2 CTA by CTA); out[warp * 32 + lane] = particle or -1 */
+long hpb_debug_push_thread_map(long cells_per_pass, int ppc, int mode, long *out, long out_len);
 /* hipace.depos_order_xy (0..3) and hipace.depos_derivative_type (0 analytic, 1 nodal, 2 centred) for
  * every particle kernel called with this context afterwards (Hipace.cpp:49-53; the reference selects
  * them at compile time through CompileTimeOptions, e.g. ExplicitDeposition.cpp:62-67).  Default 2 / 2.

@@ -128,3 +128,28 @@ def test_command_line_driver_check_mode():
     assert 'nx=64;ny=64;nz=64;' in p.stdout and 'max_step=3;' in p.stdout
     p = subprocess.run([exe, '--check', deck, 'hipace.depos_order_xy=5'], capture_output=True, text=True)
     assert p.returncode == 1 and 'depos_order_xy' in p.stderr
+
+
+@pytest.mark.parametrize('n,ppc', [(1024 * 1024, 4), (63 * 63, 4), (100 * 36, 9), (5, 2), (128, 1)])
+def test_push_thread_maps_are_permutations(n, ppc):
+    """the lattice-ordered thread -> particle maps of the push kernel (linear, passes interleaved
+    warp by warp, passes interleaved CTA by CTA) each visit every particle exactly once"""
+    import ctypes as C
+    import numpy as np
+    import hipace_b200 as hp
+    L = hp.lib()
+    L.hpb_debug_push_thread_map.restype = C.c_long
+    L.hpb_debug_push_thread_map.argtypes = [C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_long]
+    for mode in (0, 1, 2):
+        nw = L.hpb_debug_push_thread_map(n, ppc, mode, None, 0)
+        out = np.full(nw * 32, -2, dtype=np.int64)
+        assert L.hpb_debug_push_thread_map(n, ppc, mode, out.ctypes.data, out.size) == nw
+        ids = out[out >= 0]
+        assert ids.size == n * ppc and np.array_equal(np.sort(ids), np.arange(n * ppc)), mode
+        assert (out >= -1).all()
+        if mode == 2 and ppc > 1 and n >= 256:
+            # the four warps of a CTA work on 128 consecutive cells of ONE pass ...
+            cta0 = out[:128]
+            assert np.array_equal(cta0, np.arange(128))
+            # ... and the next CTA on the same cells of the next pass
+            assert np.array_equal(out[128:256], n + np.arange(128))

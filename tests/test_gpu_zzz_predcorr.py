@@ -99,3 +99,25 @@ def test_xz_diagnostic_checksums_match_oracle(repo_root):
         want = Oracle(deck, ov).evolve(30)
         _compare(got, want, floor=1e-12)
         sim.close()
+
+
+def test_cta_interleaved_push_map_gives_the_same_result(repo_root):
+    """HPB_ORDER=9: explicit deposition with the warp-interleaved map (the default) and the push with
+    the CTA-interleaved map (the experiment of ROADMAP.md section 2.1) -- a permutation of threads, so
+    the blowout golden must come out the same.  ppc 4 so that there are passes to interleave."""
+    import subprocess
+    from oracle.hipace_oracle import Simulation as Oracle
+    exe = os.path.join(repo_root, 'hipace_b200', 'bin', 'hpb200_run')
+    deck = os.path.join(repo_root, 'examples', 'blowout_wake_normalized.in')
+    ov = {'amr.n_cell': '64 64 100', 'plasma.ppc': '2 2'}
+    env = dict(os.environ, HPB_ORDER='9')
+    p = subprocess.run([exe, deck] + [f'{k}={v}' for k, v in ov.items()], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr + p.stdout
+    got = {}
+    for line in p.stdout.splitlines():
+        t = line.split()
+        if len(t) == 2 and line.startswith('  '):
+            got[t[0]] = float(t[1])
+    want = Oracle(open(deck).read(), ov).evolve()
+    for k, w in want.items():
+        assert abs(got[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (k, got[k], w)
