@@ -12,7 +12,9 @@ from oracle.hipace_oracle import Simulation as Oracle
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
 
-@pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank'])
+@pytest.mark.parametrize('case', ['linear_wake.normalized.1Rank', 'blowout_wake_explicit.2Rank',
+                                  'gaussian_linear_wake.normalized.1Rank', 'gaussian_linear_wake.SI.1Rank',
+                                  'linear_wake.SI.1Rank'])
 def test_cport_matches_reference_golden(case, repo_root):
     meta = json.load(open(os.path.join(GOLD, case + '.json')))
     deck = open(os.path.join(repo_root, meta['deck'])).read()
