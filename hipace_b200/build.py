@@ -99,7 +99,8 @@ def build_host_check(force: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     lib = os.path.join(BUILD, 'libhpb200_hostcheck.so')
     deps = [os.path.join(CSRC, f) for f in ('host_check.cu', 'generic_order.cuh', 'push_math.cuh',
-                                            'shapes.cuh', 'common.cuh', 'insitu.cuh', 'pc_fields.cuh')]
+                                            'shapes.cuh', 'common.cuh', 'insitu.cuh', 'pc_fields.cuh',
+                                            'laser_advance.cuh')]
     deps.append(os.path.join(ROOT, 'include', 'hpb200.h'))
     if (not force and os.path.exists(lib)
             and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps)):

@@ -7,6 +7,7 @@
 #include "generic_order.cuh"
 #include "insitu.cuh"
 #include "pc_fields.cuh"
+#include "laser_advance.cuh"
 
 namespace {
 struct HostAdd {
@@ -279,4 +280,44 @@ extern "C" void hc_field_insitu(double *planes, const HcGrid *hg, const int *com
                                a.comp(comps7[4])[o], a.comp(comps7[5])[o], a.comp(comps7[6])[o], clight, t);
             for (int k = 0; k < 10; ++k) out10[k] += t[k];
         }
+}
+
+// ---- laser envelope advance (laser_advance.cuh) ------------------------------------------------
+// planes8: nm1j00 nm1jp1 nm1jp2 n00j00 n00jp1 n00jp2 np1jp1 np1jp2 (complex, [ny][nx]); h3: the three
+// on-axis sums (re, im pairs); out: rhs[ny][nx] complex; phase_out: exp1 (2), exp2 (2), djn
+extern "C" void hc_laser_rhs(const hpb_c2 *const *planes8, const double *chi, const LaserAdvPar *par,
+                             const double *h3, int use_phase, hpb_c2 *rhs, double *phase_out)
+{
+    const LaserPlanes L = {planes8[0], planes8[1], planes8[2], planes8[3], planes8[4], planes8[5], planes8[6],
+                           planes8[7]};
+    const LaserPhase ph = laser_phase(c2(h3[0], h3[1]), c2(h3[2], h3[3]), c2(h3[4], h3[5]), par->dz, use_phase);
+    phase_out[0] = ph.exp1.re; phase_out[1] = ph.exp1.im; phase_out[2] = ph.exp2.re; phase_out[3] = ph.exp2.im;
+    phase_out[4] = ph.djn;
+    for (int j = 0; j < par->ny; ++j)
+        for (int i = 0; i < par->nx; ++i) rhs[(long)j * par->nx + i] = laser_rhs_cell(L, chi, i, j, *par, ph);
+}
+extern "C" void hc_laser_spectral(hpb_c2 *rhs_f, const LaserAdvPar *par, const double *phase5)
+{
+    LaserPhase ph;
+    ph.exp1 = c2(phase5[0], phase5[1]); ph.exp2 = c2(phase5[2], phase5[3]); ph.djn = phase5[4];
+    for (int j = 0; j < par->ny; ++j)
+        for (int i = 0; i < par->nx; ++i) {
+            const long o = (long)j * par->nx + i;
+            rhs_f[o] = laser_spectral_cell(rhs_f[o], i, j, *par, ph);
+        }
+}
+extern "C" void hc_laser_chi_aabs(double *planes, const HcGrid *hg, int c_chi, const double *chi_initial,
+                                  const hpb_c2 *env, int nx, int ny, double dx, double dy, int order,
+                                  double *chi_out, double *aabs_out)
+{
+    const SliceView a = view(planes, hg->nx_tot, hg->ny_tot, hg->g);
+    const int g = hg->g;
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i)
+            chi_out[(long)j * nx + i] = laser_chi_cell(a, c_chi, chi_initial, i, j, nx, ny, g, dx, dy, hg->x_off,
+                                                       hg->y_off, order);
+    for (int j = -g; j < ny + g; ++j)
+        for (int i = -g; i < nx + g; ++i)
+            aabs_out[(long)(j + g) * hg->nx_tot + (i + g)] = laser_aabs_cell(env, i, j, nx, ny, dx, dy, hg->x_off,
+                                                                             hg->y_off, order);
 }

@@ -362,3 +362,70 @@ def test_device_open_boundary_and_bxby_rhs_match_oracle(hc):
     want_by = 1.3 * O._ddx(planes[0], geom.dx, g) + (-1.3) * dz_jx
     assert np.abs(stage[0] - want_bx).max() <= 1e-13 * np.abs(want_bx).max()
     assert np.abs(stage[1] - want_by).max() <= 1e-13 * np.abs(want_by).max()
+
+
+class LaserAdvPar(C.Structure):
+    _fields_ = [('nx', C.c_int), ('ny', C.c_int), ('step0', C.c_int)] + \
+               [(k, C.c_double) for k in ('dx', 'dy', 'dz', 'c', 'dt', 'k0', 'dkx', 'dky')]
+
+
+@pytest.mark.parametrize('step0', [1, 0])
+@pytest.mark.parametrize('nx,ny', [(32, 24), (17, 21)])
+def test_device_laser_advance_matches_oracle(hc, step0, nx, ny):
+    """laser_advance.cuh on the host: right-hand side, on-axis phase and spectral division of
+    AdvanceSliceFFT around NumPy's FFT reproduce the oracle's laser_advance_fft (which the
+    reference's laser_evolution golden pins); InterpolateChi and UpdateLaserAabs from a stored slice"""
+    rng = np.random.default_rng(21 + nx)
+    geom = O.Geometry(nx, ny, 10, (-6e-5, -5e-5, -8e-5), (6e-5, 5e-5, 6e-5), 0, 2)
+    pc = O.PhysConst.make(False)
+    lam, dt = 0.8e-6, 70e-6 / pc.c
+    L = O.LaserSlices(ny, nx)
+    x = (np.arange(nx) - nx / 2 + 0.5)[None, :] / nx
+    y = (np.arange(ny) - ny / 2 + 0.5)[:, None] / ny
+    env = np.exp(-20 * (x * x + y * y))
+    names = ('nm1j00', 'nm1jp1', 'nm1jp2', 'n00j00', 'n00jp1', 'n00jp2', 'np1jp1', 'np1jp2')
+    for k, nm in enumerate(names):
+        setattr(L, nm, env * np.exp(1j * (0.3 * k + 2.0 * x)) * (1 + 0.05 * rng.normal(size=(ny, nx))))
+    chi = rng.uniform(0, 1e9, (ny, nx))
+    O.laser_advance_fft(L, chi, geom, pc, lam, dt, 0 if step0 else 3, True)
+    want = L.np1j00
+    # the same through the device functions
+    par = LaserAdvPar(nx, ny, step0, geom.dx, geom.dy, geom.dz, pc.c, dt, 2 * np.pi / lam,
+                      2 * np.pi / (geom.hi[0] - geom.lo[0]), 2 * np.pi / (geom.hi[1] - geom.lo[1]))
+    planes = [np.ascontiguousarray(getattr(L, nm)) for nm in names]
+    imid, jmid = (nx + 1) // 2, (ny + 1) // 2
+    kx = [imid - 1, imid] if nx % 2 == 0 else [imid]
+    ky = [jmid - 1, jmid] if ny % 2 == 0 else [jmid]
+    h3 = np.array([[h.real, h.imag] for h in (L.n00j00[np.ix_(ky, kx)].sum(), L.n00jp1[np.ix_(ky, kx)].sum(),
+                                              L.n00jp2[np.ix_(ky, kx)].sum())]).ravel()
+    rhs = np.zeros((ny, nx), dtype=complex)
+    phase = np.zeros(5)
+    chi_c = np.ascontiguousarray(chi)
+    hc.hc_laser_rhs(_ptrs(planes), _dp(chi_c), C.byref(par), _dp(h3), 1, _dp(rhs), _dp(phase))
+    rhs_f = np.ascontiguousarray(np.fft.fft2(rhs))
+    hc.hc_laser_spectral(_dp(rhs_f), C.byref(par), _dp(phase))
+    got = np.fft.ifft2(rhs_f) * (nx * ny)                 # cuFFT's inverse is unnormalised
+    assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
+    assert np.abs(want).max() > 0
+
+
+def test_device_laser_chi_and_aabs_match_oracle(hc):
+    rng = np.random.default_rng(30)
+    for order in (0, 1, 2):
+        geom = O.Geometry(20, 26, 8, (-3e-5, -2e-5, 0.0), (5e-5, 7e-5, 1e-5), 2, 2)
+        g = geom.g
+        chi_field = rng.uniform(0, 1, (geom.ny + 2 * g, geom.nx + 2 * g))
+        chi_init = rng.uniform(0, 1, (geom.ny, geom.nx))
+        env = rng.normal(size=(geom.ny, geom.nx)) + 1j * rng.normal(size=(geom.ny, geom.nx))
+        want_chi = O.laser_interpolate_chi(chi_field, chi_init, geom, order)
+        want_aabs = np.zeros_like(chi_field)
+        O.update_laser_aabs(env, want_aabs, geom, order)
+        planes = np.ascontiguousarray(chi_field[None])
+        hg = _grid(geom)
+        chi_out = np.zeros((geom.ny, geom.nx))
+        aabs_out = np.zeros_like(chi_field)
+        ci, ev = np.ascontiguousarray(chi_init), np.ascontiguousarray(env)
+        hc.hc_laser_chi_aabs(_dp(planes), C.byref(hg), 0, _dp(ci), _dp(ev), geom.nx, geom.ny,
+                             C.c_double(geom.dx), C.c_double(geom.dy), order, _dp(chi_out), _dp(aabs_out))
+        assert np.abs(chi_out - want_chi).max() <= 1e-14
+        assert np.abs(aabs_out - want_aabs).max() <= 1e-13 * np.abs(want_aabs).max()
