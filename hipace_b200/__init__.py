@@ -66,6 +66,8 @@ EXPORTS = (
     'hpb_fields_rel_b_error', 'hpb_fields_lincomb2', 'hpb_beam_min_uz_slice', 'hpb_adaptive_dt_next',
     'hpb_abs_sum_xz', 'hpb_plasma_insitu_slice', 'hpb_insitu_write_plasma',
     'hpb_fields_insitu_slice', 'hpb_insitu_write_fields', 'hpb_debug_push_thread_map',
+    'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
+    'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
 )
 NCCL_ID_BYTES = 128
 

@@ -4,9 +4,13 @@
 // (:214-291): |a|^2 interpolated onto the grown field slice.  The envelope is never stored: every
 // field cell evaluates the (<= 9) laser cells it interpolates from -- a few hundred flops per cell
 // once per slice, against planes of HBM traffic for a stored complex slice.
-// The envelope ADVANCE over time steps (AdvanceSliceMG, hpmg type 2) is not implemented.
+// The envelope ADVANCE over time steps (second half of this file) stores the slices and solves with the
+// fft solver (lasers.solver_type = fft, MultiLaser::AdvanceSliceFFT); hpmg type 2 is not implemented.
 #include "common.cuh"
+#include "laser_advance.cuh"
 #include <cuda/std/complex>
+#include <dlfcn.h>
+#include <vector>
 
 namespace {
 
@@ -115,5 +119,314 @@ extern "C" int hpb_laser_update_aabs(hpb_ctx *ctx, hpb_slice sl, int c_aabs, con
 #undef HPB_AABS
     hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// =================================================================================================
+// Envelope ADVANCE over time steps, fft solver (second part)
+//   MultiLaser::AdvanceSliceFFT  src/laser/MultiLaser.cpp:609-801
+//   InterpolateChi :334-407, UpdateLaserAabs :214-291, ShiftLaserSlices :180-212,
+//   the hand-over of A^{n+1}, A^n to the next time step: src/utils/MultiBuffer.cpp:840-851, 913-923
+// Per-cell arithmetic: laser_advance.cuh (verified on the host against the oracle).  The 2-D complex
+// FFT of the laser grid is cuFFT (a plain library transform, like the reference's AnyFFT), loaded
+// with dlopen on first use so that libhpb200.so carries no link-time dependency on it.
+// =================================================================================================
+namespace {
+
+// ---- cuFFT through dlopen ----------------------------------------------------------------------
+struct CufftApi {
+    void *h = nullptr;
+    int (*plan2d)(int *, int, int, int) = nullptr;
+    int (*exec_z2z)(int, void *, void *, int) = nullptr;
+    int (*set_stream)(int, cudaStream_t) = nullptr;
+    int (*destroy)(int) = nullptr;
+};
+CufftApi *cufft_api()
+{
+    static CufftApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char *name : {"libcufft.so.11", "libcufft.so.12", "libcufft.so"}) {
+            api.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (api.h) break;
+        }
+        if (api.h) {
+            api.plan2d = (int (*)(int *, int, int, int))dlsym(api.h, "cufftPlan2d");
+            api.exec_z2z = (int (*)(int, void *, void *, int))dlsym(api.h, "cufftExecZ2Z");
+            api.set_stream = (int (*)(int, cudaStream_t))dlsym(api.h, "cufftSetStream");
+            api.destroy = (int (*)(int))dlsym(api.h, "cufftDestroy");
+            if (!api.plan2d || !api.exec_z2z || !api.set_stream || !api.destroy) api.h = nullptr;
+        }
+    }
+    return api.h ? &api : nullptr;
+}
+constexpr int kCufftZ2Z = 0x69, kCufftForward = -1, kCufftInverse = 1;
+
+constexpr int kLT = 256;
+
+__global__ void __launch_bounds__(kLT)
+k_laser_init_slice(LaserSet ls, hpb_c2 *__restrict__ dst, int nx, int ny, double dx, double dy, double x_off,
+                   double y_off, double z)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nx) return;
+    const cplx e = laser_envelope(ls, i * dx + x_off, j * dy + y_off, z);
+    dst[(long)j * nx + i] = c2(e.real(), e.imag());
+}
+
+__global__ void __launch_bounds__(kLT)
+k_laser_aabs_slice(SliceView a, int c_aabs, const hpb_c2 *__restrict__ env, int nx, int ny, int g, double dx,
+                   double dy, double x_off, double y_off, int order)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x - g, j = (int)blockIdx.y - g;
+    if (i >= nx + g) return;
+    a.comp(c_aabs)[a.idx(i, j)] = laser_aabs_cell(env, i, j, nx, ny, dx, dy, x_off, y_off, order);
+}
+
+// sum |A| of the diagnostic (xyz: the valid box; xz: the y = mid-domain line, order-1 interpolation)
+__global__ void __launch_bounds__(kLT)
+k_laser_abs_sum(const hpb_c2 *__restrict__ env, int nx, int ny, int xz, double *out)
+{
+    hpb_pdl_prologue();
+    __shared__ double sm[kLT];
+    double acc = 0.;
+    if (xz) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+            hpb_c2 v = env[(long)(ny / 2) * nx + i];
+            if (ny % 2 == 0) v = 0.5 * (env[(long)(ny / 2 - 1) * nx + i] + v);
+            acc += sqrt(v.re * v.re + v.im * v.im);
+        }
+    } else {
+        const long n = (long)nx * ny;
+        for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
+            acc += sqrt(env[q].re * env[q].re + env[q].im * env[q].im);
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = kLT / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sm[0] != 0.) atomicAdd(out, sm[0]);
+}
+
+__global__ void __launch_bounds__(kLT)
+k_laser_chi(SliceView a, int c_chi, const double *__restrict__ chi_initial, double *__restrict__ chi_out, int nx,
+            int ny, int g, double dx, double dy, double x_off, double y_off, int order)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nx) return;
+    chi_out[(long)j * nx + i] = laser_chi_cell(a, c_chi, chi_initial, i, j, nx, ny, g, dx, dy, x_off, y_off, order);
+}
+
+// the three on-axis sums and the phase terms: one thread
+__global__ void k_laser_phase(const hpb_c2 *n00j00, const hpb_c2 *n00jp1, const hpb_c2 *n00jp2, int nx, int ny,
+                              double dz, int use_phase, LaserPhase *out)
+{
+    hpb_pdl_prologue();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int imid = (nx + 1) / 2, jmid = (ny + 1) / 2;
+    const int i_lo = nx % 2 == 0 ? imid - 1 : imid, j_lo = ny % 2 == 0 ? jmid - 1 : jmid;
+    hpb_c2 h0 = c2(0., 0.), h1 = c2(0., 0.), h2 = c2(0., 0.);
+    for (int j = j_lo; j <= jmid; ++j)
+        for (int i = i_lo; i <= imid; ++i) {
+            const long o = (long)j * nx + i;
+            h0 = h0 + n00j00[o]; h1 = h1 + n00jp1[o]; h2 = h2 + n00jp2[o];
+        }
+    *out = laser_phase(h0, h1, h2, dz, use_phase);
+}
+
+__global__ void __launch_bounds__(kLT)
+k_laser_rhs(LaserPlanes L, const double *__restrict__ chi, LaserAdvPar par, const LaserPhase *__restrict__ ph,
+            hpb_c2 *__restrict__ rhs)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= par.nx) return;
+    rhs[(long)j * par.nx + i] = laser_rhs_cell(L, chi, i, j, par, *ph);
+}
+
+__global__ void __launch_bounds__(kLT)
+k_laser_spectral(hpb_c2 *__restrict__ rhs_f, LaserAdvPar par, const LaserPhase *__restrict__ ph)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= par.nx) return;
+    const long o = (long)j * par.nx + i;
+    rhs_f[o] = laser_spectral_cell(rhs_f[o], i, j, par, *ph);
+}
+
+}  // namespace
+
+// the nine complex work slices (time levels n-1, n, n+1 at slices j, j+1, j+2: MultiLaser.H:24-48), the
+// per-step storage of A^n and A^{n-1} for every slice, and the solver scratch
+struct hpb_laser_state {
+    int nx = 0, ny = 0, nz = 0, interp_order = 1, use_phase = 1;
+    LaserSet ls;
+    hpb_c2 *work = nullptr;             // 9 planes
+    hpb_c2 *w[9] = {};                  // nm1j00 nm1jp1 nm1jp2 n00j00 n00jp1 n00jp2 np1j00 np1jp1 np1jp2
+    hpb_c2 *store[4] = {};              // this step's {A^n, A^{n-1}}, next step's {A^{n+1}, A^n}: nz planes each
+    hpb_c2 *rhs = nullptr;
+    double *chi = nullptr, *chi_initial = nullptr;
+    LaserPhase *phase = nullptr;
+    int plan = -1;
+};
+enum { L_NM1J00 = 0, L_NM1JP1, L_NM1JP2, L_N00J00, L_N00JP1, L_N00JP2, L_NP1J00, L_NP1JP1, L_NP1JP2 };
+
+extern "C" void hpb_laser_state_destroy(hpb_laser_state *st)
+{
+    if (!st) return;
+    if (st->plan >= 0 && cufft_api()) cufft_api()->destroy(st->plan);
+    cudaFree(st->work); cudaFree(st->rhs); cudaFree(st->chi); cudaFree(st->chi_initial); cudaFree(st->phase);
+    for (auto p : st->store) cudaFree(p);
+    delete st;
+}
+
+extern "C" int hpb_laser_state_create(hpb_laser_state **out, hpb_ctx *ctx, int nz, const hpb_laser *lasers,
+                                      int nlasers, double lambda0, int interp_order, int use_phase)
+{
+    if (!out || !ctx || nz < 1 || !lasers || nlasers < 1 || nlasers > HPB_MAX_LASERS || lambda0 <= 0.
+        || interp_order < 0 || interp_order > 2) return HPB_ERR_ARG;
+    CufftApi *fft = cufft_api();
+    if (!fft) { hpb_set_error("laser envelope advance: libcufft could not be loaded"); return HPB_ERR_UNSUPPORTED; }
+    hpb_laser_state *st = new hpb_laser_state();
+    st->nx = ctx->g.nx; st->ny = ctx->g.ny; st->nz = nz; st->interp_order = interp_order; st->use_phase = use_phase;
+    st->ls.n = nlasers;
+    for (int l = 0; l < nlasers; ++l) st->ls.L[l] = lasers[l];
+    st->ls.k0 = 2.0 * 3.14159265358979323846 / lambda0;
+    const size_t plane = (size_t)st->nx * st->ny;
+    bool ok = cudaMalloc(&st->work, 9 * plane * sizeof(hpb_c2)) == cudaSuccess
+        && cudaMalloc(&st->rhs, plane * sizeof(hpb_c2)) == cudaSuccess
+        && cudaMalloc(&st->chi, plane * sizeof(double)) == cudaSuccess
+        && cudaMalloc(&st->chi_initial, plane * sizeof(double)) == cudaSuccess
+        && cudaMalloc(&st->phase, sizeof(LaserPhase)) == cudaSuccess;
+    for (int k = 0; ok && k < 4; ++k)
+        ok = cudaMalloc(&st->store[k], (size_t)nz * plane * sizeof(hpb_c2)) == cudaSuccess
+             && cudaMemset(st->store[k], 0, (size_t)nz * plane * sizeof(hpb_c2)) == cudaSuccess;
+    // cufftPlan2d(plan, n_slowest, n_fastest, type): rows are y
+    if (ok && fft->plan2d(&st->plan, st->ny, st->nx, kCufftZ2Z) != 0) { st->plan = -1; ok = false; }
+    if (!ok) {
+        hpb_set_error("laser envelope advance: allocation or cuFFT plan failed (%zu bytes per slice plane, %d slices)",
+                      plane * sizeof(hpb_c2), nz);
+        hpb_laser_state_destroy(st);
+        return HPB_ERR_CUDA;
+    }
+    for (int k = 0; k < 9; ++k) st->w[k] = st->work + k * plane;
+    *out = st;
+    return HPB_OK;
+}
+
+// start of a time step: empty work slices (ResetAllQuantities), the unperturbed chi on the laser grid
+// (MultiLaser::SetInitialChi :293-332, computed by the caller from the plasma density profiles)
+extern "C" int hpb_laser_begin_step(hpb_laser_state *st, hpb_ctx *ctx, const double *h_chi_initial)
+{
+    if (!st || !ctx || !h_chi_initial) return HPB_ERR_ARG;
+    const size_t plane = (size_t)st->nx * st->ny;
+    HPB_CUDA_CHECK(cudaMemsetAsync(st->work, 0, 9 * plane * sizeof(hpb_c2), ctx->stream));
+    for (int k = 0; k < 9; ++k) st->w[k] = st->work + k * plane;
+    HPB_CUDA_CHECK(cudaMemcpyAsync(st->chi_initial, h_chi_initial, plane * sizeof(double), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+    return HPB_OK;
+}
+
+// the envelope of slice `islice` arrives (time step 0: the analytic pulse, InitLaserSlice; later: A^n
+// and A^{n-1} stored by the previous step), |a|^2 goes onto the field slice, sum |A| into the checksum
+extern "C" int hpb_laser_get_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_aabs, int islice,
+                                   int step, double z_slice, double *d_env_abs_sum, int diag_xz)
+{
+    if (!st || !ctx || c_aabs < 0 || islice < 0 || islice >= st->nz) return HPB_ERR_ARG;
+    const hpb_geom &g = ctx->g;
+    const size_t plane = (size_t)st->nx * st->ny;
+    const int ng = -sl.lo_x;
+    dim3 grid((st->nx + kLT - 1) / kLT, st->ny);
+    if (step == 0) {
+        hpb_launch(k_laser_init_slice, grid, kLT, 0, ctx->stream, st->ls, st->w[L_N00J00], st->nx, st->ny, g.dx,
+                   g.dy, g.x_off, g.y_off, z_slice);
+        hpb_count_launch(ctx);
+    } else {
+        HPB_CUDA_CHECK(cudaMemcpyAsync(st->w[L_N00J00], st->store[0] + (size_t)islice * plane, plane * sizeof(hpb_c2),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+        HPB_CUDA_CHECK(cudaMemcpyAsync(st->w[L_NM1J00], st->store[1] + (size_t)islice * plane, plane * sizeof(hpb_c2),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    dim3 gridg((st->nx + 2 * ng + kLT - 1) / kLT, st->ny + 2 * ng);
+    hpb_launch(k_laser_aabs_slice, gridg, kLT, 0, ctx->stream, make_view(sl), c_aabs,
+               (const hpb_c2 *)st->w[L_N00J00], st->nx, st->ny, ng, g.dx, g.dy, g.x_off, g.y_off, st->interp_order);
+    hpb_count_launch(ctx);
+    if (d_env_abs_sum) {
+        hpb_launch(k_laser_abs_sum, diag_xz ? 1u : 64u, kLT, 0, ctx->stream, (const hpb_c2 *)st->w[L_N00J00],
+                   st->nx, st->ny, diag_xz, d_env_abs_sum);
+        hpb_count_launch(ctx);
+    }
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// AdvanceSliceFFT once chi of the slice is known; A^{n+1}, A^n of the slice are kept for the next step
+extern "C" int hpb_laser_advance_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_chi, int islice,
+                                       double dt, int step, double prob_len_x, double prob_len_y)
+{
+    if (!st || !ctx || c_chi < 0 || islice < 0 || islice >= st->nz) return HPB_ERR_ARG;
+    if (dt == 0.) return HPB_OK;                                      // MultiLaser.cpp:418
+    CufftApi *fft = cufft_api();
+    const hpb_geom &g = ctx->g;
+    const size_t plane = (size_t)st->nx * st->ny;
+    const int ng = -sl.lo_x;
+    dim3 grid((st->nx + kLT - 1) / kLT, st->ny);
+    hpb_launch(k_laser_chi, grid, kLT, 0, ctx->stream, make_view(sl), c_chi, (const double *)st->chi_initial,
+               st->chi, st->nx, st->ny, ng, g.dx, g.dy, g.x_off, g.y_off, st->interp_order);
+    hpb_launch(k_laser_phase, 1, 32, 0, ctx->stream, (const hpb_c2 *)st->w[L_N00J00],
+               (const hpb_c2 *)st->w[L_N00JP1], (const hpb_c2 *)st->w[L_N00JP2], st->nx, st->ny, g.dz,
+               st->use_phase, st->phase);
+    const LaserPlanes L = {st->w[L_NM1J00], st->w[L_NM1JP1], st->w[L_NM1JP2], st->w[L_N00J00], st->w[L_N00JP1],
+                           st->w[L_N00JP2], st->w[L_NP1JP1], st->w[L_NP1JP2]};
+    const double pi2 = 2.0 * 3.14159265358979323846;
+    const LaserAdvPar par = {st->nx, st->ny, step == 0 ? 1 : 0, g.dx, g.dy, g.dz, g.c, dt, st->ls.k0,
+                             pi2 / prob_len_x, pi2 / prob_len_y};
+    hpb_launch(k_laser_rhs, grid, kLT, 0, ctx->stream, L, (const double *)st->chi, par,
+               (const LaserPhase *)st->phase, st->rhs);
+    hpb_count_launch(ctx, 3);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    if (fft->set_stream(st->plan, ctx->stream) != 0
+        || fft->exec_z2z(st->plan, st->rhs, st->rhs, kCufftForward) != 0) {
+        hpb_set_error("laser envelope advance: cuFFT forward transform failed");
+        return HPB_ERR_CUDA;
+    }
+    hpb_launch(k_laser_spectral, grid, kLT, 0, ctx->stream, st->rhs, par, (const LaserPhase *)st->phase);
+    hpb_count_launch(ctx);
+    if (fft->exec_z2z(st->plan, st->rhs, st->w[L_NP1J00], kCufftInverse) != 0) {
+        hpb_set_error("laser envelope advance: cuFFT inverse transform failed");
+        return HPB_ERR_CUDA;
+    }
+    // MultiBuffer::pack_data: A^{n+1} and A^n of this slice go to the next time step
+    HPB_CUDA_CHECK(cudaMemcpyAsync(st->store[2] + (size_t)islice * plane, st->w[L_NP1J00], plane * sizeof(hpb_c2),
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    HPB_CUDA_CHECK(cudaMemcpyAsync(st->store[3] + (size_t)islice * plane, st->w[L_N00J00], plane * sizeof(hpb_c2),
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+// ShiftLaserSlices (:180-212): j+1 -> j+2, j -> j+1 on every time level (pointer rotation)
+extern "C" int hpb_laser_shift_slices(hpb_laser_state *st)
+{
+    if (!st) return HPB_ERR_ARG;
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        hpb_c2 *j00 = st->w[3 * lvl], *jp1 = st->w[3 * lvl + 1], *jp2 = st->w[3 * lvl + 2];
+        st->w[3 * lvl + 2] = jp1; st->w[3 * lvl + 1] = j00; st->w[3 * lvl] = jp2;     // jp2's memory is reused for j00
+    }
+    return HPB_OK;
+}
+
+// end of a time step: what the advance stored becomes the next step's input
+extern "C" int hpb_laser_end_step(hpb_laser_state *st)
+{
+    if (!st) return HPB_ERR_ARG;
+    std::swap(st->store[0], st->store[2]);
+    std::swap(st->store[1], st->store[3]);
     return HPB_OK;
 }

@@ -358,11 +358,16 @@ int read_deck(hpb_sim *s)
         if (s->laser_lambda0 <= 0.) throw std::runtime_error("lasers.lambda0 must be given");
         for (const char *k : {"lasers.n_cell", "lasers.patch_lo", "lasers.patch_hi"})
             if (d.find(k)) throw std::runtime_error(std::string(k) + ": only the default laser grid (= field grid) is supported");
-        if (s->max_step > 0)
-            throw std::runtime_error("lasers: the envelope advance (max_step > 0) is not implemented");
+        if (s->max_step > 0 && d.str("lasers.solver_type", "multigrid") != "fft")
+            throw std::runtime_error("lasers: the envelope advance (max_step > 0) is implemented for "
+                                     "lasers.solver_type = fft only (hpmg type 2, the default, is not)");
+        if (s->max_step > 0 && s->adaptive_dt)
+            throw std::runtime_error("lasers cannot be combined with an adaptive time step");       // Hipace.cpp:407-409
+        s->laser_use_phase = (int)d.num("lasers.use_phase", 1) != 0;
         if (!s->explicit_solver)
             throw std::runtime_error("lasers are only supported with hipace.bxby_solver = explicit");
-        if (s->diag_xz) throw std::runtime_error("lasers: only diagnostic.diag_type = xyz is supported (the laserEnvelope checksum)");
+        if (s->diag_xz && !(s->max_step > 0 && s->dt != 0.))
+            throw std::runtime_error("lasers: diagnostic.diag_type = xz needs the stored envelope (max_step > 0, dt != 0)");
         if ((int)ln.size() > HPB_MAX_LASERS) throw std::runtime_error("too many lasers");
         for (auto &nm : ln) {
             if (d.str(nm + ".init_type", "gaussian") != "gaussian")
@@ -694,6 +699,31 @@ int begin_step(hpb_sim *s, int step)
         s->time = s->dt * step;
     }
     const double c_t = s->g.c * s->time;
+    if (s->use_laser && s->max_step > 0 && s->dt != 0.) {            // the envelope is stored and advanced
+        if (hpb_pipeline_active(s)) {
+            hpb_set_error("the laser envelope advance is not available with a multi-rank pipeline");
+            return HPB_ERR_UNSUPPORTED;
+        }
+        if (!s->laser_state) {
+            int rc = hpb_laser_state_create(&s->laser_state, s->ctx, s->nz, s->lasers.data(), (int)s->lasers.size(),
+                                            s->laser_lambda0, s->laser_interp_order, s->laser_use_phase);
+            if (rc) return rc;
+        }
+        // MultiLaser::SetInitialChi (laser/MultiLaser.cpp:293-332): sum over species of density * q^2 mu0 / m
+        std::vector<double> chi0((size_t)s->g.nx * s->g.ny, 0.);
+        for (auto &sp : s->plasmas) {
+            const double f = sp.charge * sp.charge * s->g.mu0 / sp.mass;
+            for (int j = 0; j < s->g.ny; ++j)
+                for (int i = 0; i < s->g.nx; ++i) {
+                    const double xyz[3] = {i * s->g.dx + s->g.x_off, j * s->g.dy + s->g.y_off, c_t};
+                    chi0[(size_t)j * s->g.nx + i] += s->deck.run(sp.density_host, xyz) * f;
+                }
+        }
+        SIM_CUDA(cudaStreamSynchronize(s->stream));          // chi0 is a temporary
+        int rc = hpb_laser_begin_step(s->laser_state, s->ctx, chi0.data());
+        if (rc) return rc;
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+    }
     for (auto &sp : s->plasmas) {                                    // Hipace.cpp:450
         int rc = init_plasma(s, sp, c_t);
         if (rc) return rc;
@@ -744,6 +774,7 @@ int end_step(hpb_sim *s)
         if (int rc = adaptive_from_min_uz(s, s->time, rho)) return rc;
     }
     if (int rc = write_beam_insitu(s)) return rc;
+    if (s->laser_state) hpb_laser_end_step(s->laser_state);
     for (auto &b : s->beams) { b.cur ^= 1; b.cs_valid = s->opt_checksums; b.initialised = true; }
     if (hpb_pipeline_active(s)) return hpb_pipeline_end_step(s, s->cur_step);
     return HPB_OK;
@@ -1080,9 +1111,13 @@ int solve_one_slice(hpb_sim *s, int islice)
         if (s->use_laser) {                                                             // :583, :603
             StageTimer t(s, ST_OTHER);
             const double z = islice * s->g.dz + (s->prob_lo[2] + 0.5 * s->g.dz);        // GetPosOffset(2)
-            if ((rc = hpb_laser_update_aabs(ctx, s->sl, C[HPB_C_AABS], s->lasers.data(), (int)s->lasers.size(),
-                                            s->laser_lambda0, s->laser_interp_order, z,
-                                            s->opt_checksums ? s->d_checksum + s->sl.ncomp : nullptr))) return rc;
+            if (s->laser_state) {
+                if ((rc = hpb_laser_get_slice(s->laser_state, ctx, s->sl, C[HPB_C_AABS], islice, s->cur_step, z,
+                                              s->opt_checksums ? s->d_checksum + s->sl.ncomp : nullptr,
+                                              s->diag_xz))) return rc;
+            } else if ((rc = hpb_laser_update_aabs(ctx, s->sl, C[HPB_C_AABS], s->lasers.data(),
+                                                   (int)s->lasers.size(), s->laser_lambda0, s->laser_interp_order, z,
+                                                   s->opt_checksums ? s->d_checksum + s->sl.ncomp : nullptr))) return rc;
         }
         {
             StageTimer t(s, ST_DEPOSIT);
@@ -1104,6 +1139,11 @@ int solve_one_slice(hpb_sim *s, int islice)
     {
         StageTimer t(s, ST_POISSON);
         if ((rc = hpb_fields_solve_psi_ez_bz(ctx, s->sl, C))) return rc;                // :633
+    }
+    if (s->laser_state) {                                                               // :637
+        StageTimer t(s, ST_OTHER);
+        if ((rc = hpb_laser_advance_slice(s->laser_state, ctx, s->sl, C[HPB_C_CHI], islice, s->dt, s->cur_step,
+                                          s->prob_hi[0] - s->prob_lo[0], s->prob_hi[1] - s->prob_lo[1]))) return rc;
     }
     if (!was_prepared) {
         StageTimer t(s, ST_OTHER);
@@ -1162,6 +1202,7 @@ int solve_one_slice(hpb_sim *s, int islice)
         StageTimer t(s, ST_OTHER);
         if ((rc = beam_push_and_send(s, islice))) return rc;
         if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;                   // :721
+        if (s->laser_state) hpb_laser_shift_slices(s->laser_state);                     // :727
     } else {
         cudaStream_t bs = side ? s->stream2 : s->stream;
         {
@@ -1354,6 +1395,7 @@ extern "C" void hpb_sim_destroy(hpb_sim *s)
     }
     cudaFree(s->d_overflow); cudaFree(s->d_slot_off);
     cudaFree(s->d_pc_rhs); cudaFree(s->d_pc_scal); cudaFree(s->d_field_insitu);
+    hpb_laser_state_destroy(s->laser_state);
     cudaFree(s->sl.p); cudaFree(s->d_checksum); cudaFree(s->d_nqsa); cudaFree(s->d_count);
     cudaFree(s->d_flag); cudaFree(s->d_offs); cudaFree(s->d_cub);
     hpb_destroy(s->ctx);

@@ -145,6 +145,10 @@ struct hpb_sim {
     double laser_lambda0 = 0.;
     int laser_interp_order = 1;
     bool use_laser = false;
+    // the envelope advance over time steps (laser.cu, second half); null for dt = 0 / max_step = 0 decks,
+    // which evaluate the analytic envelope per cell instead of storing it
+    hpb_laser_state *laser_state = nullptr;
+    bool laser_use_phase = true;
     bool opt_fuse = true;
     // beam-side work of the fused order (beam push / re-binning / hand-off of this slice, beam
     // deposits and the Sx, Sy seed of the next one) runs on a second stream beside the plasma push

@@ -199,6 +199,27 @@ int hpb_beam_min_uz_slice(hpb_ctx *ctx, hpb_beam_slice bm, double *d_acc);
 int hpb_adaptive_dt_next(const hpb_adaptive_par *par, int nbeams, const double *ts, const double *charge,
                          const double *mass, double rho, double t_next, double dt_in, double *dt_out,
                          double *min_uz_mq);
+/* Laser envelope ADVANCE over time steps with the fft solver (second part):
+ * MultiLaser::AdvanceSliceFFT (src/laser/MultiLaser.cpp:609-801), InterpolateChi (:334-407),
+ * UpdateLaserAabs (:214-291), ShiftLaserSlices (:180-212) and the hand-over of A^{n+1}, A^n to the next
+ * time step (src/utils/MultiBuffer.cpp:840-851, 913-923).  The state owns the nine complex work
+ * slices, 4 x nz stored slice planes and the solver scratch; laser grid = field grid.
+ *   begin_step: empty work slices; h_chi_initial = nx*ny host values of the unperturbed chi (:293-332)
+ *   get_slice:  the envelope of slice islice (step 0: the analytic pulse; later: from the store), |a|^2
+ *               into component c_aabs, sum |A| of the diagnostic into d_env_abs_sum (may be NULL)
+ *   advance_slice: after the Poisson solves of the slice (Hipace.cpp:637); no-op for dt = 0
+ *   shift_slices: end of the slice (Hipace.cpp:727); end_step: after the last slice */
+typedef struct hpb_laser_state hpb_laser_state;
+int hpb_laser_state_create(hpb_laser_state **out, hpb_ctx *ctx, int nz, const hpb_laser *lasers, int nlasers,
+                           double lambda0, int interp_order, int use_phase);
+void hpb_laser_state_destroy(hpb_laser_state *st);
+int hpb_laser_begin_step(hpb_laser_state *st, hpb_ctx *ctx, const double *h_chi_initial);
+int hpb_laser_get_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_aabs, int islice, int step,
+                        double z_slice, double *d_env_abs_sum, int diag_xz);
+int hpb_laser_advance_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_chi, int islice, double dt,
+                            int step, double prob_len_x, double prob_len_y);
+int hpb_laser_shift_slices(hpb_laser_state *st);
+int hpb_laser_end_step(hpb_laser_state *st);
 /* shiftSlippedParticles (src/particles/sorting/SliceSort.cpp:13-67) fused with the packing of
  * MultiBuffer::put_data (src/utils/MultiBuffer.cpp:730-905): invalid particles are dropped, the
  * particles with z >= min_z go (stable order) to `stay` whose counts d_stay_np[0..1] are set,

@@ -121,3 +121,31 @@ def test_cta_interleaved_push_map_gives_the_same_result(repo_root):
     want = Oracle(open(deck).read(), ov).evolve()
     for k, w in want.items():
         assert abs(got[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (k, got[k], w)
+
+
+def test_laser_evolution_golden(repo_root):
+    """the laser envelope ADVANCE on the GPU (fft solver): the reference's laser_evolution.SI.2Rank
+    golden -- 31 time steps of a focusing pulse in vacuum, xz diagnostic"""
+    import hipace_b200 as hp
+    meta = json.load(open(os.path.join(GOLD, 'laser_evolution.SI.2Rank.json')))
+    ov = dict(meta['overrides'])
+    sim = hp.Simulation(open(os.path.join(repo_root, meta['deck'])).read(), ov)
+    cs = sim.evolve(0, 30)
+    for name, want in meta['checksums']['lev=0'].items():
+        assert abs(cs[name] - want) <= 1e-8 * abs(want) + 1e-40, (name, cs[name], want)
+    sim.close()
+
+
+def test_laser_advance_with_plasma_matches_oracle(repo_root):
+    """two time steps of the laser-driven blow-out deck with the fft envelope solver against the oracle"""
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    meta = json.load(open(os.path.join(GOLD, 'laser_blowout_wake_explicit.1Rank.json')))
+    deck = open(os.path.join(repo_root, meta['deck'])).read()
+    ov = dict(meta['overrides'], **{'amr.n_cell': '32 32 60', 'max_step': 2, 'hipace.dt': 4.,
+                                    'lasers.solver_type': 'fft'})
+    sim = hp.Simulation(deck, ov)
+    got = sim.evolve(0, 2)
+    want = Oracle(deck, ov).evolve(step_end=2)
+    _compare(got, want, floor=1e-12)
+    sim.close()
