@@ -1,17 +1,19 @@
-"""GPU parity for hipace.bxby_solver = predictor-corrector and boundary.field = Open.
+"""GPU parity for the features written after this round's GPU minutes were spent:
+hipace.bxby_solver = predictor-corrector, boundary.field = Open, hipace.dt = adaptive,
+diagnostic.diag_type = xz, the laser envelope advance (fft solver), the CTA-interleaved push map.
 
-Written after this round's GPU minutes were spent: the slice loop below is built from kernels that
-HAVE run on the B200 (push incl. the temporary-slice mode, deposits, DST Poisson solves) plus the
-new field kernels of csrc/pc_fields.cu, whose per-cell arithmetic is verified on the CPU
-(tests/test_device_math_host.py) -- but the loop as a whole has not run on hardware yet.  The tests
-are therefore non-strict xfails until the round-end suite has shown them passing (XPASS)."""
+Each slice loop below is built from kernels that HAVE run on the B200 (push incl. the temporary-slice
+mode, deposits, DST Poisson solves) plus new kernels whose per-cell arithmetic is verified on the CPU
+(tests/test_device_math_host.py) -- but none of these paths has run on hardware yet.  The tests are
+therefore non-strict xfails, placed last in the suite, until the round-end run has shown them passing
+(XPASS); ROADMAP.md section 1 lists what each one exercises."""
 import json
 import os
 
 import pytest
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first hardware run of the predictor-corrector loop')]
+              pytest.mark.xfail(strict=False, reason='first hardware run of this code path')]
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 RTOL_SUM = 1e-9
