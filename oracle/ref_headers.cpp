@@ -1,6 +1,7 @@
 // C entry points around the reference's OWN header-only arithmetic, compiled from where the
 // headers lie under /root/reference/src (never copied): ShapeFactors.H (every order 0..3 and
-// derivative type 0..2), FieldGather.H (field gather and laser gather, every order), PushPlasmaParticles.H + DualNumbers.H (the momentum derivative for
+// derivative type 0..2), FieldGather.H (field gather and laser gather, every order), fields/OpenBoundary.H (the multipole
+// expansion of the open field boundary), PushPlasmaParticles.H + DualNumbers.H (the momentum derivative for
 // plain reals and for dual numbers).  Built by oracle/refhdr.py into oracle/_ref/ and used by
 // tests/test_oracle_refheaders.py to pin the NumPy restatement to the reference itself.
 // TEST INFRASTRUCTURE ONLY.
@@ -10,6 +11,7 @@
 #include "particles/pusher/PushPlasmaParticles.H"
 #define HIPACE_GPUUTIL_H_   /* Array3 comes from the shim, see there */
 #include "particles/particles_utils/FieldGather.H"
+#include "fields/OpenBoundary.H"
 
 namespace {
 template <int ORDER>
@@ -138,4 +140,22 @@ extern "C" int ref_laser_gather(int order, long n, const double *xp, const doubl
     case 3: laser_gather_all<3>(n, xp, yp, arr, dx_inv, dy_inv, x_off, y_off, out); return 0;
     }
     return 1;
+}
+
+// Open boundary (fields/OpenBoundary.H): the 37 coefficients summed over n sources (s, x, y) and the
+// field value they give at m points (xd, yd) -- all coordinates already scaled
+namespace {
+template <std::size_t... I>
+void tuple_add(MultipoleTuple &acc, const MultipoleTuple &t, std::index_sequence<I...>)
+{
+    ((amrex::get<I>(acc) += amrex::get<I>(t)), ...);
+}
+}
+extern "C" void ref_open_boundary(long n, const double *s, const double *x, const double *y, int monopole,
+                                  long m, const double *xd, const double *yd, double *out)
+{
+    MultipoleTuple acc{};
+    for (long k = 0; k < n; ++k) tuple_add(acc, GetMultipoleCoeffs(s[k], x[k], y[k]), std::make_index_sequence<37>{});
+    if (!monopole) amrex::get<0>(acc) = 0.;
+    for (long k = 0; k < m; ++k) out[k] = GetFieldMultipole(acc, xd[k], yd[k]);
 }

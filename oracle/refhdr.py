@@ -135,3 +135,14 @@ def ref_laser_gather(order, xp, yp, plane, g, dx_inv, dy_inv, x_off, y_off):
                             C.c_double(y_off), _dp(out))
     assert rc == 0
     return out
+
+
+def ref_open_boundary(s, x, y, monopole, xd, yd):
+    """fields/OpenBoundary.H: GetMultipoleCoeffs summed over the sources, GetFieldMultipole at the
+    points (all coordinates scaled as Fields::SetBoundaryCondition scales them)"""
+    L = lib()
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (s, x, y, xd, yd)]
+    out = np.zeros(a[3].size)
+    L.ref_open_boundary(C.c_long(a[0].size), _dp(a[0]), _dp(a[1]), _dp(a[2]), C.c_int(int(monopole)),
+                        C.c_long(a[3].size), _dp(a[3]), _dp(a[4]), _dp(out))
+    return out

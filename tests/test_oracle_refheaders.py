@@ -103,3 +103,33 @@ def test_field_gather_and_laser_gather_match_reference_header(order):
     assert np.abs(A - r[0]).max() <= 1e-14 and np.abs(A - r[3]).max() <= 1e-14
     assert np.abs(ADx - r[1]).max() <= 1e-13 / geom.dx
     assert np.abs(ADy - r[2]).max() <= 1e-13 / geom.dy
+
+
+@pytest.mark.parametrize('monopole', [True, False])
+def test_open_boundary_multipoles_match_reference_header(monopole):
+    """the complex-moment form of the open-boundary expansion (oracle open_boundary_rhs) against the
+    37 tabulated polynomials of the reference's fields/OpenBoundary.H: sources inside the cut-off
+    circle, field values on the ring of guard cells"""
+    rng = np.random.default_rng(17)
+    geom = O.Geometry(40, 32, 4, (-4.0, -3.0, -1.0), (5.0, 3.5, 1.0), 2, 2)
+    nx, ny, dx, dy = geom.nx, geom.ny, geom.dx, geom.dy
+    rhs = rng.normal(0, 1, (ny, nx))
+    got = O.open_boundary_rhs(rhs, geom, monopole) - rhs              # what the boundary adds
+    # the same from the reference's functions, assembled as Fields::SetBoundaryCondition does
+    off_x = 0.5 * (geom.lo[0] + geom.hi[0] - dx * (nx - 1))
+    off_y = 0.5 * (geom.lo[1] + geom.hi[1] - dy * (ny - 1))
+    scale = 3.0 / np.hypot(geom.hi[0] - geom.lo[0], geom.hi[1] - geom.lo[1])
+    radius = min(abs(geom.lo[0]), abs(geom.hi[0]), abs(geom.lo[1]), abs(geom.hi[1]))
+    X, Y = np.meshgrid((np.arange(nx) * dx + off_x) * scale, (np.arange(ny) * dy + off_y) * scale)
+    inside = ~(X * X + Y * Y > (0.95 * radius * scale) ** 2)
+    xi, yj = np.arange(nx) * dx + off_x, np.arange(ny) * dy + off_y
+    edges = [(xi, np.full(nx, -dy + off_y), dy * dy, (0, slice(None))),
+             (xi, np.full(nx, ny * dy + off_y), dy * dy, (ny - 1, slice(None))),
+             (np.full(ny, -dx + off_x), yj, dx * dx, (slice(None), 0)),
+             (np.full(ny, nx * dx + off_x), yj, dx * dx, (slice(None), nx - 1))]
+    want = np.zeros_like(rhs)
+    for xd, yd, dd, where in edges:
+        phi = refhdr.ref_open_boundary(rhs[inside], X[inside], Y[inside], monopole, xd * scale, yd * scale)
+        want[where] += -(dx * dy / (4 * np.pi)) * phi / dd
+    assert np.abs(want).max() > 0
+    assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
