@@ -290,7 +290,11 @@ extern "C" void hc_laser_rhs(const hpb_c2 *const *planes8, const double *chi, co
 {
     const LaserPlanes L = {planes8[0], planes8[1], planes8[2], planes8[3], planes8[4], planes8[5], planes8[6],
                            planes8[7]};
-    const LaserPhase ph = laser_phase(c2(h3[0], h3[1]), c2(h3[2], h3[3]), c2(h3[4], h3[5]), par->dz, use_phase);
+    // h3 == NULL: the on-axis sums come from the device function too
+    hpb_c2 h[3];
+    if (h3) { h[0] = c2(h3[0], h3[1]); h[1] = c2(h3[2], h3[3]); h[2] = c2(h3[4], h3[5]); }
+    else laser_axis_sums(planes8[3], planes8[4], planes8[5], par->nx, par->ny, h);
+    const LaserPhase ph = laser_phase(h[0], h[1], h[2], par->dz, use_phase);
     phase_out[0] = ph.exp1.re; phase_out[1] = ph.exp1.im; phase_out[2] = ph.exp2.re; phase_out[3] = ph.exp2.im;
     phase_out[4] = ph.djn;
     for (int j = 0; j < par->ny; ++j)
@@ -320,4 +324,11 @@ extern "C" void hc_laser_chi_aabs(double *planes, const HcGrid *hg, int c_chi, c
         for (int i = -g; i < nx + g; ++i)
             aabs_out[(long)(j + g) * hg->nx_tot + (i + g)] = laser_aabs_cell(env, i, j, nx, ny, dx, dy, hg->x_off,
                                                                              hg->y_off, order);
+}
+
+extern "C" double hc_laser_diag_xz_sum(const hpb_c2 *env, int nx, int ny)
+{
+    double acc = 0.;
+    for (int i = 0; i < nx; ++i) acc += laser_diag_xz_abs(env, i, nx, ny);
+    return acc;
 }

@@ -194,11 +194,8 @@ k_laser_abs_sum(const hpb_c2 *__restrict__ env, int nx, int ny, int xz, double *
     __shared__ double sm[kLT];
     double acc = 0.;
     if (xz) {
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-            hpb_c2 v = env[(long)(ny / 2) * nx + i];
-            if (ny % 2 == 0) v = 0.5 * (env[(long)(ny / 2 - 1) * nx + i] + v);
-            acc += sqrt(v.re * v.re + v.im * v.im);
-        }
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x)
+            acc += laser_diag_xz_abs(env, i, nx, ny);
     } else {
         const long n = (long)nx * ny;
         for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x)
@@ -229,15 +226,9 @@ __global__ void k_laser_phase(const hpb_c2 *n00j00, const hpb_c2 *n00jp1, const 
 {
     hpb_pdl_prologue();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int imid = (nx + 1) / 2, jmid = (ny + 1) / 2;
-    const int i_lo = nx % 2 == 0 ? imid - 1 : imid, j_lo = ny % 2 == 0 ? jmid - 1 : jmid;
-    hpb_c2 h0 = c2(0., 0.), h1 = c2(0., 0.), h2 = c2(0., 0.);
-    for (int j = j_lo; j <= jmid; ++j)
-        for (int i = i_lo; i <= imid; ++i) {
-            const long o = (long)j * nx + i;
-            h0 = h0 + n00j00[o]; h1 = h1 + n00jp1[o]; h2 = h2 + n00jp2[o];
-        }
-    *out = laser_phase(h0, h1, h2, dz, use_phase);
+    hpb_c2 h[3];
+    laser_axis_sums(n00j00, n00jp1, n00jp2, nx, ny, h);
+    *out = laser_phase(h[0], h[1], h[2], dz, use_phase);
 }
 
 __global__ void __launch_bounds__(kLT)

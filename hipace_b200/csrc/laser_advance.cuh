@@ -45,6 +45,30 @@ HPB_HD LaserPhase laser_phase(hpb_c2 h0, hpb_c2 h1, hpb_c2 h2, double dz, int us
     return p;
 }
 
+// the sums of the three n-level slices over the centre cell(s) of the grid (:651-664): two cells per
+// direction for an even size, one for an odd size
+HPB_HD void laser_axis_sums(const hpb_c2 *n00j00, const hpb_c2 *n00jp1, const hpb_c2 *n00jp2, int nx, int ny,
+                            hpb_c2 h[3])
+{
+    const int imid = (nx + 1) / 2, jmid = (ny + 1) / 2;
+    const int i_lo = nx % 2 == 0 ? imid - 1 : imid, j_lo = ny % 2 == 0 ? jmid - 1 : jmid;
+    h[0] = h[1] = h[2] = c2(0., 0.);
+    for (int j = j_lo; j <= jmid; ++j)
+        for (int i = i_lo; i <= imid; ++i) {
+            const long o = (long)j * nx + i;
+            h[0] = h[0] + n00j00[o]; h[1] = h[1] + n00jp1[o]; h[2] = h[2] + n00jp2[o];
+        }
+}
+
+// |A| of the diagnostic at column i: the y = mid-domain line of an xz diagnostic (order-1
+// interpolation: mean of the two central rows for even ny, diagnostics/Diagnostic.cpp:393-407)
+HPB_HD double laser_diag_xz_abs(const hpb_c2 *env, int i, int nx, int ny)
+{
+    hpb_c2 v = env[(long)(ny / 2) * nx + i];
+    if (ny % 2 == 0) v = 0.5 * (env[(long)(ny / 2 - 1) * nx + i] + v);
+    return sqrt(v.re * v.re + v.im * v.im);
+}
+
 struct LaserAdvPar {
     int nx, ny, step0;                 // step0: first time step (only two time levels exist)
     double dx, dy, dz, c, dt, k0;

@@ -402,6 +402,13 @@ def test_device_laser_advance_matches_oracle(hc, step0, nx, ny):
     phase = np.zeros(5)
     chi_c = np.ascontiguousarray(chi)
     hc.hc_laser_rhs(_ptrs(planes), _dp(chi_c), C.byref(par), _dp(h3), 1, _dp(rhs), _dp(phase))
+    rhs2, phase2 = np.zeros((ny, nx), dtype=complex), np.zeros(5)      # on-axis sums by the device function
+    hc.hc_laser_rhs(_ptrs(planes), _dp(chi_c), C.byref(par), None, 1, _dp(rhs2), _dp(phase2))
+    assert np.allclose(phase, phase2, rtol=1e-12, atol=0) and np.abs(rhs - rhs2).max() <= 1e-12 * np.abs(rhs).max()
+    hc.hc_laser_diag_xz_sum.restype = C.c_double
+    env0 = planes[3]
+    line = 0.5 * (env0[ny // 2 - 1] + env0[ny // 2]) if ny % 2 == 0 else env0[ny // 2]
+    assert hc.hc_laser_diag_xz_sum(_dp(env0), nx, ny) == pytest.approx(np.abs(line).sum(), rel=1e-14)
     rhs_f = np.ascontiguousarray(np.fft.fft2(rhs))
     hc.hc_laser_spectral(_dp(rhs_f), C.byref(par), _dp(phase))
     got = np.fft.ifft2(rhs_f) * (nx * ny)                 # cuFFT's inverse is unnormalised
