@@ -68,6 +68,7 @@ EXPORTS = (
     'hpb_fields_insitu_slice', 'hpb_insitu_write_fields', 'hpb_debug_push_thread_map',
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
+    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser',
 )
 NCCL_ID_BYTES = 128
 
@@ -239,6 +240,17 @@ def insitu_write_fields(path, time, step, z_lo, z_hi, normalized, dxdydz, sums):
                                           C.c_int, C.c_double, C.c_void_p]
     _check(L.hpb_insitu_write_fields(str(path).encode(), time, step, a.shape[1], z_lo, z_hi, int(normalized),
                                      dxdydz, a.ctypes.data), 'hpb_insitu_write_fields')
+
+
+def insitu_write_laser(path, time, step, z_lo, z_hi, normalized, dxdydz, nx, ny, sums):
+    """hpb_insitu_write_laser (host only): raw per-slice values[8, n_slices] -> one appended record"""
+    a = np.ascontiguousarray(sums, dtype=np.float64)
+    assert a.ndim == 2 and a.shape[0] == 8
+    L = lib()
+    L.hpb_insitu_write_laser.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                         C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    _check(L.hpb_insitu_write_laser(str(path).encode(), time, step, a.shape[1], z_lo, z_hi, int(normalized),
+                                    dxdydz, nx, ny, a.ctypes.data), 'hpb_insitu_write_laser')
 
 
 def read_insitu(path):

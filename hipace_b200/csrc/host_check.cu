@@ -332,3 +332,17 @@ extern "C" double hc_laser_diag_xz_sum(const hpb_c2 *env, int nx, int ny)
     for (int i = 0; i < nx; ++i) acc += laser_diag_xz_abs(env, i, nx, ny);
     return acc;
 }
+
+// the 8 raw laser in-situ values of one stored slice (laser_advance.cuh)
+extern "C" void hc_laser_insitu(const hpb_c2 *env, int nx, int ny, double dx, double dy, double x_off,
+                                double y_off, double *out8)
+{
+    for (int k = 0; k < 8; ++k) out8[k] = 0.;
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            double t[8];
+            insitu_laser_terms(env, i, j, nx, ny, dx, dy, x_off, y_off, t);
+            out8[0] = out8[0] > t[0] ? out8[0] : t[0];
+            for (int k = 1; k < 8; ++k) out8[k] += t[k];
+        }
+}

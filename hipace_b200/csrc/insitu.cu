@@ -340,6 +340,43 @@ extern "C" int hpb_insitu_write_fields(const char *path, double time, int step, 
     return HPB_OK;
 }
 
+// Host only.  sums: [8][n_slices] RAW per-slice values of hpb_laser_insitu_slice (max |a|^2, five sums,
+// the on-axis sum re / im); nx, ny decide the on-axis averaging factor
+// (MultiLaser::InSituWriteToFile, src/laser/MultiLaser.cpp:1003-1075)
+extern "C" int hpb_insitu_write_laser(const char *path, double time, int step, int n_slices, double z_lo,
+                                      double z_hi, int is_normalized_units, double dxdydz, int nx, int ny,
+                                      const double *sums)
+{
+    if (!path || !sums || n_slices < 1) return HPB_ERR_ARG;
+    const size_t ns = (size_t)n_slices;
+    const double mid_factor = ((nx - 1) / 2 == nx / 2 ? 1. : 0.5) * ((ny - 1) / 2 == ny / 2 ? 1. : 0.5);   // :946-947
+    std::vector<double> r(6 * ns), tot(6, 0.), axis(2 * ns);
+    for (size_t s = ns; s-- > 0;) {
+        r[s] = sums[s];
+        tot[0] = tot[0] > sums[s] ? tot[0] : sums[s];                                   // :984-986
+        for (int i = 1; i < 6; ++i) { r[i * ns + s] = sums[i * ns + s] * dxdydz; tot[i] += r[i * ns + s]; }
+        axis[2 * s] = sums[6 * ns + s] * mid_factor;
+        axis[2 * s + 1] = sums[7 * ns + s] * mid_factor;
+    }
+    static const char *names[6] = {"max(|a|^2)", "[|a|^2]", "[|a|^2*x]", "[|a|^2*x*x]", "[|a|^2*y]", "[|a|^2*y*y]"};
+    std::vector<Node> all = {f8("time", &time), i4("step", &step), i4("n_slices", &n_slices), f8("z_lo", &z_lo),
+                             f8("z_hi", &z_hi), i4("is_normalized_units", &is_normalized_units)};
+    for (int i = 0; i < 6; ++i) all.push_back(f8(names[i], &r[i * ns], ns));
+    all.push_back(leaf("axis(a)", "<c16", axis.data(), 16, ns));
+    Node integ; integ.name = "integrated";
+    for (int i = 0; i < 6; ++i) integ.sub.push_back(f8(names[i], &tot[i]));
+    all.push_back(integ);
+    FILE *f = fopen(path, "ab");
+    if (!f) { hpb_set_error("in-situ diagnostics: cannot open %s (does the directory exist?)", path); return HPB_ERR_ARG; }
+    std::string out;
+    fseek(f, 0, SEEK_END);
+    if (ftell(f) == 0) header(all, out, "");
+    payload(all, out);
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (fclose(f) != 0 || !ok) { hpb_set_error("in-situ diagnostics: error while writing %s", path); return HPB_ERR_ARG; }
+    return HPB_OK;
+}
+
 // d_acc[4] = {min uz / c, sum w, sum w uz / c, sum w uz^2 / c^2}, accumulated over the slices of a step
 extern "C" int hpb_beam_min_uz_slice(hpb_ctx *ctx, hpb_beam_slice bm, double *d_acc)
 {

@@ -251,6 +251,52 @@ k_laser_spectral(hpb_c2 *__restrict__ rhs_f, LaserAdvPar par, const LaserPhase *
     rhs_f[o] = laser_spectral_cell(rhs_f[o], i, j, par, *ph);
 }
 
+__device__ __forceinline__ void atomic_max_double(double *addr, double v)
+{
+    unsigned long long *a = (unsigned long long *)addr, old = *a;
+    while (__longlong_as_double((long long)old) < v) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+// rec[k * stride]: k = 0 maximum of |a|^2, 1..5 sums, 6, 7 the on-axis sum (re, im)
+__global__ void __launch_bounds__(kLT)
+k_laser_insitu(const hpb_c2 *__restrict__ env, int nx, int ny, double dx, double dy, double x_off, double y_off,
+               double *__restrict__ rec, long stride)
+{
+    hpb_pdl_prologue();
+    __shared__ double red[kLT / 32][8];
+    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    const long n = (long)nx * ny;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(q / nx), i = (int)(q - (long)j * nx);
+        double t[8];
+        insitu_laser_terms(env, i, j, nx, ny, dx, dy, x_off, y_off, t);
+        acc[0] = fmax(acc[0], t[0]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) acc[k] += t[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = k == 0 ? fmax(v, u) : v + u;
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int k = threadIdx.x;
+        double v = red[0][k];
+        for (int w = 1; w < kLT / 32; ++w) v = k == 0 ? fmax(v, red[w][k]) : v + red[w][k];
+        if (k == 0) atomic_max_double(rec, v);
+        else if (v != 0.) atomicAdd(rec + k * stride, v);
+    }
+}
+
 }  // namespace
 
 // the nine complex work slices (time levels n-1, n, n+1 at slices j, j+1, j+2: MultiLaser.H:24-48), the
@@ -419,5 +465,17 @@ extern "C" int hpb_laser_end_step(hpb_laser_state *st)
     if (!st) return HPB_ERR_ARG;
     std::swap(st->store[0], st->store[2]);
     std::swap(st->store[1], st->store[3]);
+    return HPB_OK;
+}
+
+// MultiLaser::InSituComputeDiags (:923-1001) of the current slice's A^n: d_record[k * stride], k = 0..7
+extern "C" int hpb_laser_insitu_slice(hpb_laser_state *st, hpb_ctx *ctx, double *d_record, long stride)
+{
+    if (!st || !ctx || !d_record || stride < 1) return HPB_ERR_ARG;
+    const hpb_geom &g = ctx->g;
+    hpb_launch(k_laser_insitu, 64, kLT, 0, ctx->stream, (const hpb_c2 *)st->w[L_N00J00], st->nx, st->ny, g.dx, g.dy,
+               g.x_off, g.y_off, d_record, stride);
+    hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
 }

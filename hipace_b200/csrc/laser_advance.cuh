@@ -69,6 +69,22 @@ HPB_HD double laser_diag_xz_abs(const hpb_c2 *env, int i, int nx, int ny)
     return sqrt(v.re * v.re + v.im * v.im);
 }
 
+// MultiLaser::InSituComputeDiags (src/laser/MultiLaser.cpp:923-1001), one laser cell: |a|^2 (for the
+// maximum and the sum), its first and second moments in x and y, and the cell's share of the on-axis
+// value (the centre cell, or the mean of the two / four centre cells)
+HPB_HD void insitu_laser_terms(const hpb_c2 *env, int i, int j, int nx, int ny, double dx, double dy,
+                               double x_off, double y_off, double out[8])
+{
+    const hpb_c2 a = env[(long)j * nx + i];
+    const double aabssq = a.re * a.re + a.im * a.im;
+    const double x = i * dx + x_off, y = j * dy + y_off;
+    const int xlo = (nx - 1) / 2, xhi = nx / 2, ylo = (ny - 1) / 2, yhi = ny / 2;
+    const bool on_axis = (i == xlo || i == xhi) && (j == ylo || j == yhi);
+    out[0] = aabssq; out[1] = aabssq; out[2] = aabssq * x; out[3] = aabssq * x * x;
+    out[4] = aabssq * y; out[5] = aabssq * y * y;
+    out[6] = on_axis ? a.re : 0.; out[7] = on_axis ? a.im : 0.;
+}
+
 struct LaserAdvPar {
     int nx, ny, step0;                 // step0: first time step (only two time levels exist)
     double dx, dy, dz, c, dt, k0;

@@ -364,6 +364,10 @@ int read_deck(hpb_sim *s)
         if (s->max_step > 0 && s->adaptive_dt)
             throw std::runtime_error("lasers cannot be combined with an adaptive time step");       // Hipace.cpp:407-409
         s->laser_use_phase = (int)d.num("lasers.use_phase", 1) != 0;
+        s->laser_insitu_period = (int)d.num("lasers.insitu_period", 0);
+        s->laser_insitu_prefix = d.str("lasers.insitu_file_prefix", "diags/laser_insitu");
+        if (s->laser_insitu_period > 0 && !(s->max_step > 0 && s->dt != 0.))
+            throw std::runtime_error("lasers.insitu_period needs the stored envelope (max_step > 0, dt != 0)");
         if (!s->explicit_solver)
             throw std::runtime_error("lasers are only supported with hipace.bxby_solver = explicit");
         if (s->diag_xz && !(s->max_step > 0 && s->dt != 0.))
@@ -846,6 +850,16 @@ int write_beam_insitu(hpb_sim *s)
                                          s->g.dx * s->g.dy * s->g.dz, h.data());
         if (rc) return rc;
     }
+    if (s->d_laser_insitu && do_diagnostics(s->laser_insitu_period, s->cur_step, s->max_step)) {   // :490
+        std::vector<double> h(8 * (size_t)s->nz);
+        SIM_CUDA(cudaStreamSynchronize(s->stream));
+        SIM_CUDA(cudaMemcpy(h.data(), s->d_laser_insitu, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        SIM_CUDA(cudaMemset(s->d_laser_insitu, 0, sizeof(double) * h.size()));
+        int rc = hpb_insitu_write_laser(insitu_path(s, s->laser_insitu_prefix, "laser").c_str(), s->time,
+                                        s->cur_step, s->nz, s->prob_lo[2], s->prob_hi[2], s->g.normalized,
+                                        s->g.dx * s->g.dy * s->g.dz, s->g.nx, s->g.ny, h.data());
+        if (rc) return rc;
+    }
     for (auto &sp : s->plasmas) {
         if (!sp.d_insitu || !do_diagnostics(sp.insitu_period, s->cur_step, s->max_step)) continue;
         std::vector<double> h(15 * (size_t)s->nz);
@@ -1173,6 +1187,14 @@ int solve_one_slice(hpb_sim *s, int islice)
         }
         if ((rc = hpb_fields_insitu_slice(ctx, s->sl, C, s->d_field_insitu + islice, s->nz))) return rc;
     }
+    if (s->laser_state && do_diagnostics(s->laser_insitu_period, s->cur_step, s->max_step)) {   // :688
+        StageTimer t(s, ST_OTHER);
+        if (!s->d_laser_insitu) {
+            SIM_CUDA(cudaMalloc(&s->d_laser_insitu, sizeof(double) * 8 * (size_t)s->nz));
+            SIM_CUDA(cudaMemsetAsync(s->d_laser_insitu, 0, sizeof(double) * 8 * (size_t)s->nz, ctx->stream));
+        }
+        if ((rc = hpb_laser_insitu_slice(s->laser_state, ctx, s->d_laser_insitu + islice, s->nz))) return rc;
+    }
     if (s->opt_checksums) {                                                             // :681-691
         StageTimer t(s, ST_OTHER);
         for (int c = 0; c < s->sl.ncomp; ++c)
@@ -1396,6 +1418,7 @@ extern "C" void hpb_sim_destroy(hpb_sim *s)
     cudaFree(s->d_overflow); cudaFree(s->d_slot_off);
     cudaFree(s->d_pc_rhs); cudaFree(s->d_pc_scal); cudaFree(s->d_field_insitu);
     hpb_laser_state_destroy(s->laser_state);
+    cudaFree(s->d_laser_insitu);
     cudaFree(s->sl.p); cudaFree(s->d_checksum); cudaFree(s->d_nqsa); cudaFree(s->d_count);
     cudaFree(s->d_flag); cudaFree(s->d_offs); cudaFree(s->d_cub);
     hpb_destroy(s->ctx);

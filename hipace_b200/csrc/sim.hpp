@@ -149,6 +149,9 @@ struct hpb_sim {
     // which evaluate the analytic envelope per cell instead of storing it
     hpb_laser_state *laser_state = nullptr;
     bool laser_use_phase = true;
+    int laser_insitu_period = 0;                  // lasers.insitu_period (MultiLaser.cpp)
+    std::string laser_insitu_prefix = "diags/laser_insitu";
+    double *d_laser_insitu = nullptr;             // [8][nz]
     bool opt_fuse = true;
     // beam-side work of the fused order (beam push / re-binning / hand-off of this slice, beam
     // deposits and the Sx, Sy seed of the next one) runs on a second stream beside the plasma push

@@ -219,6 +219,11 @@ int hpb_laser_get_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_a
 int hpb_laser_advance_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_chi, int islice, double dt,
                             int step, double prob_len_x, double prob_len_y);
 int hpb_laser_shift_slices(hpb_laser_state *st);
+/* MultiLaser::InSituComputeDiags / InSituWriteToFile (src/laser/MultiLaser.cpp:923-1075): 8 raw values per
+ * slice (max |a|^2, [|a|^2], its x, x^2, y, y^2 moments, the on-axis sum re / im) and the host writer */
+int hpb_laser_insitu_slice(hpb_laser_state *st, hpb_ctx *ctx, double *d_record, long stride);
+int hpb_insitu_write_laser(const char *path, double time, int step, int n_slices, double z_lo, double z_hi,
+                           int is_normalized_units, double dxdydz, int nx, int ny, const double *h_sums);
 int hpb_laser_end_step(hpb_laser_state *st);
 /* shiftSlippedParticles (src/particles/sorting/SliceSort.cpp:13-67) fused with the packing of
  * MultiBuffer::put_data (src/utils/MultiBuffer.cpp:730-905): invalid particles are dropped, the

@@ -1636,6 +1636,47 @@ def insitu_field_record(sums, time, step, z_lo, z_hi, normalized, dxdydz):
     return dt, rec
 
 
+LASER_INSITU_NAMES = ('max(|a|^2)', '[|a|^2]', '[|a|^2*x]', '[|a|^2*x*x]', '[|a|^2*y]', '[|a|^2*y*y]')
+
+
+def laser_insitu_sums(env, geom: 'Geometry'):
+    """MultiLaser::InSituComputeDiags, laser/MultiLaser.cpp:923-1001: raw values of one slice --
+    max |a|^2, five sums, and the sum of a over the centre cell(s) (re, im)"""
+    ny, nx = env.shape
+    a2 = env.real ** 2 + env.imag ** 2
+    x = (np.arange(nx) * geom.dx + geom.pos_offset(0))[None, :]
+    y = (np.arange(ny) * geom.dy + geom.pos_offset(1))[:, None]
+    xs = sorted({(nx - 1) // 2, nx // 2})
+    ys = sorted({(ny - 1) // 2, ny // 2})
+    axis = env[np.ix_(ys, xs)].sum()
+    return np.array([a2.max(), a2.sum(), (a2 * x).sum(), (a2 * x * x).sum(), (a2 * y).sum(),
+                     (a2 * y * y).sum(), axis.real, axis.imag])
+
+
+def insitu_laser_record(sums, time, step, z_lo, z_hi, normalized, dxdydz, nx, ny):
+    """MultiLaser::InSituWriteToFile, laser/MultiLaser.cpp:1003-1075"""
+    ns = sums.shape[1]
+    mid = (1.0 if (nx - 1) // 2 == nx // 2 else 0.5) * (1.0 if (ny - 1) // 2 == ny // 2 else 0.5)
+    per = sums[:6].copy()
+    per[1:] *= dxdydz
+    tot = np.zeros(6)
+    for isl in range(ns - 1, -1, -1):
+        tot[0] = max(tot[0], per[0, isl])
+        tot[1:] += per[1:, isl]
+    N = LASER_INSITU_NAMES
+    dt = np.dtype([('time', '<f8'), ('step', '<i4'), ('n_slices', '<i4'), ('z_lo', '<f8'), ('z_hi', '<f8'),
+                   ('is_normalized_units', '<i4')] + [(nm, '<f8', (ns,)) for nm in N]
+                  + [('axis(a)', '<c16', (ns,)), ('integrated', [(nm, '<f8') for nm in N])])
+    rec = np.zeros((), dtype=dt)
+    rec['time'], rec['step'], rec['n_slices'] = time, step, ns
+    rec['z_lo'], rec['z_hi'], rec['is_normalized_units'] = z_lo, z_hi, int(normalized)
+    for k, nm in enumerate(N):
+        rec[nm] = per[k]
+        rec['integrated'][nm] = tot[k]
+    rec['axis(a)'] = (sums[6] + 1j * sums[7]) * mid
+    return dt, rec
+
+
 def insitu_beam_record(sums, time, step, charge, mass, z_lo, z_hi, density_factor, normalized):
     """InSituWriteToFile, particles/beam/BeamParticleContainer.cpp:596-732: (numpy dtype, record)
     of one time step from the raw sums[23, n_slices]; format of utils/InsituUtil.H"""
@@ -1927,6 +1968,8 @@ class Simulation:
         assert not (self.field_insitu_period and not self.explicit), \
             'Must use explicit solver for field insitu diagnostic'
         self.field_insitu, self.field_insitu_records = None, []
+        self.laser_insitu_period = _get(d, 'lasers.insitu_period', 0, typ=int) if self.use_laser else 0
+        self.laser_insitu, self.laser_insitu_records = None, []
 
     # -- deck readers ----------------------------------------------------------------------
     def _species_charge_mass(self, pre, default_element=None):
@@ -2335,6 +2378,11 @@ class Simulation:
             if self.field_insitu is None:
                 self.field_insitu = np.zeros((10, g.nz))
             self.field_insitu[:, islice] = field_insitu_sums(F, g, pc)
+        if self.laser_insitu_period > 0 and (self.step == self.max_step
+                                             or self.step % self.laser_insitu_period == 0):   # :688
+            if self.laser_insitu is None:
+                self.laser_insitu = np.zeros((8, g.nz))
+            self.laser_insitu[:, islice] = laser_insitu_sums(self.L.n00j00, g)
         self._accumulate_checksums(islice)                                        # :691
         for b in self.beams:                                                      # :682-683 (before the push)
             bs = self.beam_slice(b, islice)
@@ -2396,7 +2444,7 @@ class Simulation:
         for step in range(step_begin, step_end + 1):
             self.checksums = {}
             self.begin_step(step)
-            self.insitu, self.plasma_insitu, self.field_insitu = {}, {}, None
+            self.insitu, self.plasma_insitu, self.field_insitu, self.laser_insitu = {}, {}, None, None
             for isl in range(g.nz - 1, stop, -1):
                 self.solve_one_slice(isl)
             if self.adaptive_dt and stop == -1:                                   # Hipace.cpp:482-483
@@ -2411,6 +2459,10 @@ class Simulation:
                 self.field_insitu_records.append(insitu_field_record(
                     self.field_insitu, self.time, step, g.lo[2], g.hi[2], self.normalized,
                     g.dx * g.dy * g.dz)[1])
+            if self.laser_insitu is not None:                                     # Hipace.cpp:490
+                self.laser_insitu_records.append(insitu_laser_record(
+                    self.laser_insitu, self.time, step, g.lo[2], g.hi[2], self.normalized,
+                    g.dx * g.dy * g.dz, g.nx, g.ny)[1])
             for pl in self.plasmas:                                               # Hipace.cpp:489
                 if pl.name in self.plasma_insitu:
                     ndf = g.dx * g.dy * g.dz if self.normalized else 1.0

@@ -151,3 +151,28 @@ def test_laser_advance_with_plasma_matches_oracle(repo_root):
     want = Oracle(deck, ov).evolve(step_end=2)
     _compare(got, want, floor=1e-12)
     sim.close()
+
+
+def test_laser_insitu_matches_oracle(repo_root, tmp_path):
+    """lasers.insitu_period: the per-slice laser diagnostics of the stored envelope against the oracle"""
+    import numpy as np
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    deck = open(os.path.join(repo_root, 'examples', 'laser_vacuum_SI.in')).read()
+    ov = {'lasers.solver_type': 'fft', 'max_step': 2, 'lasers.insitu_period': 1, 'amr.n_cell': '64 64 50',
+          'lasers.insitu_file_prefix': str(tmp_path / 'l')}
+    sim = hp.Simulation(deck, ov)
+    sim.evolve(0, 2)
+    sim.close()
+    got = hp.read_insitu(tmp_path / 'l' / 'reduced_laser.0000.txt')
+    ref = Oracle(deck, ov)
+    ref.evolve(step_end=2)
+    assert got.shape == (3,)
+    for k, want in enumerate(ref.laser_insitu_records):
+        for nm in want.dtype.names:
+            if nm == 'integrated':
+                for sub in want[nm].dtype.names:
+                    assert got[k][nm][sub] == pytest.approx(want[nm][sub], rel=1e-8), (k, sub)
+            else:
+                scale = np.abs(want[nm]).max() if np.ndim(want[nm]) else abs(want[nm])
+                assert np.allclose(got[k][nm], want[nm], rtol=1e-8, atol=1e-9 * scale), (k, nm)

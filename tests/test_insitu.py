@@ -320,3 +320,39 @@ def test_cuda_field_insitu_matches_oracle(repo_root, tmp_path):
                 assert got[0][nm][sub] == pytest.approx(want[nm][sub], rel=1e-9, abs=1e-12 * scale), sub
         else:
             assert np.allclose(got[0][nm], want[nm], rtol=1e-9, atol=1e-12 * scale), nm
+
+
+def test_laser_insitu_writer_terms_and_oracle(tmp_path, repo_root):
+    import hipace_b200 as hp
+    from hipace_b200.build import build_host_check
+    rng = np.random.default_rng(13)
+    hc = C.CDLL(build_host_check())
+    for nx, ny in ((16, 12), (15, 11), (16, 11)):        # 4, 1 and 2 centre cells
+        sums = rng.uniform(0.1, 2.0, (8, 5))
+        path = tmp_path / f'reduced_laser.{nx}.{ny}.txt'
+        hp.insitu_write_laser(path, 0.5, 3, -1e-4, 1e-4, False, 1e-18, nx, ny, sums)
+        ours = hp.read_insitu(path)
+        dt, rec = O.insitu_laser_record(sums, 0.5, 3, -1e-4, 1e-4, False, 1e-18, nx, ny)
+        assert dt == ours.dtype and ours[0].tobytes() == rec.tobytes()
+        assert ours[0]['integrated']['max(|a|^2)'] == sums[0].max()
+        # terms on the host against the oracle
+        geom = O.Geometry(nx, ny, 5, (-3e-5, -2e-5, 0.0), (5e-5, 7e-5, 1e-5), 2, 2)
+        env = np.ascontiguousarray(rng.normal(size=(ny, nx)) + 1j * rng.normal(size=(ny, nx)))
+        want = O.laser_insitu_sums(env, geom)
+        out = np.zeros(8)
+        hc.hc_laser_insitu(env.ctypes.data_as(C.c_void_p), nx, ny, C.c_double(geom.dx), C.c_double(geom.dy),
+                           C.c_double(geom.pos_offset(0)), C.c_double(geom.pos_offset(1)),
+                           out.ctypes.data_as(C.c_void_p))
+        assert np.allclose(out, want, rtol=1e-12, atol=1e-25)
+    if os.path.isdir(REF_TOOLS):
+        sys.path.insert(0, REF_TOOLS)
+        import read_insitu_diagnostics as R
+        theirs = R.read_file(str(tmp_path / 'reduced_laser.16.12.txt'))
+        assert theirs.dtype['axis(a)'].base == np.dtype('<c16')
+    # content: the vacuum pulse keeps its energy from step to step (3 steps of the golden's deck)
+    deck = open(os.path.join(repo_root, 'examples', 'laser_vacuum_SI.in')).read()
+    sim = O.Simulation(deck, {'lasers.solver_type': 'fft', 'max_step': 2, 'lasers.insitu_period': 1,
+                              'amr.n_cell': '64 64 50'})
+    sim.evolve(step_end=2)
+    e = [float(r['integrated']['[|a|^2]']) for r in sim.laser_insitu_records]
+    assert len(e) == 3 and abs(e[2] - e[0]) <= 2e-3 * e[0]
