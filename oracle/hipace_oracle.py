@@ -5,22 +5,28 @@ bench.py's cpu_baseline / --impl reference legs may import it.  The product path
 (hipace_b200/ + libhpb200.so) never calls into this file.
 
 Parity status: PINNED.  tests/test_oracle_golden.py checks the checksums this oracle produces
-against the reference's own golden files
-  tests/checksum/benchmarks_json/linear_wake.normalized.1Rank.json   (rtol 1e-9)
-  tests/checksum/benchmarks_json/blowout_wake_explicit.2Rank.json    (rtol 1e-9)
-  tests/checksum/benchmarks_json/beam_evolution.1Rank.json           (rtol 1e-9; 20 time steps with
-      dt = 3: pins the beam push, the external fields and the multi-step beam hand-off)
-(copies of the numbers are committed under tests/golden/ with the script that extracted them).
+against FOURTEEN of the reference's own golden files (tests/checksum/benchmarks_json/, rtol 1e-9;
+copies of the numbers are committed under tests/golden/ with the script that extracted them) --
+every golden of the reference that does not depend on AMReX's random number streams:
+  linear_wake.{normalized,SI}.1Rank, gaussian_linear_wake.{normalized,SI}.1Rank,
+  blowout_wake_explicit.2Rank, beam_evolution.1Rank (20 time steps), beam_in_vacuum.{normalized,SI}.1Rank
+  (deposition order 0), grid_current.1Rank, adaptive_time_step.1Rank (hipace.dt = adaptive),
+  beam_in_vacuum_open_boundary.normalized.1Rank (predictor-corrector solver, open field boundaries),
+  laser_blowout_wake_explicit.{1Rank,SI.1Rank} (laser at step 0), laser_evolution.SI.2Rank (envelope advance).
+tests/test_oracle_refheaders.py additionally holds the shape factors (every order and derivative
+type), the field / laser gathers, the momentum derivative (plain and dual, bit-identical) and the
+open-boundary multipoles to the reference's OWN headers, compiled in place by oracle/ref_headers.cpp.
 
 Each function cites the reference file:line (relative to /root/reference/src) it restates.
-Scope: level 0, explicit Bx/By solver, depos_order_xy = 2,
-depos_derivative_type = 2, Dirichlet field boundary, no laser, no ionization, no MR,
-fixed_ppc beams, u_std = 0 plasma (no RNG anywhere).  Beam slippage between slices
-(particles/sorting/SliceSort.cpp) is restated but no golden of the reference exercises it with a
-deterministic beam: that one function is "parity unpinned" (property-tested only).
+Scope (SURVEY.md section 8 and its "next" rows): level 0; explicit (hpmg) and predictor-corrector
+Bx/By solvers; depos_order_xy 0..3, depos_derivative_type 0..2; Dirichlet and Open field
+boundaries; gaussian lasers incl. the envelope advance (fft and multigrid solvers); fixed and
+adaptive time step; in-situ diagnostics; no ionization, no MR; fixed_ppc beams, u_std = 0 plasma (no
+RNG anywhere).  Not pinned by any golden: the hpmg type 2 laser solver (held to the fft solver), the
+plasma half of the predictor-corrector loop (held to the explicit solver).
 
 Array convention: every slice component is a 2-D array a[j + g, i + g] (x fastest) over the
-grown box [-g, n-1+g]^2, g = 2 guard cells (fields/Fields.cpp:63-64).
+grown box [-g, n-1+g]^2, g = (depos_order_xy + 1) / 2 + 1 guard cells (fields/Fields.cpp:63-64).
 """
 from __future__ import annotations
 
@@ -424,8 +430,8 @@ class Beam:
 # Kernels
 # --------------------------------------------------------------------------------------------
 
-# ---- laser envelope (step 0 only: analytic envelope, |a|^2 on the field grid and the
-# ponderomotive terms of the particle kernels -- the envelope ADVANCE (hpmg type 2) is not restated)
+# ---- laser envelope: analytic envelope at step 0, |a|^2 on the field grid, the
+# ponderomotive terms of the particle kernels, and the envelope advance (fft and multigrid solvers)
 
 @dataclass
 class Laser:
@@ -520,9 +526,9 @@ class LaserSlices:
 
 
 def laser_interpolate_chi(chi_field, chi_initial, geom: 'Geometry', interp_order: int):
-    G = geom.g
     """MultiLaser::InterpolateChi, laser/MultiLaser.cpp:334-407 for coinciding grids: chi of the
     field slice inside the field box shrunk by 2 guard widths, the initial chi outside"""
+    G = geom.g
     ii, jj = np.arange(geom.nx), np.arange(geom.ny)
     xmid = ((ii * geom.dx + geom.pos_offset(0)) - geom.pos_offset(0)) * (1.0 / geom.dx)
     ymid = ((jj * geom.dy + geom.pos_offset(1)) - geom.pos_offset(1)) * (1.0 / geom.dy)
