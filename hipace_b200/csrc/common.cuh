@@ -1,6 +1,7 @@
 // Shared device helpers for the hpb200 hot path (sm_100a, fp64).
 // Shape-factor arithmetic follows src/particles/particles_utils/ShapeFactors.H of the reference
-// (order 2 only: the default hipace.depos_order_xy and the one every BASELINE config uses).
+// (order 2, the default hipace.depos_order_xy and the one every BASELINE config uses; the other
+// orders and derivative types: shapes.cuh).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -15,7 +15,7 @@
  *
  * Memory layouts (identical to what an AMReX build of the reference holds):
  *   slice array : component-major, p[(i - lo_x) + (j - lo_y)*jstride + n*nstride], box
- *                 [-g, n-1+g]^2 with g = 2 guard cells (src/utils/GPUUtil.H:98-182,
+ *                 [-g, n-1+g]^2 with g = (depos_order_xy+1)/2 + 1 guard cells, 2 by default (src/utils/GPUUtil.H:98-182,
  *                 src/fields/Fields.cpp:63-64,169-174)
  *   plasma      : pure SoA in PlasmaIdx order (src/particles/plasma/PlasmaParticleContainer.H:
  *                 21-46): x y w ux uy psi x_prev y_prev ux_half_step uy_half_step psi_half_step,
@@ -128,7 +128,7 @@ int hpb_deposit_current_laser(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double 
  * d_envelope_abs_sum (device, may be NULL) accumulates sum |a| over the slice (the laserEnvelope
  * checksum).  With comps[HPB_C_AABS] >= 0, hpb_explicit_deposition and
  * hpb_advance_plasma_particles apply the ponderomotive terms of ExplicitDeposition.cpp:167-250
- * and PushPlasmaParticles.H:59-69.  The envelope ADVANCE (hpmg type 2) is not implemented. */
+ * and PushPlasmaParticles.H:59-69.  The envelope ADVANCE: hpb_laser_state_* below (fft solver). */
 typedef struct {
     double a0, w0, cep, propagation_angle_yz, pft_yz, L0, focal_distance, position_mean[3];
 } hpb_laser;
