@@ -41,8 +41,15 @@ def deck_and_overrides(nxy, nz, ppc):
     return deck, ov
 
 
+# the benchmark line is BASELINE configs[2]; the others are extra lines (profiles/) and parity cases
+WORKLOADS = {'configs2': (1024, 1024, 2, 'BASELINE configs[2]'),
+             'configs1': (256, 512, 2, 'BASELINE configs[1]'),
+             'n1023': (1023, 1024, 2, 'configs[2] on the reference\'s recommended 2^n - 1 grid')}
+
+
 def workload_name(nxy, nz, ppc):
-    return f'blowout_wake_explicit normalized {nxy}x{nxy}x{nz} ppc={ppc * ppc} (BASELINE configs[2])'
+    tag = next((t for n, z, p, t in WORKLOADS.values() if (n, z, p) == (nxy, nz, ppc)), 'custom size')
+    return f'blowout_wake_explicit normalized {nxy}x{nxy}x{nz} ppc={ppc * ppc} ({tag})'
 
 
 # ------------------------------------------------------------------------------------------------
@@ -105,6 +112,8 @@ def cpu_arm(nxy, nz, ppc, steps, warmup, sample_slices):
     Each step is a bounded sample: `sample_slices` consecutive slices of the same deck starting
     at the beam head (the reference cannot be built here: AMReX/FFTW/MPI absent)."""
     from oracle import cport
+    # all physical host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets 1)
+    cport.set_threads(cport.physical_cores())
     deck, ov = deck_and_overrides(nxy, nz, ppc)
     sim = cport.Simulation(deck, ov)
     sim.begin_step()
@@ -133,19 +142,28 @@ def main():
     ap.add_argument('--nxy', type=int, default=1024)
     ap.add_argument('--nz', type=int, default=1024)
     ap.add_argument('--ppc', type=int, default=2, help='per direction (2 -> ppc 4)')
-    ap.add_argument('--dt', type=float, default=0.0, help='hipace.dt (0: the beam is pushed but does not move)')
+    ap.add_argument('--dt', type=float, default=1.0,
+                    help='hipace.dt in 1/omega_p (> 0: the beam evolves from step to step, particles slip '
+                         'between slices and every pipeline packet differs from the last)')
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
+                    help='named size (overrides --nxy/--nz/--ppc); the default line is configs2')
+    ap.add_argument('--opt', action='append', default=[], metavar='KEY=VALUE',
+                    help='hpb_sim_set_option switch for A/B runs (e.g. order=9, fuse=0); recorded in config')
+    ap.add_argument('--no-verify', action='store_true', help='skip the N > 1 pipeline-vs-single-GPU check')
     ap.add_argument('--cpu-sample-slices', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     args = ap.parse_args()
 
+    if args.workload:
+        args.nxy, args.nz, args.ppc = WORKLOADS[args.workload][:3]
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     K, W = args.steps, max(args.warmup, 0)
     cfg = {'workload': workload_name(args.nxy, args.nz, args.ppc), 'nx': args.nxy, 'ny': args.nxy,
-           'nz': args.nz, 'ppc': args.ppc * args.ppc, 'units': 'normalized',
+           'nz': args.nz, 'ppc': args.ppc * args.ppc, 'units': 'normalized', 'dt': args.dt,
            'solver': 'explicit (FFT/DST Poisson x3 + multigrid BxBy)',
            'l2_policy': 'working set per slice (~600 MB) > L2 (126 MB); no flush needed',
            'parallelism': f'time-step pipeline x{world}' if world > 1 else 'single GPU'}
@@ -189,6 +207,11 @@ def main():
         ov['hipace.dt'] = args.dt
     sim = hp.Simulation(deck, ov, device=local_rank)
     sim.set_option('checksums', 0)
+    for kv in args.opt:
+        k, v = kv.split('=', 1)
+        sim.set_option(k, float(v))
+    if args.opt:
+        cfg['options'] = list(args.opt)
     sim.pipeline_init(rank, world, dist)
 
     # ---- device-resident leg ---------------------------------------------------------------
@@ -264,6 +287,39 @@ def main():
                       + ('' if world == 1 else '; steps > 0 receive their beam from the upstream GPU (NCCL p2p)')}
         sim.set_option('checksums', 0)
 
+    # ---- N > 1: the pipeline's result against a single-GPU run of the same steps (untimed) -----
+    # Steps 0 .. world-1 through the ring (one per rank, dt > 0: the beam rank r receives is the one
+    # rank r-1 pushed), then the rank that owns the last step replays all `world` steps alone on its
+    # own GPU: beam moments and field checksums of the last step must agree to 1e-9.
+    verify = None
+    if world > 1 and not args.no_verify:
+        sim.set_option('checksums', 1)
+        sim.run(world - 1, rank, world)
+        barrier()
+        if rank == world - 1:
+            got_f, got_b = sim.checksums(), sim.beam_checksums(0)
+            solo = hp.Simulation(deck, ov, device=local_rank)
+            solo.pipeline_init(0, 1, None)
+            solo.set_option('max_step', world - 1)
+            want_f = solo.evolve(0, world - 1)
+            want_b = solo.beam_checksums(0)
+            solo.close()
+            worst = 0.
+            for want, got in ((want_f, got_f), (want_b, got_b)):
+                for k, w in want.items():
+                    err = abs(got[k] - w) / max(abs(w), 1e-300) if w != 0. else abs(got[k])
+                    worst = max(worst, err)
+            verify = {'steps': world, 'rank': rank, 'worst_rel_err': worst,
+                      'checked': sorted(want_f) + ['beam:' + k for k in sorted(want_b)]}
+            if not worst <= 1e-9:
+                raise SystemExit(f'bench.py: pipeline result differs from the single-GPU run: {verify}')
+        sim.set_option('checksums', 0)
+        barrier()
+        if dist is not None:
+            box = [verify]
+            dist.broadcast_object_list(box, src=world - 1)
+            verify = box[0]
+
     # ---- per-stage profile + roofline of the dominant kernel (extra, untimed pass) -----------
     roofline = None
     stages = None
@@ -336,7 +392,7 @@ def main():
                 'ns_per_particle_step': ns_per_push, 'ms_per_slice': job_ms / (K * args.nz),
                 'slice_loop_ms_per_step_rank0': loop_ms / K,
                 'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
-                'stage_ms_per_slice': stages, 'cpu_baseline': cpu_baseline,
+                'stage_ms_per_slice': stages, 'cpu_baseline': cpu_baseline, 'pipeline_verify': verify,
                 'wall_ms_per_step': wall_ms_max / K}
         print(json.dumps(line))
     barrier()

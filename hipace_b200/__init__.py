@@ -68,7 +68,7 @@ EXPORTS = (
     'hpb_fields_insitu_slice', 'hpb_insitu_write_fields', 'hpb_debug_push_thread_map',
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
-    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser',
+    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option',
 )
 NCCL_ID_BYTES = 128
 
@@ -169,6 +169,9 @@ def lib():
     L.hpb_sim_set_beam.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     L.hpb_sim_get_stats.argtypes = [C.c_void_p, C.POINTER(hpb_sim_stats)]
     L.hpb_sim_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.hpb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.hpb_sim_get_mg_iters.restype = C.c_long
+    L.hpb_sim_get_mg_iters.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_long]
     L.hpb_extfields_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_char_p)]
     L.hpb_extfields_destroy.argtypes = [C.c_void_p]
     L.hpb_extfields_destroy.restype = None
@@ -315,9 +318,11 @@ class Simulation:
     def set_option(self, key: str, value: float):
         _check(self._L.hpb_sim_set_option(self._h, key.encode(), float(value)), 'hpb_sim_set_option')
 
-    def evolve(self, step_begin: int = 0, step_end: int = 0, n_slices: int = 0):
-        """Hipace::Evolve for steps [step_begin, step_end]; returns the checksum dict."""
-        _check(self._L.hpb_sim_evolve(self._h, step_begin, step_end, n_slices), 'hpb_sim_evolve')
+    def evolve(self, step_begin: int = 0, step_end: int | None = None, n_slices: int = 0):
+        """Hipace::Evolve for steps [step_begin, step_end] (default: up to the deck's max_step);
+        returns the checksum dict."""
+        _check(self._L.hpb_sim_evolve(self._h, step_begin, -1 if step_end is None else step_end, n_slices),
+               'hpb_sim_evolve')
         return self.checksums()
 
     def begin_step(self, step: int = 0):
@@ -435,6 +440,13 @@ class Simulation:
             for k, v in self.stats().items():
                 tot[k] = tot.get(k, 0) + v
         return tot
+
+    def mg_iters(self) -> list:
+        """V-cycles of every slice of the last evolve (head first)"""
+        n = self._L.hpb_sim_get_mg_iters(self._h, None, 0)
+        buf = (C.c_int * max(n, 1))()
+        self._L.hpb_sim_get_mg_iters(self._h, buf, n)
+        return list(buf[:n])
 
     def stats(self) -> dict:
         st = hpb_sim_stats()

@@ -94,20 +94,20 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_host_check(force: bool = False) -> str:
-    """TEST artefact: csrc/host_check.cu -> build/libhpb200_hostcheck.so, the __host__ __device__
+    """TEST artefact: tests/host_check.cu -> build/libhpb200_hostcheck.so, the __host__ __device__
     arithmetic of the kernels compiled for the CPU (tests/test_device_math_host.py)."""
     os.makedirs(BUILD, exist_ok=True)
     lib = os.path.join(BUILD, 'libhpb200_hostcheck.so')
-    deps = [os.path.join(CSRC, f) for f in ('host_check.cu', 'generic_order.cuh', 'push_math.cuh',
-                                            'shapes.cuh', 'common.cuh', 'insitu.cuh', 'pc_fields.cuh',
-                                            'laser_advance.cuh')]
+    deps = [os.path.join(ROOT, 'tests', 'host_check.cu')]
+    deps += [os.path.join(CSRC, f) for f in ('generic_order.cuh', 'push_math.cuh', 'shapes.cuh', 'common.cuh',
+                                             'insitu.cuh', 'pc_fields.cuh', 'laser_advance.cuh')]
     deps.append(os.path.join(ROOT, 'include', 'hpb200.h'))
     if (not force and os.path.exists(lib)
             and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps)):
         return lib
     # -ffp-contract=off: the host run is compared with the (non-contracting) reference headers
     cmd = [_nvcc()] + ARCH + ['-O2', '-std=c++17', '-Xcompiler', '-fPIC,-ffp-contract=off', '-shared',
-                              '--cudart', 'shared', '-o', lib, deps[0]]
+                              '--cudart', 'shared', '-I', CSRC, '-o', lib, deps[0]]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError('host_check build failed:\n' + p.stdout + p.stderr)

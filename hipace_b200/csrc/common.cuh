@@ -256,6 +256,9 @@ struct hpb_ctx {
     // the specialised kernels of particles.cu.  Anything else: generic_order.cu)
     int depos_order, depos_dtype;
     int force_generic;        // run the generic kernels for the default order too (cross-check)
+    // kernel variants for A/B measurements (hpb_set_option; never read from the environment)
+    int tune_order;           // bit mask of the particle kernels using the pass-interleaved map (default 1)
+    int tune_expl_variant, tune_push_variant, tune_fft_variant, tune_mg_wide, tune_mg_fuse;
 };
 // true when the particle kernels must take the generic-order path
 bool hpb_use_generic_order(const hpb_ctx *ctx);

@@ -22,18 +22,32 @@ void hpb_set_error(const char *fmt, ...)
 
 void hpb_count_launch(hpb_ctx *ctx, int n) { ctx->n_launch += n; }
 
-bool hpb_pdl_enabled()
-{
-    static int on = -1;
-    if (on < 0) { const char *e = getenv("HPB_PDL"); on = e ? (atoi(e) != 0) : 1; }
-    return on != 0;
-}
+// programmatic dependent launch of the kernel chain: process-wide (the launch helper has no context)
+static int g_pdl = 1;
+bool hpb_pdl_enabled() { return g_pdl != 0; }
 
 bool hpb_use_generic_order(const hpb_ctx *ctx)
 {
-    static int force = -1;       // HPB_GENERIC=1: the generic kernels also for order 2 / centred (cross-check)
-    if (force < 0) { const char *e = getenv("HPB_GENERIC"); force = e ? (atoi(e) != 0) : 0; }
-    return force || ctx->force_generic || ctx->depos_order != 2 || ctx->depos_dtype != 2;
+    return ctx->force_generic || ctx->depos_order != 2 || ctx->depos_dtype != 2;
+}
+
+// Behaviour switches of the library (A/B measurements, cross-checks).  A drop-in library takes
+// them through this call, never from the host's environment.
+extern "C" int hpb_set_option(hpb_ctx *ctx, const char *key, double value)
+{
+    if (!key) return HPB_ERR_ARG;
+    const int v = (int)value;
+    if (!strcmp(key, "pdl")) { g_pdl = v != 0; return HPB_OK; }
+    if (!ctx) return HPB_ERR_ARG;
+    if (!strcmp(key, "generic")) ctx->force_generic = v != 0;
+    else if (!strcmp(key, "order")) ctx->tune_order = v;
+    else if (!strcmp(key, "expl_variant")) ctx->tune_expl_variant = v;
+    else if (!strcmp(key, "push_variant")) ctx->tune_push_variant = v;
+    else if (!strcmp(key, "fft_variant")) ctx->tune_fft_variant = v;
+    else if (!strcmp(key, "mg_wide")) ctx->tune_mg_wide = v;
+    else if (!strcmp(key, "mg_fuse")) ctx->tune_mg_fuse = v;
+    else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }
+    return HPB_OK;
 }
 
 extern "C" int hpb_set_deposition_order(hpb_ctx *ctx, int order_xy, int derivative_type)
@@ -69,6 +83,7 @@ extern "C" int hpb_create(hpb_ctx **out, const hpb_geom *geom, void *stream)
     ctx->g = *geom;
     ctx->stream = (cudaStream_t)stream;
     ctx->depos_order = 2; ctx->depos_dtype = 2;
+    ctx->tune_order = 1; ctx->tune_expl_variant = 4;
     int rc = hpb_poisson_init(ctx);
     if (rc == HPB_OK) rc = hpb_mg_init(ctx);
     if (rc == HPB_OK && cudaMalloc(&ctx->d_scalar_i, 16 * sizeof(int)) != cudaSuccess) rc = HPB_ERR_CUDA;

@@ -7,6 +7,7 @@
 #pragma once
 #include <cmath>
 #include <map>
+#include <set>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -22,6 +23,11 @@ constexpr int kMaxRpn = 64;
 
 struct Deck {
     std::map<std::string, std::vector<std::string>> kv;
+    // keys the reader has asked for (has / find / num / str ...): whatever is left over after
+    // read_deck is an option this implementation does not know, and the run must not go on with
+    // different physics than the deck asks for (the reference aborts on unused parameters too,
+    // amrex::ParmParse::QueryUnusedInputs + hipace's "unused_param" check)
+    mutable std::set<std::string> used;
 
     void parse(const std::string &text)
     {
@@ -55,13 +61,27 @@ struct Deck {
         }
     }
 
-    bool has(const std::string &k) const { return kv.count(k) != 0; }
+    bool has(const std::string &k) const { used.insert(k); return kv.count(k) != 0; }
     const std::vector<std::string> *find(const std::string &k, const std::string &alt = "") const
     {
+        used.insert(k);
+        if (!alt.empty()) used.insert(alt);
         auto it = kv.find(k);
         if (it != kv.end()) return &it->second;
         if (!alt.empty()) { it = kv.find(alt); if (it != kv.end()) return &it->second; }
         return nullptr;
+    }
+    // keys of the deck nobody asked for, except those under the given prefixes
+    std::vector<std::string> unused(const std::vector<std::string> &allow_prefix) const
+    {
+        std::vector<std::string> out;
+        for (auto &e : kv) {
+            if (used.count(e.first)) continue;
+            bool ok = false;
+            for (auto &p : allow_prefix) if (e.first.compare(0, p.size(), p) == 0) ok = true;
+            if (!ok) out.push_back(e.first);
+        }
+        return out;
     }
     std::string str(const std::string &k, const std::string &def, const std::string &alt = "") const
     {

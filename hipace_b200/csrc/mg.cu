@@ -810,8 +810,7 @@ int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, cons
     const int FX = CX - 2 * EO, FY = CY * RH - 2 * EO;
     const int nvx = g.vhix - g.vlo + 1, nvy = g.vhiy - g.vlo + 1;
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
-    static int wide = -1;
-    if (wide < 0) { const char *e = getenv("HPB_MG_WIDE"); wide = e ? atoi(e) : 0; }
+    const int wide = ctx->tune_mg_wide;
     // levels whose tiles do not even fill the GPU once are latency bound: 1024 threads per tile
     // (HPB_MG_WIDE=1; faster in isolation, but no gain in the un-profiled slice loop, where a
     // 1024-thread x 62-register CTA leaves no room for the next kernel of the PDL chain: off)
@@ -1019,9 +1018,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     // Speculative V-cycles: as many as the previous solve needed, enqueued without a host round
     // trip; each kernel is a no-op once the device-side test (:1391) has passed.  One
     // synchronisation then tells us whether more are needed.
-    static int fuse_env = -1;
-    if (fuse_env < 0) { const char *e = getenv("HPB_MG_FUSE"); fuse_env = e ? atoi(e) : 0; }
-    const bool fused = fuse_env != 0;
+    const bool fused = ctx->tune_mg_fuse != 0;
     // fused: V-cycle k (1-based) reads buf[(k-1) % 2] and writes buf[k % 2], buf = {cor0 buffer, sol};
     // the cycles that actually run are a prefix of the enqueued ones, so after `iters` executed
     // cycles the iterate lives in buf[iters % 2].  Unfused: sol is only the scratch iterate.

@@ -11,7 +11,6 @@
 //   src/utils/DualNumbers.H:13-43, src/particles/pusher/GetAndSetPosition.H:29-99
 #include "common.cuh"
 #include "push_math.cuh"
-#include <stdlib.h>
 
 namespace {
 
@@ -41,8 +40,7 @@ PlasmaPtrs to_ptrs(const hpb_plasma &pl)
 PlasmaPtrs to_ptrs(const hpb_ctx *ctx, const hpb_plasma &pl, int which)
 {
     PlasmaPtrs p = to_ptrs(pl);
-    static int on = -1;
-    if (on < 0) { const char *e = getenv("HPB_ORDER"); on = e ? atoi(e) : 1; }
+    const int on = ctx->tune_order;
     // bits 4 / 8 (= which << 2): the same, interleaved CTA by CTA instead of warp by warp -- the next
     // thing to measure for the push (ROADMAP.md): the ppc passes of a cell group then run in
     // consecutive CTAs (co-resident on different SMs) instead of in the four warps of one CTA, so the
@@ -598,8 +596,6 @@ __device__ __forceinline__ void cp_async_wait_all()
 // from registers into jx, jy, chi, rhomjz (which the caller has already shifted / initialised for
 // the next slice), saving the 56 B/particle re-read and one launch per slice.
 struct DepositArgs {
-    int exp_extra;      // TIMING EXPERIMENT ONLY (HPB_EXP_DEP12): two more 4-plane deposits into scratch
-    int cx[8];
     int c_jx, c_jy, c_chi, c_rhomjz;
     double clightinv, charge_invvol, charge_mu0_mass_ratio, max_qsa;
     int *n_qsa_violation;
@@ -766,16 +762,6 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
                                                 active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
                                                 vx_c, vy_c, gamma_psi,
                                                 dep.charge_mu0_mass_ratio * psi_inv);
-    if (dep.exp_extra) {
-        deposit_aggregated<true, false, true, true>(a, dep.cx[0], dep.cx[1], -1, dep.cx[2], dep.cx[3],
-                                                    active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
-                                                    vx_c * vy_c, vy_c * vy_c, gamma_psi,
-                                                    dep.charge_mu0_mass_ratio * psi_inv * vx_c);
-        deposit_aggregated<true, false, true, true>(a, dep.cx[4], dep.cx[5], -1, dep.cx[6], dep.cx[7],
-                                                    active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
-                                                    vx_c * vx_c, gamma_psi - vy_c, gamma_psi,
-                                                    dep.charge_mu0_mass_ratio * psi_inv * vy_c);
-    }
 }
 
 inline unsigned nblocks(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
@@ -914,8 +900,7 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     if (hpb_use_generic_order(ctx)) return hpb_gen_explicit_deposition(ctx, pl, sl, charge, mass, comps);
     const hpb_geom &g = ctx->g;
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
-    static int variant = -1;
-    if (variant < 0) { const char *e = getenv("HPB_EXPL_VARIANT"); variant = e ? atoi(e) : 4; }
+    const int variant = ctx->tune_expl_variant;
     // (the laser variant uses the plain particle order)
     const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 1);
     const long nwarps = lattice_warps(pp, kExplOwn);
@@ -965,8 +950,7 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
                                       bc_hi, comps);
     }
     const hpb_geom &g = ctx->g;
-    static int variant = -1;
-    if (variant < 0) { const char *e = getenv("HPB_PUSH_VARIANT"); variant = e ? atoi(e) : 0; }
+    const int variant = ctx->tune_push_variant;
     DepositArgs dep = {};
     if (deposit) {
         const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
@@ -975,11 +959,6 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         dep.clightinv = 1.0 / g.c; dep.charge_invvol = charge * invvol;
         dep.charge_mu0_mass_ratio = charge * g.mu0 / mass;
         dep.max_qsa = max_qsa; dep.n_qsa_violation = d_n_qsa_violation;
-        static int exp12 = -1;
-        if (exp12 < 0) { const char *e = getenv("HPB_EXP_DEP12"); exp12 = e ? atoi(e) : 0; }
-        dep.exp_extra = exp12;
-        const int cx[8] = {HPB_C_SY, HPB_C_SX, HPB_C_EXMBY, HPB_C_EYPBX, HPB_C_PSI, HPB_C_EZ, HPB_C_BZ, HPB_C_EXMBY};
-        for (int k = 0; k < 8; ++k) dep.cx[k] = comps[cx[k]];
     }
     const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 2);
     const long nwarps = lattice_warps(pp, 32, kPushThreads / 32);

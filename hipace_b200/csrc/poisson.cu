@@ -499,8 +499,7 @@ int launch_rows_v(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs,
 template <class Src>
 int launch_rows(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, int nbatch, double scale)
 {
-    static int variant = -1;
-    if (variant < 0) { const char *e = getenv("HPB_FFT_VARIANT"); variant = e ? atoi(e) : 0; }
+    const int variant = ctx->tune_fft_variant;
     // 6 CTAs / SM: 1536 row-pair CTAs of a 1024^2 batch fit in two waves of 148 x 6 (measured best)
     if (variant == 1) return launch_rows_v<Src, kFftThreads, 5>(ctx, src, out, out_rs, nbatch, scale);
     return launch_rows_v<Src, kFftThreads, 6>(ctx, src, out, out_rs, nbatch, scale);

@@ -446,6 +446,29 @@ int read_deck(hpb_sim *s)
             s->beams.push_back(b);
         }
     }
+    // options whose default is what this implementation does: accepted at that value only
+    if ((int)d.num("amr.max_level", 0) != 0) throw std::runtime_error("amr.max_level > 0 (mesh refinement) is not supported");
+    if ((int)d.num("hipace.do_beam_jz_minus_rho", 0) != 0) throw std::runtime_error("hipace.do_beam_jz_minus_rho is not supported");
+    if (d.has("hipace.max_time")) throw std::runtime_error("hipace.max_time is not supported (use max_step)");
+    // Anything the deck sets that was not read above is an option of the reference this
+    // implementation does not have (ionisation, collisions, mesh refinement, SALAME, ...): refuse
+    // instead of running different physics.  Output-only and runtime-tuning groups are harmless.
+    const auto left = d.unused({"my_constants.", "amrex.", "diagnostic.", "hipace.verbose", "hipace.tile_size",
+                                "hipace.do_tiling", "hipace.output_period", "hipace.file_prefix",
+                                "hipace.openpmd_backend", "hipace.comms_buffer_", "hipace.do_device_synchronize",
+                                "hipace.m_numprocs", "hipace.numprocs_", "hipace.MG_verbose",
+                                "hipace.use_small_dst", "hipace.do_shared_depos"});
+    // (blocks of names the deck does not activate -- "beam.*" next to beams.names = no_beam --
+    // are inert in the reference as well)
+    std::set<std::string> groups = {"hipace", "amr", "geometry", "boundary", "plasmas", "beams", "lasers",
+                                    "grid_current", "max_step", "fields"};
+    for (auto &sp : s->plasmas) groups.insert(sp.name);
+    for (auto &b : s->beams) groups.insert(b.name);
+    for (auto &nm : d.strs("lasers.names")) groups.insert(nm);
+    std::string msg;
+    for (auto &k : left)
+        if (groups.count(k.substr(0, k.find('.')))) msg += " " + k;
+    if (!msg.empty()) throw std::runtime_error("unsupported or unknown input parameter(s):" + msg);
     return HPB_OK;
 }
 
@@ -700,7 +723,10 @@ int begin_step(hpb_sim *s, int step)
             SIM_CUDA(cudaMemcpyAsync(b.d_ts, b.ts, 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         }
     } else {
-        s->time = s->dt * step;
+        // the reference accumulates next_time = time + dt from step to step (Hipace.cpp:411-434);
+        // replaying the sum gives the same rounding on whichever rank owns the step
+        s->time = 0.;
+        for (int k = 0; k < step; ++k) s->time += s->dt;
     }
     const double c_t = s->g.c * s->time;
     if (s->use_laser && s->max_step > 0 && s->dt != 0.) {            // the envelope is stored and advanced
@@ -897,6 +923,10 @@ int beam_push_and_send(hpb_sim *s, int islice)
     const double min_z = s->prob_lo[2] + islice * s->g.dz;
     const double time = s->time;
     if ((rc = hpb_pipeline_wait_out_slot(s, islice))) return rc;
+    // the slipped particles of this slice are appended to the NEXT slice's packet: its receive must
+    // have landed whichever solver branch called us (the predictor-corrector branch only waits for
+    // it when it deposits the next slice's beam currents)
+    if (islice > 0 && (rc = hpb_pipeline_wait_slice(s, islice - 1))) return rc;
     for (auto &b : s->beams) {
         const BeamRing &in = b.ring[b.cur], &out = b.ring[b.cur ^ 1];
         const hpb_beam_slice bm = in.view(slot);
@@ -1344,7 +1374,6 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
         return HPB_ERR_PARSE;
     }
     s->device = device;
-    if (const char *e = getenv("HPB_FUSE")) s->opt_fuse = atoi(e) != 0;       // tuning / A-B runs
     SIM_CUDA(cudaSetDevice(device));
     SIM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     build_components(s.get());
@@ -1381,7 +1410,6 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     }
     SIM_CUDA(cudaEventCreate(&s->ev0));
     SIM_CUDA(cudaEventCreate(&s->ev1));
-    if (const char *e = getenv("HPB_SIDE_STREAM")) s->opt_side_stream = atoi(e) != 0;
     {
         // highest priority: the side stream's small kernels must get CTA slots while the plasma
         // push (tens of thousands of CTAs, launched at about the same time) is being dispatched
@@ -1450,7 +1478,9 @@ extern "C" int hpb_sim_solve_one_slice(hpb_sim *s, int islice)
 
 extern "C" int hpb_sim_evolve(hpb_sim *s, int step_begin, int step_end, int n_slices)
 {
-    if (!s || step_end < step_begin) return HPB_ERR_ARG;
+    if (!s) return HPB_ERR_ARG;
+    if (step_end < 0) step_end = s->max_step;        // the whole run of the deck (Hipace.cpp:401)
+    if (step_end < step_begin) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
     s->stats = hpb_sim_stats();
     s->mg_iters.clear();
@@ -1690,6 +1720,14 @@ extern "C" int hpb_sim_get_stats(hpb_sim *s, hpb_sim_stats *out)
     return HPB_OK;
 }
 
+extern "C" long hpb_sim_get_mg_iters(hpb_sim *s, int *h_out, long n)
+{
+    if (!s) return -1;
+    const long cnt = (long)s->mg_iters.size();
+    if (h_out) for (long k = 0; k < cnt && k < n; ++k) h_out[k] = s->mg_iters[k];
+    return cnt;
+}
+
 extern "C" int hpb_sim_timer_start(hpb_sim *s)
 {
     if (!s) return HPB_ERR_ARG;
@@ -1732,6 +1770,6 @@ extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
     else if (k == "side_stream") s->opt_side_stream = value != 0.;
     else if (k == "profile") s->opt_profile = value != 0.;
     else if (k == "max_step") s->max_step = (int)value;
-    else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }
+    else return hpb_set_option(s->ctx, key, value);      // kernel variants: the context's switches
     return HPB_OK;
 }

@@ -333,6 +333,12 @@ long hpb_debug_push_thread_map(long cells_per_pass, int ppc, int mode, long *out
  * hpb_slice.lo_x = lo_y = -guards.  The default has warp-aggregated, staged kernels; every other
  * combination runs one-thread-per-particle kernels (csrc/generic_order.cu). */
 int hpb_set_deposition_order(hpb_ctx *ctx, int order_xy, int derivative_type);
+/* behaviour switches of the kernels (A/B measurements and cross-checks; the library never reads the
+ * host's environment): "pdl" (programmatic dependent launch, process-wide, ctx may be NULL),
+ * "generic" (generic-order kernels for the default order too), "order" (bit mask: which particle
+ * kernels use the pass-interleaved thread map), "expl_variant", "push_variant", "fft_variant",
+ * "mg_wide", "mg_fuse" (launch geometry variants).  Unknown keys return HPB_ERR_ARG. */
+int hpb_set_option(hpb_ctx *ctx, const char *key, double value);
 int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
                                              double charge, double mass, int n_subcycles,
                                              int particle_bc, const double bc_lo[2],
@@ -375,7 +381,8 @@ int hpb_deck_check(const char *deck, const char *overrides, char *summary, size_
 void hpb_sim_destroy(hpb_sim *sim);
 
 /* Hipace::Evolve for time steps [step_begin, step_end] on this rank (all slices, or only the
- * first n_slices from the head if n_slices > 0).  Blocks until the device is idle. */
+ * first n_slices from the head if n_slices > 0); step_end < 0: up to the deck's max_step.
+ * Blocks until the device is idle. */
 int hpb_sim_evolve(hpb_sim *sim, int step_begin, int step_end, int n_slices);
 
 /* finer control for tests: begin a time step (plasma re-init + neutralising background,
@@ -422,6 +429,10 @@ typedef struct {
     double ms_deposit, ms_poisson, ms_explicit, ms_mg, ms_push, ms_other; /* if profiling on */
 } hpb_sim_stats;
 int hpb_sim_get_stats(hpb_sim *sim, hpb_sim_stats *out);
+/* multigrid V-cycles (or predictor-corrector iterations) of every slice of the last evolve, in
+ * slice-loop order (head first): what hpmg::MultiGrid::solve1 reports per call
+ * (src/mg_solver/HpMultiGrid.cpp:1307-1427).  Copies min(n, count) entries; returns the count. */
+long hpb_sim_get_mg_iters(hpb_sim *sim, int *h_out, long n);
 /* device-side stopwatch on the simulation stream: start records an event, stop records a second
  * one, waits for it and returns the elapsed device time (bench.py's timed region) */
 int hpb_sim_timer_start(hpb_sim *sim);

@@ -94,8 +94,35 @@ def lib():
         L.hpc_mg_solve1.restype = C.c_int
         L.hpc_mg_solve1.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
         L.hpc_num_threads.restype = C.c_int
+        L.hpc_set_num_threads.restype = C.c_int
+        L.hpc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
+
+
+def physical_cores():
+    """physical cores this process may run on (the reference's `nosmt` policy, Parser.H:80-82)"""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or avail
+    except Exception:
+        phys = avail
+    return max(1, min(avail, phys))
+
+
+_threads_override = None
+
+
+def set_threads(n):
+    """force the thread count of the C kernels AND of SciPy's DST (workers), whatever
+    OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)"""
+    global _threads_override
+    _threads_override = lib().hpc_set_num_threads(int(n))
+    return _threads_override
 
 
 class Simulation(O.Simulation):
@@ -180,9 +207,9 @@ class Simulation(O.Simulation):
         # three Poisson solves (Fields.cpp:880-918)
         L.hpc_poisson_rhs(_p(T('rhomjz')), _p(T('jx')), _p(T('jy')), g.nx, g.ny, _p(self._rhs),
                           -1.0 / pc.ep0, 1.0 / (pc.ep0 * pc.c), pc.mu0, g.dx, g.dy)
-        spec = _dstn(self._rhs, type=1, axes=(1, 2), workers=-1)
+        spec = _dstn(self._rhs, type=1, axes=(1, 2), workers=(_threads_override or -1))
         spec *= self.eig
-        sol = _dstn(spec, type=1, axes=(1, 2), workers=-1)
+        sol = _dstn(spec, type=1, axes=(1, 2), workers=(_threads_override or -1))
         for k, nm in enumerate(('Psi', 'Ez', 'Bz')):
             L.hpc_store_valid(_p(T(nm)), _p(sol[k]), g.nx, g.ny)
         L.hpc_exmby_eypbx(_p(T('Psi')), _p(T('ExmBy')), _p(T('EypBx')), g.nx, g.ny, g.dx, g.dy)

@@ -35,6 +35,19 @@ int hpc_num_threads(void)
 #endif
 }
 
+/* the caller decides the thread count (bench.py: the host's physical cores, whatever
+ * OMP_NUM_THREADS a launcher such as torchrun exported); returns the count in effect */
+int hpc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* ---- shape factors (src/particles/particles_utils/ShapeFactors.H) ----------------------- */
 
 /* compute_single_shape_factor<false,2>, :165-174 */

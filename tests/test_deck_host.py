@@ -83,6 +83,20 @@ def test_overrides_constants_and_expressions():
     ({'amr.n_cell': '64 64'}, '3 values'),
     ({'diagnostic.diag_type': 'yz'}, 'diag_type'),
     ({'beam.profile': 'parabolic'}, 'profile'),
+    # physics-changing options of the reference this implementation does not have: refused, never
+    # silently ignored (unknown keys used to be dropped)
+    ({'plasma.can_ionize': 1}, 'plasma.can_ionize'),
+    ({'plasma.ionization_product': 'elec'}, 'plasma.ionization_product'),
+    ({'hipace.collisions': 'c1'}, 'hipace.collisions'),
+    ({'plasma.do_symmetrize': 1}, 'plasma.do_symmetrize'),
+    ({'plasma.temperature_in_ev': 10.}, 'plasma.temperature_in_ev'),
+    ({'plasma.fine_patch(x,y)': '1'}, 'fine_patch'),
+    ({'beam.do_salame': 1}, 'beam.do_salame'),
+    ({'beam.random_ppc': '1 1 1'}, 'beam.random_ppc'),
+    ({'hipace.max_time': 3.}, 'max_time'),
+    ({'amr.max_level': 1}, 'max_level'),
+    ({'hipace.do_beam_jz_minus_rho': 1}, 'do_beam_jz_minus_rho'),
+    ({'hipace.no_such_option': 1}, 'hipace.no_such_option'),
 ])
 def test_unsupported_options_fail_loudly(ov, msg):
     import hipace_b200 as hp
@@ -90,6 +104,15 @@ def test_unsupported_options_fail_loudly(ov, msg):
     with pytest.raises(hp.HpbError) as e:
         hp.deck_check(text, ov)
     assert msg in str(e.value)
+
+
+def test_inert_and_output_only_keys_are_accepted():
+    """keys that cannot change the physics of the path (verbosity, diagnostics selection, AMReX
+    runtime switches) and blocks of names the deck does not activate are accepted, like the reference"""
+    import hipace_b200 as hp
+    text = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
+    hp.deck_check(text, {'hipace.verbose': 2, 'diagnostic.output_period': 3, 'amrex.the_arena_is_managed': 1,
+                         'amr.max_level': 0, 'other_beam.density': 3.})
 
 
 def test_laser_deck_is_accepted_for_step_zero_only():

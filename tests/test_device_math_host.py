@@ -1,6 +1,6 @@
 """The arithmetic of the CUDA particle kernels, RUN ON THE CPU.
 
-shapes.cuh / push_math.cuh / generic_order.cuh are __host__ __device__: csrc/host_check.cu calls the
+shapes.cuh / push_math.cuh / generic_order.cuh are __host__ __device__: tests/host_check.cu calls the
 very functions the kernels call (per-particle bodies of deposit, beam deposit, explicit deposition,
 gather, push; a plain += in place of the fp64 RED) and this file holds them to
   * the reference's own headers (oracle/ref_headers.cpp: ShapeFactors.H, FieldGather.H,

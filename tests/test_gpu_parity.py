@@ -176,6 +176,37 @@ def test_full_size_driver_orders_agree(repo_root):
         assert st['n_mg_vcycles'] == st0['n_mg_vcycles'], name
 
 
+@pytest.mark.parametrize('n_cell,nsl', [('1024 1024 1024', 48), ('1023 1023 1024', 48), ('256 256 512', 160)],
+                         ids=['configs2_1024', 'recommended_1023', 'configs1_256x512'])
+def test_full_size_matches_cport(n_cell, nsl, repo_root):
+    """The CUDA slice loop against the CPU restatement (oracle/cport: the C/OpenMP companion of the
+    NumPy oracle, itself pinned to the reference goldens in tests/test_cport.py) AT the benchmark
+    sizes: BASELINE configs[2] (1024 x 1024, ppc 4), the reference's recommended 2^n - 1 grid
+    (1023 x 1023) and configs[1] (256 x 256 x 512, ppc 4) -- nsl slices from the head of the box
+    through the beam head.  Field checksums to 1e-9, particle validity bit-exact, particle state to
+    1e-9, the same multigrid V-cycle count on every slice."""
+    import hipace_b200 as hp
+    from oracle import cport
+    text = _deck(repo_root, 'blowout_wake_normalized.in')
+    ov = {'amr.n_cell': n_cell, 'plasma.ppc': '2 2'}
+    cport.set_threads(cport.physical_cores())
+    ref = cport.Simulation(text, ov)
+    want = ref.evolve(nsl)
+    sim = hp.Simulation(text, ov)
+    got = sim.evolve(0, 0, nsl)
+    for k, w in want.items():
+        assert abs(got[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (k, got[k], w)
+    assert sim.mg_iters() == list(ref.mg_cycles), 'V-cycles per slice'
+    assert max(ref.mg_cycles) >= 2, 'the sample must reach the beam (more than the vacuum V-cycle)'
+    o, p = ref.plasmas[0], sim.plasma()
+    assert np.array_equal(p['valid'], o.valid)
+    for nm in ('x', 'y', 'ux', 'uy', 'psi', 'w'):
+        want_a = getattr(o, nm)
+        scale = max(np.abs(want_a).max(), 1e-300)
+        assert np.abs(p[nm] - want_a).max() / scale <= 1e-9, nm
+    sim.close()
+
+
 def test_si_units_deck_matches_oracle(repo_root):
     """hipace.normalized_units = 0: the SI constants, invvol = 1/(dx dy dz) and the dx dy dz / ppc
     weights through every kernel (the reference's examples/blowout_wake/inputs_SI restated).  The
