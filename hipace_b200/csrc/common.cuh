@@ -259,7 +259,14 @@ struct hpb_ctx {
     // kernel variants for A/B measurements (hpb_set_option; never read from the environment)
     int tune_order;           // bit mask of the particle kernels using the pass-interleaved map (default 1)
     int tune_expl_variant, tune_push_variant, tune_fft_variant, tune_mg_wide, tune_mg_fuse;
+    // TMA tensor maps over the caller's slice array (tma.cuh), re-encoded when the view changes:
+    // [0] the 40 x 6 gather patch of the push, [1] the patch of the explicit deposition
+    alignas(64) unsigned char tmap[2][128];
+    hpb_slice tmap_key[2];
+    int tmap_ok[2];
 };
+// the cached tensor map `which` for boxes of box_w x box_h cells of sl, or nullptr (-> cp.async path)
+const void *hpb_slice_tmap(hpb_ctx *ctx, int which, const hpb_slice &sl, int box_w, int box_h);
 // true when the particle kernels must take the generic-order path
 bool hpb_use_generic_order(const hpb_ctx *ctx);
 // fields.cu: ExmBy / EypBx from Psi (Fields.cpp:931-956), shared by the fused and the staged Poisson paths

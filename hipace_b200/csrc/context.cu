@@ -1,5 +1,6 @@
 // hpb_ctx life cycle and error reporting.
 #include "common.cuh"
+#include "tma.cuh"
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,6 +49,51 @@ extern "C" int hpb_set_option(hpb_ctx *ctx, const char *key, double value)
     else if (!strcmp(key, "mg_fuse")) ctx->tune_mg_fuse = v;
     else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }
     return HPB_OK;
+}
+
+bool hpb_encode_slice_tmap(const hpb_slice &sl, int box_w, int box_h, CUtensorMap *out)
+{
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess
+            && q == cudaDriverEntryPointSuccess)
+            encode = (EncodeTiled)fp;
+        else
+            (void)cudaGetLastError();
+    }
+    if (!encode || !sl.p || !out) return false;
+    // TMA needs a 16-byte aligned base and strides that are multiples of 16 bytes; the inner box
+    // extent must be a multiple of 16 bytes as well
+    if (((uintptr_t)sl.p & 15) || (sl.jstride & 1) || (sl.nstride & 1) || (box_w & 1) || box_w > 256
+        || box_h > 256 || sl.jstride < sl.nx_tot)
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)sl.nx_tot, (cuuint64_t)sl.ny_tot, (cuuint64_t)sl.ncomp};
+    const cuuint64_t strides[2] = {(cuuint64_t)sl.jstride * sizeof(double), (cuuint64_t)sl.nstride * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, sl.p, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+const void *hpb_slice_tmap(hpb_ctx *ctx, int which, const hpb_slice &sl, int box_w, int box_h)
+{
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    hpb_slice &k = ctx->tmap_key[which];
+    if (!(k.p == sl.p && k.nx_tot == sl.nx_tot && k.ny_tot == sl.ny_tot && k.jstride == sl.jstride
+          && k.nstride == sl.nstride && k.ncomp == sl.ncomp)) {
+        k = sl;
+        ctx->tmap_ok[which] = hpb_encode_slice_tmap(sl, box_w, box_h, (CUtensorMap *)ctx->tmap[which]) ? 1 : 0;
+    }
+    return ctx->tmap_ok[which] ? ctx->tmap[which] : nullptr;
 }
 
 extern "C" int hpb_set_deposition_order(hpb_ctx *ctx, int order_xy, int derivative_type)

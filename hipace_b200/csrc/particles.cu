@@ -11,6 +11,8 @@
 //   src/utils/DualNumbers.H:13-43, src/particles/pusher/GetAndSetPosition.H:29-99
 #include "common.cuh"
 #include "push_math.cuh"
+#include "tma.cuh"
+#include <string.h>
 
 namespace {
 
@@ -764,6 +766,587 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
                                                 dep.charge_mu0_mass_ratio * psi_inv);
 }
 
+
+// -------------------------------------------------------------------------------------------
+// CTA-tile gather + push + deposit (the default for lattice-ordered plasmas with ppc 4 or 9)
+// -------------------------------------------------------------------------------------------
+// The NW = ppc warps of a CTA work on the NW passes of the SAME 32 lattice cells (InitParticles
+// order: pass p of cell c is particle p * lat_n + c), so until the plasma has been stirred all
+// 32 * NW particles of a CTA sit in one ~35 x 5 cell patch.  Three things follow:
+//   * the five gathered field patches are staged ONCE per CTA -- by five TMA box loads
+//     (cp.async.bulk.tensor.3d, one elected thread, completion on an mbarrier) instead of ~50
+//     LDGSTS per warp; that per-warp staging loop was 27 % of all executed instructions of the
+//     round-1 kernel (ncu source page) in an issue-bound kernel;
+//   * every slice plane is fetched from DRAM once per slice instead of once per ppc pass
+//     (round 1: 1.46 x the algorithmic DRAM traffic);
+//   * the deposits of the NW passes go to the same cells: after the warp-shuffle aggregation of
+//     neighbouring lanes the NW warps combine their centre columns through shared memory (plain
+//     stores and loads, no shared-memory atomics) and issue 12 / NW fp64 reductions per lane
+//     instead of 12 -- the same-address RED contention that made the pass-interleaved map lose
+//     in round 1 is gone.
+// Lanes whose particle has left the patch (sheath, trajectory crossing) gather with direct loads
+// and deposit with their own reductions: the result never depends on the particle order.
+constexpr int kCW = 40, kCH = 6;
+constexpr uint32_t kCtaTileBytes = 5 * kCH * kCW * sizeof(double);
+constexpr int kNoCell = -(1 << 28);
+
+template <int NW>
+struct CtaShared {
+    alignas(128) double tile[5][kCH][kCW];   // Psi, Ez, Bx, By, Bz patch (TMA destination)
+    double comb[NW][12][32];                 // per warp: {jx, jy, chi, rhomjz} x 3 rows of the centre column
+    int ref_cc[32], ref_j0[32];              // warp 0's deposit cells: the cells the CTA combines on
+    int wbox[NW][4];                         // per warp: min i0, min j0 (gather stencil origins)
+    alignas(8) uint64_t mbar;
+};
+
+// Neighbour-lane aggregation of deposit_aggregated, but the centre column is RETURNED (v[comp * 3 +
+// row], comp = jx, jy, chi, rhomjz) instead of reduced; side columns without an aligned neighbour
+// lane are reduced here by the particle itself.  Must be called by all 32 lanes.
+__device__ __forceinline__ void
+deposit_centre_column(const SliceView &a, int c_jx, int c_jy, int c_chi, int c_rhomjz, bool active, int lane,
+                      int i0, int j0, const double sx[3], const double sy[3], double q_invvol, double vx_c,
+                      double vy_c, double chi_fac, double v[12])
+{
+    const int cc = active ? i0 + 1 : kNoCell - 3 * lane;
+    const int cL = __shfl_up_sync(kFull, cc, 1), jL = __shfl_up_sync(kFull, j0, 1);
+    const int cR = __shfl_down_sync(kFull, cc, 1), jR = __shfl_down_sync(kFull, j0, 1);
+    const bool L_ok = active && lane > 0 && cL == cc - 1 && jL == j0;
+    const bool R_ok = active && lane < 31 && cR == cc + 1 && jR == j0;
+    const double vxL = __shfl_up_sync(kFull, vx_c, 1), vxR = __shfl_down_sync(kFull, vx_c, 1);
+    const double vyL = __shfl_up_sync(kFull, vy_c, 1), vyR = __shfl_down_sync(kFull, vy_c, 1);
+    const double cfL = __shfl_up_sync(kFull, chi_fac, 1), cfR = __shfl_down_sync(kFull, chi_fac, 1);
+    double P0[3], P2[3];
+#pragma unroll
+    for (int iy = 0; iy < 3; ++iy) {
+        P0[iy] = q_invvol * sx[0] * sy[iy];
+        const double P1 = q_invvol * sx[1] * sy[iy];
+        P2[iy] = q_invvol * sx[2] * sy[iy];
+        double PL = __shfl_up_sync(kFull, P2[iy], 1);        // right column of the left neighbour
+        double PR = __shfl_down_sync(kFull, P0[iy], 1);      // left column of the right neighbour
+        if (!L_ok) PL = 0.;
+        if (!R_ok) PR = 0.;
+        v[0 + iy] = P1 * vx_c + PL * vxL + PR * vxR;
+        v[3 + iy] = P1 * vy_c + PL * vyL + PR * vyR;
+        v[6 + iy] = P1 * chi_fac + PL * cfL + PR * cfR;
+        v[9 + iy] = P1 + PL + PR;
+    }
+    if (!active || (L_ok && R_ok)) return;
+    double *jx = a.comp(c_jx), *jy = a.comp(c_jy), *chi = a.comp(c_chi), *rmj = a.comp(c_rhomjz);
+#pragma unroll
+    for (int iy = 0; iy < 3; ++iy) {
+        const long o = a.idx(cc, j0 + iy);
+        if (!L_ok) {
+            red_add(jx + o - 1, P0[iy] * vx_c); red_add(jy + o - 1, P0[iy] * vy_c);
+            red_add(chi + o - 1, P0[iy] * chi_fac); red_add(rmj + o - 1, P0[iy]);
+        }
+        if (!R_ok) {
+            red_add(jx + o + 1, P2[iy] * vx_c); red_add(jy + o + 1, P2[iy] * vy_c);
+            red_add(chi + o + 1, P2[iy] * chi_fac); red_add(rmj + o + 1, P2[iy]);
+        }
+    }
+}
+
+template <int NW, int MINB, bool DEPOSIT, bool TMA>
+__global__ void __launch_bounds__(NW * 32, MINB)
+k_advance_plasma_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtensorMap tmap, int nx_tot,
+                     int ny_tot, int lat_nx, int c_psi, int c_ez, int c_bx, int c_by, int c_bz, double x_off,
+                     double y_off, double dx_inv, double dy_inv, double clight, double qmc, double dz,
+                     int n_subcycles, int temp_slice, int bc, double lox, double loy, double hix, double hiy,
+                     DepositArgs dep)
+{
+    __shared__ CtaShared<NW> sh;
+    hpb_pdl_prologue();
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // the 32 lattice cells of this CTA: a run inside one lattice row when the row length is known
+    long cell;
+    bool in_range;
+    if (lat_nx > 0) {
+        const unsigned gpr = (unsigned)(lat_nx + 31) >> 5, g = blockIdx.x;
+        const unsigned row = g / gpr, col = (g - row * gpr) * 32 + lane;
+        cell = (long)row * lat_nx + col;
+        in_range = col < (unsigned)lat_nx && cell < pl.lat_n;
+    } else {
+        cell = (long)blockIdx.x * 32 + lane;
+        in_range = cell < pl.lat_n;
+    }
+    const long ip = (long)w * pl.lat_n + cell;
+    uint64_t idcpu = 0;
+    double xp0 = 0., yp0 = 0., ux0 = 0., uy0 = 0., psi0 = 1., wq = 0.;
+    if (in_range) {
+        idcpu = ld_stream(&pl.idcpu[ip]);
+        xp0 = ld_stream(&pl.r[HPB_X_PREV][ip]);
+        yp0 = ld_stream(&pl.r[HPB_Y_PREV][ip]);
+        ux0 = ld_stream(&pl.r[HPB_UX_HALF][ip]);
+        uy0 = ld_stream(&pl.r[HPB_UY_HALF][ip]);
+        psi0 = ld_stream(&pl.r[HPB_PSI_HALF][ip]);
+        if (DEPOSIT) wq = ld_stream(&pl.r[HPB_W][ip]);
+    }
+    // Prefetch: the lattice says where the CTA's particles started, and most of the plasma has moved
+    // less than a cell or two from there -- the patch around the home cells is requested NOW, in the
+    // shadow of the particle loads, instead of after them (one DRAM/L2 round trip instead of two).
+    int bi = 0, bj = 0;
+    const bool prefetched = TMA && lat_nx > 0;
+    if (TMA && tid == 0) {
+        hpb_tma_prefetch_desc(&tmap);
+        hpb_mbar_init(&sh.mbar, 1);
+    }
+    if (prefetched) {
+        const unsigned gpr = (unsigned)(lat_nx + 31) >> 5, g = blockIdx.x;
+        const unsigned row = g / gpr;
+        bi = (int)((g - row * gpr) * 32) - 4;     // stencil origins col - 2 .. col - 1, 4 wide: cols col - 2 .. col + 2
+        bj = (int)row - 3;                         // rows row - 2 .. row + 2
+        if (tid == 0) {
+            const int ax = bi - a.lo_x, ay = bj - a.lo_y;
+            hpb_mbar_arrive_expect_tx(&sh.mbar, kCtaTileBytes);
+            hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_psi);
+            hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
+            hpb_tma_load_3d(&sh.tile[2][0][0], &tmap, &sh.mbar, ax, ay, c_bx);
+            hpb_tma_load_3d(&sh.tile[3][0][0], &tmap, &sh.mbar, ax, ay, c_by);
+            hpb_tma_load_3d(&sh.tile[4][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
+        }
+    }
+    bool valid = in_range && hpb_is_valid(idcpu);
+    const double clight_inv = 1.0 / clight;
+    const double *F0 = a.comp(c_psi), *F1 = a.comp(c_ez), *F2 = a.comp(c_bx);
+    const double *F3 = a.comp(c_by), *F4 = a.comp(c_bz);
+    double xp = xp0, yp = yp0, ux = ux0, uy = uy0, psi = psi0;
+    uint32_t phase = 0;
+
+    for (int isc = 0; isc < n_subcycles; ++isc) {
+        xp = xp0; yp = yp0;
+        double sx[4], dsx[4], sy[4], dsy[4];
+        const int i0 = dshape2_nodal((xp - x_off) * dx_inv, sx, dsx);
+        const int j0 = dshape2_nodal((yp - y_off) * dy_inv, sy, dsy);
+        // bounding box of the CTA's stencil origins
+        const int big = 1 << 30;
+        const int imin = __reduce_min_sync(kFull, valid ? i0 : big), imax = __reduce_max_sync(kFull, valid ? i0 : -big);
+        const int jmin = __reduce_min_sync(kFull, valid ? j0 : big), jmax = __reduce_max_sync(kFull, valid ? j0 : -big);
+        if (lane == 0) { sh.wbox[w][0] = imin; sh.wbox[w][1] = jmin; sh.wbox[w][2] = imax; sh.wbox[w][3] = jmax; }
+        __syncthreads();        // (also: the old tile has been consumed)
+        int ci = big, cj = big, ei = -big, ej = -big;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            ci = min(ci, sh.wbox[q][0]); cj = min(cj, sh.wbox[q][1]);
+            ei = max(ei, sh.wbox[q][2]); ej = max(ej, sh.wbox[q][3]);
+        }
+        const bool any = ci != big;
+        // the prefetched patch serves if every stencil of the CTA lies inside it; otherwise the patch
+        // is (re)staged at the bounding box origin, and particles that do not fit even that (a stirred
+        // group) gather with direct loads
+        const bool pre_ok = prefetched && isc == 0 && any && ci >= bi && ei + 4 <= bi + kCW && cj >= bj
+                            && ej + 4 <= bj + kCH;
+        if (prefetched && isc == 0 && !pre_ok) {   // drain the prefetch before its buffer is rewritten
+            hpb_mbar_wait(&sh.mbar, phase); phase ^= 1u;
+            __syncthreads();
+        }
+        if (any && !pre_ok) {
+            bi = ci; bj = cj;
+            const int ax = bi - a.lo_x, ay = bj - a.lo_y;      // array coordinates of the patch origin
+            if (TMA) {
+                if (tid == 0) {
+                    hpb_fence_proxy_async();
+                    hpb_mbar_arrive_expect_tx(&sh.mbar, kCtaTileBytes);
+                    hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_psi);
+                    hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
+                    hpb_tma_load_3d(&sh.tile[2][0][0], &tmap, &sh.mbar, ax, ay, c_bx);
+                    hpb_tma_load_3d(&sh.tile[3][0][0], &tmap, &sh.mbar, ax, ay, c_by);
+                    hpb_tma_load_3d(&sh.tile[4][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
+                }
+            } else {
+                // the same patch with asynchronous 8-byte copies by all threads (arrays the TMA unit
+                // cannot address: odd row length); cells outside the array are never read
+#pragma unroll 1
+                for (int e = tid; e < 5 * kCH * kCW; e += NW * 32) {
+                    const int f = e / (kCH * kCW), rem = e - f * (kCH * kCW), r = rem / kCW, c = rem - r * kCW;
+                    const double *F = f == 0 ? F0 : f == 1 ? F1 : f == 2 ? F2 : f == 3 ? F3 : F4;
+                    if (ax + c >= 0 && ay + r >= 0 && ax + c < nx_tot && ay + r < ny_tot)
+                        cp_async_8(&sh.tile[f][r][c], F + (long)(ay + r) * a.jstride + (ax + c));
+                }
+                cp_async_wait_all();
+                __syncthreads();
+            }
+        }
+        const bool staged = any && i0 >= bi && i0 + 4 <= bi + kCW && j0 >= bj && j0 + 4 <= bj + kCH;
+        if (TMA && any) { hpb_mbar_wait(&sh.mbar, phase); phase ^= 1u; }
+        if (valid) {
+            PushFields f;
+            if (staged) {
+                const double *t0 = &sh.tile[0][j0 - bj][i0 - bi];
+                f = gather_rows([&](int fi, int ix, int iy) { return t0[fi * (kCH * kCW) + iy * kCW + ix]; },
+                                sx, dsx, sy, dsy, dx_inv, dy_inv);
+            } else {
+                const long o = a.idx(i0, j0);
+                const long js = a.jstride;
+                f = gather_rows([&](int fi, int ix, int iy) {
+                        const double *F = fi == 0 ? F0 : fi == 1 ? F1 : fi == 2 ? F2 : fi == 3 ? F3 : F4;
+                        return F[o + iy * js + ix];
+                    }, sx, dsx, sy, dsy, dx_inv, dy_inv);
+            }
+            f.Bx_c *= clight;
+            f.By_c *= clight;
+            const PushLaser las = {0., 0., 0.};
+            constexpr int nsub = 4;
+            const double sdz = dz / nsub;
+            ux = ux0; uy = uy0; psi = psi0;
+#pragma unroll 1
+            for (int isub = 0; isub < nsub; ++isub) push_substep<false>(ux, uy, psi, f, clight_inv, qmc, sdz, las);
+
+            xp += dz * clight_inv * (ux * (1.0 / psi));
+            yp += dz * clight_inv * (uy * (1.0 / psi));
+            if (enforce_bc(xp, yp, ux, uy, bc, lox, loy, hix, hiy)) {
+                st_stream(&pl.r[HPB_W][ip], 0.0);
+                st_stream(&pl.idcpu[ip], hpb_make_invalid(idcpu));
+                valid = false;
+            } else {
+                st_stream(&pl.r[HPB_X][ip], xp);
+                st_stream(&pl.r[HPB_Y][ip], yp);
+                if (!temp_slice) {
+                    st_stream(&pl.r[HPB_UX_HALF][ip], ux);
+                    st_stream(&pl.r[HPB_UY_HALF][ip], uy);
+                    st_stream(&pl.r[HPB_PSI_HALF][ip], psi);
+                    st_stream(&pl.r[HPB_X_PREV][ip], xp);
+                    st_stream(&pl.r[HPB_Y_PREV][ip], yp);
+                    xp0 = xp; yp0 = yp; ux0 = ux; uy0 = uy; psi0 = psi;
+                }
+#pragma unroll 1
+                for (int isub = 0; isub < nsub / 2; ++isub) push_substep<false>(ux, uy, psi, f, clight_inv, qmc, sdz, las);
+                st_stream(&pl.r[HPB_UX][ip], ux);
+                st_stream(&pl.r[HPB_UY][ip], uy);
+                st_stream(&pl.r[HPB_PSI][ip], psi);
+            }
+        }
+    }
+    if (!DEPOSIT) return;
+
+    // ::DepositCurrent of the pushed particle (same expressions as k_deposit_current)
+    bool active = valid;
+    const double psi_inv = 1.0 / psi;
+    const double vx_c = ux * psi_inv, vy_c = uy * psi_inv;
+    double q_invvol = dep.charge_invvol * wq;
+    const double gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * dep.clightinv * dep.clightinv
+                                    + vy_c * vy_c * dep.clightinv * dep.clightinv + 1.0);
+    if (active && (gamma_psi < 0.0 || gamma_psi > dep.max_qsa || psi_inv < 0.0)) {
+        if (dep.n_qsa_violation) atomicAdd(dep.n_qsa_violation, 1);
+        st_stream(&pl.r[HPB_W][ip], 0.0);
+        st_stream(&pl.idcpu[ip], hpb_make_invalid(idcpu));
+        active = false;
+    }
+    double dsx3[3] = {0., 0., 0.}, dsy3[3] = {0., 0., 0.};
+    int di0 = 0, dj0 = 0;
+    if (active) {
+        di0 = shape2((xp - x_off) * dx_inv, dsx3);
+        dj0 = shape2((yp - y_off) * dy_inv, dsy3);
+    } else {
+        q_invvol = 0.;
+    }
+    double v[12];
+    deposit_centre_column(a, dep.c_jx, dep.c_jy, dep.c_chi, dep.c_rhomjz, active, lane, di0, dj0, dsx3, dsy3,
+                          q_invvol, vx_c, vy_c, dep.charge_mu0_mass_ratio * psi_inv, v);
+    // combine the centre columns of the NW passes on warp 0's cells
+    const int cc = active ? di0 + 1 : kNoCell - 3 * lane;
+    if (w == 0) { sh.ref_cc[lane] = cc; sh.ref_j0[lane] = dj0; }
+    __syncthreads();
+    const int rcc = sh.ref_cc[lane], rj0 = sh.ref_j0[lane];
+    const bool match = active && cc == rcc && dj0 == rj0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) sh.comb[w][k][lane] = match ? v[k] : 0.;
+    if (active && !match) {     // this pass has left warp 0's cell: its own reductions
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+            const long o = a.idx(cc, dj0 + iy);
+            red_add(a.comp(dep.c_jx) + o, v[0 + iy]);
+            red_add(a.comp(dep.c_jy) + o, v[3 + iy]);
+            red_add(a.comp(dep.c_chi) + o, v[6 + iy]);
+            red_add(a.comp(dep.c_rhomjz) + o, v[9 + iy]);
+        }
+    }
+    __syncthreads();
+    if (rcc <= kNoCell) return;     // warp 0's lane holds no particle: nobody matched it
+#pragma unroll
+    for (int kk = 0; kk < (12 + NW - 1) / NW; ++kk) {
+        const int k = w + kk * NW;
+        if (k >= 12) break;
+        double sum = 0.;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) sum += sh.comb[q][k][lane];
+        const int comp = k < 3 ? dep.c_jx : k < 6 ? dep.c_jy : k < 9 ? dep.c_chi : dep.c_rhomjz;
+        const int row = k - (k / 3) * 3;
+        red_add(a.comp(comp) + a.idx(rcc, rj0 + row), sum);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// CTA-tile explicit deposition (lattice-ordered plasmas with ppc 4 or 9)
+// -------------------------------------------------------------------------------------------
+// Same idea as k_advance_plasma_cta: the NW warps of a CTA hold the NW passes of the same 28
+// lattice cells (+ 2 feed-only lanes on each side, see k_explicit_deposition).  The four field
+// planes the owned centre columns read (Bz, Ez, ExmBy, EypBx: 3 rows each) arrive as ONE TMA patch
+// per CTA, requested before the particle loads return (the round-1 kernel was latency bound on the
+// second, dependent round trip: long-scoreboard stalls 3.4 per issue at 26 % occupancy), and the 10
+// accumulated values of every centre column are combined across the passes in shared memory before
+// the fp64 reductions: 10 / NW REDs per lane instead of 10.
+constexpr int kEW = 40, kEH = 6;
+constexpr uint32_t kExplTileBytes = 4 * kEH * kEW * sizeof(double);
+
+template <int NW>
+struct ExplShared {
+    alignas(128) double tile[4][kEH][kEW];   // Bz, Ez, ExmBy, EypBx
+    double comb[NW][10][32];                 // per warp: Sy rows 0..4, Sx rows 0..4 of the centre column
+    int ref_cc[32], ref_j0[32];
+    int wbox[NW][4];
+    alignas(8) uint64_t mbar;
+};
+
+template <int NW, int MINB, bool TMA>
+__global__ void __launch_bounds__(NW * 32, MINB)
+k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtensorMap tmap, int nx_tot,
+                          int ny_tot, int lat_nx, int c_sy, int c_sx, int c_bz, int c_ez, int c_exmby,
+                          int c_eypbx, double x_off, double y_off, double dx_inv, double dy_inv,
+                          double a_clight, double clight_inv, double charge_invvol_mu0, double q_mass_ratio)
+{
+    __shared__ ExplShared<NW> sh;
+    hpb_pdl_prologue();
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // 28 owned lattice cells per CTA, lanes 0, 1, 30, 31 only feed their neighbours
+    long cell;
+    bool active;
+    int col0 = 0, row = 0;
+    if (lat_nx > 0) {
+        const unsigned gpr = (unsigned)(lat_nx + kExplOwn - 1) / kExplOwn, g = blockIdx.x;
+        row = (int)(g / gpr);
+        col0 = (int)(g - (unsigned)row * gpr) * kExplOwn;
+        const int col = col0 - 2 + lane;
+        cell = (long)row * lat_nx + col;
+        active = col >= 0 && col < lat_nx && cell < pl.lat_n;
+    } else {
+        cell = (long)blockIdx.x * kExplOwn - 2 + lane;
+        active = cell >= 0 && cell < pl.lat_n;
+    }
+    const long ip = (long)w * pl.lat_n + cell;
+    const bool owner = lane >= 2 && lane < 2 + kExplOwn;
+
+    int bi = 0, bj = 0;
+    const bool prefetched = TMA && lat_nx > 0;
+    if (TMA && tid == 0) {
+        hpb_tma_prefetch_desc(&tmap);
+        hpb_mbar_init(&sh.mbar, 1);
+    }
+    if (prefetched) {
+        bi = col0 - 6;          // owned centre columns col0 .. col0 + 27, 6 cells of slack on each side
+        bj = row - 3;           // rows row - 1 .. row + 1, two / one row(s) of slack
+        if (tid == 0) {
+            const int ax = bi - a.lo_x, ay = bj - a.lo_y;
+            hpb_mbar_arrive_expect_tx(&sh.mbar, kExplTileBytes);
+            hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
+            hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
+            hpb_tma_load_3d(&sh.tile[2][0][0], &tmap, &sh.mbar, ax, ay, c_exmby);
+            hpb_tma_load_3d(&sh.tile[3][0][0], &tmap, &sh.mbar, ax, ay, c_eypbx);
+        }
+    }
+
+    double vx = 0., vy = 0., gamma_psi = 1., yint = 0.;
+    double sx[5] = {0., 0., 0., 0., 0.}, dsx[5] = {0., 0., 0., 0., 0.};
+    ExplPart e = {};
+    int i0 = 0, j0 = 0;
+    if (active) {
+        const uint64_t idcpu = ld_stream(&pl.idcpu[ip]);
+        const double psi = ld_stream(&pl.r[HPB_PSI][ip]);
+        const double xp = ld_stream(&pl.r[HPB_X][ip]);
+        const double yp = ld_stream(&pl.r[HPB_Y][ip]);
+        const double ux = ld_stream(&pl.r[HPB_UX][ip]);
+        const double uy = ld_stream(&pl.r[HPB_UY][ip]);
+        const double wt = ld_stream(&pl.r[HPB_W][ip]);
+        active = hpb_is_valid(idcpu);
+        if (active) {
+            const double psi_inv = 1.0 / psi;
+            vx = ux * psi_inv * clight_inv;
+            vy = uy * psi_inv * clight_inv;
+            const double cdm = charge_invvol_mu0 * wt;
+            gamma_psi = 0.5 * (psi_inv * psi_inv + vx * vx + vy * vy + 1.0);
+            i0 = dshape2_centered((xp - x_off) * dx_inv, sx, dsx);
+            const double ym = (yp - y_off) * dy_inv + 0.5;
+            const double yfl = floor(ym);
+            yint = ym - yfl;
+            j0 = (int)yfl - 2;
+            e = expl_part(vx, vy, gamma_psi, cdm, psi_inv, q_mass_ratio, a_clight);
+        }
+    }
+    const int cc = active ? i0 + 2 : kNoCell - 7 * lane;      // centre column / sentinel
+    const double *Bz = a.comp(c_bz), *Ez = a.comp(c_ez);
+    const double *ExmBy = a.comp(c_exmby), *EypBx = a.comp(c_eypbx);
+    double *Sy = a.comp(c_sy), *Sx = a.comp(c_sx);
+
+    // bounding box of the owned centre cells (rows j0 + 1 .. j0 + 3) of the whole CTA
+    {
+        const int big = 1 << 30;
+        const bool own = active && owner;
+        const int imin = __reduce_min_sync(kFull, own ? cc : big), imax = __reduce_max_sync(kFull, own ? cc : -big);
+        const int jmin = __reduce_min_sync(kFull, own ? j0 + 1 : big), jmax = __reduce_max_sync(kFull, own ? j0 + 3 : -big);
+        if (lane == 0) { sh.wbox[w][0] = imin; sh.wbox[w][1] = jmin; sh.wbox[w][2] = imax; sh.wbox[w][3] = jmax; }
+    }
+    __syncthreads();
+    bool any;
+    {
+        const int big = 1 << 30;
+        int ci = big, cj = big, ei = -big, ej = -big;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            ci = min(ci, sh.wbox[q][0]); cj = min(cj, sh.wbox[q][1]);
+            ei = max(ei, sh.wbox[q][2]); ej = max(ej, sh.wbox[q][3]);
+        }
+        any = ci != big;
+        const bool pre_ok = prefetched && any && ci >= bi && ei < bi + kEW && cj >= bj && ej < bj + kEH;
+        if (prefetched && !pre_ok) {       // drain the prefetch before its buffer is rewritten
+            hpb_mbar_wait(&sh.mbar, 0);
+            __syncthreads();
+        }
+        if (any && !pre_ok) {
+            bi = ci - 2; bj = cj;
+            const int ax = bi - a.lo_x, ay = bj - a.lo_y;
+            if (TMA) {
+                if (tid == 0) {
+                    hpb_fence_proxy_async();
+                    hpb_mbar_arrive_expect_tx(&sh.mbar, kExplTileBytes);
+                    hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
+                    hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
+                    hpb_tma_load_3d(&sh.tile[2][0][0], &tmap, &sh.mbar, ax, ay, c_exmby);
+                    hpb_tma_load_3d(&sh.tile[3][0][0], &tmap, &sh.mbar, ax, ay, c_eypbx);
+                }
+            } else {
+#pragma unroll 1
+                for (int q = tid; q < 4 * kEH * kEW; q += NW * 32) {
+                    const int f = q / (kEH * kEW), rem = q - f * (kEH * kEW), r = rem / kEW, c = rem - r * kEW;
+                    const double *F = f == 0 ? Bz : f == 1 ? Ez : f == 2 ? ExmBy : EypBx;
+                    if (ax + c >= 0 && ay + r >= 0 && ax + c < nx_tot && ay + r < ny_tot)
+                        cp_async_8(&sh.tile[f][r][c], F + (long)(ay + r) * a.jstride + (ax + c));
+                }
+                cp_async_wait_all();
+                __syncthreads();
+            }
+        }
+        if (TMA && any) hpb_mbar_wait(&sh.mbar, (prefetched && !pre_ok) ? 1u : 0u);
+    }
+
+    // fields at the three inner rows of the owned column: from the patch, or straight from the slice
+    // if the particle has left it
+    double fBz[3], fEz[3], fEx[3], fEy[3];
+    const bool staged = any && active && owner && cc >= bi && cc < bi + kEW && j0 + 1 >= bj && j0 + 3 < bj + kEH;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        fBz[r] = fEz[r] = fEx[r] = fEy[r] = 0.;
+        if (staged) {
+            const double *t = &sh.tile[0][j0 + 1 + r - bj][cc - bi];
+            fBz[r] = t[0]; fEz[r] = t[kEH * kEW]; fEx[r] = t[2 * kEH * kEW]; fEy[r] = t[3 * kEH * kEW];
+        } else if (active && owner) {
+            const long o = a.idx(cc, j0 + 1 + r);
+            fBz[r] = Bz[o]; fEz[r] = Ez[o]; fEx[r] = ExmBy[o]; fEy[r] = EypBx[o];
+        }
+    }
+    double accy[5] = {0., 0., 0., 0., 0.}, accx[5] = {0., 0., 0., 0., 0.};
+    unsigned absorbed = 0;      // bit ix set: my column ix is deposited by the lane that owns it
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) {
+        const int src = lane + d;
+        const int srcl = src < 0 ? 0 : (src > 31 ? 31 : src);
+        const ExplCol mine = expl_col(e, sx[2 - d], dsx[2 - d], dx_inv, dy_inv);
+        if (d == -2 || d == 2) {
+            const int c_s = __shfl_sync(kFull, cc, srcl), j_s = __shfl_sync(kFull, j0, srcl);
+            const double B = __shfl_sync(kFull, mine.B, srcl), Bp = __shfl_sync(kFull, mine.Bp, srcl);
+            const double yint_s = __shfl_sync(kFull, yint, srcl);
+            const bool ok = active && owner && src >= 0 && src <= 31 && c_s == cc + d && j_s == j0;
+            if (ok) {
+                absorbed |= 1u << (2 + d);
+                double shy[5], shdy[5];
+                dshape2_centered_frac(yint_s, shy, shdy);
+#pragma unroll
+                for (int r = 1; r <= 3; ++r) { accy[r] += shy[r] * B; accx[r] += shy[r] * Bp; }
+            }
+        } else {
+            ExplCol k;
+            double vx_s, vy_s, gp_s, yint_s;
+            bool ok;
+            if (d == 0) {
+                k = mine; vx_s = vx; vy_s = vy; gp_s = gamma_psi; yint_s = yint; ok = active && owner;
+            } else {
+                const int c_s = __shfl_sync(kFull, cc, srcl), j_s = __shfl_sync(kFull, j0, srcl);
+                k.A = __shfl_sync(kFull, mine.A, srcl);   k.B = __shfl_sync(kFull, mine.B, srcl);
+                k.C = __shfl_sync(kFull, mine.C, srcl);   k.Ap = -k.A;
+                k.Bp = __shfl_sync(kFull, mine.Bp, srcl); k.Cp = __shfl_sync(kFull, mine.Cp, srcl);
+                vx_s = __shfl_sync(kFull, vx, srcl);      vy_s = __shfl_sync(kFull, vy, srcl);
+                gp_s = __shfl_sync(kFull, gamma_psi, srcl);
+                yint_s = __shfl_sync(kFull, yint, srcl);
+                ok = active && owner && src >= 0 && src <= 31 && c_s == cc + d && j_s == j0;
+                if (ok) absorbed |= 1u << (2 + d);
+            }
+            if (ok) {
+                const double a3 = -vx_s * vy_s, a4 = gp_s - vy_s * vy_s, a5 = gp_s - vx_s * vx_s;
+                double shy[5], shdy[5];
+                dshape2_centered_frac(yint_s, shy, shdy);
+                accy[0] += shdy[0] * k.C; accx[0] += shdy[0] * k.Cp;      // shy[0] = shy[4] = 0
+                accy[4] += shdy[4] * k.C; accx[4] += shdy[4] * k.Cp;
+#pragma unroll
+                for (int r = 1; r <= 3; ++r)
+                    expl_cell(k, vx_s, vy_s, a3, a4, a5, shy[r], shdy[r], fBz[r - 1], fEz[r - 1],
+                              fEx[r - 1], fEy[r - 1], clight_inv, accy[r], accx[r]);
+            }
+        }
+    }
+    // combine the centre columns of the NW passes on warp 0's cells
+    const bool own = active && owner;
+    if (w == 0) { sh.ref_cc[lane] = own ? cc : kNoCell - 7 * lane; sh.ref_j0[lane] = j0; }
+    __syncthreads();
+    const int rcc = sh.ref_cc[lane], rj0 = sh.ref_j0[lane];
+    const bool match = own && cc == rcc && j0 == rj0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        sh.comb[w][k][lane] = match ? accy[k] : 0.;
+        sh.comb[w][5 + k][lane] = match ? accx[k] : 0.;
+    }
+    if (own && !match) {
+#pragma unroll
+        for (int iy = 0; iy < 5; ++iy) {
+            const long o = a.idx(cc, j0 + iy);
+            red_add(Sy + o, accy[iy]);
+            red_add(Sx + o, accx[iy]);
+        }
+    }
+    __syncthreads();
+    if (rcc > kNoCell) {
+#pragma unroll
+        for (int kk = 0; kk < (10 + NW - 1) / NW; ++kk) {
+            const int k = w + kk * NW;
+            if (k < 10) {
+                double sum = 0.;
+#pragma unroll
+                for (int q = 0; q < NW; ++q) sum += sh.comb[q][k][lane];
+                const int iy = k < 5 ? k : k - 5;
+                red_add((k < 5 ? Sy : Sx) + a.idx(rcc, rj0 + iy), sum);
+            }
+        }
+    }
+    if (!own || absorbed == 0x1bu) return;       // columns 0, 1, 3, 4 all owned by aligned neighbours
+    // scatter the columns nobody owns (same expressions, fields read at the target cells)
+    double shy[5], shdy[5];
+    dshape2_centered_frac(yint, shy, shdy);
+#pragma unroll 1
+    for (int ix = 0; ix < 5; ++ix) {
+        if (ix == 2 || ((absorbed >> ix) & 1u)) continue;
+        const double wx = ix == 0 ? sx[0] : ix == 1 ? sx[1] : ix == 3 ? sx[3] : sx[4];
+        const double wdx = ix == 0 ? dsx[0] : ix == 1 ? dsx[1] : ix == 3 ? dsx[3] : dsx[4];
+        const ExplCol k = expl_col(e, wx, wdx, dx_inv, dy_inv);
+#pragma unroll
+        for (int iy = 0; iy < 5; ++iy) {
+            if ((ix == 0 || ix == 4) && (iy == 0 || iy == 4)) continue;
+            const long o = a.idx(i0 + ix, j0 + iy);
+            double vy_ = 0., vx_ = 0.;
+            expl_cell(k, e.vx, e.vy, e.a3, e.a4, e.a5, shy[iy], shdy[iy], Bz[o], Ez[o], ExmBy[o],
+                      EypBx[o], clight_inv, vy_, vx_);
+            red_add(Sy + o, vy_);
+            red_add(Sx + o, vx_);
+        }
+    }
+}
+
 inline unsigned nblocks(long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -901,6 +1484,32 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     const hpb_geom &g = ctx->g;
     const double invvol = g.normalized ? 1.0 : (1.0 / g.dx) * (1.0 / g.dy) * (1.0 / g.dz);
     const int variant = ctx->tune_expl_variant;
+    // expl_variant 4 (default) / 7: the CTA-tile kernel (TMA / cp.async staging) whenever the particles
+    // carry the lattice order with ppc 4 or 9 and there is no laser; 0: the round-1 warp kernel
+    const bool lattice = ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np;
+    if ((variant == 4 || variant == 7 || variant == 8) && comps[HPB_C_AABS] < 0 && lattice
+        && (ctx->order_ppc == 4 || ctx->order_ppc == 9)) {
+        PlasmaPtrs pp = to_ptrs(pl);
+        pp.lat_n = ctx->order_n; pp.lat_ppc = ctx->order_ppc; pp.lat_mode = 1;
+        const int lat_nx = pp.lat_n == (long)g.nx * g.ny ? g.nx : 0;
+        const long groups = lat_nx > 0 ? (long)g.ny * ((lat_nx + kExplOwn - 1) / kExplOwn)
+                                       : (pp.lat_n + kExplOwn - 1) / kExplOwn + 1;
+        const CUtensorMap *tm = variant != 7 ? (const CUtensorMap *)hpb_slice_tmap(ctx, 1, sl, kEW, kEH) : nullptr;
+        CUtensorMap none;
+        memset(&none, 0, sizeof(none));
+#define HPB_LAUNCH_ECTA(NW, MB, TMA_)                                                              \
+        hpb_launch(k_explicit_deposition_cta<NW, MB, TMA_>, (unsigned)groups, NW * 32, 0, ctx->stream, \
+                   pp, make_view(sl), TMA_ ? *tm : none, sl.nx_tot, sl.ny_tot, lat_nx, comps[HPB_C_SY],  \
+                   comps[HPB_C_SX], comps[HPB_C_BZ], comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], \
+                   g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass)
+        if (ctx->order_ppc == 4 && variant == 8 && tm) HPB_LAUNCH_ECTA(4, 4, true);      // 128 registers
+        else if (ctx->order_ppc == 4) { if (tm) HPB_LAUNCH_ECTA(4, 5, true); else HPB_LAUNCH_ECTA(4, 5, false); }
+        else { if (tm) HPB_LAUNCH_ECTA(9, 2, true); else HPB_LAUNCH_ECTA(9, 2, false); }
+#undef HPB_LAUNCH_ECTA
+        hpb_count_launch(ctx);
+        HPB_CUDA_CHECK(cudaGetLastError());
+        return HPB_OK;
+    }
     // (the laser variant uses the plain particle order)
     const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 1);
     const long nwarps = lattice_warps(pp, kExplOwn);
@@ -960,13 +1569,44 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         dep.charge_mu0_mass_ratio = charge * g.mu0 / mass;
         dep.max_qsa = max_qsa; dep.n_qsa_violation = d_n_qsa_violation;
     }
-    const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 2);
-    const long nwarps = lattice_warps(pp, 32, kPushThreads / 32);
     PushLaserArgs lasa = {comps[HPB_C_AABS], 0.};
     if (lasa.c_aabs >= 0) {
         if (deposit) { hpb_set_error("advance+deposit: not available with a laser"); return HPB_ERR_UNSUPPORTED; }
         lasa.norm = (charge / g.q_e) * (g.m_e / mass) * (charge / g.q_e) * (g.m_e / mass);
     }
+    // push_variant 0 (default) / 4: the CTA-tile kernel (TMA / cp.async staging) whenever the particles
+    // carry the lattice order with ppc 4 or 9; 2: the round-1 warp-staged kernel, 1: direct loads,
+    // 3: warp-staged with 128 registers
+    const bool lattice = ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np;
+    if ((variant == 0 || variant == 4 || variant == 5) && lasa.c_aabs < 0 && lattice && (ctx->order_ppc == 4 || ctx->order_ppc == 9)) {
+        PlasmaPtrs pp = to_ptrs(pl);
+        pp.lat_n = ctx->order_n; pp.lat_ppc = ctx->order_ppc; pp.lat_mode = 1;
+        // lattice row length: known when the lattice is the whole box (x fastest)
+        const int lat_nx = pp.lat_n == (long)g.nx * g.ny ? g.nx : 0;
+        const long groups = lat_nx > 0 ? (long)g.ny * ((lat_nx + 31) / 32) : (pp.lat_n + 31) / 32;
+        const CUtensorMap *tm = variant != 4 ? (const CUtensorMap *)hpb_slice_tmap(ctx, 0, sl, kCW, kCH) : nullptr;
+        CUtensorMap none;
+        memset(&none, 0, sizeof(none));
+#define HPB_LAUNCH_CTA(NW, MB, DEP, TMA_)                                                          \
+        hpb_launch(k_advance_plasma_cta<NW, MB, DEP, TMA_>, (unsigned)groups, NW * 32, 0, ctx->stream, \
+                   pp, make_view(sl), TMA_ ? *tm : none, sl.nx_tot, sl.ny_tot, lat_nx, comps[HPB_C_PSI], \
+                   comps[HPB_C_EZ], comps[HPB_C_BX], comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off,  \
+                   1.0 / g.dx, 1.0 / g.dy, g.c, charge / (mass * g.c), g.dz / n_subcycles, n_subcycles,  \
+                   temp_slice, particle_bc, bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep)
+#define HPB_LAUNCH_CTA_NW(NW, MB)                                                                 \
+        do { if (deposit) { if (tm) HPB_LAUNCH_CTA(NW, MB, true, true); else HPB_LAUNCH_CTA(NW, MB, true, false); } \
+             else { if (tm) HPB_LAUNCH_CTA(NW, MB, false, true); else HPB_LAUNCH_CTA(NW, MB, false, false); } } while (0)
+        if (ctx->order_ppc == 4 && variant == 5) HPB_LAUNCH_CTA_NW(4, 4);       // 128 registers
+        else if (ctx->order_ppc == 4) HPB_LAUNCH_CTA_NW(4, 5);
+        else HPB_LAUNCH_CTA_NW(9, 2);
+#undef HPB_LAUNCH_CTA_NW
+#undef HPB_LAUNCH_CTA
+        hpb_count_launch(ctx);
+        HPB_CUDA_CHECK(cudaGetLastError());
+        return HPB_OK;
+    }
+    const PlasmaPtrs pp = comps[HPB_C_AABS] >= 0 ? to_ptrs(pl) : to_ptrs(ctx, pl, 2);
+    const long nwarps = lattice_warps(pp, 32, kPushThreads / 32);
 #define HPB_LAUNCH_PUSH(MB, DEP, STG)                                                             \
     do { if (pp.lat_n > 0 && pp.lat_mode == 2) HPB_LAUNCH_PUSH_(MB, DEP, STG, 2, false);           \
          else if (pp.lat_n > 0) HPB_LAUNCH_PUSH_(MB, DEP, STG, 1, false);                          \
@@ -979,7 +1619,7 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,          \
         charge / (mass * g.c), g.dz / n_subcycles, n_subcycles, temp_slice, particle_bc,         \
         bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep, lasa)
-    // variants: 0 = staged gather, 5 blocks / SM (the shared-memory limit; default),
+    // round-1 kernels: staged gather, 5 blocks / SM (the shared-memory limit; variants 0 / 2 / 4),
     // 1 = direct loads only, 3 = staged with 128 registers
     if (lasa.c_aabs >= 0) {
         HPB_LAUNCH_PUSH_(4, false, true, 0, true);          // laser: staged gather, plain order, 128 registers

@@ -184,7 +184,9 @@ def test_full_size_matches_cport(n_cell, nsl, repo_root):
     sizes: BASELINE configs[2] (1024 x 1024, ppc 4), the reference's recommended 2^n - 1 grid
     (1023 x 1023) and configs[1] (256 x 256 x 512, ppc 4) -- nsl slices from the head of the box
     through the beam head.  Field checksums to 1e-9, particle validity bit-exact, particle state to
-    1e-9, the same multigrid V-cycle count on every slice."""
+    1e-9, the same multigrid V-cycle count on every slice.  (Bz vanishes by symmetry for this deck:
+    its checksum is the sum of round-off sized values and is held to 1e-12 of the largest checksum,
+    like the other symmetry-zero quantities of this suite.)"""
     import hipace_b200 as hp
     from oracle import cport
     text = _deck(repo_root, 'blowout_wake_normalized.in')
@@ -194,8 +196,9 @@ def test_full_size_matches_cport(n_cell, nsl, repo_root):
     want = ref.evolve(nsl)
     sim = hp.Simulation(text, ov)
     got = sim.evolve(0, 0, nsl)
+    atol = 1e-12 * max(abs(w) for w in want.values())
     for k, w in want.items():
-        assert abs(got[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (k, got[k], w)
+        assert abs(got[k] - w) <= RTOL_SUM * abs(w) + atol, (k, got[k], w)
     assert sim.mg_iters() == list(ref.mg_cycles), 'V-cycles per slice'
     assert max(ref.mg_cycles) >= 2, 'the sample must reach the beam (more than the vacuum V-cycle)'
     o, p = ref.plasmas[0], sim.plasma()
