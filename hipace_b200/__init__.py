@@ -68,7 +68,7 @@ EXPORTS = (
     'hpb_fields_insitu_slice', 'hpb_insitu_write_fields', 'hpb_debug_push_thread_map',
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
-    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option',
+    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder',
 )
 NCCL_ID_BYTES = 128
 
@@ -105,7 +105,7 @@ class hpb_sim_stats(C.Structure):
                 ('n_slices', C.c_long), ('n_mg_vcycles', C.c_long), ('n_qsa_violation', C.c_long),
                 ('n_kernel_launches', C.c_long), ('ms_deposit', C.c_double),
                 ('ms_poisson', C.c_double), ('ms_explicit', C.c_double), ('ms_mg', C.c_double),
-                ('ms_push', C.c_double), ('ms_other', C.c_double)]
+                ('ms_push', C.c_double), ('ms_other', C.c_double), ('n_reorders', C.c_long)]
 
 
 _lib = None

@@ -34,6 +34,7 @@ SOURCES = {
     'generic_order.cu': [],
     'insitu.cu': [],
     'pc_fields.cu': [],
+    'reorder.cu': [],
 }
 
 

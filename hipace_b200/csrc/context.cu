@@ -10,6 +10,7 @@ int hpb_poisson_init(hpb_ctx *ctx);
 void hpb_poisson_free(hpb_ctx *ctx);
 int hpb_mg_init(hpb_ctx *ctx);
 void hpb_mg_free(hpb_ctx *ctx);
+void hpb_reorder_free(hpb_ctx *ctx);
 
 static thread_local char g_err[1024] = "";
 
@@ -143,6 +144,7 @@ extern "C" void hpb_destroy(hpb_ctx *ctx)
     if (!ctx) return;
     hpb_poisson_free(ctx);
     hpb_mg_free(ctx);
+    hpb_reorder_free(ctx);
     cudaFree(ctx->d_scalar_i);
     delete ctx;
 }

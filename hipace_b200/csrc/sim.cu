@@ -334,6 +334,13 @@ int read_deck(hpb_sim *s)
             sp.neutralize = (int)d.num(nm + ".neutralize_background", 1, "plasmas.neutralize_background") != 0;
             sp.max_qsa = d.num(nm + ".max_qsa_weighting_factor", 35., "plasmas.max_qsa_weighting_factor");
             sp.n_subcycles = (int)d.num(nm + ".n_subcycles", 1, "plasmas.n_subcycles");
+            sp.reorder_period = (int)d.num(nm + ".reorder_period", 0, "plasmas.reorder_period");
+            {
+                const auto it = d.nums(nm + ".reorder_idx_type", {0., 0.}, "plasmas.reorder_idx_type");
+                if (it.size() != 2) throw std::runtime_error("reorder_idx_type needs 2 values");
+                // 0: cell, 1: node, 2: both (two sorts in the reference; binned by cell here)
+                sp.reorder_idx[0] = (int)it[0] == 1; sp.reorder_idx[1] = (int)it[1] == 1;
+            }
             sp.insitu_period = (int)d.num(nm + ".insitu_period", 0, "plasmas.insitu_period");
             sp.insitu_radius = d.num(nm + ".insitu_radius", INFINITY, "plasmas.insitu_radius");
             sp.insitu_file_prefix = d.str(nm + ".insitu_file_prefix", "diags/plasma_insitu", "plasmas.insitu_file_prefix");
@@ -1129,8 +1136,34 @@ int plasma_insitu(hpb_sim *s, int islice)
     return HPB_OK;
 }
 
+// MultiPlasma::ReorderParticles (Hipace.cpp:595): every reorder_period slices the species is sorted by
+// cell into its second SoA and the two are swapped; the InitParticles lattice order is gone afterwards
+int reorder_plasma(hpb_sim *s, int islice)
+{
+    for (auto &sp : s->plasmas) {
+        if (sp.reorder_period <= 0 || islice % sp.reorder_period != 0 || sp.d.np == 0) continue;
+        if (sp.capacity2 < sp.d.np) {
+            for (int k = 0; k < HPB_PLASMA_NREAL; ++k) { cudaFree(sp.d2.r[k]); sp.d2.r[k] = nullptr; }
+            cudaFree(sp.d2.idcpu); sp.d2.idcpu = nullptr;
+            for (int k = 0; k < HPB_PLASMA_NREAL; ++k) SIM_CUDA(cudaMalloc(&sp.d2.r[k], sizeof(double) * sp.capacity));
+            SIM_CUDA(cudaMalloc(&sp.d2.idcpu, sizeof(uint64_t) * sp.capacity));
+            sp.capacity2 = sp.capacity;
+        }
+        sp.d2.np = sp.d.np;
+        int rc = hpb_plasma_reorder(s->ctx, sp.d, sp.d2, s->prob_lo[0], s->prob_lo[1], sp.reorder_idx[0],
+                                    sp.reorder_idx[1]);
+        if (rc) return rc;
+        std::swap(sp.d, sp.d2);
+        std::swap(sp.capacity, sp.capacity2);
+        sp.lattice_n = 0;
+        s->stats.n_reorders += 1;
+    }
+    return HPB_OK;
+}
+
 int solve_one_slice(hpb_sim *s, int islice)
 {
+    if (int rcr = reorder_plasma(s, islice)) return rcr;
     if (int rci = plasma_insitu(s, islice)) return rci;
     if (!s->explicit_solver) return solve_one_slice_pc(s, islice);
     hpb_ctx *ctx = s->ctx;
@@ -1434,6 +1467,8 @@ extern "C" void hpb_sim_destroy(hpb_sim *s)
     for (auto &sp : s->plasmas) {
         for (int k = 0; k < HPB_PLASMA_NREAL; ++k) cudaFree(sp.d.r[k]);
         cudaFree(sp.d.idcpu);
+        for (int k = 0; k < HPB_PLASMA_NREAL; ++k) cudaFree(sp.d2.r[k]);
+        cudaFree(sp.d2.idcpu);
         cudaFree(sp.d_insitu);
     }
     hpb_pipeline_destroy(s);

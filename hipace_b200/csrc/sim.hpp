@@ -62,6 +62,11 @@ struct Species {
     double u_mean[3] = {0, 0, 0};
     hpb_plasma d = {};
     long capacity = 0;
+    // <plasma>.reorder_period / reorder_idx_type (PlasmaParticleContainer.cpp:147-151): the sort target
+    int reorder_period = 0;
+    int reorder_idx[2] = {0, 0};
+    hpb_plasma d2 = {};
+    long capacity2 = 0;
 };
 
 struct BeamSp {

@@ -323,6 +323,14 @@ int hpb_fields_shift_and_initialize(hpb_ctx *ctx, hpb_slice sl, int *comps);
  * from / reduces into are fetched from HBM once per slice instead of once per pass.  Results do
  * not depend on it; cells_per_pass = 0 clears the hint. */
 int hpb_set_plasma_lattice_hint(hpb_ctx *ctx, long cells_per_pass, int ppc);
+/* PlasmaParticleContainer::ReorderParticles (src/particles/plasma/PlasmaParticleContainer.cpp:196-208,
+ * called every <plasma>.reorder_period slices, src/Hipace.cpp:595): counting sort of the particle
+ * SoA by transverse cell (idx_type 0) or node (1) per direction (<plasma>.reorder_idx_type), x
+ * fastest, invalid particles last.  `out` is a second SoA of the same capacity (the caller swaps
+ * them afterwards); the particle set and every value are unchanged, the order inside a cell is
+ * unspecified.  After a reorder the lattice hint above no longer holds. */
+int hpb_plasma_reorder(hpb_ctx *ctx, hpb_plasma in, hpb_plasma out, double prob_lo_x, double prob_lo_y,
+                       int idx_type_x, int idx_type_y);
 /* test hook, host only: the thread -> particle map the push kernel uses with that hint (mode 0 linear,
  * 1 passes interleaved warp by warp, 2 CTA by CTA); out[warp * 32 + lane] = particle or -1 */
 long hpb_debug_push_thread_map(long cells_per_pass, int ppc, int mode, long *out, long out_len);
@@ -427,6 +435,7 @@ typedef struct {
     double slice_loop_ms;           /* device time of the slice loop(s) of the last evolve */
     long n_slices, n_mg_vcycles, n_qsa_violation, n_kernel_launches;
     double ms_deposit, ms_poisson, ms_explicit, ms_mg, ms_push, ms_other; /* if profiling on */
+    long n_reorders;                /* plasma sorts (<plasma>.reorder_period) */
 } hpb_sim_stats;
 int hpb_sim_get_stats(hpb_sim *sim, hpb_sim_stats *out);
 /* multigrid V-cycles (or predictor-corrector iterations) of every slice of the last evolve, in

@@ -210,6 +210,54 @@ def test_full_size_matches_cport(n_cell, nsl, repo_root):
     sim.close()
 
 
+@pytest.mark.parametrize('idx_type', ['0 0', '1 1'])
+def test_plasma_reorder_invariance(idx_type, repo_root):
+    """plasmas.reorder_period = 4: the reference re-runs its blowout_wake_explicit golden with the plasma
+    sorted by cell every 4 slices and expects the same checksums
+    (/root/reference/tests/blowout_wake_explicit.2Rank.sh:45-58).  Here: the reference golden itself with
+    the sort on, plus -- against the un-sorted run -- the same particle SET (sorted values bit-exact at the
+    sort, states equal to 1e-9 after 100 slices, multiset comparison) and V-cycle counts."""
+    import hipace_b200 as hp
+    meta = json.load(open(os.path.join(GOLD, 'blowout_wake_explicit.2Rank.json')))
+    text = open(os.path.join(repo_root, meta['deck'])).read()
+    ov = dict(meta['overrides'])
+    ov.pop('max_step', None)
+    ov['plasma.ppc'] = '2 2'
+    runs = {}
+    for period in (0, 4):
+        sim = hp.Simulation(text, dict(ov, **{'plasmas.reorder_period': period, 'plasmas.reorder_idx_type': idx_type}))
+        cs = sim.evolve()
+        runs[period] = (cs, sim.plasma(), sim.stats(), sim.mg_iters())
+        sim.close()
+    cs0, p0, st0, it0 = runs[0]
+    cs4, p4, st4, it4 = runs[4]
+    assert st0['n_reorders'] == 0 and st4['n_reorders'] == 25          # 100 slices, every 4th
+    for k, w in cs0.items():
+        assert abs(cs4[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (k, cs4[k], w)
+    assert it4 == it0
+    assert p4['valid'].sum() == p0['valid'].sum()
+    # the same particles in another order: the order statistics of every component agree
+    for nm in ('x', 'y', 'ux', 'uy', 'psi', 'w'):
+        a, b = np.sort(p0[nm][p0['valid']]), np.sort(p4[nm][p4['valid']])
+        scale = max(np.abs(a).max(), 1e-300)
+        assert np.abs(a - b).max() / scale <= 1e-8, nm
+
+
+def test_reference_golden_with_reordering(repo_root):
+    """the reference's own check: the blowout_wake_explicit golden must come out with reorder_period = 4"""
+    import hipace_b200 as hp
+    meta = json.load(open(os.path.join(GOLD, 'blowout_wake_explicit.2Rank.json')))
+    ov = dict(meta['overrides'])
+    ov.pop('max_step', None)
+    ov['plasmas.reorder_period'] = 4
+    sim = hp.Simulation(open(os.path.join(repo_root, meta['deck'])).read(), ov)
+    cs = sim.evolve()
+    for name, want in meta['checksums']['lev=0'].items():
+        assert abs(cs[name] - want) <= RTOL_SUM * abs(want) + 1e-40, (name, cs[name], want)
+    assert sim.stats()['n_reorders'] == 25
+    sim.close()
+
+
 def test_si_units_deck_matches_oracle(repo_root):
     """hipace.normalized_units = 0: the SI constants, invvol = 1/(dx dy dz) and the dx dy dz / ppc
     weights through every kernel (the reference's examples/blowout_wake/inputs_SI restated).  The
