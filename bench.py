@@ -138,7 +138,14 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--impl', default='native', choices=['native', 'reference', 'cufft_ref', 'naive'],
+                    help='native: the product path.  reference: the CPU restatement on the host cores.  '
+                         'cufft_ref: the product path with the Poisson stage replaced by the reference\'s '
+                         'FFTPoissonSolverDirichletFast sequence on cuFFT (csrc/ref_gpu_arm.cu).  naive: a '
+                         'straight restatement of the reference\'s GPU algorithm on this box -- one thread '
+                         'per particle with plain fp64 atomics and per-particle gathers (generic-order '
+                         'kernels), cuFFT Poisson, the reference call order (no fusion, no side stream, no '
+                         'programmatic dependent launch)')
     ap.add_argument('--nxy', type=int, default=1024)
     ap.add_argument('--nz', type=int, default=1024)
     ap.add_argument('--ppc', type=int, default=2, help='per direction (2 -> ppc 4)')
@@ -207,6 +214,9 @@ def main():
         ov['hipace.dt'] = args.dt
     sim = hp.Simulation(deck, ov, device=local_rank)
     sim.set_option('checksums', 0)
+    arm_opts = {'cufft_ref': ['poisson_impl=1'],
+                'naive': ['poisson_impl=1', 'generic_order_kernels=1', 'fuse=0', 'side_stream=0', 'pdl=0']}
+    args.opt = arm_opts.get(args.impl, []) + args.opt
     for kv in args.opt:
         k, v = kv.split('=', 1)
         sim.set_option(k, float(v))
@@ -366,11 +376,26 @@ def main():
                 traffic_src = tr.get('source')
         except Exception:
             pass
+        # second roof: fp64.  flops per particle = 2 DFMA + DMUL + DADD thread instructions of the ncu
+        # op counters (smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on, profiles/r01f_particles_raw.csv)
+        # divided by the particles of the launch; the peak is measured on this box (csrc/peaks.cu)
+        flops_pp = {'push': 1075.0, 'explicit': 518.0}
+        try:
+            fp64_peak = hp.measure_fp64_peak(local_rank)
+        except Exception:
+            fp64_peak = None
+        fp64 = {}
+        for k, fpp in flops_pp.items():
+            if k in stages and stages[k] > 0 and fp64_peak:
+                tf = fpp * P / (stages[k] * 1e-3) / 1e12
+                fp64[k] = {'achieved': tf, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': tf / fp64_peak,
+                           'flops_per_particle': fpp}
         roofline = {'kernel': kernel_of[dom],
                     'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                     'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': alg[dom], 'avg_launch_ms': stages[dom],
                     'deposit_fused_into_push': fused_deposit,
+                    'fp64': fp64, 'fp64_peak_source': 'measured on this box: DFMA kernel, best of 5 (csrc/peaks.cu)',
                     'all': {k: {'GBps': alg[k] / (stages[k] * 1e-3) / 1e9, 'ms': stages[k],
                                 'frac': alg[k] / (stages[k] * 1e-3) / 1e9 / peak} for k in alg}}
 
@@ -387,6 +412,7 @@ def main():
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+                **({'impl': args.impl} if args.impl != 'native' else {}),
                 'ms_per_step': job_ms / K, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
                 'ns_per_particle_step': ns_per_push, 'ms_per_slice': job_ms / (K * args.nz),

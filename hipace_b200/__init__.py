@@ -68,7 +68,7 @@ EXPORTS = (
     'hpb_fields_insitu_slice', 'hpb_insitu_write_fields', 'hpb_debug_push_thread_map',
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
-    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder',
+    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder', 'hpb_measure_fp64_peak',
 )
 NCCL_ID_BYTES = 128
 
@@ -170,6 +170,7 @@ def lib():
     L.hpb_sim_get_stats.argtypes = [C.c_void_p, C.POINTER(hpb_sim_stats)]
     L.hpb_sim_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     L.hpb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.hpb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.hpb_sim_get_mg_iters.restype = C.c_long
     L.hpb_sim_get_mg_iters.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_long]
     L.hpb_extfields_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_char_p)]
@@ -452,6 +453,13 @@ class Simulation:
         st = hpb_sim_stats()
         _check(self._L.hpb_sim_get_stats(self._h, C.byref(st)), 'hpb_sim_get_stats')
         return {f: getattr(st, f) for f, _ in st._fields_}
+
+
+def measure_fp64_peak(device: int = 0, reps: int = 5) -> float:
+    """fp64 FMA peak of the device in TFLOP/s (measured, csrc/peaks.cu)"""
+    out = C.c_double(0.)
+    _check(lib().hpb_measure_fp64_peak(device, reps, C.byref(out)), 'hpb_measure_fp64_peak')
+    return out.value
 
 
 class Context:

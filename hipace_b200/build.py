@@ -35,6 +35,8 @@ SOURCES = {
     'insitu.cu': [],
     'pc_fields.cu': [],
     'reorder.cu': [],
+    'peaks.cu': [],
+    'ref_gpu_arm.cu': [],
 }
 
 

@@ -261,6 +261,8 @@ struct hpb_ctx {
     int tune_expl_variant, tune_push_variant, tune_fft_variant, tune_mg_wide, tune_mg_fuse;
     // TMA tensor maps over the caller's slice array (tma.cuh), re-encoded when the view changes:
     // [0] the 40 x 6 gather patch of the push, [1] the patch of the explicit deposition
+    void *ref_arm;            // ref_gpu_arm.cu: cuFFT plans and buffers of the reference-algorithm arm
+    int tune_poisson_impl;    // 0: product solver, 1: the reference's DirichletFast sequence on cuFFT
     // plasma reordering scratch (reorder.cu)
     unsigned *d_reorder_key, *d_reorder_rank, *d_reorder_hist, *d_reorder_sums;
     long reorder_np_cap, reorder_bins_cap;

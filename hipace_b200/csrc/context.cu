@@ -11,6 +11,7 @@ void hpb_poisson_free(hpb_ctx *ctx);
 int hpb_mg_init(hpb_ctx *ctx);
 void hpb_mg_free(hpb_ctx *ctx);
 void hpb_reorder_free(hpb_ctx *ctx);
+void hpb_ref_arm_free(hpb_ctx *ctx);
 
 static thread_local char g_err[1024] = "";
 
@@ -48,6 +49,7 @@ extern "C" int hpb_set_option(hpb_ctx *ctx, const char *key, double value)
     else if (!strcmp(key, "fft_variant")) ctx->tune_fft_variant = v;
     else if (!strcmp(key, "mg_wide")) ctx->tune_mg_wide = v;
     else if (!strcmp(key, "mg_fuse")) ctx->tune_mg_fuse = v;
+    else if (!strcmp(key, "poisson_impl")) ctx->tune_poisson_impl = v;
     else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }
     return HPB_OK;
 }
@@ -145,6 +147,7 @@ extern "C" void hpb_destroy(hpb_ctx *ctx)
     hpb_poisson_free(ctx);
     hpb_mg_free(ctx);
     hpb_reorder_free(ctx);
+    hpb_ref_arm_free(ctx);
     cudaFree(ctx->d_scalar_i);
     delete ctx;
 }

@@ -787,6 +787,19 @@ k_advance_plasma(PlasmaPtrs pl, SliceView a, int c_psi, int c_ez, int c_bx, int 
 // Lanes whose particle has left the patch (sheath, trajectory crossing) gather with direct loads
 // and deposit with their own reductions: the result never depends on the particle order.
 constexpr int kCW = 40, kCH = 6;
+// Array coordinate (>= 0) of a patch that should start at cell `want`: clamped so that the whole box
+// lies inside the array, and rounded down to an even column (a 16-byte aligned row start).  Boxes that
+// hang over the upper edge of the array in y made the TMA copy never complete on the B200
+// (gpurun_out/r02c_debug*.txt: the mbarrier wait timed out once particles near the wall had moved
+// up by a cell); a clamped box still holds every cell a stencil inside the array can touch.
+__device__ __forceinline__ int patch_origin(int want, int lo, int tot, int ext, bool even)
+{
+    int a = want - lo;
+    a = a > tot - ext ? tot - ext : a;
+    a = a < 0 ? 0 : a;
+    if (even) a &= ~1;
+    return a;
+}
 constexpr uint32_t kCtaTileBytes = 5 * kCH * kCW * sizeof(double);
 constexpr int kNoCell = -(1 << 28);
 
@@ -893,10 +906,11 @@ k_advance_plasma_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtenso
     if (prefetched) {
         const unsigned gpr = (unsigned)(lat_nx + 31) >> 5, g = blockIdx.x;
         const unsigned row = g / gpr;
-        bi = (int)((g - row * gpr) * 32) - 4;     // stencil origins col - 2 .. col - 1, 4 wide: cols col - 2 .. col + 2
-        bj = (int)row - 3;                         // rows row - 2 .. row + 2
+        // stencil origins col - 2 .. col - 1, 4 wide: cols col - 2 .. col + 2, rows row - 2 .. row + 2
+        const int ax = patch_origin((int)((g - row * gpr) * 32) - 4, a.lo_x, nx_tot, kCW, true);
+        const int ay = patch_origin((int)row - 3, a.lo_y, ny_tot, kCH, false);
+        bi = ax + a.lo_x; bj = ay + a.lo_y;
         if (tid == 0) {
-            const int ax = bi - a.lo_x, ay = bj - a.lo_y;
             hpb_mbar_arrive_expect_tx(&sh.mbar, kCtaTileBytes);
             hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_psi);
             hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
@@ -940,8 +954,9 @@ k_advance_plasma_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtenso
             __syncthreads();
         }
         if (any && !pre_ok) {
-            bi = ci; bj = cj;
-            const int ax = bi - a.lo_x, ay = bj - a.lo_y;      // array coordinates of the patch origin
+            const int ax = patch_origin(ci, a.lo_x, nx_tot, kCW, TMA);      // array coordinates of the patch origin
+            const int ay = patch_origin(cj, a.lo_y, ny_tot, kCH, false);
+            bi = ax + a.lo_x; bj = ay + a.lo_y;
             if (TMA) {
                 if (tid == 0) {
                     hpb_fence_proxy_async();
@@ -1132,10 +1147,12 @@ k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CU
         hpb_mbar_init(&sh.mbar, 1);
     }
     if (prefetched) {
-        bi = col0 - 6;          // owned centre columns col0 .. col0 + 27, 6 cells of slack on each side
-        bj = row - 3;           // rows row - 1 .. row + 1, two / one row(s) of slack
+        // owned centre columns col0 .. col0 + 27 with 6 cells of slack on each side; rows row - 1 ..
+        // row + 1 with two / one row(s) of slack
+        const int ax = patch_origin(col0 - 6, a.lo_x, nx_tot, kEW, true);
+        const int ay = patch_origin(row - 3, a.lo_y, ny_tot, kEH, false);
+        bi = ax + a.lo_x; bj = ay + a.lo_y;
         if (tid == 0) {
-            const int ax = bi - a.lo_x, ay = bj - a.lo_y;
             hpb_mbar_arrive_expect_tx(&sh.mbar, kExplTileBytes);
             hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
             hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
@@ -1201,8 +1218,9 @@ k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CU
             __syncthreads();
         }
         if (any && !pre_ok) {
-            bi = ci - 2; bj = cj;
-            const int ax = bi - a.lo_x, ay = bj - a.lo_y;
+            const int ax = patch_origin(ci - 2, a.lo_x, nx_tot, kEW, TMA);
+            const int ay = patch_origin(cj, a.lo_y, ny_tot, kEH, false);
+            bi = ax + a.lo_x; bj = ay + a.lo_y;
             if (TMA) {
                 if (tid == 0) {
                     hpb_fence_proxy_async();

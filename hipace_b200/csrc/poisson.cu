@@ -672,9 +672,12 @@ extern "C" int hpb_poisson_solve(hpb_ctx *ctx, const double *d_rhs, hpb_slice sl
     return poisson_finish(ctx, sl, c_lhs, nbatch);
 }
 
+int hpb_ref_arm_solve_psi_ez_bz(hpb_ctx *ctx, hpb_slice sl, const int *comps);
+
 extern "C" int hpb_fields_solve_psi_ez_bz(hpb_ctx *ctx, hpb_slice sl, const int *comps)
 {
     if (!ctx || !comps) return HPB_ERR_ARG;
+    if (ctx->tune_poisson_impl == 1) return hpb_ref_arm_solve_psi_ez_bz(ctx, sl, comps);    // measurement arm
     const hpb_geom &g = ctx->g;
     const long plane = (long)g.nx * g.ny;
     OutPtrs o1;

@@ -341,11 +341,17 @@ long hpb_debug_push_thread_map(long cells_per_pass, int ppc, int mode, long *out
  * hpb_slice.lo_x = lo_y = -guards.  The default has warp-aggregated, staged kernels; every other
  * combination runs one-thread-per-particle kernels (csrc/generic_order.cu). */
 int hpb_set_deposition_order(hpb_ctx *ctx, int order_xy, int derivative_type);
+/* measurement infrastructure (bench.py): the fp64 FMA peak of `device` in TFLOP/s (2 flops per DFMA),
+ * best of `reps` launches of a register-resident DFMA kernel -- the compute roof the particle kernels
+ * are reported against beside the HBM roof */
+int hpb_measure_fp64_peak(int device, int reps, double *tflops);
 /* behaviour switches of the kernels (A/B measurements and cross-checks; the library never reads the
  * host's environment): "pdl" (programmatic dependent launch, process-wide, ctx may be NULL),
  * "generic" (generic-order kernels for the default order too), "order" (bit mask: which particle
  * kernels use the pass-interleaved thread map), "expl_variant", "push_variant", "fft_variant",
- * "mg_wide", "mg_fuse" (launch geometry variants).  Unknown keys return HPB_ERR_ARG. */
+ * "mg_wide", "mg_fuse" (launch geometry variants), "poisson_impl" (1: the measurement arm that runs
+ * the reference's FFTPoissonSolverDirichletFast sequence on cuFFT, csrc/ref_gpu_arm.cu).  Unknown keys
+ * return HPB_ERR_ARG. */
 int hpb_set_option(hpb_ctx *ctx, const char *key, double value);
 int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
                                              double charge, double mass, int n_subcycles,

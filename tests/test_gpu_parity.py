@@ -199,7 +199,13 @@ def test_full_size_matches_cport(n_cell, nsl, repo_root):
     atol = 1e-12 * max(abs(w) for w in want.values())
     for k, w in want.items():
         assert abs(got[k] - w) <= RTOL_SUM * abs(w) + atol, (k, got[k], w)
-    assert sim.mg_iters() == list(ref.mg_cycles), 'V-cycles per slice'
+    # V-cycles per slice.  Ahead of the beam the right-hand side is zero up to the round-off of the
+    # deposition sums (exactly zero on some grids and summation orders, 1e-20 on others): hpmg's
+    # relative stopping rule then iterates on noise or not at all, so only slices where the
+    # reference solver has a physical source (>= 1 V-cycle) are compared
+    got_it, want_it = sim.mg_iters(), list(ref.mg_cycles)
+    assert len(got_it) == len(want_it)
+    assert [g for g, w in zip(got_it, want_it) if w > 0] == [w for w in want_it if w > 0], 'V-cycles per slice'
     assert max(ref.mg_cycles) >= 2, 'the sample must reach the beam (more than the vacuum V-cycle)'
     o, p = ref.plasmas[0], sim.plasma()
     assert np.array_equal(p['valid'], o.valid)
@@ -208,6 +214,25 @@ def test_full_size_matches_cport(n_cell, nsl, repo_root):
         scale = max(np.abs(want_a).max(), 1e-300)
         assert np.abs(p[nm] - want_a).max() / scale <= 1e-9, nm
     sim.close()
+
+
+def test_reference_gpu_arm_matches_the_product_solver(repo_root):
+    """bench.py --impl cufft_ref / naive: the reference's DirichletFast sequence on cuFFT (ref_gpu_arm.cu)
+    and the generic one-thread-per-particle kernels in the reference call order must reproduce the
+    reference golden like the product path does -- otherwise the bar they set would be meaningless"""
+    import hipace_b200 as hp
+    meta = json.load(open(os.path.join(GOLD, 'blowout_wake_explicit.2Rank.json')))
+    ov = dict(meta['overrides'])
+    ov.pop('max_step', None)
+    text = open(os.path.join(repo_root, meta['deck'])).read()
+    for opts in ({'poisson_impl': 1}, {'poisson_impl': 1, 'generic_order_kernels': 1, 'fuse': 0, 'side_stream': 0}):
+        sim = hp.Simulation(text, ov)
+        for k, v in opts.items():
+            sim.set_option(k, v)
+        cs = sim.evolve()
+        for name, want in meta['checksums']['lev=0'].items():
+            assert abs(cs[name] - want) <= RTOL_SUM * abs(want) + 1e-40, (opts, name, cs[name], want)
+        sim.close()
 
 
 @pytest.mark.parametrize('idx_type', ['0 0', '1 1'])
