@@ -68,7 +68,8 @@ EXPORTS = (
     'hpb_fields_insitu_slice', 'hpb_insitu_write_fields', 'hpb_debug_push_thread_map',
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
-    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder', 'hpb_measure_fp64_peak',
+    'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder', 'hpb_measure_fp64_peak', 'hpb_mg_solve2', 'hpb_laser_set_solver',
+    'hpb_laser_mg_vcycles',
 )
 NCCL_ID_BYTES = 128
 
@@ -171,6 +172,8 @@ def lib():
     L.hpb_sim_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     L.hpb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     L.hpb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.hpb_mg_solve2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                C.c_double, C.c_int, C.POINTER(C.c_int)]
     L.hpb_sim_get_mg_iters.restype = C.c_long
     L.hpb_sim_get_mg_iters.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_long]
     L.hpb_extfields_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_char_p)]
@@ -586,6 +589,15 @@ class Context:
 
     def sxsy_from_beam(self, sl, comps):
         _check(self._L.hpb_fields_sxsy_from_beam(self._h, sl, comps), 'hpb_fields_sxsy_from_beam')
+
+    def mg_solve2(self, t_sol, t_rhs, t_acf_r, acf_i, tol_rel=1e-4, tol_abs=0.0, max_iters=200) -> int:
+        """hpmg solve2 on float64 CUDA tensors: t_sol [2, ny, nx] (initial guess in, solution out),
+        t_rhs [2, ny, nx], t_acf_r [ny, nx]; acf_i scalar"""
+        it = C.c_int(0)
+        _check(self._L.hpb_mg_solve2(self._h, C.c_void_p(t_sol.data_ptr()), C.c_void_p(t_rhs.data_ptr()),
+                                     C.c_void_p(t_acf_r.data_ptr()), C.c_double(acf_i), C.c_double(tol_rel),
+                                     C.c_double(tol_abs), max_iters, C.byref(it)), 'hpb_mg_solve2')
+        return it.value
 
     def mg_solve1(self, sl, c_sol, c_rhs, c_acf, tol_rel=1e-4, tol_abs=np.finfo(float).tiny,
                   max_iters=200) -> int:

@@ -37,6 +37,7 @@ SOURCES = {
     'reorder.cu': [],
     'peaks.cu': [],
     'ref_gpu_arm.cu': [],
+    'fft2d.cu': [],
 }
 
 

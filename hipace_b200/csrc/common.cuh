@@ -261,14 +261,15 @@ struct hpb_ctx {
     int tune_expl_variant, tune_push_variant, tune_fft_variant, tune_mg_wide, tune_mg_fuse;
     // TMA tensor maps over the caller's slice array (tma.cuh), re-encoded when the view changes:
     // [0] the 40 x 6 gather patch of the push, [1] the patch of the explicit deposition
+    void *mg2;                // mg.cu: level coefficient arrays of the type-2 (complex Helmholtz) solver
     void *ref_arm;            // ref_gpu_arm.cu: cuFFT plans and buffers of the reference-algorithm arm
     int tune_poisson_impl;    // 0: product solver, 1: the reference's DirichletFast sequence on cuFFT
     // plasma reordering scratch (reorder.cu)
     unsigned *d_reorder_key, *d_reorder_rank, *d_reorder_hist, *d_reorder_sums;
     long reorder_np_cap, reorder_bins_cap;
-    alignas(64) unsigned char tmap[2][128];
-    hpb_slice tmap_key[2];
-    int tmap_ok[2];
+    alignas(64) unsigned char tmap[3][128];      // [2]: the 136 x 6 patch of the row-tile push
+    hpb_slice tmap_key[3];
+    int tmap_ok[3];
 };
 // the cached tensor map `which` for boxes of box_w x box_h cells of sl, or nullptr (-> cp.async path)
 const void *hpb_slice_tmap(hpb_ctx *ctx, int which, const hpb_slice &sl, int box_w, int box_h);

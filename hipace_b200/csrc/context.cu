@@ -132,7 +132,9 @@ extern "C" int hpb_create(hpb_ctx **out, const hpb_geom *geom, void *stream)
     ctx->g = *geom;
     ctx->stream = (cudaStream_t)stream;
     ctx->depos_order = 2; ctx->depos_dtype = 2;
-    ctx->tune_order = 1; ctx->tune_expl_variant = 4;
+    // defaults = the measured best on the 1024^2 ppc 4 deck (profiles/README.md): the row-tile TMA
+    // push, the round-1 warp-aggregated explicit deposition
+    ctx->tune_order = 1; ctx->tune_expl_variant = 0; ctx->tune_push_variant = 6;
     int rc = hpb_poisson_init(ctx);
     if (rc == HPB_OK) rc = hpb_mg_init(ctx);
     if (rc == HPB_OK && cudaMalloc(&ctx->d_scalar_i, 16 * sizeof(int)) != cudaSuccess) rc = HPB_ERR_CUDA;

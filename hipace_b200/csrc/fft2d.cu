@@ -1,0 +1,142 @@
+// 2-D complex-to-complex FFT of the laser grid (the transform MultiLaser::AdvanceSliceFFT needs,
+// src/laser/MultiLaser.cpp:610-800; the reference calls AnyFFT / cufftExecZ2Z, WrapCuFFT.cpp:126-137).
+// Hand-written for sm_100a on the shared-memory Stockham FFT of fft_smem.cuh: one CTA per row, then
+// one CTA per column (the whole sequence lives in shared memory, every global element is read and
+// written once per pass; a 512 x 512 complex grid is 4 MB and stays in the L2 between the passes).
+// Same conventions as cuFFT: unnormalised, forward = exp(-i ...), inverse = exp(+i ...); in place or
+// out of place.
+#include "fft_smem.cuh"
+#include <math.h>
+#include <vector>
+
+namespace {
+
+struct Plan1D {
+    FftPlan plan;
+    double2 *d_root = nullptr;
+    double *d_cos[kMaxRad] = {}, *d_sin[kMaxRad] = {};
+};
+
+template <class T>
+bool to_device(T **dptr, const std::vector<T> &h)
+{
+    return cudaMalloc(dptr, sizeof(T) * h.size()) == cudaSuccess
+           && cudaMemcpy(*dptr, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+bool build_plan(int N, Plan1D &p)
+{
+    p.plan.N = N; p.plan.nrad = 0;
+    int n = N;
+    const int pref[] = {4, 2, 3, 5};
+    for (int r : pref) while (n % r == 0) { p.plan.rad[p.plan.nrad++] = r; n /= r; }
+    for (int q = 7; n > 1; q += 2) while (n % q == 0) { p.plan.rad[p.plan.nrad++] = q; n /= q; }
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int i = 0; i < p.plan.nrad; ++i) {
+        p.plan.cs_cos[i] = p.plan.cs_sin[i] = nullptr;
+        const int q = p.plan.rad[i];
+        if (q <= 5) continue;
+        const int h = (q - 1) / 2;
+        std::vector<double> tc((size_t)(h + 1) * h), ts((size_t)(h + 1) * h);
+        for (int b = 0; b <= h; ++b)
+            for (int t = 1; t <= h; ++t) {
+                const long tb = ((long)t * b) % q;
+                tc[(size_t)b * h + t - 1] = (double)cosl(2.0L * pi * tb / q);
+                ts[(size_t)b * h + t - 1] = (double)sinl(2.0L * pi * tb / q);
+            }
+        if (!to_device(&p.d_cos[i], tc) || !to_device(&p.d_sin[i], ts)) return false;
+        p.plan.cs_cos[i] = p.d_cos[i]; p.plan.cs_sin[i] = p.d_sin[i];
+    }
+    std::vector<double2> root(N);
+    for (int t = 0; t < N; ++t) {
+        root[t].x = (double)cosl(-2.0L * pi * t / N);
+        root[t].y = (double)sinl(-2.0L * pi * t / N);
+    }
+    return to_device(&p.d_root, root);
+}
+void free_plan(Plan1D &p)
+{
+    cudaFree(p.d_root);
+    for (int i = 0; i < kMaxRad; ++i) { cudaFree(p.d_cos[i]); cudaFree(p.d_sin[i]); }
+}
+
+// One sequence of N complex numbers per CTA: element e of sequence s is at in[s * seq_stride + e *
+// elem_stride] (rows: seq_stride = nx, elem_stride = 1; columns: seq_stride = 1, elem_stride = nx).
+// INV: conj in, forward transform, conj out = the inverse (unnormalised) transform.
+template <bool INV>
+__global__ void __launch_bounds__(kFftThreads)
+k_fft_seq(const double2 *__restrict__ in, double2 *__restrict__ out, long seq_stride, long elem_stride,
+          FftPlan plan, const double2 *__restrict__ root)
+{
+    hpb_pdl_prologue();
+    extern __shared__ double2 fsm[];
+    const int N = plan.N;
+    double2 *b0 = fsm, *b1 = fsm + N;
+    const long base = (long)blockIdx.x * seq_stride;
+    for (int e = threadIdx.x; e < N; e += blockDim.x) {
+        double2 v = in[base + (long)e * elem_stride];
+        if (INV) v.y = -v.y;
+        b0[e] = v;
+    }
+    __syncthreads();
+    const double2 *F = fft_smem(b0, b1, plan, root);
+    for (int e = threadIdx.x; e < N; e += blockDim.x) {
+        double2 v = F[e];
+        if (INV) v.y = -v.y;
+        out[base + (long)e * elem_stride] = v;
+    }
+}
+
+}  // namespace
+
+struct hpb_fft2d {
+    int nx = 0, ny = 0;
+    Plan1D px, py;
+};
+
+int hpb_fft2d_create(hpb_fft2d **out, int nx, int ny)
+{
+    if (!out || nx < 2 || ny < 2) return HPB_ERR_ARG;
+    hpb_fft2d *f = new hpb_fft2d();
+    f->nx = nx; f->ny = ny;
+    const size_t smem = 2 * sizeof(double2) * (size_t)std::max(nx, ny);
+    if (smem > 220 * 1024 || !build_plan(nx, f->px) || !build_plan(ny, f->py)) {
+        hpb_set_error("fft2d: %d x %d not supported by the shared-memory FFT", nx, ny);
+        free_plan(f->px); free_plan(f->py);
+        delete f;
+        return HPB_ERR_UNSUPPORTED;
+    }
+    cudaFuncSetAttribute(k_fft_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_fft_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    *out = f;
+    return HPB_OK;
+}
+
+void hpb_fft2d_destroy(hpb_fft2d *f)
+{
+    if (!f) return;
+    free_plan(f->px); free_plan(f->py);
+    delete f;
+}
+
+// data[j * nx + i]; dir < 0 forward, dir > 0 inverse; in == out allowed
+int hpb_fft2d_exec(hpb_fft2d *f, hpb_ctx *ctx, const double2 *in, double2 *out, int dir)
+{
+    if (!f || !ctx || !in || !out) return HPB_ERR_ARG;
+    const int nx = f->nx, ny = f->ny;
+    const size_t smx = 2 * sizeof(double2) * (size_t)nx, smy = 2 * sizeof(double2) * (size_t)ny;
+    if (dir < 0) {
+        hpb_launch(k_fft_seq<false>, (unsigned)ny, kFftThreads, smx, ctx->stream, in, out, (long)nx, 1L, f->px.plan,
+                   (const double2 *)f->px.d_root);
+        hpb_launch(k_fft_seq<false>, (unsigned)nx, kFftThreads, smy, ctx->stream, (const double2 *)out, out, 1L, (long)nx,
+                   f->py.plan, (const double2 *)f->py.d_root);
+    } else {
+        hpb_launch(k_fft_seq<true>, (unsigned)ny, kFftThreads, smx, ctx->stream, in, out, (long)nx, 1L, f->px.plan,
+                   (const double2 *)f->px.d_root);
+        hpb_launch(k_fft_seq<true>, (unsigned)nx, kFftThreads, smy, ctx->stream, (const double2 *)out, out, 1L, (long)nx,
+                   f->py.plan, (const double2 *)f->py.d_root);
+    }
+    hpb_count_launch(ctx, 2);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}

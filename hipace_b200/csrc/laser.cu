@@ -8,8 +8,13 @@
 // fft solver (lasers.solver_type = fft, MultiLaser::AdvanceSliceFFT); hpmg type 2 is not implemented.
 #include "common.cuh"
 #include "laser_advance.cuh"
+
+// fft2d.cu
+struct hpb_fft2d;
+int hpb_fft2d_create(hpb_fft2d **out, int nx, int ny);
+void hpb_fft2d_destroy(hpb_fft2d *f);
+int hpb_fft2d_exec(hpb_fft2d *f, hpb_ctx *ctx, const double2 *in, double2 *out, int dir);
 #include <cuda/std/complex>
-#include <dlfcn.h>
 #include <vector>
 
 namespace {
@@ -128,40 +133,9 @@ extern "C" int hpb_laser_update_aabs(hpb_ctx *ctx, hpb_slice sl, int c_aabs, con
 //   InterpolateChi :334-407, UpdateLaserAabs :214-291, ShiftLaserSlices :180-212,
 //   the hand-over of A^{n+1}, A^n to the next time step: src/utils/MultiBuffer.cpp:840-851, 913-923
 // Per-cell arithmetic: laser_advance.cuh (verified on the host against the oracle).  The 2-D complex
-// FFT of the laser grid is cuFFT (a plain library transform, like the reference's AnyFFT), loaded
-// with dlopen on first use so that libhpb200.so carries no link-time dependency on it.
+// FFT of the laser grid is our own shared-memory transform (fft2d.cu), not cuFFT.
 // =================================================================================================
 namespace {
-
-// ---- cuFFT through dlopen ----------------------------------------------------------------------
-struct CufftApi {
-    void *h = nullptr;
-    int (*plan2d)(int *, int, int, int) = nullptr;
-    int (*exec_z2z)(int, void *, void *, int) = nullptr;
-    int (*set_stream)(int, cudaStream_t) = nullptr;
-    int (*destroy)(int) = nullptr;
-};
-CufftApi *cufft_api()
-{
-    static CufftApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        for (const char *name : {"libcufft.so.11", "libcufft.so.12", "libcufft.so"}) {
-            api.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-            if (api.h) break;
-        }
-        if (api.h) {
-            api.plan2d = (int (*)(int *, int, int, int))dlsym(api.h, "cufftPlan2d");
-            api.exec_z2z = (int (*)(int, void *, void *, int))dlsym(api.h, "cufftExecZ2Z");
-            api.set_stream = (int (*)(int, cudaStream_t))dlsym(api.h, "cufftSetStream");
-            api.destroy = (int (*)(int))dlsym(api.h, "cufftDestroy");
-            if (!api.plan2d || !api.exec_z2z || !api.set_stream || !api.destroy) api.h = nullptr;
-        }
-    }
-    return api.h ? &api : nullptr;
-}
-constexpr int kCufftZ2Z = 0x69, kCufftForward = -1, kCufftInverse = 1;
 
 constexpr int kLT = 256;
 
@@ -241,6 +215,34 @@ k_laser_rhs(LaserPlanes L, const double *__restrict__ chi, LaserAdvPar par, cons
     rhs[(long)j * par.nx + i] = laser_rhs_cell(L, chi, i, j, par, *ph);
 }
 
+// multigrid variant: planar right-hand side [2][ny][nx], real coefficient plane, and the initial guess
+// (whatever np1j00 holds: the previous slice's solution, MultiLaser.cpp:598-606) in planar form
+__global__ void __launch_bounds__(kLT)
+k_laser_rhs_mg(LaserPlanes L, const double *__restrict__ chi, LaserAdvPar par, const LaserPhase *__restrict__ ph,
+               int do_avg_rhs, const hpb_c2 *__restrict__ guess, double *__restrict__ rhs2, double *__restrict__ acf_r,
+               double *__restrict__ sol2)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= par.nx) return;
+    const long o = (long)j * par.nx + i, plane = (long)par.nx * par.ny;
+    double ar;
+    const hpb_c2 r = laser_rhs_mg_cell(L, chi, i, j, par, *ph, do_avg_rhs, ar);
+    rhs2[o] = r.re; rhs2[plane + o] = r.im;
+    acf_r[o] = ar;
+    const hpb_c2 g = guess[o];
+    sol2[o] = g.re; sol2[plane + o] = g.im;
+}
+__global__ void __launch_bounds__(kLT)
+k_laser_from_planar(const double *__restrict__ sol2, hpb_c2 *__restrict__ dst, int nx, int ny)
+{
+    hpb_pdl_prologue();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nx) return;
+    const long o = (long)j * nx + i, plane = (long)nx * ny;
+    dst[o] = c2(sol2[o], sol2[plane + o]);
+}
+
 __global__ void __launch_bounds__(kLT)
 k_laser_spectral(hpb_c2 *__restrict__ rhs_f, LaserAdvPar par, const LaserPhase *__restrict__ ph)
 {
@@ -310,15 +312,21 @@ struct hpb_laser_state {
     hpb_c2 *rhs = nullptr;
     double *chi = nullptr, *chi_initial = nullptr;
     LaserPhase *phase = nullptr;
-    int plan = -1;
+    hpb_fft2d *fft = nullptr;           // 2-D complex transform of the laser grid (fft2d.cu)
+    // lasers.solver_type = multigrid (the reference's default): hpmg type 2 (mg.cu: hpb_mg_solve2)
+    int use_mg = 0, mg_avg_rhs = 1;
+    double mg_tol_rel = 1e-4, mg_tol_abs = 0.;
+    double *mg_rhs2 = nullptr, *mg_sol2 = nullptr, *mg_acf = nullptr;    // planar [2][ny][nx], [ny][nx]
+    long mg_vcycles = 0;
 };
 enum { L_NM1J00 = 0, L_NM1JP1, L_NM1JP2, L_N00J00, L_N00JP1, L_N00JP2, L_NP1J00, L_NP1JP1, L_NP1JP2 };
 
 extern "C" void hpb_laser_state_destroy(hpb_laser_state *st)
 {
     if (!st) return;
-    if (st->plan >= 0 && cufft_api()) cufft_api()->destroy(st->plan);
+    hpb_fft2d_destroy(st->fft);
     cudaFree(st->work); cudaFree(st->rhs); cudaFree(st->chi); cudaFree(st->chi_initial); cudaFree(st->phase);
+    cudaFree(st->mg_rhs2); cudaFree(st->mg_sol2); cudaFree(st->mg_acf);
     for (auto p : st->store) cudaFree(p);
     delete st;
 }
@@ -328,8 +336,6 @@ extern "C" int hpb_laser_state_create(hpb_laser_state **out, hpb_ctx *ctx, int n
 {
     if (!out || !ctx || nz < 1 || !lasers || nlasers < 1 || nlasers > HPB_MAX_LASERS || lambda0 <= 0.
         || interp_order < 0 || interp_order > 2) return HPB_ERR_ARG;
-    CufftApi *fft = cufft_api();
-    if (!fft) { hpb_set_error("laser envelope advance: libcufft could not be loaded"); return HPB_ERR_UNSUPPORTED; }
     hpb_laser_state *st = new hpb_laser_state();
     st->nx = ctx->g.nx; st->ny = ctx->g.ny; st->nz = nz; st->interp_order = interp_order; st->use_phase = use_phase;
     st->ls.n = nlasers;
@@ -344,10 +350,9 @@ extern "C" int hpb_laser_state_create(hpb_laser_state **out, hpb_ctx *ctx, int n
     for (int k = 0; ok && k < 4; ++k)
         ok = cudaMalloc(&st->store[k], (size_t)nz * plane * sizeof(hpb_c2)) == cudaSuccess
              && cudaMemset(st->store[k], 0, (size_t)nz * plane * sizeof(hpb_c2)) == cudaSuccess;
-    // cufftPlan2d(plan, n_slowest, n_fastest, type): rows are y
-    if (ok && fft->plan2d(&st->plan, st->ny, st->nx, kCufftZ2Z) != 0) { st->plan = -1; ok = false; }
+    if (ok && hpb_fft2d_create(&st->fft, st->nx, st->ny) != HPB_OK) ok = false;
     if (!ok) {
-        hpb_set_error("laser envelope advance: allocation or cuFFT plan failed (%zu bytes per slice plane, %d slices)",
+        hpb_set_error("laser envelope advance: allocation or FFT plan failed (%zu bytes per slice plane, %d slices)",
                       plane * sizeof(hpb_c2), nz);
         hpb_laser_state_destroy(st);
         return HPB_ERR_CUDA;
@@ -409,7 +414,6 @@ extern "C" int hpb_laser_advance_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_sl
 {
     if (!st || !ctx || c_chi < 0 || islice < 0 || islice >= st->nz) return HPB_ERR_ARG;
     if (dt == 0.) return HPB_OK;                                      // MultiLaser.cpp:418
-    CufftApi *fft = cufft_api();
     const hpb_geom &g = ctx->g;
     const size_t plane = (size_t)st->nx * st->ny;
     const int ng = -sl.lo_x;
@@ -424,21 +428,47 @@ extern "C" int hpb_laser_advance_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_sl
     const double pi2 = 2.0 * 3.14159265358979323846;
     const LaserAdvPar par = {st->nx, st->ny, step == 0 ? 1 : 0, g.dx, g.dy, g.dz, g.c, dt, st->ls.k0,
                              pi2 / prob_len_x, pi2 / prob_len_y};
+    if (st->use_mg) {
+        // MultiLaser::AdvanceSliceMG (:429-607)
+        if (!st->mg_rhs2) {
+            HPB_CUDA_CHECK(cudaMalloc(&st->mg_rhs2, 2 * plane * sizeof(double)));
+            HPB_CUDA_CHECK(cudaMalloc(&st->mg_sol2, 2 * plane * sizeof(double)));
+            HPB_CUDA_CHECK(cudaMalloc(&st->mg_acf, plane * sizeof(double)));
+        }
+        hpb_launch(k_laser_rhs_mg, grid, kLT, 0, ctx->stream, L, (const double *)st->chi, par,
+                   (const LaserPhase *)st->phase, st->mg_avg_rhs, (const hpb_c2 *)st->w[L_NP1J00], st->mg_rhs2,
+                   st->mg_acf, st->mg_sol2);
+        hpb_count_launch(ctx, 3);
+        // acoeff_imag (:518-519) needs djn: one small read-back per slice (the V-cycle loop synchronises
+        // on its convergence test anyway)
+        LaserPhase hph;
+        HPB_CUDA_CHECK(cudaMemcpyAsync(&hph, st->phase, sizeof(hph), cudaMemcpyDeviceToHost, ctx->stream));
+        HPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const double acoeff_imag = (step == 0 ? -4.0 : -2.0) * (st->ls.k0 + hph.djn) / (g.c * dt);
+        int iters = 0;
+        int rcm = hpb_mg_solve2(ctx, st->mg_sol2, st->mg_rhs2, st->mg_acf, acoeff_imag, st->mg_tol_rel, st->mg_tol_abs,
+                                200, &iters);
+        if (rcm) return rcm;
+        st->mg_vcycles += iters;
+        hpb_launch(k_laser_from_planar, grid, kLT, 0, ctx->stream, (const double *)st->mg_sol2, st->w[L_NP1J00],
+                   st->nx, st->ny);
+        hpb_count_launch(ctx);
+        HPB_CUDA_CHECK(cudaMemcpyAsync(st->store[2] + (size_t)islice * plane, st->w[L_NP1J00], plane * sizeof(hpb_c2),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+        HPB_CUDA_CHECK(cudaMemcpyAsync(st->store[3] + (size_t)islice * plane, st->w[L_N00J00], plane * sizeof(hpb_c2),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+        HPB_CUDA_CHECK(cudaGetLastError());
+        return HPB_OK;
+    }
     hpb_launch(k_laser_rhs, grid, kLT, 0, ctx->stream, L, (const double *)st->chi, par,
                (const LaserPhase *)st->phase, st->rhs);
     hpb_count_launch(ctx, 3);
     HPB_CUDA_CHECK(cudaGetLastError());
-    if (fft->set_stream(st->plan, ctx->stream) != 0
-        || fft->exec_z2z(st->plan, st->rhs, st->rhs, kCufftForward) != 0) {
-        hpb_set_error("laser envelope advance: cuFFT forward transform failed");
-        return HPB_ERR_CUDA;
-    }
+    int rc = hpb_fft2d_exec(st->fft, ctx, (const double2 *)st->rhs, (double2 *)st->rhs, -1);
+    if (rc) return rc;
     hpb_launch(k_laser_spectral, grid, kLT, 0, ctx->stream, st->rhs, par, (const LaserPhase *)st->phase);
     hpb_count_launch(ctx);
-    if (fft->exec_z2z(st->plan, st->rhs, st->w[L_NP1J00], kCufftInverse) != 0) {
-        hpb_set_error("laser envelope advance: cuFFT inverse transform failed");
-        return HPB_ERR_CUDA;
-    }
+    if ((rc = hpb_fft2d_exec(st->fft, ctx, (const double2 *)st->rhs, (double2 *)st->w[L_NP1J00], +1))) return rc;
     // MultiBuffer::pack_data: A^{n+1} and A^n of this slice go to the next time step
     HPB_CUDA_CHECK(cudaMemcpyAsync(st->store[2] + (size_t)islice * plane, st->w[L_NP1J00], plane * sizeof(hpb_c2),
                                    cudaMemcpyDeviceToDevice, ctx->stream));
@@ -449,6 +479,16 @@ extern "C" int hpb_laser_advance_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_sl
 }
 
 // ShiftLaserSlices (:180-212): j+1 -> j+2, j -> j+1 on every time level (pointer rotation)
+// lasers.solver_type / MG_tolerance_rel / MG_tolerance_abs / MG_average_rhs (MultiLaser.cpp:40-56)
+extern "C" int hpb_laser_set_solver(hpb_laser_state *st, int use_multigrid, double tol_rel, double tol_abs,
+                                    int average_rhs)
+{
+    if (!st) return HPB_ERR_ARG;
+    st->use_mg = use_multigrid != 0; st->mg_tol_rel = tol_rel; st->mg_tol_abs = tol_abs; st->mg_avg_rhs = average_rhs != 0;
+    return HPB_OK;
+}
+extern "C" long hpb_laser_mg_vcycles(hpb_laser_state *st) { return st ? st->mg_vcycles : -1; }
+
 extern "C" int hpb_laser_shift_slices(hpb_laser_state *st)
 {
     if (!st) return HPB_ERR_ARG;

@@ -127,6 +127,36 @@ HPB_HD hpb_c2 laser_rhs_cell(const LaserPlanes &L, const double *chi, int i, int
     return t1 + t2 + t3 - t4 + f * am1;
 }
 
+// right-hand side and real coefficient of the multigrid variant (MultiLaser::AdvanceSliceMG :536-592):
+// chi enters the operator (do_avg_rhs) and the right-hand side carries chi * A once, or the fft
+// variant's 2 chi A^n (MG_average_rhs = 0)
+HPB_HD hpb_c2 laser_rhs_mg_cell(const LaserPlanes &L, const double *chi, int i, int j, const LaserAdvPar &p,
+                                const LaserPhase &ph, int do_avg_rhs, double &acf_real)
+{
+    const long o = (long)j * p.nx + i;
+    const double cdt = p.c * p.dt, cdtdz = p.c * p.dt * p.dz;
+    const hpb_c2 a00 = L.n00j00[o];
+    const double acoeff_real = p.step0 ? 6.0 / cdtdz : 3.0 / cdtdz + 2.0 / (p.c * p.c * p.dt * p.dt);
+    acf_real = do_avg_rhs ? acoeff_real + chi[o] : acoeff_real;
+    if (p.step0) {
+        const hpb_c2 t1 = (8.0 / cdtdz) * ((L.n00jp1[o] - L.np1jp1[o]) * ph.exp1);
+        const hpb_c2 t2 = (2.0 / cdtdz) * ((L.np1jp2[o] - L.n00jp2[o]) * ph.exp2);
+        const hpb_c2 t4 = laser_lap(L.n00j00, i, j, p);
+        const hpb_c2 f = c2(-6.0 / cdtdz, 4.0 * ph.djn / cdt + 4.0 * p.k0 / cdt);
+        const hpb_c2 r = t1 + t2 - t4 + f * a00;
+        return r + (do_avg_rhs ? chi[o] : 2.0 * chi[o]) * a00;
+    }
+    const double c2dt2 = p.c * p.c * p.dt * p.dt;
+    const hpb_c2 am1 = L.nm1j00[o];
+    const hpb_c2 t1 = (4.0 / cdtdz) * ((L.nm1jp1[o] - L.np1jp1[o]) * ph.exp1);
+    const hpb_c2 t2 = (1.0 / cdtdz) * ((L.np1jp2[o] - L.nm1jp2[o]) * ph.exp2);
+    const hpb_c2 t3 = (-4.0 / c2dt2) * a00;
+    const hpb_c2 t4 = laser_lap(L.nm1j00, i, j, p);
+    const hpb_c2 f = c2(-3.0 / cdtdz + 2.0 / c2dt2, 2.0 * ph.djn / cdt + 2.0 * p.k0 / cdt);
+    const hpb_c2 r = t1 + t2 + t3 - t4 + f * am1;
+    return r + (do_avg_rhs ? chi[o] * am1 : (2.0 * chi[o]) * a00);
+}
+
 // spectral solve (:765-795): -rhs_f / (kx^2 + ky^2 + acoeff), times 1 / (nx ny) for the unnormalised
 // inverse transform
 HPB_HD hpb_c2 laser_spectral_cell(hpb_c2 rhs_f, int i, int j, const LaserAdvPar &p, const LaserPhase &ph)

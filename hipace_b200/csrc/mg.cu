@@ -842,6 +842,176 @@ CoarseArgs coarse_args(hpb_ctx *ctx)
     return A;
 }
 
+
+// =================================================================================================
+// hpmg system type 2: the complex Helmholtz system  lap(A) - (a_r + i a_i) A = rhs  of the laser
+// envelope solver (MultiLaser::AdvanceSliceMG, src/laser/MultiLaser.cpp:429-607) as two coupled real
+// components: gs2 (HpMultiGrid.cpp:296-334), residual2r / residual2i (:192-208), solve2 (:1192-1296).
+// V-cycle, transfer operators and stopping rule are those of type 1 (solve_doit :1307-1427, vcycle
+// :1429-1512, bottomsolve :1514-1594).  First implementation: one plain global-memory kernel per
+// level operator (a red-black half-sweep, a residual, a restriction, an interpolation), the level
+// arrays of the type-1 solver reused as scratch.  Correct against the oracle's MultiGrid2; not yet
+// tile-fused like the type-1 path.
+// =================================================================================================
+struct MG2 {
+    double *acf[32] = {};       // per level: 2 components (a_r, a_i) over the level box
+    double *sol0 = nullptr, *rhs0 = nullptr;     // level-0 iterate and right-hand side (2 comps, level box)
+};
+
+// one red-black half-sweep of gs2 on the valid points with (i + j + color) even
+__global__ void k2_gsrb(LevelGeom g, V2 phi, V2 rhs, V2 acf, int color)
+{
+    hpb_pdl_prologue();
+    const int nvx = g.vhix - g.vlo + 1;
+    const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nv) return;
+    const int j = (int)(s / nvx) + g.vlo, i = (int)(s % nvx) + g.vlo;
+    if (((i + j + color) & 1) != 0) return;
+    double lap0, lap1;
+    double c0 = -2.0 * (g.facx + g.facy);
+    if (g.cc && i == g.vlo) {
+        lap0 = g.facx * (4. / 3.) * phi.at(i + 1, j, 0); lap1 = g.facx * (4. / 3.) * phi.at(i + 1, j, 1);
+        c0 -= 2.0 * g.facx;
+    } else if (g.cc && i == g.vhix) {
+        lap0 = g.facx * (4. / 3.) * phi.at(i - 1, j, 0); lap1 = g.facx * (4. / 3.) * phi.at(i - 1, j, 1);
+        c0 -= 2.0 * g.facx;
+    } else {
+        lap0 = g.facx * (phi.at(i - 1, j, 0) + phi.at(i + 1, j, 0));
+        lap1 = g.facx * (phi.at(i - 1, j, 1) + phi.at(i + 1, j, 1));
+    }
+    if (g.cc && j == g.vlo) {
+        lap0 += g.facy * (4. / 3.) * phi.at(i, j + 1, 0); lap1 += g.facy * (4. / 3.) * phi.at(i, j + 1, 1);
+        c0 -= 2.0 * g.facy;
+    } else if (g.cc && j == g.vhiy) {
+        lap0 += g.facy * (4. / 3.) * phi.at(i, j - 1, 0); lap1 += g.facy * (4. / 3.) * phi.at(i, j - 1, 1);
+        c0 -= 2.0 * g.facy;
+    } else {
+        lap0 += g.facy * (phi.at(i, j - 1, 0) + phi.at(i, j + 1, 0));
+        lap1 += g.facy * (phi.at(i, j - 1, 1) + phi.at(i, j + 1, 1));
+    }
+    double cr = c0 - acf.at(i, j, 0), ci = -acf.at(i, j, 1);
+    const double cmag = 1.0 / (cr * cr + ci * ci);
+    cr *= cmag; ci *= cmag;
+    const double dr = rhs.at(i, j, 0) - lap0, di = rhs.at(i, j, 1) - lap1;
+    phi.at(i, j, 0) = dr * cr + di * ci;
+    phi.at(i, j, 1) = di * cr - dr * ci;
+}
+
+__device__ __forceinline__ double lap_global(const LevelGeom &g, const V2 &phi, int i, int j, int n)
+{
+    double lap = -2.0 * (g.facx + g.facy) * phi.at(i, j, n);
+    if (g.cc && i == g.vlo) lap += g.facx * ((4. / 3.) * phi.at(i + 1, j, n) - 2.0 * phi.at(i, j, n));
+    else if (g.cc && i == g.vhix) lap += g.facx * ((4. / 3.) * phi.at(i - 1, j, n) - 2.0 * phi.at(i, j, n));
+    else lap += g.facx * (phi.at(i - 1, j, n) + phi.at(i + 1, j, n));
+    if (g.cc && j == g.vlo) lap += g.facy * ((4. / 3.) * phi.at(i, j + 1, n) - 2.0 * phi.at(i, j, n));
+    else if (g.cc && j == g.vhiy) lap += g.facy * ((4. / 3.) * phi.at(i, j - 1, n) - 2.0 * phi.at(i, j, n));
+    else lap += g.facy * (phi.at(i, j - 1, n) + phi.at(i, j + 1, n));
+    return lap;
+}
+
+// out = residual2(phi) on the valid points; norm (may be null): [0] = max|out|, [1] = max|rhs|
+__global__ void k2_residual(LevelGeom g, V2 out, V2 phi, V2 rhs, V2 acf, double *norm)
+{
+    hpb_pdl_prologue();
+    const int nvx = g.vhix - g.vlo + 1;
+    const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    double nres = 0., nrhs = 0.;
+    if (s < nv) {
+        const int j = (int)(s / nvx) + g.vlo, i = (int)(s % nvx) + g.vlo;
+        const double ar = acf.at(i, j, 0), ai = acf.at(i, j, 1);
+        const double pr = phi.at(i, j, 0), pi = phi.at(i, j, 1);
+        const double r0 = rhs.at(i, j, 0) + ar * pr - ai * pi - lap_global(g, phi, i, j, 0);
+        const double r1 = rhs.at(i, j, 1) + ai * pr + ar * pi - lap_global(g, phi, i, j, 1);
+        out.at(i, j, 0) = r0;
+        out.at(i, j, 1) = r1;
+        nres = fmax(fabs(r0), fabs(r1));
+        nrhs = fmax(fabs(rhs.at(i, j, 0)), fabs(rhs.at(i, j, 1)));
+    }
+    if (!norm) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nres = fmax(nres, __shfl_xor_sync(0xffffffffu, nres, o));
+        nrhs = fmax(nrhs, __shfl_xor_sync(0xffffffffu, nrhs, o));
+    }
+    if ((threadIdx.x & 31) == 0 && (nres > 0. || nrhs > 0.)) {
+        atomicMax((unsigned long long *)&norm[0], (unsigned long long)__double_as_longlong(nres));
+        atomicMax((unsigned long long *)&norm[1], (unsigned long long)__double_as_longlong(nrhs));
+    }
+}
+
+// crse = R(fine) for 2 components on the valid coarse points (restrict_cc / restrict_nd :29-52)
+__global__ void k2_restrict(LevelGeom gc, V2 crse, V2 fine)
+{
+    hpb_pdl_prologue();
+    const int nvx = gc.vhix - gc.vlo + 1;
+    const long nv = (long)nvx * (gc.vhiy - gc.vlo + 1);
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nv) return;
+    const int j = (int)(s / nvx) + gc.vlo, i = (int)(s % nvx) + gc.vlo;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+        const double *f = fine.p + n * fine.cs + (2 * i) + (long)(2 * j) * fine.rs;
+        const long w = fine.rs;
+        double v;
+        if (gc.cc) v = 0.25 * (f[0] + f[1] + f[w] + f[w + 1]);
+        else v = (1. / 16.) * (f[-w - 1] + 2. * f[-w] + f[-w + 1] + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                               + f[w - 1] + 2. * f[w] + f[w + 1]);
+        crse.at(i, j, n) = v;
+    }
+}
+
+// out = fine + I(crse) on the valid fine points (interpcpy_cc / interpcpy_nd :88-121); out may be fine
+__global__ void k2_interp_add(LevelGeom g, V2 out, V2 fine, V2 crse)
+{
+    hpb_pdl_prologue();
+    const int nvx = g.vhix - g.vlo + 1;
+    const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nv) return;
+    const int j = (int)(s / nvx) + g.vlo, i = (int)(s % nvx) + g.vlo;
+    out.at(i, j, 0) = fine.at(i, j, 0) + interp_at(crse, i, j, 0, g.cc);
+    out.at(i, j, 1) = fine.at(i, j, 1) + interp_at(crse, i, j, 1, g.cc);
+}
+
+// level-0 embedding: planar valid-box arrays [2][ny][nx] <-> the level box (offset vlo)
+__global__ void k2_embed(LevelGeom g, V2 lvl, const double *valid2, const double *valid_r, double scalar_i, int nxv,
+                         int nyv, int mode)
+{
+    hpb_pdl_prologue();
+    const long nv = (long)nxv * nyv;
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nv) return;
+    const int jv = (int)(s / nxv), iv = (int)(s % nxv);
+    const int i = iv + g.vlo, j = jv + g.vlo;
+    if (mode == 0) {            // two planar components in
+        lvl.at(i, j, 0) = valid2[s];
+        lvl.at(i, j, 1) = valid2[nv + s];
+    } else {                    // coefficient: array real part, scalar imaginary part
+        lvl.at(i, j, 0) = valid_r[s];
+        lvl.at(i, j, 1) = scalar_i;
+    }
+}
+__global__ void k2_extract(LevelGeom g, V2 lvl, double *valid2, int nxv, int nyv)
+{
+    hpb_pdl_prologue();
+    const long nv = (long)nxv * nyv;
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nv) return;
+    const int jv = (int)(s / nxv), iv = (int)(s % nxv);
+    valid2[s] = lvl.at(iv + g.vlo, jv + g.vlo, 0);
+    valid2[nv + s] = lvl.at(iv + g.vlo, jv + g.vlo, 1);
+}
+
+int mg2_sweeps(hpb_ctx *ctx, const LevelGeom &g, V2 phi, V2 rhs, V2 acf, int nsweeps)
+{
+    const long nv = (long)(g.vhix - g.vlo + 1) * (g.vhiy - g.vlo + 1);
+    for (int ic = 0; ic < nsweeps; ++ic) hpb_launch(k2_gsrb, nb(nv), 256, 0, ctx->stream, g, phi, rhs, acf, ic);
+    hpb_count_launch(ctx, nsweeps);
+    return HPB_OK;
+}
+
 }  // namespace
 
 int hpb_mg_init(hpb_ctx *ctx)
@@ -912,8 +1082,11 @@ int hpb_mg_init(hpb_ctx *ctx)
     return HPB_OK;
 }
 
+void hpb_mg2_free(hpb_ctx *ctx);
+
 void hpb_mg_free(hpb_ctx *ctx)
 {
+    hpb_mg2_free(ctx);
     for (int l = 0; l < ctx->mg_nlev; ++l) {
         cudaFree(ctx->mg[l].acf); cudaFree(ctx->mg[l].c0i); cudaFree(ctx->mg[l].res);
         cudaFree(ctx->mg[l].cor); cudaFree(ctx->mg[l].rescor);
@@ -1062,6 +1235,127 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
         hpb_launch(k_copy2, nb(nv0), 256, 0, ctx->stream, g0, sol, cur);
         hpb_count_launch(ctx);
     }
+    HPB_CUDA_CHECK(cudaGetLastError());
+    if (h_iters) *h_iters = iters;
+    return HPB_OK;
+}
+
+void hpb_mg2_free(hpb_ctx *ctx)
+{
+    MG2 *m = (MG2 *)ctx->mg2;
+    if (!m) return;
+    for (int l = 0; l < 32; ++l) cudaFree(m->acf[l]);
+    cudaFree(m->sol0); cudaFree(m->rhs0);
+    delete m;
+    ctx->mg2 = nullptr;
+}
+
+// hpmg::MultiGrid::solve2 with an array real coefficient and a scalar imaginary one (the laser case).
+// d_sol2 / d_rhs2: planar [2][ny][nx] over the valid box (real, imaginary), d_sol2 holds the initial
+// guess and receives the solution; d_acf_r: [ny][nx].
+extern "C" int hpb_mg_solve2(hpb_ctx *ctx, double *d_sol2, const double *d_rhs2, const double *d_acf_r,
+                             double acf_i, double tol_rel, double tol_abs, int max_iters, int *h_iters)
+{
+    if (!ctx || !d_sol2 || !d_rhs2 || !d_acf_r) return HPB_ERR_ARG;
+    const int nl = ctx->mg_nlev;
+    MG2 *m = (MG2 *)ctx->mg2;
+    if (!m) {
+        m = new MG2();
+        ctx->mg2 = m;
+        for (int l = 0; l < nl; ++l) {
+            const size_t n = 2 * (size_t)ctx->mg[l].nx * ctx->mg[l].ny * sizeof(double);
+            HPB_CUDA_CHECK(cudaMalloc(&m->acf[l], n));
+            HPB_CUDA_CHECK(cudaMemset(m->acf[l], 0, n));
+        }
+        const size_t n0 = 2 * (size_t)ctx->mg[0].nx * ctx->mg[0].ny * sizeof(double);
+        HPB_CUDA_CHECK(cudaMalloc(&m->sol0, n0));
+        HPB_CUDA_CHECK(cudaMalloc(&m->rhs0, n0));
+        HPB_CUDA_CHECK(cudaMemset(m->sol0, 0, n0));
+        HPB_CUDA_CHECK(cudaMemset(m->rhs0, 0, n0));
+    }
+    const int nxv = ctx->g.nx, nyv = ctx->g.ny;
+    const long nvv = (long)nxv * nyv;
+    auto G = [&](int l) { return level_geom(ctx, l); };
+    auto NV = [&](int l) { const LevelGeom g = G(l); return (long)(g.vhix - g.vlo + 1) * (g.vhiy - g.vlo + 1); };
+    auto ACF = [&](int l) { return lvl_view(ctx, l, m->acf[l]); };
+    auto bytes2 = [&](int l) { return 2 * (size_t)ctx->mg[l].nx * ctx->mg[l].ny * sizeof(double); };
+    const V2 sol0 = lvl_view(ctx, 0, m->sol0), rhs0 = lvl_view(ctx, 0, m->rhs0);
+    const V2 cor0 = lvl_view(ctx, 0, ctx->mg[0].cor), rescor0 = lvl_view(ctx, 0, ctx->mg[0].rescor);
+    // (the type-1 solver keeps 1 / c0 planes and its iterate in the same arrays: nothing of it
+    // survives a type-2 solve, and it rebuilds them on every solve)
+    hpb_launch(k2_embed, nb(nvv), 256, 0, ctx->stream, G(0), ACF(0), (const double *)nullptr, d_acf_r, acf_i, nxv, nyv, 1);
+    hpb_launch(k2_embed, nb(nvv), 256, 0, ctx->stream, G(0), sol0, (const double *)d_sol2, (const double *)nullptr, 0., nxv, nyv, 0);
+    hpb_launch(k2_embed, nb(nvv), 256, 0, ctx->stream, G(0), rhs0, d_rhs2, (const double *)nullptr, 0., nxv, nyv, 0);
+    for (int l = 1; l < nl; ++l) hpb_launch(k2_restrict, nb(NV(l)), 256, 0, ctx->stream, G(l), ACF(l), ACF(l - 1));
+    hpb_count_launch(ctx, 3 + nl - 1);
+    HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, 2 * sizeof(double), ctx->stream));
+    // cor0 = GSRB^4(sol), rescor0 = residual(cor0)   (:1326-1327)
+    HPB_CUDA_CHECK(cudaMemcpyAsync(cor0.p, sol0.p, bytes2(0), cudaMemcpyDeviceToDevice, ctx->stream));
+    mg2_sweeps(ctx, G(0), cor0, rhs0, ACF(0), 4);
+    hpb_launch(k2_residual, nb(NV(0)), 256, 0, ctx->stream, G(0), rescor0, cor0, rhs0, ACF(0), ctx->d_mg_norm);
+    hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 0, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
+    hpb_count_launch(ctx, 2);
+    int iters = 0;
+    while (true) {
+        HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_istate, ctx->d_mg_istate, 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+        HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_norm, ctx->d_mg_state, 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+        HPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        iters = ctx->h_mg_istate[1];
+        if (ctx->h_mg_istate[2]) {
+            hpb_set_error("hpmg (type 2) failing so lets stop here (resid/max_norm = %g)",
+                          ctx->h_mg_norm[2] / ctx->h_mg_norm[1]);
+            return HPB_ERR_MG_DIVERGED;
+        }
+        if (ctx->h_mg_istate[0]) break;
+        if (iters >= max_iters) { hpb_set_error("hpmg (type 2) failed to converge after %d iterations", max_iters); return HPB_ERR_MG_DIVERGED; }
+        // ---- one V-cycle (:1429-1512) ----
+        for (int l = 0; l < nl - 1; ++l) {
+            const V2 rescor = lvl_view(ctx, l, ctx->mg[l].rescor);
+            if (l > 0) {
+                const V2 cor = lvl_view(ctx, l, ctx->mg[l].cor), res = lvl_view(ctx, l, ctx->mg[l].res);
+                HPB_CUDA_CHECK(cudaMemsetAsync(cor.p, 0, bytes2(l), ctx->stream));
+                mg2_sweeps(ctx, G(l), cor, res, ACF(l), 4);
+                hpb_launch(k2_residual, nb(NV(l)), 256, 0, ctx->stream, G(l), rescor, cor, res, ACF(l), (double *)nullptr);
+                hpb_count_launch(ctx);
+            }
+            hpb_launch(k2_restrict, nb(NV(l + 1)), 256, 0, ctx->stream, G(l + 1), lvl_view(ctx, l + 1, ctx->mg[l + 1].res), rescor);
+            hpb_count_launch(ctx);
+        }
+        {
+            const int l = nl - 1;
+            const LevelGeom gb = G(l);
+            int nsw = 16;
+            const int mx = gb.nx > gb.ny ? gb.nx : gb.ny;
+            if ((mx + 1) / 2 * 2 > nsw) nsw = (mx + 1) / 2 * 2;       // :1587
+            const V2 cor = lvl_view(ctx, l, ctx->mg[l].cor);
+            HPB_CUDA_CHECK(cudaMemsetAsync(cor.p, 0, bytes2(l), ctx->stream));
+            mg2_sweeps(ctx, gb, cor, lvl_view(ctx, l, ctx->mg[l].res), ACF(l), nsw);
+        }
+        for (int l = nl - 2; l >= 0; --l) {
+            const V2 crse = lvl_view(ctx, l + 1, ctx->mg[l + 1].cor);
+            if (l == 0) {
+                // sol = GSRB^4(cor0 + I(cor1))
+                HPB_CUDA_CHECK(cudaMemcpyAsync(sol0.p, cor0.p, bytes2(0), cudaMemcpyDeviceToDevice, ctx->stream));
+                hpb_launch(k2_interp_add, nb(NV(0)), 256, 0, ctx->stream, G(0), sol0, cor0, crse);
+                mg2_sweeps(ctx, G(0), sol0, rhs0, ACF(0), 4);
+            } else {
+                const V2 cor = lvl_view(ctx, l, ctx->mg[l].cor);
+                hpb_launch(k2_interp_add, nb(NV(l)), 256, 0, ctx->stream, G(l), cor, cor, crse);
+                mg2_sweeps(ctx, G(l), cor, lvl_view(ctx, l, ctx->mg[l].res), ACF(l), 4);
+            }
+            hpb_count_launch(ctx);
+        }
+        // cor0 = GSRB^4(sol), rescor0 = residual(cor0)   (:1501-1503)
+        HPB_CUDA_CHECK(cudaMemcpyAsync(cor0.p, sol0.p, bytes2(0), cudaMemcpyDeviceToDevice, ctx->stream));
+        mg2_sweeps(ctx, G(0), cor0, rhs0, ACF(0), 4);
+        hpb_launch(k2_residual, nb(NV(0)), 256, 0, ctx->stream, G(0), rescor0, cor0, rhs0, ACF(0), ctx->d_mg_norm);
+        hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
+        hpb_count_launch(ctx, 2);
+    }
+    hpb_launch(k2_extract, nb(nvv), 256, 0, ctx->stream, G(0), cor0, d_sol2, nxv, nyv);
+    hpb_count_launch(ctx);
     HPB_CUDA_CHECK(cudaGetLastError());
     if (h_iters) *h_iters = iters;
     return HPB_OK;

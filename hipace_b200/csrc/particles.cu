@@ -1091,6 +1091,216 @@ k_advance_plasma_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtenso
 }
 
 // -------------------------------------------------------------------------------------------
+// Row-tile gather + push + deposit: the round-1 thread map (128 consecutive particles per CTA, in
+// lattice order a run of 128 cells of one row and one ppc pass) with the per-warp LDGSTS staging
+// loop -- 27 % of all executed instructions of that kernel -- replaced by ONE 136 x 6 TMA patch per
+// field and CTA, requested before the particle loads return.  No shared-memory combine is needed: the
+// warps of a CTA deposit into different cells, the aggregation of neighbouring lanes is the warp-shuffle
+// scheme of deposit_aggregated.  Works for any particle order (lanes outside the patch use direct
+// loads); the lattice hint only supplies the prefetch position.
+constexpr int kRowThreads = 128;
+constexpr int kRW = 136;
+constexpr uint32_t kRowTileBytes = 5 * kCH * kRW * sizeof(double);
+struct RowShared {
+    alignas(128) double tile[5][kCH][kRW];
+    int wbox[kRowThreads / 32][4];
+    alignas(8) uint64_t mbar;
+};
+
+template <int MINB, bool DEPOSIT, bool TMA>
+__global__ void __launch_bounds__(kRowThreads, MINB)
+k_advance_plasma_row(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtensorMap tmap, int nx_tot,
+                     int ny_tot, int lat_nx, int c_psi, int c_ez, int c_bx, int c_by, int c_bz, double x_off,
+                     double y_off, double dx_inv, double dy_inv, double clight, double qmc, double dz,
+                     int n_subcycles, int temp_slice, int bc, double lox, double loy, double hix, double hiy,
+                     DepositArgs dep)
+{
+    constexpr int NW = kRowThreads / 32;
+    __shared__ RowShared sh;
+    hpb_pdl_prologue();
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // kRowThreads consecutive particles: in lattice order a run of cells of one row and one pass
+    const long ip = (long)blockIdx.x * kRowThreads + tid;
+    const bool in_range = ip < pl.np;
+    uint64_t idcpu = 0;
+    double xp0 = 0., yp0 = 0., ux0 = 0., uy0 = 0., psi0 = 1., wq = 0.;
+    if (in_range) {
+        idcpu = ld_stream(&pl.idcpu[ip]);
+        xp0 = ld_stream(&pl.r[HPB_X_PREV][ip]);
+        yp0 = ld_stream(&pl.r[HPB_Y_PREV][ip]);
+        ux0 = ld_stream(&pl.r[HPB_UX_HALF][ip]);
+        uy0 = ld_stream(&pl.r[HPB_UY_HALF][ip]);
+        psi0 = ld_stream(&pl.r[HPB_PSI_HALF][ip]);
+        if (DEPOSIT) wq = ld_stream(&pl.r[HPB_W][ip]);
+    }
+    // Prefetch: the lattice says where the CTA's particles started, and most of the plasma has moved
+    // less than a cell or two from there -- the patch around the home cells is requested NOW, in the
+    // shadow of the particle loads, instead of after them (one DRAM/L2 round trip instead of two).
+    int bi = 0, bj = 0;
+    // home cell of the CTA's first particle (lattice order: particle = pass * lat_n + cell, x fastest)
+    const long cell0 = pl.lat_n > 0 ? ((long)blockIdx.x * kRowThreads) % pl.lat_n : 0;
+    const int hrow = lat_nx > 0 ? (int)(cell0 / lat_nx) : 0, hcol = lat_nx > 0 ? (int)(cell0 - (long)hrow * lat_nx) : 0;
+    // (a run that crosses the end of a lattice row does not fit one patch: no prefetch for it)
+    const bool prefetched = TMA && lat_nx > 0 && hcol + kRowThreads <= lat_nx;
+    if (TMA && tid == 0) {
+        hpb_tma_prefetch_desc(&tmap);
+        hpb_mbar_init(&sh.mbar, 1);
+    }
+    if (prefetched) {
+        const int ax = patch_origin(hcol - 4, a.lo_x, nx_tot, kRW, true);
+        const int ay = patch_origin(hrow - 3, a.lo_y, ny_tot, kCH, false);
+        bi = ax + a.lo_x; bj = ay + a.lo_y;
+        if (tid == 0) {
+            hpb_mbar_arrive_expect_tx(&sh.mbar, kRowTileBytes);
+            hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_psi);
+            hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
+            hpb_tma_load_3d(&sh.tile[2][0][0], &tmap, &sh.mbar, ax, ay, c_bx);
+            hpb_tma_load_3d(&sh.tile[3][0][0], &tmap, &sh.mbar, ax, ay, c_by);
+            hpb_tma_load_3d(&sh.tile[4][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
+        }
+    }
+    bool valid = in_range && hpb_is_valid(idcpu);
+    const double clight_inv = 1.0 / clight;
+    const double *F0 = a.comp(c_psi), *F1 = a.comp(c_ez), *F2 = a.comp(c_bx);
+    const double *F3 = a.comp(c_by), *F4 = a.comp(c_bz);
+    double xp = xp0, yp = yp0, ux = ux0, uy = uy0, psi = psi0;
+    uint32_t phase = 0;
+
+    for (int isc = 0; isc < n_subcycles; ++isc) {
+        xp = xp0; yp = yp0;
+        double sx[4], dsx[4], sy[4], dsy[4];
+        const int i0 = dshape2_nodal((xp - x_off) * dx_inv, sx, dsx);
+        const int j0 = dshape2_nodal((yp - y_off) * dy_inv, sy, dsy);
+        // bounding box of the CTA's stencil origins
+        const int big = 1 << 30;
+        const int imin = __reduce_min_sync(kFull, valid ? i0 : big), imax = __reduce_max_sync(kFull, valid ? i0 : -big);
+        const int jmin = __reduce_min_sync(kFull, valid ? j0 : big), jmax = __reduce_max_sync(kFull, valid ? j0 : -big);
+        if (lane == 0) { sh.wbox[w][0] = imin; sh.wbox[w][1] = jmin; sh.wbox[w][2] = imax; sh.wbox[w][3] = jmax; }
+        __syncthreads();        // (also: the old tile has been consumed)
+        int ci = big, cj = big, ei = -big, ej = -big;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            ci = min(ci, sh.wbox[q][0]); cj = min(cj, sh.wbox[q][1]);
+            ei = max(ei, sh.wbox[q][2]); ej = max(ej, sh.wbox[q][3]);
+        }
+        const bool any = ci != big;
+        // the prefetched patch serves if every stencil of the CTA lies inside it; otherwise the patch
+        // is (re)staged at the bounding box origin, and particles that do not fit even that (a stirred
+        // group) gather with direct loads
+        const bool pre_ok = prefetched && isc == 0 && any && ci >= bi && ei + 4 <= bi + kRW && cj >= bj
+                            && ej + 4 <= bj + kCH;
+        if (prefetched && isc == 0 && !pre_ok) {   // drain the prefetch before its buffer is rewritten
+            hpb_mbar_wait(&sh.mbar, phase); phase ^= 1u;
+            __syncthreads();
+        }
+        if (any && !pre_ok) {
+            const int ax = patch_origin(ci, a.lo_x, nx_tot, kRW, TMA);      // array coordinates of the patch origin
+            const int ay = patch_origin(cj, a.lo_y, ny_tot, kCH, false);
+            bi = ax + a.lo_x; bj = ay + a.lo_y;
+            if (TMA) {
+                if (tid == 0) {
+                    hpb_fence_proxy_async();
+                    hpb_mbar_arrive_expect_tx(&sh.mbar, kRowTileBytes);
+                    hpb_tma_load_3d(&sh.tile[0][0][0], &tmap, &sh.mbar, ax, ay, c_psi);
+                    hpb_tma_load_3d(&sh.tile[1][0][0], &tmap, &sh.mbar, ax, ay, c_ez);
+                    hpb_tma_load_3d(&sh.tile[2][0][0], &tmap, &sh.mbar, ax, ay, c_bx);
+                    hpb_tma_load_3d(&sh.tile[3][0][0], &tmap, &sh.mbar, ax, ay, c_by);
+                    hpb_tma_load_3d(&sh.tile[4][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
+                }
+            } else {
+                // the same patch with asynchronous 8-byte copies by all threads (arrays the TMA unit
+                // cannot address: odd row length); cells outside the array are never read
+#pragma unroll 1
+                for (int e = tid; e < 5 * kCH * kRW; e += kRowThreads) {
+                    const int f = e / (kCH * kRW), rem = e - f * (kCH * kRW), r = rem / kRW, c = rem - r * kRW;
+                    const double *F = f == 0 ? F0 : f == 1 ? F1 : f == 2 ? F2 : f == 3 ? F3 : F4;
+                    if (ax + c >= 0 && ay + r >= 0 && ax + c < nx_tot && ay + r < ny_tot)
+                        cp_async_8(&sh.tile[f][r][c], F + (long)(ay + r) * a.jstride + (ax + c));
+                }
+                cp_async_wait_all();
+                __syncthreads();
+            }
+        }
+        const bool staged = any && i0 >= bi && i0 + 4 <= bi + kRW && j0 >= bj && j0 + 4 <= bj + kCH;
+        if (TMA && any) { hpb_mbar_wait(&sh.mbar, phase); phase ^= 1u; }
+        if (valid) {
+            PushFields f;
+            if (staged) {
+                const double *t0 = &sh.tile[0][j0 - bj][i0 - bi];
+                f = gather_rows([&](int fi, int ix, int iy) { return t0[fi * (kCH * kRW) + iy * kRW + ix]; },
+                                sx, dsx, sy, dsy, dx_inv, dy_inv);
+            } else {
+                const long o = a.idx(i0, j0);
+                const long js = a.jstride;
+                f = gather_rows([&](int fi, int ix, int iy) {
+                        const double *F = fi == 0 ? F0 : fi == 1 ? F1 : fi == 2 ? F2 : fi == 3 ? F3 : F4;
+                        return F[o + iy * js + ix];
+                    }, sx, dsx, sy, dsy, dx_inv, dy_inv);
+            }
+            f.Bx_c *= clight;
+            f.By_c *= clight;
+            const PushLaser las = {0., 0., 0.};
+            constexpr int nsub = 4;
+            const double sdz = dz / nsub;
+            ux = ux0; uy = uy0; psi = psi0;
+#pragma unroll 1
+            for (int isub = 0; isub < nsub; ++isub) push_substep<false>(ux, uy, psi, f, clight_inv, qmc, sdz, las);
+
+            xp += dz * clight_inv * (ux * (1.0 / psi));
+            yp += dz * clight_inv * (uy * (1.0 / psi));
+            if (enforce_bc(xp, yp, ux, uy, bc, lox, loy, hix, hiy)) {
+                st_stream(&pl.r[HPB_W][ip], 0.0);
+                st_stream(&pl.idcpu[ip], hpb_make_invalid(idcpu));
+                valid = false;
+            } else {
+                st_stream(&pl.r[HPB_X][ip], xp);
+                st_stream(&pl.r[HPB_Y][ip], yp);
+                if (!temp_slice) {
+                    st_stream(&pl.r[HPB_UX_HALF][ip], ux);
+                    st_stream(&pl.r[HPB_UY_HALF][ip], uy);
+                    st_stream(&pl.r[HPB_PSI_HALF][ip], psi);
+                    st_stream(&pl.r[HPB_X_PREV][ip], xp);
+                    st_stream(&pl.r[HPB_Y_PREV][ip], yp);
+                    xp0 = xp; yp0 = yp; ux0 = ux; uy0 = uy; psi0 = psi;
+                }
+#pragma unroll 1
+                for (int isub = 0; isub < nsub / 2; ++isub) push_substep<false>(ux, uy, psi, f, clight_inv, qmc, sdz, las);
+                st_stream(&pl.r[HPB_UX][ip], ux);
+                st_stream(&pl.r[HPB_UY][ip], uy);
+                st_stream(&pl.r[HPB_PSI][ip], psi);
+            }
+        }
+    }
+    if (!DEPOSIT) return;
+
+    // ::DepositCurrent of the pushed particle (same expressions as k_deposit_current)
+    bool active = valid;
+    const double psi_inv = 1.0 / psi;
+    const double vx_c = ux * psi_inv, vy_c = uy * psi_inv;
+    double q_invvol = dep.charge_invvol * wq;
+    const double gamma_psi = 0.5 * (psi_inv * psi_inv + vx_c * vx_c * dep.clightinv * dep.clightinv
+                                    + vy_c * vy_c * dep.clightinv * dep.clightinv + 1.0);
+    if (active && (gamma_psi < 0.0 || gamma_psi > dep.max_qsa || psi_inv < 0.0)) {
+        if (dep.n_qsa_violation) atomicAdd(dep.n_qsa_violation, 1);
+        st_stream(&pl.r[HPB_W][ip], 0.0);
+        st_stream(&pl.idcpu[ip], hpb_make_invalid(idcpu));
+        active = false;
+    }
+    double dsx3[3] = {0., 0., 0.}, dsy3[3] = {0., 0., 0.};
+    int di0 = 0, dj0 = 0;
+    if (active) {
+        di0 = shape2((xp - x_off) * dx_inv, dsx3);
+        dj0 = shape2((yp - y_off) * dy_inv, dsy3);
+    } else {
+        q_invvol = 0.;
+    }
+    deposit_aggregated<true, false, true, true>(a, dep.c_jx, dep.c_jy, -1, dep.c_chi, dep.c_rhomjz,
+                                                active, true, lane, di0, dj0, dsx3, dsy3, q_invvol,
+                                                vx_c, vy_c, gamma_psi,
+                                                dep.charge_mu0_mass_ratio * psi_inv);
+}
+
+// -------------------------------------------------------------------------------------------
 // CTA-tile explicit deposition (lattice-ordered plasmas with ppc 4 or 9)
 // -------------------------------------------------------------------------------------------
 // Same idea as k_advance_plasma_cta: the NW warps of a CTA hold the NW passes of the same 28
@@ -1112,7 +1322,7 @@ struct ExplShared {
     alignas(8) uint64_t mbar;
 };
 
-template <int NW, int MINB, bool TMA>
+template <int NW, int MINB, bool TMA, bool COMBINE>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtensorMap tmap, int nx_tot,
                           int ny_tot, int lat_nx, int c_sy, int c_sx, int c_bz, int c_ez, int c_exmby,
@@ -1309,27 +1519,40 @@ k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CU
             }
         }
     }
-    // combine the centre columns of the NW passes on warp 0's cells
     const bool own = active && owner;
-    if (w == 0) { sh.ref_cc[lane] = own ? cc : kNoCell - 7 * lane; sh.ref_j0[lane] = j0; }
-    __syncthreads();
-    const int rcc = sh.ref_cc[lane], rj0 = sh.ref_j0[lane];
-    const bool match = own && cc == rcc && j0 == rj0;
+    if (!COMBINE) {
+        // every pass reduces its own centre column (the round-1 scheme; the patch prefetch is the gain)
+        if (own) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        sh.comb[w][k][lane] = match ? accy[k] : 0.;
-        sh.comb[w][5 + k][lane] = match ? accx[k] : 0.;
-    }
-    if (own && !match) {
-#pragma unroll
-        for (int iy = 0; iy < 5; ++iy) {
-            const long o = a.idx(cc, j0 + iy);
-            red_add(Sy + o, accy[iy]);
-            red_add(Sx + o, accx[iy]);
+            for (int iy = 0; iy < 5; ++iy) {
+                const long o = a.idx(cc, j0 + iy);
+                red_add(Sy + o, accy[iy]);
+                red_add(Sx + o, accx[iy]);
+            }
         }
     }
-    __syncthreads();
-    if (rcc > kNoCell) {
+    // combine the centre columns of the NW passes on warp 0's cells
+    if (COMBINE && w == 0) { sh.ref_cc[lane] = own ? cc : kNoCell - 7 * lane; sh.ref_j0[lane] = j0; }
+    if (COMBINE) __syncthreads();
+    const int rcc = COMBINE ? sh.ref_cc[lane] : kNoCell, rj0 = COMBINE ? sh.ref_j0[lane] : 0;
+    const bool match = own && cc == rcc && j0 == rj0;
+    if (COMBINE) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            sh.comb[w][k][lane] = match ? accy[k] : 0.;
+            sh.comb[w][5 + k][lane] = match ? accx[k] : 0.;
+        }
+        if (own && !match) {
+#pragma unroll
+            for (int iy = 0; iy < 5; ++iy) {
+                const long o = a.idx(cc, j0 + iy);
+                red_add(Sy + o, accy[iy]);
+                red_add(Sx + o, accx[iy]);
+            }
+        }
+        __syncthreads();
+    }
+    if (COMBINE && rcc > kNoCell) {
 #pragma unroll
         for (int kk = 0; kk < (10 + NW - 1) / NW; ++kk) {
             const int k = w + kk * NW;
@@ -1505,7 +1728,7 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     // expl_variant 4 (default) / 7: the CTA-tile kernel (TMA / cp.async staging) whenever the particles
     // carry the lattice order with ppc 4 or 9 and there is no laser; 0: the round-1 warp kernel
     const bool lattice = ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np;
-    if ((variant == 4 || variant == 7 || variant == 8) && comps[HPB_C_AABS] < 0 && lattice
+    if ((variant == 4 || (variant >= 7 && variant <= 10)) && comps[HPB_C_AABS] < 0 && lattice
         && (ctx->order_ppc == 4 || ctx->order_ppc == 9)) {
         PlasmaPtrs pp = to_ptrs(pl);
         pp.lat_n = ctx->order_n; pp.lat_ppc = ctx->order_ppc; pp.lat_mode = 1;
@@ -1515,14 +1738,16 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
         const CUtensorMap *tm = variant != 7 ? (const CUtensorMap *)hpb_slice_tmap(ctx, 1, sl, kEW, kEH) : nullptr;
         CUtensorMap none;
         memset(&none, 0, sizeof(none));
-#define HPB_LAUNCH_ECTA(NW, MB, TMA_)                                                              \
-        hpb_launch(k_explicit_deposition_cta<NW, MB, TMA_>, (unsigned)groups, NW * 32, 0, ctx->stream, \
+#define HPB_LAUNCH_ECTA(NW, MB, TMA_, CMB)                                                         \
+        hpb_launch(k_explicit_deposition_cta<NW, MB, TMA_, CMB>, (unsigned)groups, NW * 32, 0, ctx->stream, \
                    pp, make_view(sl), TMA_ ? *tm : none, sl.nx_tot, sl.ny_tot, lat_nx, comps[HPB_C_SY],  \
                    comps[HPB_C_SX], comps[HPB_C_BZ], comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], \
                    g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass)
-        if (ctx->order_ppc == 4 && variant == 8 && tm) HPB_LAUNCH_ECTA(4, 4, true);      // 128 registers
-        else if (ctx->order_ppc == 4) { if (tm) HPB_LAUNCH_ECTA(4, 5, true); else HPB_LAUNCH_ECTA(4, 5, false); }
-        else { if (tm) HPB_LAUNCH_ECTA(9, 2, true); else HPB_LAUNCH_ECTA(9, 2, false); }
+        if (ctx->order_ppc == 4 && variant == 8 && tm) HPB_LAUNCH_ECTA(4, 4, true, true);      // 128 registers
+        else if (ctx->order_ppc == 4 && variant == 9 && tm) HPB_LAUNCH_ECTA(4, 5, true, false);  // no combine
+        else if (ctx->order_ppc == 4 && variant == 10 && tm) HPB_LAUNCH_ECTA(4, 4, true, false); // no combine, 128 regs
+        else if (ctx->order_ppc == 4) { if (tm) HPB_LAUNCH_ECTA(4, 5, true, true); else HPB_LAUNCH_ECTA(4, 5, false, true); }
+        else { if (tm) HPB_LAUNCH_ECTA(9, 2, true, true); else HPB_LAUNCH_ECTA(9, 2, false, true); }
 #undef HPB_LAUNCH_ECTA
         hpb_count_launch(ctx);
         HPB_CUDA_CHECK(cudaGetLastError());
@@ -1596,6 +1821,33 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
     // carry the lattice order with ppc 4 or 9; 2: the round-1 warp-staged kernel, 1: direct loads,
     // 3: warp-staged with 128 registers
     const bool lattice = ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np;
+    // push_variant 6 / 7 / 8: the row-tile kernel (round-1 thread map, one TMA patch per CTA; 96 / 128
+    // registers / cp.async staging); any particle order
+    if ((variant == 6 || variant == 7 || variant == 8) && lasa.c_aabs < 0) {
+        PlasmaPtrs pp = to_ptrs(pl);
+        const bool lat = ctx->order_n > 0 && ctx->order_n * ctx->order_ppc == pl.np;
+        pp.lat_n = lat ? ctx->order_n : 0; pp.lat_ppc = lat ? ctx->order_ppc : 1;
+        const int lat_nx = lat && pp.lat_n == (long)g.nx * g.ny ? g.nx : 0;
+        const long nblk = (pl.np + kRowThreads - 1) / kRowThreads;
+        const CUtensorMap *tm = variant != 8 ? (const CUtensorMap *)hpb_slice_tmap(ctx, 2, sl, kRW, kCH) : nullptr;
+        CUtensorMap none;
+        memset(&none, 0, sizeof(none));
+#define HPB_LAUNCH_ROW(MB, DEP, TMA_)                                                              \
+        hpb_launch(k_advance_plasma_row<MB, DEP, TMA_>, (unsigned)nblk, kRowThreads, 0, ctx->stream, \
+                   pp, make_view(sl), TMA_ ? *tm : none, sl.nx_tot, sl.ny_tot, lat_nx, comps[HPB_C_PSI], \
+                   comps[HPB_C_EZ], comps[HPB_C_BX], comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off,  \
+                   1.0 / g.dx, 1.0 / g.dy, g.c, charge / (mass * g.c), g.dz / n_subcycles, n_subcycles,  \
+                   temp_slice, particle_bc, bc_lo[0], bc_lo[1], bc_hi[0], bc_hi[1], dep)
+#define HPB_LAUNCH_ROW_MB(MB)                                                                     \
+        do { if (deposit) { if (tm) HPB_LAUNCH_ROW(MB, true, true); else HPB_LAUNCH_ROW(MB, true, false); } \
+             else { if (tm) HPB_LAUNCH_ROW(MB, false, true); else HPB_LAUNCH_ROW(MB, false, false); } } while (0)
+        if (variant == 7) HPB_LAUNCH_ROW_MB(4); else HPB_LAUNCH_ROW_MB(5);
+#undef HPB_LAUNCH_ROW_MB
+#undef HPB_LAUNCH_ROW
+        hpb_count_launch(ctx);
+        HPB_CUDA_CHECK(cudaGetLastError());
+        return HPB_OK;
+    }
     if ((variant == 0 || variant == 4 || variant == 5) && lasa.c_aabs < 0 && lattice && (ctx->order_ppc == 4 || ctx->order_ppc == 9)) {
         PlasmaPtrs pp = to_ptrs(pl);
         pp.lat_n = ctx->order_n; pp.lat_ppc = ctx->order_ppc; pp.lat_mode = 1;

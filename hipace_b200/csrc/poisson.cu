@@ -18,217 +18,14 @@
 // Two transform passes instead of four, no transposes, and the three solves of a slice
 // (Psi, Ez, Bz) are batched into every launch (grid.y = batch).
 #include "common.cuh"
+#include "fft_smem.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
 
 namespace {
 
-constexpr int kFftThreads = 256;
-constexpr int kMaxRad = 32;
-
-struct FftPlan {
-    int N; int nrad; int rad[kMaxRad];
-    const double *cs_cos[kMaxRad];     // per prime stage: cos(2 pi t b / p), [b = 0..h][t = 1..h]
-    const double *cs_sin[kMaxRad];
-};
 struct OutPtrs { double *p[4]; };
-
-__device__ __forceinline__ double2 cmul(double2 a, double2 b)
-{
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-
-// j / d and j % d for 0 <= j < 2^21 and a run-time divisor: a float reciprocal instead of the
-// ~20-instruction integer division sequence (the stage loops are instruction-issue bound)
-struct FastDiv {
-    int d; float inv;
-    __device__ __forceinline__ explicit FastDiv(int d_) : d(d_), inv(1.0f / (float)d_) {}
-    __device__ __forceinline__ int div(int j) const
-    {
-        int q = (int)(((float)j + 0.5f) * inv);
-        // the float estimate is off by at most one
-        const int r = j - q * d;
-        q += (r >= d) - (r < 0);
-        return q;
-    }
-    __device__ __forceinline__ int mod(int j) const { return j - div(j) * d; }
-};
-
-// Stockham stage of radix r with Ns = product of the previous radices:
-//   out[(j-k) r + k + b Ns] = sum_t ( in[j + t N/r] w_N^{t k N/(Ns r)} ) w_r^{t b},  k = j mod Ns
-
-__device__ __forceinline__ void fft_stage_r2(const double2 *__restrict__ in, double2 *__restrict__ out,
-                                             const double2 *__restrict__ root, int N, int Ns)
-{
-    const int Nr = N >> 1, tw = N / (Ns * 2);
-    const FastDiv fd(Ns);
-    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = fd.mod(j);
-        double2 v0 = in[j], v1 = in[j + Nr];
-        if (k) v1 = cmul(v1, __ldg(&root[k * tw]));
-        const int o = (j - k) * 2 + k;
-        out[o] = cadd(v0, v1);
-        out[o + Ns] = csub(v0, v1);
-    }
-}
-
-__device__ __forceinline__ void fft_stage_r3(const double2 *__restrict__ in, double2 *__restrict__ out,
-                                             const double2 *__restrict__ root, int N, int Ns)
-{
-    const int Nr = N / 3, tw = N / (Ns * 3);
-    const double c1 = -0.5, s1 = 0.86602540378443864676;
-    const FastDiv fd(Ns);
-    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = fd.mod(j);
-        double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr];
-        if (k) { v1 = cmul(v1, __ldg(&root[k * tw])); v2 = cmul(v2, __ldg(&root[2 * k * tw])); }
-        const double2 a = cadd(v1, v2), d = csub(v1, v2);
-        const double2 P = make_double2(v0.x + c1 * a.x, v0.y + c1 * a.y);
-        const double2 Q = make_double2(s1 * d.x, s1 * d.y);
-        const int o = (j - k) * 3 + k;
-        out[o] = cadd(v0, a);
-        out[o + Ns] = make_double2(P.x + Q.y, P.y - Q.x);          // P - iQ
-        out[o + 2 * Ns] = make_double2(P.x - Q.y, P.y + Q.x);      // P + iQ
-    }
-}
-
-// radix-4 stage, one butterfly per thread iteration (4 inputs read once)
-__device__ __forceinline__ void fft_stage_r4(const double2 *__restrict__ in, double2 *__restrict__ out,
-                                             const double2 *__restrict__ root, int N, int Ns)
-{
-    const int Nr = N >> 2;
-    const int tw = N / (Ns * 4);
-    const FastDiv fd(Ns);
-    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = fd.mod(j);
-        double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr], v3 = in[j + 3 * Nr];
-        if (k) {
-            v1 = cmul(v1, __ldg(&root[k * tw]));
-            v2 = cmul(v2, __ldg(&root[2 * k * tw]));
-            v3 = cmul(v3, __ldg(&root[3 * k * tw]));
-        }
-        const double2 s02 = cadd(v0, v2), d02 = csub(v0, v2), s13 = cadd(v1, v3), d13 = csub(v1, v3);
-        const int o = (j - k) * 4 + k;
-        out[o] = cadd(s02, s13);
-        out[o + Ns] = make_double2(d02.x + d13.y, d02.y - d13.x);       // d02 - i d13
-        out[o + 2 * Ns] = csub(s02, s13);
-        out[o + 3 * Ns] = make_double2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
-    }
-}
-
-__device__ __forceinline__ void fft_stage_r5(const double2 *__restrict__ in, double2 *__restrict__ out,
-                                             const double2 *__restrict__ root, int N, int Ns)
-{
-    const int Nr = N / 5, tw = N / (Ns * 5);
-    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
-    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
-    const FastDiv fd(Ns);
-    for (int j = threadIdx.x; j < Nr; j += blockDim.x) {
-        const int k = fd.mod(j);
-        double2 v0 = in[j], v1 = in[j + Nr], v2 = in[j + 2 * Nr], v3 = in[j + 3 * Nr], v4 = in[j + 4 * Nr];
-        if (k) {
-            v1 = cmul(v1, __ldg(&root[k * tw]));
-            v2 = cmul(v2, __ldg(&root[2 * k * tw]));
-            v3 = cmul(v3, __ldg(&root[3 * k * tw]));
-            v4 = cmul(v4, __ldg(&root[4 * k * tw]));
-        }
-        const double2 a1 = cadd(v1, v4), a2 = cadd(v2, v3), d1 = csub(v1, v4), d2 = csub(v2, v3);
-        const double2 P1 = make_double2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
-        const double2 P2 = make_double2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
-        const double2 Q1 = make_double2(s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y);
-        const double2 Q2 = make_double2(s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y);
-        const int o = (j - k) * 5 + k;
-        out[o] = make_double2(v0.x + a1.x + a2.x, v0.y + a1.y + a2.y);
-        out[o + Ns] = make_double2(P1.x + Q1.y, P1.y - Q1.x);
-        out[o + 4 * Ns] = make_double2(P1.x - Q1.y, P1.y + Q1.x);
-        out[o + 2 * Ns] = make_double2(P2.x + Q2.y, P2.y - Q2.x);
-        out[o + 3 * Ns] = make_double2(P2.x - Q2.y, P2.y + Q2.x);
-    }
-}
-
-// any odd prime radix p = 2h+1.  Two sub-steps through `tmp` (N entries):
-//   A: x_t = in[j + t Nr] w^{t k tw};  U[t][j] = x_t + x_{p-t},  V[t][j] = x_t - x_{p-t},  X0[j]
-//   B: X_b = x0 + sum_t U_t cos(2 pi t b/p) - i sum_t V_t sin(2 pi t b/p),  X_{p-b} = conj-sign
-// Result is written back into `in` (no buffer swap for this stage).
-__device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double2 *__restrict__ tmp,
-                                                const double2 *__restrict__ root, int N, int Ns, int p,
-                                                const double *__restrict__ tcos,
-                                                const double *__restrict__ tsin)
-{
-    const int Nr = N / p, h = (p - 1) / 2, tw = N / (Ns * p);
-    const FastDiv fNr(Nr), fNs(Ns);
-    for (int e = threadIdx.x; e < Nr * h; e += blockDim.x) {
-        const int tq = fNr.div(e);
-        const int t = tq + 1, j = e - tq * Nr;
-        const int k = fNs.mod(j);
-        double2 a = in[j + t * Nr], b = in[j + (p - t) * Nr];
-        if (k) {
-            // t k tw < p Ns N / (Ns p) = N: the twiddle index needs no reduction
-            a = cmul(a, __ldg(&root[t * k * tw]));
-            b = cmul(b, __ldg(&root[(p - t) * k * tw]));
-        }
-        tmp[(t - 1) * Nr + j] = cadd(a, b);
-        tmp[(h + t - 1) * Nr + j] = csub(a, b);
-    }
-    for (int j = threadIdx.x; j < Nr; j += blockDim.x) tmp[2 * h * Nr + j] = in[j];
-    __syncthreads();
-    // BB outputs b per work item share the shared-memory reads of U_t, V_t (BB > 1 measured slower:
-    // the extra accumulators spill at 6 CTAs / SM)
-    constexpr int BB = 1;
-    const int nbg = (h + BB) / BB;              // ceil((h + 1) / BB)
-    for (int e = threadIdx.x; e < Nr * nbg; e += blockDim.x) {
-        const int bg = fNr.div(e), j = e - bg * Nr;
-        const int b0 = bg * BB;
-        const int k = fNs.mod(j);
-        const double2 x0 = tmp[2 * h * Nr + j];
-        double2 P[BB], Q[BB];
-#pragma unroll
-        for (int bb = 0; bb < BB; ++bb) { P[bb] = x0; Q[bb] = make_double2(0., 0.); }
-#pragma unroll 2
-        for (int t = 0; t < h; ++t) {
-            const double2 u = tmp[t * Nr + j], v = tmp[(h + t) * Nr + j];
-#pragma unroll
-            for (int bb = 0; bb < BB; ++bb) {
-                const int b = min(b0 + bb, h);          // (a clamped duplicate is simply not stored)
-                const double c = __ldg(&tcos[b * h + t]), sn = __ldg(&tsin[b * h + t]);
-                P[bb].x += c * u.x; P[bb].y += c * u.y;
-                Q[bb].x += sn * v.x; Q[bb].y += sn * v.y;
-            }
-        }
-        const int o = (j - k) * p + k;
-#pragma unroll
-        for (int bb = 0; bb < BB; ++bb) {
-            const int b = b0 + bb;
-            if (b > h) break;
-            in[o + b * Ns] = make_double2(P[bb].x + Q[bb].y, P[bb].y - Q[bb].x);                    // P - iQ
-            if (b) in[o + (p - b) * Ns] = make_double2(P[bb].x - Q[bb].y, P[bb].y + Q[bb].x);       // P + iQ
-        }
-    }
-}
-
-// forward complex FFT of length N on shared memory; returns the buffer holding the result
-__device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const FftPlan &plan,
-                                             const double2 *__restrict__ root)
-{
-    const int N = plan.N;
-    int Ns = 1;
-    for (int s = 0; s < plan.nrad; ++s) {
-        const int r = plan.rad[s];
-        bool swap = true;
-        if (r == 4) fft_stage_r4(src, dst, root, N, Ns);
-        else if (r == 2) fft_stage_r2(src, dst, root, N, Ns);
-        else if (r == 5) fft_stage_r5(src, dst, root, N, Ns);
-        else if (r == 3) fft_stage_r3(src, dst, root, N, Ns);
-        else { fft_stage_prime(src, dst, root, N, Ns, r, plan.cs_cos[s], plan.cs_sin[s]); swap = false; }
-        __syncthreads();
-        if (swap) { double2 *t = src; src = dst; dst = t; }
-        Ns *= r;
-    }
-    return src;
-}
 
 // ---- row sources ---------------------------------------------------------------------------
 struct SrcStage {            // plain rows: in[b][j][i]

@@ -365,9 +365,14 @@ int read_deck(hpb_sim *s)
         if (s->laser_lambda0 <= 0.) throw std::runtime_error("lasers.lambda0 must be given");
         for (const char *k : {"lasers.n_cell", "lasers.patch_lo", "lasers.patch_hi"})
             if (d.find(k)) throw std::runtime_error(std::string(k) + ": only the default laser grid (= field grid) is supported");
-        if (s->max_step > 0 && d.str("lasers.solver_type", "multigrid") != "fft")
-            throw std::runtime_error("lasers: the envelope advance (max_step > 0) is implemented for "
-                                     "lasers.solver_type = fft only (hpmg type 2, the default, is not)");
+        {
+            const std::string st = d.str("lasers.solver_type", "multigrid");
+            if (st != "fft" && st != "multigrid") throw std::runtime_error("lasers.solver_type must be fft or multigrid");
+            s->laser_use_mg = st == "multigrid";
+            s->laser_mg_tol_rel = d.num("lasers.MG_tolerance_rel", 1e-4);
+            s->laser_mg_tol_abs = d.num("lasers.MG_tolerance_abs", 0.);
+            s->laser_mg_avg_rhs = (int)d.num("lasers.MG_average_rhs", 1) != 0;
+        }
         if (s->max_step > 0 && s->adaptive_dt)
             throw std::runtime_error("lasers cannot be combined with an adaptive time step");       // Hipace.cpp:407-409
         s->laser_use_phase = (int)d.num("lasers.use_phase", 1) != 0;
@@ -745,6 +750,8 @@ int begin_step(hpb_sim *s, int step)
             int rc = hpb_laser_state_create(&s->laser_state, s->ctx, s->nz, s->lasers.data(), (int)s->lasers.size(),
                                             s->laser_lambda0, s->laser_interp_order, s->laser_use_phase);
             if (rc) return rc;
+            hpb_laser_set_solver(s->laser_state, s->laser_use_mg, s->laser_mg_tol_rel, s->laser_mg_tol_abs,
+                                 s->laser_mg_avg_rhs);
         }
         // MultiLaser::SetInitialChi (laser/MultiLaser.cpp:293-332): sum over species of density * q^2 mu0 / m
         std::vector<double> chi0((size_t)s->g.nx * s->g.ny, 0.);

@@ -154,6 +154,8 @@ struct hpb_sim {
     // which evaluate the analytic envelope per cell instead of storing it
     hpb_laser_state *laser_state = nullptr;
     bool laser_use_phase = true;
+    bool laser_use_mg = true, laser_mg_avg_rhs = true;      // lasers.solver_type = multigrid (the default)
+    double laser_mg_tol_rel = 1e-4, laser_mg_tol_abs = 0.;
     int laser_insitu_period = 0;                  // lasers.insitu_period (MultiLaser.cpp)
     std::string laser_insitu_prefix = "diags/laser_insitu";
     double *d_laser_insitu = nullptr;             // [8][nz]

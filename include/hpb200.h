@@ -219,6 +219,16 @@ int hpb_laser_get_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_a
 int hpb_laser_advance_slice(hpb_laser_state *st, hpb_ctx *ctx, hpb_slice sl, int c_chi, int islice, double dt,
                             int step, double prob_len_x, double prob_len_y);
 int hpb_laser_shift_slices(hpb_laser_state *st);
+/* lasers.solver_type (0: fft, MultiLaser::AdvanceSliceFFT; 1: multigrid, AdvanceSliceMG on hpmg type 2,
+ * the reference's default), lasers.MG_tolerance_rel / MG_tolerance_abs / MG_average_rhs
+ * (src/laser/MultiLaser.cpp:40-56, 429-607) */
+int hpb_laser_set_solver(hpb_laser_state *st, int use_multigrid, double tol_rel, double tol_abs, int average_rhs);
+long hpb_laser_mg_vcycles(hpb_laser_state *st);
+/* hpmg::MultiGrid::solve2 (src/mg_solver/HpMultiGrid.cpp:1192-1296): lap(A) - (a_r + i a_i) A = rhs with an
+ * array real coefficient and a scalar imaginary one; planar [2][ny][nx] arrays over the valid box,
+ * d_sol2 holds the initial guess on entry */
+int hpb_mg_solve2(hpb_ctx *ctx, double *d_sol2, const double *d_rhs2, const double *d_acf_r, double acf_i,
+                  double tol_rel, double tol_abs, int max_iters, int *h_iters);
 /* MultiLaser::InSituComputeDiags / InSituWriteToFile (src/laser/MultiLaser.cpp:923-1075): 8 raw values per
  * slice (max |a|^2, [|a|^2], its x, x^2, y, y^2 moments, the on-axis sum re / im) and the host writer */
 int hpb_laser_insitu_slice(hpb_laser_state *st, hpb_ctx *ctx, double *d_record, long stride);

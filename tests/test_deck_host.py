@@ -7,8 +7,9 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# decks the oracle runs but the CUDA driver must refuse (with the reason), not mis-run
-ORACLE_ONLY = {'laser_vacuum_SI.in': 'envelope advance'}     # the laser envelope advance over time steps
+# decks the oracle runs but the CUDA driver must refuse (with the reason), not mis-run: none any more
+# (the laser envelope advance with the multigrid solver, hpmg type 2, was the last one)
+ORACLE_ONLY = {}
 DECKS = sorted(p for p in glob.glob(os.path.join(ROOT, 'examples', '*.in'))
                if os.path.basename(p) not in ORACLE_ONLY)
 
@@ -34,14 +35,6 @@ def test_parser_agrees_with_oracle(path):
     for k, b in enumerate(ref.beams):
         assert got[f'beam{k}.charge'] == pytest.approx(b.charge, rel=1e-15)
         assert got[f'beam{k}.mass'] == pytest.approx(b.mass, rel=1e-15)
-
-
-@pytest.mark.parametrize('name,reason', sorted(ORACLE_ONLY.items()))
-def test_oracle_only_decks_are_refused(name, reason):
-    import hipace_b200 as hp
-    with pytest.raises(hp.HpbError) as e:
-        hp.deck_check(open(os.path.join(ROOT, 'examples', name)).read())
-    assert reason in str(e.value)
 
 
 def test_deposition_orders_and_the_combination_the_reference_rejects():
@@ -115,16 +108,20 @@ def test_inert_and_output_only_keys_are_accepted():
                          'amr.max_level': 0, 'other_beam.density': 3.})
 
 
-def test_laser_deck_is_accepted_for_step_zero_only():
+def test_laser_deck_is_accepted_with_both_envelope_solvers():
     import hipace_b200 as hp
     import json
     meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'laser_blowout_wake_explicit.SI.1Rank.json')))
     text = open(os.path.join(ROOT, meta['deck'])).read()
     got = hp.deck_check(text, meta['overrides'])
     assert got['n_lasers'] == 1 and got['n_beams'] == 0 and (got['nx'], got['nz']) == (128, 100)
+    # the envelope advance over time steps: the reference's default (multigrid, hpmg type 2) and fft
+    for ov in ({'max_step': 2}, {'max_step': 2, 'lasers.solver_type': 'fft'},
+               {'max_step': 2, 'lasers.MG_tolerance_rel': 1e-5, 'lasers.MG_average_rhs': 0}):
+        hp.deck_check(text, dict(meta['overrides'], **ov))
     with pytest.raises(hp.HpbError) as e:
-        hp.deck_check(text, dict(meta['overrides'], max_step=2))
-    assert 'envelope advance' in str(e.value)
+        hp.deck_check(text, dict(meta['overrides'], **{'lasers.solver_type': 'spectral'}))
+    assert 'solver_type' in str(e.value)
 
 
 def test_no_gpu_means_error_not_fallback():

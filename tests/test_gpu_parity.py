@@ -382,6 +382,34 @@ def test_mg_solve1_matches_hpmg_oracle(nx, ny):
     ctx.close()
 
 
+@pytest.mark.parametrize('nx,ny', [(64, 64), (63, 63), (96, 64), (127, 63), (128, 128)])
+def test_mg_solve2_matches_hpmg_oracle(nx, ny):
+    """hpmg solve2 (system type 2, the laser envelope's complex Helmholtz system): same V-cycle count and
+    the same values as the oracle's MultiGrid2 (gs2 / residual2r / residual2i restated)."""
+    import torch
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import MultiGrid2
+    rng = np.random.default_rng(3 * nx + ny)
+    dx, dy = 16. / nx, 16. / ny
+    yy, xx = np.meshgrid(np.linspace(-1, 1, ny), np.linspace(-1, 1, nx), indexing='ij')
+    acf_r = 40.0 + 5.0 * np.exp(-4 * (xx ** 2 + yy ** 2)) + 0.5 * rng.random((ny, nx))
+    acf_i = -300.0
+    rhs = np.stack([np.exp(-8 * ((xx - .2) ** 2 + yy ** 2)) + 0.01 * rng.standard_normal((ny, nx)),
+                    xx * np.exp(-6 * (xx ** 2 + (yy + .1) ** 2))])
+    guess = 0.001 * rng.standard_normal((2, ny, nx))
+    mg = MultiGrid2(dx, dy, nx, ny)
+    want = guess.copy()
+    mg.solve2(want, rhs, acf_r, acf_i, 1e-4, 0.0, 200)
+    ctx = hp.Context(nx, ny, dx, dy, 0.1, -8 + dx / 2, -8 + dy / 2)
+    t_sol, t_rhs, t_acf = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (guess, rhs, acf_r))
+    iters = ctx.mg_solve2(t_sol, t_rhs, t_acf, acf_i, 1e-4, 0.0)
+    torch.cuda.synchronize()
+    got = t_sol.cpu().numpy()
+    assert iters == mg.n_vcycles_last and iters >= 1
+    assert np.abs(got - want).max() / np.abs(want).max() <= 1e-12
+    ctx.close()
+
+
 def test_command_line_driver_reproduces_golden(repo_root):
     """the C++ driver binary end to end: deck file + key=value overrides in, checksums out"""
     import subprocess

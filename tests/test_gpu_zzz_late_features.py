@@ -142,6 +142,24 @@ def test_laser_advance_with_plasma_matches_oracle(repo_root):
     sim.close()
 
 
+@pytest.mark.parametrize('avg_rhs', [1, 0])
+def test_laser_advance_multigrid_matches_oracle(avg_rhs, repo_root):
+    """lasers.solver_type = multigrid (the reference's default: MultiLaser::AdvanceSliceMG on hpmg type 2):
+    two time steps of the laser-driven blow-out deck and of the vacuum pulse against the oracle"""
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    meta = json.load(open(os.path.join(GOLD, 'laser_blowout_wake_explicit.1Rank.json')))
+    deck = open(os.path.join(repo_root, meta['deck'])).read()
+    ov = dict(meta['overrides'], **{'amr.n_cell': '32 32 60', 'max_step': 2, 'hipace.dt': 4.,
+                                    'lasers.solver_type': 'multigrid', 'lasers.MG_average_rhs': avg_rhs})
+    sim = hp.Simulation(deck, ov)
+    got = sim.evolve(0, 2)
+    ref = Oracle(deck, ov)
+    want = ref.evolve(step_end=2)
+    _compare(got, want, floor=1e-12)
+    sim.close()
+
+
 def test_laser_insitu_matches_oracle(repo_root, tmp_path):
     """lasers.insitu_period: the per-slice laser diagnostics of the stored envelope against the oracle"""
     import numpy as np

@@ -8,7 +8,7 @@ deck = open('examples/blowout_wake_normalized.in').read()
 ov = {'amr.n_cell': f'{nxy} {nxy} {nz}', 'plasma.ppc': '2 2'}
 for combo in sys.argv[3:]:
     sim = hp.Simulation(deck, ov)
-    sim.set_option('checksums', 0)
+    sim.set_option('checksums', 1)
     for kv in combo.split():
         k, v = kv.split('=')
         sim.set_option(k, float(v))
@@ -18,8 +18,8 @@ for combo in sys.argv[3:]:
         for isl in range(nz - 1, -1, -1):
             sim.solve_one_slice(isl)
             last = isl
-        st = sim.stats()
-        print(combo, ': all', nz, 'slices ok', flush=True)
+        cs = sim.checksums()
+        print(combo, ': all', nz, 'slices ok;', ' '.join(f'{k}={cs[k]:.12e}' for k in ('Bx', 'ExmBy', 'Ez', 'jx', 'chi') if k in cs), flush=True)
     except Exception as e:
         print(combo, ': FAILED after slice', last, '->', str(e)[-160:], flush=True)
     try:
