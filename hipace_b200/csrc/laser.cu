@@ -318,6 +318,7 @@ struct hpb_laser_state {
     double mg_tol_rel = 1e-4, mg_tol_abs = 0.;
     double *mg_rhs2 = nullptr, *mg_sol2 = nullptr, *mg_acf = nullptr;    // planar [2][ny][nx], [ny][nx]
     long mg_vcycles = 0;
+    int pipelined = 0;                  // the stored slices travel between ranks (pipeline.cu)
 };
 enum { L_NM1J00 = 0, L_NM1JP1, L_NM1JP2, L_N00J00, L_N00JP1, L_N00JP2, L_NP1J00, L_NP1JP1, L_NP1JP2 };
 
@@ -503,9 +504,25 @@ extern "C" int hpb_laser_shift_slices(hpb_laser_state *st)
 extern "C" int hpb_laser_end_step(hpb_laser_state *st)
 {
     if (!st) return HPB_ERR_ARG;
-    std::swap(st->store[0], st->store[2]);
-    std::swap(st->store[1], st->store[3]);
+    // single rank: this step's {A^{n+1}, A^n} are the next step's {A^n, A^{n-1}}.  In a multi-rank
+    // pipeline the next owned step gets them slice by slice from the upstream rank instead (below).
+    if (!st->pipelined) {
+        std::swap(st->store[0], st->store[2]);
+        std::swap(st->store[1], st->store[3]);
+    }
     return HPB_OK;
+}
+
+// The laser part of the per-slice hand-over between time steps (MultiBuffer::pack_data /
+// unpack_data, src/utils/MultiBuffer.cpp:444-490, 840-851, 913-923): A^{n+1} and A^n of slice
+// `islice` leave from send[0..1], the upstream rank's pair lands in recv[0..1] (this step's A^n, A^{n-1}).
+void hpb_laser_packet(hpb_laser_state *st, int islice, void *recv[2], void *send[2], size_t *bytes)
+{
+    const size_t plane = (size_t)st->nx * st->ny;
+    recv[0] = st->store[0] + (size_t)islice * plane; recv[1] = st->store[1] + (size_t)islice * plane;
+    send[0] = st->store[2] + (size_t)islice * plane; send[1] = st->store[3] + (size_t)islice * plane;
+    *bytes = plane * sizeof(hpb_c2);
+    st->pipelined = 1;
 }
 
 // MultiLaser::InSituComputeDiags (:923-1001) of the current slice's A^n: d_record[k * stride], k = 0..7

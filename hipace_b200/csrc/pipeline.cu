@@ -203,6 +203,12 @@ static int post_receives(hpb_sim *s, int upto)
             const BeamRing &in = b.ring[b.cur];
             HPB_NCCL(N->Recv(in.packet(slot), in.msg_bytes(), ncclUint8, 0, p->comm_recv, p->s_recv));
         }
+        if (s->laser_state) {       // A^n, A^{n-1} of this slice (MultiBuffer.cpp:444-490)
+            void *rv[2], *sd[2]; size_t nb = 0;
+            hpb_laser_packet(s->laser_state, s->nz - 1 - slot, rv, sd, &nb);
+            HPB_NCCL(N->Recv(rv[0], nb, ncclUint8, 0, p->comm_recv, p->s_recv));
+            HPB_NCCL(N->Recv(rv[1], nb, ncclUint8, 0, p->comm_recv, p->s_recv));
+        }
         HPB_NCCL(N->GroupEnd());
         SIM_CUDA(cudaEventRecord(p->ev_recv[slot], p->s_recv));
     }
@@ -226,15 +232,19 @@ int hpb_pipeline_begin_step(hpb_sim *s, int step)
     return post_receives(s, p->lookahead);
 }
 
-int hpb_pipeline_wait_slice(hpb_sim *s, int islice)
+int hpb_pipeline_wait_slice_on(hpb_sim *s, int islice, cudaStream_t st)
 {
     hpb_pipeline *p = s->pipe;
     if (!p || !p->receiving) return HPB_OK;
     const int slot = s->nz - 1 - islice;
     int rc = post_receives(s, slot + 1 + p->lookahead);
     if (rc) return rc;
-    SIM_CUDA(cudaStreamWaitEvent(s->beam_stream ? s->beam_stream : s->stream, p->ev_recv[slot], 0));
+    SIM_CUDA(cudaStreamWaitEvent(st, p->ev_recv[slot], 0));
     return HPB_OK;
+}
+int hpb_pipeline_wait_slice(hpb_sim *s, int islice)
+{
+    return hpb_pipeline_wait_slice_on(s, islice, s->beam_stream ? s->beam_stream : s->stream);
 }
 
 int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step)
@@ -250,6 +260,12 @@ int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step)
         const BeamRing &out = b.ring[b.cur ^ 1];
         HPB_NCCL(N->Send(out.packet(slot), out.msg_bytes(), ncclUint8, 1, p->comm_send, p->s_send));
     }
+    if (s->laser_state) {           // A^{n+1}, A^n of this slice for the next time step
+        void *rv[2], *sd[2]; size_t nb = 0;
+        hpb_laser_packet(s->laser_state, islice, rv, sd, &nb);
+        HPB_NCCL(N->Send(sd[0], nb, ncclUint8, 1, p->comm_send, p->s_send));
+        HPB_NCCL(N->Send(sd[1], nb, ncclUint8, 1, p->comm_send, p->s_send));
+    }
     HPB_NCCL(N->GroupEnd());
     SIM_CUDA(cudaEventRecord(p->ev_sent[slot], p->s_send));
     p->sent_pending[slot] = 1;
@@ -259,16 +275,20 @@ int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step)
 
 // the compute stream is about to overwrite slot `slot` of the output ring: the send of the slice
 // it held (previous owned step) must have left the buffer
-int hpb_pipeline_wait_out_slot(hpb_sim *s, int islice)
+int hpb_pipeline_wait_out_slot_on(hpb_sim *s, int islice, cudaStream_t st)
 {
     hpb_pipeline *p = s->pipe;
     if (!hpb_pipeline_active(s)) return HPB_OK;
     const int slot = s->nz - 1 - islice;
     if (p->sent_pending[slot]) {
-        SIM_CUDA(cudaStreamWaitEvent(s->beam_stream ? s->beam_stream : s->stream, p->ev_sent[slot], 0));
+        SIM_CUDA(cudaStreamWaitEvent(st, p->ev_sent[slot], 0));
         p->sent_pending[slot] = 0;
     }
     return HPB_OK;
+}
+int hpb_pipeline_wait_out_slot(hpb_sim *s, int islice)
+{
+    return hpb_pipeline_wait_out_slot_on(s, islice, s->beam_stream ? s->beam_stream : s->stream);
 }
 
 bool hpb_pipeline_out_ring_busy(const hpb_sim *s)

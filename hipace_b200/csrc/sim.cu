@@ -742,10 +742,6 @@ int begin_step(hpb_sim *s, int step)
     }
     const double c_t = s->g.c * s->time;
     if (s->use_laser && s->max_step > 0 && s->dt != 0.) {            // the envelope is stored and advanced
-        if (hpb_pipeline_active(s)) {
-            hpb_set_error("the laser envelope advance is not available with a multi-rank pipeline");
-            return HPB_ERR_UNSUPPORTED;
-        }
         if (!s->laser_state) {
             int rc = hpb_laser_state_create(&s->laser_state, s->ctx, s->nz, s->lasers.data(), (int)s->lasers.size(),
                                             s->laser_lambda0, s->laser_interp_order, s->laser_use_phase);
@@ -932,7 +928,8 @@ int write_beam_insitu(hpb_sim *s)
 int beam_push_and_send(hpb_sim *s, int islice)
 {
     int rc;
-    if (s->beams.empty()) return HPB_OK;
+    // (a laser-only deck still hands its envelope slices to the next time step)
+    if (s->beams.empty()) return s->laser_state ? hpb_pipeline_send_slice(s, islice, s->cur_step) : HPB_OK;
     const int slot = s->nz - 1 - islice;
     const double min_z = s->prob_lo[2] + islice * s->g.dz;
     const double time = s->time;
@@ -1196,6 +1193,8 @@ int solve_one_slice(hpb_sim *s, int islice)
             StageTimer t(s, ST_OTHER);
             const double z = islice * s->g.dz + (s->prob_lo[2] + 0.5 * s->g.dz);        // GetPosOffset(2)
             if (s->laser_state) {
+                // the stored A^n, A^{n-1} of this slice come from the upstream rank in a pipeline
+                if ((rc = hpb_pipeline_wait_slice_on(s, islice, ctx->stream))) return rc;
                 if ((rc = hpb_laser_get_slice(s->laser_state, ctx, s->sl, C[HPB_C_AABS], islice, s->cur_step, z,
                                               s->opt_checksums ? s->d_checksum + s->sl.ncomp : nullptr,
                                               s->diag_xz))) return rc;
@@ -1226,6 +1225,8 @@ int solve_one_slice(hpb_sim *s, int islice)
     }
     if (s->laser_state) {                                                               // :637
         StageTimer t(s, ST_OTHER);
+        // (the slots A^{n+1}, A^n of this slice are written into may still be leaving for the downstream rank)
+        if ((rc = hpb_pipeline_wait_out_slot_on(s, islice, ctx->stream))) return rc;
         if ((rc = hpb_laser_advance_slice(s->laser_state, ctx, s->sl, C[HPB_C_CHI], islice, s->dt, s->cur_step,
                                           s->prob_hi[0] - s->prob_lo[0], s->prob_hi[1] - s->prob_lo[1]))) return rc;
     }

@@ -213,6 +213,10 @@ int hpb_beam_ring_scatter(hpb_sim *s, BeamSp &b, const BeamRing &r, const long *
 void hpb_pipeline_destroy(hpb_sim *s);
 int hpb_pipeline_begin_step(hpb_sim *s, int step);          // post receives / order ring reuse
 int hpb_pipeline_wait_slice(hpb_sim *s, int islice);        // compute stream waits for slice islice
+int hpb_pipeline_wait_slice_on(hpb_sim *s, int islice, cudaStream_t st);       // ... a given stream
+int hpb_pipeline_wait_out_slot_on(hpb_sim *s, int islice, cudaStream_t st);    // out slot free, on a given stream
+struct hpb_laser_state;
+void hpb_laser_packet(hpb_laser_state *st, int islice, void *recv[2], void *send[2], size_t *bytes);
 int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step);
 int hpb_pipeline_wait_out_slot(hpb_sim *s, int islice);     // out-ring slot free (its last send left)
 bool hpb_pipeline_out_ring_busy(const hpb_sim *s);          // sends of the previous owned step pending

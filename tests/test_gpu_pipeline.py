@@ -58,6 +58,61 @@ def _free_port():
     return p
 
 
+def _laser_case():
+    import json
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'laser_blowout_wake_explicit.1Rank.json')))
+    deck = open(os.path.join(ROOT, meta['deck'])).read()
+    ov = dict(meta['overrides'], **{'amr.n_cell': '32 32 40', 'max_step': 3, 'hipace.dt': 4.})
+    return deck, ov
+
+
+def _laser_worker(rank, world, port, out_dir, solver):
+    sys.path.insert(0, ROOT)
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('HPB_TEST_WATCHDOG', '240')), exit=True)
+    import torch
+    import torch.distributed as dist
+    import hipace_b200 as hp
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    deck, ov = _laser_case()
+    ov['lasers.solver_type'] = solver
+    sim = hp.Simulation(deck, ov, device=rank)
+    sim.pipeline_init(rank, world, dist)
+    sim.run(ov['max_step'], rank, world)
+    pickle.dump({'cs': sim.checksums()}, open(os.path.join(out_dir, f'rank{rank}.pkl'), 'wb'))
+    torch.cuda.synchronize()
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('solver', ['fft', 'multigrid'])
+def test_two_gpu_laser_pipeline_matches_single_gpu(solver):
+    """the laser envelope slices A^{n+1}, A^n travel with the per-slice hand-over (MultiBuffer.cpp:444-490):
+    4 time steps of the laser-driven blow-out deck on 2 ranks == the same steps on one GPU"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    import hipace_b200 as hp
+    world = 2
+    deck, ov = _laser_case()
+    ov['lasers.solver_type'] = solver
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_laser_worker, args=(world, _free_port(), d, solver), nprocs=world, join=True)
+        res = [pickle.load(open(os.path.join(d, f'rank{r}.pkl'), 'rb')) for r in range(world)]
+    last = res[ov['max_step'] % world]
+    sim = hp.Simulation(deck, ov)
+    cs = sim.evolve(0, ov['max_step'])
+    big = max(abs(v) for v in cs.values())
+    for k, v in cs.items():
+        assert abs(last['cs'][k] - v) <= 1e-9 * abs(v) + 1e-12 * big, k
+    sim.close()
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     # a hung rank must never hold the GPU box: dump where it is stuck and exit
