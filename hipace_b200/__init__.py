@@ -458,6 +458,11 @@ class Simulation:
         return {f: getattr(st, f) for f, _ in st._fields_}
 
 
+def set_global_option(key: str, value: float):
+    """process-wide library switches (hpb_set_option with a NULL context): "pdl", "bluestein_min_prime" """
+    _check(lib().hpb_set_option(None, key.encode(), C.c_double(value)), 'hpb_set_option')
+
+
 def measure_fp64_peak(device: int = 0, reps: int = 5) -> float:
     """fp64 FMA peak of the device in TFLOP/s (measured, csrc/peaks.cu)"""
     out = C.c_double(0.)

@@ -37,6 +37,7 @@ __device__ __forceinline__ void hpb_pdl_prologue()
 #endif
 }
 bool hpb_pdl_enabled();
+int hpb_bluestein_min_prime();     // context.cu: FFT lengths with a larger prime factor use Bluestein
 
 template <class... KA, class... A>
 inline cudaError_t hpb_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem,
@@ -229,6 +230,8 @@ struct hpb_ctx {
     long n_launch;
     // Poisson (poisson.cu)
     int fftN;                 // nx + 1
+    int fftM;                 // > 0: Bluestein length (nx + 1 has a prime factor > 64), fft_smem.cuh
+    double2 *d_chirp, *d_bhat;
     int nrad; int radices[32];
     double *d_cs_cos[32], *d_cs_sin[32];         // per odd-prime stage: DFT-p cos / sin tables
     double2 *d_root;          // exp(-2 pi i t / N), t = 0..N-1

@@ -28,6 +28,9 @@ void hpb_count_launch(hpb_ctx *ctx, int n) { ctx->n_launch += n; }
 // programmatic dependent launch of the kernel chain: process-wide (the launch helper has no context)
 static int g_pdl = 1;
 bool hpb_pdl_enabled() { return g_pdl != 0; }
+// FFT plans are built when a context is created: the Bluestein threshold is process-wide as well
+static int g_bluestein_min_prime = 64;
+int hpb_bluestein_min_prime() { return g_bluestein_min_prime; }
 
 bool hpb_use_generic_order(const hpb_ctx *ctx)
 {
@@ -41,6 +44,7 @@ extern "C" int hpb_set_option(hpb_ctx *ctx, const char *key, double value)
     if (!key) return HPB_ERR_ARG;
     const int v = (int)value;
     if (!strcmp(key, "pdl")) { g_pdl = v != 0; return HPB_OK; }
+    if (!strcmp(key, "bluestein_min_prime")) { g_bluestein_min_prime = v < 5 ? 5 : v; return HPB_OK; }
     if (!ctx) return HPB_ERR_ARG;
     if (!strcmp(key, "generic")) ctx->force_generic = v != 0;
     else if (!strcmp(key, "order")) ctx->tune_order = v;

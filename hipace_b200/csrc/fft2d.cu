@@ -13,7 +13,7 @@ namespace {
 
 struct Plan1D {
     FftPlan plan;
-    double2 *d_root = nullptr;
+    double2 *d_root = nullptr, *d_chirp = nullptr, *d_bhat = nullptr;
     double *d_cos[kMaxRad] = {}, *d_sin[kMaxRad] = {};
 };
 
@@ -26,11 +26,10 @@ bool to_device(T **dptr, const std::vector<T> &h)
 
 bool build_plan(int N, Plan1D &p)
 {
-    p.plan.N = N; p.plan.nrad = 0;
-    int n = N;
-    const int pref[] = {4, 2, 3, 5};
-    for (int r : pref) while (n % r == 0) { p.plan.rad[p.plan.nrad++] = r; n /= r; }
-    for (int q = 7; n > 1; q += 2) while (n % q == 0) { p.plan.rad[p.plan.nrad++] = q; n /= q; }
+    p.plan.N = N;
+    p.plan.M = fft_factorize(N, p.plan.rad, p.plan.nrad);
+    p.plan.chirp = p.plan.bhat = nullptr;
+    const int L = p.plan.M > 0 ? p.plan.M : N;
     const long double pi = 3.14159265358979323846264338327950288L;
     for (int i = 0; i < p.plan.nrad; ++i) {
         p.plan.cs_cos[i] = p.plan.cs_sin[i] = nullptr;
@@ -47,16 +46,22 @@ bool build_plan(int N, Plan1D &p)
         if (!to_device(&p.d_cos[i], tc) || !to_device(&p.d_sin[i], ts)) return false;
         p.plan.cs_cos[i] = p.d_cos[i]; p.plan.cs_sin[i] = p.d_sin[i];
     }
-    std::vector<double2> root(N);
-    for (int t = 0; t < N; ++t) {
-        root[t].x = (double)cosl(-2.0L * pi * t / N);
-        root[t].y = (double)sinl(-2.0L * pi * t / N);
+    std::vector<double2> root(L);
+    for (int t = 0; t < L; ++t) {
+        root[t].x = (double)cosl(-2.0L * pi * t / L);
+        root[t].y = (double)sinl(-2.0L * pi * t / L);
+    }
+    if (p.plan.M > 0) {
+        std::vector<double2> chirp(N), bhat(p.plan.M);
+        fft_bluestein_tables(N, p.plan.M, chirp.data(), bhat.data());
+        if (!to_device(&p.d_chirp, chirp) || !to_device(&p.d_bhat, bhat)) return false;
+        p.plan.chirp = p.d_chirp; p.plan.bhat = p.d_bhat;
     }
     return to_device(&p.d_root, root);
 }
 void free_plan(Plan1D &p)
 {
-    cudaFree(p.d_root);
+    cudaFree(p.d_root); cudaFree(p.d_chirp); cudaFree(p.d_bhat);
     for (int i = 0; i < kMaxRad; ++i) { cudaFree(p.d_cos[i]); cudaFree(p.d_sin[i]); }
 }
 
@@ -71,7 +76,7 @@ k_fft_seq(const double2 *__restrict__ in, double2 *__restrict__ out, long seq_st
     hpb_pdl_prologue();
     extern __shared__ double2 fsm[];
     const int N = plan.N;
-    double2 *b0 = fsm, *b1 = fsm + N;
+    double2 *b0 = fsm, *b1 = fsm + plan.buf_len();
     const long base = (long)blockIdx.x * seq_stride;
     for (int e = threadIdx.x; e < N; e += blockDim.x) {
         double2 v = in[base + (long)e * elem_stride];
@@ -99,8 +104,8 @@ int hpb_fft2d_create(hpb_fft2d **out, int nx, int ny)
     if (!out || nx < 2 || ny < 2) return HPB_ERR_ARG;
     hpb_fft2d *f = new hpb_fft2d();
     f->nx = nx; f->ny = ny;
-    const size_t smem = 2 * sizeof(double2) * (size_t)std::max(nx, ny);
-    if (smem > 220 * 1024 || !build_plan(nx, f->px) || !build_plan(ny, f->py)) {
+    if (!build_plan(nx, f->px) || !build_plan(ny, f->py)
+        || 2 * sizeof(double2) * (size_t)std::max(f->px.plan.buf_len(), f->py.plan.buf_len()) > 220 * 1024) {
         hpb_set_error("fft2d: %d x %d not supported by the shared-memory FFT", nx, ny);
         free_plan(f->px); free_plan(f->py);
         delete f;
@@ -124,7 +129,8 @@ int hpb_fft2d_exec(hpb_fft2d *f, hpb_ctx *ctx, const double2 *in, double2 *out, 
 {
     if (!f || !ctx || !in || !out) return HPB_ERR_ARG;
     const int nx = f->nx, ny = f->ny;
-    const size_t smx = 2 * sizeof(double2) * (size_t)nx, smy = 2 * sizeof(double2) * (size_t)ny;
+    const size_t smx = 2 * sizeof(double2) * (size_t)f->px.plan.buf_len();
+    const size_t smy = 2 * sizeof(double2) * (size_t)f->py.plan.buf_len();
     if (dir < 0) {
         hpb_launch(k_fft_seq<false>, (unsigned)ny, kFftThreads, smx, ctx->stream, in, out, (long)nx, 1L, f->px.plan,
                    (const double2 *)f->px.d_root);

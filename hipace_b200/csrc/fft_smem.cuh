@@ -4,6 +4,8 @@
 // transforms one sequence held in shared memory; `root` is exp(-2 pi i t / N), t = 0 .. N-1.
 #pragma once
 #include "common.cuh"
+#include <math.h>
+#include <vector>
 
 namespace {
 
@@ -14,6 +16,12 @@ struct FftPlan {
     int N; int nrad; int rad[kMaxRad];
     const double *cs_cos[kMaxRad];     // per prime stage: cos(2 pi t b / p), [b = 0..h][t = 1..h]
     const double *cs_sin[kMaxRad];
+    // Bluestein (chirp-z) for lengths with a large prime factor (257, 2049 = 3 * 683, ...): M = the
+    // power of two >= 2N - 2 (enough because the chirp is even), rad[] then factor M, `root` passed to
+    // fft_smem is exp(-2 pi i t / M); chirp[n] = exp(-i pi n^2 / N), bhat = FFT_M(conj chirp, wrapped) / M
+    int M;
+    const double2 *chirp, *bhat;
+    __host__ __device__ int buf_len() const { return M > 0 ? M : N; }     // complex elements per buffer
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
@@ -191,20 +199,20 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
     }
 }
 
-// forward complex FFT of length N on shared memory; returns the buffer holding the result
-__device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const FftPlan &plan,
-                                             const double2 *__restrict__ root)
+// the Stockham stages of a plan on a sequence of length L held in src (scratch dst); returns the
+// buffer holding the result
+__device__ __forceinline__ double2 *fft_stages(double2 *src, double2 *dst, const FftPlan &plan, int L,
+                                               const double2 *__restrict__ root)
 {
-    const int N = plan.N;
     int Ns = 1;
     for (int s = 0; s < plan.nrad; ++s) {
         const int r = plan.rad[s];
         bool swap = true;
-        if (r == 4) fft_stage_r4(src, dst, root, N, Ns);
-        else if (r == 2) fft_stage_r2(src, dst, root, N, Ns);
-        else if (r == 5) fft_stage_r5(src, dst, root, N, Ns);
-        else if (r == 3) fft_stage_r3(src, dst, root, N, Ns);
-        else { fft_stage_prime(src, dst, root, N, Ns, r, plan.cs_cos[s], plan.cs_sin[s]); swap = false; }
+        if (r == 4) fft_stage_r4(src, dst, root, L, Ns);
+        else if (r == 2) fft_stage_r2(src, dst, root, L, Ns);
+        else if (r == 5) fft_stage_r5(src, dst, root, L, Ns);
+        else if (r == 3) fft_stage_r3(src, dst, root, L, Ns);
+        else { fft_stage_prime(src, dst, root, L, Ns, r, plan.cs_cos[s], plan.cs_sin[s]); swap = false; }
         __syncthreads();
         if (swap) { double2 *t = src; src = dst; dst = t; }
         Ns *= r;
@@ -212,5 +220,81 @@ __device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const F
     return src;
 }
 
+// forward complex FFT of length N on shared memory (both buffers hold plan.buf_len() elements, the
+// input is src[0 .. N-1]); returns the buffer holding the result
+__device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const FftPlan &plan,
+                                             const double2 *__restrict__ root)
+{
+    if (plan.M == 0) return fft_stages(src, dst, plan, plan.N, root);
+    // Bluestein: X[k] = c[k] sum_n (x[n] c[n]) conj(c)[k - n],  c[n] = exp(-i pi n^2 / N): a circular
+    // convolution of length M through two power-of-two FFTs
+    const int N = plan.N, M = plan.M;
+    for (int n = threadIdx.x; n < M; n += blockDim.x)
+        dst[n] = n < N ? cmul(src[n], __ldg(&plan.chirp[n])) : make_double2(0., 0.);
+    __syncthreads();
+    double2 *A = fft_stages(dst, src, plan, M, root);
+    double2 *B = (A == dst) ? src : dst;
+    // times bhat; conjugated so that the second forward FFT is the inverse transform
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const double2 v = cmul(A[m], __ldg(&plan.bhat[m]));
+        A[m] = make_double2(v.x, -v.y);
+    }
+    __syncthreads();
+    double2 *Cv = fft_stages(A, B, plan, M, root);
+    double2 *out = (Cv == A) ? B : A;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const double2 v = make_double2(Cv[k].x, -Cv[k].y);
+        out[k] = cmul(v, __ldg(&plan.chirp[k]));
+    }
+    __syncthreads();
+    return out;
+}
+
+// ---- host: plan construction shared by poisson.cu and fft2d.cu ----------------------------------------
+// Factorisation of N; lengths whose largest prime factor exceeds hpb_bluestein_min_prime() (default 64,
+// process-wide option "bluestein_min_prime") switch to Bluestein (returns M > 0 and factors M instead).
+inline int fft_factorize(int N, int *rad, int &nrad)
+{
+    auto factor = [&](int n) {
+        nrad = 0;
+        const int pref[] = {4, 2, 3, 5};
+        for (int r : pref) while (n % r == 0) { rad[nrad++] = r; n /= r; }
+        int largest = nrad ? 5 : 1;
+        for (int q = 7; n > 1; q += 2) while (n % q == 0) { rad[nrad++] = q; n /= q; largest = q; }
+        return largest;
+    };
+    if (factor(N) <= hpb_bluestein_min_prime()) return 0;
+    int M = 1;
+    while (M < 2 * N - 2) M <<= 1;
+    factor(M);
+    return M;
+}
+
+// chirp[n] = exp(-i pi n^2 / N) (n < N) and bhat = FFT_M(b) / M with b[m] = exp(+i pi m^2 / N) wrapped
+// (b[M - m] = b[m]); long-double arithmetic, O(M^2) on the host once per plan
+inline void fft_bluestein_tables(int N, int M, double2 *chirp, double2 *bhat)
+{
+    const long double pi = 3.14159265358979323846264338327950288L;
+    std::vector<long double> br(M, 0.0L), bi(M, 0.0L);
+    for (int n = 0; n < N; ++n) {
+        const long long q = ((long long)n * n) % (2LL * N);          // n^2 mod 2N keeps the argument small
+        const long double a = pi * (long double)q / (long double)N;
+        chirp[n].x = (double)cosl(a); chirp[n].y = (double)-sinl(a);
+        br[n] = cosl(a); bi[n] = sinl(a);
+        if (n > 0) { br[M - n] = cosl(a); bi[M - n] = sinl(a); }
+    }
+    std::vector<long double> wr(M), wi(M);
+    for (int t = 0; t < M; ++t) { wr[t] = cosl(-2.0L * pi * t / M); wi[t] = sinl(-2.0L * pi * t / M); }
+    for (int k = 0; k < M; ++k) {
+        long double sr = 0.0L, si = 0.0L;
+        for (int m = 0; m < M; ++m) {
+            if (br[m] == 0.0L && bi[m] == 0.0L) continue;
+            const int t = (int)(((long long)k * m) % M);
+            sr += br[m] * wr[t] - bi[m] * wi[t];
+            si += br[m] * wi[t] + bi[m] * wr[t];
+        }
+        bhat[k].x = (double)(sr / M); bhat[k].y = (double)(si / M);
+    }
+}
 
 }  // namespace

@@ -19,6 +19,7 @@
 #include "sim.hpp"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -115,6 +116,11 @@ extern "C" int hpb_sim_pipeline_init(hpb_sim *s, int rank, int world, const char
     s->pipe = p;
     if (world == 1) return HPB_OK;
     if (!id_recv || !id_send) return HPB_ERR_ARG;
+    // one channel (= one CTA) per point-to-point kernel unless the user decided otherwise: the packets
+    // are small and the CTAs of a waiting receive otherwise occupy many SMs (takes effect only if NCCL
+    // has not read its parameters yet; bench.py and hipace_b200.pipeline set it before torch starts NCCL)
+    setenv("NCCL_MAX_P2P_NCHANNELS", "1", 0);
+    setenv("NCCL_MIN_P2P_NCHANNELS", "1", 0);
     NcclApi *N = nccl();
     if (!N) return HPB_ERR_NCCL;
     ncclUniqueId idr, ids;

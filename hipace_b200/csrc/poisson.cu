@@ -76,7 +76,7 @@ k_dst_rows(Src src, OutPtrs out, long out_rs, int nx, int ny, FftPlan plan,
     extern __shared__ double2 smem[];
     const int N = plan.N, n = nx;
     double2 *buf0 = smem;
-    double2 *buf1 = smem + N;
+    double2 *buf1 = smem + plan.buf_len() + 4;
     const int b = blockIdx.y;
     const int ja = 2 * blockIdx.x, jb = ja + 1;
     const bool has_b = jb < ny;
@@ -245,14 +245,8 @@ k_thomas_reduced(const double *__restrict__ yf, const double *__restrict__ ye, d
 void factorize(int N, FftPlan &plan)
 {
     plan.N = N;
-    plan.nrad = 0;
-    int n = N;
-    const int pref[] = {4, 2, 3, 5};
-    for (int r : pref)
-        while (n % r == 0) { plan.rad[plan.nrad++] = r; n /= r; }
-    for (int p = 7; n > 1; p += 2)
-        while (n % p == 0) { plan.rad[plan.nrad++] = p; n /= p; }
-    // small radices last would also work; Stockham stages are order independent
+    plan.M = fft_factorize(N, plan.rad, plan.nrad);      // M > 0: Bluestein, the radices factor M
+    plan.chirp = plan.bhat = nullptr;
 }
 
 template <class T>
@@ -267,6 +261,7 @@ FftPlan make_plan(const hpb_ctx *ctx)
 {
     FftPlan plan;
     plan.N = ctx->fftN; plan.nrad = ctx->nrad;
+    plan.M = ctx->fftM; plan.chirp = ctx->d_chirp; plan.bhat = ctx->d_bhat;
     for (int i = 0; i < plan.nrad; ++i) {
         plan.rad[i] = ctx->radices[i];
         plan.cs_cos[i] = ctx->d_cs_cos[i];
@@ -278,8 +273,9 @@ FftPlan make_plan(const hpb_ctx *ctx)
 template <class Src, int NTHR, int MINB>
 int launch_rows_v(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, int nbatch, double scale)
 {
-    const int nx = ctx->g.nx, ny = ctx->g.ny, N = ctx->fftN;
-    const size_t smem = 2 * sizeof(double2) * (size_t)(N + 4);
+    const int nx = ctx->g.nx, ny = ctx->g.ny;
+    const int L = ctx->fftM > 0 ? ctx->fftM : ctx->fftN;
+    const size_t smem = 2 * sizeof(double2) * (size_t)(L + 4);
     static bool attr_set = false;       // per instantiation; the limit covers every supported N
     if (!attr_set) {
         HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src, NTHR, MINB>,
@@ -314,6 +310,8 @@ int hpb_poisson_init(hpb_ctx *ctx)
     FftPlan plan;
     factorize(N, plan);
     ctx->nrad = plan.nrad;
+    ctx->fftM = plan.M;
+    const int Lfft = plan.M > 0 ? plan.M : N;            // length of the root table / of the stages
     const long double pi = 3.14159265358979323846264338327950288L;
     for (int i = 0; i < plan.nrad; ++i) {
         ctx->radices[i] = plan.rad[i];
@@ -332,11 +330,17 @@ int hpb_poisson_init(hpb_ctx *ctx)
             rc = upload(&ctx->d_cs_sin[i], ts); if (rc) return rc;
         }
     }
-    std::vector<double2> root(N);
+    std::vector<double2> root(Lfft);
     std::vector<double> sinf(nx);
-    for (int t = 0; t < N; ++t) {
-        root[t].x = (double)cosl(-2.0L * pi * t / N);
-        root[t].y = (double)sinl(-2.0L * pi * t / N);
+    for (int t = 0; t < Lfft; ++t) {
+        root[t].x = (double)cosl(-2.0L * pi * t / Lfft);
+        root[t].y = (double)sinl(-2.0L * pi * t / Lfft);
+    }
+    if (plan.M > 0) {
+        std::vector<double2> chirp(N), bhat(plan.M);
+        fft_bluestein_tables(N, plan.M, chirp.data(), bhat.data());
+        int rcb = upload(&ctx->d_chirp, chirp); if (rcb) return rcb;
+        rcb = upload(&ctx->d_bhat, bhat); if (rcb) return rcb;
     }
     for (int i = 0; i < nx; ++i) sinf[i] = (double)(1.0L / (2.0L * sinl(pi * (i + 1) / N)));
     int rc = upload(&ctx->d_root, root); if (rc) return rc;
@@ -413,7 +417,7 @@ int hpb_poisson_init(hpb_ctx *ctx)
     HPB_CUDA_CHECK(cudaMalloc(&ctx->d_spec, 3 * bytes));
     HPB_CUDA_CHECK(cudaMalloc(&ctx->d_iface, 4 * 3 * sizeof(double) * (size_t)C * nx));
     HPB_CUDA_CHECK(cudaMemset(ctx->d_iface, 0, 4 * 3 * sizeof(double) * (size_t)C * nx));
-    const size_t smem = 2 * sizeof(double2) * (size_t)(N + 4);
+    const size_t smem = 2 * sizeof(double2) * (size_t)(Lfft + 4);
     if (smem > 220 * 1024) {
         hpb_set_error("poisson: nx = %d too large for the shared-memory row FFT", nx);
         return HPB_ERR_UNSUPPORTED;
@@ -426,7 +430,7 @@ void hpb_poisson_free(hpb_ctx *ctx)
     cudaFree(ctx->d_root); cudaFree(ctx->d_sinf); cudaFree(ctx->d_tri_m); cudaFree(ctx->d_tri_c);
     cudaFree(ctx->d_tri_p); cudaFree(ctx->d_tri_q); cudaFree(ctx->d_red_pe); cudaFree(ctx->d_red_pf);
     cudaFree(ctx->d_red_b); cudaFree(ctx->d_red_inv); cudaFree(ctx->d_red_del);
-    cudaFree(ctx->d_spec); cudaFree(ctx->d_iface);
+    cudaFree(ctx->d_spec); cudaFree(ctx->d_iface); cudaFree(ctx->d_chirp); cudaFree(ctx->d_bhat);
     for (int i = 0; i < ctx->nrad; ++i) { cudaFree(ctx->d_cs_cos[i]); cudaFree(ctx->d_cs_sin[i]); }
 }
 

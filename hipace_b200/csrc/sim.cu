@@ -1296,6 +1296,38 @@ int solve_one_slice(hpb_sim *s, int islice)
         if ((rc = beam_push_and_send(s, islice))) return rc;
         if ((rc = hpb_fields_shift_slices(ctx, s->sl, C))) return rc;                   // :721
         if (s->laser_state) hpb_laser_shift_slices(s->laser_state);                     // :727
+    } else if (side && s->opt_side_late) {
+        // Host issue order matters as much as the stream graph: the plasma push (the longest kernel of the
+        // slice, on the main stream) is enqueued BEFORE the side stream's dozen small beam launches and
+        // the NCCL send / receive bookkeeping, so that the GPU is busy while the host works through them
+        // (with the beam work enqueued first the main stream sat idle for the host time of those calls:
+        // ~80 us per slice as soon as the pipeline hand-off was on, SCALE_r01).  The side-stream kernels
+        // still read this slice's field planes: they get the component map from before the rotation.
+        cudaStream_t bs = s->stream2;
+        SIM_CUDA(cudaEventRecord(s->ev_fields, s->stream));
+        SIM_CUDA(cudaStreamWaitEvent(bs, s->ev_fields, 0));
+        int before[HPB_C_COUNT], after[HPB_C_COUNT];
+        memcpy(before, s->comps, sizeof(before));
+        if ((rc = hpb_fields_shift_and_initialize(ctx, s->sl, s->comps))) return rc;
+        if (islice > 0) SIM_CUDA(cudaEventRecord(s->ev_shift, s->stream));
+        if ((rc = push_plasma(true))) return rc;
+        memcpy(after, s->comps, sizeof(after));
+        memcpy(s->comps, before, sizeof(before));
+        {
+            StreamScope sc(s, bs);
+            rc = beam_push_and_send(s, islice);
+        }
+        memcpy(s->comps, after, sizeof(after));
+        if (rc) return rc;
+        if (islice > 0) {       // the beam deposits of the next slice go into freshly zeroed planes
+            SIM_CUDA(cudaStreamWaitEvent(bs, s->ev_shift, 0));
+            StreamScope sc(s, bs);
+            if ((rc = beam_deposit_jz(s, islice - 1))) return rc;
+            if ((rc = beam_next_and_sxsy(s, islice - 1))) return rc;
+        }
+        SIM_CUDA(cudaEventRecord(s->ev_side, bs));
+        SIM_CUDA(cudaStreamWaitEvent(s->stream, s->ev_side, 0));
+        s->prepared = islice > 0;
     } else {
         cudaStream_t bs = side ? s->stream2 : s->stream;
         {
@@ -1811,6 +1843,8 @@ extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
     else if (k == "fuse") s->opt_fuse = value != 0.;
     else if (k == "generic_order_kernels") s->ctx->force_generic = value != 0.;
     else if (k == "side_stream") s->opt_side_stream = value != 0.;
+    else if (k == "side_late") s->opt_side_late = value != 0.;
+    else if (k == "beam_from_host") { for (auto &b : s->beams) b.from_host = value != 0.; }   // 0: step 0 re-creates the deck's beam
     else if (k == "profile") s->opt_profile = value != 0.;
     else if (k == "max_step") s->max_step = (int)value;
     else return hpb_set_option(s->ctx, key, value);      // kernel variants: the context's switches

@@ -163,6 +163,7 @@ struct hpb_sim {
     // beam-side work of the fused order (beam push / re-binning / hand-off of this slice, beam
     // deposits and the Sx, Sy seed of the next one) runs on a second stream beside the plasma push
     bool opt_side_stream = true;
+    bool opt_side_late = true;       // enqueue the side stream's beam work behind the plasma push (host order)
     cudaStream_t stream2 = nullptr;
     cudaStream_t beam_stream = nullptr;     // where the pipeline's per-slice waits / records go
     cudaEvent_t ev_fields = nullptr, ev_shift = nullptr, ev_side = nullptr;

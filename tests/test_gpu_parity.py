@@ -141,6 +141,33 @@ def test_two_mobile_species_ion_motion(fuse, repo_root):
     sim.close()
 
 
+def test_production_shape_ppc9_two_species(repo_root):
+    """BASELINE configs[4] in miniature: ppc 9 (3 x 3) for BOTH mobile species (electrons + ions, ion motion
+    on, no neutralising background) on 96 x 96 -- the shape of the reference's production deck -- against
+    the oracle: field checksums of 30 slices, validity bit-exact, the state of both species to 1e-9"""
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import Simulation as Oracle
+    text = _deck(repo_root, 'ion_motion_normalized.in')
+    ov = {'amr.n_cell': '96 96 100', 'elec.ppc': '3 3', 'ions.ppc': '3 3'}
+    nsl = 30
+    ref = Oracle(text, ov)
+    want = ref.evolve(nsl)
+    sim = hp.Simulation(text, ov)
+    got = sim.evolve(0, 0, nsl)
+    for k, w in want.items():
+        assert abs(got[k] - w) <= RTOL_SUM * abs(w) + 1e-30, (k, got[k], w)
+    assert sim.stats()['n_qsa_violation'] == 0
+    for isp, o in enumerate(ref.plasmas):
+        p = sim.plasma(isp)
+        assert p['x'].size == 9 * 96 * 96
+        assert np.array_equal(p['valid'], o.valid)
+        v = o.valid
+        for nm, ov_ in (('x', o.x), ('y', o.y), ('ux', o.ux), ('uy', o.uy), ('psi', o.psi)):
+            scale = max(np.abs(ov_[v]).max(), 1e-300)
+            assert np.abs(p[nm][v] - ov_[v]).max() / scale <= 1e-9, (isp, nm)
+    sim.close()
+
+
 def test_full_size_driver_orders_agree(repo_root):
     """BASELINE configs[2] transverse size (1024 x 1024, ppc 4; the oracle would need minutes per
     slice here): the reference call order, the fused order and the fused order with the side
@@ -323,7 +350,9 @@ def test_plasma_init_is_bit_exact(repo_root):
 
 
 @pytest.mark.parametrize('nx,ny', [(64, 64), (63, 63), (100, 36), (255, 129), (1024, 1024),
-                                   (1023, 1023)])
+                                   (1023, 1023),
+                                   # nx + 1 with a large prime factor: the Bluestein path of fft_smem.cuh
+                                   (256, 256), (2048, 48), (682, 40)])
 def test_poisson_solve_matches_dst_oracle(nx, ny):
     """FFTPoissonSolverDirichlet: lhs = DST2D(DST2D(rhs) * eigenvalues) (oracle) vs the CUDA
     row-DST + tridiagonal formulation, incl. non power-of-two N = nx + 1 (1025 = 5*5*41)."""
