@@ -43,6 +43,16 @@ UNIT = 'slices/s'
 
 
 def deck_and_overrides(nxy, nz, ppc):
+    if (nxy, nz, ppc) == WORKLOADS['configs3'][:3]:
+        # laser_blowout_wake_explicit in SI units (the reference's golden deck of that name, scaled up):
+        # no beam, a laser pulse drives the wake, the envelope is advanced every slice (multigrid solver,
+        # the reference's default) and its slices travel through the pipeline
+        meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'laser_blowout_wake_explicit.SI.1Rank.json')))
+        deck = open(os.path.join(ROOT, meta['deck'])).read()
+        ov = dict(meta['overrides'])
+        ov.pop('max_step', None)
+        ov.update({'amr.n_cell': f'{nxy} {nxy} {nz}', 'plasma.ppc': f'{ppc} {ppc}'})
+        return deck, ov
     if (nxy, nz, ppc) == WORKLOADS['configs4'][:3]:
         # the shape of the reference's production deck: two mobile species (ion motion), ppc 9 each
         deck = open(os.path.join(ROOT, 'examples', 'ion_motion_normalized.in')).read()
@@ -56,6 +66,7 @@ def deck_and_overrides(nxy, nz, ppc):
 WORKLOADS = {'configs2': (1024, 1024, 2, 'BASELINE configs[2]'),
              'configs1': (256, 512, 2, 'BASELINE configs[1]'),
              'n1023': (1023, 1024, 2, 'configs[2] on the reference\'s recommended 2^n - 1 grid'),
+             'configs3': (512, 1024, 1, 'BASELINE configs[3]: laser_blowout_wake_explicit SI with the envelope solve'),
              'configs4': (2048, 2048, 3, 'BASELINE configs[4] shape: ion motion, two species, ppc 9, normalised units')}
 
 
@@ -161,7 +172,7 @@ def main():
     ap.add_argument('--nxy', type=int, default=1024)
     ap.add_argument('--nz', type=int, default=1024)
     ap.add_argument('--ppc', type=int, default=2, help='per direction (2 -> ppc 4)')
-    ap.add_argument('--dt', type=float, default=1.0,
+    ap.add_argument('--dt', type=float, default=None,
                     help='hipace.dt in 1/omega_p (> 0: the beam evolves from step to step, particles slip '
                          'between slices and every pipeline packet differs from the last)')
     ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
@@ -177,6 +188,9 @@ def main():
 
     if args.workload:
         args.nxy, args.nz, args.ppc = WORKLOADS[args.workload][:3]
+    if args.dt is None:
+        # normalised decks: 1 / omega_p; the SI laser deck: 4 / omega_p of its 2e24 m^-3 plasma in seconds
+        args.dt = 4.0 * 10.e-6 / 299792458. if (args.nxy, args.nz, args.ppc) == WORKLOADS['configs3'][:3] else 1.0
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     # a stuck rank must say where it is stuck and leave, never hold the box until an outer limit
@@ -232,6 +246,9 @@ def main():
     for kv in list(args.opt):          # process-wide switches take effect when a context is created
         if kv.split('=', 1)[0] in ('bluestein_min_prime',):
             hp.set_global_option(kv.split('=', 1)[0], float(kv.split('=', 1)[1]))
+    n_beams = int(hp.deck_check(deck, ov)['n_beams'])
+    if n_beams == 0:
+        args.no_e2e = True          # the end-to-end leg moves the beam through host memory: nothing to move
     sim = hp.Simulation(deck, ov, device=local_rank)
     sim.set_option('checksums', 0)
     arm_opts = {'cufft_ref': ['poisson_impl=1'],
@@ -328,16 +345,17 @@ def main():
     verify = None
     if world > 1 and not args.no_verify:
         sim.set_option('checksums', 1)
-        sim.set_option('beam_from_host', 0)     # the e2e leg uploaded a beam: step 0 starts from the deck's again
+        if n_beams:
+            sim.set_option('beam_from_host', 0)     # the e2e leg uploaded a beam: step 0 starts from the deck's again
         sim.run(world - 1, rank, world)
         barrier()
         if rank == world - 1:
-            got_f, got_b = sim.checksums(), sim.beam_checksums(0)
+            got_f, got_b = sim.checksums(), (sim.beam_checksums(0) if n_beams else {})
             solo = hp.Simulation(deck, ov, device=local_rank)
             solo.pipeline_init(0, 1, None)
             solo.set_option('max_step', world - 1)
             want_f = solo.evolve(0, world - 1)
-            want_b = solo.beam_checksums(0)
+            want_b = solo.beam_checksums(0) if n_beams else {}
             solo.close()
             worst = 0.
             for want, got in ((want_f, got_f), (want_b, got_b)):
@@ -366,7 +384,9 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
         sim.set_option('profile', 1)
-        sim.set_option('max_step', 0)      # a lone step: nothing is handed downstream
+        # a lone step: nothing is handed downstream (the laser deck keeps max_step = 1 on a single GPU so
+        # that the envelope solve is part of the profiled slice)
+        sim.set_option('max_step', 1 if (n_beams == 0 and world == 1) else 0)
         sim.evolve(0, 0)
         sp = sim.stats()
         sim.set_option('profile', 0)

@@ -68,7 +68,7 @@ void free_plan(Plan1D &p)
 // One sequence of N complex numbers per CTA: element e of sequence s is at in[s * seq_stride + e *
 // elem_stride] (rows: seq_stride = nx, elem_stride = 1; columns: seq_stride = 1, elem_stride = nx).
 // INV: conj in, forward transform, conj out = the inverse (unnormalised) transform.
-template <bool INV>
+template <bool INV, bool BLUE>
 __global__ void __launch_bounds__(kFftThreads)
 k_fft_seq(const double2 *__restrict__ in, double2 *__restrict__ out, long seq_stride, long elem_stride,
           FftPlan plan, const double2 *__restrict__ root)
@@ -84,7 +84,7 @@ k_fft_seq(const double2 *__restrict__ in, double2 *__restrict__ out, long seq_st
         b0[e] = v;
     }
     __syncthreads();
-    const double2 *F = fft_smem(b0, b1, plan, root);
+    const double2 *F = fft_smem<BLUE>(b0, b1, plan, root);
     for (int e = threadIdx.x; e < N; e += blockDim.x) {
         double2 v = F[e];
         if (INV) v.y = -v.y;
@@ -111,8 +111,10 @@ int hpb_fft2d_create(hpb_fft2d **out, int nx, int ny)
         delete f;
         return HPB_ERR_UNSUPPORTED;
     }
-    cudaFuncSetAttribute(k_fft_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_fft_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_fft_seq<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_fft_seq<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_fft_seq<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_fft_seq<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     *out = f;
     return HPB_OK;
 }
@@ -131,17 +133,19 @@ int hpb_fft2d_exec(hpb_fft2d *f, hpb_ctx *ctx, const double2 *in, double2 *out, 
     const int nx = f->nx, ny = f->ny;
     const size_t smx = 2 * sizeof(double2) * (size_t)f->px.plan.buf_len();
     const size_t smy = 2 * sizeof(double2) * (size_t)f->py.plan.buf_len();
-    if (dir < 0) {
-        hpb_launch(k_fft_seq<false>, (unsigned)ny, kFftThreads, smx, ctx->stream, in, out, (long)nx, 1L, f->px.plan,
-                   (const double2 *)f->px.d_root);
-        hpb_launch(k_fft_seq<false>, (unsigned)nx, kFftThreads, smy, ctx->stream, (const double2 *)out, out, 1L, (long)nx,
-                   f->py.plan, (const double2 *)f->py.d_root);
-    } else {
-        hpb_launch(k_fft_seq<true>, (unsigned)ny, kFftThreads, smx, ctx->stream, in, out, (long)nx, 1L, f->px.plan,
-                   (const double2 *)f->px.d_root);
-        hpb_launch(k_fft_seq<true>, (unsigned)nx, kFftThreads, smy, ctx->stream, (const double2 *)out, out, 1L, (long)nx,
-                   f->py.plan, (const double2 *)f->py.d_root);
-    }
+    auto pass = [&](const double2 *src, double2 *dst, unsigned nseq, size_t smem, long seq_stride, long elem_stride,
+                    const Plan1D &p) {
+        const bool blue = p.plan.M > 0;
+        if (dir < 0) {
+            if (blue) hpb_launch(k_fft_seq<false, true>, nseq, kFftThreads, smem, ctx->stream, src, dst, seq_stride, elem_stride, p.plan, (const double2 *)p.d_root);
+            else hpb_launch(k_fft_seq<false, false>, nseq, kFftThreads, smem, ctx->stream, src, dst, seq_stride, elem_stride, p.plan, (const double2 *)p.d_root);
+        } else {
+            if (blue) hpb_launch(k_fft_seq<true, true>, nseq, kFftThreads, smem, ctx->stream, src, dst, seq_stride, elem_stride, p.plan, (const double2 *)p.d_root);
+            else hpb_launch(k_fft_seq<true, false>, nseq, kFftThreads, smem, ctx->stream, src, dst, seq_stride, elem_stride, p.plan, (const double2 *)p.d_root);
+        }
+    };
+    pass(in, out, (unsigned)ny, smx, (long)nx, 1L, f->px);                       // rows
+    pass((const double2 *)out, out, (unsigned)nx, smy, 1L, (long)nx, f->py);     // columns
     hpb_count_launch(ctx, 2);
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;

@@ -222,10 +222,13 @@ __device__ __forceinline__ double2 *fft_stages(double2 *src, double2 *dst, const
 
 // forward complex FFT of length N on shared memory (both buffers hold plan.buf_len() elements, the
 // input is src[0 .. N-1]); returns the buffer holding the result
+// BLUE is a compile-time switch: the radix-only instantiation keeps the register budget it was tuned
+// with (the chirp-z branch costs k_dst_rows 170 bytes of spills at 40 registers when it is merely present)
+template <bool BLUE>
 __device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const FftPlan &plan,
                                              const double2 *__restrict__ root)
 {
-    if (plan.M == 0) return fft_stages(src, dst, plan, plan.N, root);
+    if (!BLUE) return fft_stages(src, dst, plan, plan.N, root);
     // Bluestein: X[k] = c[k] sum_n (x[n] c[n]) conj(c)[k - n],  c[n] = exp(-i pi n^2 / N): a circular
     // convolution of length M through two power-of-two FFTs
     const int N = plan.N, M = plan.M;

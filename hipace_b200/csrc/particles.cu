@@ -1823,7 +1823,11 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
     const bool lattice = ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np;
     // push_variant 6 / 7 / 8: the row-tile kernel (round-1 thread map, one TMA patch per CTA; 96 / 128
     // registers / cp.async staging); any particle order
-    if ((variant == 6 || variant == 7 || variant == 8) && lasa.c_aabs < 0) {
+    // (an array the TMA unit cannot address -- odd row length, e.g. the 1023 + 4 cells of a 2^n - 1 grid --
+    // runs the round-1 warp-staged kernel below: the cooperative cp.async staging of variant 8 is the
+    // slowest of the three, 0.55 vs 0.34 vs 0.29 ms at 1024^2 ppc 4)
+    const bool row_tma_ok = variant == 8 || hpb_slice_tmap(ctx, 2, sl, kRW, kCH) != nullptr;
+    if ((variant == 6 || variant == 7 || variant == 8) && lasa.c_aabs < 0 && row_tma_ok) {
         PlasmaPtrs pp = to_ptrs(pl);
         const bool lat = ctx->order_n > 0 && ctx->order_n * ctx->order_ppc == pl.np;
         pp.lat_n = lat ? ctx->order_n : 0; pp.lat_ppc = lat ? ctx->order_ppc : 1;

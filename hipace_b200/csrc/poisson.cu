@@ -67,7 +67,7 @@ struct SrcSpec {             // chunk-local Thomas solution + interface correcti
 };
 
 // DST-I along x of two rows per CTA (unnormalised, FFTW RODFT00 convention, times `scale`).
-template <class Src, int NTHR, int MINB>
+template <class Src, int NTHR, int MINB, bool BLUE>
 __global__ void __launch_bounds__(NTHR, MINB)
 k_dst_rows(Src src, OutPtrs out, long out_rs, int nx, int ny, FftPlan plan,
            const double2 *__restrict__ root, const double *__restrict__ sinf, double scale)
@@ -76,7 +76,7 @@ k_dst_rows(Src src, OutPtrs out, long out_rs, int nx, int ny, FftPlan plan,
     extern __shared__ double2 smem[];
     const int N = plan.N, n = nx;
     double2 *buf0 = smem;
-    double2 *buf1 = smem + plan.buf_len() + 4;
+    double2 *buf1 = smem + (BLUE ? plan.M + 4 : N);      // (N: the layout the radix plans were tuned with)
     const int b = blockIdx.y;
     const int ja = 2 * blockIdx.x, jb = ja + 1;
     const bool has_b = jb < ny;
@@ -115,7 +115,7 @@ k_dst_rows(Src src, OutPtrs out, long out_rs, int nx, int ny, FftPlan plan,
         if (i > 0 && N - i > nh) buf0[N - i] = make_double2(re.x + im.y, im.x - re.y);   // conj(V[N-i])
     }
     __syncthreads();
-    const double2 *F = fft_smem(buf0, buf1, plan, root);
+    const double2 *F = fft_smem<BLUE>(buf0, buf1, plan, root);
     // z_a = Re F, z_b = -Im F;  out[i] = 0.5 (z[n-i] - z[i+1] + (z[i+1] + z[n-i]) sinf[i])
     double *out_a = out.p[b] + (long)ja * out_rs;
     double *out_b = out_a + out_rs;
@@ -278,13 +278,19 @@ int launch_rows_v(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs,
     const size_t smem = 2 * sizeof(double2) * (size_t)(L + 4);
     static bool attr_set = false;       // per instantiation; the limit covers every supported N
     if (!attr_set) {
-        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src, NTHR, MINB>,
+        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src, NTHR, MINB, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src, NTHR, MINB, true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     dim3 grid((ny + 1) / 2, nbatch);
-    hpb_launch(k_dst_rows<Src, NTHR, MINB>, grid, NTHR, smem, ctx->stream, src, out, out_rs, nx, ny,
-               make_plan(ctx), ctx->d_root, ctx->d_sinf, scale);
+    if (ctx->fftM > 0)
+        hpb_launch(k_dst_rows<Src, NTHR, MINB, true>, grid, NTHR, smem, ctx->stream, src, out, out_rs, nx, ny,
+                   make_plan(ctx), ctx->d_root, ctx->d_sinf, scale);
+    else
+        hpb_launch(k_dst_rows<Src, NTHR, MINB, false>, grid, NTHR, smem, ctx->stream, src, out, out_rs, nx, ny,
+                   make_plan(ctx), ctx->d_root, ctx->d_sinf, scale);
     hpb_count_launch(ctx);
     return HPB_OK;
 }
