@@ -56,7 +56,12 @@ def deck_and_overrides(nxy, nz, ppc):
     if (nxy, nz, ppc) == WORKLOADS['configs4'][:3]:
         # the shape of the reference's production deck: two mobile species (ion motion), ppc 9 each
         deck = open(os.path.join(ROOT, 'examples', 'ion_motion_normalized.in')).read()
-        return deck, {'amr.n_cell': f'{nxy} {nxy} {nz}', 'elec.ppc': f'{ppc} {ppc}', 'ions.ppc': f'{ppc} {ppc}'}
+        # (fixed_ppc with one particle per cell in z puts a whole beam slice at ONE z: all of it slips into
+        # the next slice in the same time step, so a slice packet transiently holds two slices' worth --
+        # the packet capacity is set accordingly, and the beam radius halved to keep the two rings at
+        # 2 x 2048 x 80 000 x 64 B = 21 GB; the plasma, which is what this configuration is about, is unchanged)
+        return deck, {'amr.n_cell': f'{nxy} {nxy} {nz}', 'elec.ppc': f'{ppc} {ppc}', 'ions.ppc': f'{ppc} {ppc}',
+                      'beam.radius': 0.8, 'beam.slice_capacity': 80000}
     deck = open(os.path.join(ROOT, 'examples', 'blowout_wake_normalized.in')).read()
     ov = {'amr.n_cell': f'{nxy} {nxy} {nz}', 'plasma.ppc': f'{ppc} {ppc}'}
     return deck, ov
@@ -72,7 +77,10 @@ WORKLOADS = {'configs2': (1024, 1024, 2, 'BASELINE configs[2]'),
 
 def workload_name(nxy, nz, ppc):
     tag = next((t for n, z, p, t in WORKLOADS.values() if (n, z, p) == (nxy, nz, ppc)), 'custom size')
-    return f'blowout_wake_explicit normalized {nxy}x{nxy}x{nz} ppc={ppc * ppc} ({tag})'
+    deck = {WORKLOADS['configs3'][:3]: 'laser_blowout_wake_explicit SI',
+            WORKLOADS['configs4'][:3]: 'ion_motion (two mobile species) normalized'}.get((nxy, nz, ppc),
+                                                                                       'blowout_wake_explicit normalized')
+    return f'{deck} {nxy}x{nxy}x{nz} ppc={ppc * ppc} ({tag})'
 
 
 # ------------------------------------------------------------------------------------------------
@@ -179,6 +187,8 @@ def main():
                     help='named size (overrides --nxy/--nz/--ppc); the default line is configs2')
     ap.add_argument('--opt', action='append', default=[], metavar='KEY=VALUE',
                     help='hpb_sim_set_option switch for A/B runs (e.g. order=9, fuse=0); recorded in config')
+    ap.add_argument('--reorder-period', type=int, default=0,
+                    help='plasmas.reorder_period: sort the plasma by cell every N slices (0: never, the default)')
     ap.add_argument('--no-verify', action='store_true', help='skip the N > 1 pipeline-vs-single-GPU check')
     ap.add_argument('--cpu-sample-slices', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -190,7 +200,12 @@ def main():
         args.nxy, args.nz, args.ppc = WORKLOADS[args.workload][:3]
     if args.dt is None:
         # normalised decks: 1 / omega_p; the SI laser deck: 4 / omega_p of its 2e24 m^-3 plasma in seconds
-        args.dt = 4.0 * 10.e-6 / 299792458. if (args.nxy, args.nz, args.ppc) == WORKLOADS['configs3'][:3] else 1.0
+        # (configs4: the oblique gamma ~ 100 beam of the ion-motion deck slips 0.024 c/omega_p per unit of
+        # dt and dz is 0.0059: with dt = 0.05 a fifth of a slice's particles slips per step, which the
+        # fixed-capacity slice packets -- initial maximum + 25 % -- hold; larger steps need
+        # <beam>.slice_capacity raised, at 64 B x nz x capacity per ring)
+        key = (args.nxy, args.nz, args.ppc)
+        args.dt = {WORKLOADS['configs3'][:3]: 4.0 * 10.e-6 / 299792458., WORKLOADS['configs4'][:3]: 0.05}.get(key, 1.0)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     # a stuck rank must say where it is stuck and leave, never hold the box until an outer limit
@@ -201,7 +216,8 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     K, W = args.steps, max(args.warmup, 0)
     cfg = {'workload': workload_name(args.nxy, args.nz, args.ppc), 'nx': args.nxy, 'ny': args.nxy,
-           'nz': args.nz, 'ppc': args.ppc * args.ppc, 'units': 'normalized', 'dt': args.dt,
+           'nz': args.nz, 'ppc': args.ppc * args.ppc,
+           'units': 'SI' if (args.nxy, args.nz, args.ppc) == WORKLOADS['configs3'][:3] else 'normalized', 'dt': args.dt,
            'solver': 'explicit (FFT/DST Poisson x3 + multigrid BxBy)',
            'l2_policy': 'working set per slice (~600 MB) > L2 (126 MB); no flush needed',
            'parallelism': f'time-step pipeline x{world}' if world > 1 else 'single GPU'}
@@ -243,6 +259,9 @@ def main():
     deck, ov = deck_and_overrides(args.nxy, args.nz, args.ppc)
     if args.dt:
         ov['hipace.dt'] = args.dt
+    if args.reorder_period:
+        ov['plasmas.reorder_period'] = args.reorder_period
+        cfg['reorder_period'] = args.reorder_period
     for kv in list(args.opt):          # process-wide switches take effect when a context is created
         if kv.split('=', 1)[0] in ('bluestein_min_prime',):
             hp.set_global_option(kv.split('=', 1)[0], float(kv.split('=', 1)[1]))

@@ -858,16 +858,9 @@ struct MG2 {
     double *sol0 = nullptr, *rhs0 = nullptr;     // level-0 iterate and right-hand side (2 comps, level box)
 };
 
-// one red-black half-sweep of gs2 on the valid points with (i + j + color) even
-__global__ void k2_gsrb(LevelGeom g, V2 phi, V2 rhs, V2 acf, int color)
+// gs2 (HpMultiGrid.cpp:296-334) at point (i, j)
+__device__ __forceinline__ void gs2_update(const LevelGeom &g, const V2 &phi, const V2 &rhs, const V2 &acf, int i, int j)
 {
-    hpb_pdl_prologue();
-    const int nvx = g.vhix - g.vlo + 1;
-    const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
-    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nv) return;
-    const int j = (int)(s / nvx) + g.vlo, i = (int)(s % nvx) + g.vlo;
-    if (((i + j + color) & 1) != 0) return;
     double lap0, lap1;
     double c0 = -2.0 * (g.facx + g.facy);
     if (g.cc && i == g.vlo) {
@@ -896,6 +889,19 @@ __global__ void k2_gsrb(LevelGeom g, V2 phi, V2 rhs, V2 acf, int color)
     const double dr = rhs.at(i, j, 0) - lap0, di = rhs.at(i, j, 1) - lap1;
     phi.at(i, j, 0) = dr * cr + di * ci;
     phi.at(i, j, 1) = di * cr - dr * ci;
+}
+
+// one red-black half-sweep of gs2 on the valid points with (i + j + color) even
+__global__ void k2_gsrb(LevelGeom g, V2 phi, V2 rhs, V2 acf, int color)
+{
+    hpb_pdl_prologue();
+    const int nvx = g.vhix - g.vlo + 1;
+    const long nv = (long)nvx * (g.vhiy - g.vlo + 1);
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nv) return;
+    const int j = (int)(s / nvx) + g.vlo, i = (int)(s % nvx) + g.vlo;
+    if (((i + j + color) & 1) != 0) return;
+    gs2_update(g, phi, rhs, acf, i, j);
 }
 
 __device__ __forceinline__ double lap_global(const LevelGeom &g, const V2 &phi, int i, int j, int n)
@@ -1002,6 +1008,87 @@ __global__ void k2_extract(LevelGeom g, V2 lvl, double *valid2, int nxv, int nyv
     const int jv = (int)(s / nxv), iv = (int)(s % nxv);
     valid2[s] = lvl.at(iv + g.vlo, jv + g.vlo, 0);
     valid2[nv + s] = lvl.at(iv + g.vlo, jv + g.vlo, 1);
+}
+
+// ---- all levels of <= kSmall2 points in ONE 1024-thread CTA (the role k_coarse plays for type 1): down
+// through the small levels, the bottom solve, and back up, with block barriers between the operators.
+// The arrays stay in global memory (they are L1 / L2 resident: <= 64 x 64 points per level).
+constexpr int kSmall2 = 66 * 66;
+struct Small2Level { LevelGeom g; V2 acf, res, cor, rescor; };
+struct Small2Args { int nl; int nsweeps_bottom; Small2Level L[16]; };
+
+__device__ void s2_gsrb(const Small2Level &L, const V2 &phi, const V2 &rhs, int nsweeps)
+{
+    const LevelGeom &g = L.g;
+    const int nvx = g.vhix - g.vlo + 1, nv = nvx * (g.vhiy - g.vlo + 1);
+    for (int ic = 0; ic < nsweeps; ++ic) {
+        for (int s = threadIdx.x; s < nv; s += blockDim.x) {
+            const int j = s / nvx + g.vlo, i = s % nvx + g.vlo;
+            if (((i + j + ic) & 1) == 0) gs2_update(g, phi, rhs, L.acf, i, j);
+        }
+        __syncthreads();
+    }
+}
+__device__ void s2_zero(const Small2Level &L, const V2 &a)
+{
+    const long n = 2L * L.g.nx * L.g.ny;
+    for (long s = threadIdx.x; s < n; s += blockDim.x) a.p[s] = 0.;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k2_small(Small2Args A, const int *done)
+{
+    hpb_pdl_prologue();
+    if (done && *(const volatile int *)done) return;
+    const int nl = A.nl;
+    for (int l = 0; l < nl - 1; ++l) {
+        const Small2Level &L = A.L[l];
+        const LevelGeom &g = L.g;
+        s2_zero(L, L.cor);
+        s2_gsrb(L, L.cor, L.res, 4);
+        const int nvx = g.vhix - g.vlo + 1, nv = nvx * (g.vhiy - g.vlo + 1);
+        for (int s = threadIdx.x; s < nv; s += blockDim.x) {
+            const int j = s / nvx + g.vlo, i = s % nvx + g.vlo;
+            const double ar = L.acf.at(i, j, 0), ai = L.acf.at(i, j, 1);
+            const double pr = L.cor.at(i, j, 0), pi = L.cor.at(i, j, 1);
+            L.rescor.at(i, j, 0) = L.res.at(i, j, 0) + ar * pr - ai * pi - lap_global(g, L.cor, i, j, 0);
+            L.rescor.at(i, j, 1) = L.res.at(i, j, 1) + ai * pr + ar * pi - lap_global(g, L.cor, i, j, 1);
+        }
+        __syncthreads();
+        const Small2Level &C = A.L[l + 1];
+        const LevelGeom &gc = C.g;
+        const int cvx = gc.vhix - gc.vlo + 1, cv = cvx * (gc.vhiy - gc.vlo + 1);
+        for (int s = threadIdx.x; s < 2 * cv; s += blockDim.x) {
+            const int n = s >= cv, q = s - n * cv;
+            const int j = q / cvx + gc.vlo, i = q % cvx + gc.vlo;
+            const double *f = L.rescor.p + n * L.rescor.cs + (2 * i) + (long)(2 * j) * L.rescor.rs;
+            const long w = L.rescor.rs;
+            double v;
+            if (gc.cc) v = 0.25 * (f[0] + f[1] + f[w] + f[w + 1]);
+            else v = (1. / 16.) * (f[-w - 1] + 2. * f[-w] + f[-w + 1] + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                                   + f[w - 1] + 2. * f[w] + f[w + 1]);
+            C.res.at(i, j, n) = v;
+        }
+        __syncthreads();
+    }
+    {
+        const Small2Level &B = A.L[nl - 1];
+        s2_zero(B, B.cor);
+        s2_gsrb(B, B.cor, B.res, A.nsweeps_bottom);
+    }
+    for (int l = nl - 2; l >= 0; --l) {
+        const Small2Level &L = A.L[l];
+        const LevelGeom &g = L.g;
+        const V2 crse = A.L[l + 1].cor;
+        const int nvx = g.vhix - g.vlo + 1, nv = nvx * (g.vhiy - g.vlo + 1);
+        for (int s = threadIdx.x; s < nv; s += blockDim.x) {
+            const int j = s / nvx + g.vlo, i = s % nvx + g.vlo;
+            L.cor.at(i, j, 0) = L.cor.at(i, j, 0) + interp_at(crse, i, j, 0, g.cc);
+            L.cor.at(i, j, 1) = L.cor.at(i, j, 1) + interp_at(crse, i, j, 1, g.cc);
+        }
+        __syncthreads();
+        s2_gsrb(L, L.cor, L.res, 4);
+    }
 }
 
 int mg2_sweeps(hpb_ctx *ctx, const LevelGeom &g, V2 phi, V2 rhs, V2 acf, int nsweeps)
@@ -1311,7 +1398,11 @@ extern "C" int hpb_mg_solve2(hpb_ctx *ctx, double *d_sol2, const double *d_rhs2,
         if (ctx->h_mg_istate[0]) break;
         if (iters >= max_iters) { hpb_set_error("hpmg (type 2) failed to converge after %d iterations", max_iters); return HPB_ERR_MG_DIVERGED; }
         // ---- one V-cycle (:1429-1512) ----
-        for (int l = 0; l < nl - 1; ++l) {
+        // ls: first level handled by the single-CTA kernel (>= 1; all levels from there down are small)
+        int ls = 1;
+        while (ls < nl - 1 && (long)ctx->mg[ls].nx * ctx->mg[ls].ny > kSmall2) ++ls;
+        if (nl - ls > 16) ls = nl - 16;
+        for (int l = 0; l < ls; ++l) {
             const V2 rescor = lvl_view(ctx, l, ctx->mg[l].rescor);
             if (l > 0) {
                 const V2 cor = lvl_view(ctx, l, ctx->mg[l].cor), res = lvl_view(ctx, l, ctx->mg[l].res);
@@ -1324,16 +1415,23 @@ extern "C" int hpb_mg_solve2(hpb_ctx *ctx, double *d_sol2, const double *d_rhs2,
             hpb_count_launch(ctx);
         }
         {
-            const int l = nl - 1;
-            const LevelGeom gb = G(l);
+            Small2Args A;
+            A.nl = nl - ls;
+            for (int l = ls; l < nl; ++l) {
+                Small2Level &L = A.L[l - ls];
+                L.g = G(l); L.acf = ACF(l);
+                L.res = lvl_view(ctx, l, ctx->mg[l].res); L.cor = lvl_view(ctx, l, ctx->mg[l].cor);
+                L.rescor = lvl_view(ctx, l, ctx->mg[l].rescor);
+            }
+            const LevelGeom gb = G(nl - 1);
             int nsw = 16;
             const int mx = gb.nx > gb.ny ? gb.nx : gb.ny;
             if ((mx + 1) / 2 * 2 > nsw) nsw = (mx + 1) / 2 * 2;       // :1587
-            const V2 cor = lvl_view(ctx, l, ctx->mg[l].cor);
-            HPB_CUDA_CHECK(cudaMemsetAsync(cor.p, 0, bytes2(l), ctx->stream));
-            mg2_sweeps(ctx, gb, cor, lvl_view(ctx, l, ctx->mg[l].res), ACF(l), nsw);
+            A.nsweeps_bottom = nsw;
+            hpb_launch(k2_small, 1, 1024, 0, ctx->stream, A, (const int *)nullptr);
+            hpb_count_launch(ctx);
         }
-        for (int l = nl - 2; l >= 0; --l) {
+        for (int l = ls - 1; l >= 0; --l) {
             const V2 crse = lvl_view(ctx, l + 1, ctx->mg[l + 1].cor);
             if (l == 0) {
                 // sol = GSRB^4(cor0 + I(cor1))

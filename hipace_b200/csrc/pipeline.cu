@@ -5,7 +5,8 @@
 // time steps is the beam: for every slice, rank r receives the slice packet that rank r-1 pushed
 // in the previous time step and sends its own pushed packet to rank r+1 (ring).  There is no
 // collective and nothing else is exchanged (plasma is re-created locally every step; the physical
-// time of a step is step * dt on every rank -- adaptive time steps are out of scope).
+// time of a step is the accumulated sum of dt on every rank; adaptive time steps are single-rank).  The laser envelope slices
+// A^{n+1}, A^n of a slice ride in the same group of sends / receives (MultiBuffer.cpp:444-490).
 //
 // Each directed edge r -> r+1 is its own 2-rank communicator with its own CUDA stream, so a
 // receive that waits for the upstream rank never blocks the sends to the downstream rank.

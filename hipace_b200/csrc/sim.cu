@@ -435,6 +435,7 @@ int read_deck(hpb_sim *s)
             b.n_subcycles = (int)d.num(nm + ".n_subcycles", 10);
             if (b.n_subcycles < 1) throw std::runtime_error(nm + ".n_subcycles must be >= 1");
             b.do_z_push = (int)d.num(nm + ".do_z_push", 1) != 0;
+            (void)d.has(nm + ".slice_capacity");        // our addition, read when the rings are allocated (init_beam)
             // "<beam name> or beams" (queryWithParserAlt)
             auto alt_num = [&](const char *key, double dflt) {
                 return d.has(nm + "." + key) ? d.num(nm + "." + key, dflt) : d.num(std::string("beams.") + key, dflt);

@@ -1,0 +1,8 @@
+#!/bin/bash
+tag=${1:-r02n}
+mkdir -p gpurun_out
+export HPB_BENCH_WATCHDOG=800
+timeout 600 python -m pytest tests -m gpu -q -rfEs --tb=short --timeout 400 -k "mg_solve2 or laser" 2>&1 | tail -8 | tee gpurun_out/${tag}_pytest.txt
+timeout 600 python bench.py --workload configs3 --steps 1 --warmup 3 --no-cpu-baseline 2> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench_configs3.json | cut -c1-250
+timeout 900 python bench.py --workload configs4 --steps 1 --warmup 3 --no-cpu-baseline 2>> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench_configs4.json | cut -c1-250
+tail -5 gpurun_out/${tag}_bench.err
