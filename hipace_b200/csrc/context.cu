@@ -139,6 +139,7 @@ extern "C" int hpb_create(hpb_ctx **out, const hpb_geom *geom, void *stream)
     // defaults = the measured best on the 1024^2 ppc 4 deck (profiles/README.md): the row-tile TMA
     // push, the round-1 warp-aggregated explicit deposition
     ctx->tune_order = 1; ctx->tune_expl_variant = 0; ctx->tune_push_variant = 6;
+    ctx->tune_mg_wide = 1;      // 1024-thread tiles on the multigrid levels that do not fill the GPU: 0.393 -> 0.367 ms
     int rc = hpb_poisson_init(ctx);
     if (rc == HPB_OK) rc = hpb_mg_init(ctx);
     if (rc == HPB_OK && cudaMalloc(&ctx->d_scalar_i, 16 * sizeof(int)) != cudaSuccess) rc = HPB_ERR_CUDA;

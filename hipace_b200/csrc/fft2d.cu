@@ -84,7 +84,7 @@ k_fft_seq(const double2 *__restrict__ in, double2 *__restrict__ out, long seq_st
         b0[e] = v;
     }
     __syncthreads();
-    const double2 *F = fft_smem<BLUE>(b0, b1, plan, root);
+    const double2 *F = fft_smem<BLUE>(b0, b1, plan, root, reinterpret_cast<double *>(fsm + 2 * plan.buf_len()));
     for (int e = threadIdx.x; e < N; e += blockDim.x) {
         double2 v = F[e];
         if (INV) v.y = -v.y;
@@ -131,8 +131,8 @@ int hpb_fft2d_exec(hpb_fft2d *f, hpb_ctx *ctx, const double2 *in, double2 *out, 
 {
     if (!f || !ctx || !in || !out) return HPB_ERR_ARG;
     const int nx = f->nx, ny = f->ny;
-    const size_t smx = 2 * sizeof(double2) * (size_t)f->px.plan.buf_len();
-    const size_t smy = 2 * sizeof(double2) * (size_t)f->py.plan.buf_len();
+    const size_t smx = 2 * sizeof(double2) * (size_t)f->px.plan.buf_len() + 2 * sizeof(double) * (size_t)f->px.plan.max_prime();
+    const size_t smy = 2 * sizeof(double2) * (size_t)f->py.plan.buf_len() + 2 * sizeof(double) * (size_t)f->py.plan.max_prime();
     auto pass = [&](const double2 *src, double2 *dst, unsigned nseq, size_t smem, long seq_stride, long elem_stride,
                     const Plan1D &p) {
         const bool blue = p.plan.M > 0;

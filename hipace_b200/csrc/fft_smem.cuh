@@ -22,6 +22,12 @@ struct FftPlan {
     int M;
     const double2 *chirp, *bhat;
     __host__ __device__ int buf_len() const { return M > 0 ? M : N; }     // complex elements per buffer
+    __host__ __device__ int max_prime() const                             // largest generic (> 5) radix, or 0
+    {
+        int q = 0;
+        for (int i = 0; i < nrad; ++i) if (rad[i] > 5 && rad[i] > q) q = rad[i];
+        return q;
+    }
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b)
@@ -143,13 +149,24 @@ __device__ __forceinline__ void fft_stage_r5(const double2 *__restrict__ in, dou
 //   A: x_t = in[j + t Nr] w^{t k tw};  U[t][j] = x_t + x_{p-t},  V[t][j] = x_t - x_{p-t},  X0[j]
 //   B: X_b = x0 + sum_t U_t cos(2 pi t b/p) - i sum_t V_t sin(2 pi t b/p),  X_{p-b} = conj-sign
 // Result is written back into `in` (no buffer swap for this stage).
+// s_tab: 2 p doubles of shared memory.  The p-th roots of unity cos / sin(2 pi m / p), m = 0 .. p-1, are
+// staged there once per stage and indexed with m = (t b) mod p kept incrementally: the inner loop's two
+// table loads per step used to be global (L1) loads -- 40 % of the row kernel's stall samples were
+// long-scoreboard waits on them (profiles: r01e source page) -- and are shared-memory broadcasts now.
 __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double2 *__restrict__ tmp,
                                                 const double2 *__restrict__ root, int N, int Ns, int p,
                                                 const double *__restrict__ tcos,
-                                                const double *__restrict__ tsin)
+                                                const double *__restrict__ tsin, double *__restrict__ s_tab)
 {
     const int Nr = N / p, h = (p - 1) / 2, tw = N / (Ns * p);
     const FastDiv fNr(Nr), fNs(Ns);
+    double *s_c = s_tab, *s_s = s_tab + p;
+    for (int m = threadIdx.x; m < p; m += blockDim.x) {
+        // row b = 1 of the (b, t) tables holds cos / sin(2 pi t / p), t = 1 .. h
+        const int mm = m <= h ? m : p - m;
+        s_c[m] = m == 0 ? 1.0 : __ldg(&tcos[h + mm - 1]);
+        s_s[m] = m == 0 ? 0.0 : (m <= h ? __ldg(&tsin[h + mm - 1]) : -__ldg(&tsin[h + mm - 1]));
+    }
     for (int e = threadIdx.x; e < Nr * h; e += blockDim.x) {
         const int tq = fNr.div(e);
         const int t = tq + 1, j = e - tq * Nr;
@@ -177,13 +194,18 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
         double2 P[BB], Q[BB];
 #pragma unroll
         for (int bb = 0; bb < BB; ++bb) { P[bb] = x0; Q[bb] = make_double2(0., 0.); }
-#pragma unroll 2
+        int m[BB];
+#pragma unroll
+        for (int bb = 0; bb < BB; ++bb) m[bb] = 0;
+#pragma unroll 4
         for (int t = 0; t < h; ++t) {
             const double2 u = tmp[t * Nr + j], v = tmp[(h + t) * Nr + j];
 #pragma unroll
             for (int bb = 0; bb < BB; ++bb) {
                 const int b = min(b0 + bb, h);          // (a clamped duplicate is simply not stored)
-                const double c = __ldg(&tcos[b * h + t]), sn = __ldg(&tsin[b * h + t]);
+                m[bb] += b;                              // ((t + 1) b) mod p
+                if (m[bb] >= p) m[bb] -= p;
+                const double c = s_c[m[bb]], sn = s_s[m[bb]];
                 P[bb].x += c * u.x; P[bb].y += c * u.y;
                 Q[bb].x += sn * v.x; Q[bb].y += sn * v.y;
             }
@@ -202,7 +224,7 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
 // the Stockham stages of a plan on a sequence of length L held in src (scratch dst); returns the
 // buffer holding the result
 __device__ __forceinline__ double2 *fft_stages(double2 *src, double2 *dst, const FftPlan &plan, int L,
-                                               const double2 *__restrict__ root)
+                                               const double2 *__restrict__ root, double *s_tab)
 {
     int Ns = 1;
     for (int s = 0; s < plan.nrad; ++s) {
@@ -212,7 +234,7 @@ __device__ __forceinline__ double2 *fft_stages(double2 *src, double2 *dst, const
         else if (r == 2) fft_stage_r2(src, dst, root, L, Ns);
         else if (r == 5) fft_stage_r5(src, dst, root, L, Ns);
         else if (r == 3) fft_stage_r3(src, dst, root, L, Ns);
-        else { fft_stage_prime(src, dst, root, L, Ns, r, plan.cs_cos[s], plan.cs_sin[s]); swap = false; }
+        else { fft_stage_prime(src, dst, root, L, Ns, r, plan.cs_cos[s], plan.cs_sin[s], s_tab); swap = false; }
         __syncthreads();
         if (swap) { double2 *t = src; src = dst; dst = t; }
         Ns *= r;
@@ -226,16 +248,16 @@ __device__ __forceinline__ double2 *fft_stages(double2 *src, double2 *dst, const
 // with (the chirp-z branch costs k_dst_rows 170 bytes of spills at 40 registers when it is merely present)
 template <bool BLUE>
 __device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const FftPlan &plan,
-                                             const double2 *__restrict__ root)
+                                             const double2 *__restrict__ root, double *s_tab)
 {
-    if (!BLUE) return fft_stages(src, dst, plan, plan.N, root);
+    if (!BLUE) return fft_stages(src, dst, plan, plan.N, root, s_tab);
     // Bluestein: X[k] = c[k] sum_n (x[n] c[n]) conj(c)[k - n],  c[n] = exp(-i pi n^2 / N): a circular
     // convolution of length M through two power-of-two FFTs
     const int N = plan.N, M = plan.M;
     for (int n = threadIdx.x; n < M; n += blockDim.x)
         dst[n] = n < N ? cmul(src[n], __ldg(&plan.chirp[n])) : make_double2(0., 0.);
     __syncthreads();
-    double2 *A = fft_stages(dst, src, plan, M, root);
+    double2 *A = fft_stages(dst, src, plan, M, root, s_tab);
     double2 *B = (A == dst) ? src : dst;
     // times bhat; conjugated so that the second forward FFT is the inverse transform
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
@@ -243,7 +265,7 @@ __device__ __forceinline__ double2 *fft_smem(double2 *src, double2 *dst, const F
         A[m] = make_double2(v.x, -v.y);
     }
     __syncthreads();
-    double2 *Cv = fft_stages(A, B, plan, M, root);
+    double2 *Cv = fft_stages(A, B, plan, M, root, s_tab);
     double2 *out = (Cv == A) ? B : A;
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
         const double2 v = make_double2(Cv[k].x, -Cv[k].y);

@@ -812,8 +812,8 @@ int launch_smooth(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, cons
     const int nbx = (nvx + FX - 1) / FX, nby = (nvy + FY - 1) / FY;
     const int wide = ctx->tune_mg_wide;
     // levels whose tiles do not even fill the GPU once are latency bound: 1024 threads per tile
-    // (HPB_MG_WIDE=1; faster in isolation, but no gain in the un-profiled slice loop, where a
-    // 1024-thread x 62-register CTA leaves no room for the next kernel of the PDL chain: off)
+    // (option "mg_wide", default on since round 2: 0.393 -> 0.367 ms per slice and +2 % slices/s in the
+    // un-profiled slice loop, profiles/r02/r02r_tune.txt; round 1 had measured no gain)
     if (RH == 1 && NS == 1 && wide && nbx * nby <= 148)
         return launch_smooth_t<INIT, RES, 1, 1, 1024>(ctx, g, in, crse, rhs, acf, acf_rs, c0i_in, c0i_out, out,
                                                       gc, res_c, norm, done, nbx, nby, EO);

@@ -1107,7 +1107,7 @@ struct RowShared {
     alignas(8) uint64_t mbar;
 };
 
-template <int MINB, bool DEPOSIT, bool TMA>
+template <int MINB, bool DEPOSIT, bool TMA, bool NOBOX = false>
 __global__ void __launch_bounds__(kRowThreads, MINB)
 k_advance_plasma_row(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtensorMap tmap, int nx_tot,
                      int ny_tot, int lat_nx, int c_psi, int c_ez, int c_bx, int c_by, int c_bz, double x_off,
@@ -1159,6 +1159,8 @@ k_advance_plasma_row(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtenso
             hpb_tma_load_3d(&sh.tile[4][0][0], &tmap, &sh.mbar, ax, ay, c_bz);
         }
     }
+    const bool nobox = NOBOX && prefetched && n_subcycles == 1;
+    if (NOBOX) __syncthreads();      // the initialised barrier is visible to every warp (they are still together)
     bool valid = in_range && hpb_is_valid(idcpu);
     const double clight_inv = 1.0 / clight;
     const double *F0 = a.comp(c_psi), *F1 = a.comp(c_ez), *F2 = a.comp(c_bx);
@@ -1171,24 +1173,28 @@ k_advance_plasma_row(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtenso
         double sx[4], dsx[4], sy[4], dsy[4];
         const int i0 = dshape2_nodal((xp - x_off) * dx_inv, sx, dsx);
         const int j0 = dshape2_nodal((yp - y_off) * dy_inv, sy, dsy);
-        // bounding box of the CTA's stencil origins
+        // NOBOX: no bounding box, no restaging, no block barrier: every lane tests its own stencil against
+        // the prefetched patch and gathers with direct loads if it lies outside
         const int big = 1 << 30;
-        const int imin = __reduce_min_sync(kFull, valid ? i0 : big), imax = __reduce_max_sync(kFull, valid ? i0 : -big);
-        const int jmin = __reduce_min_sync(kFull, valid ? j0 : big), jmax = __reduce_max_sync(kFull, valid ? j0 : -big);
-        if (lane == 0) { sh.wbox[w][0] = imin; sh.wbox[w][1] = jmin; sh.wbox[w][2] = imax; sh.wbox[w][3] = jmax; }
-        __syncthreads();        // (also: the old tile has been consumed)
         int ci = big, cj = big, ei = -big, ej = -big;
+        if (!nobox) {
+            // bounding box of the CTA's stencil origins
+            const int imin = __reduce_min_sync(kFull, valid ? i0 : big), imax = __reduce_max_sync(kFull, valid ? i0 : -big);
+            const int jmin = __reduce_min_sync(kFull, valid ? j0 : big), jmax = __reduce_max_sync(kFull, valid ? j0 : -big);
+            if (lane == 0) { sh.wbox[w][0] = imin; sh.wbox[w][1] = jmin; sh.wbox[w][2] = imax; sh.wbox[w][3] = jmax; }
+            __syncthreads();        // (also: the old tile has been consumed)
 #pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            ci = min(ci, sh.wbox[q][0]); cj = min(cj, sh.wbox[q][1]);
-            ei = max(ei, sh.wbox[q][2]); ej = max(ej, sh.wbox[q][3]);
+            for (int q = 0; q < NW; ++q) {
+                ci = min(ci, sh.wbox[q][0]); cj = min(cj, sh.wbox[q][1]);
+                ei = max(ei, sh.wbox[q][2]); ej = max(ej, sh.wbox[q][3]);
+            }
         }
-        const bool any = ci != big;
+        const bool any = nobox || ci != big;
         // the prefetched patch serves if every stencil of the CTA lies inside it; otherwise the patch
         // is (re)staged at the bounding box origin, and particles that do not fit even that (a stirred
         // group) gather with direct loads
-        const bool pre_ok = prefetched && isc == 0 && any && ci >= bi && ei + 4 <= bi + kRW && cj >= bj
-                            && ej + 4 <= bj + kCH;
+        const bool pre_ok = nobox || (prefetched && isc == 0 && any && ci >= bi && ei + 4 <= bi + kRW && cj >= bj
+                                      && ej + 4 <= bj + kCH);
         if (prefetched && isc == 0 && !pre_ok) {   // drain the prefetch before its buffer is rewritten
             hpb_mbar_wait(&sh.mbar, phase); phase ^= 1u;
             __syncthreads();
@@ -1322,7 +1328,7 @@ struct ExplShared {
     alignas(8) uint64_t mbar;
 };
 
-template <int NW, int MINB, bool TMA, bool COMBINE>
+template <int NW, int MINB, bool TMA, bool COMBINE, bool NOBOX = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CUtensorMap tmap, int nx_tot,
                           int ny_tot, int lat_nx, int c_sy, int c_sx, int c_bz, int c_ez, int c_exmby,
@@ -1370,6 +1376,7 @@ k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CU
             hpb_tma_load_3d(&sh.tile[3][0][0], &tmap, &sh.mbar, ax, ay, c_eypbx);
         }
     }
+    if (NOBOX) __syncthreads();      // the initialised barrier is visible to every warp (they are still together)
 
     double vx = 0., vy = 0., gamma_psi = 1., yint = 0.;
     double sx[5] = {0., 0., 0., 0., 0.}, dsx[5] = {0., 0., 0., 0., 0.};
@@ -1403,6 +1410,13 @@ k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CU
     const double *ExmBy = a.comp(c_exmby), *EypBx = a.comp(c_eypbx);
     double *Sy = a.comp(c_sy), *Sx = a.comp(c_sx);
 
+    // NOBOX: no bounding box, no restaging, no block barrier -- every lane tests its own cells against the
+    // prefetched patch and falls back to direct loads; the warps of the CTA never wait for each other
+    const bool nobox = NOBOX && prefetched;
+    bool any = true;
+    if (nobox) {
+        hpb_mbar_wait(&sh.mbar, 0);
+    } else {
     // bounding box of the owned centre cells (rows j0 + 1 .. j0 + 3) of the whole CTA
     {
         const int big = 1 << 30;
@@ -1412,7 +1426,6 @@ k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CU
         if (lane == 0) { sh.wbox[w][0] = imin; sh.wbox[w][1] = jmin; sh.wbox[w][2] = imax; sh.wbox[w][3] = jmax; }
     }
     __syncthreads();
-    bool any;
     {
         const int big = 1 << 30;
         int ci = big, cj = big, ei = -big, ej = -big;
@@ -1453,6 +1466,7 @@ k_explicit_deposition_cta(PlasmaPtrs pl, SliceView a, const __grid_constant__ CU
             }
         }
         if (TMA && any) hpb_mbar_wait(&sh.mbar, (prefetched && !pre_ok) ? 1u : 0u);
+    }
     }
 
     // fields at the three inner rows of the owned column: from the patch, or straight from the slice
@@ -1728,7 +1742,7 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     // expl_variant 4 (default) / 7: the CTA-tile kernel (TMA / cp.async staging) whenever the particles
     // carry the lattice order with ppc 4 or 9 and there is no laser; 0: the round-1 warp kernel
     const bool lattice = ctx->order_n > 0 && ctx->order_ppc > 1 && ctx->order_n * ctx->order_ppc == pl.np;
-    if ((variant == 4 || (variant >= 7 && variant <= 10)) && comps[HPB_C_AABS] < 0 && lattice
+    if ((variant == 4 || (variant >= 7 && variant <= 12)) && comps[HPB_C_AABS] < 0 && lattice
         && (ctx->order_ppc == 4 || ctx->order_ppc == 9)) {
         PlasmaPtrs pp = to_ptrs(pl);
         pp.lat_n = ctx->order_n; pp.lat_ppc = ctx->order_ppc; pp.lat_mode = 1;
@@ -1738,14 +1752,16 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
         const CUtensorMap *tm = variant != 7 ? (const CUtensorMap *)hpb_slice_tmap(ctx, 1, sl, kEW, kEH) : nullptr;
         CUtensorMap none;
         memset(&none, 0, sizeof(none));
-#define HPB_LAUNCH_ECTA(NW, MB, TMA_, CMB)                                                         \
-        hpb_launch(k_explicit_deposition_cta<NW, MB, TMA_, CMB>, (unsigned)groups, NW * 32, 0, ctx->stream, \
+#define HPB_LAUNCH_ECTA(NW, MB, TMA_, CMB, ...)                                                    \
+        hpb_launch(k_explicit_deposition_cta<NW, MB, TMA_, CMB, ##__VA_ARGS__>, (unsigned)groups, NW * 32, 0, ctx->stream, \
                    pp, make_view(sl), TMA_ ? *tm : none, sl.nx_tot, sl.ny_tot, lat_nx, comps[HPB_C_SY],  \
                    comps[HPB_C_SX], comps[HPB_C_BZ], comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], \
                    g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass)
         if (ctx->order_ppc == 4 && variant == 8 && tm) HPB_LAUNCH_ECTA(4, 4, true, true);      // 128 registers
         else if (ctx->order_ppc == 4 && variant == 9 && tm) HPB_LAUNCH_ECTA(4, 5, true, false);  // no combine
         else if (ctx->order_ppc == 4 && variant == 10 && tm) HPB_LAUNCH_ECTA(4, 4, true, false); // no combine, 128 regs
+        else if (ctx->order_ppc == 4 && variant == 11 && tm) HPB_LAUNCH_ECTA(4, 5, true, false, true);   // + no bounding box
+        else if (ctx->order_ppc == 4 && variant == 12 && tm) HPB_LAUNCH_ECTA(4, 4, true, false, true);   // + 128 regs
         else if (ctx->order_ppc == 4) { if (tm) HPB_LAUNCH_ECTA(4, 5, true, true); else HPB_LAUNCH_ECTA(4, 5, false, true); }
         else { if (tm) HPB_LAUNCH_ECTA(9, 2, true, true); else HPB_LAUNCH_ECTA(9, 2, false, true); }
 #undef HPB_LAUNCH_ECTA
@@ -1827,7 +1843,7 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
     // runs the round-1 warp-staged kernel below: the cooperative cp.async staging of variant 8 is the
     // slowest of the three, 0.55 vs 0.34 vs 0.29 ms at 1024^2 ppc 4)
     const bool row_tma_ok = variant == 8 || hpb_slice_tmap(ctx, 2, sl, kRW, kCH) != nullptr;
-    if ((variant == 6 || variant == 7 || variant == 8) && lasa.c_aabs < 0 && row_tma_ok) {
+    if ((variant >= 6 && variant <= 9) && lasa.c_aabs < 0 && row_tma_ok) {
         PlasmaPtrs pp = to_ptrs(pl);
         const bool lat = ctx->order_n > 0 && ctx->order_n * ctx->order_ppc == pl.np;
         pp.lat_n = lat ? ctx->order_n : 0; pp.lat_ppc = lat ? ctx->order_ppc : 1;
@@ -1836,8 +1852,8 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         const CUtensorMap *tm = variant != 8 ? (const CUtensorMap *)hpb_slice_tmap(ctx, 2, sl, kRW, kCH) : nullptr;
         CUtensorMap none;
         memset(&none, 0, sizeof(none));
-#define HPB_LAUNCH_ROW(MB, DEP, TMA_)                                                              \
-        hpb_launch(k_advance_plasma_row<MB, DEP, TMA_>, (unsigned)nblk, kRowThreads, 0, ctx->stream, \
+#define HPB_LAUNCH_ROW(MB, DEP, TMA_, ...)                                                         \
+        hpb_launch(k_advance_plasma_row<MB, DEP, TMA_, ##__VA_ARGS__>, (unsigned)nblk, kRowThreads, 0, ctx->stream, \
                    pp, make_view(sl), TMA_ ? *tm : none, sl.nx_tot, sl.ny_tot, lat_nx, comps[HPB_C_PSI], \
                    comps[HPB_C_EZ], comps[HPB_C_BX], comps[HPB_C_BY], comps[HPB_C_BZ], g.x_off, g.y_off,  \
                    1.0 / g.dx, 1.0 / g.dy, g.c, charge / (mass * g.c), g.dz / n_subcycles, n_subcycles,  \
@@ -1845,7 +1861,8 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
 #define HPB_LAUNCH_ROW_MB(MB)                                                                     \
         do { if (deposit) { if (tm) HPB_LAUNCH_ROW(MB, true, true); else HPB_LAUNCH_ROW(MB, true, false); } \
              else { if (tm) HPB_LAUNCH_ROW(MB, false, true); else HPB_LAUNCH_ROW(MB, false, false); } } while (0)
-        if (variant == 7) HPB_LAUNCH_ROW_MB(4); else HPB_LAUNCH_ROW_MB(5);
+        if (variant == 9 && tm) { if (deposit) HPB_LAUNCH_ROW(5, true, true, true); else HPB_LAUNCH_ROW(5, false, true, true); }
+        else if (variant == 7) HPB_LAUNCH_ROW_MB(4); else HPB_LAUNCH_ROW_MB(5);
 #undef HPB_LAUNCH_ROW_MB
 #undef HPB_LAUNCH_ROW
         hpb_count_launch(ctx);

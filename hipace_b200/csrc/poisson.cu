@@ -115,7 +115,9 @@ k_dst_rows(Src src, OutPtrs out, long out_rs, int nx, int ny, FftPlan plan,
         if (i > 0 && N - i > nh) buf0[N - i] = make_double2(re.x + im.y, im.x - re.y);   // conj(V[N-i])
     }
     __syncthreads();
-    const double2 *F = fft_smem<BLUE>(buf0, buf1, plan, root);
+    // (the prime-stage table sits behind the two buffers: 2 (L + 4) complex elements)
+    double *s_tab = reinterpret_cast<double *>(smem + 2 * (plan.buf_len() + 4));
+    const double2 *F = fft_smem<BLUE>(buf0, buf1, plan, root, s_tab);
     // z_a = Re F, z_b = -Im F;  out[i] = 0.5 (z[n-i] - z[i+1] + (z[i+1] + z[n-i]) sinf[i])
     double *out_a = out.p[b] + (long)ja * out_rs;
     double *out_b = out_a + out_rs;
@@ -275,7 +277,8 @@ int launch_rows_v(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs,
 {
     const int nx = ctx->g.nx, ny = ctx->g.ny;
     const int L = ctx->fftM > 0 ? ctx->fftM : ctx->fftN;
-    const size_t smem = 2 * sizeof(double2) * (size_t)(L + 4);
+    const FftPlan pl_ = make_plan(ctx);
+    const size_t smem = 2 * sizeof(double2) * (size_t)(L + 4) + 2 * sizeof(double) * (size_t)pl_.max_prime();
     static bool attr_set = false;       // per instantiation; the limit covers every supported N
     if (!attr_set) {
         HPB_CUDA_CHECK(cudaFuncSetAttribute(k_dst_rows<Src, NTHR, MINB, false>,
