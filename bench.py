@@ -480,7 +480,8 @@ def main():
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
                 'ns_per_particle_step': ns_per_push, 'ms_per_slice': job_ms / (K * args.nz),
                 'slice_loop_ms_per_step_rank0': loop_ms / K,
-                'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
+                'gpu_launches': int(launches), 'fused_driver_order': bool(st_last.get('n_fused_slices', 0) > 0),
+                'clocks': clocks, 'e2e': e2e, 'roofline': roofline,
                 'stage_ms_per_slice': stages, 'cpu_baseline': cpu_baseline, 'pipeline_verify': verify,
                 'wall_ms_per_step': wall_ms_max / K}
         print(json.dumps(line))

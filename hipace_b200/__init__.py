@@ -106,7 +106,7 @@ class hpb_sim_stats(C.Structure):
                 ('n_slices', C.c_long), ('n_mg_vcycles', C.c_long), ('n_qsa_violation', C.c_long),
                 ('n_kernel_launches', C.c_long), ('ms_deposit', C.c_double),
                 ('ms_poisson', C.c_double), ('ms_explicit', C.c_double), ('ms_mg', C.c_double),
-                ('ms_push', C.c_double), ('ms_other', C.c_double), ('n_reorders', C.c_long)]
+                ('ms_push', C.c_double), ('ms_other', C.c_double), ('n_reorders', C.c_long), ('n_fused_slices', C.c_long)]
 
 
 _lib = None

@@ -290,11 +290,20 @@ inline unsigned nblk(long n) { return (unsigned)((n + kBT - 1) / kBT); }
 // ---------------------------------------------------------------------------------------------
 // C-ABI seams
 // ---------------------------------------------------------------------------------------------
+// with the constants of a deck (my_constants.* of the input file) visible to the expressions
+int hpb_extfields_create_deck(hpb_extfields **out, const char *const expr[6], const hpb::Deck *deck);
+
 extern "C" int hpb_extfields_create(hpb_extfields **out, const char *const expr[6])
+{
+    return hpb_extfields_create_deck(out, expr, nullptr);
+}
+
+int hpb_extfields_create_deck(hpb_extfields **out, const char *const expr[6], const hpb::Deck *deck)
 {
     if (!out || !expr) return HPB_ERR_ARG;
     std::vector<DevRpn> prog(6);
-    hpb::Deck d;
+    const hpb::Deck empty;
+    const hpb::Deck &d = deck ? *deck : empty;
     try {
         for (int k = 0; k < 6; ++k) {
             std::vector<hpb::RpnInstr> code;

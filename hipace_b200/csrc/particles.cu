@@ -360,34 +360,25 @@ __device__ __forceinline__ void expl_cell(const ExplCol &k, double vx, double vy
 
 struct ExplLaser { int c_aabs; double fac_c, a_norm; };     // laser_fac * c, laser_fac * q_mass_ratio^2
 
-template <int NTHR, int MINB, bool LAT, bool LASER>
-__global__ void __launch_bounds__(NTHR, MINB)
-k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, int c_ez,
-                      int c_exmby, int c_eypbx, double x_off, double y_off, double dx_inv,
-                      double dy_inv, double a_clight, double clight_inv,
-                      double charge_invvol_mu0, double q_mass_ratio, ExplLaser las)
+// The particle-independent part of the explicit deposition of ONE group of lanes (one particle per lane,
+// its seven stream values already in registers): everything of k_explicit_deposition after the loads.
+// Must be called by all 32 lanes of the warp (shuffles inside).
+struct ExplRaw { uint64_t idcpu; double psi, xp, yp, ux, uy, w; };
+template <bool LASER>
+__device__ __forceinline__ void
+expl_group(const SliceView &a, int c_sy, int c_sx, int c_bz, int c_ez, int c_exmby, int c_eypbx, double x_off,
+           double y_off, double dx_inv, double dy_inv, double a_clight, double clight_inv,
+           double charge_invvol_mu0, double q_mass_ratio, const ExplLaser &las, int lane, bool active, bool owner,
+           const ExplRaw &raw)
 {
-    hpb_pdl_prologue();
-    // warps overlap by two lanes on each side (see k_deposit_current)
-    const int lane = threadIdx.x & 31;
-    const long warp = (long)blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
-    bool active;
-    const long ip = lattice_particle<LAT ? 1 : 0>(pl, warp, lane, kExplOwn, 2, active);
-    const bool owner = lane >= 2 && lane < 2 + kExplOwn;
-
     double vx = 0., vy = 0., gamma_psi = 1., yint = 0.;
     double qp = 0.;             // 0.25 q_mass_ratio psi_inv (laser term factor of this particle)
     double sx[5] = {0., 0., 0., 0., 0.}, dsx[5] = {0., 0., 0., 0., 0.};
     ExplPart e = {};
     int i0 = 0, j0 = 0;
     if (active) {
-        const uint64_t idcpu = ld_stream(&pl.idcpu[ip]);
-        const double psi = ld_stream(&pl.r[HPB_PSI][ip]);
-        const double xp = ld_stream(&pl.r[HPB_X][ip]);
-        const double yp = ld_stream(&pl.r[HPB_Y][ip]);
-        const double ux = ld_stream(&pl.r[HPB_UX][ip]);
-        const double uy = ld_stream(&pl.r[HPB_UY][ip]);
-        const double w = ld_stream(&pl.r[HPB_W][ip]);
+        const uint64_t idcpu = raw.idcpu;
+        const double psi = raw.psi, xp = raw.xp, yp = raw.yp, ux = raw.ux, uy = raw.uy, w = raw.w;
         active = hpb_is_valid(idcpu);
         if (active) {
             const double psi_inv = 1.0 / psi;
@@ -519,6 +510,78 @@ k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, 
             red_add(Sy + o, vy_);
             red_add(Sx + o, vx_);
         }
+    }
+}
+
+template <int NTHR, int MINB, bool LAT, bool LASER>
+__global__ void __launch_bounds__(NTHR, MINB)
+k_explicit_deposition(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, int c_ez,
+                      int c_exmby, int c_eypbx, double x_off, double y_off, double dx_inv,
+                      double dy_inv, double a_clight, double clight_inv,
+                      double charge_invvol_mu0, double q_mass_ratio, ExplLaser las)
+{
+    hpb_pdl_prologue();
+    // warps overlap by two lanes on each side (see k_deposit_current)
+    const int lane = threadIdx.x & 31;
+    const long warp = (long)blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
+    bool active;
+    const long ip = lattice_particle<LAT ? 1 : 0>(pl, warp, lane, kExplOwn, 2, active);
+    const bool owner = lane >= 2 && lane < 2 + kExplOwn;
+    ExplRaw raw = {0, 1., 0., 0., 0., 0., 0.};
+    if (active) {
+        raw.idcpu = ld_stream(&pl.idcpu[ip]);
+        raw.psi = ld_stream(&pl.r[HPB_PSI][ip]);
+        raw.xp = ld_stream(&pl.r[HPB_X][ip]);
+        raw.yp = ld_stream(&pl.r[HPB_Y][ip]);
+        raw.ux = ld_stream(&pl.r[HPB_UX][ip]);
+        raw.uy = ld_stream(&pl.r[HPB_UY][ip]);
+        raw.w = ld_stream(&pl.r[HPB_W][ip]);
+    }
+    expl_group<LASER>(a, c_sy, c_sx, c_bz, c_ez, c_exmby, c_eypbx, x_off, y_off, dx_inv, dy_inv, a_clight, clight_inv,
+                      charge_invvol_mu0, q_mass_ratio, las, lane, active, owner, raw);
+}
+
+// Persistent, software-pipelined variant: a fixed grid of warps walks over the particle groups; the seven
+// stream values of the NEXT group are requested before the current group is processed, so the DRAM latency
+// of the particle streams (the round-1 kernel's dominant stall: long scoreboard 3.4 per issue at 26 %
+// occupancy) is hidden behind ~1000 instructions of work instead of being waited for by every warp.
+template <int NTHR, int MINB, bool LAT>
+__global__ void __launch_bounds__(NTHR, MINB)
+k_explicit_deposition_pipe(PlasmaPtrs pl, SliceView a, int c_sy, int c_sx, int c_bz, int c_ez,
+                           int c_exmby, int c_eypbx, double x_off, double y_off, double dx_inv,
+                           double dy_inv, double a_clight, double clight_inv,
+                           double charge_invvol_mu0, double q_mass_ratio, long nwarps)
+{
+    hpb_pdl_prologue();
+    const int lane = threadIdx.x & 31;
+    const long stride = (long)gridDim.x * (NTHR / 32);
+    const bool owner = lane >= 2 && lane < 2 + kExplOwn;
+    const ExplLaser las = {-1, 0., 0.};
+    auto fetch = [&](long warp, ExplRaw &raw) -> bool {
+        bool in_range;
+        const long ip = lattice_particle<LAT ? 1 : 0>(pl, warp, lane, kExplOwn, 2, in_range);
+        raw.idcpu = 0; raw.psi = 1.; raw.xp = raw.yp = raw.ux = raw.uy = raw.w = 0.;
+        if (in_range) {
+            raw.idcpu = ld_stream(&pl.idcpu[ip]);
+            raw.psi = ld_stream(&pl.r[HPB_PSI][ip]);
+            raw.xp = ld_stream(&pl.r[HPB_X][ip]);
+            raw.yp = ld_stream(&pl.r[HPB_Y][ip]);
+            raw.ux = ld_stream(&pl.r[HPB_UX][ip]);
+            raw.uy = ld_stream(&pl.r[HPB_UY][ip]);
+            raw.w = ld_stream(&pl.r[HPB_W][ip]);
+        }
+        return in_range;
+    };
+    long warp = (long)blockIdx.x * (NTHR / 32) + (threadIdx.x >> 5);
+    if (warp >= nwarps) return;
+    ExplRaw cur, nxt;
+    bool cur_in = fetch(warp, cur), nxt_in = false;
+    for (; warp < nwarps; warp += stride) {
+        const bool more = warp + stride < nwarps;
+        if (more) nxt_in = fetch(warp + stride, nxt);
+        expl_group<false>(a, c_sy, c_sx, c_bz, c_ez, c_exmby, c_eypbx, x_off, y_off, dx_inv, dy_inv, a_clight,
+                          clight_inv, charge_invvol_mu0, q_mass_ratio, las, lane, cur_in, owner, cur);
+        cur = nxt; cur_in = nxt_in;
     }
 }
 
@@ -1789,6 +1852,24 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
         pp, make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ],             \
         comps[HPB_C_EZ], comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.x_off, g.y_off, 1.0 / g.dx,     \
         1.0 / g.dy, g.c, 1.0 / g.c, charge * invvol * g.mu0, charge / mass, las)
+    if ((variant == 13 || variant == 14 || variant == 15) && las.c_aabs < 0) {
+        // persistent, software-pipelined kernel: 4 (variant 13, 128 registers), 5 (14) or 3 (15) CTAs per SM
+        int dev = 0, nsm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = variant == 13 ? 4 : variant == 14 ? 5 : 3;
+        long ncta = (nwarps + 3) / 4;
+        if (ncta > (long)nsm * per_sm) ncta = (long)nsm * per_sm;
+#define HPB_LAUNCH_PIPE(MB, LAT)                                                                   \
+        hpb_launch(k_explicit_deposition_pipe<128, MB, LAT>, (unsigned)ncta, 128, 0, ctx->stream,  \
+            pp, make_view(sl), comps[HPB_C_SY], comps[HPB_C_SX], comps[HPB_C_BZ], comps[HPB_C_EZ],   \
+            comps[HPB_C_EXMBY], comps[HPB_C_EYPBX], g.x_off, g.y_off, 1.0 / g.dx, 1.0 / g.dy, g.c,   \
+            1.0 / g.c, charge * invvol * g.mu0, charge / mass, nwarps)
+        if (variant == 13) { if (pp.lat_n > 0) HPB_LAUNCH_PIPE(4, true); else HPB_LAUNCH_PIPE(4, false); }
+        else if (variant == 14) { if (pp.lat_n > 0) HPB_LAUNCH_PIPE(5, true); else HPB_LAUNCH_PIPE(5, false); }
+        else { if (pp.lat_n > 0) HPB_LAUNCH_PIPE(3, true); else HPB_LAUNCH_PIPE(3, false); }
+#undef HPB_LAUNCH_PIPE
+    } else
     if (variant == 2) HPB_LAUNCH_EXPL(256, 2);
     else if (variant == 3) HPB_LAUNCH_EXPL(128, 3);
     else if (variant == 5) HPB_LAUNCH_EXPL(128, 6);

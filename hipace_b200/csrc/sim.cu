@@ -1361,6 +1361,7 @@ int solve_one_slice(hpb_sim *s, int islice)
     }
     s->stats.n_cells_updated += (double)s->g.nx * s->g.ny;
     s->stats.n_slices += 1;
+    if (fuse) s->stats.n_fused_slices += 1;
     return HPB_OK;
 }
 
@@ -1479,7 +1480,7 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
         if (b.use_ext) {
             const char *ex[6];
             for (int k = 0; k < 6; ++k) ex[k] = b.ext_expr[k].c_str();
-            if ((rc = hpb_extfields_create(&b.ext, ex))) return rc;
+            if ((rc = hpb_extfields_create_deck(&b.ext, ex, &s->deck))) return rc;     // my_constants.* visible
         }
     }
     SIM_CUDA(cudaEventCreate(&s->ev0));

@@ -216,6 +216,7 @@ int hpb_pipeline_begin_step(hpb_sim *s, int step);          // post receives / o
 int hpb_pipeline_wait_slice(hpb_sim *s, int islice);        // compute stream waits for slice islice
 int hpb_pipeline_wait_slice_on(hpb_sim *s, int islice, cudaStream_t st);       // ... a given stream
 int hpb_pipeline_wait_out_slot_on(hpb_sim *s, int islice, cudaStream_t st);    // out slot free, on a given stream
+int hpb_extfields_create_deck(hpb_extfields **out, const char *const expr[6], const hpb::Deck *deck);
 struct hpb_laser_state;
 void hpb_laser_packet(hpb_laser_state *st, int islice, void *recv[2], void *send[2], size_t *bytes);
 int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step);

@@ -452,6 +452,9 @@ typedef struct {
     long n_slices, n_mg_vcycles, n_qsa_violation, n_kernel_launches;
     double ms_deposit, ms_poisson, ms_explicit, ms_mg, ms_push, ms_other; /* if profiling on */
     long n_reorders;                /* plasma sorts (<plasma>.reorder_period) */
+    long n_fused_slices;            /* slices that ran the fused driver order (push + next deposit in one kernel);
+                                     * 0 means the deck switched it off: laser, rho diagnostic, grid current,
+                                     * non-default deposition order, plasma in-situ diagnostics, n_subcycles < 1 */
 } hpb_sim_stats;
 int hpb_sim_get_stats(hpb_sim *sim, hpb_sim_stats *out);
 /* multigrid V-cycles (or predictor-corrector iterations) of every slice of the last evolve, in
