@@ -1091,6 +1091,121 @@ __global__ void __launch_bounds__(1024) k2_small(Small2Args A, const int *done)
     }
 }
 
+// ---- tile smoother for the large levels: phi_out = GSRB^4(init) on a 32 x 32 tile with a 5-cell halo held
+// in shared memory (after four half-sweeps the values four cells inside the loaded region are exact, one
+// more ring for the residual), the per-cell inverse coefficient (c0 - a_r, -a_i) / |.|^2 of gs2 computed
+// once per tile, optional residual2 + max-norms.  One launch replaces four half-sweep launches and the
+// residual launch.  INIT 0: phi = 0, 1: phi = phi_in, 2: phi = phi_in + I(crse).
+constexpr int kT2 = 32, kH2 = 5, kR2 = kT2 + 2 * kH2;          // tile, halo, region side (42)
+constexpr int kT2Threads = 256;
+template <int INIT, bool RES>
+__global__ void __launch_bounds__(kT2Threads, 2)
+k2_smooth4(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, V2 acf, V2 phi_out, V2 res_out, double *norm, int ntx)
+{
+    extern __shared__ double sm2[];
+    double *p0 = sm2, *p1 = sm2 + kR2 * kR2, *r0 = sm2 + 2 * kR2 * kR2, *r1 = sm2 + 3 * kR2 * kR2;
+    double *cr = sm2 + 4 * kR2 * kR2, *ci = sm2 + 5 * kR2 * kR2;
+    hpb_pdl_prologue();
+    const int tx = blockIdx.x % ntx, ty = blockIdx.x / ntx;
+    const int ox = g.vlo + tx * kT2 - kH2, oy = g.vlo + ty * kT2 - kH2;       // level index of region cell (0, 0)
+    const double fx43 = g.facx * (4. / 3.), fy43 = g.facy * (4. / 3.);
+    for (int e = threadIdx.x; e < kR2 * kR2; e += kT2Threads) {
+        const int lj = e / kR2, li = e - lj * kR2;
+        const int i = ox + li, j = oy + lj;
+        double a = 0., b = 0., q0 = 0., q1 = 0., c_r = 0., c_i = 0.;
+        if (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy) {
+            if (INIT >= 1) { a = phi_in.at(i, j, 0); b = phi_in.at(i, j, 1); }
+            if (INIT == 2) { a = a + interp_at(crse, i, j, 0, g.cc); b = b + interp_at(crse, i, j, 1, g.cc); }
+            q0 = rhs.at(i, j, 0); q1 = rhs.at(i, j, 1);
+            double c0 = -2.0 * (g.facx + g.facy);
+            if (g.cc && (i == g.vlo || i == g.vhix)) c0 -= 2.0 * g.facx;
+            if (g.cc && (j == g.vlo || j == g.vhiy)) c0 -= 2.0 * g.facy;
+            c_r = c0 - acf.at(i, j, 0); c_i = -acf.at(i, j, 1);
+            const double cmag = 1.0 / (c_r * c_r + c_i * c_i);
+            c_r *= cmag; c_i *= cmag;
+        }
+        p0[e] = a; p1[e] = b; r0[e] = q0; r1[e] = q1; cr[e] = c_r; ci[e] = c_i;
+    }
+    __syncthreads();
+    for (int ic = 0; ic < 4; ++ic) {
+        // interior of the region only (the outermost ring has no neighbours in shared memory)
+        for (int e = threadIdx.x; e < (kR2 - 2) * (kR2 - 2); e += kT2Threads) {
+            const int lj = e / (kR2 - 2) + 1, li = e - (lj - 1) * (kR2 - 2) + 1;
+            const int i = ox + li, j = oy + lj;
+            if (((i + j + ic) & 1) != 0 || i < g.vlo || i > g.vhix || j < g.vlo || j > g.vhiy) continue;
+            const int o = lj * kR2 + li;
+            const double wx = (g.cc && (i == g.vlo || i == g.vhix)) ? fx43 : g.facx;
+            const double wy = (g.cc && (j == g.vlo || j == g.vhiy)) ? fy43 : g.facy;
+            double lap0 = wx * (p0[o - 1] + p0[o + 1]);
+            double lap1 = wx * (p1[o - 1] + p1[o + 1]);
+            lap0 += wy * (p0[o - kR2] + p0[o + kR2]);
+            lap1 += wy * (p1[o - kR2] + p1[o + kR2]);
+            const double dr = r0[o] - lap0, di = r1[o] - lap1;
+            p0[o] = dr * cr[o] + di * ci[o];
+            p1[o] = di * cr[o] - dr * ci[o];
+        }
+        __syncthreads();
+    }
+    double nres = 0., nrhs = 0.;
+    for (int e = threadIdx.x; e < kT2 * kT2; e += kT2Threads) {
+        const int lj = e / kT2 + kH2, li = e - (lj - kH2) * kT2 + kH2;
+        const int i = ox + li, j = oy + lj;
+        if (i > g.vhix || j > g.vhiy) continue;
+        const int o = lj * kR2 + li;
+        phi_out.at(i, j, 0) = p0[o];
+        phi_out.at(i, j, 1) = p1[o];
+        if (RES) {
+            double lap[2];
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const double *c = (n ? p1 : p0) + o;
+                double l = -2.0 * (g.facx + g.facy) * c[0];
+                if (g.cc && i == g.vlo) l += g.facx * ((4. / 3.) * c[1] - 2.0 * c[0]);
+                else if (g.cc && i == g.vhix) l += g.facx * ((4. / 3.) * c[-1] - 2.0 * c[0]);
+                else l += g.facx * (c[-1] + c[1]);
+                if (g.cc && j == g.vlo) l += g.facy * ((4. / 3.) * c[kR2] - 2.0 * c[0]);
+                else if (g.cc && j == g.vhiy) l += g.facy * ((4. / 3.) * c[-kR2] - 2.0 * c[0]);
+                else l += g.facy * (c[-kR2] + c[kR2]);
+                lap[n] = l;
+            }
+            const double ar = acf.at(i, j, 0), ai = acf.at(i, j, 1);
+            const double v0 = r0[o] + ar * p0[o] - ai * p1[o] - lap[0];
+            const double v1 = r1[o] + ai * p0[o] + ar * p1[o] - lap[1];
+            res_out.at(i, j, 0) = v0;
+            res_out.at(i, j, 1) = v1;
+            nres = fmax(nres, fmax(fabs(v0), fabs(v1)));
+            nrhs = fmax(nrhs, fmax(fabs(r0[o]), fabs(r1[o])));
+        }
+    }
+    if (!RES || !norm) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nres = fmax(nres, __shfl_xor_sync(0xffffffffu, nres, o));
+        nrhs = fmax(nrhs, __shfl_xor_sync(0xffffffffu, nrhs, o));
+    }
+    if ((threadIdx.x & 31) == 0 && (nres > 0. || nrhs > 0.)) {
+        atomicMax((unsigned long long *)&norm[0], (unsigned long long)__double_as_longlong(nres));
+        atomicMax((unsigned long long *)&norm[1], (unsigned long long)__double_as_longlong(nrhs));
+    }
+}
+
+template <int INIT, bool RES>
+int mg2_smooth4(hpb_ctx *ctx, const LevelGeom &g, V2 phi_in, V2 crse, V2 rhs, V2 acf, V2 phi_out, V2 res_out,
+                double *norm)
+{
+    const size_t smem = 6 * sizeof(double) * kR2 * kR2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HPB_CUDA_CHECK(cudaFuncSetAttribute(k2_smooth4<INIT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int ntx = (g.vhix - g.vlo + kT2) / kT2, nty = (g.vhiy - g.vlo + kT2) / kT2;
+    hpb_launch(k2_smooth4<INIT, RES>, (unsigned)(ntx * nty), kT2Threads, smem, ctx->stream, g, phi_in, crse, rhs, acf,
+               phi_out, res_out, norm, ntx);
+    hpb_count_launch(ctx);
+    return HPB_OK;
+}
+
 int mg2_sweeps(hpb_ctx *ctx, const LevelGeom &g, V2 phi, V2 rhs, V2 acf, int nsweeps)
 {
     const long nv = (long)(g.vhix - g.vlo + 1) * (g.vhiy - g.vlo + 1);
@@ -1376,12 +1491,15 @@ extern "C" int hpb_mg_solve2(hpb_ctx *ctx, double *d_sol2, const double *d_rhs2,
     for (int l = 1; l < nl; ++l) hpb_launch(k2_restrict, nb(NV(l)), 256, 0, ctx->stream, G(l), ACF(l), ACF(l - 1));
     hpb_count_launch(ctx, 3 + nl - 1);
     HPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_mg_norm, 0, 2 * sizeof(double), ctx->stream));
+    const V2 none{};
     // cor0 = GSRB^4(sol), rescor0 = residual(cor0)   (:1326-1327)
-    HPB_CUDA_CHECK(cudaMemcpyAsync(cor0.p, sol0.p, bytes2(0), cudaMemcpyDeviceToDevice, ctx->stream));
-    mg2_sweeps(ctx, G(0), cor0, rhs0, ACF(0), 4);
-    hpb_launch(k2_residual, nb(NV(0)), 256, 0, ctx->stream, G(0), rescor0, cor0, rhs0, ACF(0), ctx->d_mg_norm);
+    { int rcs = mg2_smooth4<1, true>(ctx, G(0), sol0, none, rhs0, ACF(0), cor0, rescor0, ctx->d_mg_norm); if (rcs) return rcs; }
     hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 0, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
-    hpb_count_launch(ctx, 2);
+    hpb_count_launch(ctx);
+    // ls: first level handled by the single-CTA kernel (>= 1; all levels from there down are small)
+    int ls = 1;
+    while (ls < nl - 1 && (long)ctx->mg[ls].nx * ctx->mg[ls].ny > kSmall2) ++ls;
+    if (nl - ls > 16) ls = nl - 16;
     int iters = 0;
     while (true) {
         HPB_CUDA_CHECK(cudaMemcpyAsync(ctx->h_mg_istate, ctx->d_mg_istate, 4 * sizeof(int), cudaMemcpyDeviceToHost,
@@ -1397,19 +1515,13 @@ extern "C" int hpb_mg_solve2(hpb_ctx *ctx, double *d_sol2, const double *d_rhs2,
         }
         if (ctx->h_mg_istate[0]) break;
         if (iters >= max_iters) { hpb_set_error("hpmg (type 2) failed to converge after %d iterations", max_iters); return HPB_ERR_MG_DIVERGED; }
-        // ---- one V-cycle (:1429-1512) ----
-        // ls: first level handled by the single-CTA kernel (>= 1; all levels from there down are small)
-        int ls = 1;
-        while (ls < nl - 1 && (long)ctx->mg[ls].nx * ctx->mg[ls].ny > kSmall2) ++ls;
-        if (nl - ls > 16) ls = nl - 16;
+        // ---- one V-cycle (:1429-1512): tile smoothers on the large levels, one CTA for the small ones ----
         for (int l = 0; l < ls; ++l) {
             const V2 rescor = lvl_view(ctx, l, ctx->mg[l].rescor);
             if (l > 0) {
-                const V2 cor = lvl_view(ctx, l, ctx->mg[l].cor), res = lvl_view(ctx, l, ctx->mg[l].res);
-                HPB_CUDA_CHECK(cudaMemsetAsync(cor.p, 0, bytes2(l), ctx->stream));
-                mg2_sweeps(ctx, G(l), cor, res, ACF(l), 4);
-                hpb_launch(k2_residual, nb(NV(l)), 256, 0, ctx->stream, G(l), rescor, cor, res, ACF(l), (double *)nullptr);
-                hpb_count_launch(ctx);
+                int rcs = mg2_smooth4<0, true>(ctx, G(l), none, none, lvl_view(ctx, l, ctx->mg[l].res), ACF(l),
+                                               lvl_view(ctx, l, ctx->mg[l].cor), rescor, nullptr);
+                if (rcs) return rcs;
             }
             hpb_launch(k2_restrict, nb(NV(l + 1)), 256, 0, ctx->stream, G(l + 1), lvl_view(ctx, l + 1, ctx->mg[l + 1].res), rescor);
             hpb_count_launch(ctx);
@@ -1431,26 +1543,26 @@ extern "C" int hpb_mg_solve2(hpb_ctx *ctx, double *d_sol2, const double *d_rhs2,
             hpb_launch(k2_small, 1, 1024, 0, ctx->stream, A, (const int *)nullptr);
             hpb_count_launch(ctx);
         }
+        // up: cor[l] <- GSRB^4(cor[l] + I(cor[l+1])), double-buffered through rescor[l] (a tile must not
+        // overwrite the halo its neighbours still read)
+        double *up_prev = ctx->mg[ls].cor;
         for (int l = ls - 1; l >= 0; --l) {
-            const V2 crse = lvl_view(ctx, l + 1, ctx->mg[l + 1].cor);
+            const V2 crse = lvl_view(ctx, l + 1, up_prev);
+            int rcs;
             if (l == 0) {
-                // sol = GSRB^4(cor0 + I(cor1))
-                HPB_CUDA_CHECK(cudaMemcpyAsync(sol0.p, cor0.p, bytes2(0), cudaMemcpyDeviceToDevice, ctx->stream));
-                hpb_launch(k2_interp_add, nb(NV(0)), 256, 0, ctx->stream, G(0), sol0, cor0, crse);
-                mg2_sweeps(ctx, G(0), sol0, rhs0, ACF(0), 4);
+                rcs = mg2_smooth4<2, false>(ctx, G(0), cor0, crse, rhs0, ACF(0), sol0, none, nullptr);      // sol
             } else {
-                const V2 cor = lvl_view(ctx, l, ctx->mg[l].cor);
-                hpb_launch(k2_interp_add, nb(NV(l)), 256, 0, ctx->stream, G(l), cor, cor, crse);
-                mg2_sweeps(ctx, G(l), cor, lvl_view(ctx, l, ctx->mg[l].res), ACF(l), 4);
+                rcs = mg2_smooth4<2, false>(ctx, G(l), lvl_view(ctx, l, ctx->mg[l].cor), crse,
+                                            lvl_view(ctx, l, ctx->mg[l].res), ACF(l),
+                                            lvl_view(ctx, l, ctx->mg[l].rescor), none, nullptr);
+                up_prev = ctx->mg[l].rescor;
             }
-            hpb_count_launch(ctx);
+            if (rcs) return rcs;
         }
         // cor0 = GSRB^4(sol), rescor0 = residual(cor0)   (:1501-1503)
-        HPB_CUDA_CHECK(cudaMemcpyAsync(cor0.p, sol0.p, bytes2(0), cudaMemcpyDeviceToDevice, ctx->stream));
-        mg2_sweeps(ctx, G(0), cor0, rhs0, ACF(0), 4);
-        hpb_launch(k2_residual, nb(NV(0)), 256, 0, ctx->stream, G(0), rescor0, cor0, rhs0, ACF(0), ctx->d_mg_norm);
+        { int rcs = mg2_smooth4<1, true>(ctx, G(0), sol0, none, rhs0, ACF(0), cor0, rescor0, ctx->d_mg_norm); if (rcs) return rcs; }
         hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
-        hpb_count_launch(ctx, 2);
+        hpb_count_launch(ctx);
     }
     hpb_launch(k2_extract, nb(nvv), 256, 0, ctx->stream, G(0), cor0, d_sol2, nxv, nyv);
     hpb_count_launch(ctx);
