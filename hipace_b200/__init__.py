@@ -69,7 +69,7 @@ EXPORTS = (
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
     'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder', 'hpb_measure_fp64_peak', 'hpb_mg_solve2', 'hpb_laser_set_solver',
-    'hpb_laser_mg_vcycles',
+    'hpb_laser_mg_vcycles', 'hpb_poisson_solve_periodic', 'hpb_fields_enforce_periodic',
 )
 NCCL_ID_BYTES = 128
 
@@ -139,6 +139,8 @@ def lib():
               'hpb_fields_solve_psi_ez_bz', 'hpb_fields_sxsy_from_beam'):
         getattr(L, f).argtypes = [C.c_void_p, hpb_slice, IP]
     L.hpb_poisson_solve.argtypes = [C.c_void_p, C.c_void_p, hpb_slice, IP, C.c_int]
+    L.hpb_poisson_solve_periodic.argtypes = [C.c_void_p, C.c_void_p, hpb_slice, IP, C.c_int]
+    L.hpb_fields_enforce_periodic.argtypes = [C.c_void_p, hpb_slice, C.c_int, IP, C.c_int]
     L.hpb_explicit_deposition.argtypes = [C.c_void_p, hpb_plasma, hpb_slice, C.c_double,
                                           C.c_double, IP]
     L.hpb_mg_solve1.argtypes = [C.c_void_p, hpb_slice, C.c_int, C.c_int, C.c_int, C.c_double,
@@ -588,6 +590,19 @@ class Context:
         nb = rhs.shape[0]
         arr = (C.c_int * nb)(*c_lhs)
         _check(self._L.hpb_poisson_solve(self._h, rhs.data_ptr(), sl, arr, nb), 'hpb_poisson_solve')
+
+    def poisson_solve_periodic(self, rhs, sl, c_lhs):
+        """fields.poisson_solver = FFTPeriodic; arguments as poisson_solve"""
+        nb = rhs.shape[0]
+        arr = (C.c_int * nb)(*c_lhs)
+        _check(self._L.hpb_poisson_solve_periodic(self._h, rhs.data_ptr(), sl, arr, nb),
+               'hpb_poisson_solve_periodic')
+
+    def enforce_periodic(self, sl, do_sum, comp_list):
+        """Fields::EnforcePeriodic: SumBoundary (do_sum) or FillBoundary of the listed components"""
+        arr = (C.c_int * len(comp_list))(*comp_list)
+        _check(self._L.hpb_fields_enforce_periodic(self._h, sl, int(bool(do_sum)), arr, len(comp_list)),
+               'hpb_fields_enforce_periodic')
 
     def solve_psi_ez_bz(self, sl, comps):
         _check(self._L.hpb_fields_solve_psi_ez_bz(self._h, sl, comps), 'hpb_fields_solve_psi_ez_bz')

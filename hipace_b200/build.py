@@ -38,6 +38,7 @@ SOURCES = {
     'peaks.cu': [],
     'ref_gpu_arm.cu': [],
     'fft2d.cu': [],
+    'periodic.cu': [],
 }
 
 

@@ -265,6 +265,7 @@ struct hpb_ctx {
     // TMA tensor maps over the caller's slice array (tma.cuh), re-encoded when the view changes:
     // [0] the 40 x 6 gather patch of the push, [1] the patch of the explicit deposition
     void *mg2;                // mg.cu: level coefficient arrays of the type-2 (complex Helmholtz) solver
+    void *periodic;           // periodic.cu: 2-D FFT plan and complex planes of the FFTPeriodic Poisson solver
     void *ref_arm;            // ref_gpu_arm.cu: cuFFT plans and buffers of the reference-algorithm arm
     int tune_poisson_impl;    // 0: product solver, 1: the reference's DirichletFast sequence on cuFFT
     // plasma reordering scratch (reorder.cu)

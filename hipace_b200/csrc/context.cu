@@ -12,6 +12,7 @@ int hpb_mg_init(hpb_ctx *ctx);
 void hpb_mg_free(hpb_ctx *ctx);
 void hpb_reorder_free(hpb_ctx *ctx);
 void hpb_ref_arm_free(hpb_ctx *ctx);
+void hpb_periodic_free(hpb_ctx *ctx);
 
 static thread_local char g_err[1024] = "";
 
@@ -155,6 +156,7 @@ extern "C" void hpb_destroy(hpb_ctx *ctx)
     hpb_mg_free(ctx);
     hpb_reorder_free(ctx);
     hpb_ref_arm_free(ctx);
+    hpb_periodic_free(ctx);
     cudaFree(ctx->d_scalar_i);
     delete ctx;
 }

@@ -265,9 +265,22 @@ int read_deck(hpb_sim *s)
     s->predcorr_max_iter = (int)d.num("hipace.predcorr_max_iterations", 30);
     s->predcorr_mix = d.num("hipace.predcorr_B_mixing_factor", 0.05);
     const std::string bfield = d.str("boundary.field", "");
-    if (bfield != "Dirichlet" && bfield != "Open")
-        throw std::runtime_error("only boundary.field = Dirichlet or Open is supported");
+    if (bfield != "Dirichlet" && bfield != "Open" && bfield != "Periodic")
+        throw std::runtime_error("boundary.field must be Dirichlet, Periodic or Open");        // Hipace.cpp:190-200
     s->open_bc = bfield == "Open";
+    s->field_periodic = bfield == "Periodic";
+    // Fields.cpp:34-40, :179-208: the GPU default is FFTDirichletFast; FFTDirichletDirect / Expanded are the
+    // same equation through other transforms (one solver here); MGDirichlet is not available
+    const std::string psolver = d.str("fields.poisson_solver", "FFTDirichletFast");
+    if (psolver == "FFTPeriodic") s->poisson_periodic = true;
+    else if (psolver != "FFTDirichletFast" && psolver != "FFTDirichletDirect" && psolver != "FFTDirichletExpanded")
+        throw std::runtime_error("fields.poisson_solver must be FFTDirichletFast, FFTDirichletDirect, "
+                                 "FFTDirichletExpanded or FFTPeriodic (MGDirichlet is not supported)");
+    if ((s->field_periodic || s->poisson_periodic) && !s->explicit_solver)
+        throw std::runtime_error("boundary.field = Periodic / fields.poisson_solver = FFTPeriodic are only "
+                                 "available with hipace.bxby_solver = explicit");
+    if (s->open_bc && s->poisson_periodic)
+        throw std::runtime_error("boundary.field = Open needs a Dirichlet Poisson solver");
     if (s->open_bc && s->explicit_solver)
         throw std::runtime_error("boundary.field = Open is only available with hipace.bxby_solver = predictor-corrector");
     const std::string pbc = d.str("boundary.particle", "");
@@ -360,6 +373,8 @@ int read_deck(hpb_sim *s)
     auto ln = d.strs("lasers.names");
     if (!ln.empty() && ln[0] != "no_laser") {
         s->use_laser = true;
+        if (s->field_periodic || s->poisson_periodic)
+            throw std::runtime_error("lasers with boundary.field = Periodic / fields.poisson_solver = FFTPeriodic are not supported");
         s->laser_lambda0 = d.num("lasers.lambda0", 0.);
         s->laser_interp_order = (int)d.num("lasers.interp_order", 1);
         if (s->laser_lambda0 <= 0.) throw std::runtime_error("lasers.lambda0 must be given");
@@ -1222,7 +1237,20 @@ int solve_one_slice(hpb_sim *s, int islice)
     s->prepared = false;
     {
         StageTimer t(s, ST_POISSON);
-        if ((rc = hpb_fields_solve_psi_ez_bz(ctx, s->sl, C))) return rc;                // :633
+        if (!s->field_periodic && !s->poisson_periodic) {
+            if ((rc = hpb_fields_solve_psi_ez_bz(ctx, s->sl, C))) return rc;            // :633
+        } else {
+            // Fields.cpp:859-861, :920-922: the periodic images of the deposits are summed into the valid
+            // box before, and the guard cells of the potentials filled after, the three solves
+            const int src[3] = {C[HPB_C_JX], C[HPB_C_JY], C[HPB_C_RHOMJZ]};
+            const int lhs[3] = {C[HPB_C_PSI], C[HPB_C_EZ], C[HPB_C_BZ]};
+            if (s->field_periodic && (rc = hpb_fields_enforce_periodic(ctx, s->sl, 1, src, 3))) return rc;
+            if ((rc = hpb_fields_psi_ez_bz_rhs(ctx, s->sl, C, s->d_pc_rhs))) return rc;
+            if ((rc = (s->poisson_periodic ? hpb_poisson_solve_periodic : hpb_poisson_solve)(
+                     ctx, s->d_pc_rhs, s->sl, lhs, 3))) return rc;
+            if (s->field_periodic && (rc = hpb_fields_enforce_periodic(ctx, s->sl, 0, lhs, 3))) return rc;
+            if ((rc = hpb_launch_exmby_eypbx(ctx, s->sl, C))) return rc;
+        }
     }
     if (s->laser_state) {                                                               // :637
         StageTimer t(s, ST_OTHER);
@@ -1246,8 +1274,12 @@ int solve_one_slice(hpb_sim *s, int islice)
     {
         StageTimer t(s, ST_MG);
         int iters = 0;                                                                  // :666
+        const int srcs[3] = {C[HPB_C_SY], C[HPB_C_SX], C[HPB_C_CHI]};                   // Hipace.cpp:817-821
+        if (s->field_periodic && (rc = hpb_fields_enforce_periodic(ctx, s->sl, 1, srcs, 3))) return rc;
         if ((rc = hpb_mg_solve1(ctx, s->sl, C[HPB_C_BX], C[HPB_C_SY], C[HPB_C_CHI], s->mg_tol_rel,
                                 s->mg_tol_abs, 200, &iters))) return rc;
+        const int bxy[2] = {C[HPB_C_BX], C[HPB_C_BY]};                                  // Hipace.cpp:924-927
+        if (s->field_periodic && (rc = hpb_fields_enforce_periodic(ctx, s->sl, 0, bxy, 2))) return rc;
         s->stats.n_mg_vcycles += iters;
         s->mg_iters.push_back(iters);
     }
@@ -1463,8 +1495,9 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     SIM_CUDA(cudaMemset(sl.p, 0, sizeof(double) * sl.nstride * sl.ncomp));
     SIM_CUDA(cudaMalloc(&s->d_checksum, sizeof(double) * (sl.ncomp + 1)));     // + laserEnvelope
     SIM_CUDA(cudaMemset(s->d_checksum, 0, sizeof(double) * (sl.ncomp + 1)));
-    if (!s->explicit_solver) {
+    if (!s->explicit_solver || s->field_periodic || s->poisson_periodic)
         SIM_CUDA(cudaMalloc(&s->d_pc_rhs, sizeof(double) * 3 * (size_t)s->g.nx * s->g.ny));
+    if (!s->explicit_solver) {
         SIM_CUDA(cudaMalloc(&s->d_pc_scal, sizeof(double) * 40));
     }
     SIM_CUDA(cudaMalloc(&s->d_nqsa, sizeof(int)));

@@ -117,6 +117,8 @@ struct hpb_sim {
     // hipace.bxby_solver = predictor-corrector (Hipace.cpp:935-1031, Hipace.H:210-222) and
     // boundary.field = Open (Fields.cpp:685-738)
     bool explicit_solver = true, open_bc = false;
+    // boundary.field = Periodic (Fields::EnforcePeriodic) / fields.poisson_solver = FFTPeriodic
+    bool field_periodic = false, poisson_periodic = false;
     double predcorr_tol = 4e-2, predcorr_mix = 0.05;
     int predcorr_max_iter = 30;
     double *d_pc_rhs = nullptr;                   // 3 staging planes nx * ny

@@ -293,6 +293,18 @@ int hpb_fields_lincomb2(hpb_ctx *ctx, hpb_slice sl, int c_dst, double fa, int c_
 int hpb_poisson_solve(hpb_ctx *ctx, const double *d_rhs, hpb_slice sl, const int *c_lhs,
                       int nbatch);
 
+/* fields.poisson_solver = FFTPeriodic: FFTPoissonSolverPeriodic::SolvePoissonEquation
+ * (src/fields/fft_poisson_solver/FFTPoissonSolverPeriodic.cpp:111-149; inv_k2 of :69-92, which is zero
+ * on the whole kx = 0 row and ky = 0 column).  Same arguments as hpb_poisson_solve. */
+int hpb_poisson_solve_periodic(hpb_ctx *ctx, const double *d_rhs, hpb_slice sl, const int *c_lhs,
+                               int nbatch);
+
+/* boundary.field = Periodic: Fields::EnforcePeriodic (src/fields/Fields.cpp:1117-1145).  do_sum != 0:
+ * AMReX SumBoundary -- the guard cells are added to their periodic images in the valid box (and keep
+ * their own values); do_sum == 0: FillBoundary -- the guard cells are overwritten with their periodic
+ * images.  comp_list: up to 12 component indices (entries < 0 are skipped). */
+int hpb_fields_enforce_periodic(hpb_ctx *ctx, hpb_slice sl, int do_sum, const int *comp_list, int n);
+
 /* Fields::SolvePoissonPsiExmByEypBxEzBz (src/fields/Fields.cpp:840-957): RHS assembly + three
  * Poisson solves + ExmBy/EypBx stencil, fused. */
 int hpb_fields_solve_psi_ez_bz(hpb_ctx *ctx, hpb_slice sl, const int *comps);

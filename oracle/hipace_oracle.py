@@ -745,6 +745,47 @@ def poisson_dirichlet(rhs, eig):
     return _dstn(_dstn(rhs, type=1) * eig, type=1)
 
 
+def poisson_periodic(rhs, dx, dy):
+    """FFTPoissonSolverPeriodic::SolvePoissonEquation (fields/fft_poisson_solver/FFTPoissonSolverPeriodic.cpp
+    :111-149): R2C 2-D FFT, times -inv_k2, C2R, times 1/N.  inv_k2 (:69-92): half spectrum along x,
+    kx = dkx i, ky = dky j (j < (Ny+1)/2) else dky (j - Ny), and ZERO wherever i == 0 or j == 0 (the whole
+    kx = 0 row and ky = 0 column, not only the origin)."""
+    ny, nx = rhs.shape
+    dkx, dky = 2 * math.pi / (nx * dx), 2 * math.pi / (ny * dy)
+    i = np.arange(nx // 2 + 1)
+    j = np.arange(ny)
+    kx = dkx * i
+    ky = np.where(j < (ny + 1) // 2, dky * j, dky * (j - ny))
+    k2 = kx[None, :] ** 2 + ky[:, None] ** 2
+    inv_k2 = np.zeros_like(k2)
+    m = (i[None, :] != 0) & (j[:, None] != 0)
+    inv_k2[m] = 1.0 / k2[m]
+    spec = np.fft.rfft2(rhs) * (-inv_k2)
+    # numpy's irfft2 carries the 1/N of the reference's final copy (:136-148)
+    return np.fft.irfft2(spec, s=(ny, nx))
+
+
+def enforce_periodic(arrs, G, do_sum):
+    """Fields::EnforcePeriodic (fields/Fields.cpp:1117-1145) for the single slice box: AMReX SumBoundary
+    (do_sum: the guard cells are ADDED to their periodic images in the valid box and keep their own
+    values) or FillBoundary (the guard cells are overwritten with their periodic images)."""
+    for a in arrs:
+        ny, nx = a.shape[0] - 2 * G, a.shape[1] - 2 * G
+        v = a[G:-G, G:-G]
+        if do_sum:
+            src = a.copy()
+            v[:, :G] += src[G:-G, nx + G:]            # (i + nx, j)
+            v[:, nx - G:] += src[G:-G, :G]            # (i - nx, j)
+            v[:G, :] += src[ny + G:, G:-G]            # (i, j + ny)
+            v[ny - G:, :] += src[:G, G:-G]            # (i, j - ny)
+            v[:G, :G] += src[ny + G:, nx + G:]        # corners
+            v[:G, nx - G:] += src[ny + G:, :G]
+            v[ny - G:, :G] += src[:G, nx + G:]
+            v[ny - G:, nx - G:] += src[:G, :G]
+        else:
+            a[...] = np.pad(v, G, mode='wrap')
+
+
 def _ddx(a, dx, G):
     """derivative<x> on the valid box, fields/Fields.cpp:223-235: (f[i+1]-f[i-1]) * 0.5/dx"""
     return (a[G:-G, G + 1:a.shape[1] - G + 1] - a[G:-G, G - 1:a.shape[1] - G - 1]) * (0.5 / dx)
@@ -802,16 +843,23 @@ def open_boundary_rhs(rhs, geom: Geometry, monopole: bool):
     return out
 
 
-def solve_poisson_psi_ez_bz(F, geom: Geometry, pc: PhysConst, eig, open_bc=False):
-    """Fields::SolvePoissonPsiExmByEypBxEzBz, fields/Fields.cpp:840-957 (lev 0, Dirichlet or Open)."""
+def solve_poisson_psi_ez_bz(F, geom: Geometry, pc: PhysConst, eig, open_bc=False, field_periodic=False,
+                            poisson_periodic_solver=False):
+    """Fields::SolvePoissonPsiExmByEypBxEzBz, fields/Fields.cpp:840-957 (lev 0; boundary.field Dirichlet,
+    Open or Periodic; fields.poisson_solver FFTDirichlet* or FFTPeriodic)."""
     dx, dy, G = geom.dx, geom.dy, geom.g
     T = lambda n: F[('This', n)]
     bc = (lambda r, mono: open_boundary_rhs(r, geom, mono)) if open_bc else (lambda r, mono: r)
-    T('Psi')[G:-G, G:-G] = poisson_dirichlet(bc((-1.0 / pc.ep0) * T('rhomjz')[G:-G, G:-G], True), eig)
+    if field_periodic:                                                           # :859-861
+        enforce_periodic([T('jx'), T('jy'), T('rhomjz')], G, True)
+    solve = (lambda r, e: poisson_periodic(r, dx, dy)) if poisson_periodic_solver else poisson_dirichlet
+    T('Psi')[G:-G, G:-G] = solve(bc((-1.0 / pc.ep0) * T('rhomjz')[G:-G, G:-G], True), eig)
     f = 1.0 / (pc.ep0 * pc.c)
-    T('Ez')[G:-G, G:-G] = poisson_dirichlet(bc(f * _ddx(T('jx'), dx, G) + f * _ddy(T('jy'), dy, G), False), eig)
-    T('Bz')[G:-G, G:-G] = poisson_dirichlet(bc(pc.mu0 * _ddy(T('jx'), dy, G)
+    T('Ez')[G:-G, G:-G] = solve(bc(f * _ddx(T('jx'), dx, G) + f * _ddy(T('jy'), dy, G), False), eig)
+    T('Bz')[G:-G, G:-G] = solve(bc(pc.mu0 * _ddy(T('jx'), dy, G)
                                                + (-pc.mu0) * _ddx(T('jy'), dx, G), False), eig)
+    if field_periodic:                                                           # :920-922
+        enforce_periodic([T('Psi'), T('Ez'), T('Bz')], G, False)
     # ExmBy / EypBx on the box grown by g-1, i.e. everything but the outermost ring (:931-956)
     psi = T('Psi')
     ny_t, nx_t = psi.shape
@@ -1866,9 +1914,15 @@ class Simulation:
         self.predcorr_mix = _get(d, 'hipace.predcorr_B_mixing_factor', 0.05)
         self.predcorr_iters = []
         bf = _get(d, 'boundary.field', typ=str)
-        assert bf in ('Dirichlet', 'Open'), 'oracle scope: Dirichlet / Open field boundaries'
-        assert bf == 'Dirichlet' or not self.explicit, 'oracle scope: Open only with predictor-corrector'
+        assert bf in ('Dirichlet', 'Open', 'Periodic')
+        assert bf != 'Open' or not self.explicit, 'oracle scope: Open only with predictor-corrector'
         self.open_bc = bf == 'Open'
+        self.field_periodic = bf == 'Periodic'
+        ps = _get(d, 'fields.poisson_solver', 'FFTDirichletFast', typ=str)     # fields/Fields.cpp:34-40, :179-208
+        assert ps in ('FFTDirichletFast', 'FFTDirichletDirect', 'FFTDirichletExpanded', 'FFTPeriodic')
+        self.poisson_periodic = ps == 'FFTPeriodic'
+        assert self.explicit or not (self.field_periodic or self.poisson_periodic), \
+            'oracle scope: periodic fields only with the explicit solver'
         self.bc_kind = _get(d, 'boundary.particle', typ=str)
         self.bc_lo = _get(d, 'boundary.particle_lo', [lo[0], lo[1]], n=2)
         self.bc_hi = _get(d, 'boundary.particle_hi', [hi[0], hi[1]], n=2)
@@ -2345,7 +2399,7 @@ class Simulation:
             grid_current_deposit(T('jz_beam'), g, islice, *self.grid_current)
         if self.slice_hook:
             self.slice_hook(self, islice, 'deposited')
-        solve_poisson_psi_ez_bz(F, g, pc, self.eig)                               # :633
+        solve_poisson_psi_ez_bz(F, g, pc, self.eig, False, self.field_periodic, self.poisson_periodic)   # :633
         if self.use_laser and self.dt != 0.0:                                     # :637 AdvanceSlice
             chi = laser_interpolate_chi(T('chi'), self.laser_chi_initial, g, self.laser_interp_order)
             if self.laser_solver == 'fft':
@@ -2373,9 +2427,13 @@ class Simulation:
         # ExplicitMGSolveBxBy, Hipace.cpp:793-933
         v = (slice(g.g, -g.g), slice(g.g, -g.g))
         sol = np.stack([T('Bx')[v], T('By')[v]])
+        if self.field_periodic:                                                   # Hipace.cpp:817-821
+            enforce_periodic([T('Sy'), T('Sx'), T('chi')], g.g, True)
         rhs = np.stack([T('Sy')[v], T('Sx')[v]])
         self.mg.solve1(sol, rhs, T('chi')[v], self.mg_tol_rel, self.mg_tol_abs, 200)
         T('Bx')[v], T('By')[v] = sol[0], sol[1]
+        if self.field_periodic:                                                   # Hipace.cpp:924-927
+            enforce_periodic([T('Bx'), T('By')], g.g, False)
         self.mg_cycles.append(self.mg.n_vcycles_last)
         if self.slice_hook:
             self.slice_hook(self, islice, 'fields')

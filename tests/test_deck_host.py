@@ -71,7 +71,9 @@ def test_overrides_constants_and_expressions():
     ({'hipace.depos_order_xy': 4}, 'depos_order_xy'),
     ({'hipace.bxby_solver': 'semi-implicit'}, 'bxby_solver'),
     ({'boundary.field': 'Open'}, 'predictor-corrector'),
-    ({'boundary.field': 'Periodic'}, 'Dirichlet'),
+    ({'boundary.field': 'Periodic', 'hipace.bxby_solver': 'predictor-corrector'}, 'explicit'),
+    ({'fields.poisson_solver': 'MGDirichlet'}, 'MGDirichlet'),
+    ({'boundary.field': 'Mirror'}, 'Dirichlet, Periodic or Open'),
     ({'plasma.u_std': '0. 0. 1e-3'}, 'RNG'),
     ({'amr.n_cell': '64 64'}, '3 values'),
     ({'diagnostic.diag_type': 'yz'}, 'diag_type'),
