@@ -69,7 +69,7 @@ EXPORTS = (
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
     'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder', 'hpb_measure_fp64_peak', 'hpb_mg_solve2', 'hpb_laser_set_solver',
-    'hpb_laser_mg_vcycles', 'hpb_poisson_solve_periodic', 'hpb_fields_enforce_periodic',
+    'hpb_laser_mg_vcycles', 'hpb_poisson_solve_periodic', 'hpb_fields_enforce_periodic', 'hpb_sim_get_time',
 )
 NCCL_ID_BYTES = 128
 
@@ -171,6 +171,7 @@ def lib():
     L.hpb_sim_get_beam.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     L.hpb_sim_set_beam.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     L.hpb_sim_get_stats.argtypes = [C.c_void_p, C.POINTER(hpb_sim_stats)]
+    L.hpb_sim_get_time.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.hpb_sim_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     L.hpb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     L.hpb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -453,6 +454,12 @@ class Simulation:
         buf = (C.c_int * max(n, 1))()
         self._L.hpb_sim_get_mg_iters(self._h, buf, n)
         return list(buf[:n])
+
+    def time(self):
+        """(physical time, dt) of the step that ran last"""
+        t, dt = C.c_double(0.), C.c_double(0.)
+        _check(self._L.hpb_sim_get_time(self._h, C.byref(t), C.byref(dt)), 'hpb_sim_get_time')
+        return t.value, dt.value
 
     def stats(self) -> dict:
         st = hpb_sim_stats()

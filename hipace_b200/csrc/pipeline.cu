@@ -4,8 +4,9 @@
 // Rank r owns the time steps r, r + R, ... (Hipace.cpp:401).  The only state that flows between
 // time steps is the beam: for every slice, rank r receives the slice packet that rank r-1 pushed
 // in the previous time step and sends its own pushed packet to rank r+1 (ring).  There is no
-// collective and nothing else is exchanged (plasma is re-created locally every step; the physical
-// time of a step is the accumulated sum of dt on every rank; adaptive time steps are single-rank).  The laser envelope slices
+// collective; besides the beam only the physical time of the next step travels (hpb_pipeline_put_time /
+// get_time = MultiBuffer::put_time / get_time, so hipace.dt = adaptive works across ranks: every rank keeps
+// its own dt and min_uz_mq exactly as the reference's ranks do); plasma is re-created locally.  The laser envelope slices
 // A^{n+1}, A^n of a slice ride in the same group of sends / receives (MultiBuffer.cpp:444-490).
 //
 // Each directed edge r -> r+1 is its own 2-rank communicator with its own CUDA stream, so a
@@ -86,9 +87,14 @@ struct hpb_pipeline {
     bool receiving = false, sent_this_step = false;
     int posted = 0;                                        // slots with a receive posted this step
     int lookahead = 8;
+    // the physical time of the next step (MultiBuffer::put_time / get_time): a ring of send slots (a slot
+    // is reused 8 owned steps later, long after its send left) and one receive slot
+    double *d_time = nullptr, *h_time = nullptr;           // [0..7] send, [8] receive; h_time pinned
+    unsigned n_time_sent = 0;
 };
 
 bool hpb_pipeline_active(const hpb_sim *s) { return s->pipe && s->pipe->world > 1; }
+int hpb_pipeline_world(const hpb_sim *s) { return s->pipe ? s->pipe->world : 1; }
 int hpb_pipeline_rank(const hpb_sim *s) { return s->pipe ? s->pipe->rank : 0; }
 
 // every time step but the first has an upstream (Hipace.cpp:410: step 0 starts from the initial
@@ -143,6 +149,8 @@ extern "C" int hpb_sim_pipeline_init(hpb_sim *s, int rank, int world, const char
     for (auto &e : p->ev_ready) SIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : p->ev_sent) SIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SIM_CUDA(cudaEventCreateWithFlags(&p->ev_step_done, cudaEventDisableTiming));
+    SIM_CUDA(cudaMalloc(&p->d_time, 9 * sizeof(double)));
+    SIM_CUDA(cudaMallocHost(&p->h_time, 9 * sizeof(double)));
     // connect both edges now: NCCL sets up its P2P channels on the first send / receive of a
     // communicator, and that set-up BLOCKS THE HOST until the peer enters the matching call.  As
     // for the communicators themselves the two edges of a rank are therefore connected in
@@ -184,6 +192,8 @@ void hpb_pipeline_destroy(hpb_sim *s)
     for (auto &e : p->ev_ready) cudaEventDestroy(e);
     for (auto &e : p->ev_sent) cudaEventDestroy(e);
     if (p->ev_step_done) cudaEventDestroy(p->ev_step_done);
+    cudaFree(p->d_time);
+    if (p->h_time) cudaFreeHost(p->h_time);
     if (p->s_recv) cudaStreamDestroy(p->s_recv);
     if (p->s_send) cudaStreamDestroy(p->s_send);
     delete p;
@@ -219,6 +229,35 @@ static int post_receives(hpb_sim *s, int upto)
         HPB_NCCL(N->GroupEnd());
         SIM_CUDA(cudaEventRecord(p->ev_recv[slot], p->s_recv));
     }
+    return HPB_OK;
+}
+
+// MultiBuffer::put_time (utils/MultiBuffer.cpp:629-651): the time at which the NEXT step starts leaves for
+// the downstream rank at the beginning of this step -- one 8-byte message per step on the edge's own
+// stream, ahead of the step's slice packets
+int hpb_pipeline_put_time(hpb_sim *s, int step, double t_next)
+{
+    hpb_pipeline *p = s->pipe;
+    if (!hpb_pipeline_active(s) || step + 1 > s->max_step) return HPB_OK;     // Hipace.cpp:445-447
+    NcclApi *N = nccl();
+    const unsigned k = p->n_time_sent++ % 8;
+    p->h_time[k] = t_next;
+    SIM_CUDA(cudaMemcpyAsync(p->d_time + k, p->h_time + k, sizeof(double), cudaMemcpyHostToDevice, p->s_send));
+    HPB_NCCL(N->Send(p->d_time + k, sizeof(double), ncclUint8, 1, p->comm_send, p->s_send));
+    return HPB_OK;
+}
+
+// MultiBuffer::get_time (:611-627): blocks the host like the reference's MPI_Recv; the upstream rank posted
+// the value when it began the step before this one
+int hpb_pipeline_get_time(hpb_sim *s, int step, double *t)
+{
+    hpb_pipeline *p = s->pipe;
+    if (!hpb_pipeline_receives(s, step)) return HPB_OK;
+    NcclApi *N = nccl();
+    HPB_NCCL(N->Recv(p->d_time + 8, sizeof(double), ncclUint8, 0, p->comm_recv, p->s_recv));
+    SIM_CUDA(cudaMemcpyAsync(p->h_time + 8, p->d_time + 8, sizeof(double), cudaMemcpyDeviceToHost, p->s_recv));
+    SIM_CUDA(cudaStreamSynchronize(p->s_recv));
+    *t = p->h_time[8];
     return HPB_OK;
 }
 

@@ -301,6 +301,7 @@ int read_deck(hpb_sim *s)
         s->adp.phase_tolerance = d.num("hipace.adaptive_phase_tolerance", 4e-4);
         s->adp.phase_substeps = (int)d.num("hipace.adaptive_phase_substeps", 2000);
         s->adp.control_phase = (int)d.num("hipace.adaptive_control_phase_advance", 1);
+        s->adp.predict_step = (int)d.num("hipace.adaptive_predict_step", 1);
         s->adp.c = g.c; s->adp.ep0 = g.ep0;
         s->adaptive_density = d.num("plasmas.adaptive_density", 0.);
         if ((int)d.num("hipace.adaptive_gather_ez", 0))
@@ -690,10 +691,22 @@ struct StageTimer {
     }
 };
 
-// CalculateFromMinUz (AdaptiveTimeStep.cpp:143-233) from the host copies BeamSp::ts
-int adaptive_from_min_uz(hpb_sim *s, double t_now, double rho)
+// MultiPlasma::maxChargeDensity (particles/plasma/MultiPlasma.cpp:63-73) as a function of z = c t
+std::function<double(double)> max_charge_density(hpb_sim *s)
 {
-    (void)t_now;
+    return [s](double z) {
+        double m = fabs(s->adaptive_density * s->g.q_e);
+        for (auto &sp : s->plasmas) {
+            const double xyz[3] = {0., 0., z};
+            m = fmax(m, fabs(sp.charge * s->deck.run(sp.density_host, xyz)));
+        }
+        return m;
+    };
+}
+
+// CalculateFromMinUz (AdaptiveTimeStep.cpp:143-233) from the host copies BeamSp::ts
+int adaptive_from_min_uz(hpb_sim *s, double t_now, const std::function<double(double)> &rho_at)
+{
     const int nb = (int)s->beams.size();
     std::vector<double> ts(4 * nb), q(nb), m(nb);
     for (int ib = 0; ib < nb; ++ib) {
@@ -701,7 +714,7 @@ int adaptive_from_min_uz(hpb_sim *s, double t_now, double rho)
         q[ib] = s->beams[ib].charge; m[ib] = s->beams[ib].mass;
     }
     double dt_out = s->dt, mq = s->min_uz_mq;
-    if (!adaptive_dt_from_min_uz(s->adp, nb, ts.data(), q.data(), m.data(), rho, s->dt, dt_out, mq)) {
+    if (!adaptive_dt_from_min_uz(s->adp, nb, ts.data(), q.data(), m.data(), rho_at, t_now, s->dt, dt_out, mq)) {
         hpb_set_error("adaptive time step: the sum of the beam weights is 0 or no plasma density > 0 is given "
                       "(plasmas.adaptive_density)");
         return HPB_ERR_ARG;
@@ -717,32 +730,28 @@ int begin_step(hpb_sim *s, int step)
     SIM_CUDA(cudaMemsetAsync(s->d_checksum, 0, sizeof(double) * (s->sl.ncomp + 1), s->stream));
     for (int k = 0; k < HPB_C_COUNT; ++k) s->comps[k] = s->comps0[k];
     s->prepared = false;
-    if (s->adaptive_dt) {                                            // Hipace.cpp:275-279, 411, 420, 434
-        if (hpb_pipeline_active(s)) {
-            hpb_set_error("hipace.dt = adaptive is not available with a multi-rank pipeline");
-            return HPB_ERR_UNSUPPORTED;
-        }
-        auto rho_at = [&](double z) {                                // MultiPlasma::maxChargeDensity
-            double m = fabs(s->adaptive_density * s->g.q_e);
-            for (auto &sp : s->plasmas) {
-                const double xyz[3] = {0., 0., z};
-                m = fmax(m, fabs(sp.charge * s->deck.run(sp.density_host, xyz)));
-            }
-            return m;
-        };
-        if (step == 0) {
+    // the physical time of a step after the first comes from the rank that owns the step before it
+    // (MultiBuffer::get_time, Hipace.cpp:411); without a pipeline it is the value this rank computed itself
+    double t_recv = s->next_time;
+    if (int rc = hpb_pipeline_get_time(s, step, &t_recv)) return rc;
+    if (s->adaptive_dt) {                                            // Hipace.cpp:275-281, 411, 420, 434
+        const auto rho_at = max_charge_density(s);
+        s->adp.numprocs = hpb_pipeline_world(s);
+        if (step == 0 || !s->adaptive_initialised) {
+            // Hipace.cpp:275-281: the head rank's estimate from the beam as specified in the deck is
+            // broadcast to every rank -- it depends on the deck only, so every rank computes it
             if (s->beams.empty()) { hpb_set_error("adaptive time step: needs a beam"); return HPB_ERR_ARG; }
             for (auto &b : s->beams) {                               // GatherMinUzSlice(initial)
                 b.ts[0] = b.u_mean_z; b.ts[1] = 1.; b.ts[2] = b.u_mean_z; b.ts[3] = b.u_mean_z * b.u_mean_z;
             }
             s->min_uz_mq = DBL_MAX;
-            int rc = adaptive_from_min_uz(s, 0., rho_at(0.));
+            s->dt = 0.;
+            int rc = adaptive_from_min_uz(s, 0., rho_at);
             if (rc) return rc;
             s->dt = adaptive_dt_from_density(s->adp, s->min_uz_mq, 0., s->dt, rho_at);
-            s->time = 0.;
-        } else {
-            s->time = s->next_time;
+            s->adaptive_initialised = true;
         }
+        s->time = step == 0 ? 0. : t_recv;
         s->dt = adaptive_dt_from_density(s->adp, s->min_uz_mq, s->time, s->dt, rho_at);
         s->next_time = s->time + s->dt;
         for (auto &b : s->beams) {                                   // CalculateFromDensity resets the data
@@ -750,12 +759,18 @@ int begin_step(hpb_sim *s, int step)
             if (!b.d_ts) SIM_CUDA(cudaMalloc(&b.d_ts, 4 * sizeof(double)));
             SIM_CUDA(cudaMemcpyAsync(b.d_ts, b.ts, 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         }
+    } else if (hpb_pipeline_receives(s, step)) {
+        s->time = t_recv;
+        s->next_time = s->time + s->dt;
     } else {
         // the reference accumulates next_time = time + dt from step to step (Hipace.cpp:411-434);
-        // replaying the sum gives the same rounding on whichever rank owns the step
+        // replaying the sum gives the same rounding whichever step a run (or a test) starts from
         s->time = 0.;
         for (int k = 0; k < step; ++k) s->time += s->dt;
+        s->next_time = s->time + s->dt;
     }
+    s->dt_step = s->dt;
+    if (int rc = hpb_pipeline_put_time(s, step, s->next_time)) return rc;             // Hipace.cpp:445-447
     const double c_t = s->g.c * s->time;
     if (s->use_laser && s->max_step > 0 && s->dt != 0.) {            // the envelope is stored and advanced
         if (!s->laser_state) {
@@ -822,12 +837,7 @@ int end_step(hpb_sim *s)
             if (s->stream2) SIM_CUDA(cudaStreamSynchronize(s->stream2));
             SIM_CUDA(cudaMemcpy(b.ts, b.d_ts, 4 * sizeof(double), cudaMemcpyDeviceToHost));
         }
-        double rho = fabs(s->adaptive_density * s->g.q_e);
-        for (auto &sp : s->plasmas) {
-            const double xyz[3] = {0., 0., s->g.c * s->time};
-            rho = fmax(rho, fabs(sp.charge * s->deck.run(sp.density_host, xyz)));
-        }
-        if (int rc = adaptive_from_min_uz(s, s->time, rho)) return rc;
+        if (int rc = adaptive_from_min_uz(s, s->time, max_charge_density(s))) return rc;
     }
     if (int rc = write_beam_insitu(s)) return rc;
     if (s->laser_state) hpb_laser_end_step(s->laser_state);
@@ -1410,7 +1420,8 @@ extern "C" int hpb_adaptive_dt_next(const hpb_adaptive_par *par, int nbeams, con
 {
     if (!par || !ts || !charge || !mass || !dt_out || !min_uz_mq) return HPB_ERR_ARG;
     double dt = dt_in, mq = *min_uz_mq;
-    if (!adaptive_dt_from_min_uz(*par, nbeams, ts, charge, mass, rho, dt_in, dt, mq)) return HPB_ERR_ARG;
+    if (!adaptive_dt_from_min_uz(*par, nbeams, ts, charge, mass, [rho](double) { return rho; }, 0., dt_in, dt, mq))
+        return HPB_ERR_ARG;
     *dt_out = adaptive_dt_from_density(*par, mq, t_next, dt, [rho](double) { return rho; });
     *min_uz_mq = mq;
     return HPB_OK;
@@ -1820,6 +1831,14 @@ extern "C" int hpb_sim_set_beam(hpb_sim *s, int beam, const double *const h_real
     b.initialised = true;
     b.from_host = true;
     b.cs_valid = false;
+    return HPB_OK;
+}
+
+extern "C" int hpb_sim_get_time(hpb_sim *s, double *time, double *dt)
+{
+    if (!s) return HPB_ERR_ARG;
+    if (time) *time = s->time;
+    if (dt) *dt = s->dt_step;
     return HPB_OK;
 }
 

@@ -130,8 +130,10 @@ struct hpb_sim {
     std::string field_insitu_prefix = "diags/field_insitu";
     double *d_field_insitu = nullptr;             // [10][nz]
     bool adaptive_dt = false;
-    hpb_adaptive_par adp = {20., INFINITY, 2., 4e-4, 2000, 1, 1., 1.};
+    hpb_adaptive_par adp = {20., INFINITY, 2., 4e-4, 2000, 1, 1., 1., 1, 1};
     double adaptive_density = 0., min_uz_mq = DBL_MAX, time = 0., next_time = 0.;
+    double dt_step = 0.;                          // the dt the current / last step runs with (end_step may already hold the next)
+    bool adaptive_initialised = false;            // this rank's dt / min_uz_mq hold the initial estimate (Hipace.cpp:275-281)
     bool use_grid_current = false;                // utils/GridCurrent.cpp
     double gc_peak = 0., gc_mean[3] = {0., 0., 0.}, gc_std[3] = {1., 1., 1.};
     int max_step = 0;
@@ -225,6 +227,11 @@ int hpb_pipeline_send_slice(hpb_sim *s, int islice, int step);
 int hpb_pipeline_wait_out_slot(hpb_sim *s, int islice);     // out-ring slot free (its last send left)
 bool hpb_pipeline_out_ring_busy(const hpb_sim *s);          // sends of the previous owned step pending
 int hpb_pipeline_end_step(hpb_sim *s, int step);
+// MultiBuffer::get_time / put_time (utils/MultiBuffer.cpp:611-651): the physical time of a step travels
+// from the rank that owns the step before it; get blocks the host until the value is there
+int hpb_pipeline_get_time(hpb_sim *s, int step, double *t);
+int hpb_pipeline_put_time(hpb_sim *s, int step, double t_next);
+int hpb_pipeline_world(const hpb_sim *s);
 bool hpb_pipeline_receives(const hpb_sim *s, int step);     // this step's beam comes from upstream
 bool hpb_pipeline_active(const hpb_sim *s);
 int hpb_pipeline_rank(const hpb_sim *s);

@@ -117,6 +117,9 @@ class HostPipeline:
         begin_step(step), solve_one_slice(islice), nz,
         put_beam_slice(ibeam, islice, bs)     install a received slice (before it is first used)
         take_beam_slice(ibeam, islice) -> bs  the pushed slice after solve_one_slice(islice)
+        set_time(t) / next_time()             optional: the physical time of a step arrives from the rank
+                                              that owns the step before it (MultiBuffer::get_time /
+                                              put_time, MultiBuffer.cpp:611-651; Hipace.cpp:411, :445-447)
 
     Order per slice (Hipace.cpp:582-585, 639-642, 716): slice nz-1 is received before the slice
     loop, slice islice-1 before slice islice is solved (it is the Next slice of the Bx/By
@@ -147,7 +150,16 @@ class HostPipeline:
         nz = engine.nz
         for step in owned_steps(self.rank, self.world, max_step):
             rx, tx = receives(step, self.world), sends(step, self.world, max_step)
+            if rx and hasattr(engine, 'set_time'):
+                import torch
+                t = torch.zeros(1, dtype=torch.float64)
+                self.dist.recv(t, src=self.up)
+                engine.set_time(float(t[0]))
             engine.begin_step(step)
+            if tx and hasattr(engine, 'next_time'):
+                import torch
+                t = torch.tensor([engine.next_time()], dtype=torch.float64)
+                self._pending.append((self.dist.isend(t, dst=self.down), t))
             if rx:
                 self._recv(engine, nz - 1)
             for isl in range(nz - 1, -1, -1):
@@ -156,6 +168,8 @@ class HostPipeline:
                 engine.solve_one_slice(isl)
                 if tx:
                     self._send(engine, isl)
+            if hasattr(engine, 'end_step'):
+                engine.end_step(step)
         for req, _ in self._pending:
             req.wait()
         self._pending = []

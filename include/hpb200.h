@@ -194,6 +194,7 @@ typedef struct {
     double nt_per_betatron, dt_max, threshold_uz, phase_tolerance;
     int phase_substeps, control_phase;
     double c, ep0;
+    int numprocs, predict_step;     /* ranks of the time-step pipeline; hipace.adaptive_predict_step */
 } hpb_adaptive_par;
 int hpb_beam_min_uz_slice(hpb_ctx *ctx, hpb_beam_slice bm, double *d_acc);
 int hpb_adaptive_dt_next(const hpb_adaptive_par *par, int nbeams, const double *ts, const double *charge,
@@ -469,6 +470,10 @@ typedef struct {
                                      * non-default deposition order, plasma in-situ diagnostics, n_subcycles < 1 */
 } hpb_sim_stats;
 int hpb_sim_get_stats(hpb_sim *sim, hpb_sim_stats *out);
+/* m_physical_time and m_dt of the step that ran last (src/Hipace.H; Hipace.cpp:411-434).  With a pipeline
+ * the time came from the upstream rank (MultiBuffer::get_time), with hipace.dt = adaptive dt is this
+ * rank's own value. */
+int hpb_sim_get_time(hpb_sim *sim, double *time, double *dt);
 /* multigrid V-cycles (or predictor-corrector iterations) of every slice of the last evolve, in
  * slice-loop order (head first): what hpmg::MultiGrid::solve1 reports per call
  * (src/mg_solver/HpMultiGrid.cpp:1307-1427).  Copies min(n, count) entries; returns the count. */

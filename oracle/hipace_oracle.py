@@ -1892,7 +1892,12 @@ def init_beam_slice(beam: Beam, islice: int, geom: Geometry, pc: PhysConst, norm
 # --------------------------------------------------------------------------------------------
 
 class Simulation:
-    def __init__(self, deck_text: str, overrides: dict | None = None):
+    def __init__(self, deck_text: str, overrides: dict | None = None, numprocs: int = 1):
+        """numprocs: the number of pipeline ranks whose adaptive-time-step bookkeeping is emulated (rank
+        r owns the steps r, r + numprocs, ...: each keeps its OWN dt and min_uz_mq, the physical time
+        travels with the beam, MultiBuffer::get_time / put_time, utils/MultiBuffer.cpp:611-651).  Everything
+        else of a run is independent of the number of ranks."""
+        self.numprocs = int(numprocs)
         d = self.deck = parse_deck(deck_text, overrides)
         self.normalized = bool(_get(d, 'hipace.normalized_units', 0, typ=int))
         self.pc = PhysConst.make(self.normalized)
@@ -1937,6 +1942,7 @@ class Simulation:
         self.adaptive_phase_tolerance = _get(d, 'hipace.adaptive_phase_tolerance', 4e-4)
         self.adaptive_phase_substeps = _get(d, 'hipace.adaptive_phase_substeps', 2000, typ=int)
         self.adaptive_control_phase = bool(_get(d, 'hipace.adaptive_control_phase_advance', 1, typ=int))
+        self.adaptive_predict_step = bool(_get(d, 'hipace.adaptive_predict_step', 1, typ=int))
         assert not (self.adaptive_dt and _get(d, 'hipace.adaptive_gather_ez', 0, typ=int)), \
             'oracle scope: hipace.adaptive_gather_ez = 0' 
         self.mg_tol_rel = _get(d, 'hipace.MG_tolerance_rel', 1e-4)
@@ -2128,8 +2134,15 @@ class Simulation:
         """Hipace::Evolve up to the slice loop, Hipace.cpp:401-475"""
         self.step = step
         if self.adaptive_dt:                                      # :411, :420, :434
-            if step == 0:
+            if step == 0 or not hasattr(self, '_rank_state'):
+                # Hipace.cpp:275-281: the head rank's initial dt and min_uz_mq are broadcast to every rank
+                # (a function of the deck only: a process that emulates one rank computes it itself)
+                self.dt = 0.0
                 self._adaptive_init()
+                self._rank_state = {r: (self.dt, self._min_uz_mq) for r in range(self.numprocs)}
+            # the rank that owns this step continues from ITS previous step's dt / min_uz_mq ...
+            self.dt, self._min_uz_mq = self._rank_state[step % self.numprocs]
+            # ... at the time its upstream neighbour computed (get_time :411, put_time :446)
             self.time = 0.0 if step == 0 else self._next_time
             self._adaptive_from_density()
             self._next_time = self.time + self.dt
@@ -2193,7 +2206,10 @@ class Simulation:
                 t['min_uz'] = min(t['min_uz'], float((uz * ci).min()))
 
     def _adaptive_from_min_uz(self, t_now):
-        """CalculateFromMinUz, :143-233 (one rank: no look-ahead over the pipeline)"""
+        """CalculateFromMinUz, :143-233.  The new dt is used numprocs steps later: with
+        hipace.adaptive_predict_step (default on) the betatron frequency is re-evaluated numprocs times
+        at the predicted times (:233-251)"""
+        niter = self.numprocs if self.adaptive_predict_step else 1
         new_dts, mq = [], []
         for b in self.beams:
             new_dt = self.dt
@@ -2208,13 +2224,16 @@ class Simulation:
             chosen = min(max(mean - 4.0 * sigma, t['min_uz']), 1e30)
             chosen = max(chosen, self.adaptive_threshold_uz)
             mq.append(abs(chosen * mcr))
-            rho = self._max_charge_density(self.pc.c * t_now)
-            assert rho > 0.0, 'A >0 plasma density must be specified to use an adaptive time step.'
-            min_uz = max(chosen, 0.001 * self.adaptive_threshold_uz)
-            omega_b = math.sqrt(rho / (2.0 * abs(min_uz * mcr) * self.pc.ep0))
-            cand = 2.0 * math.pi / omega_b / self.nt_per_betatron
-            if min_uz > self.adaptive_threshold_uz:
-                new_dt = cand
+            cand, new_time, min_uz = self.dt, t_now, chosen
+            for _ in range(niter):
+                rho = self._max_charge_density(self.pc.c * new_time)
+                assert rho > 0.0, 'A >0 plasma density must be specified to use an adaptive time step.'
+                min_uz = max(min_uz, 0.001 * self.adaptive_threshold_uz)
+                omega_b = math.sqrt(rho / (2.0 * abs(min_uz * mcr) * self.pc.ep0))
+                cand = 2.0 * math.pi / omega_b / self.nt_per_betatron
+                new_time += cand
+                if min_uz > self.adaptive_threshold_uz:
+                    new_dt = cand
             new_dts.append(new_dt)
         self._min_uz_mq = min(mq)
         self.dt = min(min(new_dts), self.dt_max)
@@ -2499,6 +2518,12 @@ class Simulation:
             if sl == 'This':
                 self.checksums[nm] = self.checksums.get(nm, 0.0) + float(np.abs(self._diag_rows(a, self.geom.g)).sum())
 
+    def end_step_adaptive(self, step):
+        """Hipace.cpp:482-483: after the last slice the owning rank derives its next dt from the beam"""
+        if self.adaptive_dt:
+            self._adaptive_from_min_uz(self.time)
+            self._rank_state[step % self.numprocs] = (self.dt, self._min_uz_mq)
+
     def evolve(self, nslices: int | None = None, step_begin: int = 0, step_end: int = 0):
         """Run time steps step_begin..step_end (Hipace.cpp:401-507); the checksums returned are
         those of the last one.  nslices limits the slice loop (from the head) for bounded
@@ -2511,8 +2536,8 @@ class Simulation:
             self.insitu, self.plasma_insitu, self.field_insitu, self.laser_insitu = {}, {}, None, None
             for isl in range(g.nz - 1, stop, -1):
                 self.solve_one_slice(isl)
-            if self.adaptive_dt and stop == -1:                                   # Hipace.cpp:482-483
-                self._adaptive_from_min_uz(self.time)
+            if stop == -1:
+                self.end_step_adaptive(step)
             for b in self.beams:                                                  # Hipace.cpp:488
                 if b.name in self.insitu:
                     ndf = g.dx * g.dy * g.dz if self.normalized else 1.0

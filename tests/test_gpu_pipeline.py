@@ -113,6 +113,86 @@ def test_two_gpu_laser_pipeline_matches_single_gpu(solver):
     sim.close()
 
 
+ADAPTIVE_STEPS = 7
+
+
+def _adaptive_case():
+    import json
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'adaptive_time_step.1Rank.json')))
+    return open(os.path.join(ROOT, meta['deck'])).read(), dict(meta['overrides'], max_step=ADAPTIVE_STEPS)
+
+
+def _adaptive_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('HPB_TEST_WATCHDOG', '240')), exit=True)
+    import torch
+    import torch.distributed as dist
+    import hipace_b200 as hp
+    from hipace_b200 import pipeline as pl
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    deck, ov = _adaptive_case()
+    sim = hp.Simulation(deck, ov, device=rank)
+    sim.pipeline_init(rank, world, dist)
+    sim.set_option('max_step', ADAPTIVE_STEPS)
+    times = {}
+    for step in pl.owned_steps(rank, world, ADAPTIVE_STEPS):
+        sim.evolve(step, step)
+        times[step] = sim.time()
+    pickle.dump({'cs': sim.checksums(), 'bcs': sim.beam_checksums(), 'times': times},
+                open(os.path.join(out_dir, f'rank{rank}.pkl'), 'wb'))
+    torch.cuda.synchronize()
+    dist.barrier()
+    sim.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_adaptive_time_step_matches_oracle_emulation():
+    """hipace.dt = adaptive over 2 NCCL ranks (the time travels with hpb_pipeline_put_time / get_time =
+    MultiBuffer::put_time / get_time, every rank keeps its own dt and min_uz_mq): the sequence of
+    (time, dt) of all 8 steps and the last step's field / beam checksums equal the oracle's emulation of
+    a 2-rank run (Simulation(numprocs = 2), itself reproduced bit for bit by 2 gloo ranks in
+    tests/test_pipeline_gloo.py); the sequence differs from the 1-rank one."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    from oracle.hipace_oracle import Simulation as Oracle
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_adaptive_worker, args=(world, _free_port(), d), nprocs=world, join=True)
+        res = [pickle.load(open(os.path.join(d, f'rank{r}.pkl'), 'rb')) for r in range(world)]
+    deck, ov = _adaptive_case()
+    seq = {}
+    for R in (1, world):
+        ref = Oracle(deck, ov, numprocs=R)
+        seq[R] = []
+        begin = ref.begin_step
+
+        def spy(step, _ref=ref, _b=begin, _s=seq[R]):
+            _b(step)
+            _s.append((_ref.time, _ref.dt))
+        ref.begin_step = spy
+        want = ref.evolve(step_end=ADAPTIVE_STEPS)
+    got = {}
+    for r in res:
+        got.update(r['times'])
+    for step in range(ADAPTIVE_STEPS + 1):
+        for a, b in zip(got[step], seq[world][step]):
+            assert abs(a - b) <= 1e-12 * abs(b), (step, got[step], seq[world][step])
+    assert max(abs(a[1] - b[1]) / b[1] for a, b in zip(seq[1], seq[world])) > 1e-4
+    last = res[ADAPTIVE_STEPS % world]
+    big = max(abs(v) for v in want.values())
+    for k, v in want.items():
+        assert abs(last['cs'][k] - v) <= 1e-9 * abs(v) + 1e-12 * big, k
+    for k, v in ref.beam_checksums()['beam'].items():
+        if k in last['bcs']:
+            assert abs(last['bcs'][k] - v) <= 1e-9 * abs(v) + 1e-30, k
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     # a hung rank must never hold the GPU box: dump where it is stuck and exit

@@ -153,18 +153,22 @@ def test_cuda_insitu_files_match_oracle(repo_root, tmp_path):
 
 class _AdaptivePar(C.Structure):
     _fields_ = [(k, C.c_double) for k in ('nt_per_betatron', 'dt_max', 'threshold_uz', 'phase_tolerance')] + \
-               [('phase_substeps', C.c_int), ('control_phase', C.c_int), ('c', C.c_double), ('ep0', C.c_double)]
+               [('phase_substeps', C.c_int), ('control_phase', C.c_int), ('c', C.c_double), ('ep0', C.c_double),
+                ('numprocs', C.c_int), ('predict_step', C.c_int)]
 
 
-def test_adaptive_time_step_host_logic_follows_the_oracle(repo_root):
+@pytest.mark.parametrize('numprocs', [1, 2, 3])
+def test_adaptive_time_step_host_logic_follows_the_oracle(numprocs, repo_root):
     """hpb_adaptive_dt_next (the C++ host arithmetic of hipace.dt = adaptive, csrc/adaptive_dt.hpp)
     fed with the per-step beam data of the oracle run that reproduces the reference's
-    adaptive_time_step golden: the same sequence of time steps, bit for bit"""
+    adaptive_time_step golden: the same sequence of time steps, bit for bit.  numprocs > 1: the
+    bookkeeping of a pipeline of that many ranks (every rank's dt comes from ITS previous step and is
+    used numprocs steps later, AdaptiveTimeStep.cpp:225-251)"""
     import hipace_b200 as hp
     import json
     meta = json.load(open(os.path.join(repo_root, 'tests', 'golden', 'adaptive_time_step.1Rank.json')))
     ov = dict(meta['overrides'], max_step=6)
-    sim = O.Simulation(open(os.path.join(repo_root, meta['deck'])).read(), ov)
+    sim = O.Simulation(open(os.path.join(repo_root, meta['deck'])).read(), ov, numprocs=numprocs)
     log = []
     orig = sim._adaptive_from_min_uz
 
@@ -180,7 +184,7 @@ def test_adaptive_time_step_host_logic_follows_the_oracle(repo_root):
     L = hp.lib()
     L.hpb_adaptive_dt_next.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_double] * 3 + [C.c_void_p] * 2
     par = _AdaptivePar(sim.nt_per_betatron, sim.dt_max, sim.adaptive_threshold_uz, sim.adaptive_phase_tolerance,
-                       sim.adaptive_phase_substeps, 1, sim.pc.c, sim.pc.ep0)
+                       sim.adaptive_phase_substeps, 1, sim.pc.c, sim.pc.ep0, numprocs, 1)
     assert len(log) == 8 and len(dts) == 7            # the initial call + one per step
     for k, (ts, dt_in, dt_after_min_uz, mq_want) in enumerate(log):
         t = ts['beam']
@@ -193,9 +197,12 @@ def test_adaptive_time_step_host_logic_follows_the_oracle(repo_root):
         assert mq.value == mq_want
         # uniform density: the phase-advance control leaves dt as CalculateFromMinUz set it
         assert dt_out.value == dt_after_min_uz
-        if k < len(dts):
-            assert dts[k] == dt_after_min_uz             # ... and that is the dt the next step ran with
-    assert len(set(dts)) == len(dts)                     # the step really adapts
+        # ... and that is the dt the owning rank's next step (numprocs steps later) ran with
+        if k + numprocs - 1 < len(dts):
+            assert dts[k + numprocs - 1] == dt_after_min_uz
+    for k in range(min(numprocs, len(dts))):             # every rank starts from the broadcast initial estimate
+        assert dts[k] == log[0][2]
+    assert len(set(dts)) == len(dts) - (numprocs - 1)    # the step really adapts (after the ranks' common start)
 
 
 def test_plasma_writer_and_terms(tmp_path, repo_root):

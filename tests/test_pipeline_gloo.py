@@ -21,10 +21,20 @@ KEYS = ('x', 'y', 'z', 'w', 'ux', 'uy', 'uz', 'id')
 
 
 class OracleEngine:
-    def __init__(self, deck, ov):
+    def __init__(self, deck, ov, numprocs=1):
         from oracle.hipace_oracle import Simulation
-        self.sim = Simulation(deck, ov)
+        self.sim = Simulation(deck, ov, numprocs=numprocs)
         self.nz = self.sim.geom.nz
+
+    def end_step(self, step):
+        self.sim.end_step_adaptive(step)
+
+    def set_time(self, t):                      # MultiBuffer::get_time
+        self.sim._next_time = t
+
+    def next_time(self):                        # MultiBuffer::put_time
+        s = self.sim
+        return s._next_time if s.adaptive_dt else s.time + s.dt
 
     def begin_step(self, step):
         self.sim.checksums = {}
@@ -48,6 +58,75 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
+
+
+def _worker_adaptive(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import json
+    import torch.distributed as dist
+    from hipace_b200 import pipeline as pl
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'adaptive_time_step.1Rank.json')))
+    ov = dict(meta['overrides'], max_step=ADAPTIVE_STEPS)
+    eng = OracleEngine(open(os.path.join(ROOT, meta['deck'])).read(), ov, numprocs=world)
+    times = {}
+    begin = eng.begin_step
+
+    def spy(step):
+        begin(step)
+        times[step] = (eng.sim.time, eng.sim.dt)
+    eng.begin_step = spy
+    pl.HostPipeline(dist, rank, world, 1, 8192).run(eng, ADAPTIVE_STEPS)
+    res = {'times': times, 'checksums': eng.sim.checksums,
+           'beam': {i: {k: bs[k][:bs['np']] for k in KEYS} for i, bs in eng.sim.beams[0].slices.items()}}
+    pickle.dump(res, open(os.path.join(out_dir, f'rank{rank}.pkl'), 'wb'))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+ADAPTIVE_STEPS = 7
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_adaptive_time_step_through_the_pipeline(world):
+    """hipace.dt = adaptive over `world` ranks: every rank keeps its own dt / min_uz_mq (computed from
+    the beam of ITS previous step, used `world` steps later), the physical time travels with put_time /
+    get_time.  `world` gloo ranks must reproduce the serial emulation Simulation(numprocs = world) bit
+    for bit -- and that run must differ from the one-rank sequence of time steps (the reference's
+    adaptive_time_step.1Rank golden run), otherwise the test would not see the per-rank state."""
+    import json
+    import torch.multiprocessing as mp
+    from oracle.hipace_oracle import Simulation
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker_adaptive, args=(world, _free_port(), d), nprocs=world, join=True)
+        res = [pickle.load(open(os.path.join(d, f'rank{r}.pkl'), 'rb')) for r in range(world)]
+    meta = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'adaptive_time_step.1Rank.json')))
+    ov = dict(meta['overrides'], max_step=ADAPTIVE_STEPS)
+    text = open(os.path.join(ROOT, meta['deck'])).read()
+    seq = {}
+    for R in (1, world):
+        ref = Simulation(text, ov, numprocs=R)
+        seq[R] = []
+        begin = ref.begin_step
+
+        def spy(step, _ref=ref, _b=begin, _s=seq[R]):
+            _b(step)
+            _s.append((_ref.time, _ref.dt))
+        ref.begin_step = spy
+        ref.evolve(step_end=ADAPTIVE_STEPS)
+    got = {}
+    for r in res:
+        got.update(r['times'])
+    assert [got[s] for s in range(ADAPTIVE_STEPS + 1)] == seq[world]
+    assert seq[world] != seq[1]
+    last = res[ADAPTIVE_STEPS % world]
+    for k, v in ref.checksums.items():
+        assert last['checksums'][k] == v, k
+    for isl, bs in ref.beams[0].slices.items():
+        for k in KEYS:
+            assert np.array_equal(last['beam'][isl][k], bs[k][:bs['np']]), (isl, k)
 
 
 def _worker(rank, world, port, out_dir):
