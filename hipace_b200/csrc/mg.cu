@@ -1302,8 +1302,10 @@ void hpb_mg_free(hpb_ctx *ctx)
 // d_mg_norm[0] holds max|rescor0|.  tmp is the second level-0 buffer.
 // fused = true: the two level-0 smoothers are ONE launch (8 half-sweeps, 64 x 64 tiles) that
 // reads cur and writes the new cor0 into tmp: the caller ping-pongs the two buffers.
+// top_out: where the unfused path's last level-0 smoother writes the new cor0 (cur itself, or -- buffer
+// rotation, option "mg_rotate" -- the caller's sol planes, so that no final copy is needed)
 static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, long chi_rs,
-                     double tol_rel, double tol_abs, bool fused)
+                     double tol_rel, double tol_abs, bool fused, V2 top_out)
 {
     const int lc = ctx->mg_lc;
     const V2 none{};
@@ -1343,11 +1345,47 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
         launch_smooth<2, false>(ctx, g0, cur, lvl_view(ctx, 1, up_prev), rhs0, chi, chi_rs,
                                 ctx->mg[0].c0i, nullptr, tmp, gnone, none, nullptr, done);
         // cor0 = GSRB^4(sol), rescor0 = rhs - L cor0 -> res[1], norm   (:1501-1503)
-        launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, ctx->mg[0].c0i, nullptr, cur, g1,
+        launch_smooth<1, true>(ctx, g0, tmp, none, rhs0, chi, chi_rs, ctx->mg[0].c0i, nullptr, top_out, g1,
                                lvl_view(ctx, 1, ctx->mg[1].res), ctx->d_mg_norm, done);
     }
     hpb_launch(k_mg_check, 1, 1, 0, ctx->stream, 1, ctx->d_mg_norm, ctx->d_mg_state, ctx->d_mg_istate, tol_rel, tol_abs);
     hpb_count_launch(ctx);
+    return HPB_OK;
+}
+
+// average_down_acoef (:1640-1700): the coefficient on every coarser level (+ 1 / c0 of the level);
+// level 0 uses chi in place (solve1 :1177-1187)
+static void mg_average_down_acf(hpb_ctx *ctx, const double *chi, long chi_rs)
+{
+    const int lc = ctx->mg_lc;
+    const double *fine = chi;
+    long fine_rs = chi_rs;
+    for (int l = 1; l < lc; ++l) {
+        const LevelGeom gc = level_geom(ctx, l);
+        const long nv = (long)(gc.vhix - gc.vlo + 1) * (gc.vhiy - gc.vlo + 1);
+        hpb_launch(k_restrict_acf, nb(nv), 256, 0, ctx->stream, gc, ctx->mg[l].acf, ctx->mg[l].c0i, fine, fine_rs);
+        hpb_count_launch(ctx);
+        fine = ctx->mg[l].acf;
+        fine_rs = gc.nx;
+    }
+    hpb_launch(k_coarse_setup, 1, kCoarseThreads, 0, ctx->stream, coarse_args(ctx), level_geom(ctx, lc - 1),
+                                                          fine, fine_rs);
+    hpb_count_launch(ctx);
+}
+
+// The coefficient hierarchy depends on chi only, which is final long before the Bx / By sources are: a
+// driver may run this chain of five small launches on another stream beside the Poisson solve and the
+// explicit deposition (the caller orders the streams); the next hpb_mg_solve1 with the same coefficient
+// plane then starts at its first smoother.  The reference computes it inside solve1 (:1177-1187).
+extern "C" int hpb_mg_prepare_acf(hpb_ctx *ctx, hpb_slice sl, int c_acf)
+{
+    if (!ctx || c_acf < 0 || c_acf >= sl.ncomp) return HPB_ERR_ARG;
+    SliceView v = make_view(sl);
+    const int sh = ctx->mg_cc ? 0 : -1;
+    const double *chi = v.comp(c_acf) + v.idx(sh, sh);
+    mg_average_down_acf(ctx, chi, v.jstride);
+    ctx->mg_acf_ready = chi;
+    HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
 }
 
@@ -1369,20 +1407,9 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     const V2 none{};
     (void)nl;
 
-    // average_down_acoef (:1640-1700); level 0 uses chi in place (solve1 :1177-1187)
-    const double *fine = chi;
-    long fine_rs = chi_rs;
-    for (int l = 1; l < lc; ++l) {
-        const LevelGeom gc = level_geom(ctx, l);
-        const long nv = (long)(gc.vhix - gc.vlo + 1) * (gc.vhiy - gc.vlo + 1);
-        hpb_launch(k_restrict_acf, nb(nv), 256, 0, ctx->stream, gc, ctx->mg[l].acf, ctx->mg[l].c0i, fine, fine_rs);
-        hpb_count_launch(ctx);
-        fine = ctx->mg[l].acf;
-        fine_rs = gc.nx;
-    }
-    hpb_launch(k_coarse_setup, 1, kCoarseThreads, 0, ctx->stream, coarse_args(ctx), level_geom(ctx, lc - 1),
-                                                          fine, fine_rs);
-    hpb_count_launch(ctx);
+    // average_down_acoef (:1640-1700) unless hpb_mg_prepare_acf did it already for this coefficient
+    if (ctx->mg_acf_ready != chi) mg_average_down_acf(ctx, chi, chi_rs);
+    ctx->mg_acf_ready = nullptr;
 
     // cor0 = GSRB^4(sol), rescor0 = rhs - L(cor0)   (:1326-1327), fused with its restriction
     V2 cur = lvl_view(ctx, 0, ctx->mg[0].cor);
@@ -1398,10 +1425,18 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     // the cycles that actually run are a prefix of the enqueued ones, so after `iters` executed
     // cycles the iterate lives in buf[iters % 2].  Unfused: sol is only the scratch iterate.
     const V2 buf[2] = {cur, sol};
+    // unfused + "mg_rotate": cycle 1 reads cor0 from its level buffer, every later cycle from the caller's sol
+    // planes, into which each cycle's last smoother writes; the up-stroke's output goes through the spare
+    // level-0 buffer.  The executed cycles are a prefix of the enqueued ones, so after >= 1 executed cycle
+    // the result already is in sol and the final copy disappears (it remains for 0 cycles).
+    const bool rotate = !fused && ctx->tune_mg_rotate != 0;
+    const V2 spare = lvl_view(ctx, 0, ctx->mg[0].rescor);
     int enq = 0;
     auto enqueue_cycle = [&]() -> int {
-        int rc = fused ? mg_vcycle(ctx, buf[enq & 1], buf[(enq + 1) & 1], rhs, chi, chi_rs, tol_rel, tol_abs, true)
-                       : mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs, tol_rel, tol_abs, false);
+        int rc;
+        if (fused) rc = mg_vcycle(ctx, buf[enq & 1], buf[(enq + 1) & 1], rhs, chi, chi_rs, tol_rel, tol_abs, true, none);
+        else if (rotate) rc = mg_vcycle(ctx, enq == 0 ? cur : sol, spare, rhs, chi, chi_rs, tol_rel, tol_abs, false, sol);
+        else rc = mg_vcycle(ctx, cur, sol, rhs, chi, chi_rs, tol_rel, tol_abs, false, cur);
         ++enq;
         return rc;
     };
@@ -1433,7 +1468,7 @@ extern "C" int hpb_mg_solve1(hpb_ctx *ctx, hpb_slice sl, int c_sol, int c_rhs, i
     }
     ctx->mg_last_iters = iters;
     // sol <- cor0 on the valid box (:1419-1426) unless the last executed cycle wrote it there
-    if (!fused || (iters & 1) == 0) {
+    if (rotate ? iters == 0 : (!fused || (iters & 1) == 0)) {
         hpb_launch(k_copy2, nb(nv0), 256, 0, ctx->stream, g0, sol, cur);
         hpb_count_launch(ctx);
     }

@@ -1245,6 +1245,19 @@ int solve_one_slice(hpb_sim *s, int islice)
                                               s->prob_lo[2] + islice * s->g.dz))) return rc;
     }
     s->prepared = false;
+    // chi of this slice is final (the deposits are done; with periodic fields it is summed later, a laser's
+    // multigrid reuses the level arrays): its coarse-level averages can be formed beside the next stages
+    const bool early_acf = s->opt_mg_early && s->stream3 && !s->field_periodic && !s->use_laser && !s->opt_profile;
+    if (early_acf) {
+        SIM_CUDA(cudaEventRecord(s->ev_chi, s->stream));
+        SIM_CUDA(cudaStreamWaitEvent(s->stream3, s->ev_chi, 0));
+        {
+            StreamScope sc(s, s->stream3);
+            rc = hpb_mg_prepare_acf(ctx, s->sl, C[HPB_C_CHI]);
+        }
+        if (rc) return rc;
+        SIM_CUDA(cudaEventRecord(s->ev_acf, s->stream3));
+    }
     {
         StageTimer t(s, ST_POISSON);
         if (!s->field_periodic && !s->poisson_periodic) {
@@ -1286,6 +1299,7 @@ int solve_one_slice(hpb_sim *s, int islice)
         int iters = 0;                                                                  // :666
         const int srcs[3] = {C[HPB_C_SY], C[HPB_C_SX], C[HPB_C_CHI]};                   // Hipace.cpp:817-821
         if (s->field_periodic && (rc = hpb_fields_enforce_periodic(ctx, s->sl, 1, srcs, 3))) return rc;
+        if (early_acf) SIM_CUDA(cudaStreamWaitEvent(s->stream, s->ev_acf, 0));
         if ((rc = hpb_mg_solve1(ctx, s->sl, C[HPB_C_BX], C[HPB_C_SY], C[HPB_C_CHI], s->mg_tol_rel,
                                 s->mg_tol_abs, 200, &iters))) return rc;
         const int bxy[2] = {C[HPB_C_BX], C[HPB_C_BY]};                                  // Hipace.cpp:924-927
@@ -1535,10 +1549,13 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
         int least = 0, greatest = 0;
         SIM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         SIM_CUDA(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, greatest));
+        SIM_CUDA(cudaStreamCreateWithPriority(&s->stream3, cudaStreamNonBlocking, greatest));
     }
     SIM_CUDA(cudaEventCreateWithFlags(&s->ev_fields, cudaEventDisableTiming));
     SIM_CUDA(cudaEventCreateWithFlags(&s->ev_shift, cudaEventDisableTiming));
     SIM_CUDA(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
+    SIM_CUDA(cudaEventCreateWithFlags(&s->ev_chi, cudaEventDisableTiming));
+    SIM_CUDA(cudaEventCreateWithFlags(&s->ev_acf, cudaEventDisableTiming));
     s->pev.resize(4);
     for (auto &e : s->pev) SIM_CUDA(cudaEventCreate(&e));
     *out = s.release();
@@ -1576,6 +1593,9 @@ extern "C" void hpb_sim_destroy(hpb_sim *s)
     if (s->ev_fields) cudaEventDestroy(s->ev_fields);
     if (s->ev_shift) cudaEventDestroy(s->ev_shift);
     if (s->ev_side) cudaEventDestroy(s->ev_side);
+    if (s->ev_chi) cudaEventDestroy(s->ev_chi);
+    if (s->ev_acf) cudaEventDestroy(s->ev_acf);
+    if (s->stream3) { cudaStreamSynchronize(s->stream3); cudaStreamDestroy(s->stream3); }
     for (auto &e : s->pev) cudaEventDestroy(e);
     cudaStreamDestroy(s->stream);
     delete s;
@@ -1898,6 +1918,7 @@ extern "C" int hpb_sim_set_option(hpb_sim *s, const char *key, double value)
     else if (k == "generic_order_kernels") s->ctx->force_generic = value != 0.;
     else if (k == "side_stream") s->opt_side_stream = value != 0.;
     else if (k == "side_late") s->opt_side_late = value != 0.;
+    else if (k == "mg_early") s->opt_mg_early = value != 0.;
     else if (k == "beam_from_host") { for (auto &b : s->beams) b.from_host = value != 0.; }   // 0: step 0 re-creates the deck's beam
     else if (k == "profile") s->opt_profile = value != 0.;
     else if (k == "max_step") s->max_step = (int)value;

@@ -168,6 +168,12 @@ struct hpb_sim {
     // deposits and the Sx, Sy seed of the next one) runs on a second stream beside the plasma push
     bool opt_side_stream = true;
     bool opt_side_late = true;       // enqueue the side stream's beam work behind the plasma push (host order)
+    // the multigrid's coefficient hierarchy (hpb_mg_prepare_acf: five small dependent launches) depends on chi
+    // only: option "mg_early" runs it on a third stream beside the Poisson solve and the explicit deposition
+    // (bit-identical results; measured: no gain over the in-stream PDL chain, 880 vs 880 slices/s, so off)
+    bool opt_mg_early = false;
+    cudaStream_t stream3 = nullptr;
+    cudaEvent_t ev_chi = nullptr, ev_acf = nullptr;
     cudaStream_t stream2 = nullptr;
     cudaStream_t beam_stream = nullptr;     // where the pipeline's per-slice waits / records go
     cudaEvent_t ev_fields = nullptr, ev_shift = nullptr, ev_side = nullptr;

@@ -310,6 +310,12 @@ int hpb_fields_enforce_periodic(hpb_ctx *ctx, hpb_slice sl, int do_sum, const in
  * Poisson solves + ExmBy/EypBx stencil, fused. */
 int hpb_fields_solve_psi_ez_bz(hpb_ctx *ctx, hpb_slice sl, const int *comps);
 
+/* hpmg average_down_acoef (src/mg_solver/HpMultiGrid.cpp:1640-1700), which the reference runs inside
+ * solve1 (:1177-1187), as a call of its own: the coefficient hierarchy depends on the coefficient plane
+ * only, so a driver may enqueue it early (ctx stream at the time of the call; the caller orders it against
+ * hpb_mg_solve1).  The next hpb_mg_solve1 with the same c_acf skips its own pass. */
+int hpb_mg_prepare_acf(hpb_ctx *ctx, hpb_slice sl, int c_acf);
+
 /* Hipace::InitializeSxSyWithBeam (src/Hipace.cpp:744-790) */
 int hpb_fields_sxsy_from_beam(hpb_ctx *ctx, hpb_slice sl, const int *comps);
 
