@@ -234,6 +234,7 @@ struct hpb_ctx {
     double2 *d_chirp, *d_bhat;
     int nrad; int radices[32];
     double *d_cs_cos[32], *d_cs_sin[32];         // per odd-prime stage: DFT-p cos / sin tables
+    double *d_cs_frag[32];                       // ... and the same in mma.m8n8k4 fragment order (fft_smem.cuh)
     double2 *d_root;          // exp(-2 pi i t / N), t = 0..N-1
     double *d_sinf;           // 1 / (2 sin(pi (i+1) / N)), i = 0..nx-1
     int th_L, th_C, th_last_base;                // partitioned Thomas: chunk length, chunks

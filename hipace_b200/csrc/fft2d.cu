@@ -14,7 +14,7 @@ namespace {
 struct Plan1D {
     FftPlan plan;
     double2 *d_root = nullptr, *d_chirp = nullptr, *d_bhat = nullptr;
-    double *d_cos[kMaxRad] = {}, *d_sin[kMaxRad] = {};
+    double *d_cos[kMaxRad] = {}, *d_sin[kMaxRad] = {}, *d_frag[kMaxRad] = {};
 };
 
 template <class T>
@@ -32,7 +32,7 @@ bool build_plan(int N, Plan1D &p)
     const int L = p.plan.M > 0 ? p.plan.M : N;
     const long double pi = 3.14159265358979323846264338327950288L;
     for (int i = 0; i < p.plan.nrad; ++i) {
-        p.plan.cs_cos[i] = p.plan.cs_sin[i] = nullptr;
+        p.plan.cs_cos[i] = p.plan.cs_sin[i] = p.plan.cs_frag[i] = nullptr;
         const int q = p.plan.rad[i];
         if (q <= 5) continue;
         const int h = (q - 1) / 2;
@@ -43,8 +43,9 @@ bool build_plan(int N, Plan1D &p)
                 tc[(size_t)b * h + t - 1] = (double)cosl(2.0L * pi * tb / q);
                 ts[(size_t)b * h + t - 1] = (double)sinl(2.0L * pi * tb / q);
             }
-        if (!to_device(&p.d_cos[i], tc) || !to_device(&p.d_sin[i], ts)) return false;
-        p.plan.cs_cos[i] = p.d_cos[i]; p.plan.cs_sin[i] = p.d_sin[i];
+        if (!to_device(&p.d_cos[i], tc) || !to_device(&p.d_sin[i], ts)
+            || !to_device(&p.d_frag[i], fft_prime_frag_table(q))) return false;
+        p.plan.cs_cos[i] = p.d_cos[i]; p.plan.cs_sin[i] = p.d_sin[i]; p.plan.cs_frag[i] = p.d_frag[i];
     }
     std::vector<double2> root(L);
     for (int t = 0; t < L; ++t) {
@@ -62,7 +63,7 @@ bool build_plan(int N, Plan1D &p)
 void free_plan(Plan1D &p)
 {
     cudaFree(p.d_root); cudaFree(p.d_chirp); cudaFree(p.d_bhat);
-    for (int i = 0; i < kMaxRad; ++i) { cudaFree(p.d_cos[i]); cudaFree(p.d_sin[i]); }
+    for (int i = 0; i < kMaxRad; ++i) { cudaFree(p.d_cos[i]); cudaFree(p.d_sin[i]); cudaFree(p.d_frag[i]); }
 }
 
 // One sequence of N complex numbers per CTA: element e of sequence s is at in[s * seq_stride + e *

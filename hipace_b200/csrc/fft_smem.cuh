@@ -16,6 +16,9 @@ struct FftPlan {
     int N; int nrad; int rad[kMaxRad];
     const double *cs_cos[kMaxRad];     // per prime stage: cos(2 pi t b / p), [b = 0..h][t = 1..h]
     const double *cs_sin[kMaxRad];
+    // per prime stage: the same coefficients in the operand-fragment order of mma.m8n8k4.f64
+    // (fft_prime_frag_table); nullptr = the scalar inner product
+    const double *cs_frag[kMaxRad];
     // Bluestein (chirp-z) for lengths with a large prime factor (257, 2049 = 3 * 683, ...): M = the
     // power of two >= 2N - 2 (enough because the chirp is even), rad[] then factor M, `root` passed to
     // fft_smem is exp(-2 pi i t / M); chirp[n] = exp(-i pi n^2 / N), bhat = FFT_M(conj chirp, wrapped) / M
@@ -153,15 +156,24 @@ __device__ __forceinline__ void fft_stage_r5(const double2 *__restrict__ in, dou
 // staged there once per stage and indexed with m = (t b) mod p kept incrementally: the inner loop's two
 // table loads per step used to be global (L1) loads -- 40 % of the row kernel's stall samples were
 // long-scoreboard waits on them (profiles: r01e source page) -- and are shared-memory broadcasts now.
+// D (8 x 8) += A (8 x 4, row) B (4 x 8, col) on the fp64 tensor-core path: lane l holds A[l / 4][l % 4],
+// B[l % 4][l / 4] and D[l / 4][2 (l % 4) + {0, 1}]
+__device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double2 *__restrict__ tmp,
                                                 const double2 *__restrict__ root, int N, int Ns, int p,
                                                 const double *__restrict__ tcos,
-                                                const double *__restrict__ tsin, double *__restrict__ s_tab)
+                                                const double *__restrict__ tsin, double *__restrict__ s_tab,
+                                                const double *__restrict__ frag)
 {
     const int Nr = N / p, h = (p - 1) / 2, tw = N / (Ns * p);
     const FastDiv fNr(Nr), fNs(Ns);
     double *s_c = s_tab, *s_s = s_tab + p;
-    for (int m = threadIdx.x; m < p; m += blockDim.x) {
+    for (int m = threadIdx.x; m < (frag ? 0 : p); m += blockDim.x) {
         // row b = 1 of the (b, t) tables holds cos / sin(2 pi t / p), t = 1 .. h
         const int mm = m <= h ? m : p - m;
         s_c[m] = m == 0 ? 1.0 : __ldg(&tcos[h + mm - 1]);
@@ -182,6 +194,43 @@ __device__ __forceinline__ void fft_stage_prime(double2 *__restrict__ in, double
     }
     for (int j = threadIdx.x; j < Nr; j += blockDim.x) tmp[2 * h * Nr + j] = in[j];
     __syncthreads();
+    if (frag) {
+        // Sub-step B as two small dense products on the tensor cores: P = C U and Q = S V with
+        // C / S[b][t] = cos / sin(2 pi t b / p) ((h+1) x h, padded to 8 x 4 tiles with zeros) and U, V the
+        // h x 2 Nr real matrices tmp already holds (row t, columns = Re / Im of the Nr sequences: the double2
+        // layout IS the row-major real matrix with leading dimension 2 Nr).  The scalar form of this step
+        // issued 2 LDS.128 + 2 conflicting LDS.64 per 4 DFMA and made the row kernels shared-memory-pipe
+        // bound (l1tex 83 % of peak, profiles/r01e); a warp-level mma reads each operand element once per
+        // 8 x 8 tile.  One output tile (8 values of b x 4 sequences) per warp and iteration.
+        const int KT = (h + 3) >> 2, MT = (h + 8) >> 3, NTl = (2 * Nr + 7) >> 3;
+        const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+        const int ld = 2 * Nr;
+        const double *T = reinterpret_cast<const double *>(tmp);
+        for (int tile = threadIdx.x >> 5; tile < MT * NTl; tile += (int)(blockDim.x >> 5)) {
+            const int nt = tile / MT, mt = tile - nt * MT;
+            const int n = nt * 8 + gid;                          // column of the B operand held by this lane
+            double p0 = 0., p1 = 0., q0 = 0., q1 = 0.;
+            const double *fr = frag + (size_t)mt * KT * 64 + lane;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int t = kt * 4 + tig;
+                const bool okb = t < h && n < ld;                // (padding must be a true 0, not 0 x garbage)
+                const double bu = okb ? T[t * ld + n] : 0.;
+                const double bv = okb ? T[(h + t) * ld + n] : 0.;
+                dmma_884(p0, p1, __ldg(fr + kt * 64), bu);
+                dmma_884(q0, q1, __ldg(fr + kt * 64 + 32), bv);
+            }
+            const int b = mt * 8 + gid, j = nt * 4 + tig;        // D fragment: (Re, Im) of sequence j, output b
+            if (b <= h && j < Nr) {
+                const double2 x0 = tmp[2 * h * Nr + j];
+                const double Px = x0.x + p0, Py = x0.y + p1;
+                const int k = fNs.mod(j);
+                const int o = (j - k) * p + k;
+                in[o + b * Ns] = make_double2(Px + q1, Py - q0);                    // P - iQ
+                if (b) in[o + (p - b) * Ns] = make_double2(Px - q1, Py + q0);       // P + iQ
+            }
+        }
+        return;
+    }
     // BB outputs b per work item share the shared-memory reads of U_t, V_t (BB > 1 measured slower:
     // the extra accumulators spill at 6 CTAs / SM)
     constexpr int BB = 1;
@@ -234,7 +283,7 @@ __device__ __forceinline__ double2 *fft_stages(double2 *src, double2 *dst, const
         else if (r == 2) fft_stage_r2(src, dst, root, L, Ns);
         else if (r == 5) fft_stage_r5(src, dst, root, L, Ns);
         else if (r == 3) fft_stage_r3(src, dst, root, L, Ns);
-        else { fft_stage_prime(src, dst, root, L, Ns, r, plan.cs_cos[s], plan.cs_sin[s], s_tab); swap = false; }
+        else { fft_stage_prime(src, dst, root, L, Ns, r, plan.cs_cos[s], plan.cs_sin[s], s_tab, plan.cs_frag[s]); swap = false; }
         __syncthreads();
         if (swap) { double2 *t = src; src = dst; dst = t; }
         Ns *= r;
@@ -293,6 +342,26 @@ inline int fft_factorize(int N, int *rad, int &nrad)
     while (M < 2 * N - 2) M <<= 1;
     factor(M);
     return M;
+}
+
+// Coefficients of the prime stage p = 2h + 1 in mma.m8n8k4 A-fragment order:
+//   tab[((mt KT + kt) 2 + cs) 32 + lane] = cos (cs = 0) / sin (cs = 1) of 2 pi t b / p,  b = 8 mt + lane / 4,
+//   t = 4 kt + lane % 4 + 1;  0 where b > h or t > h
+inline std::vector<double> fft_prime_frag_table(int p)
+{
+    const int h = (p - 1) / 2, KT = (h + 3) / 4, MT = (h + 8) / 8;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    std::vector<double> tab((size_t)MT * KT * 64, 0.0);
+    for (int mt = 0; mt < MT; ++mt)
+        for (int kt = 0; kt < KT; ++kt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int b = 8 * mt + lane / 4, t = 4 * kt + lane % 4 + 1;
+                if (b > h || t > h) continue;
+                const long tb = ((long)t * b) % p;
+                tab[((size_t)(mt * KT + kt) * 2 + 0) * 32 + lane] = (double)cosl(2.0L * pi * tb / p);
+                tab[((size_t)(mt * KT + kt) * 2 + 1) * 32 + lane] = (double)sinl(2.0L * pi * tb / p);
+            }
+    return tab;
 }
 
 // chirp[n] = exp(-i pi n^2 / N) (n < N) and bhat = FFT_M(b) / M with b[m] = exp(+i pi m^2 / N) wrapped

@@ -268,6 +268,8 @@ FftPlan make_plan(const hpb_ctx *ctx)
         plan.rad[i] = ctx->radices[i];
         plan.cs_cos[i] = ctx->d_cs_cos[i];
         plan.cs_sin[i] = ctx->d_cs_sin[i];
+        // fft_variant 2: the scalar prime stage (the A/B partner of the tensor-core one)
+        plan.cs_frag[i] = ctx->tune_fft_variant == 2 ? nullptr : ctx->d_cs_frag[i];
     }
     return plan;
 }
@@ -324,7 +326,7 @@ int hpb_poisson_init(hpb_ctx *ctx)
     const long double pi = 3.14159265358979323846264338327950288L;
     for (int i = 0; i < plan.nrad; ++i) {
         ctx->radices[i] = plan.rad[i];
-        ctx->d_cs_cos[i] = ctx->d_cs_sin[i] = nullptr;
+        ctx->d_cs_cos[i] = ctx->d_cs_sin[i] = ctx->d_cs_frag[i] = nullptr;
         const int p = plan.rad[i];
         if (p > 5) {
             const int h = (p - 1) / 2;
@@ -337,6 +339,7 @@ int hpb_poisson_init(hpb_ctx *ctx)
                 }
             int rc = upload(&ctx->d_cs_cos[i], tc); if (rc) return rc;
             rc = upload(&ctx->d_cs_sin[i], ts); if (rc) return rc;
+            rc = upload(&ctx->d_cs_frag[i], fft_prime_frag_table(p)); if (rc) return rc;
         }
     }
     std::vector<double2> root(Lfft);
@@ -440,7 +443,7 @@ void hpb_poisson_free(hpb_ctx *ctx)
     cudaFree(ctx->d_tri_p); cudaFree(ctx->d_tri_q); cudaFree(ctx->d_red_pe); cudaFree(ctx->d_red_pf);
     cudaFree(ctx->d_red_b); cudaFree(ctx->d_red_inv); cudaFree(ctx->d_red_del);
     cudaFree(ctx->d_spec); cudaFree(ctx->d_iface); cudaFree(ctx->d_chirp); cudaFree(ctx->d_bhat);
-    for (int i = 0; i < ctx->nrad; ++i) { cudaFree(ctx->d_cs_cos[i]); cudaFree(ctx->d_cs_sin[i]); }
+    for (int i = 0; i < ctx->nrad; ++i) { cudaFree(ctx->d_cs_cos[i]); cudaFree(ctx->d_cs_sin[i]); cudaFree(ctx->d_cs_frag[i]); }
 }
 
 // K2 + K3 + K4 on ctx->d_spec (already holding the row transforms of nbatch right-hand sides)
