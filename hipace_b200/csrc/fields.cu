@@ -134,6 +134,28 @@ __global__ void k_abs_sum(SliceView a, int c, int nx, int ny, double *out)
     if (threadIdx.x == 0) atomicAdd(out, sm[0]);
 }
 
+// sum|Q| of up to 24 components in ONE launch (blockIdx.y = entry): the driver's per-slice checksums were
+// one launch per component (16 launches per slice, ~60 us of launch chain for 25 us of memory traffic)
+struct AbsSumList { int c[24]; int slot[24]; };
+__global__ void k_abs_sum_multi(SliceView a, AbsSumList l, int nx, int ny, double *out)
+{
+    hpb_pdl_prologue();
+    __shared__ double sm[kThreads];
+    double acc = 0.0;
+    const double *p = a.comp(l.c[blockIdx.y]);
+    for (int j = blockIdx.x; j < ny; j += gridDim.x) {
+        const double *row = p + a.idx(0, j);
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) acc += fabs(row[i]);
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = kThreads / 2; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out + l.slot[blockIdx.y], sm[0]);
+}
+
 // the same for an xz diagnostic (diagnostics/Diagnostic.cpp:393-407, Fields::Copy with order-1
 // interpolation to y = mid-domain): the mean of the two central rows for even ny, else the central row
 __global__ void k_abs_sum_xz(SliceView a, int c, int nx, int ny, double *out)
@@ -315,6 +337,26 @@ extern "C" int hpb_abs_sum_xz(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out)
     if (!ctx || c < 0 || !d_out) return HPB_ERR_ARG;
     hpb_launch(k_abs_sum_xz, 1, kThreads, 0, ctx->stream, make_view(sl), c, ctx->g.nx, ctx->g.ny, d_out);
     hpb_count_launch(ctx);
+    HPB_CUDA_CHECK(cudaGetLastError());
+    return HPB_OK;
+}
+
+extern "C" int hpb_abs_sum_multi(hpb_ctx *ctx, hpb_slice sl, const int *comp_list, const int *slots, int n,
+                                 double *d_out)
+{
+    if (!ctx || !comp_list || !slots || !d_out || n < 0) return HPB_ERR_ARG;
+    const hpb_geom &g = ctx->g;
+    for (int k0 = 0; k0 < n; k0 += 24) {
+        AbsSumList l;
+        const int m = n - k0 < 24 ? n - k0 : 24;
+        for (int k = 0; k < m; ++k) {
+            if (comp_list[k0 + k] < 0 || comp_list[k0 + k] >= sl.ncomp) return HPB_ERR_ARG;
+            l.c[k] = comp_list[k0 + k]; l.slot[k] = slots[k0 + k];
+        }
+        const unsigned bx = g.ny < 74 ? g.ny : 74;          // 74 x 16 components = 8 CTAs per SM
+        hpb_launch(k_abs_sum_multi, dim3(bx, m), kThreads, 0, ctx->stream, make_view(sl), l, g.nx, g.ny, d_out);
+        hpb_count_launch(ctx);
+    }
     HPB_CUDA_CHECK(cudaGetLastError());
     return HPB_OK;
 }

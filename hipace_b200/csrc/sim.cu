@@ -545,6 +545,19 @@ void build_components(hpb_sim *s)
 // physical plane of a logical component (they differ once the beam-current planes have rotated)
 inline int phys_comp(const hpb_sim *s, int logical) { return s->comps[s->comp_id[logical]]; }
 
+// sum|Q| of every This-slice component of the finished slice into the step's checksums
+// (tests/checksum/backend/openpmd_backend.py:40-45, one slice at a time): one launch for all components
+int slice_checksums(hpb_sim *s)
+{
+    int comps[64], slots[64], n = 0;
+    for (int c = 0; c < s->sl.ncomp && n < 64; ++c)
+        if (s->comp_names[c].first == "This") { comps[n] = phys_comp(s, c); slots[n] = c; ++n; }
+    if (!s->diag_xz) return hpb_abs_sum_multi(s->ctx, s->sl, comps, slots, n, s->d_checksum);
+    for (int k = 0; k < n; ++k)
+        if (int rc = hpb_abs_sum_xz(s->ctx, s->sl, comps[k], s->d_checksum + slots[k])) return rc;
+    return HPB_OK;
+}
+
 int init_plasma(hpb_sim *s, Species &sp, double c_t)
 {
     const hpb_geom &g = s->g;
@@ -1123,9 +1136,7 @@ int solve_one_slice_pc(hpb_sim *s, int islice)
     }
     if (s->opt_checksums) {
         StageTimer t(s, ST_OTHER);
-        for (int c = 0; c < sl.ncomp; ++c)
-            if (s->comp_names[c].first == "This")
-                if ((rc = (s->diag_xz ? hpb_abs_sum_xz : hpb_abs_sum)(ctx, sl, phys_comp(s, c), s->d_checksum + c))) return rc;
+        if ((rc = slice_checksums(s))) return rc;
     }
     {
         StageTimer t(s, ST_PUSH);
@@ -1325,9 +1336,7 @@ int solve_one_slice(hpb_sim *s, int islice)
     }
     if (s->opt_checksums) {                                                             // :681-691
         StageTimer t(s, ST_OTHER);
-        for (int c = 0; c < s->sl.ncomp; ++c)
-            if (s->comp_names[c].first == "This")
-                if ((rc = (s->diag_xz ? hpb_abs_sum_xz : hpb_abs_sum)(ctx, s->sl, phys_comp(s, c), s->d_checksum + c))) return rc;
+        if ((rc = slice_checksums(s))) return rc;
     }
     auto push_plasma = [&](bool with_deposit) -> int {
         StageTimer t(s, ST_PUSH);

@@ -392,6 +392,9 @@ int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_sl
 /* sum|Q| over the valid box of component c -> d_out[0] += ...   (checksum of
  * tests/checksum/backend/openpmd_backend.py:40-45, one slice at a time) */
 int hpb_abs_sum(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out);
+/* n components in one launch: d_out[slots[k]] += sum|Q| of component comp_list[k] */
+int hpb_abs_sum_multi(hpb_ctx *ctx, hpb_slice sl, const int *comp_list, const int *slots, int n,
+                      double *d_out);
 /* the same for diagnostic.diag_type = xz: the slice contributes its y = mid-domain line (order-1
  * interpolation: mean of the two central rows for even ny; src/diagnostics/Diagnostic.cpp:393-407) */
 int hpb_abs_sum_xz(hpb_ctx *ctx, hpb_slice sl, int c, double *d_out);
