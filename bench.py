@@ -440,9 +440,10 @@ def main():
         except Exception:
             pass
         # second roof: fp64.  flops per particle = 2 DFMA + DMUL + DADD thread instructions of the ncu
-        # op counters (smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on, profiles/r01f_particles_raw.csv)
-        # divided by the particles of the launch; the peak is measured on this box (csrc/peaks.cu)
-        flops_pp = {'push': 1075.0, 'explicit': 518.0}
+        # op counters (smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on, profiles/r02/r02F_particles_raw.csv:
+        # the round-2 default kernels, slice 623) divided by the particles of the launch; the peak is measured on
+        # this box (csrc/peaks.cu)
+        flops_pp = {'push': 1021.2, 'explicit': 496.3}
         try:
             fp64_peak = hp.measure_fp64_peak(local_rank)
         except Exception:

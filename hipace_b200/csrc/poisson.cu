@@ -304,9 +304,12 @@ template <class Src>
 int launch_rows(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, int nbatch, double scale)
 {
     const int variant = ctx->tune_fft_variant;
-    // 6 CTAs / SM: 1536 row-pair CTAs of a 1024^2 batch fit in two waves of 148 x 6 (measured best)
-    if (variant == 1) return launch_rows_v<Src, kFftThreads, 5>(ctx, src, out, out_rs, nbatch, scale);
-    return launch_rows_v<Src, kFftThreads, 6>(ctx, src, out, out_rs, nbatch, scale);
+    // 5 CTAs / SM (48 registers, no spills) since the prime stage runs on the tensor cores: Poisson stage
+    // 0.138 -> 0.129 ms (profiles/r02/r02F_tune.txt).  With the scalar prime stage the kernel was bound by the
+    // shared-memory pipe and 6 CTAs / SM (40 registers, two waves of 148 x 6 for the 1536 row pairs of a
+    // 1024^2 batch) measured best: fft_variant 1 keeps that geometry, 2 also the scalar stage.
+    if (variant == 1 || variant == 2) return launch_rows_v<Src, kFftThreads, 6>(ctx, src, out, out_rs, nbatch, scale);
+    return launch_rows_v<Src, kFftThreads, 5>(ctx, src, out, out_rs, nbatch, scale);
 }
 
 }  // namespace

@@ -48,7 +48,8 @@ if a.traffic:
     k = {}
     for (name, grid), d in agg.items():
         base = re.sub(r'<.*', '', name)
-        if base in ('k_advance_plasma', 'k_explicit_deposition', 'k_deposit_current'):
-            k[base] = (d['rd'] + d['wr']) / d['n']
+        for stem in ('k_advance_plasma', 'k_explicit_deposition', 'k_deposit_current'):
+            if base.startswith(stem):          # k_advance_plasma_row / _cta: the push of the current default
+                k[stem] = (d['rd'] + d['wr']) / d['n']
     json.dump({'nxy': a.nxy, 'ppc': a.ppc, 'source': a.source or a.raw, 'unit': 'bytes per launch',
                'kernels': k}, open(a.traffic, 'w'), indent=1)
