@@ -1875,7 +1875,10 @@ extern "C" int hpb_explicit_deposition(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl
     else if (variant == 5) HPB_LAUNCH_EXPL(128, 6);
     else if (variant == 6) HPB_LAUNCH_EXPL(128, 8);
     else if (variant == 1) HPB_LAUNCH_EXPL(256, 1);
-    else HPB_LAUNCH_EXPL(128, 5);
+    else if (variant == 16) HPB_LAUNCH_EXPL(128, 5);    // the default until r02H: 96 registers, 200 bytes of spills
+    // 4 CTAs / SM, 124 registers, no spills: the kernel's L1TEX pipe (72 % of peak, r02F) also carried the
+    // spill traffic -- 0.244 -> 0.228 ms, 929 -> 951 slices/s (profiles/r02/r02H_tune.txt)
+    else HPB_LAUNCH_EXPL(128, 4);
 #undef HPB_LAUNCH_EXPL
 #undef HPB_LAUNCH_EXPL_
     hpb_count_launch(ctx);
@@ -1924,7 +1927,7 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
     // runs the round-1 warp-staged kernel below: the cooperative cp.async staging of variant 8 is the
     // slowest of the three, 0.55 vs 0.34 vs 0.29 ms at 1024^2 ppc 4)
     const bool row_tma_ok = variant == 8 || hpb_slice_tmap(ctx, 2, sl, kRW, kCH) != nullptr;
-    if ((variant >= 6 && variant <= 9) && lasa.c_aabs < 0 && row_tma_ok) {
+    if ((variant >= 6 && variant <= 10) && lasa.c_aabs < 0 && row_tma_ok) {
         PlasmaPtrs pp = to_ptrs(pl);
         const bool lat = ctx->order_n > 0 && ctx->order_n * ctx->order_ppc == pl.np;
         pp.lat_n = lat ? ctx->order_n : 0; pp.lat_ppc = lat ? ctx->order_ppc : 1;
@@ -1943,7 +1946,7 @@ static int advance_plasma(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl, double char
         do { if (deposit) { if (tm) HPB_LAUNCH_ROW(MB, true, true); else HPB_LAUNCH_ROW(MB, true, false); } \
              else { if (tm) HPB_LAUNCH_ROW(MB, false, true); else HPB_LAUNCH_ROW(MB, false, false); } } while (0)
         if (variant == 9 && tm) { if (deposit) HPB_LAUNCH_ROW(5, true, true, true); else HPB_LAUNCH_ROW(5, false, true, true); }
-        else if (variant == 7) HPB_LAUNCH_ROW_MB(4); else HPB_LAUNCH_ROW_MB(5);
+        else if (variant == 7) HPB_LAUNCH_ROW_MB(4); else if (variant == 10) HPB_LAUNCH_ROW_MB(6); else HPB_LAUNCH_ROW_MB(5);
 #undef HPB_LAUNCH_ROW_MB
 #undef HPB_LAUNCH_ROW
         hpb_count_launch(ctx);
