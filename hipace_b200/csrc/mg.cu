@@ -95,7 +95,7 @@ template <int INIT, bool RES, int RH, int NS, int NTHR>
 __global__ void __launch_bounds__(NTHR, (RH == 2 || NTHR == 1024) ? 1 : 2)
 k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
          const double *__restrict__ c0i_in, double *__restrict__ c0i_out, V2 phi_out, LevelGeom gc,
-         V2 res_c, double *norm, int nbx, int EO, const int *done)
+         V2 res_c, double *norm, int nbx, int EO, const int *done, int lean)
 {
     // c0i_in: plane of 1 / c0 (row stride g.nx) written by an earlier launch of this solve -- the
     // four fp64 divisions per thread are then loads; c0i_out: where the first launch stores it
@@ -117,6 +117,175 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     // the whole tile (with its ring) lies strictly inside the valid range: no bounds or
     // boundary-stencil cases anywhere (block-uniform)
     const bool inner = ox - 1 > g.vlo && ox + CX < g.vhix && oy - 1 > g.vlo && oy + CYr < g.vhiy;
+
+    // ---- restriction of the residual held in shared memory (owned region) + the max-norms: the tail both
+    //      tile paths share
+    auto restrict_and_norm = [&](double nres, double nrhs) {
+        // restriction of the owned region [X0, X0 + FX) x [Y0, Y0 + FY) (level indices)
+        const int X0 = ox + EO, Y0 = oy + EO;
+        // coarse points owned by this tile: cc: fine cells (2I, 2I+1); nodal: fine node 2I
+        const int I0 = (X0 + 1) >> 1, J0 = (Y0 + 1) >> 1;
+        const int I1 = (X0 + FX + 1) >> 1, J1 = (Y0 + FY + 1) >> 1;     // exclusive
+        // thread -> coarse points (I0 + lane, J0 + warp + m NTHR/32): FX/2 <= 29 columns
+        {
+            const int I = I0 + (tid & 31);
+            for (int J = J0 + (tid >> 5); J < J1; J += NTHR / 32) {
+                if (I < I1 && I >= gc.vlo && I <= gc.vhix && J >= gc.vlo && J <= gc.vhiy) {
+                    const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;     // smem index of fine (2I, 2J)
+                    const long oc = I + (long)J * res_c.rs;
+#pragma unroll
+                    for (int n = 0; n < 2; ++n) {
+                        const double *f = (n ? sm1 : sm0) + lj * AX + li;
+                        double v;
+                        if (g.cc) {
+                            v = 0.25 * (f[0] + f[1] + f[AX] + f[AX + 1]);
+                        } else {
+                            v = (1. / 16.) * (f[-AX - 1] + 2. * f[-AX] + f[-AX + 1]
+                                              + 2. * f[-1] + 4. * f[0] + 2. * f[1]
+                                              + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
+                        }
+                        res_c.p[oc + n * res_c.cs] = v;
+                    }
+                }
+            }
+        }
+        if (norm) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                nres = fmax(nres, __shfl_xor_sync(0xffffffffu, nres, o));
+                nrhs = fmax(nrhs, __shfl_xor_sync(0xffffffffu, nrhs, o));
+            }
+            if ((tid & 31) == 0 && (nres > 0. || nrhs > 0.)) {
+                // bit pattern of non-negative doubles is monotone: exact, order-independent max
+                atomicMax((unsigned long long *)&norm[0], (unsigned long long)__double_as_longlong(nres));
+                atomicMax((unsigned long long *)&norm[1], (unsigned long long)__double_as_longlong(nrhs));
+            }
+        }
+    };
+
+    // ---- lean path for tiles strictly inside the valid range (85 % of the level-0 tiles): no bounds or
+    //      boundary-stencil cases, the per-cell invariants are loaded straight into the colour sets (the
+    //      general path below loads them per row and re-selects them with FSEL pairs in every half-sweep
+    //      because both orders do not fit 64 registers), one warp per tile row in the load.  Every cell goes
+    //      through exactly the operations of the general path in the same order: bit-identical results.
+    if (RH == 1 && NS == 1 && NTHR == 512 && lean && inner) {
+        // thread (lane = tx, warp = ty) owns rows 2 ty, 2 ty + 1 of columns tx and tx + 32; of each vertical
+        // pair the cell with (i + j) even is updated by colours 0 and 2 (set A), the other by 1 and 3 (set B)
+        const int hA = (ox + tx + oy) & 1;
+        double rA0[2], rA1[2], cA[2], aA[2], rB0[2], rB1[2], cB[2], aB[2];
+        const double f2 = 2.0 * (g.facx + g.facy);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int i = ox + tx + 32 * p;
+            const int jA = oy + 2 * ty + hA, jB = oy + 2 * ty + (hA ^ 1);
+            const long oa = i + (long)jA * rhs.rs, ob = i + (long)jB * rhs.rs;
+            rA0[p] = rhs.p[oa]; rA1[p] = rhs.p[oa + rhs.cs];
+            rB0[p] = rhs.p[ob]; rB1[p] = rhs.p[ob + rhs.cs];
+            if (c0i_in) {
+                cA[p] = c0i_in[i + (long)jA * g.nx]; cB[p] = c0i_in[i + (long)jB * g.nx];
+                aA[p] = RES ? acf[i + (long)jA * acf_rs] : 0.;
+                aB[p] = RES ? acf[i + (long)jB * acf_rs] : 0.;
+            } else {
+                aA[p] = acf[i + (long)jA * acf_rs]; aB[p] = acf[i + (long)jB * acf_rs];
+                cA[p] = 1.0 / (-(aA[p] + f2));                          // gs1 :265-292, interior cell
+                cB[p] = 1.0 / (-(aB[p] + f2));
+            }
+        }
+        // tile rows ty, ty + 16, ty + 32 (< 34): columns lane, lane + 32 and (lanes 0, 1) 64 + lane
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+            const int lj = ty + 16 * rr;
+            if (lj < AYr) {
+                const int j = oy - 1 + lj;
+#pragma unroll
+                for (int cg = 0; cg < 3; ++cg) {
+                    const int li = tx + 32 * cg;
+                    if (li < AX) {
+                        double v0 = 0., v1 = 0.;
+                        if (INIT != 0) {
+                            const int i = ox - 1 + li;
+                            const long o = i + (long)j * phi_in.rs;
+                            v0 = phi_in.p[o];
+                            v1 = phi_in.p[o + phi_in.cs];
+                            if (INIT == 2) {
+                                v0 = v0 + interp_at(crse, i, j, 0, g.cc);
+                                v1 = v1 + interp_at(crse, i, j, 1, g.cc);
+                            }
+                        }
+                        sm0[lj * AX + li] = v0; sm1[lj * AX + li] = v1;
+                    }
+                }
+            }
+        }
+        if (is_done) return;            // block-uniform; nothing has been written to global memory yet
+        int oA[2], oB[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            oA[p] = (2 * ty + hA + 1) * AX + tx + 32 * p + 1;
+            oB[p] = (2 * ty + (hA ^ 1) + 1) * AX + tx + 32 * p + 1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int icolor = 0; icolor < 4; ++icolor) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const bool b = (icolor & 1) != 0;
+                double *c = sm0 + (b ? oB[p] : oA[p]);
+                double *e = sm1 + (b ? oB[p] : oA[p]);
+                const double lap0 = g.facx * (c[-1] + c[1]) + g.facy * (c[-AX] + c[AX]);
+                const double lap1 = g.facx * (e[-1] + e[1]) + g.facy * (e[-AX] + e[AX]);
+                c[0] = ((b ? rB0[p] : rA0[p]) - lap0) * (b ? cB[p] : cA[p]);
+                e[0] = ((b ? rB1[p] : rA1[p]) - lap1) * (b ? cB[p] : cA[p]);
+            }
+            __syncthreads();
+        }
+        double nres = 0., nrhs = 0.;
+        double qs0[2][2], qs1[2][2];            // residuals of [set A | B][p]
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int cix = tx + 32 * p, cjh = 2 * ty + (s ? (hA ^ 1) : hA);
+                const int so = s ? oB[p] : oA[p];
+                const double r0v = s ? rB0[p] : rA0[p], r1v = s ? rB1[p] : rA1[p];
+                const double acv = s ? aB[p] : aA[p], civ = s ? cB[p] : cA[p];
+                qs0[s][p] = qs1[s][p] = 0.;
+                if (RES && cix >= EO - 1 && cix < CX - EO + 1 && cjh >= EO - 1 && cjh < CYr - EO + 1) {
+                    // residual1 (:184-190), interior form -- the operation order of the general path
+                    const double *c = sm0 + so, *e = sm1 + so;
+                    double lap = -2.0 * (g.facx + g.facy) * c[0];
+                    lap += g.facx * (c[-1] + c[1]);
+                    lap += g.facy * (c[-AX] + c[AX]);
+                    qs0[s][p] = r0v + acv * c[0] - lap;
+                    lap = -2.0 * (g.facx + g.facy) * e[0];
+                    lap += g.facx * (e[-1] + e[1]);
+                    lap += g.facy * (e[-AX] + e[AX]);
+                    qs1[s][p] = r1v + acv * e[0] - lap;
+                }
+                if (cix >= EO && cix < CX - EO && cjh >= EO && cjh < CYr - EO) {
+                    const int i = ox + cix, j = oy + cjh;
+                    const long o = i + (long)j * phi_out.rs;
+                    phi_out.p[o] = sm0[so];
+                    phi_out.p[o + phi_out.cs] = sm1[so];
+                    if (c0i_out) c0i_out[i + (long)j * g.nx] = civ;
+                    if (RES && norm) {
+                        nres = fmax(nres, fmax(fabs(qs0[s][p]), fabs(qs1[s][p])));
+                        nrhs = fmax(nrhs, fmax(fabs(r0v), fabs(r1v)));
+                    }
+                }
+            }
+        }
+        if (!RES) return;
+        __syncthreads();                   // everyone is done reading phi from shared memory
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            sm0[oA[p]] = qs0[0][p]; sm1[oA[p]] = qs1[0][p];
+            sm0[oB[p]] = qs0[1][p]; sm1[oB[p]] = qs1[1][p];
+        }
+        __syncthreads();
+        restrict_and_norm(nres, nrhs);
+        return;
+    }
 
     // ---- tile load (with ring), linear over the AYr x AX shared array; all loads are independent
     constexpr int NLD = (AYr * AX + NTHR - 1) / NTHR;
@@ -272,46 +441,7 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
         }
     }
     __syncthreads();
-    // restriction of the owned region [X0, X0 + FX) x [Y0, Y0 + FY) (level indices)
-    const int X0 = ox + EO, Y0 = oy + EO;
-    // coarse points owned by this tile: cc: fine cells (2I, 2I+1); nodal: fine node 2I
-    const int I0 = (X0 + 1) >> 1, J0 = (Y0 + 1) >> 1;
-    const int I1 = (X0 + FX + 1) >> 1, J1 = (Y0 + FY + 1) >> 1;     // exclusive
-    // thread -> coarse points (I0 + lane, J0 + warp + m NTHR/32): FX/2 <= 29 columns
-    {
-        const int I = I0 + (tid & 31);
-        for (int J = J0 + (tid >> 5); J < J1; J += NTHR / 32) {
-            if (I < I1 && I >= gc.vlo && I <= gc.vhix && J >= gc.vlo && J <= gc.vhiy) {
-                const int li = 2 * I - ox + 1, lj = 2 * J - oy + 1;     // smem index of fine (2I, 2J)
-                const long oc = I + (long)J * res_c.rs;
-#pragma unroll
-                for (int n = 0; n < 2; ++n) {
-                    const double *f = (n ? sm1 : sm0) + lj * AX + li;
-                    double v;
-                    if (g.cc) {
-                        v = 0.25 * (f[0] + f[1] + f[AX] + f[AX + 1]);
-                    } else {
-                        v = (1. / 16.) * (f[-AX - 1] + 2. * f[-AX] + f[-AX + 1]
-                                          + 2. * f[-1] + 4. * f[0] + 2. * f[1]
-                                          + f[AX - 1] + 2. * f[AX] + f[AX + 1]);
-                    }
-                    res_c.p[oc + n * res_c.cs] = v;
-                }
-            }
-        }
-    }
-    if (norm) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            nres = fmax(nres, __shfl_xor_sync(0xffffffffu, nres, o));
-            nrhs = fmax(nrhs, __shfl_xor_sync(0xffffffffu, nrhs, o));
-        }
-        if ((tid & 31) == 0 && (nres > 0. || nrhs > 0.)) {
-            // bit pattern of non-negative doubles is monotone: exact, order-independent max
-            atomicMax((unsigned long long *)&norm[0], (unsigned long long)__double_as_longlong(nres));
-            atomicMax((unsigned long long *)&norm[1], (unsigned long long)__double_as_longlong(nrhs));
-        }
-    }
+    restrict_and_norm(nres, nrhs);
 }
 
 // ---- single-CTA part of the V-cycle: all levels with <= 34 x 34 points -------------------------
@@ -792,7 +922,7 @@ int launch_smooth_t(hpb_ctx *ctx, const LevelGeom &g, V2 in, V2 crse, V2 rhs, co
         attr_set = true;
     }
     hpb_launch(k_smooth<INIT, RES, RH, NS, NTHR>, nbx * nby, NTHR, smem, ctx->stream, g, in, crse, rhs,
-               acf, acf_rs, c0i_in, c0i_out, out, gc, res_c, norm, nbx, EO, done);
+               acf, acf_rs, c0i_in, c0i_out, out, gc, res_c, norm, nbx, EO, done, ctx->tune_mg_lean);
     hpb_count_launch(ctx);
     return HPB_OK;
 }
