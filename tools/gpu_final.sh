@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl cufft_ref --no-cpu-baseline --no-e2e 2>> gpur
 timeout 300 python bench.py --impl naive --no-cpu-baseline --no-e2e 2>> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench_naive.json | cut -c1-200
 timeout 300 python bench.py --workload configs1 --no-cpu-baseline --no-e2e 2>> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench_configs1.json | cut -c1-200
 timeout 300 python bench.py --workload n1023 --no-cpu-baseline --no-e2e 2>> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench_n1023.json | cut -c1-200
-timeout 300 bash tools/tune.sh "-" "fft_variant=1" 2>&1 | tee gpurun_out/${tag}_tune.txt
+timeout 300 bash tools/tune.sh "-" 2>&1 | tee gpurun_out/${tag}_tune.txt
 timeout 400 python bench.py --workload configs3 --steps 1 --warmup 3 --no-cpu-baseline 2>> gpurun_out/${tag}_bench.err | tee gpurun_out/${tag}_bench_configs3.json | cut -c1-200
 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${tag}_launches.csv python tools/profile_slices.py --skip 400 --slices 2 2>&1 | tail -1
