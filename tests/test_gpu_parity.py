@@ -379,6 +379,33 @@ def test_poisson_solve_matches_dst_oracle(nx, ny):
     ctx.close()
 
 
+@pytest.mark.parametrize('p,m', [(7, 8), (11, 6), (13, 4), (17, 4), (19, 4), (23, 4), (29, 2), (31, 2), (37, 2),
+                                 (41, 2), (43, 2), (47, 2), (53, 2), (59, 2), (61, 2), (41, 25), (7, 49)])
+def test_poisson_prime_stage_on_tensor_cores(p, m):
+    """the odd-prime FFT stage (fft_smem.cuh: P = C U, Q = S V as mma.m8n8k4.f64 tiles) for EVERY prime the
+    generic stage serves (7 .. 61: all paddings of the (h+1) x h coefficient matrices to 8 x 4 tiles, all
+    tile counts of the 2 Nr columns), row length nx + 1 = p m, against the DST oracle"""
+    import torch
+    import hipace_b200 as hp
+    from oracle.hipace_oracle import poisson_dirichlet, poisson_eigenvalues
+    nx, ny = p * m - 1, (15 if (p * m - 1) % 2 else 16)
+    rng = np.random.default_rng(p * 100 + m)
+    dx, dy = 16. / nx, 12. / ny
+    rhs = rng.standard_normal((3, ny, nx))
+    ctx = hp.Context(nx, ny, dx, dy, 0.1, -8 + dx / 2, -6 + dy / 2)
+    g = hp.NGUARD
+    sl_t = torch.zeros((3, ny + 2 * g, nx + 2 * g), dtype=torch.float64, device='cuda')
+    ctx.poisson_solve(torch.from_numpy(rhs).cuda(), ctx.slice_view(sl_t), [0, 1, 2])
+    torch.cuda.synchronize()
+    out = sl_t.cpu().numpy()
+    eig = poisson_eigenvalues(nx, ny, dx, dy)
+    for b in range(3):
+        want = poisson_dirichlet(rhs[b], eig)
+        err = np.abs(out[b, g:-g, g:-g] - want).max() / np.abs(want).max()
+        assert err <= 1e-11, (p, m, b, err)
+    ctx.close()
+
+
 @pytest.mark.parametrize('nx,ny', [(64, 64), (63, 63), (96, 64), (127, 63), (256, 256)])
 def test_mg_solve1_matches_hpmg_oracle(nx, ny):
     """hpmg solve1: same V-cycle count and the same values as the oracle restatement."""
