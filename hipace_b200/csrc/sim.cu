@@ -1524,7 +1524,10 @@ extern "C" int hpb_sim_create(hpb_sim **out, const char *deck, const char *overr
     if ((rc = hpb_set_deposition_order(s->ctx, s->depos_order, s->depos_dtype))) return rc;
     sl.lo_x = sl.lo_y = -s->ng;
     sl.nx_tot = s->g.nx + 2 * s->ng; sl.ny_tot = s->g.ny + 2 * s->ng;
-    sl.jstride = sl.nx_tot; sl.nstride = (long)sl.nx_tot * sl.ny_tot;
+    // rows padded to an even number of cells: every row and plane then starts on a 16-byte boundary, which
+    // the TMA tensor maps of the particle kernels need (an odd grid -- the reference's recommended 2^n - 1
+    // cells -- otherwise ran the round-1 push without the TMA patch)
+    sl.jstride = (sl.nx_tot + 1) & ~1; sl.nstride = (long)sl.jstride * sl.ny_tot;
     SIM_CUDA(cudaMalloc(&sl.p, sizeof(double) * sl.nstride * sl.ncomp));
     SIM_CUDA(cudaMemset(sl.p, 0, sizeof(double) * sl.nstride * sl.ncomp));
     SIM_CUDA(cudaMalloc(&s->d_checksum, sizeof(double) * (sl.ncomp + 1)));     // + laserEnvelope
@@ -1698,8 +1701,9 @@ extern "C" int hpb_sim_get_field(hpb_sim *s, int comp, double *h_out)
     if (!s || comp < 0 || comp >= s->sl.ncomp || !h_out) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
     SIM_CUDA(cudaStreamSynchronize(s->stream));
-    SIM_CUDA(cudaMemcpy(h_out, s->sl.p + phys_comp(s, comp) * s->sl.nstride,
-                        sizeof(double) * s->sl.nstride, cudaMemcpyDeviceToHost));
+    SIM_CUDA(cudaMemcpy2D(h_out, sizeof(double) * s->sl.nx_tot, s->sl.p + phys_comp(s, comp) * s->sl.nstride,
+                          sizeof(double) * s->sl.jstride, sizeof(double) * s->sl.nx_tot, s->sl.ny_tot,
+                          cudaMemcpyDeviceToHost));
     return HPB_OK;
 }
 
@@ -1708,8 +1712,9 @@ extern "C" int hpb_sim_set_field(hpb_sim *s, int comp, const double *h_in)
     if (!s || comp < 0 || comp >= s->sl.ncomp || !h_in) return HPB_ERR_ARG;
     SIM_CUDA(cudaSetDevice(s->device));
     SIM_CUDA(cudaStreamSynchronize(s->stream));
-    SIM_CUDA(cudaMemcpy(s->sl.p + phys_comp(s, comp) * s->sl.nstride, h_in,
-                        sizeof(double) * s->sl.nstride, cudaMemcpyHostToDevice));
+    SIM_CUDA(cudaMemcpy2D(s->sl.p + phys_comp(s, comp) * s->sl.nstride, sizeof(double) * s->sl.jstride, h_in,
+                          sizeof(double) * s->sl.nx_tot, sizeof(double) * s->sl.nx_tot, s->sl.ny_tot,
+                          cudaMemcpyHostToDevice));
     return HPB_OK;
 }
 
