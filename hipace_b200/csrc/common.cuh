@@ -253,6 +253,8 @@ struct hpb_ctx {
     int mg_last_iters;        // V-cycles of the previous solve = speculation depth of the next
     const double *mg_acf_ready;   // hpb_mg_prepare_acf ran for this coefficient plane (consumed by the next solve1)
     int tune_mg_lean;         // the lean interior-tile path of k_smooth
+    int tune_mg_persist;      // the mid levels + the single-CTA levels of a V-cycle in one persistent launch (k_mid)
+    void *d_mg_bar;           // its grid barrier
     int tune_mg_rotate;       // level-0 buffer rotation: the last smoother of a V-cycle writes into sol (no final copy)
     // misc
     int *d_scalar_i;          // scratch ints

@@ -56,6 +56,7 @@ extern "C" int hpb_set_option(hpb_ctx *ctx, const char *key, double value)
     else if (!strcmp(key, "mg_fuse")) ctx->tune_mg_fuse = v;
     else if (!strcmp(key, "mg_rotate")) ctx->tune_mg_rotate = v;
     else if (!strcmp(key, "mg_lean")) ctx->tune_mg_lean = v;
+    else if (!strcmp(key, "mg_persist")) ctx->tune_mg_persist = v;
     else if (!strcmp(key, "poisson_impl")) ctx->tune_poisson_impl = v;
     else { hpb_set_error("unknown option %s", key); return HPB_ERR_ARG; }
     return HPB_OK;

@@ -55,17 +55,23 @@ __device__ __forceinline__ double residual_smem(const double *ph, int li, int lj
     return rhs + acf * c[0] - lap;
 }
 
+// CG: load through the L2 only (ld.global.cg).  The persistent mid-level kernel (k_mid) reads arrays that
+// CTAs on OTHER SMs wrote earlier in the same launch; the L1 is not coherent across SMs.
+template <bool CG>
+__device__ __forceinline__ double ldv(const double *p) { return CG ? __ldcg(p) : *p; }
+
 // I(crse)(i, j): interpcpy_cc / interpcpy_nd (:88-121)
+template <bool CG = false>
 __device__ __forceinline__ double interp_at(const V2 &crse, int i, int j, int n, int cc)
 {
     const int ic = i >> 1, jc = j >> 1;
-    if (cc) return crse.at(ic, jc, n);
+    auto at = [&](int a, int b) { return ldv<CG>(&crse.at(a, b, n)); };
+    if (cc) return at(ic, jc);
     const bool io = (ic * 2 != i), jo = (jc * 2 != j);
-    if (io && jo) return (crse.at(ic, jc, n) + crse.at(ic + 1, jc, n) + crse.at(ic, jc + 1, n)
-                          + crse.at(ic + 1, jc + 1, n)) * 0.25;
-    if (io) return (crse.at(ic, jc, n) + crse.at(ic + 1, jc, n)) * 0.5;
-    if (jo) return (crse.at(ic, jc, n) + crse.at(ic, jc + 1, n)) * 0.5;
-    return crse.at(ic, jc, n);
+    if (io && jo) return (at(ic, jc) + at(ic + 1, jc) + at(ic, jc + 1) + at(ic + 1, jc + 1)) * 0.25;
+    if (io) return (at(ic, jc) + at(ic + 1, jc)) * 0.5;
+    if (jo) return (at(ic, jc) + at(ic, jc + 1)) * 0.5;
+    return at(ic, jc);
 }
 
 // One tile: phi = GSRB^4(init); optional residual -> restricted into res_c (+ max-norms).
@@ -91,25 +97,23 @@ struct SmCell {
 //     one of the next, cor0 = GSRB^4(sol), at the price of a 4-cell deeper halo).
 // NTHR: 512 (two columns per thread) or 1024 (one column per thread: half the dependent work per
 //       thread -- used on the small levels, whose launches are latency bound, not throughput bound)
-template <int INIT, bool RES, int RH, int NS, int NTHR>
-__global__ void __launch_bounds__(NTHR, (RH == 2 || NTHR == 1024) ? 1 : 2)
-k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
-         const double *__restrict__ c0i_in, double *__restrict__ c0i_out, V2 phi_out, LevelGeom gc,
-         V2 res_c, double *norm, int nbx, int EO, const int *done, int lean)
+// tile: index of the tile in the level's nbx x nby tiling (blockIdx.x of k_smooth; the persistent k_mid loops
+// over tiles); sm_dyn: 2 x AYr x AX doubles of shared memory; is_done: the solve has converged (no-op)
+template <int INIT, bool RES, int RH, int NS, int NTHR, bool CG = false>
+__device__ __forceinline__ void
+smooth_tile(const LevelGeom &g, const V2 &phi_in, const V2 &crse, const V2 &rhs, const double *__restrict__ acf,
+            long acf_rs, const double *__restrict__ c0i_in, double *__restrict__ c0i_out, const V2 &phi_out,
+            const LevelGeom &gc, const V2 &res_c, double *norm, int nbx, int EO, int is_done, int lean,
+            double *sm_dyn, int tile)
 {
     // c0i_in: plane of 1 / c0 (row stride g.nx) written by an earlier launch of this solve -- the
     // four fp64 divisions per thread are then loads; c0i_out: where the first launch stores it
     constexpr int TXN = NTHR / 16;              // threads along x: 32 or 64
     constexpr int CH = CX / TXN;                // column halves per thread: 2 or 1
     constexpr int CYr = CY * RH, AYr = CYr + 2, NP = CH * RH;
-    extern __shared__ double sm_dyn[];
     double *const sm0 = sm_dyn, *const sm1 = sm_dyn + AYr * AX;
-    hpb_pdl_prologue();
-    // converged: the speculatively enqueued V-cycle is a no-op.  The flag is fetched here but only
-    // tested after the tile loads have been issued, so its L2 round trip is not serialised.
-    const int is_done = done ? *(const volatile int *)done : 0;
     const int FX = CX - 2 * EO, FY = CYr - 2 * EO;
-    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+    const int bx = tile % nbx, by = tile / nbx;
     const int ox = bx * FX - EO + g.vlo;          // level index of compute cell (0, 0)
     const int oy = by * FY - EO + g.vlo;
     const int tid = threadIdx.x;
@@ -179,8 +183,8 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             const int i = ox + tx + 32 * p;
             const int jA = oy + 2 * ty + hA, jB = oy + 2 * ty + (hA ^ 1);
             const long oa = i + (long)jA * rhs.rs, ob = i + (long)jB * rhs.rs;
-            rA0[p] = rhs.p[oa]; rA1[p] = rhs.p[oa + rhs.cs];
-            rB0[p] = rhs.p[ob]; rB1[p] = rhs.p[ob + rhs.cs];
+            rA0[p] = ldv<CG>(rhs.p + oa); rA1[p] = ldv<CG>(rhs.p + oa + rhs.cs);
+            rB0[p] = ldv<CG>(rhs.p + ob); rB1[p] = ldv<CG>(rhs.p + ob + rhs.cs);
             if (c0i_in) {
                 cA[p] = c0i_in[i + (long)jA * g.nx]; cB[p] = c0i_in[i + (long)jB * g.nx];
                 aA[p] = RES ? acf[i + (long)jA * acf_rs] : 0.;
@@ -205,11 +209,11 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
                         if (INIT != 0) {
                             const int i = ox - 1 + li;
                             const long o = i + (long)j * phi_in.rs;
-                            v0 = phi_in.p[o];
-                            v1 = phi_in.p[o + phi_in.cs];
+                            v0 = ldv<CG>(phi_in.p + o);
+                            v1 = ldv<CG>(phi_in.p + o + phi_in.cs);
                             if (INIT == 2) {
-                                v0 = v0 + interp_at(crse, i, j, 0, g.cc);
-                                v1 = v1 + interp_at(crse, i, j, 1, g.cc);
+                                v0 = v0 + interp_at<CG>(crse, i, j, 0, g.cc);
+                                v1 = v1 + interp_at<CG>(crse, i, j, 1, g.cc);
                             }
                         }
                         sm0[lj * AX + li] = v0; sm1[lj * AX + li] = v1;
@@ -299,11 +303,11 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             const int i = ox - 1 + li, j = oy - 1 + lj;
             if (e < AYr * AX && (inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy))) {
                 const long o = i + (long)j * phi_in.rs;
-                v0[k] = phi_in.p[o];
-                v1[k] = phi_in.p[o + phi_in.cs];
+                v0[k] = ldv<CG>(phi_in.p + o);
+                v1[k] = ldv<CG>(phi_in.p + o + phi_in.cs);
                 if (INIT == 2) {
-                    v0[k] = v0[k] + interp_at(crse, i, j, 0, g.cc);
-                    v1[k] = v1[k] + interp_at(crse, i, j, 1, g.cc);
+                    v0[k] = v0[k] + interp_at<CG>(crse, i, j, 0, g.cc);
+                    v1[k] = v1[k] + interp_at<CG>(crse, i, j, 1, g.cc);
                 }
             }
         }
@@ -321,8 +325,8 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
             const bool ok = inner || (i >= g.vlo && i <= g.vhix && j >= g.vlo && j <= g.vhiy);
             okc[p][h] = ok;
             const long o = i + (long)j * rhs.rs;
-            r0[p][h] = ok ? rhs.p[o] : 0.;
-            r1[p][h] = ok ? rhs.p[o + rhs.cs] : 0.;
+            r0[p][h] = ok ? ldv<CG>(rhs.p + o) : 0.;
+            r1[p][h] = ok ? ldv<CG>(rhs.p + o + rhs.cs) : 0.;
             const bool xb = !inner && g.cc && (i == g.vlo || i == g.vhix);
             const bool yb = !inner && g.cc && (j == g.vlo || j == g.vhiy);
             if (c0i_in) {
@@ -442,6 +446,21 @@ k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf
     }
     __syncthreads();
     restrict_and_norm(nres, nrhs);
+}
+
+template <int INIT, bool RES, int RH, int NS, int NTHR>
+__global__ void __launch_bounds__(NTHR, (RH == 2 || NTHR == 1024) ? 1 : 2)
+k_smooth(LevelGeom g, V2 phi_in, V2 crse, V2 rhs, const double *__restrict__ acf, long acf_rs,
+         const double *__restrict__ c0i_in, double *__restrict__ c0i_out, V2 phi_out, LevelGeom gc,
+         V2 res_c, double *norm, int nbx, int EO, const int *done, int lean)
+{
+    extern __shared__ double sm_dyn[];
+    hpb_pdl_prologue();
+    // converged: the speculatively enqueued V-cycle is a no-op.  The flag is fetched here but only
+    // tested after the tile loads have been issued, so its L2 round trip is not serialised.
+    const int is_done = done ? *(const volatile int *)done : 0;
+    smooth_tile<INIT, RES, RH, NS, NTHR>(g, phi_in, crse, rhs, acf, acf_rs, c0i_in, c0i_out, phi_out, gc, res_c, norm,
+                                         nbx, EO, is_done, lean, sm_dyn, (int)blockIdx.x);
 }
 
 // ---- single-CTA part of the V-cycle: all levels with <= 34 x 34 points -------------------------
@@ -694,12 +713,12 @@ __device__ __forceinline__ void s_interp_add(const SLevel &Lf, int l, const SCel
     level_bar(l, Lf.T);
 }
 
-__global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const int *done)
+// all levels of A in one 1024-thread CTA (csm: the dynamic shared array holding every level).  CG: the
+// restricted residual of the first level was written by other SMs earlier in the same launch (k_mid)
+template <bool CG>
+__device__ __forceinline__ void coarse_body(const CoarseArgs &A, double *csm)
 {
-    extern __shared__ double csm[];
     __shared__ SLevel S[12];
-    hpb_pdl_prologue();
-    if (*done) return;
     const int nl = A.nl;
     const int cc = A.L[0].g.cc;
     const int tid = threadIdx.x;
@@ -726,8 +745,8 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const i
         for (int s = tid; s < L.n; s += blockDim.x) {
             csm[L.o_acf + s] = A.L[l].acf[s];
             csm[L.o_c0i + s] = A.L[l].c0i[s];
-            csm[L.o_res + s] = l == 0 ? A.L[0].res[s] : 0.;             // boundary nodes stay 0
-            csm[L.o_res + L.n + s] = l == 0 ? A.L[0].res[L.n + s] : 0.;
+            csm[L.o_res + s] = l == 0 ? ldv<CG>(A.L[0].res + s) : 0.;             // boundary nodes stay 0
+            csm[L.o_res + L.n + s] = l == 0 ? ldv<CG>(A.L[0].res + L.n + s) : 0.;
             csm[L.o_cor + s] = 0.;    csm[L.o_cor + L.n + s] = 0.;
             csm[L.o_rescor + s] = 0.; csm[L.o_rescor + L.n + s] = 0.;
         }
@@ -762,6 +781,78 @@ __global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const i
     {
         const SLevel L = S[0];
         for (int s = tid; s < 2 * L.n; s += blockDim.x) A.L[0].cor[s] = csm[L.o_cor + s];
+    }
+}
+
+__global__ void __launch_bounds__(kCoarseThreads) k_coarse(CoarseArgs A, const int *done)
+{
+    extern __shared__ double csm[];
+    hpb_pdl_prologue();
+    if (*done) return;
+    coarse_body<false>(A, csm);
+}
+
+// ---- the mid levels of a V-cycle in ONE persistent launch --------------------------------------------
+// Levels whose tiling has at most one tile per SM are latency chains: every launch (down-stroke smoother,
+// the single-CTA coarse part, up-stroke smoother) costs 8-10 us whatever its size, 14 launches per V-cycle
+// at 1024^2.  k_mid runs the phases  down(l0) .. down(lc-1), coarse, up(lc-1) .. up(l0)  back to back in
+// one cooperative launch of (largest tile count) CTAs with a grid-wide barrier between the phases; the
+// phases are the SAME device functions the separate launches run (smooth_tile, coarse_body), so the result
+// is bit-identical.  Arrays written in one phase and read in a later one by other SMs are read through the
+// L2 (CG).
+struct GridBar { unsigned count, gen; };
+__device__ __forceinline__ void grid_barrier(GridBar *bar)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned gen = *(volatile unsigned *)&bar->gen;
+        if (atomicAdd(&bar->count, 1u) == gridDim.x - 1) {
+            bar->count = 0;
+            __threadfence();
+            atomicAdd(&bar->gen, 1u);
+        } else {
+            while (*(volatile unsigned *)&bar->gen == gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct MidLevel {
+    LevelGeom g, gc;
+    V2 res, cor, rescor, res_c, up_crse;       // res_c: res of the next coarser level; up_crse: what the up-stroke interpolates
+    const double *acf, *c0i;
+    int nbx_d, nt_d, EO_d, nbx_u, nt_u, EO_u;  // tiling of the down / up smoother (different halo widths)
+};
+struct MidArgs { int nlev; MidLevel L[6]; CoarseArgs coarse; };
+
+__global__ void __launch_bounds__(kCoarseThreads, 1) k_mid(MidArgs A, const int *done, GridBar *bar, int lean)
+{
+    extern __shared__ double msm[];
+    hpb_pdl_prologue();
+    if (*(const volatile int *)done) return;           // uniform over the grid: the barrier is never entered
+    const V2 none{};
+    const LevelGeom gnone{};
+    for (int l = 0; l < A.nlev; ++l) {                  // down: cor = GSRB^4(0; res), res_c = R(residual)
+        const MidLevel &L = A.L[l];
+        for (int t = blockIdx.x; t < L.nt_d; t += gridDim.x) {
+            smooth_tile<0, true, 1, 1, kCoarseThreads, true>(L.g, none, none, L.res, L.acf, L.g.nx, L.c0i, nullptr, L.cor,
+                                                             L.gc, L.res_c, nullptr, L.nbx_d, L.EO_d, 0, lean, msm, t);
+            __syncthreads();
+        }
+        grid_barrier(bar);
+    }
+    if (blockIdx.x == 0) coarse_body<true>(A.coarse, msm);
+    grid_barrier(bar);
+    for (int l = A.nlev - 1; l >= 0; --l) {             // up: rescor = GSRB^4(cor + I(up_crse))
+        const MidLevel &L = A.L[l];
+        for (int t = blockIdx.x; t < L.nt_u; t += gridDim.x) {
+            smooth_tile<2, false, 1, 1, kCoarseThreads, true>(L.g, L.cor, L.up_crse, L.res, L.acf, L.g.nx, L.c0i, nullptr,
+                                                              L.rescor, gnone, none, nullptr, L.nbx_u, L.EO_u, 0, lean, msm, t);
+            __syncthreads();
+        }
+        if (l > 0) grid_barrier(bar);
     }
 }
 
@@ -1407,6 +1498,8 @@ int hpb_mg_init(hpb_ctx *ctx)
     HPB_CUDA_CHECK(cudaMemset(ctx->d_mg_norm, 0, 2 * sizeof(double)));
     HPB_CUDA_CHECK(cudaMalloc(&ctx->d_mg_state, 4 * sizeof(double)));
     HPB_CUDA_CHECK(cudaMalloc(&ctx->d_mg_istate, 4 * sizeof(int)));
+    HPB_CUDA_CHECK(cudaMalloc(&ctx->d_mg_bar, 2 * sizeof(unsigned)));
+    HPB_CUDA_CHECK(cudaMemset(ctx->d_mg_bar, 0, 2 * sizeof(unsigned)));
     HPB_CUDA_CHECK(cudaMemset(ctx->d_mg_istate, 0, 4 * sizeof(int)));
     HPB_CUDA_CHECK(cudaMallocHost(&ctx->h_mg_norm, 4 * sizeof(double)));
     HPB_CUDA_CHECK(cudaMallocHost(&ctx->h_mg_istate, 4 * sizeof(int)));
@@ -1423,7 +1516,7 @@ void hpb_mg_free(hpb_ctx *ctx)
         cudaFree(ctx->mg[l].acf); cudaFree(ctx->mg[l].c0i); cudaFree(ctx->mg[l].res);
         cudaFree(ctx->mg[l].cor); cudaFree(ctx->mg[l].rescor);
     }
-    cudaFree(ctx->d_mg_norm); cudaFree(ctx->d_mg_state); cudaFree(ctx->d_mg_istate);
+    cudaFree(ctx->d_mg_norm); cudaFree(ctx->d_mg_state); cudaFree(ctx->d_mg_istate); cudaFree(ctx->d_mg_bar);
     cudaFreeHost(ctx->h_mg_norm); cudaFreeHost(ctx->h_mg_istate);
 }
 
@@ -1441,20 +1534,76 @@ static int mg_vcycle(hpb_ctx *ctx, V2 cur, V2 tmp, V2 rhs0, const double *chi, l
     const V2 none{};
     const LevelGeom gnone{};
     const int *done = ctx->d_mg_istate;
-    for (int l = 1; l < lc; ++l) {                 // down, tile levels
+    // the levels [lm, lc) whose tilings have at most one tile per SM + the single-CTA levels: one persistent
+    // launch (k_mid) instead of 2 (lc - lm) + 1
+    int lm = lc;
+    auto tiles = [&](int l, int EO, int &nbx) {
+        const LevelGeom g = level_geom(ctx, l);
+        const int FX = CX - 2 * EO, FY = CY - 2 * EO;
+        nbx = (g.vhix - g.vlo + 1 + FX - 1) / FX;
+        return nbx * ((g.vhiy - g.vlo + 1 + FY - 1) / FY);
+    };
+    const int EOd = ctx->mg_cc ? 4 : 5, EOu = 3;
+    if (ctx->tune_mg_persist && ctx->mg_coarse_smem > 0 && ctx->d_mg_bar) {
+        int nbx;
+        while (lm > 1 && lc - (lm - 1) <= 6 && tiles(lm - 1, EOd, nbx) <= 148 && tiles(lm - 1, EOu, nbx) <= 148) --lm;
+    }
+    for (int l = 1; l < lm; ++l) {                 // down, tile levels
         const LevelGeom g = level_geom(ctx, l), gc = level_geom(ctx, l + 1);
         launch_smooth<0, true>(ctx, g, none, none, lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf,
                                g.nx, ctx->mg[l].c0i, nullptr, lvl_view(ctx, l, ctx->mg[l].cor), gc,
                                lvl_view(ctx, l + 1, ctx->mg[l + 1].res), nullptr, done);
     }
-    if (ctx->mg_coarse_smem > 0)
-        hpb_launch(k_coarse, 1, kCoarseThreads, ctx->mg_coarse_smem, ctx->stream, coarse_args(ctx), done);
-    else
-        hpb_launch(k_coarse_global, 1, kCoarseThreads, 0, ctx->stream, coarse_args(ctx), done);
-    hpb_count_launch(ctx);
+    if (lm < lc) {
+        MidArgs A;
+        A.nlev = lc - lm;
+        int grid = 1;
+        for (int l = lm; l < lc; ++l) {
+            MidLevel &L = A.L[l - lm];
+            L.g = level_geom(ctx, l); L.gc = level_geom(ctx, l + 1);
+            L.res = lvl_view(ctx, l, ctx->mg[l].res); L.cor = lvl_view(ctx, l, ctx->mg[l].cor);
+            L.rescor = lvl_view(ctx, l, ctx->mg[l].rescor);
+            L.res_c = lvl_view(ctx, l + 1, ctx->mg[l + 1].res);
+            L.up_crse = lvl_view(ctx, l + 1, l + 1 == lc ? ctx->mg[lc].cor : ctx->mg[l + 1].rescor);
+            L.acf = ctx->mg[l].acf; L.c0i = ctx->mg[l].c0i;
+            L.EO_d = EOd; L.nt_d = tiles(l, EOd, L.nbx_d);
+            L.EO_u = EOu; L.nt_u = tiles(l, EOu, L.nbx_u);
+            grid = std::max(grid, std::max(L.nt_d, L.nt_u));
+        }
+        A.coarse = coarse_args(ctx);
+        const size_t smem = std::max((size_t)ctx->mg_coarse_smem, 2 * sizeof(double) * (size_t)(CY + 2) * AX);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HPB_CUDA_CHECK(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        // cooperative: the launch fails instead of dead-locking if the CTAs cannot all be resident
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kCoarseThreads); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        if (ctx->tune_mg_persist == 2) {
+            // plain PDL launch: at most one CTA per SM and fewer CTAs than SMs, nothing else on the device
+            // waits for this kernel, so all CTAs become resident as their predecessors drain
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = hpb_pdl_enabled() ? 1 : 0;
+        } else {
+            at[0].id = cudaLaunchAttributeCooperative;
+            at[0].val.cooperative = 1;
+        }
+        cfg.attrs = at; cfg.numAttrs = 1;
+        HPB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_mid, A, done, (GridBar *)ctx->d_mg_bar, ctx->tune_mg_lean));
+        hpb_count_launch(ctx);
+    }
+    if (lm == lc) {
+        if (ctx->mg_coarse_smem > 0)
+            hpb_launch(k_coarse, 1, kCoarseThreads, ctx->mg_coarse_smem, ctx->stream, coarse_args(ctx), done);
+        else
+            hpb_launch(k_coarse_global, 1, kCoarseThreads, 0, ctx->stream, coarse_args(ctx), done);
+        hpb_count_launch(ctx);
+    }
     // up, tile levels: cor[l] <- GSRB^4(cor[l] + I(cor[l+1])); double-buffered through rescor[l]
-    double *up_prev = ctx->mg[lc].cor;
-    for (int l = lc - 1; l >= 1; --l) {
+    double *up_prev = lm == lc ? ctx->mg[lc].cor : ctx->mg[lm].rescor;
+    for (int l = lm - 1; l >= 1; --l) {
         const LevelGeom g = level_geom(ctx, l);
         launch_smooth<2, false>(ctx, g, lvl_view(ctx, l, ctx->mg[l].cor), lvl_view(ctx, l + 1, up_prev),
                                 lvl_view(ctx, l, ctx->mg[l].res), ctx->mg[l].acf, g.nx,
