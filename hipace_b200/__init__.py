@@ -69,7 +69,7 @@ EXPORTS = (
     'hpb_laser_state_create', 'hpb_laser_state_destroy', 'hpb_laser_begin_step', 'hpb_laser_get_slice',
     'hpb_laser_advance_slice', 'hpb_laser_shift_slices', 'hpb_laser_end_step',
     'hpb_laser_insitu_slice', 'hpb_insitu_write_laser', 'hpb_sim_get_mg_iters', 'hpb_set_option', 'hpb_plasma_reorder', 'hpb_measure_fp64_peak', 'hpb_mg_solve2', 'hpb_laser_set_solver',
-    'hpb_laser_mg_vcycles', 'hpb_poisson_solve_periodic', 'hpb_fields_enforce_periodic', 'hpb_sim_get_time', 'hpb_mg_prepare_acf', 'hpb_abs_sum_multi',
+    'hpb_laser_mg_vcycles', 'hpb_poisson_solve_periodic', 'hpb_fields_enforce_periodic', 'hpb_sim_get_time', 'hpb_mg_prepare_acf', 'hpb_abs_sum_multi', 'hpb_debug_fft_prime_table',
 )
 NCCL_ID_BYTES = 128
 

@@ -316,6 +316,14 @@ int launch_rows(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, i
 
 int hpb_launch_exmby_eypbx(hpb_ctx *ctx, const hpb_slice &sl, const int *comps);
 
+extern "C" long hpb_debug_fft_prime_table(int p, double *out, long out_len)
+{
+    if (p < 3 || (p & 1) == 0) return -1;
+    const std::vector<double> t = fft_prime_frag_table(p);
+    if (out) for (long k = 0; k < out_len && k < (long)t.size(); ++k) out[k] = t[k];
+    return (long)t.size();
+}
+
 int hpb_poisson_init(hpb_ctx *ctx)
 {
     const hpb_geom &g = ctx->g;

@@ -363,6 +363,10 @@ int hpb_plasma_reorder(hpb_ctx *ctx, hpb_plasma in, hpb_plasma out, double prob_
 /* test hook, host only: the thread -> particle map the push kernel uses with that hint (mode 0 linear,
  * 1 passes interleaved warp by warp, 2 CTA by CTA); out[warp * 32 + lane] = particle or -1 */
 long hpb_debug_push_thread_map(long cells_per_pass, int ppc, int mode, long *out, long out_len);
+/* Host-only: the coefficient table of the odd-prime FFT stage p in mma.m8n8k4 A-fragment order
+ * (csrc/fft_smem.cuh: fft_prime_frag_table), for the CPU tests.  Copies min(out_len, count) doubles,
+ * returns the count = ceil((h+1)/8) * ceil(h/4) * 64 with h = (p-1)/2. */
+long hpb_debug_fft_prime_table(int p, double *out, long out_len);
 /* hipace.depos_order_xy (0..3) and hipace.depos_derivative_type (0 analytic, 1 nodal, 2 centred) for
  * every particle kernel called with this context afterwards (Hipace.cpp:49-53; the reference selects
  * them at compile time through CompileTimeOptions, e.g. ExplicitDeposition.cpp:62-67).  Default 2 / 2.

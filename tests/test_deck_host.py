@@ -175,3 +175,53 @@ def test_push_thread_maps_are_permutations(n, ppc):
             assert np.array_equal(cta0, np.arange(128))
             # ... and the next CTA on the same cells of the next pass
             assert np.array_equal(out[128:256], n + np.arange(128))
+
+
+@pytest.mark.parametrize('p', [7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61])
+def test_prime_stage_tensor_core_table(p):
+    """the fragment-ordered coefficient table of the odd-prime FFT stage (fft_smem.cuh): with it, the padded
+    8 x 4 tiles of mma.m8n8k4 (lane l holds A[l / 4][l % 4]) must reproduce the DFT of length p through
+    P = C U, Q = S V, X_b = x_0 + P_b - i Q_b, X_{p-b} = x_0 + P_b + i Q_b -- emulated here tile by tile in
+    NumPy exactly as the kernel walks the table"""
+    import ctypes as C
+    import numpy as np
+    import hipace_b200 as hp
+    L = hp.lib()
+    L.hpb_debug_fft_prime_table.restype = C.c_long
+    L.hpb_debug_fft_prime_table.argtypes = [C.c_int, C.c_void_p, C.c_long]
+    n = L.hpb_debug_fft_prime_table(p, None, 0)
+    h = (p - 1) // 2
+    KT, MT = (h + 3) // 4, (h + 8) // 8
+    assert n == MT * KT * 64
+    tab = np.zeros(n)
+    assert L.hpb_debug_fft_prime_table(p, tab.ctypes.data, n) == n
+    tab = tab.reshape(MT, KT, 2, 32)
+    rng = np.random.default_rng(p)
+    x = rng.standard_normal(p) + 1j * rng.standard_normal(p)
+    U = np.array([x[t] + x[p - t] for t in range(1, h + 1)])          # rows t = 1 .. h
+    V = np.array([x[t] - x[p - t] for t in range(1, h + 1)])
+    X = np.zeros(p, complex)
+    lanes = np.arange(32)
+    for mt in range(MT):
+        Pm = np.zeros(8, complex)
+        Qm = np.zeros(8, complex)
+        for kt in range(KT):
+            A_c = np.zeros((8, 4)); A_s = np.zeros((8, 4))
+            A_c[lanes // 4, lanes % 4] = tab[mt, kt, 0]
+            A_s[lanes // 4, lanes % 4] = tab[mt, kt, 1]
+            t = 4 * kt + np.arange(4)
+            ok = t < h
+            bu = np.where(ok, U[np.minimum(t, h - 1)], 0.)
+            bv = np.where(ok, V[np.minimum(t, h - 1)], 0.)
+            Pm += A_c @ bu
+            Qm += A_s @ bv
+        for r in range(8):
+            b = 8 * mt + r
+            if b > h:
+                assert abs(Pm[r]) == 0. and abs(Qm[r]) == 0.          # padded rows are exact zeros
+                continue
+            X[b] = x[0] + Pm[r] - 1j * Qm[r]
+            if b:
+                X[p - b] = x[0] + Pm[r] + 1j * Qm[r]
+    want = np.fft.fft(x)
+    assert np.abs(X - want).max() <= 1e-13 * np.abs(want).max()
