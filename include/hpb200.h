@@ -381,10 +381,14 @@ int hpb_measure_fp64_peak(int device, int reps, double *tflops);
 /* behaviour switches of the kernels (A/B measurements and cross-checks; the library never reads the
  * host's environment): "pdl" (programmatic dependent launch, process-wide, ctx may be NULL),
  * "generic" (generic-order kernels for the default order too), "order" (bit mask: which particle
- * kernels use the pass-interleaved thread map), "expl_variant", "push_variant", "fft_variant",
- * "mg_wide", "mg_fuse" (launch geometry variants), "poisson_impl" (1: the measurement arm that runs
- * the reference's FFTPoissonSolverDirichletFast sequence on cuFFT, csrc/ref_gpu_arm.cu).  Unknown keys
- * return HPB_ERR_ARG. */
+ * kernels use the pass-interleaved thread map), "expl_variant", "push_variant" (launch geometry /
+ * staging variants of the particle kernels), "fft_variant" (0: 5 CTAs per SM + the tensor-core prime
+ * stage, 1: 6 CTAs per SM, 2: 6 CTAs per SM + the scalar prime stage), "mg_wide", "mg_fuse", "mg_rotate"
+ * (level-0 buffer rotation, no final copy), "mg_lean" (lean interior-tile path of the tile smoother),
+ * "mg_persist" (1 / 2: the mid levels of a V-cycle in one persistent launch, cooperative / plain --
+ * measured slower, off), "poisson_impl" (1: the measurement arm that runs the reference's
+ * FFTPoissonSolverDirichletFast sequence on cuFFT, csrc/ref_gpu_arm.cu).  All variants give the same
+ * results (the mg_* ones bit-identical).  Unknown keys return HPB_ERR_ARG. */
 int hpb_set_option(hpb_ctx *ctx, const char *key, double value);
 int hpb_advance_plasma_particles_and_deposit(hpb_ctx *ctx, hpb_plasma pl, hpb_slice sl,
                                              double charge, double mass, int n_subcycles,
