@@ -308,6 +308,10 @@ int launch_rows(hpb_ctx *ctx, const Src &src, const OutPtrs &out, long out_rs, i
     // 0.138 -> 0.129 ms (profiles/r02/r02F_tune.txt).  With the scalar prime stage the kernel was bound by the
     // shared-memory pipe and 6 CTAs / SM (40 registers, two waves of 148 x 6 for the 1536 row pairs of a
     // 1024^2 batch) measured best: fft_variant 1 keeps that geometry, 2 also the scalar stage.
+    // long Bluestein transforms (M >= 2048: 2 x 64 KB and more of shared memory, one CTA per SM): 1024 threads
+    // per row pair instead of 256 -- the only parallelism an SM has then is inside its one CTA
+    // (2048^2, M = 4096: the configs[4] shape; fft_variant 3 keeps 256 threads for the A/B)
+    if (ctx->fftM >= 2048 && variant != 3) return launch_rows_v<Src, 1024, 1>(ctx, src, out, out_rs, nbatch, scale);
     if (variant == 1 || variant == 2) return launch_rows_v<Src, kFftThreads, 6>(ctx, src, out, out_rs, nbatch, scale);
     return launch_rows_v<Src, kFftThreads, 5>(ctx, src, out, out_rs, nbatch, scale);
 }
